@@ -1,0 +1,206 @@
+/*
+ * evp_b200.h -- C ABI of the B200-native EVP momentum subcycle for MPAS-Seaice.
+ *
+ * Drop-in boundary: the body of subroutine subcycle_velocity_solver
+ * (reference: src/shared/mpas_seaice_velocity_solver.F:2404-2464) and the device-residency
+ * lifecycle the reference already has in module seaice_mesh_pool
+ * (src/shared/mpas_seaice_mesh_pool.F:76-177 create, :261-281 update, :188-250 destroy).
+ * The Fortran host binds these symbols with ISO_C_BINDING (fortran/seaice_evp_b200.F90,
+ * INTEGRATION.md); nothing here mentions torch, C++ or CUDA types.
+ *
+ * Conventions for every array argument (what c_loc() of an MPAS pool array gives):
+ *   - contiguous, Fortran column-major, first dimension maxEdges / vertexDegree;
+ *   - index VALUES are 1-based; an invalid neighbour is any value outside 1..n (MPAS uses n+1);
+ *   - cell arrays hold at least nCells (owned + halo) columns, vertex arrays at least nVertices
+ *     entries; the MPAS junk element n+1 may be present and is never dereferenced;
+ *   - the library copies what it needs during the call and never keeps or frees a host pointer.
+ *
+ * Every function returns 0 on success, non-zero on error (EVP_ERR_*); evp_last_error_string()
+ * gives the text.  No function throws.  One handle <-> one GPU <-> one rank (block); a handle is not
+ * re-entrant, matching the single main thread of an MPAS rank (mesh_pool.F:98-105).
+ */
+#ifndef EVP_B200_H
+#define EVP_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct evp_handle evp_handle;
+
+enum {
+    EVP_OK = 0,
+    EVP_ERR_ARGUMENT = 1,     /* NULL / out-of-range / unsupported combination */
+    EVP_ERR_CUDA = 2,         /* a CUDA runtime call failed (no device, OOM, launch failure) */
+    EVP_ERR_NCCL = 3,         /* NCCL missing or a NCCL call failed */
+    EVP_ERR_STATE = 4         /* call order violated (e.g. run before update_step) */
+};
+
+/* config_constitutive_relation_type
+ * (src/shared/mpas_seaice_velocity_solver_constitutive_relation.F:34-38) */
+enum { EVP_CR_EVP = 1, EVP_CR_EVP_REVISED = 2, EVP_CR_LINEAR = 3, EVP_CR_NONE = 4 };
+/* config_ocean_stress_type (src/shared/mpas_seaice_velocity_solver.F:55-57) */
+enum { EVP_OCEAN_QUADRATIC = 1, EVP_OCEAN_LINEAR = 2 };
+/* vertexBoundaryType (src/shared/mpas_seaice_special_boundaries.F:35-39) */
+enum { EVP_VB_NONE = 0, EVP_VB_PERIODIC = 1, EVP_VB_REVERSE = 2, EVP_VB_ZERO = 3 };
+
+/* evp_options.flags */
+enum {
+    EVP_FLAG_PIN_HOST = 1     /* host arrays passed to update_step / fetch live at stable addresses for the
+                                 life of the handle (true for MPAS pool arrays): page-lock them once with
+                                 cudaHostRegister so the per-step copies run at full PCIe speed */
+};
+
+/* Static description of one block: the variable list of module seaice_mesh_pool
+ * (mesh_pool.F:23-57, :146-171) plus variationalDenominator (passed as an argument at
+ * velocity_solver.F:2852) and the special-boundary maps (special_boundaries.F:295-296). */
+typedef struct {
+    int nCells;              /* owned + halo: loop bound of the strain / stress loops (variational.F:633,860) */
+    int nCellsSolve;         /* owned cells (informational) */
+    int nVertices;           /* owned + halo */
+    int nVerticesSolve;      /* owned: loop bound of divergence / drag / solve (variational.F:1135) */
+    int maxEdges;            /* 4, 6 or 8 supported (7 is handled by the 8 instantiation) */
+    int vertexDegree;        /* 3 or 4 */
+    const int *nEdgesOnCell;             /* (nCells) */
+    const int *verticesOnCell;           /* (maxEdges, nCells) */
+    const int *cellsOnVertex;            /* (vertexDegree, nVertices) */
+    const int *cellVerticesAtVertex;     /* (vertexDegree, nVertices); 0 = vertex not in that cell */
+    const double *basisGradientU;        /* (maxEdges, maxEdges, nCells)  (iBasisVertex, iGradientVertex, iCell) */
+    const double *basisGradientV;
+    const double *basisIntegralsU;       /* (maxEdges, maxEdges, nCells)  (iStressVertex, iVelocityVertex, iCell) */
+    const double *basisIntegralsV;
+    const double *basisIntegralsMetric;
+    const double *tanLatVertexRotatedOverRadius; /* (nVertices) */
+    const double *variationalDenominator;        /* (nVertices) */
+    const int *vertexBoundaryType;        /* (nVertices) or NULL when special boundaries are off */
+    const int *vertexBoundarySourceLocal; /* (nVertices) or NULL */
+} evp_mesh_desc;
+
+/* Namelist options that shape the subcycle (src/Registry.xml:566-647) and the scalars of
+ * seaice_init_evp (constitutive_relation.F:125,154-162). */
+typedef struct {
+    int constitutive_relation_type;           /* EVP_CR_*  */
+    int ocean_stress_type;                    /* EVP_OCEAN_* */
+    int use_ocean_stress;                     /* config_use_ocean_stress */
+    int use_special_boundaries_velocity;      /* config_use_special_boundaries_velocity */
+    int device;                               /* CUDA device ordinal, -1 = current device */
+    int flags;                                /* EVP_FLAG_* */
+    double elasticTimeStep;                   /* velocity_solver.F:157 */
+    double dynamicsTimeStep;                  /* velocity_solver.F:155 */
+    double dampingTimescale;                  /* constitutive_relation.F:125 */
+    double numericalInertiaCoefficient;       /* constitutive_relation.F:159 (evp_revised only) */
+} evp_options;
+
+/* Per-dynamics-step inputs: what seaice_mesh_pool_update refreshes (mesh_pool.F:269-278) plus the
+ * vertex fields read by ocean_stress_coefficient / solve_velocity that the reference kept on the
+ * host (velocity_solver.F:3036-3042, 3152-3167).  All (nVertices) / (nCells) / (maxEdges, nCells). */
+typedef struct {
+    const int *solveStress;               /* (nCells) */
+    const int *solveVelocity;             /* (nVertices) */
+    const double *icePressure;            /* (nCells) */
+    const double *uVelocity;              /* (nVertices) */
+    const double *vVelocity;
+    const double *stress11;               /* (maxEdges, nCells) */
+    const double *stress22;
+    const double *stress12;
+    const double *totalMassVertex;        /* (nVertices) */
+    const double *totalMassVertexfVertex;
+    const double *iceAreaVertex;
+    const double *airStressVertexU;
+    const double *airStressVertexV;
+    const double *surfaceTiltForceU;
+    const double *surfaceTiltForceV;
+    const double *oceanStressU;
+    const double *oceanStressV;
+    const double *uOceanVelocityVertex;
+    const double *vOceanVelocityVertex;
+    const double *uVelocityInitial;       /* evp_revised only, else may be NULL */
+    const double *vVelocityInitial;
+} evp_step_fields;
+
+/* Outputs consumed by velocity_solver_post_subcycle (velocity_solver.F:3360-3380) and by the
+ * restart stream (src/Registry.xml:1937-1957).  Any pointer may be NULL (= not wanted). */
+typedef struct {
+    double *uVelocity;                    /* (nVertices) */
+    double *vVelocity;
+    double *stress11;                     /* (maxEdges, nCells) */
+    double *stress22;
+    double *stress12;
+    double *strain11;                     /* (maxEdges, nCells): strain of the LAST subcycle */
+    double *strain22;
+    double *strain12;
+    double *replacementPressure;          /* (maxEdges, nCells) */
+    double *stressDivergenceU;            /* (nVertices) */
+    double *stressDivergenceV;
+    double *oceanStressCoeff;             /* (nVertices) */
+} evp_out_fields;
+
+/* seaice_mesh_pool_create equivalent.  Must be called AFTER seaice_init_velocity_solver filled the
+ * basis arrays (initialize.F:121).  The five basis pointers may all be NULL if
+ * evp_precompute_wachspress() is going to fill them on the device. */
+int evp_create(evp_handle **handle, const evp_mesh_desc *mesh, const evp_options *options);
+
+/* Change the scalars / switches without rebuilding the mesh (e.g. config_dt changed). */
+int evp_set_options(evp_handle *handle, const evp_options *options);
+
+/* Device version of seaice_init_velocity_solver_wachspress
+ * (src/shared/mpas_seaice_velocity_solver_wachspress.F:46-161) writing straight into the device layout.
+ * xLocal, yLocal: (maxEdges, nCells) from seaice_calc_local_coords.  integrationType 0 = dunavant
+ * (orders 1..8), 1 = trapezoidal.  Bit-identical to the FP64 non-FMA evaluation of the reference formulas. */
+int evp_precompute_wachspress(evp_handle *handle, const double *xLocal, const double *yLocal,
+                              int integrationType, int integrationOrder);
+
+/* Copy the basis arrays back to host arrays in the Registry layout (any pointer may be NULL). */
+int evp_fetch_basis(evp_handle *handle, double *basisGradientU, double *basisGradientV,
+                    double *basisIntegralsU, double *basisIntegralsV, double *basisIntegralsMetric);
+
+/* seaice_mesh_pool_update equivalent: upload one dynamics step's inputs. */
+int evp_update_step(evp_handle *handle, const evp_step_fields *fields);
+
+/* Replace the masks by the special-boundary masks (seaice_set_special_boundaries_velocity_masks,
+ * special_boundaries.F:345-401).  Optional. */
+int evp_set_masks(evp_handle *handle, const int *solveStress, const int *solveVelocity);
+
+/* subcycle_velocity_solver: nSubcycles x (strain -> stress -> divergence -> drag -> solve -> halo),
+ * special boundaries before the loop and after every subcycle.  Asynchronous on the handle's
+ * stream; evp_fetch / evp_synchronize block. */
+int evp_run_subcycles(evp_handle *handle, int nSubcycles);
+
+int evp_synchronize(evp_handle *handle);
+
+/* Blocking copy of the results into host arrays. */
+int evp_fetch(evp_handle *handle, const evp_out_fields *out);
+
+/* seaice_mesh_pool_destroy equivalent. */
+int evp_destroy(evp_handle *handle);
+
+const char *evp_last_error_string(void);
+
+/* ---- multi-GPU: the per-subcycle uVelocity/vVelocity halo exchange (velocity_solver.F:2543-2584) ----
+ * One rank per GPU.  Exchange lists come from the host's decomposition (in MPAS: the
+ * mpas_dmpar exchange lists of the 'velocityHaloExchangeGroup', velocity_solver.F:259-349):
+ * for neighbour k, sendIndex[sendOffset[k] .. sendOffset[k+1]) are the local 1-based owned vertices
+ * whose (u,v) this rank sends to rank neighbourRank[k]; recvIndex likewise are the local halo
+ * vertices filled from that rank, in the sender's send order. */
+int evp_comm_get_unique_id(char *id128);   /* rank 0 calls this, host broadcasts the 128 bytes (MPI_Bcast) */
+int evp_comm_init(evp_handle *handle, int rank, int nRanks, const char *id128);
+int evp_set_halo(evp_handle *handle, int nNeighbours, const int *neighbourRank,
+                 const int *sendOffset, const int *sendIndex,
+                 const int *recvOffset, const int *recvIndex);
+
+/* ---- instrumentation (bench.py, tests) ---- */
+/* Time of the last evp_run_subcycles in milliseconds (CUDA events on the handle's stream). */
+int evp_last_run_ms(evp_handle *handle, float *ms);
+/* Number of kernel launches (graph kernel nodes) one evp_run_subcycles(nSubcycles) issues. */
+int evp_launch_count(evp_handle *handle, int nSubcycles, int *count);
+/* Raw stream / device pointers for profiling harnesses; not needed by the Fortran host. */
+int evp_get_stream(evp_handle *handle, void **cudaStream);
+/* Bytes of device memory owned by the handle. */
+int evp_device_bytes(evp_handle *handle, unsigned long long *bytes);
+/* Use (1, default) or bypass (0) CUDA-graph replay of the subcycle loop. */
+int evp_set_use_graph(evp_handle *handle, int useGraph);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVP_B200_H */

@@ -1,0 +1,112 @@
+// evp_internal.cuh -- handle layout and helpers shared by the translation units of libevp_b200.so.
+//
+// Device data layout (all SoA, the cell / vertex index is the FASTEST dimension so that a warp
+// of 32 consecutive cells reads 32 consecutive elements of every array):
+//
+//   G    [j][i][c] double2 = (basisGradientU(i,j,c), basisGradientV(i,j,c))      16*M*M B / cell
+//   Suv  [j][i][c] double2 = (basisIntegralsU(i,j,c), basisIntegralsV(i,j,c))    16*M*M B / cell
+//   Sm   [j][i][c] double  =  basisIntegralsMetric(i,j,c)                         8*M*M B / cell
+//   sig  [i][c]    double2 = (stress11(i,c), stress22(i,c));  sig12[i][c] double
+//   contrib[j][c]  double2 = per-cell partial sums (stressDivergenceUCell, stressDivergenceVCell)
+//                            of reference variational.F:1151-1173 for velocity vertex slot j
+//   voc  [i][c]    int     = verticesOnCell(i,c)-1
+//   uv   [v]       double2 = (uVelocity(v), vVelocity(v))
+//   vertex fields are packed in double2 pairs (U,V) / (mass, mass*f) / (iceArea, denominator).
+//
+// c strides are padded to a multiple of 64 elements (nCp, nVp) so every row starts 512-B aligned.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/evp_b200.h"
+
+void evp_set_error(const char *fmt, ...);
+
+#define EVP_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            evp_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return EVP_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+#define EVP_REQUIRE(cond, msg)                                     \
+    do {                                                           \
+        if (!(cond)) {                                             \
+            evp_set_error("%s:%d: %s", __FILE__, __LINE__, msg);   \
+            return EVP_ERR_ARGUMENT;                               \
+        }                                                          \
+    } while (0)
+
+struct evp_halo;  // evp_halo.cu
+
+struct evp_dev {
+    // static
+    uint8_t *nEdges = nullptr;
+    int *voc = nullptr;
+    double2 *G = nullptr, *Suv = nullptr;
+    double *Sm = nullptr;
+    double *tanLat = nullptr;
+    int *gidx = nullptr;          // [D][nVp] index into contrib (j*nCp + c) or -1
+    // per step
+    uint8_t *solveStress = nullptr, *solveVel = nullptr;
+    double *P = nullptr;
+    double2 *uv = nullptr, *sig = nullptr, *contrib = nullptr;
+    double *sig12 = nullptr;
+    double2 *massf = nullptr, *air = nullptr, *tilt = nullptr, *ocnStress = nullptr, *ocnVel = nullptr;
+    double2 *areaDen = nullptr;   // (iceAreaVertex, variationalDenominator)
+    double2 *uvInit = nullptr;
+    // outputs of the last subcycle
+    double *e11 = nullptr, *e22 = nullptr, *e12 = nullptr, *repP = nullptr;
+    double2 *sdiv = nullptr;
+    double *ocoef = nullptr;
+    // special boundaries (resolved to pre-loop sources, see evp_abi.cu)
+    int nSB = 0;
+    int *sbDst = nullptr, *sbSrc = nullptr;
+    double *sbSign = nullptr;
+    double2 *sbTmp = nullptr;
+    // staging
+    void *stage = nullptr;
+    size_t stageBytes = 0;
+};
+
+struct evp_handle {
+    int device = 0;
+    int nCells = 0, nCellsSolve = 0, nVertices = 0, nVerticesSolve = 0, D = 0;
+    int Mh = 0;                   // maxEdges of the host arrays
+    int M = 0;                    // slots per cell of the device layout / kernel instantiation (4, 6 or 8)
+    size_t nCp = 0, nVp = 0;
+    evp_options opt{};
+    bool metric = false;          // any tanLatVertexRotatedOverRadius != 0
+    bool haveBasis = false, haveStep = false, haveSB = false, useGraph = true, pinHost = false, timed = false;
+    evp_dev d;
+    cudaStream_t stream = nullptr, commStream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaGraphExec_t graphExec = nullptr;
+    int graphN = -1;
+    float lastMs = 0.f;
+    unsigned long long devBytes = 0;
+    std::vector<void *> allocs;
+    std::vector<void *> pinned;   // host ranges registered with cudaHostRegister
+    void *pinStage[2] = {nullptr, nullptr};
+    cudaEvent_t pinEv[2] = {nullptr, nullptr};
+    int pinNext = 0;
+    evp_halo *halo = nullptr;
+};
+
+// evp_kernels.cu
+int evp_enqueue_subcycles(evp_handle *h, int nSub, cudaStream_t s);
+int evp_count_launches(evp_handle *h, int nSub);
+int evp_enqueue_cell_pass(evp_handle *h, bool diag, cudaStream_t s);
+int evp_enqueue_vertex_pass(evp_handle *h, bool diag, cudaStream_t s);
+int evp_enqueue_special_boundaries(evp_handle *h, cudaStream_t s);
+
+// evp_halo.cu
+int evp_halo_enqueue(evp_handle *h, cudaStream_t s);
+int evp_halo_launches(evp_handle *h);
+void evp_halo_destroy(evp_handle *h);
+
+// layout kernels (evp_abi.cu)
+int evp_dev_alloc(evp_handle *h, void **p, size_t bytes);

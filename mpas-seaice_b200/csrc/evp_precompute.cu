@@ -1,0 +1,297 @@
+// evp_precompute.cu -- device version of seaice_init_velocity_solver_wachspress
+// (reference: src/shared/mpas_seaice_velocity_solver_wachspress.F:46-161): Wachspress coefficients
+// (:535-614), basis gradients at the cell vertices (:1083-1206) and the basis integrals by
+// sub-triangle quadrature (:179-467), written straight into the SoA device layout.
+//
+// One thread per cell.  Compiled with --fmad=false and written in the reference's operation order, so
+// the result is bit-identical to an FP64 non-FMA CPU evaluation (checked against the oracle in
+// tests/test_gpu_parity.py).  At 10.5 M cells this replaces ~15 GB of host->device traffic and minutes
+// of host time by well under a second of device time.
+#include "evp_internal.cuh"
+
+namespace {
+
+constexpr int QMAX = 64;
+__constant__ double cQu[QMAX], cQv[QMAX], cQw[QMAX];
+
+// Quadrature tables: D. A. Dunavant, Int. J. Num. Meth. Engng 21 (1985) 1129-1148, with the
+// reference's truncated literals (wachspress.F:1441-1597) -- the digits must not be "improved".
+struct Rule { int n; double norm; double u[QMAX], v[QMAX], w[QMAX]; };
+
+int make_rule(int type, int order, Rule &r)
+{
+    if (type == 1) {   // trapezoidal (wachspress.F:1301-1387)
+        const int nT = order;
+        const int np = ((nT + 1) * (nT + 1) + (nT + 1)) / 2;
+        if (nT < 1 || np > QMAX) return 1;
+        r.n = np;
+        int ij = 0;
+        for (int i = 0; i <= nT; i++)
+            for (int j = 0; j <= nT - i; j++) {
+                r.u[ij] = (double)i / (double)nT;
+                r.v[ij] = (double)j / (double)nT;
+                double w = 0.0;
+                if (i <= nT - j) {
+                    if (i == nT || j == nT || (i == 0 && j == 0)) w = 1.0;
+                    else if ((j == 0 && i != 0 && i != nT) || (i == 0 && j != 0 && j != nT) ||
+                             (i == nT - j && i != 0 && j != 0)) w = 3.0;
+                    else w = 6.0;
+                }
+                r.w[ij++] = w;
+            }
+        r.norm = 6.0 * ((double)nT * (double)nT);
+        return 0;
+    }
+    if (type != 0) return 1;
+    r.norm = 2.0;
+    // each rule: a list of (u, v, w) triplets
+    static const double d1[] = {0.33333333333333, 0.33333333333333, 1.00000000000000};
+    static const double d2[] = {0.16666666666667, 0.16666666666667, 0.33333333333333,
+                                0.16666666666667, 0.66666666666667, 0.33333333333333,
+                                0.66666666666667, 0.16666666666667, 0.33333333333333};
+    static const double d3[] = {0.33333333333333, 0.33333333333333, -0.56250000000000,
+                                0.20000000000000, 0.20000000000000, 0.52083333333333,
+                                0.20000000000000, 0.60000000000000, 0.52083333333333,
+                                0.60000000000000, 0.20000000000000, 0.52083333333333};
+    static const double d4[] = {0.44594849091597, 0.44594849091597, 0.22338158967801,
+                                0.44594849091597, 0.10810301816807, 0.22338158967801,
+                                0.10810301816807, 0.44594849091597, 0.22338158967801,
+                                0.09157621350977, 0.09157621350977, 0.10995174365532,
+                                0.09157621350977, 0.81684757298046, 0.10995174365532,
+                                0.81684757298046, 0.09157621350977, 0.10995174365532};
+    static const double d5[] = {0.33333333333333, 0.33333333333333, 0.22500000000000,
+                                0.47014206410511, 0.47014206410511, 0.13239415278851,
+                                0.47014206410511, 0.05971587178977, 0.13239415278851,
+                                0.05971587178977, 0.47014206410511, 0.13239415278851,
+                                0.10128650732346, 0.10128650732346, 0.12593918054483,
+                                0.10128650732346, 0.79742698535309, 0.12593918054483,
+                                0.79742698535309, 0.10128650732346, 0.12593918054483};
+    static const double d6[] = {0.24928674517091, 0.24928674517091, 0.11678627572638,
+                                0.24928674517091, 0.50142650965818, 0.11678627572638,
+                                0.50142650965818, 0.24928674517091, 0.11678627572638,
+                                0.06308901449150, 0.06308901449150, 0.05084490637021,
+                                0.06308901449150, 0.87382197101700, 0.05084490637021,
+                                0.87382197101700, 0.06308901449150, 0.05084490637021,
+                                0.31035245103378, 0.63650249912140, 0.08285107561837,
+                                0.63650249912140, 0.05314504984482, 0.08285107561837,
+                                0.05314504984482, 0.31035245103378, 0.08285107561837,
+                                0.63650249912140, 0.31035245103378, 0.08285107561837,
+                                0.31035245103378, 0.05314504984482, 0.08285107561837,
+                                0.05314504984482, 0.63650249912140, 0.08285107561837};
+    static const double d7[] = {0.33333333333333, 0.33333333333333, -0.14957004446768,
+                                0.26034596607904, 0.26034596607904, 0.17561525743321,
+                                0.26034596607904, 0.47930806784192, 0.17561525743321,
+                                0.47930806784192, 0.26034596607904, 0.17561525743321,
+                                0.06513010290222, 0.06513010290222, 0.05334723560884,
+                                0.06513010290222, 0.86973979419557, 0.05334723560884,
+                                0.86973979419557, 0.06513010290222, 0.05334723560884,
+                                0.31286549600487, 0.63844418856981, 0.07711376089026,
+                                0.63844418856981, 0.04869031542532, 0.07711376089026,
+                                0.04869031542532, 0.31286549600487, 0.07711376089026,
+                                0.63844418856981, 0.31286549600487, 0.07711376089026,
+                                0.31286549600487, 0.04869031542532, 0.07711376089026,
+                                0.04869031542532, 0.63844418856981, 0.07711376089026};
+    static const double d8[] = {0.33333333333333, 0.33333333333333, 0.14431560767779,
+                                0.45929258829272, 0.45929258829272, 0.09509163426728,
+                                0.45929258829272, 0.08141482341455, 0.09509163426728,
+                                0.08141482341455, 0.45929258829272, 0.09509163426728,
+                                0.17056930775176, 0.17056930775176, 0.10321737053472,
+                                0.17056930775176, 0.65886138449648, 0.10321737053472,
+                                0.65886138449648, 0.17056930775176, 0.10321737053472,
+                                0.05054722831703, 0.05054722831703, 0.03245849762320,
+                                0.05054722831703, 0.89890554336594, 0.03245849762320,
+                                0.89890554336594, 0.05054722831703, 0.03245849762320,
+                                0.26311282963464, 0.72849239295540, 0.02723031417443,
+                                0.72849239295540, 0.00839477740996, 0.02723031417443,
+                                0.00839477740996, 0.26311282963464, 0.02723031417443,
+                                0.72849239295540, 0.26311282963464, 0.02723031417443,
+                                0.26311282963464, 0.00839477740996, 0.02723031417443,
+                                0.00839477740996, 0.72849239295540, 0.02723031417443};
+    const double *tabs[] = {nullptr, d1, d2, d3, d4, d5, d6, d7, d8};
+    const int counts[] = {0, 1, 3, 4, 6, 7, 12, 13, 16};
+    if (order < 1 || order > 8) return 1;
+    r.n = counts[order];
+    for (int k = 0; k < r.n; k++) {
+        r.u[k] = tabs[order][3 * k];
+        r.v[k] = tabs[order][3 * k + 1];
+        r.w[k] = tabs[order][3 * k + 2];
+    }
+    return 0;
+}
+
+template <int M>
+struct WCell {
+    int n;
+    double x[M], y[M], A[M], B[M], kappa[M];
+};
+
+__device__ __forceinline__ int wrap1(int input, int n)   // seaice_wrapped_index, 1-based
+{
+    int m = (input - 1) % n;
+    if (m < 0) m += n;
+    return m + 1;
+}
+
+// numerators (wachspress.F:864-925), their derivatives (:939-1035), then all basis functions
+// (:682-749) and derivatives (:763-850) at one point.  kappa(j,i) of the reference does not depend
+// on i, so the numerators are shared by all basis indices.
+template <int M>
+__device__ void eval_all(const WCell<M> &c, double x, double y, double *phi, double *dpx, double *dpy)
+{
+    const int n = c.n;
+    double num[M], dnx[M], dny[M], e[M];
+    double denominator = 0.0, sdx = 0.0, sdy = 0.0;
+    for (int k = 0; k < n; k++) e[k] = 1.0 - c.A[k] * x - c.B[k] * y;     // wachspress_edge_equation (:1049-1069)
+    for (int j = 1; j <= n; j++) {
+        const int i1 = j, i2 = wrap1(j + 1, n);
+        int sub[M], ns = 0;
+        for (int k = 1; k <= n; k++)
+            if (k != i1 && k != i2) sub[ns++] = k - 1;                    // wachspress_indexes (:628-668)
+        double numerator = 1.0;
+        for (int k = 0; k < ns; k++) numerator = numerator * e[sub[k]];
+        numerator = numerator * c.kappa[j - 1];
+        num[j - 1] = numerator;
+        denominator = denominator + numerator;
+        double spx = 0.0, spy = 0.0;
+        for (int k = 0; k < ns; k++) {
+            double px = 1.0, py = 1.0;
+            for (int l = 0; l < k; l++) { px = px * e[sub[l]]; py = py * e[sub[l]]; }
+            px = px * (-c.A[sub[k]]);
+            py = py * (-c.B[sub[k]]);
+            for (int l = k + 1; l < ns; l++) { px = px * e[sub[l]]; py = py * e[sub[l]]; }
+            spx = spx + px;
+            spy = spy + py;
+        }
+        dnx[j - 1] = spx * c.kappa[j - 1];
+        dny[j - 1] = spy * c.kappa[j - 1];
+        sdx = sdx + dnx[j - 1];
+        sdy = sdy + dny[j - 1];
+    }
+    for (int i = 0; i < n; i++) {
+        if (phi) phi[i] = num[i] / denominator;
+        dpx[i] = dnx[i] / denominator - (num[i] / (denominator * denominator)) * sdx;
+        dpy[i] = dny[i] / denominator - (num[i] / (denominator * denominator)) * sdy;
+    }
+}
+
+template <int M>
+__global__ void __launch_bounds__(64) k_wachspress(int nCells, size_t nCp, int Mh, const uint8_t *__restrict__ nEdges,
+                                                    const double *__restrict__ xl, const double *__restrict__ yl,
+                                                    int nq, double norm, double2 *__restrict__ G,
+                                                    double2 *__restrict__ Suv, double *__restrict__ Sm)
+{
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= nCells) return;
+    const int n = nEdges[cell];
+    if (n < 3 || n > M) return;
+    WCell<M> c;
+    c.n = n;
+    for (int i = 0; i < n; i++) { c.x[i] = xl[(size_t)Mh * cell + i]; c.y[i] = yl[(size_t)Mh * cell + i]; }
+    // calc_wachspress_coefficients (:535-614)
+    for (int iv = 1; iv <= n; iv++) {
+        int i1 = iv - 1, i2 = iv;
+        if (i1 < 1) i1 = i1 + n;
+        const double den = c.x[i1 - 1] * c.y[i2 - 1] - c.x[i2 - 1] * c.y[i1 - 1];
+        c.A[iv - 1] = (c.y[i2 - 1] - c.y[i1 - 1]) / den;
+        c.B[iv - 1] = (c.x[i1 - 1] - c.x[i2 - 1]) / den;
+    }
+    c.kappa[0] = 1.0;
+    for (int j = 2; j <= n; j++) {
+        int i0 = j - 1, i1 = j, i2 = j + 1;
+        if (i2 > n) i2 = i2 - n;
+        c.kappa[j - 1] = c.kappa[j - 2] *
+            (c.A[i2 - 1] * (c.x[i0 - 1] - c.x[i1 - 1]) + c.B[i2 - 1] * (c.y[i0 - 1] - c.y[i1 - 1])) /
+            (c.A[i0 - 1] * (c.x[i1 - 1] - c.x[i0 - 1]) + c.B[i0 - 1] * (c.y[i1 - 1] - c.y[i0 - 1]));
+    }
+    // gradients at the vertices: kept only for iGradientVertex in {i-1, i, i+1} (:1178-1191)
+    for (int jg = 1; jg <= n; jg++) {
+        double dx[M], dy[M];
+        eval_all<M>(c, c.x[jg - 1], c.y[jg - 1], nullptr, dx, dy);
+        for (int ib = 1; ib <= n; ib++) {
+            double2 g = make_double2(0.0, 0.0);
+            if (jg == ib || jg == wrap1(ib - 1, n) || jg == wrap1(ib + 1, n)) g = make_double2(dx[ib - 1], dy[ib - 1]);
+            G[(size_t)((jg - 1) * M + (ib - 1)) * nCp + cell] = g;
+        }
+    }
+    // integrals (:304-467): per pair (iStress, iVelocity): sum over sub-triangles of (sum over points) / norm
+    double bU[M][M], bV[M][M], bM[M][M];     // [iVel][iStr]
+    for (int a = 0; a < n; a++)
+        for (int b = 0; b < n; b++) { bU[a][b] = 0.0; bV[a][b] = 0.0; bM[a][b] = 0.0; }
+    for (int s = 1; s <= n; s++) {
+        const int i1 = s, i2 = wrap1(s + 1, n);
+        // get_triangle_mapping (:485-517) with (x1,y1) = (1,0), (x2,y2) = (0,1)
+        const double x1 = 1.0, y1 = 0.0, x2 = 0.0, y2 = 1.0;
+        const double u1 = c.x[i1 - 1], v1 = c.y[i1 - 1], u2 = c.x[i2 - 1], v2 = c.y[i2 - 1];
+        const double m11 = (u2 * y1 - u1 * y2) / (x2 * y1 - x1 * y2);
+        const double m12 = (u1 * x2 - u2 * x1) / (y1 * x2 - y2 * x1);
+        const double m21 = (v2 * y1 - v1 * y2) / (x2 * y1 - x1 * y2);
+        const double m22 = (v1 * x2 - v2 * x1) / (y1 * x2 - y2 * x1);
+        const double jac = m11 * m22 - m12 * m21;
+        double sU[M][M], sV[M][M], sM[M][M];
+        for (int a = 0; a < n; a++)
+            for (int b = 0; b < n; b++) { sU[a][b] = 0.0; sV[a][b] = 0.0; sM[a][b] = 0.0; }
+        for (int p = 0; p < nq; p++) {
+            const double x = m11 * cQu[p] + m12 * cQv[p];
+            const double y = m21 * cQu[p] + m22 * cQv[p];
+            double phi[M], dpx[M], dpy[M];
+            eval_all<M>(c, x, y, phi, dpx, dpy);
+            for (int is = 0; is < n; is++) {
+                const double tmp = jac * cQw[p] * phi[is];
+                for (int iv = 0; iv < n; iv++) {
+                    sU[iv][is] = sU[iv][is] + tmp * dpx[iv];
+                    sV[iv][is] = sV[iv][is] + tmp * dpy[iv];
+                    sM[iv][is] = sM[iv][is] + tmp * phi[iv];
+                }
+            }
+        }
+        for (int a = 0; a < n; a++)
+            for (int b = 0; b < n; b++) {
+                bU[a][b] = bU[a][b] + sU[a][b] / norm;
+                bV[a][b] = bV[a][b] + sV[a][b] / norm;
+                bM[a][b] = bM[a][b] + sM[a][b] / norm;
+            }
+    }
+    for (int iv = 0; iv < n; iv++)
+        for (int is = 0; is < n; is++) {
+            const size_t q = (size_t)(iv * M + is) * nCp + cell;
+            Suv[q] = make_double2(bU[iv][is], bV[iv][is]);
+            Sm[q] = bM[iv][is];
+        }
+}
+
+}  // namespace
+
+extern "C" int evp_precompute_wachspress(evp_handle *h, const double *xLocal, const double *yLocal,
+                                         int integrationType, int integrationOrder)
+{
+    EVP_REQUIRE(h != nullptr && xLocal != nullptr && yLocal != nullptr, "NULL argument");
+    Rule r;
+    if (make_rule(integrationType, integrationOrder, r)) {
+        evp_set_error("unsupported integration rule (type %d, order %d)", integrationType, integrationOrder);
+        return EVP_ERR_ARGUMENT;
+    }
+    EVP_CUDA(cudaSetDevice(h->device));
+    const size_t nC = h->nCells;
+    if (nC == 0) { h->haveBasis = true; return EVP_OK; }
+    const size_t bytes = (size_t)h->Mh * nC * sizeof(double);
+    EVP_REQUIRE(2 * bytes + 512 <= h->d.stageBytes, "staging area too small for the local coordinates");
+    EVP_CUDA(cudaStreamSynchronize(h->stream));
+    EVP_CUDA(cudaMemcpyToSymbolAsync(cQu, r.u, sizeof(double) * r.n, 0, cudaMemcpyHostToDevice, h->stream));
+    EVP_CUDA(cudaMemcpyToSymbolAsync(cQv, r.v, sizeof(double) * r.n, 0, cudaMemcpyHostToDevice, h->stream));
+    EVP_CUDA(cudaMemcpyToSymbolAsync(cQw, r.w, sizeof(double) * r.n, 0, cudaMemcpyHostToDevice, h->stream));
+    double *dx = (double *)h->d.stage;
+    double *dy = (double *)((char *)h->d.stage + ((bytes + 255) & ~(size_t)255));
+    EVP_CUDA(cudaMemcpyAsync(dx, xLocal, bytes, cudaMemcpyHostToDevice, h->stream));
+    EVP_CUDA(cudaMemcpyAsync(dy, yLocal, bytes, cudaMemcpyHostToDevice, h->stream));
+    const int block = 64;
+    const unsigned grid = (unsigned)((nC + block - 1) / block);
+    switch (h->M) {
+    case 4: k_wachspress<4><<<grid, block, 0, h->stream>>>((int)nC, h->nCp, h->Mh, h->d.nEdges, dx, dy, r.n, r.norm, h->d.G, h->d.Suv, h->d.Sm); break;
+    case 6: k_wachspress<6><<<grid, block, 0, h->stream>>>((int)nC, h->nCp, h->Mh, h->d.nEdges, dx, dy, r.n, r.norm, h->d.G, h->d.Suv, h->d.Sm); break;
+    default: k_wachspress<8><<<grid, block, 0, h->stream>>>((int)nC, h->nCp, h->Mh, h->d.nEdges, dx, dy, r.n, r.norm, h->d.G, h->d.Suv, h->d.Sm); break;
+    }
+    EVP_CUDA(cudaGetLastError());
+    EVP_CUDA(cudaStreamSynchronize(h->stream));
+    h->haveBasis = true;
+    return EVP_OK;
+}

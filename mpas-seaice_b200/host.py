@@ -1,0 +1,270 @@
+"""ctypes mirror of the C-ABI (include/evp_b200.h) for hosts written in Python (tests, bench.py).
+
+The Fortran host binds the very same symbols through fortran/seaice_evp_b200.F90; this module is the
+Python spelling of that shim and keeps the reference's names for the lifecycle
+(src/shared/mpas_seaice_mesh_pool.F:76-281, src/shared/mpas_seaice_velocity_solver.F:2404-2464):
+
+    seaice_mesh_pool_create   -> EvpSolver(...)            (evp_create)
+    seaice_mesh_pool_update   -> EvpSolver.update_step     (evp_update_step)
+    subcycle_velocity_solver  -> EvpSolver.run_subcycles   (evp_run_subcycles)
+    seaice_mesh_pool_destroy  -> EvpSolver.destroy         (evp_destroy)
+
+There is NO CPU fallback: if libevp_b200.so is missing or no CUDA device answers, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libevp_b200.so")
+_lib = None
+
+CR = {"evp": 1, "evp_revised": 2, "linear": 3, "none": 4}
+OCEAN = {"quadratic": 1, "linear": 2}
+FLAG_PIN_HOST = 1
+
+EXPORTS = (
+    "evp_create", "evp_set_options", "evp_precompute_wachspress", "evp_fetch_basis", "evp_update_step",
+    "evp_set_masks", "evp_run_subcycles", "evp_synchronize", "evp_fetch", "evp_destroy",
+    "evp_last_error_string", "evp_comm_get_unique_id", "evp_comm_init", "evp_set_halo", "evp_last_run_ms",
+    "evp_launch_count", "evp_get_stream", "evp_device_bytes", "evp_set_use_graph",
+)
+
+
+class EvpError(RuntimeError):
+    pass
+
+
+class MeshDesc(C.Structure):
+    _fields_ = ([(n, C.c_int) for n in ("nCells", "nCellsSolve", "nVertices", "nVerticesSolve", "maxEdges",
+                                        "vertexDegree")]
+                + [(n, C.c_void_p) for n in ("nEdgesOnCell", "verticesOnCell", "cellsOnVertex",
+                                             "cellVerticesAtVertex", "basisGradientU", "basisGradientV",
+                                             "basisIntegralsU", "basisIntegralsV", "basisIntegralsMetric",
+                                             "tanLatVertexRotatedOverRadius", "variationalDenominator",
+                                             "vertexBoundaryType", "vertexBoundarySourceLocal")])
+
+
+class Options(C.Structure):
+    _fields_ = ([(n, C.c_int) for n in ("constitutive_relation_type", "ocean_stress_type", "use_ocean_stress",
+                                        "use_special_boundaries_velocity", "device", "flags")]
+                + [(n, C.c_double) for n in ("elasticTimeStep", "dynamicsTimeStep", "dampingTimescale",
+                                             "numericalInertiaCoefficient")])
+
+
+STEP_FIELDS = ("solveStress", "solveVelocity", "icePressure", "uVelocity", "vVelocity", "stress11", "stress22",
+               "stress12", "totalMassVertex", "totalMassVertexfVertex", "iceAreaVertex", "airStressVertexU",
+               "airStressVertexV", "surfaceTiltForceU", "surfaceTiltForceV", "oceanStressU", "oceanStressV",
+               "uOceanVelocityVertex", "vOceanVelocityVertex", "uVelocityInitial", "vVelocityInitial")
+OUT_FIELDS = ("uVelocity", "vVelocity", "stress11", "stress22", "stress12", "strain11", "strain22", "strain12",
+              "replacementPressure", "stressDivergenceU", "stressDivergenceV", "oceanStressCoeff")
+_CELL2D = {"stress11", "stress22", "stress12", "strain11", "strain22", "strain12", "replacementPressure"}
+
+
+class StepFields(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in STEP_FIELDS]
+
+
+class OutFields(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in OUT_FIELDS]
+
+
+def load_library(path: str | None = None):
+    """dlopen libevp_b200.so; raises EvpError (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise EvpError(f"{p} not found: build it with `make -C {os.path.dirname(p)}` "
+                       f"(or __graft_entry__.build()); there is no CPU fallback")
+    lib = C.CDLL(p)
+    lib.evp_last_error_string.restype = C.c_char_p
+    for name in EXPORTS:
+        getattr(lib, name)  # AttributeError if the ABI drifted
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _ptr(a, dtype):
+    if a is None:
+        return None
+    assert isinstance(a, np.ndarray) and a.dtype == dtype and a.flags["C_CONTIGUOUS"], \
+        f"expected contiguous {dtype} array, got {getattr(a, 'dtype', type(a))}"
+    return a.ctypes.data
+
+
+def make_options(opts: dict, device: int = -1, pin_host: bool = False) -> Options:
+    o = Options()
+    o.constitutive_relation_type = CR[opts.get("constitutive_relation_type", "evp")]
+    o.ocean_stress_type = OCEAN[opts.get("ocean_stress_type", "quadratic")]
+    o.use_ocean_stress = int(opts.get("use_ocean_stress", True))
+    o.use_special_boundaries_velocity = int(opts.get("use_special_boundaries_velocity", False))
+    o.device = device
+    o.flags = FLAG_PIN_HOST if pin_host else 0
+    o.elasticTimeStep = opts["elasticTimeStep"]
+    o.dynamicsTimeStep = opts["dynamicsTimeStep"]
+    o.dampingTimescale = opts["dampingTimescale"]
+    o.numericalInertiaCoefficient = opts.get("numericalInertiaCoefficient", 0.0)
+    return o
+
+
+class EvpSolver:
+    """One handle <-> one GPU <-> one block.  ``mesh`` is a meshgen.Mesh (or any mapping with the
+    Registry mesh fields); ``var`` holds the Registry ``velocity_variational`` static fields
+    (cellVerticesAtVertex, tanLatVertexRotatedOverRadius, variationalDenominator and, unless
+    ``local_coords`` is given, the five basis arrays)."""
+
+    def __init__(self, mesh, var, opts, *, device=-1, pin_host=False, local_coords=None,
+                 integration=("dunavant", 8), special_boundaries=None, n_vertices_solve=None,
+                 n_cells_solve=None):
+        self.lib = load_library()
+        self.nCells, self.nVertices = int(mesh["nCells"]), int(mesh["nVertices"])
+        self.maxEdges, self.vertexDegree = int(mesh["maxEdges"]), int(mesh["vertexDegree"])
+        md = MeshDesc()
+        md.nCells = self.nCells
+        md.nCellsSolve = self.nCells if n_cells_solve is None else int(n_cells_solve)
+        md.nVertices = self.nVertices
+        md.nVerticesSolve = self.nVertices if n_vertices_solve is None else int(n_vertices_solve)
+        md.maxEdges, md.vertexDegree = self.maxEdges, self.vertexDegree
+        keep = []
+
+        def put(name, arr, dtype):
+            keep.append(arr)
+            setattr(md, name, _ptr(arr, dtype))
+
+        put("nEdgesOnCell", mesh["nEdgesOnCell"], np.int32)
+        put("verticesOnCell", mesh["verticesOnCell"], np.int32)
+        put("cellsOnVertex", mesh["cellsOnVertex"], np.int32)
+        put("cellVerticesAtVertex", var["cellVerticesAtVertex"], np.int32)
+        if local_coords is None:
+            for n in ("basisGradientU", "basisGradientV", "basisIntegralsU", "basisIntegralsV",
+                      "basisIntegralsMetric"):
+                put(n, var[n], np.float64)
+        put("tanLatVertexRotatedOverRadius", var["tanLatVertexRotatedOverRadius"], np.float64)
+        put("variationalDenominator", var["variationalDenominator"], np.float64)
+        if special_boundaries is not None:
+            put("vertexBoundaryType", special_boundaries[0], np.int32)
+            put("vertexBoundarySourceLocal", special_boundaries[1], np.int32)
+        self.opts = dict(opts)
+        self._o = make_options(opts, device, pin_host)
+        self._h = C.c_void_p()
+        self._check(self.lib.evp_create(C.byref(self._h), C.byref(md), C.byref(self._o)))
+        if local_coords is not None:
+            xl, yl = local_coords
+            itype = {"dunavant": 0, "trapezoidal": 1}[integration[0]]
+            self._check(self.lib.evp_precompute_wachspress(self._h, C.c_void_p(_ptr(xl, np.float64)),
+                                                           C.c_void_p(_ptr(yl, np.float64)),
+                                                           C.c_int(itype), C.c_int(integration[1])))
+
+    # -- error handling ------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise EvpError(f"libevp_b200 error {rc}: {self.lib.evp_last_error_string().decode()}")
+
+    # -- lifecycle -----------------------------------------------------------------------------
+    def set_options(self, opts, pin_host=None):
+        self.opts = dict(opts)
+        pin = bool(self._o.flags & FLAG_PIN_HOST) if pin_host is None else pin_host
+        self._o = make_options(opts, self._o.device, pin)
+        self._check(self.lib.evp_set_options(self._h, C.byref(self._o)))
+
+    def update_step(self, step):
+        sf = StepFields()
+        self._keep = []
+        for n in STEP_FIELDS:
+            a = step.get(n)
+            dt = np.int32 if n in ("solveStress", "solveVelocity") else np.float64
+            self._keep.append(a)
+            setattr(sf, n, _ptr(a, dt))
+        self._check(self.lib.evp_update_step(self._h, C.byref(sf)))
+
+    def set_masks(self, solve_stress, solve_velocity):
+        self._check(self.lib.evp_set_masks(self._h, C.c_void_p(_ptr(solve_stress, np.int32)),
+                                           C.c_void_p(_ptr(solve_velocity, np.int32))))
+
+    def run_subcycles(self, n):
+        self._check(self.lib.evp_run_subcycles(self._h, C.c_int(int(n))))
+
+    def synchronize(self):
+        self._check(self.lib.evp_synchronize(self._h))
+
+    def fetch(self, into=None, names=OUT_FIELDS):
+        """Blocking copy of the outputs; allocates Registry-shaped arrays unless ``into`` has them."""
+        of = OutFields()
+        out = {} if into is None else into
+        for n in names:
+            a = out.get(n)
+            if a is None:
+                a = np.zeros((self.nCells + 1, self.maxEdges)) if n in _CELL2D else np.zeros(self.nVertices + 1)
+                out[n] = a
+            setattr(of, n, _ptr(a, np.float64))
+        self._check(self.lib.evp_fetch(self._h, C.byref(of)))
+        return out
+
+    def fetch_basis(self):
+        shape = (self.nCells + 1, self.maxEdges, self.maxEdges)
+        arrs = [np.zeros(shape) for _ in range(5)]
+        self._check(self.lib.evp_fetch_basis(self._h, *[C.c_void_p(a.ctypes.data) for a in arrs]))
+        return dict(zip(("basisGradientU", "basisGradientV", "basisIntegralsU", "basisIntegralsV",
+                         "basisIntegralsMetric"), arrs))
+
+    def last_run_ms(self):
+        ms = C.c_float(0)
+        self._check(self.lib.evp_last_run_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self, n):
+        c = C.c_int(0)
+        self._check(self.lib.evp_launch_count(self._h, C.c_int(n), C.byref(c)))
+        return c.value
+
+    def device_bytes(self):
+        b = C.c_ulonglong(0)
+        self._check(self.lib.evp_device_bytes(self._h, C.byref(b)))
+        return b.value
+
+    def set_use_graph(self, flag):
+        self._check(self.lib.evp_set_use_graph(self._h, C.c_int(int(flag))))
+
+    # -- multi-GPU -----------------------------------------------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        lib = load_library()
+        buf = C.create_string_buffer(128)
+        rc = lib.evp_comm_get_unique_id(buf)
+        if rc != 0:
+            raise EvpError(f"libevp_b200 error {rc}: {lib.evp_last_error_string().decode()}")
+        return buf.raw
+
+    def comm_init(self, rank, n_ranks, unique_id: bytes):
+        self._check(self.lib.evp_comm_init(self._h, C.c_int(rank), C.c_int(n_ranks), C.c_char_p(unique_id)))
+
+    def set_halo(self, neighbour_rank, send_offset, send_index, recv_offset, recv_index):
+        arrs = [np.ascontiguousarray(a, dtype=np.int32) for a in
+                (neighbour_rank, send_offset, send_index, recv_offset, recv_index)]
+        self._check(self.lib.evp_set_halo(self._h, C.c_int(len(arrs[0])), *[C.c_void_p(a.ctypes.data) for a in arrs]))
+
+    def destroy(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.evp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    # reference-named aliases
+    seaice_mesh_pool_update = update_step
+    subcycle_velocity_solver = run_subcycles
+    seaice_mesh_pool_destroy = destroy
+
+
+def seaice_mesh_pool_create(mesh, var, opts, **kw) -> EvpSolver:
+    return EvpSolver(mesh, var, opts, **kw)
