@@ -193,6 +193,9 @@ int evp_set_halo(evp_handle *handle, int nNeighbours, const int *neighbourRank,
 int evp_last_run_ms(evp_handle *handle, float *ms);
 /* Number of kernel launches (graph kernel nodes) one evp_run_subcycles(nSubcycles) issues. */
 int evp_launch_count(evp_handle *handle, int nSubcycles, int *count);
+/* Average device time (ms) of the cell kernel, the vertex kernel and the rest (halo + special
+ * boundaries) over nSubcycles un-graphed subcycles; CUDA events on the handle's stream. */
+int evp_profile_passes(evp_handle *handle, int nSubcycles, float *cellMs, float *vertexMs, float *otherMs);
 /* Raw stream / device pointers for profiling harnesses; not needed by the Fortran host. */
 int evp_get_stream(evp_handle *handle, void **cudaStream);
 /* Bytes of device memory owned by the handle. */

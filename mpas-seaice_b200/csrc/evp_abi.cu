@@ -105,6 +105,12 @@ __global__ void k_gidx(const int *__restrict__ cov, const int *__restrict__ cvav
 
 inline unsigned grid_for(size_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
+struct NoPin {   // one-shot transfers (static data, basis read-back) never page-lock caller memory
+    evp_handle *h; bool saved;
+    explicit NoPin(evp_handle *h_) : h(h_), saved(h_->pinHost) { h->pinHost = false; }
+    ~NoPin() { h->pinHost = saved; }
+};
+
 struct Stage {   // bump allocator over the device staging area
     char *base; size_t cap, off;
     void *take(size_t bytes) {
@@ -385,6 +391,7 @@ extern "C" int evp_create(evp_handle **out, const evp_mesh_desc *m, const evp_op
     CUDA_FAIL(cudaMemsetAsync(d.tanLat, 0, sizeof(double) * nVp, h->stream));
 
     // ---- static uploads -------------------------------------------------------------------
+    NoPin noPin(h);
     Stage st{(char *)d.stage, d.stageBytes, 0};
     if (nC > 0) {
         int *rawN = (int *)st.take(nC * 4);
@@ -667,6 +674,7 @@ extern "C" int evp_fetch_basis(evp_handle *h, double *gu, double *gv, double *su
     EVP_REQUIRE(h != nullptr, "handle is NULL");
     if (!h->haveBasis) { evp_set_error("no basis on the device"); return EVP_ERR_STATE; }
     EVP_CUDA(cudaSetDevice(h->device));
+    NoPin noPin(h);
     evp_dev &d = h->d;
     int rc;
     if (h->nCells == 0) return EVP_OK;

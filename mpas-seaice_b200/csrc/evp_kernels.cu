@@ -430,3 +430,39 @@ int evp_count_launches(evp_handle *h, int nSub)
     const int perSub = (h->nCells ? 1 : 0) + (h->nVerticesSolve ? 1 : 0) + evp_halo_launches(h) + sb;
     return sb + nSub * perSub;
 }
+
+// Instrumentation for bench.py: average device time of the cell pass, the vertex pass and the rest
+// (halo + special boundaries) over nSub subcycles, CUDA events on the launching stream, no graph.
+extern "C" int evp_profile_passes(evp_handle *h, int nSub, float *cellMs, float *vertexMs, float *otherMs)
+{
+    EVP_REQUIRE(h != nullptr && nSub > 0, "bad argument");
+    if (!h->haveBasis || !h->haveStep) { evp_set_error("evp_profile_passes before create/update_step"); return EVP_ERR_STATE; }
+    EVP_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    cudaEvent_t e[4];
+    for (auto &x : e) EVP_CUDA(cudaEventCreate(&x));
+    double acc[3] = {0, 0, 0};
+    int rc = EVP_OK;
+    for (int k = 0; k < nSub && rc == EVP_OK; k++) {
+        EVP_CUDA(cudaEventRecord(e[0], s));
+        if ((rc = evp_enqueue_cell_pass(h, false, s))) break;
+        EVP_CUDA(cudaEventRecord(e[1], s));
+        if ((rc = evp_enqueue_vertex_pass(h, false, s))) break;
+        EVP_CUDA(cudaEventRecord(e[2], s));
+        if ((rc = evp_halo_enqueue(h, s))) break;
+        if ((rc = evp_enqueue_special_boundaries(h, s))) break;
+        EVP_CUDA(cudaEventRecord(e[3], s));
+        EVP_CUDA(cudaEventSynchronize(e[3]));
+        for (int i = 0; i < 3; i++) {
+            float ms = 0.f;
+            EVP_CUDA(cudaEventElapsedTime(&ms, e[i], e[i + 1]));
+            acc[i] += ms;
+        }
+    }
+    for (auto &x : e) cudaEventDestroy(x);
+    if (rc) return rc;
+    if (cellMs) *cellMs = (float)(acc[0] / nSub);
+    if (vertexMs) *vertexMs = (float)(acc[1] / nSub);
+    if (otherMs) *otherMs = (float)(acc[2] / nSub);
+    return EVP_OK;
+}

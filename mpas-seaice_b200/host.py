@@ -30,7 +30,7 @@ EXPORTS = (
     "evp_create", "evp_set_options", "evp_precompute_wachspress", "evp_fetch_basis", "evp_update_step",
     "evp_set_masks", "evp_run_subcycles", "evp_synchronize", "evp_fetch", "evp_destroy",
     "evp_last_error_string", "evp_comm_get_unique_id", "evp_comm_init", "evp_set_halo", "evp_last_run_ms",
-    "evp_launch_count", "evp_get_stream", "evp_device_bytes", "evp_set_use_graph",
+    "evp_launch_count", "evp_get_stream", "evp_device_bytes", "evp_set_use_graph", "evp_profile_passes",
 )
 
 
@@ -217,6 +217,12 @@ class EvpSolver:
         ms = C.c_float(0)
         self._check(self.lib.evp_last_run_ms(self._h, C.byref(ms)))
         return ms.value
+
+    def profile_passes(self, n):
+        """(cell_ms, vertex_ms, other_ms) averaged over n un-graphed subcycles (CUDA events)."""
+        a, b, c = C.c_float(0), C.c_float(0), C.c_float(0)
+        self._check(self.lib.evp_profile_passes(self._h, C.c_int(int(n)), C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     def launch_count(self, n):
         c = C.c_int(0)

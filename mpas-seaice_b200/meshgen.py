@@ -271,8 +271,7 @@ def _subdivide(p, f):
     hi = e.max(axis=1)
     key = lo * np.int64(nP) + hi
     ukey, inv = np.unique(key, return_inverse=True)
-    mid = p[ukey // nP] + p[ukey % nP]
-    mid /= np.linalg.norm(mid, axis=1)[:, None]
+    mid = _normalize(p[ukey // nP] + p[ukey % nP])
     p2 = np.concatenate([p, mid], axis=0)
     nF = f.shape[0]
     mab = nP + inv[:nF]
@@ -287,10 +286,36 @@ def _subdivide(p, f):
     return p2, f2.reshape(-1, 3)
 
 
+def _cross(a, b):
+    """Row-wise cross product (much faster than np.cross for (n, 3) arrays)."""
+    out = np.empty_like(a)
+    out[:, 0] = a[:, 1] * b[:, 2] - a[:, 2] * b[:, 1]
+    out[:, 1] = a[:, 2] * b[:, 0] - a[:, 0] * b[:, 2]
+    out[:, 2] = a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]
+    return out
+
+
+def _dot(a, b):
+    return a[:, 0] * b[:, 0] + a[:, 1] * b[:, 1] + a[:, 2] * b[:, 2]
+
+
+def _normalize(a):
+    a /= np.sqrt(_dot(a, a))[:, None]
+    return a
+
+
+def _first_index(keys, n):
+    """first_index[k] = smallest i with keys[i] == k (keys in 0..n-1, every k present)."""
+    out = np.full(n, keys.shape[0], dtype=np.int64)
+    idx = np.arange(keys.shape[0] - 1, -1, -1, dtype=np.int64)
+    out[keys[::-1]] = idx          # repeated indices: the last assignment (= smallest i) wins
+    return out
+
+
 def _sph_tri_area(a, b, c):
     """Spherical triangle area on the unit sphere (Van Oosterom & Strackee), vectorised."""
-    num = np.abs(np.einsum("ij,ij->i", a, np.cross(b, c)))
-    den = 1.0 + np.einsum("ij,ij->i", a, b) + np.einsum("ij,ij->i", b, c) + np.einsum("ij,ij->i", c, a)
+    num = np.abs(_dot(a, _cross(b, c)))
+    den = 1.0 + _dot(a, b) + _dot(b, c) + _dot(c, a)
     return 2.0 * np.arctan2(num, den)
 
 
@@ -304,9 +329,7 @@ def icosphere(level: int, radius: float = EARTH_RADIUS) -> Mesh:
     nC0 = p.shape[0]
     nV = f.shape[0]
     # renumber cells by first incident triangle (triangles are in quadtree order)
-    first_tri = np.full(nC0, nV, dtype=np.int64)
-    for k in range(3):
-        np.minimum.at(first_tri, f[:, k], np.arange(nV))
+    first_tri = _first_index(f.reshape(-1), nC0) // 3
     perm = np.argsort(first_tri, kind="stable")      # new -> old
     inv_perm = np.empty(nC0, dtype=np.int64)
     inv_perm[perm] = np.arange(nC0)
@@ -316,8 +339,8 @@ def icosphere(level: int, radius: float = EARTH_RADIUS) -> Mesh:
 
     # MPAS vertices = triangle circumcentres on the sphere
     a, b, c = p[f[:, 0]], p[f[:, 1]], p[f[:, 2]]
-    vpos = np.cross(b - a, c - a)
-    vpos /= np.linalg.norm(vpos, axis=1)[:, None]
+    vpos = _normalize(_cross(b - a, c - a))
+    del a, b, c
 
     # rings: record r = (triangle t, corner k): cell = f[t,k], next vertex = f[t,k+1], prev = f[t,k+2]
     # going CCW around a cell, the triangle after (cell, nxt, prv) is the one whose "nxt" equals prv.
@@ -331,8 +354,7 @@ def icosphere(level: int, radius: float = EARTH_RADIUS) -> Mesh:
     link = np.searchsorted(key_s, cell * np.int64(nC) + prv)
     nxt_rec = order[link]                               # record index of the next triangle around cell
     # start record per cell: the record with the smallest triangle id
-    start = np.full(nC, 3 * nV, dtype=np.int64)
-    np.minimum.at(start, cell, np.arange(3 * nV))
+    start = _first_index(cell, nC)
     ring = np.empty((nC, 6), dtype=np.int64)
     ringn = np.empty((nC, 6), dtype=np.int64)           # neighbour cell across edge s (between tri s and s+1)
     cur = start.copy()
@@ -377,8 +399,8 @@ def icosphere(level: int, radius: float = EARTH_RADIUS) -> Mesh:
     ev2[inv] = nxt_v[valid]
 
     def arc(u, v):
-        cr = np.linalg.norm(np.cross(u, v), axis=1)
-        return np.arctan2(cr, np.einsum("ij,ij->i", u, v))
+        w = _cross(u, v)
+        return np.arctan2(np.sqrt(_dot(w, w)), _dot(u, v))
 
     dv_edge = arc(vpos[ev1], vpos[ev2]) * radius
     dc_edge = arc(p[ec1], p[ec2]) * radius
@@ -394,10 +416,8 @@ def icosphere(level: int, radius: float = EARTH_RADIUS) -> Mesh:
         cc = p[f[:, k]]
         cn = p[f[:, (k + 1) % 3]]
         cp = p[f[:, (k + 2) % 3]]
-        m1 = cc + cn
-        m1 /= np.linalg.norm(m1, axis=1)[:, None]
-        m2 = cc + cp
-        m2 /= np.linalg.norm(m2, axis=1)[:, None]
+        m1 = _normalize(cc + cn)
+        m2 = _normalize(cc + cp)
         kite[:, k] = _sph_tri_area(cc, m1, vpos) + _sph_tri_area(cc, vpos, m2)
     kite *= radius * radius
     area_cell *= radius * radius

@@ -1,0 +1,107 @@
+"""Host-side (numpy, vectorised) mirror of the cheap parts of seaice_init_velocity_solver_variational
+(reference: src/shared/mpas_seaice_velocity_solver_variational.F:108-344): metric terms,
+cellVerticesAtVertex, local tangent-plane coordinates, interior vertices and the 'original'
+denominator.  The expensive part -- the Wachspress basis -- is computed on the device by
+evp_precompute_wachspress() from the local coordinates produced here.
+
+In a real MPAS-Seaice run these arrays come from the Fortran init and this module is not needed; it
+exists so that bench.py and the synthetic hosts can set up 10 M-cell problems in seconds.  The
+arithmetic order follows the cited lines (checked bit-for-bit against the oracle in the tests).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def metric_terms(mesh, rotate=True, include=True):
+    """seaice_calc_variational_metric_terms (variational_shared.F:293-358)"""
+    nV = mesh.nVertices
+    out = np.zeros(nV + 1)
+    if include:
+        z = mesh.xVertex[:nV] if rotate else mesh.zVertex[:nV]      # rotation (x,y,z) -> (-z, y, x): zp = x
+        lat = np.arcsin(z / mesh.sphere_radius)
+        out[:nV] = np.tan(lat) / mesh.sphere_radius
+    return out
+
+
+def cell_vertices_at_vertex(mesh):
+    """seaice_cell_vertices_at_vertex (src/shared/mpas_seaice_mesh.F:632-685); the reference keeps the
+    LAST matching slot, 0 if the cell does not hold the vertex."""
+    nV, nC, D, M = mesh.nVertices, mesh.nCells, mesh.vertexDegree, mesh.maxEdges
+    cov = mesh.cellsOnVertex
+    out = np.zeros((nV + 1, D), dtype=np.int32)
+    vid = np.arange(1, nV + 1, dtype=np.int32)
+    for k in range(D):
+        c = cov[:nV, k] - 1                       # junk cell (nC) has nEdgesOnCell = 0
+        n = mesh.nEdgesOnCell[c]
+        for j in range(M):
+            hit = (j < n) & (mesh.verticesOnCell[c, j] == vid)
+            out[:nV, k][hit] = j + 1
+    return out
+
+
+def interior_vertex(mesh):
+    """interior_vertices (mesh.F:423-488)"""
+    out = np.zeros(mesh.nVertices + 1, dtype=np.int32)
+    cov = mesh.cellsOnVertex[:mesh.nVertices]
+    out[:mesh.nVertices] = np.all((cov >= 1) & (cov <= mesh.nCells), axis=1)
+    return out
+
+
+def local_coords(mesh, rotate=True):
+    """seaice_calc_local_coords (variational_shared.F:42-279) with
+    seaice_project_3D_vector_onto_local_2D (mesh.F:2021-2061, 2272-2332)."""
+    nC, M = mesh.nCells, mesh.maxEdges
+    xl = np.zeros((nC + 1, M))
+    yl = np.zeros((nC + 1, M))
+    n = mesh.nEdgesOnCell[:nC]
+    voc = mesh.verticesOnCell[:nC] - 1
+    if not mesh.on_a_sphere:
+        for j in range(M):
+            ok = j < n
+            v = voc[ok, j]
+            xl[:nC][ok, j] = mesh.xVertex[v] - mesh.xCell[:nC][ok]
+            yl[:nC][ok, j] = mesh.yVertex[v] - mesh.yCell[:nC][ok]
+        return xl, yl
+    if rotate:
+        xc, yc, zc = -mesh.zCell[:nC], mesh.yCell[:nC], mesh.xCell[:nC]
+        vxr, vyr, vzr = -mesh.zVertex, mesh.yVertex, mesh.xVertex
+    else:
+        xc, yc, zc = mesh.xCell[:nC], mesh.yCell[:nC], mesh.zCell[:nC]
+        vxr, vyr, vzr = mesh.xVertex, mesh.yVertex, mesh.zVertex
+    with np.errstate(all="ignore"):
+        e0, e1, e2 = -yc, xc, np.zeros(nC)
+        mag = np.sqrt(e0 * e0 + e1 * e1 + e2 * e2)
+        e0, e1, e2 = e0 / mag, e1 / mag, e2 / mag
+        n0, n1, n2 = -xc, -yc, (xc * xc + yc * yc) / zc
+        mag = np.sqrt(n0 * n0 + n1 * n1 + n2 * n2)
+        n0, n1, n2 = n0 / mag, n1 / mag, n2 / mag
+        south = zc < 0.0
+        n0 = np.where(south, -n0, n0)
+        n1 = np.where(south, -n1, n1)
+        n2 = np.where(south, -n2, n2)
+        eq = zc == 0.0
+        n0 = np.where(eq, 0.0, n0)
+        n1 = np.where(eq, 0.0, n1)
+        n2 = np.where(eq, 1.0, n2)
+    for j in range(M):
+        ok = j < n
+        v = voc[ok, j]
+        xl[:nC][ok, j] = vxr[v] * e0[ok] + vyr[v] * e1[ok] + vzr[v] * e2[ok]
+        yl[:nC][ok, j] = vxr[v] * n0[ok] + vyr[v] * n1[ok] + vzr[v] * n2[ok]
+    return xl, yl
+
+
+def init_static(mesh, rotate=None, metric=None):
+    """The static ``velocity_variational`` fields except the basis arrays ('original' denominator =
+    areaTriangle, variational.F:433-437) plus the local coordinates the device precompute consumes."""
+    on_sphere = bool(mesh.on_a_sphere)
+    rotate = on_sphere if rotate is None else rotate
+    metric = on_sphere if metric is None else metric
+    xl, yl = local_coords(mesh, rotate)
+    den = np.zeros(mesh.nVertices + 1)
+    den[:mesh.nVertices] = mesh.areaTriangle[:mesh.nVertices]
+    return dict(tanLatVertexRotatedOverRadius=metric_terms(mesh, rotate, metric),
+                cellVerticesAtVertex=cell_vertices_at_vertex(mesh),
+                interiorVertex=interior_vertex(mesh),
+                variationalDenominator=den, xLocal=xl, yLocal=yl)

@@ -1,0 +1,56 @@
+"""The BASELINE.json configurations as ready-to-run workloads (product side: no oracle involved).
+
+  square  : planar hex 82 x 94, dc = 16 km, analytic wind / ocean, EVP 120 subcycles   (configs[1])
+  qu240   : icosahedral sphere 10 242 cells                                             (configs[2])
+  qu60    : 163 842 cells                                                               (configs[3])
+  qu30 / qu15 : 655 362 / 2 621 442 cells (intermediate sizes)
+  qu7.5   : 10 485 762 cells, config_dt = 120 s                                         (configs[4])
+
+Per-grid config_dt from bld/namelist_files/namelist_defaults_mpassi.xml:9-16.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from . import meshgen, synthetic, variational_init
+
+SPHERES = {  # name -> (icosphere level, config_dt)
+    "qu240": (5, 3600.0), "qu120": (6, 1800.0), "qu60": (7, 900.0), "qu30": (8, 450.0),
+    "qu15": (9, 240.0), "qu7.5": (10, 120.0),
+}
+ALGO_BYTES_PER_CELL = 1912.0        # cell part of one cell-subcycle (hex sphere)
+ALGO_BYTES_PER_VERTEX = 164.0       # per owned vertex
+ALGO_BYTES_PER_CELL_SUBCYCLE = 2240.0
+
+
+def build(name: str, state: str = "A", n_elastic: int = 120, verbose=None):
+    """Returns dict(mesh, static, step, opts, name, timings)."""
+    t0 = time.time()
+    log = verbose or (lambda *a: None)
+    if name == "square":
+        mesh = meshgen.planar_hex(82, 94, 16000.0)
+        config_dt = 3600.0
+        st = synthetic.square_state(mesh)
+    elif name in SPHERES:
+        level, config_dt = SPHERES[name]
+        mesh = meshgen.icosphere(level)
+        st = synthetic.sphere_state(mesh, kind=state)
+    else:
+        raise ValueError(f"unknown workload {name!r}")
+    t1 = time.time()
+    log(f"mesh {name}: {mesh.nCells} cells, {mesh.nVertices} vertices in {t1 - t0:.1f}s")
+    static = variational_init.init_static(mesh)
+    t2 = time.time()
+    step, opts = synthetic.pre_subcycle(mesh, st, config_dt, n_elastic=n_elastic)
+    t3 = time.time()
+    log(f"init_static {t2 - t1:.1f}s, pre_subcycle {t3 - t2:.1f}s")
+    return dict(name=name, mesh=mesh, static=static, step=step, opts=opts, config_dt=config_dt,
+                timings=dict(mesh_s=t1 - t0, init_s=t2 - t1, pre_subcycle_s=t3 - t2))
+
+
+def active_counts(w):
+    mesh, step = w["mesh"], w["step"]
+    return (int((step["solveStress"][:mesh.nCells] == 1).sum()),
+            int((step["solveVelocity"][:mesh.nVertices] == 1).sum()))
