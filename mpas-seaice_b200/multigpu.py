@@ -1,0 +1,61 @@
+"""One block per rank (= per GPU): what a decomposed MPAS-Seaice host hands to the C-ABI on each rank.
+
+The reference reaches this state through the MPAS framework (block creator reading
+graph.info.part.N, dmpar exchange lists) and the halo exchanges of the pre-subcycle
+(src/shared/mpas_seaice_velocity_solver.F:842-861, 919-937, 1298-1317, 1480-1498, 1597-1616,
+2087-2106); here every rank generates the same global synthetic mesh and per-step fields
+deterministically, keeps only its block (partition.build_block / restrict_step) and frees the rest.
+The only inter-rank traffic at set-up is the halo request lists and the 128-byte NCCL id, both
+through the host's own communicator (torch.distributed here, MPI in the Fortran host).
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from . import partition, variational_init, workloads
+
+
+def build_rank_workload(name, rank, world, dist=None, verbose=None, method="auto", n_halos=None, state="A"):
+    """Like workloads.build() but for the block of ``rank`` out of ``world``."""
+    log = verbose or (lambda *a: None)
+    w = workloads.build(name, state=state, verbose=verbose, with_static=False)
+    gmesh, gstep = w["mesh"], w["step"]
+    nCg, nVg = int(gmesh.nCells), int(gmesh.nVertices)
+    t0 = time.time()
+    part = partition.partition_cells(gmesh, world, method)
+    blk = partition.build_block(gmesh, part, rank, n_halos)
+    step = partition.restrict_step(blk, gstep, nCg, nVg)
+    nVs, nCs = int(blk.nVerticesSolve), int(blk.nCellsSolve)
+    active = (int((step["solveStress"][:nCs] == 1).sum()), int((step["solveVelocity"][:nVs] == 1).sum()))
+    active_local_cells = int((step["solveStress"][:blk.nCells] == 1).sum())
+    del gstep, w["step"], w["mesh"], gmesh
+    static = variational_init.init_static(blk)
+    requests = partition.halo_requests(blk)
+    log(f"partition '{method}' into {world}: block {rank} has {nCs} owned + {blk.nCells - nCs} halo cells, "
+        f"{nVs} owned + {blk.nVertices - nVs} halo vertices ({time.time() - t0:.1f}s)")
+    return dict(name=name, mesh=blk, static=static, step=step, opts=w["opts"], config_dt=w["config_dt"],
+                nVerticesSolve=nVs, nCellsSolve=nCs, active=active, active_local_cells=active_local_cells,
+                global_cells=nCg, global_vertices=nVg, requests=requests,
+                partition=f"{method} cell-graph partition into {world} blocks, "
+                          f"{blk.nHalos} halo layer(s), vertex owner = first cell of cellsOnVertex")
+
+
+def gather_requests(requests, rank, world, dist):
+    """All ranks' halo request lists, through the host communicator."""
+    if dist is None or world == 1:
+        return {rank: requests}
+    allreq = [None] * world
+    dist.all_gather_object(allreq, requests)
+    return {q: r for q, r in enumerate(allreq)}
+
+
+def attach_halo(solver, w, rank, world, dist):
+    """evp_comm_init + evp_set_halo on this rank's handle."""
+    ids = [solver.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    solver.comm_init(rank, world, ids[0])
+    lists = partition.exchange_lists(w["mesh"], gather_requests(w["requests"], rank, world, dist))
+    solver.set_halo(*lists)
+    return lists

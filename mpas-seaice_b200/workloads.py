@@ -25,23 +25,24 @@ ALGO_BYTES_PER_VERTEX = 164.0       # per owned vertex
 ALGO_BYTES_PER_CELL_SUBCYCLE = 2240.0
 
 
-def build(name: str, state: str = "A", n_elastic: int = 120, verbose=None):
-    """Returns dict(mesh, static, step, opts, name, timings)."""
+def build(name: str, state: str = "A", n_elastic: int = 120, verbose=None, with_static: bool = True):
+    """Returns dict(mesh, static, step, opts, name, timings).  ``with_static=False`` skips the static
+    variational fields (multi-GPU hosts compute them per block, see multigpu.py)."""
     t0 = time.time()
     log = verbose or (lambda *a: None)
     if name == "square":
         mesh = meshgen.planar_hex(82, 94, 16000.0)
         config_dt = 3600.0
         st = synthetic.square_state(mesh)
-    elif name in SPHERES:
-        level, config_dt = SPHERES[name]
+    elif name in SPHERES or (name.startswith("ico") and name[3:].isdigit()):
+        level, config_dt = SPHERES[name] if name in SPHERES else (int(name[3:]), 3600.0)   # icoN: test sizes
         mesh = meshgen.icosphere(level)
         st = synthetic.sphere_state(mesh, kind=state)
     else:
         raise ValueError(f"unknown workload {name!r}")
     t1 = time.time()
     log(f"mesh {name}: {mesh.nCells} cells, {mesh.nVertices} vertices in {t1 - t0:.1f}s")
-    static = variational_init.init_static(mesh)
+    static = variational_init.init_static(mesh) if with_static else None
     t2 = time.time()
     step, opts = synthetic.pre_subcycle(mesh, st, config_dt, n_elastic=n_elastic)
     t3 = time.time()

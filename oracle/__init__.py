@@ -210,3 +210,105 @@ def set_num_threads(n: int) -> None:
     """OpenMP thread count used by the oracle loops that the reference marks ``!$omp parallel do``."""
     gomp = C.CDLL("libgomp.so.1")
     gomp.omp_set_num_threads(C.c_int(int(n)))
+
+
+# ---------------------------------------------------------------------------------------------
+# pre- / post-subcycle (the host side of the boundary, restated so tests can build identical inputs)
+# ---------------------------------------------------------------------------------------------
+
+def pre_subcycle(mesh, state, config_dt, *, n_elastic=120, use_air_stress=True, use_ocean_stress=True,
+                 use_surface_tilt=True, interior_vertex=None):
+    """velocity_solver_pre_subcycle (velocity_solver.F:613-671) from a cold start, single category,
+    Hibler strength, constant_air_stress, geostrophic tilt -- call order of the reference.
+    Returns the same dict of per-step fields as mpas_seaice_b200.synthetic.pre_subcycle."""
+    L = lib()
+    nC, nV, M, D = mesh.nCells, mesh.nVertices, mesh.maxEdges, mesh.vertexDegree
+    z = lambda n: np.zeros(n)
+    f = {}
+    area = np.ascontiguousarray(state["iceAreaCell"], dtype=np.float64)
+    vol = np.ascontiguousarray(state["iceVolumeCell"], dtype=np.float64)
+    snow = np.ascontiguousarray(state["snowVolumeCell"], dtype=np.float64)
+    mass = z(nC + 1)
+    L.orc_total_mass(_i(nC + 1), _p(vol), _p(snow), _p(mass))
+
+    def c2v(cell):
+        out = z(nV + 1)
+        L.orc_interpolate_cell_to_vertex(_i(nV), _i(D), _p(mesh.cellsOnVertex), _p(mesh.areaCell),
+                                         _p(np.ascontiguousarray(cell, dtype=np.float64)), _p(out))
+        return out
+
+    with np.errstate(all="ignore"):
+        f["iceAreaVertex"] = c2v(area)
+        f["totalMassVertex"] = c2v(mass)
+        land = np.zeros(nC + 1, dtype=np.int32)
+        landv = np.zeros(nV + 1, dtype=np.int32)
+        ss = np.zeros(nC + 1, dtype=np.int32)
+        L.orc_stress_calculation_mask(_i(nC), _i(M), _p(mesh.nEdgesOnCell), _p(mesh.cellsOnCell), _p(area), _p(mass),
+                                      _p(land), _p(ss))
+        if interior_vertex is None:
+            interior_vertex = np.zeros(nV + 1, dtype=np.int32)
+            L.orc_interior_vertices(_p(interior_vertex), _i(nV), _i(D), _i(nC), _p(mesh.cellsOnVertex))
+        sv = np.zeros(nV + 1, dtype=np.int32)
+        L.orc_velocity_calculation_mask(_i(nV), _i(nV), _p(interior_vertex), _p(landv), _p(f["iceAreaVertex"]),
+                                        _p(f["totalMassVertex"]), _p(sv))
+        f["solveStress"], f["solveVelocity"] = ss, sv
+        f["uOceanVelocityVertex"] = c2v(state["uOceanVelocity"])
+        f["vOceanVelocityVertex"] = c2v(state["vOceanVelocity"])
+        u, v = z(nV + 1), z(nV + 1)
+        svp = sv.copy()
+        sdu, sdv, osu, osv = z(nV + 1), z(nV + 1), z(nV + 1), z(nV + 1)
+        ui, vi = z(nV + 1), z(nV + 1)
+        L.orc_new_ice_velocities(_i(nV), _i(nV), _p(sv), _p(svp), _p(f["uOceanVelocityVertex"]),
+                                 _p(f["vOceanVelocityVertex"]), _p(u), _p(v), _p(sdu), _p(sdv), _p(osu), _p(osv),
+                                 _p(ui), _p(vi))
+        f["solveVelocityPrevious"], f["uVelocityInitial"], f["vVelocityInitial"] = svp, ui, vi
+        P = z(nC + 1)
+        L.orc_ice_strength_hibler(_i(nC), _p(ss), _p(vol), _p(area), _p(P))
+        f["icePressure"] = P
+        au, av = z(nC + 1), z(nC + 1)
+        if use_air_stress:
+            L.orc_constant_air_stress(_i(nC + 1), _p(np.ascontiguousarray(state["uAirVelocity"])),
+                                      _p(np.ascontiguousarray(state["vAirVelocity"])),
+                                      _p(np.ascontiguousarray(state["airDensity"])), _p(area), _p(au), _p(av))
+        f["airStressVertexU"], f["airStressVertexV"] = c2v(au), c2v(av)
+        mf = z(nV + 1)
+        L.orc_coriolis_force_coefficient(_i(nV + 1), _p(f["totalMassVertex"]), _p(mesh.fVertex), _p(mf))
+        f["totalMassVertexfVertex"] = mf
+        L.orc_ocean_stress(_i(nV), _i(nV), _i(use_ocean_stress), _p(sv), _p(f["uOceanVelocityVertex"]),
+                           _p(f["vOceanVelocityVertex"]), _p(mesh.fVertex), _p(osu), _p(osv))
+        f["oceanStressU"], f["oceanStressV"] = osu, osv
+        tu, tv = z(nV + 1), z(nV + 1)
+        L.orc_surface_tilt(_i(nV), _i(nV), _i(use_surface_tilt), _p(sv), _p(mesh.fVertex), _p(f["totalMassVertex"]),
+                           _p(f["uOceanVelocityVertex"]), _p(f["vOceanVelocityVertex"]), _p(tu), _p(tv))
+        f["surfaceTiltForceU"], f["surfaceTiltForceV"] = tu, tv
+    oc = z(nV + 1)
+    e = [np.zeros((nC + 1, M)) for _ in range(3)]
+    s = [np.zeros((nC + 1, M)) for _ in range(3)]
+    L.orc_init_subcycle_variables(_i(nC), _i(nV), _i(nV), _i(M), _p(ss), _p(sv), _p(sdu), _p(sdv), _p(u), _p(v), _p(oc),
+                                  _p(e[0]), _p(e[1]), _p(e[2]), _p(s[0]), _p(s[1]), _p(s[2]))
+    f.update(stressDivergenceU=sdu, stressDivergenceV=sdv, oceanStressCoeff=oc, uVelocity=u, vVelocity=v,
+             strain11=e[0], strain22=e[1], strain12=e[2], stress11=s[0], stress22=s[1], stress12=s[2],
+             replacementPressure=np.zeros((nC + 1, M)))
+    return f
+
+
+def final_divergence_shear(mesh, step):
+    """seaice_final_divergence_shear_variational (variational.F:1198-1330)"""
+    L = lib()
+    nC = mesh.nCells
+    out = [np.zeros(nC + 1) for _ in range(4)]
+    L.orc_final_divergence_shear_variational(_i(nC), _i(mesh.maxEdges), _p(mesh.nEdgesOnCell), _p(step["solveStress"]),
+                                             _p(step["strain11"]), _p(step["strain22"]), _p(step["strain12"]),
+                                             *[_p(a) for a in out])
+    return dict(zip(("divergence", "shear", "ridgeConvergence", "ridgeShear"), out))
+
+
+def principal_stresses(mesh, step, n_cells_solve=None):
+    """principal_stresses_driver, variational branch (velocity_solver.F:3443-3610)"""
+    L = lib()
+    nC, M = mesh.nCells, mesh.maxEdges
+    p1, p2 = np.zeros((nC + 1, M)), np.zeros((nC + 1, M))
+    L.orc_principal_stresses_variational(_i(nC if n_cells_solve is None else n_cells_solve), _i(M),
+                                         _p(mesh.nEdgesOnCell), _p(step["stress11"]), _p(step["stress22"]),
+                                         _p(step["stress12"]), _p(step["replacementPressure"]), _p(p1), _p(p2))
+    return p1, p2

@@ -92,3 +92,59 @@ def masks_for(mesh, step):
     vm = np.zeros(nV + 1, dtype=bool)
     vm[:nV] = step["solveVelocity"][:nV] == 1
     return cm[:, None] & slot, vm
+
+
+# ---------------------------------------------------------------------------------------------
+# decomposed runs (host-side emulation of the MPI / NCCL path with the oracle as the block solver)
+# ---------------------------------------------------------------------------------------------
+
+def make_blocks(mesh, n_parts, method="auto", n_halos=None, basis="wachspress"):
+    """[(block mesh, block var)] + the evp_set_halo lists of every rank."""
+    from mpas_seaice_b200 import partition
+    part = partition.partition_cells(mesh, n_parts, method)
+    blocks = [partition.build_block(mesh, part, r, n_halos) for r in range(n_parts)]
+    requests = {r: partition.halo_requests(b) for r, b in enumerate(blocks)}
+    lists = [partition.exchange_lists(b, requests) for b in blocks]
+    return part, blocks, lists
+
+
+def exchange_halos(fields_by_rank, lists, names=("uVelocity", "vVelocity")):
+    """What the per-subcycle halo exchange does (velocity_solver.F:2543-2584): owner -> halo copies."""
+    n = len(lists)
+    for r in range(n):
+        nbr, soff, sidx, roff, ridx = lists[r]
+        for k, q in enumerate(nbr):
+            q = int(q)
+            qn, qsoff, qsidx, qroff, qridx = lists[q]
+            kk = int(np.nonzero(qn == r)[0][0])
+            src = qsidx[qsoff[kk]:qsoff[kk + 1]] - 1
+            dst = ridx[roff[k]:roff[k + 1]] - 1
+            assert src.shape == dst.shape
+            for name in names:
+                fields_by_rank[r][name][dst] = fields_by_rank[q][name][src]
+
+
+def run_oracle_blocks(mesh, step, opts, n_sub, n_parts, method="auto", n_halos=None, basis="wachspress"):
+    """n_sub subcycles on n_parts blocks, halo exchange after every subcycle; returns the gathered
+    global fields (owned entries of every block) and the blocks."""
+    from mpas_seaice_b200 import partition
+    part, blocks, lists = make_blocks(mesh, n_parts, method, n_halos)
+    nC, nV = mesh.nCells, mesh.nVertices
+    bvars = [oracle.init_variational(b, basis=basis) for b in blocks]
+    bsteps = [partition.restrict_step(b, step, nC, nV) for b in blocks]
+    bopts = [dict(opts, nVerticesSolve=int(b.nVerticesSolve)) for b in blocks]
+    for _ in range(n_sub):
+        for b, v, s, o in zip(blocks, bvars, bsteps, bopts):
+            oracle.subcycle_velocity_solver(b, v, s, o, 1)
+        exchange_halos(bsteps, lists)
+    out = {}
+    for k in COMPARE_CELL:
+        out[k] = np.zeros_like(step[k])
+    for k in COMPARE_VERTEX:
+        out[k] = np.zeros_like(step[k])
+    for b, s in zip(blocks, bsteps):
+        for k in COMPARE_CELL:
+            partition.scatter_owned(b, s[k], out[k], "cell")
+        for k in COMPARE_VERTEX:
+            partition.scatter_owned(b, s[k], out[k], "vertex")
+    return out, blocks, lists

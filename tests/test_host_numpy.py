@@ -1,0 +1,78 @@
+"""The vectorised numpy host helpers (variational_init.py, synthetic.py) against the oracle's loop-for-loop
+restatement of the same reference routines: integer maps bit-exact, FP64 fields bit-exact where the
+operation order is the reference's, else <= 2 ulp (documented per field)."""
+import numpy as np
+import pytest
+
+import common
+import oracle
+from mpas_seaice_b200 import meshgen, synthetic, variational_init, workloads
+
+
+@pytest.mark.parametrize("kind", ["hex20", "quad40", "ico3", "ico5"])
+def test_init_static_matches_oracle(kind):
+    mesh, var = common.mesh_case(kind)
+    st = variational_init.init_static(mesh)
+    assert np.array_equal(st["cellVerticesAtVertex"], var["cellVerticesAtVertex"])
+    assert np.array_equal(st["interiorVertex"], var["interiorVertex"])
+    assert np.array_equal(st["variationalDenominator"], var["variationalDenominator"])
+    assert np.array_equal(st["xLocal"], var["xLocal"])
+    assert np.array_equal(st["yLocal"], var["yLocal"])
+    # tan(asin(z/R))/R: numpy and libm may differ in the last bit of tan / asin
+    a, b = st["tanLatVertexRotatedOverRadius"], var["tanLatVertexRotatedOverRadius"]
+    assert np.allclose(a, b, rtol=1e-14, atol=0.0)   # tan amplifies the asin ulp near the rotated poles
+
+
+@pytest.mark.parametrize("kind", ["hex20", "ico3"])
+def test_pre_subcycle_matches_oracle(kind):
+    mesh, _ = common.mesh_case(kind)
+    state = synthetic.sphere_state(mesh, "B") if mesh.on_a_sphere else synthetic.square_state(mesh)
+    f, opts = synthetic.pre_subcycle(mesh, state, 3600.0)
+    g = oracle.pre_subcycle(mesh, state, 3600.0)
+    nV = mesh.nVertices
+    for k in ("solveStress", "solveVelocity", "solveVelocityPrevious"):
+        assert np.array_equal(f[k], g[k]), k
+    vm = f["solveVelocity"][:nV] == 1
+    assert vm.sum() > 0 and (~vm).sum() > 0
+    for k in ("iceAreaVertex", "totalMassVertex", "uOceanVelocityVertex", "vOceanVelocityVertex", "airStressVertexU",
+              "airStressVertexV", "totalMassVertexfVertex", "oceanStressU", "oceanStressV", "surfaceTiltForceU",
+              "surfaceTiltForceV", "uVelocity", "vVelocity", "uVelocityInitial", "vVelocityInitial"):
+        # consumers read these only where solveVelocity == 1
+        assert np.array_equal(f[k][:nV][vm], g[k][:nV][vm]), k
+    # exp() of numpy vs libm: last-bit differences allowed
+    assert np.allclose(f["icePressure"], g["icePressure"], rtol=4e-16, atol=0.0)
+    for k in ("stress11", "stress22", "stress12", "strain11", "replacementPressure", "stressDivergenceU"):
+        assert np.array_equal(f[k], g[k]), k
+    assert opts["elasticTimeStep"] == 30.0 and opts["dampingTimescale"] == 0.36 * 3600.0
+    L = oracle.lib()
+    assert opts["dampingTimescale"] == L.orc_damping_timescale(3600.0)
+    dv = float(mesh.dvEdge[:-1].min())
+    assert opts["numericalInertiaCoefficient"] == L.orc_numerical_inertia_coefficient(3600.0, dv)
+
+
+def test_mesh_generators_are_valid_mpas_meshes():
+    for mesh in (meshgen.planar_hex(12, 14, 1000.0), meshgen.planar_quad(9, 7, 500.0), meshgen.icosphere(2)):
+        meshgen.check_mesh(mesh)
+        nC, nV = mesh.nCells, mesh.nVertices
+        assert mesh.areaCell[nC] == meshgen.JUNK_AREA and mesh.nEdgesOnCell[nC] == 0
+        if mesh.on_a_sphere:
+            assert nC == 10 * 4 ** 2 + 2 and nV == 20 * 4 ** 2 and (mesh.nEdgesOnCell[:nC] == 5).sum() == 12
+            R = mesh.sphere_radius
+            assert abs(mesh.areaCell[:nC].sum() / (4 * np.pi * R * R) - 1.0) < 1e-12
+            assert abs(mesh.areaTriangle[:nV].sum() / (4 * np.pi * R * R) - 1.0) < 1e-12
+        else:
+            # kites tile the cells: interior vertices' triangles + boundary remainders = total cell area
+            assert abs(mesh.kiteAreasOnVertex.sum() / mesh.areaCell[:nC].sum() - 1.0) < 1e-12
+
+
+def test_workload_registry():
+    w = workloads.build("square")
+    mesh = w["mesh"]
+    assert (mesh.nx, mesh.ny, mesh.dc) == (82, 94, 16000.0) and w["config_dt"] == 3600.0   # BASELINE configs[1]
+    assert w["opts"]["elasticTimeStep"] == 30.0 and w["opts"]["n_elastic"] == 120
+    nC_act, nV_act = workloads.active_counts(w)
+    assert 0 < nC_act <= mesh.nCells and 0 < nV_act < mesh.nVertices
+    assert workloads.SPHERES["qu7.5"] == (10, 120.0) and workloads.SPHERES["qu60"] == (7, 900.0)
+    assert 10 * 4 ** 10 + 2 == 10485762
+    with pytest.raises(ValueError):
+        workloads.build("nope")

@@ -1,0 +1,85 @@
+"""N > 1: the decomposed path end to end, one process per rank.
+
+CPU (gloo, world_size 2 and 3): host logic -- per-rank block construction, request exchange through the
+host communicator, the evp_set_halo lists driving real point-to-point messages -- with the oracle as
+block solver; owned results must be BIT-identical to the single-rank oracle run.
+GPU (nccl, needs >= 2 devices): the same through libevp_b200.so and its in-graph NCCL exchange."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import common
+from mpas_seaice_b200 import workloads
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _launch(mode, name, nsub, world, out_path, method="auto", timeout=600):
+    port = _free_port()
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), OMP_NUM_THREADS="2")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "_rank_worker.py"), mode, name, str(nsub),
+                                       out_path, method], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    outs = []
+    try:
+        for p in procs:
+            o, _ = p.communicate(timeout=timeout)
+            outs.append(o.decode(errors="replace"))
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+    for r, p in enumerate(procs):
+        assert p.returncode == 0, f"rank {r} failed:\n{outs[r][-3000:]}"
+    return dict(np.load(out_path))
+
+
+def _reference(name, nsub):
+    import oracle
+    w = workloads.build(name, with_static=False)
+    mesh, step, opts = w["mesh"], w["step"], w["opts"]
+    var = oracle.init_variational(mesh)
+    ref = common.run_oracle(mesh, var, step, opts, nsub)
+    return mesh, step, ref
+
+
+def _assert_equal(mesh, step, ref, out):
+    cm, vm = common.masks_for(mesh, step)
+    for k in common.COMPARE_CELL:
+        assert np.array_equal(out[k][cm], ref[k][cm]), k
+    for k in common.COMPARE_VERTEX:
+        assert np.array_equal(out[k][vm], ref[k][vm]), k
+    assert np.abs(ref["uVelocity"]).max() > 0
+
+
+@pytest.mark.parametrize("world,method", [(2, "auto"), (3, "rcb")])
+def test_gloo_ranks_match_single_rank(tmp_path, world, method):
+    name, nsub = "ico3", 6
+    out = _launch("oracle", name, nsub, world, str(tmp_path / "out.npz"), method)
+    mesh, step, ref = _reference(name, nsub)
+    _assert_equal(mesh, step, ref, out)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,nsub", [("ico4", 120), ("square", 120)])
+def test_nccl_ranks_match_single_rank(evp_lib, tmp_path, name, nsub):
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 4 if n >= 4 else 2
+    out = _launch("gpu", name, nsub, world, str(tmp_path / "out.npz"))
+    mesh, step, ref = _reference(name, nsub)
+    _assert_equal(mesh, step, ref, out)

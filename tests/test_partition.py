@@ -1,0 +1,108 @@
+"""Decomposition, halo maps and exchange lists (host logic, CPU only).
+
+The reference pins none of these maps numerically (they live in the un-vendored MPAS framework and in
+METIS output): SURVEY.md 8(c) -> "parity unpinned" for the maps themselves.  What IS asserted:
+self-consistency of the maps, and the reference's own parallelism policy
+(testing_and_setup/testing/tests/parallelism.py:75-85): owned results are BIT-identical for every
+rank count."""
+import numpy as np
+import pytest
+
+import common
+from mpas_seaice_b200 import partition
+
+
+@pytest.mark.parametrize("kind,n_parts,method", [("hex20", 2, "rcb"), ("hex20", 5, "rcb"), ("ico3", 4, "block"),
+                                                 ("ico3", 8, "rcb"), ("quad40", 3, "rcb"), ("ico3", 1, "block")])
+def test_blocks_are_consistent(kind, n_parts, method):
+    mesh, _ = common.mesh_case(kind)
+    nC, nV, M, D = mesh.nCells, mesh.nVertices, mesh.maxEdges, mesh.vertexDegree
+    part, blocks, lists = common.make_blocks(mesh, n_parts, method)
+    counts = np.bincount(part, minlength=n_parts)
+    assert counts.max() - counts.min() <= 1                      # balanced
+    assert np.array_equal(part, partition.partition_cells(mesh, n_parts, method))   # deterministic
+    cell_owned = np.zeros(nC, dtype=int)
+    vert_owned = np.zeros(nV, dtype=int)
+    for b in blocks:
+        nCs, nVs = b.nCellsSolve, b.nVerticesSolve
+        gc = b.indexToCellID.astype(np.int64) - 1
+        gv = b.indexToVertexID.astype(np.int64) - 1
+        cell_owned[gc[:nCs]] += 1
+        vert_owned[gv[:nVs]] += 1
+        assert np.all(np.diff(gc[:nCs]) > 0) and np.all(np.diff(gv[:nVs]) > 0)
+        assert len(np.unique(gc)) == len(gc) and len(np.unique(gv)) == len(gv)
+        assert np.all(part[gc[:nCs]] == b.rank) and np.all(part[gc[nCs:]] != b.rank)
+        # connectivity maps back to the global one, slot by slot
+        n = b.nEdgesOnCell[:b.nCells]
+        assert np.array_equal(n, mesh.nEdgesOnCell[gc])
+        assert b.nEdgesOnCell[b.nCells] == 0
+        for s in range(M):
+            ok = n > s
+            assert np.array_equal(gv[b.verticesOnCell[:b.nCells][ok, s] - 1], mesh.verticesOnCell[gc[ok], s] - 1)
+        cov_l = b.cellsOnVertex[:b.nVertices]
+        cov_g = mesh.cellsOnVertex[gv]
+        local = cov_l <= b.nCells
+        assert np.array_equal(gc[cov_l[local] - 1], cov_g[local] - 1)
+        # a cell that is not local is either the global junk cell or a non-local cell
+        assert np.all(cov_l[~local] == b.nCells + 1)
+        # stencil closure for owned vertices
+        own_valid = (cov_g[:nVs] >= 1) & (cov_g[:nVs] <= nC)
+        assert np.all(local[:nVs] == own_valid)
+        # geometry travels
+        assert np.array_equal(b.xVertex[:b.nVertices], mesh.xVertex[gv])
+        assert np.array_equal(b.areaCell[:b.nCells], mesh.areaCell[gc]) and b.areaCell[b.nCells] == mesh.areaCell[nC]
+    assert np.all(cell_owned == 1) and np.all(vert_owned == 1)
+    # exchange lists: what q sends to r is exactly what r expects from q, in the same order
+    for r, (nbr, soff, sidx, roff, ridx) in enumerate(lists):
+        b = blocks[r]
+        assert np.all(np.diff(nbr) > 0) and r not in nbr
+        assert np.all(sidx >= 1) and np.all(sidx <= b.nVerticesSolve)
+        assert np.all(ridx > b.nVerticesSolve) and np.all(ridx <= b.nVertices)
+        # every halo vertex is received exactly once; the recv slices are contiguous and in order
+        assert np.array_equal(ridx, np.arange(b.nVerticesSolve + 1, b.nVertices + 1))
+        for k, q in enumerate(nbr):
+            qn, qsoff, qsidx, qroff, qridx = lists[q]
+            kk = int(np.nonzero(qn == r)[0][0])
+            sent = blocks[q].indexToVertexID[qsidx[qsoff[kk]:qsoff[kk + 1]] - 1]
+            want = b.indexToVertexID[ridx[roff[k]:roff[k + 1]] - 1]
+            assert np.array_equal(sent, want)
+
+
+def test_too_few_halos_is_rejected():
+    mesh, _ = common.mesh_case("quad40")
+    part = partition.partition_cells(mesh, 4, "rcb")
+    with pytest.raises(ValueError, match="halo"):
+        partition.build_block(mesh, part, 0, n_halos=1)
+
+
+def test_graph_files_roundtrip(tmp_path):
+    mesh, _ = common.mesh_case("hex20")
+    part = partition.partition_cells(mesh, 3, "rcb")
+    partition.write_graph_info(mesh, str(tmp_path / "graph.info"))
+    partition.write_graph_part(part, str(tmp_path / "graph.info.part.3"))
+    assert np.array_equal(partition.read_graph_part(str(tmp_path / "graph.info.part.3"), mesh.nCells), part)
+    with open(tmp_path / "graph.info") as f:
+        head = f.readline().split()
+        lines = f.read().strip().split("\n")
+    assert int(head[0]) == mesh.nCells == len(lines)
+    deg = sum(len(l.split()) for l in lines)
+    assert deg == 2 * int(head[1])
+    with pytest.raises(ValueError):
+        partition.read_graph_part(str(tmp_path / "graph.info.part.3"), mesh.nCells + 1)
+
+
+@pytest.mark.parametrize("kind,n_parts,method,nsub", [("hex20", 2, "rcb", 12), ("hex20", 3, "block", 12),
+                                                      ("ico3", 4, "block", 12), ("ico3", 3, "rcb", 12),
+                                                      ("quad40", 2, "rcb", 6)])
+def test_owned_results_bit_identical_across_rank_counts(kind, n_parts, method, nsub):
+    """The reference's parallelism policy with the oracle as the per-block solver."""
+    mesh, var = common.mesh_case(kind)
+    step, opts = common.step_case(mesh)
+    ref = common.run_oracle(mesh, var, step, opts, nsub)
+    out, blocks, _ = common.run_oracle_blocks(mesh, step, opts, nsub, n_parts, method)
+    cm, vm = common.masks_for(mesh, step)
+    for k in common.COMPARE_CELL:
+        assert np.array_equal(out[k][cm], ref[k][cm]), k
+    for k in common.COMPARE_VERTEX:
+        assert np.array_equal(out[k][vm], ref[k][vm]), k
+    assert np.abs(ref["uVelocity"]).max() > 0
