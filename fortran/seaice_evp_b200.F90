@@ -1,0 +1,595 @@
+!|||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||
+!
+!  seaice_evp_b200
+!
+!> \brief ISO_C_BINDING shim between MPAS-Seaice and libevp_b200.so (include/evp_b200.h)
+!>
+!> Drop-in for the body of subcycle_velocity_solver
+!> (src/shared/mpas_seaice_velocity_solver.F:2404-2464) and for the device-residency lifecycle of
+!> module seaice_mesh_pool (src/shared/mpas_seaice_mesh_pool.F:76-281):
+!>
+!>    seaice_mesh_pool_create  ->  seaice_evp_b200_create   (after seaice_init_velocity_solver,
+!>                                                           src/shared/mpas_seaice_initialize.F:121)
+!>    seaice_mesh_pool_update  ->  seaice_evp_b200_update   (end of velocity_solver_pre_subcycle,
+!>                                                           velocity_solver.F:668)
+!>    subcycle_velocity_solver ->  seaice_evp_b200_subcycle (velocity_solver.F:585)
+!>    seaice_mesh_pool_destroy ->  seaice_evp_b200_destroy  (src/model_forward/mpas_seaice_core.F:431)
+!>
+!> seaice_run_velocity_solver(domain, clock) keeps its signature, its namelist options and its
+!> Registry fields.  Combinations the CUDA path does not cover (weak strain / weak divergence,
+!> config_average_variational_strain) are reported by seaice_evp_b200_supported() = .false. and the
+!> caller keeps using the original Fortran subcycle -- the ORIGINAL code, not a CPU copy of this one.
+!>
+!> The bind(C) types below mirror include/evp_b200.h field for field (tests/test_fortran_shim.py
+!> checks names, order and types against the header).  This file cannot be compiled in the build
+!> container (no Fortran compiler, no MPAS framework); see INTEGRATION.md.
+!
+!-----------------------------------------------------------------------
+
+module seaice_evp_b200
+
+  use, intrinsic :: iso_c_binding
+
+#ifndef EVP_B200_STANDALONE
+  use mpass_derived_types
+  use mpass_pool_routines
+  use mpass_log, only: mpas_log_write
+#endif
+
+  implicit none
+
+  private
+  save
+
+#ifndef EVP_B200_STANDALONE
+  public :: &
+       seaice_evp_b200_supported, &
+       seaice_evp_b200_create, &
+       seaice_evp_b200_update, &
+       seaice_evp_b200_subcycle, &
+       seaice_evp_b200_destroy
+#endif
+
+  ! ---- enums of include/evp_b200.h ----
+  integer(c_int), parameter, public :: &
+       EVP_OK = 0, &
+       EVP_CR_EVP = 1, EVP_CR_EVP_REVISED = 2, EVP_CR_LINEAR = 3, EVP_CR_NONE = 4, &
+       EVP_OCEAN_QUADRATIC = 1, EVP_OCEAN_LINEAR = 2, &
+       EVP_FLAG_PIN_HOST = 1
+
+  ! ---- struct evp_mesh_desc ----
+  type, bind(C), public :: evp_mesh_desc
+     integer(c_int) :: nCells
+     integer(c_int) :: nCellsSolve
+     integer(c_int) :: nVertices
+     integer(c_int) :: nVerticesSolve
+     integer(c_int) :: maxEdges
+     integer(c_int) :: vertexDegree
+     type(c_ptr) :: nEdgesOnCell
+     type(c_ptr) :: verticesOnCell
+     type(c_ptr) :: cellsOnVertex
+     type(c_ptr) :: cellVerticesAtVertex
+     type(c_ptr) :: basisGradientU
+     type(c_ptr) :: basisGradientV
+     type(c_ptr) :: basisIntegralsU
+     type(c_ptr) :: basisIntegralsV
+     type(c_ptr) :: basisIntegralsMetric
+     type(c_ptr) :: tanLatVertexRotatedOverRadius
+     type(c_ptr) :: variationalDenominator
+     type(c_ptr) :: vertexBoundaryType
+     type(c_ptr) :: vertexBoundarySourceLocal
+  end type evp_mesh_desc
+
+  ! ---- struct evp_options ----
+  type, bind(C), public :: evp_options
+     integer(c_int) :: constitutive_relation_type
+     integer(c_int) :: ocean_stress_type
+     integer(c_int) :: use_ocean_stress
+     integer(c_int) :: use_special_boundaries_velocity
+     integer(c_int) :: device
+     integer(c_int) :: flags
+     real(c_double) :: elasticTimeStep
+     real(c_double) :: dynamicsTimeStep
+     real(c_double) :: dampingTimescale
+     real(c_double) :: numericalInertiaCoefficient
+  end type evp_options
+
+  ! ---- struct evp_step_fields ----
+  type, bind(C), public :: evp_step_fields
+     type(c_ptr) :: solveStress
+     type(c_ptr) :: solveVelocity
+     type(c_ptr) :: icePressure
+     type(c_ptr) :: uVelocity
+     type(c_ptr) :: vVelocity
+     type(c_ptr) :: stress11
+     type(c_ptr) :: stress22
+     type(c_ptr) :: stress12
+     type(c_ptr) :: totalMassVertex
+     type(c_ptr) :: totalMassVertexfVertex
+     type(c_ptr) :: iceAreaVertex
+     type(c_ptr) :: airStressVertexU
+     type(c_ptr) :: airStressVertexV
+     type(c_ptr) :: surfaceTiltForceU
+     type(c_ptr) :: surfaceTiltForceV
+     type(c_ptr) :: oceanStressU
+     type(c_ptr) :: oceanStressV
+     type(c_ptr) :: uOceanVelocityVertex
+     type(c_ptr) :: vOceanVelocityVertex
+     type(c_ptr) :: uVelocityInitial
+     type(c_ptr) :: vVelocityInitial
+  end type evp_step_fields
+
+  ! ---- struct evp_out_fields ----
+  type, bind(C), public :: evp_out_fields
+     type(c_ptr) :: uVelocity
+     type(c_ptr) :: vVelocity
+     type(c_ptr) :: stress11
+     type(c_ptr) :: stress22
+     type(c_ptr) :: stress12
+     type(c_ptr) :: strain11
+     type(c_ptr) :: strain22
+     type(c_ptr) :: strain12
+     type(c_ptr) :: replacementPressure
+     type(c_ptr) :: stressDivergenceU
+     type(c_ptr) :: stressDivergenceV
+     type(c_ptr) :: oceanStressCoeff
+  end type evp_out_fields
+
+  ! ---- functions of include/evp_b200.h ----
+  interface
+
+     function evp_create(handle, mesh, options) bind(C, name="evp_create") result(ierr)
+       import :: c_ptr, c_int, evp_mesh_desc, evp_options
+       type(c_ptr), intent(out) :: handle
+       type(evp_mesh_desc), intent(in) :: mesh
+       type(evp_options), intent(in) :: options
+       integer(c_int) :: ierr
+     end function evp_create
+
+     function evp_set_options(handle, options) bind(C, name="evp_set_options") result(ierr)
+       import :: c_ptr, c_int, evp_options
+       type(c_ptr), value :: handle
+       type(evp_options), intent(in) :: options
+       integer(c_int) :: ierr
+     end function evp_set_options
+
+     function evp_update_step(handle, fields) bind(C, name="evp_update_step") result(ierr)
+       import :: c_ptr, c_int, evp_step_fields
+       type(c_ptr), value :: handle
+       type(evp_step_fields), intent(in) :: fields
+       integer(c_int) :: ierr
+     end function evp_update_step
+
+     function evp_set_masks(handle, solveStress, solveVelocity) bind(C, name="evp_set_masks") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: handle
+       type(c_ptr), value :: solveStress
+       type(c_ptr), value :: solveVelocity
+       integer(c_int) :: ierr
+     end function evp_set_masks
+
+     function evp_run_subcycles(handle, nSubcycles) bind(C, name="evp_run_subcycles") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: handle
+       integer(c_int), value :: nSubcycles
+       integer(c_int) :: ierr
+     end function evp_run_subcycles
+
+     function evp_synchronize(handle) bind(C, name="evp_synchronize") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: handle
+       integer(c_int) :: ierr
+     end function evp_synchronize
+
+     function evp_fetch(handle, out) bind(C, name="evp_fetch") result(ierr)
+       import :: c_ptr, c_int, evp_out_fields
+       type(c_ptr), value :: handle
+       type(evp_out_fields), intent(in) :: out
+       integer(c_int) :: ierr
+     end function evp_fetch
+
+     function evp_destroy(handle) bind(C, name="evp_destroy") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: handle
+       integer(c_int) :: ierr
+     end function evp_destroy
+
+     function evp_last_error_string() bind(C, name="evp_last_error_string") result(str)
+       import :: c_ptr
+       type(c_ptr) :: str
+     end function evp_last_error_string
+
+     function evp_comm_get_unique_id(id128) bind(C, name="evp_comm_get_unique_id") result(ierr)
+       import :: c_char, c_int
+       character(kind=c_char), intent(out) :: id128(128)
+       integer(c_int) :: ierr
+     end function evp_comm_get_unique_id
+
+     function evp_comm_init(handle, rank, nRanks, id128) bind(C, name="evp_comm_init") result(ierr)
+       import :: c_ptr, c_char, c_int
+       type(c_ptr), value :: handle
+       integer(c_int), value :: rank
+       integer(c_int), value :: nRanks
+       character(kind=c_char), intent(in) :: id128(128)
+       integer(c_int) :: ierr
+     end function evp_comm_init
+
+     function evp_set_halo(handle, nNeighbours, neighbourRank, sendOffset, sendIndex, recvOffset, recvIndex) &
+          bind(C, name="evp_set_halo") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: handle
+       integer(c_int), value :: nNeighbours
+       integer(c_int), intent(in) :: neighbourRank(*)
+       integer(c_int), intent(in) :: sendOffset(*)
+       integer(c_int), intent(in) :: sendIndex(*)
+       integer(c_int), intent(in) :: recvOffset(*)
+       integer(c_int), intent(in) :: recvIndex(*)
+       integer(c_int) :: ierr
+     end function evp_set_halo
+
+  end interface
+
+  ! one block per rank (mesh_pool.F:98-105) <-> one handle <-> one GPU
+  type(c_ptr) :: evpHandle = c_null_ptr
+
+  integer(c_int) :: nElasticSubcycle = 120
+
+contains
+
+#ifndef EVP_B200_STANDALONE
+
+!|||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||
+!  seaice_evp_b200_supported
+!
+!> \brief Is this namelist combination covered by the CUDA path?  (velocity_solver.F:168-198)
+!-----------------------------------------------------------------------
+
+  function seaice_evp_b200_supported(domain) result(supported)
+
+    type(domain_type), intent(in) :: domain
+    logical :: supported
+
+    character(len=strKIND), pointer :: &
+         config_strain_scheme, &
+         config_stress_divergence_scheme
+    logical, pointer :: &
+         config_average_variational_strain
+
+    call MPAS_pool_get_config(domain % configs, "config_strain_scheme", config_strain_scheme)
+    call MPAS_pool_get_config(domain % configs, "config_stress_divergence_scheme", config_stress_divergence_scheme)
+    call MPAS_pool_get_config(domain % configs, "config_average_variational_strain", config_average_variational_strain)
+
+    supported = trim(config_strain_scheme) == "variational" .and. &
+                trim(config_stress_divergence_scheme) == "variational" .and. &
+                .not. config_average_variational_strain
+
+  end function seaice_evp_b200_supported
+
+!|||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||
+!  evp_b200_check
+!
+!> \brief C status -> MPAS critical error, the reference's convention (velocity_solver.F:262-265)
+!-----------------------------------------------------------------------
+
+  subroutine evp_b200_check(ierr, where)
+
+    integer(c_int), intent(in) :: ierr
+    character(len=*), intent(in) :: where
+
+    character(kind=c_char), dimension(:), pointer :: cmsg
+    character(len=512) :: msg
+    integer :: i
+
+    if (ierr /= EVP_OK) then
+       msg = " "
+       call c_f_pointer(evp_last_error_string(), cmsg, [512])
+       do i = 1, 512
+          if (cmsg(i) == c_null_char) exit
+          msg(i:i) = cmsg(i)
+       enddo
+       call mpas_log_write("libevp_b200: "//trim(where)//": "//trim(msg), MPAS_LOG_CRIT)
+    endif
+
+  end subroutine evp_b200_check
+
+!|||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||
+!  fill_options
+!-----------------------------------------------------------------------
+
+  subroutine fill_options(domain, options)
+
+    use seaice_velocity_solver_constitutive_relation, only: &
+         constitutiveRelationType, dampingTimescale, numericalInertiaCoefficient
+
+    type(domain_type), intent(in) :: domain
+    type(evp_options), intent(out) :: options
+
+    type(MPAS_pool_type), pointer :: velocitySolverPool
+    real(kind=RKIND), pointer :: elasticTimeStep, dynamicsTimeStep
+    character(len=strKIND), pointer :: config_ocean_stress_type
+    logical, pointer :: config_use_ocean_stress, config_use_special_boundaries_velocity
+    integer, pointer :: config_elastic_subcycle_number
+
+    call MPAS_pool_get_subpool(domain % blocklist % structs, "velocity_solver", velocitySolverPool)
+    call MPAS_pool_get_array(velocitySolverPool, "elasticTimeStep", elasticTimeStep)
+    call MPAS_pool_get_array(velocitySolverPool, "dynamicsTimeStep", dynamicsTimeStep)
+    call MPAS_pool_get_config(domain % configs, "config_ocean_stress_type", config_ocean_stress_type)
+    call MPAS_pool_get_config(domain % configs, "config_use_ocean_stress", config_use_ocean_stress)
+    call MPAS_pool_get_config(domain % configs, "config_use_special_boundaries_velocity", &
+                                                 config_use_special_boundaries_velocity)
+    call MPAS_pool_get_config(domain % configs, "config_elastic_subcycle_number", config_elastic_subcycle_number)
+
+    nElasticSubcycle = config_elastic_subcycle_number
+
+    ! EVP_CR_* are numbered like the reference's own constants (constitutive_relation.F:34-38)
+    options % constitutive_relation_type = constitutiveRelationType
+    if (trim(config_ocean_stress_type) == "quadratic") then
+       options % ocean_stress_type = EVP_OCEAN_QUADRATIC
+    else
+       options % ocean_stress_type = EVP_OCEAN_LINEAR
+    endif
+    options % use_ocean_stress = merge(1, 0, config_use_ocean_stress)
+    options % use_special_boundaries_velocity = merge(1, 0, config_use_special_boundaries_velocity)
+    options % device = -1                    ! the device the host selected (cudaSetDevice / CUDA_VISIBLE_DEVICES)
+    options % flags = EVP_FLAG_PIN_HOST      ! MPAS pool arrays live at stable addresses
+    options % elasticTimeStep = elasticTimeStep
+    options % dynamicsTimeStep = dynamicsTimeStep
+    options % dampingTimescale = dampingTimescale
+    options % numericalInertiaCoefficient = numericalInertiaCoefficient
+
+  end subroutine fill_options
+
+!|||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||
+!  seaice_evp_b200_create
+!
+!> \brief seaice_mesh_pool_create equivalent: upload connectivity + basis, build the handle
+!-----------------------------------------------------------------------
+
+  subroutine seaice_evp_b200_create(domain, variationalDenominator)
+
+    type(domain_type), intent(inout) :: domain
+    real(kind=RKIND), dimension(:), target, intent(in) :: &
+         variationalDenominator   !< the module array of seaice_velocity_solver_variational (variational.F:358-445)
+
+    type(MPAS_pool_type), pointer :: meshPool, velocityVariationalPool, specialBoundariesPool
+    type(evp_mesh_desc) :: mesh
+    type(evp_options) :: options
+
+    integer, pointer :: nCells, nCellsSolve, nVertices, nVerticesSolve, maxEdges, vertexDegree
+    integer, dimension(:), pointer :: nEdgesOnCell, vertexBoundaryType, vertexBoundarySourceLocal
+    integer, dimension(:,:), pointer :: verticesOnCell, cellsOnVertex, cellVerticesAtVertex
+    real(kind=RKIND), dimension(:), pointer :: tanLatVertexRotatedOverRadius
+    real(kind=RKIND), dimension(:,:,:), pointer :: &
+         basisGradientU, basisGradientV, basisIntegralsU, basisIntegralsV, basisIntegralsMetric
+    logical, pointer :: config_use_special_boundaries_velocity
+
+    call MPAS_pool_get_subpool(domain % blocklist % structs, "mesh", meshPool)
+    call MPAS_pool_get_subpool(domain % blocklist % structs, "velocity_variational", velocityVariationalPool)
+
+    call MPAS_pool_get_dimension(meshPool, "nCells", nCells)
+    call MPAS_pool_get_dimension(meshPool, "nCellsSolve", nCellsSolve)
+    call MPAS_pool_get_dimension(meshPool, "nVertices", nVertices)
+    call MPAS_pool_get_dimension(meshPool, "nVerticesSolve", nVerticesSolve)
+    call MPAS_pool_get_dimension(meshPool, "maxEdges", maxEdges)
+    call MPAS_pool_get_dimension(meshPool, "vertexDegree", vertexDegree)
+
+    call MPAS_pool_get_array(meshPool, "nEdgesOnCell", nEdgesOnCell)
+    call MPAS_pool_get_array(meshPool, "verticesOnCell", verticesOnCell)
+    call MPAS_pool_get_array(meshPool, "cellsOnVertex", cellsOnVertex)
+
+    call MPAS_pool_get_array(velocityVariationalPool, "cellVerticesAtVertex", cellVerticesAtVertex)
+    call MPAS_pool_get_array(velocityVariationalPool, "basisGradientU", basisGradientU)
+    call MPAS_pool_get_array(velocityVariationalPool, "basisGradientV", basisGradientV)
+    call MPAS_pool_get_array(velocityVariationalPool, "basisIntegralsU", basisIntegralsU)
+    call MPAS_pool_get_array(velocityVariationalPool, "basisIntegralsV", basisIntegralsV)
+    call MPAS_pool_get_array(velocityVariationalPool, "basisIntegralsMetric", basisIntegralsMetric)
+    call MPAS_pool_get_array(velocityVariationalPool, "tanLatVertexRotatedOverRadius", tanLatVertexRotatedOverRadius)
+
+    mesh % nCells = nCells
+    mesh % nCellsSolve = nCellsSolve
+    mesh % nVertices = nVertices
+    mesh % nVerticesSolve = nVerticesSolve
+    mesh % maxEdges = maxEdges
+    mesh % vertexDegree = vertexDegree
+    mesh % nEdgesOnCell = c_loc(nEdgesOnCell)
+    mesh % verticesOnCell = c_loc(verticesOnCell)
+    mesh % cellsOnVertex = c_loc(cellsOnVertex)
+    mesh % cellVerticesAtVertex = c_loc(cellVerticesAtVertex)
+    mesh % basisGradientU = c_loc(basisGradientU)
+    mesh % basisGradientV = c_loc(basisGradientV)
+    mesh % basisIntegralsU = c_loc(basisIntegralsU)
+    mesh % basisIntegralsV = c_loc(basisIntegralsV)
+    mesh % basisIntegralsMetric = c_loc(basisIntegralsMetric)
+    mesh % tanLatVertexRotatedOverRadius = c_loc(tanLatVertexRotatedOverRadius)
+    mesh % variationalDenominator = c_loc(variationalDenominator)
+    mesh % vertexBoundaryType = c_null_ptr
+    mesh % vertexBoundarySourceLocal = c_null_ptr
+
+    call MPAS_pool_get_config(domain % configs, "config_use_special_boundaries_velocity", &
+                                                 config_use_special_boundaries_velocity)
+    if (config_use_special_boundaries_velocity) then
+       call MPAS_pool_get_subpool(domain % blocklist % structs, "special_boundaries", specialBoundariesPool)
+       call MPAS_pool_get_array(specialBoundariesPool, "vertexBoundaryType", vertexBoundaryType)
+       call MPAS_pool_get_array(specialBoundariesPool, "vertexBoundarySourceLocal", vertexBoundarySourceLocal)
+       mesh % vertexBoundaryType = c_loc(vertexBoundaryType)
+       mesh % vertexBoundarySourceLocal = c_loc(vertexBoundarySourceLocal)
+    endif
+
+    call fill_options(domain, options)
+
+    call evp_b200_check(evp_create(evpHandle, mesh, options), "evp_create")
+
+    ! multi-rank runs: the velocityHaloExchangeGroup lists (velocity_solver.F:259-349) go to
+    ! evp_set_halo here; see INTEGRATION.md section 4 for how they are read off the dmpar exchange lists.
+
+  end subroutine seaice_evp_b200_create
+
+!|||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||
+!  seaice_evp_b200_update
+!
+!> \brief seaice_mesh_pool_update equivalent: one dynamics step's inputs, host -> device
+!-----------------------------------------------------------------------
+
+  subroutine seaice_evp_b200_update(domain)
+
+    type(domain_type), intent(inout) :: domain
+
+    type(MPAS_pool_type), pointer :: velocitySolverPool, velocityVariationalPool, icestatePool
+    type(evp_step_fields) :: f
+    type(evp_options) :: options
+
+    integer, dimension(:), pointer :: solveStress, solveVelocity
+    real(kind=RKIND), dimension(:), pointer :: &
+         icePressure, uVelocity, vVelocity, totalMassVertex, totalMassVertexfVertex, iceAreaVertex, &
+         airStressVertexU, airStressVertexV, surfaceTiltForceU, surfaceTiltForceV, oceanStressU, oceanStressV, &
+         uOceanVelocityVertex, vOceanVelocityVertex, uVelocityInitial, vVelocityInitial
+    real(kind=RKIND), dimension(:,:), pointer :: stress11, stress22, stress12
+
+    call MPAS_pool_get_subpool(domain % blocklist % structs, "velocity_solver", velocitySolverPool)
+    call MPAS_pool_get_subpool(domain % blocklist % structs, "velocity_variational", velocityVariationalPool)
+    call MPAS_pool_get_subpool(domain % blocklist % structs, "icestate", icestatePool)
+
+    call MPAS_pool_get_array(velocitySolverPool, "solveStress", solveStress)
+    call MPAS_pool_get_array(velocitySolverPool, "solveVelocity", solveVelocity)
+    call MPAS_pool_get_array(velocitySolverPool, "icePressure", icePressure)
+    call MPAS_pool_get_array(velocitySolverPool, "uVelocity", uVelocity)
+    call MPAS_pool_get_array(velocitySolverPool, "vVelocity", vVelocity)
+    call MPAS_pool_get_array(velocityVariationalPool, "stress11", stress11)
+    call MPAS_pool_get_array(velocityVariationalPool, "stress22", stress22)
+    call MPAS_pool_get_array(velocityVariationalPool, "stress12", stress12)
+    call MPAS_pool_get_array(icestatePool, "totalMassVertex", totalMassVertex)
+    call MPAS_pool_get_array(icestatePool, "iceAreaVertex", iceAreaVertex)
+    call MPAS_pool_get_array(velocitySolverPool, "totalMassVertexfVertex", totalMassVertexfVertex)
+    call MPAS_pool_get_array(velocitySolverPool, "airStressVertexU", airStressVertexU)
+    call MPAS_pool_get_array(velocitySolverPool, "airStressVertexV", airStressVertexV)
+    call MPAS_pool_get_array(velocitySolverPool, "surfaceTiltForceU", surfaceTiltForceU)
+    call MPAS_pool_get_array(velocitySolverPool, "surfaceTiltForceV", surfaceTiltForceV)
+    call MPAS_pool_get_array(velocitySolverPool, "oceanStressU", oceanStressU)
+    call MPAS_pool_get_array(velocitySolverPool, "oceanStressV", oceanStressV)
+    call MPAS_pool_get_array(velocitySolverPool, "uOceanVelocityVertex", uOceanVelocityVertex)
+    call MPAS_pool_get_array(velocitySolverPool, "vOceanVelocityVertex", vOceanVelocityVertex)
+    call MPAS_pool_get_array(velocitySolverPool, "uVelocityInitial", uVelocityInitial)
+    call MPAS_pool_get_array(velocitySolverPool, "vVelocityInitial", vVelocityInitial)
+
+    f % solveStress = c_loc(solveStress)
+    f % solveVelocity = c_loc(solveVelocity)
+    f % icePressure = c_loc(icePressure)
+    f % uVelocity = c_loc(uVelocity)
+    f % vVelocity = c_loc(vVelocity)
+    f % stress11 = c_loc(stress11)
+    f % stress22 = c_loc(stress22)
+    f % stress12 = c_loc(stress12)
+    f % totalMassVertex = c_loc(totalMassVertex)
+    f % totalMassVertexfVertex = c_loc(totalMassVertexfVertex)
+    f % iceAreaVertex = c_loc(iceAreaVertex)
+    f % airStressVertexU = c_loc(airStressVertexU)
+    f % airStressVertexV = c_loc(airStressVertexV)
+    f % surfaceTiltForceU = c_loc(surfaceTiltForceU)
+    f % surfaceTiltForceV = c_loc(surfaceTiltForceV)
+    f % oceanStressU = c_loc(oceanStressU)
+    f % oceanStressV = c_loc(oceanStressV)
+    f % uOceanVelocityVertex = c_loc(uOceanVelocityVertex)
+    f % vOceanVelocityVertex = c_loc(vOceanVelocityVertex)
+    f % uVelocityInitial = c_loc(uVelocityInitial)
+    f % vVelocityInitial = c_loc(vVelocityInitial)
+
+    ! config_dt may change between steps (coupled runs): refresh the scalars, cheap
+    call fill_options(domain, options)
+    call evp_b200_check(evp_set_options(evpHandle, options), "evp_set_options")
+
+    call evp_b200_check(evp_update_step(evpHandle, f), "evp_update_step")
+
+  end subroutine seaice_evp_b200_update
+
+!|||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||
+!  seaice_evp_b200_subcycle
+!
+!> \brief Replacement body of subcycle_velocity_solver (velocity_solver.F:2404-2464)
+!>
+!> The special-boundary velocity copies before the loop and after every subcycle, the
+!> config_elastic_subcycle_number subcycles and the per-subcycle halo exchange all run inside one
+!> CUDA graph on the device; afterwards everything velocity_solver_post_subcycle and the restart
+!> stream read is copied back into the pool arrays.
+!-----------------------------------------------------------------------
+
+  subroutine seaice_evp_b200_subcycle(domain)
+
+    use seaice_special_boundaries, only: &
+         seaice_set_special_boundaries_velocity_masks
+
+    type(domain_type), intent(inout) :: domain
+
+    type(MPAS_pool_type), pointer :: velocitySolverPool, velocityVariationalPool
+    type(evp_out_fields) :: o
+
+    integer, dimension(:), pointer :: solveStress, solveVelocity
+    real(kind=RKIND), dimension(:), pointer :: &
+         uVelocity, vVelocity, stressDivergenceU, stressDivergenceV, oceanStressCoeff
+    real(kind=RKIND), dimension(:,:), pointer :: &
+         stress11, stress22, stress12, strain11, strain22, strain12, replacementPressure
+    logical, pointer :: config_use_special_boundaries_velocity_masks
+
+    call MPAS_pool_get_subpool(domain % blocklist % structs, "velocity_solver", velocitySolverPool)
+    call MPAS_pool_get_subpool(domain % blocklist % structs, "velocity_variational", velocityVariationalPool)
+
+    ! the mask variant of the special boundaries only overwrites the two integer masks with constant
+    ! arrays (special_boundaries.F:345-401): apply it once on the host, then push the masks
+    call MPAS_pool_get_config(domain % configs, "config_use_special_boundaries_velocity_masks", &
+                                                 config_use_special_boundaries_velocity_masks)
+    if (config_use_special_boundaries_velocity_masks) then
+       call seaice_set_special_boundaries_velocity_masks(domain)
+       call MPAS_pool_get_array(velocitySolverPool, "solveStress", solveStress)
+       call MPAS_pool_get_array(velocitySolverPool, "solveVelocity", solveVelocity)
+       call evp_b200_check(evp_set_masks(evpHandle, c_loc(solveStress), c_loc(solveVelocity)), "evp_set_masks")
+    endif
+
+    call evp_b200_check(evp_run_subcycles(evpHandle, nElasticSubcycle), "evp_run_subcycles")
+
+    call MPAS_pool_get_array(velocitySolverPool, "uVelocity", uVelocity)
+    call MPAS_pool_get_array(velocitySolverPool, "vVelocity", vVelocity)
+    call MPAS_pool_get_array(velocitySolverPool, "stressDivergenceU", stressDivergenceU)
+    call MPAS_pool_get_array(velocitySolverPool, "stressDivergenceV", stressDivergenceV)
+    call MPAS_pool_get_array(velocitySolverPool, "oceanStressCoeff", oceanStressCoeff)
+    call MPAS_pool_get_array(velocityVariationalPool, "stress11", stress11)
+    call MPAS_pool_get_array(velocityVariationalPool, "stress22", stress22)
+    call MPAS_pool_get_array(velocityVariationalPool, "stress12", stress12)
+    call MPAS_pool_get_array(velocityVariationalPool, "strain11", strain11)
+    call MPAS_pool_get_array(velocityVariationalPool, "strain22", strain22)
+    call MPAS_pool_get_array(velocityVariationalPool, "strain12", strain12)
+    call MPAS_pool_get_array(velocityVariationalPool, "replacementPressure", replacementPressure)
+
+    o % uVelocity = c_loc(uVelocity)
+    o % vVelocity = c_loc(vVelocity)
+    o % stress11 = c_loc(stress11)
+    o % stress22 = c_loc(stress22)
+    o % stress12 = c_loc(stress12)
+    o % strain11 = c_loc(strain11)
+    o % strain22 = c_loc(strain22)
+    o % strain12 = c_loc(strain12)
+    o % replacementPressure = c_loc(replacementPressure)
+    o % stressDivergenceU = c_loc(stressDivergenceU)
+    o % stressDivergenceV = c_loc(stressDivergenceV)
+    o % oceanStressCoeff = c_loc(oceanStressCoeff)
+
+    call evp_b200_check(evp_fetch(evpHandle, o), "evp_fetch")
+
+  end subroutine seaice_evp_b200_subcycle
+
+!|||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||
+!  seaice_evp_b200_destroy
+!
+!> \brief seaice_mesh_pool_destroy equivalent
+!-----------------------------------------------------------------------
+
+  subroutine seaice_evp_b200_destroy(err)
+
+    integer, intent(out) :: err
+
+    err = evp_destroy(evpHandle)
+    evpHandle = c_null_ptr
+
+  end subroutine seaice_evp_b200_destroy
+
+#endif
+
+end module seaice_evp_b200

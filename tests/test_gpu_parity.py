@@ -44,3 +44,287 @@ def test_evp_subcycles_match_oracle(evp_lib, kind, nsub):
     cm, vm = common.masks_for(mesh, step)
     nV = mesh.nVertices
     assert np.all(out["uVelocity"][:nV][~vm[:nV]] == 0.0)
+
+
+@pytest.mark.parametrize("kind", ["hex20", "quad40", "ico3", "ico5"])
+def test_device_wachspress_precompute_bit_exact(evp_lib, kind):
+    """evp_precompute_wachspress against the oracle's seaice_init_velocity_solver_wachspress
+    (wachspress.F:46-161): all five basis arrays bit-identical, then a run from the device basis."""
+    from mpas_seaice_b200 import host
+    mesh, var = common.mesh_case(kind)
+    step, opts = common.step_case(mesh)
+    solver = host.EvpSolver(mesh, var, opts, local_coords=(var["xLocal"], var["yLocal"]))
+    try:
+        got = solver.fetch_basis()
+        nC = mesh.nCells
+        for k, a in got.items():
+            assert np.array_equal(a[:nC], var[k][:nC]), k
+        solver.update_step(step)
+        solver.run_subcycles(5)
+        out = solver.fetch()
+    finally:
+        solver.destroy()
+    ref = common.run_oracle(mesh, var, step, opts, 5)
+    _compare(mesh, step, ref, out)
+
+
+@pytest.mark.parametrize("itype,order", [("dunavant", 1), ("dunavant", 4), ("dunavant", 7), ("trapezoidal", 3)])
+def test_device_precompute_other_quadratures(evp_lib, itype, order):
+    from mpas_seaice_b200 import host
+    import oracle
+    mesh, _ = common.mesh_case("hex20")
+    var = oracle.init_variational(mesh, integration_type=itype, integration_order=order)
+    step, opts = common.step_case(mesh)
+    solver = host.EvpSolver(mesh, var, opts, local_coords=(var["xLocal"], var["yLocal"]), integration=(itype, order))
+    try:
+        got = solver.fetch_basis()
+    finally:
+        solver.destroy()
+    for k, a in got.items():
+        assert np.array_equal(a[:mesh.nCells], var[k][:mesh.nCells]), k
+
+
+@pytest.mark.parametrize("cr,ocean", [("evp_revised", "quadratic"), ("evp", "linear"), ("linear", "quadratic"),
+                                      ("none", "quadratic")])
+@pytest.mark.parametrize("kind", ["hex20", "ico3"])
+def test_namelist_options(evp_lib, kind, cr, ocean):
+    """config_constitutive_relation_type x config_ocean_stress_type behind the boundary."""
+    mesh, var = common.mesh_case(kind)
+    step, opts = common.step_case(mesh, constitutive_relation_type=cr)
+    opts = dict(opts, ocean_stress_type=ocean)
+    if cr in ("linear", "none"):
+        # operator-test style: a non-trivial velocity field that stays fixed (velocity_solver.F:2529-2541)
+        nV = mesh.nVertices
+        x = np.arange(nV + 1, dtype=np.float64)
+        step["uVelocity"] = np.where(step["solveVelocity"] == 1, 0.1 * np.sin(0.37 * x), 0.0)
+        step["vVelocity"] = np.where(step["solveVelocity"] == 1, 0.1 * np.cos(0.11 * x), 0.0)
+        if cr == "none":
+            step["stress11"][:] = np.where(step["solveStress"][:, None] == 1, 3.0, 0.0)
+            step["stress12"][:] = np.where(step["solveStress"][:, None] == 1, -1.5, 0.0)
+    nsub = 30
+    ref = common.run_oracle(mesh, var, step, opts, nsub)
+    out = common.run_device(mesh, var, step, opts, nsub)
+    fields_cell = common.COMPARE_CELL if cr != "none" else ("stress11", "stress22", "stress12", "strain11",
+                                                            "strain22", "strain12")
+    _compare(mesh, step, ref, out, fields_cell=fields_cell)
+    if cr in ("linear", "none"):
+        assert np.array_equal(out["uVelocity"], step["uVelocity"])
+
+
+def test_no_ocean_stress(evp_lib):
+    mesh, var = common.mesh_case("hex20")
+    step, opts = common.step_case(mesh, use_ocean_stress=False)
+    ref = common.run_oracle(mesh, var, step, opts, 20)
+    out = common.run_device(mesh, var, step, opts, 20)
+    _compare(mesh, step, ref, out)
+    assert np.all(out["oceanStressCoeff"] == 0.0)
+
+
+@pytest.mark.parametrize("kind,state", [("ico5", "B"), ("hex82", "square")])
+def test_partial_ice_cover_masks(evp_lib, kind, state):
+    """State B (ice caps) / the square ramp: inactive cells and vertices next to active ones."""
+    mesh, var = common.mesh_case(kind)
+    step, opts = common.step_case(mesh, state_kind=state)
+    nC, nV = mesh.nCells, mesh.nVertices
+    assert 0 < (step["solveStress"][:nC] == 1).sum() < nC or state == "square"
+    assert 0 < (step["solveVelocity"][:nV] == 1).sum() < nV
+    ref = common.run_oracle(mesh, var, step, opts, 120)
+    out = common.run_device(mesh, var, step, opts, 120)
+    _compare(mesh, step, ref, out)
+    off = step["solveStress"][:nC] != 1
+    for k in ("stress11", "stress22", "stress12", "strain11", "replacementPressure"):
+        assert np.all(out[k][:nC][off] == 0.0), k
+
+
+def test_pwl_basis_dense_gradients(evp_lib):
+    """config_variational_basis = 'pwl': gradients are dense (pwl.F:259-274), uploaded from the host."""
+    mesh, var = common.mesh_case("ico3", basis="pwl")
+    step, opts = common.step_case(mesh)
+    ref = common.run_oracle(mesh, var, step, opts, 60)
+    out = common.run_device(mesh, var, step, opts, 60)
+    _compare(mesh, step, ref, out)
+
+
+def test_alternate_denominator(evp_lib):
+    mesh, var = common.mesh_case("ico3", denominator="alternate")
+    step, opts = common.step_case(mesh)
+    ref = common.run_oracle(mesh, var, step, opts, 60)
+    out = common.run_device(mesh, var, step, opts, 60)
+    _compare(mesh, step, ref, out)
+
+
+def test_state_carried_across_dynamics_steps(evp_lib):
+    """Two dynamics steps: u, v, stresses and solveVelocityPrevious carried, the second
+    step starts from non-zero stress; CUDA-graph replay (second call reuses the instantiated graph)."""
+    from mpas_seaice_b200 import host, synthetic
+    mesh, var = common.mesh_case("ico3")
+    state = synthetic.sphere_state(mesh, "A")
+    step, opts = synthetic.pre_subcycle(mesh, state, 3600.0)
+    solver = host.EvpSolver(mesh, var, opts)
+    try:
+        prev_dev, prev_ref = None, None
+        for it in range(2):
+            s_dev, _ = synthetic.pre_subcycle(mesh, state, 3600.0, prev=prev_dev)
+            s_ref, _ = synthetic.pre_subcycle(mesh, state, 3600.0, prev=prev_ref)
+            solver.update_step(s_dev)
+            solver.run_subcycles(120)
+            out = solver.fetch()
+            ref = common.run_oracle(mesh, var, s_ref, opts, 120)
+            _compare(mesh, s_ref, ref, out)
+            prev_dev = dict(out, solveVelocityPrevious=s_dev["solveVelocityPrevious"])
+            prev_ref = dict(ref, solveVelocityPrevious=s_ref["solveVelocityPrevious"])
+        assert np.abs(s_ref["stress11"]).max() > 0
+    finally:
+        solver.destroy()
+
+
+def test_graph_and_stream_paths_agree(evp_lib):
+    from mpas_seaice_b200 import host
+    mesh, var = common.mesh_case("hex20")
+    step, opts = common.step_case(mesh)
+    outs = []
+    for use_graph in (1, 0):
+        solver = host.EvpSolver(mesh, var, opts)
+        try:
+            solver.set_use_graph(use_graph)
+            solver.update_step(step)
+            solver.run_subcycles(7)
+            solver.run_subcycles(3)          # a second call with a different count re-instantiates
+            outs.append(solver.fetch())
+            assert solver.launch_count(10) == 20
+        finally:
+            solver.destroy()
+    for k in common.COMPARE_CELL + common.COMPARE_VERTEX:
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+    ref = common.run_oracle(mesh, var, step, opts, 10)
+    # strain / divergence diagnostics are those of the LAST subcycle in both
+    _compare(mesh, step, ref, outs[0])
+
+
+def test_pinned_host_path(evp_lib):
+    """EVP_FLAG_PIN_HOST (cudaHostRegister of the caller's arrays) gives the same bits as the bounce path."""
+    mesh, var = common.mesh_case("ico5")
+    step, opts = common.step_case(mesh)
+    a = common.run_device(mesh, var, step, opts, 10)
+    b = common.run_device(mesh, var, step, opts, 10, pin_host=True)
+    for k in common.COMPARE_CELL + common.COMPARE_VERTEX:
+        assert np.array_equal(a[k], b[k]), k
+
+
+def _special_boundary_case():
+    """1D_velocity_hex-like set-up (testing_and_setup/testcases/square/1D_velocity_hex): periodic in x
+    (type 1), reversed copies (type 2) and zero-velocity vertices (type 3), with a chain
+    (a boundary vertex whose source is itself a boundary vertex)."""
+    mesh, var = common.mesh_case("hex20")
+    step, opts = common.step_case(mesh)
+    nV = mesh.nVertices
+    vbt = np.zeros(nV + 1, dtype=np.int32)
+    src = np.zeros(nV + 1, dtype=np.int32)
+    active = np.nonzero(step["solveVelocity"][:nV] == 1)[0]
+    inactive = np.nonzero(step["solveVelocity"][:nV] != 1)[0]
+    rng = np.random.default_rng(3)
+    pick = rng.choice(inactive, size=min(60, inactive.size), replace=False)
+    for i, v in enumerate(pick):
+        t = 1 + (i % 3)
+        vbt[v] = t
+        if t in (1, 2):
+            src[v] = int(rng.choice(active)) + 1
+    # chains: earlier and later boundary vertices as sources
+    chain = pick[vbt[pick] == 1]
+    if chain.size >= 4:
+        src[chain[0]] = chain[3] + 1     # source updated LATER in the sequential loop (old value seen)
+        src[chain[2]] = chain[1] + 1     # source updated EARLIER (new value seen)
+    return mesh, var, step, opts, vbt, src
+
+
+def test_special_boundaries_velocity(evp_lib):
+    """seaice_set_special_boundaries_velocity (special_boundaries.F:253-331) inside the captured loop."""
+    mesh, var, step, opts, vbt, src = _special_boundary_case()
+    opts = dict(opts, use_special_boundaries_velocity=True)
+    ostep = common.clone_step(step)
+    ostep["vertexBoundaryType"], ostep["vertexBoundarySourceLocal"] = vbt, src
+    ref = common.run_oracle(mesh, var, ostep, opts, 25)
+    out = common.run_device(mesh, var, step, opts, 25, special_boundaries=(vbt, src))
+    _compare(mesh, step, ref, out)
+    nV = mesh.nVertices
+    b = vbt[:nV] != 0
+    assert np.array_equal(out["uVelocity"][:nV][b], ref["uVelocity"][:nV][b])
+    assert np.array_equal(out["vVelocity"][:nV][b], ref["vVelocity"][:nV][b])
+    assert np.abs(ref["uVelocity"][:nV][b]).max() > 0
+
+
+def test_set_masks(evp_lib):
+    """seaice_set_special_boundaries_velocity_masks (special_boundaries.F:345-401): masks replaced by
+    externally supplied arrays."""
+    from mpas_seaice_b200 import host
+    mesh, var = common.mesh_case("hex20")
+    step, opts = common.step_case(mesh)
+    nC, nV = mesh.nCells, mesh.nVertices
+    ss = step["solveStress"].copy()
+    sv = step["solveVelocity"].copy()
+    sv[:nV:7] = 0
+    ss[:nC:5] = 0
+    solver = host.EvpSolver(mesh, var, opts)
+    try:
+        solver.update_step(step)
+        solver.set_masks(ss, sv)
+        solver.run_subcycles(15)
+        out = solver.fetch()
+    finally:
+        solver.destroy()
+    ostep = common.clone_step(step)
+    ostep["solveStress"], ostep["solveVelocity"] = ss, sv
+    ref = common.run_oracle(mesh, var, ostep, opts, 15)
+    _compare(mesh, ostep, ref, out)
+
+
+def test_call_order_errors(evp_lib):
+    from mpas_seaice_b200 import host
+    mesh, var = common.mesh_case("hex20")
+    step, opts = common.step_case(mesh)
+    solver = host.EvpSolver(mesh, var, opts)
+    try:
+        with pytest.raises(host.EvpError, match="update_step"):
+            solver.run_subcycles(1)
+        with pytest.raises(host.EvpError):
+            solver.last_run_ms()
+        bad = dict(step)
+        bad["icePressure"] = None
+        with pytest.raises(host.EvpError, match="NULL"):
+            solver.update_step(bad)
+        with pytest.raises(host.EvpError, match="special boundaries"):
+            solver.set_options(dict(opts, use_special_boundaries_velocity=True))
+    finally:
+        solver.destroy()
+
+
+def test_linearity_of_the_stress_divergence_at_full_size(evp_lib):
+    """Size-independent property at a BASELINE-sized mesh the oracle would need minutes for (QU60,
+    163 842 cells): with the linear constitutive relation the strain -> stress -> divergence chain is
+    linear in (u, v): D(a*u1 + u2) == a*D(u1) + D(u2) to round-off, and a constant velocity on the
+    rotated sphere has zero strain where the metric term vanishes is NOT assumed -- only linearity."""
+    from mpas_seaice_b200 import host, workloads
+    w = workloads.build("qu60")
+    mesh, static, step, opts = w["mesh"], w["static"], w["step"], w["opts"]
+    opts = dict(opts, constitutive_relation_type="linear")
+    nV = mesh.nVertices
+    lat, lon = mesh.latVertex, mesh.lonVertex
+    u1, v1 = np.cos(lat) * np.sin(3 * lon), np.sin(2 * lat) * np.cos(lon)
+    u2, v2 = np.sin(lat) ** 2 * np.cos(2 * lon), np.cos(lat) * np.sin(5 * lon)
+    solver = host.EvpSolver(mesh, static, opts, local_coords=(static["xLocal"], static["yLocal"]))
+    res = []
+    try:
+        for (u, v) in ((u1, v1), (u2, v2), (2.5 * u1 + u2, 2.5 * v1 + v2)):
+            s = dict(step)
+            s["uVelocity"], s["vVelocity"] = np.ascontiguousarray(u), np.ascontiguousarray(v)
+            solver.update_step(s)
+            solver.run_subcycles(1)
+            res.append(solver.fetch(names=("stressDivergenceU", "stressDivergenceV", "strain12")))
+    finally:
+        solver.destroy()
+    for k in ("stressDivergenceU", "stressDivergenceV", "strain12"):
+        lhs = res[2][k]
+        rhs = 2.5 * res[0][k] + res[1][k]
+        scale = np.abs(rhs).max()
+        assert scale > 0
+        assert np.abs(lhs - rhs).max() <= 1e-12 * scale, k
