@@ -181,7 +181,10 @@ const char *evp_last_error_string(void);
  * mpas_dmpar exchange lists of the 'velocityHaloExchangeGroup', velocity_solver.F:259-349):
  * for neighbour k, sendIndex[sendOffset[k] .. sendOffset[k+1]) are the local 1-based owned vertices
  * whose (u,v) this rank sends to rank neighbourRank[k]; recvIndex likewise are the local halo
- * vertices filled from that rank, in the sender's send order. */
+ * vertices filled from that rank, in the sender's send order.
+ * evp_comm_init and evp_set_halo are COLLECTIVE: every rank of the communicator must call them (set_halo
+ * performs one eager warm-up exchange so that NCCL's lazy connection set-up never happens inside the
+ * captured subcycle graph). */
 int evp_comm_get_unique_id(char *id128);   /* rank 0 calls this, host broadcasts the 128 bytes (MPI_Bcast) */
 int evp_comm_init(evp_handle *handle, int rank, int nRanks, const char *id128);
 int evp_set_halo(evp_handle *handle, int nNeighbours, const int *neighbourRank,

@@ -4,6 +4,7 @@
 // (reference: src/shared/mpas_seaice_mesh_pool.F:76-281).
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <new>
@@ -28,8 +29,9 @@ namespace {
 
 constexpr size_t kPinChunk = 32u << 20;   // pinned bounce buffers (2 x 32 MiB)
 
-// Host block of `count` cells, each (Mh) or (Mh, Mh) doubles with the first index fastest, to the SoA
-// rows dst[(row*stride + c0 + c)*ncomp + comp], row = i (1-D) or j*Mk + i (2-D).
+// Host block of `count` cells, each (Mh) or (Mh, Mh) doubles with the first index fastest, to the device
+// layout: 1-D -> row-SoA dst[(i*stride + c0 + c)*ncomp + comp]; 2-D (basis arrays) -> tiled,
+// dst[evp_tix(j*Mk + i, c0 + c, Mk*Mk)*ncomp + comp].
 __global__ void k_rows_in(const double *__restrict__ src, double *__restrict__ dst, int Mh, int Mk, int dims,
                           size_t count, size_t c0, size_t stride, int ncomp, int comp)
 {
@@ -39,7 +41,7 @@ __global__ void k_rows_in(const double *__restrict__ src, double *__restrict__ d
     const double *s = src + (size_t)Mh * nj * c;
     for (int j = 0; j < nj; j++)
         for (int i = 0; i < Mh; i++)
-            dst[((size_t)(j * Mk + i) * stride + c0 + c) * ncomp + comp] = s[j * Mh + i];
+            dst[(dims == 2 ? evp_tix(j * Mk + i, c0 + c, Mk * Mk) : (size_t)i * stride + c0 + c) * ncomp + comp] = s[j * Mh + i];
 }
 __global__ void k_rows_out(double *__restrict__ raw, const double *__restrict__ soa, int Mh, int Mk, int dims,
                            size_t count, size_t c0, size_t stride, int ncomp, int comp)
@@ -50,7 +52,7 @@ __global__ void k_rows_out(double *__restrict__ raw, const double *__restrict__ 
     double *s = raw + (size_t)Mh * nj * c;
     for (int j = 0; j < nj; j++)
         for (int i = 0; i < Mh; i++)
-            s[j * Mh + i] = soa[((size_t)(j * Mk + i) * stride + c0 + c) * ncomp + comp];
+            s[j * Mh + i] = soa[(dims == 2 ? evp_tix(j * Mk + i, c0 + c, Mk * Mk) : (size_t)i * stride + c0 + c) * ncomp + comp];
 }
 __global__ void k_voc_in(const int *__restrict__ src, int *__restrict__ dst, const int *__restrict__ nEdgesRaw,
                          int Mh, size_t count, size_t c0, size_t stride, int nVertices)
@@ -103,6 +105,61 @@ __global__ void k_gidx(const int *__restrict__ cov, const int *__restrict__ cvav
     }
 }
 
+// increasing-i order of the three band entries of gradient vertex j (0-based) in a cell with n vertices
+__device__ __forceinline__ void band_rows(int j, int n, int &i0, int &i1, int &i2)
+{
+    i0 = j - 1; i1 = j; i2 = j + 1;
+    if (j == 0) { i0 = 0; i1 = 1; i2 = n - 1; }
+    else if (j == n - 1) { i0 = 0; i1 = n - 2; i2 = n - 1; }
+}
+// flag[0] |= 1 when some basisGradient(i,j,c) outside the cyclic band i in {j-1,j,j+1} is non-zero
+__global__ void k_band_check(const double2 *__restrict__ G, const uint8_t *__restrict__ nEdges, int M, size_t nC,
+                             size_t nCp, int *flag)
+{
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nC) return;
+    const int n = nEdges[c];
+    bool bad = n < 3 && n > 0;
+    for (int j = 0; j < n; j++) {
+        int i0, i1, i2;
+        band_rows(j, n, i0, i1, i2);
+        for (int i = 0; i < n; i++) {
+            if (i == i0 || i == i1 || i == i2) continue;
+            const double2 g = G[evp_tix(j * M + i, c, M * M)];
+            bad |= (g.x != 0.0) | (g.y != 0.0);
+        }
+    }
+    if (bad) atomicOr(flag, 1);
+}
+__global__ void k_band_pack(const double2 *__restrict__ G, double2 *__restrict__ Gb, const uint8_t *__restrict__ nEdges,
+                            int M, size_t nC, size_t nCp)
+{
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nC) return;
+    const int n = nEdges[c];
+    for (int j = 0; j < M; j++) {
+        double2 g[3] = {make_double2(0.0, 0.0), make_double2(0.0, 0.0), make_double2(0.0, 0.0)};
+        if (j < n) {
+            int i[3];
+            band_rows(j, n, i[0], i[1], i[2]);
+            for (int k = 0; k < 3; k++) g[k] = G[evp_tix(j * M + i[k], c, M * M)];
+        }
+        for (int k = 0; k < 3; k++) Gb[evp_tix(k * M + j, c, 3 * M)] = g[k];
+    }
+}
+__global__ void k_band_unpack(const double2 *__restrict__ Gb, double2 *__restrict__ G, const uint8_t *__restrict__ nEdges,
+                              int M, size_t nC, size_t nCp)
+{
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nC) return;
+    const int n = nEdges[c];
+    for (int j = 0; j < n; j++) {
+        int i[3];
+        band_rows(j, n, i[0], i[1], i[2]);
+        for (int k = 0; k < 3; k++) G[evp_tix(j * M + i[k], c, M * M)] = Gb[evp_tix(k * M + j, c, 3 * M)];
+    }
+}
+
 inline unsigned grid_for(size_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
 struct NoPin {   // one-shot transfers (static data, basis read-back) never page-lock caller memory
@@ -129,6 +186,61 @@ int evp_dev_alloc(evp_handle *h, void **p, size_t bytes)
     EVP_CUDA(cudaMalloc(p, bytes));
     h->allocs.push_back(*p);
     h->devBytes += bytes;
+    return EVP_OK;
+}
+
+void evp_dev_free(evp_handle *h, void *p, size_t bytes)
+{
+    if (!p) return;
+    for (size_t i = 0; i < h->allocs.size(); i++)
+        if (h->allocs[i] == p) { h->allocs.erase(h->allocs.begin() + i); break; }
+    cudaFree(p);
+    h->devBytes -= std::min<unsigned long long>(h->devBytes, bytes);
+}
+
+static void invalidate_graph(evp_handle *h);
+
+int evp_basis_begin(evp_handle *h)
+{
+    invalidate_graph(h);
+    const size_t bytes = sizeof(double2) * h->M * h->M * h->nCp;
+    if (!h->d.G) {
+        int rc = evp_dev_alloc(h, (void **)&h->d.G, bytes);
+        if (rc) return rc;
+    }
+    EVP_CUDA(cudaMemsetAsync(h->d.G, 0, bytes, h->stream));
+    if (h->d.Gb) {
+        EVP_CUDA(cudaStreamSynchronize(h->stream));
+        evp_dev_free(h, h->d.Gb, sizeof(double2) * 3 * h->M * h->nCp);
+        h->d.Gb = nullptr;
+    }
+    h->haveBasis = false;
+    return EVP_OK;
+}
+
+// Wachspress gradients are band-sparse: keep only the band (saves 16*(M*M - 3*M) B per cell and per
+// subcycle of HBM traffic).  Any other pattern (PWL: dense, pwl.F:259-274) keeps the dense array.
+int evp_basis_finalize(evp_handle *h)
+{
+    h->haveBasis = true;
+    if (h->nCells == 0 || getenv("EVP_B200_DENSE_GRADIENT")) return EVP_OK;
+    const size_t nC = h->nCells;
+    int *flag = (int *)h->d.stage, bad = 0;
+    EVP_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), h->stream));
+    k_band_check<<<grid_for(nC, 128), 128, 0, h->stream>>>(h->d.G, h->d.nEdges, h->M, nC, h->nCp, flag);
+    EVP_CUDA(cudaGetLastError());
+    EVP_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    EVP_CUDA(cudaStreamSynchronize(h->stream));
+    if (bad) return EVP_OK;
+    const size_t bytes = sizeof(double2) * 3 * h->M * h->nCp;
+    int rc = evp_dev_alloc(h, (void **)&h->d.Gb, bytes);
+    if (rc) return rc;
+    EVP_CUDA(cudaMemsetAsync(h->d.Gb, 0, bytes, h->stream));
+    k_band_pack<<<grid_for(nC, 128), 128, 0, h->stream>>>(h->d.G, h->d.Gb, h->d.nEdges, h->M, nC, h->nCp);
+    EVP_CUDA(cudaGetLastError());
+    EVP_CUDA(cudaStreamSynchronize(h->stream));
+    evp_dev_free(h, h->d.G, sizeof(double2) * h->M * h->M * h->nCp);
+    h->d.G = nullptr;
     return EVP_OK;
 }
 
@@ -346,7 +458,6 @@ extern "C" int evp_create(evp_handle **out, const evp_mesh_desc *m, const evp_op
     evp_dev &d = h->d;
     FAIL_IF(evp_dev_alloc(h, (void **)&d.nEdges, nCp));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.voc, sizeof(int) * Mk * nCp));
-    FAIL_IF(evp_dev_alloc(h, (void **)&d.G, sizeof(double2) * Mk * Mk * nCp));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.Suv, sizeof(double2) * Mk * Mk * nCp));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.Sm, sizeof(double) * Mk * Mk * nCp));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.tanLat, sizeof(double) * nVp));
@@ -380,7 +491,6 @@ extern "C" int evp_create(evp_handle **out, const evp_mesh_desc *m, const evp_op
     // zero everything a kernel may read before the host wrote it
     CUDA_FAIL(cudaMemsetAsync(d.voc, 0, sizeof(int) * Mk * nCp, h->stream));
     CUDA_FAIL(cudaMemsetAsync(d.nEdges, 0, nCp, h->stream));
-    CUDA_FAIL(cudaMemsetAsync(d.G, 0, sizeof(double2) * Mk * Mk * nCp, h->stream));
     CUDA_FAIL(cudaMemsetAsync(d.Suv, 0, sizeof(double2) * Mk * Mk * nCp, h->stream));
     CUDA_FAIL(cudaMemsetAsync(d.Sm, 0, sizeof(double) * Mk * Mk * nCp, h->stream));
     CUDA_FAIL(cudaMemsetAsync(d.contrib, 0, sizeof(double2) * Mk * nCp, h->stream));
@@ -432,13 +542,14 @@ extern "C" int evp_create(evp_handle **out, const evp_mesh_desc *m, const evp_op
             if (m->tanLatVertexRotatedOverRadius[i] != 0.0) { h->metric = true; break; }
     }
     if (allBasis && nC > 0) {
+        FAIL_IF(evp_basis_begin(h));
         FAIL_IF(upload_rows(h, m->basisGradientU, (double *)d.G, 2, 2, 0));
         FAIL_IF(upload_rows(h, m->basisGradientV, (double *)d.G, 2, 2, 1));
         FAIL_IF(upload_rows(h, m->basisIntegralsU, (double *)d.Suv, 2, 2, 0));
         FAIL_IF(upload_rows(h, m->basisIntegralsV, (double *)d.Suv, 2, 2, 1));
         FAIL_IF(upload_rows(h, m->basisIntegralsMetric, d.Sm, 2, 1, 0));
         CUDA_FAIL(cudaStreamSynchronize(h->stream));
-        h->haveBasis = true;
+        FAIL_IF(evp_basis_finalize(h));
     }
 
     // ---- special boundaries: resolve the sequential in-place loop (special_boundaries.F:301-324) ----
@@ -678,8 +789,20 @@ extern "C" int evp_fetch_basis(evp_handle *h, double *gu, double *gv, double *su
     evp_dev &d = h->d;
     int rc;
     if (h->nCells == 0) return EVP_OK;
-    if (gu && (rc = download_rows(h, gu, (const double *)d.G, 2, 2, 0))) return rc;
-    if (gv && (rc = download_rows(h, gv, (const double *)d.G, 2, 2, 1))) return rc;
+    if (gu || gv) {
+        double2 *G = d.G;
+        const size_t gBytes = sizeof(double2) * h->M * h->M * h->nCp;
+        if (!G) {   // banded on the device: expand into a temporary dense array
+            EVP_CUDA(cudaMalloc((void **)&G, gBytes));
+            cudaMemsetAsync(G, 0, gBytes, h->stream);
+            k_band_unpack<<<grid_for(h->nCells, 128), 128, 0, h->stream>>>(d.Gb, G, d.nEdges, h->M, h->nCells, h->nCp);
+        }
+        rc = EVP_OK;
+        if (gu) rc = download_rows(h, gu, (const double *)G, 2, 2, 0);
+        if (!rc && gv) rc = download_rows(h, gv, (const double *)G, 2, 2, 1);
+        if (!d.G) { cudaStreamSynchronize(h->stream); cudaFree(G); }
+        if (rc) return rc;
+    }
     if (su && (rc = download_rows(h, su, (const double *)d.Suv, 2, 2, 0))) return rc;
     if (sv && (rc = download_rows(h, sv, (const double *)d.Suv, 2, 2, 1))) return rc;
     if (sm && (rc = download_rows(h, sm, d.Sm, 2, 1, 0))) return rc;

@@ -146,6 +146,21 @@ extern "C" int evp_set_halo(evp_handle *h, int nNb, const int *nbRank, const int
     if (H.nSend) EVP_CUDA(cudaMemcpy(H.dSendIdx, s0.data(), sizeof(int) * H.nSend, cudaMemcpyHostToDevice));
     if (H.nRecv) EVP_CUDA(cudaMemcpy(H.dRecvIdx, r0.data(), sizeof(int) * H.nRecv, cudaMemcpyHostToDevice));
     if (h->graphExec) { cudaGraphExecDestroy(h->graphExec); h->graphExec = nullptr; h->graphN = -1; }
+    // NCCL opens its point-to-point connections lazily inside the first ncclGroupEnd that uses them: a
+    // host-side handshake between the ranks plus allocations, none of which may happen while the stream is
+    // being captured into the subcycle graph.  Do one eager exchange of the (still meaningless) pack
+    // buffers now -- evp_set_halo is therefore COLLECTIVE over the ranks of the communicator.
+    if (H.comm && nNb > 0) {
+        EVP_CUDA(cudaMemsetAsync(H.dSendBuf, 0, sizeof(double2) * (H.nSend + 1), h->stream));
+        EVP_NCCL(g_nccl.GroupStart());
+        for (int k = 0; k < H.nNb; k++) {
+            const int ns = H.sendOff[k + 1] - H.sendOff[k], nr = H.recvOff[k + 1] - H.recvOff[k];
+            if (ns) EVP_NCCL(g_nccl.Send(H.dSendBuf + H.sendOff[k], (size_t)2 * ns, ncclDouble, H.nbRank[k], H.comm, h->stream));
+            if (nr) EVP_NCCL(g_nccl.Recv(H.dRecvBuf + H.recvOff[k], (size_t)2 * nr, ncclDouble, H.nbRank[k], H.comm, h->stream));
+        }
+        EVP_NCCL(g_nccl.GroupEnd());
+        EVP_CUDA(cudaStreamSynchronize(h->stream));
+    }
     return EVP_OK;
 }
 

@@ -1,11 +1,19 @@
 // evp_internal.cuh -- handle layout and helpers shared by the translation units of libevp_b200.so.
 //
-// Device data layout (all SoA, the cell / vertex index is the FASTEST dimension so that a warp
-// of 32 consecutive cells reads 32 consecutive elements of every array):
+// Device data layout.  The cell / vertex index is always the FASTEST dimension, so a warp of 32
+// consecutive cells reads 32 consecutive elements of every row.
 //
-//   G    [j][i][c] double2 = (basisGradientU(i,j,c), basisGradientV(i,j,c))      16*M*M B / cell
-//   Suv  [j][i][c] double2 = (basisIntegralsU(i,j,c), basisIntegralsV(i,j,c))    16*M*M B / cell
-//   Sm   [j][i][c] double  =  basisIntegralsMetric(i,j,c)                         8*M*M B / cell
+// Static basis arrays are TILED: the rows of a tile of EVP_TILE = 32 cells are contiguous
+// (element (row, c) lives at ((c/32)*nRows + row)*32 + c%32, see evp_tix), so that one block of the
+// cell kernel fetches the whole basis of its 32 cells with three bulk copies (cp.async.bulk, 9-18 KB
+// each) into shared memory:
+//   Gb   [tile][k*M+j][32] double2, k = 0..2: the three non-zero (basisGradientU,V)(i,j,c), i in
+//        {j-1, j, j+1} cyclic (Wachspress, wachspress.F:1178-1191) in increasing-i order   48*M B / cell
+//   G    [tile][j*M+i][32] double2 = (basisGradientU(i,j,c), basisGradientV(i,j,c))     16*M*M B / cell
+//        -- only while the basis is being built, and kept instead of Gb when the gradients are dense (PWL)
+//   Suv  [tile][j*M+i][32] double2 = (basisIntegralsU(i,j,c), basisIntegralsV(i,j,c))   16*M*M B / cell
+//   Sm   [tile][j*M+i][32] double  =  basisIntegralsMetric(i,j,c)                         8*M*M B / cell
+// State and connectivity are plain row-SoA with row stride nCp:
 //   sig  [i][c]    double2 = (stress11(i,c), stress22(i,c));  sig12[i][c] double
 //   contrib[j][c]  double2 = per-cell partial sums (stressDivergenceUCell, stressDivergenceVCell)
 //                            of reference variational.F:1151-1173 for velocity vertex slot j
@@ -22,6 +30,13 @@
 #include "../../include/evp_b200.h"
 
 void evp_set_error(const char *fmt, ...);
+
+constexpr int EVP_TILE = 32;
+// element index of (row, cell) in a tiled basis array with nRows rows per tile
+__host__ __device__ __forceinline__ size_t evp_tix(int row, size_t c, int nRows)
+{
+    return ((c / EVP_TILE) * (size_t)nRows + (size_t)row) * EVP_TILE + (c % EVP_TILE);
+}
 
 #define EVP_CUDA(call)                                                                          \
     do {                                                                                        \
@@ -46,7 +61,7 @@ struct evp_dev {
     // static
     uint8_t *nEdges = nullptr;
     int *voc = nullptr;
-    double2 *G = nullptr, *Suv = nullptr;
+    double2 *G = nullptr, *Gb = nullptr, *Suv = nullptr;
     double *Sm = nullptr;
     double *tanLat = nullptr;
     int *gidx = nullptr;          // [D][nVp] index into contrib (j*nCp + c) or -1
@@ -110,3 +125,7 @@ void evp_halo_destroy(evp_handle *h);
 
 // layout kernels (evp_abi.cu)
 int evp_dev_alloc(evp_handle *h, void **p, size_t bytes);
+void evp_dev_free(evp_handle *h, void *p, size_t bytes);
+// dense G (re)allocated and zeroed, ready to be filled; then band-compressed when the pattern allows
+int evp_basis_begin(evp_handle *h);
+int evp_basis_finalize(evp_handle *h);

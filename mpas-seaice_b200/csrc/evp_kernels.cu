@@ -14,6 +14,7 @@
 // vertex kernel = outer sum + denominator of the stress divergence (variational.F:1139-1178)
 //              + ocean_stress_coefficient (velocity_solver.F:2986-3082)
 //              + solve_velocity / solve_velocity_revised (velocity_solver.F:3096-3342)
+#include <stdlib.h>
 #include "evp_internal.cuh"
 
 namespace {
@@ -36,7 +37,8 @@ struct CellArgs {
     const uint8_t *__restrict__ nEdges;
     const uint8_t *__restrict__ solveStress;
     const int *__restrict__ voc;
-    const double2 *__restrict__ G;
+    const double2 *__restrict__ G;      // dense [j][i][c] (PWL / unknown pattern) or nullptr
+    const double2 *__restrict__ Gb;     // banded [k][j][c], k = 0..2 (Wachspress) or nullptr
     const double2 *__restrict__ Suv;
     const double *__restrict__ Sm;
     const double2 *__restrict__ uv;
@@ -85,114 +87,212 @@ __device__ __forceinline__ void constitutive(double &s11, double &s22, double &s
     }
 }
 
-template <int M, bool METRIC, int CR, bool DIAG>
-__global__ void __launch_bounds__(128) evp_cell_kernel(const CellArgs a)
+// ---- mbarrier + bulk-copy PTX (cp.async.bulk = SASS UBLKCP on sm_100a; completion counted in bytes on
+// an mbarrier in shared memory) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.nCells) return;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+// Shared memory of one block of the cell kernel = one tile of EVP_TILE cells.
+template <int M, bool METRIC, bool GBAND>
+struct CellSmem {
+    static constexpr int GR = GBAND ? 3 * M : M * M;
+    double2 G[GR][EVP_TILE];                         // bulk-copied basis gradients of the tile
+    double2 S[M * M][EVP_TILE];                      // bulk-copied basisIntegralsU/V
+    double Sm[METRIC ? M * M : 1][EVP_TILE];         // bulk-copied basisIntegralsMetric
+    double u[M][EVP_TILE], v[M][EVP_TILE];           // velocity at the cell's vertices
+    double s11[M][EVP_TILE], s22[M][EVP_TILE], s12[M][EVP_TILE];   // stress after the update
+    unsigned long long barG, barS;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Cell kernel: one block per tile of 32 cells, one thread per (cell, cell-vertex slot);
+// blockDim = (32 cells, M slots), i.e. warp j handles slot j of the 32 cells, so every row is read as
+// one contiguous segment.
+//   start    one thread arms two mbarriers and issues three bulk copies (cp.async.bulk) that bring the
+//            tile's basis arrays (contiguous in the tiled layout, 9-18 KB each) into shared memory;
+//            they are in flight while phases 0/1 run, and several blocks are resident per SM, so the
+//            HBM pipe stays full without holding the data in registers;
+//   phase 0  slot j gathers (u,v) and tan(lat)/R of its vertex and stages them in shared memory;
+//   phase 1  slot j = stress point j: strain (variational.F:633-668) + constitutive relation
+//            (constitutive_relation.F:178-373); new stress to HBM and to shared memory;
+//   phase 2  slot j = velocity vertex j: the cell's partial sum of the stress divergence
+//            (variational.F:1151-1173) -> contrib[j][c].
+// Sums run over i = 1..nEdgesOnCell in increasing i exactly like the reference loops.  With the
+// Wachspress basis basisGradientU/V(i,j,c) is exactly zero unless i is j-1, j or j+1 (cyclic;
+// wachspress.F:1178-1191); GBAND reads only those three entries, stored in increasing-i order.
+// Dropping the +-0 products leaves every partial sum bit-identical for finite velocities (x + +-0 == x,
+// and a partial sum that starts at +0 never becomes -0 in round-to-nearest).
+// Tiles without any solved cell issue no bulk copy (ice-free ocean costs ~26 B per cell).
+// ---------------------------------------------------------------------------------------------
+template <int M, bool METRIC, int CR, bool DIAG, bool GBAND>
+__global__ void __launch_bounds__(EVP_TILE *M) evp_cell_kernel(const CellArgs a)
+{
+    using Smem = CellSmem<M, METRIC, GBAND>;
+    extern __shared__ __align__(128) unsigned char evp_smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(evp_smem_raw);
+    constexpr int GR = Smem::GR;
+
+    const int cx = threadIdx.x;
+    const int j = threadIdx.y;
+    const size_t tile = blockIdx.x;
+    const size_t c = tile * EVP_TILE + cx;
     const size_t nCp = a.nCp;
-    const int n = a.nEdges[c];
-    const bool solve = a.solveStress[c] == 1;
-
-    double s11[M], s22[M], s12[M], tv[M];
-
-    if (solve) {
-        double u[M], v[M];
-#pragma unroll
-        for (int i = 0; i < M; i++) {
-            u[i] = 0.0; v[i] = 0.0; tv[i] = 0.0;
-            if (i < n) {
-                const int vi = a.voc[(size_t)i * nCp + c];
-                const double2 w = a.uv[vi];
-                u[i] = w.x; v[i] = w.y;
-                if (METRIC) tv[i] = a.tanLat[vi];
-            }
-        }
-        const double P = a.P[c];
-#pragma unroll
-        for (int j = 0; j < M; j++) {
-            s11[j] = 0.0; s22[j] = 0.0; s12[j] = 0.0;
-            if (j < n) {
-                double e11 = 0.0, e22 = 0.0, e12 = 0.0;
-#pragma unroll
-                for (int i = 0; i < M; i++) {
-                    if (i < n) {
-                        const double2 g = a.G[(size_t)(j * M + i) * nCp + c];
-                        e11 = e11 + u[i] * g.x;
-                        e22 = e22 + v[i] * g.y;
-                        e12 = e12 + 0.5 * (u[i] * g.y + v[i] * g.x);
-                    }
-                }
-                // metric terms (variational.F:658-662); tv == 0 when METRIC is off
-                e11 = e11 - v[j] * tv[j];
-                e12 = e12 + u[j] * tv[j] * 0.5;
-                const size_t q = (size_t)j * nCp + c;
-                const double2 s = a.sig[q];
-                double x11 = s.x, x22 = s.y, x12 = a.sig12[q], rep = 0.0;
-                constitutive<CR>(x11, x22, x12, e11, e22, e12, P, rep, a.dte, a.damping);
-                if (CR != EVP_CR_NONE) {
-                    a.sig[q] = make_double2(x11, x22);
-                    a.sig12[q] = x12;
-                }
-                s11[j] = x11; s22[j] = x22; s12[j] = x12;
-                if (DIAG) {
-                    a.e11[q] = e11; a.e22[q] = e22; a.e12[q] = e12;
-                    if (CR == EVP_CR_EVP || CR == EVP_CR_EVP_REVISED) a.repP[q] = rep;
-                }
-            }
-        }
-    } else {
-        // cell not solved: the stress is whatever the host left there (zero after
-        // init_subcycle_variables, velocity_solver.F:2335-2345) and still enters the divergence.
-        bool anyNonZero = false;
-#pragma unroll
-        for (int j = 0; j < M; j++) {
-            s11[j] = 0.0; s22[j] = 0.0; s12[j] = 0.0; tv[j] = 0.0;
-            if (j < n) {
-                const size_t q = (size_t)j * nCp + c;
-                const double2 s = a.sig[q];
-                s11[j] = s.x; s22[j] = s.y; s12[j] = a.sig12[q];
-                anyNonZero |= (s.x != 0.0) | (s.y != 0.0) | (s12[j] != 0.0);
-                if (DIAG && CR == EVP_CR_EVP) a.repP[q] = 0.0;   // variational.F:862
-            }
-        }
-        if (!anyNonZero) {
-            // all-zero stress: every partial sum is exactly +0 (0 - 0*S), skip reading the integrals
-#pragma unroll
-            for (int j = 0; j < M; j++)
-                if (j < n) a.contrib[(size_t)j * nCp + c] = make_double2(0.0, 0.0);
-            return;
-        }
-        if (METRIC) {
-#pragma unroll
-            for (int i = 0; i < M; i++)
-                if (i < n) tv[i] = a.tanLat[a.voc[(size_t)i * nCp + c]];
-        }
+    const bool leader = (cx == 0) && (j == 0);
+    int n = 0;
+    bool solve = false;
+    if (c < (size_t)a.nCells) {
+        n = a.nEdges[c];
+        solve = a.solveStress[c] == 1;
+    }
+    if (leader) {
+        mbar_init(&sm.barG, 1);
+        mbar_init(&sm.barS, 1);
+        mbar_fence_init();
+    }
+    const bool staged = __syncthreads_or(solve) != 0;      // block-uniform; also publishes the mbarrier init
+    if (staged && leader) {
+        const double2 *gsrc = (GBAND ? a.Gb : a.G) + tile * (size_t)(GR * EVP_TILE);
+        mbar_expect_tx(&sm.barG, (uint32_t)sizeof(sm.G));
+        bulk_g2s(&sm.G[0][0], gsrc, (uint32_t)sizeof(sm.G), &sm.barG);
+        mbar_expect_tx(&sm.barS, (uint32_t)(sizeof(sm.S) + (METRIC ? sizeof(sm.Sm) : 0)));
+        bulk_g2s(&sm.S[0][0], a.Suv + tile * (size_t)(M * M * EVP_TILE), (uint32_t)sizeof(sm.S), &sm.barS);
+        if (METRIC) bulk_g2s(&sm.Sm[0][0], a.Sm + tile * (size_t)(M * M * EVP_TILE), (uint32_t)sizeof(sm.Sm), &sm.barS);
     }
 
-    // per-cell partial sums of the stress divergence for each velocity vertex slot jv
-#pragma unroll
-    for (int jv = 0; jv < M; jv++) {
-        if (jv < n) {
-            double cU = 0.0, cV = 0.0;
+    const bool act = j < n;                       // false for every slot of an out-of-range cell
+    const size_t q = (size_t)j * nCp + c;
+    double uj = 0.0, vj = 0.0, tj = 0.0, x11 = 0.0, x22 = 0.0, x12 = 0.0;
+    if (act) {
+        const int vi = a.voc[q];
+        if (solve) {
+            const double2 w = a.uv[vi];
+            uj = w.x; vj = w.y;
+        }
+        if (METRIC) tj = a.tanLat[vi];
+        const double2 s = a.sig[q];
+        x11 = s.x; x22 = s.y; x12 = a.sig12[q];
+    }
+    sm.u[j][cx] = uj;
+    sm.v[j][cx] = vj;
+    __syncthreads();
+
+    if (act && solve) {
+        double e11 = 0.0, e22 = 0.0, e12 = 0.0;
+        const double P = a.P[c];
+        mbar_wait(&sm.barG, 0);
+        if (GBAND) {
+            int i0 = j - 1, i1 = j, i2 = j + 1;
+            if (j == 0) { i0 = 0; i1 = 1; i2 = n - 1; }
+            else if (j == n - 1) { i0 = 0; i1 = n - 2; i2 = n - 1; }
+            const double2 g0 = sm.G[0 * M + j][cx];
+            const double2 g1 = sm.G[1 * M + j][cx];
+            const double2 g2 = sm.G[2 * M + j][cx];
+            double u, v;
+            u = sm.u[i0][cx]; v = sm.v[i0][cx];
+            e11 = e11 + u * g0.x; e22 = e22 + v * g0.y; e12 = e12 + 0.5 * (u * g0.y + v * g0.x);
+            u = sm.u[i1][cx]; v = sm.v[i1][cx];
+            e11 = e11 + u * g1.x; e22 = e22 + v * g1.y; e12 = e12 + 0.5 * (u * g1.y + v * g1.x);
+            u = sm.u[i2][cx]; v = sm.v[i2][cx];
+            e11 = e11 + u * g2.x; e22 = e22 + v * g2.y; e12 = e12 + 0.5 * (u * g2.y + v * g2.x);
+        } else {
 #pragma unroll
             for (int i = 0; i < M; i++) {
                 if (i < n) {
-                    const size_t b = (size_t)(jv * M + i) * nCp + c;
-                    const double2 S = a.Suv[b];
-                    if (METRIC) {
-                        const double sm = a.Sm[b];
-                        cU = cU - s11[i] * S.x - s12[i] * S.y - s12[i] * sm * tv[jv];
-                        cV = cV - s22[i] * S.y - s12[i] * S.x + s11[i] * sm * tv[jv];
-                    } else {
-                        cU = cU - s11[i] * S.x - s12[i] * S.y;
-                        cV = cV - s22[i] * S.y - s12[i] * S.x;
-                    }
+                    const double2 g = sm.G[(GBAND ? 0 : j * M) + i][cx];
+                    const double u = sm.u[i][cx], v = sm.v[i][cx];
+                    e11 = e11 + u * g.x;
+                    e22 = e22 + v * g.y;
+                    e12 = e12 + 0.5 * (u * g.y + v * g.x);
                 }
             }
-            a.contrib[(size_t)jv * nCp + c] = make_double2(cU, cV);
+        }
+        // metric terms (variational.F:658-662); tj == 0 when METRIC is off
+        e11 = e11 - vj * tj;
+        e12 = e12 + uj * tj * 0.5;
+        double rep = 0.0;
+        constitutive<CR>(x11, x22, x12, e11, e22, e12, P, rep, a.dte, a.damping);
+        if (CR != EVP_CR_NONE) {
+            a.sig[q] = make_double2(x11, x22);
+            a.sig12[q] = x12;
+        }
+        if (DIAG) {
+            a.e11[q] = e11; a.e22[q] = e22; a.e12[q] = e12;
+            if (CR == EVP_CR_EVP || CR == EVP_CR_EVP_REVISED) a.repP[q] = rep;
+        }
+    } else if (act) {
+        // cell not solved: the stress is whatever the host left there (zero after
+        // init_subcycle_variables, velocity_solver.F:2335-2345) and still enters the divergence
+        if (DIAG && CR == EVP_CR_EVP) a.repP[q] = 0.0;   // variational.F:862
+    }
+    sm.s11[j][cx] = x11;
+    sm.s22[j][cx] = x22;
+    sm.s12[j][cx] = x12;
+    __syncthreads();
+    if (!act) return;
+
+    if (!solve) {
+        bool anyNonZero = false;
+#pragma unroll
+        for (int i = 0; i < M; i++)
+            if (i < n) anyNonZero |= (sm.s11[i][cx] != 0.0) | (sm.s22[i][cx] != 0.0) | (sm.s12[i][cx] != 0.0);
+        if (!anyNonZero) {
+            // all-zero stress: every partial sum is exactly +0 (0 - 0*S), skip reading the integrals
+            a.contrib[q] = make_double2(0.0, 0.0);
+            return;
         }
     }
+    if (staged) mbar_wait(&sm.barS, 0);
+    double cU = 0.0, cV = 0.0;
+#pragma unroll
+    for (int i = 0; i < M; i++) {
+        if (i < n) {
+            const double s11 = sm.s11[i][cx], s22 = sm.s22[i][cx], s12 = sm.s12[i][cx];
+            double2 S;
+            double m = 0.0;
+            if (staged) {
+                S = sm.S[j * M + i][cx];
+                if (METRIC) m = sm.Sm[j * M + i][cx];
+            } else {   // unsolved cell with left-over stress in a tile without any solved cell
+                const size_t b = evp_tix(j * M + i, c, M * M);
+                S = a.Suv[b];
+                if (METRIC) m = a.Sm[b];
+            }
+            if (METRIC) {
+                cU = cU - s11 * S.x - s12 * S.y - s12 * m * tj;
+                cV = cV - s22 * S.y - s12 * S.x + s11 * m * tj;
+            } else {
+                cU = cU - s11 * S.x - s12 * S.y;
+                cV = cV - s22 * S.y - s12 * S.x;
+            }
+        }
+    }
+    a.contrib[q] = make_double2(cU, cV);
 }
 
 struct VertexArgs {
@@ -299,14 +399,29 @@ __global__ void evp_sb_scatter(int n, const int *__restrict__ dst, const double2
     uv[dst[k]] = tmp[k];
 }
 
+template <int M, bool METRIC, int CR, bool DIAG, bool GBAND>
+int launch_cell_k(const CellArgs &a, cudaStream_t s)
+{
+    auto kern = evp_cell_kernel<M, METRIC, CR, DIAG, GBAND>;
+    constexpr size_t smem = sizeof(CellSmem<M, METRIC, GBAND>);
+    static bool configured[16] = {};      // per device: opt in to > 48 KB of dynamic shared memory
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 16 && !configured[dev]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
+        configured[dev] = true;
+    }
+    const dim3 block(EVP_TILE, M);
+    const unsigned grid = (unsigned)((a.nCells + EVP_TILE - 1) / EVP_TILE);
+    kern<<<grid, block, smem, s>>>(a);
+    return 0;
+}
 template <int M, bool METRIC, int CR>
 int launch_cell_d(const CellArgs &a, bool diag, cudaStream_t s)
 {
-    const int block = 128;
-    const int grid = (a.nCells + block - 1) / block;
-    if (diag) evp_cell_kernel<M, METRIC, CR, true><<<grid, block, 0, s>>>(a);
-    else      evp_cell_kernel<M, METRIC, CR, false><<<grid, block, 0, s>>>(a);
-    return 0;
+    const bool band = a.Gb != nullptr;
+    if (diag) return band ? launch_cell_k<M, METRIC, CR, true, true>(a, s) : launch_cell_k<M, METRIC, CR, true, false>(a, s);
+    return band ? launch_cell_k<M, METRIC, CR, false, true>(a, s) : launch_cell_k<M, METRIC, CR, false, false>(a, s);
 }
 template <int M, bool METRIC>
 int launch_cell_cr(const CellArgs &a, int cr, bool diag, cudaStream_t s)
@@ -351,19 +466,21 @@ int evp_enqueue_cell_pass(evp_handle *h, bool diag, cudaStream_t s)
     CellArgs a;
     a.nCells = h->nCells; a.nCp = h->nCp;
     a.nEdges = h->d.nEdges; a.solveStress = h->d.solveStress; a.voc = h->d.voc;
-    a.G = h->d.G; a.Suv = h->d.Suv; a.Sm = h->d.Sm;
+    a.G = h->d.G; a.Gb = h->d.Gb; a.Suv = h->d.Suv; a.Sm = h->d.Sm;
     a.uv = h->d.uv; a.tanLat = h->d.tanLat; a.P = h->d.P;
     a.sig = h->d.sig; a.sig12 = h->d.sig12; a.contrib = h->d.contrib;
     a.e11 = h->d.e11; a.e22 = h->d.e22; a.e12 = h->d.e12; a.repP = h->d.repP;
     a.dte = h->opt.elasticTimeStep; a.damping = h->opt.dampingTimescale;
     const int cr = h->opt.constitutive_relation_type;
+    int rc = 0;
     switch (h->M) {
-    case 4: launch_cell_m<4>(a, h->metric, cr, diag, s); break;
-    case 6: launch_cell_m<6>(a, h->metric, cr, diag, s); break;
+    case 4: rc = launch_cell_m<4>(a, h->metric, cr, diag, s); break;
+    case 6: rc = launch_cell_m<6>(a, h->metric, cr, diag, s); break;
     case 7:
-    case 8: launch_cell_m<8>(a, h->metric, cr, diag, s); break;
+    case 8: rc = launch_cell_m<8>(a, h->metric, cr, diag, s); break;
     default: evp_set_error("unsupported maxEdges %d", h->M); return EVP_ERR_ARGUMENT;
     }
+    if (rc) { evp_set_error("cell kernel: cannot opt in to its dynamic shared memory size"); return EVP_ERR_CUDA; }
     EVP_CUDA(cudaGetLastError());
     return EVP_OK;
 }

@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(64) k_wachspress(int nCells, size_t nCp, int M
         for (int ib = 1; ib <= n; ib++) {
             double2 g = make_double2(0.0, 0.0);
             if (jg == ib || jg == wrap1(ib - 1, n) || jg == wrap1(ib + 1, n)) g = make_double2(dx[ib - 1], dy[ib - 1]);
-            G[(size_t)((jg - 1) * M + (ib - 1)) * nCp + cell] = g;
+            G[evp_tix((jg - 1) * M + (ib - 1), cell, M * M)] = g;
         }
     }
     // integrals (:304-467): per pair (iStress, iVelocity): sum over sub-triangles of (sum over points) / norm
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(64) k_wachspress(int nCells, size_t nCp, int M
     }
     for (int iv = 0; iv < n; iv++)
         for (int is = 0; is < n; is++) {
-            const size_t q = (size_t)(iv * M + is) * nCp + cell;
+            const size_t q = evp_tix(iv * M + is, cell, M * M);
             Suv[q] = make_double2(bU[iv][is], bV[iv][is]);
             Sm[q] = bM[iv][is];
         }
@@ -273,6 +273,10 @@ extern "C" int evp_precompute_wachspress(evp_handle *h, const double *xLocal, co
     EVP_CUDA(cudaSetDevice(h->device));
     const size_t nC = h->nCells;
     if (nC == 0) { h->haveBasis = true; return EVP_OK; }
+    {
+        int rc = evp_basis_begin(h);
+        if (rc) return rc;
+    }
     const size_t bytes = (size_t)h->Mh * nC * sizeof(double);
     EVP_REQUIRE(2 * bytes + 512 <= h->d.stageBytes, "staging area too small for the local coordinates");
     EVP_CUDA(cudaStreamSynchronize(h->stream));
@@ -292,6 +296,5 @@ extern "C" int evp_precompute_wachspress(evp_handle *h, const double *xLocal, co
     }
     EVP_CUDA(cudaGetLastError());
     EVP_CUDA(cudaStreamSynchronize(h->stream));
-    h->haveBasis = true;
-    return EVP_OK;
+    return evp_basis_finalize(h);
 }

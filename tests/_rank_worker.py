@@ -15,8 +15,16 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+def stage(msg):
+    print(f"[rank {os.environ.get('RANK')}] {msg}", flush=True)
+
+
 def main():
     mode, name, nsub, out_path = sys.argv[1], sys.argv[2], int(sys.argv[3]), sys.argv[4]
+    after = int(os.environ.get("EVP_RANK_TRACE_AFTER", "0"))
+    if after > 0:
+        import faulthandler
+        faulthandler.dump_traceback_later(after, exit=True)
     method = sys.argv[5] if len(sys.argv) > 5 else "auto"
     import torch
     import torch.distributed as dist
@@ -35,10 +43,14 @@ def main():
         solver = host.EvpSolver(blk, w["static"], opts, device=rank,
                                 local_coords=(w["static"]["xLocal"], w["static"]["yLocal"]),
                                 n_vertices_solve=w["nVerticesSolve"], n_cells_solve=w["nCellsSolve"])
+        stage("evp_create done")
         multigpu.attach_halo(solver, w, rank, world, dist)
+        stage("evp_comm_init + evp_set_halo done")
         solver.update_step(step)
         solver.run_subcycles(nsub)
+        stage("evp_run_subcycles enqueued")
         res = solver.fetch()
+        stage("evp_fetch done")
         solver.destroy()
     else:
         import oracle

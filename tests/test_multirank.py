@@ -24,25 +24,36 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _launch(mode, name, nsub, world, out_path, method="auto", timeout=600):
+def _launch(mode, name, nsub, world, out_path, method="auto", timeout=240):
+    """One process per rank; each rank's output goes to a file so that a hang can be diagnosed (the
+    workers dump their Python stacks shortly before the timeout)."""
     port = _free_port()
-    procs = []
+    procs, logs = [], []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
-                   MASTER_PORT=str(port), OMP_NUM_THREADS="2")
+                   MASTER_PORT=str(port), OMP_NUM_THREADS="2", EVP_RANK_TRACE_AFTER=str(max(10, timeout - 20)))
+        log = open(out_path + f".rank{r}.log", "wb")
+        logs.append(log)
         procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "_rank_worker.py"), mode, name, str(nsub),
-                                       out_path, method], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
-    outs = []
+                                       out_path, method], env=env, stdout=log, stderr=subprocess.STDOUT))
+    import time
+    t_end = time.time() + timeout
     try:
-        for p in procs:
-            o, _ = p.communicate(timeout=timeout)
-            outs.append(o.decode(errors="replace"))
+        while time.time() < t_end and any(p.poll() is None for p in procs):
+            if any(p.poll() not in (None, 0) for p in procs):
+                break                       # one rank failed: do not wait for the others to time out
+            time.sleep(0.2)
     finally:
         for p in procs:
             if p.poll() is None:
                 p.kill()
+                p.wait()
+        for log in logs:
+            log.close()
+    outs = [open(out_path + f".rank{r}.log", errors="replace").read() for r in range(world)]
     for r, p in enumerate(procs):
-        assert p.returncode == 0, f"rank {r} failed:\n{outs[r][-3000:]}"
+        assert p.returncode == 0, f"rank {r} rc={p.returncode}:\n" + "\n".join(
+            f"--- rank {q} ---\n{o[-3000:]}" for q, o in enumerate(outs))
     return dict(np.load(out_path))
 
 
