@@ -191,6 +191,15 @@ int evp_set_halo(evp_handle *handle, int nNeighbours, const int *neighbourRank,
                  const int *sendOffset, const int *sendIndex,
                  const int *recvOffset, const int *recvIndex);
 
+/* ---- host-side helper for non-Fortran hosts (plain CPU code, no device needed) ----
+ * seaice_calc_variational_metric_terms (src/shared/mpas_seaice_velocity_solver_variational_shared.F:293-358):
+ * tanLatVertexRotatedOverRadius[v] = tan(asin(zVertexRotated[v] / sphereRadius)) / sphereRadius, evaluated
+ * element by element with the scalar libm, so the value of a vertex does not depend on where it sits in
+ * the array (vectorised math libraries give position-dependent last bits, which would break the
+ * bit-equality of owned results across rank counts).  A Fortran host computes this field itself. */
+int evp_host_metric_terms(int nVertices, const double *zVertexRotated, double sphereRadius,
+                          double *tanLatVertexRotatedOverRadius);
+
 /* ---- instrumentation (bench.py, tests) ---- */
 /* Time of the last evp_run_subcycles in milliseconds (CUDA events on the handle's stream). */
 int evp_last_run_ms(evp_handle *handle, float *ms);

@@ -2,6 +2,7 @@
 // Registry (Fortran column-major, AoS-in-cell) layout and the SoA device layout, CUDA-graph replay
 // of the subcycle loop.  Mirrors the lifecycle of module seaice_mesh_pool
 // (reference: src/shared/mpas_seaice_mesh_pool.F:76-281).
+#include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -815,8 +816,9 @@ extern "C" int evp_destroy(evp_handle *h)
     if (!h) return EVP_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    evp_halo_destroy(h);
+    // the graph first: ncclCommDestroy waits for every captured graph that references the communicator
     invalidate_graph(h);
+    evp_halo_destroy(h);
     for (void *p : h->pinned) cudaHostUnregister(p);
     for (void *p : h->allocs) cudaFree(p);
     for (int i = 0; i < 2; i++) {
@@ -829,6 +831,17 @@ extern "C" int evp_destroy(evp_handle *h)
     if (h->commStream) cudaStreamDestroy(h->commStream);
     cudaGetLastError();
     delete h;
+    return EVP_OK;
+}
+
+extern "C" int evp_host_metric_terms(int nVertices, const double *zRot, double radius, double *out)
+{
+    EVP_REQUIRE(nVertices >= 0 && (nVertices == 0 || (zRot && out)), "NULL argument");
+    EVP_REQUIRE(radius > 0.0, "sphereRadius must be > 0");
+    for (int v = 0; v < nVertices; v++) {
+        const double lat = asin(zRot[v] / radius);      // variational_shared.F:342
+        out[v] = tan(lat) / radius;                     // :344
+    }
     return EVP_OK;
 }
 

@@ -31,6 +31,7 @@ EXPORTS = (
     "evp_set_masks", "evp_run_subcycles", "evp_synchronize", "evp_fetch", "evp_destroy",
     "evp_last_error_string", "evp_comm_get_unique_id", "evp_comm_init", "evp_set_halo", "evp_last_run_ms",
     "evp_launch_count", "evp_get_stream", "evp_device_bytes", "evp_set_use_graph", "evp_profile_passes",
+    "evp_host_metric_terms",
 )
 
 
@@ -96,6 +97,18 @@ def _ptr(a, dtype):
     assert isinstance(a, np.ndarray) and a.dtype == dtype and a.flags["C_CONTIGUOUS"], \
         f"expected contiguous {dtype} array, got {getattr(a, 'dtype', type(a))}"
     return a.ctypes.data
+
+
+def host_metric_terms(z_rotated: np.ndarray, sphere_radius: float) -> np.ndarray:
+    """evp_host_metric_terms: tan(asin(z/R))/R with the scalar libm (position-independent bits)."""
+    lib = load_library()
+    z = np.ascontiguousarray(z_rotated, dtype=np.float64)
+    out = np.zeros_like(z)
+    rc = lib.evp_host_metric_terms(C.c_int(z.size), C.c_void_p(z.ctypes.data), C.c_double(float(sphere_radius)),
+                                   C.c_void_p(out.ctypes.data))
+    if rc != 0:
+        raise EvpError(f"libevp_b200 error {rc}: {lib.evp_last_error_string().decode()}")
+    return out
 
 
 def make_options(opts: dict, device: int = -1, pin_host: bool = False) -> Options:

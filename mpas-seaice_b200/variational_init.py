@@ -19,8 +19,10 @@ def metric_terms(mesh, rotate=True, include=True):
     out = np.zeros(nV + 1)
     if include:
         z = mesh.xVertex[:nV] if rotate else mesh.zVertex[:nV]      # rotation (x,y,z) -> (-z, y, x): zp = x
-        lat = np.arcsin(z / mesh.sphere_radius)
-        out[:nV] = np.tan(lat) / mesh.sphere_radius
+        # NOT np.tan(np.arcsin(.)): numpy's SIMD transcendental loops give position-dependent last bits,
+        # and a block-local evaluation must reproduce the global one bit for bit
+        from . import host
+        out[:nV] = host.host_metric_terms(z, mesh.sphere_radius)
     return out
 
 

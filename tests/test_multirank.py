@@ -66,12 +66,23 @@ def _reference(name, nsub):
     return mesh, step, ref
 
 
+def _diff_report(k, a, b):
+    bad = np.nonzero(a != b)[0]
+    rel = np.abs(a[bad] - b[bad]) / np.maximum(np.abs(b[bad]), 1e-300)
+    return (f"{k}: {bad.size} of {a.size} entries differ, max rel diff {rel.max():.3e}, first flat indices "
+            f"{bad[:8].tolist()}, got {a[bad[:3]].tolist()} expected {b[bad[:3]].tolist()}")
+
+
 def _assert_equal(mesh, step, ref, out):
     cm, vm = common.masks_for(mesh, step)
+    problems = []
     for k in common.COMPARE_CELL:
-        assert np.array_equal(out[k][cm], ref[k][cm]), k
+        if not np.array_equal(out[k][cm], ref[k][cm]):
+            problems.append(_diff_report(k, out[k][cm], ref[k][cm]))
     for k in common.COMPARE_VERTEX:
-        assert np.array_equal(out[k][vm], ref[k][vm]), k
+        if not np.array_equal(out[k][vm], ref[k][vm]):
+            problems.append(_diff_report(k, out[k][vm], ref[k][vm]))
+    assert not problems, "\n".join(problems)
     assert np.abs(ref["uVelocity"]).max() > 0
 
 
@@ -91,6 +102,6 @@ def test_nccl_ranks_match_single_rank(evp_lib, tmp_path, name, nsub):
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 4 if n >= 4 else 2
-    out = _launch("gpu", name, nsub, world, str(tmp_path / "out.npz"))
+    out = _launch("gpu", name, nsub, world, str(tmp_path / "out.npz"), timeout=150)
     mesh, step, ref = _reference(name, nsub)
     _assert_equal(mesh, step, ref, out)
