@@ -55,7 +55,7 @@ module seaice_evp_b200
        EVP_OK = 0, &
        EVP_CR_EVP = 1, EVP_CR_EVP_REVISED = 2, EVP_CR_LINEAR = 3, EVP_CR_NONE = 4, &
        EVP_OCEAN_QUADRATIC = 1, EVP_OCEAN_LINEAR = 2, &
-       EVP_FLAG_PIN_HOST = 1
+       EVP_FLAG_PIN_HOST = 1, EVP_FLAG_OVERLAP_HALO = 2
 
   ! ---- struct evp_mesh_desc ----
   type, bind(C), public :: evp_mesh_desc

@@ -46,6 +46,10 @@ enum { EVP_VB_NONE = 0, EVP_VB_PERIODIC = 1, EVP_VB_REVERSE = 2, EVP_VB_ZERO = 3
 
 /* evp_options.flags */
 enum {
+    EVP_FLAG_OVERLAP_HALO = 2,/* multi-rank: solve the boundary-owned vertices first and run pack / NCCL / unpack on a
+                                 forked high-priority branch while the interior vertices are solved.  Off by
+                                 default: inside the replayed graph the plain in-order exchange measured the
+                                 same or faster on NVLink */
     EVP_FLAG_PIN_HOST = 1     /* host arrays passed to update_step / fetch live at stable addresses for the
                                  life of the handle (true for MPAS pool arrays): page-lock them once with
                                  cudaHostRegister so the per-step copies run at full PCIe speed */

@@ -390,6 +390,12 @@ extern "C" int evp_set_options(evp_handle *h, const evp_options *o)
     h->opt.device = dev;
     h->pinHost = (o->flags & EVP_FLAG_PIN_HOST) != 0;
     invalidate_graph(h);
+    if (h->haveStep) {      // EVP_FLAG_OVERLAP_HALO may have changed: refresh the boundary bit of the mask
+        EVP_CUDA(cudaSetDevice(h->device));
+        int rc2 = evp_halo_mark_masks(h);
+        if (rc2) return rc2;
+        EVP_CUDA(cudaStreamSynchronize(h->stream));
+    }
     return EVP_OK;
 }
 
@@ -448,9 +454,15 @@ extern "C" int evp_create(evp_handle **out, const evp_mesh_desc *m, const evp_op
         return EVP_ERR_ARGUMENT;
     }
     CUDA_FAIL(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CUDA_FAIL(cudaStreamCreateWithFlags(&h->commStream, cudaStreamNonBlocking));
+    {   // the halo branch must not queue behind the thousands of blocks of the interior vertex pass
+        int prLow = 0, prHigh = 0;
+        CUDA_FAIL(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
+        CUDA_FAIL(cudaStreamCreateWithPriority(&h->commStream, cudaStreamNonBlocking, prHigh));
+    }
     CUDA_FAIL(cudaEventCreate(&h->ev0));
     CUDA_FAIL(cudaEventCreate(&h->ev1));
+    CUDA_FAIL(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
+    CUDA_FAIL(cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming));
     CUDA_FAIL(cudaEventCreateWithFlags(&h->pinEv[0], cudaEventDisableTiming));
     CUDA_FAIL(cudaEventCreateWithFlags(&h->pinEv[1], cudaEventDisableTiming));
     CUDA_FAIL(cudaMallocHost(&h->pinStage[0], kPinChunk));
@@ -612,6 +624,7 @@ extern "C" int evp_set_masks(evp_handle *h, const int *solveStress, const int *s
     if (nC) k_u8_in<<<grid_for(nC, 256), 256, 0, h->stream>>>(rawMs, d.solveStress, nC, 1, 1);
     if (nV) k_u8_in<<<grid_for(nV, 256), 256, 0, h->stream>>>(rawMv, d.solveVel, nV, 1, 1);
     EVP_CUDA(cudaGetLastError());
+    if ((rc = evp_halo_mark_masks(h))) return rc;
     EVP_CUDA(cudaStreamSynchronize(h->stream));
     return EVP_OK;
 }
@@ -643,6 +656,7 @@ extern "C" int evp_update_step(evp_handle *h, const evp_step_fields *f)
     if ((rc = h2d(h, rawMv, f->solveVelocity, nV * 4))) return rc;
     if (nC) k_u8_in<<<grid_for(nC, 256), 256, 0, s>>>(rawMs, d.solveStress, nC, 1, 1);
     if (nV) k_u8_in<<<grid_for(nV, 256), 256, 0, s>>>(rawMv, d.solveVel, nV, 1, 1);
+    if ((rc = evp_halo_mark_masks(h))) return rc;
     if ((rc = h2d(h, d.P, f->icePressure, nC * 8))) return rc;
 
     struct { const double *a, *b; double2 *dst; } pairs[] = {
@@ -827,6 +841,8 @@ extern "C" int evp_destroy(evp_handle *h)
     }
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->evFork) cudaEventDestroy(h->evFork);
+    if (h->evJoin) cudaEventDestroy(h->evJoin);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->commStream) cudaStreamDestroy(h->commStream);
     cudaGetLastError();

@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <stdlib.h>
+#include <algorithm>
 #include "evp_internal.cuh"
 
 namespace {
@@ -69,6 +70,17 @@ __global__ void k_pack(int n, const int *__restrict__ idx, const double2 *__rest
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n) buf[k] = uv[idx[k]];
 }
+// bit 1 of the velocity mask byte marks the boundary-owned vertices (see evp_vertex_kernel)
+__global__ void k_mark_boundary(int n, const int *__restrict__ idx, uint8_t *__restrict__ mask)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) mask[idx[k]] |= 2;
+}
+__global__ void k_clear_boundary(size_t n, uint8_t *__restrict__ mask)
+{
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) mask[k] &= 1;
+}
 __global__ void k_unpack(int n, const int *__restrict__ idx, const double2 *__restrict__ buf, double2 *__restrict__ uv)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -82,6 +94,8 @@ struct evp_halo {
     int rank = 0, nRanks = 1;
     int nNb = 0, nSend = 0, nRecv = 0;
     std::vector<int> nbRank, sendOff, recvOff;
+    int nBoundary = 0;            // unique send-list vertices
+    int *dBoundary = nullptr;
     int *dSendIdx = nullptr, *dRecvIdx = nullptr;
     double2 *dSendBuf = nullptr, *dRecvBuf = nullptr;
 };
@@ -143,6 +157,15 @@ extern "C" int evp_set_halo(evp_handle *h, int nNb, const int *nbRank, const int
     if ((rc = evp_dev_alloc(h, (void **)&H.dRecvIdx, sizeof(int) * (H.nRecv + 1)))) return rc;
     if ((rc = evp_dev_alloc(h, (void **)&H.dSendBuf, sizeof(double2) * (H.nSend + 1)))) return rc;
     if ((rc = evp_dev_alloc(h, (void **)&H.dRecvBuf, sizeof(double2) * (H.nRecv + 1)))) return rc;
+    {   // boundary-owned vertices = the distinct entries of the send lists, ascending
+        std::vector<int> b(s0);
+        std::sort(b.begin(), b.end());
+        b.erase(std::unique(b.begin(), b.end()), b.end());
+        H.nBoundary = (int)b.size();
+        if ((rc = evp_dev_alloc(h, (void **)&H.dBoundary, sizeof(int) * (b.size() + 1)))) return rc;
+        if (!b.empty()) EVP_CUDA(cudaMemcpy(H.dBoundary, b.data(), sizeof(int) * b.size(), cudaMemcpyHostToDevice));
+        if ((rc = evp_halo_mark_masks(h))) return rc;
+    }
     if (H.nSend) EVP_CUDA(cudaMemcpy(H.dSendIdx, s0.data(), sizeof(int) * H.nSend, cudaMemcpyHostToDevice));
     if (H.nRecv) EVP_CUDA(cudaMemcpy(H.dRecvIdx, r0.data(), sizeof(int) * H.nRecv, cudaMemcpyHostToDevice));
     if (h->graphExec) { cudaGraphExecDestroy(h->graphExec); h->graphExec = nullptr; h->graphN = -1; }
@@ -161,6 +184,25 @@ extern "C" int evp_set_halo(evp_handle *h, int nNb, const int *nbRank, const int
         EVP_NCCL(g_nccl.GroupEnd());
         EVP_CUDA(cudaStreamSynchronize(h->stream));
     }
+    return EVP_OK;
+}
+
+int evp_halo_boundary_count(evp_handle *h)
+{
+    if (!h->halo || !h->halo->comm || h->halo->nNb == 0 || !(h->opt.flags & EVP_FLAG_OVERLAP_HALO)) return 0;
+    return h->halo->nBoundary;
+}
+const int *evp_halo_boundary_list(evp_handle *h) { return h->halo ? h->halo->dBoundary : nullptr; }
+
+// (re)apply the boundary bit to the velocity mask; called after every mask upload
+int evp_halo_mark_masks(evp_handle *h)
+{
+    if (!h->halo || h->nVertices == 0) return EVP_OK;
+    k_clear_boundary<<<(unsigned)((h->nVp + 255) / 256), 256, 0, h->stream>>>(h->nVp, h->d.solveVel);
+    if (h->halo->nBoundary && (h->opt.flags & EVP_FLAG_OVERLAP_HALO))
+        k_mark_boundary<<<(h->halo->nBoundary + 255) / 256, 256, 0, h->stream>>>(h->halo->nBoundary, h->halo->dBoundary,
+                                                                                 h->d.solveVel);
+    EVP_CUDA(cudaGetLastError());
     return EVP_OK;
 }
 

@@ -98,7 +98,7 @@ struct evp_handle {
     bool haveBasis = false, haveStep = false, haveSB = false, useGraph = true, pinHost = false, timed = false;
     evp_dev d;
     cudaStream_t stream = nullptr, commStream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evFork = nullptr, evJoin = nullptr;
     cudaGraphExec_t graphExec = nullptr;
     int graphN = -1;
     float lastMs = 0.f;
@@ -115,12 +115,15 @@ struct evp_handle {
 int evp_enqueue_subcycles(evp_handle *h, int nSub, cudaStream_t s);
 int evp_count_launches(evp_handle *h, int nSub);
 int evp_enqueue_cell_pass(evp_handle *h, bool diag, cudaStream_t s);
-int evp_enqueue_vertex_pass(evp_handle *h, bool diag, cudaStream_t s);
+int evp_enqueue_vertex_pass(evp_handle *h, bool diag, cudaStream_t s, const int *list, int nList);
 int evp_enqueue_special_boundaries(evp_handle *h, cudaStream_t s);
 
 // evp_halo.cu
 int evp_halo_enqueue(evp_handle *h, cudaStream_t s);
 int evp_halo_launches(evp_handle *h);
+int evp_halo_mark_masks(evp_handle *h);
+int evp_halo_boundary_count(evp_handle *h);        // boundary-owned vertices (unique send-list entries)
+const int *evp_halo_boundary_list(evp_handle *h);  // device array of their 0-based indices
 void evp_halo_destroy(evp_handle *h);
 
 // layout kernels (evp_abi.cu)

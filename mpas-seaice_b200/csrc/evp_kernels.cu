@@ -296,7 +296,8 @@ __global__ void __launch_bounds__(EVP_TILE *M) evp_cell_kernel(const CellArgs a)
 }
 
 struct VertexArgs {
-    int nVerticesSolve;
+    int nVerticesSolve;                 // number of threads: owned vertices, or entries of `list`
+    const int *__restrict__ list;       // LIST: the boundary-owned vertices (those some neighbour rank needs)
     size_t nVp;
     const uint8_t *__restrict__ solveVel;
     const int *__restrict__ gidx;
@@ -315,12 +316,16 @@ struct VertexArgs {
     int useOcean, oceanType;
 };
 
-template <int D, int CR, bool DIAG>
+// solveVel[v]: bit 0 = solveVelocity(v) == 1, bit 1 = boundary-owned vertex (set only when a halo exchange is
+// attached).  The plain pass takes the vertices whose byte is exactly 1; the LIST pass runs first over the
+// boundary-owned vertices so that their (u,v) can travel while the plain pass does the interior.
+template <int D, int CR, bool DIAG, bool LIST>
 __global__ void __launch_bounds__(256) evp_vertex_kernel(const VertexArgs a)
 {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= a.nVerticesSolve) return;
-    if (a.solveVel[v] != 1) return;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.nVerticesSolve) return;
+    const int v = LIST ? a.list[k] : k;
+    if (LIST ? (a.solveVel[v] & 1) == 0 : a.solveVel[v] != 1) return;
 
     double sdU = 0.0, sdV = 0.0;
 #pragma unroll
@@ -444,8 +449,13 @@ int launch_vertex_d(const VertexArgs &a, bool diag, cudaStream_t s)
 {
     const int block = 256;
     const int grid = (a.nVerticesSolve + block - 1) / block;
-    if (diag) evp_vertex_kernel<D, CR, true><<<grid, block, 0, s>>>(a);
-    else      evp_vertex_kernel<D, CR, false><<<grid, block, 0, s>>>(a);
+    if (a.list) {
+        if (diag) evp_vertex_kernel<D, CR, true, true><<<grid, block, 0, s>>>(a);
+        else      evp_vertex_kernel<D, CR, false, true><<<grid, block, 0, s>>>(a);
+    } else {
+        if (diag) evp_vertex_kernel<D, CR, true, false><<<grid, block, 0, s>>>(a);
+        else      evp_vertex_kernel<D, CR, false, false><<<grid, block, 0, s>>>(a);
+    }
     return 0;
 }
 template <int D>
@@ -485,11 +495,13 @@ int evp_enqueue_cell_pass(evp_handle *h, bool diag, cudaStream_t s)
     return EVP_OK;
 }
 
-int evp_enqueue_vertex_pass(evp_handle *h, bool diag, cudaStream_t s)
+// list == nullptr: every owned vertex whose mask byte is 1; else the nList boundary-owned vertices.
+int evp_enqueue_vertex_pass(evp_handle *h, bool diag, cudaStream_t s, const int *list, int nList)
 {
-    if (h->nVerticesSolve == 0) return EVP_OK;
+    const int nThreads = list ? nList : h->nVerticesSolve;
+    if (nThreads == 0) return EVP_OK;
     VertexArgs a;
-    a.nVerticesSolve = h->nVerticesSolve; a.nVp = h->nVp;
+    a.nVerticesSolve = nThreads; a.list = list; a.nVp = h->nVp;
     a.solveVel = h->d.solveVel; a.gidx = h->d.gidx; a.contrib = h->d.contrib;
     a.areaDen = h->d.areaDen; a.massf = h->d.massf; a.air = h->d.air; a.tilt = h->d.tilt;
     a.ocnStress = h->d.ocnStress; a.ocnVel = h->d.ocnVel; a.uvInit = h->d.uvInit;
@@ -527,6 +539,28 @@ static inline bool diag_always(const evp_handle *h)
 // { internal stress, drag coefficient, velocity solve, halo exchange, special boundaries }.
 // Strain, replacementPressure, stressDivergence and oceanStressCoeff are only consumed after the
 // loop (velocity_solver.F:3360-3380), so only the last subcycle stores them (DIAG).
+// One subcycle after the cell pass: vertex pass + halo exchange.  With a halo attached the boundary-owned
+// vertices are solved first, their (u,v) are packed and exchanged on the communication stream (a forked
+// branch of the graph) while the interior vertices are solved on the main stream; the two join before
+// the next cell pass reads the halo.
+int evp_enqueue_vertex_and_halo(evp_handle *h, bool diag, cudaStream_t s)
+{
+    int rc;
+    const int nB = evp_halo_boundary_count(h);
+    if (nB == 0) {
+        if ((rc = evp_enqueue_vertex_pass(h, diag, s, nullptr, 0))) return rc;
+        return evp_halo_enqueue(h, s);          // no-op without neighbours
+    }
+    if ((rc = evp_enqueue_vertex_pass(h, diag, s, evp_halo_boundary_list(h), nB))) return rc;
+    EVP_CUDA(cudaEventRecord(h->evFork, s));
+    EVP_CUDA(cudaStreamWaitEvent(h->commStream, h->evFork, 0));
+    if ((rc = evp_halo_enqueue(h, h->commStream))) return rc;
+    EVP_CUDA(cudaEventRecord(h->evJoin, h->commStream));
+    if ((rc = evp_enqueue_vertex_pass(h, diag, s, nullptr, 0))) return rc;
+    EVP_CUDA(cudaStreamWaitEvent(s, h->evJoin, 0));
+    return EVP_OK;
+}
+
 int evp_enqueue_subcycles(evp_handle *h, int nSub, cudaStream_t s)
 {
     int rc;
@@ -534,8 +568,7 @@ int evp_enqueue_subcycles(evp_handle *h, int nSub, cudaStream_t s)
     for (int k = 0; k < nSub; k++) {
         const bool diag = (k == nSub - 1) || diag_always(h);
         if ((rc = evp_enqueue_cell_pass(h, diag, s))) return rc;
-        if ((rc = evp_enqueue_vertex_pass(h, diag, s))) return rc;
-        if ((rc = evp_halo_enqueue(h, s))) return rc;
+        if ((rc = evp_enqueue_vertex_and_halo(h, diag, s))) return rc;
         if ((rc = evp_enqueue_special_boundaries(h, s))) return rc;
     }
     return EVP_OK;
@@ -544,7 +577,8 @@ int evp_enqueue_subcycles(evp_handle *h, int nSub, cudaStream_t s)
 int evp_count_launches(evp_handle *h, int nSub)
 {
     const int sb = (h->opt.use_special_boundaries_velocity && h->d.nSB) ? 2 : 0;
-    const int perSub = (h->nCells ? 1 : 0) + (h->nVerticesSolve ? 1 : 0) + evp_halo_launches(h) + sb;
+    const int perSub = (h->nCells ? 1 : 0) + (h->nVerticesSolve ? 1 : 0) + (evp_halo_boundary_count(h) ? 1 : 0) +
+                       evp_halo_launches(h) + sb;
     return sb + nSub * perSub;
 }
 
@@ -564,9 +598,8 @@ extern "C" int evp_profile_passes(evp_handle *h, int nSub, float *cellMs, float 
         EVP_CUDA(cudaEventRecord(e[0], s));
         if ((rc = evp_enqueue_cell_pass(h, false, s))) break;
         EVP_CUDA(cudaEventRecord(e[1], s));
-        if ((rc = evp_enqueue_vertex_pass(h, false, s))) break;
+        if ((rc = evp_enqueue_vertex_and_halo(h, false, s))) break;
         EVP_CUDA(cudaEventRecord(e[2], s));
-        if ((rc = evp_halo_enqueue(h, s))) break;
         if ((rc = evp_enqueue_special_boundaries(h, s))) break;
         EVP_CUDA(cudaEventRecord(e[3], s));
         EVP_CUDA(cudaEventSynchronize(e[3]));

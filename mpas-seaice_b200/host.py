@@ -25,6 +25,7 @@ _lib = None
 CR = {"evp": 1, "evp_revised": 2, "linear": 3, "none": 4}
 OCEAN = {"quadratic": 1, "linear": 2}
 FLAG_PIN_HOST = 1
+FLAG_OVERLAP_HALO = 2
 
 EXPORTS = (
     "evp_create", "evp_set_options", "evp_precompute_wachspress", "evp_fetch_basis", "evp_update_step",
@@ -118,7 +119,7 @@ def make_options(opts: dict, device: int = -1, pin_host: bool = False) -> Option
     o.use_ocean_stress = int(opts.get("use_ocean_stress", True))
     o.use_special_boundaries_velocity = int(opts.get("use_special_boundaries_velocity", False))
     o.device = device
-    o.flags = FLAG_PIN_HOST if pin_host else 0
+    o.flags = (FLAG_PIN_HOST if pin_host else 0) | (FLAG_OVERLAP_HALO if opts.get("overlap_halo", False) else 0)
     o.elasticTimeStep = opts["elasticTimeStep"]
     o.dynamicsTimeStep = opts["dynamicsTimeStep"]
     o.dampingTimescale = opts["dampingTimescale"]

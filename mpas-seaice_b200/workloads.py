@@ -25,6 +25,33 @@ ALGO_BYTES_PER_VERTEX = 164.0       # per owned vertex
 ALGO_BYTES_PER_CELL_SUBCYCLE = 2240.0
 
 
+def _cached_icosphere(level: int):
+    """meshgen.icosphere(level), optionally cached as an uncompressed .npz under $EVP_B200_MESH_CACHE
+    (mesh generation is deterministic; the cache only saves the ~1 min a 10 M-cell mesh takes when
+    several runs share a machine, e.g. a plain run followed by the same run under ncu)."""
+    import os
+    cache = os.environ.get("EVP_B200_MESH_CACHE")
+    if not cache or level < 8:
+        return meshgen.icosphere(level)
+    path = os.path.join(cache, f"icosphere_{level}.npz")
+    if os.path.exists(path):
+        with np.load(path, allow_pickle=False) as z:
+            m = meshgen.Mesh()
+            for k in z.files:
+                a = z[k]
+                m[k] = a.item() if a.ndim == 0 else a
+            return m
+    m = meshgen.icosphere(level)
+    try:
+        os.makedirs(cache, exist_ok=True)
+        tmp = path + f".{os.getpid()}.tmp.npz"
+        np.savez(tmp, **{k: np.asarray(v) for k, v in m.items()})
+        os.replace(tmp, path)
+    except OSError:
+        pass
+    return m
+
+
 def build(name: str, state: str = "A", n_elastic: int = 120, verbose=None, with_static: bool = True):
     """Returns dict(mesh, static, step, opts, name, timings).  ``with_static=False`` skips the static
     variational fields (multi-GPU hosts compute them per block, see multigpu.py)."""
@@ -36,7 +63,7 @@ def build(name: str, state: str = "A", n_elastic: int = 120, verbose=None, with_
         st = synthetic.square_state(mesh)
     elif name in SPHERES or (name.startswith("ico") and name[3:].isdigit()):
         level, config_dt = SPHERES[name] if name in SPHERES else (int(name[3:]), 3600.0)   # icoN: test sizes
-        mesh = meshgen.icosphere(level)
+        mesh = _cached_icosphere(level)
         st = synthetic.sphere_state(mesh, kind=state)
     else:
         raise ValueError(f"unknown workload {name!r}")

@@ -31,6 +31,9 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     from mpas_seaice_b200 import multigpu, partition
     import common
+    overlap = mode == "gpu-overlap"      # EVP_FLAG_OVERLAP_HALO: boundary-first vertex pass, forked exchange
+    if overlap:
+        mode = "gpu"
     if mode == "gpu":
         torch.cuda.set_device(rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
@@ -40,7 +43,7 @@ def main():
     blk, step, opts = w["mesh"], w["step"], w["opts"]
     if mode == "gpu":
         from mpas_seaice_b200 import host
-        solver = host.EvpSolver(blk, w["static"], opts, device=rank,
+        solver = host.EvpSolver(blk, w["static"], dict(opts, overlap_halo=overlap), device=rank,
                                 local_coords=(w["static"]["xLocal"], w["static"]["yLocal"]),
                                 n_vertices_solve=w["nVerticesSolve"], n_cells_solve=w["nCellsSolve"])
         stage("evp_create done")

@@ -95,13 +95,13 @@ def test_gloo_ranks_match_single_rank(tmp_path, world, method):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,nsub", [("ico4", 120), ("square", 120)])
-def test_nccl_ranks_match_single_rank(evp_lib, tmp_path, name, nsub):
+@pytest.mark.parametrize("name,nsub,mode", [("ico4", 120, "gpu"), ("square", 120, "gpu"), ("ico4", 120, "gpu-overlap")])
+def test_nccl_ranks_match_single_rank(evp_lib, tmp_path, name, nsub, mode):
     import torch
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 4 if n >= 4 else 2
-    out = _launch("gpu", name, nsub, world, str(tmp_path / "out.npz"), timeout=150)
+    out = _launch(mode, name, nsub, world, str(tmp_path / "out.npz"), timeout=150)
     mesh, step, ref = _reference(name, nsub)
     _assert_equal(mesh, step, ref, out)
