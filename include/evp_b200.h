@@ -195,6 +195,106 @@ int evp_set_halo(evp_handle *handle, int nNeighbours, const int *neighbourRank,
                  const int *sendOffset, const int *sendIndex,
                  const int *recvOffset, const int *recvIndex);
 
+
+/* ======================================================================================================
+ * Widening: the steps on either side of the subcycle on the device, so that one
+ * dynamics step moves CELL fields in and a handful of fields out instead of ~20 vertex fields each way,
+ * and u, v, stress11/22/12 and solveVelocityPrevious stay resident between steps.
+ *   evp_pre_subcycle  = velocity_solver_pre_subcycle  (src/shared/mpas_seaice_velocity_solver.F:613-671)
+ *   evp_post_subcycle = velocity_solver_post_subcycle (velocity_solver.F:3360-3380)
+ * What stays on the host: aggregate_mass_and_area (:685-752, sums over ice categories) and the ice
+ * strength itself (:1341-1436: Hibler needs exp(), colpkg_ice_strength is column physics) -- the host
+ * passes icePressure for every cell that may be solved and the device applies solveStress.
+ * ====================================================================================================== */
+
+/* Mesh fields the pre-/post-subcycle read in addition to evp_mesh_desc (src/Registry.xml:2251-2367,
+ * boundary pool interiorVertex, ocean_coupling landIceMaskVertex). */
+typedef struct {
+    const int *cellsOnCell;          /* (maxEdges, nCells)  stress_calculation_mask, velocity_solver.F:1030-1040 */
+    const int *interiorVertex;       /* (nVertices)  src/shared/mpas_seaice_mesh.F:423-488 */
+    const int *landIceMaskVertex;    /* (nVertices) or NULL = no land ice (velocity_solver.F:481-544) */
+    const double *areaCell;          /* (nCells)     weights of seaice_interpolate_cell_to_vertex, mesh.F:2835-2851 */
+    const double *areaTriangle;      /* (nVertices)  weights of seaice_interpolate_vertex_to_cell, mesh.F:2958-2971 */
+    const double *fVertex;           /* (nVertices) */
+} evp_mesh_ext;
+
+/* Cell inputs of one dynamics step, all (nCells).  Optional groups are NULL when unused. */
+typedef struct {
+    const double *iceAreaCellInitial;   /* masks + vertex interpolation (velocity_solver.F:860-880) */
+    const double *iceAreaCell;          /* constant_air_stress (:1716-1723); may alias iceAreaCellInitial */
+    const double *totalMassCell;        /* aggregate_mass_and_area (:742-744) */
+    const double *icePressure;          /* ice strength, unmasked; the device zeroes it where solveStress /= 1 */
+    const double *uOceanVelocity;       /* ocean_coupling pool */
+    const double *vOceanVelocity;
+    const double *airStressCellU;       /* either the coupler's stresses ...                                   */
+    const double *airStressCellV;
+    const double *uAirVelocity;         /* ... or the inputs of constant_air_stress (used when airStressCellU is NULL) */
+    const double *vAirVelocity;
+    const double *airDensity;
+    const double *seaSurfaceTiltU;      /* surface_tilt_ssh_gradient (:2024-2170) only */
+    const double *seaSurfaceTiltV;
+    const int *landIceMask;             /* (nCells) or NULL = no land ice */
+    const int *solveStress;             /* config_calc_velocity_masks = false: masks given by the host ...   */
+    const int *solveVelocity;           /* ... (nCells) / (nVertices), else NULL                              */
+} evp_pre_fields;
+
+/* Namelist switches of the pre-subcycle (src/Registry.xml:566-647). */
+typedef struct {
+    int use_air_stress;                 /* config_use_air_stress */
+    int use_surface_tilt;               /* config_use_surface_tilt */
+    int geostrophic_surface_tilt;       /* config_geostrophic_surface_tilt */
+    int calc_velocity_masks;            /* config_calc_velocity_masks */
+    int cold_start;                     /* 1: u = v = 0, stresses = 0 and solveVelocityPrevious = solveVelocity
+                                           (first step from rest); 0: use the state resident on the device
+                                           (previous step, or seeded with evp_update_step / evp_set_state) */
+} evp_pre_options;
+
+/* Outputs of one dynamics step; any pointer may be NULL (= not wanted, nothing computed for it beyond what
+ * others need).  Cell arrays (nCells), vertex arrays (nVertices), *Var (maxEdges, nCells). */
+typedef struct {
+    double *uVelocity;                  /* -> advection */
+    double *vVelocity;
+    double *divergence;                 /* seaice_final_divergence_shear_variational, variational.F:1198-1330 */
+    double *shear;
+    double *ridgeConvergence;           /* -> ridging */
+    double *ridgeShear;
+    double *principalStress1Var;        /* principal_stresses_driver, velocity_solver.F:3443-3610 */
+    double *principalStress2Var;
+    double *oceanStressCellU;           /* ocean_stress_final, velocity_solver.F:3624-3848 -> coupler */
+    double *oceanStressCellV;
+    double *oceanStressU;               /* (nVertices) as left by ocean_stress_final */
+    double *oceanStressV;
+    double *oceanStressCoeff;
+} evp_post_fields;
+
+int evp_set_mesh_ext(evp_handle *handle, const evp_mesh_ext *ext);
+
+/* Seed the state that is carried between dynamics steps (restart: src/Registry.xml:1937-1957). */
+int evp_set_state(evp_handle *handle, const double *uVelocity, const double *vVelocity,
+                  const double *stress11, const double *stress22, const double *stress12,
+                  const int *solveVelocityPrevious);
+
+/* velocity_solver_pre_subcycle on the device; afterwards the handle is ready for evp_run_subcycles.
+ * Multi-rank: ends with the uVelocity/vVelocity halo exchange of new_ice_velocities (:1281-1320). */
+int evp_pre_subcycle(evp_handle *handle, const evp_pre_fields *fields, const evp_pre_options *options);
+
+/* velocity_solver_post_subcycle on the device + copy of the wanted results. */
+int evp_post_subcycle(evp_handle *handle, const evp_post_fields *out);
+
+/* The fields evp_pre_subcycle produced, for hosts that still need them (and for the parity tests):
+ * same struct as evp_update_step consumes, every non-NULL pointer is filled. */
+typedef struct {
+    int *solveStress; int *solveVelocity; int *solveVelocityPrevious;
+    double *icePressure;
+    double *iceAreaVertex; double *totalMassVertex; double *totalMassVertexfVertex;
+    double *airStressVertexU; double *airStressVertexV;
+    double *surfaceTiltForceU; double *surfaceTiltForceV;
+    double *oceanStressU; double *oceanStressV;
+    double *uOceanVelocityVertex; double *vOceanVelocityVertex;
+    double *uVelocityInitial; double *vVelocityInitial;
+} evp_pre_out_fields;
+int evp_fetch_pre(evp_handle *handle, const evp_pre_out_fields *out);
+
 /* ---- host-side helper for non-Fortran hosts (plain CPU code, no device needed) ----
  * seaice_calc_variational_metric_terms (src/shared/mpas_seaice_velocity_solver_variational_shared.F:293-358):
  * tanLatVertexRotatedOverRadius[v] = tan(asin(zVertexRotated[v] / sphereRadius)) / sphereRadius, evaluated

@@ -92,7 +92,7 @@ __global__ void k_pair_out(double *__restrict__ a, double *__restrict__ b, const
     if (b) b[i] = w.y;
 }
 __global__ void k_gidx(const int *__restrict__ cov, const int *__restrict__ cvav, const uint8_t *__restrict__ nEdges,
-                       int *__restrict__ gidx, int D, size_t nV, size_t nVp, int nCells, size_t nCp)
+                       int *__restrict__ gidx, int *__restrict__ cov0, int D, size_t nV, size_t nVp, int nCells, size_t nCp)
 {
     const size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nV) return;
@@ -103,6 +103,7 @@ __global__ void k_gidx(const int *__restrict__ cov, const int *__restrict__ cvav
         // the reference's inner loop runs 1..nEdgesOnCell(iCell); the junk cell has 0 edges
         if (c >= 1 && c <= nCells && j >= 1 && j <= (int)nEdges[c - 1]) g = (int)((size_t)(j - 1) * nCp + (size_t)(c - 1));
         gidx[(size_t)s * nVp + v] = g;
+        cov0[(size_t)s * nVp + v] = (c >= 1 && c <= nCells) ? c - 1 : -1;     // pre-/post-subcycle interpolation
     }
 }
 
@@ -161,22 +162,11 @@ __global__ void k_band_unpack(const double2 *__restrict__ Gb, double2 *__restric
     }
 }
 
-inline unsigned grid_for(size_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
 struct NoPin {   // one-shot transfers (static data, basis read-back) never page-lock caller memory
     evp_handle *h; bool saved;
     explicit NoPin(evp_handle *h_) : h(h_), saved(h_->pinHost) { h->pinHost = false; }
     ~NoPin() { h->pinHost = saved; }
-};
-
-struct Stage {   // bump allocator over the device staging area
-    char *base; size_t cap, off;
-    void *take(size_t bytes) {
-        size_t o = (off + 255) & ~(size_t)255;
-        if (o + bytes > cap) return nullptr;
-        off = o + bytes;
-        return base + o;
-    }
 };
 
 }  // namespace
@@ -260,7 +250,7 @@ static bool host_is_pinned(evp_handle *h, const void *p, size_t bytes)
 }
 
 // host -> device on h->stream; pageable sources go through two pinned bounce buffers
-static int h2d(evp_handle *h, void *dst, const void *src, size_t bytes)
+int evp_h2d(evp_handle *h, void *dst, const void *src, size_t bytes)
 {
     if (bytes == 0) return EVP_OK;
     if (host_is_pinned(h, src, bytes)) {
@@ -282,7 +272,7 @@ static int h2d(evp_handle *h, void *dst, const void *src, size_t bytes)
 }
 
 // device -> host; blocking for pageable destinations, stream-ordered for pinned ones
-static int d2h(evp_handle *h, void *dst, const void *src, size_t bytes)
+int evp_d2h(evp_handle *h, void *dst, const void *src, size_t bytes)
 {
     if (bytes == 0) return EVP_OK;
     if (host_is_pinned(h, dst, bytes)) {
@@ -317,14 +307,14 @@ static int d2h(evp_handle *h, void *dst, const void *src, size_t bytes)
 }
 
 // upload a (Mh[,Mh], nCells) host array into SoA rows, chunked through the device staging area
-static int upload_rows(evp_handle *h, const double *host, double *dst, int dims, int ncomp, int comp)
+int evp_upload_rows(evp_handle *h, const double *host, double *dst, int dims, int ncomp, int comp)
 {
     const size_t nC = (size_t)h->nCells;
     const size_t perCell = (size_t)h->Mh * (dims == 2 ? h->Mh : 1) * sizeof(double);
     const size_t chunkCells = std::max<size_t>(1, std::min(nC, h->d.stageBytes / perCell));
     for (size_t c0 = 0; c0 < nC; c0 += chunkCells) {
         const size_t cnt = std::min(chunkCells, nC - c0);
-        int rc = h2d(h, h->d.stage, (const char *)host + c0 * perCell, cnt * perCell);
+        int rc = evp_h2d(h, h->d.stage, (const char *)host + c0 * perCell, cnt * perCell);
         if (rc) return rc;
         k_rows_in<<<grid_for(cnt, 128), 128, 0, h->stream>>>((const double *)h->d.stage, dst, h->Mh, h->M, dims, cnt,
                                                               c0, h->nCp, ncomp, comp);
@@ -334,7 +324,7 @@ static int upload_rows(evp_handle *h, const double *host, double *dst, int dims,
     return EVP_OK;
 }
 
-static int download_rows(evp_handle *h, double *host, const double *soa, int dims, int ncomp, int comp)
+int evp_download_rows(evp_handle *h, double *host, const double *soa, int dims, int ncomp, int comp)
 {
     const size_t nC = (size_t)h->nCells;
     const size_t perCell = (size_t)h->Mh * (dims == 2 ? h->Mh : 1) * sizeof(double);
@@ -344,7 +334,7 @@ static int download_rows(evp_handle *h, double *host, const double *soa, int dim
         k_rows_out<<<grid_for(cnt, 128), 128, 0, h->stream>>>((double *)h->d.stage, soa, h->Mh, h->M, dims, cnt, c0,
                                                                h->nCp, ncomp, comp);
         EVP_CUDA(cudaGetLastError());
-        int rc = d2h(h, (char *)host + c0 * perCell, h->d.stage, cnt * perCell);
+        int rc = evp_d2h(h, (char *)host + c0 * perCell, h->d.stage, cnt * perCell);
         if (rc) return rc;
         // pinned destinations: the copy is asynchronous and the staging area is about to be reused
         EVP_CUDA(cudaStreamSynchronize(h->stream));
@@ -475,6 +465,8 @@ extern "C" int evp_create(evp_handle **out, const evp_mesh_desc *m, const evp_op
     FAIL_IF(evp_dev_alloc(h, (void **)&d.Sm, sizeof(double) * Mk * Mk * nCp));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.tanLat, sizeof(double) * nVp));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.gidx, sizeof(int) * D * nVp));
+    FAIL_IF(evp_dev_alloc(h, (void **)&d.cov, sizeof(int) * D * nVp));
+    FAIL_IF(evp_dev_alloc(h, (void **)&d.solveVelPrev, nVp));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.solveStress, nCp));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.solveVel, nVp));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.P, sizeof(double) * nCp));
@@ -504,6 +496,10 @@ extern "C" int evp_create(evp_handle **out, const evp_mesh_desc *m, const evp_op
     // zero everything a kernel may read before the host wrote it
     CUDA_FAIL(cudaMemsetAsync(d.voc, 0, sizeof(int) * Mk * nCp, h->stream));
     CUDA_FAIL(cudaMemsetAsync(d.nEdges, 0, nCp, h->stream));
+    CUDA_FAIL(cudaMemsetAsync(d.solveVelPrev, 0, nVp, h->stream));
+    CUDA_FAIL(cudaMemsetAsync(d.solveVel, 0, nVp, h->stream));
+    CUDA_FAIL(cudaMemsetAsync(d.solveStress, 0, nCp, h->stream));
+    CUDA_FAIL(cudaMemsetAsync(d.uv, 0, sizeof(double2) * nVp, h->stream));
     CUDA_FAIL(cudaMemsetAsync(d.Suv, 0, sizeof(double2) * Mk * Mk * nCp, h->stream));
     CUDA_FAIL(cudaMemsetAsync(d.Sm, 0, sizeof(double) * Mk * Mk * nCp, h->stream));
     CUDA_FAIL(cudaMemsetAsync(d.contrib, 0, sizeof(double2) * Mk * nCp, h->stream));
@@ -518,13 +514,13 @@ extern "C" int evp_create(evp_handle **out, const evp_mesh_desc *m, const evp_op
     Stage st{(char *)d.stage, d.stageBytes, 0};
     if (nC > 0) {
         int *rawN = (int *)st.take(nC * 4);
-        FAIL_IF(h2d(h, rawN, m->nEdgesOnCell, nC * 4));
+        FAIL_IF(evp_h2d(h, rawN, m->nEdgesOnCell, nC * 4));
         k_u8_in<<<grid_for(nC, 256), 256, 0, h->stream>>>(rawN, d.nEdges, nC, 0, Mh);
         const size_t chunk = std::max<size_t>(1, std::min(nC, (st.cap - st.off - 4096) / ((size_t)Mh * 4)));
         int *rawV = (int *)st.take(chunk * Mh * 4);
         for (size_t c0 = 0; c0 < nC; c0 += chunk) {
             const size_t cnt = std::min(chunk, nC - c0);
-            FAIL_IF(h2d(h, rawV, m->verticesOnCell + c0 * Mh, cnt * Mh * 4));
+            FAIL_IF(evp_h2d(h, rawV, m->verticesOnCell + c0 * Mh, cnt * Mh * 4));
             k_voc_in<<<grid_for(cnt, 128), 128, 0, h->stream>>>(rawV, d.voc, rawN + c0, Mh, cnt, c0, nCp, (int)nV);
         }
         CUDA_FAIL(cudaGetLastError());
@@ -537,16 +533,16 @@ extern "C" int evp_create(evp_handle **out, const evp_mesh_desc *m, const evp_op
         int *rawCv = (int *)st.take(chunk * D * 4);
         for (size_t v0 = 0; v0 < nV; v0 += chunk) {
             const size_t cnt = std::min(chunk, nV - v0);
-            FAIL_IF(h2d(h, rawCov, m->cellsOnVertex + v0 * D, cnt * D * 4));
-            FAIL_IF(h2d(h, rawCv, m->cellVerticesAtVertex + v0 * D, cnt * D * 4));
-            k_gidx<<<grid_for(cnt, 256), 256, 0, h->stream>>>(rawCov, rawCv, d.nEdges, d.gidx + v0, D, cnt, nVp,
+            FAIL_IF(evp_h2d(h, rawCov, m->cellsOnVertex + v0 * D, cnt * D * 4));
+            FAIL_IF(evp_h2d(h, rawCv, m->cellVerticesAtVertex + v0 * D, cnt * D * 4));
+            k_gidx<<<grid_for(cnt, 256), 256, 0, h->stream>>>(rawCov, rawCv, d.nEdges, d.gidx + v0, d.cov + v0, D, cnt, nVp,
                                                                (int)nC, nCp);
         }
         CUDA_FAIL(cudaGetLastError());
-        FAIL_IF(h2d(h, d.tanLat, m->tanLatVertexRotatedOverRadius, nV * 8));
+        FAIL_IF(evp_h2d(h, d.tanLat, m->tanLatVertexRotatedOverRadius, nV * 8));
         st.off = 0;
         double *rawD = (double *)st.take(nV * 8);
-        FAIL_IF(h2d(h, rawD, m->variationalDenominator, nV * 8));
+        FAIL_IF(evp_h2d(h, rawD, m->variationalDenominator, nV * 8));
         k_pair_in<<<grid_for(nV, 256), 256, 0, h->stream>>>(nullptr, rawD, d.areaDen, nV);   // .y = denominator
         CUDA_FAIL(cudaGetLastError());
         CUDA_FAIL(cudaStreamSynchronize(h->stream));
@@ -556,11 +552,11 @@ extern "C" int evp_create(evp_handle **out, const evp_mesh_desc *m, const evp_op
     }
     if (allBasis && nC > 0) {
         FAIL_IF(evp_basis_begin(h));
-        FAIL_IF(upload_rows(h, m->basisGradientU, (double *)d.G, 2, 2, 0));
-        FAIL_IF(upload_rows(h, m->basisGradientV, (double *)d.G, 2, 2, 1));
-        FAIL_IF(upload_rows(h, m->basisIntegralsU, (double *)d.Suv, 2, 2, 0));
-        FAIL_IF(upload_rows(h, m->basisIntegralsV, (double *)d.Suv, 2, 2, 1));
-        FAIL_IF(upload_rows(h, m->basisIntegralsMetric, d.Sm, 2, 1, 0));
+        FAIL_IF(evp_upload_rows(h, m->basisGradientU, (double *)d.G, 2, 2, 0));
+        FAIL_IF(evp_upload_rows(h, m->basisGradientV, (double *)d.G, 2, 2, 1));
+        FAIL_IF(evp_upload_rows(h, m->basisIntegralsU, (double *)d.Suv, 2, 2, 0));
+        FAIL_IF(evp_upload_rows(h, m->basisIntegralsV, (double *)d.Suv, 2, 2, 1));
+        FAIL_IF(evp_upload_rows(h, m->basisIntegralsMetric, d.Sm, 2, 1, 0));
         CUDA_FAIL(cudaStreamSynchronize(h->stream));
         FAIL_IF(evp_basis_finalize(h));
     }
@@ -619,8 +615,8 @@ extern "C" int evp_set_masks(evp_handle *h, const int *solveStress, const int *s
     int *rawMs = (int *)st.take(nC * 4), *rawMv = (int *)st.take(nV * 4);
     int rc;
     EVP_CUDA(cudaStreamSynchronize(h->stream));
-    if ((rc = h2d(h, rawMs, solveStress, nC * 4))) return rc;
-    if ((rc = h2d(h, rawMv, solveVelocity, nV * 4))) return rc;
+    if ((rc = evp_h2d(h, rawMs, solveStress, nC * 4))) return rc;
+    if ((rc = evp_h2d(h, rawMv, solveVelocity, nV * 4))) return rc;
     if (nC) k_u8_in<<<grid_for(nC, 256), 256, 0, h->stream>>>(rawMs, d.solveStress, nC, 1, 1);
     if (nV) k_u8_in<<<grid_for(nV, 256), 256, 0, h->stream>>>(rawMv, d.solveVel, nV, 1, 1);
     EVP_CUDA(cudaGetLastError());
@@ -652,12 +648,12 @@ extern "C" int evp_update_step(evp_handle *h, const evp_step_fields *f)
 
     int *rawMs = (int *)st.take(nC * 4), *rawMv = (int *)st.take(nV * 4);
     EVP_REQUIRE(rawMs && rawMv, "staging area exhausted");
-    if ((rc = h2d(h, rawMs, f->solveStress, nC * 4))) return rc;
-    if ((rc = h2d(h, rawMv, f->solveVelocity, nV * 4))) return rc;
+    if ((rc = evp_h2d(h, rawMs, f->solveStress, nC * 4))) return rc;
+    if ((rc = evp_h2d(h, rawMv, f->solveVelocity, nV * 4))) return rc;
     if (nC) k_u8_in<<<grid_for(nC, 256), 256, 0, s>>>(rawMs, d.solveStress, nC, 1, 1);
     if (nV) k_u8_in<<<grid_for(nV, 256), 256, 0, s>>>(rawMv, d.solveVel, nV, 1, 1);
     if ((rc = evp_halo_mark_masks(h))) return rc;
-    if ((rc = h2d(h, d.P, f->icePressure, nC * 8))) return rc;
+    if ((rc = evp_h2d(h, d.P, f->icePressure, nC * 8))) return rc;
 
     struct { const double *a, *b; double2 *dst; } pairs[] = {
         {f->uVelocity, f->vVelocity, d.uv},
@@ -673,8 +669,8 @@ extern "C" int evp_update_step(evp_handle *h, const evp_step_fields *f)
         if (!p.a || nV == 0) continue;
         double *ra = (double *)st.take(nV * 8), *rb = p.b ? (double *)st.take(nV * 8) : nullptr;
         EVP_REQUIRE(ra && (rb || !p.b), "staging area exhausted");
-        if ((rc = h2d(h, ra, p.a, nV * 8))) return rc;
-        if (p.b && (rc = h2d(h, rb, p.b, nV * 8))) return rc;
+        if ((rc = evp_h2d(h, ra, p.a, nV * 8))) return rc;
+        if (p.b && (rc = evp_h2d(h, rb, p.b, nV * 8))) return rc;
         k_pair_in<<<grid_for(nV, 256), 256, 0, s>>>(ra, rb, p.dst, nV);
     }
     if (nC) {
@@ -684,7 +680,7 @@ extern "C" int evp_update_step(evp_handle *h, const evp_step_fields *f)
         for (int a = 0; a < 3; a++) {
             double *raw = (double *)st.take((size_t)Mh * nC * 8);
             EVP_REQUIRE(raw, "staging area exhausted");
-            if ((rc = h2d(h, raw, src[a], (size_t)Mh * nC * 8))) return rc;
+            if ((rc = evp_h2d(h, raw, src[a], (size_t)Mh * nC * 8))) return rc;
             k_rows_in<<<grid_for(nC, 128), 128, 0, s>>>(raw, dst[a], Mh, Mk, 1, nC, 0, nCp, ncomp[a], comp[a]);
         }
     }
@@ -774,12 +770,12 @@ extern "C" int evp_fetch(evp_handle *h, const evp_out_fields *o)
         double *ra = (double *)st.take(nV * 8), *rb = (double *)st.take(nV * 8);
         k_pair_out<<<grid_for(nV, 256), 256, 0, s>>>(ra, rb, p.src, nV);
         EVP_CUDA(cudaGetLastError());
-        if (p.a && (rc = d2h(h, p.a, ra, nV * 8))) return rc;
-        if (p.b && (rc = d2h(h, p.b, rb, nV * 8))) return rc;
+        if (p.a && (rc = evp_d2h(h, p.a, ra, nV * 8))) return rc;
+        if (p.b && (rc = evp_d2h(h, p.b, rb, nV * 8))) return rc;
         EVP_CUDA(cudaStreamSynchronize(s));
     }
     if (o->oceanStressCoeff && nV) {
-        if ((rc = d2h(h, o->oceanStressCoeff, d.ocoef, nV * 8))) return rc;
+        if ((rc = evp_d2h(h, o->oceanStressCoeff, d.ocoef, nV * 8))) return rc;
     }
     struct { double *host; const double *soa; int ncomp, comp; } rows[] = {
         {o->stress11, (const double *)d.sig, 2, 0}, {o->stress22, (const double *)d.sig, 2, 1},
@@ -789,7 +785,7 @@ extern "C" int evp_fetch(evp_handle *h, const evp_out_fields *o)
     };
     for (auto &r : rows) {
         if (!r.host || h->nCells == 0) continue;
-        if ((rc = download_rows(h, r.host, r.soa, 1, r.ncomp, r.comp))) return rc;
+        if ((rc = evp_download_rows(h, r.host, r.soa, 1, r.ncomp, r.comp))) return rc;
     }
     EVP_CUDA(cudaStreamSynchronize(s));
     return EVP_OK;
@@ -813,14 +809,14 @@ extern "C" int evp_fetch_basis(evp_handle *h, double *gu, double *gv, double *su
             k_band_unpack<<<grid_for(h->nCells, 128), 128, 0, h->stream>>>(d.Gb, G, d.nEdges, h->M, h->nCells, h->nCp);
         }
         rc = EVP_OK;
-        if (gu) rc = download_rows(h, gu, (const double *)G, 2, 2, 0);
-        if (!rc && gv) rc = download_rows(h, gv, (const double *)G, 2, 2, 1);
+        if (gu) rc = evp_download_rows(h, gu, (const double *)G, 2, 2, 0);
+        if (!rc && gv) rc = evp_download_rows(h, gv, (const double *)G, 2, 2, 1);
         if (!d.G) { cudaStreamSynchronize(h->stream); cudaFree(G); }
         if (rc) return rc;
     }
-    if (su && (rc = download_rows(h, su, (const double *)d.Suv, 2, 2, 0))) return rc;
-    if (sv && (rc = download_rows(h, sv, (const double *)d.Suv, 2, 2, 1))) return rc;
-    if (sm && (rc = download_rows(h, sm, d.Sm, 2, 1, 0))) return rc;
+    if (su && (rc = evp_download_rows(h, su, (const double *)d.Suv, 2, 2, 0))) return rc;
+    if (sv && (rc = evp_download_rows(h, sv, (const double *)d.Suv, 2, 2, 1))) return rc;
+    if (sm && (rc = evp_download_rows(h, sm, d.Sm, 2, 1, 0))) return rc;
     EVP_CUDA(cudaStreamSynchronize(h->stream));
     return EVP_OK;
 }

@@ -212,12 +212,14 @@ int evp_halo_launches(evp_handle *h)
     return (h->halo->nSend ? 1 : 0) + (h->halo->nRecv ? 1 : 0);   // pack + unpack (NCCL's own kernel not counted)
 }
 
-int evp_halo_enqueue(evp_handle *h, cudaStream_t s)
+int evp_halo_enqueue(evp_handle *h, cudaStream_t s) { return evp_halo_exchange(h, s, h->d.uv); }
+
+int evp_halo_exchange(evp_handle *h, cudaStream_t s, double2 *field)
 {
     if (!h->halo || h->halo->nNb == 0) return EVP_OK;
     evp_halo &H = *h->halo;
     if (!H.comm) { evp_set_error("evp_set_halo without evp_comm_init"); return EVP_ERR_STATE; }
-    if (H.nSend) k_pack<<<(H.nSend + 255) / 256, 256, 0, s>>>(H.nSend, H.dSendIdx, h->d.uv, H.dSendBuf);
+    if (H.nSend) k_pack<<<(H.nSend + 255) / 256, 256, 0, s>>>(H.nSend, H.dSendIdx, field, H.dSendBuf);
     EVP_NCCL(g_nccl.GroupStart());
     for (int k = 0; k < H.nNb; k++) {
         const int ns = H.sendOff[k + 1] - H.sendOff[k], nr = H.recvOff[k + 1] - H.recvOff[k];
@@ -225,7 +227,7 @@ int evp_halo_enqueue(evp_handle *h, cudaStream_t s)
         if (nr) EVP_NCCL(g_nccl.Recv(H.dRecvBuf + H.recvOff[k], (size_t)2 * nr, ncclDouble, H.nbRank[k], H.comm, s));
     }
     EVP_NCCL(g_nccl.GroupEnd());
-    if (H.nRecv) k_unpack<<<(H.nRecv + 255) / 256, 256, 0, s>>>(H.nRecv, H.dRecvIdx, H.dRecvBuf, h->d.uv);
+    if (H.nRecv) k_unpack<<<(H.nRecv + 255) / 256, 256, 0, s>>>(H.nRecv, H.dRecvIdx, H.dRecvBuf, field);
     EVP_CUDA(cudaGetLastError());
     return EVP_OK;
 }

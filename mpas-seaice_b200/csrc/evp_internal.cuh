@@ -65,6 +65,14 @@ struct evp_dev {
     double *Sm = nullptr;
     double *tanLat = nullptr;
     int *gidx = nullptr;          // [D][nVp] index into contrib (j*nCp + c) or -1
+    int *cov = nullptr;           // [D][nVp] cellsOnVertex - 1, or -1 when not a local cell
+    // pre-/post-subcycle mesh extension (evp_set_mesh_ext)
+    int *coc = nullptr;           // [M][nCp] cellsOnCell - 1 or -1
+    uint8_t *vflags = nullptr;    // bit 0 interiorVertex, bit 1 landIceMaskVertex
+    double *areaCell = nullptr, *areaTri = nullptr, *fVertex = nullptr;
+    double2 *airCell = nullptr;   // (airStressCellU, airStressCellV) of the current step
+    double2 *osFinal = nullptr;   // ocean_stress_final's oceanStressU/V
+    uint8_t *solveVelPrev = nullptr;
     // per step
     uint8_t *solveStress = nullptr, *solveVel = nullptr;
     double *P = nullptr;
@@ -95,6 +103,7 @@ struct evp_handle {
     size_t nCp = 0, nVp = 0;
     evp_options opt{};
     bool metric = false;          // any tanLatVertexRotatedOverRadius != 0
+    bool haveExt = false;
     bool haveBasis = false, haveStep = false, haveSB = false, useGraph = true, pinHost = false, timed = false;
     evp_dev d;
     cudaStream_t stream = nullptr, commStream = nullptr;
@@ -119,14 +128,31 @@ int evp_enqueue_vertex_pass(evp_handle *h, bool diag, cudaStream_t s, const int 
 int evp_enqueue_special_boundaries(evp_handle *h, cudaStream_t s);
 
 // evp_halo.cu
-int evp_halo_enqueue(evp_handle *h, cudaStream_t s);
+int evp_halo_enqueue(evp_handle *h, cudaStream_t s);             // exchanges d.uv
+int evp_halo_exchange(evp_handle *h, cudaStream_t s, double2 *field);   // any (nVp) double2 vertex field
 int evp_halo_launches(evp_handle *h);
 int evp_halo_mark_masks(evp_handle *h);
 int evp_halo_boundary_count(evp_handle *h);        // boundary-owned vertices (unique send-list entries)
 const int *evp_halo_boundary_list(evp_handle *h);  // device array of their 0-based indices
 void evp_halo_destroy(evp_handle *h);
 
-// layout kernels (evp_abi.cu)
+inline unsigned grid_for(size_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+struct Stage {   // bump allocator over the device staging area
+    char *base; size_t cap, off;
+    void *take(size_t bytes) {
+        size_t o = (off + 255) & ~(size_t)255;
+        if (o + bytes > cap) return nullptr;
+        off = o + bytes;
+        return base + o;
+    }
+};
+
+// layout kernels and transfers (evp_abi.cu)
+int evp_h2d(evp_handle *h, void *dst, const void *src, size_t bytes);
+int evp_d2h(evp_handle *h, void *dst, const void *src, size_t bytes);
+int evp_upload_rows(evp_handle *h, const double *host, double *dst, int dims, int ncomp, int comp);
+int evp_download_rows(evp_handle *h, double *host, const double *soa, int dims, int ncomp, int comp);
 int evp_dev_alloc(evp_handle *h, void **p, size_t bytes);
 void evp_dev_free(evp_handle *h, void *p, size_t bytes);
 // dense G (re)allocated and zeroed, ready to be filled; then band-compressed when the pattern allows

@@ -32,7 +32,8 @@ EXPORTS = (
     "evp_set_masks", "evp_run_subcycles", "evp_synchronize", "evp_fetch", "evp_destroy",
     "evp_last_error_string", "evp_comm_get_unique_id", "evp_comm_init", "evp_set_halo", "evp_last_run_ms",
     "evp_launch_count", "evp_get_stream", "evp_device_bytes", "evp_set_use_graph", "evp_profile_passes",
-    "evp_host_metric_terms",
+    "evp_host_metric_terms", "evp_set_mesh_ext", "evp_set_state", "evp_pre_subcycle", "evp_post_subcycle",
+    "evp_fetch_pre",
 )
 
 
@@ -72,6 +73,48 @@ class StepFields(C.Structure):
 
 class OutFields(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in OUT_FIELDS]
+
+
+# ---- pre-/post-subcycle on the device (include/evp_b200.h, "Widening") ----
+MESH_EXT_FIELDS = ("cellsOnCell", "interiorVertex", "landIceMaskVertex", "areaCell", "areaTriangle", "fVertex")
+PRE_FIELDS = ("iceAreaCellInitial", "iceAreaCell", "totalMassCell", "icePressure", "uOceanVelocity", "vOceanVelocity",
+              "airStressCellU", "airStressCellV", "uAirVelocity", "vAirVelocity", "airDensity", "seaSurfaceTiltU",
+              "seaSurfaceTiltV", "landIceMask", "solveStress", "solveVelocity")
+_PRE_INT = {"landIceMask", "solveStress", "solveVelocity"}
+POST_FIELDS = ("uVelocity", "vVelocity", "divergence", "shear", "ridgeConvergence", "ridgeShear", "principalStress1Var",
+               "principalStress2Var", "oceanStressCellU", "oceanStressCellV", "oceanStressU", "oceanStressV",
+               "oceanStressCoeff")
+_POST_CELL = {"divergence", "shear", "ridgeConvergence", "ridgeShear", "oceanStressCellU", "oceanStressCellV"}
+_POST_CELL2D = {"principalStress1Var", "principalStress2Var"}
+POST_DEFAULT = ("uVelocity", "vVelocity", "divergence", "shear", "ridgeConvergence", "ridgeShear", "oceanStressCellU",
+                "oceanStressCellV")       # what the model needs every step: advection, ridging, coupler
+PRE_OUT_FIELDS = ("solveStress", "solveVelocity", "solveVelocityPrevious", "icePressure", "iceAreaVertex",
+                  "totalMassVertex", "totalMassVertexfVertex", "airStressVertexU", "airStressVertexV",
+                  "surfaceTiltForceU", "surfaceTiltForceV", "oceanStressU", "oceanStressV", "uOceanVelocityVertex",
+                  "vOceanVelocityVertex", "uVelocityInitial", "vVelocityInitial")
+_PRE_OUT_INT = {"solveStress", "solveVelocity", "solveVelocityPrevious"}
+_PRE_OUT_CELL = {"solveStress", "icePressure"}
+
+
+class MeshExt(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in MESH_EXT_FIELDS]
+
+
+class PreFields(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in PRE_FIELDS]
+
+
+class PreOptions(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("use_air_stress", "use_surface_tilt", "geostrophic_surface_tilt",
+                                       "calc_velocity_masks", "cold_start")]
+
+
+class PostFields(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in POST_FIELDS]
+
+
+class PreOutFields(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in PRE_OUT_FIELDS]
 
 
 def load_library(path: str | None = None):
@@ -250,6 +293,63 @@ class EvpSolver:
 
     def set_use_graph(self, flag):
         self._check(self.lib.evp_set_use_graph(self._h, C.c_int(int(flag))))
+
+    # -- pre-/post-subcycle on the device --------------------------------------------------------------
+    def set_mesh_ext(self, mesh, interior_vertex, land_ice_mask_vertex=None):
+        """evp_set_mesh_ext: the mesh fields velocity_solver_pre/post_subcycle read."""
+        e = MeshExt()
+        self._ext_keep = dict(cellsOnCell=mesh["cellsOnCell"], interiorVertex=interior_vertex,
+                              landIceMaskVertex=land_ice_mask_vertex, areaCell=mesh["areaCell"],
+                              areaTriangle=mesh["areaTriangle"], fVertex=mesh["fVertex"])
+        for n, a in self._ext_keep.items():
+            setattr(e, n, _ptr(a, np.int32 if n in ("cellsOnCell", "interiorVertex", "landIceMaskVertex") else np.float64))
+        self._check(self.lib.evp_set_mesh_ext(self._h, C.byref(e)))
+
+    def set_state(self, prev):
+        """evp_set_state: seed (uVelocity, vVelocity, stress11/22/12, solveVelocityPrevious), any may be absent."""
+        g = lambda n, dt: C.c_void_p(_ptr(prev.get(n), dt))
+        self._check(self.lib.evp_set_state(self._h, g("uVelocity", np.float64), g("vVelocity", np.float64),
+                                           g("stress11", np.float64), g("stress22", np.float64),
+                                           g("stress12", np.float64), g("solveVelocityPrevious", np.int32)))
+
+    def pre_subcycle(self, cells, *, use_air_stress=True, use_surface_tilt=True, geostrophic_surface_tilt=True,
+                     calc_velocity_masks=True, cold_start=False):
+        """evp_pre_subcycle: velocity_solver_pre_subcycle on the device from CELL fields."""
+        pf = PreFields()
+        self._pre_keep = []
+        for n in PRE_FIELDS:
+            a = cells.get(n)
+            self._pre_keep.append(a)
+            setattr(pf, n, _ptr(a, np.int32 if n in _PRE_INT else np.float64))
+        po = PreOptions(int(use_air_stress), int(use_surface_tilt), int(geostrophic_surface_tilt),
+                        int(calc_velocity_masks), int(cold_start))
+        self._check(self.lib.evp_pre_subcycle(self._h, C.byref(pf), C.byref(po)))
+
+    def post_subcycle(self, into=None, names=POST_DEFAULT):
+        """evp_post_subcycle: velocity_solver_post_subcycle on the device + copy of the wanted results."""
+        of = PostFields()
+        out = {} if into is None else into
+        for n in names:
+            a = out.get(n)
+            if a is None:
+                if n in _POST_CELL2D:
+                    a = np.zeros((self.nCells + 1, self.maxEdges))
+                else:
+                    a = np.zeros((self.nCells if n in _POST_CELL else self.nVertices) + 1)
+                out[n] = a
+            setattr(of, n, _ptr(a, np.float64))
+        self._check(self.lib.evp_post_subcycle(self._h, C.byref(of)))
+        return out
+
+    def fetch_pre(self, names=PRE_OUT_FIELDS):
+        of = PreOutFields()
+        out = {}
+        for n in names:
+            size = (self.nCells if n in _PRE_OUT_CELL else self.nVertices) + 1
+            out[n] = np.zeros(size, dtype=np.int32 if n in _PRE_OUT_INT else np.float64)
+            setattr(of, n, _ptr(out[n], out[n].dtype.type))
+        self._check(self.lib.evp_fetch_pre(self._h, C.byref(of)))
+        return out
 
     # -- multi-GPU -----------------------------------------------------------------------------
     @staticmethod

@@ -217,9 +217,12 @@ def set_num_threads(n: int) -> None:
 # ---------------------------------------------------------------------------------------------
 
 def pre_subcycle(mesh, state, config_dt, *, n_elastic=120, use_air_stress=True, use_ocean_stress=True,
-                 use_surface_tilt=True, interior_vertex=None):
+                 use_surface_tilt=True, interior_vertex=None, prev=None, geostrophic_surface_tilt=True):
     """velocity_solver_pre_subcycle (velocity_solver.F:613-671) from a cold start, single category,
     Hibler strength, constant_air_stress, geostrophic tilt -- call order of the reference.
+    ``prev`` (uVelocity, vVelocity, stress11/22/12, solveVelocityPrevious) = the state carried from the previous
+    dynamics step instead of a cold start; ``geostrophic_surface_tilt=False`` uses state["seaSurfaceTiltU/V"]
+    (surface_tilt_ssh_gradient, :2024-2170).
     Returns the same dict of per-step fields as mpas_seaice_b200.synthetic.pre_subcycle."""
     L = lib()
     nC, nV, M, D = mesh.nCells, mesh.nVertices, mesh.maxEdges, mesh.vertexDegree
@@ -254,8 +257,13 @@ def pre_subcycle(mesh, state, config_dt, *, n_elastic=120, use_air_stress=True, 
         f["solveStress"], f["solveVelocity"] = ss, sv
         f["uOceanVelocityVertex"] = c2v(state["uOceanVelocity"])
         f["vOceanVelocityVertex"] = c2v(state["vOceanVelocity"])
-        u, v = z(nV + 1), z(nV + 1)
-        svp = sv.copy()
+        if prev is None:
+            u, v = z(nV + 1), z(nV + 1)
+            svp = sv.copy()
+        else:
+            u = np.array(prev["uVelocity"], dtype=np.float64)
+            v = np.array(prev["vVelocity"], dtype=np.float64)
+            svp = np.array(prev["solveVelocityPrevious"], dtype=np.int32)
         sdu, sdv, osu, osv = z(nV + 1), z(nV + 1), z(nV + 1), z(nV + 1)
         ui, vi = z(nV + 1), z(nV + 1)
         L.orc_new_ice_velocities(_i(nV), _i(nV), _p(sv), _p(svp), _p(f["uOceanVelocityVertex"]),
@@ -278,12 +286,21 @@ def pre_subcycle(mesh, state, config_dt, *, n_elastic=120, use_air_stress=True, 
                            _p(f["vOceanVelocityVertex"]), _p(mesh.fVertex), _p(osu), _p(osv))
         f["oceanStressU"], f["oceanStressV"] = osu, osv
         tu, tv = z(nV + 1), z(nV + 1)
-        L.orc_surface_tilt(_i(nV), _i(nV), _i(use_surface_tilt), _p(sv), _p(mesh.fVertex), _p(f["totalMassVertex"]),
-                           _p(f["uOceanVelocityVertex"]), _p(f["vOceanVelocityVertex"]), _p(tu), _p(tv))
+        if use_surface_tilt and not geostrophic_surface_tilt:
+            f["seaSurfaceTiltVertexU"] = c2v(state["seaSurfaceTiltU"])
+            f["seaSurfaceTiltVertexV"] = c2v(state["seaSurfaceTiltV"])
+            L.orc_surface_tilt_ssh_gradient(_i(nV), _p(sv), _p(f["totalMassVertex"]), _p(f["seaSurfaceTiltVertexU"]),
+                                            _p(f["seaSurfaceTiltVertexV"]), _p(tu), _p(tv))
+        else:
+            L.orc_surface_tilt(_i(nV), _i(nV), _i(use_surface_tilt), _p(sv), _p(mesh.fVertex), _p(f["totalMassVertex"]),
+                               _p(f["uOceanVelocityVertex"]), _p(f["vOceanVelocityVertex"]), _p(tu), _p(tv))
         f["surfaceTiltForceU"], f["surfaceTiltForceV"] = tu, tv
     oc = z(nV + 1)
     e = [np.zeros((nC + 1, M)) for _ in range(3)]
-    s = [np.zeros((nC + 1, M)) for _ in range(3)]
+    if prev is None:
+        s = [np.zeros((nC + 1, M)) for _ in range(3)]
+    else:
+        s = [np.array(prev[k], dtype=np.float64) for k in ("stress11", "stress22", "stress12")]
     L.orc_init_subcycle_variables(_i(nC), _i(nV), _i(nV), _i(M), _p(ss), _p(sv), _p(sdu), _p(sdv), _p(u), _p(v), _p(oc),
                                   _p(e[0]), _p(e[1]), _p(e[2]), _p(s[0]), _p(s[1]), _p(s[2]))
     f.update(stressDivergenceU=sdu, stressDivergenceV=sdv, oceanStressCoeff=oc, uVelocity=u, vVelocity=v,
@@ -301,6 +318,41 @@ def final_divergence_shear(mesh, step):
                                              _p(step["strain11"]), _p(step["strain22"]), _p(step["strain12"]),
                                              *[_p(a) for a in out])
     return dict(zip(("divergence", "shear", "ridgeConvergence", "ridgeShear"), out))
+
+
+def hibler_strength_unmasked(state, n_cells):
+    """seaiceIceStrengthConstantHiblerP * iceVolumeCell * exp(-C*(1-iceAreaCell)) for EVERY cell (libm exp), i.e.
+    ice_strength (velocity_solver.F:1419-1436) before its solveStress mask: what a host hands to evp_pre_subcycle."""
+    L = lib()
+    ones = np.ones(n_cells + 1, dtype=np.int32)
+    P = np.zeros(n_cells + 1)
+    L.orc_ice_strength_hibler(_i(n_cells), _p(ones), _p(np.ascontiguousarray(state["iceVolumeCell"], dtype=np.float64)),
+                              _p(np.ascontiguousarray(state["iceAreaCell"], dtype=np.float64)), _p(P))
+    return P
+
+
+def ocean_stress_final(mesh, step, opts, interior_vertex, n_vertices_solve=None, n_cells_solve=None):
+    """ocean_stress_final (velocity_solver.F:3624-3848) on the fields of ``step`` AFTER the subcycle: refreshes
+    oceanStressCoeff with the final velocities, returns (oceanStressU, oceanStressV, oceanStressCellU,
+    oceanStressCellV, oceanStressCoeff)."""
+    L = lib()
+    nC, nV, M = mesh.nCells, mesh.nVertices, mesh.maxEdges
+    nVs = nV if n_vertices_solve is None else n_vertices_solve
+    nCs = nC if n_cells_solve is None else n_cells_solve
+    use_ocean = int(opts.get("use_ocean_stress", True))
+    otype = {"quadratic": 1, "linear": 2}[opts.get("ocean_stress_type", "quadratic")]
+    coef = np.array(step["oceanStressCoeff"], dtype=np.float64)
+    L.orc_ocean_stress_coefficient(_i(nVs), _i(nV), _i(use_ocean), _i(otype), _p(step["solveVelocity"]),
+                                   _p(step["iceAreaVertex"]), _p(step["uOceanVelocityVertex"]),
+                                   _p(step["vOceanVelocityVertex"]), _p(step["uVelocity"]), _p(step["vVelocity"]), _p(coef))
+    osu, osv = np.zeros(nV + 1), np.zeros(nV + 1)
+    ocu, ocv = np.zeros(nC + 1), np.zeros(nC + 1)
+    L.orc_ocean_stress_final(_i(nVs), _i(nV), _i(nCs), _i(nC), _i(M), _i(use_ocean), _p(step["solveVelocity"]), _p(coef),
+                             _p(step["uOceanVelocityVertex"]), _p(step["vOceanVelocityVertex"]), _p(step["uVelocity"]),
+                             _p(step["vVelocity"]), _p(mesh.fVertex), _p(step["iceAreaVertex"]), _p(mesh.nEdgesOnCell),
+                             _p(mesh.verticesOnCell), _p(mesh.areaTriangle), _p(interior_vertex), _p(osu), _p(osv),
+                             _p(ocu), _p(ocv))
+    return osu, osv, ocu, ocv, coef
 
 
 def principal_stresses(mesh, step, n_cells_solve=None):

@@ -714,6 +714,85 @@ void orc_principal_stresses_variational(int nCellsSolve, int maxEdges, const int
     }
 }
 
+/* seaice_interpolate_vertex_to_cell (src/shared/mpas_seaice_mesh.F:2906-2976) */
+void orc_interpolate_vertex_to_cell(int nCellsSolve, int maxEdges, const int *nEdgesOnCell, const int *verticesOnCell,
+                                    const double *areaTriangle, const int *interiorVertex,
+                                    const double *variableVertex, double *variableCell)
+{
+    const int M = maxEdges;
+    for (int iCell = 1; iCell <= nCellsSolve; iCell++) {
+        double totalArea = 0.0;
+        variableCell[iCell - 1] = 0.0;
+        for (int k = 1; k <= nEdgesOnCell[iCell - 1]; k++) {
+            const int iVertex = verticesOnCell[IDX2(k, iCell, M)];
+            variableCell[iCell - 1] = variableCell[iCell - 1] +
+                areaTriangle[iVertex - 1] * variableVertex[iVertex - 1] * (double)interiorVertex[iVertex - 1];
+            totalArea = totalArea + areaTriangle[iVertex - 1] * (double)interiorVertex[iVertex - 1];
+        }
+        if (totalArea > 0.0) variableCell[iCell - 1] = variableCell[iCell - 1] / totalArea;
+    }
+}
+
+/* ocean_stress_final (src/shared/mpas_seaice_velocity_solver.F:3624-3848); the caller has already run
+ * ocean_stress_coefficient on the final velocities (:3686) and exchanged the halo where there is one */
+void orc_ocean_stress_final(int nVerticesSolve, int nVertices, int nCellsSolve, int nCells, int maxEdges,
+                            int useOceanStress, const int *solveVelocity, const double *oceanStressCoeff,
+                            const double *uOceanVelocityVertex, const double *vOceanVelocityVertex,
+                            const double *uVelocity, const double *vVelocity, const double *fVertex,
+                            const double *iceAreaVertex, const int *nEdgesOnCell, const int *verticesOnCell,
+                            const double *areaTriangle, const int *interiorVertex,
+                            double *oceanStressU, double *oceanStressV, double *oceanStressCellU, double *oceanStressCellV)
+{
+    if (useOceanStress) {
+        for (int i = 0; i < nVerticesSolve; i++) {
+            if (solveVelocity[i] == 1) {
+                const double sgn = copysign(1.0, fVertex[i]);
+                oceanStressU[i] = oceanStressCoeff[i] *
+                    ((uOceanVelocityVertex[i] - uVelocity[i]) * cosOceanTurningAngle -
+                     (vOceanVelocityVertex[i] - vVelocity[i]) * sinOceanTurningAngle * sgn);
+                oceanStressV[i] = oceanStressCoeff[i] *
+                    ((vOceanVelocityVertex[i] - vVelocity[i]) * cosOceanTurningAngle +
+                     (uOceanVelocityVertex[i] - uVelocity[i]) * sinOceanTurningAngle * sgn);
+                oceanStressU[i] = oceanStressU[i] / iceAreaVertex[i];
+                oceanStressV[i] = oceanStressV[i] / iceAreaVertex[i];
+            } else {
+                oceanStressU[i] = 0.0;
+                oceanStressV[i] = 0.0;
+            }
+        }
+        orc_interpolate_vertex_to_cell(nCellsSolve, maxEdges, nEdgesOnCell, verticesOnCell, areaTriangle, interiorVertex,
+                                       oceanStressU, oceanStressCellU);
+        orc_interpolate_vertex_to_cell(nCellsSolve, maxEdges, nEdgesOnCell, verticesOnCell, areaTriangle, interiorVertex,
+                                       oceanStressV, oceanStressCellV);
+        for (int i = 0; i < nVerticesSolve; i++) {
+            if (solveVelocity[i] == 1) {
+                oceanStressU[i] = oceanStressU[i] * iceAreaVertex[i];
+                oceanStressV[i] = oceanStressV[i] * iceAreaVertex[i];
+            }
+        }
+    } else {
+        for (int i = 0; i < nVertices + 1; i++) { oceanStressU[i] = 0.0; oceanStressV[i] = 0.0; }
+        for (int i = 0; i < nCells + 1; i++) { oceanStressCellU[i] = 0.0; oceanStressCellV[i] = 0.0; }
+    }
+}
+
+/* surface_tilt_ssh_gradient, the vertex loop (velocity_solver.F:2140-2160); seaiceGravity = 9.80616 */
+void orc_surface_tilt_ssh_gradient(int nVerticesSolve, const int *solveVelocity, const double *totalMassVertex,
+                                   const double *seaSurfaceTiltVertexU, const double *seaSurfaceTiltVertexV,
+                                   double *surfaceTiltForceU, double *surfaceTiltForceV)
+{
+    const double seaiceGravity = 9.80616;
+    for (int i = 0; i < nVerticesSolve; i++) {
+        if (solveVelocity[i] == 1) {
+            surfaceTiltForceU[i] = -seaiceGravity * totalMassVertex[i] * seaSurfaceTiltVertexU[i];
+            surfaceTiltForceV[i] = -seaiceGravity * totalMassVertex[i] * seaSurfaceTiltVertexV[i];
+        } else {
+            surfaceTiltForceU[i] = 0.0;
+            surfaceTiltForceV[i] = 0.0;
+        }
+    }
+}
+
 /* seaice_init_evp scalars (constitutive_relation.F:125, 154-162) */
 double orc_damping_timescale(double dynamicsTimeStep) { return 0.36 * dynamicsTimeStep; }
 double orc_numerical_inertia_coefficient(double dynamicsTimeStep, double dvEdgeMinGlobal)

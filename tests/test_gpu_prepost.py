@@ -1,0 +1,273 @@
+"""GPU parity of the widened boundary: velocity_solver_pre_subcycle and
+velocity_solver_post_subcycle on the device (evp_pre_subcycle / evp_post_subcycle) against the oracle's
+restatement of the same reference routines (velocity_solver.F:613-671, 3360-3380).  Bit-exact: the
+device kernels keep the reference's operation order and are built without FMA contraction; exp() of
+the Hibler strength stays on the host (same libm on both sides)."""
+import numpy as np
+import pytest
+
+import common
+import oracle
+from mpas_seaice_b200 import synthetic, variational_init
+
+pytestmark = pytest.mark.gpu
+
+PRE_VERTEX = ("iceAreaVertex", "totalMassVertex", "totalMassVertexfVertex", "airStressVertexU", "airStressVertexV",
+              "surfaceTiltForceU", "surfaceTiltForceV", "oceanStressU", "oceanStressV", "uOceanVelocityVertex",
+              "vOceanVelocityVertex", "uVelocityInitial", "vVelocityInitial")
+
+
+def _state(mesh, kind):
+    if kind == "square":
+        if abs(mesh.Lx - 1.28e6) > 1.0:      # the square forcing is written for Lx = Ly = 1.28e6 m
+            from mpas_seaice_b200 import meshgen
+            scaled = meshgen.Mesh(mesh)
+            scaled.xCell = mesh.xCell * (1.28e6 / mesh.Lx)
+            scaled.yCell = mesh.yCell * (1.28e6 / mesh.Ly)
+            return synthetic.square_state(scaled)
+        return synthetic.square_state(mesh)
+    return synthetic.sphere_state(mesh, kind=kind)
+
+
+def _cells(mesh, state, **extra):
+    """What a host hands to evp_pre_subcycle: cell fields only (aggregate + strength done on the host)."""
+    nC = mesh.nCells
+    area = np.ascontiguousarray(state["iceAreaCell"], dtype=np.float64)
+    mass = np.zeros(nC + 1)
+    oracle.lib().orc_total_mass(nC + 1, oracle._p(np.ascontiguousarray(state["iceVolumeCell"], dtype=np.float64)),
+                                oracle._p(np.ascontiguousarray(state["snowVolumeCell"], dtype=np.float64)), oracle._p(mass))
+    c = dict(iceAreaCellInitial=area, iceAreaCell=area, totalMassCell=mass,
+             icePressure=oracle.hibler_strength_unmasked(state, nC),
+             uOceanVelocity=np.ascontiguousarray(state["uOceanVelocity"], dtype=np.float64),
+             vOceanVelocity=np.ascontiguousarray(state["vOceanVelocity"], dtype=np.float64),
+             uAirVelocity=np.ascontiguousarray(state["uAirVelocity"], dtype=np.float64),
+             vAirVelocity=np.ascontiguousarray(state["vAirVelocity"], dtype=np.float64),
+             airDensity=np.ascontiguousarray(state["airDensity"], dtype=np.float64))
+    c.update(extra)
+    return c
+
+
+def _solver(mesh, var, opts):
+    from mpas_seaice_b200 import host
+    solver = host.EvpSolver(mesh, var, opts)
+    solver.set_mesh_ext(mesh, variational_init.interior_vertex(mesh))
+    return solver
+
+
+def _compare_pre(mesh, ref, got):
+    nC, nV = mesh.nCells, mesh.nVertices
+    assert np.array_equal(got["solveStress"][:nC], ref["solveStress"][:nC])
+    assert np.array_equal(got["solveVelocity"][:nV], ref["solveVelocity"][:nV])
+    assert np.array_equal(got["solveVelocityPrevious"][:nV], ref["solveVelocityPrevious"][:nV])
+    assert np.array_equal(got["icePressure"][:nC], ref["icePressure"][:nC])
+    vm = ref["solveVelocity"][:nV] == 1
+    assert vm.any()
+    for k in PRE_VERTEX:
+        assert np.array_equal(got[k][:nV][vm], ref[k][:nV][vm]), k
+    # forcing terms are exactly zero where the vertex is not solved
+    for k in ("surfaceTiltForceU", "oceanStressU", "uVelocityInitial"):
+        assert np.all(got[k][:nV][~vm] == 0.0), k
+
+
+@pytest.mark.parametrize("kind,state_kind", [("hex82", "square"), ("ico4", "A"), ("ico5", "B"), ("quad40", "square")])
+def test_pre_subcycle_cold_start_matches_oracle(evp_lib, kind, state_kind):
+    mesh, var = common.mesh_case(kind)
+    state = _state(mesh, state_kind)
+    ref = oracle.pre_subcycle(mesh, state, 3600.0)
+    _, opts = synthetic.pre_subcycle(mesh, state, 3600.0)
+    solver = _solver(mesh, var, opts)
+    try:
+        solver.pre_subcycle(_cells(mesh, state), cold_start=True)
+        got = solver.fetch_pre()
+        out = solver.fetch(names=("uVelocity", "vVelocity", "stress11", "stress22", "stress12"))
+    finally:
+        solver.destroy()
+    _compare_pre(mesh, ref, got)
+    nV = mesh.nVertices
+    assert np.array_equal(out["uVelocity"][:nV], ref["uVelocity"][:nV])
+    assert np.all(out["stress11"] == 0.0)
+
+
+@pytest.mark.parametrize("use_air,use_tilt,geo", [(False, True, True), (True, False, True), (True, True, False)])
+def test_pre_subcycle_switches(evp_lib, use_air, use_tilt, geo):
+    """config_use_air_stress / config_use_surface_tilt / config_geostrophic_surface_tilt."""
+    mesh, var = common.mesh_case("ico4")
+    state = dict(_state(mesh, "B"))
+    nC = mesh.nCells
+    state["seaSurfaceTiltU"] = np.zeros(nC + 1)
+    state["seaSurfaceTiltV"] = np.zeros(nC + 1)
+    state["seaSurfaceTiltU"][:nC] = 1e-6 * np.sin(3 * mesh.lonCell[:nC]) * np.cos(mesh.latCell[:nC])
+    state["seaSurfaceTiltV"][:nC] = -2e-6 * np.cos(2 * mesh.lonCell[:nC]) * np.cos(mesh.latCell[:nC])
+    ref = oracle.pre_subcycle(mesh, state, 3600.0, use_air_stress=use_air, use_surface_tilt=use_tilt,
+                              geostrophic_surface_tilt=geo)
+    _, opts = synthetic.pre_subcycle(mesh, state, 3600.0)
+    solver = _solver(mesh, var, opts)
+    try:
+        solver.pre_subcycle(_cells(mesh, state, seaSurfaceTiltU=state["seaSurfaceTiltU"],
+                                   seaSurfaceTiltV=state["seaSurfaceTiltV"]),
+                            use_air_stress=use_air, use_surface_tilt=use_tilt, geostrophic_surface_tilt=geo,
+                            cold_start=True)
+        got = solver.fetch_pre()
+    finally:
+        solver.destroy()
+    _compare_pre(mesh, ref, got)
+    if use_tilt and not geo:
+        assert np.abs(ref["surfaceTiltForceU"]).max() > 0
+
+
+def test_pre_subcycle_given_air_stress_and_masks(evp_lib):
+    """Coupled-model style: the coupler's air stresses at cells, and config_calc_velocity_masks = false."""
+    mesh, var = common.mesh_case("ico4")
+    state = _state(mesh, "A")
+    nC, nV = mesh.nCells, mesh.nVertices
+    ref = oracle.pre_subcycle(mesh, state, 3600.0)
+    _, opts = synthetic.pre_subcycle(mesh, state, 3600.0)
+    cells = _cells(mesh, state)
+    area, ua, va, rho = cells["iceAreaCell"], cells["uAirVelocity"], cells["vAirVelocity"], cells["airDensity"]
+    air_u, air_v = np.zeros(nC + 1), np.zeros(nC + 1)
+    oracle.lib().orc_constant_air_stress(nC + 1, oracle._p(ua), oracle._p(va), oracle._p(rho), oracle._p(area),
+                                         oracle._p(air_u), oracle._p(air_v))
+    cells = {k: v for k, v in cells.items() if k not in ("uAirVelocity", "vAirVelocity", "airDensity")}
+    cells.update(airStressCellU=air_u, airStressCellV=air_v, solveStress=ref["solveStress"], solveVelocity=ref["solveVelocity"])
+    solver = _solver(mesh, var, opts)
+    try:
+        solver.pre_subcycle(cells, calc_velocity_masks=False, cold_start=True)
+        got = solver.fetch_pre()
+    finally:
+        solver.destroy()
+    _compare_pre(mesh, ref, got)
+
+
+def _post_reference(mesh, step, opts, interior):
+    ds = oracle.final_divergence_shear(mesh, step)
+    p1, p2 = oracle.principal_stresses(mesh, step)
+    osu, osv, ocu, ocv, coef = oracle.ocean_stress_final(mesh, step, opts, interior)
+    return dict(ds, principalStress1Var=p1, principalStress2Var=p2, oceanStressU=osu, oceanStressV=osv,
+                oceanStressCellU=ocu, oceanStressCellV=ocv, oceanStressCoeff=coef,
+                uVelocity=step["uVelocity"], vVelocity=step["vVelocity"])
+
+
+def _compare_post(mesh, ref_step, ref, got):
+    nC, nV = mesh.nCells, mesh.nVertices
+    cm = ref_step["solveStress"][:nC] == 1
+    vm = ref_step["solveVelocity"][:nV] == 1
+    for k in ("divergence", "shear", "ridgeConvergence", "ridgeShear", "oceanStressCellU", "oceanStressCellV"):
+        assert np.array_equal(got[k][:nC], ref[k][:nC]), k
+    for k in ("principalStress1Var", "principalStress2Var"):
+        n = mesh.nEdgesOnCell[:nC]
+        valid = np.arange(mesh.maxEdges)[None, :] < n[:, None]
+        assert np.array_equal(got[k][:nC][valid], ref[k][:nC][valid]), k
+    for k in ("uVelocity", "vVelocity", "oceanStressU", "oceanStressV", "oceanStressCoeff"):
+        assert np.array_equal(got[k][:nV][vm], ref[k][:nV][vm]), k
+    assert np.abs(ref["divergence"][:nC][cm]).max() > 0
+    assert np.abs(ref["oceanStressCellU"][:nC]).max() > 0
+
+
+@pytest.mark.parametrize("kind,state_kind", [("hex82", "square"), ("ico5", "B")])
+def test_full_dynamics_step_on_device(evp_lib, kind, state_kind):
+    """seaice_run_velocity_solver end to end: cell fields in -> pre -> 120 subcycles -> post -> results out."""
+    from mpas_seaice_b200 import host
+    mesh, var = common.mesh_case(kind)
+    state = _state(mesh, state_kind)
+    interior = variational_init.interior_vertex(mesh)
+    ref_step = oracle.pre_subcycle(mesh, state, 3600.0)
+    _, opts = synthetic.pre_subcycle(mesh, state, 3600.0)
+    oracle.subcycle_velocity_solver(mesh, var, ref_step, opts, 120)
+    ref = _post_reference(mesh, ref_step, opts, interior)
+    solver = _solver(mesh, var, opts)
+    try:
+        solver.pre_subcycle(_cells(mesh, state), cold_start=True)
+        solver.run_subcycles(120)
+        got = solver.post_subcycle(names=host.POST_FIELDS)
+        inner = solver.fetch(names=("stress11", "stress22", "stress12"))
+    finally:
+        solver.destroy()
+    _compare_post(mesh, ref_step, ref, got)
+    cm, _ = common.masks_for(mesh, ref_step)
+    for k in ("stress11", "stress22", "stress12"):
+        assert np.array_equal(inner[k][cm], ref_step[k][cm]), k
+
+
+def test_state_stays_resident_across_steps(evp_lib):
+    """Three dynamics steps with a MOVING ice edge: vertices that become ice-covered start from the ocean
+    velocity (new_ice_velocities, velocity_solver.F:1250-1279), vertices that lose their ice are zeroed, stresses
+    of cells that drop out are reset -- all from the state kept on the device, never re-uploaded."""
+    from mpas_seaice_b200 import host
+    mesh, var = common.mesh_case("ico4")
+    interior = variational_init.interior_vertex(mesh)
+    nC = mesh.nCells
+    base = _state(mesh, "B")
+    _, opts = synthetic.pre_subcycle(mesh, base, 3600.0)
+    solver = _solver(mesh, var, opts)
+    prev = None
+    try:
+        for it, lat0 in enumerate((70.0, 62.0, 75.0)):
+            state = dict(base)
+            cap = (np.degrees(mesh.latCell[:nC]) > lat0) | (np.degrees(mesh.latCell[:nC]) < -60.0)
+            for k, val in (("iceAreaCell", 1.0), ("iceVolumeCell", 1.0)):
+                a = np.zeros(nC + 1)
+                a[:nC] = np.where(cap, val, 0.0)
+                state[k] = a
+            ref_step = oracle.pre_subcycle(mesh, state, 3600.0, prev=prev)
+            if it > 0:
+                new_ice = (ref_step["solveVelocity"] == 1) & (prev["solveVelocityPrevious"] == 0)
+                lost_ice = (ref_step["solveVelocity"] == 0) & (prev["solveVelocityPrevious"] == 1)
+                assert (new_ice.any() if it == 1 else lost_ice.any())
+            solver.pre_subcycle(_cells(mesh, state), cold_start=(it == 0))
+            got_pre = solver.fetch_pre()
+            _compare_pre(mesh, ref_step, got_pre)
+            oracle.subcycle_velocity_solver(mesh, var, ref_step, opts, 40)
+            solver.run_subcycles(40)
+            ref = _post_reference(mesh, ref_step, opts, interior)
+            got = solver.post_subcycle(names=host.POST_FIELDS)
+            _compare_post(mesh, ref_step, ref, got)
+            prev = dict(uVelocity=ref_step["uVelocity"], vVelocity=ref_step["vVelocity"],
+                        stress11=ref_step["stress11"], stress22=ref_step["stress22"], stress12=ref_step["stress12"],
+                        solveVelocityPrevious=ref_step["solveVelocityPrevious"])
+    finally:
+        solver.destroy()
+
+
+def test_set_state_seeds_a_restart(evp_lib):
+    """Restart: u, v, stresses and solveVelocityPrevious come from the restart stream (Registry.xml:1937-1957)."""
+    mesh, var = common.mesh_case("ico4")
+    state = _state(mesh, "A")
+    first = oracle.pre_subcycle(mesh, state, 3600.0)
+    _, opts = synthetic.pre_subcycle(mesh, state, 3600.0)
+    oracle.subcycle_velocity_solver(mesh, var, first, opts, 30)
+    prev = dict(uVelocity=first["uVelocity"], vVelocity=first["vVelocity"], stress11=first["stress11"],
+                stress22=first["stress22"], stress12=first["stress12"],
+                solveVelocityPrevious=first["solveVelocityPrevious"])
+    ref_step = oracle.pre_subcycle(mesh, state, 3600.0, prev=prev)
+    oracle.subcycle_velocity_solver(mesh, var, ref_step, opts, 30)
+    solver = _solver(mesh, var, opts)
+    try:
+        solver.set_state(prev)
+        solver.pre_subcycle(_cells(mesh, state), cold_start=False)
+        solver.run_subcycles(30)
+        out = solver.fetch()
+    finally:
+        solver.destroy()
+    cm, vm = common.masks_for(mesh, ref_step)
+    for k in ("uVelocity", "vVelocity"):
+        assert np.array_equal(out[k][vm], ref_step[k][vm]), k
+    for k in ("stress11", "stress22", "stress12"):
+        assert np.array_equal(out[k][cm], ref_step[k][cm]), k
+    assert np.abs(ref_step["stress11"]).max() > 0
+
+
+def test_prepost_call_order_errors(evp_lib):
+    from mpas_seaice_b200 import host
+    mesh, var = common.mesh_case("hex20")
+    step, opts = common.step_case(mesh)
+    solver = host.EvpSolver(mesh, var, opts)
+    try:
+        with pytest.raises(host.EvpError, match="evp_set_mesh_ext"):
+            solver.pre_subcycle({}, cold_start=True)
+        solver.set_mesh_ext(mesh, variational_init.interior_vertex(mesh))
+        with pytest.raises(host.EvpError, match="NULL"):
+            solver.pre_subcycle({}, cold_start=True)
+        with pytest.raises(host.EvpError, match="before any dynamics step"):
+            solver.post_subcycle()
+    finally:
+        solver.destroy()
