@@ -47,6 +47,8 @@ module seaice_evp_b200
        seaice_evp_b200_create, &
        seaice_evp_b200_update, &
        seaice_evp_b200_subcycle, &
+       seaice_evp_b200_set_mesh_ext, &
+       seaice_evp_b200_step, &
        seaice_evp_b200_destroy
 #endif
 
@@ -134,6 +136,62 @@ module seaice_evp_b200
      type(c_ptr) :: stressDivergenceV
      type(c_ptr) :: oceanStressCoeff
   end type evp_out_fields
+
+  ! ---- struct evp_mesh_ext ----
+  type, bind(C), public :: evp_mesh_ext
+     type(c_ptr) :: cellsOnCell
+     type(c_ptr) :: interiorVertex
+     type(c_ptr) :: landIceMaskVertex
+     type(c_ptr) :: areaCell
+     type(c_ptr) :: areaTriangle
+     type(c_ptr) :: fVertex
+  end type evp_mesh_ext
+
+  ! ---- struct evp_pre_fields ----
+  type, bind(C), public :: evp_pre_fields
+     type(c_ptr) :: iceAreaCellInitial
+     type(c_ptr) :: iceAreaCell
+     type(c_ptr) :: totalMassCell
+     type(c_ptr) :: icePressure
+     type(c_ptr) :: uOceanVelocity
+     type(c_ptr) :: vOceanVelocity
+     type(c_ptr) :: airStressCellU
+     type(c_ptr) :: airStressCellV
+     type(c_ptr) :: uAirVelocity
+     type(c_ptr) :: vAirVelocity
+     type(c_ptr) :: airDensity
+     type(c_ptr) :: seaSurfaceTiltU
+     type(c_ptr) :: seaSurfaceTiltV
+     type(c_ptr) :: landIceMask
+     type(c_ptr) :: solveStress
+     type(c_ptr) :: solveVelocity
+  end type evp_pre_fields
+
+  ! ---- struct evp_pre_options ----
+  type, bind(C), public :: evp_pre_options
+     integer(c_int) :: use_air_stress
+     integer(c_int) :: use_surface_tilt
+     integer(c_int) :: geostrophic_surface_tilt
+     integer(c_int) :: calc_velocity_masks
+     integer(c_int) :: cold_start
+  end type evp_pre_options
+
+  ! ---- struct evp_post_fields ----
+  type, bind(C), public :: evp_post_fields
+     type(c_ptr) :: uVelocity
+     type(c_ptr) :: vVelocity
+     type(c_ptr) :: divergence
+     type(c_ptr) :: shear
+     type(c_ptr) :: ridgeConvergence
+     type(c_ptr) :: ridgeShear
+     type(c_ptr) :: principalStress1Var
+     type(c_ptr) :: principalStress2Var
+     type(c_ptr) :: oceanStressCellU
+     type(c_ptr) :: oceanStressCellV
+     type(c_ptr) :: oceanStressU
+     type(c_ptr) :: oceanStressV
+     type(c_ptr) :: oceanStressCoeff
+  end type evp_post_fields
 
   ! ---- functions of include/evp_b200.h ----
   interface
@@ -226,6 +284,35 @@ module seaice_evp_b200
        integer(c_int), intent(in) :: recvIndex(*)
        integer(c_int) :: ierr
      end function evp_set_halo
+
+     function evp_set_mesh_ext(handle, ext) bind(C, name="evp_set_mesh_ext") result(ierr)
+       import :: c_ptr, c_int, evp_mesh_ext
+       type(c_ptr), value :: handle
+       type(evp_mesh_ext), intent(in) :: ext
+       integer(c_int) :: ierr
+     end function evp_set_mesh_ext
+
+     function evp_set_state(handle, uVelocity, vVelocity, stress11, stress22, stress12, solveVelocityPrevious) &
+          bind(C, name="evp_set_state") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: handle, uVelocity, vVelocity, stress11, stress22, stress12, solveVelocityPrevious
+       integer(c_int) :: ierr
+     end function evp_set_state
+
+     function evp_pre_subcycle(handle, fields, options) bind(C, name="evp_pre_subcycle") result(ierr)
+       import :: c_ptr, c_int, evp_pre_fields, evp_pre_options
+       type(c_ptr), value :: handle
+       type(evp_pre_fields), intent(in) :: fields
+       type(evp_pre_options), intent(in) :: options
+       integer(c_int) :: ierr
+     end function evp_pre_subcycle
+
+     function evp_post_subcycle(handle, out) bind(C, name="evp_post_subcycle") result(ierr)
+       import :: c_ptr, c_int, evp_post_fields
+       type(c_ptr), value :: handle
+       type(evp_post_fields), intent(in) :: out
+       integer(c_int) :: ierr
+     end function evp_post_subcycle
 
   end interface
 
@@ -574,6 +661,179 @@ contains
     call evp_b200_check(evp_fetch(evpHandle, o), "evp_fetch")
 
   end subroutine seaice_evp_b200_subcycle
+
+!|||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||
+!  seaice_evp_b200_set_mesh_ext
+!
+!> \brief Mesh fields velocity_solver_pre/post_subcycle read (once, after seaice_evp_b200_create)
+!-----------------------------------------------------------------------
+
+  subroutine seaice_evp_b200_set_mesh_ext(domain)
+
+    type(domain_type), intent(inout) :: domain
+
+    type(MPAS_pool_type), pointer :: meshPool, boundaryPool, oceanCouplingPool
+    type(evp_mesh_ext) :: ext
+    integer, dimension(:,:), pointer :: cellsOnCell
+    integer, dimension(:), pointer :: interiorVertex, landIceMaskVertex
+    real(kind=RKIND), dimension(:), pointer :: areaCell, areaTriangle, fVertex
+
+    call MPAS_pool_get_subpool(domain % blocklist % structs, "mesh", meshPool)
+    call MPAS_pool_get_subpool(domain % blocklist % structs, "boundary", boundaryPool)
+    call MPAS_pool_get_subpool(domain % blocklist % structs, "ocean_coupling", oceanCouplingPool)
+
+    call MPAS_pool_get_array(meshPool, "cellsOnCell", cellsOnCell)
+    call MPAS_pool_get_array(meshPool, "areaCell", areaCell)
+    call MPAS_pool_get_array(meshPool, "areaTriangle", areaTriangle)
+    call MPAS_pool_get_array(meshPool, "fVertex", fVertex)
+    call MPAS_pool_get_array(boundaryPool, "interiorVertex", interiorVertex)
+    call MPAS_pool_get_array(oceanCouplingPool, "landIceMaskVertex", landIceMaskVertex)
+
+    ext % cellsOnCell = c_loc(cellsOnCell)
+    ext % interiorVertex = c_loc(interiorVertex)
+    ext % landIceMaskVertex = c_loc(landIceMaskVertex)
+    ext % areaCell = c_loc(areaCell)
+    ext % areaTriangle = c_loc(areaTriangle)
+    ext % fVertex = c_loc(fVertex)
+
+    call evp_b200_check(evp_set_mesh_ext(evpHandle, ext), "evp_set_mesh_ext")
+
+  end subroutine seaice_evp_b200_set_mesh_ext
+
+!|||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||
+!  seaice_evp_b200_step
+!
+!> \brief One dynamics step with pre-subcycle, subcycle and post-subcycle on the device
+!>
+!> Replaces, inside seaice_run_velocity_solver (velocity_solver.F:577-593), everything after
+!> aggregate_mass_and_area and the (unmasked) ice strength -- see INTEGRATION.md section 6.  The caller
+!> has filled iceAreaCell / iceAreaCellInitial / totalMassCell (aggregate_mass_and_area, :685-752 and
+!> :820-836) and icePressure for every cell that may be solved (ice_strength, :1419-1460, evaluated
+!> without its solveStress test; the device applies the mask).  u, v, the stresses and
+!> solveVelocityPrevious stay on the device between steps; coldStart = .true. on the first step of a
+!> run from rest, after a restart call evp_set_state first.
+!-----------------------------------------------------------------------
+
+  subroutine seaice_evp_b200_step(domain, coldStart)
+
+    type(domain_type), intent(inout) :: domain
+    logical, intent(in) :: coldStart
+
+    type(MPAS_pool_type), pointer :: velocitySolverPool, icestatePool, tracersAggregatePool, &
+         oceanCouplingPool, atmosCouplingPool, ridgingPool
+    type(evp_pre_fields) :: f
+    type(evp_pre_options) :: po
+    type(evp_post_fields) :: o
+    type(evp_options) :: options
+
+    real(kind=RKIND), dimension(:), pointer :: &
+         iceAreaCellInitial, iceAreaCell, totalMassCell, icePressure, uOceanVelocity, vOceanVelocity, &
+         airStressCellU, airStressCellV, uAirVelocity, vAirVelocity, airDensity, seaSurfaceTiltU, seaSurfaceTiltV, &
+         uVelocity, vVelocity, divergence, shear, ridgeConvergence, ridgeShear, oceanStressCellU, oceanStressCellV
+    integer, dimension(:), pointer :: landIceMask, solveStress, solveVelocity
+    logical, pointer :: config_use_air_stress, config_use_surface_tilt, config_geostrophic_surface_tilt, &
+         config_calc_velocity_masks, config_use_column_package, config_use_column_vertical_thermodynamics
+
+    call MPAS_pool_get_config(domain % configs, "config_use_air_stress", config_use_air_stress)
+    call MPAS_pool_get_config(domain % configs, "config_use_surface_tilt", config_use_surface_tilt)
+    call MPAS_pool_get_config(domain % configs, "config_geostrophic_surface_tilt", config_geostrophic_surface_tilt)
+    call MPAS_pool_get_config(domain % configs, "config_calc_velocity_masks", config_calc_velocity_masks)
+    call MPAS_pool_get_config(domain % configs, "config_use_column_package", config_use_column_package)
+    call MPAS_pool_get_config(domain % configs, "config_use_column_vertical_thermodynamics", &
+                                                 config_use_column_vertical_thermodynamics)
+
+    call MPAS_pool_get_subpool(domain % blocklist % structs, "velocity_solver", velocitySolverPool)
+    call MPAS_pool_get_subpool(domain % blocklist % structs, "icestate", icestatePool)
+    call MPAS_pool_get_subpool(domain % blocklist % structs, "tracers_aggregate", tracersAggregatePool)
+    call MPAS_pool_get_subpool(domain % blocklist % structs, "ocean_coupling", oceanCouplingPool)
+    call MPAS_pool_get_subpool(domain % blocklist % structs, "atmos_coupling", atmosCouplingPool)
+    call MPAS_pool_get_subpool(domain % blocklist % structs, "ridging", ridgingPool)
+
+    call MPAS_pool_get_array(icestatePool, "iceAreaCellInitial", iceAreaCellInitial)
+    call MPAS_pool_get_array(tracersAggregatePool, "iceAreaCell", iceAreaCell)
+    call MPAS_pool_get_array(icestatePool, "totalMassCell", totalMassCell)
+    call MPAS_pool_get_array(velocitySolverPool, "icePressure", icePressure)
+    call MPAS_pool_get_array(oceanCouplingPool, "uOceanVelocity", uOceanVelocity)
+    call MPAS_pool_get_array(oceanCouplingPool, "vOceanVelocity", vOceanVelocity)
+    call MPAS_pool_get_array(oceanCouplingPool, "seaSurfaceTiltU", seaSurfaceTiltU)
+    call MPAS_pool_get_array(oceanCouplingPool, "seaSurfaceTiltV", seaSurfaceTiltV)
+    call MPAS_pool_get_array(oceanCouplingPool, "landIceMask", landIceMask)
+    call MPAS_pool_get_array(velocitySolverPool, "airStressCellU", airStressCellU)
+    call MPAS_pool_get_array(velocitySolverPool, "airStressCellV", airStressCellV)
+    call MPAS_pool_get_array(atmosCouplingPool, "uAirVelocity", uAirVelocity)
+    call MPAS_pool_get_array(atmosCouplingPool, "vAirVelocity", vAirVelocity)
+    call MPAS_pool_get_array(atmosCouplingPool, "airDensity", airDensity)
+    call MPAS_pool_get_array(velocitySolverPool, "solveStress", solveStress)
+    call MPAS_pool_get_array(velocitySolverPool, "solveVelocity", solveVelocity)
+
+    f % iceAreaCellInitial = c_loc(iceAreaCellInitial)
+    f % iceAreaCell = c_loc(iceAreaCell)
+    f % totalMassCell = c_loc(totalMassCell)
+    f % icePressure = c_loc(icePressure)
+    f % uOceanVelocity = c_loc(uOceanVelocity)
+    f % vOceanVelocity = c_loc(vOceanVelocity)
+    ! air_stress (velocity_solver.F:1560-1580): constant_air_stress without the column thermodynamics,
+    ! else the stresses the column package / coupler left in airStressCellU/V
+    if (.not. config_use_column_package .or. &
+         (config_use_column_package .and. .not. config_use_column_vertical_thermodynamics)) then
+       f % airStressCellU = c_null_ptr
+       f % airStressCellV = c_null_ptr
+       f % uAirVelocity = c_loc(uAirVelocity)
+       f % vAirVelocity = c_loc(vAirVelocity)
+       f % airDensity = c_loc(airDensity)
+    else
+       f % airStressCellU = c_loc(airStressCellU)
+       f % airStressCellV = c_loc(airStressCellV)
+       f % uAirVelocity = c_null_ptr
+       f % vAirVelocity = c_null_ptr
+       f % airDensity = c_null_ptr
+    endif
+    f % seaSurfaceTiltU = c_loc(seaSurfaceTiltU)
+    f % seaSurfaceTiltV = c_loc(seaSurfaceTiltV)
+    f % landIceMask = c_loc(landIceMask)
+    f % solveStress = c_loc(solveStress)          ! read only when config_calc_velocity_masks = .false.
+    f % solveVelocity = c_loc(solveVelocity)
+
+    po % use_air_stress = merge(1, 0, config_use_air_stress)
+    po % use_surface_tilt = merge(1, 0, config_use_surface_tilt)
+    po % geostrophic_surface_tilt = merge(1, 0, config_geostrophic_surface_tilt)
+    po % calc_velocity_masks = merge(1, 0, config_calc_velocity_masks)
+    po % cold_start = merge(1, 0, coldStart)
+
+    call fill_options(domain, options)
+    call evp_b200_check(evp_set_options(evpHandle, options), "evp_set_options")
+    call evp_b200_check(evp_pre_subcycle(evpHandle, f, po), "evp_pre_subcycle")
+    call evp_b200_check(evp_run_subcycles(evpHandle, nElasticSubcycle), "evp_run_subcycles")
+
+    ! what the rest of the model reads every step: advection (u, v), ridging (divergence, shear,
+    ! ridgeConvergence, ridgeShear), coupler (oceanStressCellU/V).  Restart / output fields are fetched
+    ! with evp_fetch / evp_post_subcycle only when those streams fire.
+    call MPAS_pool_get_array(velocitySolverPool, "uVelocity", uVelocity)
+    call MPAS_pool_get_array(velocitySolverPool, "vVelocity", vVelocity)
+    call MPAS_pool_get_array(velocitySolverPool, "divergence", divergence)
+    call MPAS_pool_get_array(velocitySolverPool, "shear", shear)
+    call MPAS_pool_get_array(ridgingPool, "ridgeConvergence", ridgeConvergence)
+    call MPAS_pool_get_array(ridgingPool, "ridgeShear", ridgeShear)
+    call MPAS_pool_get_array(velocitySolverPool, "oceanStressCellU", oceanStressCellU)
+    call MPAS_pool_get_array(velocitySolverPool, "oceanStressCellV", oceanStressCellV)
+
+    o % uVelocity = c_loc(uVelocity)
+    o % vVelocity = c_loc(vVelocity)
+    o % divergence = c_loc(divergence)
+    o % shear = c_loc(shear)
+    o % ridgeConvergence = c_loc(ridgeConvergence)
+    o % ridgeShear = c_loc(ridgeShear)
+    o % principalStress1Var = c_null_ptr
+    o % principalStress2Var = c_null_ptr
+    o % oceanStressCellU = c_loc(oceanStressCellU)
+    o % oceanStressCellV = c_loc(oceanStressCellV)
+    o % oceanStressU = c_null_ptr
+    o % oceanStressV = c_null_ptr
+    o % oceanStressCoeff = c_null_ptr
+
+    call evp_b200_check(evp_post_subcycle(evpHandle, o), "evp_post_subcycle")
+
+  end subroutine seaice_evp_b200_step
 
 !|||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||
 !  seaice_evp_b200_destroy

@@ -27,15 +27,19 @@ def build_rank_workload(name, rank, world, dist=None, verbose=None, method="auto
     part = partition.partition_cells(gmesh, world, method)
     blk = partition.build_block(gmesh, part, rank, n_halos)
     step = partition.restrict_step(blk, gstep, nCg, nVg)
+    cells = partition.restrict_step(blk, w["cells"], nCg, nVg)
+    cells["iceAreaCell"] = cells["iceAreaCellInitial"]          # one array on the host, uploaded once
+    interior = partition.restrict_field(blk, w["interiorVertex"], nCg, nVg)    # the global flags, halo included
     nVs, nCs = int(blk.nVerticesSolve), int(blk.nCellsSolve)
     active = (int((step["solveStress"][:nCs] == 1).sum()), int((step["solveVelocity"][:nVs] == 1).sum()))
     active_local_cells = int((step["solveStress"][:blk.nCells] == 1).sum())
-    del gstep, w["step"], w["mesh"], gmesh
+    del gstep, w["step"], w["mesh"], gmesh, w["cells"], w["interiorVertex"]
     static = variational_init.init_static(blk)
     requests = partition.halo_requests(blk)
     log(f"partition '{method}' into {world}: block {rank} has {nCs} owned + {blk.nCells - nCs} halo cells, "
         f"{nVs} owned + {blk.nVertices - nVs} halo vertices ({time.time() - t0:.1f}s)")
-    return dict(name=name, mesh=blk, static=static, step=step, opts=w["opts"], config_dt=w["config_dt"],
+    return dict(name=name, mesh=blk, static=static, step=step, opts=w["opts"], config_dt=w["config_dt"], cells=cells,
+                interiorVertex=interior,
                 nVerticesSolve=nVs, nCellsSolve=nCs, active=active, active_local_cells=active_local_cells,
                 global_cells=nCg, global_vertices=nVg, requests=requests,
                 partition=f"{method} cell-graph partition into {world} blocks, "

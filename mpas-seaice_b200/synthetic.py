@@ -90,6 +90,22 @@ def sphere_state(mesh, kind="A", perturb=True):
     return st
 
 
+def cell_inputs(state):
+    """The CELL fields a host hands to evp_pre_subcycle (include/evp_b200.h, evp_pre_fields): what stays on
+    the host of velocity_solver_pre_subcycle -- aggregate_mass_and_area for a single category
+    (velocity_solver.F:738-746) and the Hibler ice strength before its solveStress mask (:1419-1436; exp()
+    is host-side on purpose) -- plus the atmosphere / ocean coupling fields as they are."""
+    area = np.ascontiguousarray(state["iceAreaCell"], dtype=np.float64)
+    vol = np.ascontiguousarray(state["iceVolumeCell"], dtype=np.float64)
+    snow = np.ascontiguousarray(state["snowVolumeCell"], dtype=np.float64)
+    c = dict(iceAreaCellInitial=area, iceAreaCell=area,
+             totalMassCell=vol * DENSITY_ICE + snow * DENSITY_SNOW,
+             icePressure=HIBLER_P * vol * np.exp(-HIBLER_C * (1.0 - area)))
+    for k in ("uOceanVelocity", "vOceanVelocity", "uAirVelocity", "vAirVelocity", "airDensity"):
+        c[k] = np.ascontiguousarray(state[k], dtype=np.float64)
+    return c
+
+
 # ---------------------------------------------------------------------------------------------
 # pre-subcycle
 # ---------------------------------------------------------------------------------------------

@@ -74,7 +74,10 @@ def build(name: str, state: str = "A", n_elastic: int = 120, verbose=None, with_
     step, opts = synthetic.pre_subcycle(mesh, st, config_dt, n_elastic=n_elastic)
     t3 = time.time()
     log(f"init_static {t2 - t1:.1f}s, pre_subcycle {t3 - t2:.1f}s")
-    return dict(name=name, mesh=mesh, static=static, step=step, opts=opts, config_dt=config_dt,
+    cells = synthetic.cell_inputs(st)                 # evp_pre_subcycle inputs (the widened boundary)
+    interior = variational_init.interior_vertex(mesh)
+    return dict(name=name, mesh=mesh, static=static, step=step, opts=opts, config_dt=config_dt, cells=cells,
+                interiorVertex=interior,
                 timings=dict(mesh_s=t1 - t0, init_s=t2 - t1, pre_subcycle_s=t3 - t2))
 
 

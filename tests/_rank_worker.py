@@ -32,14 +32,16 @@ def main():
     from mpas_seaice_b200 import multigpu, partition
     import common
     overlap = mode == "gpu-overlap"      # EVP_FLAG_OVERLAP_HALO: boundary-first vertex pass, forked exchange
-    if overlap:
+    full = mode == "gpu-full"            # pre-subcycle + subcycle + post-subcycle on the device (state B, 2 halo layers)
+    if overlap or full:
         mode = "gpu"
     if mode == "gpu":
         torch.cuda.set_device(rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
     else:
         dist.init_process_group("gloo")
-    w = multigpu.build_rank_workload(name, rank, world, dist, method=method)
+    w = multigpu.build_rank_workload(name, rank, world, dist, method=method, n_halos=2 if full else None,
+                                     state="B" if full else "A")
     blk, step, opts = w["mesh"], w["step"], w["opts"]
     if mode == "gpu":
         from mpas_seaice_b200 import host
@@ -49,10 +51,18 @@ def main():
         stage("evp_create done")
         multigpu.attach_halo(solver, w, rank, world, dist)
         stage("evp_comm_init + evp_set_halo done")
-        solver.update_step(step)
-        solver.run_subcycles(nsub)
+        post = {}
+        if full:
+            solver.set_mesh_ext(blk, w["interiorVertex"])
+            solver.pre_subcycle(w["cells"], cold_start=True)
+            solver.run_subcycles(nsub)
+            post = solver.post_subcycle(names=common.POST_CELL + common.POST_VERTEX)
+        else:
+            solver.update_step(step)
+            solver.run_subcycles(nsub)
         stage("evp_run_subcycles enqueued")
         res = solver.fetch()
+        res.update(post)
         stage("evp_fetch done")
         solver.destroy()
     else:
@@ -80,24 +90,26 @@ def main():
         res = step
     nCs, nVs = w["nCellsSolve"], w["nVerticesSolve"]
     payload = dict(cell_id=blk.indexToCellID[:nCs], vertex_id=blk.indexToVertexID[:nVs])
-    for k in common.COMPARE_CELL:
+    cell_keys = common.COMPARE_CELL + (common.POST_CELL if full else ())
+    vertex_keys = common.COMPARE_VERTEX + (common.POST_VERTEX if full else ())
+    for k in cell_keys:
         payload[k] = res[k][:nCs]
-    for k in common.COMPARE_VERTEX:
+    for k in vertex_keys:
         payload[k] = res[k][:nVs]
     gathered = [None] * world if rank == 0 else None
     dist.gather_object(payload, gathered, dst=0)
     if rank == 0:
         nC, nV, M = w["global_cells"], w["global_vertices"], blk.maxEdges
-        out = {k: np.zeros((nC + 1, M)) for k in common.COMPARE_CELL}
-        out.update({k: np.zeros(nV + 1) for k in common.COMPARE_VERTEX})
+        out = {k: (np.zeros((nC + 1, M)) if k in common.COMPARE_CELL else np.zeros(nC + 1)) for k in cell_keys}
+        out.update({k: np.zeros(nV + 1) for k in vertex_keys})
         seen_c, seen_v = np.zeros(nC, dtype=int), np.zeros(nV, dtype=int)
         for p in gathered:
             ci, vi = p["cell_id"].astype(np.int64) - 1, p["vertex_id"].astype(np.int64) - 1
             seen_c[ci] += 1
             seen_v[vi] += 1
-            for k in common.COMPARE_CELL:
+            for k in cell_keys:
                 out[k][ci] = p[k]
-            for k in common.COMPARE_VERTEX:
+            for k in vertex_keys:
                 out[k][vi] = p[k]
         assert np.all(seen_c == 1) and np.all(seen_v == 1)
         np.savez(out_path, **out)

@@ -11,6 +11,8 @@ from mpas_seaice_b200 import meshgen, synthetic
 
 COMPARE_CELL = ("stress11", "stress22", "stress12", "strain11", "strain22", "strain12", "replacementPressure")
 COMPARE_VERTEX = ("uVelocity", "vVelocity", "stressDivergenceU", "stressDivergenceV", "oceanStressCoeff")
+POST_CELL = ("divergence", "shear", "ridgeConvergence", "ridgeShear", "oceanStressCellU", "oceanStressCellV")
+POST_VERTEX = ("oceanStressU", "oceanStressV")
 
 
 @functools.lru_cache(maxsize=None)

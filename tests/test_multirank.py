@@ -95,6 +95,46 @@ def test_gloo_ranks_match_single_rank(tmp_path, world, method):
 
 
 @pytest.mark.gpu
+def test_nccl_full_dynamics_step_matches_single_rank(evp_lib, tmp_path):
+    """pre-subcycle + 120 subcycles + post-subcycle on the device, decomposed (2 halo layers, ice caps):
+    the u,v exchange that closes new_ice_velocities and the oceanStress exchange of ocean_stress_final
+    (velocity_solver.F:1281-1320, 3735-3760) ride on the same NCCL lists."""
+    import torch
+    import oracle
+    from mpas_seaice_b200 import synthetic, variational_init
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 4 if n >= 4 else 2
+    name, nsub = "ico4", 120
+    out = _launch("gpu-full", name, nsub, world, str(tmp_path / "out.npz"), timeout=150)
+    w = workloads.build(name, state="B", with_static=False)
+    mesh, opts = w["mesh"], w["opts"]
+    var = oracle.init_variational(mesh)
+    state = synthetic.sphere_state(mesh, "B")
+    ref = oracle.pre_subcycle(mesh, state, w["config_dt"])
+    oracle.subcycle_velocity_solver(mesh, var, ref, opts, nsub)
+    interior = variational_init.interior_vertex(mesh)
+    ref.update(oracle.final_divergence_shear(mesh, ref))
+    osu, osv, ocu, ocv, coef = oracle.ocean_stress_final(mesh, ref, opts, interior)
+    post_ref = dict(ref, oceanStressU=osu, oceanStressV=osv, oceanStressCellU=ocu, oceanStressCellV=ocv)
+    nC, nV = mesh.nCells, mesh.nVertices
+    cm, vm = common.masks_for(mesh, ref)
+    problems = []
+    for k in ("stress11", "stress22", "stress12"):
+        if not np.array_equal(out[k][cm], ref[k][cm]):
+            problems.append(_diff_report(k, out[k][cm], ref[k][cm]))
+    for k in ("uVelocity", "vVelocity") + common.POST_VERTEX:
+        if not np.array_equal(out[k][vm], post_ref[k][vm]):
+            problems.append(_diff_report(k, out[k][vm], post_ref[k][vm]))
+    for k in common.POST_CELL:
+        if not np.array_equal(out[k][:nC], post_ref[k][:nC]):
+            problems.append(_diff_report(k, out[k][:nC], post_ref[k][:nC]))
+    assert not problems, "\n".join(problems)
+    assert np.abs(post_ref["oceanStressCellU"]).max() > 0 and 0 < cm.sum() < cm.size
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name,nsub,mode", [("ico4", 120, "gpu"), ("square", 120, "gpu"), ("ico4", 120, "gpu-overlap")])
 def test_nccl_ranks_match_single_rank(evp_lib, tmp_path, name, nsub, mode):
     import torch
