@@ -292,7 +292,9 @@ def main():
                       "h2d_bytes_per_step": step_bytes(step, host.STEP_FIELDS),
                       "d2h_bytes_per_step": int(sum(a.nbytes for a in out.values())),
                       "ms_per_step": 1e3 * w_narrow / n_e2e}
-        del out
+        # `out` stays alive until solver.destroy(): with EVP_FLAG_PIN_HOST its arrays are registered with CUDA for
+        # the life of the handle (the contract of the flag); freeing them earlier leaves stale registrations that
+        # can collide with later device allocations (seen as 'resource already mapped' at N = 8)
 
         cells = w["cells"]
         solver.set_mesh_ext(mesh, w["interiorVertex"])

@@ -52,7 +52,9 @@ enum {
                                  same or faster on NVLink */
     EVP_FLAG_PIN_HOST = 1     /* host arrays passed to update_step / fetch live at stable addresses for the
                                  life of the handle (true for MPAS pool arrays): page-lock them once with
-                                 cudaHostRegister so the per-step copies run at full PCIe speed */
+                                 cudaHostRegister so the per-step copies run at full PCIe speed.  The arrays must
+                                 NOT be freed while registered: call evp_release_host_memory() first (or
+                                 evp_destroy) -- a stale registration can collide with later allocations */
 };
 
 /* Static description of one block: the variable list of module seaice_mesh_pool
@@ -174,6 +176,10 @@ int evp_synchronize(evp_handle *handle);
 
 /* Blocking copy of the results into host arrays. */
 int evp_fetch(evp_handle *handle, const evp_out_fields *out);
+
+/* Undo every cudaHostRegister done under EVP_FLAG_PIN_HOST (before the host frees or reallocates arrays it
+ * passed to update_step / fetch / pre_subcycle / post_subcycle). */
+int evp_release_host_memory(evp_handle *handle);
 
 /* seaice_mesh_pool_destroy equivalent. */
 int evp_destroy(evp_handle *handle);

@@ -821,6 +821,17 @@ extern "C" int evp_fetch_basis(evp_handle *h, double *gu, double *gv, double *su
     return EVP_OK;
 }
 
+extern "C" int evp_release_host_memory(evp_handle *h)
+{
+    EVP_REQUIRE(h != nullptr, "handle is NULL");
+    EVP_CUDA(cudaSetDevice(h->device));
+    EVP_CUDA(cudaStreamSynchronize(h->stream));
+    for (void *p : h->pinned) cudaHostUnregister(p);
+    h->pinned.clear();
+    cudaGetLastError();
+    return EVP_OK;
+}
+
 extern "C" int evp_destroy(evp_handle *h)
 {
     if (!h) return EVP_OK;

@@ -19,7 +19,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libevp_b200.so")
+# EVP_B200_LIB selects another build of the same sources (e.g. the FMA-contracted perf build)
+LIB_PATH = os.environ.get("EVP_B200_LIB") or os.path.join(_HERE, "csrc", "libevp_b200.so")
 _lib = None
 
 CR = {"evp": 1, "evp_revised": 2, "linear": 3, "none": 4}
@@ -33,7 +34,7 @@ EXPORTS = (
     "evp_last_error_string", "evp_comm_get_unique_id", "evp_comm_init", "evp_set_halo", "evp_last_run_ms",
     "evp_launch_count", "evp_get_stream", "evp_device_bytes", "evp_set_use_graph", "evp_profile_passes",
     "evp_host_metric_terms", "evp_set_mesh_ext", "evp_set_state", "evp_pre_subcycle", "evp_post_subcycle",
-    "evp_fetch_pre",
+    "evp_fetch_pre", "evp_release_host_memory",
 )
 
 
@@ -368,6 +369,10 @@ class EvpSolver:
         arrs = [np.ascontiguousarray(a, dtype=np.int32) for a in
                 (neighbour_rank, send_offset, send_index, recv_offset, recv_index)]
         self._check(self.lib.evp_set_halo(self._h, C.c_int(len(arrs[0])), *[C.c_void_p(a.ctypes.data) for a in arrs]))
+
+    def release_host_memory(self):
+        """evp_release_host_memory: undo the page-locking of every array passed under pin_host."""
+        self._check(self.lib.evp_release_host_memory(self._h))
 
     def destroy(self):
         if getattr(self, "_h", None) is not None and self._h.value:

@@ -20,7 +20,7 @@ from . import partition, variational_init, workloads
 def build_rank_workload(name, rank, world, dist=None, verbose=None, method="auto", n_halos=None, state="A"):
     """Like workloads.build() but for the block of ``rank`` out of ``world``."""
     log = verbose or (lambda *a: None)
-    w = workloads.build(name, state=state, verbose=verbose, with_static=False)
+    w = _build_global(name, state, rank, world, dist, verbose)
     gmesh, gstep = w["mesh"], w["step"]
     nCg, nVg = int(gmesh.nCells), int(gmesh.nVertices)
     t0 = time.time()
@@ -44,6 +44,34 @@ def build_rank_workload(name, rank, world, dist=None, verbose=None, method="auto
                 global_cells=nCg, global_vertices=nVg, requests=requests,
                 partition=f"{method} cell-graph partition into {world} blocks, "
                           f"{blk.nHalos} halo layer(s), vertex owner = first cell of cellsOnVertex")
+
+
+def _build_global(name, state, rank, world, dist, verbose):
+    """The global synthetic workload on every rank.  Large spheres are generated ONCE: rank 0 writes the mesh
+    to a node-local cache, the others read it after a barrier (a 10 M-cell mesh takes ~1 min of numpy per
+    generation; eight copies of that work on one host would dominate the set-up time)."""
+    import os
+    import tempfile
+    level = workloads.SPHERES.get(name, (0, 0))[0]
+    if dist is None or world == 1 or level < 8 or os.environ.get("EVP_B200_MESH_CACHE"):
+        return workloads.build(name, state=state, verbose=verbose, with_static=False)
+    cache = [tempfile.mkdtemp(prefix="evp_b200_mesh_") if rank == 0 else None]
+    dist.broadcast_object_list(cache, src=0)
+    os.environ["EVP_B200_MESH_CACHE"] = cache[0]
+    try:
+        w = None
+        if rank == 0:
+            w = workloads.build(name, state=state, verbose=verbose, with_static=False)
+        dist.barrier()
+        if rank != 0:
+            w = workloads.build(name, state=state, verbose=verbose, with_static=False)
+        dist.barrier()
+    finally:
+        del os.environ["EVP_B200_MESH_CACHE"]
+        if rank == 0:
+            import shutil
+            shutil.rmtree(cache[0], ignore_errors=True)
+    return w
 
 
 def gather_requests(requests, rank, world, dist):
