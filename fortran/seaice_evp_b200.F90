@@ -90,6 +90,7 @@ module seaice_evp_b200
      integer(c_int) :: use_special_boundaries_velocity
      integer(c_int) :: device
      integer(c_int) :: flags
+     integer(c_int) :: average_variational_strain
      real(c_double) :: elasticTimeStep
      real(c_double) :: dynamicsTimeStep
      real(c_double) :: dampingTimescale
@@ -346,9 +347,9 @@ contains
     call MPAS_pool_get_config(domain % configs, "config_stress_divergence_scheme", config_stress_divergence_scheme)
     call MPAS_pool_get_config(domain % configs, "config_average_variational_strain", config_average_variational_strain)
 
+    ! config_average_variational_strain is covered (it needs seaice_evp_b200_set_mesh_ext for areaCell)
     supported = trim(config_strain_scheme) == "variational" .and. &
-                trim(config_stress_divergence_scheme) == "variational" .and. &
-                .not. config_average_variational_strain
+                trim(config_stress_divergence_scheme) == "variational"
 
   end function seaice_evp_b200_supported
 
@@ -394,7 +395,8 @@ contains
     type(MPAS_pool_type), pointer :: velocitySolverPool
     real(kind=RKIND), pointer :: elasticTimeStep, dynamicsTimeStep
     character(len=strKIND), pointer :: config_ocean_stress_type
-    logical, pointer :: config_use_ocean_stress, config_use_special_boundaries_velocity
+    logical, pointer :: config_use_ocean_stress, config_use_special_boundaries_velocity, &
+         config_average_variational_strain
     integer, pointer :: config_elastic_subcycle_number
 
     call MPAS_pool_get_subpool(domain % blocklist % structs, "velocity_solver", velocitySolverPool)
@@ -405,6 +407,7 @@ contains
     call MPAS_pool_get_config(domain % configs, "config_use_special_boundaries_velocity", &
                                                  config_use_special_boundaries_velocity)
     call MPAS_pool_get_config(domain % configs, "config_elastic_subcycle_number", config_elastic_subcycle_number)
+    call MPAS_pool_get_config(domain % configs, "config_average_variational_strain", config_average_variational_strain)
 
     nElasticSubcycle = config_elastic_subcycle_number
 
@@ -419,6 +422,7 @@ contains
     options % use_special_boundaries_velocity = merge(1, 0, config_use_special_boundaries_velocity)
     options % device = -1                    ! the device the host selected (cudaSetDevice / CUDA_VISIBLE_DEVICES)
     options % flags = EVP_FLAG_PIN_HOST      ! MPAS pool arrays live at stable addresses
+    options % average_variational_strain = merge(1, 0, config_average_variational_strain)
     options % elasticTimeStep = elasticTimeStep
     options % dynamicsTimeStep = dynamicsTimeStep
     options % dampingTimescale = dampingTimescale

@@ -91,6 +91,8 @@ typedef struct {
     int use_special_boundaries_velocity;      /* config_use_special_boundaries_velocity */
     int device;                               /* CUDA device ordinal, -1 = current device */
     int flags;                                /* EVP_FLAG_* */
+    int average_variational_strain;           /* config_average_variational_strain (seaice_average_strains_on_vertex,
+                                                 variational.F:684-763); needs evp_set_mesh_ext (areaCell) */
     double elasticTimeStep;                   /* velocity_solver.F:157 */
     double dynamicsTimeStep;                  /* velocity_solver.F:155 */
     double dampingTimescale;                  /* constitutive_relation.F:125 */

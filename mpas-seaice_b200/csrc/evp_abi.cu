@@ -703,6 +703,10 @@ extern "C" int evp_run_subcycles(evp_handle *h, int nSub)
 {
     EVP_REQUIRE(h != nullptr, "handle is NULL");
     EVP_REQUIRE(nSub >= 0, "nSubcycles must be >= 0");
+    if (h->opt.average_variational_strain && !h->haveExt) {
+        evp_set_error("average_variational_strain needs areaCell: call evp_set_mesh_ext first");
+        return EVP_ERR_STATE;
+    }
     if (!h->haveBasis) { evp_set_error("basis arrays were neither given to evp_create nor precomputed"); return EVP_ERR_STATE; }
     if (!h->haveStep) { evp_set_error("evp_update_step must be called before evp_run_subcycles"); return EVP_ERR_STATE; }
     EVP_CUDA(cudaSetDevice(h->device));

@@ -150,7 +150,10 @@ struct CellSmem {
 // and a partial sum that starts at +0 never becomes -0 in round-to-nearest).
 // Tiles without any solved cell issue no bulk copy (ice-free ocean costs ~26 B per cell).
 // ---------------------------------------------------------------------------------------------
-template <int M, bool METRIC, int CR, bool DIAG, bool GBAND>
+// PHASE 0: the fused kernel.  config_average_variational_strain splits it around the vertex averaging of
+// the strains (seaice_average_strains_on_vertex, variational.F:684-763): PHASE 1 stops after the strain and
+// stores it, PHASE 2 starts from the stored (averaged) strain.
+template <int M, bool METRIC, int CR, bool DIAG, bool GBAND, int PHASE>
 __global__ void __launch_bounds__(EVP_TILE *M) evp_cell_kernel(const CellArgs a)
 {
     using Smem = CellSmem<M, METRIC, GBAND>;
@@ -177,12 +180,16 @@ __global__ void __launch_bounds__(EVP_TILE *M) evp_cell_kernel(const CellArgs a)
     }
     const bool staged = __syncthreads_or(solve) != 0;      // block-uniform; also publishes the mbarrier init
     if (staged && leader) {
-        const double2 *gsrc = (GBAND ? a.Gb : a.G) + tile * (size_t)(GR * EVP_TILE);
-        mbar_expect_tx(&sm.barG, (uint32_t)sizeof(sm.G));
-        bulk_g2s(&sm.G[0][0], gsrc, (uint32_t)sizeof(sm.G), &sm.barG);
-        mbar_expect_tx(&sm.barS, (uint32_t)(sizeof(sm.S) + (METRIC ? sizeof(sm.Sm) : 0)));
-        bulk_g2s(&sm.S[0][0], a.Suv + tile * (size_t)(M * M * EVP_TILE), (uint32_t)sizeof(sm.S), &sm.barS);
-        if (METRIC) bulk_g2s(&sm.Sm[0][0], a.Sm + tile * (size_t)(M * M * EVP_TILE), (uint32_t)sizeof(sm.Sm), &sm.barS);
+        if (PHASE != 2) {
+            const double2 *gsrc = (GBAND ? a.Gb : a.G) + tile * (size_t)(GR * EVP_TILE);
+            mbar_expect_tx(&sm.barG, (uint32_t)sizeof(sm.G));
+            bulk_g2s(&sm.G[0][0], gsrc, (uint32_t)sizeof(sm.G), &sm.barG);
+        }
+        if (PHASE != 1) {
+            mbar_expect_tx(&sm.barS, (uint32_t)(sizeof(sm.S) + (METRIC ? sizeof(sm.Sm) : 0)));
+            bulk_g2s(&sm.S[0][0], a.Suv + tile * (size_t)(M * M * EVP_TILE), (uint32_t)sizeof(sm.S), &sm.barS);
+            if (METRIC) bulk_g2s(&sm.Sm[0][0], a.Sm + tile * (size_t)(M * M * EVP_TILE), (uint32_t)sizeof(sm.Sm), &sm.barS);
+        }
     }
 
     const bool act = j < n;                       // false for every slot of an out-of-range cell
@@ -190,13 +197,15 @@ __global__ void __launch_bounds__(EVP_TILE *M) evp_cell_kernel(const CellArgs a)
     double uj = 0.0, vj = 0.0, tj = 0.0, x11 = 0.0, x22 = 0.0, x12 = 0.0;
     if (act) {
         const int vi = a.voc[q];
-        if (solve) {
+        if (solve && PHASE != 2) {
             const double2 w = a.uv[vi];
             uj = w.x; vj = w.y;
         }
         if (METRIC) tj = a.tanLat[vi];
-        const double2 s = a.sig[q];
-        x11 = s.x; x22 = s.y; x12 = a.sig12[q];
+        if (PHASE != 1) {
+            const double2 s = a.sig[q];
+            x11 = s.x; x22 = s.y; x12 = a.sig12[q];
+        }
     }
     sm.u[j][cx] = uj;
     sm.v[j][cx] = vj;
@@ -204,7 +213,10 @@ __global__ void __launch_bounds__(EVP_TILE *M) evp_cell_kernel(const CellArgs a)
 
     if (act && solve) {
         double e11 = 0.0, e22 = 0.0, e12 = 0.0;
-        const double P = a.P[c];
+        const double P = (PHASE == 1) ? 0.0 : a.P[c];
+        if (PHASE == 2) {
+            e11 = a.e11[q]; e22 = a.e22[q]; e12 = a.e12[q];
+        } else {
         mbar_wait(&sm.barG, 0);
         if (GBAND) {
             int i0 = j - 1, i1 = j, i2 = j + 1;
@@ -235,6 +247,11 @@ __global__ void __launch_bounds__(EVP_TILE *M) evp_cell_kernel(const CellArgs a)
         // metric terms (variational.F:658-662); tj == 0 when METRIC is off
         e11 = e11 - vj * tj;
         e12 = e12 + uj * tj * 0.5;
+        }
+        if (PHASE == 1) {
+            a.e11[q] = e11; a.e22[q] = e22; a.e12[q] = e12;
+            return;                       // no barrier follows in this instantiation
+        }
         double rep = 0.0;
         constitutive<CR>(x11, x22, x12, e11, e22, e12, P, rep, a.dte, a.damping);
         if (CR != EVP_CR_NONE) {
@@ -242,7 +259,7 @@ __global__ void __launch_bounds__(EVP_TILE *M) evp_cell_kernel(const CellArgs a)
             a.sig12[q] = x12;
         }
         if (DIAG) {
-            a.e11[q] = e11; a.e22[q] = e22; a.e12[q] = e12;
+            if (PHASE == 0) { a.e11[q] = e11; a.e22[q] = e22; a.e12[q] = e12; }
             if (CR == EVP_CR_EVP || CR == EVP_CR_EVP_REVISED) a.repP[q] = rep;
         }
     } else if (act) {
@@ -250,6 +267,7 @@ __global__ void __launch_bounds__(EVP_TILE *M) evp_cell_kernel(const CellArgs a)
         // init_subcycle_variables, velocity_solver.F:2335-2345) and still enters the divergence
         if (DIAG && CR == EVP_CR_EVP) a.repP[q] = 0.0;   // variational.F:862
     }
+    if (PHASE == 1) return;
     sm.s11[j][cx] = x11;
     sm.s22[j][cx] = x22;
     sm.s12[j][cx] = x12;
@@ -293,6 +311,50 @@ __global__ void __launch_bounds__(EVP_TILE *M) evp_cell_kernel(const CellArgs a)
         }
     }
     a.contrib[q] = make_double2(cU, cV);
+}
+
+// seaice_average_strains_on_vertex (variational.F:684-763): for every OWNED vertex the cell-area weighted
+// mean of the strains its vertexDegree cells hold at that vertex, written back to each of them.  A
+// (cell, slot) entry belongs to exactly one vertex, so one thread per vertex is race-free; the reference runs
+// this loop serially.  gidx is the (slot, cell) index already resolved for the divergence gather.
+template <int D>
+__global__ void __launch_bounds__(256) evp_average_strain_kernel(int nVerticesSolve, size_t nVp, size_t nCp,
+                                                                  const int *__restrict__ gidx,
+                                                                  const int *__restrict__ cov,
+                                                                  const double *__restrict__ areaCell,
+                                                                  double *__restrict__ e11, double *__restrict__ e22,
+                                                                  double *__restrict__ e12)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nVerticesSolve) return;
+    int idx[D];
+    double a11 = 0.0, a22 = 0.0, a12 = 0.0, denominator = 0.0;
+#pragma unroll
+    for (int s = 0; s < D; s++) {
+        idx[s] = gidx[(size_t)s * nVp + v];
+        const int c = cov[(size_t)s * nVp + v];
+        if (c >= 0) {
+            // a cell that does not list the vertex (cellVerticesAtVertex = 0) cannot occur on a valid mesh
+            const double area = areaCell[c];
+            if (idx[s] >= 0) {
+                a11 = a11 + e11[idx[s]] * area;
+                a22 = a22 + e22[idx[s]] * area;
+                a12 = a12 + e12[idx[s]] * area;
+            }
+            denominator = denominator + area;
+        }
+    }
+    a11 = a11 / denominator;
+    a22 = a22 / denominator;
+    a12 = a12 / denominator;
+#pragma unroll
+    for (int s = 0; s < D; s++) {
+        if (idx[s] >= 0) {
+            e11[idx[s]] = a11;
+            e22[idx[s]] = a22;
+            e12[idx[s]] = a12;
+        }
+    }
 }
 
 struct VertexArgs {
@@ -404,10 +466,10 @@ __global__ void evp_sb_scatter(int n, const int *__restrict__ dst, const double2
     uv[dst[k]] = tmp[k];
 }
 
-template <int M, bool METRIC, int CR, bool DIAG, bool GBAND>
+template <int M, bool METRIC, int CR, bool DIAG, bool GBAND, int PHASE>
 int launch_cell_k(const CellArgs &a, cudaStream_t s)
 {
-    auto kern = evp_cell_kernel<M, METRIC, CR, DIAG, GBAND>;
+    auto kern = evp_cell_kernel<M, METRIC, CR, DIAG, GBAND, PHASE>;
     constexpr size_t smem = sizeof(CellSmem<M, METRIC, GBAND>);
     static bool configured[16] = {};      // per device: opt in to > 48 KB of dynamic shared memory
     int dev = 0;
@@ -421,27 +483,34 @@ int launch_cell_k(const CellArgs &a, cudaStream_t s)
     kern<<<grid, block, smem, s>>>(a);
     return 0;
 }
+template <int M, bool METRIC, int CR, bool DIAG, bool GBAND>
+int launch_cell_p(const CellArgs &a, int phase, cudaStream_t s)
+{
+    if (phase == 1) return launch_cell_k<M, METRIC, EVP_CR_NONE, false, GBAND, 1>(a, s);   // strain only
+    if (phase == 2) return launch_cell_k<M, METRIC, CR, DIAG, GBAND, 2>(a, s);
+    return launch_cell_k<M, METRIC, CR, DIAG, GBAND, 0>(a, s);
+}
 template <int M, bool METRIC, int CR>
-int launch_cell_d(const CellArgs &a, bool diag, cudaStream_t s)
+int launch_cell_d(const CellArgs &a, bool diag, int phase, cudaStream_t s)
 {
     const bool band = a.Gb != nullptr;
-    if (diag) return band ? launch_cell_k<M, METRIC, CR, true, true>(a, s) : launch_cell_k<M, METRIC, CR, true, false>(a, s);
-    return band ? launch_cell_k<M, METRIC, CR, false, true>(a, s) : launch_cell_k<M, METRIC, CR, false, false>(a, s);
+    if (diag) return band ? launch_cell_p<M, METRIC, CR, true, true>(a, phase, s) : launch_cell_p<M, METRIC, CR, true, false>(a, phase, s);
+    return band ? launch_cell_p<M, METRIC, CR, false, true>(a, phase, s) : launch_cell_p<M, METRIC, CR, false, false>(a, phase, s);
 }
 template <int M, bool METRIC>
-int launch_cell_cr(const CellArgs &a, int cr, bool diag, cudaStream_t s)
+int launch_cell_cr(const CellArgs &a, int cr, bool diag, int phase, cudaStream_t s)
 {
     switch (cr) {
-    case EVP_CR_EVP: return launch_cell_d<M, METRIC, EVP_CR_EVP>(a, diag, s);
-    case EVP_CR_EVP_REVISED: return launch_cell_d<M, METRIC, EVP_CR_EVP_REVISED>(a, diag, s);
-    case EVP_CR_LINEAR: return launch_cell_d<M, METRIC, EVP_CR_LINEAR>(a, diag, s);
-    default: return launch_cell_d<M, METRIC, EVP_CR_NONE>(a, diag, s);
+    case EVP_CR_EVP: return launch_cell_d<M, METRIC, EVP_CR_EVP>(a, diag, phase, s);
+    case EVP_CR_EVP_REVISED: return launch_cell_d<M, METRIC, EVP_CR_EVP_REVISED>(a, diag, phase, s);
+    case EVP_CR_LINEAR: return launch_cell_d<M, METRIC, EVP_CR_LINEAR>(a, diag, phase, s);
+    default: return launch_cell_d<M, METRIC, EVP_CR_NONE>(a, diag, phase, s);
     }
 }
 template <int M>
-int launch_cell_m(const CellArgs &a, bool metric, int cr, bool diag, cudaStream_t s)
+int launch_cell_m(const CellArgs &a, bool metric, int cr, bool diag, int phase, cudaStream_t s)
 {
-    return metric ? launch_cell_cr<M, true>(a, cr, diag, s) : launch_cell_cr<M, false>(a, cr, diag, s);
+    return metric ? launch_cell_cr<M, true>(a, cr, diag, phase, s) : launch_cell_cr<M, false>(a, cr, diag, phase, s);
 }
 
 template <int D, int CR>
@@ -470,9 +539,30 @@ int launch_vertex_cr(const VertexArgs &a, int cr, bool diag, cudaStream_t s)
 
 }  // namespace
 
+static int enqueue_cell_phase(evp_handle *h, bool diag, int phase, cudaStream_t s);
+
+// strain -> [vertex averaging] -> stress -> per-cell divergence sums
 int evp_enqueue_cell_pass(evp_handle *h, bool diag, cudaStream_t s)
 {
     if (h->nCells == 0) return EVP_OK;
+    if (!h->opt.average_variational_strain) return enqueue_cell_phase(h, diag, 0, s);
+    int rc;
+    if ((rc = enqueue_cell_phase(h, diag, 1, s))) return rc;
+    if (h->nVerticesSolve) {
+        const int block = 256, grid = (h->nVerticesSolve + block - 1) / block;
+        if (h->D == 3)
+            evp_average_strain_kernel<3><<<grid, block, 0, s>>>(h->nVerticesSolve, h->nVp, h->nCp, h->d.gidx, h->d.cov,
+                                                                h->d.areaCell, h->d.e11, h->d.e22, h->d.e12);
+        else
+            evp_average_strain_kernel<4><<<grid, block, 0, s>>>(h->nVerticesSolve, h->nVp, h->nCp, h->d.gidx, h->d.cov,
+                                                                h->d.areaCell, h->d.e11, h->d.e22, h->d.e12);
+        EVP_CUDA(cudaGetLastError());
+    }
+    return enqueue_cell_phase(h, diag, 2, s);
+}
+
+static int enqueue_cell_phase(evp_handle *h, bool diag, int phase, cudaStream_t s)
+{
     CellArgs a;
     a.nCells = h->nCells; a.nCp = h->nCp;
     a.nEdges = h->d.nEdges; a.solveStress = h->d.solveStress; a.voc = h->d.voc;
@@ -484,10 +574,10 @@ int evp_enqueue_cell_pass(evp_handle *h, bool diag, cudaStream_t s)
     const int cr = h->opt.constitutive_relation_type;
     int rc = 0;
     switch (h->M) {
-    case 4: rc = launch_cell_m<4>(a, h->metric, cr, diag, s); break;
-    case 6: rc = launch_cell_m<6>(a, h->metric, cr, diag, s); break;
+    case 4: rc = launch_cell_m<4>(a, h->metric, cr, diag, phase, s); break;
+    case 6: rc = launch_cell_m<6>(a, h->metric, cr, diag, phase, s); break;
     case 7:
-    case 8: rc = launch_cell_m<8>(a, h->metric, cr, diag, s); break;
+    case 8: rc = launch_cell_m<8>(a, h->metric, cr, diag, phase, s); break;
     default: evp_set_error("unsupported maxEdges %d", h->M); return EVP_ERR_ARGUMENT;
     }
     if (rc) { evp_set_error("cell kernel: cannot opt in to its dynamic shared memory size"); return EVP_ERR_CUDA; }
@@ -577,7 +667,8 @@ int evp_enqueue_subcycles(evp_handle *h, int nSub, cudaStream_t s)
 int evp_count_launches(evp_handle *h, int nSub)
 {
     const int sb = (h->opt.use_special_boundaries_velocity && h->d.nSB) ? 2 : 0;
-    const int perSub = (h->nCells ? 1 : 0) + (h->nVerticesSolve ? 1 : 0) + (evp_halo_boundary_count(h) ? 1 : 0) +
+    const int avg = h->opt.average_variational_strain ? (h->nCells ? 1 : 0) + (h->nVerticesSolve ? 1 : 0) : 0;
+    const int perSub = avg + (h->nCells ? 1 : 0) + (h->nVerticesSolve ? 1 : 0) + (evp_halo_boundary_count(h) ? 1 : 0) +
                        evp_halo_launches(h) + sb;
     return sb + nSub * perSub;
 }

@@ -54,7 +54,8 @@ class MeshDesc(C.Structure):
 
 class Options(C.Structure):
     _fields_ = ([(n, C.c_int) for n in ("constitutive_relation_type", "ocean_stress_type", "use_ocean_stress",
-                                        "use_special_boundaries_velocity", "device", "flags")]
+                                        "use_special_boundaries_velocity", "device", "flags",
+                                        "average_variational_strain")]
                 + [(n, C.c_double) for n in ("elasticTimeStep", "dynamicsTimeStep", "dampingTimescale",
                                              "numericalInertiaCoefficient")])
 
@@ -164,6 +165,7 @@ def make_options(opts: dict, device: int = -1, pin_host: bool = False) -> Option
     o.use_special_boundaries_velocity = int(opts.get("use_special_boundaries_velocity", False))
     o.device = device
     o.flags = (FLAG_PIN_HOST if pin_host else 0) | (FLAG_OVERLAP_HALO if opts.get("overlap_halo", False) else 0)
+    o.average_variational_strain = int(opts.get("average_variational_strain", False))
     o.elasticTimeStep = opts["elasticTimeStep"]
     o.dynamicsTimeStep = opts["dynamicsTimeStep"]
     o.dampingTimescale = opts["dampingTimescale"]

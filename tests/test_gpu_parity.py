@@ -328,3 +328,55 @@ def test_linearity_of_the_stress_divergence_at_full_size(evp_lib):
         scale = np.abs(rhs).max()
         assert scale > 0
         assert np.abs(lhs - rhs).max() <= 1e-12 * scale, k
+
+
+@pytest.mark.parametrize("kind", ["hex20", "ico4", "quad40"])
+def test_average_variational_strain(evp_lib, kind):
+    """config_average_variational_strain: seaice_average_strains_on_vertex (variational.F:684-763) between the
+    strain and the stress update -- the fused cell kernel splits into strain / vertex average / stress."""
+    from mpas_seaice_b200 import host, variational_init
+    mesh, var = common.mesh_case(kind)
+    step, opts = common.step_case(mesh)
+    opts = dict(opts, average_variational_strain=True)
+    nsub = 30
+    ref = common.run_oracle(mesh, var, step, opts, nsub)
+    plain = common.run_oracle(mesh, var, step, dict(opts, average_variational_strain=False), nsub)
+    solver = host.EvpSolver(mesh, var, opts)
+    try:
+        solver.update_step(step)
+        with pytest.raises(host.EvpError, match="evp_set_mesh_ext"):
+            solver.run_subcycles(nsub)
+        solver.set_mesh_ext(mesh, variational_init.interior_vertex(mesh))
+        solver.run_subcycles(nsub)
+        out = solver.fetch()
+        assert solver.launch_count(nsub) == 4 * nsub
+    finally:
+        solver.destroy()
+    _compare(mesh, step, ref, out)
+    cm, _ = common.masks_for(mesh, step)
+    assert not np.array_equal(ref["stress11"][cm], plain["stress11"][cm])      # the option does change the answer
+
+
+def test_split_subcycle_counts_at_full_size(evp_lib):
+    """Size-independent property at QU60 (BASELINE configs[3], 163 842 cells): 120 subcycles in one call, in two
+    calls of 60, and without graph replay give the same bits for every carried field (u, v, stresses), because
+    nothing but those fields is carried between subcycles."""
+    from mpas_seaice_b200 import host, workloads
+    w = workloads.build("qu60")
+    mesh, static, step, opts = w["mesh"], w["static"], w["step"], w["opts"]
+    names = ("uVelocity", "vVelocity", "stress11", "stress22", "stress12", "strain11", "stressDivergenceU")
+    solver = host.EvpSolver(mesh, static, opts, local_coords=(static["xLocal"], static["yLocal"]))
+    res = []
+    try:
+        for plan, graph in (((120,), 1), ((60, 60), 1), ((119, 1), 0)):
+            solver.set_use_graph(graph)
+            solver.update_step(step)
+            for n in plan:
+                solver.run_subcycles(n)
+            res.append(solver.fetch(names=names))
+    finally:
+        solver.destroy()
+    assert np.abs(res[0]["uVelocity"]).max() > 0
+    for other in res[1:]:
+        for k in names:
+            assert np.array_equal(res[0][k], other[k]), k

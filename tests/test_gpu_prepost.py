@@ -163,9 +163,10 @@ def _compare_post(mesh, ref_step, ref, got):
     assert np.abs(ref["oceanStressCellU"][:nC]).max() > 0
 
 
-@pytest.mark.parametrize("kind,state_kind", [("hex82", "square"), ("ico5", "B")])
+@pytest.mark.parametrize("kind,state_kind", [("hex82", "square"), ("ico5", "B"), ("ico7", "A")])
 def test_full_dynamics_step_on_device(evp_lib, kind, state_kind):
-    """seaice_run_velocity_solver end to end: cell fields in -> pre -> 120 subcycles -> post -> results out."""
+    """seaice_run_velocity_solver end to end: cell fields in -> pre -> 120 subcycles -> post -> results out.
+    hex82 = BASELINE configs[1] (square test case), ico5 = configs[2] (QU240), ico7 = configs[3] (QU60) at full size."""
     from mpas_seaice_b200 import host
     mesh, var = common.mesh_case(kind)
     state = _state(mesh, state_kind)
