@@ -54,6 +54,7 @@ class ClockSampler:
     def __init__(self, device):
         self.device = device
         self.lines = []
+        self.first = 0
         self.proc = None
 
     def start(self):
@@ -70,6 +71,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """Start of the timed region: earlier samples (warm-up) are used only if none arrives afterwards."""
+        self.first = len(self.lines)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -80,7 +85,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines = self.lines[self.first:] or self.lines[-3:]
+        for ln in lines:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -210,12 +216,13 @@ def main():
         nC_tot, nV_tot = nC_act, nV_act
 
     # ---- device-resident throughput -----------------------------------------------------------
-    for _ in range(args.warmup):
+    sampler = ClockSampler(local_rank)
+    sampler.start()                  # nvidia-smi needs ~0.1-0.2 s to deliver its first sample: start it before the
+    for _ in range(args.warmup):     # warm-up so that short timed regions (small meshes, many GPUs) are covered too
         solver.run_subcycles(N_ELASTIC)
     solver.synchronize()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark()
     t0 = time.perf_counter()
     dev_ms = 0.0
     for _ in range(args.steps):
