@@ -57,7 +57,8 @@ module seaice_evp_b200
        EVP_OK = 0, &
        EVP_CR_EVP = 1, EVP_CR_EVP_REVISED = 2, EVP_CR_LINEAR = 3, EVP_CR_NONE = 4, &
        EVP_OCEAN_QUADRATIC = 1, EVP_OCEAN_LINEAR = 2, &
-       EVP_FLAG_PIN_HOST = 1, EVP_FLAG_OVERLAP_HALO = 2
+       EVP_FLAG_PIN_HOST = 1, EVP_FLAG_OVERLAP_HALO = 2, &
+       EVP_SCHEME_VARIATIONAL = 1, EVP_SCHEME_WEAK = 2
 
   ! ---- struct evp_mesh_desc ----
   type, bind(C), public :: evp_mesh_desc
@@ -91,6 +92,8 @@ module seaice_evp_b200
      integer(c_int) :: device
      integer(c_int) :: flags
      integer(c_int) :: average_variational_strain
+     integer(c_int) :: strain_scheme
+     integer(c_int) :: stress_divergence_scheme
      real(c_double) :: elasticTimeStep
      real(c_double) :: dynamicsTimeStep
      real(c_double) :: dampingTimescale
@@ -423,6 +426,8 @@ contains
     options % device = -1                    ! the device the host selected (cudaSetDevice / CUDA_VISIBLE_DEVICES)
     options % flags = EVP_FLAG_PIN_HOST      ! MPAS pool arrays live at stable addresses
     options % average_variational_strain = merge(1, 0, config_average_variational_strain)
+    options % strain_scheme = EVP_SCHEME_VARIATIONAL             ! the weak schemes stay on the Fortran path in this
+    options % stress_divergence_scheme = EVP_SCHEME_VARIATIONAL  ! shim (seaice_evp_b200_supported); see INTEGRATION.md
     options % elasticTimeStep = elasticTimeStep
     options % dynamicsTimeStep = dynamicsTimeStep
     options % dampingTimescale = dampingTimescale

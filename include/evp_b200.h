@@ -44,6 +44,11 @@ enum { EVP_OCEAN_QUADRATIC = 1, EVP_OCEAN_LINEAR = 2 };
 /* vertexBoundaryType (src/shared/mpas_seaice_special_boundaries.F:35-39) */
 enum { EVP_VB_NONE = 0, EVP_VB_PERIODIC = 1, EVP_VB_REVERSE = 2, EVP_VB_ZERO = 3 };
 
+/* config_strain_scheme / config_stress_divergence_scheme (src/shared/mpas_seaice_velocity_solver.F:168-198);
+ * 0 is read as variational.  weak strain + variational divergence is allowed, the reverse is rejected
+ * like the reference does (:195-198). */
+enum { EVP_SCHEME_VARIATIONAL = 1, EVP_SCHEME_WEAK = 2 };
+
 /* evp_options.flags */
 enum {
     EVP_FLAG_OVERLAP_HALO = 2,/* multi-rank: solve the boundary-owned vertices first and run pack / NCCL / unpack on a
@@ -93,6 +98,8 @@ typedef struct {
     int flags;                                /* EVP_FLAG_* */
     int average_variational_strain;           /* config_average_variational_strain (seaice_average_strains_on_vertex,
                                                  variational.F:684-763); needs evp_set_mesh_ext (areaCell) */
+    int strain_scheme;                        /* EVP_SCHEME_*; weak needs evp_set_weak_mesh */
+    int stress_divergence_scheme;             /* EVP_SCHEME_* */
     double elasticTimeStep;                   /* velocity_solver.F:157 */
     double dynamicsTimeStep;                  /* velocity_solver.F:155 */
     double dampingTimescale;                  /* constitutive_relation.F:125 */
@@ -302,6 +309,47 @@ typedef struct {
     double *uVelocityInitial; double *vVelocityInitial;
 } evp_pre_out_fields;
 int evp_fetch_pre(evp_handle *handle, const evp_pre_out_fields *out);
+
+
+/* ======================================================================================================
+ * Weak operators: config_strain_scheme / config_stress_divergence_scheme = 'weak'
+ * (src/shared/mpas_seaice_velocity_solver_weak.F): line-integral strain on cells with ONE stress point per
+ * cell, line-integral stress divergence on vertices.  The normal vectors come from the host
+ * (seaice_normal_vectors, src/shared/mpas_seaice_mesh.F:703-2007, is not part of this library).
+ * ====================================================================================================== */
+typedef struct {
+    int nEdges;
+    double sphere_radius;                  /* mesh attribute; 0 is read as 1 like weak.F:208 */
+    const int *edgesOnCell;                /* (maxEdges, nCells) */
+    const int *verticesOnEdge;             /* (2, nEdges) */
+    const int *edgesOnVertex;              /* (vertexDegree, nVertices) */
+    const int *cellsOnEdge;                /* (2, nEdges) */
+    const double *dvEdge;                  /* (nEdges) */
+    const double *dcEdge;                  /* (nEdges) */
+    const double *areaCell;                /* (nCells) */
+    const double *areaTriangle;            /* (nVertices) */
+    const double *normalVectorPolygon;     /* (2, maxEdges, nCells) */
+    const double *normalVectorTriangle;    /* (2, vertexDegree, nVertices) */
+    const double *latCellRotated;          /* (nCells)    tan() is taken on the host at this call */
+    const double *latVertexRotated;        /* (nVertices) */
+} evp_weak_mesh;
+
+/* velocity_weak pool fields (src/Registry.xml, var_struct velocity_weak), all (nCells); any may be NULL */
+typedef struct {
+    double *stress11Weak;
+    double *stress22Weak;
+    double *stress12Weak;
+    double *strain11Weak;
+    double *strain22Weak;
+    double *strain12Weak;
+    double *replacementPressureWeak;
+} evp_weak_fields;
+
+int evp_set_weak_mesh(evp_handle *handle, const evp_weak_mesh *mesh);
+/* Upload the carried weak stresses (the three stress pointers of `fields`; the rest is ignored). */
+int evp_update_weak_state(evp_handle *handle, const evp_weak_fields *fields);
+/* Blocking copy of the weak fields into host arrays. */
+int evp_fetch_weak(evp_handle *handle, const evp_weak_fields *fields);
 
 /* ---- host-side helper for non-Fortran hosts (plain CPU code, no device needed) ----
  * seaice_calc_variational_metric_terms (src/shared/mpas_seaice_velocity_solver_variational_shared.F:293-358):

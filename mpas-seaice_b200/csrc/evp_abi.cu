@@ -358,6 +358,13 @@ static int check_options(const evp_options *o)
                 "constitutive_relation_type must be 1..4");
     EVP_REQUIRE(o->ocean_stress_type == EVP_OCEAN_QUADRATIC || o->ocean_stress_type == EVP_OCEAN_LINEAR,
                 "ocean_stress_type must be 1 or 2");
+    EVP_REQUIRE(o->strain_scheme >= 0 && o->strain_scheme <= EVP_SCHEME_WEAK && o->stress_divergence_scheme >= 0 &&
+                o->stress_divergence_scheme <= EVP_SCHEME_WEAK, "strain / stress divergence scheme must be 0..2");
+    // velocity_solver.F:195-198: "variational strain scheme with weak stress divergence scheme" is rejected
+    EVP_REQUIRE(!(o->strain_scheme != EVP_SCHEME_WEAK && o->stress_divergence_scheme == EVP_SCHEME_WEAK),
+                "variational strain with weak stress divergence is not a valid combination");
+    EVP_REQUIRE(!(o->strain_scheme == EVP_SCHEME_WEAK && o->average_variational_strain),
+                "average_variational_strain applies to the variational strain scheme only");
     if (o->constitutive_relation_type == EVP_CR_EVP)
         EVP_REQUIRE(o->elasticTimeStep > 0.0 && o->dampingTimescale > 0.0,
                     "elasticTimeStep and dampingTimescale must be > 0");
@@ -703,6 +710,10 @@ extern "C" int evp_run_subcycles(evp_handle *h, int nSub)
 {
     EVP_REQUIRE(h != nullptr, "handle is NULL");
     EVP_REQUIRE(nSub >= 0, "nSubcycles must be >= 0");
+    if (h->opt.strain_scheme == EVP_SCHEME_WEAK && !h->haveWeak) {
+        evp_set_error("the weak schemes need evp_set_weak_mesh first");
+        return EVP_ERR_STATE;
+    }
     if (h->opt.average_variational_strain && !h->haveExt) {
         evp_set_error("average_variational_strain needs areaCell: call evp_set_mesh_ext first");
         return EVP_ERR_STATE;

@@ -55,7 +55,11 @@ __host__ __device__ __forceinline__ size_t evp_tix(int row, size_t c, int nRows)
         }                                                          \
     } while (0)
 
-struct evp_halo;  // evp_halo.cu
+struct evp_halo;  // evp_weak.cu
+int evp_enqueue_weak_cell_pass(evp_handle *h, bool diag, cudaStream_t s);    // strain [+ stress] on cells
+int evp_enqueue_weak_to_variational(evp_handle *h, cudaStream_t s);          // interpolate_strains_weak_to_variational
+
+// evp_halo.cu
 
 struct evp_dev {
     // static
@@ -73,6 +77,19 @@ struct evp_dev {
     double2 *airCell = nullptr;   // (airStressCellU, airStressCellV) of the current step
     double2 *osFinal = nullptr;   // ocean_stress_final's oceanStressU/V
     uint8_t *solveVelPrev = nullptr;
+    // weak operators (evp_set_weak_mesh): per cell-slot / vertex-slot edge data, one stress point per cell
+    int2 *wEdgeV = nullptr;       // [M][nCp] the two vertices of edge k of the cell (0-based)
+    double2 *wNp = nullptr;       // [M][nCp] normalVectorPolygon
+    double *wDv = nullptr;        // [M][nCp] dvEdge of that edge
+    int2 *wEdgeC = nullptr;       // [D][nVp] the two cells of edge s of the vertex (0-based, -1 = none)
+    double2 *wNt = nullptr;       // [D][nVp] normalVectorTriangle
+    double *wDc = nullptr;        // [D][nVp] dcEdge
+    double *wTanC = nullptr, *wTanV = nullptr;     // tan(latCellRotated), tan(latVertexRotated) (host libm)
+    double *wAreaC = nullptr, *wAreaT = nullptr;   // areaCell, areaTriangle
+    double2 *sigW = nullptr;      // (stress11Weak, stress22Weak)
+    double *sigW12 = nullptr, *eW11 = nullptr, *eW22 = nullptr, *eW12 = nullptr, *repPW = nullptr;
+    double *eV11 = nullptr, *eV22 = nullptr, *eV12 = nullptr;   // strainXXVertex of interpolate_strains_weak_to_variational
+    double wRadius = 1.0;
     // per step
     uint8_t *solveStress = nullptr, *solveVel = nullptr;
     double *P = nullptr;
@@ -103,7 +120,7 @@ struct evp_handle {
     size_t nCp = 0, nVp = 0;
     evp_options opt{};
     bool metric = false;          // any tanLatVertexRotatedOverRadius != 0
-    bool haveExt = false;
+    bool haveExt = false, haveWeak = false;
     bool haveBasis = false, haveStep = false, haveSB = false, useGraph = true, pinHost = false, timed = false;
     evp_dev d;
     cudaStream_t stream = nullptr, commStream = nullptr;
@@ -126,6 +143,10 @@ int evp_count_launches(evp_handle *h, int nSub);
 int evp_enqueue_cell_pass(evp_handle *h, bool diag, cudaStream_t s);
 int evp_enqueue_vertex_pass(evp_handle *h, bool diag, cudaStream_t s, const int *list, int nList);
 int evp_enqueue_special_boundaries(evp_handle *h, cudaStream_t s);
+
+// evp_weak.cu
+int evp_enqueue_weak_cell_pass(evp_handle *h, bool diag, cudaStream_t s);    // strain [+ stress] on cells
+int evp_enqueue_weak_to_variational(evp_handle *h, cudaStream_t s);          // interpolate_strains_weak_to_variational
 
 // evp_halo.cu
 int evp_halo_enqueue(evp_handle *h, cudaStream_t s);             // exchanges d.uv

@@ -376,12 +376,20 @@ struct VertexArgs {
     double *__restrict__ ocoef;
     double dte, dtDyn, beta;
     int useOcean, oceanType;
+    // weak stress divergence (seaice_stress_divergence_weak, weak.F:493-640)
+    const int *__restrict__ cov;
+    const int2 *__restrict__ wEdgeC;
+    const double2 *__restrict__ wNt;
+    const double *__restrict__ wDc, *__restrict__ wTanV, *__restrict__ wAreaT;
+    const double2 *__restrict__ sigW;
+    const double *__restrict__ sigW12;
+    double wRadius;
 };
 
 // solveVel[v]: bit 0 = solveVelocity(v) == 1, bit 1 = boundary-owned vertex (set only when a halo exchange is
 // attached).  The plain pass takes the vertices whose byte is exactly 1; the LIST pass runs first over the
 // boundary-owned vertices so that their (u,v) can travel while the plain pass does the interior.
-template <int D, int CR, bool DIAG, bool LIST>
+template <int D, int CR, bool DIAG, bool LIST, bool WEAK>
 __global__ void __launch_bounds__(256) evp_vertex_kernel(const VertexArgs a)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -390,17 +398,47 @@ __global__ void __launch_bounds__(256) evp_vertex_kernel(const VertexArgs a)
     if (LIST ? (a.solveVel[v] & 1) == 0 : a.solveVel[v] != 1) return;
 
     double sdU = 0.0, sdV = 0.0;
-#pragma unroll
-    for (int s = 0; s < D; s++) {
-        const int idx = a.gidx[(size_t)s * a.nVp + v];
-        double2 cc = make_double2(0.0, 0.0);
-        if (idx >= 0) cc = a.contrib[idx];
-        sdU = sdU + cc.x;
-        sdV = sdV + cc.y;
-    }
     const double2 ad = a.areaDen[v];
-    sdU = sdU / ad.y;
-    sdV = sdV / ad.y;
+    if (WEAK) {
+        // line integral around the dual triangle: the stress on edge s is the mean of its two cells; a cell
+        // that does not exist is the junk cell with zero stress (only at vertices that are never solved)
+        double s11V = 0.0, s22V = 0.0, s12V = 0.0;
+#pragma unroll
+        for (int s = 0; s < D; s++) {
+            const size_t q = (size_t)s * a.nVp + v;
+            const int c = a.cov[q];
+            if (c >= 0) {
+                const double2 x = a.sigW[c];
+                s11V = s11V + x.x; s22V = s22V + x.y; s12V = s12V + a.sigW12[c];
+            }
+            const int2 ec = a.wEdgeC[q];
+            double e11 = 0.0, e22 = 0.0, e12 = 0.0;
+            if (ec.x >= 0) { const double2 x = a.sigW[ec.x]; e11 = e11 + x.x; e22 = e22 + x.y; e12 = e12 + a.sigW12[ec.x]; }
+            if (ec.y >= 0) { const double2 x = a.sigW[ec.y]; e11 = e11 + x.x; e22 = e22 + x.y; e12 = e12 + a.sigW12[ec.y]; }
+            e11 = e11 / 2.0; e22 = e22 / 2.0; e12 = e12 / 2.0;
+            const double2 nv = a.wNt[q];
+            const double dc = a.wDc[q];
+            sdU = sdU + (e11 * nv.x + e12 * nv.y) * dc;
+            sdV = sdV + (e22 * nv.y + e12 * nv.x) * dc;
+        }
+        s11V = s11V / (double)D; s22V = s22V / (double)D; s12V = s12V / (double)D;
+        const double areaT = a.wAreaT[v], t = a.wTanV[v];
+        sdU = sdU / areaT;
+        sdV = sdV / areaT;
+        sdU = sdU - (t * s12V * 2.0) / a.wRadius;
+        sdV = sdV + (t * (s11V - s22V)) / a.wRadius;
+    } else {
+#pragma unroll
+        for (int s = 0; s < D; s++) {
+            const int idx = a.gidx[(size_t)s * a.nVp + v];
+            double2 cc = make_double2(0.0, 0.0);
+            if (idx >= 0) cc = a.contrib[idx];
+            sdU = sdU + cc.x;
+            sdV = sdV + cc.y;
+        }
+        sdU = sdU / ad.y;
+        sdV = sdV / ad.y;
+    }
 
     const double2 w = a.uv[v];
     double coef = 0.0;
@@ -513,19 +551,24 @@ int launch_cell_m(const CellArgs &a, bool metric, int cr, bool diag, int phase, 
     return metric ? launch_cell_cr<M, true>(a, cr, diag, phase, s) : launch_cell_cr<M, false>(a, cr, diag, phase, s);
 }
 
-template <int D, int CR>
-int launch_vertex_d(const VertexArgs &a, bool diag, cudaStream_t s)
+template <int D, int CR, bool WEAK>
+int launch_vertex_w(const VertexArgs &a, bool diag, cudaStream_t s)
 {
     const int block = 256;
     const int grid = (a.nVerticesSolve + block - 1) / block;
     if (a.list) {
-        if (diag) evp_vertex_kernel<D, CR, true, true><<<grid, block, 0, s>>>(a);
-        else      evp_vertex_kernel<D, CR, false, true><<<grid, block, 0, s>>>(a);
+        if (diag) evp_vertex_kernel<D, CR, true, true, WEAK><<<grid, block, 0, s>>>(a);
+        else      evp_vertex_kernel<D, CR, false, true, WEAK><<<grid, block, 0, s>>>(a);
     } else {
-        if (diag) evp_vertex_kernel<D, CR, true, false><<<grid, block, 0, s>>>(a);
-        else      evp_vertex_kernel<D, CR, false, false><<<grid, block, 0, s>>>(a);
+        if (diag) evp_vertex_kernel<D, CR, true, false, WEAK><<<grid, block, 0, s>>>(a);
+        else      evp_vertex_kernel<D, CR, false, false, WEAK><<<grid, block, 0, s>>>(a);
     }
     return 0;
+}
+template <int D, int CR>
+int launch_vertex_d(const VertexArgs &a, bool diag, cudaStream_t s)
+{
+    return a.sigW ? launch_vertex_w<D, CR, true>(a, diag, s) : launch_vertex_w<D, CR, false>(a, diag, s);
 }
 template <int D>
 int launch_vertex_cr(const VertexArgs &a, int cr, bool diag, cudaStream_t s)
@@ -545,8 +588,16 @@ static int enqueue_cell_phase(evp_handle *h, bool diag, int phase, cudaStream_t 
 int evp_enqueue_cell_pass(evp_handle *h, bool diag, cudaStream_t s)
 {
     if (h->nCells == 0) return EVP_OK;
-    if (!h->opt.average_variational_strain) return enqueue_cell_phase(h, diag, 0, s);
     int rc;
+    if (h->opt.strain_scheme == EVP_SCHEME_WEAK) {
+        if ((rc = evp_enqueue_weak_cell_pass(h, diag, s))) return rc;
+        if (h->opt.stress_divergence_scheme == EVP_SCHEME_WEAK) return EVP_OK;
+        // weak strain + variational divergence: interpolate_strains_weak_to_variational, then the stress /
+        // divergence half of the cell kernel from the stored strain
+        if ((rc = evp_enqueue_weak_to_variational(h, s))) return rc;
+        return enqueue_cell_phase(h, diag, 2, s);
+    }
+    if (!h->opt.average_variational_strain) return enqueue_cell_phase(h, diag, 0, s);
     if ((rc = enqueue_cell_phase(h, diag, 1, s))) return rc;
     if (h->nVerticesSolve) {
         const int block = 256, grid = (h->nVerticesSolve + block - 1) / block;
@@ -599,6 +650,9 @@ int evp_enqueue_vertex_pass(evp_handle *h, bool diag, cudaStream_t s, const int 
     a.dte = h->opt.elasticTimeStep; a.dtDyn = h->opt.dynamicsTimeStep;
     a.beta = h->opt.numericalInertiaCoefficient;
     a.useOcean = h->opt.use_ocean_stress; a.oceanType = h->opt.ocean_stress_type;
+    const bool weak = h->opt.stress_divergence_scheme == EVP_SCHEME_WEAK;
+    a.cov = h->d.cov; a.wEdgeC = h->d.wEdgeC; a.wNt = h->d.wNt; a.wDc = h->d.wDc; a.wTanV = h->d.wTanV;
+    a.wAreaT = h->d.wAreaT; a.sigW = weak ? h->d.sigW : nullptr; a.sigW12 = h->d.sigW12; a.wRadius = h->d.wRadius;
     const int cr = h->opt.constitutive_relation_type;
     switch (h->D) {
     case 3: launch_vertex_cr<3>(a, cr, diag, s); break;
@@ -667,7 +721,9 @@ int evp_enqueue_subcycles(evp_handle *h, int nSub, cudaStream_t s)
 int evp_count_launches(evp_handle *h, int nSub)
 {
     const int sb = (h->opt.use_special_boundaries_velocity && h->d.nSB) ? 2 : 0;
-    const int avg = h->opt.average_variational_strain ? (h->nCells ? 1 : 0) + (h->nVerticesSolve ? 1 : 0) : 0;
+    int avg = h->opt.average_variational_strain ? (h->nCells ? 1 : 0) + (h->nVerticesSolve ? 1 : 0) : 0;
+    if (h->opt.strain_scheme == EVP_SCHEME_WEAK)      // weak/weak: 1 cell kernel; weak/variational: 1 + 2 + phase 2
+        avg = h->opt.stress_divergence_scheme == EVP_SCHEME_WEAK ? 0 : (h->nCells ? 2 : 0) + (h->nVerticesSolve ? 1 : 0);
     const int perSub = avg + (h->nCells ? 1 : 0) + (h->nVerticesSolve ? 1 : 0) + (evp_halo_boundary_count(h) ? 1 : 0) +
                        evp_halo_launches(h) + sb;
     return sb + nSub * perSub;

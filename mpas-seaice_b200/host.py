@@ -25,6 +25,7 @@ _lib = None
 
 CR = {"evp": 1, "evp_revised": 2, "linear": 3, "none": 4}
 OCEAN = {"quadratic": 1, "linear": 2}
+SCHEME = {"variational": 1, "weak": 2}
 FLAG_PIN_HOST = 1
 FLAG_OVERLAP_HALO = 2
 
@@ -34,7 +35,7 @@ EXPORTS = (
     "evp_last_error_string", "evp_comm_get_unique_id", "evp_comm_init", "evp_set_halo", "evp_last_run_ms",
     "evp_launch_count", "evp_get_stream", "evp_device_bytes", "evp_set_use_graph", "evp_profile_passes",
     "evp_host_metric_terms", "evp_set_mesh_ext", "evp_set_state", "evp_pre_subcycle", "evp_post_subcycle",
-    "evp_fetch_pre", "evp_release_host_memory",
+    "evp_fetch_pre", "evp_release_host_memory", "evp_set_weak_mesh", "evp_update_weak_state", "evp_fetch_weak",
 )
 
 
@@ -55,7 +56,7 @@ class MeshDesc(C.Structure):
 class Options(C.Structure):
     _fields_ = ([(n, C.c_int) for n in ("constitutive_relation_type", "ocean_stress_type", "use_ocean_stress",
                                         "use_special_boundaries_velocity", "device", "flags",
-                                        "average_variational_strain")]
+                                        "average_variational_strain", "strain_scheme", "stress_divergence_scheme")]
                 + [(n, C.c_double) for n in ("elasticTimeStep", "dynamicsTimeStep", "dampingTimescale",
                                              "numericalInertiaCoefficient")])
 
@@ -119,6 +120,23 @@ class PreOutFields(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in PRE_OUT_FIELDS]
 
 
+# ---- weak operators ----
+WEAK_MESH_INT = ("edgesOnCell", "verticesOnEdge", "edgesOnVertex", "cellsOnEdge")
+WEAK_MESH_REAL = ("dvEdge", "dcEdge", "areaCell", "areaTriangle", "normalVectorPolygon", "normalVectorTriangle",
+                  "latCellRotated", "latVertexRotated")
+WEAK_FIELDS = ("stress11Weak", "stress22Weak", "stress12Weak", "strain11Weak", "strain22Weak", "strain12Weak",
+               "replacementPressureWeak")
+
+
+class WeakMesh(C.Structure):
+    _fields_ = ([("nEdges", C.c_int), ("sphere_radius", C.c_double)]
+                + [(n, C.c_void_p) for n in WEAK_MESH_INT + WEAK_MESH_REAL])
+
+
+class WeakFields(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in WEAK_FIELDS]
+
+
 def load_library(path: str | None = None):
     """dlopen libevp_b200.so; raises EvpError (never falls back) when it has not been built."""
     global _lib
@@ -166,6 +184,8 @@ def make_options(opts: dict, device: int = -1, pin_host: bool = False) -> Option
     o.device = device
     o.flags = (FLAG_PIN_HOST if pin_host else 0) | (FLAG_OVERLAP_HALO if opts.get("overlap_halo", False) else 0)
     o.average_variational_strain = int(opts.get("average_variational_strain", False))
+    o.strain_scheme = SCHEME[opts.get("strain_scheme", "variational")]
+    o.stress_divergence_scheme = SCHEME[opts.get("stress_divergence_scheme", "variational")]
     o.elasticTimeStep = opts["elasticTimeStep"]
     o.dynamicsTimeStep = opts["dynamicsTimeStep"]
     o.dampingTimescale = opts["dampingTimescale"]
@@ -352,6 +372,34 @@ class EvpSolver:
             out[n] = np.zeros(size, dtype=np.int32 if n in _PRE_OUT_INT else np.float64)
             setattr(of, n, _ptr(out[n], out[n].dtype.type))
         self._check(self.lib.evp_fetch_pre(self._h, C.byref(of)))
+        return out
+
+    # -- weak operators ------------------------------------------------------------------------------
+    def set_weak_mesh(self, mesh, weak):
+        """evp_set_weak_mesh; ``weak`` holds verticesOnEdge, edgesOnVertex, normalVectorPolygon/Triangle,
+        latCellRotated, latVertexRotated (weakmesh.weak_fields), the rest comes from ``mesh``."""
+        wm = WeakMesh()
+        wm.nEdges = int(mesh["nEdges"])
+        wm.sphere_radius = float(mesh["sphere_radius"]) if mesh["on_a_sphere"] else 0.0
+        self._weak_keep = []
+        for n in WEAK_MESH_INT + WEAK_MESH_REAL:
+            a = weak[n] if n in weak else mesh[n]
+            self._weak_keep.append(a)
+            setattr(wm, n, _ptr(a, np.int32 if n in WEAK_MESH_INT else np.float64))
+        self._check(self.lib.evp_set_weak_mesh(self._h, C.byref(wm)))
+
+    def update_weak_state(self, step):
+        wf = WeakFields()
+        for n in WEAK_FIELDS[:3]:
+            setattr(wf, n, _ptr(step[n], np.float64))
+        self._check(self.lib.evp_update_weak_state(self._h, C.byref(wf)))
+
+    def fetch_weak(self):
+        wf = WeakFields()
+        out = {n: np.zeros(self.nCells + 1) for n in WEAK_FIELDS}
+        for n in WEAK_FIELDS:
+            setattr(wf, n, _ptr(out[n], np.float64))
+        self._check(self.lib.evp_fetch_weak(self._h, C.byref(wf)))
         return out
 
     # -- multi-GPU -----------------------------------------------------------------------------

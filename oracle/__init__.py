@@ -127,6 +127,12 @@ def integration_factors(integration_type="dunavant", order=8):
 # subcycle
 # ---------------------------------------------------------------------------------------------
 
+_WEAK_STATIC = ("edgesOnCell", "verticesOnEdge", "edgesOnVertex", "cellsOnEdge", "dvEdge", "dcEdge", "areaTriangle",
+                "normalVectorPolygon", "normalVectorTriangle", "latCellRotated", "latVertexRotated")
+_WEAK_STEP = ("stress11Weak", "stress22Weak", "stress12Weak", "strain11Weak", "strain22Weak", "strain12Weak",
+              "replacementPressureWeak", "strain11Vertex", "strain22Vertex", "strain12Vertex")
+
+
 class _SubcycleArgs(C.Structure):
     _ints = ["nCells", "nVertices", "nVerticesSolve", "maxEdges", "vertexDegree"]
     _fields_ = (
@@ -150,6 +156,8 @@ class _SubcycleArgs(C.Structure):
                                      "uVelocity", "vVelocity", "stress11", "stress22", "stress12",
                                      "strain11", "strain22", "strain12", "replacementPressure",
                                      "stressDivergenceU", "stressDivergenceV", "oceanStressCoeff")]
+        + [("strainScheme", C.c_int), ("stressDivergenceScheme", C.c_int), ("sphere_radius", C.c_double)]
+        + [(n, C.c_void_p) for n in _WEAK_STATIC + _WEAK_STEP]
     )
 
 
@@ -202,6 +210,26 @@ def subcycle_velocity_solver(mesh, var, step, opts, n_subcycles):
     a.dynamicsTimeStep = opts["dynamicsTimeStep"]
     a.dampingTimescale = opts["dampingTimescale"]
     a.numericalInertiaCoefficient = opts.get("numericalInertiaCoefficient", 0.0)
+    # weak operators: opts strain_scheme / stress_divergence_scheme = 'weak'; the static fields come from
+    # var["weak"] (mpas_seaice_b200.weakmesh.weak_fields) or the mesh, the weak state from ``step``
+    scheme = {"variational": 1, "weak": 2}
+    a.strainScheme = scheme[opts.get("strain_scheme", "variational")]
+    a.stressDivergenceScheme = scheme[opts.get("stress_divergence_scheme", "variational")]
+    a.sphere_radius = 0.0
+    if a.strainScheme == 2:
+        a.sphere_radius = float(mesh.sphere_radius) if mesh.on_a_sphere else 0.0
+        weak = var["weak"]
+        for name in _WEAK_STATIC:
+            arr = weak[name] if name in weak else mesh[name]
+            assert arr.flags["C_CONTIGUOUS"]
+            keep.append(arr)
+            setattr(a, name, arr.ctypes.data)
+        nC, nV = mesh.nCells, mesh.nVertices
+        for name in _WEAK_STEP:
+            if name not in step:
+                step[name] = np.zeros((nV if name.endswith("Vertex") else nC) + 1)
+            keep.append(step[name])
+            setattr(a, name, step[name].ctypes.data)
     L.orc_subcycle_velocity_solver(C.byref(a), _i(n_subcycles))
     return step
 

@@ -371,6 +371,202 @@ void orc_set_special_boundaries_velocity(int nVertices, const int *vertexBoundar
     }
 }
 
+/* ==========================================================================================
+ * weak operators (src/shared/mpas_seaice_velocity_solver_weak.F): one stress point per cell
+ * ========================================================================================== */
+#define NV2(d, k, c, M) ((size_t)((d) - 1) + 2 * ((size_t)((k) - 1) + (size_t)(M) * (size_t)((c) - 1)))
+
+/* seaice_strain_tensor_weak (weak.F:112-253) */
+void orc_strain_tensor_weak(int nCells, int maxEdges, const int *nEdgesOnCell, const int *verticesOnCell,
+                            const int *edgesOnCell, const int *verticesOnEdge, const double *dvEdge,
+                            const double *areaCell, double sphere_radius, const int *solveStress,
+                            const double *uVelocity, const double *vVelocity,
+                            const double *normalVectorPolygon, const double *latCellRotated,
+                            double *strain11, double *strain22, double *strain12)
+{
+    const int M = maxEdges;
+    double sphereRadius = sphere_radius;
+    if (sphereRadius == 0.0) sphereRadius = 1.0;
+    for (int iCell = 1; iCell <= nCells; iCell++) {
+        strain11[iCell - 1] = 0.0;
+        strain22[iCell - 1] = 0.0;
+        strain12[iCell - 1] = 0.0;
+        if (solveStress[iCell - 1] == 1) {
+            double uCellCentre = 0.0, vCellCentre = 0.0;
+            for (int k = 1; k <= nEdgesOnCell[iCell - 1]; k++) {
+                int iVertex = verticesOnCell[IDX2(k, iCell, M)];
+                uCellCentre = uCellCentre + uVelocity[iVertex - 1];
+                vCellCentre = vCellCentre + vVelocity[iVertex - 1];
+                const int iEdge = edgesOnCell[IDX2(k, iCell, M)];
+                double uVelocityEdge = 0.0, vVelocityEdge = 0.0;
+                for (int e = 1; e <= 2; e++) {
+                    iVertex = verticesOnEdge[IDX2(e, iEdge, 2)];
+                    uVelocityEdge = uVelocityEdge + uVelocity[iVertex - 1];
+                    vVelocityEdge = vVelocityEdge + vVelocity[iVertex - 1];
+                }
+                uVelocityEdge = uVelocityEdge / 2.0;
+                vVelocityEdge = vVelocityEdge / 2.0;
+                const double nx = normalVectorPolygon[NV2(1, k, iCell, M)], ny = normalVectorPolygon[NV2(2, k, iCell, M)];
+                strain11[iCell - 1] = strain11[iCell - 1] + uVelocityEdge * nx * dvEdge[iEdge - 1];
+                strain22[iCell - 1] = strain22[iCell - 1] + vVelocityEdge * ny * dvEdge[iEdge - 1];
+                strain12[iCell - 1] = strain12[iCell - 1] + 0.5 * (uVelocityEdge * ny + vVelocityEdge * nx) * dvEdge[iEdge - 1];
+            }
+            uCellCentre = uCellCentre / (double)nEdgesOnCell[iCell - 1];
+            vCellCentre = vCellCentre / (double)nEdgesOnCell[iCell - 1];
+            strain11[iCell - 1] = strain11[iCell - 1] / areaCell[iCell - 1];
+            strain22[iCell - 1] = strain22[iCell - 1] / areaCell[iCell - 1];
+            strain12[iCell - 1] = strain12[iCell - 1] / areaCell[iCell - 1];
+            strain11[iCell - 1] = strain11[iCell - 1] - (vCellCentre * tan(latCellRotated[iCell - 1])) / sphereRadius;
+            strain12[iCell - 1] = strain12[iCell - 1] + (uCellCentre * tan(latCellRotated[iCell - 1]) * 0.5) / sphereRadius;
+        }
+    }
+}
+
+/* seaice_stress_tensor_weak (weak.F:267-385): unlike the variational routine it zeroes the stress of
+ * cells that are not solved, and it never touches replacementPressure of those cells */
+void orc_stress_tensor_weak(int nCells, const int *solveStress, int constitutiveRelationType,
+                            double dtElastic, double dampingTimescale, const double *icePressure,
+                            const double *strain11, const double *strain22, const double *strain12,
+                            double *stress11, double *stress22, double *stress12, double *replacementPressure)
+{
+    if (constitutiveRelationType != EVP && constitutiveRelationType != EVP_REVISED && constitutiveRelationType != LINEAR)
+        return;
+    for (int i = 0; i < nCells; i++) {
+        if (solveStress[i] == 1) {
+            if (constitutiveRelationType == EVP)
+                evp_constitutive_relation(&stress11[i], &stress22[i], &stress12[i], strain11[i], strain22[i], strain12[i],
+                                          icePressure[i], &replacementPressure[i], dtElastic, dampingTimescale);
+            else if (constitutiveRelationType == EVP_REVISED)
+                evp_constitutive_relation_revised(&stress11[i], &stress22[i], &stress12[i], strain11[i], strain22[i],
+                                                  strain12[i], icePressure[i], &replacementPressure[i]);
+            else {
+                stress11[i] = 1.0 * strain11[i];
+                stress22[i] = 1.0 * strain22[i];
+                stress12[i] = 1.0 * strain12[i];
+            }
+        } else {
+            stress11[i] = 0.0;
+            stress22[i] = 0.0;
+            stress12[i] = 0.0;
+        }
+    }
+}
+
+/* seaice_stress_divergence_weak (weak.F:493-640) */
+void orc_stress_divergence_weak(int nVerticesSolve, int vertexDegree, const int *cellsOnVertex, const int *edgesOnVertex,
+                                const int *cellsOnEdge, const double *dcEdge, const double *areaTriangle,
+                                double sphere_radius, const int *solveVelocity,
+                                const double *stress11, const double *stress22, const double *stress12,
+                                const double *normalVectorTriangle, const double *latVertexRotated,
+                                double *stressDivergenceU, double *stressDivergenceV)
+{
+    const int D = vertexDegree;
+    double sphereRadius = sphere_radius;
+    if (sphereRadius == 0.0) sphereRadius = 1.0;
+    for (int iVertex = 1; iVertex <= nVerticesSolve; iVertex++) {
+        stressDivergenceU[iVertex - 1] = 0.0;
+        stressDivergenceV[iVertex - 1] = 0.0;
+        if (solveVelocity[iVertex - 1] == 1) {
+            double stress11Vertex = 0.0, stress22Vertex = 0.0, stress12Vertex = 0.0;
+            for (int k = 1; k <= D; k++) {
+                int iCell = cellsOnVertex[IDX2(k, iVertex, D)];
+                stress11Vertex = stress11Vertex + stress11[iCell - 1];
+                stress22Vertex = stress22Vertex + stress22[iCell - 1];
+                stress12Vertex = stress12Vertex + stress12[iCell - 1];
+                const int iEdge = edgesOnVertex[IDX2(k, iVertex, D)];
+                double stress11Edge = 0.0, stress22Edge = 0.0, stress12Edge = 0.0;
+                for (int e = 1; e <= 2; e++) {
+                    iCell = cellsOnEdge[IDX2(e, iEdge, 2)];
+                    stress11Edge = stress11Edge + stress11[iCell - 1];
+                    stress22Edge = stress22Edge + stress22[iCell - 1];
+                    stress12Edge = stress12Edge + stress12[iCell - 1];
+                }
+                stress11Edge = stress11Edge / 2.0;
+                stress22Edge = stress22Edge / 2.0;
+                stress12Edge = stress12Edge / 2.0;
+                const double nx = normalVectorTriangle[NV2(1, k, iVertex, D)], ny = normalVectorTriangle[NV2(2, k, iVertex, D)];
+                stressDivergenceU[iVertex - 1] = stressDivergenceU[iVertex - 1] +
+                    (stress11Edge * nx + stress12Edge * ny) * dcEdge[iEdge - 1];
+                stressDivergenceV[iVertex - 1] = stressDivergenceV[iVertex - 1] +
+                    (stress22Edge * ny + stress12Edge * nx) * dcEdge[iEdge - 1];
+            }
+            stress11Vertex = stress11Vertex / (double)D;
+            stress22Vertex = stress22Vertex / (double)D;
+            stress12Vertex = stress12Vertex / (double)D;
+            stressDivergenceU[iVertex - 1] = stressDivergenceU[iVertex - 1] / areaTriangle[iVertex - 1];
+            stressDivergenceV[iVertex - 1] = stressDivergenceV[iVertex - 1] / areaTriangle[iVertex - 1];
+            stressDivergenceU[iVertex - 1] = stressDivergenceU[iVertex - 1] -
+                (tan(latVertexRotated[iVertex - 1]) * stress12Vertex * 2.0) / sphereRadius;
+            stressDivergenceV[iVertex - 1] = stressDivergenceV[iVertex - 1] +
+                (tan(latVertexRotated[iVertex - 1]) * (stress11Vertex - stress22Vertex)) / sphereRadius;
+        }
+    }
+}
+
+/* interpolate_strains_weak_to_variational (velocity_solver.F:2877-2972); strainXXVertex are work arrays
+ * (nVertices+1) that keep whatever they held at the halo vertices, as in the reference */
+void orc_interpolate_strains_weak_to_variational(int nCells, int nVerticesSolve, int vertexDegree, int maxEdges,
+                                                 const int *nEdgesOnCell, const int *verticesOnCell,
+                                                 const int *cellsOnVertex, const double *areaCell,
+                                                 const double *strain11weak, const double *strain22weak,
+                                                 const double *strain12weak,
+                                                 double *strain11Vertex, double *strain22Vertex, double *strain12Vertex,
+                                                 double *strain11var, double *strain22var, double *strain12var)
+{
+    const int M = maxEdges, D = vertexDegree;
+    for (int iVertex = 1; iVertex <= nVerticesSolve; iVertex++) {
+        double denom = 0.0;
+        strain11Vertex[iVertex - 1] = 0.0;
+        strain22Vertex[iVertex - 1] = 0.0;
+        strain12Vertex[iVertex - 1] = 0.0;
+        for (int k = 1; k <= D; k++) {
+            const int iCell = cellsOnVertex[IDX2(k, iVertex, D)];
+            if (iCell >= 1 && iCell <= nCells) {
+                strain11Vertex[iVertex - 1] = strain11Vertex[iVertex - 1] + areaCell[iCell - 1] * strain11weak[iCell - 1];
+                strain22Vertex[iVertex - 1] = strain22Vertex[iVertex - 1] + areaCell[iCell - 1] * strain22weak[iCell - 1];
+                strain12Vertex[iVertex - 1] = strain12Vertex[iVertex - 1] + areaCell[iCell - 1] * strain12weak[iCell - 1];
+                denom = denom + areaCell[iCell - 1];
+            }
+        }
+        strain11Vertex[iVertex - 1] = strain11Vertex[iVertex - 1] / denom;
+        strain22Vertex[iVertex - 1] = strain22Vertex[iVertex - 1] / denom;
+        strain12Vertex[iVertex - 1] = strain12Vertex[iVertex - 1] / denom;
+    }
+    for (int iCell = 1; iCell <= nCells; iCell++) {
+        for (int k = 1; k <= nEdgesOnCell[iCell - 1]; k++) {
+            const int iVertex = verticesOnCell[IDX2(k, iCell, M)];
+            strain11var[IDX2(k, iCell, M)] = strain11Vertex[iVertex - 1];
+            strain22var[IDX2(k, iCell, M)] = strain22Vertex[iVertex - 1];
+            strain12var[IDX2(k, iCell, M)] = strain12Vertex[iVertex - 1];
+        }
+    }
+}
+
+/* seaice_final_divergence_shear_weak (weak.F:651-751).  NOTE the reference assigns the WHOLE work array
+ * ("Delta = sqrt(...)", weak.F:729) inside the cell loop, so after the loop every Delta(i) holds the value of
+ * the last owned cell; ridgeShear is computed from that.  Restated as written. */
+void orc_final_divergence_shear_weak(int nCellsSolve, const double *strain11, const double *strain22,
+                                     const double *strain12, double *divergence, double *shear,
+                                     double *ridgeConvergence, double *ridgeShear)
+{
+    double Delta = 0.0;
+    for (int i = 0; i < nCellsSolve; i++) {
+        const double strainDivergence = strain11[i] + strain22[i];
+        const double strainTension = strain11[i] - strain22[i];
+        const double strainShearing = strain12[i] * 2.0;
+        Delta = sqrt(strainDivergence * strainDivergence +
+                     (strainTension * strainTension + strainShearing * strainShearing) / eccentricitySquared);
+        divergence[i] = strainDivergence;
+        shear[i] = sqrt(strainTension * strainTension + strainShearing * strainShearing);
+    }
+    if (ridgeConvergence) {
+        for (int i = 0; i < nCellsSolve; i++) {
+            ridgeConvergence[i] = -fmin(divergence[i], 0.0);
+            ridgeShear[i] = 0.5 * (Delta - fabs(divergence[i]));
+        }
+    }
+}
+
 /* The argument block of one dynamics step of the subcycle; mirrors module seaice_mesh_pool
  * (src/shared/mpas_seaice_mesh_pool.F:23-57) plus the host-side vertex fields of a8/a9. */
 typedef struct {
@@ -391,6 +587,14 @@ typedef struct {
     double *uVelocity, *vVelocity, *stress11, *stress22, *stress12;
     double *strain11, *strain22, *strain12, *replacementPressure;
     double *stressDivergenceU, *stressDivergenceV, *oceanStressCoeff;
+    /* weak operators (config_strain_scheme / config_stress_divergence_scheme = 'weak'); 1 = variational, 2 = weak */
+    int strainScheme, stressDivergenceScheme;
+    double sphere_radius;
+    const int *edgesOnCell, *verticesOnEdge, *edgesOnVertex, *cellsOnEdge;
+    const double *dvEdge, *dcEdge, *areaTriangle, *normalVectorPolygon, *normalVectorTriangle;
+    const double *latCellRotated, *latVertexRotated;
+    double *stress11Weak, *stress22Weak, *stress12Weak, *strain11Weak, *strain22Weak, *strain12Weak;
+    double *replacementPressureWeak, *strain11Vertex, *strain22Vertex, *strain12Vertex;
 } orc_subcycle_args;
 
 static void special_boundaries(const orc_subcycle_args *a)
@@ -409,22 +613,46 @@ static void special_boundaries(const orc_subcycle_args *a)
  * (:2606-2863, variational/variational branch).  Single block, so the halo exchange is a no-op. */
 void orc_single_subcycle(const orc_subcycle_args *a)
 {
-    orc_strain_tensor_variational(a->nCells, a->maxEdges, a->nEdgesOnCell, a->verticesOnCell, a->solveStress,
-                                  a->uVelocity, a->vVelocity, a->basisGradientU, a->basisGradientV,
-                                  a->tanLatVertexRotatedOverRadius, a->strain11, a->strain22, a->strain12);
-    if (a->averageVariationalStrains)
+    const int weakStrain = a->strainScheme == 2, weakDivergence = a->stressDivergenceScheme == 2;
+    /* seaice_internal_stress (velocity_solver.F:2606-2863) */
+    if (weakStrain)
+        orc_strain_tensor_weak(a->nCells, a->maxEdges, a->nEdgesOnCell, a->verticesOnCell, a->edgesOnCell,
+                               a->verticesOnEdge, a->dvEdge, a->areaCell, a->sphere_radius, a->solveStress,
+                               a->uVelocity, a->vVelocity, a->normalVectorPolygon, a->latCellRotated,
+                               a->strain11Weak, a->strain22Weak, a->strain12Weak);
+    else
+        orc_strain_tensor_variational(a->nCells, a->maxEdges, a->nEdgesOnCell, a->verticesOnCell, a->solveStress,
+                                      a->uVelocity, a->vVelocity, a->basisGradientU, a->basisGradientV,
+                                      a->tanLatVertexRotatedOverRadius, a->strain11, a->strain22, a->strain12);
+    if (!weakStrain && a->averageVariationalStrains)
         orc_average_strains_on_vertex(a->nCells, a->nVerticesSolve, a->vertexDegree, a->maxEdges, a->cellsOnVertex,
                                       a->cellVerticesAtVertex, a->areaCell, a->strain11, a->strain22, a->strain12);
-    orc_stress_tensor_variational(a->nCells, a->maxEdges, a->nEdgesOnCell, a->solveStress,
-                                  a->constitutiveRelationType, a->elasticTimeStep, a->dampingTimescale,
-                                  a->icePressure, a->strain11, a->strain22, a->strain12,
-                                  a->stress11, a->stress22, a->stress12, a->replacementPressure);
-    orc_stress_divergence_variational(a->nVerticesSolve, a->vertexDegree, a->maxEdges, a->nEdgesOnCell,
-                                      a->cellsOnVertex, a->cellVerticesAtVertex, a->solveVelocity,
-                                      a->stress11, a->stress22, a->stress12,
-                                      a->basisIntegralsU, a->basisIntegralsV, a->basisIntegralsMetric,
-                                      a->variationalDenominator, a->tanLatVertexRotatedOverRadius,
-                                      a->stressDivergenceU, a->stressDivergenceV);
+    if (weakStrain && !weakDivergence)
+        orc_interpolate_strains_weak_to_variational(a->nCells, a->nVerticesSolve, a->vertexDegree, a->maxEdges,
+                                                    a->nEdgesOnCell, a->verticesOnCell, a->cellsOnVertex, a->areaCell,
+                                                    a->strain11Weak, a->strain22Weak, a->strain12Weak,
+                                                    a->strain11Vertex, a->strain22Vertex, a->strain12Vertex,
+                                                    a->strain11, a->strain22, a->strain12);
+    if (weakDivergence) {
+        orc_stress_tensor_weak(a->nCells, a->solveStress, a->constitutiveRelationType, a->elasticTimeStep,
+                               a->dampingTimescale, a->icePressure, a->strain11Weak, a->strain22Weak, a->strain12Weak,
+                               a->stress11Weak, a->stress22Weak, a->stress12Weak, a->replacementPressureWeak);
+        orc_stress_divergence_weak(a->nVerticesSolve, a->vertexDegree, a->cellsOnVertex, a->edgesOnVertex,
+                                   a->cellsOnEdge, a->dcEdge, a->areaTriangle, a->sphere_radius, a->solveVelocity,
+                                   a->stress11Weak, a->stress22Weak, a->stress12Weak, a->normalVectorTriangle,
+                                   a->latVertexRotated, a->stressDivergenceU, a->stressDivergenceV);
+    } else {
+        orc_stress_tensor_variational(a->nCells, a->maxEdges, a->nEdgesOnCell, a->solveStress,
+                                      a->constitutiveRelationType, a->elasticTimeStep, a->dampingTimescale,
+                                      a->icePressure, a->strain11, a->strain22, a->strain12,
+                                      a->stress11, a->stress22, a->stress12, a->replacementPressure);
+        orc_stress_divergence_variational(a->nVerticesSolve, a->vertexDegree, a->maxEdges, a->nEdgesOnCell,
+                                          a->cellsOnVertex, a->cellVerticesAtVertex, a->solveVelocity,
+                                          a->stress11, a->stress22, a->stress12,
+                                          a->basisIntegralsU, a->basisIntegralsV, a->basisIntegralsMetric,
+                                          a->variationalDenominator, a->tanLatVertexRotatedOverRadius,
+                                          a->stressDivergenceU, a->stressDivergenceV);
+    }
     orc_ocean_stress_coefficient(a->nVerticesSolve, a->nVertices, a->useOceanStress, a->oceanStressType,
                                  a->solveVelocity, a->iceAreaVertex, a->uOceanVelocityVertex, a->vOceanVelocityVertex,
                                  a->uVelocity, a->vVelocity, a->oceanStressCoeff);
