@@ -48,6 +48,7 @@ module seaice_evp_b200
        seaice_evp_b200_update, &
        seaice_evp_b200_subcycle, &
        seaice_evp_b200_set_mesh_ext, &
+       seaice_evp_b200_set_weak_mesh, &
        seaice_evp_b200_step, &
        seaice_evp_b200_destroy
 #endif
@@ -195,7 +196,38 @@ module seaice_evp_b200
      type(c_ptr) :: oceanStressU
      type(c_ptr) :: oceanStressV
      type(c_ptr) :: oceanStressCoeff
+     type(c_ptr) :: principalStress1Weak
+     type(c_ptr) :: principalStress2Weak
   end type evp_post_fields
+
+  ! ---- struct evp_weak_mesh ----
+  type, bind(C), public :: evp_weak_mesh
+     integer(c_int) :: nEdges
+     real(c_double) :: sphere_radius
+     type(c_ptr) :: edgesOnCell
+     type(c_ptr) :: verticesOnEdge
+     type(c_ptr) :: edgesOnVertex
+     type(c_ptr) :: cellsOnEdge
+     type(c_ptr) :: dvEdge
+     type(c_ptr) :: dcEdge
+     type(c_ptr) :: areaCell
+     type(c_ptr) :: areaTriangle
+     type(c_ptr) :: normalVectorPolygon
+     type(c_ptr) :: normalVectorTriangle
+     type(c_ptr) :: latCellRotated
+     type(c_ptr) :: latVertexRotated
+  end type evp_weak_mesh
+
+  ! ---- struct evp_weak_fields ----
+  type, bind(C), public :: evp_weak_fields
+     type(c_ptr) :: stress11Weak
+     type(c_ptr) :: stress22Weak
+     type(c_ptr) :: stress12Weak
+     type(c_ptr) :: strain11Weak
+     type(c_ptr) :: strain22Weak
+     type(c_ptr) :: strain12Weak
+     type(c_ptr) :: replacementPressureWeak
+  end type evp_weak_fields
 
   ! ---- functions of include/evp_b200.h ----
   interface
@@ -318,6 +350,27 @@ module seaice_evp_b200
        integer(c_int) :: ierr
      end function evp_post_subcycle
 
+     function evp_set_weak_mesh(handle, mesh) bind(C, name="evp_set_weak_mesh") result(ierr)
+       import :: c_ptr, c_int, evp_weak_mesh
+       type(c_ptr), value :: handle
+       type(evp_weak_mesh), intent(in) :: mesh
+       integer(c_int) :: ierr
+     end function evp_set_weak_mesh
+
+     function evp_update_weak_state(handle, fields) bind(C, name="evp_update_weak_state") result(ierr)
+       import :: c_ptr, c_int, evp_weak_fields
+       type(c_ptr), value :: handle
+       type(evp_weak_fields), intent(in) :: fields
+       integer(c_int) :: ierr
+     end function evp_update_weak_state
+
+     function evp_fetch_weak(handle, fields) bind(C, name="evp_fetch_weak") result(ierr)
+       import :: c_ptr, c_int, evp_weak_fields
+       type(c_ptr), value :: handle
+       type(evp_weak_fields), intent(in) :: fields
+       integer(c_int) :: ierr
+     end function evp_fetch_weak
+
   end interface
 
   ! one block per rank (mesh_pool.F:98-105) <-> one handle <-> one GPU
@@ -349,10 +402,15 @@ contains
     call MPAS_pool_get_config(domain % configs, "config_strain_scheme", config_strain_scheme)
     call MPAS_pool_get_config(domain % configs, "config_stress_divergence_scheme", config_stress_divergence_scheme)
     call MPAS_pool_get_config(domain % configs, "config_average_variational_strain", config_average_variational_strain)
+    call MPAS_pool_get_config(domain % configs, "config_strain_scheme", config_strain_scheme)
+    call MPAS_pool_get_config(domain % configs, "config_stress_divergence_scheme", config_stress_divergence_scheme)
 
-    ! config_average_variational_strain is covered (it needs seaice_evp_b200_set_mesh_ext for areaCell)
-    supported = trim(config_strain_scheme) == "variational" .and. &
-                trim(config_stress_divergence_scheme) == "variational"
+    ! variational / variational (with or without config_average_variational_strain, which needs
+    ! seaice_evp_b200_set_mesh_ext for areaCell), weak / weak and weak strain + variational divergence (both need
+    ! seaice_evp_b200_set_weak_mesh) are all covered; the pkgVariational arrays must exist because evp_create
+    ! takes them, so a pure weak run without that package stays on the Fortran path
+    supported = trim(config_stress_divergence_scheme) == "variational" .or. &
+                trim(config_strain_scheme) == "weak"
 
   end function seaice_evp_b200_supported
 
@@ -397,7 +455,7 @@ contains
 
     type(MPAS_pool_type), pointer :: velocitySolverPool
     real(kind=RKIND), pointer :: elasticTimeStep, dynamicsTimeStep
-    character(len=strKIND), pointer :: config_ocean_stress_type
+    character(len=strKIND), pointer :: config_ocean_stress_type, config_strain_scheme, config_stress_divergence_scheme
     logical, pointer :: config_use_ocean_stress, config_use_special_boundaries_velocity, &
          config_average_variational_strain
     integer, pointer :: config_elastic_subcycle_number
@@ -426,8 +484,9 @@ contains
     options % device = -1                    ! the device the host selected (cudaSetDevice / CUDA_VISIBLE_DEVICES)
     options % flags = EVP_FLAG_PIN_HOST      ! MPAS pool arrays live at stable addresses
     options % average_variational_strain = merge(1, 0, config_average_variational_strain)
-    options % strain_scheme = EVP_SCHEME_VARIATIONAL             ! the weak schemes stay on the Fortran path in this
-    options % stress_divergence_scheme = EVP_SCHEME_VARIATIONAL  ! shim (seaice_evp_b200_supported); see INTEGRATION.md
+    options % strain_scheme = merge(EVP_SCHEME_WEAK, EVP_SCHEME_VARIATIONAL, trim(config_strain_scheme) == "weak")
+    options % stress_divergence_scheme = merge(EVP_SCHEME_WEAK, EVP_SCHEME_VARIATIONAL, &
+                                               trim(config_stress_divergence_scheme) == "weak")
     options % elasticTimeStep = elasticTimeStep
     options % dynamicsTimeStep = dynamicsTimeStep
     options % dampingTimescale = dampingTimescale
@@ -533,6 +592,7 @@ contains
     type(MPAS_pool_type), pointer :: velocitySolverPool, velocityVariationalPool, icestatePool
     type(evp_step_fields) :: f
     type(evp_options) :: options
+    type(evp_weak_fields) :: wf
 
     integer, dimension(:), pointer :: solveStress, solveVelocity
     real(kind=RKIND), dimension(:), pointer :: &
@@ -595,6 +655,11 @@ contains
 
     call evp_b200_check(evp_update_step(evpHandle, f), "evp_update_step")
 
+    if (options % stress_divergence_scheme == EVP_SCHEME_WEAK) then
+       call weak_state_pointers(domain, wf)
+       call evp_b200_check(evp_update_weak_state(evpHandle, wf), "evp_update_weak_state")
+    endif
+
   end subroutine seaice_evp_b200_update
 
 !|||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||
@@ -617,6 +682,8 @@ contains
 
     type(MPAS_pool_type), pointer :: velocitySolverPool, velocityVariationalPool
     type(evp_out_fields) :: o
+    type(evp_weak_fields) :: wf
+    character(len=strKIND), pointer :: config_strain_scheme
 
     integer, dimension(:), pointer :: solveStress, solveVelocity
     real(kind=RKIND), dimension(:), pointer :: &
@@ -669,6 +736,12 @@ contains
 
     call evp_b200_check(evp_fetch(evpHandle, o), "evp_fetch")
 
+    call MPAS_pool_get_config(domain % configs, "config_strain_scheme", config_strain_scheme)
+    if (trim(config_strain_scheme) == "weak") then
+       call weak_state_pointers(domain, wf)
+       call evp_b200_check(evp_fetch_weak(evpHandle, wf), "evp_fetch_weak")
+    endif
+
   end subroutine seaice_evp_b200_subcycle
 
 !|||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||
@@ -708,6 +781,96 @@ contains
     call evp_b200_check(evp_set_mesh_ext(evpHandle, ext), "evp_set_mesh_ext")
 
   end subroutine seaice_evp_b200_set_mesh_ext
+
+!|||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||
+!  seaice_evp_b200_set_weak_mesh
+!
+!> \brief Edge connectivity + normal vectors of the weak operators (once, after seaice_evp_b200_create and
+!>        after seaice_init_velocity_solver_weak filled normalVectorPolygon / normalVectorTriangle)
+!-----------------------------------------------------------------------
+
+  subroutine seaice_evp_b200_set_weak_mesh(domain)
+
+    type(domain_type), intent(inout) :: domain
+
+    type(MPAS_pool_type), pointer :: meshPool, velocityWeakPool
+    type(evp_weak_mesh) :: wm
+    integer, pointer :: nEdges
+    real(kind=RKIND), pointer :: sphere_radius
+    integer, dimension(:,:), pointer :: edgesOnCell, verticesOnEdge, edgesOnVertex, cellsOnEdge
+    real(kind=RKIND), dimension(:), pointer :: dvEdge, dcEdge, areaCell, areaTriangle, latCellRotated, latVertexRotated
+    real(kind=RKIND), dimension(:,:,:), pointer :: normalVectorPolygon, normalVectorTriangle
+
+    call MPAS_pool_get_subpool(domain % blocklist % structs, "mesh", meshPool)
+    call MPAS_pool_get_subpool(domain % blocklist % structs, "velocity_weak", velocityWeakPool)
+
+    call MPAS_pool_get_dimension(meshPool, "nEdges", nEdges)
+    call MPAS_pool_get_config(meshPool, "sphere_radius", sphere_radius)
+    call MPAS_pool_get_array(meshPool, "edgesOnCell", edgesOnCell)
+    call MPAS_pool_get_array(meshPool, "verticesOnEdge", verticesOnEdge)
+    call MPAS_pool_get_array(meshPool, "edgesOnVertex", edgesOnVertex)
+    call MPAS_pool_get_array(meshPool, "cellsOnEdge", cellsOnEdge)
+    call MPAS_pool_get_array(meshPool, "dvEdge", dvEdge)
+    call MPAS_pool_get_array(meshPool, "dcEdge", dcEdge)
+    call MPAS_pool_get_array(meshPool, "areaCell", areaCell)
+    call MPAS_pool_get_array(meshPool, "areaTriangle", areaTriangle)
+    call MPAS_pool_get_array(velocityWeakPool, "normalVectorPolygon", normalVectorPolygon)
+    call MPAS_pool_get_array(velocityWeakPool, "normalVectorTriangle", normalVectorTriangle)
+    call MPAS_pool_get_array(velocityWeakPool, "latCellRotated", latCellRotated)
+    call MPAS_pool_get_array(velocityWeakPool, "latVertexRotated", latVertexRotated)
+
+    wm % nEdges = nEdges
+    wm % sphere_radius = sphere_radius
+    wm % edgesOnCell = c_loc(edgesOnCell)
+    wm % verticesOnEdge = c_loc(verticesOnEdge)
+    wm % edgesOnVertex = c_loc(edgesOnVertex)
+    wm % cellsOnEdge = c_loc(cellsOnEdge)
+    wm % dvEdge = c_loc(dvEdge)
+    wm % dcEdge = c_loc(dcEdge)
+    wm % areaCell = c_loc(areaCell)
+    wm % areaTriangle = c_loc(areaTriangle)
+    wm % normalVectorPolygon = c_loc(normalVectorPolygon)
+    wm % normalVectorTriangle = c_loc(normalVectorTriangle)
+    wm % latCellRotated = c_loc(latCellRotated)
+    wm % latVertexRotated = c_loc(latVertexRotated)
+
+    call evp_b200_check(evp_set_weak_mesh(evpHandle, wm), "evp_set_weak_mesh")
+
+  end subroutine seaice_evp_b200_set_weak_mesh
+
+!|||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||
+!  weak_state_pointers
+!
+!> \brief The velocity_weak pool fields as evp_weak_fields (src/Registry.xml:3730-3745)
+!-----------------------------------------------------------------------
+
+  subroutine weak_state_pointers(domain, wf)
+
+    type(domain_type), intent(inout) :: domain
+    type(evp_weak_fields), intent(out) :: wf
+
+    type(MPAS_pool_type), pointer :: velocityWeakPool
+    real(kind=RKIND), dimension(:), pointer :: stress11, stress22, stress12, strain11, strain22, strain12, &
+         replacementPressure
+
+    call MPAS_pool_get_subpool(domain % blocklist % structs, "velocity_weak", velocityWeakPool)
+    call MPAS_pool_get_array(velocityWeakPool, "stress11", stress11)
+    call MPAS_pool_get_array(velocityWeakPool, "stress22", stress22)
+    call MPAS_pool_get_array(velocityWeakPool, "stress12", stress12)
+    call MPAS_pool_get_array(velocityWeakPool, "strain11", strain11)
+    call MPAS_pool_get_array(velocityWeakPool, "strain22", strain22)
+    call MPAS_pool_get_array(velocityWeakPool, "strain12", strain12)
+    call MPAS_pool_get_array(velocityWeakPool, "replacementPressure", replacementPressure)
+
+    wf % stress11Weak = c_loc(stress11)
+    wf % stress22Weak = c_loc(stress22)
+    wf % stress12Weak = c_loc(stress12)
+    wf % strain11Weak = c_loc(strain11)
+    wf % strain22Weak = c_loc(strain22)
+    wf % strain12Weak = c_loc(strain12)
+    wf % replacementPressureWeak = c_loc(replacementPressure)
+
+  end subroutine weak_state_pointers
 
 !|||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||||
 !  seaice_evp_b200_step
@@ -839,6 +1002,8 @@ contains
     o % oceanStressU = c_null_ptr
     o % oceanStressV = c_null_ptr
     o % oceanStressCoeff = c_null_ptr
+    o % principalStress1Weak = c_null_ptr
+    o % principalStress2Weak = c_null_ptr
 
     call evp_b200_check(evp_post_subcycle(evpHandle, o), "evp_post_subcycle")
 

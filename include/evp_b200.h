@@ -269,7 +269,10 @@ typedef struct {
 typedef struct {
     double *uVelocity;                  /* -> advection */
     double *vVelocity;
-    double *divergence;                 /* seaice_final_divergence_shear_variational, variational.F:1198-1330 */
+    double *divergence;                 /* seaice_final_divergence_shear_variational, variational.F:1198-1330, or with
+                                           the weak divergence scheme seaice_final_divergence_shear_weak, weak.F:651-751
+                                           (no unit change there, and ridgeShear from the last owned cell's Delta --
+                                           the reference assigns its whole Delta work array inside the loop, :729) */
     double *shear;
     double *ridgeConvergence;           /* -> ridging */
     double *ridgeShear;
@@ -280,6 +283,8 @@ typedef struct {
     double *oceanStressU;               /* (nVertices) as left by ocean_stress_final */
     double *oceanStressV;
     double *oceanStressCoeff;
+    double *principalStress1Weak;       /* (nCells) weak stress divergence scheme only (velocity_solver.F:3500-3515) */
+    double *principalStress2Weak;
 } evp_post_fields;
 
 int evp_set_mesh_ext(evp_handle *handle, const evp_mesh_ext *ext);

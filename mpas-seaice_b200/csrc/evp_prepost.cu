@@ -50,6 +50,8 @@ struct PreArgs {
     double2 *__restrict__ airCell;
     double2 *__restrict__ sig;
     double *__restrict__ sig12;
+    double2 *__restrict__ sigW;          // weak stress divergence scheme: stress11/22Weak, stress12Weak (else nullptr)
+    double *__restrict__ sigW12;
     double2 *__restrict__ uv, *__restrict__ uvInit, *__restrict__ areaDen, *__restrict__ massf, *__restrict__ air,
         *__restrict__ tilt, *__restrict__ ocnStress, *__restrict__ ocnVel;
 };
@@ -98,9 +100,14 @@ __global__ void __launch_bounds__(256) k_pre_cells(const PreArgs a)
     a.airCell[c] = air;
 
     if (!solve || a.coldStart) {
-        for (int j = 0; j < a.M; j++) {
-            a.sig[(size_t)j * a.nCp + c] = make_double2(0.0, 0.0);
-            a.sig12[(size_t)j * a.nCp + c] = 0.0;
+        if (a.sigW) {                     // init_subcycle_variables, weak branch (:2350-2365)
+            a.sigW[c] = make_double2(0.0, 0.0);
+            a.sigW12[c] = 0.0;
+        } else {
+            for (int j = 0; j < a.M; j++) {
+                a.sig[(size_t)j * a.nCp + c] = make_double2(0.0, 0.0);
+                a.sig12[(size_t)j * a.nCp + c] = 0.0;
+            }
         }
     }
 }
@@ -276,6 +283,46 @@ __global__ void __launch_bounds__(256) k_post_principal(const PostArgs a)
             }
         }
         a.principal[q] = p;
+    }
+}
+
+// seaice_final_divergence_shear_weak (weak.F:651-751) over the owned cells.  As written in the reference the
+// whole Delta work array is assigned inside the loop (:729), so ridgeShear sees the Delta of the LAST owned cell.
+__global__ void __launch_bounds__(256) k_post_div_shear_weak(int nCellsSolve, const double *__restrict__ e11,
+                                                             const double *__restrict__ e22, const double *__restrict__ e12,
+                                                             double *__restrict__ div, double *__restrict__ shear,
+                                                             double *__restrict__ ridgeConv, double *__restrict__ ridgeShear)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCellsSolve) return;
+    const int last = nCellsSolve - 1;
+    const double ld = e11[last] + e22[last], lt = e11[last] - e22[last], ls = e12[last] * 2.0;
+    const double Delta = sqrt(ld * ld + (lt * lt + ls * ls) / kEccentricitySquared);
+    const double sd = e11[c] + e22[c], st = e11[c] - e22[c], ss = e12[c] * 2.0;
+    div[c] = sd;
+    shear[c] = sqrt(st * st + ss * ss);
+    ridgeConv[c] = -fmin(sd, 0.0);
+    ridgeShear[c] = 0.5 * (Delta - fabs(sd));
+}
+
+// principal_stresses (velocity_solver.F:3565-3610) at the single stress point of every owned cell (:3500-3515)
+__global__ void __launch_bounds__(256) k_post_principal_weak(int nCellsSolve, const double2 *__restrict__ sigW,
+                                                             const double *__restrict__ sigW12,
+                                                             const double *__restrict__ repPW,
+                                                             double *__restrict__ p1, double *__restrict__ p2)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCellsSolve) return;
+    const double rep = repPW[c];
+    if (rep > kPuny) {
+        const double2 s = sigW[c];
+        const double s12 = sigW12[c];
+        const double sqrtContents = (s.x + s.y) * (s.x + s.y) - 4.0 * s.x * s.y + 4.0 * (s12 * s12);
+        p1[c] = (0.5 * (s.x + s.y) + 0.5 * sqrt(sqrtContents)) / rep;
+        p2[c] = (0.5 * (s.x + s.y) - 0.5 * sqrt(sqrtContents)) / rep;
+    } else {
+        p1[c] = 1.0e30;
+        p2[c] = 1.0e30;
     }
 }
 
@@ -545,6 +592,9 @@ extern "C" int evp_pre_subcycle(evp_handle *h, const evp_pre_fields *f, const ev
     if (rc) return rc;
     a.solveStress = d.solveStress; a.solveVel = d.solveVel; a.solveVelPrev = d.solveVelPrev;
     a.P = d.P; a.airCell = d.airCell; a.sig = d.sig; a.sig12 = d.sig12;
+    const bool weakDiv = h->opt.stress_divergence_scheme == EVP_SCHEME_WEAK;
+    if (weakDiv && !h->haveWeak) { evp_set_error("the weak schemes need evp_set_weak_mesh first"); return EVP_ERR_STATE; }
+    a.sigW = weakDiv ? d.sigW : nullptr; a.sigW12 = weakDiv ? d.sigW12 : nullptr;
     a.uv = d.uv; a.uvInit = d.uvInit; a.areaDen = d.areaDen; a.massf = d.massf; a.air = d.air; a.tilt = d.tilt;
     a.ocnStress = d.ocnStress; a.ocnVel = d.ocnVel;
 
@@ -560,6 +610,11 @@ extern "C" int evp_pre_subcycle(evp_handle *h, const evp_pre_fields *f, const ev
     EVP_CUDA(cudaMemsetAsync(d.repP, 0, rowBytes, s));
     EVP_CUDA(cudaMemsetAsync(d.sdiv, 0, sizeof(double2) * h->nVp, s));
     EVP_CUDA(cudaMemsetAsync(d.ocoef, 0, sizeof(double) * h->nVp, s));
+    if (h->haveWeak) {
+        EVP_CUDA(cudaMemsetAsync(d.eW11, 0, sizeof(double) * h->nCp, s));
+        EVP_CUDA(cudaMemsetAsync(d.eW22, 0, sizeof(double) * h->nCp, s));
+        EVP_CUDA(cudaMemsetAsync(d.eW12, 0, sizeof(double) * h->nCp, s));
+    }
     if ((rc = evp_halo_mark_masks(h))) return rc;
     // the velocity halo exchange that closes new_ice_velocities (:1281-1320)
     if ((rc = evp_halo_exchange(h, s, d.uv))) return rc;
@@ -589,7 +644,7 @@ extern "C" int evp_post_subcycle(evp_handle *h, const evp_post_fields *o)
     a.osFinal = d.osFinal; a.ocoef = d.ocoef;
 
     Stage st{(char *)d.stage, d.stageBytes, 0};
-    double *cellOut[6];
+    double *cellOut[8];
     for (auto &p : cellOut) { p = (double *)st.take(nC * 8 + 8); EVP_REQUIRE(p, "staging area exhausted"); }
     a.div = cellOut[0]; a.shear = cellOut[1]; a.ridgeConv = cellOut[2]; a.ridgeShear = cellOut[3];
     a.oscU = cellOut[4]; a.oscV = cellOut[5];
@@ -598,7 +653,27 @@ extern "C" int evp_post_subcycle(evp_handle *h, const evp_post_fields *o)
 
     const bool wantDiv = o->divergence || o->shear || o->ridgeConvergence || o->ridgeShear;
     const bool wantOcean = o->oceanStressCellU || o->oceanStressCellV || o->oceanStressU || o->oceanStressV || o->oceanStressCoeff;
-    if (wantDiv && nC) k_post_div_shear<<<grid_for(nC, 256), 256, 0, s>>>(a);
+    const bool weakDiv = h->opt.stress_divergence_scheme == EVP_SCHEME_WEAK;
+    if (weakDiv && !h->haveWeak) { evp_set_error("the weak schemes need evp_set_weak_mesh first"); return EVP_ERR_STATE; }
+    if (wantDiv && nC) {
+        if (weakDiv) {
+            // the reference leaves the halo entries untouched; here they read 0
+            for (int i = 0; i < 4; i++) EVP_CUDA(cudaMemsetAsync(cellOut[i], 0, nC * 8, s));
+            if (h->nCellsSolve)
+                k_post_div_shear_weak<<<grid_for(h->nCellsSolve, 256), 256, 0, s>>>(h->nCellsSolve, d.eW11, d.eW22, d.eW12, a.div,
+                                                                                   a.shear, a.ridgeConv, a.ridgeShear);
+        } else {
+            k_post_div_shear<<<grid_for(nC, 256), 256, 0, s>>>(a);
+        }
+    }
+    if ((o->principalStress1Weak || o->principalStress2Weak) && nC) {
+        if (!weakDiv) { evp_set_error("principalStress*Weak needs the weak stress divergence scheme"); return EVP_ERR_ARGUMENT; }
+        EVP_CUDA(cudaMemsetAsync(cellOut[6], 0, nC * 8, s));
+        EVP_CUDA(cudaMemsetAsync(cellOut[7], 0, nC * 8, s));
+        if (h->nCellsSolve)
+            k_post_principal_weak<<<grid_for(h->nCellsSolve, 256), 256, 0, s>>>(h->nCellsSolve, d.sigW, d.sigW12, d.repPW,
+                                                                               cellOut[6], cellOut[7]);
+    }
     if (wantOcean) {
         if (nV) k_post_ocean_vertices<<<grid_for(nV, 256), 256, 0, s>>>(a);
         EVP_CUDA(cudaGetLastError());
@@ -610,7 +685,7 @@ extern "C" int evp_post_subcycle(evp_handle *h, const evp_post_fields *o)
     struct { double *host; const double *dev; size_t n; } copies[] = {
         {o->divergence, a.div, nC}, {o->shear, a.shear, nC}, {o->ridgeConvergence, a.ridgeConv, nC},
         {o->ridgeShear, a.ridgeShear, nC}, {o->oceanStressCellU, a.oscU, nC}, {o->oceanStressCellV, a.oscV, nC},
-        {o->oceanStressCoeff, d.ocoef, nV},
+        {o->oceanStressCoeff, d.ocoef, nV}, {o->principalStress1Weak, cellOut[6], nC}, {o->principalStress2Weak, cellOut[7], nC},
     };
     for (auto &c : copies)
         if (c.host && c.n && (rc = evp_d2h(h, c.host, c.dev, c.n * 8))) return rc;

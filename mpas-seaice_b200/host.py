@@ -86,8 +86,10 @@ PRE_FIELDS = ("iceAreaCellInitial", "iceAreaCell", "totalMassCell", "icePressure
 _PRE_INT = {"landIceMask", "solveStress", "solveVelocity"}
 POST_FIELDS = ("uVelocity", "vVelocity", "divergence", "shear", "ridgeConvergence", "ridgeShear", "principalStress1Var",
                "principalStress2Var", "oceanStressCellU", "oceanStressCellV", "oceanStressU", "oceanStressV",
-               "oceanStressCoeff")
-_POST_CELL = {"divergence", "shear", "ridgeConvergence", "ridgeShear", "oceanStressCellU", "oceanStressCellV"}
+               "oceanStressCoeff", "principalStress1Weak", "principalStress2Weak")
+POST_FIELDS_VARIATIONAL = tuple(n for n in POST_FIELDS if not n.endswith("Weak"))
+_POST_CELL = {"divergence", "shear", "ridgeConvergence", "ridgeShear", "oceanStressCellU", "oceanStressCellV",
+              "principalStress1Weak", "principalStress2Weak"}
 _POST_CELL2D = {"principalStress1Var", "principalStress2Var"}
 POST_DEFAULT = ("uVelocity", "vVelocity", "divergence", "shear", "ridgeConvergence", "ridgeShear", "oceanStressCellU",
                 "oceanStressCellV")       # what the model needs every step: advection, ridging, coupler

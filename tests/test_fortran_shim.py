@@ -35,7 +35,7 @@ def _f_type(name):
 
 def test_bind_c_types_mirror_the_header():
     for name in ("evp_mesh_desc", "evp_options", "evp_step_fields", "evp_out_fields", "evp_mesh_ext", "evp_pre_fields",
-                 "evp_pre_options", "evp_post_fields"):
+                 "evp_pre_options", "evp_post_fields", "evp_weak_mesh", "evp_weak_fields"):
         assert _f_type(name) == _c_struct(name), name
 
 
@@ -55,7 +55,8 @@ def test_bound_names_are_exported(evp_lib):
 
 def test_enum_values_agree():
     for name in ("EVP_CR_EVP", "EVP_CR_EVP_REVISED", "EVP_CR_LINEAR", "EVP_CR_NONE", "EVP_OCEAN_QUADRATIC",
-                 "EVP_OCEAN_LINEAR", "EVP_FLAG_PIN_HOST", "EVP_FLAG_OVERLAP_HALO", "EVP_OK"):
+                 "EVP_OCEAN_LINEAR", "EVP_FLAG_PIN_HOST", "EVP_FLAG_OVERLAP_HALO", "EVP_SCHEME_VARIATIONAL",
+                 "EVP_SCHEME_WEAK", "EVP_OK"):
         c = int(re.search(name + r"\s*=\s*(\d+)", HDR).group(1))
         f = int(re.search(name + r"\s*=\s*(\d+)", F90).group(1))
         assert c == f, name

@@ -179,7 +179,7 @@ def test_full_dynamics_step_on_device(evp_lib, kind, state_kind):
     try:
         solver.pre_subcycle(_cells(mesh, state), cold_start=True)
         solver.run_subcycles(120)
-        got = solver.post_subcycle(names=host.POST_FIELDS)
+        got = solver.post_subcycle(names=host.POST_FIELDS_VARIATIONAL)
         inner = solver.fetch(names=("stress11", "stress22", "stress12"))
     finally:
         solver.destroy()
@@ -220,7 +220,7 @@ def test_state_stays_resident_across_steps(evp_lib):
             oracle.subcycle_velocity_solver(mesh, var, ref_step, opts, 40)
             solver.run_subcycles(40)
             ref = _post_reference(mesh, ref_step, opts, interior)
-            got = solver.post_subcycle(names=host.POST_FIELDS)
+            got = solver.post_subcycle(names=host.POST_FIELDS_VARIATIONAL)
             _compare_post(mesh, ref_step, ref, got)
             prev = dict(uVelocity=ref_step["uVelocity"], vVelocity=ref_step["vVelocity"],
                         stress11=ref_step["stress11"], stress22=ref_step["stress22"], stress12=ref_step["stress12"],

@@ -82,3 +82,52 @@ def test_invalid_scheme_combination_is_rejected(evp_lib):
     step, opts = common.step_case(mesh)
     with pytest.raises(host.EvpError, match="not a valid combination"):
         host.EvpSolver(mesh, var, dict(opts, strain_scheme="variational", stress_divergence_scheme="weak"))
+
+
+def test_weak_full_dynamics_step_on_device(evp_lib):
+    """pre-subcycle + weak subcycle + post-subcycle on the device: init_subcycle_variables' weak branch
+    (velocity_solver.F:2350-2365), seaice_final_divergence_shear_weak (weak.F:651-751, incl. its last-cell Delta) and
+    the weak principal stresses (velocity_solver.F:3500-3515)."""
+    import oracle
+    from mpas_seaice_b200 import host, synthetic, variational_init
+    mesh, var = common.mesh_case("ico4")
+    weak = weakmesh.weak_fields(mesh)
+    state = synthetic.sphere_state(mesh, "B")
+    nC, nV = mesh.nCells, mesh.nVertices
+    ref = oracle.pre_subcycle(mesh, state, 3600.0)
+    _, opts = synthetic.pre_subcycle(mesh, state, 3600.0)
+    opts = dict(opts, strain_scheme="weak", stress_divergence_scheme="weak")
+    oracle.subcycle_velocity_solver(mesh, dict(var, weak=weak), ref, opts, 60)
+    L = oracle.lib()
+    want = {k: np.zeros(nC + 1) for k in ("divergence", "shear", "ridgeConvergence", "ridgeShear", "p1", "p2")}
+    L.orc_final_divergence_shear_weak(nC, oracle._p(ref["strain11Weak"]), oracle._p(ref["strain22Weak"]),
+                                      oracle._p(ref["strain12Weak"]), oracle._p(want["divergence"]), oracle._p(want["shear"]),
+                                      oracle._p(want["ridgeConvergence"]), oracle._p(want["ridgeShear"]))
+    one = np.ones(nC + 1, dtype=np.int32)
+    L.orc_principal_stresses_variational(nC, 1, oracle._p(one), oracle._p(ref["stress11Weak"]), oracle._p(ref["stress22Weak"]),
+                                         oracle._p(ref["stress12Weak"]), oracle._p(ref["replacementPressureWeak"]),
+                                         oracle._p(want["p1"]), oracle._p(want["p2"]))
+    cells = synthetic.cell_inputs(state)
+    cells["icePressure"] = oracle.hibler_strength_unmasked(state, nC)         # same libm exp() on both sides
+    solver = host.EvpSolver(mesh, var, opts)
+    try:
+        solver.set_mesh_ext(mesh, variational_init.interior_vertex(mesh))
+        solver.set_weak_mesh(mesh, weak)
+        solver.pre_subcycle(cells, cold_start=True)
+        solver.run_subcycles(60)
+        got = solver.post_subcycle(names=("uVelocity", "vVelocity", "divergence", "shear", "ridgeConvergence", "ridgeShear",
+                                          "principalStress1Weak", "principalStress2Weak"))
+        wk = solver.fetch_weak()
+    finally:
+        solver.destroy()
+    vm = ref["solveVelocity"][:nV] == 1
+    assert vm.any() and not vm.all()
+    for k in ("uVelocity", "vVelocity"):
+        assert np.array_equal(got[k][:nV][vm], ref[k][:nV][vm]), k
+    for k in ("stress11Weak", "stress22Weak", "stress12Weak", "strain11Weak", "replacementPressureWeak"):
+        assert np.array_equal(wk[k][:nC], ref[k][:nC]), k
+    for k in ("divergence", "shear", "ridgeConvergence", "ridgeShear"):
+        assert np.array_equal(got[k][:nC], want[k][:nC]), k
+    assert np.array_equal(got["principalStress1Weak"][:nC], want["p1"][:nC])
+    assert np.array_equal(got["principalStress2Weak"][:nC], want["p2"][:nC])
+    assert np.abs(want["ridgeShear"]).max() > 0
