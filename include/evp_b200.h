@@ -165,6 +165,13 @@ int evp_set_options(evp_handle *handle, const evp_options *options);
 int evp_precompute_wachspress(evp_handle *handle, const double *xLocal, const double *yLocal,
                               int integrationType, int integrationOrder);
 
+/* Device version of seaice_init_velocity_solver_pwl (src/shared/mpas_seaice_velocity_solver_pwl.F:44-373,
+ * config_variational_basis = 'pwl'), incl. the 3x3 LU solves of src/shared/mpas_seaice_numerics.F:44-212.
+ * edgesOnCell (maxEdges, nCells), dvEdge (nEdges), areaCell (nCells).  Bit-identical to the non-FMA host
+ * evaluation; the gradients are dense, so the cell kernel takes its dense-gradient path. */
+int evp_precompute_pwl(evp_handle *handle, const double *xLocal, const double *yLocal, const int *edgesOnCell,
+                       const double *dvEdge, int nEdges, const double *areaCell);
+
 /* Copy the basis arrays back to host arrays in the Registry layout (any pointer may be NULL). */
 int evp_fetch_basis(evp_handle *handle, double *basisGradientU, double *basisGradientV,
                     double *basisIntegralsU, double *basisIntegralsV, double *basisIntegralsMetric);

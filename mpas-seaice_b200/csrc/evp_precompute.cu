@@ -259,6 +259,173 @@ __global__ void __launch_bounds__(64) k_wachspress(int nCells, size_t nCp, int M
         }
 }
 
+// ------------------------------------------------------------------------------------------
+// PWL basis (reference: src/shared/mpas_seaice_velocity_solver_pwl.F:44-373) with the 3x3 LU solve of
+// src/shared/mpas_seaice_numerics.F:44-212 (Crout, implicit scaling, partial pivoting).  Only + - * / sqrt
+// and comparisons: bit-identical to the non-FMA host evaluation.
+// ------------------------------------------------------------------------------------------
+__device__ void lu_decomposition3(double a[3][3], int indices[3])
+{
+    const double tiny = 1.0e-20;
+    double maxa[3];
+    for (int i = 0; i < 3; i++) {
+        double m = 0.0;
+        for (int j = 0; j < 3; j++) if (fabs(a[i][j]) > m) m = fabs(a[i][j]);
+        maxa[i] = 1.0 / m;
+    }
+    for (int j = 0; j < 3; j++) {
+        int jmax = j;
+        double best = maxa[j] * fabs(a[j][j]);
+        for (int i = j + 1; i < 3; i++) {          // maxloc: first maximum
+            const double val = maxa[i] * fabs(a[i][j]);
+            if (val > best) { best = val; jmax = i; }
+        }
+        if (j != jmax) {
+            for (int k = 0; k < 3; k++) { const double t = a[jmax][k]; a[jmax][k] = a[j][k]; a[j][k] = t; }
+            maxa[jmax] = maxa[j];
+        }
+        indices[j] = jmax;
+        if (a[j][j] == 0.0) a[j][j] = tiny;
+        for (int i = j + 1; i < 3; i++) a[i][j] = a[i][j] / a[j][j];
+        for (int i = j + 1; i < 3; i++)
+            for (int k = j + 1; k < 3; k++) a[i][k] = a[i][k] - a[i][j] * a[j][k];
+    }
+}
+__device__ void lu_back_substitution3(double a[3][3], const int indices[3], double b[3])
+{
+    int j = -1;
+    for (int i = 0; i < 3; i++) {
+        const int k = indices[i];
+        double sums = b[k];
+        b[k] = b[i];
+        if (j != -1) {
+            double dot = 0.0;
+            for (int l = j; l <= i - 1; l++) dot = dot + a[i][l] * b[l];
+            sums = sums - dot;
+        } else if (sums != 0.0) {
+            j = i;
+        }
+        b[i] = sums;
+    }
+    for (int i = 2; i >= 0; i--) {
+        double dot = 0.0;
+        for (int l = i + 1; l < 3; l++) dot = dot + a[i][l] * b[l];
+        b[i] = (b[i] - dot) / a[i][i];
+    }
+}
+__device__ void solve_linear_basis_system3(const double left[3][3], const double rhs[3], double sol[3])
+{
+    double a[3][3];
+    int indices[3];
+    for (int i = 0; i < 3; i++) {
+        sol[i] = rhs[i];
+        for (int j = 0; j < 3; j++) a[i][j] = left[i][j];
+    }
+    lu_decomposition3(a, indices);
+    lu_back_substitution3(a, indices, sol);
+}
+
+template <int M>
+__global__ void __launch_bounds__(64) k_pwl(int nCells, int Mh, const uint8_t *__restrict__ nEdges,
+                                             const double *__restrict__ xlAll, const double *__restrict__ ylAll,
+                                             const int *__restrict__ edgesOnCell, const double *__restrict__ dvEdge,
+                                             int nEdgesTotal, const double *__restrict__ areaCell,
+                                             double2 *__restrict__ G, double2 *__restrict__ Suv, double *__restrict__ Sm)
+{
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= nCells) return;
+    const int n = nEdges[cell];
+    if (n < 3 || n > M) return;
+    double xl[M], yl[M];
+    for (int i = 0; i < n; i++) { xl[i] = xlAll[(size_t)Mh * cell + i]; yl[i] = ylAll[(size_t)Mh * cell + i]; }
+    const double alphaPWL = 1.0 / (double)n;
+    double xC = 0.0, yC = 0.0;
+    for (int j = 0; j < n; j++) { xC = xC + alphaPWL * xl[j]; yC = yC + alphaPWL * yl[j]; }
+    // sub-triangle areas by Heron with dvEdge as the outer side, rescaled to areaCell (:159-183)
+    double subArea[M], subAreaSum = 0.0;
+    for (int s = 1; s <= n; s++) {
+        int iEdge = edgesOnCell[(size_t)Mh * cell + (s - 1)];
+        if (iEdge < 1 || iEdge > nEdgesTotal) iEdge = 1;
+        const int v1 = s, v2 = wrap1(s + 1, n);
+        const double c = dvEdge[iEdge - 1];
+        const double a = sqrt((xl[v1 - 1] - xC) * (xl[v1 - 1] - xC) + (yl[v1 - 1] - yC) * (yl[v1 - 1] - yC));
+        const double b = sqrt((xl[v2 - 1] - xC) * (xl[v2 - 1] - xC) + (yl[v2 - 1] - yC) * (yl[v2 - 1] - yC));
+        const double sp = (a + b + c) * 0.5;
+        subArea[s - 1] = sqrt(sp * (sp - a) * (sp - b) * (sp - c));
+        subAreaSum = subAreaSum + subArea[s - 1];
+    }
+    {
+        const double scale = areaCell[cell] / subAreaSum;
+        for (int s = 0; s < n; s++) subArea[s] = subArea[s] * scale;
+    }
+    // linear basis on each sub-triangle: two 3x3 solves (:186-231)
+    double sbU[M][3], sbV[M][3];
+    for (int s = 1; s <= n; s++) {
+        const int v1 = s, v2 = wrap1(s + 1, n);
+        const double left[3][3] = {{xl[v1 - 1] - xC, yl[v1 - 1] - yC, 1.0},
+                                   {xl[v2 - 1] - xC, yl[v2 - 1] - yC, 1.0},
+                                   {0.0, 0.0, 1.0}};
+        const double rhs1[3] = {1.0, 0.0, 0.0}, rhs2[3] = {0.0, 1.0, 0.0};
+        double sol[3];
+        solve_linear_basis_system3(left, rhs1, sol);
+        sbU[s - 1][0] = sol[0]; sbV[s - 1][0] = sol[1];
+        solve_linear_basis_system3(left, rhs2, sol);
+        sbU[s - 1][1] = sol[0]; sbV[s - 1][1] = sol[1];
+        sbU[s - 1][2] = -sbU[s - 1][0] - sbU[s - 1][1];
+        sbV[s - 1][2] = -sbV[s - 1][0] - sbV[s - 1][1];
+    }
+    // gradient of basis function ib on sub-cell s (:234-257)
+    double scU[M][M], scV[M][M];
+    for (int ib = 1; ib <= n; ib++) {
+        for (int s = 1; s <= n; s++) {
+            scU[ib - 1][s - 1] = sbU[s - 1][2] * alphaPWL;
+            scV[ib - 1][s - 1] = sbV[s - 1][2] * alphaPWL;
+            if (s == ib) {
+                scU[ib - 1][s - 1] = scU[ib - 1][s - 1] + sbU[s - 1][0];
+                scV[ib - 1][s - 1] = scV[ib - 1][s - 1] + sbV[s - 1][0];
+            } else if (s == wrap1(ib - 1, n)) {
+                scU[ib - 1][s - 1] = scU[ib - 1][s - 1] + sbU[s - 1][1];
+                scV[ib - 1][s - 1] = scV[ib - 1][s - 1] + sbV[s - 1][1];
+            }
+        }
+    }
+    // gradient at a vertex = mean of its two sub-cells (:260-274): dense in (ib, ig)
+    for (int ib = 1; ib <= n; ib++) {
+        for (int ig = 1; ig <= n; ig++) {
+            const int s1 = ig, s2 = wrap1(ig - 1, n);
+            G[evp_tix((ig - 1) * M + (ib - 1), cell, M * M)] =
+                make_double2(0.5 * (scU[ib - 1][s1 - 1] + scU[ib - 1][s2 - 1]), 0.5 * (scV[ib - 1][s1 - 1] + scV[ib - 1][s2 - 1]));
+        }
+    }
+    // integrals (:277-362)
+    for (int is = 1; is <= n; is++) {
+        for (int iv = 1; iv <= n; iv++) {
+            double bU = 0.0, bV = 0.0, bM = 0.0;
+            for (int s = 1; s <= n; s++) {
+                double basisIntegral;
+                if (s == is || s == wrap1(is - 1, n)) basisIntegral = ((alphaPWL + 1) * subArea[s - 1]) / 3.0;
+                else basisIntegral = (alphaPWL * subArea[s - 1]) / 3.0;
+                bU = bU + scU[iv - 1][s - 1] * basisIntegral;
+                bV = bV + scV[iv - 1][s - 1] * basisIntegral;
+            }
+            for (int s = 1; s <= n; s++) {
+                const int tS = (s == is) ? 1 : (s == wrap1(is - 1, n)) ? 2 : 3;
+                const int tV = (s == iv) ? 1 : (s == wrap1(iv - 1, n)) ? 2 : 3;
+                double val = 0.0;
+                if ((tS == 1 && tV == 1) || (tS == 2 && tV == 2)) val = 2.0 * (alphaPWL * alphaPWL) + 2.0 * alphaPWL + 2.0;
+                else if ((tS == 1 && tV == 2) || (tS == 2 && tV == 1)) val = 2.0 * (alphaPWL * alphaPWL) + 2.0 * alphaPWL + 1.0;
+                else if (tS == 3 && tV == 3) val = 2.0 * (alphaPWL * alphaPWL);
+                else val = 2.0 * (alphaPWL * alphaPWL) + alphaPWL;
+                val = val * subArea[s - 1] / 12.0;
+                bM = bM + val;
+            }
+            const size_t q = evp_tix((iv - 1) * M + (is - 1), cell, M * M);
+            Suv[q] = make_double2(bU, bV);
+            Sm[q] = bM;
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int evp_precompute_wachspress(evp_handle *h, const double *xLocal, const double *yLocal,
@@ -293,6 +460,44 @@ extern "C" int evp_precompute_wachspress(evp_handle *h, const double *xLocal, co
     case 4: k_wachspress<4><<<grid, block, 0, h->stream>>>((int)nC, h->nCp, h->Mh, h->d.nEdges, dx, dy, r.n, r.norm, h->d.G, h->d.Suv, h->d.Sm); break;
     case 6: k_wachspress<6><<<grid, block, 0, h->stream>>>((int)nC, h->nCp, h->Mh, h->d.nEdges, dx, dy, r.n, r.norm, h->d.G, h->d.Suv, h->d.Sm); break;
     default: k_wachspress<8><<<grid, block, 0, h->stream>>>((int)nC, h->nCp, h->Mh, h->d.nEdges, dx, dy, r.n, r.norm, h->d.G, h->d.Suv, h->d.Sm); break;
+    }
+    EVP_CUDA(cudaGetLastError());
+    EVP_CUDA(cudaStreamSynchronize(h->stream));
+    return evp_basis_finalize(h);
+}
+
+extern "C" int evp_precompute_pwl(evp_handle *h, const double *xLocal, const double *yLocal, const int *edgesOnCell,
+                                  const double *dvEdge, int nEdges, const double *areaCell)
+{
+    EVP_REQUIRE(h != nullptr && xLocal && yLocal && edgesOnCell && dvEdge && areaCell, "NULL argument");
+    EVP_REQUIRE(nEdges >= 1, "nEdges must be >= 1");
+    EVP_CUDA(cudaSetDevice(h->device));
+    const size_t nC = h->nCells;
+    if (nC == 0) { h->haveBasis = true; return EVP_OK; }
+    {
+        int rc = evp_basis_begin(h);
+        if (rc) return rc;
+    }
+    EVP_CUDA(cudaMemsetAsync(h->d.Suv, 0, sizeof(double2) * h->M * h->M * h->nCp, h->stream));
+    EVP_CUDA(cudaMemsetAsync(h->d.Sm, 0, sizeof(double) * h->M * h->M * h->nCp, h->stream));
+    EVP_CUDA(cudaStreamSynchronize(h->stream));
+    Stage st{(char *)h->d.stage, h->d.stageBytes, 0};
+    const size_t rowBytes = (size_t)h->Mh * nC * sizeof(double);
+    double *dx = (double *)st.take(rowBytes), *dy = (double *)st.take(rowBytes);
+    int *de = (int *)st.take((size_t)h->Mh * nC * sizeof(int));
+    double *dv = (double *)st.take((size_t)nEdges * sizeof(double)), *da = (double *)st.take(nC * sizeof(double));
+    EVP_REQUIRE(dx && dy && de && dv && da, "staging area too small for the PWL inputs");
+    EVP_CUDA(cudaMemcpyAsync(dx, xLocal, rowBytes, cudaMemcpyHostToDevice, h->stream));
+    EVP_CUDA(cudaMemcpyAsync(dy, yLocal, rowBytes, cudaMemcpyHostToDevice, h->stream));
+    EVP_CUDA(cudaMemcpyAsync(de, edgesOnCell, (size_t)h->Mh * nC * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    EVP_CUDA(cudaMemcpyAsync(dv, dvEdge, (size_t)nEdges * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    EVP_CUDA(cudaMemcpyAsync(da, areaCell, nC * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    const int block = 64;
+    const unsigned grid = (unsigned)((nC + block - 1) / block);
+    switch (h->M) {
+    case 4: k_pwl<4><<<grid, block, 0, h->stream>>>((int)nC, h->Mh, h->d.nEdges, dx, dy, de, dv, nEdges, da, h->d.G, h->d.Suv, h->d.Sm); break;
+    case 6: k_pwl<6><<<grid, block, 0, h->stream>>>((int)nC, h->Mh, h->d.nEdges, dx, dy, de, dv, nEdges, da, h->d.G, h->d.Suv, h->d.Sm); break;
+    default: k_pwl<8><<<grid, block, 0, h->stream>>>((int)nC, h->Mh, h->d.nEdges, dx, dy, de, dv, nEdges, da, h->d.G, h->d.Suv, h->d.Sm); break;
     }
     EVP_CUDA(cudaGetLastError());
     EVP_CUDA(cudaStreamSynchronize(h->stream));

@@ -36,6 +36,7 @@ EXPORTS = (
     "evp_launch_count", "evp_get_stream", "evp_device_bytes", "evp_set_use_graph", "evp_profile_passes",
     "evp_host_metric_terms", "evp_set_mesh_ext", "evp_set_state", "evp_pre_subcycle", "evp_post_subcycle",
     "evp_fetch_pre", "evp_release_host_memory", "evp_set_weak_mesh", "evp_update_weak_state", "evp_fetch_weak",
+    "evp_precompute_pwl",
 )
 
 
@@ -203,7 +204,7 @@ class EvpSolver:
 
     def __init__(self, mesh, var, opts, *, device=-1, pin_host=False, local_coords=None,
                  integration=("dunavant", 8), special_boundaries=None, n_vertices_solve=None,
-                 n_cells_solve=None):
+                 n_cells_solve=None, basis="wachspress"):
         self.lib = load_library()
         self.nCells, self.nVertices = int(mesh["nCells"]), int(mesh["nVertices"])
         self.maxEdges, self.vertexDegree = int(mesh["maxEdges"]), int(mesh["vertexDegree"])
@@ -236,7 +237,13 @@ class EvpSolver:
         self._o = make_options(opts, device, pin_host)
         self._h = C.c_void_p()
         self._check(self.lib.evp_create(C.byref(self._h), C.byref(md), C.byref(self._o)))
-        if local_coords is not None:
+        if local_coords is not None and basis == "pwl":
+            xl, yl = local_coords
+            self._check(self.lib.evp_precompute_pwl(
+                self._h, C.c_void_p(_ptr(xl, np.float64)), C.c_void_p(_ptr(yl, np.float64)),
+                C.c_void_p(_ptr(mesh["edgesOnCell"], np.int32)), C.c_void_p(_ptr(mesh["dvEdge"], np.float64)),
+                C.c_int(int(mesh["nEdges"])), C.c_void_p(_ptr(mesh["areaCell"], np.float64))))
+        elif local_coords is not None:
             xl, yl = local_coords
             itype = {"dunavant": 0, "trapezoidal": 1}[integration[0]]
             self._check(self.lib.evp_precompute_wachspress(self._h, C.c_void_p(_ptr(xl, np.float64)),

@@ -380,3 +380,25 @@ def test_split_subcycle_counts_at_full_size(evp_lib):
     for other in res[1:]:
         for k in names:
             assert np.array_equal(res[0][k], other[k]), k
+
+
+@pytest.mark.parametrize("kind", ["hex20", "quad40", "ico4"])
+def test_device_pwl_precompute_bit_exact(evp_lib, kind):
+    """evp_precompute_pwl against the oracle's seaice_init_velocity_solver_pwl (pwl.F:44-373, LU solves of
+    numerics.F:44-212): all five basis arrays bit-identical, then a run from the device basis (dense gradients)."""
+    from mpas_seaice_b200 import host
+    mesh, var = common.mesh_case(kind, basis="pwl")
+    step, opts = common.step_case(mesh)
+    solver = host.EvpSolver(mesh, var, opts, local_coords=(var["xLocal"], var["yLocal"]), basis="pwl")
+    try:
+        got = solver.fetch_basis()
+        nC = mesh.nCells
+        for k, a in got.items():
+            assert np.array_equal(a[:nC], var[k][:nC]), k
+        solver.update_step(step)
+        solver.run_subcycles(20)
+        out = solver.fetch()
+    finally:
+        solver.destroy()
+    ref = common.run_oracle(mesh, var, step, opts, 20)
+    _compare(mesh, step, ref, out)
