@@ -55,6 +55,32 @@ def test_argument_errors_do_not_need_a_device(evp_lib):
     assert evp_lib.evp_create(C.byref(h), C.byref(md), C.byref(o)) == 1
     assert evp_lib.evp_run_subcycles(None, 1) == 1
     assert evp_lib.evp_destroy(None) == 0
+    # the widened entry points validate their arguments before touching the device too
+    for fn in ("evp_set_mesh_ext", "evp_pre_subcycle", "evp_post_subcycle", "evp_fetch_pre", "evp_set_weak_mesh",
+               "evp_update_weak_state", "evp_fetch_weak", "evp_release_host_memory"):
+        f = getattr(evp_lib, fn)
+        n_args = {"evp_pre_subcycle": 3, "evp_release_host_memory": 1}.get(fn, 2)
+        assert f(*([None] * n_args)) == 1, fn
+        assert b"NULL" in evp_lib.evp_last_error_string(), fn
+    # scheme combinations (velocity_solver.F:195-198)
+    o = host.make_options(dict(elasticTimeStep=30.0, dynamicsTimeStep=3600.0, dampingTimescale=1296.0,
+                               strain_scheme="variational", stress_divergence_scheme="weak"))
+    md.maxEdges, md.vertexDegree = 6, 3
+    assert evp_lib.evp_create(C.byref(h), C.byref(md), C.byref(o)) == 1
+    assert b"not a valid combination" in evp_lib.evp_last_error_string()
+
+
+def test_host_metric_terms_is_scalar_libm():
+    """evp_host_metric_terms (no device needed): tan(asin(z/R))/R element by element, independent of the position
+    of the element in the array (the property numpy's SIMD loops do not have)."""
+    import math
+    rng = np.random.default_rng(5)
+    R = 6371229.0
+    z = R * np.sin(rng.uniform(-1.5, 1.5, 1001))
+    out = host.host_metric_terms(z, R)
+    want = np.array([math.tan(math.asin(v / R)) / R for v in z])
+    assert np.array_equal(out, want)
+    assert np.array_equal(host.host_metric_terms(z[3:40].copy(), R), out[3:40])
 
 
 def test_no_cpu_fallback_without_a_device(evp_lib):
