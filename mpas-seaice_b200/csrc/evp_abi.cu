@@ -567,6 +567,7 @@ extern "C" int evp_create(evp_handle **out, const evp_mesh_desc *m, const evp_op
         CUDA_FAIL(cudaStreamSynchronize(h->stream));
         FAIL_IF(evp_basis_finalize(h));
     }
+    if (nC == 0) h->haveBasis = true;      // an empty block (a rank without cells) has nothing to precompute
 
     // ---- special boundaries: resolve the sequential in-place loop (special_boundaries.F:301-324) ----
     if (haveSB && nV > 0) {

@@ -402,3 +402,92 @@ def test_device_pwl_precompute_bit_exact(evp_lib, kind):
         solver.destroy()
     ref = common.run_oracle(mesh, var, step, opts, 20)
     _compare(mesh, step, ref, out)
+
+
+def _pad_max_edges(mesh, var, step, new_m):
+    """The same mesh stored with a larger maxEdges (MPAS meshes with a few 7-sided cells have maxEdges = 7):
+    every (maxEdges, ...) array gets extra, unused columns."""
+    from mpas_seaice_b200 import meshgen
+    M = mesh.maxEdges
+    nC = mesh.nCells
+
+    def pad_last(a, fill):
+        out = np.full(a.shape[:-1] + (new_m,), fill, dtype=a.dtype)
+        out[..., :M] = a
+        return np.ascontiguousarray(out)
+
+    m2 = meshgen.Mesh(mesh)
+    m2["maxEdges"] = new_m
+    for k in ("verticesOnCell", "edgesOnCell", "cellsOnCell"):
+        fill = {"verticesOnCell": mesh.nVertices + 1, "edgesOnCell": mesh.nEdges + 1, "cellsOnCell": nC + 1}[k]
+        m2[k] = pad_last(mesh[k], fill)
+    v2 = dict(var)
+    for k in ("basisGradientU", "basisGradientV", "basisIntegralsU", "basisIntegralsV", "basisIntegralsMetric"):
+        a = np.zeros((nC + 1, new_m, new_m))
+        a[:, :M, :M] = var[k]
+        v2[k] = a
+    for k in ("xLocal", "yLocal"):
+        if k in var:
+            v2[k] = pad_last(var[k], 0.0)
+    s2 = dict(step)
+    for k in ("stress11", "stress22", "stress12", "strain11", "strain22", "strain12", "replacementPressure"):
+        s2[k] = pad_last(step[k], 0.0)
+    return m2, v2, s2
+
+
+@pytest.mark.parametrize("new_m", [7, 8])
+def test_host_max_edges_larger_than_any_cell(evp_lib, new_m):
+    """maxEdges = 7 (handled by the 8-slot instantiation) and 8 on a mesh whose cells have 5-6 vertices:
+    the host layout (Mh) and the device layout (M) differ."""
+    mesh, var = common.mesh_case("ico3")
+    step, opts = common.step_case(mesh)
+    m2, v2, s2 = _pad_max_edges(mesh, var, step, new_m)
+    ref = common.run_oracle(m2, v2, s2, opts, 30)
+    out = common.run_device(m2, v2, s2, opts, 30)
+    _compare(m2, s2, ref, out)
+    plain = common.run_oracle(mesh, var, step, opts, 30)
+    assert np.array_equal(ref["uVelocity"], plain["uVelocity"])            # padding changes nothing
+    # device Wachspress precompute with the padded local coordinates
+    from mpas_seaice_b200 import host
+    solver = host.EvpSolver(m2, v2, opts, local_coords=(v2["xLocal"], v2["yLocal"]))
+    try:
+        got = solver.fetch_basis()
+    finally:
+        solver.destroy()
+    for k, a in got.items():
+        assert np.array_equal(a[:mesh.nCells], v2[k][:mesh.nCells]), k
+
+
+def test_no_ice_anywhere_and_empty_block(evp_lib):
+    """Edge cases: every mask off (ice-free ocean: nothing is read but the masks, everything stays zero), and a
+    block without any cell or vertex (a rank whose partition is empty)."""
+    from mpas_seaice_b200 import host
+    mesh, var = common.mesh_case("ico3")
+    step, opts = common.step_case(mesh)
+    s = common.clone_step(step)
+    s["solveStress"][:] = 0
+    s["solveVelocity"][:] = 0
+    for k in ("uVelocity", "vVelocity"):
+        s[k][:] = 0.0
+    out = common.run_device(mesh, var, s, opts, 10)
+    for k in ("uVelocity", "vVelocity", "stress11", "stress12", "strain11", "replacementPressure", "stressDivergenceU"):
+        assert not out[k].any(), k
+    from mpas_seaice_b200 import meshgen
+    empty = meshgen.Mesh(nCells=0, nVertices=0, maxEdges=6, vertexDegree=3,
+                         nEdgesOnCell=np.zeros(1, dtype=np.int32), verticesOnCell=np.ones((1, 6), dtype=np.int32),
+                         cellsOnVertex=np.ones((1, 3), dtype=np.int32))
+    evar = dict(cellVerticesAtVertex=np.zeros((1, 3), dtype=np.int32), tanLatVertexRotatedOverRadius=np.zeros(1),
+                variationalDenominator=np.zeros(1))
+    for k in ("basisGradientU", "basisGradientV", "basisIntegralsU", "basisIntegralsV", "basisIntegralsMetric"):
+        evar[k] = np.zeros((1, 6, 6))
+    estep = {k: (np.zeros((1, 6)) if v.ndim == 2 else np.zeros(1, dtype=v.dtype)) for k, v in step.items()
+             if isinstance(v, np.ndarray)}
+    solver = host.EvpSolver(empty, evar, opts)
+    try:
+        solver.update_step(estep)
+        solver.run_subcycles(5)
+        assert solver.launch_count(5) == 0
+        res = solver.fetch()
+    finally:
+        solver.destroy()
+    assert res["uVelocity"].shape == (1,)
