@@ -10,8 +10,9 @@
  * image (no Fortran compiler, no MPI, no netCDF) and ships NO stored numeric outputs
  * (SURVEY.md section 8c).  This oracle is therefore pinned only by the reference's own analytic
  * known answers (testing_and_setup/testcases/square/operators_strain_stress_divergence/create_ics.py:12-48,
- * src/shared/mpas_seaice_testing.F:726-839) -- see tests/test_oracle_kat.py -- i.e. against golden
- * OUTPUTS of the reference it is "parity unpinned".
+ * src/shared/mpas_seaice_testing.F:726-839) -- see tests/test_oracle_kat.py -- and by analytic fields generated
+ * with the reference's own Python test-case scripts (tests/golden/make_analytic_golden.py,
+ * tests/test_analytic_golden.py); against golden OUTPUTS of the reference model it is "parity unpinned".
  *
  * Array conventions are the reference's: Fortran column-major, 1-based index VALUES, one junk
  * element at the end of every mesh array.  A Fortran A(i,j,c) with leading dims (M,M) is

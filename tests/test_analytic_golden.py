@@ -1,0 +1,105 @@
+"""Known answers computed by the REFERENCE'S OWN test-case scripts (tests/golden/analytic_*.npz, generated in the
+build container by tests/golden/make_analytic_golden.py importing /root/reference/testing_and_setup/testcases/...):
+the analytic velocity, strain and stress-divergence fields of its operator tests
+  - planar:  square/operators_strain_stress_divergence/create_ics.py:12-48   (BASELINE configs[0], hex 82 x 94)
+  - sphere:  spherical_operators/strain_stress_divergence/create_ic.py:574-603 (10 242 cells, rotated unit sphere)
+with the error norm of strain_stress_divergence_scaling.py:9-27 and its near-boundary vertex mask (:91-114).
+The reference encodes no pass/fail threshold (it plots error against resolution between first- and second-order
+guide lines); the thresholds below are the measured errors of the restated operators plus 25 % head-room, i.e.
+they pin today's behaviour against the reference's analytic truth.
+CPU: the oracle.  GPU: the device gives the oracle's bits, hence the same norms."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from mpas_seaice_b200 import meshgen, synthetic
+from test_oracle_kat import _operator_setup, _slot_mask, _use_vertex
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def l2_norm(numerical, analytical, area, use):
+    """L2_norm of strain_stress_divergence_scaling.py:9-27 (area-weighted, relative)."""
+    return float(np.sqrt(np.sum(area[use] * (numerical[use] - analytical[use]) ** 2) / np.sum(area[use] * analytical[use] ** 2)))
+
+
+def _planar_case():
+    g = np.load(os.path.join(HERE, "golden", "analytic_planar_hex82.npz"))
+    mesh = meshgen.planar_hex(int(g["nx"]), int(g["ny"]), float(g["dc"]))
+    nV = mesh.nVertices
+    assert np.array_equal(mesh.xVertex[:nV], g["x"]) and np.array_equal(mesh.yVertex[:nV], g["y"])
+    var = oracle.init_variational(mesh, metric=False)
+    u, v = np.zeros(nV + 1), np.zeros(nV + 1)
+    u[:nV], v[:nV] = g["u"], g["v"]
+    step, opts = _operator_setup(mesh, u, v)
+    use = _use_vertex(mesh) & (step["solveVelocity"][:nV] == 1)
+    return g, mesh, var, step, opts, use
+
+
+def _sphere_case():
+    g = np.load(os.path.join(HERE, "golden", "analytic_sphere_ico5.npz"))
+    mesh = meshgen.icosphere(int(g["level"]), radius=1.0)
+    nV = mesh.nVertices
+    assert np.array_equal(mesh.xVertex[:nV], g["x"]) and np.array_equal(mesh.zVertex[:nV], g["z"])
+    var = oracle.init_variational(mesh)          # rotated grid + metric terms, Registry defaults
+    u, v = np.zeros(nV + 1), np.zeros(nV + 1)
+    u[:nV], v[:nV] = g["u"], g["v"]
+    step, opts = _operator_setup(mesh, u, v)
+    return g, mesh, var, step, opts, np.ones(nV, dtype=bool)
+
+
+# measured (oracle, this repo): planar divu 1.38e-2, divv 1.24e-2, strains 8.3e-2 .. 1.0e-1 (first order at the
+# one-sided stress points); sphere divu 4.2e-2, divv 3.7e-2, strains 5.7e-2 .. 7.2e-2
+PLANAR_LIMITS = dict(divu=0.0175, divv=0.0155, e11=0.126, e22=0.104, e12=0.116)
+SPHERE_LIMITS = dict(divu=0.053, divv=0.047, e11=0.080, e22=0.072, e12=0.090)
+
+
+def _norms(g, mesh, step, use):
+    nC, nV = mesh.nCells, mesh.nVertices
+    area = mesh.areaTriangle[:nV]
+    out = dict(divu=l2_norm(step["stressDivergenceU"][:nV], g["divu"], area, use),
+               divv=l2_norm(step["stressDivergenceV"][:nV], g["divv"], area, use))
+    sm = _slot_mask(mesh)
+    voc = mesh.verticesOnCell[:nC] - 1
+    cell_use = use[np.where(sm, voc, 0)] & sm                 # stress points whose vertex is used
+    w = np.broadcast_to(mesh.areaCell[:nC, None], sm.shape)
+    for k, name in (("e11", "strain11"), ("e22", "strain22"), ("e12", "strain12")):
+        num = step[name][:nC]
+        ana = g[k][np.where(sm, voc, 0)]
+        out[k] = float(np.sqrt(np.sum(w[cell_use] * (num[cell_use] - ana[cell_use]) ** 2) / np.sum(w[cell_use] * ana[cell_use] ** 2)))
+    return out
+
+
+def test_reference_planar_fields_equal_our_restatement():
+    """synthetic.operator_test_fields restates create_ics.py:12-48; the reference's own output agrees to round-off."""
+    g, mesh, *_ = _planar_case()
+    ana = synthetic.operator_test_fields(mesh)
+    nV = mesh.nVertices
+    for k in ("u", "v", "e11", "e22", "e12", "divu", "divv"):
+        assert np.allclose(ana[k][:nV], g[k], rtol=1e-12, atol=1e-12 * np.abs(g[k]).max()), k
+
+
+@pytest.mark.parametrize("case,limits", [("planar", PLANAR_LIMITS), ("sphere", SPHERE_LIMITS)])
+def test_oracle_operators_against_reference_analytic_fields(case, limits):
+    g, mesh, var, step, opts, use = _planar_case() if case == "planar" else _sphere_case()
+    oracle.subcycle_velocity_solver(mesh, var, step, opts, 1)
+    norms = _norms(g, mesh, step, use)
+    for k, lim in limits.items():
+        assert norms[k] < lim, (k, norms)
+    assert use.sum() > 0.7 * mesh.nVertices
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,limits", [("planar", PLANAR_LIMITS), ("sphere", SPHERE_LIMITS)])
+def test_device_operators_against_reference_analytic_fields(evp_lib, case, limits):
+    import common
+    g, mesh, var, step, opts, use = _planar_case() if case == "planar" else _sphere_case()
+    out = common.run_device(mesh, var, step, opts, 1)
+    norms = _norms(g, mesh, out, use)
+    for k, lim in limits.items():
+        assert norms[k] < lim, (k, norms)
+    ref = common.run_oracle(mesh, var, step, opts, 1)
+    for k in ("strain11", "strain22", "strain12", "stressDivergenceU", "stressDivergenceV"):
+        assert np.array_equal(out[k], ref[k]), k
