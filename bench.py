@@ -139,8 +139,9 @@ def run_reference(args, rank):
         "ms_per_step": 1e3 * dt / args.steps * (N_ELASTIC / sub), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "vertex_updates_per_sec": value * nV_act,
-        "config": {"workload": name, "cells": mesh.nCells, "vertices": mesh.nVertices,
-                   "subcycles_per_step": N_ELASTIC, "state": "A"},
+        "config": {"workload": name, "cells": int(mesh.nCells), "vertices": int(mesh.nVertices),
+                   "active_cells": nC_act, "active_vertices": nV_act, "subcycles_per_step": N_ELASTIC, "state": "A",
+                   "basis": "wachspress/dunavant-8", "partition": "none (OpenMP threads share one block)"},
         "cpu_baseline": {"value": value, "unit": "subcycles/s", "cores": cores, "kind": "port",
                          "sample": f"{sub} of {N_ELASTIC} subcycles per step on the full {name} mesh"},
         "e2e": {"value": value, "unit": "subcycles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
