@@ -11,7 +11,8 @@ import common
 from mpas_seaice_b200 import meshgen
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-FILES = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
+FILES = sorted(f for f in glob.glob(os.path.join(HERE, "golden", "*.npz"))
+               if not os.path.basename(f).startswith("analytic_"))      # those belong to test_analytic_golden.py
 
 
 def _load(path):
