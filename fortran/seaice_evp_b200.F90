@@ -396,19 +396,14 @@ contains
     character(len=strKIND), pointer :: &
          config_strain_scheme, &
          config_stress_divergence_scheme
-    logical, pointer :: &
-         config_average_variational_strain
 
-    call MPAS_pool_get_config(domain % configs, "config_strain_scheme", config_strain_scheme)
-    call MPAS_pool_get_config(domain % configs, "config_stress_divergence_scheme", config_stress_divergence_scheme)
-    call MPAS_pool_get_config(domain % configs, "config_average_variational_strain", config_average_variational_strain)
     call MPAS_pool_get_config(domain % configs, "config_strain_scheme", config_strain_scheme)
     call MPAS_pool_get_config(domain % configs, "config_stress_divergence_scheme", config_stress_divergence_scheme)
 
     ! variational / variational (with or without config_average_variational_strain, which needs
     ! seaice_evp_b200_set_mesh_ext for areaCell), weak / weak and weak strain + variational divergence (both need
-    ! seaice_evp_b200_set_weak_mesh) are all covered; the pkgVariational arrays must exist because evp_create
-    ! takes them, so a pure weak run without that package stays on the Fortran path
+    ! seaice_evp_b200_set_weak_mesh) are all covered; in a pure weak run pkgVariational is inactive and the
+    ! velocity_variational fields are simply not passed (c_null_ptr)
     supported = trim(config_stress_divergence_scheme) == "variational" .or. &
                 trim(config_strain_scheme) == "weak"
 
@@ -469,6 +464,8 @@ contains
                                                  config_use_special_boundaries_velocity)
     call MPAS_pool_get_config(domain % configs, "config_elastic_subcycle_number", config_elastic_subcycle_number)
     call MPAS_pool_get_config(domain % configs, "config_average_variational_strain", config_average_variational_strain)
+    call MPAS_pool_get_config(domain % configs, "config_strain_scheme", config_strain_scheme)
+    call MPAS_pool_get_config(domain % configs, "config_stress_divergence_scheme", config_stress_divergence_scheme)
 
     nElasticSubcycle = config_elastic_subcycle_number
 
@@ -500,11 +497,9 @@ contains
 !> \brief seaice_mesh_pool_create equivalent: upload connectivity + basis, build the handle
 !-----------------------------------------------------------------------
 
-  subroutine seaice_evp_b200_create(domain, variationalDenominator)
+  subroutine seaice_evp_b200_create(domain)
 
     type(domain_type), intent(inout) :: domain
-    real(kind=RKIND), dimension(:), target, intent(in) :: &
-         variationalDenominator   !< the module array of seaice_velocity_solver_variational (variational.F:358-445)
 
     type(MPAS_pool_type), pointer :: meshPool, velocityVariationalPool, specialBoundariesPool
     type(evp_mesh_desc) :: mesh
@@ -513,10 +508,10 @@ contains
     integer, pointer :: nCells, nCellsSolve, nVertices, nVerticesSolve, maxEdges, vertexDegree
     integer, dimension(:), pointer :: nEdgesOnCell, vertexBoundaryType, vertexBoundarySourceLocal
     integer, dimension(:,:), pointer :: verticesOnCell, cellsOnVertex, cellVerticesAtVertex
-    real(kind=RKIND), dimension(:), pointer :: tanLatVertexRotatedOverRadius
+    real(kind=RKIND), dimension(:), pointer :: tanLatVertexRotatedOverRadius, variationalDenominator
     real(kind=RKIND), dimension(:,:,:), pointer :: &
          basisGradientU, basisGradientV, basisIntegralsU, basisIntegralsV, basisIntegralsMetric
-    logical, pointer :: config_use_special_boundaries_velocity
+    logical, pointer :: config_use_special_boundaries_velocity, pkgVariationalActive
 
     call MPAS_pool_get_subpool(domain % blocklist % structs, "mesh", meshPool)
     call MPAS_pool_get_subpool(domain % blocklist % structs, "velocity_variational", velocityVariationalPool)
@@ -532,6 +527,18 @@ contains
     call MPAS_pool_get_array(meshPool, "verticesOnCell", verticesOnCell)
     call MPAS_pool_get_array(meshPool, "cellsOnVertex", cellsOnVertex)
 
+    ! a pure weak configuration has no velocity_variational fields (pkgVariational inactive,
+    ! src/model_forward/mpas_seaice_core_interface.F:158-185): every pointer below stays c_null_ptr
+    mesh % cellVerticesAtVertex = c_null_ptr
+    mesh % basisGradientU = c_null_ptr
+    mesh % basisGradientV = c_null_ptr
+    mesh % basisIntegralsU = c_null_ptr
+    mesh % basisIntegralsV = c_null_ptr
+    mesh % basisIntegralsMetric = c_null_ptr
+    mesh % tanLatVertexRotatedOverRadius = c_null_ptr
+    mesh % variationalDenominator = c_null_ptr
+    call MPAS_pool_get_package(domain % packages, "pkgVariationalActive", pkgVariationalActive)
+    if (pkgVariationalActive) then
     call MPAS_pool_get_array(velocityVariationalPool, "cellVerticesAtVertex", cellVerticesAtVertex)
     call MPAS_pool_get_array(velocityVariationalPool, "basisGradientU", basisGradientU)
     call MPAS_pool_get_array(velocityVariationalPool, "basisGradientV", basisGradientV)
@@ -539,6 +546,17 @@ contains
     call MPAS_pool_get_array(velocityVariationalPool, "basisIntegralsV", basisIntegralsV)
     call MPAS_pool_get_array(velocityVariationalPool, "basisIntegralsMetric", basisIntegralsMetric)
     call MPAS_pool_get_array(velocityVariationalPool, "tanLatVertexRotatedOverRadius", tanLatVertexRotatedOverRadius)
+    ! filled by variational_denominator (variational.F:358-445); read the same way at velocity_solver.F:2718
+    call MPAS_pool_get_array(velocityVariationalPool, "variationalDenominator", variationalDenominator)
+    mesh % cellVerticesAtVertex = c_loc(cellVerticesAtVertex)
+    mesh % basisGradientU = c_loc(basisGradientU)
+    mesh % basisGradientV = c_loc(basisGradientV)
+    mesh % basisIntegralsU = c_loc(basisIntegralsU)
+    mesh % basisIntegralsV = c_loc(basisIntegralsV)
+    mesh % basisIntegralsMetric = c_loc(basisIntegralsMetric)
+    mesh % tanLatVertexRotatedOverRadius = c_loc(tanLatVertexRotatedOverRadius)
+    mesh % variationalDenominator = c_loc(variationalDenominator)
+    endif
 
     mesh % nCells = nCells
     mesh % nCellsSolve = nCellsSolve
@@ -549,14 +567,6 @@ contains
     mesh % nEdgesOnCell = c_loc(nEdgesOnCell)
     mesh % verticesOnCell = c_loc(verticesOnCell)
     mesh % cellsOnVertex = c_loc(cellsOnVertex)
-    mesh % cellVerticesAtVertex = c_loc(cellVerticesAtVertex)
-    mesh % basisGradientU = c_loc(basisGradientU)
-    mesh % basisGradientV = c_loc(basisGradientV)
-    mesh % basisIntegralsU = c_loc(basisIntegralsU)
-    mesh % basisIntegralsV = c_loc(basisIntegralsV)
-    mesh % basisIntegralsMetric = c_loc(basisIntegralsMetric)
-    mesh % tanLatVertexRotatedOverRadius = c_loc(tanLatVertexRotatedOverRadius)
-    mesh % variationalDenominator = c_loc(variationalDenominator)
     mesh % vertexBoundaryType = c_null_ptr
     mesh % vertexBoundarySourceLocal = c_null_ptr
 
@@ -600,6 +610,7 @@ contains
          airStressVertexU, airStressVertexV, surfaceTiltForceU, surfaceTiltForceV, oceanStressU, oceanStressV, &
          uOceanVelocityVertex, vOceanVelocityVertex, uVelocityInitial, vVelocityInitial
     real(kind=RKIND), dimension(:,:), pointer :: stress11, stress22, stress12
+    logical, pointer :: pkgVariationalActive
 
     call MPAS_pool_get_subpool(domain % blocklist % structs, "velocity_solver", velocitySolverPool)
     call MPAS_pool_get_subpool(domain % blocklist % structs, "velocity_variational", velocityVariationalPool)
@@ -610,9 +621,12 @@ contains
     call MPAS_pool_get_array(velocitySolverPool, "icePressure", icePressure)
     call MPAS_pool_get_array(velocitySolverPool, "uVelocity", uVelocity)
     call MPAS_pool_get_array(velocitySolverPool, "vVelocity", vVelocity)
-    call MPAS_pool_get_array(velocityVariationalPool, "stress11", stress11)
-    call MPAS_pool_get_array(velocityVariationalPool, "stress22", stress22)
-    call MPAS_pool_get_array(velocityVariationalPool, "stress12", stress12)
+    call MPAS_pool_get_package(domain % packages, "pkgVariationalActive", pkgVariationalActive)
+    if (pkgVariationalActive) then
+       call MPAS_pool_get_array(velocityVariationalPool, "stress11", stress11)
+       call MPAS_pool_get_array(velocityVariationalPool, "stress22", stress22)
+       call MPAS_pool_get_array(velocityVariationalPool, "stress12", stress12)
+    endif
     call MPAS_pool_get_array(icestatePool, "totalMassVertex", totalMassVertex)
     call MPAS_pool_get_array(icestatePool, "iceAreaVertex", iceAreaVertex)
     call MPAS_pool_get_array(velocitySolverPool, "totalMassVertexfVertex", totalMassVertexfVertex)
@@ -632,9 +646,14 @@ contains
     f % icePressure = c_loc(icePressure)
     f % uVelocity = c_loc(uVelocity)
     f % vVelocity = c_loc(vVelocity)
-    f % stress11 = c_loc(stress11)
-    f % stress22 = c_loc(stress22)
-    f % stress12 = c_loc(stress12)
+    f % stress11 = c_null_ptr
+    f % stress22 = c_null_ptr
+    f % stress12 = c_null_ptr
+    if (pkgVariationalActive) then
+       f % stress11 = c_loc(stress11)
+       f % stress22 = c_loc(stress22)
+       f % stress12 = c_loc(stress12)
+    endif
     f % totalMassVertex = c_loc(totalMassVertex)
     f % totalMassVertexfVertex = c_loc(totalMassVertexfVertex)
     f % iceAreaVertex = c_loc(iceAreaVertex)
@@ -690,7 +709,7 @@ contains
          uVelocity, vVelocity, stressDivergenceU, stressDivergenceV, oceanStressCoeff
     real(kind=RKIND), dimension(:,:), pointer :: &
          stress11, stress22, stress12, strain11, strain22, strain12, replacementPressure
-    logical, pointer :: config_use_special_boundaries_velocity_masks
+    logical, pointer :: config_use_special_boundaries_velocity_masks, pkgVariationalActive
 
     call MPAS_pool_get_subpool(domain % blocklist % structs, "velocity_solver", velocitySolverPool)
     call MPAS_pool_get_subpool(domain % blocklist % structs, "velocity_variational", velocityVariationalPool)
@@ -713,23 +732,35 @@ contains
     call MPAS_pool_get_array(velocitySolverPool, "stressDivergenceU", stressDivergenceU)
     call MPAS_pool_get_array(velocitySolverPool, "stressDivergenceV", stressDivergenceV)
     call MPAS_pool_get_array(velocitySolverPool, "oceanStressCoeff", oceanStressCoeff)
-    call MPAS_pool_get_array(velocityVariationalPool, "stress11", stress11)
-    call MPAS_pool_get_array(velocityVariationalPool, "stress22", stress22)
-    call MPAS_pool_get_array(velocityVariationalPool, "stress12", stress12)
-    call MPAS_pool_get_array(velocityVariationalPool, "strain11", strain11)
-    call MPAS_pool_get_array(velocityVariationalPool, "strain22", strain22)
-    call MPAS_pool_get_array(velocityVariationalPool, "strain12", strain12)
-    call MPAS_pool_get_array(velocityVariationalPool, "replacementPressure", replacementPressure)
+    call MPAS_pool_get_package(domain % packages, "pkgVariationalActive", pkgVariationalActive)
+    if (pkgVariationalActive) then
+       call MPAS_pool_get_array(velocityVariationalPool, "stress11", stress11)
+       call MPAS_pool_get_array(velocityVariationalPool, "stress22", stress22)
+       call MPAS_pool_get_array(velocityVariationalPool, "stress12", stress12)
+       call MPAS_pool_get_array(velocityVariationalPool, "strain11", strain11)
+       call MPAS_pool_get_array(velocityVariationalPool, "strain22", strain22)
+       call MPAS_pool_get_array(velocityVariationalPool, "strain12", strain12)
+       call MPAS_pool_get_array(velocityVariationalPool, "replacementPressure", replacementPressure)
+    endif
 
     o % uVelocity = c_loc(uVelocity)
     o % vVelocity = c_loc(vVelocity)
-    o % stress11 = c_loc(stress11)
-    o % stress22 = c_loc(stress22)
-    o % stress12 = c_loc(stress12)
-    o % strain11 = c_loc(strain11)
-    o % strain22 = c_loc(strain22)
-    o % strain12 = c_loc(strain12)
-    o % replacementPressure = c_loc(replacementPressure)
+    o % stress11 = c_null_ptr
+    o % stress22 = c_null_ptr
+    o % stress12 = c_null_ptr
+    o % strain11 = c_null_ptr
+    o % strain22 = c_null_ptr
+    o % strain12 = c_null_ptr
+    o % replacementPressure = c_null_ptr
+    if (pkgVariationalActive) then
+       o % stress11 = c_loc(stress11)
+       o % stress22 = c_loc(stress22)
+       o % stress12 = c_loc(stress12)
+       o % strain11 = c_loc(strain11)
+       o % strain22 = c_loc(strain22)
+       o % strain12 = c_loc(strain12)
+       o % replacementPressure = c_loc(replacementPressure)
+    endif
     o % stressDivergenceU = c_loc(stressDivergenceU)
     o % stressDivergenceV = c_loc(stressDivergenceV)
     o % oceanStressCoeff = c_loc(oceanStressCoeff)

@@ -406,10 +406,14 @@ extern "C" int evp_create(evp_handle **out, const evp_mesh_desc *m, const evp_op
     EVP_REQUIRE(m->nVerticesSolve >= 0 && m->nVerticesSolve <= m->nVertices, "nVerticesSolve out of range");
     EVP_REQUIRE(m->maxEdges >= 3 && m->maxEdges <= 8, "maxEdges must be 3..8");
     EVP_REQUIRE(m->vertexDegree == 3 || m->vertexDegree == 4, "vertexDegree must be 3 or 4");
-    EVP_REQUIRE(m->nEdgesOnCell && m->verticesOnCell && m->cellsOnVertex && m->cellVerticesAtVertex,
-                "connectivity arrays must not be NULL");
-    EVP_REQUIRE(m->tanLatVertexRotatedOverRadius && m->variationalDenominator,
-                "tanLatVertexRotatedOverRadius / variationalDenominator must not be NULL");
+    EVP_REQUIRE(m->nEdgesOnCell && m->verticesOnCell && m->cellsOnVertex, "connectivity arrays must not be NULL");
+    // a pure weak configuration (pkgVariational inactive in the host) has no velocity_variational fields at all
+    const bool pureWeak = o->stress_divergence_scheme == EVP_SCHEME_WEAK;
+    if (!pureWeak) {
+        EVP_REQUIRE(m->cellVerticesAtVertex, "cellVerticesAtVertex must not be NULL");
+        EVP_REQUIRE(m->tanLatVertexRotatedOverRadius && m->variationalDenominator,
+                    "tanLatVertexRotatedOverRadius / variationalDenominator must not be NULL");
+    }
     const bool anyBasis = m->basisGradientU || m->basisGradientV || m->basisIntegralsU || m->basisIntegralsV ||
                           m->basisIntegralsMetric;
     const bool allBasis = m->basisGradientU && m->basisGradientV && m->basisIntegralsU && m->basisIntegralsV &&
@@ -541,20 +545,23 @@ extern "C" int evp_create(evp_handle **out, const evp_mesh_desc *m, const evp_op
         for (size_t v0 = 0; v0 < nV; v0 += chunk) {
             const size_t cnt = std::min(chunk, nV - v0);
             FAIL_IF(evp_h2d(h, rawCov, m->cellsOnVertex + v0 * D, cnt * D * 4));
-            FAIL_IF(evp_h2d(h, rawCv, m->cellVerticesAtVertex + v0 * D, cnt * D * 4));
+            if (m->cellVerticesAtVertex) FAIL_IF(evp_h2d(h, rawCv, m->cellVerticesAtVertex + v0 * D, cnt * D * 4));
+            else CUDA_FAIL(cudaMemsetAsync(rawCv, 0, cnt * D * 4, h->stream));      // slot 0 = "not in that cell"
             k_gidx<<<grid_for(cnt, 256), 256, 0, h->stream>>>(rawCov, rawCv, d.nEdges, d.gidx + v0, d.cov + v0, D, cnt, nVp,
                                                                (int)nC, nCp);
         }
         CUDA_FAIL(cudaGetLastError());
-        FAIL_IF(evp_h2d(h, d.tanLat, m->tanLatVertexRotatedOverRadius, nV * 8));
-        st.off = 0;
-        double *rawD = (double *)st.take(nV * 8);
-        FAIL_IF(evp_h2d(h, rawD, m->variationalDenominator, nV * 8));
-        k_pair_in<<<grid_for(nV, 256), 256, 0, h->stream>>>(nullptr, rawD, d.areaDen, nV);   // .y = denominator
+        if (m->tanLatVertexRotatedOverRadius) FAIL_IF(evp_h2d(h, d.tanLat, m->tanLatVertexRotatedOverRadius, nV * 8));
+        if (m->variationalDenominator) {
+            st.off = 0;
+            double *rawD = (double *)st.take(nV * 8);
+            FAIL_IF(evp_h2d(h, rawD, m->variationalDenominator, nV * 8));
+            k_pair_in<<<grid_for(nV, 256), 256, 0, h->stream>>>(nullptr, rawD, d.areaDen, nV);   // .y = denominator
+        }
         CUDA_FAIL(cudaGetLastError());
         CUDA_FAIL(cudaStreamSynchronize(h->stream));
         h->metric = false;
-        for (size_t i = 0; i < nV; i++)
+        for (size_t i = 0; m->tanLatVertexRotatedOverRadius && i < nV; i++)
             if (m->tanLatVertexRotatedOverRadius[i] != 0.0) { h->metric = true; break; }
     }
     if (allBasis && nC > 0) {
@@ -636,8 +643,12 @@ extern "C" int evp_set_masks(evp_handle *h, const int *solveStress, const int *s
 extern "C" int evp_update_step(evp_handle *h, const evp_step_fields *f)
 {
     EVP_REQUIRE(h != nullptr && f != nullptr, "handle/fields is NULL");
-    EVP_REQUIRE(f->solveStress && f->solveVelocity && f->icePressure && f->uVelocity && f->vVelocity &&
-                f->stress11 && f->stress22 && f->stress12, "mesh-pool step fields must not be NULL");
+    EVP_REQUIRE(f->solveStress && f->solveVelocity && f->icePressure && f->uVelocity && f->vVelocity,
+                "mesh-pool step fields must not be NULL");
+    // the variational stresses do not exist in a pure weak configuration (evp_update_weak_state carries its state)
+    const bool needVarStress = h->opt.stress_divergence_scheme != EVP_SCHEME_WEAK;
+    EVP_REQUIRE((f->stress11 && f->stress22 && f->stress12) || (!needVarStress && !f->stress11 && !f->stress22 && !f->stress12),
+                "stress11/22/12 must not be NULL (all three may be NULL only with the weak stress divergence scheme)");
     EVP_REQUIRE(f->totalMassVertex && f->totalMassVertexfVertex && f->iceAreaVertex && f->airStressVertexU &&
                 f->airStressVertexV && f->surfaceTiltForceU && f->surfaceTiltForceV && f->oceanStressU &&
                 f->oceanStressV && f->uOceanVelocityVertex && f->vOceanVelocityVertex,
@@ -681,7 +692,7 @@ extern "C" int evp_update_step(evp_handle *h, const evp_step_fields *f)
         if (p.b && (rc = evp_h2d(h, rb, p.b, nV * 8))) return rc;
         k_pair_in<<<grid_for(nV, 256), 256, 0, s>>>(ra, rb, p.dst, nV);
     }
-    if (nC) {
+    if (nC && f->stress11) {
         const double *src[3] = {f->stress11, f->stress22, f->stress12};
         double *dst[3] = {(double *)d.sig, (double *)d.sig, d.sig12};
         const int ncomp[3] = {2, 2, 1}, comp[3] = {0, 1, 0};
@@ -719,7 +730,10 @@ extern "C" int evp_run_subcycles(evp_handle *h, int nSub)
         evp_set_error("average_variational_strain needs areaCell: call evp_set_mesh_ext first");
         return EVP_ERR_STATE;
     }
-    if (!h->haveBasis) { evp_set_error("basis arrays were neither given to evp_create nor precomputed"); return EVP_ERR_STATE; }
+    if (!h->haveBasis && h->opt.stress_divergence_scheme != EVP_SCHEME_WEAK) {
+        evp_set_error("basis arrays were neither given to evp_create nor precomputed");
+        return EVP_ERR_STATE;
+    }
     if (!h->haveStep) { evp_set_error("evp_update_step must be called before evp_run_subcycles"); return EVP_ERR_STATE; }
     EVP_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;

@@ -223,13 +223,16 @@ class EvpSolver:
         put("nEdgesOnCell", mesh["nEdgesOnCell"], np.int32)
         put("verticesOnCell", mesh["verticesOnCell"], np.int32)
         put("cellsOnVertex", mesh["cellsOnVertex"], np.int32)
-        put("cellVerticesAtVertex", var["cellVerticesAtVertex"], np.int32)
-        if local_coords is None:
+        pure_weak = opts.get("stress_divergence_scheme", "variational") == "weak" and "cellVerticesAtVertex" not in var
+        if not pure_weak:
+            put("cellVerticesAtVertex", var["cellVerticesAtVertex"], np.int32)
+        if local_coords is None and not pure_weak:
             for n in ("basisGradientU", "basisGradientV", "basisIntegralsU", "basisIntegralsV",
                       "basisIntegralsMetric"):
                 put(n, var[n], np.float64)
-        put("tanLatVertexRotatedOverRadius", var["tanLatVertexRotatedOverRadius"], np.float64)
-        put("variationalDenominator", var["variationalDenominator"], np.float64)
+        if not pure_weak:
+            put("tanLatVertexRotatedOverRadius", var["tanLatVertexRotatedOverRadius"], np.float64)
+            put("variationalDenominator", var["variationalDenominator"], np.float64)
         if special_boundaries is not None:
             put("vertexBoundaryType", special_boundaries[0], np.int32)
             put("vertexBoundarySourceLocal", special_boundaries[1], np.int32)

@@ -131,3 +131,31 @@ def test_weak_full_dynamics_step_on_device(evp_lib):
     assert np.array_equal(got["principalStress1Weak"][:nC], want["p1"][:nC])
     assert np.array_equal(got["principalStress2Weak"][:nC], want["p2"][:nC])
     assert np.abs(want["ridgeShear"]).max() > 0
+
+
+def test_pure_weak_configuration_without_variational_fields(evp_lib):
+    """pkgVariational inactive in the host (config_strain_scheme = config_stress_divergence_scheme = 'weak'): no basis
+    arrays, no cellVerticesAtVertex, no variational stresses cross the boundary at all."""
+    from mpas_seaice_b200 import host
+    mesh, var = common.mesh_case("ico4")
+    weak = weakmesh.weak_fields(mesh)
+    step, opts = common.step_case(mesh)
+    opts = dict(opts, strain_scheme="weak", stress_divergence_scheme="weak")
+    nC, nV = mesh.nCells, mesh.nVertices
+    ref = common.run_oracle(mesh, dict(var, weak=weak), step, opts, 40)
+    s2 = {k: v for k, v in step.items() if k not in ("stress11", "stress22", "stress12")}
+    solver = host.EvpSolver(mesh, {}, opts)
+    try:
+        solver.set_weak_mesh(mesh, weak)
+        solver.update_step(s2)
+        solver.update_weak_state({k: np.zeros(nC + 1) for k in WEAK_CELL[:3]})
+        solver.run_subcycles(40)
+        out = solver.fetch(names=common.COMPARE_VERTEX)
+        out.update(solver.fetch_weak())
+    finally:
+        solver.destroy()
+    cm, vm = common.masks_for(mesh, step)
+    for k in common.COMPARE_VERTEX:
+        assert np.array_equal(out[k][vm], ref[k][vm]), k
+    for k in WEAK_CELL:
+        assert np.array_equal(out[k][:nC], ref[k][:nC]), k
