@@ -383,9 +383,22 @@ extern "C" int evp_set_options(evp_handle *h, const evp_options *o)
         return EVP_ERR_ARGUMENT;
     }
     const int dev = h->device;
-    h->opt = *o;
-    h->opt.device = dev;
+    evp_options next = *o;
+    next.device = dev;
+    // the Fortran shim refreshes the options every dynamics step (config_dt may change in coupled runs): keep the
+    // instantiated graph when nothing changed -- kernel arguments such as the time steps are baked into its nodes
+    const evp_options &p = h->opt;      // field by field: the struct has padding
+    const bool same = next.constitutive_relation_type == p.constitutive_relation_type &&
+                      next.ocean_stress_type == p.ocean_stress_type && next.use_ocean_stress == p.use_ocean_stress &&
+                      next.use_special_boundaries_velocity == p.use_special_boundaries_velocity &&
+                      next.flags == p.flags && next.average_variational_strain == p.average_variational_strain &&
+                      next.strain_scheme == p.strain_scheme && next.stress_divergence_scheme == p.stress_divergence_scheme &&
+                      next.elasticTimeStep == p.elasticTimeStep && next.dynamicsTimeStep == p.dynamicsTimeStep &&
+                      next.dampingTimescale == p.dampingTimescale &&
+                      next.numericalInertiaCoefficient == p.numericalInertiaCoefficient;
+    h->opt = next;
     h->pinHost = (o->flags & EVP_FLAG_PIN_HOST) != 0;
+    if (same) return EVP_OK;
     invalidate_graph(h);
     if (h->haveStep) {      // EVP_FLAG_OVERLAP_HALO may have changed: refresh the boundary bit of the mask
         EVP_CUDA(cudaSetDevice(h->device));

@@ -491,3 +491,32 @@ def test_no_ice_anywhere_and_empty_block(evp_lib):
     finally:
         solver.destroy()
     assert res["uVelocity"].shape == (1,)
+
+
+def test_set_options_between_steps(evp_lib):
+    """evp_set_options every dynamics step (what the Fortran shim does): unchanged options keep the instantiated
+    graph, changed scalars (config_dt changed -> elasticTimeStep, dampingTimescale) rebuild it -- the time steps are
+    kernel arguments baked into the graph nodes."""
+    from mpas_seaice_b200 import host
+    mesh, var = common.mesh_case("ico3")
+    step, opts = common.step_case(mesh)
+    opts2 = dict(opts, elasticTimeStep=opts["elasticTimeStep"] / 2.0, dynamicsTimeStep=opts["dynamicsTimeStep"] / 2.0,
+                 dampingTimescale=opts["dampingTimescale"] / 2.0)
+    solver = host.EvpSolver(mesh, var, opts)
+    try:
+        outs = []
+        for o in (opts, opts, opts2, opts):
+            solver.set_options(o)
+            solver.update_step(step)
+            solver.run_subcycles(40)
+            outs.append(solver.fetch())
+    finally:
+        solver.destroy()
+    ref1 = common.run_oracle(mesh, var, step, opts, 40)
+    ref2 = common.run_oracle(mesh, var, step, opts2, 40)
+    _compare(mesh, step, ref1, outs[0])
+    _compare(mesh, step, ref1, outs[1])
+    _compare(mesh, step, ref2, outs[2])
+    _compare(mesh, step, ref1, outs[3])
+    cm, vm = common.masks_for(mesh, step)
+    assert not np.array_equal(ref1["uVelocity"][vm], ref2["uVelocity"][vm])
