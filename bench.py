@@ -117,7 +117,7 @@ def run_reference(args, rank):
     import oracle
     from mpas_seaice_b200 import workloads
     name = args.workload
-    w = workloads.build(name, verbose=log)
+    w = workloads.build(name, state=args.state, verbose=log)
     mesh, step, opts = w["mesh"], w["step"], w["opts"]
     cores = os.cpu_count() or 1
     oracle.set_num_threads(cores)
@@ -140,7 +140,7 @@ def run_reference(args, rank):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "vertex_updates_per_sec": value * nV_act,
         "config": {"workload": name, "cells": int(mesh.nCells), "vertices": int(mesh.nVertices),
-                   "active_cells": nC_act, "active_vertices": nV_act, "subcycles_per_step": N_ELASTIC, "state": "A",
+                   "active_cells": nC_act, "active_vertices": nV_act, "subcycles_per_step": N_ELASTIC, "state": args.state,
                    "basis": "wachspress/dunavant-8", "partition": "none (OpenMP threads share one block)"},
         "cpu_baseline": {"value": value, "unit": "subcycles/s", "cores": cores, "kind": "port",
                          "sample": f"{sub} of {N_ELASTIC} subcycles per step on the full {name} mesh"},
@@ -157,6 +157,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default=os.environ.get("EVP_BENCH_WORKLOAD", "qu7.5"))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--state", default="A", choices=["A", "B"],
+                    help="synthetic ice state: A = full cover (every cell active, the roofline case), B = polar caps "
+                         "(lat > 70N or < 60S, about 10 %% of the cells: what the masks skip)")
     ap.add_argument("--ref-subcycles", type=int, default=2, help="subcycles per step of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -193,9 +196,9 @@ def main():
     name = args.workload
     if world > 1:
         from mpas_seaice_b200 import multigpu
-        w = multigpu.build_rank_workload(name, rank, world, dist, verbose=log if rank == 0 else None)
+        w = multigpu.build_rank_workload(name, rank, world, dist, verbose=log if rank == 0 else None, state=args.state)
     else:
-        w = workloads.build(name, verbose=log)
+        w = workloads.build(name, state=args.state, verbose=log)
     mesh, static, step, opts = w["mesh"], w["static"], w["step"], w["opts"]
 
     t0 = time.time()
@@ -364,7 +367,7 @@ def main():
             "config": {"workload": name, "cells": int(w.get("global_cells", mesh.nCells)),
                        "vertices": int(w.get("global_vertices", mesh.nVertices)),
                        "active_cells": nC_tot, "active_vertices": nV_tot,
-                       "subcycles_per_step": N_ELASTIC, "state": "A", "basis": "wachspress/dunavant-8",
+                       "subcycles_per_step": N_ELASTIC, "state": args.state, "basis": "wachspress/dunavant-8",
                        "l2": "inputs larger than L2 (no flush needed)" if nC_tot * 2240 > 4 * 126e6
                              else "working set fits L2: flush not applied, see DESIGN.md",
                        "partition": w.get("partition", "none")},

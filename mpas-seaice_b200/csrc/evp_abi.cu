@@ -492,6 +492,7 @@ extern "C" int evp_create(evp_handle **out, const evp_mesh_desc *m, const evp_op
     FAIL_IF(evp_dev_alloc(h, (void **)&d.cov, sizeof(int) * D * nVp));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.solveVelPrev, nVp));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.solveStress, nCp));
+    FAIL_IF(evp_dev_alloc(h, (void **)&d.tileWork, nCp / EVP_TILE + 1));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.solveVel, nVp));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.P, sizeof(double) * nCp));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.uv, sizeof(double2) * nVp));
@@ -523,6 +524,7 @@ extern "C" int evp_create(evp_handle **out, const evp_mesh_desc *m, const evp_op
     CUDA_FAIL(cudaMemsetAsync(d.solveVelPrev, 0, nVp, h->stream));
     CUDA_FAIL(cudaMemsetAsync(d.solveVel, 0, nVp, h->stream));
     CUDA_FAIL(cudaMemsetAsync(d.solveStress, 0, nCp, h->stream));
+    CUDA_FAIL(cudaMemsetAsync(d.tileWork, 1, nCp / EVP_TILE + 1, h->stream));
     CUDA_FAIL(cudaMemsetAsync(d.uv, 0, sizeof(double2) * nVp, h->stream));
     CUDA_FAIL(cudaMemsetAsync(d.Suv, 0, sizeof(double2) * Mk * Mk * nCp, h->stream));
     CUDA_FAIL(cudaMemsetAsync(d.Sm, 0, sizeof(double) * Mk * Mk * nCp, h->stream));
@@ -649,6 +651,7 @@ extern "C" int evp_set_masks(evp_handle *h, const int *solveStress, const int *s
     if (nV) k_u8_in<<<grid_for(nV, 256), 256, 0, h->stream>>>(rawMv, d.solveVel, nV, 1, 1);
     EVP_CUDA(cudaGetLastError());
     if ((rc = evp_halo_mark_masks(h))) return rc;
+    if ((rc = evp_refresh_tile_flags(h, h->stream))) return rc;
     EVP_CUDA(cudaStreamSynchronize(h->stream));
     return EVP_OK;
 }
@@ -725,6 +728,7 @@ extern "C" int evp_update_step(evp_handle *h, const evp_step_fields *f)
     EVP_CUDA(cudaMemsetAsync(d.sdiv, 0, sizeof(double2) * nVp, s));
     EVP_CUDA(cudaMemsetAsync(d.ocoef, 0, sizeof(double) * nVp, s));
     EVP_CUDA(cudaGetLastError());
+    if ((rc = evp_refresh_tile_flags(h, s))) return rc;
     // pinned sources are copied asynchronously: do not return before the host may touch them again
     EVP_CUDA(cudaStreamSynchronize(s));
     h->haveStep = true;

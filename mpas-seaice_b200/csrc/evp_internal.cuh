@@ -92,6 +92,7 @@ struct evp_dev {
     double wRadius = 1.0;
     // per step
     uint8_t *solveStress = nullptr, *solveVel = nullptr;
+    uint8_t *tileWork = nullptr;  // per tile of EVP_TILE cells: 1 = some cell is solved or holds a non-zero stress
     double *P = nullptr;
     double2 *uv = nullptr, *sig = nullptr, *contrib = nullptr;
     double *sig12 = nullptr;
@@ -143,6 +144,9 @@ int evp_count_launches(evp_handle *h, int nSub);
 int evp_enqueue_cell_pass(evp_handle *h, bool diag, cudaStream_t s);
 int evp_enqueue_vertex_pass(evp_handle *h, bool diag, cudaStream_t s, const int *list, int nList);
 int evp_enqueue_special_boundaries(evp_handle *h, cudaStream_t s);
+// recompute tileWork from the masks and stresses on the device (and zero contrib of tiles without work); must
+// follow every change of solveStress / sig outside the subcycle kernels
+int evp_refresh_tile_flags(evp_handle *h, cudaStream_t s);
 
 // evp_weak.cu
 int evp_enqueue_weak_cell_pass(evp_handle *h, bool diag, cudaStream_t s);    // strain [+ stress] on cells

@@ -36,6 +36,7 @@ struct CellArgs {
     size_t nCp;
     const uint8_t *__restrict__ nEdges;
     const uint8_t *__restrict__ solveStress;
+    const uint8_t *__restrict__ tileWork;
     const int *__restrict__ voc;
     const double2 *__restrict__ G;      // dense [j][i][c] (PWL / unknown pattern) or nullptr
     const double2 *__restrict__ Gb;     // banded [k][j][c], k = 0..2 (Wachspress) or nullptr
@@ -167,12 +168,17 @@ __global__ void __launch_bounds__(EVP_TILE *M) evp_cell_kernel(const CellArgs a)
     const size_t c = tile * EVP_TILE + cx;
     const size_t nCp = a.nCp;
     const bool leader = (cx == 0) && (j == 0);
+    // three independent loads in flight together; the tile flag decides first
+    const uint8_t tileHasWork = a.tileWork[tile];
     int n = 0;
     bool solve = false;
     if (c < (size_t)a.nCells) {
         n = a.nEdges[c];
         solve = a.solveStress[c] == 1;
     }
+    // ice-free ocean: a tile without a solved cell and without left-over stress has nothing to compute and its
+    // contrib rows already hold zeros (evp_refresh_tile_flags)
+    if (tileHasWork == 0) return;
     if (leader) {
         mbar_init(&sm.barG, 1);
         mbar_init(&sm.barS, 1);
@@ -616,7 +622,7 @@ static int enqueue_cell_phase(evp_handle *h, bool diag, int phase, cudaStream_t 
 {
     CellArgs a;
     a.nCells = h->nCells; a.nCp = h->nCp;
-    a.nEdges = h->d.nEdges; a.solveStress = h->d.solveStress; a.voc = h->d.voc;
+    a.nEdges = h->d.nEdges; a.solveStress = h->d.solveStress; a.tileWork = h->d.tileWork; a.voc = h->d.voc;
     a.G = h->d.G; a.Gb = h->d.Gb; a.Suv = h->d.Suv; a.Sm = h->d.Sm;
     a.uv = h->d.uv; a.tanLat = h->d.tanLat; a.P = h->d.P;
     a.sig = h->d.sig; a.sig12 = h->d.sig12; a.contrib = h->d.contrib;
@@ -659,6 +665,46 @@ int evp_enqueue_vertex_pass(evp_handle *h, bool diag, cudaStream_t s, const int 
     case 4: launch_vertex_cr<4>(a, cr, diag, s); break;
     default: evp_set_error("unsupported vertexDegree %d", h->D); return EVP_ERR_ARGUMENT;
     }
+    EVP_CUDA(cudaGetLastError());
+    return EVP_OK;
+}
+
+namespace {
+// one warp per tile: lane = cell.  work = solved, or a non-solved cell still carrying stress (it enters the
+// divergence, variational.F:1151-1170).  Tiles without work get their contrib rows zeroed once, here.
+__global__ void __launch_bounds__(256) k_tile_flags(int nCells, size_t nCp, int M, const uint8_t *__restrict__ nEdges,
+                                                    const uint8_t *__restrict__ solveStress, const double2 *__restrict__ sig,
+                                                    const double *__restrict__ sig12, double2 *__restrict__ contrib,
+                                                    uint8_t *__restrict__ tileWork, size_t nTiles)
+{
+    const size_t tile = (size_t)blockIdx.x * (blockDim.x / EVP_TILE) + threadIdx.x / EVP_TILE;
+    if (tile >= nTiles) return;
+    const int lane = threadIdx.x % EVP_TILE;
+    const size_t c = tile * EVP_TILE + lane;
+    bool work = false;
+    if (c < (size_t)nCells) {
+        work = solveStress[c] == 1;
+        if (!work) {
+            const int n = nEdges[c];
+            for (int j = 0; j < n; j++) {
+                const double2 s = sig[(size_t)j * nCp + c];
+                work |= (s.x != 0.0) | (s.y != 0.0) | (sig12[(size_t)j * nCp + c] != 0.0);
+            }
+        }
+    }
+    const bool any = __any_sync(0xffffffffu, work);
+    if (lane == 0) tileWork[tile] = any ? 1 : 0;
+    if (!any)
+        for (int j = 0; j < M; j++) contrib[(size_t)j * nCp + c] = make_double2(0.0, 0.0);
+}
+}  // namespace
+
+int evp_refresh_tile_flags(evp_handle *h, cudaStream_t s)
+{
+    const size_t nTiles = h->nCp / EVP_TILE;
+    const int tilesPerBlock = 256 / EVP_TILE;
+    k_tile_flags<<<(unsigned)((nTiles + tilesPerBlock - 1) / tilesPerBlock), 256, 0, s>>>(
+        h->nCells, h->nCp, h->M, h->d.nEdges, h->d.solveStress, h->d.sig, h->d.sig12, h->d.contrib, h->d.tileWork, nTiles);
     EVP_CUDA(cudaGetLastError());
     return EVP_OK;
 }

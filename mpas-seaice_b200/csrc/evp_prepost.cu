@@ -528,6 +528,7 @@ extern "C" int evp_set_state(evp_handle *h, const double *u, const double *v, co
         if ((rc = evp_upload_rows(h, s11, (double *)d.sig, 1, 2, 0))) return rc;
         if ((rc = evp_upload_rows(h, s22, (double *)d.sig, 1, 2, 1))) return rc;
         if ((rc = evp_upload_rows(h, s12, d.sig12, 1, 1, 0))) return rc;
+        if ((rc = evp_refresh_tile_flags(h, s))) return rc;
     }
     EVP_CUDA(cudaStreamSynchronize(s));
     return EVP_OK;
@@ -616,6 +617,7 @@ extern "C" int evp_pre_subcycle(evp_handle *h, const evp_pre_fields *f, const ev
         EVP_CUDA(cudaMemsetAsync(d.eW12, 0, sizeof(double) * h->nCp, s));
     }
     if ((rc = evp_halo_mark_masks(h))) return rc;
+    if ((rc = evp_refresh_tile_flags(h, s))) return rc;
     // the velocity halo exchange that closes new_ice_velocities (:1281-1320)
     if ((rc = evp_halo_exchange(h, s, d.uv))) return rc;
     EVP_CUDA(cudaStreamSynchronize(s));           // pinned sources were copied asynchronously
@@ -708,6 +710,8 @@ extern "C" int evp_post_subcycle(evp_handle *h, const evp_post_fields *o)
         EVP_CUDA(cudaGetLastError());
         if (o->principalStress1Var && (rc = evp_download_rows(h, o->principalStress1Var, (const double *)d.contrib, 1, 2, 0))) return rc;
         if (o->principalStress2Var && (rc = evp_download_rows(h, o->principalStress2Var, (const double *)d.contrib, 1, 2, 1))) return rc;
+        // contrib served as scratch: tiles without work rely on their contrib rows being zero
+        if ((rc = evp_refresh_tile_flags(h, s))) return rc;
     }
     EVP_CUDA(cudaStreamSynchronize(s));
     return EVP_OK;
