@@ -93,6 +93,8 @@ struct evp_dev {
     // per step
     uint8_t *solveStress = nullptr, *solveVel = nullptr;
     uint8_t *tileWork = nullptr;  // per tile of EVP_TILE cells: 1 = some cell is solved or holds a non-zero stress
+    int *tileList = nullptr;      // the tiles with work, compacted (cell kernel grid = their number)
+    int *tileCount = nullptr;     // device counter behind tileList
     double *P = nullptr;
     double2 *uv = nullptr, *sig = nullptr, *contrib = nullptr;
     double *sig12 = nullptr;
@@ -119,6 +121,7 @@ struct evp_handle {
     int Mh = 0;                   // maxEdges of the host arrays
     int M = 0;                    // slots per cell of the device layout / kernel instantiation (4, 6 or 8)
     size_t nCp = 0, nVp = 0;
+    int nActiveTiles = -1;        // tiles with work (host copy); -1 = not computed yet
     evp_options opt{};
     bool metric = false;          // any tanLatVertexRotatedOverRadius != 0
     bool haveExt = false, haveWeak = false;

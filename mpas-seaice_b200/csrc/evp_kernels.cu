@@ -33,10 +33,11 @@ constexpr double kRhow = 1026.0;
 
 struct CellArgs {
     int nCells;
+    int nTiles;                         // grid size: tiles with work
     size_t nCp;
     const uint8_t *__restrict__ nEdges;
     const uint8_t *__restrict__ solveStress;
-    const uint8_t *__restrict__ tileWork;
+    const int *__restrict__ tileList;   // compacted list of the tiles with work, or nullptr when every tile has work
     const int *__restrict__ voc;
     const double2 *__restrict__ G;      // dense [j][i][c] (PWL / unknown pattern) or nullptr
     const double2 *__restrict__ Gb;     // banded [k][j][c], k = 0..2 (Wachspress) or nullptr
@@ -164,21 +165,18 @@ __global__ void __launch_bounds__(EVP_TILE *M) evp_cell_kernel(const CellArgs a)
 
     const int cx = threadIdx.x;
     const int j = threadIdx.y;
-    const size_t tile = blockIdx.x;
+    // ice-free ocean: tiles without a solved cell and without left-over stress are not launched at all -- the grid
+    // runs over the compacted list of tiles with work (evp_refresh_tile_flags), their contrib rows hold zeros
+    const size_t tile = a.tileList ? (size_t)a.tileList[blockIdx.x] : (size_t)blockIdx.x;
     const size_t c = tile * EVP_TILE + cx;
     const size_t nCp = a.nCp;
     const bool leader = (cx == 0) && (j == 0);
-    // three independent loads in flight together; the tile flag decides first
-    const uint8_t tileHasWork = a.tileWork[tile];
     int n = 0;
     bool solve = false;
     if (c < (size_t)a.nCells) {
         n = a.nEdges[c];
         solve = a.solveStress[c] == 1;
     }
-    // ice-free ocean: a tile without a solved cell and without left-over stress has nothing to compute and its
-    // contrib rows already hold zeros (evp_refresh_tile_flags)
-    if (tileHasWork == 0) return;
     if (leader) {
         mbar_init(&sm.barG, 1);
         mbar_init(&sm.barS, 1);
@@ -523,8 +521,8 @@ int launch_cell_k(const CellArgs &a, cudaStream_t s)
         configured[dev] = true;
     }
     const dim3 block(EVP_TILE, M);
-    const unsigned grid = (unsigned)((a.nCells + EVP_TILE - 1) / EVP_TILE);
-    kern<<<grid, block, smem, s>>>(a);
+    const unsigned grid = (unsigned)a.nTiles;
+    if (grid) kern<<<grid, block, smem, s>>>(a);
     return 0;
 }
 template <int M, bool METRIC, int CR, bool DIAG, bool GBAND>
@@ -622,7 +620,10 @@ static int enqueue_cell_phase(evp_handle *h, bool diag, int phase, cudaStream_t 
 {
     CellArgs a;
     a.nCells = h->nCells; a.nCp = h->nCp;
-    a.nEdges = h->d.nEdges; a.solveStress = h->d.solveStress; a.tileWork = h->d.tileWork; a.voc = h->d.voc;
+    const int allTiles = (h->nCells + EVP_TILE - 1) / EVP_TILE;
+    a.nTiles = h->nActiveTiles < 0 ? allTiles : h->nActiveTiles;
+    a.tileList = (a.nTiles == allTiles) ? nullptr : h->d.tileList;
+    a.nEdges = h->d.nEdges; a.solveStress = h->d.solveStress; a.voc = h->d.voc;
     a.G = h->d.G; a.Gb = h->d.Gb; a.Suv = h->d.Suv; a.Sm = h->d.Sm;
     a.uv = h->d.uv; a.tanLat = h->d.tanLat; a.P = h->d.P;
     a.sig = h->d.sig; a.sig12 = h->d.sig12; a.contrib = h->d.contrib;
@@ -699,13 +700,49 @@ __global__ void __launch_bounds__(256) k_tile_flags(int nCells, size_t nCp, int 
 }
 }  // namespace
 
+namespace {
+// ordered inside a block of 256 tiles (warp ballots + a shared prefix), blocks land in atomicAdd order: the list
+// keeps the mesh's locality in runs of 256 tiles, and the order has no influence on any result
+__global__ void __launch_bounds__(256) k_tile_compact(int nTiles, const uint8_t *__restrict__ tileWork, int *__restrict__ list,
+                                                      int *__restrict__ count)
+{
+    __shared__ int warpSum[8];
+    __shared__ int base;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = t < nTiles && tileWork[t] != 0;
+    const unsigned ballot = __ballot_sync(0xffffffffu, on);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) warpSum[warp] = __popc(ballot);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int total = 0;
+        for (int w = 0; w < 8; w++) { const int v = warpSum[w]; warpSum[w] = total; total += v; }
+        base = total ? atomicAdd(count, total) : 0;
+    }
+    __syncthreads();
+    if (on) list[base + warpSum[warp] + __popc(ballot & ((1u << lane) - 1u))] = t;
+}
+}  // namespace
+
 int evp_refresh_tile_flags(evp_handle *h, cudaStream_t s)
 {
     const size_t nTiles = h->nCp / EVP_TILE;
     const int tilesPerBlock = 256 / EVP_TILE;
     k_tile_flags<<<(unsigned)((nTiles + tilesPerBlock - 1) / tilesPerBlock), 256, 0, s>>>(
         h->nCells, h->nCp, h->M, h->d.nEdges, h->d.solveStress, h->d.sig, h->d.sig12, h->d.contrib, h->d.tileWork, nTiles);
+    EVP_CUDA(cudaMemsetAsync(h->d.tileCount, 0, sizeof(int), s));
+    const int realTiles = (h->nCells + EVP_TILE - 1) / EVP_TILE;
+    if (realTiles) k_tile_compact<<<(realTiles + 255) / 256, 256, 0, s>>>(realTiles, h->d.tileWork, h->d.tileList, h->d.tileCount);
     EVP_CUDA(cudaGetLastError());
+    int count = 0;
+    EVP_CUDA(cudaMemcpyAsync(&count, h->d.tileCount, sizeof(int), cudaMemcpyDeviceToHost, s));
+    EVP_CUDA(cudaStreamSynchronize(s));
+    if (count != h->nActiveTiles) {
+        // the grid of the cell kernel is baked into the graph nodes: a different number of tiles needs a new graph
+        h->nActiveTiles = count;
+        if (h->graphExec) { cudaGraphExecDestroy(h->graphExec); h->graphExec = nullptr; }
+        h->graphN = -1;
+    }
     return EVP_OK;
 }
 
@@ -767,11 +804,18 @@ int evp_enqueue_subcycles(evp_handle *h, int nSub, cudaStream_t s)
 int evp_count_launches(evp_handle *h, int nSub)
 {
     const int sb = (h->opt.use_special_boundaries_velocity && h->d.nSB) ? 2 : 0;
-    int avg = h->opt.average_variational_strain ? (h->nCells ? 1 : 0) + (h->nVerticesSolve ? 1 : 0) : 0;
-    if (h->opt.strain_scheme == EVP_SCHEME_WEAK)      // weak/weak: 1 cell kernel; weak/variational: 1 + 2 + phase 2
-        avg = h->opt.stress_divergence_scheme == EVP_SCHEME_WEAK ? 0 : (h->nCells ? 2 : 0) + (h->nVerticesSolve ? 1 : 0);
-    const int perSub = avg + (h->nCells ? 1 : 0) + (h->nVerticesSolve ? 1 : 0) + (evp_halo_boundary_count(h) ? 1 : 0) +
-                       evp_halo_launches(h) + sb;
+    const bool cells = h->nCells > 0, work = cells && h->nActiveTiles != 0, verts = h->nVerticesSolve > 0;
+    int cellKernels;                                   // per subcycle, before the vertex pass
+    if (h->opt.strain_scheme == EVP_SCHEME_WEAK) {
+        cellKernels = cells ? 1 : 0;                   // k_weak_cells runs over every cell
+        if (h->opt.stress_divergence_scheme != EVP_SCHEME_WEAK)   // strain -> vertex, vertex -> stress points, PHASE 2
+            cellKernels += (verts ? 1 : 0) + (cells ? 1 : 0) + (work ? 1 : 0);
+    } else if (h->opt.average_variational_strain) {
+        cellKernels = (work ? 1 : 0) + (verts ? 1 : 0) + (work ? 1 : 0);   // PHASE 1, vertex average, PHASE 2
+    } else {
+        cellKernels = work ? 1 : 0;
+    }
+    const int perSub = cellKernels + (verts ? 1 : 0) + (evp_halo_boundary_count(h) ? 1 : 0) + evp_halo_launches(h) + sb;
     return sb + nSub * perSub;
 }
 
