@@ -495,6 +495,9 @@ extern "C" int evp_create(evp_handle **out, const evp_mesh_desc *m, const evp_op
     FAIL_IF(evp_dev_alloc(h, (void **)&d.tileWork, nCp / EVP_TILE + 1));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.tileList, sizeof(int) * (nCp / EVP_TILE + 1)));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.tileCount, sizeof(int)));
+    FAIL_IF(evp_dev_alloc(h, (void **)&d.vblockWork, nVp / 256 + 2));
+    FAIL_IF(evp_dev_alloc(h, (void **)&d.vblockList, sizeof(int) * (nVp / 256 + 2)));
+    FAIL_IF(evp_dev_alloc(h, (void **)&d.vblockCount, sizeof(int)));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.solveVel, nVp));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.P, sizeof(double) * nCp));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.uv, sizeof(double2) * nVp));

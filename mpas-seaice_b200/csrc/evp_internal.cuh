@@ -95,6 +95,8 @@ struct evp_dev {
     uint8_t *tileWork = nullptr;  // per tile of EVP_TILE cells: 1 = some cell is solved or holds a non-zero stress
     int *tileList = nullptr;      // the tiles with work, compacted (cell kernel grid = their number)
     int *tileCount = nullptr;     // device counter behind tileList
+    uint8_t *vblockWork = nullptr;  // per block of 256 owned vertices: 1 = some vertex is solved
+    int *vblockList = nullptr, *vblockCount = nullptr;
     double *P = nullptr;
     double2 *uv = nullptr, *sig = nullptr, *contrib = nullptr;
     double *sig12 = nullptr;
@@ -122,6 +124,7 @@ struct evp_handle {
     int M = 0;                    // slots per cell of the device layout / kernel instantiation (4, 6 or 8)
     size_t nCp = 0, nVp = 0;
     int nActiveTiles = -1;        // tiles with work (host copy); -1 = not computed yet
+    int nActiveVBlocks = -1;      // 256-vertex blocks with a solved vertex; -1 = not computed yet
     evp_options opt{};
     bool metric = false;          // any tanLatVertexRotatedOverRadius != 0
     bool haveExt = false, haveWeak = false;

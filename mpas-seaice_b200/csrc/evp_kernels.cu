@@ -364,6 +364,8 @@ __global__ void __launch_bounds__(256) evp_average_strain_kernel(int nVerticesSo
 struct VertexArgs {
     int nVerticesSolve;                 // number of threads: owned vertices, or entries of `list`
     const int *__restrict__ list;       // LIST: the boundary-owned vertices (those some neighbour rank needs)
+    const int *__restrict__ vblockList; // plain pass: compacted list of the 256-vertex blocks with a solved vertex, or nullptr
+    int nBlocks;                        // plain pass: grid size
     size_t nVp;
     const uint8_t *__restrict__ solveVel;
     const int *__restrict__ gidx;
@@ -396,7 +398,8 @@ struct VertexArgs {
 template <int D, int CR, bool DIAG, bool LIST, bool WEAK>
 __global__ void __launch_bounds__(256) evp_vertex_kernel(const VertexArgs a)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int blk = (!LIST && a.vblockList) ? a.vblockList[blockIdx.x] : (int)blockIdx.x;
+    const int k = blk * blockDim.x + threadIdx.x;
     if (k >= a.nVerticesSolve) return;
     const int v = LIST ? a.list[k] : k;
     if (LIST ? (a.solveVel[v] & 1) == 0 : a.solveVel[v] != 1) return;
@@ -559,7 +562,8 @@ template <int D, int CR, bool WEAK>
 int launch_vertex_w(const VertexArgs &a, bool diag, cudaStream_t s)
 {
     const int block = 256;
-    const int grid = (a.nVerticesSolve + block - 1) / block;
+    const int grid = a.list ? (a.nVerticesSolve + block - 1) / block : a.nBlocks;
+    if (grid == 0) return 0;
     if (a.list) {
         if (diag) evp_vertex_kernel<D, CR, true, true, WEAK><<<grid, block, 0, s>>>(a);
         else      evp_vertex_kernel<D, CR, false, true, WEAK><<<grid, block, 0, s>>>(a);
@@ -650,6 +654,9 @@ int evp_enqueue_vertex_pass(evp_handle *h, bool diag, cudaStream_t s, const int 
     if (nThreads == 0) return EVP_OK;
     VertexArgs a;
     a.nVerticesSolve = nThreads; a.list = list; a.nVp = h->nVp;
+    const int allBlocks = (h->nVerticesSolve + 255) / 256;
+    a.nBlocks = h->nActiveVBlocks < 0 ? allBlocks : h->nActiveVBlocks;
+    a.vblockList = (a.nBlocks == allBlocks) ? nullptr : h->d.vblockList;
     a.solveVel = h->d.solveVel; a.gidx = h->d.gidx; a.contrib = h->d.contrib;
     a.areaDen = h->d.areaDen; a.massf = h->d.massf; a.air = h->d.air; a.tilt = h->d.tilt;
     a.ocnStress = h->d.ocnStress; a.ocnVel = h->d.ocnVel; a.uvInit = h->d.uvInit;
@@ -724,6 +731,17 @@ __global__ void __launch_bounds__(256) k_tile_compact(int nTiles, const uint8_t 
 }
 }  // namespace
 
+namespace {
+__global__ void __launch_bounds__(256) k_vblock_flags(int nVerticesSolve, const uint8_t *__restrict__ solveVel,
+                                                      uint8_t *__restrict__ vblockWork)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    const int on = v < nVerticesSolve && (solveVel[v] & 1);
+    const int any = __syncthreads_or(on);
+    if (threadIdx.x == 0) vblockWork[blockIdx.x] = any ? 1 : 0;
+}
+}  // namespace
+
 int evp_refresh_tile_flags(evp_handle *h, cudaStream_t s)
 {
     const size_t nTiles = h->nCp / EVP_TILE;
@@ -734,12 +752,22 @@ int evp_refresh_tile_flags(evp_handle *h, cudaStream_t s)
     const int realTiles = (h->nCells + EVP_TILE - 1) / EVP_TILE;
     if (realTiles) k_tile_compact<<<(realTiles + 255) / 256, 256, 0, s>>>(realTiles, h->d.tileWork, h->d.tileList, h->d.tileCount);
     EVP_CUDA(cudaGetLastError());
-    int count = 0;
+    // the same for the vertex pass: blocks of 256 owned vertices without a solved vertex are not launched
+    const int vBlocks = (h->nVerticesSolve + 255) / 256;
+    EVP_CUDA(cudaMemsetAsync(h->d.vblockCount, 0, sizeof(int), s));
+    if (vBlocks) {
+        k_vblock_flags<<<vBlocks, 256, 0, s>>>(h->nVerticesSolve, h->d.solveVel, h->d.vblockWork);
+        k_tile_compact<<<(vBlocks + 255) / 256, 256, 0, s>>>(vBlocks, h->d.vblockWork, h->d.vblockList, h->d.vblockCount);
+    }
+    EVP_CUDA(cudaGetLastError());
+    int count = 0, vcount = 0;
     EVP_CUDA(cudaMemcpyAsync(&count, h->d.tileCount, sizeof(int), cudaMemcpyDeviceToHost, s));
+    EVP_CUDA(cudaMemcpyAsync(&vcount, h->d.vblockCount, sizeof(int), cudaMemcpyDeviceToHost, s));
     EVP_CUDA(cudaStreamSynchronize(s));
-    if (count != h->nActiveTiles) {
-        // the grid of the cell kernel is baked into the graph nodes: a different number of tiles needs a new graph
+    if (count != h->nActiveTiles || vcount != h->nActiveVBlocks) {
+        // the grids are baked into the graph nodes: a different number of tiles / vertex blocks needs a new graph
         h->nActiveTiles = count;
+        h->nActiveVBlocks = vcount;
         if (h->graphExec) { cudaGraphExecDestroy(h->graphExec); h->graphExec = nullptr; }
         h->graphN = -1;
     }
@@ -805,6 +833,7 @@ int evp_count_launches(evp_handle *h, int nSub)
 {
     const int sb = (h->opt.use_special_boundaries_velocity && h->d.nSB) ? 2 : 0;
     const bool cells = h->nCells > 0, work = cells && h->nActiveTiles != 0, verts = h->nVerticesSolve > 0;
+    const bool vwork = verts && h->nActiveVBlocks != 0;
     int cellKernels;                                   // per subcycle, before the vertex pass
     if (h->opt.strain_scheme == EVP_SCHEME_WEAK) {
         cellKernels = cells ? 1 : 0;                   // k_weak_cells runs over every cell
@@ -815,7 +844,7 @@ int evp_count_launches(evp_handle *h, int nSub)
     } else {
         cellKernels = work ? 1 : 0;
     }
-    const int perSub = cellKernels + (verts ? 1 : 0) + (evp_halo_boundary_count(h) ? 1 : 0) + evp_halo_launches(h) + sb;
+    const int perSub = cellKernels + (vwork ? 1 : 0) + (evp_halo_boundary_count(h) ? 1 : 0) + evp_halo_launches(h) + sb;
     return sb + nSub * perSub;
 }
 
