@@ -76,3 +76,43 @@ def test_workload_registry():
     assert 10 * 4 ** 10 + 2 == 10485762
     with pytest.raises(ValueError):
         workloads.build("nope")
+
+
+@pytest.mark.parametrize("kind", ["hex20", "quad40", "ico3"])
+def test_weak_mesh_helper_geometry(kind):
+    """weakmesh.weak_fields (synthetic stand-in for the mesh file's verticesOnEdge / edgesOnVertex and for
+    seaice_normal_vectors): connectivity is consistent and the unit normals close every polygon / dual triangle."""
+    from mpas_seaice_b200 import weakmesh
+    mesh, _ = common.mesh_case(kind)
+    w = weakmesh.weak_fields(mesh)
+    nC, nV, nE, M, D = mesh.nCells, mesh.nVertices, mesh.nEdges, mesh.maxEdges, mesh.vertexDegree
+    voe, eov = w["verticesOnEdge"], w["edgesOnVertex"]
+    assert np.all((voe[:nE] >= 1) & (voe[:nE] <= nV))
+    # every edge of a cell joins two of that cell's vertices; both cells of an edge contain both vertices
+    for c in (0, nC // 2, nC - 1):
+        verts = set(mesh.verticesOnCell[c, :mesh.nEdgesOnCell[c]])
+        for k in range(mesh.nEdgesOnCell[c]):
+            e = mesh.edgesOnCell[c, k] - 1
+            assert set(voe[e]) <= verts
+    # an edge listed at a vertex has that vertex as one of its ends
+    v = np.arange(nV)
+    for s in range(D):
+        e = eov[:nV, s]
+        ok = e <= nE
+        assert np.all((voe[e[ok] - 1, 0] == v[ok] + 1) | (voe[e[ok] - 1, 1] == v[ok] + 1))
+    nvp, nvt = w["normalVectorPolygon"], w["normalVectorTriangle"]
+    slot = np.arange(M)[None, :] < mesh.nEdgesOnCell[:nC, None]
+    assert np.allclose(np.hypot(nvp[:nC, :, 0], nvp[:nC, :, 1])[slot], 1.0, rtol=1e-12)
+    acc = np.zeros((nC, 2))
+    for k in range(M):
+        ok = slot[:, k]
+        acc[ok] += nvp[:nC][ok, k, :] * mesh.dvEdge[mesh.edgesOnCell[:nC][ok, k] - 1][:, None]
+    tol = 1e-12 if not mesh.on_a_sphere else 2e-2            # tangent-plane projection on the sphere
+    assert np.abs(acc).max() <= tol * mesh.dvEdge[:nE].max()
+    interior = np.all(mesh.cellsOnVertex[:nV] <= nC, axis=1)
+    acc = np.zeros((nV, 2))
+    for s in range(D):
+        e = eov[:nV, s] - 1
+        ok = e < nE
+        acc[ok] += nvt[:nV][ok, s, :] * mesh.dcEdge[e[ok]][:, None]
+    assert np.abs(acc[interior]).max() <= tol * mesh.dcEdge[:nE].max()
