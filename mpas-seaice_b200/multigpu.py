@@ -47,30 +47,20 @@ def build_rank_workload(name, rank, world, dist=None, verbose=None, method="auto
 
 
 def _build_global(name, state, rank, world, dist, verbose):
-    """The global synthetic workload on every rank.  Large spheres are generated ONCE: rank 0 writes the mesh
-    to a node-local cache, the others read it after a barrier (a 10 M-cell mesh takes ~1 min of numpy per
-    generation; eight copies of that work on one host would dominate the set-up time)."""
+    """The global synthetic workload on every rank.  Large spheres are generated ONCE per machine: rank 0 fills
+    the mesh cache (workloads.mesh_cache_path) if needed, the others read it after a barrier -- a 10 M-cell mesh
+    takes ~1 min of numpy per generation, eight copies of that work on one host would dominate the set-up."""
     import os
-    import tempfile
     level = workloads.SPHERES.get(name, (0, 0))[0]
-    if dist is None or world == 1 or level < 8 or os.environ.get("EVP_B200_MESH_CACHE"):
+    path = workloads.mesh_cache_path(level)
+    if dist is None or world == 1 or path is None:
         return workloads.build(name, state=state, verbose=verbose, with_static=False)
-    cache = [tempfile.mkdtemp(prefix="evp_b200_mesh_") if rank == 0 else None]
-    dist.broadcast_object_list(cache, src=0)
-    os.environ["EVP_B200_MESH_CACHE"] = cache[0]
-    try:
-        w = None
-        if rank == 0:
-            w = workloads.build(name, state=state, verbose=verbose, with_static=False)
-        dist.barrier()
-        if rank != 0:
-            w = workloads.build(name, state=state, verbose=verbose, with_static=False)
-        dist.barrier()
-    finally:
-        del os.environ["EVP_B200_MESH_CACHE"]
-        if rank == 0:
-            import shutil
-            shutil.rmtree(cache[0], ignore_errors=True)
+    w = None
+    if rank == 0 or os.path.exists(path):
+        w = workloads.build(name, state=state, verbose=verbose, with_static=False)
+    dist.barrier()
+    if w is None:
+        w = workloads.build(name, state=state, verbose=verbose, with_static=False)
     return w
 
 

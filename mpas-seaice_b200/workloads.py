@@ -25,25 +25,43 @@ ALGO_BYTES_PER_VERTEX = 164.0       # per owned vertex
 ALGO_BYTES_PER_CELL_SUBCYCLE = 2240.0
 
 
-def _cached_icosphere(level: int):
-    """meshgen.icosphere(level), optionally cached as an uncompressed .npz under $EVP_B200_MESH_CACHE
-    (mesh generation is deterministic; the cache only saves the ~1 min a 10 M-cell mesh takes when
-    several runs share a machine, e.g. a plain run followed by the same run under ncu)."""
+def mesh_cache_dir():
+    """Directory of the generated-mesh cache, or None when disabled.  Default: <repo>/.mesh_cache (git- and
+    gpurun-ignored); EVP_B200_MESH_CACHE names another directory, or switches the cache off with 0 / off / none."""
     import os
-    cache = os.environ.get("EVP_B200_MESH_CACHE")
-    if not cache or level < 8:
+    v = os.environ.get("EVP_B200_MESH_CACHE")
+    if v is not None:
+        return None if v.strip().lower() in ("", "0", "off", "none") else v
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), ".mesh_cache")
+
+
+def mesh_cache_path(level: int):
+    import os
+    d = mesh_cache_dir()
+    return None if (d is None or level < 8) else os.path.join(d, f"icosphere_{level}.npz")
+
+
+def _cached_icosphere(level: int):
+    """meshgen.icosphere(level), cached as an uncompressed .npz for level >= 8 (mesh generation is deterministic;
+    the cache only saves the ~1 min a 10 M-cell mesh takes when several runs share a machine: the reference arm
+    and our arm of bench.py, the N = 1, 2, 4, 8 scaling runs, a plain run followed by the same run under ncu)."""
+    import os
+    path = mesh_cache_path(level)
+    if path is None:
         return meshgen.icosphere(level)
-    path = os.path.join(cache, f"icosphere_{level}.npz")
     if os.path.exists(path):
-        with np.load(path, allow_pickle=False) as z:
-            m = meshgen.Mesh()
-            for k in z.files:
-                a = z[k]
-                m[k] = a.item() if a.ndim == 0 else a
-            return m
+        try:
+            with np.load(path, allow_pickle=False) as z:
+                m = meshgen.Mesh()
+                for k in z.files:
+                    a = z[k]
+                    m[k] = a.item() if a.ndim == 0 else a
+                return m
+        except Exception:
+            pass                                   # truncated / foreign file: regenerate
     m = meshgen.icosphere(level)
     try:
-        os.makedirs(cache, exist_ok=True)
+        os.makedirs(os.path.dirname(path), exist_ok=True)
         tmp = path + f".{os.getpid()}.tmp.npz"
         np.savez(tmp, **{k: np.asarray(v) for k, v in m.items()})
         os.replace(tmp, path)
