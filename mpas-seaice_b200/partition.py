@@ -235,6 +235,12 @@ def build_block(mesh, part: np.ndarray, rank: int, n_halos: int | None = None) -
                 out[:nEl] = mesh[k][edges]
                 b[k] = out
         b.indexToEdgeID = (edges + 1).astype(np.int32)
+        if "cellsOnEdge" in mesh:          # weak stress divergence reads the two cells of an edge (weak.F:585-592)
+            coe_g = mesh.cellsOnEdge[edges].astype(np.int64) - 1
+            coe_ok = (coe_g >= 0) & (coe_g < nC)
+            coe_l = np.full((nEl + 1, 2), nCl + 1, dtype=np.int32)
+            coe_l[:nEl] = np.where(coe_ok, g2l_cell[np.where(coe_ok, coe_g, nC)] + 1, nCl + 1)
+            b.cellsOnEdge = coe_l
 
     for k in CELL_FIELDS_1D:
         b[k] = cell1d(mesh[k], JUNK_AREA if k == "areaCell" else 0.0)
@@ -331,6 +337,30 @@ def restrict_field(block, a: np.ndarray, n_global_cells: int, n_global_vertices:
         raise ValueError(f"field of length {a.shape[0]} is neither a cell nor a vertex field")
     out = np.zeros((idx.shape[0] + 1,) + a.shape[1:], dtype=a.dtype)
     out[:-1] = a[idx]
+    return out
+
+
+def restrict_weak(block, gmesh, gweak: dict) -> dict:
+    """The weak-operator fields of weakmesh.weak_fields(global mesh) restricted to ``block``: cell- and
+    vertex-indexed arrays by rows, edge-indexed ones through the block's edge numbering.  Restricting the global
+    arrays (instead of recomputing them per block) keeps every value bit-identical on every rank count."""
+    nCg, nVg, nEg = int(gmesh.nCells), int(gmesh.nVertices), int(gmesh.nEdges)
+    nVl, nEl = int(block.nVertices), int(block.nEdges)
+    out = {}
+    for k in ("normalVectorPolygon", "normalVectorTriangle", "latCellRotated", "latVertexRotated"):
+        out[k] = np.ascontiguousarray(restrict_field(block, gweak[k], nCg, nVg))
+    g2l_vert = np.full(nVg + 2, nVl + 1, dtype=np.int64)
+    g2l_vert[block.indexToVertexID.astype(np.int64)] = np.arange(1, nVl + 1)
+    g2l_edge = np.full(nEg + 2, nEl + 1, dtype=np.int64)
+    g2l_edge[block.indexToEdgeID.astype(np.int64)] = np.arange(1, nEl + 1)
+    edges_g = block.indexToEdgeID.astype(np.int64) - 1
+    voe = np.full((nEl + 1, 2), nVl + 1, dtype=np.int32)
+    voe[:nEl] = g2l_vert[gweak["verticesOnEdge"][edges_g].astype(np.int64)].astype(np.int32)
+    out["verticesOnEdge"] = voe
+    verts_g = block.indexToVertexID.astype(np.int64) - 1
+    eov = np.full((nVl + 1, gweak["edgesOnVertex"].shape[1]), nEl + 1, dtype=np.int32)
+    eov[:nVl] = g2l_edge[gweak["edgesOnVertex"][verts_g].astype(np.int64)].astype(np.int32)
+    out["edgesOnVertex"] = eov
     return out
 
 

@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 import common
+import oracle
 from mpas_seaice_b200 import partition
 
 
@@ -105,4 +106,40 @@ def test_owned_results_bit_identical_across_rank_counts(kind, n_parts, method, n
         assert np.array_equal(out[k][cm], ref[k][cm]), k
     for k in common.COMPARE_VERTEX:
         assert np.array_equal(out[k][vm], ref[k][vm]), k
+    assert np.abs(ref["uVelocity"]).max() > 0
+
+
+@pytest.mark.parametrize("kind,n_parts,method,schemes", [("ico3", 3, "rcb", ("weak", "weak")),
+                                                         ("hex20", 2, "block", ("weak", "weak")),
+                                                         ("quad40", 2, "rcb", ("weak", "weak"))])
+def test_weak_operators_bit_identical_across_rank_counts(kind, n_parts, method, schemes):
+    """The weak operators decomposed: edge-indexed mesh data goes through the block's edge numbering
+    (partition.build_block: edgesOnCell, cellsOnEdge, dvEdge, dcEdge; partition.restrict_weak: verticesOnEdge,
+    edgesOnVertex, the normal vectors); owned results equal the single-rank run bit for bit."""
+    from mpas_seaice_b200 import partition, weakmesh
+    mesh, var = common.mesh_case(kind)
+    gweak = weakmesh.weak_fields(mesh)
+    step, opts = common.step_case(mesh)
+    opts = dict(opts, strain_scheme=schemes[0], stress_divergence_scheme=schemes[1])
+    nsub = 8
+    ref = common.run_oracle(mesh, dict(var, weak=gweak), step, opts, nsub)
+    part, blocks, lists = common.make_blocks(mesh, n_parts, method)
+    bsteps = [partition.restrict_step(b, step, mesh.nCells, mesh.nVertices) for b in blocks]
+    bvars = []
+    for b in blocks:
+        v = oracle.init_variational(b)
+        v["weak"] = partition.restrict_weak(b, mesh, gweak)
+        bvars.append(v)
+    for _ in range(nsub):
+        for b, v, s in zip(blocks, bvars, bsteps):
+            oracle.subcycle_velocity_solver(b, v, s, dict(opts, nVerticesSolve=int(b.nVerticesSolve)), 1)
+        common.exchange_halos(bsteps, lists)
+    for b, s in zip(blocks, bsteps):
+        nVs, nCs = int(b.nVerticesSolve), int(b.nCellsSolve)
+        gv = b.indexToVertexID[:nVs].astype(np.int64) - 1
+        gc = b.indexToCellID[:nCs].astype(np.int64) - 1
+        for k in ("uVelocity", "vVelocity", "stressDivergenceU", "stressDivergenceV"):
+            assert np.array_equal(s[k][:nVs], ref[k][gv]), k
+        for k in ("stress11Weak", "stress22Weak", "stress12Weak", "strain11Weak", "strain12Weak"):
+            assert np.array_equal(s[k][:nCs], ref[k][gc]), k
     assert np.abs(ref["uVelocity"]).max() > 0
