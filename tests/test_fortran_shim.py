@@ -60,3 +60,62 @@ def test_enum_values_agree():
         c = int(re.search(name + r"\s*=\s*(\d+)", HDR).group(1))
         f = int(re.search(name + r"\s*=\s*(\d+)", F90).group(1))
         assert c == f, name
+
+
+def _code_lines():
+    """Source lines without comments and preprocessor lines, continuations joined."""
+    out, cur = [], ""
+    for raw in F90.split("\n"):
+        line = raw.split("!")[0].rstrip() if not raw.lstrip().startswith("!") else ""
+        if raw.lstrip().startswith("#") or not line.strip():
+            continue
+        if line.rstrip().endswith("&"):
+            cur += line.rstrip()[:-1] + " "
+            continue
+        out.append((cur + line).strip())
+        cur = ""
+    assert cur == ""
+    return out
+
+
+def test_free_form_line_length_and_block_balance():
+    """No Fortran compiler here: at least the block structure must balance and no line may exceed the 132 columns of
+    free-form source."""
+    for i, raw in enumerate(F90.split("\n"), 1):
+        assert len(raw) <= 132, f"line {i} has {len(raw)} columns"
+    lines = [l.lower() for l in _code_lines()]
+    opens = dict(subroutine=0, function=0, interface=0, module=0, do=0)
+    ifs = types = 0
+    for l in lines:
+        w = l.split()
+        if re.match(r"^(end\s*subroutine)\b", l): opens["subroutine"] -= 1
+        elif re.match(r"^(end\s*function)\b", l): opens["function"] -= 1
+        elif re.match(r"^(end\s*interface)\b", l): opens["interface"] -= 1
+        elif re.match(r"^(end\s*module)\b", l): opens["module"] -= 1
+        elif re.match(r"^(end\s*do)\b", l): opens["do"] -= 1
+        elif re.match(r"^(end\s*if)\b", l): ifs -= 1
+        elif re.match(r"^(end\s*type)\b", l): types -= 1
+        elif w[0] == "subroutine": opens["subroutine"] += 1
+        elif w[0] == "function" or re.match(r"^.*\bfunction\s+\w+\s*\(", l) and "bind(c" in l: opens["function"] += 1
+        elif w[0] == "interface": opens["interface"] += 1
+        elif w[0] == "module": opens["module"] += 1
+        elif re.match(r"^do\b", l): opens["do"] += 1
+        elif re.match(r"^if\s*\(.*\)\s*then$", l) or re.match(r"^else\s*if\s*\(.*\)\s*then$", l) and False: ifs += 1
+        elif re.match(r"^type\s*,", l): types += 1
+    assert all(v == 0 for v in opens.values()), opens
+    assert ifs == 0 and types == 0, (ifs, types)
+
+
+def test_every_called_c_function_is_bound_and_every_c_loc_target_is_declared():
+    bound = set(re.findall(r'bind\(C, name="(\w+)"\)', F90))
+    called = set(re.findall(r"\b(evp_[a-z_0-9]+)\s*\(", "\n".join(_code_lines())))
+    types = {"evp_mesh_desc", "evp_options", "evp_step_fields", "evp_out_fields", "evp_mesh_ext", "evp_pre_fields",
+             "evp_pre_options", "evp_post_fields", "evp_weak_mesh", "evp_weak_fields"}
+    assert called - types - {"evp_b200_check"} <= bound, called - types - bound
+    # inside every routine, each c_loc(x) argument is a declared pointer / target
+    src = "\n".join(_code_lines())
+    for m in re.finditer(r"subroutine\s+(\w+)\s*\(.*?end subroutine \1", src, flags=re.S | re.I):
+        body = m.group(0)
+        decl = " ".join(l for l in body.split("\n") if "::" in l)
+        for var in set(re.findall(r"c_loc\((\w+)\)", body)):
+            assert re.search(r"\b" + var + r"\b", decl), (m.group(1), var)
