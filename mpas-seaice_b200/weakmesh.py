@@ -3,8 +3,10 @@
 In MPAS-Seaice ``verticesOnEdge`` / ``edgesOnVertex`` come from the mesh file and the normal vectors
 from seaice_normal_vectors (reference: src/shared/mpas_seaice_mesh.F:703-2007, weak schemes only --
 out of scope of this library).  The generators of meshgen.py do not emit
-them, so this module derives the connectivity and builds geometrically sensible unit normals in the
-local tangent planes.  Operator parity (device vs oracle) does not depend on how the normals were
+them, so this module derives the connectivity; on planar meshes the normals follow the reference's
+normal_vectors_planar_polygon / _triangle (mesh.F:858-1024), on the sphere they are geometrically
+sensible unit normals in the local tangent planes (the reference's great-circle construction,
+mesh.F:1038-1744, is not restated).  Operator parity (device vs oracle) does not depend on how the normals were
 made: both sides read the same arrays.
 """
 from __future__ import annotations
@@ -60,12 +62,50 @@ def edge_connectivity(mesh):
     return voe, eov
 
 
+def _planar_fields(mesh, voe, eov):
+    """Planar meshes: the reference's own definitions, normal_vectors_planar_polygon / _triangle
+    (src/shared/mpas_seaice_mesh.F:858-943, 957-1024), with xEdge / yEdge = the edge midpoint."""
+    nC, nV, nE, M, D = mesh.nCells, mesh.nVertices, mesh.nEdges, mesh.maxEdges, mesh.vertexDegree
+    xv, yv = mesh.xVertex, mesh.yVertex
+    xe = np.zeros(nE + 1)
+    ye = np.zeros(nE + 1)
+    v1, v2 = voe[:nE, 0] - 1, voe[:nE, 1] - 1
+    xe[:nE] = 0.5 * (xv[v1] + xv[v2])
+    ye[:nE] = 0.5 * (yv[v1] + yv[v2])
+    nvp = np.zeros((nC + 1, M, 2))
+    for k in range(M):
+        c = np.nonzero(mesh.nEdgesOnCell[:nC] > k)[0]
+        e = mesh.edgesOnCell[c, k] - 1
+        a, b = voe[e, 0] - 1, voe[e, 1] - 1
+        tx, ty = xv[b] - xv[a], yv[b] - yv[a]
+        tmag = np.sqrt(tx ** 2 + ty ** 2)
+        tx, ty = tx / tmag, ty / tmag
+        nx, ny = xe[e] - mesh.xCell[c], ye[e] - mesh.yCell[c]
+        flip = (nx * ty - ny * tx) < 0.0
+        tx = np.where(flip, -tx, tx)
+        ty = np.where(flip, -ty, ty)
+        nvp[c, k, 0] = ty
+        nvp[c, k, 1] = -tx
+    nvt = np.zeros((nV + 1, D, 2))
+    interior = variational_init.interior_vertex(mesh)[:nV] == 1
+    v = np.nonzero(interior)[0]
+    for s in range(D):
+        e = eov[v, s] - 1
+        dx, dy = xe[e] - xv[v], ye[e] - yv[v]
+        nvt[v, s, 0] = dx / np.sqrt(dx ** 2 + dy ** 2)
+        nvt[v, s, 1] = dy / np.sqrt(dx ** 2 + dy ** 2)
+    return dict(verticesOnEdge=voe, edgesOnVertex=eov, normalVectorPolygon=nvp, normalVectorTriangle=nvt,
+                latCellRotated=np.zeros(nC + 1), latVertexRotated=np.zeros(nV + 1))
+
+
 def weak_fields(mesh):
     """dict(verticesOnEdge, edgesOnVertex, normalVectorPolygon (nCells+1, maxEdges, 2), normalVectorTriangle
     (nVertices+1, vertexDegree, 2), latCellRotated, latVertexRotated) in Registry layouts."""
     nC, nV, M, D = mesh.nCells, mesh.nVertices, mesh.maxEdges, mesh.vertexDegree
     voe, eov = edge_connectivity(mesh)
     on_sphere = bool(mesh.on_a_sphere)
+    if not on_sphere:
+        return _planar_fields(mesh, voe, eov)
     xl, yl = variational_init.local_coords(mesh, rotate=on_sphere)       # vertices in the cell's tangent plane
     n_on = mesh.nEdgesOnCell
     nvp = np.zeros((nC + 1, M, 2))
