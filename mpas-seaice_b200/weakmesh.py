@@ -1,13 +1,13 @@
-"""Edge connectivity and normal vectors for the weak operators, for synthetic hosts.
+"""Edge connectivity and normal vectors for the weak operators, for non-Fortran hosts.
 
-In MPAS-Seaice ``verticesOnEdge`` / ``edgesOnVertex`` come from the mesh file and the normal vectors
-from seaice_normal_vectors (reference: src/shared/mpas_seaice_mesh.F:703-2007, weak schemes only --
-out of scope of this library).  The generators of meshgen.py do not emit
-them, so this module derives the connectivity; on planar meshes the normals follow the reference's
-normal_vectors_planar_polygon / _triangle (mesh.F:858-1024), on the sphere they are geometrically
-sensible unit normals in the local tangent planes (the reference's great-circle construction,
-mesh.F:1038-1744, is not restated).  Operator parity (device vs oracle) does not depend on how the normals were
-made: both sides read the same arrays.
+In MPAS-Seaice ``verticesOnEdge`` / ``edgesOnVertex`` come from the mesh file and the normal vectors from
+seaice_normal_vectors (reference: src/shared/mpas_seaice_mesh.F:703-2007), which the Fortran host keeps
+computing itself.  The generators of meshgen.py emit neither, so this module derives the connectivity (with the
+MPAS orientation of verticesOnEdge against cellsOnEdge) and restates the reference's normal vectors:
+planar meshes normal_vectors_planar_polygon / _triangle (mesh.F:858-1024), spherical meshes
+normal_vectors_spherical_polygon_metric / _triangle_metric (mesh.F:1038-1606) with removeMetricTerms = .true.
+as seaice_init_velocity_solver_weak calls them (weak.F:87-96).  tests/test_analytic_golden.py checks the result
+through the weak operators against the reference's analytic operator-test fields.
 """
 from __future__ import annotations
 
@@ -98,6 +98,88 @@ def _planar_fields(mesh, voe, eov):
                 latCellRotated=np.zeros(nC + 1), latVertexRotated=np.zeros(nV + 1))
 
 
+def _sphere_fields(mesh, voe, eov):
+    """Spherical meshes: normal_vectors_spherical_polygon_metric / _triangle_metric of the reference
+    (src/shared/mpas_seaice_mesh.F:1038-1241, 1393-1606) with config_rotate_cartesian_grid = true and
+    removeMetricTerms = .true. as seaice_init_velocity_solver_weak passes it (weak.F:87-96): every cell (vertex) is
+    first rotated to lon = 0, lat = 0 of the rotated grid, where east / north are the axes of its tangent plane; the
+    horizontal unit normal of the side (tangent x position) is then expressed by its eastward component and the
+    signed remainder.  xEdge / yEdge / zEdge = the vertex midpoint pushed back onto the sphere.  The reference's sign
+    rule relies on the MPAS orientation of verticesOnEdge against cellsOnEdge (tangent = radial x normal), which is
+    established here first."""
+    nC, nV, nE, M, D = mesh.nCells, mesh.nVertices, mesh.nEdges, mesh.maxEdges, mesh.vertexDegree
+    R = float(mesh.sphere_radius)
+    rot = lambda x, y, z: (-z, y, x)                       # seaice_grid_rotation_forward, mesh.F:2367-2379
+    cx, cy, cz = rot(mesh.xCell, mesh.yCell, mesh.zCell)
+    vx, vy, vz = rot(mesh.xVertex, mesh.yVertex, mesh.zVertex)
+    coe = mesh.cellsOnEdge[:nE].astype(np.int64) - 1
+    a, b = voe[:nE, 0].astype(np.int64) - 1, voe[:nE, 1].astype(np.int64) - 1
+    ex, ey, ez = 0.5 * (vx[a] + vx[b]), 0.5 * (vy[a] + vy[b]), 0.5 * (vz[a] + vz[b])
+    en = np.sqrt(ex * ex + ey * ey + ez * ez) / R
+    ex, ey, ez = ex / en, ey / en, ez / en
+    # orientation: (v2 - v1) . (r x (c2 - c1)) > 0
+    nx_, ny_, nz_ = cx[coe[:, 1]] - cx[coe[:, 0]], cy[coe[:, 1]] - cy[coe[:, 0]], cz[coe[:, 1]] - cz[coe[:, 0]]
+    tx_, ty_, tz_ = ey * nz_ - ez * ny_, ez * nx_ - ex * nz_, ex * ny_ - ey * nx_
+    swap = ((vx[b] - vx[a]) * tx_ + (vy[b] - vy[a]) * ty_ + (vz[b] - vz[a]) * tz_) < 0.0
+    voe = voe.copy()
+    voe[:nE][swap] = voe[:nE][swap][:, ::-1]
+    a, b = voe[:nE, 0].astype(np.int64) - 1, voe[:nE, 1].astype(np.int64) - 1
+
+    def to_equator(px, py, pz, lat, lon):
+        """yRotationMatrix . zRotationMatrix . p  (mesh.F:1118-1127): the point (lat, lon) goes to (R, 0, 0)."""
+        cl, sl = np.cos(-lon), np.sin(-lon)
+        x1, y1, z1 = cl * px - sl * py, sl * px + cl * py, pz
+        ct, st = np.cos(lat), np.sin(lat)
+        return ct * x1 + st * z1, y1, -st * x1 + ct * z1
+
+    def components(gx, gy, gz, qx, qy):
+        """Unit horizontal normal (gx,gy,gz) at the rotated edge position (qx,qy,.) -> (eastward component, signed
+        remainder), mesh.F:1205-1225."""
+        gn = np.sqrt(gx ** 2 + gy ** 2 + gz ** 2)
+        gx, gy, gz = gx / gn, gy / gn, gz / gn
+        east_x, east_y = -qy, qx
+        east_n = np.sqrt(east_x ** 2 + east_y ** 2)
+        east_x, east_y = east_x / east_n, east_y / east_n
+        n1 = gx * east_x + gy * east_y + gz * 0.0
+        n2 = np.copysign(1.0, gz) * np.sqrt(1.0 - np.maximum(np.minimum(n1, 1.0), -1.0) ** 2)
+        return n1, n2
+
+    lat_cell = np.arcsin(np.clip(cz[:nC] / R, -1.0, 1.0))
+    lon_cell = np.arctan2(cy[:nC], cx[:nC])
+    nvp = np.zeros((nC + 1, M, 2))
+    for k in range(M):
+        c = np.nonzero(mesh.nEdgesOnCell[:nC] > k)[0]
+        e = mesh.edgesOnCell[c, k].astype(np.int64) - 1
+        la, lo = lat_cell[c], lon_cell[c]
+        qx, qy, qz = to_equator(ex[e], ey[e], ez[e], la, lo)
+        ax_, ay_, az_ = to_equator(vx[a[e]], vy[a[e]], vz[a[e]], la, lo)
+        bx_, by_, bz_ = to_equator(vx[b[e]], vy[b[e]], vz[b[e]], la, lo)
+        wx, wy, wz = bx_ - ax_, by_ - ay_, bz_ - az_
+        gx, gy, gz = wy * qz - wz * qy, wz * qx - wx * qz, wx * qy - wy * qx
+        flip = np.where(c == coe[e, 1], -1.0, 1.0)
+        nvp[c, k, 0], nvp[c, k, 1] = components(gx * flip, gy * flip, gz * flip, qx, qy)
+    nvt = np.zeros((nV + 1, D, 2))
+    interior = variational_init.interior_vertex(mesh)[:nV] == 1
+    v = np.nonzero(interior)[0]
+    lat_vert = np.arcsin(np.clip(vz[v] / R, -1.0, 1.0))
+    lon_vert = np.arctan2(vy[v], vx[v])
+    for s_ in range(D):
+        e = eov[v, s_].astype(np.int64) - 1
+        qx, qy, qz = to_equator(ex[e], ey[e], ez[e], lat_vert, lon_vert)
+        c1x, c1y, c1z = to_equator(cx[coe[e, 0]], cy[coe[e, 0]], cz[coe[e, 0]], lat_vert, lon_vert)
+        c2x, c2y, c2z = to_equator(cx[coe[e, 1]], cy[coe[e, 1]], cz[coe[e, 1]], lat_vert, lon_vert)
+        wx, wy, wz = c2x - c1x, c2y - c1y, c2z - c1z
+        gx, gy, gz = wy * qz - wz * qy, wz * qx - wx * qz, wx * qy - wy * qx
+        flip = np.where(v == a[e], -1.0, 1.0)
+        nvt[v, s_, 0], nvt[v, s_, 1] = components(gx * flip, gy * flip, gz * flip, qx, qy)
+    lat_c = np.zeros(nC + 1)
+    lat_v = np.zeros(nV + 1)
+    lat_c[:nC] = np.arcsin(np.clip(cz[:nC] / R, -1.0, 1.0))
+    lat_v[:nV][interior] = np.arcsin(np.clip(vz[:nV][interior] / R, -1.0, 1.0))
+    return dict(verticesOnEdge=voe, edgesOnVertex=eov, normalVectorPolygon=nvp, normalVectorTriangle=nvt,
+                latCellRotated=lat_c, latVertexRotated=lat_v)
+
+
 def weak_fields(mesh):
     """dict(verticesOnEdge, edgesOnVertex, normalVectorPolygon (nCells+1, maxEdges, 2), normalVectorTriangle
     (nVertices+1, vertexDegree, 2), latCellRotated, latVertexRotated) in Registry layouts."""
@@ -106,74 +188,4 @@ def weak_fields(mesh):
     on_sphere = bool(mesh.on_a_sphere)
     if not on_sphere:
         return _planar_fields(mesh, voe, eov)
-    xl, yl = variational_init.local_coords(mesh, rotate=on_sphere)       # vertices in the cell's tangent plane
-    n_on = mesh.nEdgesOnCell
-    nvp = np.zeros((nC + 1, M, 2))
-    # which neighbour vertex closes edge k: decided exactly as in edge_connectivity (re-derive from verticesOnEdge)
-    voc = mesh.verticesOnCell
-    for k in range(M):
-        valid = n_on[:nC] > k
-        c = np.nonzero(valid)[0]
-        e = mesh.edgesOnCell[c, k]
-        other = np.where(voe[e - 1, 0] == voc[c, k], voe[e - 1, 1], voe[e - 1, 0])
-        # slot of the other vertex inside the cell
-        slot = np.argmax(voc[c, :] == other[:, None], axis=1)
-        dx = xl[c, slot] - xl[c, k]
-        dy = yl[c, slot] - yl[c, k]
-        nx, ny = dy, -dx
-        # outward: pointing away from the cell centre (the origin of the local coordinates)
-        mx, my = 0.5 * (xl[c, slot] + xl[c, k]), 0.5 * (yl[c, slot] + yl[c, k])
-        flip = (nx * mx + ny * my) < 0.0
-        nx = np.where(flip, -nx, nx)
-        ny = np.where(flip, -ny, ny)
-        ln = np.sqrt(nx * nx + ny * ny)
-        nvp[c, k, 0] = nx / ln
-        nvp[c, k, 1] = ny / ln
-    # dual triangle: edge s of vertex v is crossed by the dual edge joining the two cells of that edge
-    if on_sphere:
-        px, py, pz = -mesh.zCell, mesh.yCell, mesh.xCell         # rotated frame, as local_coords uses
-        vx, vy, vz = -mesh.zVertex, mesh.yVertex, mesh.xVertex
-        r = np.sqrt(vx * vx + vy * vy + vz * vz)
-        r[r == 0] = 1.0
-        ux, uy, uz = vx / r, vy / r, vz / r
-        ex, ey, ez = -uy, ux, np.zeros_like(ux)                   # east
-        en = np.sqrt(ex * ex + ey * ey)
-        en[en == 0] = 1.0
-        ex, ey = ex / en, ey / en
-        nx3, ny3, nz3 = uy * ez - uz * ey, uz * ex - ux * ez, ux * ey - uy * ex   # north = up x east
-
-        def local(v, c):
-            dx, dy, dz = px[c] - vx[v], py[c] - vy[v], pz[c] - vz[v]
-            return dx * ex[v] + dy * ey[v] + dz * ez[v], dx * nx3[v] + dy * ny3[v] + dz * nz3[v]
-    else:
-        def local(v, c):
-            return mesh.xCell[c] - mesh.xVertex[v], mesh.yCell[c] - mesh.yVertex[v]
-    nvt = np.zeros((nV + 1, D, 2))
-    v = np.arange(nV)
-    for s in range(D):
-        e = eov[:nV, s]
-        ok = e <= mesh.nEdges
-        vv = v[ok]
-        ca = mesh.cellsOnEdge[e[ok] - 1, 0] - 1
-        cb = mesh.cellsOnEdge[e[ok] - 1, 1] - 1
-        good = (ca < nC) & (cb < nC) & (ca >= 0) & (cb >= 0)
-        vv, ca, cb = vv[good], ca[good], cb[good]
-        ax, ay = local(vv, ca)
-        bx, by = local(vv, cb)
-        dx, dy = bx - ax, by - ay
-        nx, ny = dy, -dx
-        mx, my = 0.5 * (ax + bx), 0.5 * (ay + by)
-        flip = (nx * mx + ny * my) < 0.0
-        nx = np.where(flip, -nx, nx)
-        ny = np.where(flip, -ny, ny)
-        ln = np.sqrt(nx * nx + ny * ny)
-        nvt[vv, s, 0] = nx / ln
-        nvt[vv, s, 1] = ny / ln
-    lat_c = np.zeros(nC + 1)
-    lat_v = np.zeros(nV + 1)
-    if on_sphere:
-        R = mesh.sphere_radius
-        lat_c[:nC] = np.arcsin(np.clip(mesh.xCell[:nC] / R, -1.0, 1.0))      # rotated pole: z' = x
-        lat_v[:nV] = np.arcsin(np.clip(mesh.xVertex[:nV] / R, -1.0, 1.0))
-    return dict(verticesOnEdge=voe, edgesOnVertex=eov, normalVectorPolygon=nvp, normalVectorTriangle=nvt,
-                latCellRotated=lat_c, latVertexRotated=lat_v)
+    return _sphere_fields(mesh, voe, eov)
