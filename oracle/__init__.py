@@ -24,7 +24,7 @@ QUADRATIC_OCEAN_STRESS, LINEAR_OCEAN_STRESS = 1, 2
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("evp_oracle.c", "evp_precompute_oracle.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("evp_oracle.c", "evp_precompute_oracle.c", "ir_oracle.c", "Makefile")]
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
     if force or stale:
