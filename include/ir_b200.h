@@ -1,0 +1,111 @@
+/* ir_b200.h -- C ABI of the B200 incremental-remapping (IR) transport of MPAS-Seaice: the consumer of the EVP
+ * velocities.
+ *
+ * Replaces the work of one call of
+ *     seaice_run_advection_incremental_remap        src/shared/mpas_seaice_advection_incremental_remap.F:2338-2730
+ * on one block, i.e. incremental_remap_block (:2740-3400) with the volume <-> thickness conversions around it
+ * (:2462-2480, :2680-2700).  Initialisation (seaice_init_advection_incremental_remap, :165-816) stays with the host
+ * model: it fills the `incremental_remap` pool (Registry.xml var_struct incremental_remap) once, and those pool arrays
+ * are what ir_create receives -- the same contract evp_b200.h has with the velocity solver's pools.
+ *
+ * STATUS (round 1): built and exported; parity against oracle/ir_oracle.c is tested by tests/test_gpu_ir.py, which
+ * has not yet run on a device (the round's GPU minutes were spent before this was written).  Single block: the
+ * tracer halo update after the call (seaice_update_tracer_halo, :2710) is still the host's.
+ *
+ * Conventions as in evp_b200.h: host pointers, Fortran (column-major) layout passed with c_loc(), 1-based index
+ * values, arrays dimensioned nCells / nEdges / nVertices carry MPAS's extra slot n+1.  Every entry point returns
+ * IR_OK or an error code; ir_last_error_string() describes the last failure of the calling thread.
+ */
+#ifndef IR_B200_H
+#define IR_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ir_handle ir_handle;
+
+enum {
+    IR_OK = 0,
+    IR_ERR_ARGUMENT = 1,
+    IR_ERR_CUDA = 2,
+    IR_ERR_STATE = 3,
+    /* conditions the reference aborts on (MPAS_LOG_CRIT), reported after the step has run */
+    IR_ERR_NEGATIVE_MASS_QP = 10,   /* negative mass at a quadrature point   incremental_remap.F:6895-6935 */
+    IR_ERR_NEGATIVE_MASS = 11,      /* new mass below -puny**2               incremental_remap.F:7465-7480 */
+    IR_ERR_PARALLEL_EDGES = 12,     /* degenerate basis in shift_vertices    incremental_remap.F:6415-6425 */
+    IR_ERR_TOO_MANY_TRIANGLES = 13  /* more than nTriPerEdgeRemap departure triangles on an edge */
+};
+
+/* Dimensions fixed by Registry.xml:59-78. */
+#define IR_N_TRI_PER_EDGE 6
+#define IR_MAX_CELLS_PER_EDGE_REMAP 6
+#define IR_MAX_EDGES_PER_EDGE_REMAP 6
+#define IR_MAX_VERTICES_PER_EDGE_REMAP 8
+
+/* Mesh pool + incremental_remap pool arrays (incremental_remap_block's pointer list, :2860-2925). */
+typedef struct ir_mesh_desc {
+    int nCells, nCellsSolve, nVertices, nEdges, maxEdges, vertexDegree;
+    int nCategories;
+    int nQuadPoints;                 /* 3 or 6 (Registry.xml:59-62) */
+    int on_a_sphere;                 /* mesh pool config on_a_sphere */
+    int rotate_cartesian_grid;       /* config_rotate_cartesian_grid */
+    /* mesh pool */
+    const int *nEdgesOnCell;         /* (nCells+1) */
+    const int *edgesOnCell;          /* (maxEdges, nCells+1) */
+    const int *cellsOnCell;          /* (maxEdges, nCells+1) */
+    const int *verticesOnCell;       /* (maxEdges, nCells+1) */
+    const int *cellsOnEdge;          /* (2, nEdges+1) */
+    const int *verticesOnEdge;       /* (2, nEdges+1) */
+    const double *areaCell;          /* (nCells+1) */
+    const double *dcEdge;            /* (nEdges+1) */
+    const double *coeffs_reconstruct;/* (3, maxEdges, nCells+1)   mpas_init_reconstruct, :744-746 */
+    /* incremental_remap pool */
+    const double *transGlobalToCell; /* (3, 3, nCells); may be NULL on a plane */
+    const double *xVertexOnCell, *yVertexOnCell;   /* (maxEdges, nCells+1) */
+    const double *xVertexOnEdge, *yVertexOnEdge;   /* (8, nEdges+1) */
+    const int *remapEdge;            /* (nEdges+1) */
+    const int *cellsOnEdgeRemap;     /* (6, nEdges+1) */
+    const int *edgesOnEdgeRemap;     /* (6, nEdges+1) */
+    /* xAvgCell yAvgCell xxAvgCell xyAvgCell yyAvgCell xxxAvgCell xxyAvgCell xyyAvgCell yyyAvgCell
+     * xxxxAvgCell xxxyAvgCell xxyyAvgCell xyyyAvgCell yyyyAvgCell, (nCells+1) each (:2051-2090) */
+    const double *geomAvgCell[14];
+} ir_mesh_desc;
+
+/* One element of the reference's tracer linked list (incremental_remap_tracers.F:26-110), parents before children
+ * (the order of seaice_add_tracers_to_linked_list after sorting, the first being the mass-like field). */
+typedef struct ir_tracer_desc {
+    int nLayers;      /* 1 for (nCategories, nCells) tracers, else the first dimension of (nLayers, nCategories, nCells) */
+    int parent;       /* index of the parent tracer in the table, -1 for the mass-like field (iceAreaCategory) */
+    int volumeLike;   /* 1 for iceVolumeCategory / snowVolumeCategory: volume in and out, thickness while transported */
+    double *array;    /* (nLayers, nCategories, nCells+1), IN/OUT */
+} ir_tracer_desc;
+
+/* Create the device copy of the mesh and geometry.  device < 0: the current CUDA device. */
+int ir_create(ir_handle **out, const ir_mesh_desc *mesh, int device);
+
+/* Declare the tracer hierarchy (sizes and parents; the array pointers are not read here).  Allocates the resident
+ * device state.  May be called again when the set of active tracers changes. */
+int ir_set_tracers(ir_handle *h, int nTracers, const ir_tracer_desc *tracers);
+
+/* One transport step: uploads the tracers and the vertex velocities ((nVertices+1) each), runs the step, writes the
+ * tracers back.  Returns one of the IR_ERR_* abort conditions if the reference would have aborted; the arrays then
+ * hold whatever the step produced, as after the reference's abort write. */
+int ir_run(ir_handle *h, int nTracers, const ir_tracer_desc *tracers, const double *uVelocity, const double *vVelocity,
+           double dt);
+
+/* Diagnostics of the last step (any pointer may be NULL):
+ * xTriangle / yTriangle (nQuadPoints, 6, nEdges) quadrature points, triangleArea (6, nEdges), iCellTriangle (6, nEdges),
+ * maskEdge (nEdges), edgeFluxMass (nLayers of the mass field, nCategories, nEdges). */
+int ir_fetch_diagnostics(ir_handle *h, double *xTriangle, double *yTriangle, double *triangleArea, int *iCellTriangle,
+                         int *maskEdge, double *edgeFluxMass);
+
+int ir_last_run_ms(ir_handle *h, float *ms);       /* device time of the last ir_run, kernels only */
+int ir_launch_count(ir_handle *h, long long *n);   /* kernels launched by this handle so far */
+int ir_destroy(ir_handle *h);
+const char *ir_last_error_string(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,1083 @@
+// ir_kernels.cu -- incremental-remapping transport on B200 (sm_100a): kernels and the C ABI of include/ir_b200.h.
+//
+// What one ir_run does (reference: incremental_remap_block, src/shared/mpas_seaice_advection_incremental_remap.F:2740):
+//   k_prepare      cell mask, volume -> thickness                                   (:2462-2480, make_masks :3404)
+//   k_reconstruct  per tracer depth: gradient, limiter, centre value, barycentre    (:3580-5250)
+//   k_triangles    per edge: departure triangles and their quadrature points        (:5255-6665)
+//   k_fluxes       per (edge, tracer row): integrate mass * tracer over triangles   (:6667-6980)
+//   k_update       per tracer depth: new mass and tracers                           (:6982-7540)
+//   k_finish       zap small masses, thickness -> volume                            (:8764-8895, :2680-2700)
+//
+// Layout: the host keeps a tracer as (nLayers, nCategories, nCells) -- all components of a cell together.  On the
+// device every (tracer, category, layer) is a ROW of one matrix val[nRows][nCp] with the cell index fastest, so a warp
+// of 32 cells reads 256 contiguous bytes of a row; the same for every per-cell / per-edge geometry array
+// ([slot][nCp]).  Rows are ordered by tracer, so rows of one depth of the hierarchy are contiguous ranges and a whole
+// depth is one launch (grid.y = rows).  Parents are resolved to row numbers once, in ir_set_tracers.
+//
+// All of it is gather-heavy FP64 streaming work bounded by HBM / L2, not tensor work.  Built with --fmad=false and in
+// the reference's operation order so that the results are bit-identical to oracle/ir_oracle.c (tests/test_gpu_ir.py).
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/ir_b200.h"
+
+// Kernel launches go through one macro so that tests/emu can compile this file for the host and step through the
+// kernels thread by thread (tests/test_ir_parity.py, "emulation" leg: a check of the kernel logic where no GPU is
+// available; it is test infrastructure and never part of the shipped library).
+#ifndef IR_LAUNCH
+#define IR_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#endif
+
+namespace {
+
+constexpr double EPS11 = 1.0e-11;
+constexpr double W1QP = 1.09951743655321885e-01, W2QP = 2.23381589678011389e-01;
+constexpr double Q1QP = 9.15762135097710761e-02, Q2QP = 8.16847572980458514e-01;
+constexpr double Q3QP = 1.08103018168070275e-01, Q4QP = 4.45948490915965612e-01;
+constexpr int NTRI = IR_N_TRI_PER_EDGE, NCER = 6, NEER = 6, NVER = 8;
+constexpr int MAXM = 8;        // maxEdges supported
+constexpr int MAX_DEPTH = 4;   // mass + three parents (incremental_remap.F:6745)
+
+enum { FLAG_NEG_QP = 1, FLAG_NEG_MASS = 2, FLAG_PARALLEL = 4, FLAG_MANY_TRI = 8 };
+
+thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+#define IR_CUDA(call)                                                                        \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return IR_ERR_CUDA;                                                              \
+        }                                                                                    \
+    } while (0)
+#define IR_REQUIRE(cond, msg)                                  \
+    do {                                                       \
+        if (!(cond)) {                                         \
+            set_error("%s:%d: %s", __FILE__, __LINE__, msg);   \
+            return IR_ERR_ARGUMENT;                            \
+        }                                                      \
+    } while (0)
+
+struct RowInfo {
+    int chain[MAX_DEPTH];  // rows of the mass field .. this row (mass first); chain[depth] == this row
+    int depth;             // number of parents
+    int hasChild;
+    int cat;               // category of the row
+    int volumeLike;
+};
+
+struct Dev {
+    // sizes
+    int nC, nCS, nV, nE, M, D, nK, nQP, sphere, rotate;
+    size_t nCp, nEp, nVp;
+    // mesh / geometry, [slot][pitch]
+    int *nEdgesOnCell, *edgesOnCell, *cellsOnCell, *verticesOnCell, *cellsOnEdge, *verticesOnEdge;
+    int *remapEdge, *coer, *eoer;
+    double *areaCell, *sdc /* signed dcEdge per (slot, cell) */, *coef /* [3*M] */, *trans /* rows 1,2 of transGlobalToCell: [6] */;
+    double *xvc, *yvc, *xve, *yve, *geom /* [14] */;
+    int *fluxSign;   // [M][nCp]: +1 if the cell is cellsOnEdge(1) of its k-th edge, else -1
+    // per step
+    double *u, *v;
+    int *maskCell, *maskEdge, *iCellTri /* [NTRI][nEp] */;
+    double *xq, *yq /* [NTRI*6][nEp] */, *triArea /* [NTRI][nEp] */;
+    // tracer state, [nRows][nCp] unless noted
+    int nRows;
+    RowInfo *rows;
+    double *val, *valNew, *center, *xGrad, *yGrad, *xBary, *yBary, *mtpNew;
+    double *edgeFlux;   // [nRows][nEp]
+    int *flags;
+    double *stage;      // raw host-layout staging
+    size_t stageBytes;
+};
+
+}  // namespace
+
+struct ir_handle {
+    int device;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    Dev d;
+    std::vector<RowInfo> rows;
+    std::vector<int> tracerRow0, tracerLayers, tracerParent, tracerVolume, tracerDepth;
+    std::vector<int> depthRow0;   // rows of depth q are [depthRow0[q], depthRow0[q+1])  (rows sorted by depth)
+    std::vector<int> rowOrder;    // device row -> (tracer, k, l) linear index on the host side
+    std::vector<void *> allocs;
+    float lastMs;
+    long long launches;
+    bool haveTracers;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ small device helpers
+
+__device__ __forceinline__ double cross2(double ax, double ay, double bx, double by) { return ax * by - ay * bx; }
+
+// point_in_half_plane as the reference executes it (its dummy arguments are (point, lineStart, lineEnd) while every
+// caller passes (V1, V2, P)): cross product of (P - V2) and (V1 - V2), incremental_remap.F:9200-9235
+__device__ __forceinline__ bool in_half_plane(double v1x, double v1y, double v2x, double v2y, double px, double py)
+{
+    return cross2(px - v2x, py - v2y, v1x - v2x, v1y - v2y) >= 0.0;
+}
+
+__device__ __forceinline__ double tri_area(double x1, double y1, double x2, double y2, double x3, double y3)
+{
+    return fabs(0.5 * ((x2 - x1) * (y3 - y1) - (y2 - y1) * (x3 - x1)));
+}
+
+// find_line_intersection, incremental_remap.F:8934
+__device__ bool line_intersection(double x1, double y1, double x2, double y2, double x3, double y3, double x4, double y4,
+                                  double &ipx, double &ipy)
+{
+    const double rx = x2 - x1, ry = y2 - y1, sx = x4 - x3, sy = y4 - y3;
+    const double rsCross = rx * sy - ry * sx;
+    const double rsCrossMin = EPS11 * sqrt((rx * rx + ry * ry) * (sx * sx + sy * sy));
+    if (fabs(rsCross) > rsCrossMin) {
+        const double t1 = (sy * (x3 - x1) - sx * (y3 - y1)) / rsCross;
+        const double t2 = (ry * (x3 - x1) - rx * (y3 - y1)) / rsCross;
+        ipx = x1 + t1 * rx;
+        ipy = y1 + t1 * ry;
+        return t1 > 0.0 && t1 < 1.0 && t2 > 0.0 && t2 < 1.0;
+    }
+    ipx = DBL_MAX;
+    ipy = DBL_MAX;
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------------------- layout kernels
+
+// host (n, w) row-major -> device [w][pitch]
+template <typename T>
+__global__ void k_rows_in(const T *__restrict__ raw, T *__restrict__ dst, size_t n, int w, size_t pitch)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int j = 0; j < w; j++) dst[(size_t)j * pitch + i] = raw[i * w + j];
+}
+
+// tracer: host (n, w) -> rows row0 .. row0+w-1 of val, and back
+__global__ void k_tracer_out(double *__restrict__ raw, const double *__restrict__ val, size_t n, int w, size_t pitch)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int j = 0; j < w; j++) raw[i * w + j] = val[(size_t)j * pitch + i];
+}
+
+// per (slot, cell): signed dcEdge and the flux sign (compute_gradient :4330-4340, update_mass_and_tracers :7260-7270)
+__global__ void k_cell_edge_signs(Dev d, const double *__restrict__ dcEdge)
+{
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= (size_t)d.nC) return;
+    for (int k = 0; k < d.M; k++) {
+        const int e = d.edgesOnCell[k * d.nCp + c];
+        double s = 1.0;
+        int fs = 1;
+        if (k < d.nEdgesOnCell[c] && e >= 1 && e <= d.nE) {
+            const bool first = ((int)c + 1 == d.cellsOnEdge[2 * ((size_t)e - 1)]);   // cellsOnEdge(1, e), host layout
+            fs = first ? 1 : -1;
+            s = (first ? 1.0 : -1.0) * dcEdge[e - 1];
+        }
+        d.sdc[k * d.nCp + c] = s;
+        d.fluxSign[k * d.nCp + c] = fs;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------- step
+
+// maskCell (make_masks :3455-3470: sum over the mass field's categories and layers > 0) and volume -> thickness
+// (volume_to_thickness :9248, every column including the extra one)
+__global__ void k_prepare(Dev d, int massRow0, int massRows)
+{
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > (size_t)d.nC) return;
+    if (c < (size_t)d.nC) {
+        double massSumCell = 0.0;
+        for (int r = 0; r < massRows; r++) massSumCell = massSumCell + d.val[(size_t)(massRow0 + r) * d.nCp + c];
+        d.maskCell[c] = massSumCell > 0.0 ? 1 : 0;
+    }
+    for (int r = 0; r < d.nRows; r++) {
+        const RowInfo &ri = d.rows[r];
+        if (!ri.volumeLike) continue;
+        const double area = d.val[(size_t)(massRow0 + ri.cat) * d.nCp + c];   // mass field with one layer: row = category
+        double *v = &d.val[(size_t)r * d.nCp + c];
+        *v = (area > 0.0) ? *v / area : 0.0;
+    }
+}
+
+__device__ __forceinline__ bool row_mask(const Dev &d, const RowInfo &ri, size_t c)
+{
+    if (c >= (size_t)d.nC) return false;                                  // the extra slot never holds ice
+    if (ri.depth == 0) return true;                                       // make_masks :3450
+    return d.val[(size_t)ri.chain[ri.depth - 1] * d.nCp + c] > EPS11;     // parent value above the threshold, :3480-3510
+}
+
+// compute_barycenter_coordinates (:4658): centre of mass * tracer chain of `n` linear fields
+__device__ void barycenter(const Dev &d, size_t c, int n, const double *mean, const double *cen, const double *gx,
+                           const double *gy, double &xB, double &yB)
+{
+    const double *G = d.geom;
+    const size_t p = d.nCp;
+    const double ax = G[0 * p + c], ay = G[1 * p + c], axx = G[2 * p + c], axy = G[3 * p + c], ayy = G[4 * p + c];
+    if (n == 1) {
+        const double c0 = cen[0], cx = gx[0], cy = gy[0];
+        const double reciprocal = (fabs(mean[0]) > 0.0) ? 1.0 / mean[0] : 0.0;
+        xB = (c0 * ax + cx * axx + cy * axy) * reciprocal;
+        yB = (c0 * ay + cx * axy + cy * ayy) * reciprocal;
+        return;
+    }
+    const double axxx = G[5 * p + c], axxy = G[6 * p + c], axyy = G[7 * p + c], ayyy = G[8 * p + c];
+    if (n == 2) {
+        const double c0 = cen[0] * cen[1];
+        const double cx = cen[0] * gx[1] + gx[0] * cen[1];
+        const double cy = cen[0] * gy[1] + gy[0] * cen[1];
+        const double cxx = gx[0] * gx[1];
+        const double cxy = gx[0] * gy[1] + gy[0] * gx[1];
+        const double cyy = gy[0] * gy[1];
+        const double prod = mean[0] * mean[1];
+        const double reciprocal = (fabs(prod) > 0.0) ? 1.0 / prod : 0.0;
+        xB = (c0 * ax + cx * axx + cy * axy + cxx * axxx + cxy * axxy + cyy * axyy) * reciprocal;
+        yB = (c0 * ay + cx * axy + cy * ayy + cxx * axxy + cxy * axyy + cyy * ayyy) * reciprocal;
+        return;
+    }
+    const double axxxx = G[9 * p + c], axxxy = G[10 * p + c], axxyy = G[11 * p + c], axyyy = G[12 * p + c], ayyyy = G[13 * p + c];
+    const double c0 = cen[0] * cen[1] * cen[2];
+    const double cx = cen[0] * cen[1] * gx[2] + cen[0] * gx[1] * cen[2] + gx[0] * cen[1] * cen[2];
+    const double cy = cen[0] * cen[1] * gy[2] + cen[0] * gy[1] * cen[2] + gy[0] * cen[1] * cen[2];
+    const double cxx = cen[0] * gx[1] * gx[2] + gx[0] * cen[1] * gx[2] + gx[0] * gx[1] * cen[2];
+    const double cxy = cen[0] * gx[1] * gy[2] + gx[0] * gy[1] * cen[2] + gy[0] * cen[1] * gx[2] + cen[0] * gy[1] * gx[2] +
+                       gx[0] * cen[1] * gy[2] + gy[0] * gx[1] * cen[2];
+    const double cyy = cen[0] * gy[1] * gy[2] + gy[0] * cen[1] * gy[2] + gy[0] * gy[1] * cen[2];
+    const double cxxx = gx[0] * gx[1] * gx[2];
+    const double cxxy = gx[0] * gx[1] * gy[2] + gx[0] * gy[1] * gx[2] + gy[0] * gx[1] * gx[2];
+    const double cxyy = gy[0] * gy[1] * gx[2] + gy[0] * gx[1] * gy[2] + gx[0] * gy[1] * gy[2];
+    const double cyyy = gy[0] * gy[1] * gy[2];
+    const double prod = mean[0] * mean[1] * mean[2];
+    const double reciprocal = (fabs(prod) > 0.0) ? 1.0 / prod : 0.0;
+    xB = (c0 * ax + cx * axx + cy * axy + cxx * axxx + cxy * axxy + cyy * axyy + cxxx * axxxx + cxxy * axxxy + cxyy * axxyy +
+          cyyy * axyyy) * reciprocal;
+    yB = (c0 * ay + cx * axy + cy * ayy + cxx * axxy + cxy * axyy + cyy * ayyy + cxxx * axxxy + cxxy * axxyy + cxyy * axyyy +
+          cyyy * ayyyy) * reciprocal;
+}
+
+// construct_linear_tracer_fields (:3580) for the rows [row0, row0 + gridDim.y) of one depth of the hierarchy:
+// compute_gradient (:4204), limit_tracer_gradient (:4802), centre value (:3735), barycentre (:3750-3840).
+__global__ void __launch_bounds__(128) k_reconstruct(Dev d, int row0)
+{
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = row0 + blockIdx.y;
+    if (c >= (size_t)d.nC) return;
+    const RowInfo ri = d.rows[r];
+    const size_t p = d.nCp;
+    const double *field = d.val + (size_t)r * p;
+    const double f0 = field[c];
+    const int pr = ri.depth > 0 ? ri.chain[ri.depth - 1] : -1;
+    double xB, yB;   // barycentre of the parent: where this row's value sits
+    if (pr >= 0) { xB = d.xBary[(size_t)pr * p + c]; yB = d.yBary[(size_t)pr * p + c]; }
+    else { xB = d.geom[c]; yB = d.geom[p + c]; }
+    double xg = 0.0, yg = 0.0;
+    const bool ice = d.maskCell[c] == 1;
+    if (ice) {
+        const int n = d.nEdgesOnCell[c];
+        const bool m0 = row_mask(d, ri, c);
+        double g1 = 0.0, g2 = 0.0, g3 = 0.0;
+        double maxNeighbor = f0, minNeighbor = f0;
+        for (int k = 0; k < n; k++) {
+            const int nb = d.cellsOnCell[k * p + c];            // 1-based, nC+1 = none
+            const bool mn = row_mask(d, ri, (size_t)nb - 1);
+            double normalGrad = 0.0;
+            const double fn = (nb >= 1 && nb <= d.nC + 1) ? field[nb - 1] : 0.0;
+            if (nb >= 1 && nb <= d.nC && m0 && mn) normalGrad = (fn - f0) / d.sdc[k * p + c];
+            g1 = g1 + d.coef[(size_t)(3 * k + 0) * p + c] * normalGrad;
+            g2 = g2 + d.coef[(size_t)(3 * k + 1) * p + c] * normalGrad;
+            g3 = g3 + d.coef[(size_t)(3 * k + 2) * p + c] * normalGrad;
+            if (mn) {
+                maxNeighbor = (maxNeighbor > fn) ? maxNeighbor : fn;
+                minNeighbor = (minNeighbor < fn) ? minNeighbor : fn;
+            }
+        }
+        if (d.rotate && d.sphere) { const double t = g1; g1 = -g3; g3 = t; }
+        if (d.sphere) {
+            xg = d.trans[0 * p + c] * g1 + d.trans[1 * p + c] * g2 + d.trans[2 * p + c] * g3;
+            yg = d.trans[3 * p + c] * g1 + d.trans[4 * p + c] * g2 + d.trans[5 * p + c] * g3;
+        } else {
+            xg = g1;
+            yg = g2;
+        }
+        maxNeighbor = maxNeighbor - f0;
+        minNeighbor = minNeighbor - f0;
+        double maxLocal = 0.0, minLocal = 0.0;
+        for (int k = 0; k < n; k++) {
+            const double dev = xg * (d.xvc[k * p + c] - xB) + yg * (d.yvc[k * p + c] - yB);
+            maxLocal = (maxLocal > dev) ? maxLocal : dev;
+            minLocal = (minLocal < dev) ? minLocal : dev;
+        }
+        double f1 = 1.0, f2 = 1.0;
+        if (fabs(maxLocal) > fabs(maxNeighbor)) { f1 = maxNeighbor / maxLocal; if (!(f1 > 0.0)) f1 = 0.0; }
+        if (fabs(minLocal) > fabs(minNeighbor)) { f2 = minNeighbor / minLocal; if (!(f2 > 0.0)) f2 = 0.0; }
+        double gradFactor = (f1 < f2) ? f1 : f2;
+        gradFactor = gradFactor - EPS11;
+        if (!(gradFactor > 0.0)) gradFactor = 0.0;
+        xg = xg * gradFactor;
+        yg = yg * gradFactor;
+    }
+    const double cen = f0 - xg * xB - yg * yB;
+    d.xGrad[(size_t)r * p + c] = xg;
+    d.yGrad[(size_t)r * p + c] = yg;
+    d.center[(size_t)r * p + c] = cen;
+    if (ri.hasChild) {
+        double bx = 0.0, by = 0.0;
+        if (ice) {
+            double mean[3], ce[3], gx[3], gy[3];
+            const int n = ri.depth + 1;
+            for (int s = 0; s < n - 1; s++) {
+                const size_t q = (size_t)ri.chain[s] * p + c;
+                mean[s] = d.val[q]; ce[s] = d.center[q]; gx[s] = d.xGrad[q]; gy[s] = d.yGrad[q];
+            }
+            mean[n - 1] = f0; ce[n - 1] = cen; gx[n - 1] = xg; gy[n - 1] = yg;
+            barycenter(d, c, n, mean, ce, gx, gy, bx, by);
+        }
+        d.xBary[(size_t)r * p + c] = bx;
+        d.yBary[(size_t)r * p + c] = by;
+    }
+}
+
+// find_departure_points + find_departure_triangles + get_triangle_quadrature_points for one edge per thread.
+struct Tri {
+    double x[3], y[3];
+    double e1x, e1y, e2x, e2y;
+    int cell, vOnEdge, vOnCell, sign;
+};
+
+__device__ int vertex_on_cell(const Dev &d, int iCell, int vGlobal, int prev)
+{
+    int r = prev;
+    if (iCell < 1 || iCell > d.nC) return r;
+    const int n = d.nEdgesOnCell[iCell - 1];
+    for (int k = 0; k < n; k++)
+        if (d.verticesOnCell[k * d.nCp + (iCell - 1)] == vGlobal) r = k + 1;
+    return r;
+}
+
+__global__ void __launch_bounds__(128) k_triangles(Dev d, double dt)
+{
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)d.nE) return;
+    const size_t pe = d.nEp, pc = d.nCp;
+    for (int t = 0; t < NTRI; t++) {
+        d.triArea[t * pe + e] = 0.0;
+        d.iCellTri[t * pe + e] = 0;
+    }
+    const int v1 = d.verticesOnEdge[e], v2 = d.verticesOnEdge[pe + e];
+    // find_departure_points (:5255): departurePoint = -velocity * dt
+    double dpx[2], dpy[2];
+    bool any = false;
+    if (d.remapEdge[e] == 1) {
+        const int vv[2] = {v1, v2};
+        for (int k = 0; k < 2; k++) {
+            dpx[k] = -d.u[vv[k] - 1] * dt;
+            dpy[k] = -d.v[vv[k] - 1] * dt;
+            if (dpx[k] * dpx[k] + dpy[k] * dpy[k] > 0.0) any = true;
+        }
+    }
+    d.maskEdge[e] = any ? 1 : 0;
+    if (!any) return;
+
+    double XE[NVER], YE[NVER];
+#pragma unroll
+    for (int k = 0; k < NVER; k++) { XE[k] = d.xve[k * pe + e]; YE[k] = d.yve[k * pe + e]; }
+    int EO[NEER], CO[NCER];
+#pragma unroll
+    for (int k = 0; k < NEER; k++) { EO[k] = d.eoer[k * pe + e]; CO[k] = d.coer[k * pe + e]; }
+    const int vg[2] = {v1, v2};
+    const double evx[2] = {XE[0], XE[1]}, evy[2] = {YE[0], YE[1]};
+    for (int k = 0; k < 2; k++) { dpx[k] = XE[k] + dpx[k]; dpy[k] = YE[k] + dpy[k]; }
+
+    Tri T[NTRI];
+    int count = 0;
+    const int D = d.D;
+    const bool sphere = d.sphere != 0;
+#define NEW_TRI(name)                                                   \
+    if (count >= NTRI) { atomicOr(d.flags, FLAG_MANY_TRI); return; }    \
+    Tri &name = T[count];                                               \
+    count++;                                                            \
+    name.e1x = name.e1y = name.e2x = name.e2y = 0.0;                    \
+    name.vOnCell = 0
+
+    // side triangles: does the segment D1-D2 cut one of the side edges E1..E4 (:5700-5900)?
+    for (int iv = 0; iv < 2; iv++) {
+        const double n0x = evx[iv], n0y = evy[iv];
+        for (int side = 0; side < 2; side++) {
+            const int ieo = (iv + 1) + 2 * side;   // E1/E3 at V1, E2/E4 at V2 (1-based)
+            const int ivr = ieo + 2;               // V3..V6 (1-based)
+            const int en = EO[ieo - 1];
+            bool hit = false;
+            double ipx = 0.0, ipy = 0.0, n1x = 0.0, n1y = 0.0;
+            if (en >= 1 && en <= d.nE) {
+                n1x = XE[ivr - 1];
+                n1y = YE[ivr - 1];
+                hit = line_intersection(dpx[0], dpy[0], dpx[1], dpy[1], n0x, n0y, n1x, n1y, ipx, ipy);
+            }
+            if (!hit) continue;
+            NEW_TRI(t);
+            t.x[0] = evx[iv]; t.y[0] = evy[iv];
+            t.x[1] = dpx[iv]; t.y[1] = dpy[iv];
+            t.x[2] = ipx;     t.y[2] = ipy;
+            t.vOnEdge = iv + 1;
+            t.cell = CO[iv + 2];
+            t.vOnCell = vertex_on_cell(d, t.cell, vg[iv], 0);
+            if (sphere) {
+                t.e1x = n1x - n0x; t.e1y = n1y - n0y;
+                int iOtherEdge;
+                if (D == 3) { iOtherEdge = ieo + 2; if (iOtherEdge > 4) iOtherEdge = iOtherEdge - 4; }
+                else iOtherEdge = iv + 1 + 4;
+                const int iOtherVertex = iOtherEdge + 2;
+                t.e2x = XE[iOtherVertex - 1] - n0x; t.e2y = YE[iOtherVertex - 1] - n0y;
+            }
+            t.sign = (side == 0) ? 1 : -1;
+            if (D == 4) {
+                const int en5 = EO[iv + 4];        // E5 at V1, E6 at V2
+                bool hitMain = false;
+                double ipmx = 0.0, ipmy = 0.0;
+                if (en5 >= 1 && en5 <= d.nE)
+                    hitMain = line_intersection(dpx[0], dpy[0], dpx[1], dpy[1], n0x, n0y, XE[iv + 6], YE[iv + 6], ipmx, ipmy);
+                if (hitMain) {
+                    t.x[2] = ipmx; t.y[2] = ipmy;
+                    if (side == 0) {
+                        t.cell = CO[iv + 4];
+                        t.vOnCell = vertex_on_cell(d, t.cell, vg[iv], t.vOnCell);
+                        if (sphere) { t.e1x = XE[ivr + 2 - 1] - n0x; t.e1y = YE[ivr + 2 - 1] - n0y; }
+                    } else if (sphere) {
+                        t.e1x = XE[ivr - 2 - 1] - n0x; t.e1y = YE[ivr - 2 - 1] - n0y;
+                    }
+                    const int prevOnEdge = t.vOnEdge, prevSign = t.sign;
+                    const double pe2x = t.e2x, pe2y = t.e2y;
+                    NEW_TRI(t2);
+                    t2.x[0] = evx[iv]; t2.y[0] = evy[iv];
+                    t2.x[1] = ipmx;    t2.y[1] = ipmy;
+                    t2.x[2] = ipx;     t2.y[2] = ipy;
+                    t2.cell = (side == 0) ? CO[iv + 2] : CO[iv + 4];
+                    t2.vOnEdge = prevOnEdge;
+                    t2.vOnCell = vertex_on_cell(d, t2.cell, vg[iv], 0);
+                    if (sphere) { t2.e1x = XE[ivr - 1] - n0x; t2.e1y = YE[ivr - 1] - n0y; t2.e2x = pe2x; t2.e2y = pe2y; }
+                    t2.sign = prevSign;
+                } else if (side != 0) {
+                    t.cell = CO[iv + 4];
+                    t.vOnCell = vertex_on_cell(d, t.cell, vg[iv], t.vOnCell);
+                }
+            }
+            dpx[iv] = ipx;   // the departure point moves to the side intersection for what follows (:5898)
+            dpy[iv] = ipy;
+        }
+    }
+
+    // central triangles in C1 / C2 (:5905-6075)
+    {
+        double ipmx, ipmy;
+        const bool hitMain = line_intersection(dpx[0], dpy[0], dpx[1], dpy[1], evx[0], evy[0], evx[1], evy[1], ipmx, ipmy);
+        bool two = hitMain;
+        if (!hitMain) {
+            const double quadArea = tri_area(evx[0], evy[0], evx[1], evy[1], dpx[1], dpy[1]) +
+                                    tri_area(evx[0], evy[0], dpx[1], dpy[1], dpx[0], dpy[0]);
+            two = quadArea > 0.0;
+        }
+        if (two) {
+            for (int iv = 0; iv < 2; iv++) {
+                NEW_TRI(t);
+                if (hitMain) {
+                    t.x[0] = evx[iv]; t.y[0] = evy[iv]; t.x[1] = dpx[iv]; t.y[1] = dpy[iv]; t.x[2] = ipmx; t.y[2] = ipmy;
+                } else if (iv == 0) {
+                    t.x[0] = evx[0]; t.y[0] = evy[0]; t.x[1] = evx[1]; t.y[1] = evy[1]; t.x[2] = dpx[0]; t.y[2] = dpy[0];
+                } else {
+                    t.x[0] = evx[1]; t.y[0] = evy[1]; t.x[1] = dpx[0]; t.y[1] = dpy[0]; t.x[2] = dpx[1]; t.y[2] = dpy[1];
+                }
+                t.vOnEdge = iv + 1;
+                const bool inHP = in_half_plane(evx[0], evy[0], evx[1], evy[1], dpx[iv], dpy[iv]);
+                t.cell = inHP ? CO[0] : CO[1];
+                t.sign = inHP ? 1 : -1;
+                t.vOnCell = vertex_on_cell(d, t.cell, vg[iv], 0);
+                if (sphere) {
+                    const int other = 1 - iv;
+                    t.e1x = evx[other] - evx[iv]; t.e1y = evy[other] - evy[iv];
+                    const int iOtherEdge = inHP ? (iv + 1) : (iv + 3);
+                    t.e2x = XE[iOtherEdge + 2 - 1] - evx[iv]; t.e2y = YE[iOtherEdge + 2 - 1] - evy[iv];
+                }
+            }
+        }
+    }
+#undef NEW_TRI
+
+    // shift_vertices_of_departure_triangle (:6270), signed area, quadrature points (:6546)
+    for (int it = 0; it < NTRI; it++) {
+        double x[3] = {0.0, 0.0, 0.0}, y[3] = {0.0, 0.0, 0.0};
+        if (it < count) {
+            Tri &t = T[it];
+            for (int q = 0; q < 3; q++) { x[q] = t.x[q]; y[q] = t.y[q]; }
+            d.iCellTri[it * pe + e] = t.cell;
+            if (t.cell >= 1 && t.cell <= d.nC) {
+                const size_t ic = (size_t)t.cell - 1;
+                const int kk = t.vOnCell < 1 ? 1 : t.vOnCell;
+                const double xv = d.xvc[(kk - 1) * pc + ic], yv = d.yvc[(kk - 1) * pc + ic];
+                const double oex = XE[t.vOnEdge - 1], oey = YE[t.vOnEdge - 1];
+                if (sphere) {
+                    double e1x = t.e1x, e1y = t.e1y, e2x = t.e2x, e2y = t.e2y;
+                    const double crossProduct = cross2(e1x, e1y, e2x, e2y);
+                    if (fabs(crossProduct) < EPS11) atomicOr(d.flags, FLAG_PARALLEL);
+                    if (crossProduct > 0.0) {
+                        const double tx = e1x, ty = e1y;
+                        e1x = e2x; e1y = e2y; e2x = tx; e2y = ty;
+                    }
+                    const int n = d.nEdgesOnCell[ic];
+                    int km1 = kk - 1; if (km1 < 1) km1 = km1 + n;
+                    int kp1 = kk + 1; if (kp1 > n) kp1 = kp1 - n;
+                    const double c1x = d.xvc[(km1 - 1) * pc + ic] - xv, c1y = d.yvc[(km1 - 1) * pc + ic] - yv;
+                    const double c2x = d.xvc[(kp1 - 1) * pc + ic] - xv, c2y = d.yvc[(kp1 - 1) * pc + ic] - yv;
+                    const double denom = e1x * e2y - e2x * e1y;
+                    for (int q = 0; q < 3; q++) {
+                        x[q] = x[q] - oex;
+                        y[q] = y[q] - oey;
+                        const double coeff_a = (x[q] * e2y - y[q] * e2x) / denom;
+                        const double coeff_b = (y[q] * e1x - x[q] * e1y) / denom;
+                        x[q] = xv + coeff_a * c1x + coeff_b * c2x;
+                        y[q] = yv + coeff_a * c1y + coeff_b * c2y;
+                    }
+                } else {
+                    for (int q = 0; q < 3; q++) {
+                        x[q] = x[q] - oex + xv;
+                        y[q] = y[q] - oey + yv;
+                    }
+                }
+                const double area = fabs(0.5 * ((x[1] - x[0]) * (y[2] - y[0]) - (y[1] - y[0]) * (x[2] - x[0])));
+                d.triArea[it * pe + e] = area * t.sign;
+            }
+        }
+        double *xo = d.xq + (size_t)it * 6 * pe + e, *yo = d.yq + (size_t)it * 6 * pe + e;
+        if (d.nQP == 3) {
+            const double xMid = (x[0] + x[1] + x[2]) / 3.0;
+            const double yMid = (x[0] + x[1] + x[2]) / 3.0;   // as the reference has it (:6598)
+            for (int q = 0; q < 3; q++) {
+                xo[q * pe] = 0.5 * (x[q] + xMid);
+                yo[q * pe] = 0.5 * (y[q] + yMid);
+            }
+        } else {
+            xo[0 * pe] = Q1QP * x[0] + Q1QP * x[1] + Q2QP * x[2]; yo[0 * pe] = Q1QP * y[0] + Q1QP * y[1] + Q2QP * y[2];
+            xo[1 * pe] = Q1QP * x[0] + Q2QP * x[1] + Q1QP * x[2]; yo[1 * pe] = Q1QP * y[0] + Q2QP * y[1] + Q1QP * y[2];
+            xo[2 * pe] = Q2QP * x[0] + Q1QP * x[1] + Q1QP * x[2]; yo[2 * pe] = Q2QP * y[0] + Q1QP * y[1] + Q1QP * y[2];
+            xo[3 * pe] = Q3QP * x[0] + Q4QP * x[1] + Q4QP * x[2]; yo[3 * pe] = Q3QP * y[0] + Q4QP * y[1] + Q4QP * y[2];
+            xo[4 * pe] = Q4QP * x[0] + Q3QP * x[1] + Q4QP * x[2]; yo[4 * pe] = Q4QP * y[0] + Q3QP * y[1] + Q4QP * y[2];
+            xo[5 * pe] = Q4QP * x[0] + Q4QP * x[1] + Q3QP * x[2]; yo[5 * pe] = Q4QP * y[0] + Q4QP * y[1] + Q3QP * y[2];
+        }
+    }
+}
+
+// integrate_fluxes_over_triangles (:6667): one thread per (edge, row).  triangleValue of a row is the product down its
+// chain of parents of the linear reconstructions at the quadrature point, the mass field first.
+__global__ void __launch_bounds__(128) k_fluxes(Dev d)
+{
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (e >= (size_t)d.nE) return;
+    const size_t pe = d.nEp, pc = d.nCp;
+    double flux = 0.0;
+    if (d.maskEdge[e] == 1) {
+        const RowInfo ri = d.rows[r];
+        const int nQP = d.nQP;
+        bool negative = false;
+        for (int t = 0; t < NTRI; t++) {
+            const double area = d.triArea[t * pe + e];
+            if (area == 0.0) continue;
+            const size_t cell = (size_t)d.iCellTri[t * pe + e] - 1;
+            double cen[MAX_DEPTH], gx[MAX_DEPTH], gy[MAX_DEPTH];
+            for (int s = 0; s <= ri.depth; s++) {
+                const size_t q = (size_t)ri.chain[s] * pc + cell;
+                cen[s] = d.center[q]; gx[s] = d.xGrad[q]; gy[s] = d.yGrad[q];
+            }
+            double tracerIntegral = 0.0;
+            for (int iqp = 0; iqp < nQP; iqp++) {
+                const double x = d.xq[(size_t)(t * 6 + iqp) * pe + e], y = d.yq[(size_t)(t * 6 + iqp) * pe + e];
+                double value = 1.0;
+                for (int s = 0; s <= ri.depth; s++) value = value * (cen[s] + gx[s] * x + gy[s] * y);
+                if (ri.depth == 0 && value < 0.0) negative = true;
+                const double w = (nQP == 3) ? (1.0 / 3.0) : (iqp < 3 ? W1QP : W2QP);
+                tracerIntegral = tracerIntegral + w * value;
+            }
+            flux = flux + area * tracerIntegral;
+        }
+        if (negative) atomicOr(d.flags, FLAG_NEG_QP);
+    }
+    d.edgeFlux[(size_t)r * pe + e] = flux;
+}
+
+// compute_mass_tracer_products (:6982) + update_mass_and_tracers (:7125) for the rows of one depth
+__global__ void __launch_bounds__(128) k_update(Dev d, int row0)
+{
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = row0 + blockIdx.y;
+    if (c > (size_t)d.nC) return;
+    const size_t pe = d.nEp, pc = d.nCp;
+    if (c >= (size_t)d.nCS) {                 // halo cells and the extra slot keep their values
+        d.valNew[(size_t)r * pc + c] = d.val[(size_t)r * pc + c];
+        return;
+    }
+    const RowInfo ri = d.rows[r];
+    const int n = d.nEdgesOnCell[c];
+    double fluxFromCell = 0.0;
+    for (int k = 0; k < n; k++) {
+        const int e = d.edgesOnCell[k * pc + c];
+        fluxFromCell = fluxFromCell + d.edgeFlux[(size_t)r * pe + (e - 1)] * (double)d.fluxSign[k * pc + c];
+    }
+    double mtpOld = 1.0;
+    for (int s = 0; s <= ri.depth; s++) mtpOld = mtpOld * d.val[(size_t)ri.chain[s] * pc + c];
+    const double pm = ri.depth > 0 ? d.mtpNew[(size_t)ri.chain[ri.depth - 1] * pc + c] : 1.0;
+    double v = 0.0;
+    if (pm > 0.0) v = (mtpOld - (fluxFromCell / d.areaCell[c])) / pm;
+    d.mtpNew[(size_t)r * pc + c] = pm * v;
+    if (ri.depth == 0) {
+        constexpr double puny2 = 1.0e-11 * 1.0e-11;   // seaicePuny**2
+        if (v < -puny2) atomicOr(d.flags, FLAG_NEG_MASS);
+        else if (v < 0.0) v = 0.0;
+    }
+    d.valNew[(size_t)r * pc + c] = v;
+}
+
+// zap_small_mass (:8764; one-layer mass field) and thickness -> volume (:9295) on the new values
+__global__ void k_finish(Dev d, int massRows, int massOneLayer)
+{
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > (size_t)d.nC) return;
+    const size_t pc = d.nCp;
+    if (massOneLayer && c < (size_t)d.nCS) {
+        for (int k = 0; k < d.nK; k++) {
+            const double m = d.valNew[(size_t)k * pc + c];
+            if (m > 0.0 && m < 1.0e-22) {
+                d.valNew[(size_t)k * pc + c] = 0.0;
+                for (int r = massRows; r < d.nRows; r++)
+                    if (d.rows[r].cat == k) d.valNew[(size_t)r * pc + c] = 0.0;
+            }
+        }
+    }
+    for (int r = massRows; r < d.nRows; r++) {
+        const RowInfo &ri = d.rows[r];
+        if (!ri.volumeLike) continue;
+        d.valNew[(size_t)r * pc + c] = d.valNew[(size_t)ri.cat * pc + c] * d.valNew[(size_t)r * pc + c];
+    }
+}
+
+// rows 1 and 2 of transGlobalToCell (3,3,nCells): trans(i,j,c) at c*9 + j*3 + i
+__global__ void k_trans_in(const double *__restrict__ raw, double *__restrict__ dst, size_t n, size_t pitch)
+{
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    for (int i = 0; i < 2; i++)
+        for (int j = 0; j < 3; j++) dst[(size_t)(i * 3 + j) * pitch + c] = raw[c * 9 + j * 3 + i];
+}
+
+inline unsigned grid_for(size_t n, int block) { return (unsigned)((n + block - 1) / block); }
+inline size_t round_up(size_t n, size_t m) { return (n + m - 1) / m * m; }
+
+template <typename T>
+int dev_alloc(ir_handle *h, T **p, size_t count)
+{
+    void *q = nullptr;
+    IR_CUDA(cudaMalloc(&q, sizeof(T) * (count ? count : 1)));
+    IR_CUDA(cudaMemsetAsync(q, 0, sizeof(T) * (count ? count : 1), h->stream));
+    h->allocs.push_back(q);
+    *p = (T *)q;
+    return IR_OK;
+}
+
+int ensure_stage(ir_handle *h, size_t bytes)
+{
+    if (h->d.stageBytes >= bytes) return IR_OK;
+    if (h->d.stage) {
+        IR_CUDA(cudaStreamSynchronize(h->stream));
+        IR_CUDA(cudaFree(h->d.stage));
+        h->d.stage = nullptr;
+        h->d.stageBytes = 0;
+    }
+    void *q = nullptr;
+    IR_CUDA(cudaMalloc(&q, bytes));
+    h->d.stage = (double *)q;
+    h->d.stageBytes = bytes;
+    return IR_OK;
+}
+
+// host (n, w) -> device [w][pitch]
+template <typename T>
+int upload_rows(ir_handle *h, T *dst, const T *host, size_t n, int w, size_t pitch)
+{
+    int rc = ensure_stage(h, n * w * sizeof(T));
+    if (rc) return rc;
+    IR_CUDA(cudaMemcpyAsync(h->d.stage, host, n * w * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    IR_LAUNCH((k_rows_in<T>), grid_for(n, 256), 256, h->stream, (const T *)h->d.stage, dst, n, w, pitch);
+    h->launches++;
+    IR_CUDA(cudaGetLastError());
+    IR_CUDA(cudaStreamSynchronize(h->stream));   // the staging area is reused by the next upload
+    return IR_OK;
+}
+
+}  // namespace
+
+// =============================================================================================================== ABI
+
+extern "C" const char *ir_last_error_string(void) { return g_err; }
+
+extern "C" int ir_create(ir_handle **out, const ir_mesh_desc *m, int device)
+{
+    IR_REQUIRE(out != nullptr && m != nullptr, "handle/mesh is NULL");
+    *out = nullptr;
+    IR_REQUIRE(m->nCells >= 0 && m->nVertices >= 0 && m->nEdges >= 0, "negative dimension");
+    IR_REQUIRE(m->nCellsSolve >= 0 && m->nCellsSolve <= m->nCells, "nCellsSolve out of range");
+    IR_REQUIRE(m->maxEdges >= 3 && m->maxEdges <= MAXM, "maxEdges must be 3..8");
+    IR_REQUIRE(m->vertexDegree == 3 || m->vertexDegree == 4, "vertexDegree must be 3 or 4");
+    IR_REQUIRE(m->nCategories >= 1, "nCategories must be positive");
+    IR_REQUIRE(m->nQuadPoints == 3 || m->nQuadPoints == 6, "nQuadPoints must be 3 or 6 (incremental_remap.F:780-787)");
+    IR_REQUIRE(m->nEdgesOnCell && m->edgesOnCell && m->cellsOnCell && m->verticesOnCell && m->cellsOnEdge && m->verticesOnEdge,
+               "connectivity arrays must not be NULL");
+    IR_REQUIRE(m->areaCell && m->dcEdge && m->coeffs_reconstruct, "areaCell / dcEdge / coeffs_reconstruct must not be NULL");
+    IR_REQUIRE(m->xVertexOnCell && m->yVertexOnCell && m->xVertexOnEdge && m->yVertexOnEdge && m->remapEdge &&
+                   m->cellsOnEdgeRemap && m->edgesOnEdgeRemap,
+               "incremental_remap pool arrays must not be NULL");
+    IR_REQUIRE(!m->on_a_sphere || m->transGlobalToCell, "transGlobalToCell is needed on a sphere");
+    for (int k = 0; k < 14; k++) IR_REQUIRE(m->geomAvgCell[k] != nullptr, "geomAvgCell arrays must not be NULL");
+    int dev = device;
+    if (dev < 0) IR_CUDA(cudaGetDevice(&dev));
+    IR_CUDA(cudaSetDevice(dev));
+    ir_handle *h = new ir_handle();
+    h->device = dev;
+    h->lastMs = 0.f;
+    h->launches = 0;
+    h->haveTracers = false;
+    memset(&h->d, 0, sizeof h->d);
+    cudaError_t ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (ce != cudaSuccess) { set_error("cudaStreamCreate -> %s", cudaGetErrorString(ce)); delete h; return IR_ERR_CUDA; }
+    cudaEventCreate(&h->ev0);
+    cudaEventCreate(&h->ev1);
+    Dev &d = h->d;
+    d.nC = m->nCells; d.nCS = m->nCellsSolve; d.nV = m->nVertices; d.nE = m->nEdges; d.M = m->maxEdges; d.D = m->vertexDegree;
+    d.nK = m->nCategories; d.nQP = m->nQuadPoints; d.sphere = m->on_a_sphere ? 1 : 0; d.rotate = m->rotate_cartesian_grid ? 1 : 0;
+    d.nCp = round_up((size_t)d.nC + 1, 32); d.nEp = round_up((size_t)d.nE + 1, 32); d.nVp = round_up((size_t)d.nV + 1, 32);
+    const size_t nC1 = (size_t)d.nC + 1, nE1 = (size_t)d.nE + 1, nV1 = (size_t)d.nV + 1;
+    const int M = d.M;
+    int rc = IR_OK;
+#define TRY(x) do { if ((rc = (x)) != IR_OK) { ir_destroy(h); return rc; } } while (0)
+    TRY(dev_alloc(h, &d.nEdgesOnCell, d.nCp));
+    TRY(dev_alloc(h, &d.edgesOnCell, M * d.nCp));
+    TRY(dev_alloc(h, &d.cellsOnCell, M * d.nCp));
+    TRY(dev_alloc(h, &d.verticesOnCell, M * d.nCp));
+    TRY(dev_alloc(h, &d.cellsOnEdge, 2 * nE1));           // host layout (nEdges+1, 2): used by k_cell_edge_signs only
+    TRY(dev_alloc(h, &d.verticesOnEdge, 2 * d.nEp));
+    TRY(dev_alloc(h, &d.remapEdge, d.nEp));
+    TRY(dev_alloc(h, &d.coer, NCER * d.nEp));
+    TRY(dev_alloc(h, &d.eoer, NEER * d.nEp));
+    TRY(dev_alloc(h, &d.areaCell, d.nCp));
+    TRY(dev_alloc(h, &d.sdc, M * d.nCp));
+    TRY(dev_alloc(h, &d.fluxSign, M * d.nCp));
+    TRY(dev_alloc(h, &d.coef, 3 * M * d.nCp));
+    TRY(dev_alloc(h, &d.trans, 6 * d.nCp));
+    TRY(dev_alloc(h, &d.xvc, M * d.nCp));
+    TRY(dev_alloc(h, &d.yvc, M * d.nCp));
+    TRY(dev_alloc(h, &d.xve, NVER * d.nEp));
+    TRY(dev_alloc(h, &d.yve, NVER * d.nEp));
+    TRY(dev_alloc(h, &d.geom, 14 * d.nCp));
+    TRY(dev_alloc(h, &d.u, d.nVp));
+    TRY(dev_alloc(h, &d.v, d.nVp));
+    TRY(dev_alloc(h, &d.maskCell, d.nCp));
+    TRY(dev_alloc(h, &d.maskEdge, d.nEp));
+    TRY(dev_alloc(h, &d.iCellTri, NTRI * d.nEp));
+    TRY(dev_alloc(h, &d.xq, NTRI * 6 * d.nEp));
+    TRY(dev_alloc(h, &d.yq, NTRI * 6 * d.nEp));
+    TRY(dev_alloc(h, &d.triArea, NTRI * d.nEp));
+    TRY(dev_alloc(h, &d.flags, 1));
+    cudaStream_t s = h->stream;
+    auto copy1 = [&](void *dst, const void *src, size_t bytes) -> int {
+        IR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+        return IR_OK;
+    };
+    TRY(copy1(d.nEdgesOnCell, m->nEdgesOnCell, nC1 * 4));
+    TRY(copy1(d.areaCell, m->areaCell, nC1 * 8));
+    TRY(copy1(d.remapEdge, m->remapEdge, nE1 * 4));
+    TRY(copy1(d.cellsOnEdge, m->cellsOnEdge, 2 * nE1 * 4));
+    for (int k = 0; k < 14; k++) TRY(copy1(d.geom + (size_t)k * d.nCp, m->geomAvgCell[k], nC1 * 8));
+    TRY(upload_rows<int>(h, d.edgesOnCell, m->edgesOnCell, nC1, M, d.nCp));
+    TRY(upload_rows<int>(h, d.cellsOnCell, m->cellsOnCell, nC1, M, d.nCp));
+    TRY(upload_rows<int>(h, d.verticesOnCell, m->verticesOnCell, nC1, M, d.nCp));
+    TRY(upload_rows<int>(h, d.verticesOnEdge, m->verticesOnEdge, nE1, 2, d.nEp));
+    TRY(upload_rows<int>(h, d.coer, m->cellsOnEdgeRemap, nE1, NCER, d.nEp));
+    TRY(upload_rows<int>(h, d.eoer, m->edgesOnEdgeRemap, nE1, NEER, d.nEp));
+    TRY(upload_rows<double>(h, d.coef, m->coeffs_reconstruct, nC1, 3 * M, d.nCp));
+    TRY(upload_rows<double>(h, d.xvc, m->xVertexOnCell, nC1, M, d.nCp));
+    TRY(upload_rows<double>(h, d.yvc, m->yVertexOnCell, nC1, M, d.nCp));
+    TRY(upload_rows<double>(h, d.xve, m->xVertexOnEdge, nE1, NVER, d.nEp));
+    TRY(upload_rows<double>(h, d.yve, m->yVertexOnEdge, nE1, NVER, d.nEp));
+    if (d.sphere && d.nC > 0) {
+        TRY(ensure_stage(h, (size_t)d.nC * 9 * 8));
+        TRY(copy1(d.stage, m->transGlobalToCell, (size_t)d.nC * 9 * 8));
+        IR_LAUNCH((k_trans_in), grid_for(d.nC, 256), 256, s, d.stage, d.trans, (size_t)d.nC, d.nCp);
+        h->launches++;
+    }
+    {   // signed dcEdge and flux signs per (slot, cell)
+        double *dc = nullptr;
+        TRY(dev_alloc(h, &dc, nE1));
+        TRY(copy1(dc, m->dcEdge, nE1 * 8));
+        if (d.nC > 0) {
+            IR_LAUNCH((k_cell_edge_signs), grid_for(d.nC, 256), 256, s, d, dc);
+            h->launches++;
+        }
+    }
+    (void)nV1;
+    cudaError_t e2 = cudaStreamSynchronize(s);
+    if (e2 == cudaSuccess) e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) { set_error("ir_create: %s", cudaGetErrorString(e2)); ir_destroy(h); return IR_ERR_CUDA; }
+#undef TRY
+    *out = h;
+    return IR_OK;
+}
+
+extern "C" int ir_set_tracers(ir_handle *h, int nTracers, const ir_tracer_desc *tr)
+{
+    IR_REQUIRE(h != nullptr && tr != nullptr, "handle/tracers is NULL");
+    IR_REQUIRE(nTracers >= 1, "at least the mass-like field is needed");
+    IR_REQUIRE(tr[0].parent == -1, "the first tracer must be the mass-like field (parent = -1)");
+    IR_CUDA(cudaSetDevice(h->device));
+    Dev &d = h->d;
+    const int nK = d.nK;
+    std::vector<int> depth(nTracers, 0), hasChild(nTracers, 0);
+    int maxLayers = 1;
+    for (int t = 0; t < nTracers; t++) {
+        IR_REQUIRE(tr[t].nLayers >= 1, "nLayers must be positive");
+        if (tr[t].nLayers > maxLayers) maxLayers = tr[t].nLayers;
+        if (t == 0) continue;
+        IR_REQUIRE(tr[t].parent >= 0 && tr[t].parent < t, "a parent must come before its children; only tracer 0 has none");
+        depth[t] = depth[tr[t].parent] + 1;
+        IR_REQUIRE(depth[t] < MAX_DEPTH, "at most three parents (incremental_remap.F:6745)");
+        const int pl = tr[tr[t].parent].nLayers;
+        IR_REQUIRE(pl == 1 || pl == tr[t].nLayers, "a layered parent must have the child's number of layers");
+        hasChild[tr[t].parent] = 1;
+        IR_REQUIRE(!tr[t].volumeLike || (tr[t].nLayers == 1 && tr[t].parent == 0 && tr[0].nLayers == 1),
+                   "volume-like tracers are one-layer children of a one-layer mass field");
+    }
+    for (int t = 0; t < nTracers; t++)
+        IR_REQUIRE(!(hasChild[t] && depth[t] >= 3), "a tracer with three parents cannot have children (incremental_remap.F:3840)");
+    // rows grouped by depth, tracers in list order within a depth
+    h->tracerRow0.assign(nTracers, 0);
+    h->tracerLayers.assign(nTracers, 1);
+    h->tracerParent.assign(nTracers, -1);
+    h->tracerVolume.assign(nTracers, 0);
+    h->tracerDepth = depth;
+    h->depthRow0.assign(MAX_DEPTH + 1, 0);
+    int row = 0;
+    for (int q = 0; q < MAX_DEPTH; q++) {
+        h->depthRow0[q] = row;
+        for (int t = 0; t < nTracers; t++)
+            if (depth[t] == q) { h->tracerRow0[t] = row; row += nK * tr[t].nLayers; }
+    }
+    h->depthRow0[MAX_DEPTH] = row;
+    const int nRows = row;
+    h->rows.assign(nRows, RowInfo());
+    for (int t = 0; t < nTracers; t++) {
+        h->tracerLayers[t] = tr[t].nLayers;
+        h->tracerParent[t] = tr[t].parent;
+        h->tracerVolume[t] = tr[t].volumeLike ? 1 : 0;
+        for (int k = 0; k < nK; k++)
+            for (int l = 0; l < tr[t].nLayers; l++) {
+                RowInfo &ri = h->rows[h->tracerRow0[t] + k * tr[t].nLayers + l];
+                ri.depth = depth[t];
+                ri.hasChild = hasChild[t];
+                ri.cat = k;
+                ri.volumeLike = tr[t].volumeLike ? 1 : 0;
+                int q = t, s = depth[t];
+                while (q >= 0) {
+                    const int ql = tr[q].nLayers;
+                    ri.chain[s] = h->tracerRow0[q] + k * ql + (ql == 1 ? 0 : l);
+                    q = tr[q].parent;
+                    s--;
+                }
+                for (int z = depth[t] + 1; z < MAX_DEPTH; z++) ri.chain[z] = 0;
+            }
+    }
+    // (re)allocate the tracer state
+    IR_CUDA(cudaStreamSynchronize(h->stream));
+    double **bufs[] = {&d.val, &d.valNew, &d.center, &d.xGrad, &d.yGrad, &d.xBary, &d.yBary, &d.mtpNew, &d.edgeFlux};
+    for (double **b : bufs)
+        if (*b) { cudaFree(*b); *b = nullptr; }
+    if (d.rows) { cudaFree(d.rows); d.rows = nullptr; }
+    d.nRows = nRows;
+    const size_t cellBytes = sizeof(double) * (size_t)nRows * d.nCp, edgeBytes = sizeof(double) * (size_t)nRows * d.nEp;
+    for (double **b : bufs) {
+        const size_t bytes = (b == &d.edgeFlux) ? edgeBytes : cellBytes;
+        IR_CUDA(cudaMalloc((void **)b, bytes));
+        IR_CUDA(cudaMemsetAsync(*b, 0, bytes, h->stream));
+    }
+    IR_CUDA(cudaMalloc((void **)&d.rows, sizeof(RowInfo) * nRows));
+    IR_CUDA(cudaMemcpyAsync(d.rows, h->rows.data(), sizeof(RowInfo) * nRows, cudaMemcpyHostToDevice, h->stream));
+    int rc = ensure_stage(h, sizeof(double) * ((size_t)d.nC + 1) * nK * maxLayers);
+    if (rc) return rc;
+    IR_CUDA(cudaStreamSynchronize(h->stream));
+    h->haveTracers = true;
+    return IR_OK;
+}
+
+extern "C" int ir_run(ir_handle *h, int nTracers, const ir_tracer_desc *tr, const double *u, const double *v, double dt)
+{
+    IR_REQUIRE(h != nullptr && tr != nullptr && u != nullptr && v != nullptr, "NULL argument");
+    if (!h->haveTracers) { set_error("ir_run before ir_set_tracers"); return IR_ERR_STATE; }
+    IR_REQUIRE(nTracers == (int)h->tracerRow0.size(), "tracer table differs from the one given to ir_set_tracers");
+    for (int t = 0; t < nTracers; t++)
+        IR_REQUIRE(tr[t].array != nullptr && tr[t].nLayers == h->tracerLayers[t] && tr[t].parent == h->tracerParent[t] &&
+                       (tr[t].volumeLike ? 1 : 0) == h->tracerVolume[t],
+                   "tracer table differs from the one given to ir_set_tracers");
+    IR_CUDA(cudaSetDevice(h->device));
+    Dev &d = h->d;
+    cudaStream_t s = h->stream;
+    const size_t nC1 = (size_t)d.nC + 1;
+    const int nK = d.nK;
+    // in: tracers (host (nCells+1, nK*nL) -> rows) and velocities
+    for (int t = 0; t < nTracers; t++) {
+        int rc = upload_rows<double>(h, d.val + (size_t)h->tracerRow0[t] * d.nCp, tr[t].array, nC1, nK * tr[t].nLayers, d.nCp);
+        if (rc) return rc;
+    }
+    IR_CUDA(cudaMemcpyAsync(d.u, u, ((size_t)d.nV + 1) * 8, cudaMemcpyHostToDevice, s));
+    IR_CUDA(cudaMemcpyAsync(d.v, v, ((size_t)d.nV + 1) * 8, cudaMemcpyHostToDevice, s));
+    IR_CUDA(cudaMemsetAsync(d.flags, 0, sizeof(int), s));
+    IR_CUDA(cudaEventRecord(h->ev0, s));
+    const int massRows = nK * h->tracerLayers[0];
+    const unsigned gc = grid_for(nC1, 128), ge = grid_for((size_t)d.nE, 128);
+    IR_LAUNCH((k_prepare), gc, 128, s, d, 0, massRows);
+    h->launches++;
+    for (int q = 0; q < MAX_DEPTH; q++) {
+        const int r0 = h->depthRow0[q], n = h->depthRow0[q + 1] - r0;
+        if (n > 0 && d.nC > 0) {
+            IR_LAUNCH((k_reconstruct), dim3(grid_for((size_t)d.nC, 128), n), 128, s, d, r0);
+            h->launches++;
+        }
+    }
+    if (d.nE > 0) {
+        IR_LAUNCH((k_triangles), ge, 128, s, d, dt);
+        IR_LAUNCH((k_fluxes), dim3(ge, d.nRows), 128, s, d);
+        h->launches += 2;
+    }
+    for (int q = 0; q < MAX_DEPTH; q++) {
+        const int r0 = h->depthRow0[q], n = h->depthRow0[q + 1] - r0;
+        if (n > 0) {
+            IR_LAUNCH((k_update), dim3(gc, n), 128, s, d, r0);
+            h->launches++;
+        }
+    }
+    IR_LAUNCH((k_finish), gc, 128, s, d, massRows, h->tracerLayers[0] == 1 ? 1 : 0);
+    h->launches++;
+    IR_CUDA(cudaEventRecord(h->ev1, s));
+    IR_CUDA(cudaGetLastError());
+    // out
+    for (int t = 0; t < nTracers; t++) {
+        const int w = nK * tr[t].nLayers;
+        IR_LAUNCH((k_tracer_out), grid_for(nC1, 256), 256, s, d.stage, d.valNew + (size_t)h->tracerRow0[t] * d.nCp, nC1, w, d.nCp);
+        h->launches++;
+        IR_CUDA(cudaMemcpyAsync(tr[t].array, d.stage, nC1 * w * 8, cudaMemcpyDeviceToHost, s));
+        IR_CUDA(cudaStreamSynchronize(s));
+    }
+    int flags = 0;
+    IR_CUDA(cudaMemcpyAsync(&flags, d.flags, sizeof(int), cudaMemcpyDeviceToHost, s));
+    IR_CUDA(cudaStreamSynchronize(s));
+    IR_CUDA(cudaEventElapsedTime(&h->lastMs, h->ev0, h->ev1));
+    if (flags & FLAG_NEG_MASS) { set_error("IR: negative mass in a cell (incremental_remap.F:7465)"); return IR_ERR_NEGATIVE_MASS; }
+    if (flags & FLAG_NEG_QP) { set_error("IR: negative mass at a quadrature point (incremental_remap.F:6895)"); return IR_ERR_NEGATIVE_MASS_QP; }
+    if (flags & FLAG_PARALLEL) { set_error("IR: parallel basis edges in shift_vertices (incremental_remap.F:6415)"); return IR_ERR_PARALLEL_EDGES; }
+    if (flags & FLAG_MANY_TRI) { set_error("IR: more than nTriPerEdgeRemap departure triangles on an edge"); return IR_ERR_TOO_MANY_TRIANGLES; }
+    return IR_OK;
+}
+
+extern "C" int ir_fetch_diagnostics(ir_handle *h, double *xTriangle, double *yTriangle, double *triangleArea,
+                                    int *iCellTriangle, int *maskEdge, double *edgeFluxMass)
+{
+    IR_REQUIRE(h != nullptr, "handle is NULL");
+    IR_CUDA(cudaSetDevice(h->device));
+    Dev &d = h->d;
+    const size_t nE = (size_t)d.nE;
+    if (nE == 0) return IR_OK;
+    cudaStream_t s = h->stream;
+    std::vector<double> tmp;
+    std::vector<int> itmp;
+    auto fetch = [&](const double *src, size_t rows) -> int {
+        tmp.resize(rows * d.nEp);
+        IR_CUDA(cudaMemcpyAsync(tmp.data(), src, rows * d.nEp * 8, cudaMemcpyDeviceToHost, s));
+        IR_CUDA(cudaStreamSynchronize(s));
+        return IR_OK;
+    };
+    int rc;
+    for (int pass = 0; pass < 2; pass++) {
+        double *dst = pass == 0 ? xTriangle : yTriangle;
+        if (!dst) continue;
+        if ((rc = fetch(pass == 0 ? d.xq : d.yq, NTRI * 6))) return rc;
+        for (size_t e = 0; e < nE; e++)
+            for (int t = 0; t < NTRI; t++)
+                for (int q = 0; q < d.nQP; q++) dst[(e * NTRI + t) * d.nQP + q] = tmp[(size_t)(t * 6 + q) * d.nEp + e];
+    }
+    if (triangleArea) {
+        if ((rc = fetch(d.triArea, NTRI))) return rc;
+        for (size_t e = 0; e < nE; e++)
+            for (int t = 0; t < NTRI; t++) triangleArea[e * NTRI + t] = tmp[(size_t)t * d.nEp + e];
+    }
+    if (iCellTriangle) {
+        itmp.resize(NTRI * d.nEp);
+        IR_CUDA(cudaMemcpyAsync(itmp.data(), d.iCellTri, NTRI * d.nEp * 4, cudaMemcpyDeviceToHost, s));
+        IR_CUDA(cudaStreamSynchronize(s));
+        for (size_t e = 0; e < nE; e++)
+            for (int t = 0; t < NTRI; t++) iCellTriangle[e * NTRI + t] = itmp[(size_t)t * d.nEp + e];
+    }
+    if (maskEdge) {
+        IR_CUDA(cudaMemcpyAsync(maskEdge, d.maskEdge, nE * 4, cudaMemcpyDeviceToHost, s));
+        IR_CUDA(cudaStreamSynchronize(s));
+    }
+    if (edgeFluxMass && h->haveTracers) {
+        const int w = d.nK * h->tracerLayers[0];
+        if ((rc = fetch(d.edgeFlux, (size_t)w))) return rc;
+        for (size_t e = 0; e < nE; e++)
+            for (int j = 0; j < w; j++) edgeFluxMass[e * w + j] = tmp[(size_t)j * d.nEp + e];
+    }
+    return IR_OK;
+}
+
+extern "C" int ir_last_run_ms(ir_handle *h, float *ms)
+{
+    IR_REQUIRE(h != nullptr && ms != nullptr, "NULL argument");
+    *ms = h->lastMs;
+    return IR_OK;
+}
+
+extern "C" int ir_launch_count(ir_handle *h, long long *n)
+{
+    IR_REQUIRE(h != nullptr && n != nullptr, "NULL argument");
+    *n = h->launches;
+    return IR_OK;
+}
+
+extern "C" int ir_destroy(ir_handle *h)
+{
+    if (!h) return IR_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    Dev &d = h->d;
+    double *bufs[] = {d.val, d.valNew, d.center, d.xGrad, d.yGrad, d.xBary, d.yBary, d.mtpNew, d.edgeFlux, d.stage};
+    for (double *b : bufs)
+        if (b) cudaFree(b);
+    if (d.rows) cudaFree(d.rows);
+    for (void *p : h->allocs) cudaFree(p);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return IR_OK;
+}

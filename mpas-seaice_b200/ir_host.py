@@ -1,0 +1,160 @@
+"""ctypes mirror of include/ir_b200.h: the incremental-remapping transport on the device.
+
+Host-side counterpart of seaice_run_advection_incremental_remap
+(src/shared/mpas_seaice_advection_incremental_remap.F:2338) for non-Fortran hosts: the arrays are numpy arrays in the
+layout c_loc() of the MPAS pool arrays has (C order with the dimensions reversed, the extra slot n+1).  There is no
+CPU fallback: without the CUDA library (or a device) construction fails.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("IR_B200_LIB", os.path.join(_HERE, "csrc", "libir_b200.so"))
+
+EXPORTS = ("ir_create", "ir_set_tracers", "ir_run", "ir_fetch_diagnostics", "ir_last_run_ms", "ir_launch_count",
+           "ir_destroy", "ir_last_error_string")
+GEOM_NAMES = ("x", "y", "xx", "xy", "yy", "xxx", "xxy", "xyy", "yyy", "xxxx", "xxxy", "xxyy", "xyyy", "yyyy")
+
+IR_OK, IR_ERR_ARGUMENT, IR_ERR_CUDA, IR_ERR_STATE = 0, 1, 2, 3
+IR_ERR_NEGATIVE_MASS_QP, IR_ERR_NEGATIVE_MASS, IR_ERR_PARALLEL_EDGES, IR_ERR_TOO_MANY_TRIANGLES = 10, 11, 12, 13
+
+
+class IrError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("ir_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+class ir_mesh_desc(C.Structure):
+    _fields_ = ([(n, C.c_int) for n in ("nCells", "nCellsSolve", "nVertices", "nEdges", "maxEdges", "vertexDegree",
+                                        "nCategories", "nQuadPoints", "on_a_sphere", "rotate_cartesian_grid")]
+                + [(n, C.c_void_p) for n in ("nEdgesOnCell", "edgesOnCell", "cellsOnCell", "verticesOnCell", "cellsOnEdge",
+                                             "verticesOnEdge", "areaCell", "dcEdge", "coeffs_reconstruct",
+                                             "transGlobalToCell", "xVertexOnCell", "yVertexOnCell", "xVertexOnEdge",
+                                             "yVertexOnEdge", "remapEdge", "cellsOnEdgeRemap", "edgesOnEdgeRemap")]
+                + [("geomAvgCell", C.c_void_p * 14)])
+
+
+class ir_tracer_desc(C.Structure):
+    _fields_ = [("nLayers", C.c_int), ("parent", C.c_int), ("volumeLike", C.c_int), ("array", C.c_void_p)]
+
+
+_libs = {}
+
+
+def load(path=None):
+    path = path or LIB_PATH
+    if path not in _libs:
+        if not os.path.exists(path):
+            raise IrError(IR_ERR_STATE, "%s is missing: build it with `python __graft_entry__.py` (no CPU fallback)" % path)
+        L = C.CDLL(path)
+        L.ir_last_error_string.restype = C.c_char_p
+        for name in EXPORTS[:-1]:
+            getattr(L, name).restype = C.c_int
+        _libs[path] = L
+    return _libs[path]
+
+
+def _ptr(a, dtype):
+    assert isinstance(a, np.ndarray) and a.dtype == dtype and a.flags["C_CONTIGUOUS"], (getattr(a, "dtype", None), dtype)
+    return a.ctypes.data
+
+
+class IrTransport:
+    """One block's transport.  ``mesh``: meshgen.Mesh (or any mapping with the MPAS mesh-pool names); ``irf``: the
+    mesh-file / framework arrays of irmesh.ir_fields; ``geom``: the incremental_remap pool arrays
+    (xVertexOnCell ... geomAvg) as seaice_init_advection_incremental_remap leaves them."""
+
+    def __init__(self, mesh, irf, geom, n_categories, n_quad_points=6, n_cells_solve=None, rotate=False, device=-1,
+                 lib_path=None):
+        self._L = load(lib_path)
+        self._h = C.c_void_p()
+        self.mesh = mesh
+        nC = mesh.nCells
+        m = ir_mesh_desc()
+        m.nCells, m.nVertices, m.nEdges, m.maxEdges, m.vertexDegree = nC, mesh.nVertices, mesh.nEdges, mesh.maxEdges, mesh.vertexDegree
+        m.nCellsSolve = nC if n_cells_solve is None else int(n_cells_solve)
+        m.nCategories, m.nQuadPoints = int(n_categories), int(n_quad_points)
+        m.on_a_sphere, m.rotate_cartesian_grid = int(bool(mesh.on_a_sphere)), int(bool(rotate))
+        self._keep = [mesh, irf, geom]
+        for name in ("nEdgesOnCell", "edgesOnCell", "cellsOnCell", "verticesOnCell", "cellsOnEdge"):
+            setattr(m, name, _ptr(mesh[name], np.int32))
+        m.verticesOnEdge = _ptr(irf["verticesOnEdge"], np.int32)
+        m.areaCell, m.dcEdge = _ptr(mesh["areaCell"], np.float64), _ptr(mesh["dcEdge"], np.float64)
+        m.coeffs_reconstruct = _ptr(irf["coeffs_reconstruct"], np.float64)
+        m.transGlobalToCell = _ptr(geom["transGlobalToCell"], np.float64) if mesh.on_a_sphere else None
+        for name in ("xVertexOnCell", "yVertexOnCell", "xVertexOnEdge", "yVertexOnEdge"):
+            setattr(m, name, _ptr(geom[name], np.float64))
+        for name in ("remapEdge", "cellsOnEdgeRemap", "edgesOnEdgeRemap"):
+            setattr(m, name, _ptr(geom[name], np.int32))
+        for k, n in enumerate(GEOM_NAMES):
+            m.geomAvgCell[k] = _ptr(geom["geomAvg"][n], np.float64)
+        self.n_categories, self.n_quad_points = int(n_categories), int(n_quad_points)
+        self._check(self._L.ir_create(C.byref(self._h), C.byref(m), C.c_int(device)))
+        self._table = None
+
+    def _check(self, rc):
+        if rc != IR_OK:
+            raise IrError(rc, self._L.ir_last_error_string().decode())
+
+    def _make_table(self, tracers):
+        """tracers: sequence of objects with .array (nCells+1, nCategories, nLayers), .parent (index or None),
+        .volume_like"""
+        table = (ir_tracer_desc * len(tracers))()
+        for i, t in enumerate(tracers):
+            assert t.array.shape[:2] == (self.mesh.nCells + 1, self.n_categories)
+            table[i].nLayers = t.array.shape[2]
+            table[i].parent = -1 if t.parent is None else int(t.parent)
+            table[i].volumeLike = int(bool(t.volume_like))
+            table[i].array = _ptr(t.array, np.float64)
+        return table
+
+    def set_tracers(self, tracers):
+        self._table = self._make_table(tracers)
+        self._check(self._L.ir_set_tracers(self._h, C.c_int(len(tracers)), self._table))
+
+    def run(self, tracers, u, v, dt, check=True):
+        """One step IN PLACE on the tracer arrays; returns the ir_run code (raises on an abort condition if check)."""
+        nV = self.mesh.nVertices
+        assert u.shape == (nV + 1,) and v.shape == (nV + 1,)
+        table = self._make_table(tracers)
+        rc = self._L.ir_run(self._h, C.c_int(len(tracers)), table, C.c_void_p(_ptr(u, np.float64)),
+                            C.c_void_p(_ptr(v, np.float64)), C.c_double(dt))
+        if check or rc in (IR_ERR_ARGUMENT, IR_ERR_CUDA, IR_ERR_STATE):
+            self._check(rc)
+        return rc
+
+    def diagnostics(self, n_mass_layers=1):
+        nE, nQ, nK = self.mesh.nEdges, self.n_quad_points, self.n_categories
+        out = dict(xTriangle=np.zeros((nE, 6, nQ)), yTriangle=np.zeros((nE, 6, nQ)), triangleArea=np.zeros((nE, 6)),
+                   iCellTriangle=np.zeros((nE, 6), np.int32), maskEdge=np.zeros(nE, np.int32),
+                   edgeFluxMass=np.zeros((nE, nK, n_mass_layers)))
+        self._check(self._L.ir_fetch_diagnostics(self._h, *[C.c_void_p(out[k].ctypes.data) for k in
+                                                            ("xTriangle", "yTriangle", "triangleArea", "iCellTriangle",
+                                                             "maskEdge", "edgeFluxMass")]))
+        return out
+
+    def last_run_ms(self):
+        ms = C.c_float(0)
+        self._check(self._L.ir_last_run_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        n = C.c_longlong(0)
+        self._check(self._L.ir_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def destroy(self):
+        if self._h:
+            self._L.ir_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass

@@ -1,0 +1,214 @@
+"""Parity of the incremental-remapping kernels (mpas-seaice_b200/csrc/ir_kernels.cu, C ABI include/ir_b200.h) with
+the oracle (oracle/ir_oracle.c): bit-exact -- FP64 work done in the reference's operation order with contraction
+off on both sides.
+
+Two legs run the same cases through the same C ABI and ctypes host:
+
+* ``cuda`` (@gpu): the shipped library on a B200.  Written after this round's GPU minutes were spent, so it has
+  not run on a device yet: non-strict xfail until it has (an XPASS is the expected outcome).
+* ``emulation`` (CPU): the SAME source file compiled with g++ against tests/emu/cuda_runtime.h, which runs every
+  kernel thread sequentially.  It checks the kernels' logic here, where there is no GPU; it is test infrastructure,
+  built under tests/_build/, and never shipped or loaded by the product.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import ir
+from mpas_seaice_b200 import ir_host
+from test_oracle_ir import case, smooth_divergent_velocity, uniform_velocity, _random_state
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "mpas-seaice_b200", "csrc", "ir_kernels.cu")
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+EMU_LIB = os.path.join(ROOT, "tests", "_build", "libir_emu.so")
+
+
+def _emulation_library():
+    deps = [SRC, os.path.join(EMU_DIR, "cuda_runtime.h"), os.path.join(ROOT, "include", "ir_b200.h")]
+    if not os.path.exists(EMU_LIB) or any(os.path.getmtime(p) > os.path.getmtime(EMU_LIB) for p in deps):
+        os.makedirs(os.path.dirname(EMU_LIB), exist_ok=True)
+        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-std=c++17", "-fPIC", "-shared", "-x", "c++",
+                        "-Wall", "-Wno-unknown-pragmas", "-I", EMU_DIR, "-o", EMU_LIB, SRC], check=True)
+    return EMU_LIB
+
+
+LEGS = [
+    pytest.param("emulation", id="emulation"),
+    pytest.param("cuda", id="cuda", marks=[
+        pytest.mark.gpu,
+        pytest.mark.xfail(strict=False, reason="written after this round's GPU minutes were spent: not yet run on a device")]),
+]
+
+
+@pytest.fixture(params=LEGS)
+def lib_path(request):
+    if request.param == "emulation":
+        return _emulation_library()
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return ir_host.LIB_PATH
+
+
+def clone(tracers):
+    return [ir.Tracer(t.name, t.array.copy(), t.parent, t.volume_like) for t in tracers]
+
+
+def run_both(kind, tracers, u, v, dt, lib_path, steps=1, n_quad_points=6, rotate=False, check=True):
+    mesh, irf, geom = case(kind)
+    if rotate:
+        geom = ir.init_geometry(mesh, irf, rotate=True)
+    ref, dev = clone(tracers), clone(tracers)
+    nK = tracers[0].array.shape[1]
+    solver = ir_host.IrTransport(mesh, irf, geom, nK, n_quad_points=n_quad_points, rotate=rotate, lib_path=lib_path)
+    try:
+        solver.set_tracers(dev)
+        codes = []
+        for _ in range(steps):
+            d_ref = ir.run(mesh, irf, geom, ref, u, v, dt, n_quad_points=n_quad_points, rotate=rotate, diagnostics=True,
+                           check=False)
+            rc = solver.run(dev, u, v, dt, check=False)
+            codes.append((d_ref["error"], rc))
+        d_dev = solver.diagnostics(tracers[0].array.shape[2])
+        launches = solver.launch_count()
+    finally:
+        solver.destroy()
+    return mesh, ref, dev, d_ref, d_dev, codes, launches
+
+
+def assert_identical(mesh, ref, dev, d_ref, d_dev):
+    nC = mesh.nCells
+    for a, b in zip(ref, dev):
+        assert np.array_equal(a.array[:nC], b.array[:nC]), a.name
+    for key in ("maskEdge", "iCellTriangle", "triangleArea", "xTriangle", "yTriangle", "edgeFluxMass"):
+        assert np.array_equal(d_ref[key], d_dev[key]), key
+
+
+@pytest.mark.parametrize("kind", ["hex16", "quad16", "ico3"])
+def test_full_hierarchy_matches_oracle(kind, lib_path):
+    """area -> {volume -> {enthalpy, salinity (layers)}, snow volume -> snow enthalpy, surface temperature}, three
+    categories, divergent flow, ice-free cells: three steps, every tracer and every departure triangle identical."""
+    mesh, irf, geom = case(kind)
+    rng = np.random.default_rng(21)
+    tracers = _random_state(mesh, rng)
+    u, v = smooth_divergent_velocity(mesh, geom)
+    mesh, ref, dev, d_ref, d_dev, codes, launches = run_both(kind, tracers, u, v, 3600.0, lib_path, steps=3)
+    assert all(c == (0, 0) for c in codes), codes
+    assert_identical(mesh, ref, dev, d_ref, d_dev)
+    assert any(np.any(a.array != t.array) for a, t in zip(ref, tracers))      # something moved
+    assert launches > 0
+
+
+@pytest.mark.parametrize("kind,vel", [("hex16", (0.05, 0.02)), ("hex16", (-0.04, -0.04)), ("quad16", (0.07, 0.0)),
+                                      ("quad16", (-0.03, 0.06)), ("quad16", (0.0, -0.05))])
+def test_uniform_flow_matches_oracle(kind, vel, lib_path):
+    """Every configuration of find_departure_triangles: side triangles left / right, a quadrilateral on one side of
+    the edge, the E5/E6 split on quads."""
+    mesh, irf, geom = case(kind)
+    nC = mesh.nCells
+    tracers = ir.default_tracers(nC, 2)
+    x, y = mesh.xCell[:nC], mesh.yCell[:nC]
+    tracers[0].array[:nC, 0, 0] = 0.3 + 1e-5 * x + 2e-5 * y
+    tracers[0].array[:nC, 1, 0] = 0.2 - 0.5e-5 * x + 1e-5 * y
+    tracers[1].array[:nC] = tracers[0].array[:nC] * 2.0
+    tracers[3].array[:nC] = -5.0
+    u, v = uniform_velocity(mesh, *vel)
+    mesh, ref, dev, d_ref, d_dev, codes, _ = run_both(kind, tracers, u, v, 3600.0, lib_path)
+    assert codes == [(0, 0)]
+    assert_identical(mesh, ref, dev, d_ref, d_dev)
+
+
+def test_three_point_quadrature_and_rotated_grid_match_oracle(lib_path):
+    """nQuadPoints = 3 (with the reference's x-for-y mid-point, :6598) on a plane, where it stays benign; the rotated
+    Cartesian grid (config_rotate_cartesian_grid: gradient components swapped, :4365-4372) on the sphere."""
+    mesh, irf, geom = case("hex16")
+    rng = np.random.default_rng(4)
+    tracers = _random_state(mesh, rng, n_cat=2, n_ice=2, n_snow=0, ice_free=0.0)
+    u, v = uniform_velocity(mesh, 0.04, -0.03)
+    mesh, ref, dev, d_ref, d_dev, codes, _ = run_both("hex16", tracers, u, v, 3600.0, lib_path, n_quad_points=3, check=False)
+    assert codes == [(0, 0)]
+    assert_identical(mesh, ref, dev, d_ref, d_dev)
+    mesh, irf, geom = case("ico3")
+    tracers = _random_state(mesh, rng, n_cat=2, n_ice=2, n_snow=0)
+    u, v = smooth_divergent_velocity(mesh, geom, cfl=0.2)
+    mesh, ref, dev, d_ref, d_dev, codes, _ = run_both("ico3", tracers, u, v, 3600.0, lib_path, rotate=True, check=False)
+    assert codes == [(0, 0)]
+    assert_identical(mesh, ref, dev, d_ref, d_dev)
+
+
+def test_abort_conditions_are_reported_like_the_oracle(lib_path):
+    """The 3-point quadrature on the sphere puts its points far outside the departure triangles (the mid-point slip,
+    :6598): masses go negative, which the reference treats as fatal (:6895, :7465).  Oracle and device must both
+    report it; departure triangles and mass fluxes, computed before the abort, are still identical."""
+    mesh, irf, geom = case("ico3")
+    rng = np.random.default_rng(4)
+    tracers = _random_state(mesh, rng, n_cat=2, n_ice=2, n_snow=0)
+    u, v = smooth_divergent_velocity(mesh, geom, cfl=0.2)
+    mesh, ref, dev, d_ref, d_dev, codes, _ = run_both("ico3", tracers, u, v, 3600.0, lib_path, n_quad_points=3, check=False)
+    oracle_code, device_code = codes[0]
+    assert oracle_code in (4, 5)
+    assert device_code in (ir_host.IR_ERR_NEGATIVE_MASS_QP, ir_host.IR_ERR_NEGATIVE_MASS)
+    for key in ("maskEdge", "iCellTriangle", "triangleArea", "xTriangle", "yTriangle", "edgeFluxMass"):
+        assert np.array_equal(d_ref[key], d_dev[key]), key
+    nC = mesh.nCells
+    assert np.array_equal(ref[0].array[:nC], dev[0].array[:nC])      # the mass field was updated before the check
+
+
+def test_rotation_test_case_matches_oracle(lib_path):
+    """The reference's advection test case (cosine bell, u = U cos(lat); create_ics.py:36-107) on the 2562-cell
+    sphere with its twelve pentagons: ten steps, identical throughout."""
+    import math
+    from test_oracle_ir import _rotation_case
+    mesh, irf, geom = case("ico4")
+    nC, nV = mesh.nCells, mesh.nVertices
+    p, field = _rotation_case(mesh, "cosine_bell")
+    tracers = ir.default_tracers(nC, 1)
+    tracers[0].array[:nC, 0, 0] = field(p)
+    tracers[1].array[:nC, 0, 0] = tracers[0].array[:nC, 0, 0] * (1.0 + 0.5 * p[:, 2])
+    u, v = np.zeros(nV + 1), np.zeros(nV + 1)
+    u[:nV] = 2.0 * math.pi * 6371229.0 / (120.0 * 86400.0) * np.cos(mesh.latVertex[:nV])
+    mesh, ref, dev, d_ref, d_dev, codes, _ = run_both("ico4", tracers, u, v, 6.0 * 3600.0, lib_path, steps=10)
+    assert all(c == (0, 0) for c in codes)
+    assert_identical(mesh, ref, dev, d_ref, d_dev)
+
+
+def test_call_order_and_argument_errors(lib_path):
+    mesh, irf, geom = case("hex12")
+    solver = ir_host.IrTransport(mesh, irf, geom, 1, lib_path=lib_path)
+    try:
+        tracers = ir.default_tracers(mesh.nCells, 1)
+        u, v = uniform_velocity(mesh, 0.0, 0.0)
+        with pytest.raises(ir_host.IrError) as e:
+            solver.run(tracers, u, v, 1.0)
+        assert e.value.code == ir_host.IR_ERR_STATE
+        bad = clone(tracers)
+        bad[2].parent = 3                      # a child before its parent
+        with pytest.raises(ir_host.IrError) as e:
+            solver.set_tracers(bad)
+        assert e.value.code == ir_host.IR_ERR_ARGUMENT
+        solver.set_tracers(tracers)
+        with pytest.raises(ir_host.IrError) as e:
+            solver.run(tracers[:3], u, v, 1.0)
+        assert e.value.code == ir_host.IR_ERR_ARGUMENT
+        assert solver.run(tracers, u, v, 1.0) == ir_host.IR_OK
+    finally:
+        solver.destroy()
+    with pytest.raises(ir_host.IrError):
+        ir_host.IrTransport(mesh, irf, geom, 1, n_quad_points=4, lib_path=lib_path)
+
+
+def test_shipped_library_exports_the_abi():
+    """include/ir_b200.h against the built CUDA library (no compute: there is no device here)."""
+    import ctypes as C
+    import re
+    header = open(os.path.join(ROOT, "include", "ir_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char \*)\s*(ir_[a-z_]+)\(", header, flags=re.M))
+    assert declared == set(ir_host.EXPORTS)
+    L = C.CDLL(ir_host.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-Wall", "-Wextra", "-x", "c", os.path.join(ROOT, "include", "ir_b200.h")],
+                   check=True)
