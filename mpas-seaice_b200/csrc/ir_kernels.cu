@@ -1,18 +1,19 @@
 // ir_kernels.cu -- incremental-remapping transport on B200 (sm_100a): kernels and the C ABI of include/ir_b200.h.
 //
 // What one ir_run does (reference: incremental_remap_block, src/shared/mpas_seaice_advection_incremental_remap.F:2740):
-//   k_prepare      cell mask, volume -> thickness                                   (:2462-2480, make_masks :3404)
-//   k_reconstruct  per tracer depth: gradient, limiter, centre value, barycentre    (:3580-5250)
-//   k_triangles    per edge: departure triangles and their quadrature points        (:5255-6665)
-//   k_fluxes       per (edge, tracer row): integrate mass * tracer over triangles   (:6667-6980)
-//   k_update       per tracer depth: new mass and tracers                           (:6982-7540)
-//   k_finish       zap small masses, thickness -> volume                            (:8764-8895, :2680-2700)
+//   k_prepare      per cell: ice mask, volume -> thickness                               (:2462-2480, make_masks :3404)
+//   k_reconstruct  per (cell, category): gradient, limiter, centre value, barycentre    (:3580-5250)
+//   k_triangles    per edge: departure triangles and their quadrature points            (:5255-6665)
+//   k_fluxes       per (edge, category): integrate mass * tracer over the triangles     (:6667-6980)
+//   k_update       per (cell, category): new mass and tracers, zap, thickness -> volume (:6982-7540, :8764-8895, :2680-2700)
+// Five launches per step whatever the number of tracers.
 //
 // Layout: the host keeps a tracer as (nLayers, nCategories, nCells) -- all components of a cell together.  On the
 // device every (tracer, category, layer) is a ROW of one matrix val[nRows][nCp] with the cell index fastest, so a warp
 // of 32 cells reads 256 contiguous bytes of a row; the same for every per-cell / per-edge geometry array
-// ([slot][nCp]).  Rows are ordered by tracer, so rows of one depth of the hierarchy are contiguous ranges and a whole
-// depth is one launch (grid.y = rows).  Parents are resolved to row numbers once, in ir_set_tracers.
+// ([slot][nCp]).  Parents are resolved to row numbers once, in ir_set_tracers.  Categories never mix, and within a
+// category a row depends on its parents in the same cell only, so the tracer kernels run one thread per
+// (cell or edge, category) that walks the category's rows parents first and reads the geometry once.
 //
 // All of it is gather-heavy FP64 streaming work bounded by HBM / L2, not tensor work.  Built with --fmad=false and in
 // the reference's operation order so that the results are bit-identical to oracle/ir_oracle.c (tests/test_gpu_ir.py).
@@ -94,8 +95,9 @@ struct Dev {
     int *maskCell, *maskEdge, *iCellTri /* [NTRI][nEp] */;
     double *xq, *yq /* [NTRI*6][nEp] */, *triArea /* [NTRI][nEp] */;
     // tracer state, [nRows][nCp] unless noted
-    int nRows;
+    int nRows, nRowsPerCat;
     RowInfo *rows;
+    int *catBaseRow, *catLayers;   // rows of category k in parents-first order: catBaseRow[j] + k * catLayers[j]
     double *val, *valNew, *center, *xGrad, *yGrad, *xBary, *yBary, *mtpNew;
     double *edgeFlux;   // [nRows][nEp]
     int *flags;
@@ -272,85 +274,108 @@ __device__ void barycenter(const Dev &d, size_t c, int n, const double *mean, co
           cyyy * ayyyy) * reciprocal;
 }
 
-// construct_linear_tracer_fields (:3580) for the rows [row0, row0 + gridDim.y) of one depth of the hierarchy:
-// compute_gradient (:4204), limit_tracer_gradient (:4802), centre value (:3735), barycentre (:3750-3840).
-__global__ void __launch_bounds__(128) k_reconstruct(Dev d, int row0)
+// construct_linear_tracer_fields (:3580): compute_gradient (:4204), limit_tracer_gradient (:4802), centre value
+// (:3735), barycentre (:3750-3840).  One thread per (cell, category) walks the rows of its category parents first:
+// a row needs its parents' results in the SAME cell only (neighbour cells contribute their input values), so the
+// whole hierarchy is one launch, and the cell's geometry (reconstruction coefficients, signed dcEdge, vertex
+// coordinates: 6 * maxEdges doubles) is read once per category instead of once per row.  It is parked in shared
+// memory as a per-thread scratch column (no thread reads another's, hence no barrier).
+constexpr int RB = 64;   // threads per block of the per-(cell, category) and per-(edge, category) kernels
+
+__global__ void __launch_bounds__(RB) k_reconstruct(Dev d)
 {
+    __shared__ double S[6 * MAXM][RB];
     const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = row0 + blockIdx.y;
+    const int cat = blockIdx.y, tx = threadIdx.x;
     if (c >= (size_t)d.nC) return;
-    const RowInfo ri = d.rows[r];
     const size_t p = d.nCp;
-    const double *field = d.val + (size_t)r * p;
-    const double f0 = field[c];
-    const int pr = ri.depth > 0 ? ri.chain[ri.depth - 1] : -1;
-    double xB, yB;   // barycentre of the parent: where this row's value sits
-    if (pr >= 0) { xB = d.xBary[(size_t)pr * p + c]; yB = d.yBary[(size_t)pr * p + c]; }
-    else { xB = d.geom[c]; yB = d.geom[p + c]; }
-    double xg = 0.0, yg = 0.0;
-    const bool ice = d.maskCell[c] == 1;
-    if (ice) {
-        const int n = d.nEdgesOnCell[c];
-        const bool m0 = row_mask(d, ri, c);
-        double g1 = 0.0, g2 = 0.0, g3 = 0.0;
-        double maxNeighbor = f0, minNeighbor = f0;
-        for (int k = 0; k < n; k++) {
-            const int nb = d.cellsOnCell[k * p + c];            // 1-based, nC+1 = none
-            const bool mn = row_mask(d, ri, (size_t)nb - 1);
-            double normalGrad = 0.0;
-            const double fn = (nb >= 1 && nb <= d.nC + 1) ? field[nb - 1] : 0.0;
-            if (nb >= 1 && nb <= d.nC && m0 && mn) normalGrad = (fn - f0) / d.sdc[k * p + c];
-            g1 = g1 + d.coef[(size_t)(3 * k + 0) * p + c] * normalGrad;
-            g2 = g2 + d.coef[(size_t)(3 * k + 1) * p + c] * normalGrad;
-            g3 = g3 + d.coef[(size_t)(3 * k + 2) * p + c] * normalGrad;
-            if (mn) {
-                maxNeighbor = (maxNeighbor > fn) ? maxNeighbor : fn;
-                minNeighbor = (minNeighbor < fn) ? minNeighbor : fn;
-            }
-        }
-        if (d.rotate && d.sphere) { const double t = g1; g1 = -g3; g3 = t; }
-        if (d.sphere) {
-            xg = d.trans[0 * p + c] * g1 + d.trans[1 * p + c] * g2 + d.trans[2 * p + c] * g3;
-            yg = d.trans[3 * p + c] * g1 + d.trans[4 * p + c] * g2 + d.trans[5 * p + c] * g3;
-        } else {
-            xg = g1;
-            yg = g2;
-        }
-        maxNeighbor = maxNeighbor - f0;
-        minNeighbor = minNeighbor - f0;
-        double maxLocal = 0.0, minLocal = 0.0;
-        for (int k = 0; k < n; k++) {
-            const double dev = xg * (d.xvc[k * p + c] - xB) + yg * (d.yvc[k * p + c] - yB);
-            maxLocal = (maxLocal > dev) ? maxLocal : dev;
-            minLocal = (minLocal < dev) ? minLocal : dev;
-        }
-        double f1 = 1.0, f2 = 1.0;
-        if (fabs(maxLocal) > fabs(maxNeighbor)) { f1 = maxNeighbor / maxLocal; if (!(f1 > 0.0)) f1 = 0.0; }
-        if (fabs(minLocal) > fabs(minNeighbor)) { f2 = minNeighbor / minLocal; if (!(f2 > 0.0)) f2 = 0.0; }
-        double gradFactor = (f1 < f2) ? f1 : f2;
-        gradFactor = gradFactor - EPS11;
-        if (!(gradFactor > 0.0)) gradFactor = 0.0;
-        xg = xg * gradFactor;
-        yg = yg * gradFactor;
+    const int M = d.M, n = d.nEdgesOnCell[c];
+    int nb[MAXM];
+    for (int k = 0; k < n; k++) {
+        nb[k] = d.cellsOnCell[k * p + c];            // 1-based, nC+1 = none
+        S[3 * k + 0][tx] = d.coef[(size_t)(3 * k + 0) * p + c];
+        S[3 * k + 1][tx] = d.coef[(size_t)(3 * k + 1) * p + c];
+        S[3 * k + 2][tx] = d.coef[(size_t)(3 * k + 2) * p + c];
+        S[3 * M + k][tx] = d.sdc[k * p + c];
+        S[4 * M + k][tx] = d.xvc[k * p + c];
+        S[5 * M + k][tx] = d.yvc[k * p + c];
     }
-    const double cen = f0 - xg * xB - yg * yB;
-    d.xGrad[(size_t)r * p + c] = xg;
-    d.yGrad[(size_t)r * p + c] = yg;
-    d.center[(size_t)r * p + c] = cen;
-    if (ri.hasChild) {
-        double bx = 0.0, by = 0.0;
+    double tr[6] = {0, 0, 0, 0, 0, 0};
+    if (d.sphere)
+        for (int q = 0; q < 6; q++) tr[q] = d.trans[q * p + c];
+    const double xAvg = d.geom[c], yAvg = d.geom[p + c];
+    const bool ice = d.maskCell[c] == 1;
+    for (int j = 0; j < d.nRowsPerCat; j++) {
+        const int r = d.catBaseRow[j] + cat * d.catLayers[j];
+        const RowInfo ri = d.rows[r];
+        const double *field = d.val + (size_t)r * p;
+        const double f0 = field[c];
+        const int pr = ri.depth > 0 ? ri.chain[ri.depth - 1] : -1;
+        double xB, yB;   // barycentre of the parent: where this row's value sits
+        if (pr >= 0) { xB = d.xBary[(size_t)pr * p + c]; yB = d.yBary[(size_t)pr * p + c]; }
+        else { xB = xAvg; yB = yAvg; }
+        double xg = 0.0, yg = 0.0;
         if (ice) {
-            double mean[3], ce[3], gx[3], gy[3];
-            const int n = ri.depth + 1;
-            for (int s = 0; s < n - 1; s++) {
-                const size_t q = (size_t)ri.chain[s] * p + c;
-                mean[s] = d.val[q]; ce[s] = d.center[q]; gx[s] = d.xGrad[q]; gy[s] = d.yGrad[q];
+            const bool m0 = row_mask(d, ri, c);
+            double g1 = 0.0, g2 = 0.0, g3 = 0.0;
+            double maxNeighbor = f0, minNeighbor = f0;
+            for (int k = 0; k < n; k++) {
+                const bool mn = row_mask(d, ri, (size_t)nb[k] - 1);
+                double normalGrad = 0.0;
+                const double fn = (nb[k] >= 1 && nb[k] <= d.nC + 1) ? field[nb[k] - 1] : 0.0;
+                if (nb[k] >= 1 && nb[k] <= d.nC && m0 && mn) normalGrad = (fn - f0) / S[3 * M + k][tx];
+                g1 = g1 + S[3 * k + 0][tx] * normalGrad;
+                g2 = g2 + S[3 * k + 1][tx] * normalGrad;
+                g3 = g3 + S[3 * k + 2][tx] * normalGrad;
+                if (mn) {
+                    maxNeighbor = (maxNeighbor > fn) ? maxNeighbor : fn;
+                    minNeighbor = (minNeighbor < fn) ? minNeighbor : fn;
+                }
             }
-            mean[n - 1] = f0; ce[n - 1] = cen; gx[n - 1] = xg; gy[n - 1] = yg;
-            barycenter(d, c, n, mean, ce, gx, gy, bx, by);
+            if (d.rotate && d.sphere) { const double t = g1; g1 = -g3; g3 = t; }
+            if (d.sphere) {
+                xg = tr[0] * g1 + tr[1] * g2 + tr[2] * g3;
+                yg = tr[3] * g1 + tr[4] * g2 + tr[5] * g3;
+            } else {
+                xg = g1;
+                yg = g2;
+            }
+            maxNeighbor = maxNeighbor - f0;
+            minNeighbor = minNeighbor - f0;
+            double maxLocal = 0.0, minLocal = 0.0;
+            for (int k = 0; k < n; k++) {
+                const double dev = xg * (S[4 * M + k][tx] - xB) + yg * (S[5 * M + k][tx] - yB);
+                maxLocal = (maxLocal > dev) ? maxLocal : dev;
+                minLocal = (minLocal < dev) ? minLocal : dev;
+            }
+            double f1 = 1.0, f2 = 1.0;
+            if (fabs(maxLocal) > fabs(maxNeighbor)) { f1 = maxNeighbor / maxLocal; if (!(f1 > 0.0)) f1 = 0.0; }
+            if (fabs(minLocal) > fabs(minNeighbor)) { f2 = minNeighbor / minLocal; if (!(f2 > 0.0)) f2 = 0.0; }
+            double gradFactor = (f1 < f2) ? f1 : f2;
+            gradFactor = gradFactor - EPS11;
+            if (!(gradFactor > 0.0)) gradFactor = 0.0;
+            xg = xg * gradFactor;
+            yg = yg * gradFactor;
         }
-        d.xBary[(size_t)r * p + c] = bx;
-        d.yBary[(size_t)r * p + c] = by;
+        const double cen = f0 - xg * xB - yg * yB;
+        d.xGrad[(size_t)r * p + c] = xg;
+        d.yGrad[(size_t)r * p + c] = yg;
+        d.center[(size_t)r * p + c] = cen;
+        if (ri.hasChild) {
+            double bx = 0.0, by = 0.0;
+            if (ice) {
+                double mean[3], ce[3], gx[3], gy[3];
+                const int nn = ri.depth + 1;
+                for (int q = 0; q < nn - 1; q++) {
+                    const size_t a = (size_t)ri.chain[q] * p + c;
+                    mean[q] = d.val[a]; ce[q] = d.center[a]; gx[q] = d.xGrad[a]; gy[q] = d.yGrad[a];
+                }
+                mean[nn - 1] = f0; ce[nn - 1] = cen; gx[nn - 1] = xg; gy[nn - 1] = yg;
+                barycenter(d, c, nn, mean, ce, gx, gy, bx, by);
+            }
+            d.xBary[(size_t)r * p + c] = bx;
+            d.yBary[(size_t)r * p + c] = by;
+        }
     }
 }
 
@@ -582,96 +607,112 @@ __global__ void __launch_bounds__(128) k_triangles(Dev d, double dt)
     }
 }
 
-// integrate_fluxes_over_triangles (:6667): one thread per (edge, row).  triangleValue of a row is the product down its
-// chain of parents of the linear reconstructions at the quadrature point, the mass field first.
-__global__ void __launch_bounds__(128) k_fluxes(Dev d)
+// integrate_fluxes_over_triangles (:6667): one thread per (edge, category).  The quadrature points of the edge's
+// departure triangles (up to 6 x 6 x 2 doubles) are parked once in a per-thread shared-memory column and reused by every
+// row of the category.  triangleValue of a row is the product down its chain of parents of the linear reconstructions
+// at the quadrature point, the mass field first.
+__global__ void __launch_bounds__(RB) k_fluxes(Dev d)
 {
+    __shared__ double Q[NTRI * 12][RB];
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y;
+    const int cat = blockIdx.y, tx = threadIdx.x;
     if (e >= (size_t)d.nE) return;
     const size_t pe = d.nEp, pc = d.nCp;
-    double flux = 0.0;
+    const int nQP = d.nQP;
+    double area[NTRI];
+    size_t cell[NTRI];
+    bool any = false;
     if (d.maskEdge[e] == 1) {
-        const RowInfo ri = d.rows[r];
-        const int nQP = d.nQP;
-        bool negative = false;
         for (int t = 0; t < NTRI; t++) {
-            const double area = d.triArea[t * pe + e];
-            if (area == 0.0) continue;
-            const size_t cell = (size_t)d.iCellTri[t * pe + e] - 1;
-            double cen[MAX_DEPTH], gx[MAX_DEPTH], gy[MAX_DEPTH];
-            for (int s = 0; s <= ri.depth; s++) {
-                const size_t q = (size_t)ri.chain[s] * pc + cell;
-                cen[s] = d.center[q]; gx[s] = d.xGrad[q]; gy[s] = d.yGrad[q];
+            area[t] = d.triArea[t * pe + e];
+            if (area[t] == 0.0) continue;
+            any = true;
+            cell[t] = (size_t)d.iCellTri[t * pe + e] - 1;
+            for (int q = 0; q < nQP; q++) {
+                Q[t * 12 + q][tx] = d.xq[(size_t)(t * 6 + q) * pe + e];
+                Q[t * 12 + 6 + q][tx] = d.yq[(size_t)(t * 6 + q) * pe + e];
             }
-            double tracerIntegral = 0.0;
-            for (int iqp = 0; iqp < nQP; iqp++) {
-                const double x = d.xq[(size_t)(t * 6 + iqp) * pe + e], y = d.yq[(size_t)(t * 6 + iqp) * pe + e];
-                double value = 1.0;
-                for (int s = 0; s <= ri.depth; s++) value = value * (cen[s] + gx[s] * x + gy[s] * y);
-                if (ri.depth == 0 && value < 0.0) negative = true;
-                const double w = (nQP == 3) ? (1.0 / 3.0) : (iqp < 3 ? W1QP : W2QP);
-                tracerIntegral = tracerIntegral + w * value;
-            }
-            flux = flux + area * tracerIntegral;
         }
-        if (negative) atomicOr(d.flags, FLAG_NEG_QP);
     }
-    d.edgeFlux[(size_t)r * pe + e] = flux;
+    bool negative = false;
+    for (int j = 0; j < d.nRowsPerCat; j++) {
+        const int r = d.catBaseRow[j] + cat * d.catLayers[j];
+        double flux = 0.0;
+        if (any) {
+            const RowInfo ri = d.rows[r];
+            for (int t = 0; t < NTRI; t++) {
+                if (area[t] == 0.0) continue;
+                double cen[MAX_DEPTH], gx[MAX_DEPTH], gy[MAX_DEPTH];
+                for (int s = 0; s <= ri.depth; s++) {
+                    const size_t q = (size_t)ri.chain[s] * pc + cell[t];
+                    cen[s] = d.center[q]; gx[s] = d.xGrad[q]; gy[s] = d.yGrad[q];
+                }
+                double tracerIntegral = 0.0;
+                for (int iqp = 0; iqp < nQP; iqp++) {
+                    const double x = Q[t * 12 + iqp][tx], y = Q[t * 12 + 6 + iqp][tx];
+                    double value = 1.0;
+                    for (int s = 0; s <= ri.depth; s++) value = value * (cen[s] + gx[s] * x + gy[s] * y);
+                    if (ri.depth == 0 && value < 0.0) negative = true;
+                    const double w = (nQP == 3) ? (1.0 / 3.0) : (iqp < 3 ? W1QP : W2QP);
+                    tracerIntegral = tracerIntegral + w * value;
+                }
+                flux = flux + area[t] * tracerIntegral;
+            }
+        }
+        d.edgeFlux[(size_t)r * pe + e] = flux;
+    }
+    if (negative) atomicOr(d.flags, FLAG_NEG_QP);
 }
 
-// compute_mass_tracer_products (:6982) + update_mass_and_tracers (:7125) for the rows of one depth
-__global__ void __launch_bounds__(128) k_update(Dev d, int row0)
+// compute_mass_tracer_products (:6982), update_mass_and_tracers (:7125), zap_small_mass (:8764; one-layer mass field)
+// and thickness -> volume (:9295): one thread per (cell, category), rows parents first -- a row needs the NEW
+// mass * tracer product of its parent in the same cell only.
+__global__ void __launch_bounds__(RB) k_update(Dev d, int massOneLayer)
 {
     const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = row0 + blockIdx.y;
+    const int cat = blockIdx.y;
     if (c > (size_t)d.nC) return;
     const size_t pe = d.nEp, pc = d.nCp;
-    if (c >= (size_t)d.nCS) {                 // halo cells and the extra slot keep their values
-        d.valNew[(size_t)r * pc + c] = d.val[(size_t)r * pc + c];
-        return;
+    const bool owned = c < (size_t)d.nCS;
+    int edge[MAXM], sign[MAXM], n = 0;
+    double area = 1.0;
+    if (owned) {
+        n = d.nEdgesOnCell[c];
+        for (int k = 0; k < n; k++) { edge[k] = d.edgesOnCell[k * pc + c]; sign[k] = d.fluxSign[k * pc + c]; }
+        area = d.areaCell[c];
     }
-    const RowInfo ri = d.rows[r];
-    const int n = d.nEdgesOnCell[c];
-    double fluxFromCell = 0.0;
-    for (int k = 0; k < n; k++) {
-        const int e = d.edgesOnCell[k * pc + c];
-        fluxFromCell = fluxFromCell + d.edgeFlux[(size_t)r * pe + (e - 1)] * (double)d.fluxSign[k * pc + c];
-    }
-    double mtpOld = 1.0;
-    for (int s = 0; s <= ri.depth; s++) mtpOld = mtpOld * d.val[(size_t)ri.chain[s] * pc + c];
-    const double pm = ri.depth > 0 ? d.mtpNew[(size_t)ri.chain[ri.depth - 1] * pc + c] : 1.0;
-    double v = 0.0;
-    if (pm > 0.0) v = (mtpOld - (fluxFromCell / d.areaCell[c])) / pm;
-    d.mtpNew[(size_t)r * pc + c] = pm * v;
-    if (ri.depth == 0) {
-        constexpr double puny2 = 1.0e-11 * 1.0e-11;   // seaicePuny**2
-        if (v < -puny2) atomicOr(d.flags, FLAG_NEG_MASS);
-        else if (v < 0.0) v = 0.0;
-    }
-    d.valNew[(size_t)r * pc + c] = v;
-}
-
-// zap_small_mass (:8764; one-layer mass field) and thickness -> volume (:9295) on the new values
-__global__ void k_finish(Dev d, int massRows, int massOneLayer)
-{
-    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c > (size_t)d.nC) return;
-    const size_t pc = d.nCp;
-    if (massOneLayer && c < (size_t)d.nCS) {
-        for (int k = 0; k < d.nK; k++) {
-            const double m = d.valNew[(size_t)k * pc + c];
-            if (m > 0.0 && m < 1.0e-22) {
-                d.valNew[(size_t)k * pc + c] = 0.0;
-                for (int r = massRows; r < d.nRows; r++)
-                    if (d.rows[r].cat == k) d.valNew[(size_t)r * pc + c] = 0.0;
-            }
+    for (int j = 0; j < d.nRowsPerCat; j++) {
+        const int r = d.catBaseRow[j] + cat * d.catLayers[j];
+        if (!owned) {                               // halo cells and the extra slot keep their values
+            d.valNew[(size_t)r * pc + c] = d.val[(size_t)r * pc + c];
+            continue;
         }
+        const RowInfo ri = d.rows[r];
+        double fluxFromCell = 0.0;
+        for (int k = 0; k < n; k++)
+            fluxFromCell = fluxFromCell + d.edgeFlux[(size_t)r * pe + (edge[k] - 1)] * (double)sign[k];
+        double mtpOld = 1.0;
+        for (int s = 0; s <= ri.depth; s++) mtpOld = mtpOld * d.val[(size_t)ri.chain[s] * pc + c];
+        const double pm = ri.depth > 0 ? d.mtpNew[(size_t)ri.chain[ri.depth - 1] * pc + c] : 1.0;
+        double v = 0.0;
+        if (pm > 0.0) v = (mtpOld - (fluxFromCell / area)) / pm;
+        d.mtpNew[(size_t)r * pc + c] = pm * v;
+        if (ri.depth == 0) {
+            constexpr double puny2 = 1.0e-11 * 1.0e-11;   // seaicePuny**2
+            if (v < -puny2) atomicOr(d.flags, FLAG_NEG_MASS);
+            else if (v < 0.0) v = 0.0;
+        }
+        d.valNew[(size_t)r * pc + c] = v;
     }
-    for (int r = massRows; r < d.nRows; r++) {
-        const RowInfo &ri = d.rows[r];
-        if (!ri.volumeLike) continue;
-        d.valNew[(size_t)r * pc + c] = d.valNew[(size_t)ri.cat * pc + c] * d.valNew[(size_t)r * pc + c];
+    if (massOneLayer) {                             // the mass row of this category is row `cat`
+        const double m = d.valNew[(size_t)cat * pc + c];
+        if (owned && m > 0.0 && m < 1.0e-22)
+            for (int j = 0; j < d.nRowsPerCat; j++)
+                d.valNew[(size_t)(d.catBaseRow[j] + cat * d.catLayers[j]) * pc + c] = 0.0;
+        for (int j = 0; j < d.nRowsPerCat; j++) {
+            const int r = d.catBaseRow[j] + cat * d.catLayers[j];
+            if (d.rows[r].volumeLike) d.valNew[(size_t)r * pc + c] = d.valNew[(size_t)cat * pc + c] * d.valNew[(size_t)r * pc + c];
+        }
     }
 }
 
@@ -914,7 +955,21 @@ extern "C" int ir_set_tracers(ir_handle *h, int nTracers, const ir_tracer_desc *
     for (double **b : bufs)
         if (*b) { cudaFree(*b); *b = nullptr; }
     if (d.rows) { cudaFree(d.rows); d.rows = nullptr; }
+    if (d.catBaseRow) { cudaFree(d.catBaseRow); d.catBaseRow = nullptr; }
+    if (d.catLayers) { cudaFree(d.catLayers); d.catLayers = nullptr; }
     d.nRows = nRows;
+    // rows of one category, parents first: tracers by depth (list order within a depth), layers innermost
+    std::vector<int> baseRow, layers;
+    for (int q = 0; q < MAX_DEPTH; q++)
+        for (int t = 0; t < nTracers; t++)
+            if (depth[t] == q)
+                for (int l = 0; l < tr[t].nLayers; l++) { baseRow.push_back(h->tracerRow0[t] + l); layers.push_back(tr[t].nLayers); }
+    d.nRowsPerCat = (int)baseRow.size();
+    IR_CUDA(cudaMalloc((void **)&d.catBaseRow, sizeof(int) * baseRow.size()));
+    IR_CUDA(cudaMalloc((void **)&d.catLayers, sizeof(int) * layers.size()));
+    IR_CUDA(cudaMemcpyAsync(d.catBaseRow, baseRow.data(), sizeof(int) * baseRow.size(), cudaMemcpyHostToDevice, h->stream));
+    IR_CUDA(cudaMemcpyAsync(d.catLayers, layers.data(), sizeof(int) * layers.size(), cudaMemcpyHostToDevice, h->stream));
+    IR_CUDA(cudaStreamSynchronize(h->stream));     // baseRow / layers go out of scope
     const size_t cellBytes = sizeof(double) * (size_t)nRows * d.nCp, edgeBytes = sizeof(double) * (size_t)nRows * d.nEp;
     for (double **b : bufs) {
         const size_t bytes = (b == &d.edgeFlux) ? edgeBytes : cellBytes;
@@ -957,26 +1012,16 @@ extern "C" int ir_run(ir_handle *h, int nTracers, const ir_tracer_desc *tr, cons
     const unsigned gc = grid_for(nC1, 128), ge = grid_for((size_t)d.nE, 128);
     IR_LAUNCH((k_prepare), gc, 128, s, d, 0, massRows);
     h->launches++;
-    for (int q = 0; q < MAX_DEPTH; q++) {
-        const int r0 = h->depthRow0[q], n = h->depthRow0[q + 1] - r0;
-        if (n > 0 && d.nC > 0) {
-            IR_LAUNCH((k_reconstruct), dim3(grid_for((size_t)d.nC, 128), n), 128, s, d, r0);
-            h->launches++;
-        }
+    if (d.nC > 0) {
+        IR_LAUNCH((k_reconstruct), dim3(grid_for((size_t)d.nC, RB), nK), RB, s, d);
+        h->launches++;
     }
     if (d.nE > 0) {
         IR_LAUNCH((k_triangles), ge, 128, s, d, dt);
-        IR_LAUNCH((k_fluxes), dim3(ge, d.nRows), 128, s, d);
+        IR_LAUNCH((k_fluxes), dim3(grid_for((size_t)d.nE, RB), nK), RB, s, d);
         h->launches += 2;
     }
-    for (int q = 0; q < MAX_DEPTH; q++) {
-        const int r0 = h->depthRow0[q], n = h->depthRow0[q + 1] - r0;
-        if (n > 0) {
-            IR_LAUNCH((k_update), dim3(gc, n), 128, s, d, r0);
-            h->launches++;
-        }
-    }
-    IR_LAUNCH((k_finish), gc, 128, s, d, massRows, h->tracerLayers[0] == 1 ? 1 : 0);
+    IR_LAUNCH((k_update), dim3(grid_for(nC1, RB), nK), RB, s, d, h->tracerLayers[0] == 1 ? 1 : 0);
     h->launches++;
     IR_CUDA(cudaEventRecord(h->ev1, s));
     IR_CUDA(cudaGetLastError());
@@ -1074,6 +1119,8 @@ extern "C" int ir_destroy(ir_handle *h)
     for (double *b : bufs)
         if (b) cudaFree(b);
     if (d.rows) cudaFree(d.rows);
+    if (d.catBaseRow) cudaFree(d.catBaseRow);
+    if (d.catLayers) cudaFree(d.catLayers);
     for (void *p : h->allocs) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);

@@ -19,6 +19,9 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
+/* shared memory: the kernels use it as per-thread scratch columns only (no thread reads another's slot and there
+ * is no barrier), so one static array reused by the sequentially executed threads behaves the same */
+#define __shared__ static
 
 struct dim3 {
     unsigned x, y, z;
