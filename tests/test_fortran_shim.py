@@ -119,3 +119,93 @@ def test_every_called_c_function_is_bound_and_every_c_loc_target_is_declared():
         decl = " ".join(l for l in body.split("\n") if "::" in l)
         for var in set(re.findall(r"c_loc\((\w+)\)", body)):
             assert re.search(r"\b" + var + r"\b", decl), (m.group(1), var)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fortran/seaice_ir_b200.F90 against include/ir_b200.h (incremental-remapping transport)
+# ---------------------------------------------------------------------------------------------------------------
+
+IR_F90 = open(os.path.join(ROOT, "fortran", "seaice_ir_b200.F90")).read()
+IR_HDR = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "ir_b200.h")).read(), flags=re.S)
+
+
+def _ir_c_struct(name):
+    body = re.search(r"typedef struct " + name + r" \{([^{}]*)\} " + name + ";", IR_HDR).group(1)
+    out = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        base = "double" if re.match(r"(const\s+)?double\b", decl) else "int"
+        for item in re.sub(r"^(const\s+)?(int|double)\s*", "", decl).split(","):
+            item = item.strip()
+            m = re.match(r"(\*?)\s*(\w+)(?:\[(\d+)\])?$", item)
+            assert m, item
+            kind = "ptr" if m.group(1) else base
+            for _ in range(int(m.group(3) or 1)):
+                out.append((m.group(2), kind))
+    return out
+
+
+def _ir_f_type(name):
+    body = re.search(r"type, bind\(C\) :: " + name + r"\n(.*?)end type " + name, IR_F90, flags=re.S).group(1)
+    out = []
+    for line in body.strip().split("\n"):
+        m = re.match(r"\s*(integer\(c_int\)|real\(c_double\)|type\(c_ptr\)) :: (.*)$", line)
+        assert m, line
+        kind = {"integer(c_int)": "int", "real(c_double)": "double", "type(c_ptr)": "ptr"}[m.group(1)]
+        for item in m.group(2).split(","):
+            mm = re.match(r"\s*(\w+)(?:\((\d+)\))?\s*$", item)
+            assert mm, item
+            for _ in range(int(mm.group(2) or 1)):
+                out.append((mm.group(1), kind))
+    return out
+
+
+def test_ir_bind_c_types_mirror_the_header():
+    for name in ("ir_mesh_desc", "ir_tracer_desc"):
+        assert _ir_f_type(name) == _ir_c_struct(name), name
+
+
+def test_ir_bound_names_are_exported_with_matching_argument_counts():
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(ROOT, "mpas-seaice_b200", "csrc", "libir_b200.so"))
+    bound = re.findall(r'bind\(C, name="(\w+)"\)', IR_F90)
+    assert set(bound) == {"ir_create", "ir_set_tracers", "ir_run", "ir_destroy", "ir_last_error_string"}
+    for n in bound:
+        assert hasattr(lib, n), n
+        proto = re.search(r"\b" + n + r"\s*\(([^)]*)\)", IR_HDR).group(1)
+        n_c = 0 if proto.strip() in ("", "void") else len(proto.split(","))
+        iface = re.search(r"function " + n + r"\(([^)]*)\)", IR_F90).group(1)
+        n_f = 0 if not iface.strip() else len(iface.split(","))
+        assert n_c == n_f, (n, n_c, n_f)
+    assert int(re.search(r"IR_OK\s*=\s*(\d+)", IR_HDR).group(1)) == int(re.search(r"IR_OK\s*=\s*(\d+)", IR_F90).group(1))
+
+
+def test_ir_shim_layout_checks():
+    for i, raw in enumerate(IR_F90.split("\n"), 1):
+        assert len(raw) <= 132, f"line {i} has {len(raw)} columns"
+    raw_code = [l.split("!")[0].strip().lower() for l in IR_F90.split("\n") if not l.lstrip().startswith("!")]
+    code, cur = [], ""
+    for l in raw_code:                      # join continuation lines
+        if not l:
+            continue
+        if l.endswith("&"):
+            cur += l[:-1] + " "
+            continue
+        code.append((cur + l).strip())
+        cur = ""
+    for opener, closer in (("subroutine", "end subroutine"), ("module", "end module"), ("interface", "end interface")):
+        n_open = sum(1 for l in code if re.match(r"^" + opener + r"\b", l))
+        n_close = sum(1 for l in code if re.match(r"^" + closer + r"\b", l))
+        assert n_open == n_close, (opener, n_open, n_close)
+    assert sum(1 for l in code if re.match(r"^do\b", l)) == sum(1 for l in code if re.match(r"^end\s*do\b", l))
+    n_if = sum(1 for l in code if re.match(r"^if\s*\(.*\)\s*then$", l))
+    assert n_if == sum(1 for l in code if re.match(r"^end\s*if\b", l))
+    # every pool array handed to c_loc is declared as a pointer in its routine
+    src = "\n".join(code)
+    for m in re.finditer(r"subroutine\s+(\w+)\s*\(.*?end subroutine \1", src, flags=re.S):
+        body = m.group(0)
+        decl = " ".join(l for l in body.split("\n") if "::" in l)
+        for var in set(re.findall(r"c_loc\((\w+)\)", body)):
+            assert re.search(r"\b" + var.lower() + r"\b", decl), (m.group(1), var)
