@@ -8,7 +8,7 @@
  * model: it fills the `incremental_remap` pool (Registry.xml var_struct incremental_remap) once, and those pool arrays
  * are what ir_create receives -- the same contract evp_b200.h has with the velocity solver's pools.
  *
- * STATUS (round 1): built and exported; parity against oracle/ir_oracle.c is tested by tests/test_gpu_ir.py, which
+ * STATUS (round 1): built and exported; parity against oracle/ir_oracle.c is tested by the `cuda` leg of tests/test_ir_parity.py, which
  * has not yet run on a device (the round's GPU minutes were spent before this was written).  Single block: the
  * tracer halo update after the call (seaice_update_tracer_halo, :2710) is still the host's.
  *
@@ -30,6 +30,7 @@ enum {
     IR_ERR_ARGUMENT = 1,
     IR_ERR_CUDA = 2,
     IR_ERR_STATE = 3,
+    IR_ERR_MESH = 4,                /* ir_init_geometry: orientation checks of the reference failed (:1296, :2010) */
     /* conditions the reference aborts on (MPAS_LOG_CRIT), reported after the step has run */
     IR_ERR_NEGATIVE_MASS_QP = 10,   /* negative mass at a quadrature point   incremental_remap.F:6895-6935 */
     IR_ERR_NEGATIVE_MASS = 11,      /* new mass below -puny**2               incremental_remap.F:7465-7480 */
@@ -80,6 +81,37 @@ typedef struct ir_tracer_desc {
     int volumeLike;   /* 1 for iceVolumeCategory / snowVolumeCategory: volume in and out, thickness while transported */
     double *array;    /* (nLayers, nCategories, nCells+1), IN/OUT */
 } ir_tracer_desc;
+
+/* For hosts that do not run seaice_init_advection_incremental_remap (:165-816): its geometry part (:446-711) --
+ * local frames, vertex coordinates in cell and edge frames, remap stencils, minimum edge length at the vertices,
+ * geometric cell averages -- computed on the device from the mesh-file arrays into the arrays of the
+ * incremental_remap pool.  A Fortran host keeps its own init and never calls this. */
+typedef struct ir_geometry_in {
+    int nCells, nCellsSolve, nVertices, nEdges, maxEdges, vertexDegree;
+    int on_a_sphere, rotate_cartesian_grid;
+    const int *nEdgesOnCell;     /* (nCells+1) */
+    const int *edgesOnCell;      /* (maxEdges, nCells+1) */
+    const int *verticesOnCell;   /* (maxEdges, nCells+1) */
+    const int *cellsOnEdge;      /* (2, nEdges+1) */
+    const int *verticesOnEdge;   /* (2, nEdges+1) */
+    const int *edgesOnVertex;    /* (vertexDegree, nVertices+1) */
+    const double *xCell, *yCell, *zCell;         /* (nCells+1) */
+    const double *xVertex, *yVertex, *zVertex;   /* (nVertices+1) */
+    const double *xEdge, *yEdge, *zEdge;         /* (nEdges+1) */
+    const double *dcEdge, *dvEdge;               /* (nEdges+1) */
+} ir_geometry_in;
+
+typedef struct ir_geometry_out {
+    double *transGlobalToCell;                   /* (3, 3, nCells); may be NULL on a plane */
+    double *xVertexOnCell, *yVertexOnCell;       /* (maxEdges, nCells+1) */
+    int *remapEdge;                              /* (nEdges+1) */
+    int *cellsOnEdgeRemap, *edgesOnEdgeRemap;    /* (6, nEdges+1) */
+    double *xVertexOnEdge, *yVertexOnEdge;       /* (8, nEdges+1) */
+    double *minLengthEdgesOnVertex;              /* (nVertices+1) */
+    double *geomAvgCell[14];                     /* as in ir_mesh_desc */
+} ir_geometry_out;
+
+int ir_init_geometry(const ir_geometry_in *in, const ir_geometry_out *out, int device);
 
 /* Create the device copy of the mesh and geometry.  device < 0: the current CUDA device. */
 int ir_create(ir_handle **out, const ir_mesh_desc *mesh, int device);

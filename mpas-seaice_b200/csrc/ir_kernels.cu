@@ -725,6 +725,279 @@ __global__ void k_trans_in(const double *__restrict__ raw, double *__restrict__ 
         for (int j = 0; j < 3; j++) dst[(size_t)(i * 3 + j) * pitch + c] = raw[c * 9 + j * 3 + i];
 }
 
+// ------------------------------------------------------------------------------------------------ init-time geometry
+// seaice_init_advection_incremental_remap's geometry (:446-711) for hosts that do not run the Fortran init: local
+// frames, vertex coordinates in cell and edge frames, remap stencils, geometric cell averages.  Init-time work, so the
+// arrays keep the host layout on the device.
+
+struct Geo {
+    int nC, nCS, nV, nE, M, D, sphere, rotate;
+    const int *nEdgesOnCell, *edgesOnCell, *verticesOnCell, *cellsOnEdge, *verticesOnEdge, *edgesOnVertex;
+    const double *xC, *yC, *zC, *xV, *yV, *zV, *xE, *yE, *zE, *dcEdge, *dvEdge;
+    double *trans, *xvc, *yvc, *xve, *yve, *minLen, *geom[14];
+    int *remapEdge, *coer, *eoer, *flags;
+};
+enum { GEO_BAD_EDGE = 1, GEO_BAD_CELL = 2 };
+
+// rotate_global_vectors (:948): (x, y, z) -> (-z, y, x) when the Cartesian grid is rotated
+__device__ __forceinline__ void point(const Geo &g, const double *x, const double *y, const double *z, int i, double *o)
+{
+    if (g.rotate && g.sphere) { o[0] = -z[i]; o[1] = y[i]; o[2] = x[i]; }
+    else { o[0] = x[i]; o[1] = y[i]; o[2] = z[i]; }
+}
+
+// define_local_to_global_transformations (:990): rows east, north, up; t(i,j) at t[(j-1)*3 + (i-1)]
+__device__ void global_to_local(const double *pt, double *t)
+{
+    double e1[3], e2[3], e3[3] = {pt[0], pt[1], pt[2]};
+    double mag = sqrt(e3[0] * e3[0] + e3[1] * e3[1] + e3[2] * e3[2]);
+    if (mag > 0.0) { e3[0] = e3[0] / mag; e3[1] = e3[1] / mag; e3[2] = e3[2] / mag; } else { e3[0] = e3[1] = e3[2] = 0.0; }
+    if (fabs(pt[0] * pt[0] + pt[1] * pt[1]) > EPS11) {
+        e1[0] = -pt[1]; e1[1] = pt[0]; e1[2] = 0.0;
+        mag = sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
+        if (mag > 0.0) { e1[0] = e1[0] / mag; e1[1] = e1[1] / mag; e1[2] = e1[2] / mag; } else { e1[0] = e1[1] = e1[2] = 0.0; }
+        e2[0] = e3[1] * e1[2] - e3[2] * e1[1];
+        e2[1] = e3[2] * e1[0] - e3[0] * e1[2];
+        e2[2] = e3[0] * e1[1] - e3[1] * e1[0];
+    } else if (pt[2] > 0.0) {
+        e1[0] = 1.0; e1[1] = 0.0; e1[2] = 0.0; e2[0] = 0.0; e2[1] = 1.0; e2[2] = 0.0;
+    } else {
+        e1[0] = 0.0; e1[1] = 1.0; e1[2] = 0.0; e2[0] = 1.0; e2[1] = 0.0; e2[2] = 0.0;
+    }
+    for (int j = 0; j < 3; j++) { t[j * 3 + 0] = e1[j]; t[j * 3 + 1] = e2[j]; t[j * 3 + 2] = e3[j]; }
+}
+
+// get_vertex_on_cell_coordinates (:1823) + compute_geometric_cell_averages (:2097)
+__global__ void k_geo_cells(Geo g)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= g.nC) return;
+    const int M = g.M, n = g.nEdgesOnCell[c];
+    double pc[3], t[9];
+    point(g, g.xC, g.yC, g.zC, c, pc);
+    if (g.sphere) {
+        global_to_local(pc, t);
+        for (int q = 0; q < 9; q++) g.trans[(size_t)c * 9 + q] = t[q];
+    }
+    double xv[MAXM], yv[MAXM];
+    for (int k = 0; k < n; k++) {
+        const int v = g.verticesOnCell[(size_t)c * M + k] - 1;
+        double pv[3];
+        point(g, g.xV, g.yV, g.zV, v, pv);
+        if (g.sphere) {
+            const double w0 = pv[0] - pc[0], w1 = pv[1] - pc[1], w2 = pv[2] - pc[2];
+            xv[k] = t[0] * w0 + t[3] * w1 + t[6] * w2;
+            yv[k] = t[1] * w0 + t[4] * w1 + t[7] * w2;
+        } else {
+            xv[k] = pv[0] - pc[0];
+            yv[k] = pv[1] - pc[1];
+        }
+        g.xvc[(size_t)c * M + k] = xv[k];
+        g.yvc[(size_t)c * M + k] = yv[k];
+    }
+    for (int k = 0; k < n; k++) {
+        const int k1 = (k + 1 >= n) ? 0 : k + 1;
+        if (!(cross2(xv[k], yv[k], xv[k1], yv[k1]) >= 0.0)) atomicOr(g.flags, GEO_BAD_CELL);
+    }
+    double frac[MAXM], sumArea = 0.0;
+    for (int k = 0; k < n; k++) {
+        const int e = g.edgesOnCell[(size_t)c * M + k] - 1;
+        frac[k] = 0.25 * g.dcEdge[e] * g.dvEdge[e];
+        sumArea = sumArea + frac[k];
+    }
+    for (int k = 0; k < n; k++) frac[k] = frac[k] / sumArea;
+    double acc[14];
+    for (int q = 0; q < 14; q++) acc[q] = 0.0;
+    for (int k = 0; k < n; k++) {
+        const int k1 = (k + 1 >= n) ? 0 : k + 1;
+        const double x1 = 0.0, y1 = 0.0, x2 = xv[k], y2 = yv[k], x3 = xv[k1], y3 = yv[k1];
+        double xq[6], yq[6];
+        xq[0] = Q1QP * x1 + Q1QP * x2 + Q2QP * x3; yq[0] = Q1QP * y1 + Q1QP * y2 + Q2QP * y3;
+        xq[1] = Q1QP * x1 + Q2QP * x2 + Q1QP * x3; yq[1] = Q1QP * y1 + Q2QP * y2 + Q1QP * y3;
+        xq[2] = Q2QP * x1 + Q1QP * x2 + Q1QP * x3; yq[2] = Q2QP * y1 + Q1QP * y2 + Q1QP * y3;
+        xq[3] = Q3QP * x1 + Q4QP * x2 + Q4QP * x3; yq[3] = Q3QP * y1 + Q4QP * y2 + Q4QP * y3;
+        xq[4] = Q4QP * x1 + Q3QP * x2 + Q4QP * x3; yq[4] = Q4QP * y1 + Q3QP * y2 + Q4QP * y3;
+        xq[5] = Q4QP * x1 + Q4QP * x2 + Q3QP * x3; yq[5] = Q4QP * y1 + Q4QP * y2 + Q3QP * y3;
+        double a[14];
+        for (int q = 0; q < 14; q++) a[q] = 0.0;
+        for (int q = 0; q < 6; q++) {
+            const double x = xq[q], y = yq[q], w = (q < 3) ? W1QP : W2QP;
+            const double x2p = x * x, y2p = y * y, x3p = x * x * x, y3p = y * y * y, x4p = (x * x) * (x * x), y4p = (y * y) * (y * y);
+            a[0] = a[0] + w * x;        a[1] = a[1] + w * y;
+            a[2] = a[2] + w * x2p;      a[3] = a[3] + w * x * y;      a[4] = a[4] + w * y2p;
+            a[5] = a[5] + w * x3p;      a[6] = a[6] + w * x2p * y;    a[7] = a[7] + w * x * y2p;   a[8] = a[8] + w * y3p;
+            a[9] = a[9] + w * x4p;      a[10] = a[10] + w * x3p * y;  a[11] = a[11] + w * x2p * y2p;
+            a[12] = a[12] + w * x * y3p; a[13] = a[13] + w * y4p;
+        }
+        for (int q = 0; q < 14; q++) acc[q] = acc[q] + frac[k] * a[q];
+    }
+    for (int q = 0; q < 14; q++) g.geom[q][c] = acc[q];
+}
+
+// get_geometry_incremental_remap (:1105), first pass per edge: remapEdge, orientation check, the stencils
+// cellsOnEdgeRemap / edgesOnEdgeRemap, the edge's own two vertices in its frame
+__global__ void k_geo_edges(Geo g)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= g.nE) return;
+    const int M = g.M, D = g.D, nC = g.nC, nE = g.nE;
+    const int c1 = g.cellsOnEdge[(size_t)e * 2], c2 = g.cellsOnEdge[(size_t)e * 2 + 1];
+    const int v1 = g.verticesOnEdge[(size_t)e * 2], v2 = g.verticesOnEdge[(size_t)e * 2 + 1];
+    // an edge of an owned cell with a cell on both sides (:1235-1262)
+    const bool both = c1 >= 1 && c1 <= nC && c2 >= 1 && c2 <= nC;
+    const bool remap = both && (c1 <= g.nCS || c2 <= g.nCS);
+    g.remapEdge[e] = remap ? 1 : 0;
+    double pe[3], t[9], p1[3], p2[3];
+    point(g, g.xE, g.yE, g.zE, e, pe);
+    const bool haveV = v1 >= 1 && v1 <= g.nV && v2 >= 1 && v2 <= g.nV;
+    if (haveV) { point(g, g.xV, g.yV, g.zV, v1 - 1, p1); point(g, g.xV, g.yV, g.zV, v2 - 1, p2); }
+    double ex[2] = {0.0, 0.0}, ey[2] = {0.0, 0.0};
+    if (g.sphere) {
+        global_to_local(pe, t);
+        if (haveV) {
+            const double w0 = p2[0] - p1[0], w1 = p2[1] - p1[1], w2 = p2[2] - p1[2];
+            const double xVector = t[0] * w0 + t[3] * w1 + t[6] * w2, yVector = t[1] * w0 + t[4] * w1 + t[7] * w2;
+            g.xve[(size_t)e * NVER + 0] = -0.5 * xVector; g.yve[(size_t)e * NVER + 0] = -0.5 * yVector;
+            g.xve[(size_t)e * NVER + 1] = 0.5 * xVector;  g.yve[(size_t)e * NVER + 1] = 0.5 * yVector;
+        }
+    } else if (remap) {
+        g.xve[(size_t)e * NVER + 0] = p1[0] - pe[0]; g.yve[(size_t)e * NVER + 0] = p1[1] - pe[1];
+        g.xve[(size_t)e * NVER + 1] = p2[0] - pe[0]; g.yve[(size_t)e * NVER + 1] = p2[1] - pe[1];
+    }
+    if (!remap) return;
+    // C1 must lie to the left of V1 -> V2, tested in the edge frame with the vertices relative to the edge point (:1270-1330)
+    {
+        double cc[2], pcell[3];
+        point(g, g.xC, g.yC, g.zC, c1 - 1, pcell);
+        const double *pp[2] = {p1, p2};
+        for (int k = 0; k < 2; k++) {
+            const double w0 = pp[k][0] - pe[0], w1 = pp[k][1] - pe[1], w2 = pp[k][2] - pe[2];
+            if (g.sphere) { ex[k] = t[0] * w0 + t[3] * w1 + t[6] * w2; ey[k] = t[1] * w0 + t[4] * w1 + t[7] * w2; }
+            else { ex[k] = w0; ey[k] = w1; }
+        }
+        const double w0 = pcell[0] - pe[0], w1 = pcell[1] - pe[1], w2 = pcell[2] - pe[2];
+        if (g.sphere) { cc[0] = t[0] * w0 + t[3] * w1 + t[6] * w2; cc[1] = t[1] * w0 + t[4] * w1 + t[7] * w2; }
+        else { cc[0] = w0; cc[1] = w1; }
+        if (!in_half_plane(ex[0], ey[0], ex[1], ey[1], cc[0], cc[1])) atomicOr(g.flags, GEO_BAD_EDGE);
+    }
+    int EO[NEER] = {0, 0, 0, 0, 0, 0}, CO[NCER] = {0, 0, 0, 0, 0, 0};
+    CO[0] = c1; CO[1] = c2;
+    for (int side = 0; side < 2; side++) {
+        const int cell = side == 0 ? c1 : c2;
+        const int n = g.nEdgesOnCell[cell - 1];
+        int iMain = 0;
+        for (int k = 1; k <= n; k++)
+            if (g.edgesOnCell[(size_t)(cell - 1) * M + k - 1] == e + 1) { iMain = k; break; }
+        int km = iMain - 1; if (km < 1) km = km + n;
+        int kp = iMain + 1; if (kp > n) kp = kp - n;
+        const int em = g.edgesOnCell[(size_t)(cell - 1) * M + km - 1], ep = g.edgesOnCell[(size_t)(cell - 1) * M + kp - 1];
+        if (side == 0) { EO[0] = em; EO[1] = ep; } else { EO[2] = ep; EO[3] = em; }
+    }
+    if (D == 4) {
+        const int vv[2] = {v1, v2};
+        for (int iv = 0; iv < 2; iv++)
+            for (int k = 0; k < D; k++) {
+                const int en = g.edgesOnVertex[(size_t)(vv[iv] - 1) * D + k];
+                if (en >= 1 && en <= nE) {
+                    bool isNew = true;
+                    for (int q = 0; q < 4; q++)
+                        if (en == EO[q] || en == e + 1) { isNew = false; break; }
+                    if (isNew) { EO[iv + 4] = en; break; }
+                }
+            }
+    }
+    if (D == 3) {
+        CO[2] = nC + 1; CO[3] = nC + 1;
+        for (int iv = 0; iv < 2; iv++) {
+            int en = EO[iv];
+            if (en < 1 || en > nE) en = EO[iv + 2];
+            if (en < 1 || en > nE) continue;
+            for (int k = 0; k < 2; k++) {
+                const int cn = g.cellsOnEdge[(size_t)(en - 1) * 2 + k];
+                if (cn >= 1 && cn <= nC && cn != CO[0] && cn != CO[1]) CO[iv + 2] = cn;
+            }
+        }
+    } else {
+        for (int q = 2; q < 6; q++) CO[q] = nC + 1;
+        for (int iv = 0; iv < 2; iv++) {
+            int en = EO[iv];
+            if (en >= 1 && en <= nE)
+                for (int k = 0; k < 2; k++) {
+                    const int cn = g.cellsOnEdge[(size_t)(en - 1) * 2 + k];
+                    if (cn >= 1 && cn <= nC && cn != CO[0]) CO[iv + 2] = cn;
+                }
+            en = EO[iv + 2];
+            if (en >= 1 && en <= nE)
+                for (int k = 0; k < 2; k++) {
+                    const int cn = g.cellsOnEdge[(size_t)(en - 1) * 2 + k];
+                    if (cn >= 1 && cn <= nC && cn != CO[1]) CO[iv + 4] = cn;
+                }
+        }
+    }
+    for (int q = 0; q < NEER; q++) { g.eoer[(size_t)e * NEER + q] = EO[q]; g.coer[(size_t)e * NCER + q] = CO[q]; }
+}
+
+// second pass per edge: the far vertices of the side edges in this edge's frame (:1690-1780)
+__global__ void k_geo_side_vertices(Geo g)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= g.nE || g.remapEdge[e] != 1) return;
+    const int nE = g.nE, nSide = (g.D == 3) ? 4 : 6;
+    const int ve[2] = {g.verticesOnEdge[(size_t)e * 2], g.verticesOnEdge[(size_t)e * 2 + 1]};
+    double pe[3];
+    point(g, g.xE, g.yE, g.zE, e, pe);
+    int count = 2;
+    for (int q = 0; q < nSide; q++) {
+        const int en = g.eoer[(size_t)e * NEER + q];
+        if (en < 1 || en > nE) continue;
+        const int vn[2] = {g.verticesOnEdge[(size_t)(en - 1) * 2], g.verticesOnEdge[(size_t)(en - 1) * 2 + 1]};
+        int n1 = 1, m1 = 1, m2 = 2, far = 0;
+        for (int n = 1; n <= 2; n++)
+            for (int m = 1; m <= 2; m++)
+                if (vn[m - 1] == ve[n - 1]) {
+                    n1 = n;
+                    if (m == 1) { m1 = 1; m2 = 2; } else { m1 = 2; m2 = 1; }
+                    far = vn[m2 - 1];
+                    if (!g.sphere) count = count + 1;
+                    break;
+                }
+        if (g.sphere) {
+            // this edge's shared vertex plus the side edge's own vector, taken in the side edge's frame as it is
+            g.xve[(size_t)e * NVER + q + 2] = g.xve[(size_t)e * NVER + n1 - 1] +
+                                              (g.xve[(size_t)(en - 1) * NVER + m2 - 1] - g.xve[(size_t)(en - 1) * NVER + m1 - 1]);
+            g.yve[(size_t)e * NVER + q + 2] = g.yve[(size_t)e * NVER + n1 - 1] +
+                                              (g.yve[(size_t)(en - 1) * NVER + m2 - 1] - g.yve[(size_t)(en - 1) * NVER + m1 - 1]);
+        } else if (count <= NVER && far >= 1) {
+            // on a plane the reference fills the slots by counting the side edges that exist (:1745-1772)
+            double pf[3];
+            point(g, g.xV, g.yV, g.zV, far - 1, pf);
+            g.xve[(size_t)e * NVER + count - 1] = pf[0] - pe[0];
+            g.yve[(size_t)e * NVER + count - 1] = pf[1] - pe[1];
+        }
+    }
+}
+
+// minLengthEdgesOnVertex (:1785-1805)
+__global__ void k_geo_vertices(Geo g)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v > g.nV) return;
+    double mn = DBL_MAX;
+    if (v < g.nV)
+        for (int k = 0; k < g.D; k++) {
+            const int e = g.edgesOnVertex[(size_t)v * g.D + k];
+            if (e >= 1 && e <= g.nE) {
+                double a[3], b[3];
+                point(g, g.xV, g.yV, g.zV, g.verticesOnEdge[(size_t)(e - 1) * 2] - 1, a);
+                point(g, g.xV, g.yV, g.zV, g.verticesOnEdge[(size_t)(e - 1) * 2 + 1] - 1, b);
+                const double w0 = b[0] - a[0], w1 = b[1] - a[1], w2 = b[2] - a[2];
+                const double len = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
+                if (len < mn) mn = len;
+            }
+        }
+    g.minLen[v] = mn;
+}
+
 inline unsigned grid_for(size_t n, int block) { return (unsigned)((n + block - 1) / block); }
 inline size_t round_up(size_t n, size_t m) { return (n + m - 1) / m * m; }
 
@@ -884,6 +1157,98 @@ extern "C" int ir_create(ir_handle **out, const ir_mesh_desc *m, int device)
     if (e2 != cudaSuccess) { set_error("ir_create: %s", cudaGetErrorString(e2)); ir_destroy(h); return IR_ERR_CUDA; }
 #undef TRY
     *out = h;
+    return IR_OK;
+}
+
+extern "C" int ir_init_geometry(const ir_geometry_in *in, const ir_geometry_out *out, int device)
+{
+    IR_REQUIRE(in != nullptr && out != nullptr, "NULL argument");
+    IR_REQUIRE(in->nCells >= 0 && in->nVertices >= 0 && in->nEdges >= 0, "negative dimension");
+    IR_REQUIRE(in->nCellsSolve >= 0 && in->nCellsSolve <= in->nCells, "nCellsSolve out of range");
+    IR_REQUIRE(in->maxEdges >= 3 && in->maxEdges <= MAXM, "maxEdges must be 3..8");
+    IR_REQUIRE(in->vertexDegree == 3 || in->vertexDegree == 4, "vertexDegree must be 3 or 4");
+    IR_REQUIRE(in->nEdgesOnCell && in->edgesOnCell && in->verticesOnCell && in->cellsOnEdge && in->verticesOnEdge && in->edgesOnVertex,
+               "connectivity arrays must not be NULL");
+    IR_REQUIRE(in->xCell && in->yCell && in->zCell && in->xVertex && in->yVertex && in->zVertex && in->xEdge && in->yEdge &&
+                   in->zEdge && in->dcEdge && in->dvEdge,
+               "coordinate arrays must not be NULL");
+    IR_REQUIRE(out->xVertexOnCell && out->yVertexOnCell && out->remapEdge && out->cellsOnEdgeRemap && out->edgesOnEdgeRemap &&
+                   out->xVertexOnEdge && out->yVertexOnEdge && out->minLengthEdgesOnVertex,
+               "output arrays must not be NULL");
+    IR_REQUIRE(!in->on_a_sphere || out->transGlobalToCell, "transGlobalToCell is needed on a sphere");
+    for (int k = 0; k < 14; k++) IR_REQUIRE(out->geomAvgCell[k] != nullptr, "geomAvgCell arrays must not be NULL");
+    int dev = device;
+    if (dev < 0) IR_CUDA(cudaGetDevice(&dev));
+    IR_CUDA(cudaSetDevice(dev));
+    const size_t nC1 = (size_t)in->nCells + 1, nE1 = (size_t)in->nEdges + 1, nV1 = (size_t)in->nVertices + 1;
+    const int M = in->maxEdges, D = in->vertexDegree;
+    std::vector<void *> bufs;
+    int rc = IR_OK;
+    auto up = [&](const void *host, size_t bytes, void **devp) -> int {
+        IR_CUDA(cudaMalloc(devp, bytes ? bytes : 1));
+        bufs.push_back(*devp);
+        if (host) IR_CUDA(cudaMemcpyAsync(*devp, host, bytes, cudaMemcpyHostToDevice, 0));
+        else IR_CUDA(cudaMemsetAsync(*devp, 0, bytes ? bytes : 1, 0));
+        return IR_OK;
+    };
+    auto cleanup = [&]() { for (void *b : bufs) cudaFree(b); };
+#define TRYG(x) do { if ((rc = (x)) != IR_OK) { cleanup(); return rc; } } while (0)
+    Geo g;
+    memset(&g, 0, sizeof g);
+    g.nC = in->nCells; g.nCS = in->nCellsSolve; g.nV = in->nVertices; g.nE = in->nEdges; g.M = M; g.D = D;
+    g.sphere = in->on_a_sphere ? 1 : 0; g.rotate = in->rotate_cartesian_grid ? 1 : 0;
+    TRYG(up(in->nEdgesOnCell, nC1 * 4, (void **)&g.nEdgesOnCell));
+    TRYG(up(in->edgesOnCell, nC1 * M * 4, (void **)&g.edgesOnCell));
+    TRYG(up(in->verticesOnCell, nC1 * M * 4, (void **)&g.verticesOnCell));
+    TRYG(up(in->cellsOnEdge, nE1 * 2 * 4, (void **)&g.cellsOnEdge));
+    TRYG(up(in->verticesOnEdge, nE1 * 2 * 4, (void **)&g.verticesOnEdge));
+    TRYG(up(in->edgesOnVertex, nV1 * D * 4, (void **)&g.edgesOnVertex));
+    TRYG(up(in->xCell, nC1 * 8, (void **)&g.xC)); TRYG(up(in->yCell, nC1 * 8, (void **)&g.yC)); TRYG(up(in->zCell, nC1 * 8, (void **)&g.zC));
+    TRYG(up(in->xVertex, nV1 * 8, (void **)&g.xV)); TRYG(up(in->yVertex, nV1 * 8, (void **)&g.yV)); TRYG(up(in->zVertex, nV1 * 8, (void **)&g.zV));
+    TRYG(up(in->xEdge, nE1 * 8, (void **)&g.xE)); TRYG(up(in->yEdge, nE1 * 8, (void **)&g.yE)); TRYG(up(in->zEdge, nE1 * 8, (void **)&g.zE));
+    TRYG(up(in->dcEdge, nE1 * 8, (void **)&g.dcEdge)); TRYG(up(in->dvEdge, nE1 * 8, (void **)&g.dvEdge));
+    const size_t nCt = in->nCells > 0 ? (size_t)in->nCells : 1;
+    TRYG(up(nullptr, nCt * 9 * 8, (void **)&g.trans));
+    TRYG(up(nullptr, nC1 * M * 8, (void **)&g.xvc)); TRYG(up(nullptr, nC1 * M * 8, (void **)&g.yvc));
+    TRYG(up(nullptr, nE1 * NVER * 8, (void **)&g.xve)); TRYG(up(nullptr, nE1 * NVER * 8, (void **)&g.yve));
+    TRYG(up(nullptr, nV1 * 8, (void **)&g.minLen));
+    for (int k = 0; k < 14; k++) TRYG(up(nullptr, nC1 * 8, (void **)&g.geom[k]));
+    TRYG(up(nullptr, nE1 * 4, (void **)&g.remapEdge));
+    TRYG(up(nullptr, nE1 * NCER * 4, (void **)&g.coer)); TRYG(up(nullptr, nE1 * NEER * 4, (void **)&g.eoer));
+    TRYG(up(nullptr, 4, (void **)&g.flags));
+    cudaStream_t s0 = 0;
+    if (g.nC > 0) IR_LAUNCH((k_geo_cells), grid_for((size_t)g.nC, 128), 128, s0, g);
+    if (g.nE > 0) {
+        IR_LAUNCH((k_geo_edges), grid_for((size_t)g.nE, 128), 128, s0, g);
+        IR_LAUNCH((k_geo_side_vertices), grid_for((size_t)g.nE, 128), 128, s0, g);
+    }
+    IR_LAUNCH((k_geo_vertices), grid_for(nV1, 128), 128, s0, g);
+    auto down = [&](void *host, const void *devp, size_t bytes) -> int {
+        IR_CUDA(cudaMemcpyAsync(host, devp, bytes, cudaMemcpyDeviceToHost, 0));
+        return IR_OK;
+    };
+    if (g.sphere && in->nCells > 0) TRYG(down(out->transGlobalToCell, g.trans, (size_t)in->nCells * 9 * 8));
+    TRYG(down(out->xVertexOnCell, g.xvc, nC1 * M * 8)); TRYG(down(out->yVertexOnCell, g.yvc, nC1 * M * 8));
+    TRYG(down(out->xVertexOnEdge, g.xve, nE1 * NVER * 8)); TRYG(down(out->yVertexOnEdge, g.yve, nE1 * NVER * 8));
+    TRYG(down(out->minLengthEdgesOnVertex, g.minLen, nV1 * 8));
+    for (int k = 0; k < 14; k++) TRYG(down(out->geomAvgCell[k], g.geom[k], nC1 * 8));
+    TRYG(down(out->remapEdge, g.remapEdge, nE1 * 4));
+    TRYG(down(out->cellsOnEdgeRemap, g.coer, nE1 * NCER * 4)); TRYG(down(out->edgesOnEdgeRemap, g.eoer, nE1 * NEER * 4));
+    int flags = 0;
+    TRYG(down(&flags, g.flags, 4));
+    cudaError_t ce = cudaStreamSynchronize(s0);
+    if (ce == cudaSuccess) ce = cudaGetLastError();
+    cleanup();
+#undef TRYG
+    if (ce != cudaSuccess) { set_error("ir_init_geometry: %s", cudaGetErrorString(ce)); return IR_ERR_CUDA; }
+    if (flags & GEO_BAD_EDGE) {
+        set_error("IR geometry: cellsOnEdge(1) is not to the left of verticesOnEdge(1) -> (2) (incremental_remap.F:1296)");
+        return IR_ERR_MESH;
+    }
+    if (flags & GEO_BAD_CELL) {
+        set_error("IR geometry: the vertices of a cell do not run counter-clockwise (incremental_remap.F:2010)");
+        return IR_ERR_MESH;
+    }
     return IR_OK;
 }
 

@@ -15,11 +15,11 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("IR_B200_LIB", os.path.join(_HERE, "csrc", "libir_b200.so"))
 
-EXPORTS = ("ir_create", "ir_set_tracers", "ir_run", "ir_fetch_diagnostics", "ir_last_run_ms", "ir_launch_count",
+EXPORTS = ("ir_init_geometry", "ir_create", "ir_set_tracers", "ir_run", "ir_fetch_diagnostics", "ir_last_run_ms", "ir_launch_count",
            "ir_destroy", "ir_last_error_string")
 GEOM_NAMES = ("x", "y", "xx", "xy", "yy", "xxx", "xxy", "xyy", "yyy", "xxxx", "xxxy", "xxyy", "xyyy", "yyyy")
 
-IR_OK, IR_ERR_ARGUMENT, IR_ERR_CUDA, IR_ERR_STATE = 0, 1, 2, 3
+IR_OK, IR_ERR_ARGUMENT, IR_ERR_CUDA, IR_ERR_STATE, IR_ERR_MESH = 0, 1, 2, 3, 4
 IR_ERR_NEGATIVE_MASS_QP, IR_ERR_NEGATIVE_MASS, IR_ERR_PARALLEL_EDGES, IR_ERR_TOO_MANY_TRIANGLES = 10, 11, 12, 13
 
 
@@ -36,6 +36,21 @@ class ir_mesh_desc(C.Structure):
                                              "verticesOnEdge", "areaCell", "dcEdge", "coeffs_reconstruct",
                                              "transGlobalToCell", "xVertexOnCell", "yVertexOnCell", "xVertexOnEdge",
                                              "yVertexOnEdge", "remapEdge", "cellsOnEdgeRemap", "edgesOnEdgeRemap")]
+                + [("geomAvgCell", C.c_void_p * 14)])
+
+
+class ir_geometry_in(C.Structure):
+    _fields_ = ([(n, C.c_int) for n in ("nCells", "nCellsSolve", "nVertices", "nEdges", "maxEdges", "vertexDegree",
+                                        "on_a_sphere", "rotate_cartesian_grid")]
+                + [(n, C.c_void_p) for n in ("nEdgesOnCell", "edgesOnCell", "verticesOnCell", "cellsOnEdge", "verticesOnEdge",
+                                             "edgesOnVertex", "xCell", "yCell", "zCell", "xVertex", "yVertex", "zVertex",
+                                             "xEdge", "yEdge", "zEdge", "dcEdge", "dvEdge")])
+
+
+class ir_geometry_out(C.Structure):
+    _fields_ = ([(n, C.c_void_p) for n in ("transGlobalToCell", "xVertexOnCell", "yVertexOnCell", "remapEdge",
+                                           "cellsOnEdgeRemap", "edgesOnEdgeRemap", "xVertexOnEdge", "yVertexOnEdge",
+                                           "minLengthEdgesOnVertex")]
                 + [("geomAvgCell", C.c_void_p * 14)])
 
 
@@ -62,6 +77,41 @@ def load(path=None):
 def _ptr(a, dtype):
     assert isinstance(a, np.ndarray) and a.dtype == dtype and a.flags["C_CONTIGUOUS"], (getattr(a, "dtype", None), dtype)
     return a.ctypes.data
+
+
+def init_geometry(mesh, irf, n_cells_solve=None, rotate=False, device=-1, lib_path=None):
+    """The incremental_remap pool arrays (what seaice_init_advection_incremental_remap computes,
+    incremental_remap.F:446-711) from the mesh-file arrays, on the device.  Returns the dict IrTransport takes."""
+    L = load(lib_path)
+    nC, nV, nE, M = mesh.nCells, mesh.nVertices, mesh.nEdges, mesh.maxEdges
+    gi, go = ir_geometry_in(), ir_geometry_out()
+    gi.nCells, gi.nVertices, gi.nEdges, gi.maxEdges, gi.vertexDegree = nC, nV, nE, M, mesh.vertexDegree
+    gi.nCellsSolve = nC if n_cells_solve is None else int(n_cells_solve)
+    gi.on_a_sphere, gi.rotate_cartesian_grid = int(bool(mesh.on_a_sphere)), int(bool(rotate))
+    for name in ("nEdgesOnCell", "edgesOnCell", "verticesOnCell", "cellsOnEdge"):
+        setattr(gi, name, _ptr(mesh[name], np.int32))
+    for name in ("verticesOnEdge", "edgesOnVertex"):
+        setattr(gi, name, _ptr(irf[name], np.int32))
+    for name in ("xCell", "yCell", "zCell", "xVertex", "yVertex", "zVertex", "dcEdge", "dvEdge"):
+        setattr(gi, name, _ptr(mesh[name], np.float64))
+    for name in ("xEdge", "yEdge", "zEdge"):
+        setattr(gi, name, _ptr(irf[name], np.float64))
+    out = dict(transGlobalToCell=np.zeros((max(nC, 1), 3, 3)),
+               xVertexOnCell=np.zeros((nC + 1, M)), yVertexOnCell=np.zeros((nC + 1, M)),
+               remapEdge=np.zeros(nE + 1, np.int32),
+               cellsOnEdgeRemap=np.zeros((nE + 1, 6), np.int32), edgesOnEdgeRemap=np.zeros((nE + 1, 6), np.int32),
+               xVertexOnEdge=np.zeros((nE + 1, 8)), yVertexOnEdge=np.zeros((nE + 1, 8)),
+               minLengthEdgesOnVertex=np.zeros(nV + 1))
+    for name, arr in out.items():
+        setattr(go, name, arr.ctypes.data)
+    geom = {n: np.zeros(nC + 1) for n in GEOM_NAMES}
+    for k, n in enumerate(GEOM_NAMES):
+        go.geomAvgCell[k] = geom[n].ctypes.data
+    rc = L.ir_init_geometry(C.byref(gi), C.byref(go), C.c_int(device))
+    if rc != IR_OK:
+        raise IrError(rc, L.ir_last_error_string().decode())
+    out["geomAvg"] = geom
+    return out
 
 
 class IrTransport:

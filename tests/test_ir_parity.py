@@ -175,6 +175,45 @@ def test_rotation_test_case_matches_oracle(lib_path):
     assert_identical(mesh, ref, dev, d_ref, d_dev)
 
 
+@pytest.mark.parametrize("kind,rotate", [("hex12", False), ("quad10", False), ("ico3", False), ("ico4", False), ("ico3", True)])
+def test_init_geometry_matches_oracle(kind, rotate, lib_path):
+    """ir_init_geometry (the incremental_remap pool arrays for hosts without the Fortran init) against
+    orc_ir_init_geometry: every array identical, on planar hexes and quads (with their boundary stencils), on the
+    sphere, and with the rotated Cartesian grid."""
+    mesh, irf, _ = case(kind)
+    ref = ir.init_geometry(mesh, irf, rotate=rotate)
+    got = ir_host.init_geometry(mesh, irf, rotate=rotate, lib_path=lib_path)
+    nC, nE, nV = mesh.nCells, mesh.nEdges, mesh.nVertices
+    for name in ("xVertexOnCell", "yVertexOnCell"):
+        assert np.array_equal(ref[name][:nC], got[name][:nC]), name
+    for name in ("remapEdge", "cellsOnEdgeRemap", "edgesOnEdgeRemap", "xVertexOnEdge", "yVertexOnEdge"):
+        assert np.array_equal(ref[name][:nE], got[name][:nE]), name
+    assert np.array_equal(ref["minLengthEdgesOnVertex"][:nV], got["minLengthEdgesOnVertex"][:nV])
+    if mesh.on_a_sphere:
+        assert np.array_equal(ref["transGlobalToCell"], got["transGlobalToCell"])
+    for name in ir_host.GEOM_NAMES:
+        assert np.array_equal(ref["geomAvg"][name][:nC], got["geomAvg"][name][:nC]), name
+
+
+def test_init_geometry_with_halo_cells_and_bad_orientation(lib_path):
+    """remapEdge covers the edges of OWNED cells only (nCellsSolve < nCells, :1235-1262); a mesh whose verticesOnEdge
+    runs the wrong way round is refused like the reference refuses it (:1296)."""
+    mesh, irf, _ = case("hex12")
+    n_solve = mesh.nCells // 2
+    ref = ir.init_geometry(mesh, irf, n_cells_solve=n_solve)
+    got = ir_host.init_geometry(mesh, irf, n_cells_solve=n_solve, lib_path=lib_path)
+    assert 0 < got["remapEdge"].sum() < case("hex12")[2]["remapEdge"].sum()
+    for name in ("remapEdge", "cellsOnEdgeRemap", "edgesOnEdgeRemap", "xVertexOnEdge", "yVertexOnEdge"):
+        assert np.array_equal(ref[name][:mesh.nEdges], got[name][:mesh.nEdges]), name
+    bad = dict(irf)
+    bad["verticesOnEdge"] = np.ascontiguousarray(irf["verticesOnEdge"][:, ::-1])
+    with pytest.raises(ir_host.IrError) as e:
+        ir_host.init_geometry(mesh, bad, lib_path=lib_path)
+    assert e.value.code == ir_host.IR_ERR_MESH
+    with pytest.raises(RuntimeError, match="edge orientation"):
+        ir.init_geometry(mesh, bad)
+
+
 def test_call_order_and_argument_errors(lib_path):
     mesh, irf, geom = case("hex12")
     solver = ir_host.IrTransport(mesh, irf, geom, 1, lib_path=lib_path)
