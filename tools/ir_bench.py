@@ -1,0 +1,125 @@
+"""Timing of the incremental-remap transport step (include/ir_b200.h) -- a measurement aid for the IR row
+(DESIGN.md section 7c), NOT the north-star bench (that is bench.py: EVP subcycles per second).
+
+    python tools/ir_bench.py [--level 7] [--steps 5] [--warmup 2] [--cpu]
+
+Product path only: meshgen -> irmesh (host arrays a Python host lacks) -> ir_init_geometry (device) -> ir_run.
+Workload: the reference's standard tracer set (iceAreaCategory, iceVolumeCategory, snowVolumeCategory,
+surfaceTemperature, iceEnthalpy, iceSalinity, snowEnthalpy; 5 categories, 7 ice layers, 5 snow layers =
+115 (category, layer) rows), smooth ice cover with open water around the equator, smooth divergent velocity at 30 %
+of the CFL limit.  Prints one JSON line: device time of the five kernels per step (CUDA events inside ir_run), wall
+time per step through the C ABI with host buffers (uploads and downloads included), cell-row updates per second.
+``--cpu`` times the oracle on the same state instead (the checker timed as a baseline, as bench.py does).
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import mpas_seaice_b200  # noqa: E402,F401
+from mpas_seaice_b200 import irmesh, workloads  # noqa: E402
+
+
+class Tracer:
+    def __init__(self, name, array, parent=None, volume_like=False):
+        self.name, self.array, self.parent, self.volume_like = name, array, parent, volume_like
+
+
+def standard_tracers(mesh, n_cat=5, n_ice=7, n_snow=5):
+    nC = mesh.nCells
+    lat, lon = mesh.latCell[:nC], mesh.lonCell[:nC]
+    cover = np.clip((np.abs(lat) - np.deg2rad(20.0)) / np.deg2rad(30.0), 0.0, 1.0) * (0.8 + 0.15 * np.sin(3 * lon))
+
+    def new(nl):
+        return np.zeros((nC + 1, n_cat, nl))
+    area, ivol, svol, tsfc = new(1), new(1), new(1), new(1)
+    ienth, isal, senth = new(n_ice), new(n_ice), new(n_snow)
+    for k in range(n_cat):
+        a = cover * (0.1 + 0.05 * k) * (1.0 + 0.2 * np.cos(2 * lon + k))
+        area[:nC, k, 0] = a
+        ivol[:nC, k, 0] = a * (0.5 + 0.6 * k) * (1.0 + 0.1 * np.sin(4 * lat))
+        svol[:nC, k, 0] = a * 0.1 * (1.0 + 0.3 * np.cos(lon))
+        tsfc[:nC, k, 0] = -10.0 - 5.0 * np.cos(lat) + k
+        for l in range(n_ice):
+            ienth[:nC, k, l] = -3.0e8 * (1.0 + 0.05 * l + 0.02 * np.sin(lon))
+            isal[:nC, k, l] = 3.0 + 0.5 * l + 0.1 * np.cos(lat)
+        for l in range(n_snow):
+            senth[:nC, k, l] = -1.2e8 * (1.0 + 0.03 * l + 0.02 * np.cos(lon))
+    return [Tracer("iceAreaCategory", area), Tracer("iceVolumeCategory", ivol, 0, True),
+            Tracer("snowVolumeCategory", svol, 0, True), Tracer("surfaceTemperature", tsfc, 0),
+            Tracer("iceEnthalpy", ienth, 1), Tracer("iceSalinity", isal, 1), Tracer("snowEnthalpy", senth, 2)]
+
+
+def smooth_velocity(mesh, min_edge, dt, cfl=0.3):
+    nV = mesh.nVertices
+    speed = cfl * min_edge / dt
+    lat, lon = mesh.latVertex[:nV], mesh.lonVertex[:nV]
+    u, v = np.zeros(nV + 1), np.zeros(nV + 1)
+    u[:nV] = speed * np.cos(lat) * np.sin(2 * lon)
+    v[:nV] = speed * np.cos(lat) * np.sin(3 * lat) * np.cos(lon)
+    return u, v
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--level", type=int, default=7, help="icosphere level: 7 = 163 842 cells (QU60), 9 = QU15, 10 = QU7.5")
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--cpu", action="store_true", help="time the oracle (CPU) instead of the device")
+    args = ap.parse_args()
+    dt = 3600.0
+    t0 = time.time()
+    mesh = workloads._cached_icosphere(args.level) if hasattr(workloads, "_cached_icosphere") else None
+    if mesh is None:
+        from mpas_seaice_b200 import meshgen
+        mesh = meshgen.icosphere(args.level)
+    irf = irmesh.ir_fields(mesh)
+    t_mesh = time.time() - t0
+    tracers = standard_tracers(mesh)
+    n_rows = sum(t.array.shape[1] * t.array.shape[2] for t in tracers)
+    rec = dict(metric="ir_cell_row_updates_per_s", unit="cell-rows/s", cells=mesh.nCells, edges=mesh.nEdges, rows=n_rows,
+               steps=args.steps, warmup=args.warmup, mesh_s=round(t_mesh, 2), data="synthetic", dtype="f64")
+    if args.cpu:
+        from oracle import ir
+        geom = ir.init_geometry(mesh, irf)
+        u, v = smooth_velocity(mesh, geom["minLengthEdgesOnVertex"][:mesh.nVertices].min(), dt)
+        otr = [ir.Tracer(t.name, t.array, t.parent, t.volume_like) for t in tracers]
+        for _ in range(args.warmup):
+            ir.run(mesh, irf, geom, otr, u, v, dt)
+        t1 = time.time()
+        for _ in range(args.steps):
+            ir.run(mesh, irf, geom, otr, u, v, dt)
+        wall = (time.time() - t1) / args.steps
+        rec.update(impl="oracle", cores=os.cpu_count(), wall_ms_per_step=round(wall * 1e3, 3),
+                   value=mesh.nCells * n_rows / wall)
+    else:
+        from mpas_seaice_b200 import ir_host
+        t1 = time.time()
+        geom = ir_host.init_geometry(mesh, irf)
+        rec["init_geometry_s"] = round(time.time() - t1, 3)
+        u, v = smooth_velocity(mesh, geom["minLengthEdgesOnVertex"][:mesh.nVertices].min(), dt)
+        solver = ir_host.IrTransport(mesh, irf, geom, tracers[0].array.shape[1])
+        try:
+            solver.set_tracers(tracers)
+            for _ in range(args.warmup):
+                solver.run(tracers, u, v, dt)
+            dev_ms, t1 = [], time.time()
+            for _ in range(args.steps):
+                solver.run(tracers, u, v, dt)
+                dev_ms.append(solver.last_run_ms())
+            wall = (time.time() - t1) / args.steps
+            rec.update(impl="cuda", kernel_ms_per_step=round(float(np.mean(dev_ms)), 3), wall_ms_per_step=round(wall * 1e3, 3),
+                       value=mesh.nCells * n_rows / (np.mean(dev_ms) * 1e-3), gpu_launches=solver.launch_count())
+        finally:
+            solver.destroy()
+    print(json.dumps(rec))
+
+
+if __name__ == "__main__":
+    main()
