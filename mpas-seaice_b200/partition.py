@@ -364,6 +364,31 @@ def restrict_weak(block, gmesh, gweak: dict) -> dict:
     return out
 
 
+def restrict_ir(block, gmesh, girf: dict) -> dict:
+    """irmesh.ir_fields(global mesh) restricted to ``block``: the mesh-file arrays (verticesOnEdge, edgesOnVertex,
+    x/y/zEdge) through the block's numbering, and coeffs_reconstruct by rows -- the reference computes it on owned
+    cells and halo-exchanges it (incremental_remap.F:744-770), which restricting the global array reproduces."""
+    nVl, nEl = int(block.nVertices), int(block.nEdges)
+    nVg, nEg = int(gmesh.nVertices), int(gmesh.nEdges)
+    verts = block.indexToVertexID.astype(np.int64) - 1
+    edges = block.indexToEdgeID.astype(np.int64) - 1
+    g2l_vert = np.full(nVg + 1, nVl, dtype=np.int64)
+    g2l_vert[verts] = np.arange(nVl)
+    g2l_edge = np.full(nEg + 1, nEl, dtype=np.int64)
+    g2l_edge[edges] = np.arange(nEl)
+    voe = np.full((nEl + 1, 2), nVl + 1, dtype=np.int32)
+    voe[:nEl] = g2l_vert[girf["verticesOnEdge"][edges].astype(np.int64) - 1] + 1
+    eov = np.full((nVl + 1, girf["edgesOnVertex"].shape[1]), nEl + 1, dtype=np.int32)
+    eov[:nVl] = g2l_edge[np.minimum(girf["edgesOnVertex"][verts].astype(np.int64) - 1, nEg)] + 1
+    out = dict(verticesOnEdge=voe, edgesOnVertex=eov)
+    for k in ("xEdge", "yEdge", "zEdge"):
+        a = np.zeros(nEl + 1)
+        a[:nEl] = girf[k][edges]
+        out[k] = a
+    out["coeffs_reconstruct"] = restrict_field(block, girf["coeffs_reconstruct"], int(gmesh.nCells), nVg)
+    return out
+
+
 def restrict_step(block, step: dict, n_global_cells: int, n_global_vertices: int) -> dict:
     """Per-step fields of the global mesh -> the block (what the reference's halo exchanges of the
     pre-subcycle leave in owned + halo entries)."""
