@@ -9,7 +9,7 @@ import pytest
 from oracle import ir
 from mpas_seaice_b200 import ir_host, partition
 from test_oracle_ir import case, smooth_divergent_velocity, _random_state
-from test_ir_parity import LEGS, _emulation_library, clone
+from test_ir_parity import clone, lib_path  # noqa: F401  (lib_path: the emulation / cuda fixture)
 
 
 def _blocks(kind, n_parts, n_halos):
@@ -70,16 +70,6 @@ def test_one_halo_layer_is_not_enough():
             partition.scatter_owned(b, tr[t].array, gathered[t].array, "cell")
     assert not np.array_equal(single[0].array, gathered[0].array)
     assert np.allclose(single[0].array, gathered[0].array, atol=5e-2)
-
-
-@pytest.fixture(params=LEGS)
-def lib_path(request):
-    if request.param == "emulation":
-        return _emulation_library()
-    import torch
-    if not torch.cuda.is_available():
-        pytest.skip("no CUDA device")
-    return ir_host.LIB_PATH
 
 
 def test_device_blocks_reproduce_the_single_block_run(lib_path):
