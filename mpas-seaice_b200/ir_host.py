@@ -208,3 +208,39 @@ class IrTransport:
             self.destroy()
         except Exception:
             pass
+
+
+class TracerHalo:
+    """Owner -> halo update of the tracer arrays between the ranks of a decomposed run: what
+    seaice_update_tracer_halo does after the transport (incremental_remap.F:2705-2712).  Host-side, over the
+    process group ``dist`` (torch.distributed with a backend that moves CPU tensors, e.g. gloo), one message per
+    neighbour carrying every tracer.  ``lists``: partition.cell_exchange_lists of this rank's block."""
+
+    def __init__(self, lists, dist):
+        self.nbrs, self.send_off, self.send_idx, self.recv_off, self.recv_idx = lists
+        self.dist = dist
+
+    def update(self, tracers):
+        import torch
+        dist = self.dist
+        ops, recv_bufs = [], []
+        for i, q in enumerate(self.nbrs):
+            s = self.send_idx[self.send_off[i]:self.send_off[i + 1]].astype(np.int64) - 1
+            r = self.recv_idx[self.recv_off[i]:self.recv_off[i + 1]].astype(np.int64) - 1
+            if s.size:
+                out = torch.from_numpy(np.concatenate([t.array[s].reshape(-1) for t in tracers]))
+                ops.append(dist.P2POp(dist.isend, out, int(q)))
+            if r.size:
+                n = sum(r.size * t.array.shape[1] * t.array.shape[2] for t in tracers)
+                buf = torch.empty(n, dtype=torch.float64)
+                ops.append(dist.P2POp(dist.irecv, buf, int(q)))
+                recv_bufs.append((r, buf))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        for r, buf in recv_bufs:
+            a, o = buf.numpy(), 0
+            for t in tracers:
+                n = r.size * t.array.shape[1] * t.array.shape[2]
+                t.array[r] = a[o:o + n].reshape((r.size,) + t.array.shape[1:])
+                o += n

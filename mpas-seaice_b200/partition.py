@@ -253,6 +253,7 @@ def build_block(mesh, part: np.ndarray, rank: int, n_halos: int | None = None) -
     b.indexToCellID = (cells + 1).astype(np.int32)
     b.indexToVertexID = (verts + 1).astype(np.int32)
     b.cellHaloLayer = layer_of
+    b.cellOwner = part[cells].astype(np.int32)              # owning rank of every local cell
     b.vertexOwner = np.concatenate([np.full(nVs, rank, dtype=np.int32), own_rank[halo_v]])
     # interiorVertex is computed on owned vertices and halo-exchanged by the reference (mesh.F:405);
     # taking it from the global mesh is that exchange
@@ -314,6 +315,53 @@ def exchange_lists(block, requests_by_rank: dict):
         r = (np.nonzero(owner == q)[0] + nVs + 1).astype(np.int32)
         if q in mine:
             assert np.array_equal(gid_halo[r - nVs - 1], np.asarray(mine[q]))
+        send_idx.append(s)
+        recv_idx.append(r)
+        send_off.append(send_off[-1] + s.shape[0])
+        recv_off.append(recv_off[-1] + r.shape[0])
+    cat = lambda l: np.concatenate(l).astype(np.int32) if l else np.zeros(0, dtype=np.int32)
+    return (np.asarray(nbrs, dtype=np.int32), np.asarray(send_off, dtype=np.int32), cat(send_idx),
+            np.asarray(recv_off, dtype=np.int32), cat(recv_idx))
+
+
+def cell_halo_requests(block) -> dict:
+    """{owner rank: ascending global ids (1-based) of the halo CELLS this block needs from it} -- the cell
+    counterpart of halo_requests, for fields that live on cells (the tracers of the transport scheme)."""
+    nCs, nCl = int(block.nCellsSolve), int(block.nCells)
+    gid, owner = block.indexToCellID[nCs:nCl].astype(np.int64), block.cellOwner[nCs:nCl]
+    return {int(q): np.sort(gid[owner == q]) for q in np.unique(owner)}
+
+
+def cell_exchange_lists(block, requests_by_rank: dict):
+    """(neighbours, send_off, send_idx, recv_off, recv_idx) with 1-based LOCAL cell indices: what this rank packs
+    for every neighbour (its owned cells, in the ascending-global-id order the neighbour asked for) and where the
+    values it receives go (its halo cells owned by that neighbour, same order)."""
+    rank = int(block.rank)
+    nCs, nCl = int(block.nCellsSolve), int(block.nCells)
+    gid = block.indexToCellID.astype(np.int64)
+    order_owned = np.argsort(gid[:nCs], kind="stable")
+    gid_owned = gid[:nCs][order_owned]
+    mine = cell_halo_requests(block)
+    send = {}
+    for q, req in requests_by_rank.items():
+        if int(q) == rank or req is None:
+            continue
+        want = req.get(rank)
+        if want is None or len(want) == 0:
+            continue
+        want = np.asarray(want, dtype=np.int64)
+        pos = np.searchsorted(gid_owned, want)
+        if np.any(pos >= nCs) or np.any(gid_owned[np.minimum(pos, nCs - 1)] != want):
+            raise ValueError(f"rank {q} requests cells rank {rank} does not own")
+        send[int(q)] = (order_owned[pos] + 1).astype(np.int32)
+    nbrs = sorted(set(send) | set(mine))
+    send_off, recv_off, send_idx, recv_idx = [0], [0], [], []
+    halo_gid, halo_owner = gid[nCs:nCl], block.cellOwner[nCs:nCl]
+    for q in nbrs:
+        s = send.get(q, np.zeros(0, dtype=np.int32))
+        loc = np.nonzero(halo_owner == q)[0]
+        loc = loc[np.argsort(halo_gid[loc], kind="stable")]
+        r = (loc + nCs + 1).astype(np.int32)
         send_idx.append(s)
         recv_idx.append(r)
         send_off.append(send_off[-1] + s.shape[0])
