@@ -180,6 +180,42 @@ def test_abort_conditions_are_reported_like_the_oracle(lib_path):
     assert np.array_equal(ref[0].array[:nC], dev[0].array[:nC])      # the mass field was updated before the check
 
 
+def test_deep_and_layered_hierarchies_match_oracle(lib_path):
+    """Three parents (area -> volume -> brine fraction -> a layered child: the depth of mobileFraction /
+    verticalAlgaeIce, incremental_remap_tracers.F:300-330) and a layered tracer under a layered parent
+    (compute_barycenter_coordinates with 3-D parents, :4040-4170); mass * tracer products conserved, device =
+    oracle."""
+    mesh, irf, geom = case("ico3")
+    nC = mesh.nCells
+    rng = np.random.default_rng(33)
+
+    def rnd(nl, lo, hi):
+        a = np.zeros((nC + 1, 2, nl))
+        a[:nC] = rng.uniform(lo, hi, (nC, 2, nl))
+        return a
+    area = rnd(1, 0.05, 0.45)
+    area[:nC, :, 0][rng.uniform(size=(nC, 2)) < 0.2] = 0.0
+    tracers = [ir.Tracer("iceAreaCategory", area),
+               ir.Tracer("iceVolumeCategory", area * rnd(1, 0.5, 3.0), 0, True),
+               ir.Tracer("layeredParent", rnd(2, 0.2, 1.0), 0),
+               ir.Tracer("brineFraction", rnd(1, 0.3, 1.0), 1),
+               ir.Tracer("layeredChild", rnd(2, 1.0, 5.0), 2),
+               ir.Tracer("mobileFraction", rnd(2, 0.1, 0.9), 3)]
+    A = mesh.areaCell[:nC, None, None]
+
+    def products(tr):
+        a, vol = tr[0].array[:nC], tr[1].array[:nC]
+        return [(a * A).sum(), (vol * A).sum(), (a * tr[2].array[:nC] * A).sum(0), (vol * tr[3].array[:nC] * A).sum(),
+                (a * tr[2].array[:nC] * tr[4].array[:nC] * A).sum(0), (vol * tr[3].array[:nC] * tr[5].array[:nC] * A).sum(0)]
+    before = products(tracers)
+    u, v = smooth_divergent_velocity(mesh, geom)
+    mesh, ref, dev, d_ref, d_dev, codes, _ = run_both("ico3", tracers, u, v, 3600.0, lib_path, steps=2)
+    assert all(c == (0, 0) for c in codes), codes
+    assert_identical(mesh, ref, dev, d_ref, d_dev)
+    for b, a in zip(before, products(ref)):
+        assert np.allclose(a, b, rtol=5e-13, atol=0)
+
+
 def test_rotation_test_case_matches_oracle(lib_path):
     """The reference's advection test case (cosine bell, u = U cos(lat); create_ics.py:36-107) on the 2562-cell
     sphere with its twelve pentagons: ten steps, identical throughout."""
