@@ -6,7 +6,7 @@
 Product path only: meshgen -> irmesh (host arrays a Python host lacks) -> ir_init_geometry (device) -> ir_run.
 Workload: the reference's standard tracer set (iceAreaCategory, iceVolumeCategory, snowVolumeCategory,
 surfaceTemperature, iceEnthalpy, iceSalinity, snowEnthalpy; 5 categories, 7 ice layers, 5 snow layers =
-115 (category, layer) rows), smooth ice cover with open water around the equator, smooth divergent velocity at 30 %
+115 (category, layer) rows), smooth ice cover with open water around the equator (where the rotated grid has its poles), smooth divergent velocity at 30 %
 of the CFL limit.  Prints one JSON line: device time of the five kernels per step (CUDA events inside ir_run), wall
 time per step through the C ABI with host buffers (uploads and downloads included), cell-row updates per second.
 ``--cpu`` times the oracle on the same state instead (the checker timed as a baseline, as bench.py does).
@@ -87,24 +87,24 @@ def main():
                steps=args.steps, warmup=args.warmup, mesh_s=round(t_mesh, 2), data="synthetic", dtype="f64")
     if args.cpu:
         from oracle import ir
-        geom = ir.init_geometry(mesh, irf)
+        geom = ir.init_geometry(mesh, irf, rotate=True)          # config_rotate_cartesian_grid: Registry default
         u, v = smooth_velocity(mesh, geom["minLengthEdgesOnVertex"][:mesh.nVertices].min(), dt)
         otr = [ir.Tracer(t.name, t.array, t.parent, t.volume_like) for t in tracers]
         for _ in range(args.warmup):
-            ir.run(mesh, irf, geom, otr, u, v, dt)
+            ir.run(mesh, irf, geom, otr, u, v, dt, rotate=True)
         t1 = time.time()
         for _ in range(args.steps):
-            ir.run(mesh, irf, geom, otr, u, v, dt)
+            ir.run(mesh, irf, geom, otr, u, v, dt, rotate=True)
         wall = (time.time() - t1) / args.steps
         rec.update(impl="oracle", cores=os.cpu_count(), wall_ms_per_step=round(wall * 1e3, 3),
                    value=mesh.nCells * n_rows / wall)
     else:
         from mpas_seaice_b200 import ir_host
         t1 = time.time()
-        geom = ir_host.init_geometry(mesh, irf)
+        geom = ir_host.init_geometry(mesh, irf, rotate=True)     # config_rotate_cartesian_grid: Registry default
         rec["init_geometry_s"] = round(time.time() - t1, 3)
         u, v = smooth_velocity(mesh, geom["minLengthEdgesOnVertex"][:mesh.nVertices].min(), dt)
-        solver = ir_host.IrTransport(mesh, irf, geom, tracers[0].array.shape[1])
+        solver = ir_host.IrTransport(mesh, irf, geom, tracers[0].array.shape[1], rotate=True)
         try:
             solver.set_tracers(tracers)
             for _ in range(args.warmup):
