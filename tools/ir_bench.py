@@ -6,8 +6,8 @@
 Product path only: meshgen -> irmesh (host arrays a Python host lacks) -> ir_init_geometry (device) -> ir_run.
 Workload: the reference's standard tracer set (iceAreaCategory, iceVolumeCategory, snowVolumeCategory,
 surfaceTemperature, iceEnthalpy, iceSalinity, snowEnthalpy; 5 categories, 7 ice layers, 5 snow layers =
-115 (category, layer) rows), smooth ice cover with open water around the equator (where the rotated grid has its poles), smooth divergent velocity at 30 %
-of the CFL limit.  Prints one JSON line: device time of the five kernels per step (CUDA events inside ir_run), wall
+115 (category, layer) rows), smooth ice cover with open water around the equator (where the rotated grid has its
+poles), smooth divergent velocity at 30 % of the CFL limit.  Prints one JSON line: device time of the five kernels per step (CUDA events inside ir_run), wall
 time per step through the C ABI with host buffers (uploads and downloads included), cell-row updates per second.
 ``--cpu`` times the oracle on the same state instead (the checker timed as a baseline, as bench.py does).
 """
