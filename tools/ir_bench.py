@@ -72,6 +72,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--cpu", action="store_true", help="time the oracle (CPU) instead of the device")
+    ap.add_argument("--check", action="store_true",
+                    help="after the timed steps, run the oracle on the same initial state and report whether the device "
+                         "fields are identical (the oracle as the checker, outside the timed region)")
     args = ap.parse_args()
     dt = 3600.0
     t0 = time.time()
@@ -82,6 +85,7 @@ def main():
     irf = irmesh.ir_fields(mesh)
     t_mesh = time.time() - t0
     tracers = standard_tracers(mesh)
+    initial = [t.array.copy() for t in tracers] if args.check else None
     n_rows = sum(t.array.shape[1] * t.array.shape[2] for t in tracers)
     rec = dict(metric="ir_cell_row_updates_per_s", unit="cell-rows/s", cells=mesh.nCells, edges=mesh.nEdges, rows=n_rows,
                steps=args.steps, warmup=args.warmup, mesh_s=round(t_mesh, 2), data="synthetic", dtype="f64")
@@ -118,6 +122,17 @@ def main():
                        value=mesh.nCells * n_rows / (np.mean(dev_ms) * 1e-3), gpu_launches=solver.launch_count())
         finally:
             solver.destroy()
+        if args.check:
+            from oracle import ir
+            geom_o = ir.init_geometry(mesh, irf, rotate=True)
+            otr = [ir.Tracer(t.name, a, t.parent, t.volume_like) for t, a in zip(tracers, initial)]
+            for _ in range(args.warmup + args.steps):
+                ir.run(mesh, irf, geom_o, otr, u, v, dt, rotate=True)
+            nC = mesh.nCells
+            rec["parity"] = bool(all(np.array_equal(t.array[:nC], o.array[:nC]) for t, o in zip(tracers, otr)))
+            rec["geometry_parity"] = bool(all(np.array_equal(geom[k][:-1], geom_o[k][:-1]) for k in
+                                              ("xVertexOnCell", "yVertexOnCell", "xVertexOnEdge", "yVertexOnEdge", "remapEdge",
+                                               "cellsOnEdgeRemap", "edgesOnEdgeRemap")))
     print(json.dumps(rec))
 
 
