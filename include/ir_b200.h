@@ -132,6 +132,11 @@ int ir_run(ir_handle *h, int nTracers, const ir_tracer_desc *tracers, const doub
 int ir_fetch_diagnostics(ir_handle *h, double *xTriangle, double *yTriangle, double *triangleArea, int *iCellTriangle,
                          int *maskEdge, double *edgeFluxMass);
 
+/* With IR_B200_PIN_HOST=1 in the environment at ir_create, ir_run page-locks the tracer and velocity arrays the first
+ * time it sees them (cudaHostRegister) so that the per-step copies run at the full PCIe rate.  Call this before the
+ * host frees or reallocates such an array (e.g. mpas_pool_destroy_pool); ir_destroy does it too.  No-op otherwise. */
+int ir_release_host_memory(ir_handle *h);
+
 int ir_last_run_ms(ir_handle *h, float *ms);       /* device time of the last ir_run, kernels only */
 int ir_launch_count(ir_handle *h, long long *n);   /* kernels launched by this handle so far */
 int ir_destroy(ir_handle *h);

@@ -23,7 +23,9 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 #include "../../include/ir_b200.h"
@@ -117,6 +119,8 @@ struct ir_handle {
     std::vector<int> depthRow0;   // rows of depth q are [depthRow0[q], depthRow0[q+1])  (rows sorted by depth)
     std::vector<int> rowOrder;    // device row -> (tracer, k, l) linear index on the host side
     std::vector<void *> allocs;
+    std::vector<std::pair<const void *, size_t>> pinned;   // host ranges registered under IR_B200_PIN_HOST
+    bool pinHost;
     float lastMs;
     long long launches;
     bool haveTracers;
@@ -1042,6 +1046,25 @@ int upload_rows(ir_handle *h, T *dst, const T *host, size_t n, int w, size_t pit
     return IR_OK;
 }
 
+// Opt-in (environment IR_B200_PIN_HOST=1 at ir_create): page-lock the host arrays the first time ir_run sees them, so
+// the per-step uploads and downloads run at the full PCIe rate.  The pool arrays of the host model live as long as
+// the model; a host that frees them earlier calls ir_release_host_memory first.  A range that cannot be registered
+// (already registered by someone else, not page-lockable) is simply copied as pageable memory.
+void pin_host(ir_handle *h, const void *p, size_t bytes)
+{
+    if (!h->pinHost || p == nullptr || bytes == 0) return;
+    for (auto &r : h->pinned)
+        if (r.first == p && r.second >= bytes) return;
+    if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) h->pinned.emplace_back(p, bytes);
+    else (void)cudaGetLastError();
+}
+
+void unpin_all(ir_handle *h)
+{
+    for (auto &r : h->pinned) cudaHostUnregister(const_cast<void *>(r.first));
+    h->pinned.clear();
+}
+
 }  // namespace
 
 // =============================================================================================================== ABI
@@ -1074,6 +1097,10 @@ extern "C" int ir_create(ir_handle **out, const ir_mesh_desc *m, int device)
     h->lastMs = 0.f;
     h->launches = 0;
     h->haveTracers = false;
+    {
+        const char *e = getenv("IR_B200_PIN_HOST");
+        h->pinHost = e != nullptr && e[0] != '\0' && e[0] != '0';
+    }
     memset(&h->d, 0, sizeof h->d);
     cudaError_t ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (ce != cudaSuccess) { set_error("cudaStreamCreate -> %s", cudaGetErrorString(ce)); delete h; return IR_ERR_CUDA; }
@@ -1365,6 +1392,9 @@ extern "C" int ir_run(ir_handle *h, int nTracers, const ir_tracer_desc *tr, cons
     const size_t nC1 = (size_t)d.nC + 1;
     const int nK = d.nK;
     // in: tracers (host (nCells+1, nK*nL) -> rows) and velocities
+    for (int t = 0; t < nTracers; t++) pin_host(h, tr[t].array, nC1 * nK * tr[t].nLayers * sizeof(double));
+    pin_host(h, u, ((size_t)d.nV + 1) * 8);
+    pin_host(h, v, ((size_t)d.nV + 1) * 8);
     for (int t = 0; t < nTracers; t++) {
         int rc = upload_rows<double>(h, d.val + (size_t)h->tracerRow0[t] * d.nCp, tr[t].array, nC1, nK * tr[t].nLayers, d.nCp);
         if (rc) return rc;
@@ -1474,11 +1504,21 @@ extern "C" int ir_launch_count(ir_handle *h, long long *n)
     return IR_OK;
 }
 
+extern "C" int ir_release_host_memory(ir_handle *h)
+{
+    IR_REQUIRE(h != nullptr, "handle is NULL");
+    IR_CUDA(cudaSetDevice(h->device));
+    IR_CUDA(cudaStreamSynchronize(h->stream));
+    unpin_all(h);
+    return IR_OK;
+}
+
 extern "C" int ir_destroy(ir_handle *h)
 {
     if (!h) return IR_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    unpin_all(h);
     Dev &d = h->d;
     double *bufs[] = {d.val, d.valNew, d.center, d.xGrad, d.yGrad, d.xBary, d.yBary, d.mtpNew, d.edgeFlux, d.stage};
     for (double *b : bufs)

@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("IR_B200_LIB", os.path.join(_HERE, "csrc", "libir_b200.so"))
 
-EXPORTS = ("ir_init_geometry", "ir_create", "ir_set_tracers", "ir_run", "ir_fetch_diagnostics", "ir_last_run_ms", "ir_launch_count",
+EXPORTS = ("ir_init_geometry", "ir_create", "ir_set_tracers", "ir_run", "ir_fetch_diagnostics", "ir_release_host_memory", "ir_last_run_ms", "ir_launch_count",
            "ir_destroy", "ir_last_error_string")
 GEOM_NAMES = ("x", "y", "xx", "xy", "yy", "xxx", "xxy", "xyy", "yyy", "xxxx", "xxxy", "xxyy", "xyyy", "yyyy")
 
@@ -187,6 +187,10 @@ class IrTransport:
                                                             ("xTriangle", "yTriangle", "triangleArea", "iCellTriangle",
                                                              "maskEdge", "edgeFluxMass")]))
         return out
+
+    def release_host_memory(self):
+        """Undo the page-locking of host arrays done under IR_B200_PIN_HOST (before they are freed)."""
+        self._check(self._L.ir_release_host_memory(self._h))
 
     def last_run_ms(self):
         ms = C.c_float(0)

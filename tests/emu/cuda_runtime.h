@@ -69,6 +69,9 @@ static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = 1; return cudaS
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+enum { cudaHostRegisterDefault = 0 };
+static inline cudaError_t cudaHostRegister(void *, size_t, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaHostUnregister(void *) { return cudaSuccess; }
 static inline int atomicOr(int *p, int v) { const int old = *p; *p = old | v; return old; }
 
 #endif
