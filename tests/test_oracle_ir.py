@@ -546,3 +546,110 @@ def test_fluxes_equal_the_exact_remap_of_the_piecewise_linear_field(kind, vel):
         assert abs(area_sum / mesh.areaCell[c] - 1.0) < 1e-12
         worst = max(worst, abs(total / mesh.areaCell[c] - a[c, 0, 0]))
     assert worst < 2e-14, worst
+
+
+def _moments(poly):
+    """area, and the integrals of x, y, x^2, xy, y^2 over a counter-clockwise polygon"""
+    a = sx = sy = sxx = sxy = syy = 0.0
+    for i in range(len(poly)):
+        (x0, y0), (x1, y1) = poly[i], poly[(i + 1) % len(poly)]
+        w = x0 * y1 - x1 * y0
+        a += w
+        sx += (x0 + x1) * w
+        sy += (y0 + y1) * w
+        sxx += (x0 * x0 + x0 * x1 + x1 * x1) * w
+        syy += (y0 * y0 + y0 * y1 + y1 * y1) * w
+        sxy += (x0 * y1 + 2.0 * x0 * y0 + 2.0 * x1 * y1 + x1 * y0) * w
+    return a / 2.0, sx / 6.0, sy / 6.0, sxx / 12.0, sxy / 24.0, syy / 12.0
+
+
+@pytest.mark.parametrize("kind", ["hex12", "quad10"])
+def test_tracer_fluxes_equal_the_exact_remap_of_mass_times_tracer(kind):
+    """The same independent check one level down the hierarchy: thickness sits at the centre of MASS of its cell
+    (compute_barycenter_coordinates, :4658) and is carried as mass * thickness, a quadratic inside every cell.  The
+    new volume of a cell must be the integral of that quadratic over the shifted cell -- evaluated here with exact
+    polygon moments and an independently computed barycentre."""
+    mesh, irf, geom = case(kind)
+    nC = mesh.nCells
+    dt, vel = 3600.0, (0.045, -0.03)
+    rng = np.random.default_rng(29)
+
+    def fresh():
+        tr = ir.default_tracers(nC, 1)
+        r = np.random.default_rng(29)
+        tr[0].array[:nC, 0, 0] = r.uniform(0.1, 0.9, nC)
+        tr[1].array[:nC, 0, 0] = tr[0].array[:nC, 0, 0] * r.uniform(0.5, 3.0, nC)
+        return tr
+    del rng
+    u, v = uniform_velocity(mesh, *vel)
+    tr = fresh()
+    a_old = tr[0].array[:nC, 0, 0].copy()
+    h_old = tr[1].array[:nC, 0, 0] / a_old
+    dm = ir.run(mesh, irf, geom, tr, u, v, dt, diagnostics=True, grad_tracer=0)
+    vol_new = tr[1].array[:nC, 0, 0].copy()
+    dh = ir.run(mesh, irf, geom, fresh(), u, v, dt, diagnostics=True, grad_tracer=1)
+    gmx, gmy = dm["xGrad"][:nC, 0, 0], dm["yGrad"][:nC, 0, 0]
+    ghx, ghy = dh["xGrad"][:nC, 0, 0], dh["yGrad"][:nC, 0, 0]
+    assert np.abs(ghx).max() > 0
+    polys = []
+    for c in range(nC):
+        vs = mesh.verticesOnCell[c, :mesh.nEdgesOnCell[c]] - 1
+        polys.append([(float(mesh.xVertex[k] - mesh.xCell[c]), float(mesh.yVertex[k] - mesh.yCell[c])) for k in vs])
+    # reconstruction coefficients in cell-centred coordinates, barycentre from exact polygon moments
+    m0, h0 = np.zeros(nC), np.zeros(nC)
+    for c in range(nC):
+        A, sx, sy, sxx, sxy, syy = _moments(polys[c])
+        m0[c] = a_old[c] - gmx[c] * sx / A - gmy[c] * sy / A
+        mass = a_old[c] * A
+        xb = (m0[c] * sx + gmx[c] * sxx + gmy[c] * sxy) / mass
+        yb = (m0[c] * sy + gmx[c] * sxy + gmy[c] * syy) / mass
+        h0[c] = h_old[c] - ghx[c] * xb - ghy[c] * yb
+    coc = mesh.cellsOnCell
+    worst = 0.0
+    for c in np.nonzero(inner_cells(mesh, 2))[0][::3]:
+        cand = {c}
+        for k in range(mesh.nEdgesOnCell[c]):
+            n1 = coc[c, k] - 1
+            cand.add(n1)
+            for kk in range(mesh.nEdgesOnCell[n1]):
+                if coc[n1, kk] <= nC:
+                    cand.add(coc[n1, kk] - 1)
+        total = 0.0
+        for s in cand:
+            ox, oy = mesh.xCell[c] - mesh.xCell[s], mesh.yCell[c] - mesh.yCell[s]
+            shifted = [(x + ox - vel[0] * dt, y + oy - vel[1] * dt) for x, y in polys[c]]   # in the frame of cell s
+            piece = _clip(shifted, polys[s])
+            if len(piece) < 3:
+                continue
+            A, sx, sy, sxx, sxy, syy = _moments(piece)
+            total += (m0[s] * h0[s] * A + (m0[s] * ghx[s] + gmx[s] * h0[s]) * sx + (m0[s] * ghy[s] + gmy[s] * h0[s]) * sy
+                      + gmx[s] * ghx[s] * sxx + (gmx[s] * ghy[s] + gmy[s] * ghx[s]) * sxy + gmy[s] * ghy[s] * syy)
+        worst = max(worst, abs(total / mesh.areaCell[c] - vol_new[c]) / vol_new[c])
+    assert worst < 5e-13, worst
+
+
+@pytest.mark.parametrize("kind", ["hex12", "quad10", "ico3"])
+def test_limited_reconstruction_stays_within_the_neighbour_range(kind):
+    """limit_tracer_gradient (:4802): at every vertex of a cell the reconstructed value lies between the smallest and
+    the largest of the values in the cell and its edge neighbours -- for the mass field about the centroid and for a
+    tracer about its parent's barycentre (here checked for the mass field, whose reference point is known)."""
+    mesh, irf, geom = case(kind)
+    nC, M = mesh.nCells, mesh.maxEdges
+    rng = np.random.default_rng(6)
+    tr = ir.default_tracers(nC, 1)
+    tr[0].array[:nC, 0, 0] = rng.uniform(0.05, 0.95, nC)
+    a = tr[0].array[:nC, 0, 0].copy()
+    u, v = uniform_velocity(mesh, 0.0, 0.0)
+    d = ir.run(mesh, irf, geom, tr, u, v, 1.0, diagnostics=True)
+    xg, yg = d["xGrad"][:nC, 0, 0], d["yGrad"][:nC, 0, 0]
+    assert np.count_nonzero(xg) > nC // 4
+    slot = np.arange(M)[None, :] < mesh.nEdgesOnCell[:nC, None]
+    nb = np.minimum(mesh.cellsOnCell[:nC], nC + 1) - 1
+    a_pad = np.append(a, np.nan)
+    lo = np.fmin(a, np.nanmin(np.where(slot, a_pad[nb], np.nan), axis=1))
+    hi = np.fmax(a, np.nanmax(np.where(slot, a_pad[nb], np.nan), axis=1))
+    xv, yv = geom["xVertexOnCell"][:nC], geom["yVertexOnCell"][:nC]
+    gx, gy = geom["geomAvg"]["x"][:nC], geom["geomAvg"]["y"][:nC]
+    val = a[:, None] + xg[:, None] * (xv - gx[:, None]) + yg[:, None] * (yv - gy[:, None])
+    assert np.all(np.where(slot, val, lo[:, None]) >= lo[:, None] - 1e-15)
+    assert np.all(np.where(slot, val, hi[:, None]) <= hi[:, None] + 1e-15)
