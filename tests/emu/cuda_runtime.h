@@ -29,21 +29,26 @@ struct dim3 {
 };
 static thread_local dim3 blockIdx, threadIdx, blockDim, gridDim;
 
+/* Threads of a launch run one after the other.  IR_EMU_ORDER=reverse runs blocks and threads last to first: a kernel
+ * whose threads depend on one another within a launch (a race on the device) gives different results in the two
+ * orders, so comparing them is a cheap race detector (tests/test_ir_parity.py). */
 template <typename F>
 static void emu_launch(dim3 grid, dim3 block, F body)
 {
     gridDim = grid;
     blockDim = block;
-    for (unsigned bz = 0; bz < grid.z; bz++)
-        for (unsigned by = 0; by < grid.y; by++)
-            for (unsigned bx = 0; bx < grid.x; bx++)
-                for (unsigned tz = 0; tz < block.z; tz++)
-                    for (unsigned ty = 0; ty < block.y; ty++)
-                        for (unsigned tx = 0; tx < block.x; tx++) {
-                            blockIdx = dim3(bx, by, bz);
-                            threadIdx = dim3(tx, ty, tz);
-                            body();
-                        }
+    const char *order = getenv("IR_EMU_ORDER");
+    const bool reverse = order != nullptr && order[0] == 'r';
+    const unsigned long long nb = (unsigned long long)grid.x * grid.y * grid.z, nt = (unsigned long long)block.x * block.y * block.z;
+    for (unsigned long long ib = 0; ib < nb; ib++) {
+        const unsigned long long b = reverse ? nb - 1 - ib : ib;
+        for (unsigned long long it = 0; it < nt; it++) {
+            const unsigned long long t = reverse ? nt - 1 - it : it;
+            blockIdx = dim3((unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y), (unsigned)(b / ((unsigned long long)grid.x * grid.y)));
+            threadIdx = dim3((unsigned)(t % block.x), (unsigned)((t / block.x) % block.y), (unsigned)(t / ((unsigned long long)block.x * block.y)));
+            body();
+        }
+    }
 }
 #define IR_LAUNCH(kernel, grid, block, stream, ...) emu_launch(dim3(grid), dim3(block), [&] { kernel(__VA_ARGS__); })
 

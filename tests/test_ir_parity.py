@@ -216,6 +216,41 @@ def test_deep_and_layered_hierarchies_match_oracle(lib_path):
         assert np.allclose(a, b, rtol=5e-13, atol=0)
 
 
+def test_emulated_kernels_do_not_depend_on_the_thread_order():
+    """The emulation runs the threads of a launch sequentially; run last-to-first (IR_EMU_ORDER=reverse) the results
+    must not change -- they would if a thread read what another thread of the same launch writes, which on the device
+    is a race.  Full hierarchy, geometry init included."""
+    lib = _emulation_library()
+    mesh, irf, _ = case("ico3")
+    rng = np.random.default_rng(21)
+    tracers = _random_state(mesh, rng)
+    results = []
+    for order in ("forward", "reverse"):
+        os.environ["IR_EMU_ORDER"] = order
+        try:
+            geom = ir_host.init_geometry(mesh, irf, lib_path=lib)
+            u, v = smooth_divergent_velocity(mesh, geom)
+            dev = clone(tracers)
+            solver = ir_host.IrTransport(mesh, irf, geom, tracers[0].array.shape[1], lib_path=lib)
+            try:
+                solver.set_tracers(dev)
+                for _ in range(2):
+                    solver.run(dev, u, v, 3600.0)
+                diag = solver.diagnostics()
+            finally:
+                solver.destroy()
+        finally:
+            os.environ.pop("IR_EMU_ORDER", None)
+        results.append((geom, dev, diag))
+    (g0, t0, d0), (g1, t1, d1) = results
+    for k in ("xVertexOnCell", "yVertexOnCell", "xVertexOnEdge", "yVertexOnEdge", "cellsOnEdgeRemap", "edgesOnEdgeRemap"):
+        assert np.array_equal(g0[k], g1[k]), k
+    for a, b in zip(t0, t1):
+        assert np.array_equal(a.array, b.array), a.name
+    for k in d0:
+        assert np.array_equal(d0[k], d1[k]), k
+
+
 def test_rotation_test_case_matches_oracle(lib_path):
     """The reference's advection test case (cosine bell, u = U cos(lat); create_ics.py:36-107) on the 2562-cell
     sphere with its twelve pentagons: ten steps, identical throughout."""
