@@ -251,6 +251,23 @@ def test_emulated_kernels_do_not_depend_on_the_thread_order():
         assert np.array_equal(d0[k], d1[k]), k
 
 
+def test_emulated_kernels_are_clean_under_address_sanitizer(tmp_path):
+    """Device-memory bounds, checked where there is no device: the kernels compiled for the host with
+    -fsanitize=address, every "device" buffer a calloc of exactly the requested size."""
+    import sys
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan is not installed")
+    lib = str(tmp_path / "libir_emu_asan.so")
+    subprocess.run(["g++", "-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer", "-ffp-contract=off", "-std=c++17",
+                    "-fPIC", "-shared", "-x", "c++", "-Wno-unknown-pragmas", "-I", EMU_DIR, "-o", lib, SRC], check=True)
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_ir_asan_worker.py"), lib], env=env, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and "AddressSanitizer" not in r.stderr, r.stderr[-3000:]
+    assert r.stdout.count("ok") == 6
+
+
 def test_rotation_test_case_matches_oracle(lib_path):
     """The reference's advection test case (cosine bell, u = U cos(lat); create_ics.py:36-107) on the 2562-cell
     sphere with its twelve pentagons: ten steps, identical throughout."""
