@@ -612,40 +612,44 @@ __global__ void __launch_bounds__(128) k_triangles(Dev d, double dt)
 }
 
 // integrate_fluxes_over_triangles (:6667): one thread per (edge, category).  The quadrature points of the edge's
-// departure triangles (up to 6 x 6 x 2 doubles) are parked once in a per-thread shared-memory column and reused by every
-// row of the category.  triangleValue of a row is the product down its chain of parents of the linear reconstructions
-// at the quadrature point, the mass field first.
+// non-empty departure triangles are parked once in a per-thread shared-memory column and reused by every row of the
+// category.  CAP = the most triangles an edge can have (4 on hexagonal meshes, 6 on quadrilateral ones,
+// find_departure_triangles :5420-5460): it sizes the scratch, i.e. the blocks that fit on an SM.  triangleValue of a
+// row is the product down its chain of parents of the linear reconstructions at the quadrature point, the mass field
+// first.
+template <int CAP>
 __global__ void __launch_bounds__(RB) k_fluxes(Dev d)
 {
-    __shared__ double Q[NTRI * 12][RB];
+    __shared__ double Q[CAP * 12][RB];
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int cat = blockIdx.y, tx = threadIdx.x;
     if (e >= (size_t)d.nE) return;
     const size_t pe = d.nEp, pc = d.nCp;
     const int nQP = d.nQP;
-    double area[NTRI];
-    size_t cell[NTRI];
-    bool any = false;
+    double area[CAP];
+    size_t cell[CAP];
+    int nt = 0;
     if (d.maskEdge[e] == 1) {
-        for (int t = 0; t < NTRI; t++) {
-            area[t] = d.triArea[t * pe + e];
-            if (area[t] == 0.0) continue;
-            any = true;
-            cell[t] = (size_t)d.iCellTri[t * pe + e] - 1;
+        for (int t = 0; t < NTRI; t++) {            // in triangle order: the order the fluxes are summed in
+            const double a = d.triArea[t * pe + e];
+            if (a == 0.0) continue;
+            if (nt == CAP) { atomicOr(d.flags, FLAG_MANY_TRI); break; }
+            area[nt] = a;
+            cell[nt] = (size_t)d.iCellTri[t * pe + e] - 1;
             for (int q = 0; q < nQP; q++) {
-                Q[t * 12 + q][tx] = d.xq[(size_t)(t * 6 + q) * pe + e];
-                Q[t * 12 + 6 + q][tx] = d.yq[(size_t)(t * 6 + q) * pe + e];
+                Q[nt * 12 + q][tx] = d.xq[(size_t)(t * 6 + q) * pe + e];
+                Q[nt * 12 + 6 + q][tx] = d.yq[(size_t)(t * 6 + q) * pe + e];
             }
+            nt++;
         }
     }
     bool negative = false;
     for (int j = 0; j < d.nRowsPerCat; j++) {
         const int r = d.catBaseRow[j] + cat * d.catLayers[j];
         double flux = 0.0;
-        if (any) {
+        if (nt > 0) {
             const RowInfo ri = d.rows[r];
-            for (int t = 0; t < NTRI; t++) {
-                if (area[t] == 0.0) continue;
+            for (int t = 0; t < nt; t++) {
                 double cen[MAX_DEPTH], gx[MAX_DEPTH], gy[MAX_DEPTH];
                 for (int s = 0; s <= ri.depth; s++) {
                     const size_t q = (size_t)ri.chain[s] * pc + cell[t];
@@ -1413,7 +1417,8 @@ extern "C" int ir_run(ir_handle *h, int nTracers, const ir_tracer_desc *tr, cons
     }
     if (d.nE > 0) {
         IR_LAUNCH((k_triangles), ge, 128, s, d, dt);
-        IR_LAUNCH((k_fluxes), dim3(grid_for((size_t)d.nE, RB), nK), RB, s, d);
+        if (d.D == 3) IR_LAUNCH((k_fluxes<4>), dim3(grid_for((size_t)d.nE, RB), nK), RB, s, d);
+        else IR_LAUNCH((k_fluxes<6>), dim3(grid_for((size_t)d.nE, RB), nK), RB, s, d);
         h->launches += 2;
     }
     IR_LAUNCH((k_update), dim3(grid_for(nC1, RB), nK), RB, s, d, h->tracerLayers[0] == 1 ? 1 : 0);
