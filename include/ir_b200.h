@@ -132,6 +132,21 @@ int ir_run(ir_handle *h, int nTracers, const ir_tracer_desc *tracers, const doub
 int ir_fetch_diagnostics(ir_handle *h, double *xTriangle, double *yTriangle, double *triangleArea, int *iCellTriangle,
                          int *maskEdge, double *edgeFluxMass);
 
+/* Work fields of the last step for one tracer, in the host layout of the tracer itself -- (nLayers, nCategories,
+ * nCells+1), or (nLayers, nCategories, nEdges+1) for IR_FIELD_EDGE_FLUX: what the reference keeps in the
+ * tracer_reconstruction / tracer_barycenter / tracer_products / tracer_edge_fluxes pools (center2D/3D, xGrad, yGrad,
+ * xBarycenter, yBarycenter, massTracerProduct, edgeFlux; incremental_remap_tracers.F:40-110).  Debugging aid. */
+enum {
+    IR_FIELD_CENTER = 0,
+    IR_FIELD_XGRAD = 1,
+    IR_FIELD_YGRAD = 2,
+    IR_FIELD_XBARYCENTER = 3,
+    IR_FIELD_YBARYCENTER = 4,
+    IR_FIELD_MASS_TRACER_PRODUCT = 5,   /* after the update */
+    IR_FIELD_EDGE_FLUX = 6
+};
+int ir_fetch_tracer_field(ir_handle *h, int which, int tracer, double *out);
+
 /* With IR_B200_PIN_HOST=1 in the environment at ir_create, ir_run page-locks the tracer and velocity arrays the first
  * time it sees them (cudaHostRegister) so that the per-step copies run at the full PCIe rate.  Call this before the
  * host frees or reallocates such an array (e.g. mpas_pool_destroy_pool); ir_destroy does it too.  No-op otherwise. */

@@ -1495,6 +1495,37 @@ extern "C" int ir_fetch_diagnostics(ir_handle *h, double *xTriangle, double *yTr
     return IR_OK;
 }
 
+extern "C" int ir_fetch_tracer_field(ir_handle *h, int which, int tracer, double *out)
+{
+    IR_REQUIRE(h != nullptr && out != nullptr, "NULL argument");
+    if (!h->haveTracers) { set_error("ir_fetch_tracer_field before ir_set_tracers"); return IR_ERR_STATE; }
+    IR_REQUIRE(tracer >= 0 && tracer < (int)h->tracerRow0.size(), "tracer index out of range");
+    IR_CUDA(cudaSetDevice(h->device));
+    Dev &d = h->d;
+    const double *src = nullptr;
+    bool onEdges = false;
+    switch (which) {
+        case IR_FIELD_CENTER: src = d.center; break;
+        case IR_FIELD_XGRAD: src = d.xGrad; break;
+        case IR_FIELD_YGRAD: src = d.yGrad; break;
+        case IR_FIELD_XBARYCENTER: src = d.xBary; break;
+        case IR_FIELD_YBARYCENTER: src = d.yBary; break;
+        case IR_FIELD_MASS_TRACER_PRODUCT: src = d.mtpNew; break;
+        case IR_FIELD_EDGE_FLUX: src = d.edgeFlux; onEdges = true; break;
+        default: IR_REQUIRE(false, "unknown field");
+    }
+    const int w = d.nK * h->tracerLayers[tracer];
+    const size_t n = onEdges ? (size_t)d.nE + 1 : (size_t)d.nC + 1, pitch = onEdges ? d.nEp : d.nCp;
+    int rc = ensure_stage(h, n * w * sizeof(double));
+    if (rc) return rc;
+    IR_LAUNCH((k_tracer_out), grid_for(n, 256), 256, h->stream, d.stage, src + (size_t)h->tracerRow0[tracer] * pitch, n, w, pitch);
+    h->launches++;
+    IR_CUDA(cudaGetLastError());
+    IR_CUDA(cudaMemcpyAsync(out, d.stage, n * w * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    IR_CUDA(cudaStreamSynchronize(h->stream));
+    return IR_OK;
+}
+
 extern "C" int ir_last_run_ms(ir_handle *h, float *ms)
 {
     IR_REQUIRE(h != nullptr && ms != nullptr, "NULL argument");

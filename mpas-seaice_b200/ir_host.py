@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("IR_B200_LIB", os.path.join(_HERE, "csrc", "libir_b200.so"))
 
-EXPORTS = ("ir_init_geometry", "ir_create", "ir_set_tracers", "ir_run", "ir_fetch_diagnostics", "ir_release_host_memory", "ir_last_run_ms", "ir_launch_count",
+EXPORTS = ("ir_init_geometry", "ir_create", "ir_set_tracers", "ir_run", "ir_fetch_diagnostics", "ir_fetch_tracer_field", "ir_release_host_memory", "ir_last_run_ms", "ir_launch_count",
            "ir_destroy", "ir_last_error_string")
 GEOM_NAMES = ("x", "y", "xx", "xy", "yy", "xxx", "xxy", "xyy", "yyy", "xxxx", "xxxy", "xxyy", "xyyy", "yyyy")
 
@@ -186,6 +186,16 @@ class IrTransport:
         self._check(self._L.ir_fetch_diagnostics(self._h, *[C.c_void_p(out[k].ctypes.data) for k in
                                                             ("xTriangle", "yTriangle", "triangleArea", "iCellTriangle",
                                                              "maskEdge", "edgeFluxMass")]))
+        return out
+
+    FIELDS = dict(center=0, xGrad=1, yGrad=2, xBarycenter=3, yBarycenter=4, massTracerProduct=5, edgeFlux=6)
+
+    def tracer_field(self, which, tracer_index, n_layers):
+        """A work field of the last step (see ir_fetch_tracer_field): (nCells+1 | nEdges+1, nCategories, nLayers)."""
+        n = (self.mesh.nEdges if which == "edgeFlux" else self.mesh.nCells) + 1
+        out = np.zeros((n, self.n_categories, n_layers))
+        self._check(self._L.ir_fetch_tracer_field(self._h, C.c_int(self.FIELDS[which]), C.c_int(tracer_index),
+                                                  C.c_void_p(out.ctypes.data)))
         return out
 
     def release_host_memory(self):

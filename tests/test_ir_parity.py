@@ -268,6 +268,33 @@ def test_emulated_kernels_are_clean_under_address_sanitizer(tmp_path):
     assert r.stdout.count("ok") == 6
 
 
+def test_work_fields_match_oracle(lib_path):
+    """ir_fetch_tracer_field: the limited gradients of a child tracer and the mass fluxes, against the oracle's."""
+    mesh, irf, geom = case("ico3")
+    rng = np.random.default_rng(5)
+    tracers = _random_state(mesh, rng, n_cat=2, n_ice=2, n_snow=0)
+    u, v = smooth_divergent_velocity(mesh, geom)
+    ref, dev = clone(tracers), clone(tracers)
+    d_ref = ir.run(mesh, irf, geom, ref, u, v, 3600.0, diagnostics=True, grad_tracer=4)
+    solver = ir_host.IrTransport(mesh, irf, geom, 2, lib_path=lib_path)
+    try:
+        solver.set_tracers(dev)
+        solver.run(dev, u, v, 3600.0)
+        nC = mesh.nCells
+        assert np.array_equal(solver.tracer_field("xGrad", 4, 2)[:nC], d_ref["xGrad"][:nC])
+        assert np.array_equal(solver.tracer_field("yGrad", 4, 2)[:nC], d_ref["yGrad"][:nC])
+        assert np.array_equal(solver.tracer_field("edgeFlux", 0, 1)[:mesh.nEdges], d_ref["edgeFluxMass"])
+        cen = solver.tracer_field("center", 0, 1)
+        xg, yg = solver.tracer_field("xGrad", 0, 1), solver.tracer_field("yGrad", 0, 1)
+        a = tracers[0].array
+        want = a[:nC, :, 0] - xg[:nC, :, 0] * geom["geomAvg"]["x"][:nC, None] - yg[:nC, :, 0] * geom["geomAvg"]["y"][:nC, None]
+        assert np.array_equal(cen[:nC, :, 0], want)
+        with pytest.raises(ir_host.IrError):
+            solver.tracer_field("center", 9, 1)
+    finally:
+        solver.destroy()
+
+
 def test_rotation_test_case_matches_oracle(lib_path):
     """The reference's advection test case (cosine bell, u = U cos(lat); create_ics.py:36-107) on the 2562-cell
     sphere with its twelve pentagons: ten steps, identical throughout."""
