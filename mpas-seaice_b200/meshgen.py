@@ -469,6 +469,84 @@ def icosphere(level: int, radius: float = EARTH_RADIUS) -> Mesh:
     return m
 
 
+def latlon_band(nlon: int, nlat: int, lat_max_deg: float = 60.0, radius: float = EARTH_RADIUS) -> Mesh:
+    """A quadrilateral mesh on the sphere: nlon x nlat cells between -lat_max and +lat_max, periodic in longitude,
+    every interior vertex of degree 4 -- the kind of mesh the reference's "spherical quad" notes refer to
+    (src/shared/mpas_seaice_advection_incremental_remap.F:105-119), here without poles.  Only the fields the
+    transport scheme reads (connectivity, coordinates, areaCell, dcEdge, dvEdge)."""
+    dlon, lat0 = 2.0 * np.pi / nlon, -np.deg2rad(lat_max_deg)
+    dlat = -2.0 * lat0 / nlat
+    nC, nV = nlon * nlat, nlon * (nlat + 1)
+    nH = nlon * (nlat + 1)                      # edges along parallels: h(i, j) joins v(i, j) and v(i+1, j)
+    nE = nH + nlon * nlat                       # edges along meridians: w(i, j) joins v(i, j) and v(i, j+1)
+    ii, jj = np.meshgrid(np.arange(nlon), np.arange(nlat), indexing="xy")
+    ii, jj = ii.ravel(), jj.ravel()             # cell c = j * nlon + i
+    ip = (ii + 1) % nlon
+    im = (ii - 1) % nlon
+
+    def vid(i, j):
+        return j * nlon + i
+
+    def unit(lon, lat):
+        return np.stack([np.cos(lat) * np.cos(lon), np.cos(lat) * np.sin(lon), np.sin(lat)], axis=-1)
+
+    def arc(a, b):
+        return radius * np.arctan2(np.linalg.norm(np.cross(a, b), axis=-1), np.sum(a * b, axis=-1))
+    voc = np.stack([vid(ii, jj), vid(ip, jj), vid(ip, jj + 1), vid(ii, jj + 1)], axis=1)            # counter-clockwise
+    eoc = np.stack([jj * nlon + ii, nH + jj * nlon + ip, (jj + 1) * nlon + ii, nH + jj * nlon + ii], axis=1)
+    south = np.where(jj > 0, (jj - 1) * nlon + ii, -1)
+    north = np.where(jj < nlat - 1, (jj + 1) * nlon + ii, -1)
+    coc = np.stack([south, jj * nlon + ip, north, jj * nlon + im], axis=1)
+    vi, vj = np.meshgrid(np.arange(nlon), np.arange(nlat + 1), indexing="xy")
+    vi, vj = vi.ravel(), vj.ravel()
+    vim = (vi - 1) % nlon
+    below, above = vj > 0, vj < nlat
+    cov = np.stack([np.where(below, (vj - 1) * nlon + vim, -1), np.where(below, (vj - 1) * nlon + vi, -1),
+                    np.where(above, vj * nlon + vi, -1), np.where(above, vj * nlon + vim, -1)], axis=1)
+    # cells of every edge: parallels have (south, north), meridians (west, east)
+    hi, hj = vi, vj
+    coe_h = np.stack([np.where(hj > 0, (hj - 1) * nlon + hi, -1), np.where(hj < nlat, hj * nlon + hi, -1)], axis=1)
+    coe_w = np.stack([jj * nlon + im, jj * nlon + ii], axis=1)
+    coe = np.concatenate([coe_h, coe_w])
+    lon_v, lat_v = vi * dlon, lat0 + vj * dlat
+    lon_c, lat_c = (ii + 0.5) * dlon, lat0 + (jj + 0.5) * dlat
+    pv, pc = unit(lon_v, lat_v), unit(lon_c, lat_c)
+    area = radius * radius * dlon * (np.sin(lat0 + (jj + 1) * dlat) - np.sin(lat0 + jj * dlat))
+    ev = np.concatenate([np.stack([vid(hi, hj), vid((hi + 1) % nlon, hj)], axis=1), np.stack([vid(ii, jj), vid(ii, jj + 1)], axis=1)])
+    dv = arc(pv[ev[:, 0]], pv[ev[:, 1]])
+    mid = pv[ev[:, 0]] + pv[ev[:, 1]]
+    mid /= np.linalg.norm(mid, axis=1)[:, None]
+    both = (coe[:, 0] >= 0) & (coe[:, 1] >= 0)
+    one = np.where(coe[:, 0] >= 0, coe[:, 0], coe[:, 1])
+    dc = np.where(both, arc(pc[np.maximum(coe[:, 0], 0)], pc[np.maximum(coe[:, 1], 0)]), 2.0 * arc(pc[one], mid))
+
+    m = Mesh()
+    m.on_a_sphere, m.sphere_radius, m.kind = True, radius, "latlon_band"
+    m.nCells, m.nVertices, m.nEdges, m.maxEdges, m.vertexDegree = nC, nV, nE, 4, 4
+
+    def pad1(a, junk, dtype):
+        out = np.empty(a.shape[0] + 1, dtype=dtype)
+        out[:-1] = a
+        out[-1] = junk
+        return out
+
+    def pad_idx(a, n_target):
+        out = np.empty((a.shape[0] + 1, a.shape[1]), dtype=np.int32)
+        out[:-1] = np.where(a >= 0, a + 1, n_target + 1)
+        out[-1] = n_target + 1
+        return out
+    m.nEdgesOnCell = pad1(np.full(nC, 4), 0, np.int32)
+    m.verticesOnCell, m.edgesOnCell, m.cellsOnCell = pad_idx(voc, nV), pad_idx(eoc, nE), pad_idx(coc, nC)
+    m.cellsOnVertex, m.cellsOnEdge = pad_idx(cov, nC), pad_idx(coe, nC)
+    m.xCell, m.yCell, m.zCell = (pad1(radius * pc[:, k], 0.0, np.float64) for k in range(3))
+    m.xVertex, m.yVertex, m.zVertex = (pad1(radius * pv[:, k], 0.0, np.float64) for k in range(3))
+    m.latCell, m.lonCell = pad1(lat_c, 0.0, np.float64), pad1(lon_c, 0.0, np.float64)
+    m.latVertex, m.lonVertex = pad1(lat_v, 0.0, np.float64), pad1(lon_v, 0.0, np.float64)
+    m.areaCell = pad1(area, JUNK_AREA, np.float64)
+    m.dvEdge, m.dcEdge = pad1(dv, 0.0, np.float64), pad1(dc, 0.0, np.float64)
+    return m
+
+
 def check_mesh(m: Mesh) -> None:
     """Structural invariants every generator must satisfy (used by tests)."""
     nC, nV, M, D = m.nCells, m.nVertices, m.maxEdges, m.vertexDegree

@@ -14,7 +14,7 @@ from oracle import ir
 from mpas_seaice_b200 import ir_host, partition
 from test_oracle_ir import case, smooth_divergent_velocity, _random_state, uniform_velocity
 lib = sys.argv[1]
-for kind in ("hex16", "quad16", "ico3"):
+for kind in ("hex16", "quad16", "ico3", "band48"):
     mesh, irf, _ = case(kind)
     geom = ir_host.init_geometry(mesh, irf, lib_path=lib)
     rng = np.random.default_rng(21)

@@ -110,7 +110,7 @@ def assert_identical(mesh, ref, dev, d_ref, d_dev):
         assert np.array_equal(d_ref[key], d_dev[key]), key
 
 
-@pytest.mark.parametrize("kind", ["hex16", "quad16", "ico3"])
+@pytest.mark.parametrize("kind", ["hex16", "quad16", "ico3", "band48"])
 def test_full_hierarchy_matches_oracle(kind, lib_path):
     """area -> {volume -> {enthalpy, salinity (layers)}, snow volume -> snow enthalpy, surface temperature}, three
     categories, divergent flow, ice-free cells: three steps, every tracer and every departure triangle identical."""
@@ -265,7 +265,7 @@ def test_emulated_kernels_are_clean_under_address_sanitizer(tmp_path):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_ir_asan_worker.py"), lib], env=env, capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0 and "AddressSanitizer" not in r.stderr, r.stderr[-3000:]
-    assert r.stdout.count("ok") == 6
+    assert r.stdout.count("ok") == 7
 
 
 def test_work_fields_match_oracle(lib_path):
@@ -313,7 +313,8 @@ def test_rotation_test_case_matches_oracle(lib_path):
     assert_identical(mesh, ref, dev, d_ref, d_dev)
 
 
-@pytest.mark.parametrize("kind,rotate", [("hex12", False), ("quad10", False), ("ico3", False), ("ico4", False), ("ico3", True)])
+@pytest.mark.parametrize("kind,rotate", [("hex12", False), ("quad10", False), ("ico3", False), ("ico4", False), ("ico3", True),
+                                         ("band48", False), ("band48", True)])
 def test_init_geometry_matches_oracle(kind, rotate, lib_path):
     """ir_init_geometry (the incremental_remap pool arrays for hosts without the Fortran init) against
     orc_ir_init_geometry: every array identical, on planar hexes and quads (with their boundary stencils), on the

@@ -30,6 +30,9 @@ def case(kind):
         elif kind.startswith("quad"):
             n = int(kind[4:])
             mesh = meshgen.planar_quad(n, n, 1000.0)
+        elif kind.startswith("band"):        # quadrilaterals on the sphere: the vertexDegree = 4 branches with frames
+            n = int(kind[4:])
+            mesh = meshgen.latlon_band(n, (5 * n) // 12, 60.0)
         else:
             mesh = meshgen.icosphere(int(kind[3:]))
         irf = irmesh.ir_fields(mesh)
@@ -100,7 +103,7 @@ def test_geometry_moments_of_regular_polygons():
     assert np.allclose(g["xxyy"][:mesh.nCells][inner], 1000.0 ** 4 / 144.0, rtol=1e-11)
 
 
-@pytest.mark.parametrize("kind", ["hex12", "quad10", "ico3"])
+@pytest.mark.parametrize("kind", ["hex12", "quad10", "ico3", "band48"])
 def test_geometry_stencils(kind):
     """remapEdge = edges with a cell on both sides; C3/C4 (and C5/C6) share exactly one vertex with the edge; the side
     vertices V3.. are the far ends of the side edges (get_geometry_incremental_remap, incremental_remap.F:1105)."""
@@ -255,7 +258,7 @@ def _products(mesh, tr):
     return out
 
 
-@pytest.mark.parametrize("kind", ["hex16", "quad16", "ico3"])
+@pytest.mark.parametrize("kind", ["hex16", "quad16", "ico3", "band48"])
 def test_conservation_of_mass_and_tracer_products(kind):
     """update_mass_and_tracers (:7125) moves edgeFlux out of one cell and into the other: area, volume, area*Tsfc,
     volume*enthalpy ... are conserved to rounding under an arbitrary (divergent) velocity field."""
@@ -273,7 +276,7 @@ def test_conservation_of_mass_and_tracer_products(kind):
         assert np.abs(after[name] - before[name]).max() <= 2e-13 * scale, name
 
 
-@pytest.mark.parametrize("kind", ["hex16", "ico3"])
+@pytest.mark.parametrize("kind", ["hex16", "ico3", "band48"])
 def test_uniform_tracers_stay_uniform_under_divergent_flow(kind):
     """Tracer consistency: with thickness / temperature / enthalpy uniform, mass*tracer fluxes are the mass fluxes
     times a constant, so the new tracer values are that constant -- however the area field changes."""
