@@ -80,6 +80,8 @@ struct RowInfo {
     int hasChild;
     int cat;               // category of the row
     int volumeLike;
+    int slot;              // row in the arrays kept for parents only (xBary, yBary, mtpNew), -1 for a childless row
+    int parentSlot;        // the parent's slot, -1 for the mass-like field
 };
 
 struct Dev {
@@ -121,6 +123,7 @@ struct ir_handle {
     std::vector<void *> allocs;
     std::vector<std::pair<const void *, size_t>> pinned;   // host ranges registered under IR_B200_PIN_HOST
     bool pinHost;
+    int nSlots;           // rows of the parent-only arrays
     float lastMs;
     long long launches;
     bool haveTracers;
@@ -316,7 +319,7 @@ __global__ void __launch_bounds__(RB) k_reconstruct(Dev d)
         const double f0 = field[c];
         const int pr = ri.depth > 0 ? ri.chain[ri.depth - 1] : -1;
         double xB, yB;   // barycentre of the parent: where this row's value sits
-        if (pr >= 0) { xB = d.xBary[(size_t)pr * p + c]; yB = d.yBary[(size_t)pr * p + c]; }
+        if (pr >= 0) { xB = d.xBary[(size_t)ri.parentSlot * p + c]; yB = d.yBary[(size_t)ri.parentSlot * p + c]; }
         else { xB = xAvg; yB = yAvg; }
         double xg = 0.0, yg = 0.0;
         if (ice) {
@@ -377,8 +380,8 @@ __global__ void __launch_bounds__(RB) k_reconstruct(Dev d)
                 mean[nn - 1] = f0; ce[nn - 1] = cen; gx[nn - 1] = xg; gy[nn - 1] = yg;
                 barycenter(d, c, nn, mean, ce, gx, gy, bx, by);
             }
-            d.xBary[(size_t)r * p + c] = bx;
-            d.yBary[(size_t)r * p + c] = by;
+            d.xBary[(size_t)ri.slot * p + c] = bx;
+            d.yBary[(size_t)ri.slot * p + c] = by;
         }
     }
 }
@@ -701,10 +704,10 @@ __global__ void __launch_bounds__(RB) k_update(Dev d, int massOneLayer)
             fluxFromCell = fluxFromCell + d.edgeFlux[(size_t)r * pe + (edge[k] - 1)] * (double)sign[k];
         double mtpOld = 1.0;
         for (int s = 0; s <= ri.depth; s++) mtpOld = mtpOld * d.val[(size_t)ri.chain[s] * pc + c];
-        const double pm = ri.depth > 0 ? d.mtpNew[(size_t)ri.chain[ri.depth - 1] * pc + c] : 1.0;
+        const double pm = ri.depth > 0 ? d.mtpNew[(size_t)ri.parentSlot * pc + c] : 1.0;
         double v = 0.0;
         if (pm > 0.0) v = (mtpOld - (fluxFromCell / area)) / pm;
-        d.mtpNew[(size_t)r * pc + c] = pm * v;
+        if (ri.slot >= 0) d.mtpNew[(size_t)ri.slot * pc + c] = pm * v;   // only children read it
         if (ri.depth == 0) {
             constexpr double puny2 = 1.0e-11 * 1.0e-11;   // seaicePuny**2
             if (v < -puny2) atomicOr(d.flags, FLAG_NEG_MASS);
@@ -1345,6 +1348,11 @@ extern "C" int ir_set_tracers(ir_handle *h, int nTracers, const ir_tracer_desc *
                 for (int z = depth[t] + 1; z < MAX_DEPTH; z++) ri.chain[z] = 0;
             }
     }
+    // barycentres and new mass * tracer products are kept for rows that have children only
+    int nSlots = 0;
+    for (int r = 0; r < nRows; r++) h->rows[r].slot = h->rows[r].hasChild ? nSlots++ : -1;
+    for (int r = 0; r < nRows; r++) h->rows[r].parentSlot = h->rows[r].depth > 0 ? h->rows[h->rows[r].chain[h->rows[r].depth - 1]].slot : -1;
+    h->nSlots = nSlots;
     // (re)allocate the tracer state
     IR_CUDA(cudaStreamSynchronize(h->stream));
     double **bufs[] = {&d.val, &d.valNew, &d.center, &d.xGrad, &d.yGrad, &d.xBary, &d.yBary, &d.mtpNew, &d.edgeFlux};
@@ -1367,8 +1375,10 @@ extern "C" int ir_set_tracers(ir_handle *h, int nTracers, const ir_tracer_desc *
     IR_CUDA(cudaMemcpyAsync(d.catLayers, layers.data(), sizeof(int) * layers.size(), cudaMemcpyHostToDevice, h->stream));
     IR_CUDA(cudaStreamSynchronize(h->stream));     // baseRow / layers go out of scope
     const size_t cellBytes = sizeof(double) * (size_t)nRows * d.nCp, edgeBytes = sizeof(double) * (size_t)nRows * d.nEp;
+    const size_t slotBytes = sizeof(double) * (size_t)(nSlots > 0 ? nSlots : 1) * d.nCp;
     for (double **b : bufs) {
-        const size_t bytes = (b == &d.edgeFlux) ? edgeBytes : cellBytes;
+        const bool parentOnly = (b == &d.xBary || b == &d.yBary || b == &d.mtpNew);
+        const size_t bytes = (b == &d.edgeFlux) ? edgeBytes : (parentOnly ? slotBytes : cellBytes);
         IR_CUDA(cudaMalloc((void **)b, bytes));
         IR_CUDA(cudaMemsetAsync(*b, 0, bytes, h->stream));
     }
@@ -1516,9 +1526,14 @@ extern "C" int ir_fetch_tracer_field(ir_handle *h, int which, int tracer, double
     }
     const int w = d.nK * h->tracerLayers[tracer];
     const size_t n = onEdges ? (size_t)d.nE + 1 : (size_t)d.nC + 1, pitch = onEdges ? d.nEp : d.nCp;
+    size_t firstRow = (size_t)h->tracerRow0[tracer];
+    if (which == IR_FIELD_XBARYCENTER || which == IR_FIELD_YBARYCENTER || which == IR_FIELD_MASS_TRACER_PRODUCT) {
+        IR_REQUIRE(h->rows[firstRow].slot >= 0, "barycentres and products are kept for tracers that have children only");
+        firstRow = (size_t)h->rows[firstRow].slot;     // the rows of one tracer have consecutive slots
+    }
     int rc = ensure_stage(h, n * w * sizeof(double));
     if (rc) return rc;
-    IR_LAUNCH((k_tracer_out), grid_for(n, 256), 256, h->stream, d.stage, src + (size_t)h->tracerRow0[tracer] * pitch, n, w, pitch);
+    IR_LAUNCH((k_tracer_out), grid_for(n, 256), 256, h->stream, d.stage, src + firstRow * pitch, n, w, pitch);
     h->launches++;
     IR_CUDA(cudaGetLastError());
     IR_CUDA(cudaMemcpyAsync(out, d.stage, n * w * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

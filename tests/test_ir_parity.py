@@ -289,8 +289,17 @@ def test_work_fields_match_oracle(lib_path):
         a = tracers[0].array
         want = a[:nC, :, 0] - xg[:nC, :, 0] * geom["geomAvg"]["x"][:nC, None] - yg[:nC, :, 0] * geom["geomAvg"]["y"][:nC, None]
         assert np.array_equal(cen[:nC, :, 0], want)
+        # the centre of mass of the reconstructed area field (compute_barycenter_coordinates, one-field branch :4700)
+        g = geom["geomAvg"]
+        ice = (tracers[0].array[:nC, :, 0].sum(axis=1) > 0)[:, None] & (a[:nC, :, 0] > 0)
+        xb = solver.tracer_field("xBarycenter", 0, 1)[:nC, :, 0]
+        want = (cen[:nC, :, 0] * g["x"][:nC, None] + xg[:nC, :, 0] * g["xx"][:nC, None] + yg[:nC, :, 0] * g["xy"][:nC, None]) \
+            / np.where(ice, a[:nC, :, 0], 1.0)
+        assert np.allclose(xb[ice], want[ice], rtol=1e-14, atol=0)
         with pytest.raises(ir_host.IrError):
             solver.tracer_field("center", 9, 1)
+        with pytest.raises(ir_host.IrError, match="children"):
+            solver.tracer_field("xBarycenter", 3, 1)         # surfaceTemperature has no children
     finally:
         solver.destroy()
 
