@@ -645,6 +645,12 @@ __global__ void __launch_bounds__(RB) k_fluxes(Dev d)
             }
             nt++;
         }
+        // Triangles whose source cells hold no ice in any category carry nothing: there the mass reconstruction is
+        // identically zero (value 0, gradients 0: k_reconstruct's fast path), so every product down the chain is a
+        // zero and the flux is the +0.0 written below.  Most of an ocean mesh is ice-free.
+        bool ice = false;
+        for (int t = 0; t < nt; t++) ice = ice || d.maskCell[cell[t]] == 1;
+        if (!ice) nt = 0;
     }
     bool negative = false;
     for (int j = 0; j < d.nRowsPerCat; j++) {
