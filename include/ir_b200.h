@@ -8,8 +8,8 @@
  * model: it fills the `incremental_remap` pool (Registry.xml var_struct incremental_remap) once, and those pool arrays
  * are what ir_create receives -- the same contract evp_b200.h has with the velocity solver's pools.
  *
- * STATUS (round 1): built and exported; parity against oracle/ir_oracle.c is tested by the `cuda` leg of tests/test_ir_parity.py, which
- * has not yet run on a device (the round's GPU minutes were spent before this was written).  Single block: the
+ * STATUS (round 1): bit-identical to oracle/ir_oracle.c under host emulation (tests/test_ir_parity.py) and in a first
+ * run on a B200 (tools/ir_quick_gpu.py, profiles/ir_r01_first_device_run.json); not yet profiled.  Single block: the
  * tracer halo update after the call (seaice_update_tracer_halo, :2710) is still the host's.
  *
  * Conventions as in evp_b200.h: host pointers, Fortran (column-major) layout passed with c_loc(), 1-based index
