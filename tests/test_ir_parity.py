@@ -57,7 +57,7 @@ def lib_path(request):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="written after this round's GPU minutes were spent: not yet run on a device")
+@pytest.mark.xfail(strict=False, reason="not yet run as a pytest session on a device (first contact with a B200: tools/ir_quick_gpu.py, all identical)")
 def test_cuda_leg_in_a_child_process():
     """Every `cuda` case of this file and of test_ir_blocks.py, in a process of its own with a time limit."""
     import sys
