@@ -1,0 +1,1609 @@
+// ir_kernels.cu -- incremental-remapping transport on B200 (sm_100a): kernels and the C ABI of include/ir_b200.h.
+//
+// What one ir_run does (reference: incremental_remap_block, src/shared/mpas_seaice_advection_incremental_remap.F:2740):
+//   k_prepare      per cell: ice mask, volume -> thickness                               (:2462-2480, make_masks :3404)
+//   k_reconstruct  per (cell, category): gradient, limiter, centre value, barycentre    (:3580-5250)
+//   k_triangles    per edge: departure triangles and their quadrature points            (:5255-6665)
+//   k_fluxes       per (edge, category): integrate mass * tracer over the triangles     (:6667-6980)
+//   k_update       per (cell, category): new mass and tracers, zap, thickness -> volume (:6982-7540, :8764-8895, :2680-2700)
+// Five launches per step whatever the number of tracers.
+//
+// EXPERIMENTAL VARIANT of ../ir_kernels.cu (same ABI, same arithmetic, same results; built as
+// libir_b200_cellmajor.so and selected with IR_B200_LIB, to be measured against the shipped layout -- DESIGN.md 10.4a).
+//
+// Layout: categories never mix, and a thread of the tracer kernels walks ALL rows (tracer, layer) of one category for one
+// cell -- or, in the flux kernel, for one SOURCE cell it gathers from.  So the tracer state is category-major and
+// cell-minor with the rows of a category innermost:
+//     V, VN   [category][cell][JP]            values, new values            (JP = rows per category padded to 4)
+//     R       [category][cell][JP][3]         centre, xGrad, yGrad packed
+//     B, MT   [category][cell][SP][2], [SP]   barycentres, new mass * tracer products of the rows that have children
+//     EF      [category][edge][JP]            edge fluxes
+// Every (category, cell) block starts on a 32-byte sector and is consumed completely by the thread that touches it:
+// a gather of a source cell's reconstruction reads 18 sectors for 23 rows instead of 69.  The per-cell / per-edge
+// geometry arrays stay [slot][nCp] (coalesced over cells).  The hierarchy is the same in every category, so the row
+// tables are per row-in-category.
+//
+// All of it is gather-heavy FP64 streaming work bounded by HBM / L2, not tensor work.  Built with --fmad=false and in
+// the reference's operation order so that the results are bit-identical to oracle/ir_oracle.c (tests/test_gpu_ir.py).
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <utility>
+#include <vector>
+
+#include "../../../include/ir_b200.h"
+
+// Kernel launches go through one macro so that tests/emu can compile this file for the host and step through the
+// kernels thread by thread (tests/test_ir_parity.py, "emulation" leg: a check of the kernel logic where no GPU is
+// available; it is test infrastructure and never part of the shipped library).
+#ifndef IR_LAUNCH
+#define IR_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#endif
+
+namespace {
+
+constexpr double EPS11 = 1.0e-11;
+constexpr double W1QP = 1.09951743655321885e-01, W2QP = 2.23381589678011389e-01;
+constexpr double Q1QP = 9.15762135097710761e-02, Q2QP = 8.16847572980458514e-01;
+constexpr double Q3QP = 1.08103018168070275e-01, Q4QP = 4.45948490915965612e-01;
+constexpr int NTRI = IR_N_TRI_PER_EDGE, NCER = 6, NEER = 6, NVER = 8;
+constexpr int MAXM = 8;        // maxEdges supported
+constexpr int MAX_DEPTH = 4;   // mass + three parents (incremental_remap.F:6745)
+
+enum { FLAG_NEG_QP = 1, FLAG_NEG_MASS = 2, FLAG_PARALLEL = 4, FLAG_MANY_TRI = 8 };
+
+thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+#define IR_CUDA(call)                                                                        \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return IR_ERR_CUDA;                                                              \
+        }                                                                                    \
+    } while (0)
+#define IR_REQUIRE(cond, msg)                                  \
+    do {                                                       \
+        if (!(cond)) {                                         \
+            set_error("%s:%d: %s", __FILE__, __LINE__, msg);   \
+            return IR_ERR_ARGUMENT;                            \
+        }                                                      \
+    } while (0)
+
+struct RowInfo {         // one per row-in-category j
+    int chain[MAX_DEPTH];  // j of the mass field .. this row (mass first); chain[depth] == this j
+    int depth;             // number of parents
+    int hasChild;
+    int cat;               // category of the row
+    int volumeLike;
+    int slot;              // row in the arrays kept for parents only (xBary, yBary, mtpNew), -1 for a childless row
+    int parentSlot;        // the parent's slot, -1 for the mass-like field
+};
+
+struct Dev {
+    // sizes
+    int nC, nCS, nV, nE, M, D, nK, nQP, sphere, rotate;
+    size_t nCp, nEp, nVp;
+    // mesh / geometry, [slot][pitch]
+    int *nEdgesOnCell, *edgesOnCell, *cellsOnCell, *verticesOnCell, *cellsOnEdge, *verticesOnEdge;
+    int *remapEdge, *coer, *eoer;
+    double *areaCell, *sdc /* signed dcEdge per (slot, cell) */, *coef /* [3*M] */, *trans /* rows 1,2 of transGlobalToCell: [6] */;
+    double *xvc, *yvc, *xve, *yve, *geom /* [14] */;
+    int *fluxSign;   // [M][nCp]: +1 if the cell is cellsOnEdge(1) of its k-th edge, else -1
+    // per step
+    double *u, *v;
+    int *maskCell, *maskEdge, *iCellTri /* [NTRI][nEp] */;
+    double *xq, *yq /* [NTRI*6][nEp] */, *triArea /* [NTRI][nEp] */;
+    // tracer state (layouts in the file header)
+    int nRows, nRowsPerCat, JP, SP;
+    RowInfo *rows;                 // [nRowsPerCat]
+    double *val, *valNew, *recon, *bary, *mtpNew;
+    double *edgeFlux;
+    int *flags;
+    double *stage;      // raw host-layout staging
+    size_t stageBytes;
+};
+
+}  // namespace
+
+struct ir_handle {
+    int device;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    Dev d;
+    std::vector<RowInfo> rows;
+    std::vector<int> tracerRow0, tracerLayers, tracerParent, tracerVolume, tracerDepth;
+    std::vector<int> depthRow0;   // rows of depth q are [depthRow0[q], depthRow0[q+1])  (rows sorted by depth)
+    std::vector<int> rowOrder;    // device row -> (tracer, k, l) linear index on the host side
+    std::vector<void *> allocs;
+    std::vector<std::pair<const void *, size_t>> pinned;   // host ranges registered under IR_B200_PIN_HOST
+    bool pinHost;
+    int nSlots;           // rows of the parent-only arrays
+    float lastMs;
+    long long launches;
+    bool haveTracers;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ small device helpers
+
+__device__ __forceinline__ double cross2(double ax, double ay, double bx, double by) { return ax * by - ay * bx; }
+
+// point_in_half_plane as the reference executes it (its dummy arguments are (point, lineStart, lineEnd) while every
+// caller passes (V1, V2, P)): cross product of (P - V2) and (V1 - V2), incremental_remap.F:9200-9235
+__device__ __forceinline__ bool in_half_plane(double v1x, double v1y, double v2x, double v2y, double px, double py)
+{
+    return cross2(px - v2x, py - v2y, v1x - v2x, v1y - v2y) >= 0.0;
+}
+
+__device__ __forceinline__ double tri_area(double x1, double y1, double x2, double y2, double x3, double y3)
+{
+    return fabs(0.5 * ((x2 - x1) * (y3 - y1) - (y2 - y1) * (x3 - x1)));
+}
+
+// find_line_intersection, incremental_remap.F:8934
+__device__ bool line_intersection(double x1, double y1, double x2, double y2, double x3, double y3, double x4, double y4,
+                                  double &ipx, double &ipy)
+{
+    const double rx = x2 - x1, ry = y2 - y1, sx = x4 - x3, sy = y4 - y3;
+    const double rsCross = rx * sy - ry * sx;
+    const double rsCrossMin = EPS11 * sqrt((rx * rx + ry * ry) * (sx * sx + sy * sy));
+    if (fabs(rsCross) > rsCrossMin) {
+        const double t1 = (sy * (x3 - x1) - sx * (y3 - y1)) / rsCross;
+        const double t2 = (ry * (x3 - x1) - rx * (y3 - y1)) / rsCross;
+        ipx = x1 + t1 * rx;
+        ipy = y1 + t1 * ry;
+        return t1 > 0.0 && t1 < 1.0 && t2 > 0.0 && t2 < 1.0;
+    }
+    ipx = DBL_MAX;
+    ipy = DBL_MAX;
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------------------- layout kernels
+
+// host (n, w) row-major -> device [w][pitch]
+template <typename T>
+__global__ void k_rows_in(const T *__restrict__ raw, T *__restrict__ dst, size_t n, int w, size_t pitch)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int j = 0; j < w; j++) dst[(size_t)j * pitch + i] = raw[i * w + j];
+}
+
+// tracer: host (n, nK, nL) <-> dev[k][i][j0 + l * stride .. ] with `inner` doubles per (category, entity) block
+__global__ void k_tracer_in(const double *__restrict__ raw, double *__restrict__ dev, size_t n, int nK, int nL, int j0,
+                            size_t pitch, int inner)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int k = 0; k < nK; k++)
+        for (int l = 0; l < nL; l++) dev[((size_t)k * pitch + i) * inner + j0 + l] = raw[(i * nK + k) * nL + l];
+}
+
+__global__ void k_tracer_out(double *__restrict__ raw, const double *__restrict__ dev, size_t n, int nK, int nL, int j0,
+                             size_t pitch, int inner, int stride, int offset)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int k = 0; k < nK; k++)
+        for (int l = 0; l < nL; l++)
+            raw[(i * nK + k) * nL + l] = dev[((size_t)k * pitch + i) * inner + (size_t)(j0 + l) * stride + offset];
+}
+
+// per (slot, cell): signed dcEdge and the flux sign (compute_gradient :4330-4340, update_mass_and_tracers :7260-7270)
+__global__ void k_cell_edge_signs(Dev d, const double *__restrict__ dcEdge)
+{
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= (size_t)d.nC) return;
+    for (int k = 0; k < d.M; k++) {
+        const int e = d.edgesOnCell[k * d.nCp + c];
+        double s = 1.0;
+        int fs = 1;
+        if (k < d.nEdgesOnCell[c] && e >= 1 && e <= d.nE) {
+            const bool first = ((int)c + 1 == d.cellsOnEdge[2 * ((size_t)e - 1)]);   // cellsOnEdge(1, e), host layout
+            fs = first ? 1 : -1;
+            s = (first ? 1.0 : -1.0) * dcEdge[e - 1];
+        }
+        d.sdc[k * d.nCp + c] = s;
+        d.fluxSign[k * d.nCp + c] = fs;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------------------- step
+
+// maskCell (make_masks :3455-3470: sum over the mass field's categories and layers > 0) and volume -> thickness
+// (volume_to_thickness :9248, every column including the extra one)
+__global__ void k_prepare(Dev d, int massLayers)
+{
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > (size_t)d.nC) return;
+    const int JP = d.JP;
+    if (c < (size_t)d.nC) {
+        double massSumCell = 0.0;
+        for (int k = 0; k < d.nK; k++)
+            for (int l = 0; l < massLayers; l++) massSumCell = massSumCell + d.val[((size_t)k * d.nCp + c) * JP + l];
+        d.maskCell[c] = massSumCell > 0.0 ? 1 : 0;
+    }
+    for (int j = 0; j < d.nRowsPerCat; j++) {
+        if (!d.rows[j].volumeLike) continue;
+        for (int k = 0; k < d.nK; k++) {
+            const size_t base = ((size_t)k * d.nCp + c) * JP;
+            const double area = d.val[base];                 // mass field with one layer: j = 0
+            d.val[base + j] = (area > 0.0) ? d.val[base + j] / area : 0.0;
+        }
+    }
+}
+
+__device__ __forceinline__ bool row_mask(const Dev &d, const RowInfo &ri, int cat, size_t c)
+{
+    if (c >= (size_t)d.nC) return false;                                  // the extra slot never holds ice
+    if (ri.depth == 0) return true;                                       // make_masks :3450
+    return d.val[((size_t)cat * d.nCp + c) * d.JP + ri.chain[ri.depth - 1]] > EPS11;   // parent value, :3480-3510
+}
+
+// compute_barycenter_coordinates (:4658): centre of mass * tracer chain of `n` linear fields
+__device__ void barycenter(const Dev &d, size_t c, int n, const double *mean, const double *cen, const double *gx,
+                           const double *gy, double &xB, double &yB)
+{
+    const double *G = d.geom;
+    const size_t p = d.nCp;
+    const double ax = G[0 * p + c], ay = G[1 * p + c], axx = G[2 * p + c], axy = G[3 * p + c], ayy = G[4 * p + c];
+    if (n == 1) {
+        const double c0 = cen[0], cx = gx[0], cy = gy[0];
+        const double reciprocal = (fabs(mean[0]) > 0.0) ? 1.0 / mean[0] : 0.0;
+        xB = (c0 * ax + cx * axx + cy * axy) * reciprocal;
+        yB = (c0 * ay + cx * axy + cy * ayy) * reciprocal;
+        return;
+    }
+    const double axxx = G[5 * p + c], axxy = G[6 * p + c], axyy = G[7 * p + c], ayyy = G[8 * p + c];
+    if (n == 2) {
+        const double c0 = cen[0] * cen[1];
+        const double cx = cen[0] * gx[1] + gx[0] * cen[1];
+        const double cy = cen[0] * gy[1] + gy[0] * cen[1];
+        const double cxx = gx[0] * gx[1];
+        const double cxy = gx[0] * gy[1] + gy[0] * gx[1];
+        const double cyy = gy[0] * gy[1];
+        const double prod = mean[0] * mean[1];
+        const double reciprocal = (fabs(prod) > 0.0) ? 1.0 / prod : 0.0;
+        xB = (c0 * ax + cx * axx + cy * axy + cxx * axxx + cxy * axxy + cyy * axyy) * reciprocal;
+        yB = (c0 * ay + cx * axy + cy * ayy + cxx * axxy + cxy * axyy + cyy * ayyy) * reciprocal;
+        return;
+    }
+    const double axxxx = G[9 * p + c], axxxy = G[10 * p + c], axxyy = G[11 * p + c], axyyy = G[12 * p + c], ayyyy = G[13 * p + c];
+    const double c0 = cen[0] * cen[1] * cen[2];
+    const double cx = cen[0] * cen[1] * gx[2] + cen[0] * gx[1] * cen[2] + gx[0] * cen[1] * cen[2];
+    const double cy = cen[0] * cen[1] * gy[2] + cen[0] * gy[1] * cen[2] + gy[0] * cen[1] * cen[2];
+    const double cxx = cen[0] * gx[1] * gx[2] + gx[0] * cen[1] * gx[2] + gx[0] * gx[1] * cen[2];
+    const double cxy = cen[0] * gx[1] * gy[2] + gx[0] * gy[1] * cen[2] + gy[0] * cen[1] * gx[2] + cen[0] * gy[1] * gx[2] +
+                       gx[0] * cen[1] * gy[2] + gy[0] * gx[1] * cen[2];
+    const double cyy = cen[0] * gy[1] * gy[2] + gy[0] * cen[1] * gy[2] + gy[0] * gy[1] * cen[2];
+    const double cxxx = gx[0] * gx[1] * gx[2];
+    const double cxxy = gx[0] * gx[1] * gy[2] + gx[0] * gy[1] * gx[2] + gy[0] * gx[1] * gx[2];
+    const double cxyy = gy[0] * gy[1] * gx[2] + gy[0] * gx[1] * gy[2] + gx[0] * gy[1] * gy[2];
+    const double cyyy = gy[0] * gy[1] * gy[2];
+    const double prod = mean[0] * mean[1] * mean[2];
+    const double reciprocal = (fabs(prod) > 0.0) ? 1.0 / prod : 0.0;
+    xB = (c0 * ax + cx * axx + cy * axy + cxx * axxx + cxy * axxy + cyy * axyy + cxxx * axxxx + cxxy * axxxy + cxyy * axxyy +
+          cyyy * axyyy) * reciprocal;
+    yB = (c0 * ay + cx * axy + cy * ayy + cxx * axxy + cxy * axyy + cyy * ayyy + cxxx * axxxy + cxxy * axxyy + cxyy * axyyy +
+          cyyy * ayyyy) * reciprocal;
+}
+
+// construct_linear_tracer_fields (:3580): compute_gradient (:4204), limit_tracer_gradient (:4802), centre value
+// (:3735), barycentre (:3750-3840).  One thread per (cell, category) walks the rows of its category parents first:
+// a row needs its parents' results in the SAME cell only (neighbour cells contribute their input values), so the
+// whole hierarchy is one launch, and the cell's geometry (reconstruction coefficients, signed dcEdge, vertex
+// coordinates: 6 * maxEdges doubles) is read once per category instead of once per row.  It is parked in shared
+// memory as a per-thread scratch column (no thread reads another's, hence no barrier).
+constexpr int RB = 64;   // threads per block of the per-(cell, category) and per-(edge, category) kernels
+
+__global__ void __launch_bounds__(RB) k_reconstruct(Dev d)
+{
+    __shared__ double S[6 * MAXM][RB];
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cat = blockIdx.y, tx = threadIdx.x;
+    if (c >= (size_t)d.nC) return;
+    const size_t p = d.nCp;
+    const int M = d.M, n = d.nEdgesOnCell[c];
+    int nb[MAXM];
+    for (int k = 0; k < n; k++) {
+        nb[k] = d.cellsOnCell[k * p + c];            // 1-based, nC+1 = none
+        S[3 * k + 0][tx] = d.coef[(size_t)(3 * k + 0) * p + c];
+        S[3 * k + 1][tx] = d.coef[(size_t)(3 * k + 1) * p + c];
+        S[3 * k + 2][tx] = d.coef[(size_t)(3 * k + 2) * p + c];
+        S[3 * M + k][tx] = d.sdc[k * p + c];
+        S[4 * M + k][tx] = d.xvc[k * p + c];
+        S[5 * M + k][tx] = d.yvc[k * p + c];
+    }
+    double tr[6] = {0, 0, 0, 0, 0, 0};
+    if (d.sphere)
+        for (int q = 0; q < 6; q++) tr[q] = d.trans[q * p + c];
+    const double xAvg = d.geom[c], yAvg = d.geom[p + c];
+    const bool ice = d.maskCell[c] == 1;
+    const int JP = d.JP, SP = d.SP;
+    const size_t base = ((size_t)cat * p + c) * JP;         // this cell's block of values
+    const size_t sbase = ((size_t)cat * p + c) * SP;        // ... of parent-only slots
+    for (int j = 0; j < d.nRowsPerCat; j++) {
+        const RowInfo ri = d.rows[j];
+        const double f0 = d.val[base + j];
+        double xB, yB;   // barycentre of the parent: where this row's value sits
+        if (ri.depth > 0) { xB = d.bary[(sbase + ri.parentSlot) * 2]; yB = d.bary[(sbase + ri.parentSlot) * 2 + 1]; }
+        else { xB = xAvg; yB = yAvg; }
+        double xg = 0.0, yg = 0.0;
+        if (ice) {
+            const bool m0 = row_mask(d, ri, cat, c);
+            double g1 = 0.0, g2 = 0.0, g3 = 0.0;
+            double maxNeighbor = f0, minNeighbor = f0;
+            for (int k = 0; k < n; k++) {
+                const bool mn = row_mask(d, ri, cat, (size_t)nb[k] - 1);
+                double normalGrad = 0.0;
+                const double fn = (nb[k] >= 1 && nb[k] <= d.nC + 1) ? d.val[((size_t)cat * p + (nb[k] - 1)) * JP + j] : 0.0;
+                if (nb[k] >= 1 && nb[k] <= d.nC && m0 && mn) normalGrad = (fn - f0) / S[3 * M + k][tx];
+                g1 = g1 + S[3 * k + 0][tx] * normalGrad;
+                g2 = g2 + S[3 * k + 1][tx] * normalGrad;
+                g3 = g3 + S[3 * k + 2][tx] * normalGrad;
+                if (mn) {
+                    maxNeighbor = (maxNeighbor > fn) ? maxNeighbor : fn;
+                    minNeighbor = (minNeighbor < fn) ? minNeighbor : fn;
+                }
+            }
+            if (d.rotate && d.sphere) { const double t = g1; g1 = -g3; g3 = t; }
+            if (d.sphere) {
+                xg = tr[0] * g1 + tr[1] * g2 + tr[2] * g3;
+                yg = tr[3] * g1 + tr[4] * g2 + tr[5] * g3;
+            } else {
+                xg = g1;
+                yg = g2;
+            }
+            maxNeighbor = maxNeighbor - f0;
+            minNeighbor = minNeighbor - f0;
+            double maxLocal = 0.0, minLocal = 0.0;
+            for (int k = 0; k < n; k++) {
+                const double dev = xg * (S[4 * M + k][tx] - xB) + yg * (S[5 * M + k][tx] - yB);
+                maxLocal = (maxLocal > dev) ? maxLocal : dev;
+                minLocal = (minLocal < dev) ? minLocal : dev;
+            }
+            double f1 = 1.0, f2 = 1.0;
+            if (fabs(maxLocal) > fabs(maxNeighbor)) { f1 = maxNeighbor / maxLocal; if (!(f1 > 0.0)) f1 = 0.0; }
+            if (fabs(minLocal) > fabs(minNeighbor)) { f2 = minNeighbor / minLocal; if (!(f2 > 0.0)) f2 = 0.0; }
+            double gradFactor = (f1 < f2) ? f1 : f2;
+            gradFactor = gradFactor - EPS11;
+            if (!(gradFactor > 0.0)) gradFactor = 0.0;
+            xg = xg * gradFactor;
+            yg = yg * gradFactor;
+        }
+        const double cen = f0 - xg * xB - yg * yB;
+        d.recon[(base + j) * 3 + 0] = cen;
+        d.recon[(base + j) * 3 + 1] = xg;
+        d.recon[(base + j) * 3 + 2] = yg;
+        if (ri.hasChild) {
+            double bx = 0.0, by = 0.0;
+            if (ice) {
+                double mean[3], ce[3], gx[3], gy[3];
+                const int nn = ri.depth + 1;
+                for (int q = 0; q < nn - 1; q++) {
+                    const size_t a = base + ri.chain[q];
+                    mean[q] = d.val[a]; ce[q] = d.recon[a * 3]; gx[q] = d.recon[a * 3 + 1]; gy[q] = d.recon[a * 3 + 2];
+                }
+                mean[nn - 1] = f0; ce[nn - 1] = cen; gx[nn - 1] = xg; gy[nn - 1] = yg;
+                barycenter(d, c, nn, mean, ce, gx, gy, bx, by);
+            }
+            d.bary[(sbase + ri.slot) * 2] = bx;
+            d.bary[(sbase + ri.slot) * 2 + 1] = by;
+        }
+    }
+}
+
+// find_departure_points + find_departure_triangles + get_triangle_quadrature_points for one edge per thread.
+struct Tri {
+    double x[3], y[3];
+    double e1x, e1y, e2x, e2y;
+    int cell, vOnEdge, vOnCell, sign;
+};
+
+__device__ int vertex_on_cell(const Dev &d, int iCell, int vGlobal, int prev)
+{
+    int r = prev;
+    if (iCell < 1 || iCell > d.nC) return r;
+    const int n = d.nEdgesOnCell[iCell - 1];
+    for (int k = 0; k < n; k++)
+        if (d.verticesOnCell[k * d.nCp + (iCell - 1)] == vGlobal) r = k + 1;
+    return r;
+}
+
+__global__ void __launch_bounds__(128) k_triangles(Dev d, double dt)
+{
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)d.nE) return;
+    const size_t pe = d.nEp, pc = d.nCp;
+    for (int t = 0; t < NTRI; t++) {
+        d.triArea[t * pe + e] = 0.0;
+        d.iCellTri[t * pe + e] = 0;
+    }
+    const int v1 = d.verticesOnEdge[e], v2 = d.verticesOnEdge[pe + e];
+    // find_departure_points (:5255): departurePoint = -velocity * dt
+    double dpx[2], dpy[2];
+    bool any = false;
+    if (d.remapEdge[e] == 1) {
+        const int vv[2] = {v1, v2};
+        for (int k = 0; k < 2; k++) {
+            dpx[k] = -d.u[vv[k] - 1] * dt;
+            dpy[k] = -d.v[vv[k] - 1] * dt;
+            if (dpx[k] * dpx[k] + dpy[k] * dpy[k] > 0.0) any = true;
+        }
+    }
+    d.maskEdge[e] = any ? 1 : 0;
+    if (!any) return;
+
+    double XE[NVER], YE[NVER];
+#pragma unroll
+    for (int k = 0; k < NVER; k++) { XE[k] = d.xve[k * pe + e]; YE[k] = d.yve[k * pe + e]; }
+    int EO[NEER], CO[NCER];
+#pragma unroll
+    for (int k = 0; k < NEER; k++) { EO[k] = d.eoer[k * pe + e]; CO[k] = d.coer[k * pe + e]; }
+    const int vg[2] = {v1, v2};
+    const double evx[2] = {XE[0], XE[1]}, evy[2] = {YE[0], YE[1]};
+    for (int k = 0; k < 2; k++) { dpx[k] = XE[k] + dpx[k]; dpy[k] = YE[k] + dpy[k]; }
+
+    Tri T[NTRI];
+    int count = 0;
+    const int D = d.D;
+    const bool sphere = d.sphere != 0;
+#define NEW_TRI(name)                                                   \
+    if (count >= NTRI) { atomicOr(d.flags, FLAG_MANY_TRI); return; }    \
+    Tri &name = T[count];                                               \
+    count++;                                                            \
+    name.e1x = name.e1y = name.e2x = name.e2y = 0.0;                    \
+    name.vOnCell = 0
+
+    // side triangles: does the segment D1-D2 cut one of the side edges E1..E4 (:5700-5900)?
+    for (int iv = 0; iv < 2; iv++) {
+        const double n0x = evx[iv], n0y = evy[iv];
+        for (int side = 0; side < 2; side++) {
+            const int ieo = (iv + 1) + 2 * side;   // E1/E3 at V1, E2/E4 at V2 (1-based)
+            const int ivr = ieo + 2;               // V3..V6 (1-based)
+            const int en = EO[ieo - 1];
+            bool hit = false;
+            double ipx = 0.0, ipy = 0.0, n1x = 0.0, n1y = 0.0;
+            if (en >= 1 && en <= d.nE) {
+                n1x = XE[ivr - 1];
+                n1y = YE[ivr - 1];
+                hit = line_intersection(dpx[0], dpy[0], dpx[1], dpy[1], n0x, n0y, n1x, n1y, ipx, ipy);
+            }
+            if (!hit) continue;
+            NEW_TRI(t);
+            t.x[0] = evx[iv]; t.y[0] = evy[iv];
+            t.x[1] = dpx[iv]; t.y[1] = dpy[iv];
+            t.x[2] = ipx;     t.y[2] = ipy;
+            t.vOnEdge = iv + 1;
+            t.cell = CO[iv + 2];
+            t.vOnCell = vertex_on_cell(d, t.cell, vg[iv], 0);
+            if (sphere) {
+                t.e1x = n1x - n0x; t.e1y = n1y - n0y;
+                int iOtherEdge;
+                if (D == 3) { iOtherEdge = ieo + 2; if (iOtherEdge > 4) iOtherEdge = iOtherEdge - 4; }
+                else iOtherEdge = iv + 1 + 4;
+                const int iOtherVertex = iOtherEdge + 2;
+                t.e2x = XE[iOtherVertex - 1] - n0x; t.e2y = YE[iOtherVertex - 1] - n0y;
+            }
+            t.sign = (side == 0) ? 1 : -1;
+            if (D == 4) {
+                const int en5 = EO[iv + 4];        // E5 at V1, E6 at V2
+                bool hitMain = false;
+                double ipmx = 0.0, ipmy = 0.0;
+                if (en5 >= 1 && en5 <= d.nE)
+                    hitMain = line_intersection(dpx[0], dpy[0], dpx[1], dpy[1], n0x, n0y, XE[iv + 6], YE[iv + 6], ipmx, ipmy);
+                if (hitMain) {
+                    t.x[2] = ipmx; t.y[2] = ipmy;
+                    if (side == 0) {
+                        t.cell = CO[iv + 4];
+                        t.vOnCell = vertex_on_cell(d, t.cell, vg[iv], t.vOnCell);
+                        if (sphere) { t.e1x = XE[ivr + 2 - 1] - n0x; t.e1y = YE[ivr + 2 - 1] - n0y; }
+                    } else if (sphere) {
+                        t.e1x = XE[ivr - 2 - 1] - n0x; t.e1y = YE[ivr - 2 - 1] - n0y;
+                    }
+                    const int prevOnEdge = t.vOnEdge, prevSign = t.sign;
+                    const double pe2x = t.e2x, pe2y = t.e2y;
+                    NEW_TRI(t2);
+                    t2.x[0] = evx[iv]; t2.y[0] = evy[iv];
+                    t2.x[1] = ipmx;    t2.y[1] = ipmy;
+                    t2.x[2] = ipx;     t2.y[2] = ipy;
+                    t2.cell = (side == 0) ? CO[iv + 2] : CO[iv + 4];
+                    t2.vOnEdge = prevOnEdge;
+                    t2.vOnCell = vertex_on_cell(d, t2.cell, vg[iv], 0);
+                    if (sphere) { t2.e1x = XE[ivr - 1] - n0x; t2.e1y = YE[ivr - 1] - n0y; t2.e2x = pe2x; t2.e2y = pe2y; }
+                    t2.sign = prevSign;
+                } else if (side != 0) {
+                    t.cell = CO[iv + 4];
+                    t.vOnCell = vertex_on_cell(d, t.cell, vg[iv], t.vOnCell);
+                }
+            }
+            dpx[iv] = ipx;   // the departure point moves to the side intersection for what follows (:5898)
+            dpy[iv] = ipy;
+        }
+    }
+
+    // central triangles in C1 / C2 (:5905-6075)
+    {
+        double ipmx, ipmy;
+        const bool hitMain = line_intersection(dpx[0], dpy[0], dpx[1], dpy[1], evx[0], evy[0], evx[1], evy[1], ipmx, ipmy);
+        bool two = hitMain;
+        if (!hitMain) {
+            const double quadArea = tri_area(evx[0], evy[0], evx[1], evy[1], dpx[1], dpy[1]) +
+                                    tri_area(evx[0], evy[0], dpx[1], dpy[1], dpx[0], dpy[0]);
+            two = quadArea > 0.0;
+        }
+        if (two) {
+            for (int iv = 0; iv < 2; iv++) {
+                NEW_TRI(t);
+                if (hitMain) {
+                    t.x[0] = evx[iv]; t.y[0] = evy[iv]; t.x[1] = dpx[iv]; t.y[1] = dpy[iv]; t.x[2] = ipmx; t.y[2] = ipmy;
+                } else if (iv == 0) {
+                    t.x[0] = evx[0]; t.y[0] = evy[0]; t.x[1] = evx[1]; t.y[1] = evy[1]; t.x[2] = dpx[0]; t.y[2] = dpy[0];
+                } else {
+                    t.x[0] = evx[1]; t.y[0] = evy[1]; t.x[1] = dpx[0]; t.y[1] = dpy[0]; t.x[2] = dpx[1]; t.y[2] = dpy[1];
+                }
+                t.vOnEdge = iv + 1;
+                const bool inHP = in_half_plane(evx[0], evy[0], evx[1], evy[1], dpx[iv], dpy[iv]);
+                t.cell = inHP ? CO[0] : CO[1];
+                t.sign = inHP ? 1 : -1;
+                t.vOnCell = vertex_on_cell(d, t.cell, vg[iv], 0);
+                if (sphere) {
+                    const int other = 1 - iv;
+                    t.e1x = evx[other] - evx[iv]; t.e1y = evy[other] - evy[iv];
+                    const int iOtherEdge = inHP ? (iv + 1) : (iv + 3);
+                    t.e2x = XE[iOtherEdge + 2 - 1] - evx[iv]; t.e2y = YE[iOtherEdge + 2 - 1] - evy[iv];
+                }
+            }
+        }
+    }
+#undef NEW_TRI
+
+    // shift_vertices_of_departure_triangle (:6270), signed area, quadrature points (:6546)
+    for (int it = 0; it < NTRI; it++) {
+        double x[3] = {0.0, 0.0, 0.0}, y[3] = {0.0, 0.0, 0.0};
+        if (it < count) {
+            Tri &t = T[it];
+            for (int q = 0; q < 3; q++) { x[q] = t.x[q]; y[q] = t.y[q]; }
+            d.iCellTri[it * pe + e] = t.cell;
+            if (t.cell >= 1 && t.cell <= d.nC) {
+                const size_t ic = (size_t)t.cell - 1;
+                const int kk = t.vOnCell < 1 ? 1 : t.vOnCell;
+                const double xv = d.xvc[(kk - 1) * pc + ic], yv = d.yvc[(kk - 1) * pc + ic];
+                const double oex = XE[t.vOnEdge - 1], oey = YE[t.vOnEdge - 1];
+                if (sphere) {
+                    double e1x = t.e1x, e1y = t.e1y, e2x = t.e2x, e2y = t.e2y;
+                    const double crossProduct = cross2(e1x, e1y, e2x, e2y);
+                    if (fabs(crossProduct) < EPS11) atomicOr(d.flags, FLAG_PARALLEL);
+                    if (crossProduct > 0.0) {
+                        const double tx = e1x, ty = e1y;
+                        e1x = e2x; e1y = e2y; e2x = tx; e2y = ty;
+                    }
+                    const int n = d.nEdgesOnCell[ic];
+                    int km1 = kk - 1; if (km1 < 1) km1 = km1 + n;
+                    int kp1 = kk + 1; if (kp1 > n) kp1 = kp1 - n;
+                    const double c1x = d.xvc[(km1 - 1) * pc + ic] - xv, c1y = d.yvc[(km1 - 1) * pc + ic] - yv;
+                    const double c2x = d.xvc[(kp1 - 1) * pc + ic] - xv, c2y = d.yvc[(kp1 - 1) * pc + ic] - yv;
+                    const double denom = e1x * e2y - e2x * e1y;
+                    for (int q = 0; q < 3; q++) {
+                        x[q] = x[q] - oex;
+                        y[q] = y[q] - oey;
+                        const double coeff_a = (x[q] * e2y - y[q] * e2x) / denom;
+                        const double coeff_b = (y[q] * e1x - x[q] * e1y) / denom;
+                        x[q] = xv + coeff_a * c1x + coeff_b * c2x;
+                        y[q] = yv + coeff_a * c1y + coeff_b * c2y;
+                    }
+                } else {
+                    for (int q = 0; q < 3; q++) {
+                        x[q] = x[q] - oex + xv;
+                        y[q] = y[q] - oey + yv;
+                    }
+                }
+                const double area = fabs(0.5 * ((x[1] - x[0]) * (y[2] - y[0]) - (y[1] - y[0]) * (x[2] - x[0])));
+                d.triArea[it * pe + e] = area * t.sign;
+            }
+        }
+        double *xo = d.xq + (size_t)it * 6 * pe + e, *yo = d.yq + (size_t)it * 6 * pe + e;
+        if (d.nQP == 3) {
+            const double xMid = (x[0] + x[1] + x[2]) / 3.0;
+            const double yMid = (x[0] + x[1] + x[2]) / 3.0;   // as the reference has it (:6598)
+            for (int q = 0; q < 3; q++) {
+                xo[q * pe] = 0.5 * (x[q] + xMid);
+                yo[q * pe] = 0.5 * (y[q] + yMid);
+            }
+        } else {
+            xo[0 * pe] = Q1QP * x[0] + Q1QP * x[1] + Q2QP * x[2]; yo[0 * pe] = Q1QP * y[0] + Q1QP * y[1] + Q2QP * y[2];
+            xo[1 * pe] = Q1QP * x[0] + Q2QP * x[1] + Q1QP * x[2]; yo[1 * pe] = Q1QP * y[0] + Q2QP * y[1] + Q1QP * y[2];
+            xo[2 * pe] = Q2QP * x[0] + Q1QP * x[1] + Q1QP * x[2]; yo[2 * pe] = Q2QP * y[0] + Q1QP * y[1] + Q1QP * y[2];
+            xo[3 * pe] = Q3QP * x[0] + Q4QP * x[1] + Q4QP * x[2]; yo[3 * pe] = Q3QP * y[0] + Q4QP * y[1] + Q4QP * y[2];
+            xo[4 * pe] = Q4QP * x[0] + Q3QP * x[1] + Q4QP * x[2]; yo[4 * pe] = Q4QP * y[0] + Q3QP * y[1] + Q4QP * y[2];
+            xo[5 * pe] = Q4QP * x[0] + Q4QP * x[1] + Q3QP * x[2]; yo[5 * pe] = Q4QP * y[0] + Q4QP * y[1] + Q3QP * y[2];
+        }
+    }
+}
+
+// integrate_fluxes_over_triangles (:6667): one thread per (edge, category).  The quadrature points of the edge's
+// non-empty departure triangles are parked once in a per-thread shared-memory column and reused by every row of the
+// category.  CAP = the most triangles an edge can have (4 on hexagonal meshes, 6 on quadrilateral ones,
+// find_departure_triangles :5420-5460): it sizes the scratch, i.e. the blocks that fit on an SM.  triangleValue of a
+// row is the product down its chain of parents of the linear reconstructions at the quadrature point, the mass field
+// first.
+template <int CAP>
+__global__ void __launch_bounds__(RB) k_fluxes(Dev d)
+{
+    __shared__ double Q[CAP * 12][RB];
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cat = blockIdx.y, tx = threadIdx.x;
+    if (e >= (size_t)d.nE) return;
+    const size_t pe = d.nEp, pc = d.nCp;
+    const int nQP = d.nQP;
+    double area[CAP];
+    size_t cell[CAP];
+    int nt = 0;
+    if (d.maskEdge[e] == 1) {
+        for (int t = 0; t < NTRI; t++) {            // in triangle order: the order the fluxes are summed in
+            const double a = d.triArea[t * pe + e];
+            if (a == 0.0) continue;
+            if (nt == CAP) { atomicOr(d.flags, FLAG_MANY_TRI); break; }
+            area[nt] = a;
+            cell[nt] = (size_t)d.iCellTri[t * pe + e] - 1;
+            for (int q = 0; q < nQP; q++) {
+                Q[nt * 12 + q][tx] = d.xq[(size_t)(t * 6 + q) * pe + e];
+                Q[nt * 12 + 6 + q][tx] = d.yq[(size_t)(t * 6 + q) * pe + e];
+            }
+            nt++;
+        }
+        // Triangles whose source cells hold no ice in any category carry nothing: there the mass reconstruction is
+        // identically zero (value 0, gradients 0: k_reconstruct's fast path), so every product down the chain is a
+        // zero and the flux is the +0.0 written below.  Most of an ocean mesh is ice-free.
+        bool ice = false;
+        for (int t = 0; t < nt; t++) ice = ice || d.maskCell[cell[t]] == 1;
+        if (!ice) nt = 0;
+    }
+    bool negative = false;
+    const int JP = d.JP;
+    size_t rbase[CAP];                                  // reconstruction blocks of the source cells
+    for (int t = 0; t < nt; t++) rbase[t] = ((size_t)cat * pc + cell[t]) * JP * 3;
+    const size_t ebase = ((size_t)cat * pe + e) * JP;
+    for (int j = 0; j < d.nRowsPerCat; j++) {
+        double flux = 0.0;
+        if (nt > 0) {
+            const RowInfo ri = d.rows[j];
+            for (int t = 0; t < nt; t++) {
+                double cen[MAX_DEPTH], gx[MAX_DEPTH], gy[MAX_DEPTH];
+                for (int s = 0; s <= ri.depth; s++) {
+                    const size_t q = rbase[t] + (size_t)ri.chain[s] * 3;
+                    cen[s] = d.recon[q]; gx[s] = d.recon[q + 1]; gy[s] = d.recon[q + 2];
+                }
+                double tracerIntegral = 0.0;
+                for (int iqp = 0; iqp < nQP; iqp++) {
+                    const double x = Q[t * 12 + iqp][tx], y = Q[t * 12 + 6 + iqp][tx];
+                    double value = 1.0;
+                    for (int s = 0; s <= ri.depth; s++) value = value * (cen[s] + gx[s] * x + gy[s] * y);
+                    if (ri.depth == 0 && value < 0.0) negative = true;
+                    const double w = (nQP == 3) ? (1.0 / 3.0) : (iqp < 3 ? W1QP : W2QP);
+                    tracerIntegral = tracerIntegral + w * value;
+                }
+                flux = flux + area[t] * tracerIntegral;
+            }
+        }
+        d.edgeFlux[ebase + j] = flux;
+    }
+    if (negative) atomicOr(d.flags, FLAG_NEG_QP);
+}
+
+// compute_mass_tracer_products (:6982), update_mass_and_tracers (:7125), zap_small_mass (:8764; one-layer mass field)
+// and thickness -> volume (:9295): one thread per (cell, category), rows parents first -- a row needs the NEW
+// mass * tracer product of its parent in the same cell only.
+__global__ void __launch_bounds__(RB) k_update(Dev d, int massOneLayer)
+{
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cat = blockIdx.y;
+    if (c > (size_t)d.nC) return;
+    const size_t pe = d.nEp, pc = d.nCp;
+    const int JP = d.JP, SP = d.SP;
+    const size_t base = ((size_t)cat * pc + c) * JP, sbase = ((size_t)cat * pc + c) * SP;
+    const bool owned = c < (size_t)d.nCS;
+    size_t ebase[MAXM];
+    int sign[MAXM], n = 0;
+    double area = 1.0;
+    if (owned) {
+        n = d.nEdgesOnCell[c];
+        for (int k = 0; k < n; k++) {
+            ebase[k] = ((size_t)cat * pe + (d.edgesOnCell[k * pc + c] - 1)) * JP;
+            sign[k] = d.fluxSign[k * pc + c];
+        }
+        area = d.areaCell[c];
+    }
+    for (int j = 0; j < d.nRowsPerCat; j++) {
+        if (!owned) {                               // halo cells and the extra slot keep their values
+            d.valNew[base + j] = d.val[base + j];
+            continue;
+        }
+        const RowInfo ri = d.rows[j];
+        double fluxFromCell = 0.0;
+        for (int k = 0; k < n; k++) fluxFromCell = fluxFromCell + d.edgeFlux[ebase[k] + j] * (double)sign[k];
+        double mtpOld = 1.0;
+        for (int s = 0; s <= ri.depth; s++) mtpOld = mtpOld * d.val[base + ri.chain[s]];
+        const double pm = ri.depth > 0 ? d.mtpNew[sbase + ri.parentSlot] : 1.0;
+        double v = 0.0;
+        if (pm > 0.0) v = (mtpOld - (fluxFromCell / area)) / pm;
+        if (ri.slot >= 0) d.mtpNew[sbase + ri.slot] = pm * v;   // only children read it
+        if (ri.depth == 0) {
+            constexpr double puny2 = 1.0e-11 * 1.0e-11;   // seaicePuny**2
+            if (v < -puny2) atomicOr(d.flags, FLAG_NEG_MASS);
+            else if (v < 0.0) v = 0.0;
+        }
+        d.valNew[base + j] = v;
+    }
+    if (massOneLayer) {                             // the mass row of this category is j = 0
+        const double m = d.valNew[base];
+        if (owned && m > 0.0 && m < 1.0e-22)
+            for (int j = 0; j < d.nRowsPerCat; j++) d.valNew[base + j] = 0.0;
+        for (int j = 0; j < d.nRowsPerCat; j++)
+            if (d.rows[j].volumeLike) d.valNew[base + j] = d.valNew[base] * d.valNew[base + j];
+    }
+}
+
+// rows 1 and 2 of transGlobalToCell (3,3,nCells): trans(i,j,c) at c*9 + j*3 + i
+__global__ void k_trans_in(const double *__restrict__ raw, double *__restrict__ dst, size_t n, size_t pitch)
+{
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    for (int i = 0; i < 2; i++)
+        for (int j = 0; j < 3; j++) dst[(size_t)(i * 3 + j) * pitch + c] = raw[c * 9 + j * 3 + i];
+}
+
+// ------------------------------------------------------------------------------------------------ init-time geometry
+// seaice_init_advection_incremental_remap's geometry (:446-711) for hosts that do not run the Fortran init: local
+// frames, vertex coordinates in cell and edge frames, remap stencils, geometric cell averages.  Init-time work, so the
+// arrays keep the host layout on the device.
+
+struct Geo {
+    int nC, nCS, nV, nE, M, D, sphere, rotate;
+    const int *nEdgesOnCell, *edgesOnCell, *verticesOnCell, *cellsOnEdge, *verticesOnEdge, *edgesOnVertex;
+    const double *xC, *yC, *zC, *xV, *yV, *zV, *xE, *yE, *zE, *dcEdge, *dvEdge;
+    double *trans, *xvc, *yvc, *xve, *yve, *minLen, *geom[14];
+    int *remapEdge, *coer, *eoer, *flags;
+};
+enum { GEO_BAD_EDGE = 1, GEO_BAD_CELL = 2 };
+
+// rotate_global_vectors (:948): (x, y, z) -> (-z, y, x) when the Cartesian grid is rotated
+__device__ __forceinline__ void point(const Geo &g, const double *x, const double *y, const double *z, int i, double *o)
+{
+    if (g.rotate && g.sphere) { o[0] = -z[i]; o[1] = y[i]; o[2] = x[i]; }
+    else { o[0] = x[i]; o[1] = y[i]; o[2] = z[i]; }
+}
+
+// define_local_to_global_transformations (:990): rows east, north, up; t(i,j) at t[(j-1)*3 + (i-1)]
+__device__ void global_to_local(const double *pt, double *t)
+{
+    double e1[3], e2[3], e3[3] = {pt[0], pt[1], pt[2]};
+    double mag = sqrt(e3[0] * e3[0] + e3[1] * e3[1] + e3[2] * e3[2]);
+    if (mag > 0.0) { e3[0] = e3[0] / mag; e3[1] = e3[1] / mag; e3[2] = e3[2] / mag; } else { e3[0] = e3[1] = e3[2] = 0.0; }
+    if (fabs(pt[0] * pt[0] + pt[1] * pt[1]) > EPS11) {
+        e1[0] = -pt[1]; e1[1] = pt[0]; e1[2] = 0.0;
+        mag = sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
+        if (mag > 0.0) { e1[0] = e1[0] / mag; e1[1] = e1[1] / mag; e1[2] = e1[2] / mag; } else { e1[0] = e1[1] = e1[2] = 0.0; }
+        e2[0] = e3[1] * e1[2] - e3[2] * e1[1];
+        e2[1] = e3[2] * e1[0] - e3[0] * e1[2];
+        e2[2] = e3[0] * e1[1] - e3[1] * e1[0];
+    } else if (pt[2] > 0.0) {
+        e1[0] = 1.0; e1[1] = 0.0; e1[2] = 0.0; e2[0] = 0.0; e2[1] = 1.0; e2[2] = 0.0;
+    } else {
+        e1[0] = 0.0; e1[1] = 1.0; e1[2] = 0.0; e2[0] = 1.0; e2[1] = 0.0; e2[2] = 0.0;
+    }
+    for (int j = 0; j < 3; j++) { t[j * 3 + 0] = e1[j]; t[j * 3 + 1] = e2[j]; t[j * 3 + 2] = e3[j]; }
+}
+
+// get_vertex_on_cell_coordinates (:1823) + compute_geometric_cell_averages (:2097)
+__global__ void k_geo_cells(Geo g)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= g.nC) return;
+    const int M = g.M, n = g.nEdgesOnCell[c];
+    double pc[3], t[9];
+    point(g, g.xC, g.yC, g.zC, c, pc);
+    if (g.sphere) {
+        global_to_local(pc, t);
+        for (int q = 0; q < 9; q++) g.trans[(size_t)c * 9 + q] = t[q];
+    }
+    double xv[MAXM], yv[MAXM];
+    for (int k = 0; k < n; k++) {
+        const int v = g.verticesOnCell[(size_t)c * M + k] - 1;
+        double pv[3];
+        point(g, g.xV, g.yV, g.zV, v, pv);
+        if (g.sphere) {
+            const double w0 = pv[0] - pc[0], w1 = pv[1] - pc[1], w2 = pv[2] - pc[2];
+            xv[k] = t[0] * w0 + t[3] * w1 + t[6] * w2;
+            yv[k] = t[1] * w0 + t[4] * w1 + t[7] * w2;
+        } else {
+            xv[k] = pv[0] - pc[0];
+            yv[k] = pv[1] - pc[1];
+        }
+        g.xvc[(size_t)c * M + k] = xv[k];
+        g.yvc[(size_t)c * M + k] = yv[k];
+    }
+    for (int k = 0; k < n; k++) {
+        const int k1 = (k + 1 >= n) ? 0 : k + 1;
+        if (!(cross2(xv[k], yv[k], xv[k1], yv[k1]) >= 0.0)) atomicOr(g.flags, GEO_BAD_CELL);
+    }
+    double frac[MAXM], sumArea = 0.0;
+    for (int k = 0; k < n; k++) {
+        const int e = g.edgesOnCell[(size_t)c * M + k] - 1;
+        frac[k] = 0.25 * g.dcEdge[e] * g.dvEdge[e];
+        sumArea = sumArea + frac[k];
+    }
+    for (int k = 0; k < n; k++) frac[k] = frac[k] / sumArea;
+    double acc[14];
+    for (int q = 0; q < 14; q++) acc[q] = 0.0;
+    for (int k = 0; k < n; k++) {
+        const int k1 = (k + 1 >= n) ? 0 : k + 1;
+        const double x1 = 0.0, y1 = 0.0, x2 = xv[k], y2 = yv[k], x3 = xv[k1], y3 = yv[k1];
+        double xq[6], yq[6];
+        xq[0] = Q1QP * x1 + Q1QP * x2 + Q2QP * x3; yq[0] = Q1QP * y1 + Q1QP * y2 + Q2QP * y3;
+        xq[1] = Q1QP * x1 + Q2QP * x2 + Q1QP * x3; yq[1] = Q1QP * y1 + Q2QP * y2 + Q1QP * y3;
+        xq[2] = Q2QP * x1 + Q1QP * x2 + Q1QP * x3; yq[2] = Q2QP * y1 + Q1QP * y2 + Q1QP * y3;
+        xq[3] = Q3QP * x1 + Q4QP * x2 + Q4QP * x3; yq[3] = Q3QP * y1 + Q4QP * y2 + Q4QP * y3;
+        xq[4] = Q4QP * x1 + Q3QP * x2 + Q4QP * x3; yq[4] = Q4QP * y1 + Q3QP * y2 + Q4QP * y3;
+        xq[5] = Q4QP * x1 + Q4QP * x2 + Q3QP * x3; yq[5] = Q4QP * y1 + Q4QP * y2 + Q3QP * y3;
+        double a[14];
+        for (int q = 0; q < 14; q++) a[q] = 0.0;
+        for (int q = 0; q < 6; q++) {
+            const double x = xq[q], y = yq[q], w = (q < 3) ? W1QP : W2QP;
+            const double x2p = x * x, y2p = y * y, x3p = x * x * x, y3p = y * y * y, x4p = (x * x) * (x * x), y4p = (y * y) * (y * y);
+            a[0] = a[0] + w * x;        a[1] = a[1] + w * y;
+            a[2] = a[2] + w * x2p;      a[3] = a[3] + w * x * y;      a[4] = a[4] + w * y2p;
+            a[5] = a[5] + w * x3p;      a[6] = a[6] + w * x2p * y;    a[7] = a[7] + w * x * y2p;   a[8] = a[8] + w * y3p;
+            a[9] = a[9] + w * x4p;      a[10] = a[10] + w * x3p * y;  a[11] = a[11] + w * x2p * y2p;
+            a[12] = a[12] + w * x * y3p; a[13] = a[13] + w * y4p;
+        }
+        for (int q = 0; q < 14; q++) acc[q] = acc[q] + frac[k] * a[q];
+    }
+    for (int q = 0; q < 14; q++) g.geom[q][c] = acc[q];
+}
+
+// get_geometry_incremental_remap (:1105), first pass per edge: remapEdge, orientation check, the stencils
+// cellsOnEdgeRemap / edgesOnEdgeRemap, the edge's own two vertices in its frame
+__global__ void k_geo_edges(Geo g)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= g.nE) return;
+    const int M = g.M, D = g.D, nC = g.nC, nE = g.nE;
+    const int c1 = g.cellsOnEdge[(size_t)e * 2], c2 = g.cellsOnEdge[(size_t)e * 2 + 1];
+    const int v1 = g.verticesOnEdge[(size_t)e * 2], v2 = g.verticesOnEdge[(size_t)e * 2 + 1];
+    // an edge of an owned cell with a cell on both sides (:1235-1262)
+    const bool both = c1 >= 1 && c1 <= nC && c2 >= 1 && c2 <= nC;
+    const bool remap = both && (c1 <= g.nCS || c2 <= g.nCS);
+    g.remapEdge[e] = remap ? 1 : 0;
+    double pe[3], t[9], p1[3], p2[3];
+    point(g, g.xE, g.yE, g.zE, e, pe);
+    const bool haveV = v1 >= 1 && v1 <= g.nV && v2 >= 1 && v2 <= g.nV;
+    if (haveV) { point(g, g.xV, g.yV, g.zV, v1 - 1, p1); point(g, g.xV, g.yV, g.zV, v2 - 1, p2); }
+    double ex[2] = {0.0, 0.0}, ey[2] = {0.0, 0.0};
+    if (g.sphere) {
+        global_to_local(pe, t);
+        if (haveV) {
+            const double w0 = p2[0] - p1[0], w1 = p2[1] - p1[1], w2 = p2[2] - p1[2];
+            const double xVector = t[0] * w0 + t[3] * w1 + t[6] * w2, yVector = t[1] * w0 + t[4] * w1 + t[7] * w2;
+            g.xve[(size_t)e * NVER + 0] = -0.5 * xVector; g.yve[(size_t)e * NVER + 0] = -0.5 * yVector;
+            g.xve[(size_t)e * NVER + 1] = 0.5 * xVector;  g.yve[(size_t)e * NVER + 1] = 0.5 * yVector;
+        }
+    } else if (remap) {
+        g.xve[(size_t)e * NVER + 0] = p1[0] - pe[0]; g.yve[(size_t)e * NVER + 0] = p1[1] - pe[1];
+        g.xve[(size_t)e * NVER + 1] = p2[0] - pe[0]; g.yve[(size_t)e * NVER + 1] = p2[1] - pe[1];
+    }
+    if (!remap) return;
+    // C1 must lie to the left of V1 -> V2, tested in the edge frame with the vertices relative to the edge point (:1270-1330)
+    {
+        double cc[2], pcell[3];
+        point(g, g.xC, g.yC, g.zC, c1 - 1, pcell);
+        const double *pp[2] = {p1, p2};
+        for (int k = 0; k < 2; k++) {
+            const double w0 = pp[k][0] - pe[0], w1 = pp[k][1] - pe[1], w2 = pp[k][2] - pe[2];
+            if (g.sphere) { ex[k] = t[0] * w0 + t[3] * w1 + t[6] * w2; ey[k] = t[1] * w0 + t[4] * w1 + t[7] * w2; }
+            else { ex[k] = w0; ey[k] = w1; }
+        }
+        const double w0 = pcell[0] - pe[0], w1 = pcell[1] - pe[1], w2 = pcell[2] - pe[2];
+        if (g.sphere) { cc[0] = t[0] * w0 + t[3] * w1 + t[6] * w2; cc[1] = t[1] * w0 + t[4] * w1 + t[7] * w2; }
+        else { cc[0] = w0; cc[1] = w1; }
+        if (!in_half_plane(ex[0], ey[0], ex[1], ey[1], cc[0], cc[1])) atomicOr(g.flags, GEO_BAD_EDGE);
+    }
+    int EO[NEER] = {0, 0, 0, 0, 0, 0}, CO[NCER] = {0, 0, 0, 0, 0, 0};
+    CO[0] = c1; CO[1] = c2;
+    for (int side = 0; side < 2; side++) {
+        const int cell = side == 0 ? c1 : c2;
+        const int n = g.nEdgesOnCell[cell - 1];
+        int iMain = 0;
+        for (int k = 1; k <= n; k++)
+            if (g.edgesOnCell[(size_t)(cell - 1) * M + k - 1] == e + 1) { iMain = k; break; }
+        int km = iMain - 1; if (km < 1) km = km + n;
+        int kp = iMain + 1; if (kp > n) kp = kp - n;
+        const int em = g.edgesOnCell[(size_t)(cell - 1) * M + km - 1], ep = g.edgesOnCell[(size_t)(cell - 1) * M + kp - 1];
+        if (side == 0) { EO[0] = em; EO[1] = ep; } else { EO[2] = ep; EO[3] = em; }
+    }
+    if (D == 4) {
+        const int vv[2] = {v1, v2};
+        for (int iv = 0; iv < 2; iv++)
+            for (int k = 0; k < D; k++) {
+                const int en = g.edgesOnVertex[(size_t)(vv[iv] - 1) * D + k];
+                if (en >= 1 && en <= nE) {
+                    bool isNew = true;
+                    for (int q = 0; q < 4; q++)
+                        if (en == EO[q] || en == e + 1) { isNew = false; break; }
+                    if (isNew) { EO[iv + 4] = en; break; }
+                }
+            }
+    }
+    if (D == 3) {
+        CO[2] = nC + 1; CO[3] = nC + 1;
+        for (int iv = 0; iv < 2; iv++) {
+            int en = EO[iv];
+            if (en < 1 || en > nE) en = EO[iv + 2];
+            if (en < 1 || en > nE) continue;
+            for (int k = 0; k < 2; k++) {
+                const int cn = g.cellsOnEdge[(size_t)(en - 1) * 2 + k];
+                if (cn >= 1 && cn <= nC && cn != CO[0] && cn != CO[1]) CO[iv + 2] = cn;
+            }
+        }
+    } else {
+        for (int q = 2; q < 6; q++) CO[q] = nC + 1;
+        for (int iv = 0; iv < 2; iv++) {
+            int en = EO[iv];
+            if (en >= 1 && en <= nE)
+                for (int k = 0; k < 2; k++) {
+                    const int cn = g.cellsOnEdge[(size_t)(en - 1) * 2 + k];
+                    if (cn >= 1 && cn <= nC && cn != CO[0]) CO[iv + 2] = cn;
+                }
+            en = EO[iv + 2];
+            if (en >= 1 && en <= nE)
+                for (int k = 0; k < 2; k++) {
+                    const int cn = g.cellsOnEdge[(size_t)(en - 1) * 2 + k];
+                    if (cn >= 1 && cn <= nC && cn != CO[1]) CO[iv + 4] = cn;
+                }
+        }
+    }
+    for (int q = 0; q < NEER; q++) { g.eoer[(size_t)e * NEER + q] = EO[q]; g.coer[(size_t)e * NCER + q] = CO[q]; }
+}
+
+// second pass per edge: the far vertices of the side edges in this edge's frame (:1690-1780)
+__global__ void k_geo_side_vertices(Geo g)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= g.nE || g.remapEdge[e] != 1) return;
+    const int nE = g.nE, nSide = (g.D == 3) ? 4 : 6;
+    const int ve[2] = {g.verticesOnEdge[(size_t)e * 2], g.verticesOnEdge[(size_t)e * 2 + 1]};
+    double pe[3];
+    point(g, g.xE, g.yE, g.zE, e, pe);
+    int count = 2;
+    for (int q = 0; q < nSide; q++) {
+        const int en = g.eoer[(size_t)e * NEER + q];
+        if (en < 1 || en > nE) continue;
+        const int vn[2] = {g.verticesOnEdge[(size_t)(en - 1) * 2], g.verticesOnEdge[(size_t)(en - 1) * 2 + 1]};
+        int n1 = 1, m1 = 1, m2 = 2, far = 0;
+        for (int n = 1; n <= 2; n++)
+            for (int m = 1; m <= 2; m++)
+                if (vn[m - 1] == ve[n - 1]) {
+                    n1 = n;
+                    if (m == 1) { m1 = 1; m2 = 2; } else { m1 = 2; m2 = 1; }
+                    far = vn[m2 - 1];
+                    if (!g.sphere) count = count + 1;
+                    break;
+                }
+        if (g.sphere) {
+            // this edge's shared vertex plus the side edge's own vector, taken in the side edge's frame as it is
+            g.xve[(size_t)e * NVER + q + 2] = g.xve[(size_t)e * NVER + n1 - 1] +
+                                              (g.xve[(size_t)(en - 1) * NVER + m2 - 1] - g.xve[(size_t)(en - 1) * NVER + m1 - 1]);
+            g.yve[(size_t)e * NVER + q + 2] = g.yve[(size_t)e * NVER + n1 - 1] +
+                                              (g.yve[(size_t)(en - 1) * NVER + m2 - 1] - g.yve[(size_t)(en - 1) * NVER + m1 - 1]);
+        } else if (count <= NVER && far >= 1) {
+            // on a plane the reference fills the slots by counting the side edges that exist (:1745-1772)
+            double pf[3];
+            point(g, g.xV, g.yV, g.zV, far - 1, pf);
+            g.xve[(size_t)e * NVER + count - 1] = pf[0] - pe[0];
+            g.yve[(size_t)e * NVER + count - 1] = pf[1] - pe[1];
+        }
+    }
+}
+
+// minLengthEdgesOnVertex (:1785-1805)
+__global__ void k_geo_vertices(Geo g)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v > g.nV) return;
+    double mn = DBL_MAX;
+    if (v < g.nV)
+        for (int k = 0; k < g.D; k++) {
+            const int e = g.edgesOnVertex[(size_t)v * g.D + k];
+            if (e >= 1 && e <= g.nE) {
+                double a[3], b[3];
+                point(g, g.xV, g.yV, g.zV, g.verticesOnEdge[(size_t)(e - 1) * 2] - 1, a);
+                point(g, g.xV, g.yV, g.zV, g.verticesOnEdge[(size_t)(e - 1) * 2 + 1] - 1, b);
+                const double w0 = b[0] - a[0], w1 = b[1] - a[1], w2 = b[2] - a[2];
+                const double len = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
+                if (len < mn) mn = len;
+            }
+        }
+    g.minLen[v] = mn;
+}
+
+inline unsigned grid_for(size_t n, int block) { return (unsigned)((n + block - 1) / block); }
+inline size_t round_up(size_t n, size_t m) { return (n + m - 1) / m * m; }
+
+template <typename T>
+int dev_alloc(ir_handle *h, T **p, size_t count)
+{
+    void *q = nullptr;
+    IR_CUDA(cudaMalloc(&q, sizeof(T) * (count ? count : 1)));
+    IR_CUDA(cudaMemsetAsync(q, 0, sizeof(T) * (count ? count : 1), h->stream));
+    h->allocs.push_back(q);
+    *p = (T *)q;
+    return IR_OK;
+}
+
+int ensure_stage(ir_handle *h, size_t bytes)
+{
+    if (h->d.stageBytes >= bytes) return IR_OK;
+    if (h->d.stage) {
+        IR_CUDA(cudaStreamSynchronize(h->stream));
+        IR_CUDA(cudaFree(h->d.stage));
+        h->d.stage = nullptr;
+        h->d.stageBytes = 0;
+    }
+    void *q = nullptr;
+    IR_CUDA(cudaMalloc(&q, bytes));
+    h->d.stage = (double *)q;
+    h->d.stageBytes = bytes;
+    return IR_OK;
+}
+
+// host (n, w) -> device [w][pitch]
+template <typename T>
+int upload_rows(ir_handle *h, T *dst, const T *host, size_t n, int w, size_t pitch)
+{
+    int rc = ensure_stage(h, n * w * sizeof(T));
+    if (rc) return rc;
+    IR_CUDA(cudaMemcpyAsync(h->d.stage, host, n * w * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    IR_LAUNCH((k_rows_in<T>), grid_for(n, 256), 256, h->stream, (const T *)h->d.stage, dst, n, w, pitch);
+    h->launches++;
+    IR_CUDA(cudaGetLastError());
+    IR_CUDA(cudaStreamSynchronize(h->stream));   // the staging area is reused by the next upload
+    return IR_OK;
+}
+
+// Opt-in (environment IR_B200_PIN_HOST=1 at ir_create): page-lock the host arrays the first time ir_run sees them, so
+// the per-step uploads and downloads run at the full PCIe rate.  The pool arrays of the host model live as long as
+// the model; a host that frees them earlier calls ir_release_host_memory first.  A range that cannot be registered
+// (already registered by someone else, not page-lockable) is simply copied as pageable memory.
+void pin_host(ir_handle *h, const void *p, size_t bytes)
+{
+    if (!h->pinHost || p == nullptr || bytes == 0) return;
+    for (auto &r : h->pinned)
+        if (r.first == p && r.second >= bytes) return;
+    if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) h->pinned.emplace_back(p, bytes);
+    else (void)cudaGetLastError();
+}
+
+void unpin_all(ir_handle *h)
+{
+    for (auto &r : h->pinned) cudaHostUnregister(const_cast<void *>(r.first));
+    h->pinned.clear();
+}
+
+}  // namespace
+
+// =============================================================================================================== ABI
+
+extern "C" const char *ir_last_error_string(void) { return g_err; }
+
+extern "C" int ir_create(ir_handle **out, const ir_mesh_desc *m, int device)
+{
+    IR_REQUIRE(out != nullptr && m != nullptr, "handle/mesh is NULL");
+    *out = nullptr;
+    IR_REQUIRE(m->nCells >= 0 && m->nVertices >= 0 && m->nEdges >= 0, "negative dimension");
+    IR_REQUIRE(m->nCellsSolve >= 0 && m->nCellsSolve <= m->nCells, "nCellsSolve out of range");
+    IR_REQUIRE(m->maxEdges >= 3 && m->maxEdges <= MAXM, "maxEdges must be 3..8");
+    IR_REQUIRE(m->vertexDegree == 3 || m->vertexDegree == 4, "vertexDegree must be 3 or 4");
+    IR_REQUIRE(m->nCategories >= 1, "nCategories must be positive");
+    IR_REQUIRE(m->nQuadPoints == 3 || m->nQuadPoints == 6, "nQuadPoints must be 3 or 6 (incremental_remap.F:780-787)");
+    IR_REQUIRE(m->nEdgesOnCell && m->edgesOnCell && m->cellsOnCell && m->verticesOnCell && m->cellsOnEdge && m->verticesOnEdge,
+               "connectivity arrays must not be NULL");
+    IR_REQUIRE(m->areaCell && m->dcEdge && m->coeffs_reconstruct, "areaCell / dcEdge / coeffs_reconstruct must not be NULL");
+    IR_REQUIRE(m->xVertexOnCell && m->yVertexOnCell && m->xVertexOnEdge && m->yVertexOnEdge && m->remapEdge &&
+                   m->cellsOnEdgeRemap && m->edgesOnEdgeRemap,
+               "incremental_remap pool arrays must not be NULL");
+    IR_REQUIRE(!m->on_a_sphere || m->transGlobalToCell, "transGlobalToCell is needed on a sphere");
+    for (int k = 0; k < 14; k++) IR_REQUIRE(m->geomAvgCell[k] != nullptr, "geomAvgCell arrays must not be NULL");
+    int dev = device;
+    if (dev < 0) IR_CUDA(cudaGetDevice(&dev));
+    IR_CUDA(cudaSetDevice(dev));
+    ir_handle *h = new ir_handle();
+    h->device = dev;
+    h->lastMs = 0.f;
+    h->launches = 0;
+    h->haveTracers = false;
+    {
+        const char *e = getenv("IR_B200_PIN_HOST");
+        h->pinHost = e != nullptr && e[0] != '\0' && e[0] != '0';
+    }
+    memset(&h->d, 0, sizeof h->d);
+    cudaError_t ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (ce != cudaSuccess) { set_error("cudaStreamCreate -> %s", cudaGetErrorString(ce)); delete h; return IR_ERR_CUDA; }
+    cudaEventCreate(&h->ev0);
+    cudaEventCreate(&h->ev1);
+    Dev &d = h->d;
+    d.nC = m->nCells; d.nCS = m->nCellsSolve; d.nV = m->nVertices; d.nE = m->nEdges; d.M = m->maxEdges; d.D = m->vertexDegree;
+    d.nK = m->nCategories; d.nQP = m->nQuadPoints; d.sphere = m->on_a_sphere ? 1 : 0; d.rotate = m->rotate_cartesian_grid ? 1 : 0;
+    d.nCp = round_up((size_t)d.nC + 1, 32); d.nEp = round_up((size_t)d.nE + 1, 32); d.nVp = round_up((size_t)d.nV + 1, 32);
+    const size_t nC1 = (size_t)d.nC + 1, nE1 = (size_t)d.nE + 1, nV1 = (size_t)d.nV + 1;
+    const int M = d.M;
+    int rc = IR_OK;
+#define TRY(x) do { if ((rc = (x)) != IR_OK) { ir_destroy(h); return rc; } } while (0)
+    TRY(dev_alloc(h, &d.nEdgesOnCell, d.nCp));
+    TRY(dev_alloc(h, &d.edgesOnCell, M * d.nCp));
+    TRY(dev_alloc(h, &d.cellsOnCell, M * d.nCp));
+    TRY(dev_alloc(h, &d.verticesOnCell, M * d.nCp));
+    TRY(dev_alloc(h, &d.cellsOnEdge, 2 * nE1));           // host layout (nEdges+1, 2): used by k_cell_edge_signs only
+    TRY(dev_alloc(h, &d.verticesOnEdge, 2 * d.nEp));
+    TRY(dev_alloc(h, &d.remapEdge, d.nEp));
+    TRY(dev_alloc(h, &d.coer, NCER * d.nEp));
+    TRY(dev_alloc(h, &d.eoer, NEER * d.nEp));
+    TRY(dev_alloc(h, &d.areaCell, d.nCp));
+    TRY(dev_alloc(h, &d.sdc, M * d.nCp));
+    TRY(dev_alloc(h, &d.fluxSign, M * d.nCp));
+    TRY(dev_alloc(h, &d.coef, 3 * M * d.nCp));
+    TRY(dev_alloc(h, &d.trans, 6 * d.nCp));
+    TRY(dev_alloc(h, &d.xvc, M * d.nCp));
+    TRY(dev_alloc(h, &d.yvc, M * d.nCp));
+    TRY(dev_alloc(h, &d.xve, NVER * d.nEp));
+    TRY(dev_alloc(h, &d.yve, NVER * d.nEp));
+    TRY(dev_alloc(h, &d.geom, 14 * d.nCp));
+    TRY(dev_alloc(h, &d.u, d.nVp));
+    TRY(dev_alloc(h, &d.v, d.nVp));
+    TRY(dev_alloc(h, &d.maskCell, d.nCp));
+    TRY(dev_alloc(h, &d.maskEdge, d.nEp));
+    TRY(dev_alloc(h, &d.iCellTri, NTRI * d.nEp));
+    TRY(dev_alloc(h, &d.xq, NTRI * 6 * d.nEp));
+    TRY(dev_alloc(h, &d.yq, NTRI * 6 * d.nEp));
+    TRY(dev_alloc(h, &d.triArea, NTRI * d.nEp));
+    TRY(dev_alloc(h, &d.flags, 1));
+    cudaStream_t s = h->stream;
+    auto copy1 = [&](void *dst, const void *src, size_t bytes) -> int {
+        IR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+        return IR_OK;
+    };
+    TRY(copy1(d.nEdgesOnCell, m->nEdgesOnCell, nC1 * 4));
+    TRY(copy1(d.areaCell, m->areaCell, nC1 * 8));
+    TRY(copy1(d.remapEdge, m->remapEdge, nE1 * 4));
+    TRY(copy1(d.cellsOnEdge, m->cellsOnEdge, 2 * nE1 * 4));
+    for (int k = 0; k < 14; k++) TRY(copy1(d.geom + (size_t)k * d.nCp, m->geomAvgCell[k], nC1 * 8));
+    TRY(upload_rows<int>(h, d.edgesOnCell, m->edgesOnCell, nC1, M, d.nCp));
+    TRY(upload_rows<int>(h, d.cellsOnCell, m->cellsOnCell, nC1, M, d.nCp));
+    TRY(upload_rows<int>(h, d.verticesOnCell, m->verticesOnCell, nC1, M, d.nCp));
+    TRY(upload_rows<int>(h, d.verticesOnEdge, m->verticesOnEdge, nE1, 2, d.nEp));
+    TRY(upload_rows<int>(h, d.coer, m->cellsOnEdgeRemap, nE1, NCER, d.nEp));
+    TRY(upload_rows<int>(h, d.eoer, m->edgesOnEdgeRemap, nE1, NEER, d.nEp));
+    TRY(upload_rows<double>(h, d.coef, m->coeffs_reconstruct, nC1, 3 * M, d.nCp));
+    TRY(upload_rows<double>(h, d.xvc, m->xVertexOnCell, nC1, M, d.nCp));
+    TRY(upload_rows<double>(h, d.yvc, m->yVertexOnCell, nC1, M, d.nCp));
+    TRY(upload_rows<double>(h, d.xve, m->xVertexOnEdge, nE1, NVER, d.nEp));
+    TRY(upload_rows<double>(h, d.yve, m->yVertexOnEdge, nE1, NVER, d.nEp));
+    if (d.sphere && d.nC > 0) {
+        TRY(ensure_stage(h, (size_t)d.nC * 9 * 8));
+        TRY(copy1(d.stage, m->transGlobalToCell, (size_t)d.nC * 9 * 8));
+        IR_LAUNCH((k_trans_in), grid_for(d.nC, 256), 256, s, d.stage, d.trans, (size_t)d.nC, d.nCp);
+        h->launches++;
+    }
+    {   // signed dcEdge and flux signs per (slot, cell)
+        double *dc = nullptr;
+        TRY(dev_alloc(h, &dc, nE1));
+        TRY(copy1(dc, m->dcEdge, nE1 * 8));
+        if (d.nC > 0) {
+            IR_LAUNCH((k_cell_edge_signs), grid_for(d.nC, 256), 256, s, d, dc);
+            h->launches++;
+        }
+    }
+    (void)nV1;
+    cudaError_t e2 = cudaStreamSynchronize(s);
+    if (e2 == cudaSuccess) e2 = cudaGetLastError();
+    if (e2 != cudaSuccess) { set_error("ir_create: %s", cudaGetErrorString(e2)); ir_destroy(h); return IR_ERR_CUDA; }
+#undef TRY
+    *out = h;
+    return IR_OK;
+}
+
+extern "C" int ir_init_geometry(const ir_geometry_in *in, const ir_geometry_out *out, int device)
+{
+    IR_REQUIRE(in != nullptr && out != nullptr, "NULL argument");
+    IR_REQUIRE(in->nCells >= 0 && in->nVertices >= 0 && in->nEdges >= 0, "negative dimension");
+    IR_REQUIRE(in->nCellsSolve >= 0 && in->nCellsSolve <= in->nCells, "nCellsSolve out of range");
+    IR_REQUIRE(in->maxEdges >= 3 && in->maxEdges <= MAXM, "maxEdges must be 3..8");
+    IR_REQUIRE(in->vertexDegree == 3 || in->vertexDegree == 4, "vertexDegree must be 3 or 4");
+    IR_REQUIRE(in->nEdgesOnCell && in->edgesOnCell && in->verticesOnCell && in->cellsOnEdge && in->verticesOnEdge && in->edgesOnVertex,
+               "connectivity arrays must not be NULL");
+    IR_REQUIRE(in->xCell && in->yCell && in->zCell && in->xVertex && in->yVertex && in->zVertex && in->xEdge && in->yEdge &&
+                   in->zEdge && in->dcEdge && in->dvEdge,
+               "coordinate arrays must not be NULL");
+    IR_REQUIRE(out->xVertexOnCell && out->yVertexOnCell && out->remapEdge && out->cellsOnEdgeRemap && out->edgesOnEdgeRemap &&
+                   out->xVertexOnEdge && out->yVertexOnEdge && out->minLengthEdgesOnVertex,
+               "output arrays must not be NULL");
+    IR_REQUIRE(!in->on_a_sphere || out->transGlobalToCell, "transGlobalToCell is needed on a sphere");
+    for (int k = 0; k < 14; k++) IR_REQUIRE(out->geomAvgCell[k] != nullptr, "geomAvgCell arrays must not be NULL");
+    int dev = device;
+    if (dev < 0) IR_CUDA(cudaGetDevice(&dev));
+    IR_CUDA(cudaSetDevice(dev));
+    const size_t nC1 = (size_t)in->nCells + 1, nE1 = (size_t)in->nEdges + 1, nV1 = (size_t)in->nVertices + 1;
+    const int M = in->maxEdges, D = in->vertexDegree;
+    std::vector<void *> bufs;
+    int rc = IR_OK;
+    auto up = [&](const void *host, size_t bytes, void **devp) -> int {
+        IR_CUDA(cudaMalloc(devp, bytes ? bytes : 1));
+        bufs.push_back(*devp);
+        if (host) IR_CUDA(cudaMemcpyAsync(*devp, host, bytes, cudaMemcpyHostToDevice, 0));
+        else IR_CUDA(cudaMemsetAsync(*devp, 0, bytes ? bytes : 1, 0));
+        return IR_OK;
+    };
+    auto cleanup = [&]() { for (void *b : bufs) cudaFree(b); };
+#define TRYG(x) do { if ((rc = (x)) != IR_OK) { cleanup(); return rc; } } while (0)
+    Geo g;
+    memset(&g, 0, sizeof g);
+    g.nC = in->nCells; g.nCS = in->nCellsSolve; g.nV = in->nVertices; g.nE = in->nEdges; g.M = M; g.D = D;
+    g.sphere = in->on_a_sphere ? 1 : 0; g.rotate = in->rotate_cartesian_grid ? 1 : 0;
+    TRYG(up(in->nEdgesOnCell, nC1 * 4, (void **)&g.nEdgesOnCell));
+    TRYG(up(in->edgesOnCell, nC1 * M * 4, (void **)&g.edgesOnCell));
+    TRYG(up(in->verticesOnCell, nC1 * M * 4, (void **)&g.verticesOnCell));
+    TRYG(up(in->cellsOnEdge, nE1 * 2 * 4, (void **)&g.cellsOnEdge));
+    TRYG(up(in->verticesOnEdge, nE1 * 2 * 4, (void **)&g.verticesOnEdge));
+    TRYG(up(in->edgesOnVertex, nV1 * D * 4, (void **)&g.edgesOnVertex));
+    TRYG(up(in->xCell, nC1 * 8, (void **)&g.xC)); TRYG(up(in->yCell, nC1 * 8, (void **)&g.yC)); TRYG(up(in->zCell, nC1 * 8, (void **)&g.zC));
+    TRYG(up(in->xVertex, nV1 * 8, (void **)&g.xV)); TRYG(up(in->yVertex, nV1 * 8, (void **)&g.yV)); TRYG(up(in->zVertex, nV1 * 8, (void **)&g.zV));
+    TRYG(up(in->xEdge, nE1 * 8, (void **)&g.xE)); TRYG(up(in->yEdge, nE1 * 8, (void **)&g.yE)); TRYG(up(in->zEdge, nE1 * 8, (void **)&g.zE));
+    TRYG(up(in->dcEdge, nE1 * 8, (void **)&g.dcEdge)); TRYG(up(in->dvEdge, nE1 * 8, (void **)&g.dvEdge));
+    const size_t nCt = in->nCells > 0 ? (size_t)in->nCells : 1;
+    TRYG(up(nullptr, nCt * 9 * 8, (void **)&g.trans));
+    TRYG(up(nullptr, nC1 * M * 8, (void **)&g.xvc)); TRYG(up(nullptr, nC1 * M * 8, (void **)&g.yvc));
+    TRYG(up(nullptr, nE1 * NVER * 8, (void **)&g.xve)); TRYG(up(nullptr, nE1 * NVER * 8, (void **)&g.yve));
+    TRYG(up(nullptr, nV1 * 8, (void **)&g.minLen));
+    for (int k = 0; k < 14; k++) TRYG(up(nullptr, nC1 * 8, (void **)&g.geom[k]));
+    TRYG(up(nullptr, nE1 * 4, (void **)&g.remapEdge));
+    TRYG(up(nullptr, nE1 * NCER * 4, (void **)&g.coer)); TRYG(up(nullptr, nE1 * NEER * 4, (void **)&g.eoer));
+    TRYG(up(nullptr, 4, (void **)&g.flags));
+    cudaStream_t s0 = 0;
+    if (g.nC > 0) IR_LAUNCH((k_geo_cells), grid_for((size_t)g.nC, 128), 128, s0, g);
+    if (g.nE > 0) {
+        IR_LAUNCH((k_geo_edges), grid_for((size_t)g.nE, 128), 128, s0, g);
+        IR_LAUNCH((k_geo_side_vertices), grid_for((size_t)g.nE, 128), 128, s0, g);
+    }
+    IR_LAUNCH((k_geo_vertices), grid_for(nV1, 128), 128, s0, g);
+    auto down = [&](void *host, const void *devp, size_t bytes) -> int {
+        IR_CUDA(cudaMemcpyAsync(host, devp, bytes, cudaMemcpyDeviceToHost, 0));
+        return IR_OK;
+    };
+    if (g.sphere && in->nCells > 0) TRYG(down(out->transGlobalToCell, g.trans, (size_t)in->nCells * 9 * 8));
+    TRYG(down(out->xVertexOnCell, g.xvc, nC1 * M * 8)); TRYG(down(out->yVertexOnCell, g.yvc, nC1 * M * 8));
+    TRYG(down(out->xVertexOnEdge, g.xve, nE1 * NVER * 8)); TRYG(down(out->yVertexOnEdge, g.yve, nE1 * NVER * 8));
+    TRYG(down(out->minLengthEdgesOnVertex, g.minLen, nV1 * 8));
+    for (int k = 0; k < 14; k++) TRYG(down(out->geomAvgCell[k], g.geom[k], nC1 * 8));
+    TRYG(down(out->remapEdge, g.remapEdge, nE1 * 4));
+    TRYG(down(out->cellsOnEdgeRemap, g.coer, nE1 * NCER * 4)); TRYG(down(out->edgesOnEdgeRemap, g.eoer, nE1 * NEER * 4));
+    int flags = 0;
+    TRYG(down(&flags, g.flags, 4));
+    cudaError_t ce = cudaStreamSynchronize(s0);
+    if (ce == cudaSuccess) ce = cudaGetLastError();
+    cleanup();
+#undef TRYG
+    if (ce != cudaSuccess) { set_error("ir_init_geometry: %s", cudaGetErrorString(ce)); return IR_ERR_CUDA; }
+    if (flags & GEO_BAD_EDGE) {
+        set_error("IR geometry: cellsOnEdge(1) is not to the left of verticesOnEdge(1) -> (2) (incremental_remap.F:1296)");
+        return IR_ERR_MESH;
+    }
+    if (flags & GEO_BAD_CELL) {
+        set_error("IR geometry: the vertices of a cell do not run counter-clockwise (incremental_remap.F:2010)");
+        return IR_ERR_MESH;
+    }
+    return IR_OK;
+}
+
+extern "C" int ir_set_tracers(ir_handle *h, int nTracers, const ir_tracer_desc *tr)
+{
+    IR_REQUIRE(h != nullptr && tr != nullptr, "handle/tracers is NULL");
+    IR_REQUIRE(nTracers >= 1, "at least the mass-like field is needed");
+    IR_REQUIRE(tr[0].parent == -1, "the first tracer must be the mass-like field (parent = -1)");
+    IR_CUDA(cudaSetDevice(h->device));
+    Dev &d = h->d;
+    const int nK = d.nK;
+    std::vector<int> depth(nTracers, 0), hasChild(nTracers, 0);
+    int maxLayers = 1;
+    for (int t = 0; t < nTracers; t++) {
+        IR_REQUIRE(tr[t].nLayers >= 1, "nLayers must be positive");
+        if (tr[t].nLayers > maxLayers) maxLayers = tr[t].nLayers;
+        if (t == 0) continue;
+        IR_REQUIRE(tr[t].parent >= 0 && tr[t].parent < t, "a parent must come before its children; only tracer 0 has none");
+        depth[t] = depth[tr[t].parent] + 1;
+        IR_REQUIRE(depth[t] < MAX_DEPTH, "at most three parents (incremental_remap.F:6745)");
+        const int pl = tr[tr[t].parent].nLayers;
+        IR_REQUIRE(pl == 1 || pl == tr[t].nLayers, "a layered parent must have the child's number of layers");
+        hasChild[tr[t].parent] = 1;
+        IR_REQUIRE(!tr[t].volumeLike || (tr[t].nLayers == 1 && tr[t].parent == 0 && tr[0].nLayers == 1),
+                   "volume-like tracers are one-layer children of a one-layer mass field");
+    }
+    for (int t = 0; t < nTracers; t++)
+        IR_REQUIRE(!(hasChild[t] && depth[t] >= 3), "a tracer with three parents cannot have children (incremental_remap.F:3840)");
+    // rows of ONE category (the hierarchy is the same in all of them), parents first: tracers by depth (list order
+    // within a depth), layers innermost.  tracerRow0[t] = the j of the tracer's first layer.
+    h->tracerRow0.assign(nTracers, 0);
+    h->tracerLayers.assign(nTracers, 1);
+    h->tracerParent.assign(nTracers, -1);
+    h->tracerVolume.assign(nTracers, 0);
+    h->tracerDepth = depth;
+    int nJ = 0;
+    for (int q = 0; q < MAX_DEPTH; q++)
+        for (int t = 0; t < nTracers; t++)
+            if (depth[t] == q) { h->tracerRow0[t] = nJ; nJ += tr[t].nLayers; }
+    h->rows.assign(nJ, RowInfo());
+    for (int t = 0; t < nTracers; t++) {
+        h->tracerLayers[t] = tr[t].nLayers;
+        h->tracerParent[t] = tr[t].parent;
+        h->tracerVolume[t] = tr[t].volumeLike ? 1 : 0;
+        for (int l = 0; l < tr[t].nLayers; l++) {
+            RowInfo &ri = h->rows[h->tracerRow0[t] + l];
+            ri.depth = depth[t];
+            ri.hasChild = hasChild[t];
+            ri.cat = 0;
+            ri.volumeLike = tr[t].volumeLike ? 1 : 0;
+            int q = t, s = depth[t];
+            while (q >= 0) {
+                ri.chain[s] = h->tracerRow0[q] + (tr[q].nLayers == 1 ? 0 : l);
+                q = tr[q].parent;
+                s--;
+            }
+            for (int z = depth[t] + 1; z < MAX_DEPTH; z++) ri.chain[z] = 0;
+        }
+    }
+    // barycentres and new mass * tracer products are kept for rows that have children only
+    int nSlots = 0;
+    for (int j = 0; j < nJ; j++) h->rows[j].slot = h->rows[j].hasChild ? nSlots++ : -1;
+    for (int j = 0; j < nJ; j++) h->rows[j].parentSlot = h->rows[j].depth > 0 ? h->rows[h->rows[j].chain[h->rows[j].depth - 1]].slot : -1;
+    h->nSlots = nSlots;
+    // (re)allocate the tracer state
+    IR_CUDA(cudaStreamSynchronize(h->stream));
+    double **bufs[] = {&d.val, &d.valNew, &d.recon, &d.bary, &d.mtpNew, &d.edgeFlux};
+    for (double **b : bufs)
+        if (*b) { cudaFree(*b); *b = nullptr; }
+    if (d.rows) { cudaFree(d.rows); d.rows = nullptr; }
+    d.nRowsPerCat = nJ;
+    d.nRows = nJ * nK;
+    d.JP = (int)round_up((size_t)nJ, 4);
+    d.SP = (int)round_up((size_t)(nSlots > 0 ? nSlots : 1), 4);
+    const size_t cells = (size_t)nK * d.nCp, edges = (size_t)nK * d.nEp;
+    const size_t sizes[] = {cells * d.JP, cells * d.JP, cells * d.JP * 3, cells * d.SP * 2, cells * d.SP, edges * d.JP};
+    for (int b = 0; b < 6; b++) {
+        IR_CUDA(cudaMalloc((void **)bufs[b], sizeof(double) * sizes[b]));
+        IR_CUDA(cudaMemsetAsync(*bufs[b], 0, sizeof(double) * sizes[b], h->stream));
+    }
+    IR_CUDA(cudaMalloc((void **)&d.rows, sizeof(RowInfo) * nJ));
+    IR_CUDA(cudaMemcpyAsync(d.rows, h->rows.data(), sizeof(RowInfo) * nJ, cudaMemcpyHostToDevice, h->stream));
+    const size_t nMax = (size_t)(d.nC > d.nE ? d.nC : d.nE) + 1;
+    int rc = ensure_stage(h, sizeof(double) * nMax * nK * maxLayers);
+    if (rc) return rc;
+    IR_CUDA(cudaStreamSynchronize(h->stream));
+    h->haveTracers = true;
+    return IR_OK;
+}
+
+extern "C" int ir_run(ir_handle *h, int nTracers, const ir_tracer_desc *tr, const double *u, const double *v, double dt)
+{
+    IR_REQUIRE(h != nullptr && tr != nullptr && u != nullptr && v != nullptr, "NULL argument");
+    if (!h->haveTracers) { set_error("ir_run before ir_set_tracers"); return IR_ERR_STATE; }
+    IR_REQUIRE(nTracers == (int)h->tracerRow0.size(), "tracer table differs from the one given to ir_set_tracers");
+    for (int t = 0; t < nTracers; t++)
+        IR_REQUIRE(tr[t].array != nullptr && tr[t].nLayers == h->tracerLayers[t] && tr[t].parent == h->tracerParent[t] &&
+                       (tr[t].volumeLike ? 1 : 0) == h->tracerVolume[t],
+                   "tracer table differs from the one given to ir_set_tracers");
+    IR_CUDA(cudaSetDevice(h->device));
+    Dev &d = h->d;
+    cudaStream_t s = h->stream;
+    const size_t nC1 = (size_t)d.nC + 1;
+    const int nK = d.nK;
+    // in: tracers (host (nCells+1, nK*nL) -> rows) and velocities
+    for (int t = 0; t < nTracers; t++) pin_host(h, tr[t].array, nC1 * nK * tr[t].nLayers * sizeof(double));
+    pin_host(h, u, ((size_t)d.nV + 1) * 8);
+    pin_host(h, v, ((size_t)d.nV + 1) * 8);
+    for (int t = 0; t < nTracers; t++) {
+        const size_t bytes = nC1 * nK * tr[t].nLayers * sizeof(double);
+        int rc = ensure_stage(h, bytes);
+        if (rc) return rc;
+        IR_CUDA(cudaMemcpyAsync(d.stage, tr[t].array, bytes, cudaMemcpyHostToDevice, s));
+        IR_LAUNCH((k_tracer_in), grid_for(nC1, 256), 256, s, d.stage, d.val, nC1, nK, tr[t].nLayers, h->tracerRow0[t], d.nCp, d.JP);
+        h->launches++;
+        IR_CUDA(cudaGetLastError());
+        IR_CUDA(cudaStreamSynchronize(s));       // the staging area is reused by the next tracer
+    }
+    IR_CUDA(cudaMemcpyAsync(d.u, u, ((size_t)d.nV + 1) * 8, cudaMemcpyHostToDevice, s));
+    IR_CUDA(cudaMemcpyAsync(d.v, v, ((size_t)d.nV + 1) * 8, cudaMemcpyHostToDevice, s));
+    IR_CUDA(cudaMemsetAsync(d.flags, 0, sizeof(int), s));
+    IR_CUDA(cudaEventRecord(h->ev0, s));
+    const unsigned gc = grid_for(nC1, 128), ge = grid_for((size_t)d.nE, 128);
+    IR_LAUNCH((k_prepare), gc, 128, s, d, h->tracerLayers[0]);
+    h->launches++;
+    if (d.nC > 0) {
+        IR_LAUNCH((k_reconstruct), dim3(grid_for((size_t)d.nC, RB), nK), RB, s, d);
+        h->launches++;
+    }
+    if (d.nE > 0) {
+        IR_LAUNCH((k_triangles), ge, 128, s, d, dt);
+        if (d.D == 3) IR_LAUNCH((k_fluxes<4>), dim3(grid_for((size_t)d.nE, RB), nK), RB, s, d);
+        else IR_LAUNCH((k_fluxes<6>), dim3(grid_for((size_t)d.nE, RB), nK), RB, s, d);
+        h->launches += 2;
+    }
+    IR_LAUNCH((k_update), dim3(grid_for(nC1, RB), nK), RB, s, d, h->tracerLayers[0] == 1 ? 1 : 0);
+    h->launches++;
+    IR_CUDA(cudaEventRecord(h->ev1, s));
+    IR_CUDA(cudaGetLastError());
+    // out
+    for (int t = 0; t < nTracers; t++) {
+        const int w = nK * tr[t].nLayers;
+        IR_LAUNCH((k_tracer_out), grid_for(nC1, 256), 256, s, d.stage, d.valNew, nC1, nK, tr[t].nLayers, h->tracerRow0[t], d.nCp, d.JP,
+                  1, 0);
+        h->launches++;
+        IR_CUDA(cudaMemcpyAsync(tr[t].array, d.stage, nC1 * w * 8, cudaMemcpyDeviceToHost, s));
+        IR_CUDA(cudaStreamSynchronize(s));
+    }
+    int flags = 0;
+    IR_CUDA(cudaMemcpyAsync(&flags, d.flags, sizeof(int), cudaMemcpyDeviceToHost, s));
+    IR_CUDA(cudaStreamSynchronize(s));
+    IR_CUDA(cudaEventElapsedTime(&h->lastMs, h->ev0, h->ev1));
+    if (flags & FLAG_NEG_MASS) { set_error("IR: negative mass in a cell (incremental_remap.F:7465)"); return IR_ERR_NEGATIVE_MASS; }
+    if (flags & FLAG_NEG_QP) { set_error("IR: negative mass at a quadrature point (incremental_remap.F:6895)"); return IR_ERR_NEGATIVE_MASS_QP; }
+    if (flags & FLAG_PARALLEL) { set_error("IR: parallel basis edges in shift_vertices (incremental_remap.F:6415)"); return IR_ERR_PARALLEL_EDGES; }
+    if (flags & FLAG_MANY_TRI) { set_error("IR: more than nTriPerEdgeRemap departure triangles on an edge"); return IR_ERR_TOO_MANY_TRIANGLES; }
+    return IR_OK;
+}
+
+extern "C" int ir_fetch_diagnostics(ir_handle *h, double *xTriangle, double *yTriangle, double *triangleArea,
+                                    int *iCellTriangle, int *maskEdge, double *edgeFluxMass)
+{
+    IR_REQUIRE(h != nullptr, "handle is NULL");
+    IR_CUDA(cudaSetDevice(h->device));
+    Dev &d = h->d;
+    const size_t nE = (size_t)d.nE;
+    if (nE == 0) return IR_OK;
+    cudaStream_t s = h->stream;
+    std::vector<double> tmp;
+    std::vector<int> itmp;
+    auto fetch = [&](const double *src, size_t rows) -> int {
+        tmp.resize(rows * d.nEp);
+        IR_CUDA(cudaMemcpyAsync(tmp.data(), src, rows * d.nEp * 8, cudaMemcpyDeviceToHost, s));
+        IR_CUDA(cudaStreamSynchronize(s));
+        return IR_OK;
+    };
+    int rc;
+    for (int pass = 0; pass < 2; pass++) {
+        double *dst = pass == 0 ? xTriangle : yTriangle;
+        if (!dst) continue;
+        if ((rc = fetch(pass == 0 ? d.xq : d.yq, NTRI * 6))) return rc;
+        for (size_t e = 0; e < nE; e++)
+            for (int t = 0; t < NTRI; t++)
+                for (int q = 0; q < d.nQP; q++) dst[(e * NTRI + t) * d.nQP + q] = tmp[(size_t)(t * 6 + q) * d.nEp + e];
+    }
+    if (triangleArea) {
+        if ((rc = fetch(d.triArea, NTRI))) return rc;
+        for (size_t e = 0; e < nE; e++)
+            for (int t = 0; t < NTRI; t++) triangleArea[e * NTRI + t] = tmp[(size_t)t * d.nEp + e];
+    }
+    if (iCellTriangle) {
+        itmp.resize(NTRI * d.nEp);
+        IR_CUDA(cudaMemcpyAsync(itmp.data(), d.iCellTri, NTRI * d.nEp * 4, cudaMemcpyDeviceToHost, s));
+        IR_CUDA(cudaStreamSynchronize(s));
+        for (size_t e = 0; e < nE; e++)
+            for (int t = 0; t < NTRI; t++) iCellTriangle[e * NTRI + t] = itmp[(size_t)t * d.nEp + e];
+    }
+    if (maskEdge) {
+        IR_CUDA(cudaMemcpyAsync(maskEdge, d.maskEdge, nE * 4, cudaMemcpyDeviceToHost, s));
+        IR_CUDA(cudaStreamSynchronize(s));
+    }
+    if (edgeFluxMass && h->haveTracers) {
+        const int nL = h->tracerLayers[0];
+        const size_t n1 = nE + 1;
+        if ((rc = ensure_stage(h, n1 * d.nK * nL * sizeof(double)))) return rc;
+        IR_LAUNCH((k_tracer_out), grid_for(n1, 256), 256, s, d.stage, d.edgeFlux, n1, d.nK, nL, 0, d.nEp, d.JP, 1, 0);
+        h->launches++;
+        IR_CUDA(cudaGetLastError());
+        IR_CUDA(cudaMemcpyAsync(edgeFluxMass, d.stage, nE * d.nK * nL * sizeof(double), cudaMemcpyDeviceToHost, s));
+        IR_CUDA(cudaStreamSynchronize(s));
+    }
+    return IR_OK;
+}
+
+extern "C" int ir_fetch_tracer_field(ir_handle *h, int which, int tracer, double *out)
+{
+    IR_REQUIRE(h != nullptr && out != nullptr, "NULL argument");
+    if (!h->haveTracers) { set_error("ir_fetch_tracer_field before ir_set_tracers"); return IR_ERR_STATE; }
+    IR_REQUIRE(tracer >= 0 && tracer < (int)h->tracerRow0.size(), "tracer index out of range");
+    IR_CUDA(cudaSetDevice(h->device));
+    Dev &d = h->d;
+    const double *src = nullptr;
+    bool onEdges = false, parentOnly = false;
+    int inner = d.JP, stride = 1, offset = 0;
+    switch (which) {
+        case IR_FIELD_CENTER: src = d.recon; inner = 3 * d.JP; stride = 3; offset = 0; break;
+        case IR_FIELD_XGRAD: src = d.recon; inner = 3 * d.JP; stride = 3; offset = 1; break;
+        case IR_FIELD_YGRAD: src = d.recon; inner = 3 * d.JP; stride = 3; offset = 2; break;
+        case IR_FIELD_XBARYCENTER: src = d.bary; inner = 2 * d.SP; stride = 2; offset = 0; parentOnly = true; break;
+        case IR_FIELD_YBARYCENTER: src = d.bary; inner = 2 * d.SP; stride = 2; offset = 1; parentOnly = true; break;
+        case IR_FIELD_MASS_TRACER_PRODUCT: src = d.mtpNew; inner = d.SP; parentOnly = true; break;
+        case IR_FIELD_EDGE_FLUX: src = d.edgeFlux; onEdges = true; break;
+        default: IR_REQUIRE(false, "unknown field");
+    }
+    const int nL = h->tracerLayers[tracer];
+    const size_t n = onEdges ? (size_t)d.nE + 1 : (size_t)d.nC + 1, pitch = onEdges ? d.nEp : d.nCp;
+    int j0 = h->tracerRow0[tracer];
+    if (parentOnly) {
+        IR_REQUIRE(h->rows[j0].slot >= 0, "barycentres and products are kept for tracers that have children only");
+        j0 = h->rows[j0].slot;                         // the layers of one tracer have consecutive slots
+    }
+    int rc = ensure_stage(h, n * d.nK * nL * sizeof(double));
+    if (rc) return rc;
+    IR_LAUNCH((k_tracer_out), grid_for(n, 256), 256, h->stream, d.stage, src, n, d.nK, nL, j0, pitch, inner, stride, offset);
+    h->launches++;
+    IR_CUDA(cudaGetLastError());
+    IR_CUDA(cudaMemcpyAsync(out, d.stage, n * d.nK * nL * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    IR_CUDA(cudaStreamSynchronize(h->stream));
+    return IR_OK;
+}
+
+extern "C" int ir_last_run_ms(ir_handle *h, float *ms)
+{
+    IR_REQUIRE(h != nullptr && ms != nullptr, "NULL argument");
+    *ms = h->lastMs;
+    return IR_OK;
+}
+
+extern "C" int ir_launch_count(ir_handle *h, long long *n)
+{
+    IR_REQUIRE(h != nullptr && n != nullptr, "NULL argument");
+    *n = h->launches;
+    return IR_OK;
+}
+
+extern "C" int ir_release_host_memory(ir_handle *h)
+{
+    IR_REQUIRE(h != nullptr, "handle is NULL");
+    IR_CUDA(cudaSetDevice(h->device));
+    IR_CUDA(cudaStreamSynchronize(h->stream));
+    unpin_all(h);
+    return IR_OK;
+}
+
+extern "C" int ir_destroy(ir_handle *h)
+{
+    if (!h) return IR_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    unpin_all(h);
+    Dev &d = h->d;
+    double *bufs[] = {d.val, d.valNew, d.recon, d.bary, d.mtpNew, d.edgeFlux, d.stage};
+    for (double *b : bufs)
+        if (b) cudaFree(b);
+    if (d.rows) cudaFree(d.rows);
+    for (void *p : h->allocs) cudaFree(p);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return IR_OK;
+}

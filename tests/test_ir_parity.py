@@ -21,9 +21,12 @@ from mpas_seaice_b200 import ir_host
 from test_oracle_ir import case, smooth_divergent_velocity, uniform_velocity, _random_state
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SRC = os.path.join(ROOT, "mpas-seaice_b200", "csrc", "ir_kernels.cu")
+# IR_B200_EMU_SRC: run the emulation leg on another source file with the same ABI (the experimental layout variants
+# under csrc/experimental/)
+SRC = os.environ.get("IR_B200_EMU_SRC") or os.path.join(ROOT, "mpas-seaice_b200", "csrc", "ir_kernels.cu")
 EMU_DIR = os.path.join(ROOT, "tests", "emu")
-EMU_LIB = os.path.join(ROOT, "tests", "_build", "libir_emu.so")
+EMU_LIB = os.path.join(ROOT, "tests", "_build", "libir_emu%s.so" % ("" if "IR_B200_EMU_SRC" not in os.environ else
+                                                                   "_" + os.path.splitext(os.path.basename(SRC))[0]))
 
 
 def _emulation_library():
