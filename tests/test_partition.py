@@ -143,3 +143,30 @@ def test_weak_operators_bit_identical_across_rank_counts(kind, n_parts, method, 
         for k in ("stress11Weak", "stress22Weak", "stress12Weak", "strain11Weak", "strain12Weak"):
             assert np.array_equal(s[k][:nCs], ref[k][gc]), k
     assert np.abs(ref["uVelocity"]).max() > 0
+
+
+@pytest.mark.parametrize("kind,n_parts,n_halos", [("ico4", 4, 2), ("hex20", 3, 2), ("quad40", 3, 3)])
+def test_cell_exchange_lists_are_consistent(kind, n_parts, n_halos):
+    """The cell halo maps of the transport (partition.cell_halo_requests / cell_exchange_lists): every halo cell is
+    received exactly once, from the rank that owns it; what a rank sends are owned cells; sender and receiver agree on
+    the order (ascending global id).  The reference's own maps live in the MPAS framework (unpinned): self-consistency
+    plus identical results across rank counts (tests/test_ir_multirank.py) is the check."""
+    mesh, _ = common.mesh_case(kind)
+    part = partition.partition_cells(mesh, n_parts)
+    blocks = [partition.build_block(mesh, part, r, n_halos) for r in range(n_parts)]
+    requests = {r: partition.cell_halo_requests(b) for r, b in enumerate(blocks)}
+    lists = [partition.cell_exchange_lists(b, requests) for b in blocks]
+    for r, b in enumerate(blocks):
+        nbrs, soff, sidx, roff, ridx = lists[r]
+        assert np.array_equal(b.cellOwner[:b.nCellsSolve], np.full(b.nCellsSolve, r))
+        got = np.sort(ridx)
+        assert np.array_equal(got, np.arange(b.nCellsSolve + 1, b.nCells + 1))          # every halo cell, once
+        assert np.all(sidx >= 1) and np.all(sidx <= b.nCellsSolve)                        # only owned cells are sent
+        for k, q in enumerate(nbrs):
+            q = int(q)
+            qn, qsoff, qsidx, qroff, qridx = lists[q]
+            kk = int(np.nonzero(qn == r)[0][0])
+            mine = ridx[roff[k]:roff[k + 1]] - 1
+            theirs = qsidx[qsoff[kk]:qsoff[kk + 1]] - 1
+            assert np.array_equal(b.indexToCellID[mine], blocks[q].indexToCellID[theirs])
+            assert np.all(b.cellOwner[mine] == q)
