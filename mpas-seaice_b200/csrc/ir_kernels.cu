@@ -616,8 +616,8 @@ __global__ void __launch_bounds__(128) k_triangles(Dev d, double dt)
 
 // integrate_fluxes_over_triangles (:6667): one thread per (edge, category).  The quadrature points of the edge's
 // non-empty departure triangles are parked once in a per-thread shared-memory column and reused by every row of the
-// category.  CAP = the most triangles an edge can have (4 on hexagonal meshes, 6 on quadrilateral ones,
-// find_departure_triangles :5420-5460): it sizes the scratch, i.e. the blocks that fit on an SM.  triangleValue of a
+// category.  CAP = the triangles parked per edge (4 on hexagonal meshes -- the most a smooth flow produces there,
+// find_departure_triangles :5420-5460 -- 6 on quadrilateral ones): it sizes the scratch, i.e. the blocks that fit on an SM.  triangleValue of a
 // row is the product down its chain of parents of the linear reconstructions at the quadrature point, the mass field
 // first.
 template <int CAP>
@@ -632,11 +632,16 @@ __global__ void __launch_bounds__(RB) k_fluxes(Dev d)
     double area[CAP];
     size_t cell[CAP];
     int nt = 0;
+    // An edge of a hexagonal mesh has at most four departure triangles when the velocity varies smoothly (the
+    // reference's own count, :5420-5460), but two side triangles at one vertex do occur in rough fields: triangles
+    // beyond CAP stay in global memory and are integrated from there, after the parked ones (they come later in
+    // triangle order, so the order of the sum is unchanged).
+    int extra[NTRI - CAP > 0 ? NTRI - CAP : 1], nx = 0;
     if (d.maskEdge[e] == 1) {
         for (int t = 0; t < NTRI; t++) {            // in triangle order: the order the fluxes are summed in
             const double a = d.triArea[t * pe + e];
             if (a == 0.0) continue;
-            if (nt == CAP) { atomicOr(d.flags, FLAG_MANY_TRI); break; }
+            if (nt == CAP) { if (nx < NTRI - CAP) extra[nx++] = t; continue; }
             area[nt] = a;
             cell[nt] = (size_t)d.iCellTri[t * pe + e] - 1;
             for (int q = 0; q < nQP; q++) {
@@ -650,13 +655,14 @@ __global__ void __launch_bounds__(RB) k_fluxes(Dev d)
         // zero and the flux is the +0.0 written below.  Most of an ocean mesh is ice-free.
         bool ice = false;
         for (int t = 0; t < nt; t++) ice = ice || d.maskCell[cell[t]] == 1;
-        if (!ice) nt = 0;
+        for (int x = 0; x < nx; x++) ice = ice || d.maskCell[d.iCellTri[extra[x] * pe + e] - 1] == 1;
+        if (!ice) { nt = 0; nx = 0; }
     }
     bool negative = false;
     for (int j = 0; j < d.nRowsPerCat; j++) {
         const int r = d.catBaseRow[j] + cat * d.catLayers[j];
         double flux = 0.0;
-        if (nt > 0) {
+        if (nt + nx > 0) {
             const RowInfo ri = d.rows[r];
             for (int t = 0; t < nt; t++) {
                 double cen[MAX_DEPTH], gx[MAX_DEPTH], gy[MAX_DEPTH];
@@ -674,6 +680,25 @@ __global__ void __launch_bounds__(RB) k_fluxes(Dev d)
                     tracerIntegral = tracerIntegral + w * value;
                 }
                 flux = flux + area[t] * tracerIntegral;
+            }
+            for (int x = 0; x < nx; x++) {          // the rare triangles that did not fit the scratch
+                const int t = extra[x];
+                const size_t cl = (size_t)d.iCellTri[t * pe + e] - 1;
+                double cen[MAX_DEPTH], gx[MAX_DEPTH], gy[MAX_DEPTH];
+                for (int s = 0; s <= ri.depth; s++) {
+                    const size_t q = (size_t)ri.chain[s] * pc + cl;
+                    cen[s] = d.center[q]; gx[s] = d.xGrad[q]; gy[s] = d.yGrad[q];
+                }
+                double tracerIntegral = 0.0;
+                for (int iqp = 0; iqp < nQP; iqp++) {
+                    const double xx = d.xq[(size_t)(t * 6 + iqp) * pe + e], yy = d.yq[(size_t)(t * 6 + iqp) * pe + e];
+                    double value = 1.0;
+                    for (int s = 0; s <= ri.depth; s++) value = value * (cen[s] + gx[s] * xx + gy[s] * yy);
+                    if (ri.depth == 0 && value < 0.0) negative = true;
+                    const double w = (nQP == 3) ? (1.0 / 3.0) : (iqp < 3 ? W1QP : W2QP);
+                    tracerIntegral = tracerIntegral + w * value;
+                }
+                flux = flux + d.triArea[t * pe + e] * tracerIntegral;
             }
         }
         d.edgeFlux[(size_t)r * pe + e] = flux;

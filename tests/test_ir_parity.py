@@ -307,6 +307,50 @@ def test_work_fields_match_oracle(lib_path):
         solver.destroy()
 
 
+@pytest.mark.parametrize("kind", ["hex16", "quad16", "ico3", "band48"])
+def test_random_states_and_velocities_match_oracle(kind, lib_path):
+    """Fuzz: random ice cover, random CFL up to 0.6, velocity fields alternately smooth and random per vertex.  The
+    rough fields reach the rare configurations -- two side triangles at one vertex (more than four departure triangles
+    on a hexagonal edge: first found by this test), departure regions leaving their source cell (the reference's abort
+    conditions).  Device and oracle must agree on the triangles and fluxes always, on every tracer when neither aborts,
+    and on whether the step is fatal."""
+    mesh, irf, geom = case(kind)
+    nC, nV = mesh.nCells, mesh.nVertices
+    solver = ir_host.IrTransport(mesh, irf, geom, 2, lib_path=lib_path)
+    seen_many = False
+    try:
+        for seed in range(8):
+            rng = np.random.default_rng(1000 + seed)
+            tracers = _random_state(mesh, rng, n_cat=2, n_ice=2, n_snow=1, ice_free=rng.uniform(0, 0.6))
+            cfl = rng.uniform(0.1, 0.6)
+            if seed % 2 == 0:
+                speed = cfl * geom["minLengthEdgesOnVertex"][:nV].min() / 3600.0
+                u, v = np.zeros(nV + 1), np.zeros(nV + 1)
+                u[:nV], v[:nV] = rng.uniform(-speed, speed, nV), rng.uniform(-speed, speed, nV)
+            else:
+                uu, vv = smooth_divergent_velocity(mesh, geom, cfl=cfl)
+                ang = rng.uniform(0, 2 * np.pi)
+                u, v = uu * np.cos(ang) - vv * np.sin(ang), uu * np.sin(ang) + vv * np.cos(ang)
+            ref, dev = clone(tracers), clone(tracers)
+            d_ref = ir.run(mesh, irf, geom, ref, u, v, 3600.0, check=False, diagnostics=True)
+            solver.set_tracers(dev)
+            rc = solver.run(dev, u, v, 3600.0, check=False)
+            d_dev = solver.diagnostics()
+            for key in d_dev:
+                assert np.array_equal(d_ref[key], d_dev[key]), (seed, key)
+            seen_many = seen_many or np.count_nonzero(d_ref["triangleArea"], axis=1).max() > 4
+            assert (d_ref["error"] != 0) == (rc != 0), (seed, d_ref["error"], rc)
+            if d_ref["error"] == 0:
+                for a, b in zip(ref, dev):
+                    assert np.array_equal(a.array[:nC], b.array[:nC]), (seed, a.name)
+            elif d_ref["error"] == 4:        # flagged after the whole step ran: the fields are still comparable
+                assert np.array_equal(ref[0].array[:nC], dev[0].array[:nC]), seed
+    finally:
+        solver.destroy()
+    if kind == "ico3":
+        assert seen_many                     # the case that needs the overflow path of k_fluxes is in the sample
+
+
 def test_rotation_test_case_matches_oracle(lib_path):
     """The reference's advection test case (cosine bell, u = U cos(lat); create_ics.py:36-107) on the 2562-cell
     sphere with its twelve pentagons: ten steps, identical throughout."""
