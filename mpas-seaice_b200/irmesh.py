@@ -64,7 +64,7 @@ def oriented_vertices_on_edge(mesh):
     return voe, eov
 
 
-def reconstruction_coefficients(mesh, x_edge, y_edge, z_edge):
+def reconstruction_coefficients(mesh, x_edge, y_edge, z_edge, chunk=262144):
     """coeffs_reconstruct (nCells+1, maxEdges, 3): gradient (or any tangent vector) at a cell centre =
     sum over the cell's edges of coeffs * (normal component at the edge, positive from cellsOnEdge(1) to (2))."""
     nC, nE, M = mesh.nCells, mesh.nEdges, mesh.maxEdges
@@ -93,28 +93,30 @@ def reconstruction_coefficients(mesh, x_edge, y_edge, z_edge):
     for n in np.unique(n_on):
         if n < 1:
             continue
-        cells = np.nonzero(n_on == n)[0]
-        e = mesh.edgesOnCell[cells, :n].astype(np.int64) - 1          # (B, n)
-        x = pe[e]                                                     # (B, n, 3)
-        nv = n_e[e]
-        c = pc[cells]
-        alpha = np.mean(0.5 * np.sqrt(np.sum((x - c[:, None, :]) ** 2, axis=2)), axis=1)   # (B,)
-        # everything in the tangent plane
-        xs = np.stack([np.sum(x * t1[cells][:, None, :], axis=2), np.sum(x * t2[cells][:, None, :], axis=2)], axis=2)
-        ns = np.stack([np.sum(nv * t1[cells][:, None, :], axis=2), np.sum(nv * t2[cells][:, None, :], axis=2)], axis=2)
-        cs = np.stack([np.sum(c * t1[cells], axis=1), np.sum(c * t2[cells], axis=1)], axis=1)
-        r2 = np.sum((xs[:, :, None, :] - xs[:, None, :, :]) ** 2, axis=3) / (alpha ** 2)[:, None, None]
-        A = np.zeros((cells.size, n + 2, n + 2))
-        A[:, :n, :n] = (1.0 / np.sqrt(1.0 + r2)) * np.sum(ns[:, :, None, :] * ns[:, None, :, :], axis=3)
-        A[:, :n, n:] = ns
-        A[:, n:, :n] = np.transpose(ns, (0, 2, 1))
-        rd = np.sum((xs - cs[:, None, :]) ** 2, axis=2) / (alpha ** 2)[:, None]
-        rhs = np.zeros((cells.size, n + 2, 2))
-        rhs[:, :n, :] = (1.0 / np.sqrt(1.0 + rd))[:, :, None] * ns
-        rhs[:, n, 0] = 1.0
-        rhs[:, n + 1, 1] = 1.0
-        sol = np.linalg.solve(A, rhs)[:, :n, :]                       # (B, n, 2)
-        out[cells, :n, :] = sol[:, :, 0:1] * t1[cells][:, None, :] + sol[:, :, 1:2] * t2[cells][:, None, :]
+        group = np.nonzero(n_on == n)[0]
+        for start in range(0, group.size, chunk):          # bounded memory: (chunk, n+2, n+2) systems at a time
+            cells = group[start:start + chunk]
+            e = mesh.edgesOnCell[cells, :n].astype(np.int64) - 1          # (B, n)
+            x = pe[e]                                                     # (B, n, 3)
+            nv = n_e[e]
+            c = pc[cells]
+            alpha = np.mean(0.5 * np.sqrt(np.sum((x - c[:, None, :]) ** 2, axis=2)), axis=1)   # (B,)
+            # everything in the tangent plane
+            xs = np.stack([np.sum(x * t1[cells][:, None, :], axis=2), np.sum(x * t2[cells][:, None, :], axis=2)], axis=2)
+            ns = np.stack([np.sum(nv * t1[cells][:, None, :], axis=2), np.sum(nv * t2[cells][:, None, :], axis=2)], axis=2)
+            cs = np.stack([np.sum(c * t1[cells], axis=1), np.sum(c * t2[cells], axis=1)], axis=1)
+            r2 = np.sum((xs[:, :, None, :] - xs[:, None, :, :]) ** 2, axis=3) / (alpha ** 2)[:, None, None]
+            A = np.zeros((cells.size, n + 2, n + 2))
+            A[:, :n, :n] = (1.0 / np.sqrt(1.0 + r2)) * np.sum(ns[:, :, None, :] * ns[:, None, :, :], axis=3)
+            A[:, :n, n:] = ns
+            A[:, n:, :n] = np.transpose(ns, (0, 2, 1))
+            rd = np.sum((xs - cs[:, None, :]) ** 2, axis=2) / (alpha ** 2)[:, None]
+            rhs = np.zeros((cells.size, n + 2, 2))
+            rhs[:, :n, :] = (1.0 / np.sqrt(1.0 + rd))[:, :, None] * ns
+            rhs[:, n, 0] = 1.0
+            rhs[:, n + 1, 1] = 1.0
+            sol = np.linalg.solve(A, rhs)[:, :n, :]                       # (B, n, 2)
+            out[cells, :n, :] = sol[:, :, 0:1] * t1[cells][:, None, :] + sol[:, :, 1:2] * t2[cells][:, None, :]
     return out
 
 
