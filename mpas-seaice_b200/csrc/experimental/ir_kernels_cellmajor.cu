@@ -1404,7 +1404,8 @@ extern "C" int ir_set_tracers(ir_handle *h, int nTracers, const ir_tracer_desc *
     for (int j = 0; j < nJ; j++) h->rows[j].slot = h->rows[j].hasChild ? nSlots++ : -1;
     for (int j = 0; j < nJ; j++) h->rows[j].parentSlot = h->rows[j].depth > 0 ? h->rows[h->rows[j].chain[h->rows[j].depth - 1]].slot : -1;
     h->nSlots = nSlots;
-    // (re)allocate the tracer state
+    // (re)allocate the tracer state; a failure from here on leaves the handle without tracers
+    h->haveTracers = false;
     IR_CUDA(cudaStreamSynchronize(h->stream));
     double **bufs[] = {&d.val, &d.valNew, &d.recon, &d.bary, &d.mtpNew, &d.edgeFlux};
     for (double **b : bufs)

@@ -1384,7 +1384,8 @@ extern "C" int ir_set_tracers(ir_handle *h, int nTracers, const ir_tracer_desc *
     for (int r = 0; r < nRows; r++) h->rows[r].slot = h->rows[r].hasChild ? nSlots++ : -1;
     for (int r = 0; r < nRows; r++) h->rows[r].parentSlot = h->rows[r].depth > 0 ? h->rows[h->rows[r].chain[h->rows[r].depth - 1]].slot : -1;
     h->nSlots = nSlots;
-    // (re)allocate the tracer state
+    // (re)allocate the tracer state; a failure from here on leaves the handle without tracers
+    h->haveTracers = false;
     IR_CUDA(cudaStreamSynchronize(h->stream));
     double **bufs[] = {&d.val, &d.valNew, &d.center, &d.xGrad, &d.yGrad, &d.xBary, &d.yBary, &d.mtpNew, &d.edgeFlux};
     for (double **b : bufs)
