@@ -59,7 +59,9 @@ module seaice_evp_b200
        EVP_CR_EVP = 1, EVP_CR_EVP_REVISED = 2, EVP_CR_LINEAR = 3, EVP_CR_NONE = 4, &
        EVP_OCEAN_QUADRATIC = 1, EVP_OCEAN_LINEAR = 2, &
        EVP_FLAG_PIN_HOST = 1, EVP_FLAG_OVERLAP_HALO = 2, &
-       EVP_SCHEME_VARIATIONAL = 1, EVP_SCHEME_WEAK = 2
+       EVP_SCHEME_VARIATIONAL = 1, EVP_SCHEME_WEAK = 2, &
+       EVP_START_RESIDENT = 0, EVP_START_FROM_REST = 1, EVP_START_FIRST_STEP = 2, &
+       EVP_HALO_NONE = 0, EVP_HALO_NCCL = 1, EVP_HALO_P2P = 2
 
   ! ---- struct evp_mesh_desc ----
   type, bind(C), public :: evp_mesh_desc
@@ -320,6 +322,15 @@ module seaice_evp_b200
        integer(c_int), intent(in) :: recvIndex(*)
        integer(c_int) :: ierr
      end function evp_set_halo
+
+     function evp_halo_mode(handle, mode, why, whyLen) bind(C, name="evp_halo_mode") result(ierr)
+       import :: c_ptr, c_char, c_int
+       type(c_ptr), value :: handle
+       integer(c_int), intent(out) :: mode
+       character(kind=c_char), intent(out) :: why(*)
+       integer(c_int), value :: whyLen
+       integer(c_int) :: ierr
+     end function evp_halo_mode
 
      function evp_set_mesh_ext(handle, ext) bind(C, name="evp_set_mesh_ext") result(ierr)
        import :: c_ptr, c_int, evp_mesh_ext
@@ -914,7 +925,8 @@ contains
 !> :820-836) and icePressure for every cell that may be solved (ice_strength, :1419-1460, evaluated
 !> without its solveStress test; the device applies the mask).  u, v, the stresses and
 !> solveVelocityPrevious stay on the device between steps; coldStart = .true. on the first step of a
-!> run from rest, after a restart call evp_set_state first.
+!> run without a restart file (solveVelocityPrevious = 0 as in the reference, so solved vertices start at
+!> the ocean velocity, velocity_solver.F:1252-1258), after a restart call evp_set_state first.
 !-----------------------------------------------------------------------
 
   subroutine seaice_evp_b200_step(domain, coldStart)
@@ -1001,7 +1013,7 @@ contains
     po % use_surface_tilt = merge(1, 0, config_use_surface_tilt)
     po % geostrophic_surface_tilt = merge(1, 0, config_geostrophic_surface_tilt)
     po % calc_velocity_masks = merge(1, 0, config_calc_velocity_masks)
-    po % cold_start = merge(1, 0, coldStart)
+    po % cold_start = merge(EVP_START_FIRST_STEP, EVP_START_RESIDENT, coldStart)
 
     call fill_options(domain, options)
     call evp_b200_check(evp_set_options(evpHandle, options), "evp_set_options")

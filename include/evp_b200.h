@@ -51,10 +51,9 @@ enum { EVP_SCHEME_VARIATIONAL = 1, EVP_SCHEME_WEAK = 2 };
 
 /* evp_options.flags */
 enum {
-    EVP_FLAG_OVERLAP_HALO = 2,/* multi-rank: solve the boundary-owned vertices first and run pack / NCCL / unpack on a
-                                 forked high-priority branch while the interior vertices are solved.  Off by
-                                 default: inside the replayed graph the plain in-order exchange measured the
-                                 same or faster on NVLink */
+    EVP_FLAG_OVERLAP_HALO = 2,/* accepted and ignored (kept for ABI stability): round 1's forked pack / NCCL / unpack branch
+                                 measured no gain and is superseded by the peer-to-peer exchange, in which the vertex
+                                 kernel itself stores boundary velocities into the neighbours (evp_set_halo) */
     EVP_FLAG_PIN_HOST = 1     /* host arrays passed to update_step / fetch live at stable addresses for the
                                  life of the handle (true for MPAS pool arrays): page-lock them once with
                                  cudaHostRegister so the per-step copies run at full PCIe speed.  The arrays must
@@ -208,14 +207,27 @@ const char *evp_last_error_string(void);
  * for neighbour k, sendIndex[sendOffset[k] .. sendOffset[k+1]) are the local 1-based owned vertices
  * whose (u,v) this rank sends to rank neighbourRank[k]; recvIndex likewise are the local halo
  * vertices filled from that rank, in the sender's send order.
- * evp_comm_init and evp_set_halo are COLLECTIVE: every rank of the communicator must call them (set_halo
- * performs one eager warm-up exchange so that NCCL's lazy connection set-up never happens inside the
- * captured subcycle graph). */
+ * evp_comm_init, evp_set_halo and (once a halo is attached) evp_destroy are COLLECTIVE: every rank of the
+ * communicator must call them.  evp_set_halo chooses the exchange:
+ *   EVP_HALO_P2P   every neighbour's velocity array could be mapped (cudaIpc*, one process per GPU on one NVLink
+ *                  node) and all ranks agreed: the vertex kernel stores the (u,v) of boundary-owned vertices straight
+ *                  into double-buffered halo slots of the neighbours and publishes a per-pass flag; the cell kernel
+ *                  waits on the flags only where it gathers a halo vertex.  No communication kernel, no NCCL node in
+ *                  the captured graph.  All ranks must then call evp_run_subcycles with the same counts.
+ *   EVP_HALO_NCCL  otherwise (or EVP_B200_HALO=nccl in the environment; also whenever the weak operators or the
+ *                  special boundaries are switched on): pack kernel + grouped ncclSend/ncclRecv on the handle's stream
+ *                  inside the graph, received in place when each neighbour's halo vertices are one contiguous run of the
+ *                  local numbering.  set_halo performs one eager warm-up exchange so that NCCL's lazy connection
+ *                  set-up never happens inside the captured subcycle graph.
+ * EVP_B200_HALO=p2p makes evp_set_halo fail instead of falling back.  Results are bit-identical either way. */
+enum { EVP_HALO_NONE = 0, EVP_HALO_NCCL = 1, EVP_HALO_P2P = 2 };
 int evp_comm_get_unique_id(char *id128);   /* rank 0 calls this, host broadcasts the 128 bytes (MPI_Bcast) */
 int evp_comm_init(evp_handle *handle, int rank, int nRanks, const char *id128);
 int evp_set_halo(evp_handle *handle, int nNeighbours, const int *neighbourRank,
                  const int *sendOffset, const int *sendIndex,
                  const int *recvOffset, const int *recvIndex);
+/* Which exchange the next evp_run_subcycles uses; `why` (may be NULL) receives the reason for a fallback. */
+int evp_halo_mode(evp_handle *handle, int *mode, char *why, int whyLen);
 
 
 /* ======================================================================================================
@@ -260,15 +272,25 @@ typedef struct {
     const int *solveVelocity;           /* ... (nCells) / (nVertices), else NULL                              */
 } evp_pre_fields;
 
+#define EVP_START_RESIDENT 0
+#define EVP_START_FROM_REST 1
+#define EVP_START_FIRST_STEP 2
+
 /* Namelist switches of the pre-subcycle (src/Registry.xml:566-647). */
 typedef struct {
     int use_air_stress;                 /* config_use_air_stress */
     int use_surface_tilt;               /* config_use_surface_tilt */
     int geostrophic_surface_tilt;       /* config_geostrophic_surface_tilt */
     int calc_velocity_masks;            /* config_calc_velocity_masks */
-    int cold_start;                     /* 1: u = v = 0, stresses = 0 and solveVelocityPrevious = solveVelocity
-                                           (first step from rest); 0: use the state resident on the device
-                                           (previous step, or seeded with evp_update_step / evp_set_state) */
+    int cold_start;                     /* EVP_START_RESIDENT (0): use the state resident on the device (previous step,
+                                           or seeded with evp_update_step / evp_set_state);
+                                           EVP_START_FROM_REST (1): u = v = 0, stresses = 0 and solveVelocityPrevious =
+                                           solveVelocity -- ice at rest that is NOT treated as new ice (what a restart
+                                           file with zero velocities gives; not the reference's first step);
+                                           EVP_START_FIRST_STEP (2): the reference's first step without a restart file:
+                                           stresses = 0 and solveVelocityPrevious = 0 (no Registry default, assigned only
+                                           at velocity_solver.F:1274), so every solved vertex is new ice and starts at the
+                                           interpolated ocean velocity (velocity_solver.F:1252-1258) */
 } evp_pre_options;
 
 /* Outputs of one dynamics step; any pointer may be NULL (= not wanted, nothing computed for it beyond what

@@ -400,7 +400,7 @@ extern "C" int evp_set_options(evp_handle *h, const evp_options *o)
     h->pinHost = (o->flags & EVP_FLAG_PIN_HOST) != 0;
     if (same) return EVP_OK;
     invalidate_graph(h);
-    if (h->haveStep) {      // EVP_FLAG_OVERLAP_HALO may have changed: refresh the boundary bit of the mask
+    if (h->haveStep) {      // keep the boundary bit of the velocity mask in step with the options
         EVP_CUDA(cudaSetDevice(h->device));
         int rc2 = evp_halo_mark_masks(h);
         if (rc2) return rc2;
@@ -628,9 +628,10 @@ extern "C" int evp_create(evp_handle **out, const evp_mesh_desc *m, const evp_op
             FAIL_IF(evp_dev_alloc(h, (void **)&d.sbSrc, sizeof(int) * d.nSB));
             FAIL_IF(evp_dev_alloc(h, (void **)&d.sbSign, sizeof(double) * d.nSB));
             FAIL_IF(evp_dev_alloc(h, (void **)&d.sbTmp, sizeof(double2) * d.nSB));
-            CUDA_FAIL(cudaMemcpy(d.sbDst, dst.data(), sizeof(int) * d.nSB, cudaMemcpyHostToDevice));
-            CUDA_FAIL(cudaMemcpy(d.sbSrc, src.data(), sizeof(int) * d.nSB, cudaMemcpyHostToDevice));
-            CUDA_FAIL(cudaMemcpy(d.sbSign, sign.data(), sizeof(double) * d.nSB, cudaMemcpyHostToDevice));
+            // through the bounce buffers on h->stream (a non-blocking stream is not ordered behind a plain cudaMemcpy)
+            FAIL_IF(evp_h2d(h, d.sbDst, dst.data(), sizeof(int) * d.nSB));
+            FAIL_IF(evp_h2d(h, d.sbSrc, src.data(), sizeof(int) * d.nSB));
+            FAIL_IF(evp_h2d(h, d.sbSign, sign.data(), sizeof(double) * d.nSB));
         }
     }
     CUDA_FAIL(cudaStreamSynchronize(h->stream));
@@ -791,7 +792,7 @@ extern "C" int evp_synchronize(evp_handle *h)
     EVP_REQUIRE(h != nullptr, "handle is NULL");
     EVP_CUDA(cudaSetDevice(h->device));
     EVP_CUDA(cudaStreamSynchronize(h->stream));
-    return EVP_OK;
+    return evp_halo_check(h);
 }
 
 extern "C" int evp_last_run_ms(evp_handle *h, float *ms)
@@ -840,7 +841,7 @@ extern "C" int evp_fetch(evp_handle *h, const evp_out_fields *o)
         if ((rc = evp_download_rows(h, r.host, r.soa, 1, r.ncomp, r.comp))) return rc;
     }
     EVP_CUDA(cudaStreamSynchronize(s));
-    return EVP_OK;
+    return evp_halo_check(h);
 }
 
 extern "C" int evp_fetch_basis(evp_handle *h, double *gu, double *gv, double *su, double *sv, double *sm)

@@ -55,7 +55,7 @@ __host__ __device__ __forceinline__ size_t evp_tix(int row, size_t c, int nRows)
         }                                                          \
     } while (0)
 
-struct evp_halo;  // evp_weak.cu
+struct evp_halo;  // evp_halo.cu
 int evp_enqueue_weak_cell_pass(evp_handle *h, bool diag, cudaStream_t s);    // strain [+ stress] on cells
 int evp_enqueue_weak_to_variational(evp_handle *h, cudaStream_t s);          // interpolate_strains_weak_to_variational
 
@@ -148,7 +148,7 @@ struct evp_handle {
 int evp_enqueue_subcycles(evp_handle *h, int nSub, cudaStream_t s);
 int evp_count_launches(evp_handle *h, int nSub);
 int evp_enqueue_cell_pass(evp_handle *h, bool diag, cudaStream_t s);
-int evp_enqueue_vertex_pass(evp_handle *h, bool diag, cudaStream_t s, const int *list, int nList);
+int evp_enqueue_vertex_pass(evp_handle *h, bool diag, cudaStream_t s);
 int evp_enqueue_special_boundaries(evp_handle *h, cudaStream_t s);
 // recompute tileWork from the masks and stresses on the device (and zero contrib of tiles without work); must
 // follow every change of solveStress / sig outside the subcycle kernels
@@ -159,13 +159,74 @@ int evp_enqueue_weak_cell_pass(evp_handle *h, bool diag, cudaStream_t s);    // 
 int evp_enqueue_weak_to_variational(evp_handle *h, cudaStream_t s);          // interpolate_strains_weak_to_variational
 
 // evp_halo.cu
-int evp_halo_enqueue(evp_handle *h, cudaStream_t s);             // exchanges d.uv
-int evp_halo_exchange(evp_handle *h, cudaStream_t s, double2 *field);   // any (nVp) double2 vertex field
+// The peer-to-peer halo exchange as the kernels see it (all-default without it, see evp_halo.cu for the protocol).
+struct evp_halo_view {
+    const int *ctr = nullptr;       // completed vertex passes of this rank (device counter)
+    const int *flagsIn = nullptr;   // [nNb] completed vertex passes of each neighbour, stored by them over NVLink
+    int *err = nullptr;             // mapped host flag: a wait ran into its time limit
+    int nNb = 0;
+    int haloFirst = 0x7fffffff;     // = nVerticesSolve: the first halo vertex
+    int shift0 = 0;                 // halo vertex v of an even pass lives at element v + shift0 ...
+    int stride = 0;                 // ... of an odd pass at v + shift0 + stride
+};
+struct evp_push_view {              // what the vertex kernel needs to store boundary-owned (u,v) into the neighbours
+    int *ctr = nullptr;
+    unsigned *done = nullptr;       // block tickets: the last block of the pass publishes the flags
+    const int *bStart = nullptr;    // [vertex blocks + 1] boundary vertices before each block of 256 owned vertices
+    const int *pushStart = nullptr; // [nBoundary + 1] CSR over the boundary vertices in ascending order
+    const int2 *push = nullptr;     // (neighbour slot, element index in that neighbour's array for an even pass)
+    double2 *const *peerUv = nullptr;   // [nNb] the neighbour's velocity array (peer mapping)
+    const int *peerStride = nullptr;    // [nNb] its distance between the two halo buffers
+    int *const *peerFlag = nullptr;     // [nNb] this rank's slot among the neighbour's incoming flags
+    int nNb = 0;
+};
+int evp_halo_enqueue(evp_handle *h, cudaStream_t s);             // in-loop exchange of d.uv on the NCCL path
+int evp_halo_exchange(evp_handle *h, cudaStream_t s, double2 *field);   // any (nVp) double2 vertex field, NCCL
 int evp_halo_launches(evp_handle *h);
 int evp_halo_mark_masks(evp_handle *h);
 int evp_halo_boundary_count(evp_handle *h);        // boundary-owned vertices (unique send-list entries)
-const int *evp_halo_boundary_list(evp_handle *h);  // device array of their 0-based indices
+bool evp_halo_p2p_active(evp_handle *h);
+evp_halo_view evp_halo_get_view(evp_handle *h);
+evp_push_view evp_halo_get_push(evp_handle *h);                  // ctr == nullptr when not active
+int evp_halo_begin_run(evp_handle *h, cudaStream_t s);           // around every run of subcycles (no-ops on the NCCL path)
+int evp_halo_end_run(evp_handle *h, cudaStream_t s);
+int evp_halo_check(evp_handle *h);                 // EVP_ERR_NCCL after a timed-out wait
 void evp_halo_destroy(evp_handle *h);
+
+#ifdef __CUDACC__
+__device__ __forceinline__ int evp_ld_acquire_sys(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void evp_st_release_sys(int *p, int v)
+{
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long evp_globaltimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Block until every neighbour has published vertex pass c (flags only grow; the comparison survives wrap-around).
+// Bounded: after 30 s the mapped error flag is raised and the caller proceeds (the host reports it).
+__device__ __forceinline__ void evp_halo_wait(const evp_halo_view &hv, int c)
+{
+    for (int i = 0; i < hv.nNb; i++) {
+        if (evp_ld_acquire_sys(hv.flagsIn + i) - c >= 0) continue;
+        const unsigned long long t0 = evp_globaltimer();
+        while (evp_ld_acquire_sys(hv.flagsIn + i) - c < 0) {
+            __nanosleep(100);
+            if (evp_globaltimer() - t0 > 30000000000ull) {
+                *(volatile int *)hv.err = 1;
+                break;
+            }
+        }
+    }
+}
+#endif
 
 inline unsigned grid_for(size_t n, int block) { return (unsigned)((n + block - 1) / block); }
 

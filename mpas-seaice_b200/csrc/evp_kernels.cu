@@ -54,6 +54,7 @@ struct CellArgs {
     double *__restrict__ e12;
     double *__restrict__ repP;
     double dte, damping;
+    evp_halo_view hv;                   // peer-to-peer halo exchange: where the current pass' halo velocities live
 };
 
 template <int CR>
@@ -202,7 +203,17 @@ __global__ void __launch_bounds__(EVP_TILE *M) evp_cell_kernel(const CellArgs a)
     if (act) {
         const int vi = a.voc[q];
         if (solve && PHASE != 2) {
-            const double2 w = a.uv[vi];
+            double2 w;
+            if (vi >= a.hv.haloFirst) {
+                // peer-to-peer halo exchange (evp_halo.cu): the neighbours' vertex kernels stored the velocity of this
+                // halo vertex into the buffer of the current pass' parity; make sure their pass is complete.  Only
+                // the few threads that gather a halo vertex ever come here, the flags are in local memory
+                const int c = *(const volatile int *)a.hv.ctr;
+                evp_halo_wait(a.hv, c);
+                w = __ldcg(&a.uv[(size_t)vi + a.hv.shift0 + (size_t)(c & 1) * a.hv.stride]);
+            } else {
+                w = a.uv[vi];
+            }
             uj = w.x; vj = w.y;
         }
         if (METRIC) tj = a.tanLat[vi];
@@ -362,10 +373,10 @@ __global__ void __launch_bounds__(256) evp_average_strain_kernel(int nVerticesSo
 }
 
 struct VertexArgs {
-    int nVerticesSolve;                 // number of threads: owned vertices, or entries of `list`
-    const int *__restrict__ list;       // LIST: the boundary-owned vertices (those some neighbour rank needs)
-    const int *__restrict__ vblockList; // plain pass: compacted list of the 256-vertex blocks with a solved vertex, or nullptr
-    int nBlocks;                        // plain pass: grid size
+    int nVerticesSolve;                 // owned vertices
+    const int *__restrict__ vblockList; // compacted list of the 256-vertex blocks with work, or nullptr
+    int nBlocks;                        // blocks with work (the grid, except that P2P launches at least one block)
+    evp_push_view pv;                   // P2P: peer-to-peer halo exchange fused into this kernel (evp_halo.cu)
     size_t nVp;
     const uint8_t *__restrict__ solveVel;
     const int *__restrict__ gidx;
@@ -392,18 +403,11 @@ struct VertexArgs {
     double wRadius;
 };
 
-// solveVel[v]: bit 0 = solveVelocity(v) == 1, bit 1 = boundary-owned vertex (set only when a halo exchange is
-// attached).  The plain pass takes the vertices whose byte is exactly 1; the LIST pass runs first over the
-// boundary-owned vertices so that their (u,v) can travel while the plain pass does the interior.
-template <int D, int CR, bool DIAG, bool LIST, bool WEAK>
-__global__ void __launch_bounds__(256) evp_vertex_kernel(const VertexArgs a)
+// one owned, solved vertex: stress divergence (variational gather or weak line integral), drag coefficient, 2x2 solve;
+// returns the vertex' (u,v) after the pass
+template <int D, int CR, bool DIAG, bool WEAK>
+__device__ __forceinline__ double2 evp_vertex_solve(const VertexArgs &a, const int v)
 {
-    const int blk = (!LIST && a.vblockList) ? a.vblockList[blockIdx.x] : (int)blockIdx.x;
-    const int k = blk * blockDim.x + threadIdx.x;
-    if (k >= a.nVerticesSolve) return;
-    const int v = LIST ? a.list[k] : k;
-    if (LIST ? (a.solveVel[v] & 1) == 0 : a.solveVel[v] != 1) return;
-
     double sdU = 0.0, sdV = 0.0;
     const double2 ad = a.areaDen[v];
     if (WEAK) {
@@ -484,7 +488,61 @@ __global__ void __launch_bounds__(256) evp_vertex_kernel(const VertexArgs a)
         const double l12 = -mf.y - coef * kSinOceanTurningAngle * sgn;
         const double l21 = mf.y + coef * kSinOceanTurningAngle * sgn;
         const double den = l11 * l22 - l12 * l21;
-        a.uv[v] = make_double2((l22 * r1 - l12 * r2) / den, (l11 * r2 - l21 * r1) / den);
+        const double2 wNew = make_double2((l22 * r1 - l12 * r2) / den, (l11 * r2 - l21 * r1) / den);
+        a.uv[v] = wNew;
+        return wNew;
+    }
+    return w;       // linear / none: no velocity update (velocity_solver.F:2529-2541)
+}
+
+// solveVel[v]: bit 0 = solveVelocity(v) == 1, bit 1 = boundary-owned vertex (some neighbour rank holds a halo copy;
+// set only while the peer-to-peer halo exchange is established).
+// P2P: the halo exchange is part of this kernel.  A boundary-owned vertex stores its (u,v) -- new, or unchanged when
+// it is not solved -- into the halo buffer of the NEXT pass' parity in every neighbour that holds a copy (NVLink
+// stores into peer-mapped memory); the last block to finish publishes "pass c+1 complete" into each neighbour's
+// flag word and advances the local pass counter.  The (neighbour, slot) list of a vertex is found from its rank
+// among the boundary vertices of its block of 256 (bStart) -- no per-vertex table is read by the other vertices.
+template <int D, int CR, bool DIAG, bool P2P, bool WEAK>
+__global__ void __launch_bounds__(256) evp_vertex_kernel(const VertexArgs a)
+{
+    int blk = a.vblockList ? ((int)blockIdx.x < a.nBlocks ? a.vblockList[blockIdx.x] : -1) : (int)blockIdx.x;
+    if (P2P && (int)blockIdx.x >= a.nBlocks) blk = -1;      // the one block launched only to publish the flags
+    const int v = blk * (int)blockDim.x + (int)threadIdx.x;
+    uint8_t mask = 0;
+    if (blk >= 0 && v < a.nVerticesSolve) mask = a.solveVel[v];
+    double2 wPush = make_double2(0.0, 0.0);
+    if (mask & 1) wPush = evp_vertex_solve<D, CR, DIAG, WEAK>(a, v);
+    else if (P2P && (mask & 2)) wPush = a.uv[v];
+    if (P2P) {
+        __shared__ int warpCount[8];
+        const bool bnd = (mask & 2) != 0;
+        const unsigned ballot = __ballot_sync(0xffffffffu, bnd);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) warpCount[warp] = __popc(ballot);
+        __syncthreads();
+        if (bnd) {
+            int e = a.pv.bStart[blk] + __popc(ballot & ((1u << lane) - 1u));
+            for (int w = 0; w < warp; w++) e += warpCount[w];
+            const int next = (*(const volatile int *)a.pv.ctr + 1) & 1;
+            const int t1 = a.pv.pushStart[e + 1];
+            for (int t = a.pv.pushStart[e]; t < t1; t++) {
+                const int2 pd = a.pv.push[t];
+                a.pv.peerUv[pd.x][(size_t)pd.y + (size_t)next * a.pv.peerStride[pd.x]] = wPush;
+            }
+            __threadfence_system();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned ticket = atomicAdd(a.pv.done, 1u);
+            if (ticket == gridDim.x - 1) {
+                __threadfence_system();
+                *a.pv.done = 0;
+                const int c1 = *(volatile int *)a.pv.ctr + 1;
+                for (int k = 0; k < a.pv.nNb; k++) evp_st_release_sys(a.pv.peerFlag[k], c1);
+                *(volatile int *)a.pv.ctr = c1;
+            }
+        }
     }
 }
 
@@ -516,13 +574,9 @@ int launch_cell_k(const CellArgs &a, cudaStream_t s)
 {
     auto kern = evp_cell_kernel<M, METRIC, CR, DIAG, GBAND, PHASE>;
     constexpr size_t smem = sizeof(CellSmem<M, METRIC, GBAND>);
-    static bool configured[16] = {};      // per device: opt in to > 48 KB of dynamic shared memory
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 16 && !configured[dev]) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
-        configured[dev] = true;
-    }
+    // opt in to > 48 KB of dynamic shared memory: per device and cheap, so set on every launch rather than cached
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
     const dim3 block(EVP_TILE, M);
     const unsigned grid = (unsigned)a.nTiles;
     if (grid) kern<<<grid, block, smem, s>>>(a);
@@ -562,11 +616,13 @@ template <int D, int CR, bool WEAK>
 int launch_vertex_w(const VertexArgs &a, bool diag, cudaStream_t s)
 {
     const int block = 256;
-    const int grid = a.list ? (a.nVerticesSolve + block - 1) / block : a.nBlocks;
+    const bool p2p = !WEAK && a.pv.ctr != nullptr;
+    // the peer-to-peer pass always runs: its last block publishes the pass to the neighbours even without work here
+    const int grid = p2p ? (a.nBlocks > 0 ? a.nBlocks : 1) : a.nBlocks;
     if (grid == 0) return 0;
-    if (a.list) {
-        if (diag) evp_vertex_kernel<D, CR, true, true, WEAK><<<grid, block, 0, s>>>(a);
-        else      evp_vertex_kernel<D, CR, false, true, WEAK><<<grid, block, 0, s>>>(a);
+    if (p2p) {
+        if (diag) evp_vertex_kernel<D, CR, true, !WEAK, WEAK><<<grid, block, 0, s>>>(a);
+        else      evp_vertex_kernel<D, CR, false, !WEAK, WEAK><<<grid, block, 0, s>>>(a);
     } else {
         if (diag) evp_vertex_kernel<D, CR, true, false, WEAK><<<grid, block, 0, s>>>(a);
         else      evp_vertex_kernel<D, CR, false, false, WEAK><<<grid, block, 0, s>>>(a);
@@ -633,6 +689,7 @@ static int enqueue_cell_phase(evp_handle *h, bool diag, int phase, cudaStream_t 
     a.sig = h->d.sig; a.sig12 = h->d.sig12; a.contrib = h->d.contrib;
     a.e11 = h->d.e11; a.e22 = h->d.e22; a.e12 = h->d.e12; a.repP = h->d.repP;
     a.dte = h->opt.elasticTimeStep; a.damping = h->opt.dampingTimescale;
+    a.hv = evp_halo_get_view(h);
     const int cr = h->opt.constitutive_relation_type;
     int rc = 0;
     switch (h->M) {
@@ -647,13 +704,12 @@ static int enqueue_cell_phase(evp_handle *h, bool diag, int phase, cudaStream_t 
     return EVP_OK;
 }
 
-// list == nullptr: every owned vertex whose mask byte is 1; else the nList boundary-owned vertices.
-int evp_enqueue_vertex_pass(evp_handle *h, bool diag, cudaStream_t s, const int *list, int nList)
+int evp_enqueue_vertex_pass(evp_handle *h, bool diag, cudaStream_t s)
 {
-    const int nThreads = list ? nList : h->nVerticesSolve;
-    if (nThreads == 0) return EVP_OK;
     VertexArgs a;
-    a.nVerticesSolve = nThreads; a.list = list; a.nVp = h->nVp;
+    a.pv = evp_halo_get_push(h);
+    if (h->nVerticesSolve == 0 && !a.pv.ctr) return EVP_OK;
+    a.nVerticesSolve = h->nVerticesSolve; a.nVp = h->nVp;
     const int allBlocks = (h->nVerticesSolve + 255) / 256;
     a.nBlocks = h->nActiveVBlocks < 0 ? allBlocks : h->nActiveVBlocks;
     a.vblockList = (a.nBlocks == allBlocks) ? nullptr : h->d.vblockList;
@@ -736,7 +792,8 @@ __global__ void __launch_bounds__(256) k_vblock_flags(int nVerticesSolve, const 
                                                       uint8_t *__restrict__ vblockWork)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    const int on = v < nVerticesSolve && (solveVel[v] & 1);
+    // bit 1 (boundary-owned, peer-to-peer exchange): the vertex stores its velocity into the neighbours every pass
+    const int on = v < nVerticesSolve && solveVel[v] != 0;
     const int any = __syncthreads_or(on);
     if (threadIdx.x == 0) vblockWork[blockIdx.x] = any ? 1 : 0;
 }
@@ -794,38 +851,27 @@ static inline bool diag_always(const evp_handle *h)
 // { internal stress, drag coefficient, velocity solve, halo exchange, special boundaries }.
 // Strain, replacementPressure, stressDivergence and oceanStressCoeff are only consumed after the
 // loop (velocity_solver.F:3360-3380), so only the last subcycle stores them (DIAG).
-// One subcycle after the cell pass: vertex pass + halo exchange.  With a halo attached the boundary-owned
-// vertices are solved first, their (u,v) are packed and exchanged on the communication stream (a forked
-// branch of the graph) while the interior vertices are solved on the main stream; the two join before
-// the next cell pass reads the halo.
+// One subcycle after the cell pass: vertex pass + halo exchange.  With the peer-to-peer exchange the vertex kernel
+// is the exchange (evp_halo.cu); otherwise pack / ncclSend+ncclRecv / [unpack] follow on the same stream.
 int evp_enqueue_vertex_and_halo(evp_handle *h, bool diag, cudaStream_t s)
 {
     int rc;
-    const int nB = evp_halo_boundary_count(h);
-    if (nB == 0) {
-        if ((rc = evp_enqueue_vertex_pass(h, diag, s, nullptr, 0))) return rc;
-        return evp_halo_enqueue(h, s);          // no-op without neighbours
-    }
-    if ((rc = evp_enqueue_vertex_pass(h, diag, s, evp_halo_boundary_list(h), nB))) return rc;
-    EVP_CUDA(cudaEventRecord(h->evFork, s));
-    EVP_CUDA(cudaStreamWaitEvent(h->commStream, h->evFork, 0));
-    if ((rc = evp_halo_enqueue(h, h->commStream))) return rc;
-    EVP_CUDA(cudaEventRecord(h->evJoin, h->commStream));
-    if ((rc = evp_enqueue_vertex_pass(h, diag, s, nullptr, 0))) return rc;
-    EVP_CUDA(cudaStreamWaitEvent(s, h->evJoin, 0));
-    return EVP_OK;
+    if ((rc = evp_enqueue_vertex_pass(h, diag, s))) return rc;
+    return evp_halo_enqueue(h, s);          // no-op without neighbours or with the peer-to-peer exchange
 }
 
 int evp_enqueue_subcycles(evp_handle *h, int nSub, cudaStream_t s)
 {
     int rc;
     if ((rc = evp_enqueue_special_boundaries(h, s))) return rc;
+    if (nSub > 0 && (rc = evp_halo_begin_run(h, s))) return rc;
     for (int k = 0; k < nSub; k++) {
         const bool diag = (k == nSub - 1) || diag_always(h);
         if ((rc = evp_enqueue_cell_pass(h, diag, s))) return rc;
         if ((rc = evp_enqueue_vertex_and_halo(h, diag, s))) return rc;
         if ((rc = evp_enqueue_special_boundaries(h, s))) return rc;
     }
+    if (nSub > 0 && (rc = evp_halo_end_run(h, s))) return rc;
     return EVP_OK;
 }
 
@@ -844,8 +890,9 @@ int evp_count_launches(evp_handle *h, int nSub)
     } else {
         cellKernels = work ? 1 : 0;
     }
-    const int perSub = cellKernels + (vwork ? 1 : 0) + (evp_halo_boundary_count(h) ? 1 : 0) + evp_halo_launches(h) + sb;
-    return sb + nSub * perSub;
+    const bool p2p = evp_halo_p2p_active(h);
+    const int perSub = cellKernels + ((vwork || p2p) ? 1 : 0) + evp_halo_launches(h) + sb;
+    return sb + nSub * perSub + ((p2p && nSub > 0) ? 2 : 0);      // + evp_halo_begin_run / evp_halo_end_run
 }
 
 // Instrumentation for bench.py: average device time of the cell pass, the vertex pass and the rest
@@ -859,7 +906,7 @@ extern "C" int evp_profile_passes(evp_handle *h, int nSub, float *cellMs, float 
     cudaEvent_t e[4];
     for (auto &x : e) EVP_CUDA(cudaEventCreate(&x));
     double acc[3] = {0, 0, 0};
-    int rc = EVP_OK;
+    int rc = evp_halo_begin_run(h, s);
     for (int k = 0; k < nSub && rc == EVP_OK; k++) {
         EVP_CUDA(cudaEventRecord(e[0], s));
         if ((rc = evp_enqueue_cell_pass(h, false, s))) break;
@@ -877,6 +924,8 @@ extern "C" int evp_profile_passes(evp_handle *h, int nSub, float *cellMs, float 
     }
     for (auto &x : e) cudaEventDestroy(x);
     if (rc) return rc;
+    if ((rc = evp_halo_end_run(h, s))) return rc;
+    EVP_CUDA(cudaStreamSynchronize(s));
     if (cellMs) *cellMs = (float)(acc[0] / nSub);
     if (vertexMs) *vertexMs = (float)(acc[1] / nSub);
     if (otherMs) *otherMs = (float)(acc[2] / nSub);

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(256) k_pre_vertices(const PreArgs a)
     }
 
     double2 w = a.coldStart ? make_double2(0.0, 0.0) : a.uv[v];
-    const int prev = a.coldStart ? solve : a.solveVelPrev[v];
+    const int prev = a.coldStart == EVP_START_FROM_REST ? solve : (a.coldStart == EVP_START_FIRST_STEP ? 0 : a.solveVelPrev[v]);
     if (solve) {
         if (prev == 0) w = make_double2(uo, vo);
     } else {
@@ -574,7 +574,7 @@ extern "C" int evp_pre_subcycle(evp_handle *h, const evp_pre_fields *f, const ev
     a.nCells = h->nCells; a.nVerticesSolve = h->nVerticesSolve; a.nVertices = h->nVertices; a.M = h->M; a.D = h->D;
     a.nCp = h->nCp; a.nVp = h->nVp;
     a.useAir = o->use_air_stress != 0; a.constantAir = constantAir; a.useOcean = h->opt.use_ocean_stress != 0;
-    a.tiltMode = tiltMode; a.calcMasks = o->calc_velocity_masks != 0; a.coldStart = o->cold_start != 0;
+    a.tiltMode = tiltMode; a.calcMasks = o->calc_velocity_masks != 0; a.coldStart = o->cold_start;
     a.cr = h->opt.constitutive_relation_type;
     a.nEdges = d.nEdges; a.coc = d.coc; a.cov = d.cov; a.vflags = d.vflags; a.areaCell = d.areaCell; a.fVertex = d.fVertex;
     a.areaInit = stage_d(f->iceAreaCellInitial, nC);

@@ -157,7 +157,15 @@ int upload_vec(evp_handle *h, T **dst, const std::vector<T> &src)
 {
     int rc = evp_dev_alloc(h, (void **)dst, sizeof(T) * std::max<size_t>(src.size(), 1));
     if (rc) return rc;
-    if (!src.empty()) EVP_CUDA(cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice));
+    // on h->stream through the pinned bounce buffers (the handle's stream is non-blocking: a plain cudaMemcpy from
+    // pageable memory is not ordered before the kernels launched on it); the source is consumed when this returns
+    if (!src.empty()) {
+        const bool pin = h->pinHost;
+        h->pinHost = false;
+        rc = evp_h2d(h, *dst, src.data(), sizeof(T) * src.size());
+        h->pinHost = pin;
+        if (rc) return rc;
+    }
     return EVP_OK;
 }
 

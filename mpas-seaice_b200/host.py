@@ -28,6 +28,7 @@ OCEAN = {"quadratic": 1, "linear": 2}
 SCHEME = {"variational": 1, "weak": 2}
 FLAG_PIN_HOST = 1
 FLAG_OVERLAP_HALO = 2
+START_RESIDENT, START_FROM_REST, START_FIRST_STEP = 0, 1, 2     # evp_pre_options.cold_start
 
 EXPORTS = (
     "evp_create", "evp_set_options", "evp_precompute_wachspress", "evp_fetch_basis", "evp_update_step",
@@ -36,7 +37,7 @@ EXPORTS = (
     "evp_launch_count", "evp_get_stream", "evp_device_bytes", "evp_set_use_graph", "evp_profile_passes",
     "evp_host_metric_terms", "evp_set_mesh_ext", "evp_set_state", "evp_pre_subcycle", "evp_post_subcycle",
     "evp_fetch_pre", "evp_release_host_memory", "evp_set_weak_mesh", "evp_update_weak_state", "evp_fetch_weak",
-    "evp_precompute_pwl",
+    "evp_precompute_pwl", "evp_halo_mode",
 )
 
 
@@ -349,7 +350,9 @@ class EvpSolver:
 
     def pre_subcycle(self, cells, *, use_air_stress=True, use_surface_tilt=True, geostrophic_surface_tilt=True,
                      calc_velocity_masks=True, cold_start=False):
-        """evp_pre_subcycle: velocity_solver_pre_subcycle on the device from CELL fields."""
+        """evp_pre_subcycle: velocity_solver_pre_subcycle on the device from CELL fields.  ``cold_start``: False /
+        START_RESIDENT, True / START_FROM_REST (ice at rest, not new ice) or START_FIRST_STEP (the reference's first
+        step without a restart file: solveVelocityPrevious = 0, solved vertices start at the ocean velocity)."""
         pf = PreFields()
         self._pre_keep = []
         for n in PRE_FIELDS:
@@ -431,6 +434,13 @@ class EvpSolver:
         arrs = [np.ascontiguousarray(a, dtype=np.int32) for a in
                 (neighbour_rank, send_offset, send_index, recv_offset, recv_index)]
         self._check(self.lib.evp_set_halo(self._h, C.c_int(len(arrs[0])), *[C.c_void_p(a.ctypes.data) for a in arrs]))
+
+    def halo_mode(self):
+        """evp_halo_mode: 'none', 'nccl (<why not peer-to-peer>)' or 'p2p' -- the exchange the next run uses."""
+        mode, why = C.c_int(0), C.create_string_buffer(256)
+        self._check(self.lib.evp_halo_mode(self._h, C.byref(mode), why, C.c_int(256)))
+        name = {0: "none", 1: "nccl", 2: "p2p"}[mode.value]
+        return f"{name} ({why.value.decode()})" if why.value else name
 
     def release_host_memory(self):
         """evp_release_host_memory: undo the page-locking of every array passed under pin_host."""

@@ -5,6 +5,8 @@
   qu60    : 163 842 cells                                                               (configs[3])
   qu30 / qu15 : 655 362 / 2 621 442 cells (intermediate sizes)
   qu7.5   : 10 485 762 cells, config_dt = 120 s                                         (configs[4])
+  hexNXxNY: planar hex NX x NY with the square case's forcing stretched over it (any size: the weak-scaling series
+            of bench.py --scaling weak, a fixed number of cells per GPU)
 
 Per-grid config_dt from bld/namelist_files/namelist_defaults_mpassi.xml:9-16.
 """
@@ -21,6 +23,7 @@ SPHERES = {  # name -> (icosphere level, config_dt)
     "qu15": (9, 240.0), "qu7.5": (10, 120.0),
 }
 ALGO_BYTES_PER_CELL = 1912.0        # cell part of one cell-subcycle (hex sphere)
+ALGO_BYTES_PER_CELL_PLANAR = 1624.0  # the same without basisIntegralsMetric (8 M^2 = 288 B): planar meshes, metric terms off
 ALGO_BYTES_PER_VERTEX = 164.0       # per owned vertex
 ALGO_BYTES_PER_CELL_SUBCYCLE = 2240.0
 
@@ -79,6 +82,14 @@ def build(name: str, state: str = "A", n_elastic: int = 120, verbose=None, with_
         mesh = meshgen.planar_hex(82, 94, 16000.0)
         config_dt = 3600.0
         st = synthetic.square_state(mesh)
+    elif name.startswith("hex") and "x" in name:
+        nx, ny = (int(t) for t in name[3:].split("x"))
+        mesh = meshgen.planar_hex(nx, ny, 16000.0)
+        config_dt = 3600.0
+        scaled = meshgen.Mesh(mesh)            # the square forcing is written for Lx = Ly = 1.28e6
+        scaled.xCell = mesh.xCell * (1.28e6 / mesh.Lx)
+        scaled.yCell = mesh.yCell * (1.28e6 / mesh.Ly)
+        st = synthetic.square_state(scaled)
     elif name in SPHERES or (name.startswith("ico") and name[3:].isdigit()):
         level, config_dt = SPHERES[name] if name in SPHERES else (int(name[3:]), 3600.0)   # icoN: test sizes
         mesh = _cached_icosphere(level)

@@ -2,8 +2,10 @@
 
   mode 'oracle' : backend gloo, the CPU oracle solves the block, halo exchange by dist.isend/irecv
                   following the very evp_set_halo lists -- covers the N>1 host logic without a GPU;
-  mode 'gpu'    : backend nccl, the block is solved by libevp_b200.so with its in-graph NCCL halo
-                  exchange.
+  mode 'gpu'    : backend nccl, the block is solved by libevp_b200.so; 'gpu-p2p' insists on the peer-to-peer halo
+                  exchange fused into the vertex kernel (EVP_B200_HALO=p2p: evp_set_halo fails if it cannot be
+                  set up), 'gpu-nccl' on the in-graph ncclSend/ncclRecv exchange, plain 'gpu' takes what
+                  evp_set_halo chooses.
 Rank 0 gathers the owned results and writes them to an .npz for the parent test to compare."""
 import os
 import sys
@@ -31,9 +33,10 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     from mpas_seaice_b200 import multigpu, partition
     import common
-    overlap = mode == "gpu-overlap"      # EVP_FLAG_OVERLAP_HALO: boundary-first vertex pass, forked exchange
     full = mode == "gpu-full"            # pre-subcycle + subcycle + post-subcycle on the device (state B, 2 halo layers)
-    if overlap or full:
+    if mode in ("gpu-p2p", "gpu-nccl"):
+        os.environ["EVP_B200_HALO"] = mode[4:]
+    if mode.startswith("gpu"):
         mode = "gpu"
     if mode == "gpu":
         torch.cuda.set_device(rank)
@@ -45,12 +48,12 @@ def main():
     blk, step, opts = w["mesh"], w["step"], w["opts"]
     if mode == "gpu":
         from mpas_seaice_b200 import host
-        solver = host.EvpSolver(blk, w["static"], dict(opts, overlap_halo=overlap), device=rank,
+        solver = host.EvpSolver(blk, w["static"], opts, device=rank,
                                 local_coords=(w["static"]["xLocal"], w["static"]["yLocal"]),
                                 n_vertices_solve=w["nVerticesSolve"], n_cells_solve=w["nCellsSolve"])
         stage("evp_create done")
         multigpu.attach_halo(solver, w, rank, world, dist)
-        stage("evp_comm_init + evp_set_halo done")
+        stage("evp_comm_init + evp_set_halo done: halo exchange " + solver.halo_mode())
         post = {}
         if full:
             solver.set_mesh_ext(blk, w["interiorVertex"])

@@ -113,7 +113,6 @@ def test_example_basis_equals_the_wachspress_precompute(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="added after this round's GPU minutes were spent: not yet run on a device")
 def test_example_runs_on_the_device(tmp_path):
     r = subprocess.run([_build(tmp_path)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr

@@ -1,15 +1,14 @@
 """Fuzz of the EVP device path against the oracle: random combinations of mesh, namelist options, masks, perturbed
 forcing and subcycle counts, bit-exact like the fixed cases of test_gpu_parity.py.  (The same idea found the one
 unhandled configuration of the transport kernels, tests/test_ir_parity.py::test_random_states_and_velocities_match_oracle.)
-Written when this round's GPU minutes were spent: non-strict xfail until it has run once on a device."""
+First device run: round 1's driver GPUTEST (all cases bit-identical); a difference fails the suite."""
 import numpy as np
 import pytest
 
 import common
 from test_gpu_parity import _compare
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="new fuzz test, not yet run on a device")]
+pytestmark = [pytest.mark.gpu]
 
 
 def _random_case(seed):

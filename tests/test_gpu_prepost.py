@@ -88,6 +88,37 @@ def test_pre_subcycle_cold_start_matches_oracle(evp_lib, kind, state_kind):
     assert np.all(out["stress11"] == 0.0)
 
 
+@pytest.mark.parametrize("via", ["first_step_flag", "set_state"])
+def test_pre_subcycle_reference_first_step(evp_lib, via):
+    """The reference's first step without a restart file: solveVelocityPrevious has no Registry default and is only
+    assigned at velocity_solver.F:1274, so it is 0 and every solved vertex starts at the interpolated ocean velocity
+    (:1252-1258).  Either EVP_START_FIRST_STEP or solveVelocityPrevious = 0 through evp_set_state."""
+    from mpas_seaice_b200 import host
+    mesh, var = common.mesh_case("ico4")
+    state = _state(mesh, "B")
+    nC, nV, M = mesh.nCells, mesh.nVertices, mesh.maxEdges
+    prev = dict(uVelocity=np.zeros(nV + 1), vVelocity=np.zeros(nV + 1), solveVelocityPrevious=np.zeros(nV + 1, dtype=np.int32),
+                stress11=np.zeros((nC + 1, M)), stress22=np.zeros((nC + 1, M)), stress12=np.zeros((nC + 1, M)))
+    ref = oracle.pre_subcycle(mesh, state, 3600.0, prev=prev)
+    _, opts = synthetic.pre_subcycle(mesh, state, 3600.0)
+    solver = _solver(mesh, var, opts)
+    try:
+        if via == "set_state":
+            solver.set_state(prev)
+            solver.pre_subcycle(_cells(mesh, state), cold_start=host.START_RESIDENT)
+        else:
+            solver.pre_subcycle(_cells(mesh, state), cold_start=host.START_FIRST_STEP)
+        got = solver.fetch_pre()
+        out = solver.fetch(names=("uVelocity", "vVelocity"))
+    finally:
+        solver.destroy()
+    _compare_pre(mesh, ref, got)
+    vm = ref["solveVelocity"][:nV] == 1
+    assert np.array_equal(out["uVelocity"][:nV], ref["uVelocity"][:nV])
+    assert np.array_equal(out["uVelocity"][:nV][vm], ref["uOceanVelocityVertex"][:nV][vm])       # new ice everywhere
+    assert np.abs(out["uVelocity"][:nV][vm]).max() > 0
+
+
 @pytest.mark.parametrize("use_air,use_tilt,geo", [(False, True, True), (True, False, True), (True, True, False)])
 def test_pre_subcycle_switches(evp_lib, use_air, use_tilt, geo):
     """config_use_air_stress / config_use_surface_tilt / config_geostrophic_surface_tilt."""

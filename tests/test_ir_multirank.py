@@ -71,7 +71,6 @@ def test_ranks_reproduce_the_single_block_run_under_emulation(world, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="not yet run as a pytest session on a device (first contact with a B200: tools/ir_quick_gpu.py, all identical)")
 def test_ranks_reproduce_the_single_block_run_on_devices(tmp_path):
     import torch
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:

@@ -5,7 +5,7 @@ off on both sides.
 Two legs run the same cases through the same C ABI and ctypes host:
 
 * ``cuda`` (@gpu): the shipped library on a B200, in a child process (see test_cuda_leg_in_a_child_process).
-  Written after this round's GPU minutes were spent: non-strict xfail until it has run once (XPASS expected).
+  First passed on a B200 in round 1's driver GPUTEST; a difference fails the suite.
 * ``emulation`` (CPU): the SAME source file compiled with g++ against tests/emu/cuda_runtime.h, which runs every
   kernel thread sequentially.  It checks the kernels' logic here, where there is no GPU; it is test infrastructure,
   built under tests/_build/, and never shipped or loaded by the product.
@@ -38,8 +38,8 @@ def _emulation_library():
     return EMU_LIB
 
 
-# The cuda leg runs in a child process (test_cuda_leg_in_a_child_process below): the kernels have not met a device
-# yet, and a fault there must not take the CUDA context -- or the process -- of the validated EVP tests with it.
+# The cuda leg runs in a child process (test_cuda_leg_in_a_child_process below) with a time limit: a fault there must
+# not take the CUDA context -- or the process -- of the EVP tests with it.
 CUDA_LEG_ENABLED = os.environ.get("IR_B200_CUDA_LEG") == "1"
 LEGS = [
     pytest.param("emulation", id="emulation"),
@@ -60,7 +60,6 @@ def lib_path(request):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="not yet run as a pytest session on a device (first contact with a B200: tools/ir_quick_gpu.py, all identical)")
 def test_cuda_leg_in_a_child_process():
     """Every `cuda` case of this file and of test_ir_blocks.py, in a process of its own with a time limit."""
     import sys

@@ -135,7 +135,8 @@ def test_nccl_full_dynamics_step_matches_single_rank(evp_lib, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,nsub,mode", [("ico4", 120, "gpu"), ("square", 120, "gpu"), ("ico4", 120, "gpu-overlap")])
+@pytest.mark.parametrize("name,nsub,mode", [("ico4", 120, "gpu-p2p"), ("square", 120, "gpu-p2p"), ("ico4", 120, "gpu-nccl"),
+                                            ("ico4", 7, "gpu-p2p"), ("ico3", 120, "gpu")])
 def test_nccl_ranks_match_single_rank(evp_lib, tmp_path, name, nsub, mode):
     import torch
     n = torch.cuda.device_count()
