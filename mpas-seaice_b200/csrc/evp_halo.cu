@@ -437,6 +437,7 @@ static int p2p_setup(evp_handle *h, const std::vector<int> &s0)
     evp_push_view pv{};
     pv.ctr = H.ctr; pv.done = H.done; pv.bStart = H.dBStart; pv.pushStart = H.dPushStart; pv.push = H.dPush;
     pv.peerUv = H.dPeerUv; pv.peerStride = H.dPeerStride; pv.peerFlag = H.dPeerFlag; pv.nNb = H.nNb;
+    for (int i = 0; i < nVBlocks; i++) pv.nPushBlocks += bStart[i + 1] > bStart[i] ? 1 : 0;
     H.pushView = pv;
     EVP_CUDA(cudaStreamSynchronize(s));
     H.p2p = true;
@@ -523,7 +524,11 @@ extern "C" int evp_set_halo(evp_handle *h, int nNb, const int *nbRank, const int
         EVP_CUDA(cudaStreamSynchronize(h->stream));
     }
     if (H.comm && (rc = p2p_setup(h, s0))) return rc;
-    return evp_halo_mark_masks(h);
+    if ((rc = evp_halo_mark_masks(h))) return rc;
+    // the lists of vertex blocks with work depend on the boundary bit just (re)applied
+    if (h->haveStep && (rc = evp_refresh_tile_flags(h, h->stream))) return rc;
+    EVP_CUDA(cudaStreamSynchronize(h->stream));
+    return EVP_OK;
 }
 
 // the peer-to-peer exchange is established AND usable with the current options (all ranks share the options, so

@@ -179,6 +179,7 @@ struct evp_push_view {              // what the vertex kernel needs to store bou
     const int *peerStride = nullptr;    // [nNb] its distance between the two halo buffers
     int *const *peerFlag = nullptr;     // [nNb] this rank's slot among the neighbour's incoming flags
     int nNb = 0;
+    int nPushBlocks = 0;                // blocks of 256 owned vertices that hold a boundary vertex (the ticket count)
 };
 int evp_halo_enqueue(evp_handle *h, cudaStream_t s);             // in-loop exchange of d.uv on the NCCL path
 int evp_halo_exchange(evp_handle *h, cudaStream_t s, double2 *field);   // any (nVp) double2 vertex field, NCCL

@@ -501,27 +501,33 @@ __device__ __forceinline__ double2 evp_vertex_solve(const VertexArgs &a, const i
 // it is not solved -- into the halo buffer of the NEXT pass' parity in every neighbour that holds a copy (NVLink
 // stores into peer-mapped memory); the last block to finish publishes "pass c+1 complete" into each neighbour's
 // flag word and advances the local pass counter.  The (neighbour, slot) list of a vertex is found from its rank
-// among the boundary vertices of its block of 256 (bStart) -- no per-vertex table is read by the other vertices.
+// among the boundary vertices of its block of 256 (bStart) -- no per-vertex table is read by the other vertices, and
+// blocks without a boundary vertex (nearly all of them) leave after one look at bStart: no barrier, no fence, no atomic.
 template <int D, int CR, bool DIAG, bool P2P, bool WEAK>
-__global__ void __launch_bounds__(256) evp_vertex_kernel(const VertexArgs a)
+__device__ __forceinline__ void evp_vertex_body(const VertexArgs &a)
 {
     int blk = a.vblockList ? ((int)blockIdx.x < a.nBlocks ? a.vblockList[blockIdx.x] : -1) : (int)blockIdx.x;
-    if (P2P && (int)blockIdx.x >= a.nBlocks) blk = -1;      // the one block launched only to publish the flags
+    if (P2P && (int)blockIdx.x >= a.nBlocks) blk = -1;      // the extra block: publishes the pass when no block pushes
     const int v = blk * (int)blockDim.x + (int)threadIdx.x;
     uint8_t mask = 0;
     if (blk >= 0 && v < a.nVerticesSolve) mask = a.solveVel[v];
     double2 wPush = make_double2(0.0, 0.0);
     if (mask & 1) wPush = evp_vertex_solve<D, CR, DIAG, WEAK>(a, v);
-    else if (P2P && (mask & 2)) wPush = a.uv[v];
     if (P2P) {
+        // blocks of 256 vertices without a boundary-owned vertex (nearly all) are done here
+        const int e0 = blk >= 0 ? a.pv.bStart[blk] : 0;
+        const int nPushers = blk >= 0 ? a.pv.bStart[blk + 1] - e0 : 0;
+        if (blk >= 0 && nPushers == 0) return;
+        if (blk < 0 && a.pv.nPushBlocks > 0) return;
         __shared__ int warpCount[8];
         const bool bnd = (mask & 2) != 0;
+        if (bnd && !(mask & 1)) wPush = a.uv[v];            // not solved: its unchanged velocity fills the other parity
         const unsigned ballot = __ballot_sync(0xffffffffu, bnd);
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         if (lane == 0) warpCount[warp] = __popc(ballot);
         __syncthreads();
         if (bnd) {
-            int e = a.pv.bStart[blk] + __popc(ballot & ((1u << lane) - 1u));
+            int e = e0 + __popc(ballot & ((1u << lane) - 1u));
             for (int w = 0; w < warp; w++) e += warpCount[w];
             const int next = (*(const volatile int *)a.pv.ctr + 1) & 1;
             const int t1 = a.pv.pushStart[e + 1];
@@ -529,21 +535,35 @@ __global__ void __launch_bounds__(256) evp_vertex_kernel(const VertexArgs a)
                 const int2 pd = a.pv.push[t];
                 a.pv.peerUv[pd.x][(size_t)pd.y + (size_t)next * a.pv.peerStride[pd.x]] = wPush;
             }
-            __threadfence_system();
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            __threadfence();
+            // one system-scope fence per pushing block: cumulative over the stores of the threads that arrived at the
+            // barrier above; then the ticket -- the last pushing block publishes the pass
+            __threadfence_system();
+            const unsigned last = a.pv.nPushBlocks > 0 ? (unsigned)a.pv.nPushBlocks - 1u : 0u;
             const unsigned ticket = atomicAdd(a.pv.done, 1u);
-            if (ticket == gridDim.x - 1) {
+            if (ticket == last) {
                 __threadfence_system();
-                *a.pv.done = 0;
+                *(volatile unsigned *)a.pv.done = 0;
                 const int c1 = *(volatile int *)a.pv.ctr + 1;
                 for (int k = 0; k < a.pv.nNb; k++) evp_st_release_sys(a.pv.peerFlag[k], c1);
                 *(volatile int *)a.pv.ctr = c1;
             }
         }
     }
+}
+
+template <int D, int CR, bool DIAG, bool WEAK>
+__global__ void __launch_bounds__(256) evp_vertex_kernel(const VertexArgs a)
+{
+    evp_vertex_body<D, CR, DIAG, false, WEAK>(a);
+}
+// 5 blocks per SM like the plain kernel (48 registers): the exchange code must not cost the interior blocks occupancy
+template <int D, int CR, bool DIAG>
+__global__ void __launch_bounds__(256, 5) evp_vertex_p2p_kernel(const VertexArgs a)
+{
+    evp_vertex_body<D, CR, DIAG, true, false>(a);
 }
 
 // seaice_set_special_boundaries_velocity (special_boundaries.F:301-324) with the sequential
@@ -617,15 +637,15 @@ int launch_vertex_w(const VertexArgs &a, bool diag, cudaStream_t s)
 {
     const int block = 256;
     const bool p2p = !WEAK && a.pv.ctr != nullptr;
-    // the peer-to-peer pass always runs: its last block publishes the pass to the neighbours even without work here
-    const int grid = p2p ? (a.nBlocks > 0 ? a.nBlocks : 1) : a.nBlocks;
+    // peer-to-peer: one extra block, which publishes the pass when this rank has no boundary-owned vertex to push
+    const int grid = p2p ? a.nBlocks + 1 : a.nBlocks;
     if (grid == 0) return 0;
     if (p2p) {
-        if (diag) evp_vertex_kernel<D, CR, true, !WEAK, WEAK><<<grid, block, 0, s>>>(a);
-        else      evp_vertex_kernel<D, CR, false, !WEAK, WEAK><<<grid, block, 0, s>>>(a);
+        if (diag) evp_vertex_p2p_kernel<D, CR, true><<<grid, block, 0, s>>>(a);
+        else      evp_vertex_p2p_kernel<D, CR, false><<<grid, block, 0, s>>>(a);
     } else {
-        if (diag) evp_vertex_kernel<D, CR, true, false, WEAK><<<grid, block, 0, s>>>(a);
-        else      evp_vertex_kernel<D, CR, false, false, WEAK><<<grid, block, 0, s>>>(a);
+        if (diag) evp_vertex_kernel<D, CR, true, WEAK><<<grid, block, 0, s>>>(a);
+        else      evp_vertex_kernel<D, CR, false, WEAK><<<grid, block, 0, s>>>(a);
     }
     return 0;
 }
