@@ -495,6 +495,7 @@ extern "C" int evp_create(evp_handle **out, const evp_mesh_desc *m, const evp_op
     FAIL_IF(evp_dev_alloc(h, (void **)&d.tileWork, nCp / EVP_TILE + 1));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.tileList, sizeof(int) * (nCp / EVP_TILE + 1)));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.tileCount, sizeof(int)));
+    FAIL_IF(evp_dev_alloc(h, (void **)&d.gridBar, sizeof(unsigned)));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.vblockWork, nVp / 256 + 2));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.vblockList, sizeof(int) * (nVp / 256 + 2)));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.vblockCount, sizeof(int)));
@@ -761,7 +762,12 @@ extern "C" int evp_run_subcycles(evp_handle *h, int nSub)
     EVP_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = h->stream;
     int rc;
-    if (h->useGraph && nSub > 0) {
+    if (h->useGraph && nSub > 0 && evp_persistent_run(h, nSub, s, true) == 0) {
+        // small mesh: the whole loop is one cooperative launch (evp_persistent_kernel)
+        EVP_CUDA(cudaEventRecord(h->ev0, s));
+        if (evp_persistent_run(h, nSub, s, false) != 0) { evp_set_error("persistent kernel launch failed"); return EVP_ERR_CUDA; }
+        EVP_CUDA(cudaEventRecord(h->ev1, s));
+    } else if (h->useGraph && nSub > 0) {
         if (!h->graphExec || h->graphN != nSub) {
             invalidate_graph(h);
             cudaGraph_t g = nullptr;

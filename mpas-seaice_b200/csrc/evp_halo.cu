@@ -182,7 +182,7 @@ struct evp_halo {
     unsigned *done = nullptr;     // device: block tickets of the vertex kernel
     int *errHost = nullptr, *errDev = nullptr;   // mapped host flag: a wait timed out
     std::vector<void *> peerBase; // cudaIpcOpenMemHandle results
-    int *dBStart = nullptr, *dPushStart = nullptr;
+    int *dBStart = nullptr, *dPushStart = nullptr, *dOrder = nullptr;
     int2 *dPush = nullptr;
     double2 **dPeerUv = nullptr;
     int *dPeerStride = nullptr;
@@ -264,7 +264,7 @@ static void halo_release(evp_handle *h, bool collective)
     if (H.errHost) { cudaFreeHost(H.errHost); H.errHost = nullptr; H.errDev = nullptr; }
     H.p2p = false;
     H.ctr = nullptr; H.done = nullptr;
-    H.dBStart = H.dPushStart = nullptr; H.dPush = nullptr; H.dPeerUv = nullptr; H.dPeerStride = nullptr;
+    H.dBStart = H.dPushStart = H.dOrder = nullptr; H.dPush = nullptr; H.dPeerUv = nullptr; H.dPeerStride = nullptr;
     H.dPeerFlag = nullptr; H.pushView = evp_push_view{};
     evp_dev_free(h, H.dSendIdx, H.bytesSendIdx); H.dSendIdx = nullptr;
     evp_dev_free(h, H.dRecvIdx, H.bytesRecvIdx); H.dRecvIdx = nullptr;
@@ -419,6 +419,14 @@ static int p2p_setup(evp_handle *h, const std::vector<int> &s0)
     if ((rc = p2p_alloc(h, (void **)&H.done, sizeof(unsigned)))) return rc;
     if ((rc = p2p_alloc(h, (void **)&H.dBStart, sizeof(int) * bStart.size()))) return rc;
     if ((rc = p2p_alloc(h, (void **)&H.dPushStart, sizeof(int) * pushStart.size()))) return rc;
+    std::vector<int> order;
+    order.reserve(nVBlocks + 1);
+    for (int i = 0; i < nVBlocks; i++) if (bStart[i + 1] > bStart[i]) order.push_back(i);
+    const int nPushBlocks = (int)order.size();
+    for (int i = 0; i < nVBlocks; i++) if (bStart[i + 1] == bStart[i]) order.push_back(i);
+    if (order.empty()) order.push_back(0);
+    if ((rc = p2p_alloc(h, (void **)&H.dOrder, sizeof(int) * order.size()))) return rc;
+    if ((rc = evp_h2d(h, H.dOrder, order.data(), sizeof(int) * order.size()))) return rc;
     if ((rc = p2p_alloc(h, (void **)&H.dPush, sizeof(int2) * push.size()))) return rc;
     if ((rc = p2p_alloc(h, (void **)&H.dPeerUv, sizeof(double2 *) * peerUv.size()))) return rc;
     if ((rc = p2p_alloc(h, (void **)&H.dPeerStride, sizeof(int) * peerStride.size()))) return rc;
@@ -437,7 +445,8 @@ static int p2p_setup(evp_handle *h, const std::vector<int> &s0)
     evp_push_view pv{};
     pv.ctr = H.ctr; pv.done = H.done; pv.bStart = H.dBStart; pv.pushStart = H.dPushStart; pv.push = H.dPush;
     pv.peerUv = H.dPeerUv; pv.peerStride = H.dPeerStride; pv.peerFlag = H.dPeerFlag; pv.nNb = H.nNb;
-    for (int i = 0; i < nVBlocks; i++) pv.nPushBlocks += bStart[i + 1] > bStart[i] ? 1 : 0;
+    pv.nPushBlocks = nPushBlocks;
+    pv.order = H.dOrder;
     H.pushView = pv;
     EVP_CUDA(cudaStreamSynchronize(s));
     H.p2p = true;
@@ -557,7 +566,19 @@ evp_halo_view evp_halo_get_view(evp_handle *h)
     return v;
 }
 
-evp_push_view evp_halo_get_push(evp_handle *h) { return evp_halo_p2p_active(h) ? h->halo->pushView : evp_push_view{}; }
+evp_push_view evp_halo_get_push(evp_handle *h)
+{
+    if (!evp_halo_p2p_active(h)) return evp_push_view{};
+    evp_push_view pv = h->halo->pushView;
+    // timing experiments (tools/gpu_job_p2p_dbg.sh): 1 = boundary stores go to local memory, 2 = no system fence in the
+    // pushing blocks, 4 = no block pushes at all (the extra block publishes), 8 = device- instead of system-scope fence
+    const char *e = getenv("EVP_B200_P2P_DEBUG");
+    if (e) {
+        pv.dbg = atoi(e);
+        if (pv.dbg & 4) pv.nPushBlocks = 0;
+    }
+    return pv;
+}
 
 int evp_halo_begin_run(evp_handle *h, cudaStream_t s)
 {

@@ -95,6 +95,7 @@ struct evp_dev {
     uint8_t *tileWork = nullptr;  // per tile of EVP_TILE cells: 1 = some cell is solved or holds a non-zero stress
     int *tileList = nullptr;      // the tiles with work, compacted (cell kernel grid = their number)
     int *tileCount = nullptr;     // device counter behind tileList
+    unsigned *gridBar = nullptr;  // grid barrier counter of the persistent whole-loop kernel
     uint8_t *vblockWork = nullptr;  // per block of 256 owned vertices: 1 = some vertex is solved
     int *vblockList = nullptr, *vblockCount = nullptr;
     double *P = nullptr;
@@ -147,6 +148,9 @@ struct evp_handle {
 // evp_kernels.cu
 int evp_enqueue_subcycles(evp_handle *h, int nSub, cudaStream_t s);
 int evp_count_launches(evp_handle *h, int nSub);
+// all nSub subcycles as ONE cooperative launch when the whole mesh can be resident (small meshes); 0 = launched (or
+// would be, with probeOnly), -1 = not eligible: use the two-kernel graph
+int evp_persistent_run(evp_handle *h, int nSub, cudaStream_t s, bool probeOnly);
 int evp_enqueue_cell_pass(evp_handle *h, bool diag, cudaStream_t s);
 int evp_enqueue_vertex_pass(evp_handle *h, bool diag, cudaStream_t s);
 int evp_enqueue_special_boundaries(evp_handle *h, cudaStream_t s);
@@ -180,6 +184,9 @@ struct evp_push_view {              // what the vertex kernel needs to store bou
     int *const *peerFlag = nullptr;     // [nNb] this rank's slot among the neighbour's incoming flags
     int nNb = 0;
     int nPushBlocks = 0;                // blocks of 256 owned vertices that hold a boundary vertex (the ticket count)
+    const int *order = nullptr;         // [vertex blocks] launch order: the pushing blocks first, so that their stores, fences
+                                        // and the publication of the pass overlap the interior vertices' work
+    int dbg = 0;                        // EVP_B200_P2P_DEBUG: timing experiments only (results are NOT valid with it)
 };
 int evp_halo_enqueue(evp_handle *h, cudaStream_t s);             // in-loop exchange of d.uv on the NCCL path
 int evp_halo_exchange(evp_handle *h, cudaStream_t s, double2 *field);   // any (nVp) double2 vertex field, NCCL

@@ -405,7 +405,8 @@ struct VertexArgs {
 
 // one owned, solved vertex: stress divergence (variational gather or weak line integral), drag coefficient, 2x2 solve;
 // returns the vertex' (u,v) after the pass
-template <int D, int CR, bool DIAG, bool WEAK>
+// COHERENT: contrib and (u,v) were written by OTHER blocks of the same (persistent) kernel: read them from L2.
+template <int D, int CR, bool DIAG, bool WEAK, bool COHERENT = false>
 __device__ __forceinline__ double2 evp_vertex_solve(const VertexArgs &a, const int v)
 {
     double sdU = 0.0, sdV = 0.0;
@@ -443,7 +444,7 @@ __device__ __forceinline__ double2 evp_vertex_solve(const VertexArgs &a, const i
         for (int s = 0; s < D; s++) {
             const int idx = a.gidx[(size_t)s * a.nVp + v];
             double2 cc = make_double2(0.0, 0.0);
-            if (idx >= 0) cc = a.contrib[idx];
+            if (idx >= 0) cc = COHERENT ? __ldcg(&a.contrib[idx]) : a.contrib[idx];
             sdU = sdU + cc.x;
             sdV = sdV + cc.y;
         }
@@ -451,7 +452,7 @@ __device__ __forceinline__ double2 evp_vertex_solve(const VertexArgs &a, const i
         sdV = sdV / ad.y;
     }
 
-    const double2 w = a.uv[v];
+    const double2 w = COHERENT ? __ldcg(&a.uv[v]) : a.uv[v];
     double coef = 0.0;
     if (a.useOcean) {
         if (a.oceanType == EVP_OCEAN_QUADRATIC) {
@@ -506,8 +507,11 @@ __device__ __forceinline__ double2 evp_vertex_solve(const VertexArgs &a, const i
 template <int D, int CR, bool DIAG, bool P2P, bool WEAK>
 __device__ __forceinline__ void evp_vertex_body(const VertexArgs &a)
 {
-    int blk = a.vblockList ? ((int)blockIdx.x < a.nBlocks ? a.vblockList[blockIdx.x] : -1) : (int)blockIdx.x;
+    int blk;
     if (P2P && (int)blockIdx.x >= a.nBlocks) blk = -1;      // the extra block: publishes the pass when no block pushes
+    else if (a.vblockList) blk = a.vblockList[blockIdx.x];
+    else if (P2P) blk = a.pv.order[blockIdx.x];             // pushing blocks first
+    else blk = (int)blockIdx.x;
     const int v = blk * (int)blockDim.x + (int)threadIdx.x;
     uint8_t mask = 0;
     if (blk >= 0 && v < a.nVerticesSolve) mask = a.solveVel[v];
@@ -517,7 +521,7 @@ __device__ __forceinline__ void evp_vertex_body(const VertexArgs &a)
         // blocks of 256 vertices without a boundary-owned vertex (nearly all) are done here
         const int e0 = blk >= 0 ? a.pv.bStart[blk] : 0;
         const int nPushers = blk >= 0 ? a.pv.bStart[blk + 1] - e0 : 0;
-        if (blk >= 0 && nPushers == 0) return;
+        if (blk >= 0 && (nPushers == 0 || (a.pv.dbg & 4))) return;
         if (blk < 0 && a.pv.nPushBlocks > 0) return;
         __shared__ int warpCount[8];
         const bool bnd = (mask & 2) != 0;
@@ -533,14 +537,16 @@ __device__ __forceinline__ void evp_vertex_body(const VertexArgs &a)
             const int t1 = a.pv.pushStart[e + 1];
             for (int t = a.pv.pushStart[e]; t < t1; t++) {
                 const int2 pd = a.pv.push[t];
-                a.pv.peerUv[pd.x][(size_t)pd.y + (size_t)next * a.pv.peerStride[pd.x]] = wPush;
+                if (a.pv.dbg & 1) a.sdiv[a.nVp - 1 - (t & 31)] = wPush;
+                else a.pv.peerUv[pd.x][(size_t)pd.y + (size_t)next * a.pv.peerStride[pd.x]] = wPush;
             }
         }
         __syncthreads();
         if (threadIdx.x == 0) {
             // one system-scope fence per pushing block: cumulative over the stores of the threads that arrived at the
             // barrier above; then the ticket -- the last pushing block publishes the pass
-            __threadfence_system();
+            if (a.pv.dbg & 8) __threadfence();
+            else if (!(a.pv.dbg & 2)) __threadfence_system();
             const unsigned last = a.pv.nPushBlocks > 0 ? (unsigned)a.pv.nPushBlocks - 1u : 0u;
             const unsigned ticket = atomicAdd(a.pv.done, 1u);
             if (ticket == last) {
@@ -564,6 +570,167 @@ template <int D, int CR, bool DIAG>
 __global__ void __launch_bounds__(256, 5) evp_vertex_p2p_kernel(const VertexArgs a)
 {
     evp_vertex_body<D, CR, DIAG, true, false>(a);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent whole-loop kernel for meshes small enough that every tile of 32 cells can have a block of its own
+// resident at the same time (square 7 708 cells, QU240 10 242 cells: BASELINE configs[1] and [2]).  There the
+// graph of 2 x nSub kernel nodes is bound by launch latency (about 3.5 us per node against about 1 us of work), so
+// ONE cooperative launch runs all nSub subcycles:
+//   * the tile's basis arrays are bulk-copied into shared memory once and stay there for the whole loop;
+//   * the stresses of a (cell, stress point) live in registers of its thread from the first subcycle to the last;
+//   * per subcycle: gather (u,v) from L2 -> strain, stress -> per-cell divergence sums to L2 | grid barrier |
+//     vertex solve for this block's share of the owned vertices | grid barrier.
+// Arithmetic, operation order and summation order are those of evp_cell_kernel / evp_vertex_solve: results are
+// bit-identical to the two-kernel path (tests/test_gpu_parity.py::test_graph_and_stream_paths_agree).
+// ---------------------------------------------------------------------------------------------
+struct PersistArgs {
+    CellArgs c;
+    VertexArgs v;
+    int nSub;
+    int vChunk;            // owned vertices per block in the vertex phase (<= threads per block)
+    unsigned *bar;         // grid barrier counter, zero at launch
+};
+
+__device__ __forceinline__ unsigned evp_ld_acquire_gpu_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// all blocks of the (cooperative) grid; `target` counts the arrivals expected so far
+__device__ __forceinline__ void evp_grid_barrier(unsigned *bar, unsigned &target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        target += gridDim.x;
+        __threadfence();                       // cumulative over what the block wrote before the barrier above
+        atomicAdd(bar, 1u);
+        while (evp_ld_acquire_gpu_u32(bar) < target) { }
+    }
+    __syncthreads();
+}
+
+template <int M, bool METRIC, int CR, int D>
+__global__ void __launch_bounds__(EVP_TILE *M) evp_persistent_kernel(const PersistArgs p)
+{
+    using Smem = CellSmem<M, METRIC, true>;
+    extern __shared__ __align__(128) unsigned char evp_smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(evp_smem_raw);
+    const CellArgs &a = p.c;
+    const int cx = threadIdx.x, j = threadIdx.y;
+    const size_t tile = blockIdx.x;
+    const size_t c = tile * EVP_TILE + cx;
+    const size_t nCp = a.nCp;
+    const bool leader = (cx == 0) && (j == 0);
+    int n = 0;
+    bool solve = false;
+    if (c < (size_t)a.nCells) {
+        n = a.nEdges[c];
+        solve = a.solveStress[c] == 1;
+    }
+    if (leader) {
+        mbar_init(&sm.barG, 1);
+        mbar_init(&sm.barS, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (leader) {       // the basis of the tile: fetched once, resident for all subcycles
+        mbar_expect_tx(&sm.barG, (uint32_t)sizeof(sm.G));
+        bulk_g2s(&sm.G[0][0], a.Gb + tile * (size_t)(Smem::GR * EVP_TILE), (uint32_t)sizeof(sm.G), &sm.barG);
+        mbar_expect_tx(&sm.barS, (uint32_t)(sizeof(sm.S) + (METRIC ? sizeof(sm.Sm) : 0)));
+        bulk_g2s(&sm.S[0][0], a.Suv + tile * (size_t)(M * M * EVP_TILE), (uint32_t)sizeof(sm.S), &sm.barS);
+        if (METRIC) bulk_g2s(&sm.Sm[0][0], a.Sm + tile * (size_t)(M * M * EVP_TILE), (uint32_t)sizeof(sm.Sm), &sm.barS);
+    }
+    const bool act = j < n;
+    const size_t q = (size_t)j * nCp + c;
+    int vi = 0;
+    double tj = 0.0, x11 = 0.0, x22 = 0.0, x12 = 0.0, P = 0.0;
+    if (act) {
+        vi = a.voc[q];
+        if (METRIC) tj = a.tanLat[vi];
+        const double2 s0 = a.sig[q];
+        x11 = s0.x; x22 = s0.y; x12 = a.sig12[q];
+        P = a.P[c];
+    }
+    // the vertex phase: block b solves the owned vertices [b * vChunk, (b + 1) * vChunk)
+    const int t = j * EVP_TILE + cx;
+    const int vtx = (int)blockIdx.x * p.vChunk + t;
+    const bool vact = t < p.vChunk && vtx < p.v.nVerticesSolve && (p.v.solveVel[vtx] & 1);
+    int i0 = j - 1, i1 = j, i2 = j + 1;
+    if (j == 0) { i0 = 0; i1 = 1; i2 = n - 1; }
+    else if (j == n - 1) { i0 = 0; i1 = n - 2; i2 = n - 1; }
+    mbar_wait(&sm.barG, 0);
+    mbar_wait(&sm.barS, 0);
+    unsigned target = 0;
+
+    for (int k = 0; k < p.nSub; k++) {
+        const bool diag = k == p.nSub - 1;
+        double uj = 0.0, vj = 0.0;
+        if (act && solve) {
+            const double2 w = __ldcg(&a.uv[vi]);        // written by other blocks in the previous subcycle
+            uj = w.x; vj = w.y;
+        }
+        sm.u[j][cx] = uj;
+        sm.v[j][cx] = vj;
+        __syncthreads();
+        if (act && solve) {
+            double e11 = 0.0, e22 = 0.0, e12 = 0.0;
+            const double2 g0 = sm.G[0 * M + j][cx];
+            const double2 g1 = sm.G[1 * M + j][cx];
+            const double2 g2 = sm.G[2 * M + j][cx];
+            double u, v;
+            u = sm.u[i0][cx]; v = sm.v[i0][cx];
+            e11 = e11 + u * g0.x; e22 = e22 + v * g0.y; e12 = e12 + 0.5 * (u * g0.y + v * g0.x);
+            u = sm.u[i1][cx]; v = sm.v[i1][cx];
+            e11 = e11 + u * g1.x; e22 = e22 + v * g1.y; e12 = e12 + 0.5 * (u * g1.y + v * g1.x);
+            u = sm.u[i2][cx]; v = sm.v[i2][cx];
+            e11 = e11 + u * g2.x; e22 = e22 + v * g2.y; e12 = e12 + 0.5 * (u * g2.y + v * g2.x);
+            e11 = e11 - vj * tj;
+            e12 = e12 + uj * tj * 0.5;
+            double rep = 0.0;
+            constitutive<CR>(x11, x22, x12, e11, e22, e12, P, rep, a.dte, a.damping);
+            if (diag) {
+                a.e11[q] = e11; a.e22[q] = e22; a.e12[q] = e12;
+                a.repP[q] = rep;
+            }
+        } else if (act && diag && CR == EVP_CR_EVP) {
+            a.repP[q] = 0.0;                             // variational.F:862
+        }
+        sm.s11[j][cx] = x11;
+        sm.s22[j][cx] = x22;
+        sm.s12[j][cx] = x12;
+        __syncthreads();
+        if (act) {
+            double cU = 0.0, cV = 0.0;
+#pragma unroll
+            for (int i = 0; i < M; i++) {
+                if (i < n) {
+                    const double s11 = sm.s11[i][cx], s22 = sm.s22[i][cx], s12 = sm.s12[i][cx];
+                    const double2 S = sm.S[j * M + i][cx];
+                    if (METRIC) {
+                        const double m = sm.Sm[j * M + i][cx];
+                        cU = cU - s11 * S.x - s12 * S.y - s12 * m * tj;
+                        cV = cV - s22 * S.y - s12 * S.x + s11 * m * tj;
+                    } else {
+                        cU = cU - s11 * S.x - s12 * S.y;
+                        cV = cV - s22 * S.y - s12 * S.x;
+                    }
+                }
+            }
+            a.contrib[q] = make_double2(cU, cV);
+        }
+        evp_grid_barrier(p.bar, target);
+        if (vact) {
+            if (diag) evp_vertex_solve<D, CR, true, false, true>(p.v, vtx);
+            else      evp_vertex_solve<D, CR, false, false, true>(p.v, vtx);
+        }
+        evp_grid_barrier(p.bar, target);
+    }
+    if (act && solve) {
+        a.sig[q] = make_double2(x11, x22);
+        a.sig12[q] = x12;
+    }
 }
 
 // seaice_set_special_boundaries_velocity (special_boundaries.F:301-324) with the sequential
@@ -696,9 +863,8 @@ int evp_enqueue_cell_pass(evp_handle *h, bool diag, cudaStream_t s)
     return enqueue_cell_phase(h, diag, 2, s);
 }
 
-static int enqueue_cell_phase(evp_handle *h, bool diag, int phase, cudaStream_t s)
+static void fill_cell_args(evp_handle *h, CellArgs &a)
 {
-    CellArgs a;
     a.nCells = h->nCells; a.nCp = h->nCp;
     const int allTiles = (h->nCells + EVP_TILE - 1) / EVP_TILE;
     a.nTiles = h->nActiveTiles < 0 ? allTiles : h->nActiveTiles;
@@ -710,6 +876,12 @@ static int enqueue_cell_phase(evp_handle *h, bool diag, int phase, cudaStream_t 
     a.e11 = h->d.e11; a.e22 = h->d.e22; a.e12 = h->d.e12; a.repP = h->d.repP;
     a.dte = h->opt.elasticTimeStep; a.damping = h->opt.dampingTimescale;
     a.hv = evp_halo_get_view(h);
+}
+
+static int enqueue_cell_phase(evp_handle *h, bool diag, int phase, cudaStream_t s)
+{
+    CellArgs a;
+    fill_cell_args(h, a);
     const int cr = h->opt.constitutive_relation_type;
     int rc = 0;
     switch (h->M) {
@@ -724,11 +896,9 @@ static int enqueue_cell_phase(evp_handle *h, bool diag, int phase, cudaStream_t 
     return EVP_OK;
 }
 
-int evp_enqueue_vertex_pass(evp_handle *h, bool diag, cudaStream_t s)
+static void fill_vertex_args(evp_handle *h, VertexArgs &a)
 {
-    VertexArgs a;
     a.pv = evp_halo_get_push(h);
-    if (h->nVerticesSolve == 0 && !a.pv.ctr) return EVP_OK;
     a.nVerticesSolve = h->nVerticesSolve; a.nVp = h->nVp;
     const int allBlocks = (h->nVerticesSolve + 255) / 256;
     a.nBlocks = h->nActiveVBlocks < 0 ? allBlocks : h->nActiveVBlocks;
@@ -743,6 +913,13 @@ int evp_enqueue_vertex_pass(evp_handle *h, bool diag, cudaStream_t s)
     const bool weak = h->opt.stress_divergence_scheme == EVP_SCHEME_WEAK;
     a.cov = h->d.cov; a.wEdgeC = h->d.wEdgeC; a.wNt = h->d.wNt; a.wDc = h->d.wDc; a.wTanV = h->d.wTanV;
     a.wAreaT = h->d.wAreaT; a.sigW = weak ? h->d.sigW : nullptr; a.sigW12 = h->d.sigW12; a.wRadius = h->d.wRadius;
+}
+
+int evp_enqueue_vertex_pass(evp_handle *h, bool diag, cudaStream_t s)
+{
+    VertexArgs a;
+    fill_vertex_args(h, a);
+    if (h->nVerticesSolve == 0 && !a.pv.ctr) return EVP_OK;
     const int cr = h->opt.constitutive_relation_type;
     switch (h->D) {
     case 3: launch_vertex_cr<3>(a, cr, diag, s); break;
@@ -895,8 +1072,92 @@ int evp_enqueue_subcycles(evp_handle *h, int nSub, cudaStream_t s)
     return EVP_OK;
 }
 
+// ---- the persistent whole-loop kernel: eligibility and launch ----
+namespace {
+template <int M, bool METRIC, int CR, int D>
+int persistent_launch(evp_handle *h, const PersistArgs &p, unsigned grid, cudaStream_t s, bool probeOnly)
+{
+    auto kern = evp_persistent_kernel<M, METRIC, CR, D>;
+    constexpr size_t smem = sizeof(CellSmem<M, METRIC, true>);
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return -1; }
+    int perSM = 0, nSM = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, EVP_TILE * M, smem) != cudaSuccess) { cudaGetLastError(); return -1; }
+    if (cudaDeviceGetAttribute(&nSM, cudaDevAttrMultiProcessorCount, h->device) != cudaSuccess) { cudaGetLastError(); return -1; }
+    if ((long long)perSM * nSM < (long long)grid) return -1;          // not every tile can be resident at once
+    if (probeOnly) return 0;
+    void *args[] = {(void *)&p};
+    if (cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(EVP_TILE, M), args, smem, s) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return 0;
+}
+template <int M, bool METRIC, int CR>
+int persistent_d(evp_handle *h, const PersistArgs &p, unsigned grid, cudaStream_t s, bool probe)
+{
+    return h->D == 3 ? persistent_launch<M, METRIC, CR, 3>(h, p, grid, s, probe) : persistent_launch<M, METRIC, CR, 4>(h, p, grid, s, probe);
+}
+template <int M, bool METRIC>
+int persistent_cr(evp_handle *h, const PersistArgs &p, unsigned grid, cudaStream_t s, bool probe)
+{
+    return h->opt.constitutive_relation_type == EVP_CR_EVP ? persistent_d<M, METRIC, EVP_CR_EVP>(h, p, grid, s, probe)
+                                                           : persistent_d<M, METRIC, EVP_CR_EVP_REVISED>(h, p, grid, s, probe);
+}
+template <int M>
+int persistent_m(evp_handle *h, const PersistArgs &p, unsigned grid, cudaStream_t s, bool probe)
+{
+    return h->metric ? persistent_cr<M, true>(h, p, grid, s, probe) : persistent_cr<M, false>(h, p, grid, s, probe);
+}
+}  // namespace
+
+static void fill_cell_args(evp_handle *h, CellArgs &a);
+static void fill_vertex_args(evp_handle *h, VertexArgs &a);
+
+// Can (and should) nSub subcycles of this handle run as ONE cooperative launch?  Default configuration only:
+// variational operators without vertex averaging, EVP / revised EVP, banded (Wachspress) gradients, one rank, no
+// special boundaries -- everything else keeps the two-kernel graph.  EVP_B200_PERSISTENT=0 switches it off,
+// =1 insists (an error if the mesh does not fit), default: used whenever every tile fits on the device at once.
+static bool persistent_configured(evp_handle *h)
+{
+    const char *e = getenv("EVP_B200_PERSISTENT");
+    if (e && e[0] == '0') return false;
+    if (!h->useGraph || h->nCells == 0 || h->nVerticesSolve == 0) return false;
+    if (h->opt.strain_scheme == EVP_SCHEME_WEAK || h->opt.stress_divergence_scheme == EVP_SCHEME_WEAK) return false;
+    if (h->opt.average_variational_strain) return false;
+    const int cr = h->opt.constitutive_relation_type;
+    if (cr != EVP_CR_EVP && cr != EVP_CR_EVP_REVISED) return false;
+    if (!h->d.Gb) return false;
+    if (h->opt.use_special_boundaries_velocity && h->d.nSB) return false;
+    if (evp_halo_launches(h) || evp_halo_p2p_active(h)) return false;
+    if (h->D != 3 && h->D != 4) return false;
+    return true;
+}
+
+// 0 = launched (or, with probeOnly, would be), -1 = not eligible
+int evp_persistent_run(evp_handle *h, int nSub, cudaStream_t s, bool probeOnly)
+{
+    if (nSub <= 0 || !persistent_configured(h)) return -1;
+    const unsigned grid = (unsigned)((h->nCells + EVP_TILE - 1) / EVP_TILE);
+    if (grid > 4096) return -1;                       // far beyond what can be co-resident: skip the occupancy query
+    PersistArgs p;
+    fill_cell_args(h, p.c);
+    fill_vertex_args(h, p.v);
+    p.nSub = nSub;
+    p.vChunk = (h->nVerticesSolve + (int)grid - 1) / (int)grid;
+    p.bar = h->d.gridBar;
+    if (p.vChunk > EVP_TILE * h->M) return -1;
+    if (!probeOnly && cudaMemsetAsync(h->d.gridBar, 0, sizeof(unsigned), s) != cudaSuccess) { cudaGetLastError(); return -1; }
+    switch (h->M) {
+    case 4: return persistent_m<4>(h, p, grid, s, probeOnly);
+    case 6: return persistent_m<6>(h, p, grid, s, probeOnly);
+    case 8: return persistent_m<8>(h, p, grid, s, probeOnly);
+    default: return -1;
+    }
+}
+
 int evp_count_launches(evp_handle *h, int nSub)
 {
+    if (evp_persistent_run(h, nSub, h->stream, true) == 0) return 1;
     const int sb = (h->opt.use_special_boundaries_velocity && h->d.nSB) ? 2 : 0;
     const bool cells = h->nCells > 0, work = cells && h->nActiveTiles != 0, verts = h->nVerticesSolve > 0;
     const bool vwork = verts && h->nActiveVBlocks != 0;

@@ -178,12 +178,16 @@ def test_state_carried_across_dynamics_steps(evp_lib):
         solver.destroy()
 
 
-def test_graph_and_stream_paths_agree(evp_lib):
+@pytest.mark.parametrize("kind", ["hex20", "quad40", "ico4"])
+def test_graph_and_stream_paths_agree(evp_lib, kind, monkeypatch):
+    """Three ways to run the same subcycles: the persistent whole-loop kernel (one cooperative launch, the default for
+    meshes whose tiles are all resident at once), the CUDA graph of cell / vertex kernel nodes, plain stream launches."""
     from mpas_seaice_b200 import host
-    mesh, var = common.mesh_case("hex20")
+    mesh, var = common.mesh_case(kind)
     step, opts = common.step_case(mesh)
     outs = []
-    for use_graph in (1, 0):
+    for mode, use_graph, persistent, launches in (("persistent", 1, "1", 1), ("graph", 1, "0", 20), ("stream", 0, "1", 20)):
+        monkeypatch.setenv("EVP_B200_PERSISTENT", persistent)
         solver = host.EvpSolver(mesh, var, opts)
         try:
             solver.set_use_graph(use_graph)
@@ -191,14 +195,34 @@ def test_graph_and_stream_paths_agree(evp_lib):
             solver.run_subcycles(7)
             solver.run_subcycles(3)          # a second call with a different count re-instantiates
             outs.append(solver.fetch())
-            assert solver.launch_count(10) == 20
+            assert solver.launch_count(10) == launches, mode
         finally:
             solver.destroy()
     for k in common.COMPARE_CELL + common.COMPARE_VERTEX:
         assert np.array_equal(outs[0][k], outs[1][k]), k
+        assert np.array_equal(outs[0][k], outs[2][k]), k
     ref = common.run_oracle(mesh, var, step, opts, 10)
-    # strain / divergence diagnostics are those of the LAST subcycle in both
+    # strain / divergence diagnostics are those of the LAST subcycle in all of them
     _compare(mesh, step, ref, outs[0])
+
+
+@pytest.mark.parametrize("cr", ["evp", "evp_revised"])
+def test_persistent_kernel_with_partial_cover(evp_lib, cr, monkeypatch):
+    """The whole-loop kernel on the polar-cap state (unsolved cells and vertices inside resident tiles) and with the
+    revised EVP relation, 120 subcycles, against the oracle."""
+    from mpas_seaice_b200 import host
+    monkeypatch.setenv("EVP_B200_PERSISTENT", "1")
+    mesh, var = common.mesh_case("ico5")
+    step, opts = common.step_case(mesh, state_kind="B", constitutive_relation_type=cr)
+    solver = host.EvpSolver(mesh, var, opts)
+    try:
+        solver.update_step(step)
+        solver.run_subcycles(120)
+        out = solver.fetch()
+        assert solver.launch_count(120) == 1
+    finally:
+        solver.destroy()
+    _compare(mesh, step, common.run_oracle(mesh, var, step, opts, 120), out)
 
 
 def test_pinned_host_path(evp_lib):
