@@ -612,7 +612,7 @@ __device__ __forceinline__ void evp_grid_barrier(unsigned *bar, unsigned &target
 }
 
 template <int M, bool METRIC, int CR, int D>
-__global__ void __launch_bounds__(EVP_TILE *M) evp_persistent_kernel(const PersistArgs p)
+__global__ void __launch_bounds__(EVP_TILE *M, 3) evp_persistent_kernel(const PersistArgs p)
 {
     using Smem = CellSmem<M, METRIC, true>;
     extern __shared__ __align__(128) unsigned char evp_smem_raw[];

@@ -1,22 +1,27 @@
 // ir_kernels.cu -- incremental-remapping transport on B200 (sm_100a): kernels and the C ABI of include/ir_b200.h.
 //
 // What one ir_run does (reference: incremental_remap_block, src/shared/mpas_seaice_advection_incremental_remap.F:2740):
-//   k_prepare      per cell: ice mask, volume -> thickness                               (:2462-2480, make_masks :3404)
-//   k_reconstruct  per (cell, category): gradient, limiter, centre value, barycentre    (:3580-5250)
-//   k_triangles    per edge: departure triangles and their quadrature points            (:5255-6665)
-//   k_fluxes       per (edge, category): integrate mass * tracer over the triangles     (:6667-6980)
-//   k_update       per (cell, category): new mass and tracers, zap, thickness -> volume (:6982-7540, :8764-8895, :2680-2700)
+//   k_prepare           per cell: ice mask, volume -> thickness                                    (:2462-2480, make_masks :3404)
+//   k_reconstruct_coop  block = 32 cells x all rows: gradient, limiter, centre value, barycentre   (:3580-5250)
+//   k_triangles         per edge: departure triangles and their quadrature points                  (:5255-6665)
+//   k_fluxes_coop       block = 32 edges x the rows of one category: mass * tracer over the triangles (:6667-6980)
+//   k_update_coop       block = 32 cells x all rows: new mass and tracers, zap, thickness -> volume (:6982-7540, :8764-8895, :2680-2700)
 // Five launches per step whatever the number of tracers.
 //
 // Layout: the host keeps a tracer as (nLayers, nCategories, nCells) -- all components of a cell together.  On the
 // device every (tracer, category, layer) is a ROW of one matrix val[nRows][nCp] with the cell index fastest, so a warp
 // of 32 cells reads 256 contiguous bytes of a row; the same for every per-cell / per-edge geometry array
 // ([slot][nCp]).  Parents are resolved to row numbers once, in ir_set_tracers.  Categories never mix, and within a
-// category a row depends on its parents in the same cell only, so the tracer kernels run one thread per
-// (cell or edge, category) that walks the category's rows parents first and reads the geometry once.
+// category a row depends on its parents in the same cell only.  The three tracer kernels are cooperative: a warp is
+// 32 consecutive cells (or edges) of ONE row, the rows of the tracer hierarchy are spread over the thread rows of the
+// block and walked depth by depth with a barrier in between, and what all rows share -- the cell's geometry, the
+// departure triangles' quadrature points, the mass reconstruction at those points -- is staged or computed once per
+// block in shared memory.  (Round 1 ran one thread per (cell or edge, category) walking its 23 rows serially: 8.2 ms
+// per QU60 step, 80 % of it in the flux kernel at 27 % occupancy and 9 % L1 hit rate, profiles/ir_r02_*.)
 //
-// All of it is gather-heavy FP64 streaming work bounded by HBM / L2, not tensor work.  Built with --fmad=false and in
-// the reference's operation order so that the results are bit-identical to oracle/ir_oracle.c (tests/test_gpu_ir.py).
+// All of it is gather-heavy FP64 streaming work bounded by HBM / L2 and, in the flux kernel, the FP64 pipe -- not tensor
+// work.  Built with --fmad=false and in the reference's operation order so that the results are bit-identical to
+// oracle/ir_oracle.c (tests/test_ir_parity.py).
 #include <cuda_runtime.h>
 
 #include <cfloat>
@@ -35,6 +40,12 @@
 // available; it is test infrastructure and never part of the shipped library).
 #ifndef IR_LAUNCH
 #define IR_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+// kernels whose threads cooperate through shared memory and __syncthreads() (the emulation runs them as fibers)
+#define IR_LAUNCH_SYNC(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define IR_DYN_SHARED(type, name)                                  \
+    extern __shared__ __align__(16) unsigned char ir_dyn_smem_raw[]; \
+    type *name = reinterpret_cast<type *>(ir_dyn_smem_raw)
+#define IR_DEVICE_BUILD 1
 #endif
 
 namespace {
@@ -84,6 +95,16 @@ struct RowInfo {
     int parentSlot;        // the parent's slot, -1 for the mass-like field
 };
 
+// One row of a category in parents-first order; the table is the same for every category k, whose device row is
+// baseRow + k * layers.  anc[q] is the position IN THIS TABLE of the ancestor of depth q (anc[depth] = the row itself).
+struct CatRow {
+    int baseRow, layers, depth;
+    int cls;                  // index among the category's rows of the same depth (kept for depth 0 and 1), else -1
+    int anc[MAX_DEPTH];
+    int hasChild, volumeLike;
+    int slotJ, parentSlotJ;   // index among the category's rows that have children: this row's / its parent's, or -1
+};
+
 struct Dev {
     // sizes
     int nC, nCS, nV, nE, M, D, nK, nQP, sphere, rotate;
@@ -102,6 +123,8 @@ struct Dev {
     int nRows, nRowsPerCat;
     RowInfo *rows;
     int *catBaseRow, *catLayers;   // rows of category k in parents-first order: catBaseRow[j] + k * catLayers[j]
+    CatRow *catRows;               // the same list with the tree structure resolved (k_fluxes)
+    int nD0, nD1, nSlotsPerCat;    // rows of depth 0 / depth 1 / rows with children, per category
     double *val, *valNew, *center, *xGrad, *yGrad, *xBary, *yBary, *mtpNew;
     double *edgeFlux;   // [nRows][nEp]
     int *flags;
@@ -282,107 +305,133 @@ __device__ void barycenter(const Dev &d, size_t c, int n, const double *mean, co
 }
 
 // construct_linear_tracer_fields (:3580): compute_gradient (:4204), limit_tracer_gradient (:4802), centre value
-// (:3735), barycentre (:3750-3840).  One thread per (cell, category) walks the rows of its category parents first:
-// a row needs its parents' results in the SAME cell only (neighbour cells contribute their input values), so the
-// whole hierarchy is one launch, and the cell's geometry (reconstruction coefficients, signed dcEdge, vertex
-// coordinates: 6 * maxEdges doubles) is read once per category instead of once per row.  It is parked in shared
-// memory as a per-thread scratch column (no thread reads another's, hence no barrier).
-constexpr int RB = 64;   // threads per block of the per-(cell, category) and per-(edge, category) kernels
+// (:3735), barycentre (:3750-3840).  One block = 32 cells (lane = cell) x CW thread rows and ALL rows of all categories.  The cell's geometry (reconstruction coefficients, signed dcEdge, vertex coordinates,
+// neighbour cells: 6 * maxEdges doubles) is staged in shared memory once per block and used by every row; the rows are
+// processed depth by depth with a barrier in between, because a row needs the barycentre of its parent (and, for its
+// own barycentre, the reconstructions of all its ancestors) in the same cell -- written by other threads of the block.
+// A row needs neighbour cells' INPUT values only, so the whole hierarchy is one launch.
+constexpr int CL = 32;   // cells per block
+constexpr int CW = 12;   // thread rows per block
 
-__global__ void __launch_bounds__(RB) k_reconstruct(Dev d)
+inline size_t ir_reconstruct_smem_bytes() { return sizeof(double) * ((size_t)CL * (6 * MAXM + 8)) + sizeof(int) * (size_t)CL * (MAXM + 2); }
+
+__global__ void __launch_bounds__(CL *CW, 3) k_reconstruct_coop(Dev d, int maxDepth)
 {
-    __shared__ double S[6 * MAXM][RB];
-    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int cat = blockIdx.y, tx = threadIdx.x;
-    if (c >= (size_t)d.nC) return;
+    IR_DYN_SHARED(double, sm);
+    double *S = sm;                                  // [6 * MAXM][CL]: coef (3M), sdc (M), xvc (M), yvc (M)
+    double *TR = S + 6 * MAXM * CL;                  // [6][CL] rows 1, 2 of transGlobalToCell
+    double *AVG = TR + 6 * CL;                       // [2][CL] geometric centre
+    int *NB = reinterpret_cast<int *>(AVG + 2 * CL); // [MAXM][CL] cellsOnCell (1-based)
+    int *NE = NB + MAXM * CL;                        // [CL] nEdgesOnCell
+    int *ICE = NE + CL;                              // [CL] maskCell
+    const int lane = threadIdx.x, ty = threadIdx.y;
+    const size_t c = (size_t)blockIdx.x * CL + lane;
+    const bool valid = c < (size_t)d.nC;
     const size_t p = d.nCp;
-    const int M = d.M, n = d.nEdgesOnCell[c];
-    int nb[MAXM];
-    for (int k = 0; k < n; k++) {
-        nb[k] = d.cellsOnCell[k * p + c];            // 1-based, nC+1 = none
-        S[3 * k + 0][tx] = d.coef[(size_t)(3 * k + 0) * p + c];
-        S[3 * k + 1][tx] = d.coef[(size_t)(3 * k + 1) * p + c];
-        S[3 * k + 2][tx] = d.coef[(size_t)(3 * k + 2) * p + c];
-        S[3 * M + k][tx] = d.sdc[k * p + c];
-        S[4 * M + k][tx] = d.xvc[k * p + c];
-        S[5 * M + k][tx] = d.yvc[k * p + c];
+    const int M = d.M;
+    // ---- stage the geometry ----
+    for (int row = ty; row < 6 * M; row += CW) {
+        double v = 0.0;
+        if (valid) {
+            if (row < 3 * M) v = d.coef[(size_t)row * p + c];
+            else if (row < 4 * M) v = d.sdc[(size_t)(row - 3 * M) * p + c];
+            else if (row < 5 * M) v = d.xvc[(size_t)(row - 4 * M) * p + c];
+            else v = d.yvc[(size_t)(row - 5 * M) * p + c];
+        }
+        S[row * CL + lane] = v;
     }
-    double tr[6] = {0, 0, 0, 0, 0, 0};
-    if (d.sphere)
-        for (int q = 0; q < 6; q++) tr[q] = d.trans[q * p + c];
-    const double xAvg = d.geom[c], yAvg = d.geom[p + c];
-    const bool ice = d.maskCell[c] == 1;
-    for (int j = 0; j < d.nRowsPerCat; j++) {
-        const int r = d.catBaseRow[j] + cat * d.catLayers[j];
-        const RowInfo ri = d.rows[r];
-        const double *field = d.val + (size_t)r * p;
-        const double f0 = field[c];
-        const int pr = ri.depth > 0 ? ri.chain[ri.depth - 1] : -1;
-        double xB, yB;   // barycentre of the parent: where this row's value sits
-        if (pr >= 0) { xB = d.xBary[(size_t)ri.parentSlot * p + c]; yB = d.yBary[(size_t)ri.parentSlot * p + c]; }
-        else { xB = xAvg; yB = yAvg; }
-        double xg = 0.0, yg = 0.0;
-        if (ice) {
-            const bool m0 = row_mask(d, ri, c);
-            double g1 = 0.0, g2 = 0.0, g3 = 0.0;
-            double maxNeighbor = f0, minNeighbor = f0;
-            for (int k = 0; k < n; k++) {
-                const bool mn = row_mask(d, ri, (size_t)nb[k] - 1);
-                double normalGrad = 0.0;
-                const double fn = (nb[k] >= 1 && nb[k] <= d.nC + 1) ? field[nb[k] - 1] : 0.0;
-                if (nb[k] >= 1 && nb[k] <= d.nC && m0 && mn) normalGrad = (fn - f0) / S[3 * M + k][tx];
-                g1 = g1 + S[3 * k + 0][tx] * normalGrad;
-                g2 = g2 + S[3 * k + 1][tx] * normalGrad;
-                g3 = g3 + S[3 * k + 2][tx] * normalGrad;
-                if (mn) {
-                    maxNeighbor = (maxNeighbor > fn) ? maxNeighbor : fn;
-                    minNeighbor = (minNeighbor < fn) ? minNeighbor : fn;
-                }
-            }
-            if (d.rotate && d.sphere) { const double t = g1; g1 = -g3; g3 = t; }
-            if (d.sphere) {
-                xg = tr[0] * g1 + tr[1] * g2 + tr[2] * g3;
-                yg = tr[3] * g1 + tr[4] * g2 + tr[5] * g3;
-            } else {
-                xg = g1;
-                yg = g2;
-            }
-            maxNeighbor = maxNeighbor - f0;
-            minNeighbor = minNeighbor - f0;
-            double maxLocal = 0.0, minLocal = 0.0;
-            for (int k = 0; k < n; k++) {
-                const double dev = xg * (S[4 * M + k][tx] - xB) + yg * (S[5 * M + k][tx] - yB);
-                maxLocal = (maxLocal > dev) ? maxLocal : dev;
-                minLocal = (minLocal < dev) ? minLocal : dev;
-            }
-            double f1 = 1.0, f2 = 1.0;
-            if (fabs(maxLocal) > fabs(maxNeighbor)) { f1 = maxNeighbor / maxLocal; if (!(f1 > 0.0)) f1 = 0.0; }
-            if (fabs(minLocal) > fabs(minNeighbor)) { f2 = minNeighbor / minLocal; if (!(f2 > 0.0)) f2 = 0.0; }
-            double gradFactor = (f1 < f2) ? f1 : f2;
-            gradFactor = gradFactor - EPS11;
-            if (!(gradFactor > 0.0)) gradFactor = 0.0;
-            xg = xg * gradFactor;
-            yg = yg * gradFactor;
-        }
-        const double cen = f0 - xg * xB - yg * yB;
-        d.xGrad[(size_t)r * p + c] = xg;
-        d.yGrad[(size_t)r * p + c] = yg;
-        d.center[(size_t)r * p + c] = cen;
-        if (ri.hasChild) {
-            double bx = 0.0, by = 0.0;
+    for (int row = ty; row < M; row += CW) NB[row * CL + lane] = valid ? d.cellsOnCell[(size_t)row * p + c] : 0;
+    for (int row = ty; row < 6; row += CW) TR[row * CL + lane] = (valid && d.sphere) ? d.trans[(size_t)row * p + c] : 0.0;
+    for (int row = ty; row < 2; row += CW) AVG[row * CL + lane] = valid ? d.geom[(size_t)row * p + c] : 0.0;
+    if (ty == 0) {
+        NE[lane] = valid ? d.nEdgesOnCell[c] : 0;
+        ICE[lane] = valid ? d.maskCell[c] : 0;
+    }
+    __syncthreads();
+    const int n = NE[lane];
+    const bool ice = ICE[lane] == 1;
+    const double xAvg = AVG[lane], yAvg = AVG[CL + lane];
+    int j0 = 0;
+    for (int q = 0; q <= maxDepth; q++) {
+        int j1 = j0;
+        while (j1 < d.nRowsPerCat && d.catRows[j1].depth == q) j1++;
+        const int cnt = j1 - j0;
+        for (int it = ty; valid && it < d.nK * cnt; it += CW) {
+            const int cat = it / cnt, j = j0 + (it - cat * cnt);
+            const int r = d.catRows[j].baseRow + cat * d.catRows[j].layers;
+            const RowInfo ri = d.rows[r];
+            const double *field = d.val + (size_t)r * p;
+            const double f0 = field[c];
+            const int pr = ri.depth > 0 ? ri.chain[ri.depth - 1] : -1;
+            double xB, yB;   // barycentre of the parent: where this row's value sits
+            if (pr >= 0) { xB = d.xBary[(size_t)ri.parentSlot * p + c]; yB = d.yBary[(size_t)ri.parentSlot * p + c]; }
+            else { xB = xAvg; yB = yAvg; }
+            double xg = 0.0, yg = 0.0;
             if (ice) {
-                double mean[3], ce[3], gx[3], gy[3];
-                const int nn = ri.depth + 1;
-                for (int q = 0; q < nn - 1; q++) {
-                    const size_t a = (size_t)ri.chain[q] * p + c;
-                    mean[q] = d.val[a]; ce[q] = d.center[a]; gx[q] = d.xGrad[a]; gy[q] = d.yGrad[a];
+                const bool m0 = row_mask(d, ri, c);
+                double g1 = 0.0, g2 = 0.0, g3 = 0.0;
+                double maxNeighbor = f0, minNeighbor = f0;
+                for (int k = 0; k < n; k++) {
+                    const int nbk = NB[k * CL + lane];
+                    const bool mn = row_mask(d, ri, (size_t)nbk - 1);
+                    double normalGrad = 0.0;
+                    const double fn = (nbk >= 1 && nbk <= d.nC + 1) ? field[nbk - 1] : 0.0;
+                    if (nbk >= 1 && nbk <= d.nC && m0 && mn) normalGrad = (fn - f0) / S[(3 * M + k) * CL + lane];
+                    g1 = g1 + S[(3 * k + 0) * CL + lane] * normalGrad;
+                    g2 = g2 + S[(3 * k + 1) * CL + lane] * normalGrad;
+                    g3 = g3 + S[(3 * k + 2) * CL + lane] * normalGrad;
+                    if (mn) {
+                        maxNeighbor = (maxNeighbor > fn) ? maxNeighbor : fn;
+                        minNeighbor = (minNeighbor < fn) ? minNeighbor : fn;
+                    }
                 }
-                mean[nn - 1] = f0; ce[nn - 1] = cen; gx[nn - 1] = xg; gy[nn - 1] = yg;
-                barycenter(d, c, nn, mean, ce, gx, gy, bx, by);
+                if (d.rotate && d.sphere) { const double t = g1; g1 = -g3; g3 = t; }
+                if (d.sphere) {
+                    xg = TR[0 * CL + lane] * g1 + TR[1 * CL + lane] * g2 + TR[2 * CL + lane] * g3;
+                    yg = TR[3 * CL + lane] * g1 + TR[4 * CL + lane] * g2 + TR[5 * CL + lane] * g3;
+                } else {
+                    xg = g1;
+                    yg = g2;
+                }
+                maxNeighbor = maxNeighbor - f0;
+                minNeighbor = minNeighbor - f0;
+                double maxLocal = 0.0, minLocal = 0.0;
+                for (int k = 0; k < n; k++) {
+                    const double dev = xg * (S[(4 * M + k) * CL + lane] - xB) + yg * (S[(5 * M + k) * CL + lane] - yB);
+                    maxLocal = (maxLocal > dev) ? maxLocal : dev;
+                    minLocal = (minLocal < dev) ? minLocal : dev;
+                }
+                double f1 = 1.0, f2 = 1.0;
+                if (fabs(maxLocal) > fabs(maxNeighbor)) { f1 = maxNeighbor / maxLocal; if (!(f1 > 0.0)) f1 = 0.0; }
+                if (fabs(minLocal) > fabs(minNeighbor)) { f2 = minNeighbor / minLocal; if (!(f2 > 0.0)) f2 = 0.0; }
+                double gradFactor = (f1 < f2) ? f1 : f2;
+                gradFactor = gradFactor - EPS11;
+                if (!(gradFactor > 0.0)) gradFactor = 0.0;
+                xg = xg * gradFactor;
+                yg = yg * gradFactor;
             }
-            d.xBary[(size_t)ri.slot * p + c] = bx;
-            d.yBary[(size_t)ri.slot * p + c] = by;
+            const double cen = f0 - xg * xB - yg * yB;
+            d.xGrad[(size_t)r * p + c] = xg;
+            d.yGrad[(size_t)r * p + c] = yg;
+            d.center[(size_t)r * p + c] = cen;
+            if (ri.hasChild) {
+                double bx = 0.0, by = 0.0;
+                if (ice) {
+                    double mean[3], ce[3], gx[3], gy[3];
+                    const int nn = ri.depth + 1;
+                    for (int z = 0; z < nn - 1; z++) {
+                        const size_t a = (size_t)ri.chain[z] * p + c;
+                        mean[z] = d.val[a]; ce[z] = d.center[a]; gx[z] = d.xGrad[a]; gy[z] = d.yGrad[a];
+                    }
+                    mean[nn - 1] = f0; ce[nn - 1] = cen; gx[nn - 1] = xg; gy[nn - 1] = yg;
+                    barycenter(d, c, nn, mean, ce, gx, gy, bx, by);
+                }
+                d.xBary[(size_t)ri.slot * p + c] = bx;
+                d.yBary[(size_t)ri.slot * p + c] = by;
+            }
         }
+        j0 = j1;
+        __syncthreads();       // the next depth reads what this one stored (same cell, other threads of the block)
     }
 }
 
@@ -614,147 +663,225 @@ __global__ void __launch_bounds__(128) k_triangles(Dev d, double dt)
     }
 }
 
-// integrate_fluxes_over_triangles (:6667): one thread per (edge, category).  The quadrature points of the edge's
-// non-empty departure triangles are parked once in a per-thread shared-memory column and reused by every row of the
-// category.  CAP = the triangles parked per edge (4 on hexagonal meshes -- the most a smooth flow produces there,
-// find_departure_triangles :5420-5460 -- 6 on quadrilateral ones): it sizes the scratch, i.e. the blocks that fit on an SM.  triangleValue of a
-// row is the product down its chain of parents of the linear reconstructions at the quadrature point, the mass field
-// first.
-template <int CAP>
-__global__ void __launch_bounds__(RB) k_fluxes(Dev d)
+// integrate_fluxes_over_triangles (:6667): one block = 32 edges (lane = edge) x FR thread rows,
+// one category per block (blockIdx.y).  The reference evaluates, for every row, at every quadrature point of every
+// departure triangle, the product down the row's chain of parents of the linear reconstructions,
+//     value = ((1 * v_0) * v_1) * ... * v_depth,   v_s = center_s + xGrad_s * x + yGrad_s * y  at the source cell.
+// All rows of a category share v_0 (the mass field), and the children of a depth-1 row share v_0 * v_1, so the
+// block computes those once into shared memory (1 * v_0 is v_0 exactly; (v_0 * v_1) is the reference's own
+// intermediate: the results stay bit-identical) and a row of depth 2 costs one reconstruction and one product per
+// point instead of three and three.  Phases (barriers between them):
+//   A  lanes compact the non-empty triangles of their edge (area, source cell) -- triangle order is kept, it is the
+//      order the reference sums in -- and drop edges whose source cells hold no ice; all threads then fetch the
+//      quadrature points into shared memory;
+//   B  v_0 at every (triangle, point) for the category's depth-0 rows; negative-mass check (:6895);
+//   C  v_0 * v_1 for the depth-1 rows;
+//   D  thread (lane, row): the row's flux through the edge -> edgeFlux[row][edge]  (one warp = 32 consecutive
+//      edges of one row: coalesced stores; shared memory is [..][lane]: conflict-free).
+constexpr int FL = 32;   // edges per block
+constexpr int FR = 24;   // thread rows per block
+constexpr int FNS = NTRI * 6;   // (triangle, point) slots per edge
+
+inline size_t ir_flux_smem_bytes(int nD0, int nD1)
 {
-    __shared__ double Q[CAP * 12][RB];
-    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int cat = blockIdx.y, tx = threadIdx.x;
-    if (e >= (size_t)d.nE) return;
+    return sizeof(double) * ((size_t)FL * (2 * FNS + (size_t)(nD0 + nD1) * FNS + NTRI) + (size_t)FL * (2 * NTRI + 1) / 2 + 8);
+}
+
+__global__ void __launch_bounds__(FL *FR, 2) k_fluxes_coop(Dev d)
+{
+    IR_DYN_SHARED(double, sm);
+    const int lane = threadIdx.x, ty = threadIdx.y, cat = blockIdx.y;
+    const size_t e = (size_t)blockIdx.x * FL + lane;
+    const bool inRange = e < (size_t)d.nE;
     const size_t pe = d.nEp, pc = d.nCp;
     const int nQP = d.nQP;
-    double area[CAP];
-    size_t cell[CAP];
-    int nt = 0;
-    // An edge of a hexagonal mesh has at most four departure triangles when the velocity varies smoothly (the
-    // reference's own count, :5420-5460), but two side triangles at one vertex do occur in rough fields: triangles
-    // beyond CAP stay in global memory and are integrated from there, after the parked ones (they come later in
-    // triangle order, so the order of the sum is unchanged).
-    int extra[NTRI - CAP > 0 ? NTRI - CAP : 1], nx = 0;
-    if (d.maskEdge[e] == 1) {
-        for (int t = 0; t < NTRI; t++) {            // in triangle order: the order the fluxes are summed in
-            const double a = d.triArea[t * pe + e];
-            if (a == 0.0) continue;
-            if (nt == CAP) { if (nx < NTRI - CAP) extra[nx++] = t; continue; }
-            area[nt] = a;
-            cell[nt] = (size_t)d.iCellTri[t * pe + e] - 1;
-            for (int q = 0; q < nQP; q++) {
-                Q[nt * 12 + q][tx] = d.xq[(size_t)(t * 6 + q) * pe + e];
-                Q[nt * 12 + 6 + q][tx] = d.yq[(size_t)(t * 6 + q) * pe + e];
+    double *xq = sm;                                   // [FNS][FL]
+    double *yq = xq + FNS * FL;                        // [FNS][FL]
+    double *vp = yq + FNS * FL;                        // [(nD0 + nD1)][FNS][FL]: v_0 of the depth-0 rows, then v_0 * v_1
+    double *area = vp + (size_t)(d.nD0 + d.nD1) * FNS * FL;   // [NTRI][FL]
+    int *cell = reinterpret_cast<int *>(area + NTRI * FL);   // [NTRI][FL] source cell (0-based) of the compacted triangle
+    int *tOf = cell + NTRI * FL;                       // [NTRI][FL] its index among the edge's NTRI triangles
+    int *ntL = tOf + NTRI * FL;                        // [FL] number of non-empty triangles
+    __shared__ int negative;
+
+    // ---- A1: compaction, one thread per edge ----
+    if (ty == 0) {
+        int nt = 0;
+        if (lane == 0) negative = 0;
+        if (inRange && d.maskEdge[e] == 1) {
+            bool ice = false;
+            for (int t = 0; t < NTRI; t++) {
+                const double a = d.triArea[t * pe + e];
+                if (a == 0.0) continue;
+                const int cl = d.iCellTri[t * pe + e] - 1;
+                area[nt * FL + lane] = a;
+                cell[nt * FL + lane] = cl;
+                tOf[nt * FL + lane] = t;
+                ice = ice || d.maskCell[cl] == 1;
+                nt++;
             }
-            nt++;
+            // source cells without ice in any category: the mass reconstruction is identically zero there, every
+            // product down the chain is a zero and the flux is the +0.0 written in phase D
+            if (!ice) nt = 0;
         }
-        // Triangles whose source cells hold no ice in any category carry nothing: there the mass reconstruction is
-        // identically zero (value 0, gradients 0: k_reconstruct's fast path), so every product down the chain is a
-        // zero and the flux is the +0.0 written below.  Most of an ocean mesh is ice-free.
-        bool ice = false;
-        for (int t = 0; t < nt; t++) ice = ice || d.maskCell[cell[t]] == 1;
-        for (int x = 0; x < nx; x++) ice = ice || d.maskCell[d.iCellTri[extra[x] * pe + e] - 1] == 1;
-        if (!ice) { nt = 0; nx = 0; }
+        ntL[lane] = nt;
     }
-    bool negative = false;
-    for (int j = 0; j < d.nRowsPerCat; j++) {
-        const int r = d.catBaseRow[j] + cat * d.catLayers[j];
+    __syncthreads();
+    const int nt = ntL[lane];
+    // ---- A2 + B: quadrature points, v_0 of the depth-0 rows ----
+    for (int s0 = ty; s0 < FNS; s0 += FR) {
+        const int k = s0 / 6, q = s0 - 6 * k;
+        if (k < nt && q < nQP) {
+            const int t = tOf[k * FL + lane];
+            const double x = d.xq[(size_t)(t * 6 + q) * pe + e], y = d.yq[(size_t)(t * 6 + q) * pe + e];
+            xq[s0 * FL + lane] = x;
+            yq[s0 * FL + lane] = y;
+            const size_t cl = (size_t)cell[k * FL + lane];
+            for (int j = 0; j < d.nD0; j++) {          // depth-0 rows come first in the table
+                const size_t a = (size_t)(d.catRows[j].baseRow + cat * d.catRows[j].layers) * pc + cl;
+                const double value = 1.0 * (d.center[a] + d.xGrad[a] * x + d.yGrad[a] * y);
+                if (value < 0.0) negative = 1;
+                vp[((size_t)j * FNS + s0) * FL + lane] = value;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- C: v_0 * v_1 of the depth-1 rows ----
+    for (int it = ty; it < d.nD1 * FNS; it += FR) {
+        const int j1 = it / FNS, s0 = it - j1 * FNS;
+        const int k = s0 / 6, q = s0 - 6 * k;
+        if (k < nt && q < nQP) {
+            const CatRow cr = d.catRows[d.nD0 + j1];   // depth-1 rows follow the depth-0 rows
+            const size_t a = (size_t)(cr.baseRow + cat * cr.layers) * pc + (size_t)cell[k * FL + lane];
+            const double x = xq[s0 * FL + lane], y = yq[s0 * FL + lane];
+            const double v0 = vp[((size_t)d.catRows[cr.anc[0]].cls * FNS + s0) * FL + lane];
+            vp[((size_t)(d.nD0 + j1) * FNS + s0) * FL + lane] = v0 * (d.center[a] + d.xGrad[a] * x + d.yGrad[a] * y);
+        }
+    }
+    __syncthreads();
+    // ---- D: the fluxes, one (edge, row) per thread ----
+    for (int j = ty; j < d.nRowsPerCat; j += FR) {
+        const CatRow cr = d.catRows[j];
+        const int r = cr.baseRow + cat * cr.layers;
         double flux = 0.0;
-        if (nt + nx > 0) {
-            const RowInfo ri = d.rows[r];
-            for (int t = 0; t < nt; t++) {
-                double cen[MAX_DEPTH], gx[MAX_DEPTH], gy[MAX_DEPTH];
-                for (int s = 0; s <= ri.depth; s++) {
-                    const size_t q = (size_t)ri.chain[s] * pc + cell[t];
-                    cen[s] = d.center[q]; gx[s] = d.xGrad[q]; gy[s] = d.yGrad[q];
+        if (nt > 0) {
+            // where this row's shared partial product sits: its own entry (depth 0, 1) or its depth-1 ancestor's
+            const int base = cr.depth == 0 ? cr.cls : d.nD0 + d.catRows[cr.anc[1]].cls;
+            const int r2 = cr.depth >= 2 ? d.catRows[cr.anc[2]].baseRow + cat * d.catRows[cr.anc[2]].layers : 0;
+            for (int k = 0; k < nt; k++) {
+                const size_t cl = (size_t)cell[k * FL + lane];
+                double c2 = 0.0, gx2 = 0.0, gy2 = 0.0, c3 = 0.0, gx3 = 0.0, gy3 = 0.0;
+                if (cr.depth >= 2) {
+                    const size_t a = (size_t)r2 * pc + cl;
+                    c2 = d.center[a]; gx2 = d.xGrad[a]; gy2 = d.yGrad[a];
+                }
+                if (cr.depth >= 3) {
+                    const size_t a = (size_t)r * pc + cl;
+                    c3 = d.center[a]; gx3 = d.xGrad[a]; gy3 = d.yGrad[a];
                 }
                 double tracerIntegral = 0.0;
-                for (int iqp = 0; iqp < nQP; iqp++) {
-                    const double x = Q[t * 12 + iqp][tx], y = Q[t * 12 + 6 + iqp][tx];
-                    double value = 1.0;
-                    for (int s = 0; s <= ri.depth; s++) value = value * (cen[s] + gx[s] * x + gy[s] * y);
-                    if (ri.depth == 0 && value < 0.0) negative = true;
-                    const double w = (nQP == 3) ? (1.0 / 3.0) : (iqp < 3 ? W1QP : W2QP);
+                for (int q = 0; q < nQP; q++) {
+                    const int s0 = k * 6 + q;
+                    double value = vp[((size_t)base * FNS + s0) * FL + lane];
+                    if (cr.depth >= 2) {
+                        const double x = xq[s0 * FL + lane], y = yq[s0 * FL + lane];
+                        value = value * (c2 + gx2 * x + gy2 * y);
+                        if (cr.depth >= 3) value = value * (c3 + gx3 * x + gy3 * y);
+                    }
+                    const double w = (nQP == 3) ? (1.0 / 3.0) : (q < 3 ? W1QP : W2QP);
                     tracerIntegral = tracerIntegral + w * value;
                 }
-                flux = flux + area[t] * tracerIntegral;
-            }
-            for (int x = 0; x < nx; x++) {          // the rare triangles that did not fit the scratch
-                const int t = extra[x];
-                const size_t cl = (size_t)d.iCellTri[t * pe + e] - 1;
-                double cen[MAX_DEPTH], gx[MAX_DEPTH], gy[MAX_DEPTH];
-                for (int s = 0; s <= ri.depth; s++) {
-                    const size_t q = (size_t)ri.chain[s] * pc + cl;
-                    cen[s] = d.center[q]; gx[s] = d.xGrad[q]; gy[s] = d.yGrad[q];
-                }
-                double tracerIntegral = 0.0;
-                for (int iqp = 0; iqp < nQP; iqp++) {
-                    const double xx = d.xq[(size_t)(t * 6 + iqp) * pe + e], yy = d.yq[(size_t)(t * 6 + iqp) * pe + e];
-                    double value = 1.0;
-                    for (int s = 0; s <= ri.depth; s++) value = value * (cen[s] + gx[s] * xx + gy[s] * yy);
-                    if (ri.depth == 0 && value < 0.0) negative = true;
-                    const double w = (nQP == 3) ? (1.0 / 3.0) : (iqp < 3 ? W1QP : W2QP);
-                    tracerIntegral = tracerIntegral + w * value;
-                }
-                flux = flux + d.triArea[t * pe + e] * tracerIntegral;
+                flux = flux + area[k * FL + lane] * tracerIntegral;
             }
         }
-        d.edgeFlux[(size_t)r * pe + e] = flux;
+        if (inRange) d.edgeFlux[(size_t)r * pe + e] = flux;
     }
-    if (negative) atomicOr(d.flags, FLAG_NEG_QP);
+    __syncthreads();
+    if (lane == 0 && ty == 0 && negative) atomicOr(d.flags, FLAG_NEG_QP);
 }
 
 // compute_mass_tracer_products (:6982), update_mass_and_tracers (:7125), zap_small_mass (:8764; one-layer mass field)
-// and thickness -> volume (:9295): one thread per (cell, category), rows parents first -- a row needs the NEW
-// mass * tracer product of its parent in the same cell only.
-__global__ void __launch_bounds__(RB) k_update(Dev d, int massOneLayer)
+// and thickness -> volume (:9295): one block = 32 cells x UW thread rows and all rows of all categories, depth by depth
+// (a row needs the NEW mass * tracer product of its parent in the same cell), the cell's edges and flux signs staged in
+// shared memory.
+constexpr int UW = 12;
+
+__global__ void __launch_bounds__(CL *UW, 4) k_update_coop(Dev d, int massOneLayer, int maxDepth)
 {
-    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int cat = blockIdx.y;
-    if (c > (size_t)d.nC) return;
-    const size_t pe = d.nEp, pc = d.nCp;
+    __shared__ int EDGE[MAXM][CL], SIGN[MAXM][CL], NE[CL];
+    __shared__ double AREA[CL];
+    const int lane = threadIdx.x, ty = threadIdx.y;
+    const size_t c = (size_t)blockIdx.x * CL + lane;
+    const bool valid = c <= (size_t)d.nC;            // the extra slot takes part (it keeps its values)
     const bool owned = c < (size_t)d.nCS;
-    int edge[MAXM], sign[MAXM], n = 0;
-    double area = 1.0;
-    if (owned) {
-        n = d.nEdgesOnCell[c];
-        for (int k = 0; k < n; k++) { edge[k] = d.edgesOnCell[k * pc + c]; sign[k] = d.fluxSign[k * pc + c]; }
-        area = d.areaCell[c];
+    const size_t pe = d.nEp, pc = d.nCp;
+    for (int k = ty; k < d.M; k += UW) {
+        EDGE[k][lane] = owned ? d.edgesOnCell[(size_t)k * pc + c] : 1;
+        SIGN[k][lane] = owned ? d.fluxSign[(size_t)k * pc + c] : 0;
     }
-    for (int j = 0; j < d.nRowsPerCat; j++) {
-        const int r = d.catBaseRow[j] + cat * d.catLayers[j];
-        if (!owned) {                               // halo cells and the extra slot keep their values
-            d.valNew[(size_t)r * pc + c] = d.val[(size_t)r * pc + c];
-            continue;
-        }
-        const RowInfo ri = d.rows[r];
-        double fluxFromCell = 0.0;
-        for (int k = 0; k < n; k++)
-            fluxFromCell = fluxFromCell + d.edgeFlux[(size_t)r * pe + (edge[k] - 1)] * (double)sign[k];
-        double mtpOld = 1.0;
-        for (int s = 0; s <= ri.depth; s++) mtpOld = mtpOld * d.val[(size_t)ri.chain[s] * pc + c];
-        const double pm = ri.depth > 0 ? d.mtpNew[(size_t)ri.parentSlot * pc + c] : 1.0;
-        double v = 0.0;
-        if (pm > 0.0) v = (mtpOld - (fluxFromCell / area)) / pm;
-        if (ri.slot >= 0) d.mtpNew[(size_t)ri.slot * pc + c] = pm * v;   // only children read it
-        if (ri.depth == 0) {
-            constexpr double puny2 = 1.0e-11 * 1.0e-11;   // seaicePuny**2
-            if (v < -puny2) atomicOr(d.flags, FLAG_NEG_MASS);
-            else if (v < 0.0) v = 0.0;
-        }
-        d.valNew[(size_t)r * pc + c] = v;
+    if (ty == 0) {
+        NE[lane] = owned ? d.nEdgesOnCell[c] : 0;
+        AREA[lane] = owned ? d.areaCell[c] : 1.0;
     }
-    if (massOneLayer) {                             // the mass row of this category is row `cat`
-        const double m = d.valNew[(size_t)cat * pc + c];
-        if (owned && m > 0.0 && m < 1.0e-22)
-            for (int j = 0; j < d.nRowsPerCat; j++)
-                d.valNew[(size_t)(d.catBaseRow[j] + cat * d.catLayers[j]) * pc + c] = 0.0;
-        for (int j = 0; j < d.nRowsPerCat; j++) {
-            const int r = d.catBaseRow[j] + cat * d.catLayers[j];
-            if (d.rows[r].volumeLike) d.valNew[(size_t)r * pc + c] = d.valNew[(size_t)cat * pc + c] * d.valNew[(size_t)r * pc + c];
+    __syncthreads();
+    const int n = NE[lane];
+    const double area = AREA[lane];
+    int j0 = 0;
+    for (int q = 0; q <= maxDepth; q++) {
+        int j1 = j0;
+        while (j1 < d.nRowsPerCat && d.catRows[j1].depth == q) j1++;
+        const int cnt = j1 - j0;
+        for (int it = ty; valid && it < d.nK * cnt; it += UW) {
+            const int cat = it / cnt, j = j0 + (it - cat * cnt);
+            const int r = d.catRows[j].baseRow + cat * d.catRows[j].layers;
+            if (!owned) {                               // halo cells and the extra slot keep their values
+                d.valNew[(size_t)r * pc + c] = d.val[(size_t)r * pc + c];
+                continue;
+            }
+            const RowInfo ri = d.rows[r];
+            double fluxFromCell = 0.0;
+            for (int k = 0; k < n; k++)
+                fluxFromCell = fluxFromCell + d.edgeFlux[(size_t)r * pe + (EDGE[k][lane] - 1)] * (double)SIGN[k][lane];
+            double mtpOld = 1.0;
+            for (int z = 0; z <= ri.depth; z++) mtpOld = mtpOld * d.val[(size_t)ri.chain[z] * pc + c];
+            const double pm = ri.depth > 0 ? d.mtpNew[(size_t)ri.parentSlot * pc + c] : 1.0;
+            double v = 0.0;
+            if (pm > 0.0) v = (mtpOld - (fluxFromCell / area)) / pm;
+            if (ri.slot >= 0) d.mtpNew[(size_t)ri.slot * pc + c] = pm * v;   // only children read it
+            if (ri.depth == 0) {
+                constexpr double puny2 = 1.0e-11 * 1.0e-11;   // seaicePuny**2
+                if (v < -puny2) atomicOr(d.flags, FLAG_NEG_MASS);
+                else if (v < 0.0) v = 0.0;
+            }
+            d.valNew[(size_t)r * pc + c] = v;
         }
+        j0 = j1;
+        __syncthreads();
+    }
+    if (!massOneLayer) return;
+    // zap_small_mass (:8764) and thickness -> volume (:9295); the mass row of category k is row k.  Every row reads
+    // the category's new mass before any of them (the mass row included) is rewritten
+    const int total = d.nK * d.nRowsPerCat;
+    const int myItems = (total - ty + UW - 1) / UW;          // items ty, ty + UW, ...
+    const int maxItems = (total + UW - 1) / UW;              // the same for every thread: the loop holds barriers
+    double vNew[16];
+    for (int base = 0; base < maxItems; base += 16) {
+        const int m = myItems - base < 16 ? (myItems - base > 0 ? myItems - base : 0) : 16;
+        for (int i = 0; valid && i < m; i++) {
+            const int it = ty + (base + i) * UW, cat = it / d.nRowsPerCat, j = it - cat * d.nRowsPerCat;
+            const int r = d.catRows[j].baseRow + cat * d.catRows[j].layers;
+            const double mass = d.valNew[(size_t)cat * pc + c];
+            const bool zap = owned && mass > 0.0 && mass < 1.0e-22;
+            double v = zap ? 0.0 : d.valNew[(size_t)r * pc + c];
+            if (d.catRows[j].volumeLike) v = (zap ? 0.0 : mass) * v;
+            vNew[i] = v;
+        }
+        __syncthreads();
+        for (int i = 0; valid && i < m; i++) {
+            const int it = ty + (base + i) * UW, cat = it / d.nRowsPerCat, j = it - cat * d.nRowsPerCat;
+            d.valNew[(size_t)(d.catRows[j].baseRow + cat * d.catRows[j].layers) * pc + c] = vNew[i];
+        }
+        __syncthreads();
     }
 }
 
@@ -1401,6 +1528,30 @@ extern "C" int ir_set_tracers(ir_handle *h, int nTracers, const ir_tracer_desc *
             if (depth[t] == q)
                 for (int l = 0; l < tr[t].nLayers; l++) { baseRow.push_back(h->tracerRow0[t] + l); layers.push_back(tr[t].nLayers); }
     d.nRowsPerCat = (int)baseRow.size();
+    {   // the same list with the tree structure resolved: positions of the ancestors, classes, parent slots
+        std::vector<CatRow> cr(baseRow.size());
+        std::vector<int> rowToJ(nRows, -1);
+        for (size_t j = 0; j < baseRow.size(); j++) rowToJ[baseRow[j]] = (int)j;      // category 0's rows
+        int nCls[MAX_DEPTH] = {0, 0, 0, 0}, nSlotJ = 0;
+        for (size_t j = 0; j < baseRow.size(); j++) {
+            const RowInfo &ri = h->rows[baseRow[j]];
+            CatRow &c = cr[j];
+            c.baseRow = baseRow[j]; c.layers = layers[j]; c.depth = ri.depth;
+            c.cls = ri.depth <= 1 ? nCls[ri.depth] : -1;
+            nCls[ri.depth]++;
+            for (int q = 0; q < MAX_DEPTH; q++) c.anc[q] = q <= ri.depth ? rowToJ[ri.chain[q]] : -1;
+            c.hasChild = ri.hasChild; c.volumeLike = ri.volumeLike;
+            c.slotJ = ri.hasChild ? nSlotJ++ : -1;
+            c.parentSlotJ = -1;
+        }
+        for (size_t j = 0; j < cr.size(); j++)
+            if (cr[j].depth > 0) cr[j].parentSlotJ = cr[cr[j].anc[cr[j].depth - 1]].slotJ;
+        d.nD0 = nCls[0]; d.nD1 = nCls[1]; d.nSlotsPerCat = nSlotJ;
+        if (d.catRows) { cudaFree(d.catRows); d.catRows = nullptr; }
+        IR_CUDA(cudaMalloc((void **)&d.catRows, sizeof(CatRow) * cr.size()));
+        IR_CUDA(cudaMemcpyAsync(d.catRows, cr.data(), sizeof(CatRow) * cr.size(), cudaMemcpyHostToDevice, h->stream));
+        IR_CUDA(cudaStreamSynchronize(h->stream));
+    }
     IR_CUDA(cudaMalloc((void **)&d.catBaseRow, sizeof(int) * baseRow.size()));
     IR_CUDA(cudaMalloc((void **)&d.catLayers, sizeof(int) * layers.size()));
     IR_CUDA(cudaMemcpyAsync(d.catBaseRow, baseRow.data(), sizeof(int) * baseRow.size(), cudaMemcpyHostToDevice, h->stream));
@@ -1454,16 +1605,27 @@ extern "C" int ir_run(ir_handle *h, int nTracers, const ir_tracer_desc *tr, cons
     IR_LAUNCH((k_prepare), gc, 128, s, d, 0, massRows);
     h->launches++;
     if (d.nC > 0) {
-        IR_LAUNCH((k_reconstruct), dim3(grid_for((size_t)d.nC, RB), nK), RB, s, d);
+        int maxDepth = 0;
+        for (int dq : h->tracerDepth) maxDepth = dq > maxDepth ? dq : maxDepth;
+        IR_LAUNCH_SYNC((k_reconstruct_coop), grid_for((size_t)d.nC, CL), dim3(CL, CW), ir_reconstruct_smem_bytes(), s, d, maxDepth);
         h->launches++;
     }
     if (d.nE > 0) {
         IR_LAUNCH((k_triangles), ge, 128, s, d, dt);
-        if (d.D == 3) IR_LAUNCH((k_fluxes<4>), dim3(grid_for((size_t)d.nE, RB), nK), RB, s, d);
-        else IR_LAUNCH((k_fluxes<6>), dim3(grid_for((size_t)d.nE, RB), nK), RB, s, d);
+        {
+            const size_t smem = ir_flux_smem_bytes(d.nD0, d.nD1);
+#ifdef IR_DEVICE_BUILD
+            IR_CUDA(cudaFuncSetAttribute(k_fluxes_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#endif
+            IR_LAUNCH_SYNC((k_fluxes_coop), dim3(grid_for((size_t)d.nE, FL), nK), dim3(FL, FR), smem, s, d);
+        }
         h->launches += 2;
     }
-    IR_LAUNCH((k_update), dim3(grid_for(nC1, RB), nK), RB, s, d, h->tracerLayers[0] == 1 ? 1 : 0);
+    {
+        int maxDepth = 0;
+        for (int dq : h->tracerDepth) maxDepth = dq > maxDepth ? dq : maxDepth;
+        IR_LAUNCH_SYNC((k_update_coop), grid_for(nC1, CL), dim3(CL, UW), 0, s, d, h->tracerLayers[0] == 1 ? 1 : 0, maxDepth);
+    }
     h->launches++;
     IR_CUDA(cudaEventRecord(h->ev1, s));
     IR_CUDA(cudaGetLastError());
@@ -1609,6 +1771,7 @@ extern "C" int ir_destroy(ir_handle *h)
     if (d.rows) cudaFree(d.rows);
     if (d.catBaseRow) cudaFree(d.catBaseRow);
     if (d.catLayers) cudaFree(d.catLayers);
+    if (d.catRows) cudaFree(d.catRows);
     for (void *p : h->allocs) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);

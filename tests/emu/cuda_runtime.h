@@ -10,18 +10,27 @@
 #ifndef TESTS_EMU_CUDA_RUNTIME_H
 #define TESTS_EMU_CUDA_RUNTIME_H
 
+#include <ucontext.h>
+
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <vector>
 
 #define __global__
 #define __device__
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
-/* shared memory: the kernels use it as per-thread scratch columns only (no thread reads another's slot and there
- * is no barrier), so one static array reused by the sequentially executed threads behaves the same */
+/* shared memory: one static array per declaration, shared by the threads of the block being executed (blocks run one
+ * after the other).  Kernels launched with IR_LAUNCH use it as per-thread scratch columns only; kernels that exchange
+ * data between threads through it are launched with IR_LAUNCH_SYNC (below), where __syncthreads() is a real barrier. */
 #define __shared__ static
+/* dynamic shared memory: one buffer, big enough for any launch of the file under test */
+static double emu_dyn_smem[64 * 1024];
+#define IR_DYN_SHARED(type, name) type *name = reinterpret_cast<type *>(emu_dyn_smem)
+#define __ldg(p) (*(p))
 
 struct dim3 {
     unsigned x, y, z;
@@ -51,6 +60,74 @@ static void emu_launch(dim3 grid, dim3 block, F body)
     }
 }
 #define IR_LAUNCH(kernel, grid, block, stream, ...) emu_launch(dim3(grid), dim3(block), [&] { kernel(__VA_ARGS__); })
+
+/* Kernels with __syncthreads(): every thread of a block is a fiber (ucontext) with a stack of its own; a fiber runs
+ * until it reaches a barrier or returns, then the next one runs; when all living fibers of the block wait at the
+ * barrier the round starts over.  Same order switch as above (IR_EMU_ORDER=reverse). */
+struct EmuFiber {
+    ucontext_t ctx;
+    char *stack = nullptr;
+    bool done = true;
+};
+static std::vector<EmuFiber> emu_fibers;
+static ucontext_t emu_sched_ctx;
+static std::function<void()> *emu_body = nullptr;
+static unsigned long long emu_current = 0;
+static const size_t EMU_STACK = 256 * 1024;
+
+static void emu_trampoline()
+{
+    (*emu_body)();
+    emu_fibers[emu_current].done = true;      /* uc_link brings control back to the scheduler */
+}
+static inline void emu_syncthreads()
+{
+    swapcontext(&emu_fibers[emu_current].ctx, &emu_sched_ctx);
+}
+#define __syncthreads() emu_syncthreads()
+
+template <typename F>
+static void emu_launch_sync(dim3 grid, dim3 block, F body)
+{
+    gridDim = grid;
+    blockDim = block;
+    const char *order = getenv("IR_EMU_ORDER");
+    const bool reverse = order != nullptr && order[0] == 'r';
+    const unsigned long long nb = (unsigned long long)grid.x * grid.y * grid.z, nt = (unsigned long long)block.x * block.y * block.z;
+    if (emu_fibers.size() < nt) emu_fibers.resize(nt);
+    for (unsigned long long t = 0; t < nt; t++)
+        if (!emu_fibers[t].stack) emu_fibers[t].stack = (char *)malloc(EMU_STACK);
+    std::function<void()> fn = body;
+    emu_body = &fn;
+    for (unsigned long long ib = 0; ib < nb; ib++) {
+        const unsigned long long b = reverse ? nb - 1 - ib : ib;
+        blockIdx = dim3((unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y), (unsigned)(b / ((unsigned long long)grid.x * grid.y)));
+        for (unsigned long long t = 0; t < nt; t++) {
+            EmuFiber &f = emu_fibers[t];
+            getcontext(&f.ctx);
+            f.ctx.uc_stack.ss_sp = f.stack;
+            f.ctx.uc_stack.ss_size = EMU_STACK;
+            f.ctx.uc_link = &emu_sched_ctx;
+            makecontext(&f.ctx, emu_trampoline, 0);
+            f.done = false;
+        }
+        unsigned long long alive = nt;
+        while (alive > 0) {
+            for (unsigned long long it = 0; it < nt; it++) {
+                const unsigned long long t = reverse ? nt - 1 - it : it;
+                EmuFiber &f = emu_fibers[t];
+                if (f.done) continue;
+                threadIdx = dim3((unsigned)(t % block.x), (unsigned)((t / block.x) % block.y), (unsigned)(t / ((unsigned long long)block.x * block.y)));
+                emu_current = t;
+                swapcontext(&emu_sched_ctx, &f.ctx);
+                if (f.done) alive--;
+            }
+        }
+    }
+    emu_body = nullptr;
+}
+#define IR_LAUNCH_SYNC(kernel, grid, block, smem, stream, ...) \
+    emu_launch_sync(dim3(grid), dim3(block), [&] { kernel(__VA_ARGS__); })
 
 typedef int cudaError_t;
 enum { cudaSuccess = 0 };

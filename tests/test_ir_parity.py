@@ -21,8 +21,7 @@ from mpas_seaice_b200 import ir_host
 from test_oracle_ir import case, smooth_divergent_velocity, uniform_velocity, _random_state
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-# IR_B200_EMU_SRC: run the emulation leg on another source file with the same ABI (the experimental layout variants
-# under csrc/experimental/)
+# IR_B200_EMU_SRC: run the emulation leg on another source file with the same ABI (a kernel variant under development)
 SRC = os.environ.get("IR_B200_EMU_SRC") or os.path.join(ROOT, "mpas-seaice_b200", "csrc", "ir_kernels.cu")
 EMU_DIR = os.path.join(ROOT, "tests", "emu")
 EMU_LIB = os.path.join(ROOT, "tests", "_build", "libir_emu%s.so" % ("" if "IR_B200_EMU_SRC" not in os.environ else

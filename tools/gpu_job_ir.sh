@@ -10,10 +10,6 @@ IR_B200_CUDA_LEG=1 timeout 600 python -m pytest -q -x -m gpu -k "cuda and not ch
 timeout 300 python tools/ir_bench.py --level 7 --steps 5 --warmup 2 --check > gpurun_out/ir_bench_qu60.json 2> gpurun_out/ir_bench_qu60.err; echo "bench qu60 rc=$?"; cat gpurun_out/ir_bench_qu60.json
 timeout 300 python tools/ir_bench.py --level 7 --steps 2 --warmup 1 --cpu > gpurun_out/ir_bench_qu60_cpu.json 2>&1; cat gpurun_out/ir_bench_qu60_cpu.json
 timeout 600 python tools/ir_bench.py --level 9 --steps 3 --warmup 1 > gpurun_out/ir_bench_qu15.json 2> gpurun_out/ir_bench_qu15.err; echo "bench qu15 rc=$?"; cat gpurun_out/ir_bench_qu15.json
-# the experimental category-major / cell-minor layout (csrc/experimental/ir_kernels_cellmajor.cu, same ABI) against the shipped one
-IR_B200_LIB=$PWD/mpas-seaice_b200/csrc/libir_b200_cellmajor.so timeout 120 python tools/ir_quick_gpu.py > gpurun_out/ir_cellmajor_parity.log 2>&1; tail -1 gpurun_out/ir_cellmajor_parity.log
-IR_B200_LIB=$PWD/mpas-seaice_b200/csrc/libir_b200_cellmajor.so timeout 300 python tools/ir_bench.py --level 7 --steps 5 --warmup 2 --check > gpurun_out/ir_bench_qu60_cellmajor.json 2> gpurun_out/ir_bench_qu60_cellmajor.err; cat gpurun_out/ir_bench_qu60_cellmajor.json
-IR_B200_LIB=$PWD/mpas-seaice_b200/csrc/libir_b200_cellmajor.so timeout 600 python tools/ir_bench.py --level 9 --steps 3 --warmup 1 > gpurun_out/ir_bench_qu15_cellmajor.json 2> gpurun_out/ir_bench_qu15_cellmajor.err; cat gpurun_out/ir_bench_qu15_cellmajor.json
 IR_B200_PIN_HOST=1 timeout 600 python tools/ir_bench.py --level 9 --steps 3 --warmup 1 > gpurun_out/ir_bench_qu15_pinned.json 2> gpurun_out/ir_bench_qu15_pinned.err; echo "bench qu15 pinned rc=$?"; cat gpurun_out/ir_bench_qu15_pinned.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/ir_launches_qu15.csv \
     python tools/ir_bench.py --level 9 --steps 1 --warmup 1 > gpurun_out/ir_ncu_list.log 2>&1; echo "ncu list rc=$?"

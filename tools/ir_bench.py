@@ -7,9 +7,14 @@ Product path only: meshgen -> irmesh (host arrays a Python host lacks) -> ir_ini
 Workload: the reference's standard tracer set (iceAreaCategory, iceVolumeCategory, snowVolumeCategory,
 surfaceTemperature, iceEnthalpy, iceSalinity, snowEnthalpy; 5 categories, 7 ice layers, 5 snow layers =
 115 (category, layer) rows), smooth ice cover with open water around the equator (where the rotated grid has its
-poles), smooth divergent velocity at 30 % of the CFL limit.  Prints one JSON line: device time of the five kernels per step (CUDA events inside ir_run), wall
-time per step through the C ABI with host buffers (uploads and downloads included), cell-row updates per second.
-``--cpu`` times the oracle on the same state instead (the checker timed as a baseline, as bench.py does).
+poles), smooth divergent velocity at 30 % of the CFL limit.  Prints one JSON line in bench.py's vocabulary:
+  value / kernel_ms_per_step   device time of the five kernels of a step (CUDA events inside ir_run), cell-row updates / s
+  e2e                          the same through the C ABI with host buffers (uploads and downloads inside the timed region)
+  roofline                     HBM: ALGORITHMIC bytes of a step (per cell-row val in 8 + centre / gradients out
+                               and in 48 + edge fluxes of 3 edges out and in 48 + new value out 8 = 112 B; per edge the
+                               departure-triangle data out and in 2 x 4 triangles x 112 B) / kernel time / measured peak
+  cpu_baseline                 with --cpu-baseline: the oracle (oracle/ir_oracle.c, kind "port") on the same state, few steps
+``--cpu`` times the oracle only (the checker timed as a baseline, as bench.py does).
 """
 import argparse
 import json
@@ -72,6 +77,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--cpu", action="store_true", help="time the oracle (CPU) instead of the device")
+    ap.add_argument("--cpu-baseline", action="store_true", help="add a cpu_baseline object: the oracle timed on 2 steps")
     ap.add_argument("--check", action="store_true",
                     help="after the timed steps, run the oracle on the same initial state and report whether the device "
                          "fields are identical (the oracle as the checker, outside the timed region)")
@@ -118,8 +124,21 @@ def main():
                 solver.run(tracers, u, v, dt)
                 dev_ms.append(solver.last_run_ms())
             wall = (time.time() - t1) / args.steps
-            rec.update(impl="cuda", kernel_ms_per_step=round(float(np.mean(dev_ms)), 3), wall_ms_per_step=round(wall * 1e3, 3),
-                       value=mesh.nCells * n_rows / (np.mean(dev_ms) * 1e-3), gpu_launches=solver.launch_count())
+            kms = float(np.mean(dev_ms))
+            algo = mesh.nCells * n_rows * 112.0 + mesh.nEdges * 2 * 4 * 112.0
+            peak = 6650.0
+            pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+            if os.path.exists(pk):
+                peak = float(json.load(open(pk))["hbm_gbs"])
+            io_bytes = int(sum(t.array.nbytes for t in tracers))
+            rec.update(impl="cuda", kernel_ms_per_step=round(kms, 4), wall_ms_per_step=round(wall * 1e3, 3),
+                       value=mesh.nCells * n_rows / (kms * 1e-3), higher_is_better=True, gpu_launches=solver.launch_count(),
+                       e2e=dict(value=mesh.nCells * n_rows / wall, unit="cell-rows/s", h2d_bytes_per_step=io_bytes + 2 * u.nbytes,
+                                d2h_bytes_per_step=io_bytes),
+                       roofline=dict(bound="hbm", achieved=algo / (kms * 1e-3) / 1e9, peak=peak, unit="GB/s",
+                                     frac=algo / (kms * 1e-3) / 1e9 / peak, algorithmic_bytes_per_step=algo, traffic=None,
+                                     kernel="the five kernels of one ir_run (k_prepare, k_reconstruct_coop, k_triangles, "
+                                            "k_fluxes_coop, k_update_coop)"))
         finally:
             solver.destroy()
         if args.check:
@@ -133,6 +152,17 @@ def main():
             rec["geometry_parity"] = bool(all(np.array_equal(geom[k][:-1], geom_o[k][:-1]) for k in
                                               ("xVertexOnCell", "yVertexOnCell", "xVertexOnEdge", "yVertexOnEdge", "remapEdge",
                                                "cellsOnEdgeRemap", "edgesOnEdgeRemap")))
+    if args.cpu_baseline and not args.cpu:
+        from oracle import ir
+        geom_o = ir.init_geometry(mesh, irf, rotate=True)
+        otr = [ir.Tracer(t.name, t.array.copy(), t.parent, t.volume_like) for t in tracers]
+        ir.run(mesh, irf, geom_o, otr, u, v, dt, rotate=True)
+        t1 = time.time()
+        for _ in range(2):
+            ir.run(mesh, irf, geom_o, otr, u, v, dt, rotate=True)
+        cw = (time.time() - t1) / 2
+        rec["cpu_baseline"] = dict(value=mesh.nCells * n_rows / cw, unit="cell-rows/s", cores=os.cpu_count(), kind="port",
+                                   sample="2 steps of the same mesh and state, oracle/ir_oracle.c (OpenMP)")
     print(json.dumps(rec))
 
 
