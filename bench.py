@@ -230,6 +230,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    if world > 1 and not os.environ.get("EVP_B200_NO_NUMA_BIND"):
+        from mpas_seaice_b200 import multigpu as _mg
+        _mg.bind_to_gpu_numa(local_rank, verbose=log if rank == 0 else None)
     os.environ["EVP_B200_HALO"] = args.halo
     dist = None
     if world > 1:

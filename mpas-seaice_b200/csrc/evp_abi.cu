@@ -495,7 +495,6 @@ extern "C" int evp_create(evp_handle **out, const evp_mesh_desc *m, const evp_op
     FAIL_IF(evp_dev_alloc(h, (void **)&d.tileWork, nCp / EVP_TILE + 1));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.tileList, sizeof(int) * (nCp / EVP_TILE + 1)));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.tileCount, sizeof(int)));
-    FAIL_IF(evp_dev_alloc(h, (void **)&d.gridBar, sizeof(unsigned)));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.vblockWork, nVp / 256 + 2));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.vblockList, sizeof(int) * (nVp / 256 + 2)));
     FAIL_IF(evp_dev_alloc(h, (void **)&d.vblockCount, sizeof(int)));

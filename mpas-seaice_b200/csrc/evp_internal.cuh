@@ -95,7 +95,8 @@ struct evp_dev {
     uint8_t *tileWork = nullptr;  // per tile of EVP_TILE cells: 1 = some cell is solved or holds a non-zero stress
     int *tileList = nullptr;      // the tiles with work, compacted (cell kernel grid = their number)
     int *tileCount = nullptr;     // device counter behind tileList
-    unsigned *gridBar = nullptr;  // grid barrier counter of the persistent whole-loop kernel
+    unsigned *gridBar = nullptr;  // persistent whole-loop kernel: release word + one arrival slot per block
+    double2 *contrib2 = nullptr;  // ... and its second buffer of the divergence sums (allocated on first use)
     uint8_t *vblockWork = nullptr;  // per block of 256 owned vertices: 1 = some vertex is solved
     int *vblockList = nullptr, *vblockCount = nullptr;
     double *P = nullptr;

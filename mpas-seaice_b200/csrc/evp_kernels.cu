@@ -405,6 +405,44 @@ struct VertexArgs {
 
 // one owned, solved vertex: stress divergence (variational gather or weak line integral), drag coefficient, 2x2 solve;
 // returns the vertex' (u,v) after the pass
+// ocean_stress_coefficient (velocity_solver.F:2986-3082)
+__device__ __forceinline__ double evp_drag_coefficient(int useOcean, int oceanType, double iceAreaVertex, double2 o, double2 w)
+{
+    double coef = 0.0;
+    if (useOcean) {
+        if (oceanType == EVP_OCEAN_QUADRATIC) {
+            const double du = o.x - w.x, dv = o.y - w.y;
+            coef = kDragio * kRhow * iceAreaVertex * sqrt(du * du + dv * dv);
+        } else {
+            coef = kDragio * kRhow * iceAreaVertex;
+        }
+    }
+    return coef;
+}
+// solve_velocity / solve_velocity_revised (velocity_solver.F:3096-3342): Cramer's rule in the reference's order
+template <int CR>
+__device__ __forceinline__ double2 evp_momentum_solve(double sdU, double sdV, double coef, double2 w, double2 mf, double2 air,
+                                                      double2 tilt, double2 os, double2 w0, double dte, double dtDyn, double beta)
+{
+    const double sgn = copysign(1.0, mf.y);
+    double l11, l22, r1, r2;
+    if (CR == EVP_CR_EVP) {
+        l11 = mf.x / dte + coef * kCosOceanTurningAngle;
+        l22 = mf.x / dte + coef * kCosOceanTurningAngle;
+        r1 = sdU + air.x + tilt.x + coef * os.x + (mf.x * w.x) / dte;
+        r2 = sdV + air.y + tilt.y + coef * os.y + (mf.x * w.y) / dte;
+    } else {
+        l11 = (beta + 1.0) * (mf.x / dtDyn) + coef * kCosOceanTurningAngle;
+        l22 = (beta + 1.0) * (mf.x / dtDyn) + coef * kCosOceanTurningAngle;
+        r1 = sdU + air.x + tilt.x + coef * os.x + (mf.x * (beta * w.x + w0.x)) / dtDyn;
+        r2 = sdV + air.y + tilt.y + coef * os.y + (mf.x * (beta * w.y + w0.y)) / dtDyn;
+    }
+    const double l12 = -mf.y - coef * kSinOceanTurningAngle * sgn;
+    const double l21 = mf.y + coef * kSinOceanTurningAngle * sgn;
+    const double den = l11 * l22 - l12 * l21;
+    return make_double2((l22 * r1 - l12 * r2) / den, (l11 * r2 - l21 * r1) / den);
+}
+
 // COHERENT: contrib and (u,v) were written by OTHER blocks of the same (persistent) kernel: read them from L2.
 template <int D, int CR, bool DIAG, bool WEAK, bool COHERENT = false>
 __device__ __forceinline__ double2 evp_vertex_solve(const VertexArgs &a, const int v)
@@ -453,43 +491,15 @@ __device__ __forceinline__ double2 evp_vertex_solve(const VertexArgs &a, const i
     }
 
     const double2 w = COHERENT ? __ldcg(&a.uv[v]) : a.uv[v];
-    double coef = 0.0;
-    if (a.useOcean) {
-        if (a.oceanType == EVP_OCEAN_QUADRATIC) {
-            const double2 o = a.ocnVel[v];
-            const double du = o.x - w.x, dv = o.y - w.y;
-            coef = kDragio * kRhow * ad.x * sqrt(du * du + dv * dv);
-        } else {
-            coef = kDragio * kRhow * ad.x;
-        }
-    }
+    const double coef = evp_drag_coefficient(a.useOcean, a.oceanType, ad.x, a.ocnVel[v], w);
     if (DIAG) {
         a.sdiv[v] = make_double2(sdU, sdV);
         a.ocoef[v] = coef;
     }
     if (CR == EVP_CR_EVP || CR == EVP_CR_EVP_REVISED) {
-        const double2 mf = a.massf[v];
-        const double2 air = a.air[v];
-        const double2 tilt = a.tilt[v];
-        const double2 os = a.ocnStress[v];
-        const double sgn = copysign(1.0, mf.y);
-        double l11, l22, r1, r2;
-        if (CR == EVP_CR_EVP) {
-            l11 = mf.x / a.dte + coef * kCosOceanTurningAngle;
-            l22 = mf.x / a.dte + coef * kCosOceanTurningAngle;
-            r1 = sdU + air.x + tilt.x + coef * os.x + (mf.x * w.x) / a.dte;
-            r2 = sdV + air.y + tilt.y + coef * os.y + (mf.x * w.y) / a.dte;
-        } else {
-            const double2 w0 = a.uvInit[v];
-            l11 = (a.beta + 1.0) * (mf.x / a.dtDyn) + coef * kCosOceanTurningAngle;
-            l22 = (a.beta + 1.0) * (mf.x / a.dtDyn) + coef * kCosOceanTurningAngle;
-            r1 = sdU + air.x + tilt.x + coef * os.x + (mf.x * (a.beta * w.x + w0.x)) / a.dtDyn;
-            r2 = sdV + air.y + tilt.y + coef * os.y + (mf.x * (a.beta * w.y + w0.y)) / a.dtDyn;
-        }
-        const double l12 = -mf.y - coef * kSinOceanTurningAngle * sgn;
-        const double l21 = mf.y + coef * kSinOceanTurningAngle * sgn;
-        const double den = l11 * l22 - l12 * l21;
-        const double2 wNew = make_double2((l22 * r1 - l12 * r2) / den, (l11 * r2 - l21 * r1) / den);
+        const double2 w0 = (CR == EVP_CR_EVP_REVISED) ? a.uvInit[v] : make_double2(0.0, 0.0);
+        const double2 wNew = evp_momentum_solve<CR>(sdU, sdV, coef, w, a.massf[v], a.air[v], a.tilt[v], a.ocnStress[v], w0,
+                                                    a.dte, a.dtDyn, a.beta);
         a.uv[v] = wNew;
         return wNew;
     }
@@ -576,11 +586,16 @@ __global__ void __launch_bounds__(256, 5) evp_vertex_p2p_kernel(const VertexArgs
 // Persistent whole-loop kernel for meshes small enough that every tile of 32 cells can have a block of its own
 // resident at the same time (square 7 708 cells, QU240 10 242 cells: BASELINE configs[1] and [2]).  There the
 // graph of 2 x nSub kernel nodes is bound by launch latency (about 3.5 us per node against about 1 us of work), so
-// ONE cooperative launch runs all nSub subcycles:
+// ONE cooperative launch runs all nSub subcycles and nothing but the per-cell divergence sums travels through L2:
 //   * the tile's basis arrays are bulk-copied into shared memory once and stay there for the whole loop;
-//   * the stresses of a (cell, stress point) live in registers of its thread from the first subcycle to the last;
-//   * per subcycle: gather (u,v) from L2 -> strain, stress -> per-cell divergence sums to L2 | grid barrier |
-//     vertex solve for this block's share of the owned vertices | grid barrier.
+//   * thread (cell, slot j) keeps in registers, from the first subcycle to the last, the stresses of its stress
+//     point AND the complete state of the vertex in slot j -- its velocity, mass, forcing, the positions of the
+//     vertexDegree divergence sums it gathers.  The vertexDegree threads that share a vertex each solve it, from
+//     identical inputs with identical instructions, so their copies never differ and no velocity is exchanged;
+//   * per subcycle: (u,v) -> shared -> strain, stress -> per-cell divergence sums -> L2 (double-buffered) |
+//     ONE grid barrier | gather vertexDegree sums from L2 -> drag coefficient, 2x2 solve -> (u,v) in registers.
+// The barrier has no atomics (same-address atomics from hundreds of blocks serialise in L2): every block stores its
+// epoch into a slot of its own, block 0 polls the slots and stores the release word the others poll.
 // Arithmetic, operation order and summation order are those of evp_cell_kernel / evp_vertex_solve: results are
 // bit-identical to the two-kernel path (tests/test_gpu_parity.py::test_graph_and_stream_paths_agree).
 // ---------------------------------------------------------------------------------------------
@@ -588,8 +603,9 @@ struct PersistArgs {
     CellArgs c;
     VertexArgs v;
     int nSub;
-    int vChunk;            // owned vertices per block in the vertex phase (<= threads per block)
-    unsigned *bar;         // grid barrier counter, zero at launch
+    double2 *contrib2;     // second buffer of the divergence sums
+    unsigned *arrive;      // [grid] epoch every block has reached, zero at launch
+    unsigned *release;     // epoch everybody may pass, zero at launch
 };
 
 __device__ __forceinline__ unsigned evp_ld_acquire_gpu_u32(const unsigned *p)
@@ -598,16 +614,24 @@ __device__ __forceinline__ unsigned evp_ld_acquire_gpu_u32(const unsigned *p)
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// all blocks of the (cooperative) grid; `target` counts the arrivals expected so far
-__device__ __forceinline__ void evp_grid_barrier(unsigned *bar, unsigned &target)
+__device__ __forceinline__ void evp_st_release_gpu_u32(unsigned *p, unsigned v)
 {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// all blocks of the (cooperative) grid have finished epoch `e` (1, 2, ...)
+__device__ __forceinline__ void evp_grid_barrier(unsigned *arrive, unsigned *release, unsigned e)
+{
+    const unsigned tid = threadIdx.y * blockDim.x + threadIdx.x, nThreads = blockDim.x * blockDim.y;
     __syncthreads();
-    if (threadIdx.x == 0 && threadIdx.y == 0) {
-        target += gridDim.x;
-        __threadfence();                       // cumulative over what the block wrote before the barrier above
-        atomicAdd(bar, 1u);
-        while (evp_ld_acquire_gpu_u32(bar) < target) { }
+    if (tid == 0) evp_st_release_gpu_u32(arrive + blockIdx.x, e);     // cumulative over the block's stores before the barrier
+    if (blockIdx.x == 0) {
+        for (unsigned b = tid; b < gridDim.x; b += nThreads)
+            while (evp_ld_acquire_gpu_u32(arrive + b) < e) { }
+        __syncthreads();
+        if (tid == 0) evp_st_release_gpu_u32(release, e);
     }
+    if (tid == 0)
+        while (evp_ld_acquire_gpu_u32(release) < e) { }
     __syncthreads();
 }
 
@@ -618,6 +642,7 @@ __global__ void __launch_bounds__(EVP_TILE *M, 3) evp_persistent_kernel(const Pe
     extern __shared__ __align__(128) unsigned char evp_smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(evp_smem_raw);
     const CellArgs &a = p.c;
+    const VertexArgs &va = p.v;
     const int cx = threadIdx.x, j = threadIdx.y;
     const size_t tile = blockIdx.x;
     const size_t c = tile * EVP_TILE + cx;
@@ -644,33 +669,45 @@ __global__ void __launch_bounds__(EVP_TILE *M, 3) evp_persistent_kernel(const Pe
     }
     const bool act = j < n;
     const size_t q = (size_t)j * nCp + c;
-    int vi = 0;
+    // ---- the stress point (cell, j) ----
     double tj = 0.0, x11 = 0.0, x22 = 0.0, x12 = 0.0, P = 0.0;
+    // ---- the vertex in slot j: everything the momentum solve reads, and where its divergence sums come from ----
+    int vi = 0, g[D];
+    bool vsolve = false, writer = false;
+    double2 w = make_double2(0.0, 0.0), ad = w, mf = w, air = w, tilt = w, os = w, ov = w, w0 = w;
+#pragma unroll
+    for (int s = 0; s < D; s++) g[s] = -1;
     if (act) {
         vi = a.voc[q];
         if (METRIC) tj = a.tanLat[vi];
         const double2 s0 = a.sig[q];
         x11 = s0.x; x22 = s0.y; x12 = a.sig12[q];
         P = a.P[c];
+        w = a.uv[vi];
+        vsolve = vi < va.nVerticesSolve && (va.solveVel[vi] & 1);
+        if (vsolve) {
+#pragma unroll
+            for (int s = 0; s < D; s++) g[s] = va.gidx[(size_t)s * va.nVp + vi];
+            // one of the threads that share the vertex stores its results: the one sitting on the first divergence sum
+            writer = false;
+#pragma unroll
+            for (int s = D - 1; s >= 0; s--) if (g[s] >= 0) writer = (size_t)g[s] == q;
+            ad = va.areaDen[vi]; mf = va.massf[vi]; air = va.air[vi]; tilt = va.tilt[vi];
+            os = va.ocnStress[vi]; ov = va.ocnVel[vi];
+            if (CR == EVP_CR_EVP_REVISED) w0 = va.uvInit[vi];
+        }
     }
-    // the vertex phase: block b solves the owned vertices [b * vChunk, (b + 1) * vChunk)
-    const int t = j * EVP_TILE + cx;
-    const int vtx = (int)blockIdx.x * p.vChunk + t;
-    const bool vact = t < p.vChunk && vtx < p.v.nVerticesSolve && (p.v.solveVel[vtx] & 1);
     int i0 = j - 1, i1 = j, i2 = j + 1;
     if (j == 0) { i0 = 0; i1 = 1; i2 = n - 1; }
     else if (j == n - 1) { i0 = 0; i1 = n - 2; i2 = n - 1; }
     mbar_wait(&sm.barG, 0);
     mbar_wait(&sm.barS, 0);
-    unsigned target = 0;
 
     for (int k = 0; k < p.nSub; k++) {
         const bool diag = k == p.nSub - 1;
-        double uj = 0.0, vj = 0.0;
-        if (act && solve) {
-            const double2 w = __ldcg(&a.uv[vi]);        // written by other blocks in the previous subcycle
-            uj = w.x; vj = w.y;
-        }
+        // the last subcycle leaves its sums in the regular buffer
+        double2 *contrib = ((p.nSub - 1 - k) & 1) ? p.contrib2 : a.contrib;
+        const double uj = (act && solve) ? w.x : 0.0, vj = (act && solve) ? w.y : 0.0;
         sm.u[j][cx] = uj;
         sm.v[j][cx] = vj;
         __syncthreads();
@@ -718,19 +755,33 @@ __global__ void __launch_bounds__(EVP_TILE *M, 3) evp_persistent_kernel(const Pe
                     }
                 }
             }
-            a.contrib[q] = make_double2(cU, cV);
+            contrib[q] = make_double2(cU, cV);
         }
-        evp_grid_barrier(p.bar, target);
-        if (vact) {
-            if (diag) evp_vertex_solve<D, CR, true, false, true>(p.v, vtx);
-            else      evp_vertex_solve<D, CR, false, false, true>(p.v, vtx);
+        evp_grid_barrier(p.arrive, p.release, (unsigned)(k + 1));
+        if (vsolve) {
+            double sdU = 0.0, sdV = 0.0;
+#pragma unroll
+            for (int s = 0; s < D; s++) {
+                double2 cc = make_double2(0.0, 0.0);
+                if (g[s] >= 0) cc = __ldcg(&contrib[g[s]]);      // written by other blocks: from L2
+                sdU = sdU + cc.x;
+                sdV = sdV + cc.y;
+            }
+            sdU = sdU / ad.y;
+            sdV = sdV / ad.y;
+            const double coef = evp_drag_coefficient(va.useOcean, va.oceanType, ad.x, ov, w);
+            if (diag && writer) {
+                va.sdiv[vi] = make_double2(sdU, sdV);
+                va.ocoef[vi] = coef;
+            }
+            w = evp_momentum_solve<CR>(sdU, sdV, coef, w, mf, air, tilt, os, w0, va.dte, va.dtDyn, va.beta);
         }
-        evp_grid_barrier(p.bar, target);
     }
     if (act && solve) {
         a.sig[q] = make_double2(x11, x22);
         a.sig12[q] = x12;
     }
+    if (vsolve && writer) va.uv[vi] = w;
 }
 
 // seaice_set_special_boundaries_velocity (special_boundaries.F:301-324) with the sequential
@@ -1130,6 +1181,7 @@ static bool persistent_configured(evp_handle *h)
     if (h->opt.use_special_boundaries_velocity && h->d.nSB) return false;
     if (evp_halo_launches(h) || evp_halo_p2p_active(h)) return false;
     if (h->D != 3 && h->D != 4) return false;
+    if (h->nVerticesSolve != h->nVertices) return false;        // one rank: every vertex of a local cell is owned
     return true;
 }
 
@@ -1143,10 +1195,16 @@ int evp_persistent_run(evp_handle *h, int nSub, cudaStream_t s, bool probeOnly)
     fill_cell_args(h, p.c);
     fill_vertex_args(h, p.v);
     p.nSub = nSub;
-    p.vChunk = (h->nVerticesSolve + (int)grid - 1) / (int)grid;
-    p.bar = h->d.gridBar;
-    if (p.vChunk > EVP_TILE * h->M) return -1;
-    if (!probeOnly && cudaMemsetAsync(h->d.gridBar, 0, sizeof(unsigned), s) != cudaSuccess) { cudaGetLastError(); return -1; }
+    if (!probeOnly) {
+        if (!h->d.contrib2) {      // second buffer of the divergence sums + the barrier words, on first use
+            if (evp_dev_alloc(h, (void **)&h->d.contrib2, sizeof(double2) * h->M * h->nCp)) return -1;
+            if (evp_dev_alloc(h, (void **)&h->d.gridBar, sizeof(unsigned) * (grid + 64))) return -1;
+        }
+        if (cudaMemsetAsync(h->d.gridBar, 0, sizeof(unsigned) * (grid + 64), s) != cudaSuccess) { cudaGetLastError(); return -1; }
+    }
+    p.contrib2 = h->d.contrib2;
+    p.arrive = h->d.gridBar + 32;
+    p.release = h->d.gridBar;
     switch (h->M) {
     case 4: return persistent_m<4>(h, p, grid, s, probeOnly);
     case 6: return persistent_m<6>(h, p, grid, s, probeOnly);

@@ -103,6 +103,9 @@ struct CatRow {
     int anc[MAX_DEPTH];
     int hasChild, volumeLike;
     int slotJ, parentSlotJ;   // index among the category's rows that have children: this row's / its parent's, or -1
+    int vpIdx;                // k_fluxes_coop: which shared partial product the row starts from (its own for depth 0 / 1,
+                              // its depth-1 ancestor's below)
+    int base2, layers2;       // ... and, for depth >= 2, the device row (category 0) / layer stride of its depth-2 ancestor
 };
 
 struct Dev {
@@ -671,9 +674,9 @@ __global__ void __launch_bounds__(128) k_triangles(Dev d, double dt)
 // block computes those once into shared memory (1 * v_0 is v_0 exactly; (v_0 * v_1) is the reference's own
 // intermediate: the results stay bit-identical) and a row of depth 2 costs one reconstruction and one product per
 // point instead of three and three.  Phases (barriers between them):
-//   A  lanes compact the non-empty triangles of their edge (area, source cell) -- triangle order is kept, it is the
-//      order the reference sums in -- and drop edges whose source cells hold no ice; all threads then fetch the
-//      quadrature points into shared memory;
+//   A  the non-empty triangles of every edge are compacted (area, source cell) -- triangle order is kept, it is the
+//      order the reference sums in -- edges whose source cells hold no ice are dropped, and a block without any
+//      edge left writes its zeros and leaves; all threads then fetch the quadrature points into shared memory;
 //   B  v_0 at every (triangle, point) for the category's depth-0 rows; negative-mass check (:6895);
 //   C  v_0 * v_1 for the depth-1 rows;
 //   D  thread (lane, row): the row's flux through the edge -> edgeFlux[row][edge]  (one warp = 32 consecutive
@@ -687,6 +690,7 @@ inline size_t ir_flux_smem_bytes(int nD0, int nD1)
     return sizeof(double) * ((size_t)FL * (2 * FNS + (size_t)(nD0 + nD1) * FNS + NTRI) + (size_t)FL * (2 * NTRI + 1) / 2 + 8);
 }
 
+template <int NQ>
 __global__ void __launch_bounds__(FL *FR, 2) k_fluxes_coop(Dev d)
 {
     IR_DYN_SHARED(double, sm);
@@ -694,68 +698,93 @@ __global__ void __launch_bounds__(FL *FR, 2) k_fluxes_coop(Dev d)
     const size_t e = (size_t)blockIdx.x * FL + lane;
     const bool inRange = e < (size_t)d.nE;
     const size_t pe = d.nEp, pc = d.nCp;
-    const int nQP = d.nQP;
+    constexpr int SL = FNS * FL;                       // doubles per (row, all slots, all lanes) plane
     double *xq = sm;                                   // [FNS][FL]
-    double *yq = xq + FNS * FL;                        // [FNS][FL]
-    double *vp = yq + FNS * FL;                        // [(nD0 + nD1)][FNS][FL]: v_0 of the depth-0 rows, then v_0 * v_1
-    double *area = vp + (size_t)(d.nD0 + d.nD1) * FNS * FL;   // [NTRI][FL]
-    int *cell = reinterpret_cast<int *>(area + NTRI * FL);   // [NTRI][FL] source cell (0-based) of the compacted triangle
-    int *tOf = cell + NTRI * FL;                       // [NTRI][FL] its index among the edge's NTRI triangles
+    double *yq = xq + SL;                              // [FNS][FL]
+    double *vp = yq + SL;                              // [(nD0 + nD1)][FNS][FL]: v_0 of the depth-0 rows, then v_0 * v_1
+    double *area = vp + (d.nD0 + d.nD1) * SL;          // [NTRI][FL] raw, then compacted
+    int *cell = reinterpret_cast<int *>(area + NTRI * FL);   // [NTRI][FL] source cell (0-based): raw, then compacted
+    int *tOf = cell + NTRI * FL;                       // [NTRI][FL] index of the compacted triangle among the edge's NTRI
     int *ntL = tOf + NTRI * FL;                        // [FL] number of non-empty triangles
-    __shared__ int negative;
+    __shared__ int negative, anyWork;
+    __shared__ double areaRaw[NTRI][FL];
+    __shared__ int cellRaw[NTRI][FL], iceRaw[NTRI][FL];
 
-    // ---- A1: compaction, one thread per edge ----
+    // ---- A1: one thread per (edge, triangle) fetches area, source cell and its ice mask ----
+    if (ty == 0 && lane == 0) { negative = 0; anyWork = 0; }
+    const bool moving = inRange && d.maskEdge[e] == 1;
+    if (ty < NTRI) {
+        double ar = 0.0;
+        int cl = 0, ic = 0;
+        if (moving) {
+            ar = d.triArea[ty * pe + e];
+            if (ar != 0.0) {
+                cl = d.iCellTri[ty * pe + e] - 1;
+                ic = d.maskCell[cl];
+            }
+        }
+        areaRaw[ty][lane] = ar; cellRaw[ty][lane] = cl; iceRaw[ty][lane] = ic;
+    }
+    __syncthreads();
+    // ---- A2: compaction per edge, triangle order kept (it is the order the reference sums in) ----
     if (ty == 0) {
         int nt = 0;
-        if (lane == 0) negative = 0;
-        if (inRange && d.maskEdge[e] == 1) {
-            bool ice = false;
-            for (int t = 0; t < NTRI; t++) {
-                const double a = d.triArea[t * pe + e];
-                if (a == 0.0) continue;
-                const int cl = d.iCellTri[t * pe + e] - 1;
-                area[nt * FL + lane] = a;
-                cell[nt * FL + lane] = cl;
-                tOf[nt * FL + lane] = t;
-                ice = ice || d.maskCell[cl] == 1;
-                nt++;
-            }
-            // source cells without ice in any category: the mass reconstruction is identically zero there, every
-            // product down the chain is a zero and the flux is the +0.0 written in phase D
-            if (!ice) nt = 0;
+        bool ice = false;
+#pragma unroll
+        for (int t = 0; t < NTRI; t++) {
+            const double ar = areaRaw[t][lane];
+            if (ar == 0.0) continue;
+            area[nt * FL + lane] = ar;
+            cell[nt * FL + lane] = cellRaw[t][lane];
+            tOf[nt * FL + lane] = t;
+            ice = ice || iceRaw[t][lane] == 1;
+            nt++;
         }
+        // source cells without ice in any category: the mass reconstruction is identically zero there, every product
+        // down the chain is a zero and the flux is the +0.0 written in phase D
+        if (!ice) nt = 0;
         ntL[lane] = nt;
+        if (nt > 0) anyWork = 1;
     }
     __syncthreads();
     const int nt = ntL[lane];
-    // ---- A2 + B: quadrature points, v_0 of the depth-0 rows ----
-    for (int s0 = ty; s0 < FNS; s0 += FR) {
-        const int k = s0 / 6, q = s0 - 6 * k;
-        if (k < nt && q < nQP) {
-            const int t = tOf[k * FL + lane];
+    if (!anyWork) {                                    // ice-free or motionless: most of an ocean mesh
+        if (inRange)
+            for (int j = ty; j < d.nRowsPerCat; j += FR)
+                d.edgeFlux[(size_t)(d.catRows[j].baseRow + cat * d.catRows[j].layers) * pe + e] = 0.0;
+        return;
+    }
+    // ---- A3 + B: quadrature points, v_0 of the depth-0 rows ----
+    for (int s0 = ty; s0 < NTRI * NQ; s0 += FR) {
+        const int k = s0 / NQ, q = s0 - NQ * k;
+        if (k < nt) {
+            const int t = tOf[k * FL + lane], so = (k * 6 + q) * FL + lane;
             const double x = d.xq[(size_t)(t * 6 + q) * pe + e], y = d.yq[(size_t)(t * 6 + q) * pe + e];
-            xq[s0 * FL + lane] = x;
-            yq[s0 * FL + lane] = y;
+            xq[so] = x;
+            yq[so] = y;
             const size_t cl = (size_t)cell[k * FL + lane];
             for (int j = 0; j < d.nD0; j++) {          // depth-0 rows come first in the table
                 const size_t a = (size_t)(d.catRows[j].baseRow + cat * d.catRows[j].layers) * pc + cl;
                 const double value = 1.0 * (d.center[a] + d.xGrad[a] * x + d.yGrad[a] * y);
                 if (value < 0.0) negative = 1;
-                vp[((size_t)j * FNS + s0) * FL + lane] = value;
+                vp[j * SL + so] = value;
             }
         }
     }
     __syncthreads();
-    // ---- C: v_0 * v_1 of the depth-1 rows ----
-    for (int it = ty; it < d.nD1 * FNS; it += FR) {
-        const int j1 = it / FNS, s0 = it - j1 * FNS;
-        const int k = s0 / 6, q = s0 - 6 * k;
-        if (k < nt && q < nQP) {
+    // ---- C: v_0 * v_1 of the depth-1 rows: thread row <-> (depth-1 row, triangle), the points unrolled ----
+    for (int it = ty; it < d.nD1 * NTRI; it += FR) {
+        const int j1 = it / NTRI, k = it - j1 * NTRI;
+        if (k < nt) {
             const CatRow cr = d.catRows[d.nD0 + j1];   // depth-1 rows follow the depth-0 rows
             const size_t a = (size_t)(cr.baseRow + cat * cr.layers) * pc + (size_t)cell[k * FL + lane];
-            const double x = xq[s0 * FL + lane], y = yq[s0 * FL + lane];
-            const double v0 = vp[((size_t)d.catRows[cr.anc[0]].cls * FNS + s0) * FL + lane];
-            vp[((size_t)(d.nD0 + j1) * FNS + s0) * FL + lane] = v0 * (d.center[a] + d.xGrad[a] * x + d.yGrad[a] * y);
+            const double c1 = d.center[a], gx1 = d.xGrad[a], gy1 = d.yGrad[a];
+            const int v0base = d.catRows[cr.anc[0]].cls * SL, out = (d.nD0 + j1) * SL;
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                const int so = (k * 6 + q) * FL + lane;
+                vp[out + so] = vp[v0base + so] * (c1 + gx1 * xq[so] + gy1 * yq[so]);
+            }
         }
     }
     __syncthreads();
@@ -765,30 +794,24 @@ __global__ void __launch_bounds__(FL *FR, 2) k_fluxes_coop(Dev d)
         const int r = cr.baseRow + cat * cr.layers;
         double flux = 0.0;
         if (nt > 0) {
-            // where this row's shared partial product sits: its own entry (depth 0, 1) or its depth-1 ancestor's
-            const int base = cr.depth == 0 ? cr.cls : d.nD0 + d.catRows[cr.anc[1]].cls;
-            const int r2 = cr.depth >= 2 ? d.catRows[cr.anc[2]].baseRow + cat * d.catRows[cr.anc[2]].layers : 0;
+            const int base = cr.vpIdx * SL;
+            const size_t row2 = (size_t)(cr.base2 + cat * cr.layers2) * pc, row3 = (size_t)r * pc;
             for (int k = 0; k < nt; k++) {
                 const size_t cl = (size_t)cell[k * FL + lane];
                 double c2 = 0.0, gx2 = 0.0, gy2 = 0.0, c3 = 0.0, gx3 = 0.0, gy3 = 0.0;
-                if (cr.depth >= 2) {
-                    const size_t a = (size_t)r2 * pc + cl;
-                    c2 = d.center[a]; gx2 = d.xGrad[a]; gy2 = d.yGrad[a];
-                }
-                if (cr.depth >= 3) {
-                    const size_t a = (size_t)r * pc + cl;
-                    c3 = d.center[a]; gx3 = d.xGrad[a]; gy3 = d.yGrad[a];
-                }
+                if (cr.depth >= 2) { c2 = d.center[row2 + cl]; gx2 = d.xGrad[row2 + cl]; gy2 = d.yGrad[row2 + cl]; }
+                if (cr.depth >= 3) { c3 = d.center[row3 + cl]; gx3 = d.xGrad[row3 + cl]; gy3 = d.yGrad[row3 + cl]; }
                 double tracerIntegral = 0.0;
-                for (int q = 0; q < nQP; q++) {
-                    const int s0 = k * 6 + q;
-                    double value = vp[((size_t)base * FNS + s0) * FL + lane];
+#pragma unroll
+                for (int q = 0; q < NQ; q++) {
+                    const int so = (k * 6 + q) * FL + lane;
+                    double value = vp[base + so];
                     if (cr.depth >= 2) {
-                        const double x = xq[s0 * FL + lane], y = yq[s0 * FL + lane];
+                        const double x = xq[so], y = yq[so];
                         value = value * (c2 + gx2 * x + gy2 * y);
                         if (cr.depth >= 3) value = value * (c3 + gx3 * x + gy3 * y);
                     }
-                    const double w = (nQP == 3) ? (1.0 / 3.0) : (q < 3 ? W1QP : W2QP);
+                    const double w = (NQ == 3) ? (1.0 / 3.0) : (q < 3 ? W1QP : W2QP);
                     tracerIntegral = tracerIntegral + w * value;
                 }
                 flux = flux + area[k * FL + lane] * tracerIntegral;
@@ -859,25 +882,31 @@ __global__ void __launch_bounds__(CL *UW, 4) k_update_coop(Dev d, int massOneLay
         __syncthreads();
     }
     if (!massOneLayer) return;
-    // zap_small_mass (:8764) and thickness -> volume (:9295); the mass row of category k is row k.  Every row reads
-    // the category's new mass before any of them (the mass row included) is rewritten
+    // zap_small_mass (:8764) and thickness -> volume (:9295); the mass row of category k is row k.  A row is rewritten
+    // only if it changes: the volume-like rows (value -> mass * value) and, in a zapped category, every row (-> 0).
+    // Every thread reads the category's new mass before any row (the mass row included) is rewritten.
     const int total = d.nK * d.nRowsPerCat;
     const int myItems = (total - ty + UW - 1) / UW;          // items ty, ty + UW, ...
     const int maxItems = (total + UW - 1) / UW;              // the same for every thread: the loop holds barriers
     double vNew[16];
+    unsigned changed = 0;
     for (int base = 0; base < maxItems; base += 16) {
         const int m = myItems - base < 16 ? (myItems - base > 0 ? myItems - base : 0) : 16;
+        changed = 0;
         for (int i = 0; valid && i < m; i++) {
             const int it = ty + (base + i) * UW, cat = it / d.nRowsPerCat, j = it - cat * d.nRowsPerCat;
-            const int r = d.catRows[j].baseRow + cat * d.catRows[j].layers;
             const double mass = d.valNew[(size_t)cat * pc + c];
             const bool zap = owned && mass > 0.0 && mass < 1.0e-22;
-            double v = zap ? 0.0 : d.valNew[(size_t)r * pc + c];
-            if (d.catRows[j].volumeLike) v = (zap ? 0.0 : mass) * v;
+            const bool vol = d.catRows[j].volumeLike != 0;
+            if (!zap && !vol) continue;
+            double v = zap ? 0.0 : d.valNew[(size_t)(d.catRows[j].baseRow + cat * d.catRows[j].layers) * pc + c];
+            if (vol) v = (zap ? 0.0 : mass) * v;
             vNew[i] = v;
+            changed |= 1u << i;
         }
         __syncthreads();
         for (int i = 0; valid && i < m; i++) {
+            if (!(changed & (1u << i))) continue;
             const int it = ty + (base + i) * UW, cat = it / d.nRowsPerCat, j = it - cat * d.nRowsPerCat;
             d.valNew[(size_t)(d.catRows[j].baseRow + cat * d.catRows[j].layers) * pc + c] = vNew[i];
         }
@@ -1544,8 +1573,13 @@ extern "C" int ir_set_tracers(ir_handle *h, int nTracers, const ir_tracer_desc *
             c.slotJ = ri.hasChild ? nSlotJ++ : -1;
             c.parentSlotJ = -1;
         }
-        for (size_t j = 0; j < cr.size(); j++)
-            if (cr[j].depth > 0) cr[j].parentSlotJ = cr[cr[j].anc[cr[j].depth - 1]].slotJ;
+        for (size_t j = 0; j < cr.size(); j++) {
+            CatRow &c = cr[j];
+            if (c.depth > 0) c.parentSlotJ = cr[c.anc[c.depth - 1]].slotJ;
+            c.vpIdx = c.depth == 0 ? c.cls : nCls[0] + cr[c.anc[1]].cls;
+            c.base2 = c.depth >= 2 ? cr[c.anc[2]].baseRow : 0;
+            c.layers2 = c.depth >= 2 ? cr[c.anc[2]].layers : 0;
+        }
         d.nD0 = nCls[0]; d.nD1 = nCls[1]; d.nSlotsPerCat = nSlotJ;
         if (d.catRows) { cudaFree(d.catRows); d.catRows = nullptr; }
         IR_CUDA(cudaMalloc((void **)&d.catRows, sizeof(CatRow) * cr.size()));
@@ -1615,9 +1649,11 @@ extern "C" int ir_run(ir_handle *h, int nTracers, const ir_tracer_desc *tr, cons
         {
             const size_t smem = ir_flux_smem_bytes(d.nD0, d.nD1);
 #ifdef IR_DEVICE_BUILD
-            IR_CUDA(cudaFuncSetAttribute(k_fluxes_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            IR_CUDA(cudaFuncSetAttribute(k_fluxes_coop<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            IR_CUDA(cudaFuncSetAttribute(k_fluxes_coop<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
-            IR_LAUNCH_SYNC((k_fluxes_coop), dim3(grid_for((size_t)d.nE, FL), nK), dim3(FL, FR), smem, s, d);
+            if (d.nQP == 3) IR_LAUNCH_SYNC((k_fluxes_coop<3>), dim3(grid_for((size_t)d.nE, FL), nK), dim3(FL, FR), smem, s, d);
+            else IR_LAUNCH_SYNC((k_fluxes_coop<6>), dim3(grid_for((size_t)d.nE, FL), nK), dim3(FL, FR), smem, s, d);
         }
         h->launches += 2;
     }

@@ -17,6 +17,49 @@ import numpy as np
 from . import partition, variational_init, workloads
 
 
+def bind_to_gpu_numa(device_index: int, verbose=None):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (what `mpirun --bind-to` / `numactl` do for the
+    Fortran host).  Pages are placed by first touch, so the host arrays allocated afterwards -- the ones the per-step
+    copies read and write -- live in the memory next to the GPU's PCIe root instead of crossing the socket link.
+    Silently does nothing when the topology cannot be read (no NVML, no sysfs)."""
+    import os
+    try:
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(visible.split(",")[device_index]) if visible and visible.split(",")[0].isdigit() else device_index
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(idx)).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+        except Exception:  # noqa: BLE001
+            import subprocess
+            bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(idx)],
+                                 capture_output=True, text=True, timeout=20, check=True).stdout.strip()
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:          # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            if verbose:
+                verbose(f"GPU {device_index} ({bus}): bound to {len(cpus)} CPUs of its NUMA node ({spec})")
+        return sorted(cpus)
+    except Exception as e:  # noqa: BLE001 -- an optimisation only
+        if verbose:
+            verbose(f"NUMA binding skipped: {type(e).__name__}: {e}")
+        return None
+
+
 def build_rank_workload(name, rank, world, dist=None, verbose=None, method="auto", n_halos=None, state="A"):
     """Like workloads.build() but for the block of ``rank`` out of ``world``."""
     log = verbose or (lambda *a: None)

@@ -12,9 +12,9 @@ print("$wl persistent=$pers", "value", round(d["value"],1), "us/subcycle", round
 PY
   done
 done
-timeout 600 python tools/ir_bench.py --level 7 --steps 10 --warmup 3 --check --cpu-baseline > gpurun_out/ir_bench_qu60_r02b.json 2> gpurun_out/ir_bench_qu60_r02b.err; echo "ir bench qu60 rc=$?"; cat gpurun_out/ir_bench_qu60_r02b.json; tail -3 gpurun_out/ir_bench_qu60_r02b.err
-timeout 600 python tools/ir_bench.py --level 9 --steps 3 --warmup 1 > gpurun_out/ir_bench_qu15_r02b.json 2> gpurun_out/ir_bench_qu15_r02b.err; echo "ir bench qu15 rc=$?"; cat gpurun_out/ir_bench_qu15_r02b.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/ir_launches_qu60_r02b.csv \
+timeout 600 python tools/ir_bench.py --level 7 --steps 10 --warmup 3 --check --cpu-baseline > gpurun_out/ir_bench_qu60_r02${TAG:-b}.json 2> gpurun_out/ir_bench_qu60_r02${TAG:-b}.err; echo "ir bench qu60 rc=$?"; cat gpurun_out/ir_bench_qu60_r02${TAG:-b}.json; tail -3 gpurun_out/ir_bench_qu60_r02${TAG:-b}.err
+[ -n "$SKIP_QU15" ] || timeout 600 python tools/ir_bench.py --level 9 --steps 3 --warmup 1 > gpurun_out/ir_bench_qu15_r02${TAG:-b}.json 2> gpurun_out/ir_bench_qu15_r02${TAG:-b}.err; echo "ir bench qu15 rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/ir_launches_qu60_r02${TAG:-b}.csv \
     python tools/ir_bench.py --level 7 --steps 1 --warmup 1 > gpurun_out/ir_ncu_list.log 2>&1; echo "ir ncu list rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_reconstruct|k_triangles|k_fluxes|k_update|k_prepare" -c 5 -o gpurun_out/ir_prof_qu60_r02b -f \
+[ -n "$SKIP_FULL" ] || timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_reconstruct|k_triangles|k_fluxes|k_update|k_prepare" -c 5 -o gpurun_out/ir_prof_qu60_r02${TAG:-b} -f \
     python tools/ir_bench.py --level 7 --steps 1 --warmup 0 > gpurun_out/ir_ncu_full.log 2>&1; echo "ir ncu full rc=$?"
