@@ -174,6 +174,14 @@ module seaice_evp_b200
      type(c_ptr) :: solveVelocity
   end type evp_pre_fields
 
+  ! ---- struct evp_category_fields ----
+  type, bind(C), public :: evp_category_fields
+     integer(c_int) :: nCategories
+     type(c_ptr) :: iceAreaCategory
+     type(c_ptr) :: iceVolumeCategory
+     type(c_ptr) :: snowVolumeCategory
+  end type evp_category_fields
+
   ! ---- struct evp_pre_options ----
   type, bind(C), public :: evp_pre_options
      integer(c_int) :: use_air_stress
@@ -353,6 +361,26 @@ module seaice_evp_b200
        type(evp_pre_options), intent(in) :: options
        integer(c_int) :: ierr
      end function evp_pre_subcycle
+
+     function evp_aggregate(handle, categories, hibler_strength) bind(C, name="evp_aggregate") result(ierr)
+       import :: c_ptr, c_int, evp_category_fields
+       type(c_ptr), value :: handle
+       type(evp_category_fields), intent(in) :: categories
+       integer(c_int), value :: hibler_strength
+       integer(c_int) :: ierr
+     end function evp_aggregate
+
+     function evp_fetch_aggregate(handle, iceAreaCell, iceVolumeCell, snowVolumeCell, totalMassCell, icePressure) &
+          bind(C, name="evp_fetch_aggregate") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: handle
+       type(c_ptr), value :: iceAreaCell
+       type(c_ptr), value :: iceVolumeCell
+       type(c_ptr), value :: snowVolumeCell
+       type(c_ptr), value :: totalMassCell
+       type(c_ptr), value :: icePressure
+       integer(c_int) :: ierr
+     end function evp_fetch_aggregate
 
      function evp_post_subcycle(handle, out) bind(C, name="evp_post_subcycle") result(ierr)
        import :: c_ptr, c_int, evp_post_fields

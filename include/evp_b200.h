@@ -236,10 +236,33 @@ int evp_halo_mode(evp_handle *handle, int *mode, char *why, int whyLen);
  * and u, v, stress11/22/12 and solveVelocityPrevious stay resident between steps.
  *   evp_pre_subcycle  = velocity_solver_pre_subcycle  (src/shared/mpas_seaice_velocity_solver.F:613-671)
  *   evp_post_subcycle = velocity_solver_post_subcycle (velocity_solver.F:3360-3380)
- * What stays on the host: aggregate_mass_and_area (:685-752, sums over ice categories) and the ice
- * strength itself (:1341-1436: Hibler needs exp(), colpkg_ice_strength is column physics) -- the host
- * passes icePressure for every cell that may be solved and the device applies solveStress.
+ * aggregate_mass_and_area (:685-752, sums over the ice categories) and the Hibler ice strength (:1419-1436) may
+ * run on the host (the caller passes iceAreaCell, totalMassCell and an unmasked icePressure) or on the device
+ * (evp_aggregate below, then evp_pre_subcycle with those pointers NULL).  colpkg_ice_strength (the Rothrock
+ * strength of the column package, :1438-1460) is column physics and stays with the host.
  * ====================================================================================================== */
+
+/* aggregate_mass_and_area on the device: the three category tracers of the `tracers` pool, layer 1, stored
+ * (nCategories, nCells) = the Registry's (ONE, nCategories, nCells).  The sums run in category order like the
+ * reference's sum() (bit-identical to a sequential host sum); totalMassCell = iceVolumeCell * rho_i + snowVolumeCell *
+ * rho_s.  With hibler_strength != 0 the unmasked Hibler strength P* h exp(-C (1 - a)) is evaluated too -- with the
+ * DEVICE's exp(), which is specified to 1 ulp and therefore need not equal the host libm's in the last bit.  Measured
+ * on QU240 (10 242 cells, polar caps in 5 categories) it does: no cell's icePressure differs from glibc's and a full
+ * dynamics step is bit-identical either way (tests/test_gpu_prepost.py::test_device_hibler_strength, which asserts
+ * <= 1 ulp and <= 1e-9 after 120 subcycles and prints the measured numbers).  Hosts that must not depend on that
+ * libm pass icePressure themselves.  The results stay on the device and feed the next evp_pre_subcycle whose
+ * iceAreaCell / totalMassCell / icePressure (and iceAreaCellInitial, if it is to be the same field) pointers are NULL;
+ * evp_fetch_aggregate copies them to the host arrays of the tracers_aggregate / icestate / velocity_solver pools. */
+typedef struct {
+    int nCategories;
+    const double *iceAreaCategory;
+    const double *iceVolumeCategory;
+    const double *snowVolumeCategory;
+} evp_category_fields;
+int evp_aggregate(evp_handle *handle, const evp_category_fields *categories, int hibler_strength);
+/* any pointer may be NULL; icePressure is the UNMASKED strength (the mask is applied by evp_pre_subcycle) */
+int evp_fetch_aggregate(evp_handle *handle, double *iceAreaCell, double *iceVolumeCell, double *snowVolumeCell,
+                        double *totalMassCell, double *icePressure);
 
 /* Mesh fields the pre-/post-subcycle read in addition to evp_mesh_desc (src/Registry.xml:2251-2367,
  * boundary pool interiorVertex, ocean_coupling landIceMaskVertex). */
@@ -254,10 +277,12 @@ typedef struct {
 
 /* Cell inputs of one dynamics step, all (nCells).  Optional groups are NULL when unused. */
 typedef struct {
-    const double *iceAreaCellInitial;   /* masks + vertex interpolation (velocity_solver.F:860-880) */
-    const double *iceAreaCell;          /* constant_air_stress (:1716-1723); may alias iceAreaCellInitial */
-    const double *totalMassCell;        /* aggregate_mass_and_area (:742-744) */
-    const double *icePressure;          /* ice strength, unmasked; the device zeroes it where solveStress /= 1 */
+    const double *iceAreaCellInitial;   /* masks + vertex interpolation (velocity_solver.F:860-880); NULL = iceAreaCell */
+    const double *iceAreaCell;          /* constant_air_stress (:1716-1723); may alias iceAreaCellInitial;
+                                           NULL = the result of evp_aggregate */
+    const double *totalMassCell;        /* aggregate_mass_and_area (:742-744); NULL = the result of evp_aggregate */
+    const double *icePressure;          /* ice strength, unmasked; the device zeroes it where solveStress /= 1;
+                                           NULL = the Hibler strength of evp_aggregate */
     const double *uOceanVelocity;       /* ocean_coupling pool */
     const double *vOceanVelocity;
     const double *airStressCellU;       /* either the coupler's stresses ...                                   */

@@ -77,6 +77,8 @@ struct evp_dev {
     double2 *airCell = nullptr;   // (airStressCellU, airStressCellV) of the current step
     double2 *osFinal = nullptr;   // ocean_stress_final's oceanStressU/V
     uint8_t *solveVelPrev = nullptr;
+    // evp_aggregate: aggregate_mass_and_area and the Hibler strength on the device (allocated on first use)
+    double *aggArea = nullptr, *aggVolIce = nullptr, *aggVolSnow = nullptr, *aggMass = nullptr, *aggP = nullptr;
     // weak operators (evp_set_weak_mesh): per cell-slot / vertex-slot edge data, one stress point per cell
     int2 *wEdgeV = nullptr;       // [M][nCp] the two vertices of edge k of the cell (0-based)
     double2 *wNp = nullptr;       // [M][nCp] normalVectorPolygon
@@ -130,6 +132,7 @@ struct evp_handle {
     evp_options opt{};
     bool metric = false;          // any tanLatVertexRotatedOverRadius != 0
     bool haveExt = false, haveWeak = false;
+    bool haveAgg = false, haveAggP = false;   // evp_aggregate ran (with the Hibler strength)
     bool haveBasis = false, haveStep = false, haveSB = false, useGraph = true, pinHost = false, timed = false;
     evp_dev d;
     cudaStream_t stream = nullptr, commStream = nullptr;

@@ -61,6 +61,31 @@ __device__ __forceinline__ bool enough_ice(const PreArgs &a, int c)
     return a.areaInit[c] > kAreaMinimum && a.mass[c] > kMassMinimum && (a.landIce == nullptr || a.landIce[c] == 0);
 }
 
+// aggregate_mass_and_area (velocity_solver.F:685-752) + the Hibler strength before its mask (:1419-1436).
+// cat arrays: (nCategories, nCells), category fastest.  The sums start from 0 and run in category order like sum().
+constexpr double kDensityIce = 917.0, kDensitySnow = 330.0;                  // ice_constants_colpkg.F90
+constexpr double kHiblerP = 2.75e4, kHiblerC = 20.0;                         // mpas_seaice_constants.F
+__global__ void __launch_bounds__(256) k_aggregate(int nCells, int nCat, const double *__restrict__ aCat,
+                                                   const double *__restrict__ viCat, const double *__restrict__ vsCat,
+                                                   double *__restrict__ area, double *__restrict__ volIce,
+                                                   double *__restrict__ volSnow, double *__restrict__ mass,
+                                                   double *__restrict__ P, int hibler)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nCells) return;
+    double a = 0.0, vi = 0.0, vs = 0.0;
+    for (int k = 0; k < nCat; k++) {
+        a = a + aCat[(size_t)c * nCat + k];
+        vi = vi + viCat[(size_t)c * nCat + k];
+        vs = vs + vsCat[(size_t)c * nCat + k];
+    }
+    area[c] = a;
+    volIce[c] = vi;
+    volSnow[c] = vs;
+    mass[c] = vi * kDensityIce + vs * kDensitySnow;
+    if (hibler) P[c] = kHiblerP * vi * exp(-kHiblerC * (1.0 - a));
+}
+
 // cells: stress_calculation_mask (:961-1059), ice_strength mask (:1419-1436), air stress at cells
 // (:1560-1580, constant_air_stress :1716-1723), stress reset of init_subcycle_variables (:2335-2345)
 __global__ void __launch_bounds__(256) k_pre_cells(const PreArgs a)
@@ -538,11 +563,15 @@ extern "C" int evp_pre_subcycle(evp_handle *h, const evp_pre_fields *f, const ev
 {
     EVP_REQUIRE(h != nullptr && f != nullptr && o != nullptr, "NULL argument");
     if (!h->haveExt) { evp_set_error("evp_pre_subcycle needs evp_set_mesh_ext first"); return EVP_ERR_STATE; }
-    EVP_REQUIRE(f->iceAreaCellInitial && f->totalMassCell && f->icePressure && f->uOceanVelocity && f->vOceanVelocity,
-                "iceAreaCellInitial, totalMassCell, icePressure and u/vOceanVelocity must not be NULL");
+    EVP_REQUIRE(f->uOceanVelocity && f->vOceanVelocity, "u/vOceanVelocity must not be NULL");
+    if (!f->iceAreaCell || !f->totalMassCell) {
+        if (!h->haveAgg) { evp_set_error("iceAreaCell / totalMassCell are NULL and evp_aggregate has not run"); return EVP_ERR_STATE; }
+    }
+    if (!f->icePressure && !h->haveAggP) { evp_set_error("icePressure is NULL and evp_aggregate has not computed the Hibler strength"); return EVP_ERR_STATE; }
+    EVP_REQUIRE(f->iceAreaCellInitial || f->iceAreaCell || h->haveAgg, "iceAreaCellInitial must not be NULL");
     const bool constantAir = o->use_air_stress && !f->airStressCellU;
     if (o->use_air_stress) {
-        if (constantAir) EVP_REQUIRE(f->uAirVelocity && f->vAirVelocity && f->airDensity && (f->iceAreaCell || f->iceAreaCellInitial),
+        if (constantAir) EVP_REQUIRE(f->uAirVelocity && f->vAirVelocity && f->airDensity && (f->iceAreaCell || f->iceAreaCellInitial || h->haveAgg),
                                      "air stress: give airStressCellU/V or u/vAirVelocity + airDensity");
         else EVP_REQUIRE(f->airStressCellV, "airStressCellV is NULL");
     }
@@ -577,10 +606,15 @@ extern "C" int evp_pre_subcycle(evp_handle *h, const evp_pre_fields *f, const ev
     a.tiltMode = tiltMode; a.calcMasks = o->calc_velocity_masks != 0; a.coldStart = o->cold_start;
     a.cr = h->opt.constitutive_relation_type;
     a.nEdges = d.nEdges; a.coc = d.coc; a.cov = d.cov; a.vflags = d.vflags; a.areaCell = d.areaCell; a.fVertex = d.fVertex;
-    a.areaInit = stage_d(f->iceAreaCellInitial, nC);
-    a.areaNow = (!f->iceAreaCell || f->iceAreaCell == f->iceAreaCellInitial) ? a.areaInit : stage_d(f->iceAreaCell, nC);
-    a.mass = stage_d(f->totalMassCell, nC);
-    a.Pin = stage_d(f->icePressure, nC);
+    // iceAreaCell: the caller's, else the aggregate on the device; iceAreaCellInitial: the caller's, else iceAreaCell
+    const double *areaNow = f->iceAreaCell ? nullptr : (h->haveAgg ? d.aggArea : nullptr);
+    if (f->iceAreaCellInitial) a.areaInit = stage_d(f->iceAreaCellInitial, nC);
+    if (f->iceAreaCell) areaNow = (f->iceAreaCell == f->iceAreaCellInitial) ? a.areaInit : stage_d(f->iceAreaCell, nC);
+    if (!areaNow) areaNow = a.areaInit;
+    if (!f->iceAreaCellInitial) a.areaInit = areaNow;
+    a.areaNow = areaNow;
+    a.mass = f->totalMassCell ? stage_d(f->totalMassCell, nC) : d.aggMass;
+    a.Pin = f->icePressure ? stage_d(f->icePressure, nC) : d.aggP;
     a.uOcn = stage_d(f->uOceanVelocity, nC);
     a.vOcn = stage_d(f->vOceanVelocity, nC);
     if (a.useAir && !constantAir) { a.airU = stage_d(f->airStressCellU, nC); a.airV = stage_d(f->airStressCellV, nC); }
@@ -622,6 +656,63 @@ extern "C" int evp_pre_subcycle(evp_handle *h, const evp_pre_fields *f, const ev
     if ((rc = evp_halo_exchange(h, s, d.uv))) return rc;
     EVP_CUDA(cudaStreamSynchronize(s));           // pinned sources were copied asynchronously
     h->haveStep = true;
+    return EVP_OK;
+}
+
+extern "C" int evp_aggregate(evp_handle *h, const evp_category_fields *cf, int hibler)
+{
+    EVP_REQUIRE(h != nullptr && cf != nullptr, "handle/categories is NULL");
+    EVP_REQUIRE(cf->nCategories >= 1 && cf->iceAreaCategory && cf->iceVolumeCategory && cf->snowVolumeCategory,
+                "nCategories >= 1 and the three category arrays are needed");
+    EVP_CUDA(cudaSetDevice(h->device));
+    evp_dev &d = h->d;
+    const size_t nC = h->nCells, nK = (size_t)cf->nCategories;
+    cudaStream_t s = h->stream;
+    int rc;
+    if (!d.aggArea) {
+        double **bufs[] = {&d.aggArea, &d.aggVolIce, &d.aggVolSnow, &d.aggMass, &d.aggP};
+        for (double **b : bufs) {
+            if ((rc = evp_dev_alloc(h, (void **)b, sizeof(double) * h->nCp))) return rc;
+            EVP_CUDA(cudaMemsetAsync(*b, 0, sizeof(double) * h->nCp, s));
+        }
+    }
+    if (nC == 0) { h->haveAgg = true; h->haveAggP = hibler != 0; return EVP_OK; }
+    EVP_CUDA(cudaStreamSynchronize(s));          // the staging area may still feed kernels of a previous call
+    // the category arrays go through the staging area in chunks of cells
+    const size_t perCell = 3 * nK * sizeof(double);
+    const size_t chunk = std::max<size_t>(1, std::min(nC, (d.stageBytes - 1024) / perCell));
+    for (size_t c0 = 0; c0 < nC; c0 += chunk) {
+        const size_t cnt = std::min(chunk, nC - c0);
+        double *sa = (double *)d.stage, *svi = sa + cnt * nK, *svs = svi + cnt * nK;
+        if ((rc = evp_h2d(h, sa, cf->iceAreaCategory + c0 * nK, cnt * nK * 8))) return rc;
+        if ((rc = evp_h2d(h, svi, cf->iceVolumeCategory + c0 * nK, cnt * nK * 8))) return rc;
+        if ((rc = evp_h2d(h, svs, cf->snowVolumeCategory + c0 * nK, cnt * nK * 8))) return rc;
+        k_aggregate<<<grid_for(cnt, 256), 256, 0, s>>>((int)cnt, (int)nK, sa, svi, svs, d.aggArea + c0, d.aggVolIce + c0,
+                                                        d.aggVolSnow + c0, d.aggMass + c0, d.aggP + c0, hibler);
+        EVP_CUDA(cudaGetLastError());
+        if (c0 + chunk < nC) EVP_CUDA(cudaStreamSynchronize(s));     // the staging area is reused by the next chunk
+    }
+    EVP_CUDA(cudaStreamSynchronize(s));           // pinned sources were copied asynchronously
+    h->haveAgg = true;
+    h->haveAggP = hibler != 0;
+    return EVP_OK;
+}
+
+extern "C" int evp_fetch_aggregate(evp_handle *h, double *iceAreaCell, double *iceVolumeCell, double *snowVolumeCell,
+                                   double *totalMassCell, double *icePressure)
+{
+    EVP_REQUIRE(h != nullptr, "handle is NULL");
+    if (!h->haveAgg) { evp_set_error("evp_fetch_aggregate before evp_aggregate"); return EVP_ERR_STATE; }
+    if (icePressure && !h->haveAggP) { evp_set_error("evp_aggregate did not compute the Hibler strength"); return EVP_ERR_STATE; }
+    EVP_CUDA(cudaSetDevice(h->device));
+    evp_dev &d = h->d;
+    const size_t nC = h->nCells;
+    int rc;
+    struct { double *host; const double *dev; } copies[] = {{iceAreaCell, d.aggArea}, {iceVolumeCell, d.aggVolIce},
+        {snowVolumeCell, d.aggVolSnow}, {totalMassCell, d.aggMass}, {icePressure, d.aggP}};
+    for (auto &c : copies)
+        if (c.host && nC && (rc = evp_d2h(h, c.host, c.dev, nC * 8))) return rc;
+    EVP_CUDA(cudaStreamSynchronize(h->stream));
     return EVP_OK;
 }
 

@@ -37,7 +37,7 @@ EXPORTS = (
     "evp_launch_count", "evp_get_stream", "evp_device_bytes", "evp_set_use_graph", "evp_profile_passes",
     "evp_host_metric_terms", "evp_set_mesh_ext", "evp_set_state", "evp_pre_subcycle", "evp_post_subcycle",
     "evp_fetch_pre", "evp_release_host_memory", "evp_set_weak_mesh", "evp_update_weak_state", "evp_fetch_weak",
-    "evp_precompute_pwl", "evp_halo_mode",
+    "evp_precompute_pwl", "evp_halo_mode", "evp_aggregate", "evp_fetch_aggregate",
 )
 
 
@@ -109,6 +109,11 @@ class MeshExt(C.Structure):
 
 class PreFields(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in PRE_FIELDS]
+
+
+class CategoryFields(C.Structure):
+    _fields_ = [("nCategories", C.c_int)] + [(n, C.c_void_p) for n in ("iceAreaCategory", "iceVolumeCategory",
+                                                                         "snowVolumeCategory")]
 
 
 class PreOptions(C.Structure):
@@ -362,6 +367,25 @@ class EvpSolver:
         po = PreOptions(int(use_air_stress), int(use_surface_tilt), int(geostrophic_surface_tilt),
                         int(calc_velocity_masks), int(cold_start))
         self._check(self.lib.evp_pre_subcycle(self._h, C.byref(pf), C.byref(po)))
+
+    def aggregate(self, ice_area_category, ice_volume_category, snow_volume_category, hibler_strength=True):
+        """evp_aggregate: aggregate_mass_and_area (and the Hibler strength, with the device's exp()) on the device from
+        (nCells + 1, nCategories) category arrays; a following pre_subcycle may leave iceAreaCell, iceAreaCellInitial,
+        totalMassCell and icePressure out."""
+        cf = CategoryFields()
+        cf.nCategories = int(ice_area_category.shape[1])
+        self._agg_keep = (ice_area_category, ice_volume_category, snow_volume_category)
+        for n, a in zip(("iceAreaCategory", "iceVolumeCategory", "snowVolumeCategory"), self._agg_keep):
+            assert a.shape == (self.nCells + 1, cf.nCategories)
+            setattr(cf, n, _ptr(a, np.float64))
+        self._check(self.lib.evp_aggregate(self._h, C.byref(cf), C.c_int(int(hibler_strength))))
+
+    def fetch_aggregate(self, ice_pressure=True):
+        names = ("iceAreaCell", "iceVolumeCell", "snowVolumeCell", "totalMassCell") + (("icePressure",) if ice_pressure else ())
+        out = {n: np.zeros(self.nCells + 1) for n in names}
+        ptrs = [C.c_void_p(out[n].ctypes.data) for n in names] + ([] if ice_pressure else [C.c_void_p()])
+        self._check(self.lib.evp_fetch_aggregate(self._h, *ptrs))
+        return out
 
     def post_subcycle(self, into=None, names=POST_DEFAULT):
         """evp_post_subcycle: velocity_solver_post_subcycle on the device + copy of the wanted results."""

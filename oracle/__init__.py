@@ -348,6 +348,18 @@ def final_divergence_shear(mesh, step):
     return dict(zip(("divergence", "shear", "ridgeConvergence", "ridgeShear"), out))
 
 
+def aggregate_mass_and_area(ice_area_category, ice_volume_category, snow_volume_category):
+    """aggregate_mass_and_area (velocity_solver.F:685-752) on (nCells + 1, nCategories) arrays; returns
+    iceAreaCell, iceVolumeCell, snowVolumeCell, totalMassCell."""
+    a = np.ascontiguousarray(ice_area_category, dtype=np.float64)
+    n, k = a.shape
+    vi = np.ascontiguousarray(ice_volume_category, dtype=np.float64)
+    vs = np.ascontiguousarray(snow_volume_category, dtype=np.float64)
+    out = [np.zeros(n) for _ in range(4)]
+    lib().orc_aggregate_mass_and_area(_i(n), _i(k), _p(a), _p(vi), _p(vs), *[_p(o) for o in out])
+    return out
+
+
 def hibler_strength_unmasked(state, n_cells):
     """seaiceIceStrengthConstantHiblerP * iceVolumeCell * exp(-C*(1-iceAreaCell)) for EVERY cell (libm exp), i.e.
     ice_strength (velocity_solver.F:1419-1436) before its solveStress mask: what a host hands to evp_pre_subcycle."""

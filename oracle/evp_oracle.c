@@ -1031,6 +1031,26 @@ double orc_numerical_inertia_coefficient(double dynamicsTimeStep, double dvEdgeM
 }
 
 /* aggregate_mass_and_area for one category (velocity_solver.F:738-746) */
+/* aggregate_mass_and_area (velocity_solver.F:685-752): sums over the categories in category order (layer 1 of the
+ * (1, nCategories, nCells) tracer arrays), then the total mass */
+void orc_aggregate_mass_and_area(int nCells, int nCategories, const double *iceAreaCategory,
+                                 const double *iceVolumeCategory, const double *snowVolumeCategory, double *iceAreaCell,
+                                 double *iceVolumeCell, double *snowVolumeCell, double *totalMassCell)
+{
+    for (int i = 0; i < nCells; i++) {
+        double a = 0.0, vi = 0.0, vs = 0.0;
+        for (int k = 0; k < nCategories; k++) {
+            a = a + iceAreaCategory[(size_t)i * nCategories + k];
+            vi = vi + iceVolumeCategory[(size_t)i * nCategories + k];
+            vs = vs + snowVolumeCategory[(size_t)i * nCategories + k];
+        }
+        iceAreaCell[i] = a;
+        iceVolumeCell[i] = vi;
+        snowVolumeCell[i] = vs;
+        totalMassCell[i] = vi * seaiceDensityIce + vs * seaiceDensitySnow;
+    }
+}
+
 void orc_total_mass(int nCells, const double *iceVolumeCell, const double *snowVolumeCell, double *totalMassCell)
 {
     for (int i = 0; i < nCells; i++)

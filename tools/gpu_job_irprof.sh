@@ -1,0 +1,6 @@
+# 1-GPU: full ncu capture of the transport step kernels (QU60, 115 rows)
+mkdir -p gpurun_out
+export EVP_B200_MESH_CACHE=/tmp/evp_cache
+timeout 300 python tools/ir_bench.py --level 7 --steps 5 --warmup 2 > gpurun_out/ir_bench_qu60_r02${TAG:-d}.json 2> gpurun_out/ir_bench_qu60_r02${TAG:-d}.err; cat gpurun_out/ir_bench_qu60_r02${TAG:-d}.json
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_reconstruct|k_triangles|k_fluxes|k_update|k_prepare" -c 5 -o gpurun_out/ir_prof_qu60_r02${TAG:-d} -f \
+    python tools/ir_bench.py --level 7 --steps 1 --warmup 0 > gpurun_out/ir_ncu_full.log 2>&1; echo "ir ncu full rc=$?"
