@@ -674,24 +674,25 @@ __global__ void __launch_bounds__(128) k_triangles(Dev d, double dt)
 // block computes those once into shared memory (1 * v_0 is v_0 exactly; (v_0 * v_1) is the reference's own
 // intermediate: the results stay bit-identical) and a row of depth 2 costs one reconstruction and one product per
 // point instead of three and three.  Phases (barriers between them):
-//   A  the non-empty triangles of every edge are compacted (area, source cell) -- triangle order is kept, it is the
-//      order the reference sums in -- edges whose source cells hold no ice are dropped, and a block without any
-//      edge left writes its zeros and leaves; all threads then fetch the quadrature points into shared memory;
-//   B  v_0 at every (triangle, point) for the category's depth-0 rows; negative-mass check (:6895);
-//   C  v_0 * v_1 for the depth-1 rows;
-//   D  thread (lane, row): the row's flux through the edge -> edgeFlux[row][edge]  (one warp = 32 consecutive
-//      edges of one row: coalesced stores; shared memory is [..][lane]: conflict-free).
+//   A    area, source cell and ice mask of the edge's triangles -> shared memory; a block without any edge whose
+//        triangles touch ice writes its zeros and leaves; every thread compacts its edge's non-empty triangles for
+//        itself (triangle order is kept, it is the order the reference sums in);
+//   B+C  thread (lane, triangle, point): the quadrature point, v_0 for the category's depth-0 rows (negative-mass
+//        check, :6895) and v_0 * v_1 for its depth-1 rows -> shared memory;
+//   D    thread (lane, row): the row's flux through the edge -> edgeFlux[row][edge]  (one warp = 32 consecutive
+//        edges of one row: coalesced stores; shared memory is [..][lane]: conflict-free).
+// Two barriers per block; 12 thread rows, three blocks per SM (58 KB of shared memory each).
 constexpr int FL = 32;   // edges per block
-constexpr int FR = 24;   // thread rows per block
+constexpr int FR = 12;   // thread rows per block
 constexpr int FNS = NTRI * 6;   // (triangle, point) slots per edge
 
 inline size_t ir_flux_smem_bytes(int nD0, int nD1)
 {
-    return sizeof(double) * ((size_t)FL * (2 * FNS + (size_t)(nD0 + nD1) * FNS + NTRI) + (size_t)FL * (2 * NTRI + 1) / 2 + 8);
+    return sizeof(double) * ((size_t)FL * (2 * FNS + (size_t)(nD0 + nD1) * FNS + NTRI) + (size_t)FL * NTRI + 8);
 }
 
 template <int NQ>
-__global__ void __launch_bounds__(FL *FR, 2) k_fluxes_coop(Dev d)
+__global__ void __launch_bounds__(FL *FR, 3) k_fluxes_coop(Dev d)
 {
     IR_DYN_SHARED(double, sm);
     const int lane = threadIdx.x, ty = threadIdx.y, cat = blockIdx.y;
@@ -702,88 +703,70 @@ __global__ void __launch_bounds__(FL *FR, 2) k_fluxes_coop(Dev d)
     double *xq = sm;                                   // [FNS][FL]
     double *yq = xq + SL;                              // [FNS][FL]
     double *vp = yq + SL;                              // [(nD0 + nD1)][FNS][FL]: v_0 of the depth-0 rows, then v_0 * v_1
-    double *area = vp + (d.nD0 + d.nD1) * SL;          // [NTRI][FL] raw, then compacted
-    int *cell = reinterpret_cast<int *>(area + NTRI * FL);   // [NTRI][FL] source cell (0-based): raw, then compacted
-    int *tOf = cell + NTRI * FL;                       // [NTRI][FL] index of the compacted triangle among the edge's NTRI
-    int *ntL = tOf + NTRI * FL;                        // [FL] number of non-empty triangles
-    __shared__ int negative, anyWork;
-    __shared__ double areaRaw[NTRI][FL];
-    __shared__ int cellRaw[NTRI][FL], iceRaw[NTRI][FL];
+    double *areaRaw = vp + (d.nD0 + d.nD1) * SL;       // [NTRI][FL] signed area of the edge's triangles (0 = empty)
+    int *cellRaw = reinterpret_cast<int *>(areaRaw + NTRI * FL);   // [NTRI][FL] source cell (0-based)
+    int *iceRaw = cellRaw + NTRI * FL;                 // [NTRI][FL] its ice mask
 
-    // ---- A1: one thread per (edge, triangle) fetches area, source cell and its ice mask ----
-    if (ty == 0 && lane == 0) { negative = 0; anyWork = 0; }
-    const bool moving = inRange && d.maskEdge[e] == 1;
+    // ---- A: one thread per (edge, triangle) fetches area, source cell and its ice mask ----
+    bool mine = false;
     if (ty < NTRI) {
         double ar = 0.0;
         int cl = 0, ic = 0;
-        if (moving) {
+        if (inRange && d.maskEdge[e] == 1) {
             ar = d.triArea[ty * pe + e];
             if (ar != 0.0) {
                 cl = d.iCellTri[ty * pe + e] - 1;
                 ic = d.maskCell[cl];
             }
         }
-        areaRaw[ty][lane] = ar; cellRaw[ty][lane] = cl; iceRaw[ty][lane] = ic;
+        areaRaw[ty * FL + lane] = ar; cellRaw[ty * FL + lane] = cl; iceRaw[ty * FL + lane] = ic;
+        mine = ar != 0.0 && ic == 1;
     }
-    __syncthreads();
-    // ---- A2: compaction per edge, triangle order kept (it is the order the reference sums in) ----
-    if (ty == 0) {
-        int nt = 0;
-        bool ice = false;
-#pragma unroll
-        for (int t = 0; t < NTRI; t++) {
-            const double ar = areaRaw[t][lane];
-            if (ar == 0.0) continue;
-            area[nt * FL + lane] = ar;
-            cell[nt * FL + lane] = cellRaw[t][lane];
-            tOf[nt * FL + lane] = t;
-            ice = ice || iceRaw[t][lane] == 1;
-            nt++;
-        }
-        // source cells without ice in any category: the mass reconstruction is identically zero there, every product
-        // down the chain is a zero and the flux is the +0.0 written in phase D
-        if (!ice) nt = 0;
-        ntL[lane] = nt;
-        if (nt > 0) anyWork = 1;
-    }
-    __syncthreads();
-    const int nt = ntL[lane];
-    if (!anyWork) {                                    // ice-free or motionless: most of an ocean mesh
+    // an edge has work when one of its non-empty triangles lies in a cell with ice: ice-free or motionless blocks
+    // (most of an ocean mesh) write their zeros and leave
+    if (!__syncthreads_or(mine)) {
         if (inRange)
             for (int j = ty; j < d.nRowsPerCat; j += FR)
                 d.edgeFlux[(size_t)(d.catRows[j].baseRow + cat * d.catRows[j].layers) * pe + e] = 0.0;
         return;
     }
-    // ---- A3 + B: quadrature points, v_0 of the depth-0 rows ----
+    // every thread compacts the non-empty triangles of its edge for itself (triangle order kept: it is the order the
+    // reference sums in): tmap holds the triangle index of compacted slot k in bits 3k .. 3k+2
+    int nt = 0;
+    unsigned tmap = 0;
+    {
+        bool ice = false;
+#pragma unroll
+        for (int t = 0; t < NTRI; t++) {
+            if (areaRaw[t * FL + lane] == 0.0) continue;
+            tmap |= (unsigned)t << (3 * nt);
+            ice = ice || iceRaw[t * FL + lane] == 1;
+            nt++;
+        }
+        // source cells without ice in any category: the mass reconstruction is identically zero there, every product
+        // down the chain is a zero and the flux is the +0.0 written in phase D
+        if (!ice) nt = 0;
+    }
+    // ---- B + C: quadrature points, v_0 of the depth-0 rows and v_0 * v_1 of the depth-1 rows, one (triangle, point)
+    //      per thread ----
     for (int s0 = ty; s0 < NTRI * NQ; s0 += FR) {
         const int k = s0 / NQ, q = s0 - NQ * k;
         if (k < nt) {
-            const int t = tOf[k * FL + lane], so = (k * 6 + q) * FL + lane;
+            const int t = (tmap >> (3 * k)) & 7, so = (k * 6 + q) * FL + lane;
             const double x = d.xq[(size_t)(t * 6 + q) * pe + e], y = d.yq[(size_t)(t * 6 + q) * pe + e];
             xq[so] = x;
             yq[so] = y;
-            const size_t cl = (size_t)cell[k * FL + lane];
+            const size_t cl = (size_t)cellRaw[t * FL + lane];
             for (int j = 0; j < d.nD0; j++) {          // depth-0 rows come first in the table
                 const size_t a = (size_t)(d.catRows[j].baseRow + cat * d.catRows[j].layers) * pc + cl;
                 const double value = 1.0 * (d.center[a] + d.xGrad[a] * x + d.yGrad[a] * y);
-                if (value < 0.0) negative = 1;
+                if (value < 0.0) atomicOr(d.flags, FLAG_NEG_QP);        // an abort condition (:6895): rare
                 vp[j * SL + so] = value;
             }
-        }
-    }
-    __syncthreads();
-    // ---- C: v_0 * v_1 of the depth-1 rows: thread row <-> (depth-1 row, triangle), the points unrolled ----
-    for (int it = ty; it < d.nD1 * NTRI; it += FR) {
-        const int j1 = it / NTRI, k = it - j1 * NTRI;
-        if (k < nt) {
-            const CatRow cr = d.catRows[d.nD0 + j1];   // depth-1 rows follow the depth-0 rows
-            const size_t a = (size_t)(cr.baseRow + cat * cr.layers) * pc + (size_t)cell[k * FL + lane];
-            const double c1 = d.center[a], gx1 = d.xGrad[a], gy1 = d.yGrad[a];
-            const int v0base = d.catRows[cr.anc[0]].cls * SL, out = (d.nD0 + j1) * SL;
-#pragma unroll
-            for (int q = 0; q < NQ; q++) {
-                const int so = (k * 6 + q) * FL + lane;
-                vp[out + so] = vp[v0base + so] * (c1 + gx1 * xq[so] + gy1 * yq[so]);
+            for (int j1 = 0; j1 < d.nD1; j1++) {       // depth-1 rows follow
+                const CatRow cr = d.catRows[d.nD0 + j1];
+                const size_t a = (size_t)(cr.baseRow + cat * cr.layers) * pc + cl;
+                vp[(d.nD0 + j1) * SL + so] = vp[d.catRows[cr.anc[0]].cls * SL + so] * (d.center[a] + d.xGrad[a] * x + d.yGrad[a] * y);
             }
         }
     }
@@ -797,7 +780,8 @@ __global__ void __launch_bounds__(FL *FR, 2) k_fluxes_coop(Dev d)
             const int base = cr.vpIdx * SL;
             const size_t row2 = (size_t)(cr.base2 + cat * cr.layers2) * pc, row3 = (size_t)r * pc;
             for (int k = 0; k < nt; k++) {
-                const size_t cl = (size_t)cell[k * FL + lane];
+                const int t = (tmap >> (3 * k)) & 7;
+                const size_t cl = (size_t)cellRaw[t * FL + lane];
                 double c2 = 0.0, gx2 = 0.0, gy2 = 0.0, c3 = 0.0, gx3 = 0.0, gy3 = 0.0;
                 if (cr.depth >= 2) { c2 = d.center[row2 + cl]; gx2 = d.xGrad[row2 + cl]; gy2 = d.yGrad[row2 + cl]; }
                 if (cr.depth >= 3) { c3 = d.center[row3 + cl]; gx3 = d.xGrad[row3 + cl]; gy3 = d.yGrad[row3 + cl]; }
@@ -814,13 +798,11 @@ __global__ void __launch_bounds__(FL *FR, 2) k_fluxes_coop(Dev d)
                     const double w = (NQ == 3) ? (1.0 / 3.0) : (q < 3 ? W1QP : W2QP);
                     tracerIntegral = tracerIntegral + w * value;
                 }
-                flux = flux + area[k * FL + lane] * tracerIntegral;
+                flux = flux + areaRaw[t * FL + lane] * tracerIntegral;
             }
         }
         if (inRange) d.edgeFlux[(size_t)r * pe + e] = flux;
     }
-    __syncthreads();
-    if (lane == 0 && ty == 0 && negative) atomicOr(d.flags, FLAG_NEG_QP);
 }
 
 // compute_mass_tracer_products (:6982), update_mass_and_tracers (:7125), zap_small_mass (:8764; one-layer mass field)

@@ -68,6 +68,7 @@ struct EmuFiber {
     ucontext_t ctx;
     char *stack = nullptr;
     bool done = true;
+    long orCount = 0;      /* number of __syncthreads_or() this fiber has passed in the current block */
 };
 static std::vector<EmuFiber> emu_fibers;
 static ucontext_t emu_sched_ctx;
@@ -85,6 +86,20 @@ static inline void emu_syncthreads()
     swapcontext(&emu_fibers[emu_current].ctx, &emu_sched_ctx);
 }
 #define __syncthreads() emu_syncthreads()
+/* __syncthreads_or: two accumulators used alternately; the first fiber to arrive for a generation clears its slot */
+static int emu_or_acc[2] = {0, 0};
+static long emu_or_gen[2] = {-1, -1};
+static inline int emu_syncthreads_or(int pred)
+{
+    EmuFiber &f = emu_fibers[emu_current];
+    const long gen = f.orCount++;
+    const int slot = (int)(gen & 1);
+    if (emu_or_gen[slot] != gen) { emu_or_gen[slot] = gen; emu_or_acc[slot] = 0; }
+    if (pred) emu_or_acc[slot] = 1;
+    emu_syncthreads();
+    return emu_or_acc[slot];
+}
+#define __syncthreads_or(p) emu_syncthreads_or(p)
 
 template <typename F>
 static void emu_launch_sync(dim3 grid, dim3 block, F body)
@@ -110,7 +125,9 @@ static void emu_launch_sync(dim3 grid, dim3 block, F body)
             f.ctx.uc_link = &emu_sched_ctx;
             makecontext(&f.ctx, emu_trampoline, 0);
             f.done = false;
+            f.orCount = 0;
         }
+        emu_or_gen[0] = emu_or_gen[1] = -1;
         unsigned long long alive = nt;
         while (alive > 0) {
             for (unsigned long long it = 0; it < nt; it++) {
