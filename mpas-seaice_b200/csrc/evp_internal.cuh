@@ -212,9 +212,9 @@ __device__ __forceinline__ int evp_ld_acquire_sys(const int *p)
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void evp_st_release_sys(int *p, int v)
+__device__ __forceinline__ void evp_st_relaxed_sys(int *p, int v)      // ordered by a preceding __threadfence_system()
 {
-    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long evp_globaltimer()
 {

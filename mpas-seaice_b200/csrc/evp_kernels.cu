@@ -560,10 +560,12 @@ __device__ __forceinline__ void evp_vertex_body(const VertexArgs &a)
             const unsigned last = a.pv.nPushBlocks > 0 ? (unsigned)a.pv.nPushBlocks - 1u : 0u;
             const unsigned ticket = atomicAdd(a.pv.done, 1u);
             if (ticket == last) {
+                // ONE system-scope fence (cumulative over the tickets observed, i.e. over every pushing block's
+                // stores), then the flags as plain system-scope stores: a release store per neighbour would repeat it
                 __threadfence_system();
                 *(volatile unsigned *)a.pv.done = 0;
                 const int c1 = *(volatile int *)a.pv.ctr + 1;
-                for (int k = 0; k < a.pv.nNb; k++) evp_st_release_sys(a.pv.peerFlag[k], c1);
+                for (int k = 0; k < a.pv.nNb; k++) evp_st_relaxed_sys(a.pv.peerFlag[k], c1);
                 *(volatile int *)a.pv.ctr = c1;
             }
         }
