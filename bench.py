@@ -454,7 +454,29 @@ def main():
             dt = time.perf_counter() - t0
             cpu = {"value": sub * reps / dt, "unit": "subcycles/s", "cores": cores, "kind": "port",
                    "sample": f"{reps} x {sub} subcycles of the same {name} mesh and state (oracle, OpenMP over "
-                             f"cells/vertices as in the reference)"}
+                             f"cells/vertices as in the reference)",
+                   "build": "C2 of BASELINE.md section 3: gcc -O2 -ffp-contract=off, all host cores"}
+            # BASELINE.md section 3 variants, reported next to it: C1 = one thread ("single CPU rank"), and the
+            # -O3 -march=native build (compiled on this machine, contraction at the compiler's default)
+            variants = {}
+            try:
+                oracle.set_num_threads(1)
+                t0 = time.perf_counter()
+                oracle.subcycle_velocity_solver(mesh, var, cstep, opts, 1)
+                variants["C1_single_thread"] = {"value": 1.0 / (time.perf_counter() - t0), "unit": "subcycles/s", "cores": 1,
+                                                "sample": "1 subcycle", "build": "gcc -O2 -ffp-contract=off"}
+                oracle.set_num_threads(cores)
+                fast = oracle.load_variant("o3native")
+                oracle.subcycle_velocity_solver(mesh, var, cstep, opts, 1, library=fast)
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    oracle.subcycle_velocity_solver(mesh, var, cstep, opts, sub, library=fast)
+                variants["C2_O3_native"] = {"value": sub * reps / (time.perf_counter() - t0), "unit": "subcycles/s",
+                                            "cores": cores, "sample": f"{reps} x {sub} subcycles",
+                                            "build": "gcc -O3 -march=native (FMA contraction allowed: timing only)"}
+            except Exception as e:  # noqa: BLE001
+                variants["error"] = str(e)
+            cpu["variants"] = variants
             del var
         except Exception as e:  # the oracle is optional test infrastructure
             cpu = {"value": None, "unit": "subcycles/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}

@@ -32,6 +32,28 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
+def build_variant(name: str = "o3native") -> str:
+    """A second build of the same sources for TIMING only ("a second -O3 -march=native build
+    is reported separately and labelled as such"): gcc -O3 -march=native with the compiler's default contraction, i.e.
+    what a production CPU build would do.  Compiled where it runs (-march=native is only valid for the machine that
+    compiles it), into oracle/_build/; never used as the checker."""
+    import platform
+    import hashlib
+    if name != "o3native":
+        raise ValueError(name)
+    tag = hashlib.md5((platform.node() + platform.processor() + platform.machine()).encode()).hexdigest()[:8]
+    out = os.path.join(_HERE, "_build", f"liboracle_{name}_{tag}.so")
+    srcs = [os.path.join(_HERE, f) for f in ("evp_oracle.c", "evp_precompute_oracle.c", "ir_oracle.c")]
+    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.run(["gcc", "-O3", "-march=native", "-fPIC", "-fopenmp", "-shared", "-o", out, *srcs, "-lm"], check=True)
+    return out
+
+
+def load_variant(name: str = "o3native"):
+    return C.CDLL(build_variant(name))
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -173,7 +195,7 @@ _STEP = ("solveStress", "solveVelocity", "vertexBoundaryType", "vertexBoundarySo
          "oceanStressCoeff")
 
 
-def subcycle_velocity_solver(mesh, var, step, opts, n_subcycles):
+def subcycle_velocity_solver(mesh, var, step, opts, n_subcycles, library=None):
     """subcycle_velocity_solver (velocity_solver.F:2404-2464) on host arrays, IN PLACE on ``step``.
 
     mesh: meshgen.Mesh; var: dict from init_variational; step: dict of per-step fields (see
@@ -181,7 +203,7 @@ def subcycle_velocity_solver(mesh, var, step, opts, n_subcycles):
     'evp_revised' | 'linear' | 'none'), ocean_stress_type, use_ocean_stress, average_variational_strain,
     elasticTimeStep, dynamicsTimeStep, dampingTimescale, numericalInertiaCoefficient.
     """
-    L = lib()
+    L = library if library is not None else lib()      # `library`: a timing variant (load_variant), never the checker
     a = _SubcycleArgs()
     a.nCells, a.nVertices = mesh.nCells, mesh.nVertices
     a.nVerticesSolve = int(opts.get("nVerticesSolve", mesh.nVertices))
