@@ -287,6 +287,9 @@ def main():
         solver.run_subcycles(N_ELASTIC)
         got = solver.fetch(names=("uVelocity", "vVelocity", "stress11", "stress22", "stress12"))
         part = checksum.owned_checksum(mesh, got)
+        # the arrays of this fetch were page-locked (EVP_FLAG_PIN_HOST): unregister them BEFORE they are freed -- a
+        # stale registration under a recycled address makes a later copy fail or land in the old pages
+        solver.release_host_memory()
         del got
         if dist is not None:
             parts = [None] * world
@@ -445,6 +448,7 @@ def main():
             parity = {"config": name, "state": args.state, "subcycles": sub, "max_rel_err": max(errs.values()),
                       "per_field": errs, "bit_exact": exact, "compared": "device vs oracle/evp_oracle.c, solved "
                       "vertices and every stress point of the solved cells", "tolerance": 1e-10}
+            solver.release_host_memory()             # `got` was page-locked by the fetch: unregister before freeing
             del got
             solver.update_step(step)
             t0 = time.perf_counter()
@@ -503,4 +507,15 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException as exc:  # noqa: BLE001
+        if isinstance(exc, SystemExit) and exc.code in (0, None):
+            raise
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        sys.stdout.flush()
+        # no interpreter shutdown: the NCCL destructors of a rank that failed would wait for the collectives its
+        # peers are blocked in; exiting at once lets the launcher stop the other ranks
+        os._exit(1 if not isinstance(exc, SystemExit) else (exc.code if isinstance(exc.code, int) else 1))

@@ -238,8 +238,11 @@ int evp_basis_finalize(evp_handle *h)
 static bool host_is_pinned(evp_handle *h, const void *p, size_t bytes)
 {
     if (!h->pinHost || bytes < (1u << 20)) return false;
-    cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost) return true;
+    // both ends: a range that only overlaps an older (possibly stale) registration must not be treated as pinned
+    cudaPointerAttributes a0, a1;
+    if (cudaPointerGetAttributes(&a0, p) == cudaSuccess && a0.type == cudaMemoryTypeHost &&
+        cudaPointerGetAttributes(&a1, (const char *)p + bytes - 1) == cudaSuccess && a1.type == cudaMemoryTypeHost)
+        return true;
     cudaGetLastError();
     if (cudaHostRegister(const_cast<void *>(p), bytes, cudaHostRegisterDefault) == cudaSuccess) {
         h->pinned.push_back(const_cast<void *>(p));
@@ -254,8 +257,8 @@ int evp_h2d(evp_handle *h, void *dst, const void *src, size_t bytes)
 {
     if (bytes == 0) return EVP_OK;
     if (host_is_pinned(h, src, bytes)) {
-        EVP_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
-        return EVP_OK;
+        if (cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream) == cudaSuccess) return EVP_OK;
+        cudaGetLastError();      // e.g. a stale registration of freed memory under this address: take the bounce path
     }
     size_t off = 0;
     while (off < bytes) {
@@ -276,8 +279,8 @@ int evp_d2h(evp_handle *h, void *dst, const void *src, size_t bytes)
 {
     if (bytes == 0) return EVP_OK;
     if (host_is_pinned(h, dst, bytes)) {
-        EVP_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
-        return EVP_OK;
+        if (cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream) == cudaSuccess) return EVP_OK;
+        cudaGetLastError();      // e.g. a stale registration of freed memory under this address: take the bounce path
     }
     size_t off = 0, pendOff[2] = {0, 0}, pendN[2] = {0, 0};
     bool pend[2] = {false, false};

@@ -228,12 +228,14 @@ __device__ __forceinline__ void evp_halo_wait(const evp_halo_view &hv, int c)
 {
     for (int i = 0; i < hv.nNb; i++) {
         if (evp_ld_acquire_sys(hv.flagsIn + i) - c >= 0) continue;
+        if (*(volatile int *)hv.err) return;              // an earlier wait already gave up: do not queue 30 s waits
         const unsigned long long t0 = evp_globaltimer();
         while (evp_ld_acquire_sys(hv.flagsIn + i) - c < 0) {
             __nanosleep(100);
             if (evp_globaltimer() - t0 > 30000000000ull) {
                 *(volatile int *)hv.err = 1;
-                break;
+                __threadfence_system();
+                return;
             }
         }
     }
