@@ -471,15 +471,8 @@ extern "C" int evp_create(evp_handle **out, const evp_mesh_desc *m, const evp_op
         return EVP_ERR_ARGUMENT;
     }
     CUDA_FAIL(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    {   // the halo branch must not queue behind the thousands of blocks of the interior vertex pass
-        int prLow = 0, prHigh = 0;
-        CUDA_FAIL(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
-        CUDA_FAIL(cudaStreamCreateWithPriority(&h->commStream, cudaStreamNonBlocking, prHigh));
-    }
     CUDA_FAIL(cudaEventCreate(&h->ev0));
     CUDA_FAIL(cudaEventCreate(&h->ev1));
-    CUDA_FAIL(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
-    CUDA_FAIL(cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming));
     CUDA_FAIL(cudaEventCreateWithFlags(&h->pinEv[0], cudaEventDisableTiming));
     CUDA_FAIL(cudaEventCreateWithFlags(&h->pinEv[1], cudaEventDisableTiming));
     CUDA_FAIL(cudaMallocHost(&h->pinStage[0], kPinChunk));
@@ -909,10 +902,7 @@ extern "C" int evp_destroy(evp_handle *h)
     }
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
-    if (h->evFork) cudaEventDestroy(h->evFork);
-    if (h->evJoin) cudaEventDestroy(h->evJoin);
     if (h->stream) cudaStreamDestroy(h->stream);
-    if (h->commStream) cudaStreamDestroy(h->commStream);
     cudaGetLastError();
     delete h;
     return EVP_OK;

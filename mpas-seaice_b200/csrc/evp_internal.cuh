@@ -135,8 +135,8 @@ struct evp_handle {
     bool haveAgg = false, haveAggP = false;   // evp_aggregate ran (with the Hibler strength)
     bool haveBasis = false, haveStep = false, haveSB = false, useGraph = true, pinHost = false, timed = false;
     evp_dev d;
-    cudaStream_t stream = nullptr, commStream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evFork = nullptr, evJoin = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaGraphExec_t graphExec = nullptr;
     int graphN = -1;
     float lastMs = 0.f;
