@@ -1168,8 +1168,8 @@ static void fill_vertex_args(evp_handle *h, VertexArgs &a);
 
 // Can (and should) nSub subcycles of this handle run as ONE cooperative launch?  Default configuration only:
 // variational operators without vertex averaging, EVP / revised EVP, banded (Wachspress) gradients, one rank, no
-// special boundaries -- everything else keeps the two-kernel graph.  EVP_B200_PERSISTENT=0 switches it off,
-// =1 insists (an error if the mesh does not fit), default: used whenever every tile fits on the device at once.
+// special boundaries -- everything else keeps the two-kernel graph.  Used whenever every tile can have a resident
+// block of its own; EVP_B200_PERSISTENT=0 in the environment switches it off (the tests compare both paths).
 static bool persistent_configured(evp_handle *h)
 {
     const char *e = getenv("EVP_B200_PERSISTENT");
