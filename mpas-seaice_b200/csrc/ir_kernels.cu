@@ -16,8 +16,8 @@
 // 32 consecutive cells (or edges) of ONE row, the rows of the tracer hierarchy are spread over the thread rows of the
 // block and walked depth by depth with a barrier in between, and what all rows share -- the cell's geometry, the
 // departure triangles' quadrature points, the mass reconstruction at those points -- is staged or computed once per
-// block in shared memory.  (Round 1 ran one thread per (cell or edge, category) walking its 23 rows serially: 8.2 ms
-// per QU60 step, 80 % of it in the flux kernel at 27 % occupancy and 9 % L1 hit rate, profiles/ir_r02_*.)
+// block in shared memory.  (Round 1 ran one thread per (cell or edge, category) walking its 23 rows serially: 8.4 ms
+// per QU60 step, 78 % of it in the flux kernel at 27 % occupancy and 9 % L1 hit rate; now 2.85 ms, profiles/ir_r02_*.)
 //
 // All of it is gather-heavy FP64 streaming work bounded by HBM / L2 and, in the flux kernel, the FP64 pipe -- not tensor
 // work.  Built with --fmad=false and in the reference's operation order so that the results are bit-identical to
@@ -666,8 +666,8 @@ __global__ void __launch_bounds__(128) k_triangles(Dev d, double dt)
     }
 }
 
-// integrate_fluxes_over_triangles (:6667): one block = 32 edges (lane = edge) x FR thread rows,
-// one category per block (blockIdx.y).  The reference evaluates, for every row, at every quadrature point of every
+// integrate_fluxes_over_triangles (:6667): one block = 32 edges (lane = edge) x FR thread rows, looping over
+// the categories (the departure triangles and their quadrature points are the same for all of them).  The reference evaluates, for every row, at every quadrature point of every
 // departure triangle, the product down the row's chain of parents of the linear reconstructions,
 //     value = ((1 * v_0) * v_1) * ... * v_depth,   v_s = center_s + xGrad_s * x + yGrad_s * y  at the source cell.
 // All rows of a category share v_0 (the mass field), and the children of a depth-1 row share v_0 * v_1, so the
@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(128) k_triangles(Dev d, double dt)
 //        check, :6895) and v_0 * v_1 for its depth-1 rows -> shared memory;
 //   D    thread (lane, row): the row's flux through the edge -> edgeFlux[row][edge]  (one warp = 32 consecutive
 //        edges of one row: coalesced stores; shared memory is [..][lane]: conflict-free).
-// Two barriers per block; 12 thread rows, three blocks per SM (58 KB of shared memory each).
+// One barrier for A, two per category; 12 thread rows, three blocks per SM (58 KB of shared memory each).
 constexpr int FL = 32;   // edges per block
 constexpr int FR = 12;   // thread rows per block
 constexpr int FNS = NTRI * 6;   // (triangle, point) slots per edge
@@ -695,7 +695,7 @@ template <int NQ>
 __global__ void __launch_bounds__(FL *FR, 3) k_fluxes_coop(Dev d)
 {
     IR_DYN_SHARED(double, sm);
-    const int lane = threadIdx.x, ty = threadIdx.y, cat = blockIdx.y;
+    const int lane = threadIdx.x, ty = threadIdx.y;
     const size_t e = (size_t)blockIdx.x * FL + lane;
     const bool inRange = e < (size_t)d.nE;
     const size_t pe = d.nEp, pc = d.nCp;
@@ -726,8 +726,10 @@ __global__ void __launch_bounds__(FL *FR, 3) k_fluxes_coop(Dev d)
     // (most of an ocean mesh) write their zeros and leave
     if (!__syncthreads_or(mine)) {
         if (inRange)
-            for (int j = ty; j < d.nRowsPerCat; j += FR)
+            for (int it = ty; it < d.nK * d.nRowsPerCat; it += FR) {
+                const int cat = it / d.nRowsPerCat, j = it - cat * d.nRowsPerCat;
                 d.edgeFlux[(size_t)(d.catRows[j].baseRow + cat * d.catRows[j].layers) * pe + e] = 0.0;
+            }
         return;
     }
     // every thread compacts the non-empty triangles of its edge for itself (triangle order kept: it is the order the
@@ -747,61 +749,71 @@ __global__ void __launch_bounds__(FL *FR, 3) k_fluxes_coop(Dev d)
         // down the chain is a zero and the flux is the +0.0 written in phase D
         if (!ice) nt = 0;
     }
-    // ---- B + C: quadrature points, v_0 of the depth-0 rows and v_0 * v_1 of the depth-1 rows, one (triangle, point)
-    //      per thread ----
+    // the quadrature points: fetched once, used by every category
     for (int s0 = ty; s0 < NTRI * NQ; s0 += FR) {
         const int k = s0 / NQ, q = s0 - NQ * k;
         if (k < nt) {
             const int t = (tmap >> (3 * k)) & 7, so = (k * 6 + q) * FL + lane;
-            const double x = d.xq[(size_t)(t * 6 + q) * pe + e], y = d.yq[(size_t)(t * 6 + q) * pe + e];
-            xq[so] = x;
-            yq[so] = y;
-            const size_t cl = (size_t)cellRaw[t * FL + lane];
-            for (int j = 0; j < d.nD0; j++) {          // depth-0 rows come first in the table
-                const size_t a = (size_t)(d.catRows[j].baseRow + cat * d.catRows[j].layers) * pc + cl;
-                const double value = 1.0 * (d.center[a] + d.xGrad[a] * x + d.yGrad[a] * y);
-                if (value < 0.0) atomicOr(d.flags, FLAG_NEG_QP);        // an abort condition (:6895): rare
-                vp[j * SL + so] = value;
-            }
-            for (int j1 = 0; j1 < d.nD1; j1++) {       // depth-1 rows follow
-                const CatRow cr = d.catRows[d.nD0 + j1];
-                const size_t a = (size_t)(cr.baseRow + cat * cr.layers) * pc + cl;
-                vp[(d.nD0 + j1) * SL + so] = vp[d.catRows[cr.anc[0]].cls * SL + so] * (d.center[a] + d.xGrad[a] * x + d.yGrad[a] * y);
-            }
+            xq[so] = d.xq[(size_t)(t * 6 + q) * pe + e];
+            yq[so] = d.yq[(size_t)(t * 6 + q) * pe + e];
         }
     }
-    __syncthreads();
-    // ---- D: the fluxes, one (edge, row) per thread ----
-    for (int j = ty; j < d.nRowsPerCat; j += FR) {
-        const CatRow cr = d.catRows[j];
-        const int r = cr.baseRow + cat * cr.layers;
-        double flux = 0.0;
-        if (nt > 0) {
-            const int base = cr.vpIdx * SL;
-            const size_t row2 = (size_t)(cr.base2 + cat * cr.layers2) * pc, row3 = (size_t)r * pc;
-            for (int k = 0; k < nt; k++) {
-                const int t = (tmap >> (3 * k)) & 7;
+    // (each thread reads back below exactly the points it stored: no barrier needed before B + C)
+    for (int cat = 0; cat < d.nK; cat++) {
+        // ---- B + C: v_0 of the depth-0 rows and v_0 * v_1 of the depth-1 rows, one (triangle, point) per thread ----
+        for (int s0 = ty; s0 < NTRI * NQ; s0 += FR) {
+            const int k = s0 / NQ, q = s0 - NQ * k;
+            if (k < nt) {
+                const int t = (tmap >> (3 * k)) & 7, so = (k * 6 + q) * FL + lane;
+                const double x = xq[so], y = yq[so];
                 const size_t cl = (size_t)cellRaw[t * FL + lane];
-                double c2 = 0.0, gx2 = 0.0, gy2 = 0.0, c3 = 0.0, gx3 = 0.0, gy3 = 0.0;
-                if (cr.depth >= 2) { c2 = d.center[row2 + cl]; gx2 = d.xGrad[row2 + cl]; gy2 = d.yGrad[row2 + cl]; }
-                if (cr.depth >= 3) { c3 = d.center[row3 + cl]; gx3 = d.xGrad[row3 + cl]; gy3 = d.yGrad[row3 + cl]; }
-                double tracerIntegral = 0.0;
-#pragma unroll
-                for (int q = 0; q < NQ; q++) {
-                    const int so = (k * 6 + q) * FL + lane;
-                    double value = vp[base + so];
-                    if (cr.depth >= 2) {
-                        const double x = xq[so], y = yq[so];
-                        value = value * (c2 + gx2 * x + gy2 * y);
-                        if (cr.depth >= 3) value = value * (c3 + gx3 * x + gy3 * y);
-                    }
-                    const double w = (NQ == 3) ? (1.0 / 3.0) : (q < 3 ? W1QP : W2QP);
-                    tracerIntegral = tracerIntegral + w * value;
+                for (int j = 0; j < d.nD0; j++) {          // depth-0 rows come first in the table
+                    const size_t a = (size_t)(d.catRows[j].baseRow + cat * d.catRows[j].layers) * pc + cl;
+                    const double value = 1.0 * (d.center[a] + d.xGrad[a] * x + d.yGrad[a] * y);
+                    if (value < 0.0) atomicOr(d.flags, FLAG_NEG_QP);        // an abort condition (:6895): rare
+                    vp[j * SL + so] = value;
                 }
-                flux = flux + areaRaw[t * FL + lane] * tracerIntegral;
+                for (int j1 = 0; j1 < d.nD1; j1++) {       // depth-1 rows follow
+                    const CatRow cr = d.catRows[d.nD0 + j1];
+                    const size_t a = (size_t)(cr.baseRow + cat * cr.layers) * pc + cl;
+                    vp[(d.nD0 + j1) * SL + so] = vp[d.catRows[cr.anc[0]].cls * SL + so] * (d.center[a] + d.xGrad[a] * x + d.yGrad[a] * y);
+                }
             }
         }
-        if (inRange) d.edgeFlux[(size_t)r * pe + e] = flux;
+        __syncthreads();
+        // ---- D: the fluxes, one (edge, row) per thread ----
+        for (int j = ty; j < d.nRowsPerCat; j += FR) {
+            const CatRow cr = d.catRows[j];
+            const int r = cr.baseRow + cat * cr.layers;
+            double flux = 0.0;
+            if (nt > 0) {
+                const int base = cr.vpIdx * SL;
+                const size_t row2 = (size_t)(cr.base2 + cat * cr.layers2) * pc, row3 = (size_t)r * pc;
+                for (int k = 0; k < nt; k++) {
+                    const int t = (tmap >> (3 * k)) & 7;
+                    const size_t cl = (size_t)cellRaw[t * FL + lane];
+                    double c2 = 0.0, gx2 = 0.0, gy2 = 0.0, c3 = 0.0, gx3 = 0.0, gy3 = 0.0;
+                    if (cr.depth >= 2) { c2 = d.center[row2 + cl]; gx2 = d.xGrad[row2 + cl]; gy2 = d.yGrad[row2 + cl]; }
+                    if (cr.depth >= 3) { c3 = d.center[row3 + cl]; gx3 = d.xGrad[row3 + cl]; gy3 = d.yGrad[row3 + cl]; }
+                    double tracerIntegral = 0.0;
+#pragma unroll
+                    for (int q = 0; q < NQ; q++) {
+                        const int so = (k * 6 + q) * FL + lane;
+                        double value = vp[base + so];
+                        if (cr.depth >= 2) {
+                            const double x = xq[so], y = yq[so];
+                            value = value * (c2 + gx2 * x + gy2 * y);
+                            if (cr.depth >= 3) value = value * (c3 + gx3 * x + gy3 * y);
+                        }
+                        const double w = (NQ == 3) ? (1.0 / 3.0) : (q < 3 ? W1QP : W2QP);
+                        tracerIntegral = tracerIntegral + w * value;
+                    }
+                    flux = flux + areaRaw[t * FL + lane] * tracerIntegral;
+                }
+            }
+            if (inRange) d.edgeFlux[(size_t)r * pe + e] = flux;
+        }
+        __syncthreads();       // the next category overwrites the shared partial products
     }
 }
 
@@ -1634,8 +1646,8 @@ extern "C" int ir_run(ir_handle *h, int nTracers, const ir_tracer_desc *tr, cons
             IR_CUDA(cudaFuncSetAttribute(k_fluxes_coop<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             IR_CUDA(cudaFuncSetAttribute(k_fluxes_coop<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #endif
-            if (d.nQP == 3) IR_LAUNCH_SYNC((k_fluxes_coop<3>), dim3(grid_for((size_t)d.nE, FL), nK), dim3(FL, FR), smem, s, d);
-            else IR_LAUNCH_SYNC((k_fluxes_coop<6>), dim3(grid_for((size_t)d.nE, FL), nK), dim3(FL, FR), smem, s, d);
+            if (d.nQP == 3) IR_LAUNCH_SYNC((k_fluxes_coop<3>), grid_for((size_t)d.nE, FL), dim3(FL, FR), smem, s, d);
+            else IR_LAUNCH_SYNC((k_fluxes_coop<6>), grid_for((size_t)d.nE, FL), dim3(FL, FR), smem, s, d);
         }
         h->launches += 2;
     }
