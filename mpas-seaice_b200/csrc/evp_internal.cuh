@@ -205,6 +205,7 @@ int evp_halo_end_run(evp_handle *h, cudaStream_t s);
 int evp_halo_check(evp_handle *h);                 // EVP_ERR_NCCL after a timed-out wait
 void evp_halo_destroy(evp_handle *h);
 
+constexpr unsigned long long EVP_HALO_WAIT_NS = 300ull * 1000ull * 1000ull * 1000ull;
 #ifdef __CUDACC__
 __device__ __forceinline__ int evp_ld_acquire_sys(const int *p)
 {
@@ -223,16 +224,17 @@ __device__ __forceinline__ unsigned long long evp_globaltimer()
     return t;
 }
 // Block until every neighbour has published vertex pass c (flags only grow; the comparison survives wrap-around).
-// Bounded: after 30 s the mapped error flag is raised and the caller proceeds (the host reports it).
+// Bounded: after EVP_HALO_WAIT_NS (5 minutes: ranks of a real host may be skewed by I/O far longer than a bench's) the mapped
+// error flag is raised and the caller proceeds; the host reports it at the next evp_synchronize / evp_fetch.
 __device__ __forceinline__ void evp_halo_wait(const evp_halo_view &hv, int c)
 {
     for (int i = 0; i < hv.nNb; i++) {
         if (evp_ld_acquire_sys(hv.flagsIn + i) - c >= 0) continue;
-        if (*(volatile int *)hv.err) return;              // an earlier wait already gave up: do not queue 30 s waits
+        if (*(volatile int *)hv.err) return;              // an earlier wait already gave up: do not queue further long waits
         const unsigned long long t0 = evp_globaltimer();
         while (evp_ld_acquire_sys(hv.flagsIn + i) - c < 0) {
             __nanosleep(100);
-            if (evp_globaltimer() - t0 > 30000000000ull) {
+            if (evp_globaltimer() - t0 > EVP_HALO_WAIT_NS) {
                 *(volatile int *)hv.err = 1;
                 __threadfence_system();
                 return;
