@@ -17,8 +17,10 @@
 !>
 !>  The volume <-> thickness conversions around the block loop (:2462-2480, :2680-2700) are done by the
 !>  library (volumeLike = 1), so the two loops that call volume_to_thickness / thickness_to_volume are
-!>  skipped when the device path is on.  Halo updates before and after (:2410-2450, :2705-2712) and
-!>  the optional conservation / monotonicity checks stay as they are.
+!>  skipped when the device path is on.  Halo updates before and after (:2410-2450, :2705-2712) stay as
+!>  they are.  The optional checks: the library computes this block's conservation sums and
+!>  check_tracer_conservation (:8126) keeps adding the ranks and testing them; the monotonicity test
+!>  (:8416) runs in the library, so the call of check_tracer_monotonicity is skipped on the device path.
 !>
 !>  Not compiled in this repository (no Fortran compiler in the build image); tests/test_fortran_shim.py
 !>  checks the interface blocks against include/ir_b200.h.
@@ -70,6 +72,15 @@ module seaice_ir_b200
      type(c_ptr) :: array
   end type ir_tracer_desc
 
+  type, bind(C) :: ir_check_report
+     integer(c_int) :: conservationViolated
+     integer(c_int) :: consTracer, consCategory, consLayer
+     real(c_double) :: sumInit, sumFinal
+     integer(c_int) :: monotonicityViolated
+     integer(c_int) :: monoTracer, monoCategory, monoLayer, monoCell
+     real(c_double) :: newValue, bound, tolerance
+  end type ir_check_report
+
   interface
 
      function ir_create(handle, mesh, device) bind(C, name="ir_create") result(ierr)
@@ -98,6 +109,29 @@ module seaice_ir_b200
        integer(c_int) :: ierr
      end function ir_run
 
+     function ir_set_checks(handle, conservation, monotonicity) bind(C, name="ir_set_checks") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: handle
+       integer(c_int), value :: conservation, monotonicity
+       integer(c_int) :: ierr
+     end function ir_set_checks
+
+     function ir_fetch_check_report(handle, report) bind(C, name="ir_fetch_check_report") result(ierr)
+       import :: c_ptr, c_int, ir_check_report
+       type(c_ptr), value :: handle
+       type(ir_check_report), intent(out) :: report
+       integer(c_int) :: ierr
+     end function ir_fetch_check_report
+
+     function ir_fetch_conservation_sums(handle, tracer, sumInit, sumFinal) &
+          bind(C, name="ir_fetch_conservation_sums") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: handle
+       integer(c_int), value :: tracer
+       type(c_ptr), value :: sumInit, sumFinal
+       integer(c_int) :: ierr
+     end function ir_fetch_conservation_sums
+
      function ir_destroy(handle) bind(C, name="ir_destroy") result(ierr)
        import :: c_ptr, c_int
        type(c_ptr), value :: handle
@@ -112,6 +146,7 @@ module seaice_ir_b200
   end interface
 
   integer(c_int), parameter :: IR_OK = 0
+  integer(c_int), parameter :: IR_ERR_MONOTONICITY = 15
 
   ! one handle per block; MPAS-Seaice runs one block per rank on the device path (mesh_pool.F:98-105)
   type(c_ptr) :: irHandle = c_null_ptr
@@ -239,6 +274,8 @@ contains
     type(tracer_type), pointer :: thisTracer, otherTracer
     integer :: nTracers, iTracer, iParent
     integer(c_int) :: ierr
+    logical, pointer :: configConservationCheck, configMonotonicityCheck
+    integer(c_int) :: consMode, monoMode
 
     call MPAS_pool_get_subpool(block % structs, 'velocity_solver', velocityPool)
     call MPAS_pool_get_array(velocityPool, 'uVelocity', uVelocity)
@@ -292,8 +329,38 @@ contains
        nTracersTable = nTracers
     endif
 
+    ! config_conservation_check / config_monotonicity_check (:2574, :2590).  Conservation in mode 2: the
+    ! library computes this block's sums, check_tracer_conservation (:8126) keeps adding the ranks and testing.
+    ! Monotonicity is tested by the library (every bound it needs lies within the two halo layers).
+    call MPAS_pool_get_config(block % configs, 'config_conservation_check', configConservationCheck)
+    call MPAS_pool_get_config(block % configs, 'config_monotonicity_check', configMonotonicityCheck)
+    consMode = 0
+    monoMode = 0
+    if (configConservationCheck) consMode = 2
+    if (configMonotonicityCheck) monoMode = 1
+    ierr = ir_set_checks(irHandle, consMode, monoMode)
+    if (ierr /= IR_OK) call ir_b200_abort('ir_set_checks')
+
     ierr = ir_run(irHandle, int(nTracers, c_int), tracerTable, c_loc(uVelocity), c_loc(vVelocity), real(dt, c_double))
     if (ierr /= IR_OK) call ir_b200_abort('ir_run')
+
+    ! the sums go where check_tracer_conservation reads them (incremental_remap_tracers.F:54-57)
+    if (configConservationCheck) then
+       iTracer = 0
+       thisTracer => tracersHead
+       do while (associated(thisTracer))
+          if (thisTracer % ndims == 2) then
+             ierr = ir_fetch_conservation_sums(irHandle, int(iTracer, c_int), &
+                  c_loc(thisTracer % globalSumInit2D), c_loc(thisTracer % globalSumFinal2D))
+          else
+             ierr = ir_fetch_conservation_sums(irHandle, int(iTracer, c_int), &
+                  c_loc(thisTracer % globalSumInit3D), c_loc(thisTracer % globalSumFinal3D))
+          endif
+          if (ierr /= IR_OK) call ir_b200_abort('ir_fetch_conservation_sums')
+          iTracer = iTracer + 1
+          thisTracer => thisTracer % next
+       enddo
+    endif
 
   end subroutine seaice_ir_b200_step
 

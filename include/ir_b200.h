@@ -8,9 +8,9 @@
  * model: it fills the `incremental_remap` pool (Registry.xml var_struct incremental_remap) once, and those pool arrays
  * are what ir_create receives -- the same contract evp_b200.h has with the velocity solver's pools.
  *
- * STATUS (round 1): bit-identical to oracle/ir_oracle.c under host emulation (tests/test_ir_parity.py) and in a first
- * run on a B200 (tools/ir_quick_gpu.py, profiles/ir_r01_first_device_run.json); not yet profiled.  Single block: the
- * tracer halo update after the call (seaice_update_tracer_halo, :2710) is still the host's.
+ * STATUS: bit-identical to oracle/ir_oracle.c on a B200 and under host emulation (tests/test_ir_parity.py); timings
+ * and ncu summaries under profiles/ir_r02_*.  One block per handle: the tracer halo update after the call
+ * (seaice_update_tracer_halo, :2710) is the host's.
  *
  * Conventions as in evp_b200.h: host pointers, Fortran (column-major) layout passed with c_loc(), 1-based index
  * values, arrays dimensioned nCells / nEdges / nVertices carry MPAS's extra slot n+1.  Every entry point returns
@@ -35,7 +35,10 @@ enum {
     IR_ERR_NEGATIVE_MASS_QP = 10,   /* negative mass at a quadrature point   incremental_remap.F:6895-6935 */
     IR_ERR_NEGATIVE_MASS = 11,      /* new mass below -puny**2               incremental_remap.F:7465-7480 */
     IR_ERR_PARALLEL_EDGES = 12,     /* degenerate basis in shift_vertices    incremental_remap.F:6415-6425 */
-    IR_ERR_TOO_MANY_TRIANGLES = 13  /* more than nTriPerEdgeRemap departure triangles on an edge */
+    IR_ERR_TOO_MANY_TRIANGLES = 13, /* more than nTriPerEdgeRemap departure triangles on an edge */
+    /* the optional checks (ir_set_checks), reported like the abort conditions above */
+    IR_ERR_CONSERVATION = 14,       /* check_tracer_conservation             incremental_remap.F:8126-8260 */
+    IR_ERR_MONOTONICITY = 15        /* check_tracer_monotonicity             incremental_remap.F:8416-8760 */
 };
 
 /* Dimensions fixed by Registry.xml:59-78. */
@@ -125,6 +128,35 @@ int ir_set_tracers(ir_handle *h, int nTracers, const ir_tracer_desc *tracers);
  * hold whatever the step produced, as after the reference's abort write. */
 int ir_run(ir_handle *h, int nTracers, const ir_tracer_desc *tracers, const double *uVelocity, const double *vVelocity,
            double dt);
+
+/* config_conservation_check / config_monotonicity_check (Registry.xml, both default .false.; incremental_remap.F
+ * :2574-2600, :2999-3015, :3259-3310).  Switched on, ir_run also computes
+ *   conservation  the area-weighted sums of every mass * tracer product over the owned cells before and after the update
+ *                 (sum_tracers :7998).  1: ir_run tests them itself (check_tracer_conservation :8126: a relative change
+ *                 above 1e-11 returns IR_ERR_CONSERVATION) -- for a block that holds the whole mesh; 2: sums only, for
+ *                 decomposed runs, where the host adds the ranks' sums first (mpas_dmpar_sum_real, :8150) and tests them;
+ *   monotonicity  for every tracer with a parent, the range of the old values over a cell and its edge neighbours
+ *                 (tracer_local_min_max :8268), widened by one more ring, against the new value
+ *                 (check_tracer_monotonicity :8416): outside by more than 1e-11 * max(1, |bound|) returns
+ *                 IR_ERR_MONOTONICITY.  Needs the two halo layers the scheme itself requires (:829).
+ * The transported fields are the same with and without the checks.  0 / 0 switches them off again. */
+int ir_set_checks(ir_handle *h, int conservation, int monotonicity);
+
+/* What the checks of the last ir_run found.  Indices as the reference logs them: tracer = position in the tracer table
+ * (0-based), category / layer / cell 1-based (cell = local index).  The first violation in the reference's loop order. */
+typedef struct ir_check_report {
+    int conservationViolated;      /* 0 / 1 */
+    int consTracer, consCategory, consLayer;
+    double sumInit, sumFinal;      /* of that (tracer, category, layer) */
+    int monotonicityViolated;      /* 0 none, 1 below the old minimum, 2 above the old maximum */
+    int monoTracer, monoCategory, monoLayer, monoCell;
+    double newValue, bound, tolerance;
+} ir_check_report;
+int ir_fetch_check_report(ir_handle *h, ir_check_report *out);
+
+/* The sums of one tracer, (nLayers, nCategories) each in Fortran order: globalSumInit / globalSumFinal before the ranks
+ * are added (incremental_remap_tracers.F:54-57). */
+int ir_fetch_conservation_sums(ir_handle *h, int tracer, double *sumInit, double *sumFinal);
 
 /* Diagnostics of the last step (any pointer may be NULL):
  * xTriangle / yTriangle (nQuadPoints, 6, nEdges) quadrature points, triangleArea (6, nEdges), iCellTriangle (6, nEdges),

@@ -133,6 +133,13 @@ struct Dev {
     int *flags;
     double *stage;      // raw host-layout staging
     size_t stageBytes;
+    // optional checks (ir_set_checks): allocated when first used
+    double *lmin, *lmax;            // [nRows][nCp]: tracer_local_min_max of the old values
+    double *sums;                   // [2][nRows]: sum_tracers before / after the update
+    int *rowT, *rowKL;              // row -> tracer index, category * maxLayers + layer (the reference's loop order)
+    unsigned long long *monoKey;    // smallest (tracer, cell, category, layer) key among the violations
+    double *monoDetail;             // [3]: new value, lower bound, upper bound of one (row, cell)
+    int maxLayers;
 };
 
 }  // namespace
@@ -153,6 +160,9 @@ struct ir_handle {
     float lastMs;
     long long launches;
     bool haveTracers;
+    int checkConservation, checkMonotonicity;   // ir_set_checks
+    ir_check_report report;                     // of the last ir_run
+    std::vector<double> sumsHost;               // [2][nRows] of the last ir_run
 };
 
 namespace {
@@ -908,6 +918,144 @@ __global__ void __launch_bounds__(CL *UW, 4) k_update_coop(Dev d, int massOneLay
     }
 }
 
+// ------------------------------------------------------------------------------------- optional checks (default off)
+// config_conservation_check / config_monotonicity_check (incremental_remap.F:2574-2600, :2999-3015, :3259-3310).  With
+// a check switched on, ir_run launches the kernels below around the update and runs zap / thickness -> volume as
+// kernels of their own (the fused tail of k_update_coop is skipped), because the reference sums the new products before
+// zap_small_mass and tests monotonicity after it but before the volumes are restored.  None of this is on the default path.
+
+// tracer_local_min_max (:8268) on the old values, masks of make_masks(threshold 0) (:3001): one thread per (cell, row).
+// Evaluated for every cell of the block; the reference computes the owned cells and fills the halo by an exchange.
+__global__ void __launch_bounds__(128) k_check_minmax(Dev d)
+{
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (c >= (size_t)d.nC) return;
+    const RowInfo ri = d.rows[r];
+    const double *val = d.val + (size_t)r * d.nCp;
+    const double *par = ri.depth > 0 ? d.val + (size_t)ri.chain[ri.depth - 1] * d.nCp : nullptr;
+    double lo = 0.0, hi = 0.0;
+    if (par == nullptr || par[c] > 0.0) { lo = val[c]; hi = val[c]; }
+    const int n = d.nEdgesOnCell[c];
+    for (int k = 0; k < n; k++) {
+        const int nb = d.cellsOnCell[(size_t)k * d.nCp + c];
+        if (nb >= 1 && nb <= d.nC) {
+            const size_t cn = (size_t)nb - 1;
+            if (par == nullptr || par[cn] > 0.0) {
+                if (val[cn] < lo) lo = val[cn];
+                if (val[cn] > hi) hi = val[cn];
+            }
+        }
+    }
+    d.lmin[(size_t)r * d.nCp + c] = lo;
+    d.lmax[(size_t)r * d.nCp + c] = hi;
+}
+
+// sum_tracers (:7998): area-weighted sum of mass * tracer products over the owned cells, one block per row.  The
+// reference adds cell after cell (and then over the ranks); here every thread adds its cells in increasing order and the
+// 256 partial sums are combined in a fixed tree, so the result is reproducible but not the serial sum's last bits.
+__global__ void __launch_bounds__(256) k_check_sums(Dev d, const double *__restrict__ src, double *__restrict__ out)
+{
+    __shared__ double part[256];
+    const int r = blockIdx.x, tid = threadIdx.x;
+    const RowInfo ri = d.rows[r];
+    double s = 0.0;
+    for (size_t c = tid; c < (size_t)d.nCS; c += 256) {
+        double mtp = 1.0;
+        for (int z = 0; z <= ri.depth; z++) mtp = mtp * src[(size_t)ri.chain[z] * d.nCp + c];
+        s = s + d.areaCell[c] * mtp;
+    }
+    part[tid] = s;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (tid < w) part[tid] = part[tid] + part[tid + w];
+        __syncthreads();
+    }
+    if (tid == 0) out[r] = part[0];
+}
+
+// zap_small_mass (:8764) as a kernel of its own: one thread per owned cell (one-layer mass field: row = category)
+__global__ void __launch_bounds__(128) k_zap(Dev d)
+{
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= (size_t)d.nCS) return;
+    for (int cat = 0; cat < d.nK; cat++) {
+        const double mass = d.valNew[(size_t)cat * d.nCp + c];
+        if (mass > 0.0 && mass < 1.0e-22)
+            for (int j = 0; j < d.nRowsPerCat; j++) d.valNew[(size_t)(d.catRows[j].baseRow + cat * d.catRows[j].layers) * d.nCp + c] = 0.0;
+    }
+}
+
+// thickness -> volume (:9295) as a kernel of its own: every column including the extra one
+__global__ void __launch_bounds__(128) k_thickness_to_volume(Dev d)
+{
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > (size_t)d.nC) return;
+    for (int r = 0; r < d.nRows; r++) {
+        if (!d.rows[r].volumeLike) continue;
+        double *v = &d.valNew[(size_t)r * d.nCp + c];
+        *v = d.valNew[(size_t)d.rows[r].cat * d.nCp + c] * *v;
+    }
+}
+
+// check_tracer_monotonicity (:8416), extendedMinMax = .true.: the bounds of (row, cell) widened by those of its edge
+// neighbours, masks of make_masks(threshold eps11) on the OLD values.  The neighbours are read in their un-extended state
+// (the reference widens in place cell after cell, so there a cell may also see what a lower-numbered neighbour has already
+// gathered: bounds that depend on the numbering and are never tighter than these).
+__device__ bool mono_bounds(const Dev &d, int r, size_t c, double &lo, double &hi)
+{
+    const RowInfo ri = d.rows[r];
+    if (!row_mask(d, ri, c)) return false;
+    lo = d.lmin[(size_t)r * d.nCp + c];
+    hi = d.lmax[(size_t)r * d.nCp + c];
+    const int n = d.nEdgesOnCell[c];
+    for (int k = 0; k < n; k++) {
+        const int nb = d.cellsOnCell[(size_t)k * d.nCp + c];
+        if (nb >= 1 && nb <= d.nC && row_mask(d, ri, (size_t)nb - 1)) {
+            const double nlo = d.lmin[(size_t)r * d.nCp + nb - 1], nhi = d.lmax[(size_t)r * d.nCp + nb - 1];
+            if (nlo < lo) lo = nlo;
+            if (nhi > hi) hi = nhi;
+        }
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(128) k_check_mono(Dev d)
+{
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (c >= (size_t)d.nCS || d.rows[r].depth == 0) return;   // monotonicity holds for tracers, not for the mass-like field
+    double lo, hi;
+    if (!mono_bounds(d, r, c, lo, hi)) return;
+    const double v = d.valNew[(size_t)r * d.nCp + c];
+    const double toleranceMin = EPS11 * fmax(1.0, fabs(lo)), toleranceMax = EPS11 * fmax(1.0, fabs(hi));
+    if (v < lo - toleranceMin || v > hi + toleranceMax) {
+        const unsigned long long key = ((unsigned long long)d.rowT[r] * ((unsigned long long)d.nC + 1) + c) *
+                                           (unsigned long long)(d.nK * d.maxLayers) + (unsigned long long)d.rowKL[r];
+        atomicMin(d.monoKey, key);
+    }
+}
+
+// the numbers of the first violation, taken before thickness -> volume rewrites the volume-like rows (one thread)
+__global__ void k_check_mono_detail(Dev d)
+{
+    const unsigned long long key = *d.monoKey;
+    if (key == ~0ull) return;
+    const unsigned long long KL = (unsigned long long)(d.nK * d.maxLayers);
+    const int kl = (int)(key % KL);
+    const unsigned long long tc = key / KL;
+    const size_t c = (size_t)(tc % ((unsigned long long)d.nC + 1));
+    const int t = (int)(tc / ((unsigned long long)d.nC + 1));
+    for (int r = 0; r < d.nRows; r++) {
+        if (d.rowT[r] != t || d.rowKL[r] != kl) continue;
+        double lo = 0.0, hi = 0.0;
+        mono_bounds(d, r, c, lo, hi);
+        d.monoDetail[0] = d.valNew[(size_t)r * d.nCp + c];
+        d.monoDetail[1] = lo;
+        d.monoDetail[2] = hi;
+    }
+}
+
 // rows 1 and 2 of transGlobalToCell (3,3,nCells): trans(i,j,c) at c*9 + j*3 + i
 __global__ void k_trans_in(const double *__restrict__ raw, double *__restrict__ dst, size_t n, size_t pitch)
 {
@@ -1253,6 +1401,48 @@ void unpin_all(ir_handle *h)
     h->pinned.clear();
 }
 
+void free_check_buffers(ir_handle *h)
+{
+    Dev &d = h->d;
+    void *bufs[] = {d.lmin, d.lmax, d.sums, d.rowT, d.rowKL, d.monoKey, d.monoDetail};
+    for (void *b : bufs)
+        if (b) cudaFree(b);
+    d.lmin = d.lmax = d.sums = d.monoDetail = nullptr;
+    d.rowT = d.rowKL = nullptr;
+    d.monoKey = nullptr;
+}
+
+// buffers of the optional checks, allocated by the first ir_run that needs them (freed when the tracer set changes)
+int ensure_check_buffers(ir_handle *h)
+{
+    Dev &d = h->d;
+    const size_t nRows = (size_t)d.nRows;
+    if (h->checkConservation && !d.sums) IR_CUDA(cudaMalloc((void **)&d.sums, sizeof(double) * 2 * nRows));
+    if (h->checkMonotonicity && !d.lmin) {
+        IR_CUDA(cudaMalloc((void **)&d.lmin, sizeof(double) * nRows * d.nCp));
+        IR_CUDA(cudaMalloc((void **)&d.lmax, sizeof(double) * nRows * d.nCp));
+        IR_CUDA(cudaMalloc((void **)&d.rowT, sizeof(int) * nRows));
+        IR_CUDA(cudaMalloc((void **)&d.rowKL, sizeof(int) * nRows));
+        IR_CUDA(cudaMalloc((void **)&d.monoKey, sizeof(unsigned long long)));
+        IR_CUDA(cudaMalloc((void **)&d.monoDetail, sizeof(double) * 3));
+        int maxLayers = 1;
+        for (int nl : h->tracerLayers) maxLayers = nl > maxLayers ? nl : maxLayers;
+        d.maxLayers = maxLayers;
+        std::vector<int> rowT(nRows), rowKL(nRows);
+        for (size_t t = 0; t < h->tracerRow0.size(); t++)
+            for (int k = 0; k < d.nK; k++)
+                for (int l = 0; l < h->tracerLayers[t]; l++) {
+                    const size_t r = (size_t)h->tracerRow0[t] + (size_t)k * h->tracerLayers[t] + l;
+                    rowT[r] = (int)t;
+                    rowKL[r] = k * maxLayers + l;
+                }
+        IR_CUDA(cudaMemcpyAsync(d.rowT, rowT.data(), sizeof(int) * nRows, cudaMemcpyHostToDevice, h->stream));
+        IR_CUDA(cudaMemcpyAsync(d.rowKL, rowKL.data(), sizeof(int) * nRows, cudaMemcpyHostToDevice, h->stream));
+        IR_CUDA(cudaStreamSynchronize(h->stream));     // the vectors go out of scope
+    }
+    return IR_OK;
+}
+
 }  // namespace
 
 // =============================================================================================================== ABI
@@ -1536,10 +1726,12 @@ extern "C" int ir_set_tracers(ir_handle *h, int nTracers, const ir_tracer_desc *
     h->nSlots = nSlots;
     // (re)allocate the tracer state; a failure from here on leaves the handle without tracers
     h->haveTracers = false;
+    h->sumsHost.clear();
     IR_CUDA(cudaStreamSynchronize(h->stream));
     double **bufs[] = {&d.val, &d.valNew, &d.center, &d.xGrad, &d.yGrad, &d.xBary, &d.yBary, &d.mtpNew, &d.edgeFlux};
     for (double **b : bufs)
         if (*b) { cudaFree(*b); *b = nullptr; }
+    free_check_buffers(h);
     if (d.rows) { cudaFree(d.rows); d.rows = nullptr; }
     if (d.catBaseRow) { cudaFree(d.catBaseRow); d.catBaseRow = nullptr; }
     if (d.catLayers) { cudaFree(d.catLayers); d.catLayers = nullptr; }
@@ -1627,11 +1819,26 @@ extern "C" int ir_run(ir_handle *h, int nTracers, const ir_tracer_desc *tr, cons
     IR_CUDA(cudaMemcpyAsync(d.u, u, ((size_t)d.nV + 1) * 8, cudaMemcpyHostToDevice, s));
     IR_CUDA(cudaMemcpyAsync(d.v, v, ((size_t)d.nV + 1) * 8, cudaMemcpyHostToDevice, s));
     IR_CUDA(cudaMemsetAsync(d.flags, 0, sizeof(int), s));
+    const bool checks = h->checkConservation != 0 || h->checkMonotonicity != 0;
+    memset(&h->report, 0, sizeof h->report);
+    if (checks) {
+        int rc = ensure_check_buffers(h);
+        if (rc) return rc;
+        if (h->checkMonotonicity) IR_CUDA(cudaMemsetAsync(d.monoKey, 0xff, sizeof(unsigned long long), s));
+    }
     IR_CUDA(cudaEventRecord(h->ev0, s));
     const int massRows = nK * h->tracerLayers[0];
     const unsigned gc = grid_for(nC1, 128), ge = grid_for((size_t)d.nE, 128);
     IR_LAUNCH((k_prepare), gc, 128, s, d, 0, massRows);
     h->launches++;
+    if (h->checkMonotonicity && d.nC > 0) {
+        IR_LAUNCH((k_check_minmax), dim3(grid_for((size_t)d.nC, 128), (unsigned)d.nRows), 128, s, d);
+        h->launches++;
+    }
+    if (h->checkConservation) {
+        IR_LAUNCH_SYNC((k_check_sums), (unsigned)d.nRows, 256, 0, s, d, (const double *)d.val, d.sums);
+        h->launches++;
+    }
     if (d.nC > 0) {
         int maxDepth = 0;
         for (int dq : h->tracerDepth) maxDepth = dq > maxDepth ? dq : maxDepth;
@@ -1654,9 +1861,30 @@ extern "C" int ir_run(ir_handle *h, int nTracers, const ir_tracer_desc *tr, cons
     {
         int maxDepth = 0;
         for (int dq : h->tracerDepth) maxDepth = dq > maxDepth ? dq : maxDepth;
-        IR_LAUNCH_SYNC((k_update_coop), grid_for(nC1, CL), dim3(CL, UW), 0, s, d, h->tracerLayers[0] == 1 ? 1 : 0, maxDepth);
+        const int massOneLayer = h->tracerLayers[0] == 1 ? 1 : 0;
+        // with a check on, zap / thickness -> volume run as kernels of their own around the checks
+        IR_LAUNCH_SYNC((k_update_coop), grid_for(nC1, CL), dim3(CL, UW), 0, s, d, checks ? 0 : massOneLayer, maxDepth);
+        h->launches++;
+        if (checks) {
+            if (h->checkConservation) {
+                IR_LAUNCH_SYNC((k_check_sums), (unsigned)d.nRows, 256, 0, s, d, (const double *)d.valNew, d.sums + d.nRows);
+                h->launches++;
+            }
+            if (massOneLayer && d.nCS > 0) {
+                IR_LAUNCH((k_zap), grid_for((size_t)d.nCS, 128), 128, s, d);
+                h->launches++;
+            }
+            if (h->checkMonotonicity && d.nCS > 0) {
+                IR_LAUNCH((k_check_mono), dim3(grid_for((size_t)d.nCS, 128), (unsigned)d.nRows), 128, s, d);
+                IR_LAUNCH((k_check_mono_detail), 1, 1, s, d);
+                h->launches += 2;
+            }
+            if (massOneLayer) {
+                IR_LAUNCH((k_thickness_to_volume), gc, 128, s, d);
+                h->launches++;
+            }
+        }
     }
-    h->launches++;
     IR_CUDA(cudaEventRecord(h->ev1, s));
     IR_CUDA(cudaGetLastError());
     // out
@@ -1675,6 +1903,86 @@ extern "C" int ir_run(ir_handle *h, int nTracers, const ir_tracer_desc *tr, cons
     if (flags & FLAG_NEG_QP) { set_error("IR: negative mass at a quadrature point (incremental_remap.F:6895)"); return IR_ERR_NEGATIVE_MASS_QP; }
     if (flags & FLAG_PARALLEL) { set_error("IR: parallel basis edges in shift_vertices (incremental_remap.F:6415)"); return IR_ERR_PARALLEL_EDGES; }
     if (flags & FLAG_MANY_TRI) { set_error("IR: more than nTriPerEdgeRemap departure triangles on an edge"); return IR_ERR_TOO_MANY_TRIANGLES; }
+    if (h->checkConservation) {
+        // check_tracer_conservation (:8126): the reference's loop order (tracer, category, layer), first violation
+        h->sumsHost.assign(2 * (size_t)d.nRows, 0.0);
+        IR_CUDA(cudaMemcpyAsync(h->sumsHost.data(), d.sums, sizeof(double) * 2 * d.nRows, cudaMemcpyDeviceToHost, s));
+        IR_CUDA(cudaStreamSynchronize(s));
+        for (int t = 0; h->checkConservation == 1 && t < nTracers && !h->report.conservationViolated; t++)
+            for (int k = 0; k < nK && !h->report.conservationViolated; k++)
+                for (int l = 0; l < tr[t].nLayers; l++) {
+                    const size_t r = (size_t)h->tracerRow0[t] + (size_t)k * tr[t].nLayers + l;
+                    const double si = h->sumsHost[r], sf = h->sumsHost[d.nRows + r];
+                    if (fabs(si) > EPS11) {
+                        const double difference = sf - si;
+                        const double ratio = difference / si;
+                        if (fabs(ratio) > EPS11) {
+                            h->report.conservationViolated = 1;
+                            h->report.consTracer = t; h->report.consCategory = k + 1; h->report.consLayer = l + 1;
+                            h->report.sumInit = si; h->report.sumFinal = sf;
+                            break;
+                        }
+                    }
+                }
+        if (h->report.conservationViolated) {
+            set_error("IR: tracer conservation error (incremental_remap.F:8170): tracer %d, category %d, layer %d: %.17g -> %.17g",
+                      h->report.consTracer, h->report.consCategory, h->report.consLayer, h->report.sumInit, h->report.sumFinal);
+            return IR_ERR_CONSERVATION;       // the reference aborts before the monotonicity check (:2577-2581)
+        }
+    }
+    if (h->checkMonotonicity) {
+        unsigned long long key = ~0ull;
+        IR_CUDA(cudaMemcpyAsync(&key, d.monoKey, sizeof key, cudaMemcpyDeviceToHost, s));
+        IR_CUDA(cudaStreamSynchronize(s));
+        if (key != ~0ull) {
+            const unsigned long long KL = (unsigned long long)nK * d.maxLayers;
+            const int kl = (int)(key % KL);
+            const unsigned long long tc = key / KL;
+            const size_t c = (size_t)(tc % ((unsigned long long)d.nC + 1));
+            const int t = (int)(tc / ((unsigned long long)d.nC + 1)), k = kl / d.maxLayers, l = kl % d.maxLayers;
+            double det[3] = {0.0, 0.0, 0.0};
+            IR_CUDA(cudaMemcpyAsync(det, d.monoDetail, sizeof det, cudaMemcpyDeviceToHost, s));
+            IR_CUDA(cudaStreamSynchronize(s));
+            const double tolMin = EPS11 * fmax(1.0, fabs(det[1])), tolMax = EPS11 * fmax(1.0, fabs(det[2]));
+            const bool below = det[0] < det[1] - tolMin;
+            h->report.monotonicityViolated = below ? 1 : 2;
+            h->report.monoTracer = t; h->report.monoCategory = k + 1; h->report.monoLayer = l + 1; h->report.monoCell = (int)c + 1;
+            h->report.newValue = det[0]; h->report.bound = below ? det[1] : det[2]; h->report.tolerance = below ? tolMin : tolMax;
+            set_error("IR: monotonicity violation (incremental_remap.F:8530): tracer %d, layer %d, category %d, cell %d: new value %.17g, old %s %.17g",
+                      t, l + 1, k + 1, (int)c + 1, det[0], below ? "minimum" : "maximum", h->report.bound);
+            return IR_ERR_MONOTONICITY;
+        }
+    }
+    return IR_OK;
+}
+
+extern "C" int ir_set_checks(ir_handle *h, int conservation, int monotonicity)
+{
+    IR_REQUIRE(h != nullptr, "handle is NULL");
+    IR_REQUIRE(conservation >= 0 && conservation <= 2, "conservation must be 0 (off), 1 (sums and check) or 2 (sums only)");
+    IR_REQUIRE(monotonicity == 0 || monotonicity == 1, "monotonicity must be 0 or 1");
+    h->checkConservation = conservation;
+    h->checkMonotonicity = monotonicity;
+    return IR_OK;
+}
+
+extern "C" int ir_fetch_check_report(ir_handle *h, ir_check_report *out)
+{
+    IR_REQUIRE(h != nullptr && out != nullptr, "NULL argument");
+    *out = h->report;
+    return IR_OK;
+}
+
+extern "C" int ir_fetch_conservation_sums(ir_handle *h, int tracer, double *sumInit, double *sumFinal)
+{
+    IR_REQUIRE(h != nullptr, "handle is NULL");
+    if (!h->haveTracers || h->sumsHost.empty()) { set_error("no conservation sums: ir_set_checks(conservation) and ir_run first"); return IR_ERR_STATE; }
+    IR_REQUIRE(tracer >= 0 && tracer < (int)h->tracerRow0.size(), "tracer index out of range");
+    const size_t n = (size_t)h->d.nK * h->tracerLayers[tracer], r0 = (size_t)h->tracerRow0[tracer], nRows = (size_t)h->d.nRows;
+    for (size_t i = 0; i < n; i++) {      // rows of a tracer: category-major, layer fastest == Fortran (nLayers, nCategories)
+        if (sumInit) sumInit[i] = h->sumsHost[r0 + i];
+        if (sumFinal) sumFinal[i] = h->sumsHost[nRows + r0 + i];
+    }
     return IR_OK;
 }
 
@@ -1802,6 +2110,7 @@ extern "C" int ir_destroy(ir_handle *h)
     if (d.catBaseRow) cudaFree(d.catBaseRow);
     if (d.catLayers) cudaFree(d.catLayers);
     if (d.catRows) cudaFree(d.catRows);
+    free_check_buffers(h);
     for (void *p : h->allocs) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);

@@ -15,12 +15,14 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("IR_B200_LIB", os.path.join(_HERE, "csrc", "libir_b200.so"))
 
-EXPORTS = ("ir_init_geometry", "ir_create", "ir_set_tracers", "ir_run", "ir_fetch_diagnostics", "ir_fetch_tracer_field", "ir_release_host_memory", "ir_last_run_ms", "ir_launch_count",
-           "ir_destroy", "ir_last_error_string")
+EXPORTS = ("ir_init_geometry", "ir_create", "ir_set_tracers", "ir_run", "ir_set_checks", "ir_fetch_check_report",
+           "ir_fetch_conservation_sums", "ir_fetch_diagnostics", "ir_fetch_tracer_field", "ir_release_host_memory",
+           "ir_last_run_ms", "ir_launch_count", "ir_destroy", "ir_last_error_string")
 GEOM_NAMES = ("x", "y", "xx", "xy", "yy", "xxx", "xxy", "xyy", "yyy", "xxxx", "xxxy", "xxyy", "xyyy", "yyyy")
 
 IR_OK, IR_ERR_ARGUMENT, IR_ERR_CUDA, IR_ERR_STATE, IR_ERR_MESH = 0, 1, 2, 3, 4
 IR_ERR_NEGATIVE_MASS_QP, IR_ERR_NEGATIVE_MASS, IR_ERR_PARALLEL_EDGES, IR_ERR_TOO_MANY_TRIANGLES = 10, 11, 12, 13
+IR_ERR_CONSERVATION, IR_ERR_MONOTONICITY = 14, 15
 
 
 class IrError(RuntimeError):
@@ -56,6 +58,13 @@ class ir_geometry_out(C.Structure):
 
 class ir_tracer_desc(C.Structure):
     _fields_ = [("nLayers", C.c_int), ("parent", C.c_int), ("volumeLike", C.c_int), ("array", C.c_void_p)]
+
+
+class ir_check_report(C.Structure):
+    _fields_ = [("conservationViolated", C.c_int), ("consTracer", C.c_int), ("consCategory", C.c_int), ("consLayer", C.c_int),
+                ("sumInit", C.c_double), ("sumFinal", C.c_double),
+                ("monotonicityViolated", C.c_int), ("monoTracer", C.c_int), ("monoCategory", C.c_int), ("monoLayer", C.c_int),
+                ("monoCell", C.c_int), ("newValue", C.c_double), ("bound", C.c_double), ("tolerance", C.c_double)]
 
 
 _libs = {}
@@ -174,9 +183,26 @@ class IrTransport:
         table = self._make_table(tracers)
         rc = self._L.ir_run(self._h, C.c_int(len(tracers)), table, C.c_void_p(_ptr(u, np.float64)),
                             C.c_void_p(_ptr(v, np.float64)), C.c_double(dt))
-        if check or rc in (IR_ERR_ARGUMENT, IR_ERR_CUDA, IR_ERR_STATE):
+        if check or rc in (IR_ERR_ARGUMENT, IR_ERR_CUDA, IR_ERR_STATE, IR_ERR_MESH):
             self._check(rc)
         return rc
+
+    def set_checks(self, conservation=0, monotonicity=0):
+        """config_conservation_check (1: sums and check, 2: sums only) / config_monotonicity_check of the next runs."""
+        self._check(self._L.ir_set_checks(self._h, C.c_int(int(conservation)), C.c_int(int(monotonicity))))
+
+    def check_report(self):
+        """ir_check_report of the last run as a dict."""
+        rep = ir_check_report()
+        self._check(self._L.ir_fetch_check_report(self._h, C.byref(rep)))
+        return {name: getattr(rep, name) for name, _ in ir_check_report._fields_}
+
+    def conservation_sums(self, tracer_index, n_layers):
+        """(sumInit, sumFinal) of one tracer after a run with the conservation check on: (nCategories, nLayers) each."""
+        a, b = np.zeros((self.n_categories, n_layers)), np.zeros((self.n_categories, n_layers))
+        self._check(self._L.ir_fetch_conservation_sums(self._h, C.c_int(tracer_index), C.c_void_p(a.ctypes.data),
+                                                       C.c_void_p(b.ctypes.data)))
+        return a, b
 
     def diagnostics(self, n_mass_layers=1):
         nE, nQ, nK = self.mesh.nEdges, self.n_quad_points, self.n_categories

@@ -10,7 +10,8 @@ from . import lib
 
 GEOM_NAMES = ("x", "y", "xx", "xy", "yy", "xxx", "xxy", "xyy", "yyy", "xxxx", "xxxy", "xxyy", "xyyy", "yyyy")
 ERRORS = {1: "edge orientation", 2: "cell orientation", 3: "parallel basis edges", 4: "negative mass at a quadrature point",
-          5: "negative mass", 6: "too many parents", 7: "too many triangles", 8: "bad argument"}
+          5: "negative mass", 6: "too many parents", 7: "too many triangles", 8: "bad argument",
+          9: "tracer conservation error", 10: "monotonicity violation"}
 
 
 class _GeomArgs(C.Structure):
@@ -43,7 +44,8 @@ class _RunArgs(C.Structure):
                    ("tracers", C.POINTER(_Tracer))]
                 + [(n, C.c_void_p) for n in ("xTriangleOut", "yTriangleOut", "triangleAreaOut", "iCellTriangleOut",
                                              "edgeFluxMassOut", "maskEdgeOut", "xGradOut", "yGradOut")]
-                + [("gradTracerOut", C.c_int)])
+                + [("gradTracerOut", C.c_int), ("conservationCheck", C.c_int), ("monotonicityCheck", C.c_int)]
+                + [(n, C.c_void_p) for n in ("sumInitOut", "sumFinalOut", "consErrOut", "monoErrOut", "monoValOut")])
 
 
 def _ptr(a, dtype):
@@ -118,8 +120,13 @@ def default_tracers(n_cells, n_categories, n_ice_layers=0, n_snow_layers=0, rng=
 
 
 def run(mesh, irf, geom, tracers, u, v, dt, n_quad_points=6, n_cells_solve=None, rotate=False, diagnostics=False,
-        grad_tracer=0, check=True):
-    """One call of seaice_run_advection_incremental_remap (single block, no halo update) IN PLACE on the tracers."""
+        grad_tracer=0, check=True, conservation_check=0, monotonicity_check=0):
+    """One call of seaice_run_advection_incremental_remap (single block, no halo update) IN PLACE on the tracers.
+    ``conservation_check`` (1: sums and check, 2: sums only) / ``monotonicity_check`` (1: the reference's in-place
+    extension of the bounds, 2: the order-independent one) switch on config_conservation_check /
+    config_monotonicity_check; the returned dict then holds ``sumInit`` / ``sumFinal`` (one (nCategories, nLayers) array
+    per tracer), ``consErr`` [violated, tracer, iCat, iLayer], ``monoErr`` [0 / 1 min / 2 max, tracer, iLayer, iCat,
+    iCell] and ``monoVal`` [new value, bound, tolerance]."""
     nC, nV, nE, M = mesh.nCells, mesh.nVertices, mesh.nEdges, mesh.maxEdges
     nK = tracers[0].array.shape[1]
     a = _RunArgs()
@@ -171,9 +178,24 @@ def run(mesh, irf, geom, tracers, u, v, dt, n_quad_points=6, n_cells_solve=None,
         a.edgeFluxMassOut, a.maskEdgeOut = diag["edgeFluxMass"].ctypes.data, diag["maskEdge"].ctypes.data
         a.xGradOut, a.yGradOut = diag["xGrad"].ctypes.data, diag["yGrad"].ctypes.data
         a.gradTracerOut = grad_tracer
+    a.conservationCheck, a.monotonicityCheck = int(conservation_check), int(monotonicity_check)
+    if conservation_check or monotonicity_check:
+        n_sum = sum(nK * t.array.shape[2] for t in tracers)
+        flat_i, flat_f = np.zeros(n_sum), np.zeros(n_sum)
+        diag["consErr"], diag["monoErr"], diag["monoVal"] = np.zeros(4, np.int32), np.zeros(5, np.int32), np.zeros(3)
+        a.sumInitOut, a.sumFinalOut = flat_i.ctypes.data, flat_f.ctypes.data
+        a.consErrOut, a.monoErrOut, a.monoValOut = (diag["consErr"].ctypes.data, diag["monoErr"].ctypes.data,
+                                                    diag["monoVal"].ctypes.data)
     L = lib()
     L.orc_ir_run.restype = C.c_int
     err = L.orc_ir_run(C.byref(a))
+    if conservation_check or monotonicity_check:
+        off, diag["sumInit"], diag["sumFinal"] = 0, [], []
+        for t in tracers:
+            n = nK * t.array.shape[2]
+            diag["sumInit"].append(flat_i[off:off + n].reshape(nK, t.array.shape[2]).copy())
+            diag["sumFinal"].append(flat_f[off:off + n].reshape(nK, t.array.shape[2]).copy())
+            off += n
     if check and err:
         raise RuntimeError("orc_ir_run: " + ERRORS.get(err, str(err)))
     diag["error"] = err

@@ -15,6 +15,9 @@
  *     shift_vertices_of_departure_triangle :6270-6545   get_triangle_quadrature_points :6546-6665
  *     integrate_fluxes_over_triangles :6667-6980   compute_mass_tracer_products :6982-7120
  *     update_mass_and_tracers :7125-7540   zap_small_mass :8764-8895   helpers :8900-9326
+ *     the optional checks (config_conservation_check, config_monotonicity_check; default off):
+ *     sum_tracers :7998-8120   check_tracer_conservation :8126-8260   tracer_local_min_max :8268-8410
+ *     check_tracer_monotonicity :8416-8760
  *
  * The reference keeps "2D" (nCategories, nCells) and "3D" (nLayers, nCategories, nCells) tracers in separate
  * code paths that differ only in the layer index; here every tracer is (nLayers, nCategories, nCells) with
@@ -62,6 +65,8 @@
 #define IR_ERR_TOO_MANY_PARENTS 6
 #define IR_ERR_TOO_MANY_TRIANGLES 7
 #define IR_ERR_BAD_ARGUMENT     8
+#define IR_ERR_CONSERVATION     9   /* check_tracer_conservation (:8126): relative change of a global sum > eps11 */
+#define IR_ERR_MONOTONICITY     10  /* check_tracer_monotonicity (:8416): new value outside the old neighbourhood range */
 
 /* 1-based accessors */
 #define A2(a, i, j, n1) ((a)[((size_t)(j) - 1) * (size_t)(n1) + ((size_t)(i) - 1)])            /* a(i,j), first dim n1 */
@@ -510,6 +515,13 @@ typedef struct {
     int *maskEdgeOut;                     /* (nEdges) */
     double *xGradOut, *yGradOut;          /* tracer `gradTracerOut`: limited gradients (nCells+1, nCategories, nLayers) */
     int gradTracerOut;
+    /* optional checks (config_conservation_check / config_monotonicity_check, both default .false.) */
+    int conservationCheck;                /* 1: sums and the check on this block's sums; 2: sums only (the caller adds the ranks) */
+    int monotonicityCheck;                /* 1: as the reference (in-place extension of the bounds); 2: order-independent extension */
+    double *sumInitOut, *sumFinalOut;     /* tracer after tracer, (nCategories, nLayers) each: globalSumInit / globalSumFinal */
+    int *consErrOut;                      /* [4]: violated, tracer (0-based), iCat, iLayer (1-based) of the first violation */
+    int *monoErrOut;                      /* [5]: 0 none / 1 below the minimum / 2 above the maximum, tracer, iLayer, iCat, iCell */
+    double *monoValOut;                   /* [3]: new value, the bound it crossed, the tolerance */
 } orc_ir_run_args;
 
 typedef struct {
@@ -891,6 +903,53 @@ int orc_ir_run(orc_ir_run_args *a)
     double *triArea = (double *)calloc((size_t)(nE > 0 ? nE : 1) * NTRI, sizeof(double));
     int *iCellTri = (int *)calloc((size_t)(nE > 0 ? nE : 1) * NTRI, sizeof(int));
 
+    /* config_monotonicity_check (:2999-3015): make_masks with threshold 0, then tracer_local_min_max (:8268) on the
+     * old values.  The reference fills localMin / localMax for the owned cells and brings the halo cells in with a
+     * halo exchange (:8450); this single-block restatement evaluates the same loop for every cell of the block
+     * instead -- for the halo cells next to owned ones (all the extension below reads) their neighbours are present
+     * with the two halo layers the scheme requires (:829), so the values are those the owner would send. */
+    double **lmin = NULL, **lmax = NULL;
+    if (a->monotonicityCheck) {
+        lmin = (double **)calloc((size_t)nT, sizeof(double *));
+        lmax = (double **)calloc((size_t)nT, sizeof(double *));
+        for (int t = 0; t < nT; t++) {
+            const orc_ir_tracer *tr = &a->tracers[t];
+            const int nL = tr->nLayers;
+            const size_t n = ((size_t)nC + 1) * nK * nL;
+            lmin[t] = (double *)calloc(n, sizeof(double));
+            lmax[t] = (double *)calloc(n, sizeof(double));
+            int *mask0 = (int *)calloc(n, sizeof(int));
+            if (tr->nParents == 0) {
+                for (int c = 1; c <= nC; c++)
+                    for (int k = 1; k <= nK; k++)
+                        for (int l = 1; l <= nL; l++) mask0[TIX(l, k, c, nL, nK)] = 1;
+            } else {
+                const orc_ir_tracer *p = &a->tracers[tr->parent];
+                for (int c = 1; c <= nC; c++)
+                    for (int k = 1; k <= nK; k++)
+                        for (int l = 1; l <= nL; l++)
+                            if (p->array[TIX((p->nLayers == 1) ? 1 : l, k, c, p->nLayers, nK)] > 0.0) mask0[TIX(l, k, c, nL, nK)] = 1;
+            }
+            for (int iCell = 1; iCell <= nC; iCell++)
+                for (int k = 1; k <= nK; k++)
+                    for (int l = 1; l <= nL; l++) {
+                        const size_t q = TIX(l, k, iCell, nL, nK);
+                        if (mask0[q] == 1) { lmin[t][q] = tr->array[q]; lmax[t][q] = tr->array[q]; }
+                        for (int iCellOnCell = 1; iCellOnCell <= a->nEdgesOnCell[iCell - 1]; iCellOnCell++) {
+                            const int iCellNeighbor = A2(a->cellsOnCell, iCellOnCell, iCell, M);
+                            if (iCellNeighbor >= 1 && iCellNeighbor <= nC) {
+                                const size_t qn = TIX(l, k, iCellNeighbor, nL, nK);
+                                if (mask0[qn] == 1) {
+                                    if (tr->array[qn] < lmin[t][q]) lmin[t][q] = tr->array[qn];
+                                    if (tr->array[qn] > lmax[t][q]) lmax[t][q] = tr->array[qn];
+                                }
+                            }
+                        }
+                    }
+            free(mask0);
+        }
+    }
+
     /* make_masks, threshold eps11 (:3404; called at :2995) */
     for (int t = 0; t < nT; t++) {
         const orc_ir_tracer *tr = &a->tracers[t];
@@ -1122,6 +1181,20 @@ int orc_ir_run(orc_ir_run_args *a)
                 }
     }
 
+    /* config_conservation_check: sum_tracers(init = .true.) (:3259-3268, :7998) */
+    size_t *sumOff = (size_t *)calloc((size_t)nT + 1, sizeof(size_t));
+    for (int t = 0; t < nT; t++) sumOff[t + 1] = sumOff[t] + (size_t)nK * a->tracers[t].nLayers;
+    double *sumInit = (double *)calloc(sumOff[nT], sizeof(double)), *sumFinal = (double *)calloc(sumOff[nT], sizeof(double));
+    if (a->conservationCheck)
+        for (int t = 0; t < nT; t++) {
+            const int nL = a->tracers[t].nLayers;
+            for (int iCell = 1; iCell <= a->nCellsSolve; iCell++)
+                for (int k = 1; k <= nK; k++)
+                    for (int l = 1; l <= nL; l++)
+                        sumInit[sumOff[t] + (size_t)(k - 1) * nL + (l - 1)] =
+                            sumInit[sumOff[t] + (size_t)(k - 1) * nL + (l - 1)] + a->areaCell[iCell - 1] * W[t].mtp[TIX(l, k, iCell, nL, nK)];
+        }
+
     /* update_mass_and_tracers (:7125) */
     for (int t = 0; t < nT && err != IR_ERR_NEGATIVE_MASS; t++) {
         orc_ir_tracer *tr = &a->tracers[t];
@@ -1156,6 +1229,25 @@ int orc_ir_run(orc_ir_run_args *a)
         }
     }
 
+    /* config_conservation_check: compute_mass_tracer_products on the new values, sum_tracers(init = .false.) (:3298-3310) */
+    if (a->conservationCheck && err != IR_ERR_NEGATIVE_MASS)
+        for (int t = 0; t < nT; t++) {
+            const orc_ir_tracer *tr = &a->tracers[t];
+            const int nL = tr->nLayers, ip = tr->parent;
+            const int pL = (ip >= 0) ? a->tracers[ip].nLayers : 1;
+            for (int c = 1; c <= nC; c++)
+                for (int k = 1; k <= nK; k++)
+                    for (int l = 1; l <= nL; l++) {
+                        const double pm = (ip >= 0) ? W[ip].mtp[TIX((pL == 1) ? 1 : l, k, c, pL, nK)] : 1.0;
+                        W[t].mtp[TIX(l, k, c, nL, nK)] = pm * tr->array[TIX(l, k, c, nL, nK)];
+                    }
+            for (int iCell = 1; iCell <= a->nCellsSolve; iCell++)
+                for (int k = 1; k <= nK; k++)
+                    for (int l = 1; l <= nL; l++)
+                        sumFinal[sumOff[t] + (size_t)(k - 1) * nL + (l - 1)] =
+                            sumFinal[sumOff[t] + (size_t)(k - 1) * nL + (l - 1)] + a->areaCell[iCell - 1] * W[t].mtp[TIX(l, k, iCell, nL, nK)];
+        }
+
     /* zap_small_mass (:8764); the reference handles a one-layer mass-like field only */
     if (mass->nLayers == 1 && err != IR_ERR_NEGATIVE_MASS) {
         const double smallMassThreshold = 1.0e-22;
@@ -1170,6 +1262,91 @@ int orc_ir_run(orc_ir_run_args *a)
                 }
             }
     }
+
+    /* check_tracer_conservation (:8126; the sums of the ranks are added first, :8150 -- the caller's job with
+     * conservationCheck = 2).  First violation in the reference's loop order: tracer, category, layer. */
+    if (a->sumInitOut) memcpy(a->sumInitOut, sumInit, sumOff[nT] * sizeof(double));
+    if (a->sumFinalOut) memcpy(a->sumFinalOut, sumFinal, sumOff[nT] * sizeof(double));
+    if (a->consErrOut) a->consErrOut[0] = a->consErrOut[1] = a->consErrOut[2] = a->consErrOut[3] = 0;
+    if (a->monoErrOut) a->monoErrOut[0] = a->monoErrOut[1] = a->monoErrOut[2] = a->monoErrOut[3] = a->monoErrOut[4] = 0;
+    int consViolated = 0;
+    if (a->conservationCheck == 1 && err == IR_OK) {
+        for (int t = 0; t < nT && !consViolated; t++) {
+            const int nL = a->tracers[t].nLayers;
+            for (int k = 1; k <= nK && !consViolated; k++)
+                for (int l = 1; l <= nL; l++) {
+                    const double si = sumInit[sumOff[t] + (size_t)(k - 1) * nL + (l - 1)], sf = sumFinal[sumOff[t] + (size_t)(k - 1) * nL + (l - 1)];
+                    if (fabs(si) > EPS11) {
+                        const double difference = sf - si;
+                        const double ratio = difference / si;
+                        if (fabs(ratio) > EPS11) {
+                            consViolated = 1;
+                            if (a->consErrOut) { a->consErrOut[0] = 1; a->consErrOut[1] = t; a->consErrOut[2] = k; a->consErrOut[3] = l; }
+                            break;
+                        }
+                    }
+                }
+        }
+        if (consViolated) err = IR_ERR_CONSERVATION;
+    }
+    /* check_tracer_monotonicity (:8416), not reached when the conservation check has aborted (:2577-2581).  The
+     * masks are those of the last make_masks call (threshold eps11, OLD values); extendedMinMax = .true. */
+    if (a->monotonicityCheck && err == IR_OK) {
+        int found = 0;
+        for (int t = 0; t < nT && !found; t++) {
+            const orc_ir_tracer *tr = &a->tracers[t];
+            if (tr->nParents == 0) continue;      /* monotonicity holds for tracers but not for the mass-like field */
+            const int nL = tr->nLayers;
+            const int *mask = W[t].mask;
+            const size_t n = ((size_t)nC + 1) * nK * nL;
+            double *emin = (double *)malloc(n * sizeof(double)), *emax = (double *)malloc(n * sizeof(double));
+            memcpy(emin, lmin[t], n * sizeof(double));
+            memcpy(emax, lmax[t], n * sizeof(double));
+            /* the reference extends in place, cell after cell (:8478-8500): a cell updated earlier in the loop is seen
+             * in its extended state by a later neighbour, so its bounds depend on the cell numbering (and are never
+             * tighter than the two-ring bounds).  monotonicityCheck = 2 is the order-independent variant the parallel
+             * device kernel computes: neighbours are read in their un-extended state. */
+            for (int iCell = 1; iCell <= a->nCellsSolve; iCell++)
+                for (int k = 1; k <= nK; k++)
+                    for (int l = 1; l <= nL; l++) {
+                        const size_t q = TIX(l, k, iCell, nL, nK);
+                        if (mask[q] != 1) continue;
+                        for (int iCellOnCell = 1; iCellOnCell <= a->nEdgesOnCell[iCell - 1]; iCellOnCell++) {
+                            const int iCellNeighbor = A2(a->cellsOnCell, iCellOnCell, iCell, M);
+                            if (iCellNeighbor >= 1 && iCellNeighbor <= nC) {
+                                const size_t qn = TIX(l, k, iCellNeighbor, nL, nK);
+                                if (mask[qn] == 1) {
+                                    const double nmin = (a->monotonicityCheck == 2) ? lmin[t][qn] : emin[qn];
+                                    const double nmax = (a->monotonicityCheck == 2) ? lmax[t][qn] : emax[qn];
+                                    if (nmin < emin[q]) emin[q] = nmin;
+                                    if (nmax > emax[q]) emax[q] = nmax;
+                                }
+                            }
+                        }
+                    }
+            for (int iCell = 1; iCell <= a->nCellsSolve && !found; iCell++)
+                for (int k = 1; k <= nK && !found; k++)
+                    for (int l = 1; l <= nL; l++) {
+                        const size_t q = TIX(l, k, iCell, nL, nK);
+                        if (mask[q] != 1) continue;
+                        const double toleranceMin = EPS11 * fmax(1.0, fabs(emin[q]));
+                        const double toleranceMax = EPS11 * fmax(1.0, fabs(emax[q]));
+                        int which = 0;
+                        if (tr->array[q] < emin[q] - toleranceMin) which = 1;
+                        else if (tr->array[q] > emax[q] + toleranceMax) which = 2;
+                        if (which) {
+                            found = 1;
+                            if (a->monoErrOut) { a->monoErrOut[0] = which; a->monoErrOut[1] = t; a->monoErrOut[2] = l; a->monoErrOut[3] = k; a->monoErrOut[4] = iCell; }
+                            if (a->monoValOut) { a->monoValOut[0] = tr->array[q]; a->monoValOut[1] = which == 1 ? emin[q] : emax[q]; a->monoValOut[2] = which == 1 ? toleranceMin : toleranceMax; }
+                            break;
+                        }
+                    }
+            free(emin); free(emax);
+        }
+        if (found) err = IR_ERR_MONOTONICITY;
+    }
+    if (lmin) { for (int t = 0; t < nT; t++) { free(lmin[t]); free(lmax[t]); } free(lmin); free(lmax); }
+    free(sumOff); free(sumInit); free(sumFinal);
 
     /* thickness -> volume (:2680-2700) with the new area */
     for (int t = 0; t < nT; t++) {

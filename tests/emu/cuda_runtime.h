@@ -172,5 +172,6 @@ enum { cudaHostRegisterDefault = 0 };
 static inline cudaError_t cudaHostRegister(void *, size_t, unsigned) { return cudaSuccess; }
 static inline cudaError_t cudaHostUnregister(void *) { return cudaSuccess; }
 static inline int atomicOr(int *p, int v) { const int old = *p; *p = old | v; return old; }
+static inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) { const unsigned long long old = *p; if (v < old) *p = v; return old; }
 
 #endif
