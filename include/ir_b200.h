@@ -179,6 +179,70 @@ enum {
 };
 int ir_fetch_tracer_field(ir_handle *h, int which, int tracer, double *out);
 
+/* ---- seaice_normal_vectors (src/shared/mpas_seaice_mesh.F:703-846) on the device, for hosts that do not run the Fortran
+ * init: the unit normals of the cell sides in the cell's local east / north frame (normalVectorPolygon, (2, maxEdges,
+ * nCells+1)), those of the dual triangles' sides at interior vertices (normalVectorTriangle, (2, vertexDegree,
+ * nVertices+1)) and the rotated latitudes.  Planar :858-1024, spherical :1038-1241 / :1393-1606.  Callers in the
+ * reference: seaice_init_velocity_solver_weak (weak.F:84-96, remove_metric_terms = 1) -- the arrays evp_set_weak_mesh of
+ * evp_b200.h takes -- and seaice_init_advection_upwind (advection_upwind.F:122-126, polygons only, remove_metric_terms
+ * = 0) -- the normalVectorEdge of ir_set_upwind_mesh below.  The device's sin / cos / asin / atan2 are accurate to 1-2
+ * ulp, not correctly rounded, so the result agrees with a host libm to round-off, not bit for bit; the second component
+ * is sign(n3) * sqrt(1 - n1**2), which loses half the digits where a side points due east or west (n1 = +-1) -- in the
+ * reference as here. */
+typedef struct ir_normals_in {
+    int nCells, nVertices, nVerticesSolve, nEdges, maxEdges, vertexDegree;
+    int on_a_sphere, rotate_cartesian_grid, remove_metric_terms;
+    double sphere_radius;
+    const int *nEdgesOnCell;     /* (nCells+1) */
+    const int *edgesOnCell;      /* (maxEdges, nCells+1) */
+    const int *verticesOnEdge;   /* (2, nEdges+1) */
+    const int *cellsOnEdge;      /* (2, nEdges+1) */
+    const int *edgesOnVertex;    /* (vertexDegree, nVertices+1); triangles only */
+    const int *interiorVertex;   /* (nVertices+1); triangles only */
+    const double *xCell, *yCell, *zCell;         /* (nCells+1); z may be NULL on a plane */
+    const double *xVertex, *yVertex, *zVertex;   /* (nVertices+1) */
+    const double *xEdge, *yEdge, *zEdge;         /* (nEdges+1) */
+} ir_normals_in;
+
+typedef struct ir_normals_out {
+    double *normalVectorPolygon;   /* (2, maxEdges, nCells+1) */
+    double *normalVectorTriangle;  /* (2, vertexDegree, nVertices+1); NULL: seaice_normal_vectors_polygon alone */
+    double *latCellRotated;        /* (nCells+1), may be NULL */
+    double *latVertexRotated;      /* (nVertices+1), may be NULL */
+} ir_normals_out;
+
+int ir_normal_vectors(const ir_normals_in *in, const ir_normals_out *out, int device);
+
+/* ---- config_advection_type = 'upwind': seaice_run_advection_upwind (src/shared/mpas_seaice_advection_upwind.F:385-520)
+ * on one block, restated AS EXECUTED with the tracer connectivity table (tracerConnectivities, :37-56, filled at
+ * :145-170) as an argument.  The handle is the one of ir_create (its mesh arrays are shared; the incremental_remap pool
+ * arrays are not read by this path).  Left to the host: the tracer halo exchange between prepare_advection and the
+ * variable loop (halo_exchange_advection :1786 -- with the values unchanged by prepare_tracers' volume -> thickness
+ * conversion only if the host exchanges thicknesses, so decomposed hosts call with halos already current), and the time-
+ * level shift of the pool (:2032).
+ *
+ * ir_set_upwind_mesh: interiorEdge (nEdges+1) of the boundary pool (mesh.F:567), dvEdge (nEdges+1), normalVectorEdge
+ * (2, maxEdges, nCells+1) of the velocity_solver pool (advection_upwind.F:122).  Once, before the first step. */
+int ir_set_upwind_mesh(ir_handle *h, const int *interiorEdge, const double *dvEdge, const double *normalVectorEdge);
+
+typedef struct ir_upwind_var {
+    int parent;            /* index of the parent in the table, -1 for 'none' (the first variable: the ice area) */
+    int volumeLike;        /* 1: divided by variable 0 before and multiplied by its new value after the step where it
+                            * exceeds iceAreaMinimum (config_convert_volume_to_thickness, :57, :1949, :2063) */
+    double childMinimum;   /* childTracerMinimum (:235); the threshold its children use as parentTracerMinimum */
+    double *array;         /* (nCategories, nCells+1): time level 1 in, the new time level out */
+} ir_upwind_var;
+
+/* One step IN PLACE on the variables' arrays, in table order (a parent before its children).  uVelocity / vVelocity
+ * (nVertices+1).  Owned cells hold the new values; halo cells hold old * parent as after the reference's update loop
+ * over nCells (:1136, :1215) and want the host's next halo exchange. */
+int ir_run_upwind(ir_handle *h, int nVars, const ir_upwind_var *vars, const double *uVelocity, const double *vVelocity,
+                  double dt);
+
+/* <variable>EdgeFlux (nCategories, nEdges+1) of the tracer_edge_fluxes pool and the edge velocity (nEdges+1) of the
+ * last ir_run_upwind; either pointer may be NULL. */
+int ir_fetch_upwind_fluxes(ir_handle *h, int var, double *edgeFlux, double *edgeVelocity);
+
 /* With IR_B200_PIN_HOST=1 in the environment at ir_create, ir_run page-locks the tracer and velocity arrays the first
  * time it sees them (cudaHostRegister) so that the per-step copies run at the full PCIe rate.  Call this before the
  * host frees or reallocates such an array (e.g. mpas_pool_destroy_pool); ir_destroy does it too.  No-op otherwise. */

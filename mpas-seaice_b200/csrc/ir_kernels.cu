@@ -142,6 +142,18 @@ struct Dev {
     int maxLayers;
 };
 
+// device state of the upwind option (ir_upwind.cuh)
+struct Upw {
+    int *interiorEdge;
+    double *dvEdge, *nve /* normalVectorEdge, [2 * slot + component][nCp] */;
+    double *oldv, *newv;               // [nVars * nK][nCp]: time levels 1 and 2
+    double *eflux;                     // [nVars * nK][nEp]: <variable>EdgeFlux
+    double *fluxUp;                    // [nK][nEp]: flux_upwind of the variable being advected
+    double *pOldNone, *pNewNone;       // [nK][nCp]: the stand-in parent of a variable without one
+    double *pFluxNone;                 // [nK][nEp]
+    double *edgeVel;                   // [nEp]
+};
+
 }  // namespace
 
 struct ir_handle {
@@ -163,6 +175,9 @@ struct ir_handle {
     int checkConservation, checkMonotonicity;   // ir_set_checks
     ir_check_report report;                     // of the last ir_run
     std::vector<double> sumsHost;               // [2][nRows] of the last ir_run
+    Upw up;                                     // ir_set_upwind_mesh / ir_run_upwind
+    int upVars;
+    bool upMesh;
 };
 
 namespace {
@@ -1401,6 +1416,8 @@ void unpin_all(ir_handle *h)
     h->pinned.clear();
 }
 
+void upwind_free_all(ir_handle *h);   // ir_upwind.cuh
+
 void free_check_buffers(ir_handle *h)
 {
     Dev &d = h->d;
@@ -2111,6 +2128,7 @@ extern "C" int ir_destroy(ir_handle *h)
     if (d.catLayers) cudaFree(d.catLayers);
     if (d.catRows) cudaFree(d.catRows);
     free_check_buffers(h);
+    upwind_free_all(h);
     for (void *p : h->allocs) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -2118,3 +2136,6 @@ extern "C" int ir_destroy(ir_handle *h)
     delete h;
     return IR_OK;
 }
+
+// the non-default options: seaice_normal_vectors on the device and the upwind transport
+#include "ir_upwind.cuh"

@@ -16,7 +16,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("IR_B200_LIB", os.path.join(_HERE, "csrc", "libir_b200.so"))
 
 EXPORTS = ("ir_init_geometry", "ir_create", "ir_set_tracers", "ir_run", "ir_set_checks", "ir_fetch_check_report",
-           "ir_fetch_conservation_sums", "ir_fetch_diagnostics", "ir_fetch_tracer_field", "ir_release_host_memory",
+           "ir_fetch_conservation_sums", "ir_fetch_diagnostics", "ir_fetch_tracer_field", "ir_normal_vectors",
+           "ir_set_upwind_mesh", "ir_run_upwind", "ir_fetch_upwind_fluxes", "ir_release_host_memory",
            "ir_last_run_ms", "ir_launch_count", "ir_destroy", "ir_last_error_string")
 GEOM_NAMES = ("x", "y", "xx", "xy", "yy", "xxx", "xxy", "xyy", "yyy", "xxxx", "xxxy", "xxyy", "xyyy", "yyyy")
 
@@ -58,6 +59,23 @@ class ir_geometry_out(C.Structure):
 
 class ir_tracer_desc(C.Structure):
     _fields_ = [("nLayers", C.c_int), ("parent", C.c_int), ("volumeLike", C.c_int), ("array", C.c_void_p)]
+
+
+class ir_normals_in(C.Structure):
+    _fields_ = ([(n, C.c_int) for n in ("nCells", "nVertices", "nVerticesSolve", "nEdges", "maxEdges", "vertexDegree",
+                                        "on_a_sphere", "rotate_cartesian_grid", "remove_metric_terms")]
+                + [("sphere_radius", C.c_double)]
+                + [(n, C.c_void_p) for n in ("nEdgesOnCell", "edgesOnCell", "verticesOnEdge", "cellsOnEdge", "edgesOnVertex",
+                                             "interiorVertex", "xCell", "yCell", "zCell", "xVertex", "yVertex", "zVertex",
+                                             "xEdge", "yEdge", "zEdge")])
+
+
+class ir_normals_out(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("normalVectorPolygon", "normalVectorTriangle", "latCellRotated", "latVertexRotated")]
+
+
+class ir_upwind_var(C.Structure):
+    _fields_ = [("parent", C.c_int), ("volumeLike", C.c_int), ("childMinimum", C.c_double), ("array", C.c_void_p)]
 
 
 class ir_check_report(C.Structure):
@@ -120,6 +138,53 @@ def init_geometry(mesh, irf, n_cells_solve=None, rotate=False, device=-1, lib_pa
     if rc != IR_OK:
         raise IrError(rc, L.ir_last_error_string().decode())
     out["geomAvg"] = geom
+    return out
+
+
+def normal_vectors(mesh, edges, interior_vertex, rotate=True, remove_metric_terms=True, triangles=True,
+                   n_vertices_solve=None, device=-1, lib_path=None):
+    """seaice_normal_vectors (src/shared/mpas_seaice_mesh.F:703) on the device: ir_normal_vectors.  ``edges`` holds
+    verticesOnEdge, edgesOnVertex, xEdge, yEdge, zEdge (mesh-file arrays; irmesh.ir_fields for generated meshes).
+    Returns dict(normalVectorPolygon (nCells+1, maxEdges, 2), latCellRotated[, normalVectorTriangle (nVertices+1,
+    vertexDegree, 2), latVertexRotated]); ``triangles=False`` is seaice_normal_vectors_polygon alone."""
+    L = load(lib_path)
+    nC, nV, nE, M, D = mesh.nCells, mesh.nVertices, mesh.nEdges, mesh.maxEdges, mesh.vertexDegree
+    a = ir_normals_in()
+    a.nCells, a.nVertices, a.nEdges, a.maxEdges, a.vertexDegree = nC, nV, nE, M, D
+    a.nVerticesSolve = nV if n_vertices_solve is None else int(n_vertices_solve)
+    a.on_a_sphere = int(bool(mesh.on_a_sphere))
+    a.rotate_cartesian_grid, a.remove_metric_terms = int(bool(rotate)), int(bool(remove_metric_terms))
+    a.sphere_radius = float(getattr(mesh, "sphere_radius", 0.0) or 0.0)
+    for name in ("nEdgesOnCell", "edgesOnCell", "cellsOnEdge"):
+        setattr(a, name, _ptr(mesh[name], np.int32))
+    for name in ("verticesOnEdge", "edgesOnVertex"):
+        setattr(a, name, _ptr(edges[name], np.int32))
+    iv = np.ascontiguousarray(interior_vertex, dtype=np.int32)
+    a.interiorVertex = iv.ctypes.data
+    for name in ("xCell", "yCell", "zCell", "xVertex", "yVertex", "zVertex"):
+        setattr(a, name, _ptr(mesh[name], np.float64))
+    for name in ("xEdge", "yEdge", "zEdge"):
+        setattr(a, name, _ptr(edges[name], np.float64))
+    out = dict(normalVectorPolygon=np.zeros((nC + 1, M, 2)), latCellRotated=np.zeros(nC + 1))
+    o = ir_normals_out()
+    o.normalVectorPolygon, o.latCellRotated = out["normalVectorPolygon"].ctypes.data, out["latCellRotated"].ctypes.data
+    if triangles:
+        out.update(normalVectorTriangle=np.zeros((nV + 1, D, 2)), latVertexRotated=np.zeros(nV + 1))
+        o.normalVectorTriangle, o.latVertexRotated = out["normalVectorTriangle"].ctypes.data, out["latVertexRotated"].ctypes.data
+    rc = L.ir_normal_vectors(C.byref(a), C.byref(o), C.c_int(device))
+    if rc != IR_OK:
+        raise IrError(rc, L.ir_last_error_string().decode())
+    return out
+
+
+def interior_edge(mesh, n_edges_solve=None):
+    """interiorEdge of the boundary pool (interior_edges, src/shared/mpas_seaice_mesh.F:567): 1 for the first nEdgesSolve
+    edges that have a cell of the block on both sides."""
+    nC, nE = mesh.nCells, mesh.nEdges
+    nES = nE if n_edges_solve is None else int(n_edges_solve)
+    out = np.zeros(nE + 1, np.int32)
+    coe = mesh.cellsOnEdge[:nES]
+    out[:nES] = ((coe[:, 0] <= nC) & (coe[:, 1] <= nC)).astype(np.int32)
     return out
 
 
@@ -203,6 +268,37 @@ class IrTransport:
         self._check(self._L.ir_fetch_conservation_sums(self._h, C.c_int(tracer_index), C.c_void_p(a.ctypes.data),
                                                        C.c_void_p(b.ctypes.data)))
         return a, b
+
+    # ---- config_advection_type = 'upwind' (seaice_run_advection_upwind, advection_upwind.F:385)
+    def set_upwind_mesh(self, interior_edge_mask, dv_edge, normal_vector_edge):
+        nC, nE, M = self.mesh.nCells, self.mesh.nEdges, self.mesh.maxEdges
+        assert interior_edge_mask.shape == (nE + 1,) and dv_edge.shape == (nE + 1,) and normal_vector_edge.shape == (nC + 1, M, 2)
+        self._check(self._L.ir_set_upwind_mesh(self._h, C.c_void_p(_ptr(interior_edge_mask, np.int32)),
+                                               C.c_void_p(_ptr(dv_edge, np.float64)),
+                                               C.c_void_p(_ptr(normal_vector_edge, np.float64))))
+
+    def run_upwind(self, variables, u, v, dt):
+        """One upwind step IN PLACE; ``variables``: objects with .array (nCells+1, nCategories), .parent (index or
+        None), .volume_like, .child_minimum -- the rows of the reference's tracerConnectivities table, in order."""
+        nV = self.mesh.nVertices
+        assert u.shape == (nV + 1,) and v.shape == (nV + 1,)
+        table = (ir_upwind_var * len(variables))()
+        for i, var in enumerate(variables):
+            assert var.array.shape == (self.mesh.nCells + 1, self.n_categories)
+            table[i].parent = -1 if var.parent is None else int(var.parent)
+            table[i].volumeLike = int(bool(var.volume_like))
+            table[i].childMinimum = float(var.child_minimum)
+            table[i].array = _ptr(var.array, np.float64)
+        self._check(self._L.ir_run_upwind(self._h, C.c_int(len(variables)), table, C.c_void_p(_ptr(u, np.float64)),
+                                          C.c_void_p(_ptr(v, np.float64)), C.c_double(dt)))
+
+    def upwind_fluxes(self, var_index):
+        """(<variable>EdgeFlux (nEdges+1, nCategories), edgeVelocity (nEdges+1)) of the last upwind step."""
+        nE = self.mesh.nEdges
+        flux, vel = np.zeros((nE + 1, self.n_categories)), np.zeros(nE + 1)
+        self._check(self._L.ir_fetch_upwind_fluxes(self._h, C.c_int(var_index), C.c_void_p(flux.ctypes.data),
+                                                   C.c_void_p(vel.ctypes.data)))
+        return flux, vel
 
     def diagnostics(self, n_mass_layers=1):
         nE, nQ, nK = self.mesh.nEdges, self.n_quad_points, self.n_categories

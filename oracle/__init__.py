@@ -24,7 +24,7 @@ QUADRATIC_OCEAN_STRESS, LINEAR_OCEAN_STRESS = 1, 2
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("evp_oracle.c", "evp_precompute_oracle.c", "ir_oracle.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("evp_oracle.c", "evp_precompute_oracle.c", "ir_oracle.c", "upwind_oracle.c", "Makefile")]
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
     if force or stale:
@@ -43,7 +43,7 @@ def build_variant(name: str = "o3native") -> str:
         raise ValueError(name)
     tag = hashlib.md5((platform.node() + platform.processor() + platform.machine()).encode()).hexdigest()[:8]
     out = os.path.join(_HERE, "_build", f"liboracle_{name}_{tag}.so")
-    srcs = [os.path.join(_HERE, f) for f in ("evp_oracle.c", "evp_precompute_oracle.c", "ir_oracle.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("evp_oracle.c", "evp_precompute_oracle.c", "ir_oracle.c", "upwind_oracle.c")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         subprocess.run(["gcc", "-O3", "-march=native", "-fPIC", "-fopenmp", "-shared", "-o", out, *srcs, "-lm"], check=True)

@@ -42,3 +42,25 @@ for r in range(3):
     s.run(btr, partition.restrict_field(b, u, mesh.nCells, mesh.nVertices), partition.restrict_field(b, v, mesh.nCells, mesh.nVertices), 3600.0)
     s.destroy()
     print("block", r, "ok")
+# the non-default options: checks, normal vectors, upwind (tests/test_transport_options.py)
+from oracle import upwind
+from mpas_seaice_b200 import variational_init
+from test_transport_options import _upwind_state
+for kind in ("hex16", "band48"):
+    mesh, irf, geom = case(kind)
+    nCS = (2 * mesh.nCells) // 3
+    tr = _random_state(mesh, np.random.default_rng(21))
+    u, v = smooth_divergent_velocity(mesh, geom)
+    s = ir_host.IrTransport(mesh, irf, geom, 3, n_cells_solve=nCS, lib_path=lib)
+    s.set_tracers(tr)
+    s.set_checks(2, 1)
+    s.run(tr, u, v, 3600.0, check=False)
+    iv = variational_init.interior_vertex(mesh)
+    for rm in (True, False):
+        nv = ir_host.normal_vectors(mesh, irf, iv, rotate=True, remove_metric_terms=rm, lib_path=lib)
+    var = _upwind_state(mesh, np.random.default_rng(3))
+    s.set_upwind_mesh(ir_host.interior_edge(mesh), mesh.dvEdge, nv["normalVectorPolygon"])
+    for _ in range(2): s.run_upwind(var, u, v, 3600.0)
+    s.upwind_fluxes(3)
+    s.destroy()
+    print(kind, "options ok")

@@ -29,7 +29,9 @@ EMU_LIB = os.path.join(ROOT, "tests", "_build", "libir_emu%s.so" % ("" if "IR_B2
 
 
 def _emulation_library():
-    deps = [SRC, os.path.join(EMU_DIR, "cuda_runtime.h"), os.path.join(ROOT, "include", "ir_b200.h")]
+    deps = [SRC, os.path.join(os.path.dirname(SRC), "ir_upwind.cuh"), os.path.join(EMU_DIR, "cuda_runtime.h"),
+            os.path.join(ROOT, "include", "ir_b200.h")]
+    deps = [p for p in deps if os.path.exists(p)]
     if not os.path.exists(EMU_LIB) or any(os.path.getmtime(p) > os.path.getmtime(EMU_LIB) for p in deps):
         os.makedirs(os.path.dirname(EMU_LIB), exist_ok=True)
         subprocess.run(["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-std=c++17", "-fPIC", "-shared", "-x", "c++",
@@ -266,7 +268,7 @@ def test_emulated_kernels_are_clean_under_address_sanitizer(tmp_path):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_ir_asan_worker.py"), lib], env=env, capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0 and "AddressSanitizer" not in r.stderr, r.stderr[-3000:]
-    assert r.stdout.count("ok") == 7
+    assert r.stdout.count("ok") == 9
 
 
 def test_work_fields_match_oracle(lib_path):

@@ -210,3 +210,244 @@ def test_checks_call_order_and_arguments(lib_path):
             s.conservation_sums(0, 1)
     finally:
         s.destroy()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# seaice_normal_vectors (src/shared/mpas_seaice_mesh.F:703-846): oracle/upwind_oracle.c and ir_normal_vectors
+# ----------------------------------------------------------------------------------------------------------------------
+from oracle import upwind                                             # noqa: E402
+from mpas_seaice_b200 import variational_init, weakmesh              # noqa: E402
+
+
+@pytest.fixture(params=LEGS)
+def leg(request):
+    if request.param == "emulation":
+        return "emulation", _emulation_library()
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return "cuda", ir_host.LIB_PATH
+
+
+def _vertex_midpoint_edges(mesh, voe, eov):
+    """x/y/zEdge as weakmesh.py takes them: the midpoint of the edge's vertices, pushed back onto the sphere."""
+    nE = mesh.nEdges
+    a, b = voe[:nE, 0] - 1, voe[:nE, 1] - 1
+    p = [0.5 * (getattr(mesh, n)[a] + getattr(mesh, n)[b]) for n in ("xVertex", "yVertex", "zVertex")]
+    if mesh.on_a_sphere:
+        s = np.sqrt(p[0] ** 2 + p[1] ** 2 + p[2] ** 2) / mesh.sphere_radius
+        p = [q / s for q in p]
+    out = {}
+    for name, q in zip(("xEdge", "yEdge", "zEdge"), p):
+        out[name] = np.zeros(nE + 1)
+        out[name][:nE] = q
+    out.update(verticesOnEdge=voe, edgesOnVertex=eov)
+    return out
+
+
+def _assert_normals_close(got, ref, exact):
+    """exact: bit for bit.  Otherwise first component to 1e-13 and the second, sign(n3) * sqrt(1 - n1**2), to what the
+    first one's round-off allows: d(n2) = -n1 d(n1) / n2, i.e. |d(n2)| * max(|n2|, sqrt(eps)) <= 1e-13."""
+    for key in ref:
+        if exact:
+            assert np.array_equal(got[key], ref[key]), key
+        elif key.startswith("lat"):
+            assert np.abs(got[key] - ref[key]).max() <= 1e-14, key
+        else:
+            d = np.abs(got[key] - ref[key])
+            assert d[..., 0].max() <= 1e-13, key
+            assert (d[..., 1] * np.maximum(np.abs(ref[key][..., 1]), 1.5e-8)).max() <= 1e-13, key
+
+
+@pytest.mark.parametrize("kind", ["hex12", "quad10", "ico3", "band48"])
+def test_oracle_normal_vectors_against_the_vectorised_restatement(kind):
+    """oracle/upwind_oracle.c (loop for loop after mesh.F) against mpas-seaice_b200/weakmesh.py (numpy, written from
+    the geometry: rotate to the equator of the cell, tangent x position, eastward component): two independent readings
+    of seaice_normal_vectors with removeMetricTerms = .true. as the weak operators call it (weak.F:87-96)."""
+    mesh, irf, _ = case(kind)
+    wf = weakmesh.weak_fields(mesh)
+    edges = _vertex_midpoint_edges(mesh, wf["verticesOnEdge"], wf["edgesOnVertex"])
+    iv = variational_init.interior_vertex(mesh)
+    o = upwind.normal_vectors(mesh, edges, iv, rotate=True, remove_metric_terms=True)
+    _assert_normals_close(o, {k: wf[k] for k in o}, exact=False)
+    n = o["normalVectorPolygon"][:mesh.nCells]
+    used = np.arange(mesh.maxEdges)[None, :] < mesh.nEdgesOnCell[:mesh.nCells, None]
+    assert np.abs((n ** 2).sum(axis=2) - 1.0)[used].max() < 1e-14          # unit vectors
+    if not mesh.on_a_sphere:
+        # a closed polygon: the side normals weighted by the side lengths add up to zero
+        dv = mesh.dvEdge[mesh.edgesOnCell[:mesh.nCells] - 1]
+        closed = (n * (dv * used)[:, :, None]).sum(axis=1)
+        assert np.abs(closed).max() < 1e-9 * mesh.dvEdge[:mesh.nEdges].max()
+
+
+@pytest.mark.parametrize("remove_metric_terms", [True, False])
+@pytest.mark.parametrize("kind", ["hex12", "quad10", "ico3", "band48"])
+def test_normal_vectors_match_oracle(kind, remove_metric_terms, leg):
+    """ir_normal_vectors against the oracle, as the weak operators (removeMetricTerms) and as the upwind transport (not)
+    call it.  Emulation: the same libm, bit for bit.  Device: CUDA's sin / cos / asin / atan2 are 1-2 ulp functions, so
+    to round-off, with the second component held to what its formula allows (see _assert_normals_close)."""
+    which, lib = leg
+    mesh, irf, _ = case(kind)
+    iv = variational_init.interior_vertex(mesh)
+    ref = upwind.normal_vectors(mesh, irf, iv, rotate=True, remove_metric_terms=remove_metric_terms)
+    got = ir_host.normal_vectors(mesh, irf, iv, rotate=True, remove_metric_terms=remove_metric_terms, lib_path=lib)
+    _assert_normals_close(got, ref, exact=(which == "emulation"))
+    ref_p = upwind.normal_vectors(mesh, irf, iv, rotate=False, remove_metric_terms=remove_metric_terms, triangles=False)
+    got_p = ir_host.normal_vectors(mesh, irf, iv, rotate=False, remove_metric_terms=remove_metric_terms, triangles=False,
+                                   lib_path=lib)
+    assert set(got_p) == {"normalVectorPolygon", "latCellRotated"}
+    _assert_normals_close(got_p, ref_p, exact=(which == "emulation"))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# config_advection_type = 'upwind' (src/shared/mpas_seaice_advection_upwind.F): oracle/upwind_oracle.c and ir_run_upwind
+# ----------------------------------------------------------------------------------------------------------------------
+
+def _upwind_setup(kind):
+    mesh, irf, geom = case(kind)
+    iv = variational_init.interior_vertex(mesh)
+    # seaice_init_advection_upwind (:122): polygons only, removeMetricTerms = .false.
+    nve = upwind.normal_vectors(mesh, irf, iv, rotate=True, remove_metric_terms=False, triangles=False)["normalVectorPolygon"]
+    return mesh, irf, geom, ir_host.interior_edge(mesh), nve
+
+
+def _upwind_state(mesh, rng, n_cat=3, table="physical", ice_free=0.3):
+    """area, ice volume, snow volume, surface temperature as (nCells+1, nCategories) arrays.  ``physical``: every tracer
+    rides on the area.  ``reference``: define_tracer_connectivities as written (:160-165): area <- surfaceTemperature <-
+    iceVolumeCategory <- snowVolumeCategory."""
+    nC = mesh.nCells
+    a = np.zeros((nC + 1, n_cat))
+    a[:nC] = rng.uniform(0.05, 0.3, size=(nC, n_cat))
+    a[:nC][rng.uniform(size=(nC, n_cat)) < ice_free] = 0.0
+    vol, snow, tsfc = np.zeros_like(a), np.zeros_like(a), np.zeros_like(a)
+    vol[:nC] = a[:nC] * rng.uniform(0.5, 3.0, size=(nC, n_cat))
+    snow[:nC] = a[:nC] * rng.uniform(0.0, 0.3, size=(nC, n_cat))
+    tsfc[:nC] = np.where(a[:nC] > 0, rng.uniform(-20.0, -1.0, size=(nC, n_cat)), 0.0)
+    if table == "physical":
+        return [upwind.Var("iceAreaCategory", a), upwind.Var("iceVolumeCategory", vol, 0, True),
+                upwind.Var("snowVolumeCategory", snow, 0, True), upwind.Var("surfaceTemperature", tsfc, 0)]
+    return [upwind.Var("iceAreaCategory", a), upwind.Var("surfaceTemperature", tsfc, 0),
+            upwind.Var("iceVolumeCategory", vol, 1, True), upwind.Var("snowVolumeCategory", snow, 2, True)]
+
+
+def _clone_vars(variables):
+    return [upwind.Var(x.name, x.array.copy(), x.parent, x.volume_like, x.child_minimum) for x in variables]
+
+
+def test_upwind_oracle_conserves_and_keeps_uniform_tracers():
+    """Planar mesh, no flux through the boundary (its edges are not interior): the upwind step conserves the total area
+    and the ice / snow volumes to round-off, a uniform thickness and a uniform temperature stay uniform wherever ice is
+    left, and the new area of an interior cell is the closed-form donor-cell update."""
+    mesh, irf, geom, interior, nve = _upwind_setup("quad16")
+    nC = mesh.nCells
+    rng = np.random.default_rng(3)
+    var = _upwind_state(mesh, rng, n_cat=2)
+    a0 = var[0].array.copy()
+    var[1].array[:] = a0 * 1.7           # uniform thickness
+    var[3].array[:] = np.where(a0 > 0, -5.0, 0.0)
+    u0 = 0.04
+    from test_oracle_ir import uniform_velocity
+    u, v = uniform_velocity(mesh, u0, 0.0)
+    dt = 3600.0
+    before = [(x.array[:nC] * mesh.areaCell[:nC, None]).sum(axis=0) for x in var[:3]]
+    d = upwind.run(mesh, irf["verticesOnEdge"], interior, nve, var, u, v, dt, diagnostics=True)
+    after = [(x.array[:nC] * mesh.areaCell[:nC, None]).sum(axis=0) for x in var[:3]]
+    for b, f in zip(before, after):
+        assert np.all(np.abs(f - b) <= 1e-13 * np.abs(b))
+    a1 = var[0].array
+    ice = a1[:nC] > 1e-11
+    assert np.abs(var[1].array[:nC][ice] / a1[:nC][ice] - 1.7).max() < 1e-13
+    assert np.abs(var[3].array[:nC][ice] + 5.0).max() < 1e-13
+    # donor cell: a_i <- a_i - (u dt / dx) (a_i - a_west) on cells whose four edges are interior and whose neighbourhood holds ice
+    dx = 1000.0
+    west = {}
+    for c in range(nC):
+        for j in range(mesh.nEdgesOnCell[c]):
+            nb = mesh.cellsOnCell[c, j] - 1
+            if nb < nC and abs(mesh.yCell[nb] - mesh.yCell[c]) < 1e-6 and mesh.xCell[nb] < mesh.xCell[c]:
+                west[c] = nb
+    from test_oracle_ir import inner_cells
+    inner = np.nonzero(inner_cells(mesh, 1))[0]
+    checked = 0
+    for c in inner:
+        w = west[c]
+        if a0[c, 0] > 1e-11 and a0[w, 0] > 1e-11 and a0[[n - 1 for n in mesh.cellsOnCell[c, :4]], 0].min() > 1e-11:
+            expect = a0[c, 0] - (u0 * dt / dx) * (a0[c, 0] - a0[w, 0])
+            assert abs(a1[c, 0] - expect) < 1e-14
+            checked += 1
+    assert checked > 20
+    assert np.abs(d["edgeVelocity"][:mesh.nEdges]).max() <= u0 * (1 + 1e-14)
+
+
+def test_upwind_oracle_with_the_reference_table_zeroes_the_volumes():
+    """define_tracer_connectivities as written chains iceVolumeCategory under surfaceTemperature (:162-164): the volume's
+    "mass" is area * temperature, which is negative for ice below the melting point, `parentTracerNew > 0` (:1217) never
+    holds and the volumes come back zero.  Recorded here as the as-executed behaviour of the reference's table; the
+    physically meaningful table is the caller's choice (ir_upwind_var.parent)."""
+    mesh, irf, geom, interior, nve = _upwind_setup("hex12")
+    var = _upwind_state(mesh, np.random.default_rng(4), n_cat=2, table="reference")
+    u, v = smooth_divergent_velocity(mesh, geom)
+    a0 = var[0].array.copy()
+    upwind.run(mesh, irf["verticesOnEdge"], interior, nve, var, u, v, 3600.0)
+    assert np.all(var[2].array == 0.0) and np.all(var[3].array == 0.0)
+    assert np.abs(var[0].array[:mesh.nCells] - a0[:mesh.nCells]).max() > 1e-6     # the area itself is transported
+
+
+@pytest.mark.parametrize("table", ["physical", "reference"])
+@pytest.mark.parametrize("kind", ["hex16", "quad16", "ico3", "band48"])
+def test_upwind_matches_oracle(kind, table, lib_path):
+    """ir_run_upwind against the oracle, bit for bit: every cell (halo and the extra slot included), the edge fluxes of
+    every variable and the edge velocity, three steps, divergent flow, ice-free cells, a block that owns two thirds of
+    its cells."""
+    mesh, irf, geom, interior, nve = _upwind_setup(kind)
+    nC = mesh.nCells
+    nCS = (2 * nC) // 3
+    var = _upwind_state(mesh, np.random.default_rng(11), table=table)
+    u, v = smooth_divergent_velocity(mesh, geom)
+    ref, dev = _clone_vars(var), _clone_vars(var)
+    s = _solver(kind, lib_path, var[0].array.shape[1], n_cells_solve=nCS)
+    try:
+        s.set_upwind_mesh(interior, mesh.dvEdge, nve)
+        for _ in range(3):
+            d = upwind.run(mesh, irf["verticesOnEdge"], interior, nve, ref, u, v, 3600.0, n_cells_solve=nCS, diagnostics=True)
+            s.run_upwind(dev, u, v, 3600.0)
+            for i, (x, y) in enumerate(zip(ref, dev)):
+                assert np.array_equal(x.array, y.array), x.name
+                flux, vel = s.upwind_fluxes(i)
+                assert np.array_equal(flux[:mesh.nEdges], d["edgeFlux"][i][:mesh.nEdges]), x.name
+                assert np.array_equal(vel[:mesh.nEdges], d["edgeVelocity"][:mesh.nEdges])
+            # what a host does between steps: halo cells back to physical values (here: owned cells' rule applied by the oracle)
+            for x, y in zip(ref, dev):
+                y.array[:] = x.array
+        assert np.abs(ref[0].array[:nCS] - var[0].array[:nCS]).max() > 1e-6
+    finally:
+        s.destroy()
+
+
+def test_upwind_call_order_and_arguments(lib_path):
+    mesh, irf, geom, interior, nve = _upwind_setup("hex12")
+    var = _upwind_state(mesh, np.random.default_rng(2), n_cat=2)
+    u, v = smooth_divergent_velocity(mesh, geom)
+    s = _solver("hex12", lib_path, 2)
+    try:
+        with pytest.raises(ir_host.IrError) as e:
+            s.run_upwind(var, u, v, 3600.0)                 # before ir_set_upwind_mesh
+        assert e.value.code == ir_host.IR_ERR_STATE
+        with pytest.raises(ir_host.IrError):
+            s.upwind_fluxes(0)
+        s.set_upwind_mesh(interior, mesh.dvEdge, nve)
+        bad = _clone_vars(var)
+        bad[1].parent = 2                                    # a parent after its child
+        with pytest.raises(ir_host.IrError) as e:
+            s.run_upwind(bad, u, v, 3600.0)
+        assert e.value.code == ir_host.IR_ERR_ARGUMENT
+        bad = _clone_vars(var)
+        bad[0].parent = 0
+        with pytest.raises(ir_host.IrError):
+            s.run_upwind(bad, u, v, 3600.0)
+        s.run_upwind(var, u, v, 3600.0)
+        s.run_upwind(var[:2], u, v, 3600.0)                  # another table: the state is reallocated
+        with pytest.raises(ir_host.IrError):
+            s.upwind_fluxes(2)
+    finally:
+        s.destroy()
