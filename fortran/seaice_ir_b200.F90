@@ -46,6 +46,7 @@ module seaice_ir_b200
   public :: &
        seaice_ir_b200_create, &
        seaice_ir_b200_step, &
+       seaice_upwind_b200_step, &
        seaice_ir_b200_destroy
 
   ! ---- C ABI (include/ir_b200.h) ----------------------------------------------------------------
@@ -71,6 +72,13 @@ module seaice_ir_b200
      integer(c_int) :: volumeLike
      type(c_ptr) :: array
   end type ir_tracer_desc
+
+  type, bind(C) :: ir_upwind_var
+     integer(c_int) :: parent
+     integer(c_int) :: volumeLike
+     real(c_double) :: childMinimum
+     type(c_ptr) :: array
+  end type ir_upwind_var
 
   type, bind(C) :: ir_check_report
      integer(c_int) :: conservationViolated
@@ -132,6 +140,24 @@ module seaice_ir_b200
        integer(c_int) :: ierr
      end function ir_fetch_conservation_sums
 
+     function ir_set_upwind_mesh(handle, interiorEdge, dvEdge, normalVectorEdge) &
+          bind(C, name="ir_set_upwind_mesh") result(ierr)
+       import :: c_ptr, c_int
+       type(c_ptr), value :: handle
+       type(c_ptr), value :: interiorEdge, dvEdge, normalVectorEdge
+       integer(c_int) :: ierr
+     end function ir_set_upwind_mesh
+
+     function ir_run_upwind(handle, nVars, vars, uVelocity, vVelocity, dt) bind(C, name="ir_run_upwind") result(ierr)
+       import :: c_ptr, c_int, c_double, ir_upwind_var
+       type(c_ptr), value :: handle
+       integer(c_int), value :: nVars
+       type(ir_upwind_var), dimension(*), intent(in) :: vars
+       type(c_ptr), value :: uVelocity, vVelocity
+       real(c_double), value :: dt
+       integer(c_int) :: ierr
+     end function ir_run_upwind
+
      function ir_destroy(handle) bind(C, name="ir_destroy") result(ierr)
        import :: c_ptr, c_int
        type(c_ptr), value :: handle
@@ -154,6 +180,9 @@ module seaice_ir_b200
   integer, parameter :: maxTracers = 128
   type(ir_tracer_desc), dimension(maxTracers), target :: tracerTable
   integer :: nTracersTable = 0
+
+  type(ir_upwind_var), dimension(4), target :: upwindTable
+  logical :: upwindMeshSet = .false.
 
 contains
 
@@ -365,6 +394,70 @@ contains
   end subroutine seaice_ir_b200_step
 
 !-----------------------------------------------------------------------
+!  seaice_upwind_b200_step: config_advection_type = 'upwind'.  Replaces, for one block, what
+!  seaice_run_advection_upwind (mpas_seaice_advection_upwind.F:385-520) does between the tracer halo
+!  exchange and the time-level shift: prepare_advection, the loop over tracerConnectivities,
+!  finalize_advection.  The table is the reference's (define_tracer_connectivities :145-170), in its
+!  order; the library works in place on time level 1, so MPAS_pool_shift_time_levels (:2032) is
+!  skipped for these four arrays.  (The reference zeroes time level 2 of iceEnthalpy, iceSalinity and
+!  snowEnthalpy (:1690-1700) and shifts it in: a host that wants that too zeroes them here.)
+!-----------------------------------------------------------------------
+
+  subroutine seaice_upwind_b200_step(block, dt)
+
+    type(block_type), intent(inout) :: block
+    real(kind=RKIND), intent(in) :: dt
+
+    type(mpas_pool_type), pointer :: meshPool, boundaryPool, tracersPool, velocityPool
+    real(kind=RKIND), dimension(:), pointer :: uVelocity, vVelocity, dvEdge
+    real(kind=RKIND), dimension(:,:,:), pointer :: normalVectorEdge
+    real(kind=RKIND), dimension(:,:,:), pointer :: iceAreaCategory, surfaceTemperature, iceVolumeCategory, snowVolumeCategory
+    integer, dimension(:), pointer :: interiorEdge
+    integer(c_int) :: ierr
+
+    call MPAS_pool_get_subpool(block % structs, 'mesh', meshPool)
+    call MPAS_pool_get_subpool(block % structs, 'boundary', boundaryPool)
+    call MPAS_pool_get_subpool(block % structs, 'tracers', tracersPool)
+    call MPAS_pool_get_subpool(block % structs, 'velocity_solver', velocityPool)
+
+    call MPAS_pool_get_array(velocityPool, 'uVelocity', uVelocity)
+    call MPAS_pool_get_array(velocityPool, 'vVelocity', vVelocity)
+
+    if (.not. upwindMeshSet) then
+       call MPAS_pool_get_array(meshPool, 'dvEdge', dvEdge)
+       call MPAS_pool_get_array(boundaryPool, 'interiorEdge', interiorEdge)
+       call MPAS_pool_get_array(velocityPool, 'normalVectorEdge', normalVectorEdge)
+       ierr = ir_set_upwind_mesh(irHandle, c_loc(interiorEdge), c_loc(dvEdge), c_loc(normalVectorEdge))
+       if (ierr /= IR_OK) call ir_b200_abort('ir_set_upwind_mesh')
+       upwindMeshSet = .true.
+    endif
+
+    call MPAS_pool_get_array(tracersPool, 'iceAreaCategory', iceAreaCategory, 1)
+    call MPAS_pool_get_array(tracersPool, 'surfaceTemperature', surfaceTemperature, 1)
+    call MPAS_pool_get_array(tracersPool, 'iceVolumeCategory', iceVolumeCategory, 1)
+    call MPAS_pool_get_array(tracersPool, 'snowVolumeCategory', snowVolumeCategory, 1)
+
+    ! (1, nCategories, nCells+1) arrays: the same memory as the (nCategories, nCells+1) the C side takes
+    upwindTable(1) % parent = -1
+    upwindTable(1) % volumeLike = 0
+    upwindTable(1) % array = c_loc(iceAreaCategory)
+    upwindTable(2) % parent = 0
+    upwindTable(2) % volumeLike = 0
+    upwindTable(2) % array = c_loc(surfaceTemperature)
+    upwindTable(3) % parent = 1
+    upwindTable(3) % volumeLike = 1
+    upwindTable(3) % array = c_loc(iceVolumeCategory)
+    upwindTable(4) % parent = 2
+    upwindTable(4) % volumeLike = 1
+    upwindTable(4) % array = c_loc(snowVolumeCategory)
+    upwindTable(:) % childMinimum = 0.0_c_double
+
+    ierr = ir_run_upwind(irHandle, 4_c_int, upwindTable, c_loc(uVelocity), c_loc(vVelocity), real(dt, c_double))
+    if (ierr /= IR_OK) call ir_b200_abort('ir_run_upwind')
+
+  end subroutine seaice_upwind_b200_step
+
+!-----------------------------------------------------------------------
 
   subroutine seaice_ir_b200_destroy()
 
@@ -374,6 +467,7 @@ contains
        ierr = ir_destroy(irHandle)
        irHandle = c_null_ptr
        nTracersTable = 0
+       upwindMeshSet = .false.
     endif
 
   end subroutine seaice_ir_b200_destroy

@@ -163,7 +163,7 @@ def _ir_f_type(name):
 
 
 def test_ir_bind_c_types_mirror_the_header():
-    for name in ("ir_mesh_desc", "ir_tracer_desc", "ir_check_report"):
+    for name in ("ir_mesh_desc", "ir_tracer_desc", "ir_check_report", "ir_upwind_var"):
         assert _ir_f_type(name) == _ir_c_struct(name), name
 
 
@@ -172,7 +172,8 @@ def test_ir_bound_names_are_exported_with_matching_argument_counts():
     lib = ctypes.CDLL(os.path.join(ROOT, "mpas-seaice_b200", "csrc", "libir_b200.so"))
     bound = re.findall(r'bind\(C, name="(\w+)"\)', IR_F90)
     assert set(bound) == {"ir_create", "ir_set_tracers", "ir_run", "ir_set_checks", "ir_fetch_check_report",
-                          "ir_fetch_conservation_sums", "ir_destroy", "ir_last_error_string"}
+                          "ir_fetch_conservation_sums", "ir_set_upwind_mesh", "ir_run_upwind", "ir_destroy",
+                          "ir_last_error_string"}
     for n in bound:
         assert hasattr(lib, n), n
         proto = re.search(r"\b" + n + r"\s*\(([^)]*)\)", IR_HDR).group(1)
