@@ -248,7 +248,10 @@ int ir_fetch_upwind_fluxes(ir_handle *h, int var, double *edgeFlux, double *edge
  * host frees or reallocates such an array (e.g. mpas_pool_destroy_pool); ir_destroy does it too.  No-op otherwise. */
 int ir_release_host_memory(ir_handle *h);
 
-int ir_last_run_ms(ir_handle *h, float *ms);       /* device time of the last ir_run, kernels only */
+int ir_last_run_ms(ir_handle *h, float *ms);       /* device time of the last ir_run / ir_run_upwind, kernels only */
+/* ... of the last ir_run by kernel, ms[5]: prepare, reconstruct, triangles, fluxes, update (each with the check kernels
+ * launched next to it, if any): CUDA events on the handle's stream */
+int ir_last_kernel_ms(ir_handle *h, float *ms);
 int ir_launch_count(ir_handle *h, long long *n);   /* kernels launched by this handle so far */
 int ir_destroy(ir_handle *h);
 const char *ir_last_error_string(void);

@@ -160,6 +160,8 @@ struct ir_handle {
     int device;
     cudaStream_t stream;
     cudaEvent_t ev0, ev1;
+    cudaEvent_t evK[4];   // between the five kernels of a step (ir_last_kernel_ms)
+    float kernelMs[5];
     Dev d;
     std::vector<RowInfo> rows;
     std::vector<int> tracerRow0, tracerLayers, tracerParent, tracerVolume, tracerDepth;
@@ -1501,6 +1503,7 @@ extern "C" int ir_create(ir_handle **out, const ir_mesh_desc *m, int device)
     if (ce != cudaSuccess) { set_error("cudaStreamCreate -> %s", cudaGetErrorString(ce)); delete h; return IR_ERR_CUDA; }
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
+    for (cudaEvent_t &ev : h->evK) cudaEventCreate(&ev);
     Dev &d = h->d;
     d.nC = m->nCells; d.nCS = m->nCellsSolve; d.nV = m->nVertices; d.nE = m->nEdges; d.M = m->maxEdges; d.D = m->vertexDegree;
     d.nK = m->nCategories; d.nQP = m->nQuadPoints; d.sphere = m->on_a_sphere ? 1 : 0; d.rotate = m->rotate_cartesian_grid ? 1 : 0;
@@ -1856,14 +1859,17 @@ extern "C" int ir_run(ir_handle *h, int nTracers, const ir_tracer_desc *tr, cons
         IR_LAUNCH_SYNC((k_check_sums), (unsigned)d.nRows, 256, 0, s, d, (const double *)d.val, d.sums);
         h->launches++;
     }
+    IR_CUDA(cudaEventRecord(h->evK[0], s));
     if (d.nC > 0) {
         int maxDepth = 0;
         for (int dq : h->tracerDepth) maxDepth = dq > maxDepth ? dq : maxDepth;
         IR_LAUNCH_SYNC((k_reconstruct_coop), grid_for((size_t)d.nC, CL), dim3(CL, CW), ir_reconstruct_smem_bytes(), s, d, maxDepth);
         h->launches++;
     }
+    IR_CUDA(cudaEventRecord(h->evK[1], s));
     if (d.nE > 0) {
         IR_LAUNCH((k_triangles), ge, 128, s, d, dt);
+        IR_CUDA(cudaEventRecord(h->evK[2], s));
         {
             const size_t smem = ir_flux_smem_bytes(d.nD0, d.nD1);
 #ifdef IR_DEVICE_BUILD
@@ -1874,7 +1880,10 @@ extern "C" int ir_run(ir_handle *h, int nTracers, const ir_tracer_desc *tr, cons
             else IR_LAUNCH_SYNC((k_fluxes_coop<6>), grid_for((size_t)d.nE, FL), dim3(FL, FR), smem, s, d);
         }
         h->launches += 2;
+    } else {
+        IR_CUDA(cudaEventRecord(h->evK[2], s));
     }
+    IR_CUDA(cudaEventRecord(h->evK[3], s));
     {
         int maxDepth = 0;
         for (int dq : h->tracerDepth) maxDepth = dq > maxDepth ? dq : maxDepth;
@@ -1916,6 +1925,10 @@ extern "C" int ir_run(ir_handle *h, int nTracers, const ir_tracer_desc *tr, cons
     IR_CUDA(cudaMemcpyAsync(&flags, d.flags, sizeof(int), cudaMemcpyDeviceToHost, s));
     IR_CUDA(cudaStreamSynchronize(s));
     IR_CUDA(cudaEventElapsedTime(&h->lastMs, h->ev0, h->ev1));
+    {
+        cudaEvent_t marks[6] = {h->ev0, h->evK[0], h->evK[1], h->evK[2], h->evK[3], h->ev1};
+        for (int i = 0; i < 5; i++) IR_CUDA(cudaEventElapsedTime(&h->kernelMs[i], marks[i], marks[i + 1]));
+    }
     if (flags & FLAG_NEG_MASS) { set_error("IR: negative mass in a cell (incremental_remap.F:7465)"); return IR_ERR_NEGATIVE_MASS; }
     if (flags & FLAG_NEG_QP) { set_error("IR: negative mass at a quadrature point (incremental_remap.F:6895)"); return IR_ERR_NEGATIVE_MASS_QP; }
     if (flags & FLAG_PARALLEL) { set_error("IR: parallel basis edges in shift_vertices (incremental_remap.F:6415)"); return IR_ERR_PARALLEL_EDGES; }
@@ -2097,6 +2110,13 @@ extern "C" int ir_last_run_ms(ir_handle *h, float *ms)
     return IR_OK;
 }
 
+extern "C" int ir_last_kernel_ms(ir_handle *h, float *ms)
+{
+    IR_REQUIRE(h != nullptr && ms != nullptr, "NULL argument");
+    for (int i = 0; i < 5; i++) ms[i] = h->kernelMs[i];
+    return IR_OK;
+}
+
 extern "C" int ir_launch_count(ir_handle *h, long long *n)
 {
     IR_REQUIRE(h != nullptr && n != nullptr, "NULL argument");
@@ -2132,6 +2152,8 @@ extern "C" int ir_destroy(ir_handle *h)
     for (void *p : h->allocs) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    for (cudaEvent_t ev : h->evK)
+        if (ev) cudaEventDestroy(ev);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return IR_OK;

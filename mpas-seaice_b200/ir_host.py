@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("IR_B200_LIB", os.path.join(_HERE, "csrc", "libir_b200
 EXPORTS = ("ir_init_geometry", "ir_create", "ir_set_tracers", "ir_run", "ir_set_checks", "ir_fetch_check_report",
            "ir_fetch_conservation_sums", "ir_fetch_diagnostics", "ir_fetch_tracer_field", "ir_normal_vectors",
            "ir_set_upwind_mesh", "ir_run_upwind", "ir_fetch_upwind_fluxes", "ir_release_host_memory",
-           "ir_last_run_ms", "ir_launch_count", "ir_destroy", "ir_last_error_string")
+           "ir_last_run_ms", "ir_last_kernel_ms", "ir_launch_count", "ir_destroy", "ir_last_error_string")
 GEOM_NAMES = ("x", "y", "xx", "xy", "yy", "xxx", "xxy", "xyy", "yyy", "xxxx", "xxxy", "xxyy", "xyyy", "yyyy")
 
 IR_OK, IR_ERR_ARGUMENT, IR_ERR_CUDA, IR_ERR_STATE, IR_ERR_MESH = 0, 1, 2, 3, 4
@@ -328,6 +328,12 @@ class IrTransport:
         ms = C.c_float(0)
         self._check(self._L.ir_last_run_ms(self._h, C.byref(ms)))
         return ms.value
+
+    def last_kernel_ms(self):
+        """Device time of the last run by kernel: dict(prepare, reconstruct, triangles, fluxes, update) in ms."""
+        ms = (C.c_float * 5)()
+        self._check(self._L.ir_last_kernel_ms(self._h, ms))
+        return dict(zip(("prepare", "reconstruct", "triangles", "fluxes", "update"), (float(x) for x in ms)))
 
     def launch_count(self):
         n = C.c_longlong(0)

@@ -71,12 +71,69 @@ def smooth_velocity(mesh, min_edge, dt, cfl=0.3):
     return u, v
 
 
+def upwind_bench(args, mesh, irf, tracers, dt, t_mesh):
+    """ir_run_upwind on the same mesh and ice state: 4 variables x 5 categories.  Algorithmic bytes of a step: per
+    (variable, category) row the old value in and the new value out per cell (16 B) and the edge flux out per edge (8 B)."""
+    from mpas_seaice_b200 import ir_host, variational_init
+    from oracle import upwind as oup
+
+    class Var:
+        def __init__(self, name, array, parent=None, volume_like=False):
+            self.name, self.array, self.parent, self.volume_like, self.child_minimum = name, array, parent, volume_like, 0.0
+    variables = [Var(t.name, np.ascontiguousarray(t.array[:, :, 0]), None if t.parent is None else 0, t.volume_like)
+                 for t in tracers[:4]]
+    geom = ir_host.init_geometry(mesh, irf, rotate=True)
+    u, v = smooth_velocity(mesh, geom["minLengthEdgesOnVertex"][:mesh.nVertices].min(), dt)
+    iv = variational_init.interior_vertex(mesh)
+    nve = ir_host.normal_vectors(mesh, irf, iv, rotate=True, remove_metric_terms=False, triangles=False)["normalVectorPolygon"]
+    interior = ir_host.interior_edge(mesh)
+    nK = variables[0].array.shape[1]
+    rows = len(variables) * nK
+    rec = dict(metric="upwind_cell_row_updates_per_s", unit="cell-rows/s", cells=mesh.nCells, edges=mesh.nEdges, rows=rows,
+               steps=args.steps, warmup=args.warmup, mesh_s=round(t_mesh, 2), data="synthetic", dtype="f64", impl="cuda")
+    initial = [x.array.copy() for x in variables]
+    solver = ir_host.IrTransport(mesh, irf, geom, nK, rotate=True)
+    try:
+        solver.set_upwind_mesh(interior, mesh.dvEdge, nve)
+        for _ in range(args.warmup):
+            solver.run_upwind(variables, u, v, dt)
+        dev_ms, t1 = [], time.time()
+        for _ in range(args.steps):
+            solver.run_upwind(variables, u, v, dt)
+            dev_ms.append(solver.last_run_ms())
+        wall = (time.time() - t1) / args.steps
+        kms = float(np.mean(dev_ms)) or float("nan")      # (0 under the host emulation, which has no clock)
+        algo = rows * (16.0 * mesh.nCells + 8.0 * mesh.nEdges)
+        peak = 6650.0
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            peak = float(json.load(open(pk))["hbm_gbs"])
+        rec.update(kernel_ms_per_step=round(kms, 4), wall_ms_per_step=round(wall * 1e3, 3), value=mesh.nCells * rows / (kms * 1e-3),
+                   higher_is_better=True, gpu_launches=solver.launch_count(),
+                   roofline=dict(bound="hbm", achieved=algo / (kms * 1e-3) / 1e9, peak=peak, unit="GB/s",
+                                 frac=algo / (kms * 1e-3) / 1e9 / peak, algorithmic_bytes_per_step=algo, traffic=None,
+                                 kernel="the kernels of one ir_run_upwind (edge velocity, prepare, per variable edge flux + update, finalize)"))
+    finally:
+        solver.destroy()
+    if args.check:
+        ref = [oup.Var(x.name, a, x.parent, x.volume_like) for x, a in zip(variables, initial)]
+        nve_o = oup.normal_vectors(mesh, irf, iv, rotate=True, remove_metric_terms=False, triangles=False)["normalVectorPolygon"]
+        rec["normals_max_abs_diff"] = float(np.abs(nve - nve_o).max())
+        for _ in range(args.warmup + args.steps):
+            oup.run(mesh, irf["verticesOnEdge"], interior, nve, ref, u, v, dt)
+        rec["parity"] = bool(all(np.array_equal(a.array, b.array) for a, b in zip(variables, ref)))
+    print(json.dumps(rec))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--level", type=int, default=7, help="icosphere level: 7 = 163 842 cells (QU60), 9 = QU15, 10 = QU7.5")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--cpu", action="store_true", help="time the oracle (CPU) instead of the device")
+    ap.add_argument("--upwind", action="store_true",
+                    help="time config_advection_type = 'upwind' (ir_run_upwind: area, ice / snow volume, surface temperature "
+                         "riding on the area) instead of the incremental remapping")
     ap.add_argument("--cpu-baseline", action="store_true", help="add a cpu_baseline object: the oracle timed on 2 steps")
     ap.add_argument("--check", action="store_true",
                     help="after the timed steps, run the oracle on the same initial state and report whether the device "
@@ -91,6 +148,8 @@ def main():
     irf = irmesh.ir_fields(mesh)
     t_mesh = time.time() - t0
     tracers = standard_tracers(mesh)
+    if args.upwind:
+        return upwind_bench(args, mesh, irf, tracers, dt, t_mesh)
     initial = [t.array.copy() for t in tracers] if args.check else None
     n_rows = sum(t.array.shape[1] * t.array.shape[2] for t in tracers)
     rec = dict(metric="ir_cell_row_updates_per_s", unit="cell-rows/s", cells=mesh.nCells, edges=mesh.nEdges, rows=n_rows,
@@ -124,13 +183,14 @@ def main():
                 solver.run(tracers, u, v, dt)
                 dev_ms.append(solver.last_run_ms())
             wall = (time.time() - t1) / args.steps
-            kms = float(np.mean(dev_ms))
+            kms = float(np.mean(dev_ms)) or float("nan")      # (0 under the host emulation, which has no clock)
             algo = mesh.nCells * n_rows * 112.0 + mesh.nEdges * 2 * 4 * 112.0
             peak = 6650.0
             pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
             if os.path.exists(pk):
                 peak = float(json.load(open(pk))["hbm_gbs"])
             io_bytes = int(sum(t.array.nbytes for t in tracers))
+            rec["kernel_ms"] = {k: round(x, 4) for k, x in solver.last_kernel_ms().items()}     # of the last timed step
             rec.update(impl="cuda", kernel_ms_per_step=round(kms, 4), wall_ms_per_step=round(wall * 1e3, 3),
                        value=mesh.nCells * n_rows / (kms * 1e-3), higher_is_better=True, gpu_launches=solver.launch_count(),
                        e2e=dict(value=mesh.nCells * n_rows / wall, unit="cell-rows/s", h2d_bytes_per_step=io_bytes + 2 * u.nbytes,
