@@ -237,7 +237,7 @@ class Parser:
             a = ("un", op, self.p_mul())
         else:
             a = self.p_mul()
-        while self.at_op("+", "-"):
+        while self.at_op("+", "-", "//"):
             op = self.take()[1]
             a = ("bin", op, a, self.p_mul())
         return a
@@ -245,6 +245,8 @@ class Parser:
     def p_mul(self):
         a = self.p_pow()
         while self.at_op("*", "/"):
+            if self.peek()[1] == "/" and self.i + 1 < len(self.t) and self.t[self.i + 1] == ("op", ")"):
+                break                                        # the closing "/)" of an array constructor
             op = self.take()[1]
             a = ("bin", op, a, self.p_pow())
         return a
@@ -298,6 +300,17 @@ class Parser:
         if tok[0] == "str":
             self.take()
             return ("str", tok[1])
+        if tok == ("op", "(") and self.i + 1 < len(self.t) and self.t[self.i + 1] == ("op", "/"):
+            self.take()
+            self.take()
+            items = []
+            while not self.at_op("/"):
+                items.append(self.expr())
+                if self.at_op(","):
+                    self.take()
+            self.take("op", "/")
+            self.take("op", ")")
+            return ("array", items)
         if tok == ("op", "("):
             self.take()
             a = self.expr()
@@ -387,6 +400,13 @@ class VarRef:
     def set(self, v):
         self.frame.set(self.name, v)
 
+    def bind(self, v):
+        cur = self.frame.vars.get(self.name)
+        if isinstance(cur, VarRef):
+            cur.bind(v)
+        else:
+            self.frame.bind(self.name, v)
+
 
 ABSENT = object()
 
@@ -427,14 +447,44 @@ def _size(x, dim=None):
     return int(x.a.shape[x.a.ndim - int(dim)])
 
 
+def _dot_product(a, b):
+    s = 0.0
+    for x, y in zip(a.a.reshape(-1), b.a.reshape(-1)):     # rank-1 arguments: one multiply and one add per element, in order
+        s = s + float(x) * float(y)
+    return s
+
+
+def _spread(x, dim, ncopies):
+    if x.a.ndim != 1:
+        raise FortranError("spread() of a rank-%d array" % x.a.ndim)
+    if dim == 2:                                            # result(i, j) = x(i): numpy layout [j][i]
+        return FArray(np.tile(x.a, (int(ncopies), 1)))
+    return FArray(np.tile(x.a[:, None], (1, int(ncopies))))  # dim = 1: result(i, j) = x(j): numpy layout [j][i]
+
+
+def _maxval(x, dim=None):
+    if dim is None:
+        return _scalar(x.a.max())
+    return FArray(x.a.max(axis=x.a.ndim - int(dim)))
+
+
 INTRINSICS = {
+    "dot_product": _dot_product, "spread": _spread, "maxval": _maxval,
+    "maxloc": lambda x: FArray(np.array([int(np.argmax(x.a.T.reshape(-1))) + 1], dtype=np.int64)),
+    "any": lambda x: bool(np.any(x.a)) if isinstance(x, FArray) else bool(x),
+    "all": lambda x: bool(np.all(x.a)) if isinstance(x, FArray) else bool(x),
     "sqrt": math.sqrt, "abs": abs, "max": max, "min": min,
     "sign": lambda a, b: math.copysign(abs(a), b) if isinstance(a, float) or isinstance(b, float) else (abs(a) if b >= 0 else -abs(a)),
     "mod": lambda a, b: math.fmod(a, b) if isinstance(a, float) else int(math.fmod(a, b)),
+    "modulo": lambda a, b: a - b * math.floor(a / b) if isinstance(a, float) or isinstance(b, float) else a % b,
     "real": lambda a, *k: float(a), "dble": float, "int": lambda a, *k: int(a), "nint": lambda a: int(round(a)),
     "sin": math.sin, "cos": math.cos, "tan": math.tan, "asin": math.asin, "acos": math.acos, "atan": math.atan,
     "atan2": math.atan2, "exp": math.exp, "log": math.log, "sum": _sum, "size": _size, "trim": lambda s: s.rstrip(),
 }
+
+
+# elementwise on whole arrays / sections (numpy's float64 sqrt, abs, maximum, minimum are the same IEEE operations)
+ARRAY_INTRINSICS = {"sqrt": np.sqrt, "abs": np.abs, "max": np.maximum, "min": np.minimum}
 
 
 class _Exit(Exception):
@@ -456,6 +506,8 @@ class Sub:
         self.name, self.args, self.file = name, args, file
         self.renames, self.decl_arrays, self.inits, self.body = {}, [], [], None
         self.lines = lines
+        self.result = None         # name of the result variable of a function
+        self.types = {}            # declared type of the names: "int" | "real" | "log" (assignment converts)
 
 
 _DECL = re.compile(r"^(real\b|integer\b|logical\b|character\b|double\s+precision\b|type\s*\(|class\s*\()", re.I)
@@ -483,6 +535,11 @@ class Frame:
         return v
 
     def set(self, name, val):
+        t = self.sub.types.get(name)
+        if t == "int" and isinstance(val, float):
+            val = int(val)                                   # assignment to an integer truncates
+        elif t == "real" and isinstance(val, int) and not isinstance(val, bool):
+            val = float(val)
         if name in self.vars:
             cur = self.vars[name]
             if isinstance(cur, (ElemRef, VarRef)):
@@ -516,7 +573,7 @@ class Interpreter:
     def __init__(self, defined=()):
         self.defined = tuple(defined)
         self.subs = {}
-        self.globals = {}          # module variables (lower-case names)
+        self.globals = {"rkind": 8, "strkind": 512}   # module variables (lower-case names); the MPAS kind parameters
         self.pool = {}             # (pool name or None, variable name) -> value for the MPAS_pool_get_* calls
         self.noop = set()          # framework calls that do nothing on a single block
         self.hooks = {}            # name -> python callable(interp, frame, args) replacing a call
@@ -532,13 +589,19 @@ class Interpreter:
         while i < len(lines):
             no, s = lines[i]
             m = re.match(r"^(?:recursive\s+|pure\s+|elemental\s+)*subroutine\s+(\w+)\s*(?:\((.*)\))?\s*$", s, re.I)
-            if m:
-                name = m.group(1).lower()
-                args = [a.strip().lower() for a in (m.group(2) or "").split(",") if a.strip()]
+            mf = None if m else re.match(
+                r"^(?:recursive\s+|pure\s+|elemental\s+|real\s*(?:\([^)]*\))?\s+|integer\s+|logical\s+|double\s+precision\s+)*"
+                r"function\s+(\w+)\s*\((.*?)\)\s*(?:result\s*\(\s*(\w+)\s*\))?\s*$", s, re.I)
+            if m or mf:
+                mm = m or mf
+                name = mm.group(1).lower()
+                args = [a.strip().lower() for a in (mm.group(2) or "").split(",") if a.strip()]
                 j = i + 1
-                while not re.match(r"^end\s*subroutine\b", lines[j][1], re.I):
+                while not re.match(r"^end\s*(subroutine|function)\b", lines[j][1], re.I):
                     j += 1
                 self.subs[name] = Sub(name, args, lines[i + 1:j], path)
+                if mf:
+                    self.subs[name].result = (mf.group(3) or name).lower()
                 i = j
             i += 1
 
@@ -615,6 +678,8 @@ class Interpreter:
             if not m:
                 continue
             name, own_dim, init = m.group(1).lower(), m.group(2), m.group(3)
+            if not attrs_l.startswith(("type", "class", "character")):
+                sub.types[name] = kind
             shape = own_dim if own_dim else (dim.group(1) if dim else None)
             if shape is not None and not deferred and ":" not in shape and name not in sub.args:
                 sub.decl_arrays.append((name, [parse_expr(x) for x in _split_top(shape)], kind))
@@ -751,10 +816,19 @@ class Interpreter:
             return node[1]
         if k == "paren":
             return self.ev(node[1], fr)
+        if k == "array":
+            vals = [self.ev(x, fr) for x in node[1]]
+            return FArray(np.array(vals, dtype=np.float64 if any(isinstance(v, float) for v in vals) else np.int64))
         if k == "name":
             return fr.get(node[1])
         if k == "un":
             v = self.ev(node[2], fr)
+            if isinstance(v, FArray):
+                if node[1] == "-":
+                    return FArray(-v.a)
+                if node[1] == "+":
+                    return v
+                return FArray(~v.a)
             if node[1] == "-":
                 return -v
             if node[1] == "+":
@@ -769,6 +843,8 @@ class Interpreter:
             a, b = self.ev(node[2], fr), self.ev(node[3], fr)
             if isinstance(a, FArray) or isinstance(b, FArray):
                 return self._array_op(op, a, b)
+            if op == "//":
+                return str(a) + str(b)
             if op == "+":
                 return a + b
             if op == "-":
@@ -820,6 +896,11 @@ class Interpreter:
             return FArray(x * y)
         if op == "/":
             return FArray(x / y)
+        if op == "**" and isinstance(y, int) and not isinstance(y, bool):
+            return FArray(powi(x, y))                        # elementwise multiplications
+        rel = {"==": np.equal, "/=": np.not_equal, "<": np.less, "<=": np.less_equal, ">": np.greater, ">=": np.greater_equal}
+        if op in rel:
+            return FArray(rel[op](x, y))
         raise FortranError("array operator %s" % op)
 
     def _index(self, args, fr):
@@ -847,9 +928,14 @@ class Interpreter:
             if name == "associated":
                 vals = [self.ev(a, fr) for _, a in args]
                 return vals[0] is not None if len(vals) == 1 else vals[0] is vals[1]
+            if name in self.subs and self.subs[name].result:
+                callee = self.invoke(name, args, fr)
+                return callee.get(self.subs[name].result)
             if name in INTRINSICS:
                 vals = [self.ev(a, fr) for kw, a in args if kw is None]
                 kws = {kw: self.ev(a, fr) for kw, a in args if kw is not None}
+                if name in ARRAY_INTRINSICS and any(isinstance(v, FArray) for v in vals):
+                    return FArray(ARRAY_INTRINSICS[name](*[v.a if isinstance(v, FArray) else v for v in vals]))
                 return INTRINSICS[name](*vals, **kws)
             raise FortranError("%s: %r is neither an array nor a known function" % (fr.sub.name, name))
         v = self.ev(base, fr)
@@ -885,6 +971,8 @@ class Interpreter:
                         break
             elif k == "do":
                 lim = [self.ev(x, fr) for x in n[3]]
+                if any(isinstance(x, float) for x in lim):
+                    raise FortranError("%s line %d: real do-loop bounds %s" % (fr.sub.name, n[1], lim))
                 lo, hi, st = lim[0], lim[1], (lim[2] if len(lim) > 2 else 1)
                 count = max((hi - lo + st) // st, 0)
                 v = lo
@@ -929,7 +1017,14 @@ class Interpreter:
             elif k == "allocate":
                 for item in n[2]:
                     shape = [int(self.ev(a, fr)) for _, a in item[2]]
-                    fr.bind(item[1][1], FArray(np.zeros(tuple(reversed(shape)))))
+                    kind = fr.sub.types.get(item[1][1], "real")
+                    dt = np.float64 if kind == "real" else (np.int64 if kind == "int" else np.bool_)
+                    new = FArray(np.zeros(tuple(reversed(shape)), dtype=dt))
+                    cur = fr.vars.get(item[1][1])
+                    if isinstance(cur, VarRef):            # an allocatable dummy: the caller's variable is allocated
+                        cur.bind(new)
+                    else:
+                        fr.bind(item[1][1], new)
             elif k in ("deallocate", "continue"):
                 pass
             else:
@@ -942,7 +1037,8 @@ class Interpreter:
         if name in self.POOL_GETTERS:
             return self._pool_get(name, args, fr)
         if name in self.subs:
-            return self.invoke(name, args, fr)
+            self.invoke(name, args, fr)
+            return None
         if name in self.noop:
             return None
         raise FortranError("%s line %d: call of %r, which is neither loaded, mapped nor declared a no-op" % (fr.sub.name, no, name))
@@ -984,7 +1080,7 @@ class Interpreter:
             self.run_block(sub.body, fr)
         except _Return:
             pass
-        return None
+        return fr
 
     def _actual(self, node, caller):
         if caller is None:

@@ -57,6 +57,7 @@ CASES = {
     "refexec_quad10_linear_1": ("quad10", "linear", 1, {}),
     "refexec_quad10_evp_avg_6": ("quad10", "evp", 6, {"average_variational_strain": True}),
     "refexec_ico2_evp_lineardrag_6": ("ico2", "evp", 6, {"ocean_stress_type": "linear"}),
+    "refexec_hex12_evp_special_boundaries_8": ("hex12", "evp", 8, {"use_special_boundaries_velocity": True}),
 }
 
 
@@ -127,6 +128,24 @@ def build(name):
         x, y = mesh.xVertex[:nV] / mesh.Lx, mesh.yVertex[:nV] / mesh.Ly
         step["uVelocity"][:nV] = np.sin(2.0 * np.pi * 2.56 * x) * np.sin(2.0 * np.pi * 2.56 * y)
         step["vVelocity"][:nV] = np.sin(2.0 * np.pi * 2.56 * x) * np.sin(2.0 * np.pi * 2.56 * y)
+    if opts.get("use_special_boundaries_velocity"):
+        # periodic (1), reversed (2) and zero-velocity (3) vertices with chained sources, as tests/test_gpu_parity.py's
+        # 1D_velocity_hex-like case: seaice_set_special_boundaries_velocity (special_boundaries.F:253-331) runs before the
+        # loop and after every subcycle (velocity_solver.F:2440-2455)
+        nV = mesh.nVertices
+        vbt, src = np.zeros(nV + 1, dtype=np.int32), np.zeros(nV + 1, dtype=np.int32)
+        active = np.nonzero(step["solveVelocity"][:nV] == 1)[0]
+        inactive = np.nonzero(step["solveVelocity"][:nV] != 1)[0]
+        rng = np.random.default_rng(3)
+        pick = rng.choice(inactive, size=min(30, inactive.size), replace=False)
+        for i, v in enumerate(pick):
+            vbt[v] = 1 + (i % 3)
+            if vbt[v] in (1, 2):
+                src[v] = int(rng.choice(active)) + 1
+        chain = pick[vbt[pick] == 1]
+        src[chain[0]] = chain[3] + 1      # a source updated LATER in the sequential loop (the old value is seen)
+        src[chain[2]] = chain[1] + 1      # a source updated EARLIER (the new value is seen)
+        step["vertexBoundaryType"], step["vertexBoundarySourceLocal"] = vbt, src
     work = common.clone_step(step)
     I, domain = interpreter(mesh, var, work, opts, nsub)
     t0 = time.time()
@@ -150,8 +169,258 @@ def build(name):
     return out, called, time.time() - t0
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# The init-time precompute: init_velocity_solver_variational_primary_mesh (variational.F:108-344) with everything below it
+# -- seaice_calc_variational_metric_terms, seaice_cell_vertices_at_vertex (mesh.F:632), seaice_calc_local_coords
+# (variational_shared.F:42-290), seaice_init_velocity_solver_wachspress (wachspress.F:46-1287 incl. the Dunavant tables) or
+# seaice_init_velocity_solver_pwl (pwl.F:44-373 with the LU solve of numerics.F), variational_denominator (:358-445).
+# Input: the mesh-file arrays; output: the eight static arrays of the velocity_variational pool.
+# ---------------------------------------------------------------------------------------------------------------------
+INIT_FILES = ("src/column/constants/cice/ice_constants_colpkg.F90", "src/shared/mpas_seaice_constants.F",
+              "src/shared/mpas_seaice_numerics.F", "src/shared/mpas_seaice_mesh.F",
+              "src/shared/mpas_seaice_velocity_solver_variational_shared.F", "src/shared/mpas_seaice_velocity_solver_wachspress.F",
+              "src/shared/mpas_seaice_velocity_solver_pwl.F", "src/shared/mpas_seaice_velocity_solver_variational.F")
+INIT_OUT = ("cellVerticesAtVertex", "tanLatVertexRotatedOverRadius", "basisGradientU", "basisGradientV", "basisIntegralsU",
+            "basisIntegralsV", "basisIntegralsMetric", "variationalDenominator")
+INIT_MESH = ("nEdgesOnCell", "verticesOnCell", "cellsOnVertex", "edgesOnCell", "xVertex", "yVertex", "zVertex", "xCell", "yCell",
+             "zCell", "areaCell", "areaTriangle", "dvEdge")
+INIT_CASES = {
+    # name: (mesh, basis, denominator, integration type, order)
+    "refexec_init_hex5_wachspress": (("planar_hex", 5, 6, 16000.0), "wachspress", "original", "dunavant", 8),
+    "refexec_init_ico1_wachspress": (("icosphere", 1), "wachspress", "original", "dunavant", 8),
+    "refexec_init_quad4_wachspress_alt": (("planar_quad", 4, 4, 16000.0), "wachspress", "alternate", "dunavant", 4),
+    "refexec_init_hex4_trapezoidal": (("planar_hex", 4, 5, 16000.0), "wachspress", "original", "trapezoidal", 3),
+    "refexec_init_hex5_pwl": (("planar_hex", 5, 6, 16000.0), "pwl", "original", "dunavant", 8),
+    "refexec_init_ico1_pwl": (("icosphere", 1), "pwl", "alternate", "dunavant", 8),
+}
+
+
+def init_mesh(spec):
+    from mpas_seaice_b200 import meshgen
+    return getattr(meshgen, spec[0])(*spec[1:])
+
+
+def build_init(name):
+    from mpas_seaice_b200 import variational_init
+    spec, basis, denominator, itype, order = INIT_CASES[name]
+    mesh = init_mesh(spec)
+    nC, nV, M, D = mesh.nCells, mesh.nVertices, mesh.maxEdges, mesh.vertexDegree
+    I = F.Interpreter(defined=())
+    for f in INIT_FILES:
+        I.load(os.path.join(REF, f))
+    I.resolve_constants()
+    I.noop |= {"mpas_timer_start", "mpas_timer_stop", "mpas_log_write"}
+    out = dict(cellVerticesAtVertex=np.zeros((nV + 1, D), np.int32), tanLatVertexRotatedOverRadius=np.zeros(nV + 1),
+               variationalDenominator=np.zeros(nV + 1))
+    for k in INIT_OUT[2:7]:
+        out[k] = np.zeros((nC + 1, M, M))
+    arrays = dict(out)
+    for k in INIT_MESH:
+        arrays[k] = mesh[k]
+    arrays["interiorVertex"] = variational_init.interior_vertex(mesh).astype(np.int32)      # boundary pool (mesh.F:423)
+    for k, v in arrays.items():
+        I.pool[k] = F.FArray(v)
+    sphere = bool(mesh.on_a_sphere)
+    I.pool.update(on_a_sphere=sphere, sphere_radius=float(getattr(mesh, "sphere_radius", 0.0) or 0.0), nCells=nC,
+                  nVertices=nV, vertexDegree=D, maxEdges=M)
+    t0 = time.time()
+    # rotateCartesianGrid / includeMetricTerms: the Registry defaults on a sphere (Registry.xml:571-578), off on a plane
+    I.call("init_velocity_solver_variational_primary_mesh", "mesh", "velocity_variational", "boundary", sphere, sphere,
+           basis, denominator, itype, order)
+    called = sorted(set(I.trace))
+    data = {"provenance": np.array("outputs computed by interpreting the reference's Fortran source "
+                                   "(tests/golden/fortran_subset.py): " + ", ".join(called)),
+            "spec": np.array(repr(spec)), "basis": np.array(basis), "denominator": np.array(denominator),
+            "integration_type": np.array(itype), "integration_order": np.int64(order)}
+    for k in INIT_MESH:
+        data["mesh_" + k] = mesh[k]
+    for k in INIT_OUT:
+        data["out_" + k] = out[k]
+    return data, called, time.time() - t0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# A whole dynamics step, the body of seaice_run_velocity_solver (velocity_solver.F:562-595):
+#   velocity_solver_pre_subcycle (:613-671: aggregate_mass_and_area, calculation_masks, new_ice_velocities, ice_strength,
+#   air_stress, coriolis_force_coefficient, ocean_stress, surface_tilt, init_subcycle_variables, with
+#   seaice_interpolate_cell_to_vertex of mesh.F) -> subcycle_velocity_solver -> velocity_solver_post_subcycle (:3360-3380:
+#   final_divergence_shear, principal_stresses_driver, ocean_stress_final with seaice_interpolate_vertex_to_cell).
+# Input: the category tracers, the coupler fields and the state carried from the previous step; output: every field the
+# three phases leave in the pools.
+# ---------------------------------------------------------------------------------------------------------------------
+STEP_FILES = ("src/column/constants/cice/ice_constants_colpkg.F90", "src/shared/mpas_seaice_constants.F",
+              "src/shared/mpas_seaice_mesh.F", "src/shared/mpas_seaice_velocity_solver_constitutive_relation.F",
+              "src/shared/mpas_seaice_velocity_solver_variational.F", "src/shared/mpas_seaice_special_boundaries.F",
+              "src/shared/mpas_seaice_velocity_solver.F")
+STEP_CASES = {
+    # name: (mesh kind, state kind, config_dt, subcycles, categories)
+    "refexec_step_ico2_stateB_6": ("ico2", "B", 3600.0, 6, 1),
+    "refexec_step_hex12_square_5": ("hex12", "square", 3600.0, 5, 1),
+    "refexec_step_ico2_stateB_3cat_4": ("ico2", "B", 3600.0, 4, 3),
+}
+STEP_OUT = {
+    "velocity_solver": ("solveStress", "solveVelocity", "solveVelocityPrevious", "icePressure", "airStressCellU", "airStressCellV",
+                        "uVelocity", "vVelocity", "uVelocityInitial", "vVelocityInitial", "stressDivergenceU", "stressDivergenceV",
+                        "oceanStressU", "oceanStressV", "oceanStressCoeff", "airStressVertexU", "airStressVertexV",
+                        "surfaceTiltForceU", "surfaceTiltForceV", "uOceanVelocityVertex", "vOceanVelocityVertex",
+                        "totalMassVertexfVertex", "divergence", "shear", "oceanStressCellU", "oceanStressCellV"),
+    "icestate": ("iceAreaVertex", "totalMassVertex", "totalMassCell", "iceAreaCellInitial"),
+    "tracers_aggregate": ("iceAreaCell", "iceVolumeCell", "snowVolumeCell"),
+    "velocity_variational": ("strain11", "strain22", "strain12", "stress11", "stress22", "stress12", "replacementPressure",
+                             "principalStress1", "principalStress2"),
+    "ridging": ("ridgeConvergence", "ridgeShear"),
+}
+
+
+def step_state(mesh, state_kind, n_cat):
+    """cell state + forcing of mpas_seaice_b200.synthetic, the ice spread over n_cat thickness categories"""
+    from mpas_seaice_b200 import meshgen, synthetic
+    if state_kind == "square":
+        scaled = meshgen.Mesh(mesh)
+        scaled.xCell = mesh.xCell * (1.28e6 / mesh.Lx)
+        scaled.yCell = mesh.yCell * (1.28e6 / mesh.Ly)
+        state = synthetic.square_state(scaled)
+    else:
+        state = synthetic.sphere_state(mesh, kind=state_kind)
+    nC = mesh.nCells
+    w = np.array([0.5, 0.3, 0.2][:n_cat]) if n_cat > 1 else np.array([1.0])
+    w = w / w.sum()
+    cat = {}
+    for k_cell, k_cat in (("iceAreaCell", "iceAreaCategory"), ("iceVolumeCell", "iceVolumeCategory"), ("snowVolumeCell", "snowVolumeCategory")):
+        a = np.zeros((nC + 1, n_cat, 1))
+        for k in range(n_cat):
+            a[:, k, 0] = state[k_cell] * w[k] * (1.0 + 0.1 * k if k_cell != "iceAreaCell" else 1.0)
+        cat[k_cat] = a
+    return state, cat
+
+
+def build_step(name):
+    from mpas_seaice_b200 import variational_init
+    kind, state_kind, config_dt, nsub, n_cat = STEP_CASES[name]
+    mesh, var = common.mesh_case(kind)
+    state, cat = step_state(mesh, state_kind, n_cat)
+    _, opts = common.step_case(mesh)                      # elasticTimeStep, dampingTimescale ... as seaice_init_evp sets them
+    opts = dict(opts)
+    nC, nV, M, D = mesh.nCells, mesh.nVertices, mesh.maxEdges, mesh.vertexDegree
+    I = F.Interpreter(defined=())
+    for f in STEP_FILES:
+        I.load(os.path.join(REF, f))
+    I.resolve_constants()
+    I.noop |= {"mpas_timer_start", "mpas_timer_stop", "mpas_log_write", "seaice_load_balance_timers", "mpas_dmpar_field_halo_exch",
+               "mpas_dmpar_exch_group_full_halo_exch", "mpas_dmpar_exch_group_reuse_halo_exch",
+               "seaice_mesh_pool_update"}         # seaice_mesh_pool's pointers ARE the pool arrays here
+    zc, zv, zcm = (lambda: np.zeros(nC + 1)), (lambda: np.zeros(nV + 1)), (lambda: np.zeros((nC + 1, M)))
+    P = {}
+    for k, a in cat.items():
+        P[("tracers", k)] = a.copy()
+    for k in STEP_OUT["tracers_aggregate"]:
+        P[("tracers_aggregate", k)] = zc()
+    for k in ("totalMassCell", "iceAreaCellInitial", "openWaterArea"):
+        P[("icestate", k)] = zc()
+    for k in ("iceAreaVertex", "totalMassVertex"):
+        P[("icestate", k)] = zv()
+    for k in ("uAirVelocity", "vAirVelocity", "airDensity"):
+        P[("atmos_coupling", k)] = np.ascontiguousarray(state[k], dtype=np.float64).copy()
+    for k in ("uOceanVelocity", "vOceanVelocity"):
+        P[("ocean_coupling", k)] = np.ascontiguousarray(state[k], dtype=np.float64).copy()
+    for k in ("seaSurfaceTiltU", "seaSurfaceTiltV"):
+        P[("ocean_coupling", k)] = zc()
+    P[("ocean_coupling", "landIceMask")] = np.zeros(nC + 1, np.int32)
+    P[("ocean_coupling", "landIceMaskVertex")] = np.zeros(nV + 1, np.int32)
+    P[("boundary", "interiorVertex")] = variational_init.interior_vertex(mesh).astype(np.int32)
+    P[("velocity_solver", "solveStress")] = np.zeros(nC + 1, np.int32)
+    for k in ("solveVelocity", "solveVelocityPrevious"):
+        P[("velocity_solver", k)] = np.zeros(nV + 1, np.int32)         # no Registry default: the first step of a run
+    for k in ("icePressure", "airStressCellU", "airStressCellV", "divergence", "shear", "oceanStressCellU", "oceanStressCellV"):
+        P[("velocity_solver", k)] = zc()
+    for k in ("uVelocity", "vVelocity", "uVelocityInitial", "vVelocityInitial", "stressDivergenceU", "stressDivergenceV",
+              "oceanStressU", "oceanStressV", "oceanStressCoeff", "airStressVertexU", "airStressVertexV", "surfaceTiltForceU",
+              "surfaceTiltForceV", "seaSurfaceTiltVertexU", "seaSurfaceTiltVertexV", "uOceanVelocityVertex",
+              "vOceanVelocityVertex", "totalMassVertexfVertex"):
+        P[("velocity_solver", k)] = zv()
+    for k in STEP_OUT["velocity_variational"]:
+        P[("velocity_variational", k)] = zcm()
+    for k in ("strain11", "strain22", "strain12", "stress11", "stress22", "stress12", "replacementPressure", "principalStress1",
+              "principalStress2"):
+        P[("velocity_weak", k)] = zc()
+    for k in STEP_OUT["ridging"]:
+        P[("ridging", k)] = zc()
+    for k in list(mesh.keys()):
+        if isinstance(mesh[k], np.ndarray):
+            P[("mesh", k)] = mesh[k]
+    for k in VAR_KEYS:
+        P[("velocity_variational", k)] = var[k]
+    for (pool, k), v in P.items():
+        fa = F.FArray(v)
+        I.pool[(pool, k)] = fa
+        I.pool.setdefault(k, fa)
+        if pool != "velocity_weak":
+            I.globals[k.lower()] = fa                  # seaice_mesh_pool's module pointers
+    dims = dict(nCells=nC, nVertices=nV, nVerticesSolve=nV, nCellsSolve=nC, vertexDegree=D, maxEdges=M, nCategories=n_cat)
+    I.pool.update(dims)
+    for k, v in dims.items():
+        I.globals[k.lower()] = v
+    I.pool.update(config_use_halo_exch=False, config_aggregate_halo_exch=False, config_reuse_halo_exch=False,
+                  config_use_column_package=False, config_use_column_vertical_thermodynamics=False,
+                  config_use_air_stress=True, config_use_ocean_stress=True, config_use_surface_tilt=True,
+                  config_geostrophic_surface_tilt=True, config_calc_velocity_masks=True,
+                  config_stress_divergence_scheme="variational", config_strain_scheme="variational",
+                  config_elastic_subcycle_number=int(nsub), config_use_special_boundaries_velocity=False,
+                  config_use_special_boundaries_velocity_masks=False,
+                  elasticTimeStep=float(opts["elasticTimeStep"]), dynamicsTimeStep=float(opts["dynamicsTimeStep"]))
+    g = I.globals
+    g["strainschemetype"] = g["variational_strain_scheme"]
+    g["stressdivergenceschemetype"] = g["variational_stress_divergence_scheme"]
+    g["averagevariationalstrains"] = False
+    g["oceanstresstype"] = g["quadratic_ocean_stress"]
+    g["constitutiverelationtype"] = g["evp_constitutive_relation"]
+    g["usespecialboundariesvelocity"] = False
+    g["usespecialboundariesvelocitymasks"] = False
+    g["dampingtimescale"] = float(opts["dampingTimescale"])
+    g["numericalinertiacoefficient"] = float(opts.get("numericalInertiaCoefficient", 0.0))
+    block = types.SimpleNamespace(structs="structs", configs="configs", dimensions="dimensions", next=None)
+    domain = types.SimpleNamespace(blocklist=block, configs="configs")
+    data = {"nsub": np.int64(nsub), "config_dt": np.float64(config_dt), "kind": np.array(kind), "state_kind": np.array(state_kind)}
+    for k, a in cat.items():
+        data["in_" + k] = a.copy()
+    for k in ("uAirVelocity", "vAirVelocity", "airDensity", "uOceanVelocity", "vOceanVelocity"):
+        data["in_" + k] = np.ascontiguousarray(state[k], dtype=np.float64)
+    for k, v in opts.items():
+        data["opt_" + k] = np.array(v)
+    t0 = time.time()
+    I.call("velocity_solver_pre_subcycle", domain)
+    for pool, names in STEP_OUT.items():
+        for k in names:
+            data["pre_" + k] = P[(pool, k)].copy()
+    I.call("subcycle_velocity_solver", domain, None)
+    I.call("velocity_solver_post_subcycle", domain)
+    for pool, names in STEP_OUT.items():
+        for k in names:
+            data["out_" + k] = P[(pool, k)].copy()
+    called = sorted(set(I.trace))
+    data["provenance"] = np.array("outputs computed by interpreting the reference's Fortran source "
+                                  "(tests/golden/fortran_subset.py): " + ", ".join(called))
+    return data, called, time.time() - t0
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
+    for name in STEP_CASES:
+        if only and name not in only:
+            continue
+        data, called, secs = build_step(name)
+        path = os.path.join(HERE, "step", name + ".npz")
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        np.savez_compressed(path, **data)
+        print("%s: %.1f s, %d KB; interpreted: %s" % (name, secs, os.path.getsize(path) // 1024, ", ".join(called)), flush=True)
+    for name in INIT_CASES:
+        if only and name not in only:
+            continue
+        data, called, secs = build_init(name)
+        path = os.path.join(HERE, "init", name + ".npz")
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        np.savez_compressed(path, **data)
+        print("%s: %.1f s, %d KB; interpreted: %s" % (name, secs, os.path.getsize(path) // 1024, ", ".join(called)), flush=True)
     for name in CASES:
         if only and name not in only:
             continue

@@ -1,6 +1,11 @@
-"""Committed golden vectors (tests/golden/*.npz, made by tests/golden/make_golden.py from the oracle):
-stored inputs -> stored outputs.  CPU: the oracle still reproduces them bit for bit (pins the checker
-against drift between rounds).  GPU: libevp_b200.so reproduces them bit for bit through the C-ABI."""
+"""Committed golden vectors (tests/golden/*.npz): stored inputs -> stored outputs, replayed bit for bit through the
+oracle (CPU) and through libevp_b200.so and the C ABI (GPU).
+
+* refexec_*.npz -- outputs computed by EXECUTING THE REFERENCE'S OWN FORTRAN SOURCE (subcycle_velocity_solver and
+  everything below it) with the interpreter tests/golden/fortran_subset.py; made by
+  tests/golden/make_reference_executed_golden.py.  These pin the oracle -- and the device -- to the reference itself.
+* the others -- made by tests/golden/make_golden.py from the oracle: longer runs on larger meshes, a guard against drift
+  between rounds."""
 import glob
 import os
 
@@ -41,6 +46,9 @@ def _check(mesh, step, want, got):
         assert np.array_equal(got[k][cm], want[k][cm]), k
     for k in common.COMPARE_VERTEX:
         assert np.array_equal(got[k][vm], want[k][vm]), k
+    if "vertexBoundaryType" in step:          # the special-boundary vertices themselves (not solved: outside vm)
+        b = step["vertexBoundaryType"] != 0
+        assert b.any() and np.array_equal(got["uVelocity"][b], want["uVelocity"][b]) and np.array_equal(got["vVelocity"][b], want["vVelocity"][b])
 
 
 def test_golden_files_exist():
@@ -59,7 +67,8 @@ def test_oracle_reproduces_golden(path):
 def test_device_reproduces_golden(evp_lib, path):
     from mpas_seaice_b200 import host
     mesh, var, step, opts, want, nsub = _load(path)
-    solver = host.EvpSolver(mesh, var, opts)
+    sb = (step["vertexBoundaryType"], step["vertexBoundarySourceLocal"]) if opts.get("use_special_boundaries_velocity") else None
+    solver = host.EvpSolver(mesh, var, opts, special_boundaries=sb)
     try:
         if opts.get("average_variational_strain"):
             interior = np.zeros(mesh.nVertices + 1, dtype=np.int32)          # not read by the averaging
