@@ -393,6 +393,11 @@ def build_step(name):
         for k in names:
             data["pre_" + k] = P[(pool, k)].copy()
     I.call("subcycle_velocity_solver", domain, None)
+    # The pre-subcycle ran with config_use_column_package = .false.: the column package is not part of this path, so the
+    # categories are aggregated here (:685) and the strength is Hibler's (:1419) instead of colpkg_ice_strength.  The
+    # ridging parameters of the post-subcycle (variational.F:1283-1300) exist only with the package on (the Registry
+    # default), and nothing else in the post-subcycle reads the switch: on from here.
+    I.pool["config_use_column_package"] = True
     I.call("velocity_solver_post_subcycle", domain)
     for pool, names in STEP_OUT.items():
         for k in names:
