@@ -121,17 +121,21 @@ def test_device_reproduces_the_reference_executed_step(evp_lib, path):
         agg = solver.fetch_aggregate(ice_pressure=True)
         for k in ("iceAreaCell", "iceVolumeCell", "snowVolumeCell", "totalMassCell"):
             assert np.array_equal(agg[k][:nC], pre[k][:nC]), k
+        # The Hibler strength holds the path's one transcendental: P* h exp(-C (1 - a)) (velocity_solver.F:1419-1436).  CUDA's
+        # exp() is a 1-ulp function, the reference's is the host libm's: the device value is held to 1 ulp here, and the step
+        # continues from the libm value (what a host that keeps ice_strength passes) so that everything after it stays
+        # a bit-for-bit comparison.
+        state = dict(iceAreaCell=agg["iceAreaCell"], iceVolumeCell=agg["iceVolumeCell"])
+        p_host = oracle.hibler_strength_unmasked(state, nC)
+        assert np.all(np.abs(agg["icePressure"][:nC] - p_host[:nC]) <= np.spacing(np.abs(p_host[:nC])))
         cells = dict(forcing, iceAreaCellInitial=agg["iceAreaCell"], iceAreaCell=agg["iceAreaCell"],
-                     totalMassCell=agg["totalMassCell"], icePressure=agg["icePressure"])
+                     totalMassCell=agg["totalMassCell"], icePressure=p_host)
         solver.pre_subcycle(cells, cold_start=host.START_FIRST_STEP)
         got_pre = solver.fetch_pre()
         vm = pre["solveVelocity"][:nV] == 1
         assert np.array_equal(got_pre["solveStress"][:nC], pre["solveStress"][:nC])
         assert np.array_equal(got_pre["solveVelocity"][:nV], pre["solveVelocity"][:nV])
-        # the device's exp() is a 1-ulp function; the strength is compared to 1 ulp, everything else bit for bit unless
-        # the strength itself differs (measured identical on the tested states)
-        same_p = np.array_equal(got_pre["icePressure"][:nC], pre["icePressure"][:nC])
-        assert np.all(np.abs(got_pre["icePressure"][:nC] - pre["icePressure"][:nC]) <= np.spacing(np.abs(pre["icePressure"][:nC])))
+        assert np.array_equal(got_pre["icePressure"][:nC], pre["icePressure"][:nC])
         for k in ("iceAreaVertex", "totalMassVertex", "totalMassVertexfVertex", "airStressVertexU", "airStressVertexV",
                   "surfaceTiltForceU", "surfaceTiltForceV", "oceanStressU", "oceanStressV", "uOceanVelocityVertex",
                   "vOceanVelocityVertex", "uVelocityInitial", "vVelocityInitial"):
@@ -142,8 +146,6 @@ def test_device_reproduces_the_reference_executed_step(evp_lib, path):
                                     "replacementPressure", "stressDivergenceU", "stressDivergenceV"))
     finally:
         solver.destroy()
-    if not same_p:
-        pytest.skip("device exp() differs from libm in the last bit of the ice strength on this state")
     cm = (pre["solveStress"][:nC] == 1)[:, None] & _valid(mesh)
     for k in POST_CELL:
         assert np.array_equal(got[k][:nC], out[k][:nC]), k
