@@ -3,9 +3,10 @@
 TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 ``--impl reference`` legs may import this package; the product never does.
 
-Parity status: the reference Fortran cannot be built here and stores no outputs, so this oracle
-is pinned by the reference's analytic known answers only (tests/test_oracle_kat.py) --
-"parity unpinned" against golden outputs of the reference itself.
+Parity status: the reference Fortran cannot be built here and stores no outputs; the EVP oracle is pinned by
+outputs of the reference's own source executed by an interpreter (tests/golden/fortran_subset.py,
+tests/test_golden.py, tests/test_refexec_init.py, tests/test_refexec_step.py: bit for bit) and by the reference's
+analytic known answers (tests/test_oracle_kat.py).  See the headers of the C files.
 """
 from __future__ import annotations
 

@@ -8,11 +8,16 @@
  *
  * PARITY PINNING: the reference (Fortran + un-vendored MPAS framework) cannot be compiled in this
  * image (no Fortran compiler, no MPI, no netCDF) and ships NO stored numeric outputs
- * (SURVEY.md section 8c).  This oracle is therefore pinned only by the reference's own analytic
- * known answers (testing_and_setup/testcases/square/operators_strain_stress_divergence/create_ics.py:12-48,
- * src/shared/mpas_seaice_testing.F:726-839) -- see tests/test_oracle_kat.py -- and by analytic fields generated
- * with the reference's own Python test-case scripts (tests/golden/make_analytic_golden.py,
- * tests/test_analytic_golden.py); against golden OUTPUTS of the reference model it is "parity unpinned".
+ * (SURVEY.md section 8c).  This oracle is pinned by OUTPUTS OF THE REFERENCE'S OWN SOURCE EXECUTED HERE: an
+ * interpreter for the Fortran subset of these routines (tests/golden/fortran_subset.py) runs
+ * subcycle_velocity_solver, velocity_solver_pre_subcycle and velocity_solver_post_subcycle with everything below them
+ * from the files under /root/reference, one IEEE operation per operator in the written order; the fixtures
+ * (tests/golden/refexec_*.npz, tests/golden/step/*.npz) are reproduced by this file bit for bit
+ * (tests/test_golden.py, tests/test_refexec_step.py).  Also: the reference's analytic known answers
+ * (testing_and_setup/testcases/square/operators_strain_stress_divergence/create_ics.py:12-48,
+ * src/shared/mpas_seaice_testing.F:726-839; tests/test_oracle_kat.py), analytic fields generated with the reference's
+ * own Python test-case scripts (tests/test_analytic_golden.py) and closed-form recurrences (tests/test_closed_forms.py).
+ * Not pinned: what a production Fortran compiler does beyond the source semantics (FMA contraction, vectorised sums).
  *
  * Array conventions are the reference's: Fortran column-major, 1-based index VALUES, one junk
  * element at the end of every mesh array.  A Fortran A(i,j,c) with leading dims (M,M) is

@@ -2,10 +2,11 @@
  * oracle/evp_precompute_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
  *
  * CPU restatement of the one-time precompute that feeds the EVP subcycle
- * (seaice_init_velocity_solver_variational and callees).  Same conventions and the same
- * "parity unpinned against stored reference outputs" caveat as evp_oracle.c; pinned by the exact
- * reproduction properties of the bases (constant / linear fields, partition of unity) in
- * tests/test_oracle_kat.py.
+ * (seaice_init_velocity_solver_variational and callees).  Same conventions as evp_oracle.c.  Pinned by outputs of
+ * the reference's own source executed here (tests/golden/fortran_subset.py interprets
+ * init_velocity_solver_variational_primary_mesh with the Wachspress / PWL routines below it; fixtures
+ * tests/golden/init/*.npz, reproduced bit for bit: tests/test_refexec_init.py), by the exact reproduction properties
+ * of the bases (tests/test_oracle_kat.py) and by an independent closed form (tests/test_wachspress_independent.py).
  *
  * Arrays: Fortran column-major, 1-based index values, junk slot at the end.
  */
