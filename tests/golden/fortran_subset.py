@@ -374,6 +374,8 @@ class FArray:
 def _scalar(v):
     if isinstance(v, (np.floating, float)):
         return float(v)
+    if not isinstance(v, (np.integer, int, np.bool_, bool)):
+        return v                                   # an element of an array of derived-type objects
     if isinstance(v, (np.bool_, bool)):
         return bool(v)
     return int(v)
@@ -462,6 +464,29 @@ def _spread(x, dim, ncopies):
     return FArray(np.tile(x.a[:, None], (1, int(ncopies))))  # dim = 1: result(i, j) = x(j): numpy layout [j][i]
 
 
+def _matmul(a, b):
+    """matmul of a rank-2 and a rank-1 (or two rank-2) arrays: result(i[,k]) = sum over j of a(i,j) * b(j[,k]), the
+    products added in increasing j starting from zero -- the loop a compiler inlines for small fixed sizes."""
+    A = a.a.T                                   # A[i, j] in Fortran index order
+    if b.a.ndim == 1:
+        out = np.zeros(A.shape[0])
+        for i in range(A.shape[0]):
+            s = 0.0
+            for j in range(A.shape[1]):
+                s = s + float(A[i, j]) * float(b.a[j])
+            out[i] = s
+        return FArray(out)
+    B = b.a.T
+    out = np.zeros((A.shape[0], B.shape[1]))
+    for i in range(A.shape[0]):
+        for k in range(B.shape[1]):
+            s = 0.0
+            for j in range(A.shape[1]):
+                s = s + float(A[i, j]) * float(B[j, k])
+            out[i, k] = s
+    return FArray(out.T.copy())
+
+
 def _maxval(x, dim=None):
     if dim is None:
         return _scalar(x.a.max())
@@ -469,7 +494,7 @@ def _maxval(x, dim=None):
 
 
 INTRINSICS = {
-    "dot_product": _dot_product, "spread": _spread, "maxval": _maxval,
+    "dot_product": _dot_product, "spread": _spread, "maxval": _maxval, "matmul": _matmul,
     "maxloc": lambda x: FArray(np.array([int(np.argmax(x.a.T.reshape(-1))) + 1], dtype=np.int64)),
     "any": lambda x: bool(np.any(x.a)) if isinstance(x, FArray) else bool(x),
     "all": lambda x: bool(np.all(x.a)) if isinstance(x, FArray) else bool(x),

@@ -408,8 +408,146 @@ def build_step(name):
     return data, called, time.time() - t0
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# The transport row's options: seaice_normal_vectors (mesh.F:703-2007) and config_advection_type = 'upwind'
+# (mpas_seaice_advection_upwind.F: define_tracer_connectivities :145 and seaice_run_advection_upwind :385 with everything
+# below them, the module's own connectivity table and logical parameters).
+# ---------------------------------------------------------------------------------------------------------------------
+OPTION_MESHES = {"hex": ("planar_hex", 8, 9, 1000.0), "quad": ("planar_quad", 8, 8, 1000.0), "ico": ("icosphere", 2),
+                 "band": ("latlon_band", 24, 10, 60.0)}
+UPWIND_NAMES = ("iceAreaCategory", "iceVolumeCategory", "snowVolumeCategory", "surfaceTemperature", "iceEnthalpy", "iceSalinity",
+                "snowEnthalpy")
+
+
+def build_normals(kind, remove_metric_terms):
+    from mpas_seaice_b200 import irmesh, variational_init
+    mesh = init_mesh(OPTION_MESHES[kind])
+    irf = irmesh.ir_fields(mesh)
+    iv = variational_init.interior_vertex(mesh).astype(np.int32)
+    nC, nV, M, D = mesh.nCells, mesh.nVertices, mesh.maxEdges, mesh.vertexDegree
+    I = F.Interpreter(defined=())
+    I.load(os.path.join(REF, "src/shared/mpas_seaice_mesh.F"))
+    I.noop |= {"mpas_log_write"}
+    for k in list(mesh.keys()):
+        if isinstance(mesh[k], np.ndarray):
+            I.pool[k] = F.FArray(mesh[k])
+    for k in ("verticesOnEdge", "edgesOnVertex", "xEdge", "yEdge", "zEdge"):
+        I.pool[k] = F.FArray(irf[k])
+    I.pool.update(nCells=nC, nVertices=nV, nVerticesSolve=nV, vertexDegree=D, maxEdges=M, on_a_sphere=bool(mesh.on_a_sphere),
+                  sphere_radius=float(getattr(mesh, "sphere_radius", 0.0) or 0.0))
+    out = dict(normalVectorPolygon=np.zeros((nC + 1, M, 2)), normalVectorTriangle=np.zeros((nV + 1, D, 2)),
+               latCellRotated=np.zeros(nC + 1), latVertexRotated=np.zeros(nV + 1))
+    I.call("seaice_normal_vectors", "mesh", F.FArray(out["normalVectorPolygon"]), F.FArray(out["normalVectorTriangle"]),
+           F.FArray(iv), True, bool(remove_metric_terms), F.FArray(out["latCellRotated"]), F.FArray(out["latVertexRotated"]))
+    data = {"spec": np.array(repr(OPTION_MESHES[kind])), "remove_metric_terms": np.array(bool(remove_metric_terms)),
+            "provenance": np.array("outputs computed by interpreting the reference's Fortran source "
+                                   "(tests/golden/fortran_subset.py): " + ", ".join(sorted(set(I.trace))))}
+    for k in ("xCell", "xVertex"):
+        data["mesh_" + k] = mesh[k]
+    for k, v in out.items():
+        data["out_" + k] = v
+    return data
+
+
+def build_upwind(kind, nsteps=2):
+    from mpas_seaice_b200 import irmesh, variational_init, ir_host
+    from oracle import ir as oir, upwind as oup          # the oracle only supplies INPUTS here: geometry for the velocity scale
+    from test_transport_options import _upwind_state
+    from test_oracle_ir import smooth_divergent_velocity
+    mesh = init_mesh(OPTION_MESHES[kind])
+    irf = irmesh.ir_fields(mesh)
+    nC, nV, nE, M = mesh.nCells, mesh.nVertices, mesh.nEdges, mesh.maxEdges
+    nK = 2
+    normals = build_normals(kind, False)                                  # normalVectorEdge: the reference's own (:122)
+    nve = normals["out_normalVectorPolygon"]
+    var = _upwind_state(mesh, np.random.default_rng(11), n_cat=nK, table="reference")
+    u, v = smooth_divergent_velocity(mesh, oir.init_geometry(mesh, irf))
+    interior = ir_host.interior_edge(mesh)
+    I = F.Interpreter(defined=())
+    for f in ("src/column/constants/cice/ice_constants_colpkg.F90", "src/shared/mpas_seaice_constants.F",
+              "src/shared/mpas_seaice_advection_upwind.F"):
+        I.load(os.path.join(REF, f))
+    I.resolve_constants()
+    I.noop |= {"mpas_log_write", "mpas_timer_start", "mpas_timer_stop"}
+    layers = dict(iceEnthalpy=3, iceSalinity=3, snowEnthalpy=2)
+    byname = {x.name: x.array for x in var}
+    L1, L2 = {}, {}
+    for n in UPWIND_NAMES:
+        nl = layers.get(n, 1)
+        a = np.zeros((nC + 1, nK, nl))
+        if n in byname:
+            a[:, :, 0] = byname[n]
+        else:
+            a[:nC] = 1.5
+        L1[n], L2[n] = a, np.full_like(a, 7.0)
+        I.pool[("tracers", n, 1)], I.pool[("tracers", n, 2)] = F.FArray(L1[n]), F.FArray(L2[n])
+        tend = F.FArray(np.full((nC + 1, nK, nl), 3.0))
+        I.pool[("tracer_tendencies", n + "Tend")] = I.pool[("tracer_tendencies", n + "Tend", 1)] = tend
+        flux = F.FArray(np.full((nE + 1, nK, nl), 4.0))
+        I.pool[("tracer_edge_fluxes", n + "EdgeFlux")] = I.pool[("tracer_edge_fluxes", n + "EdgeFlux", 1)] = flux
+        for lvl in (1, 2):
+            I.pool[("tracer_conservation", n + "Cons", lvl)] = F.FArray(np.zeros(nK))
+    for k in list(mesh.keys()):
+        if isinstance(mesh[k], np.ndarray):
+            I.pool[k] = F.FArray(mesh[k])
+    I.pool["verticesOnEdge"] = F.FArray(irf["verticesOnEdge"])
+    I.pool.update(uVelocity=F.FArray(u), vVelocity=F.FArray(v), normalVectorEdge=F.FArray(nve), interiorEdge=F.FArray(interior),
+                  dynamicsTimeStep=3600.0, nCells=nC, nCellsSolve=nC, nEdges=nE, nVertices=nV, maxEdges=M, nCategories=nK, ONE=1,
+                  config_conservation_check=False)
+    I.globals["tracerconnectivities"] = F.FArray(np.array([types.SimpleNamespace() for _ in range(7)], dtype=object))
+
+    def get_field(interp, fr, args):
+        pool, key = interp.ev(args[0][1], fr), interp.ev(args[1][1], fr)
+        lvl = interp.ev(args[3][1], fr) if len(args) > 3 else 1
+        fr.bind(args[2][1][1], types.SimpleNamespace(array=interp.pool[(pool, key, lvl)]))
+
+    def field_info(interp, fr, args):
+        fr.bind(args[2][1][1], types.SimpleNamespace(ndims=3))
+
+    def shift(interp, fr, args):                       # MPAS_pool_shift_time_levels: the new level becomes the current one
+        for n in UPWIND_NAMES:
+            t = L1[n].copy()
+            L1[n][...] = L2[n]
+            L2[n][...] = t
+
+    I.hooks.update(mpas_pool_get_field=get_field, mpas_pool_get_field_info=field_info, mpas_pool_shift_time_levels=shift,
+                   halo_exchange_advection=lambda *a: None)        # one block: nothing to exchange
+    block = types.SimpleNamespace(structs="structs", configs="configs", dimensions="dimensions", next=None)
+    domain = types.SimpleNamespace(blocklist=block, configs="configs")
+    data = {"spec": np.array(repr(OPTION_MESHES[kind])), "nsteps": np.int64(nsteps), "dt": np.float64(3600.0),
+            "in_uVelocity": u, "in_vVelocity": v, "in_normalVectorEdge": nve, "in_interiorEdge": interior}
+    for x in var:
+        data["in_" + x.name] = x.array.copy()
+    I.call("define_tracer_connectivities", True)
+    table = I.globals["tracerconnectivities"].a
+    data["table"] = np.array(repr([(t.childtracername.strip(), t.parenttracername.strip()) for t in table if t.defined == 1]))
+    for step in range(nsteps):
+        I.call("seaice_run_advection_upwind", domain, None)
+        for x in var:
+            data["out%d_%s" % (step + 1, x.name)] = L1[x.name][:, :, 0].copy()
+        for n in ("iceEnthalpy", "iceSalinity", "snowEnthalpy"):
+            data["out%d_%s" % (step + 1, n)] = L1[n].copy()
+    data["provenance"] = np.array("outputs computed by interpreting the reference's Fortran source "
+                                  "(tests/golden/fortran_subset.py): " + ", ".join(sorted(set(I.trace))))
+    return data
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
+    os.makedirs(os.path.join(HERE, "options"), exist_ok=True)
+    for kind in OPTION_MESHES:
+        for rm in (True, False):
+            name = "refexec_normals_%s_%s" % (kind, "nometric" if rm else "metric")
+            if only and name not in only:
+                continue
+            np.savez_compressed(os.path.join(HERE, "options", name + ".npz"), **build_normals(kind, rm))
+            print(name, flush=True)
+    for kind in ("hex", "quad", "ico"):
+        name = "refexec_upwind_%s" % kind
+        if only and name not in only:
+            continue
+        np.savez_compressed(os.path.join(HERE, "options", name + ".npz"), **build_upwind(kind))
+        print(name, flush=True)
     for name in STEP_CASES:
         if only and name not in only:
             continue

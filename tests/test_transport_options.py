@@ -451,3 +451,94 @@ def test_upwind_call_order_and_arguments(lib_path):
             s.upwind_fluxes(2)
     finally:
         s.destroy()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Reference-executed fixtures (tests/golden/options/*.npz): outputs of the reference's own Fortran source -- mesh.F's
+# seaice_normal_vectors and advection_upwind.F's define_tracer_connectivities / seaice_run_advection_upwind -- interpreted
+# by tests/golden/fortran_subset.py (generator: tests/golden/make_reference_executed_golden.py).
+# ----------------------------------------------------------------------------------------------------------------------
+import ast      # noqa: E402
+import glob     # noqa: E402
+
+from mpas_seaice_b200 import irmesh, meshgen     # noqa: E402
+
+_OPT = os.path.join(ROOT, "tests", "golden", "options")
+NORMAL_FILES = sorted(glob.glob(os.path.join(_OPT, "refexec_normals_*.npz")))
+UPWIND_FILES = sorted(glob.glob(os.path.join(_OPT, "refexec_upwind_*.npz")))
+
+
+def _fixture_mesh(z):
+    spec = ast.literal_eval(str(z["spec"]))
+    mesh = getattr(meshgen, spec[0])(*spec[1:])
+    for k in z.files:
+        if k.startswith("mesh_"):
+            assert np.array_equal(mesh[k[5:]], z[k]), "meshgen no longer produces the fixture's mesh"
+    return mesh, irmesh.ir_fields(mesh)
+
+
+def test_reference_executed_option_fixtures_exist():
+    assert len(NORMAL_FILES) == 8 and len(UPWIND_FILES) == 3
+    seen = set()
+    for f in NORMAL_FILES + UPWIND_FILES:
+        prov = str(np.load(f)["provenance"])
+        assert "interpreting the reference's Fortran source" in prov
+        seen |= {w.strip() for w in prov.split(":", 1)[1].split(",")}
+    for name in ("seaice_normal_vectors", "normal_vectors_planar_polygon", "normal_vectors_planar_triangle",
+                 "normal_vectors_spherical_polygon_metric", "normal_vectors_spherical_triangle_metric",
+                 "define_tracer_connectivities", "seaice_run_advection_upwind", "edge_from_vertex_velocity",
+                 "prepare_none_parent_tracer", "upwind_tendencies", "run_advection_subvariable", "scale_tracers_back_3d"):
+        assert name in seen, name
+    # the table the reference's own define_tracer_connectivities builds (:160-165), read back from the interpreter
+    table = ast.literal_eval(str(np.load(UPWIND_FILES[0])["table"]))
+    assert table == [("iceAreaCategory", "none"), ("surfaceTemperature", "iceAreaCategory"),
+                     ("iceVolumeCategory", "surfaceTemperature"), ("snowVolumeCategory", "iceVolumeCategory")]
+
+
+@pytest.mark.parametrize("path", NORMAL_FILES, ids=[os.path.basename(f)[16:-4] for f in NORMAL_FILES])
+def test_normal_vectors_reproduce_the_reference_executed_arrays(path, leg):
+    """oracle/upwind_oracle.c: bit for bit.  ir_normal_vectors: bit for bit under emulation (same libm), to round-off on
+    the device (CUDA's trigonometric functions are 1-2 ulp; tolerance model in _assert_normals_close)."""
+    which, lib = leg
+    z = np.load(path)
+    mesh, irf = _fixture_mesh(z)
+    iv = variational_init.interior_vertex(mesh)
+    rm = bool(z["remove_metric_terms"])
+    want = {k[4:]: z[k] for k in z.files if k.startswith("out_")}
+    _assert_normals_close(upwind.normal_vectors(mesh, irf, iv, rotate=True, remove_metric_terms=rm), want, exact=True)
+    got = ir_host.normal_vectors(mesh, irf, iv, rotate=True, remove_metric_terms=rm, lib_path=lib)
+    _assert_normals_close(got, want, exact=(which == "emulation"))
+
+
+@pytest.mark.parametrize("path", UPWIND_FILES, ids=[os.path.basename(f)[15:-4] for f in UPWIND_FILES])
+def test_upwind_reproduces_the_reference_executed_steps(path, lib_path):
+    """Two steps of seaice_run_advection_upwind as the reference's source executes them, its own connectivity table:
+    the oracle and ir_run_upwind reproduce the four advected arrays bit for bit (every cell; the volumes come out zero,
+    see test_upwind_oracle_with_the_reference_table_zeroes_the_volumes).  The fixture also records what the reference
+    does to the tracers that are NOT in its table: the time-level shift leaves them zero."""
+    z = np.load(path)
+    mesh, irf = _fixture_mesh(z)
+    names = ("iceAreaCategory", "surfaceTemperature", "iceVolumeCategory", "snowVolumeCategory")
+    parents = {"iceAreaCategory": None, "surfaceTemperature": 0, "iceVolumeCategory": 1, "snowVolumeCategory": 2}
+    make = lambda: [upwind.Var(n, z["in_" + n].copy(), parents[n], n.endswith("VolumeCategory")) for n in names]
+    ref, dev = make(), make()
+    u, v, nve, interior = z["in_uVelocity"], z["in_vVelocity"], z["in_normalVectorEdge"], z["in_interiorEdge"]
+    s = ir_host.IrTransport(mesh, irf, case_geometry(mesh, irf), ref[0].array.shape[1], lib_path=lib_path)
+    try:
+        s.set_upwind_mesh(interior, mesh.dvEdge, nve)
+        for step in range(1, int(z["nsteps"]) + 1):
+            upwind.run(mesh, irf["verticesOnEdge"], interior, nve, ref, u, v, float(z["dt"]))
+            s.run_upwind(dev, u, v, float(z["dt"]))
+            for x, y in zip(ref, dev):
+                want = z["out%d_%s" % (step, x.name)]
+                assert np.array_equal(x.array, want), ("oracle", x.name, step)
+                assert np.array_equal(y.array, want), ("device", x.name, step)
+            for n in ("iceEnthalpy", "iceSalinity", "snowEnthalpy"):
+                assert np.all(z["out%d_%s" % (step, n)] == 0.0)
+        assert np.abs(z["out2_iceAreaCategory"] - z["in_iceAreaCategory"]).max() > 1e-6
+    finally:
+        s.destroy()
+
+
+def case_geometry(mesh, irf):
+    return ir.init_geometry(mesh, irf)
