@@ -16,10 +16,13 @@
  * TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may call this; the product never
  * does.  Build with -ffp-contract=off: the reference's operation order, one IEEE operation at a time.
  *
- * Parity status: "parity unpinned" against the reference itself (no Fortran compiler in the image).  The
- * normal vectors are pinned by an independent vectorised restatement (mpas-seaice_b200/weakmesh.py) and, through the weak
- * operators, by the reference's analytic operator fields (tests/test_analytic_golden.py); the upwind step by conservation,
- * exact translation of a uniform field and the closed-form one-cell update (tests/test_transport_options.py).
+ * Parity status: the reference cannot be compiled in this image; both parts are pinned by OUTPUTS OF THE
+ * REFERENCE'S OWN SOURCE EXECUTED HERE by the Fortran-subset interpreter tests/golden/fortran_subset.py (mesh.F's
+ * seaice_normal_vectors; advection_upwind.F's define_tracer_connectivities and seaice_run_advection_upwind with the
+ * module's own table and parameters): fixtures tests/golden/options/*.npz, reproduced by this file bit for bit
+ * (tests/test_transport_options.py).  Also: an independent vectorised reading of the normal vectors
+ * (mpas-seaice_b200/weakmesh.py), the reference's analytic operator fields through the weak operators
+ * (tests/test_analytic_golden.py), conservation, uniform tracers and the closed-form donor-cell update.
  *
  * The upwind module is restated AS EXECUTED, with the tracer connectivity table as an input.  What the reference's own
  * table does (define_tracer_connectivities :145-170) is noted in tests/test_transport_options.py: the chain

@@ -44,8 +44,10 @@ from make_golden import MESH_KEYS, VAR_KEYS  # noqa: E402
 REF = os.environ.get("MPAS_SEAICE_REFERENCE", "/root/reference")
 FILES = ("src/column/constants/cice/ice_constants_colpkg.F90",
          "src/shared/mpas_seaice_constants.F",
+         "src/shared/mpas_seaice_mesh.F",
          "src/shared/mpas_seaice_velocity_solver_constitutive_relation.F",
          "src/shared/mpas_seaice_velocity_solver_variational.F",
+         "src/shared/mpas_seaice_velocity_solver_weak.F",
          "src/shared/mpas_seaice_special_boundaries.F",
          "src/shared/mpas_seaice_velocity_solver.F")
 
@@ -58,10 +60,20 @@ CASES = {
     "refexec_quad10_evp_avg_6": ("quad10", "evp", 6, {"average_variational_strain": True}),
     "refexec_ico2_evp_lineardrag_6": ("ico2", "evp", 6, {"ocean_stress_type": "linear"}),
     "refexec_hex12_evp_special_boundaries_8": ("hex12", "evp", 8, {"use_special_boundaries_velocity": True}),
+    # the weak operators (src/shared/mpas_seaice_velocity_solver_weak.F) and the weak-strain / variational-divergence mix
+    # (interpolate_strains_weak_to_variational, velocity_solver.F:2877-2972)
+    "refexec_hex12_weak_evp_8": ("hex12", "evp", 8, {"strain_scheme": "weak", "stress_divergence_scheme": "weak"}),
+    "refexec_ico2_weak_evp_6": ("ico2", "evp", 6, {"strain_scheme": "weak", "stress_divergence_scheme": "weak"}),
+    "refexec_quad10_weak_revised_5": ("quad10", "evp_revised", 5, {"strain_scheme": "weak", "stress_divergence_scheme": "weak"}),
+    "refexec_ico2_weakvar_evp_5": ("ico2", "evp", 5, {"strain_scheme": "weak", "stress_divergence_scheme": "variational"}),
 }
+WEAK_STATIC = ("verticesOnEdge", "edgesOnVertex", "normalVectorPolygon", "normalVectorTriangle", "latCellRotated", "latVertexRotated")
+WEAK_MESH = ("edgesOnCell", "cellsOnEdge", "dvEdge", "dcEdge", "areaTriangle")
+WEAK_STATE = ("stress11Weak", "stress22Weak", "stress12Weak", "strain11Weak", "strain22Weak", "strain12Weak",
+              "replacementPressureWeak", "strain11Vertex", "strain22Vertex", "strain12Vertex")
 
 
-def interpreter(mesh, var, step, opts, nsub):
+def interpreter(mesh, var, step, opts, nsub, weak=None):
     I = F.Interpreter(defined=())          # no macros: the plain CPU build (no MPAS_OPENMP, no offload, no CPRINTEL)
     for f in FILES:
         I.load(os.path.join(REF, f))
@@ -80,9 +92,23 @@ def interpreter(mesh, var, step, opts, nsub):
         if isinstance(v, np.ndarray):
             arrays[k] = v
     for k, v in arrays.items():
+        if k in WEAK_STATE:
+            continue
         fa = F.FArray(v)
         I.globals[k.lower()] = fa          # seaice_mesh_pool's module pointers carry the pool arrays' names
         I.pool[k] = fa
+    if weak is not None:
+        # the velocity_weak pool (Registry.xml:3700-3745) and the mesh arrays the weak routines fetch themselves
+        for k in WEAK_STATIC:
+            I.pool[k] = F.FArray(weak[k])
+        for k in WEAK_MESH:
+            I.pool[k] = F.FArray(mesh[k])
+        for k in WEAK_STATE[:7]:
+            I.pool[("velocity_weak", k[:-4])] = F.FArray(step[k])
+        for k in WEAK_STATE[7:]:
+            I.pool[("velocity_weak_variational", k)] = F.FArray(step[k])
+        I.pool.update(nEdges=int(mesh.nEdges), on_a_sphere=bool(mesh.on_a_sphere),
+                      sphere_radius=float(getattr(mesh, "sphere_radius", 0.0) or 0.0))
     # dimensions (seaice_mesh_pool: nCells, nVerticesSolve, vertexDegree) and the pool scalars / configs the routines read
     dims = dict(nCells=nC, nVertices=nV, nVerticesSolve=int(opts.get("nVerticesSolve", nV)), vertexDegree=mesh.vertexDegree,
                 maxEdges=mesh.maxEdges)
@@ -99,8 +125,8 @@ def interpreter(mesh, var, step, opts, nsub):
     # what seaice_init_velocity_solver / seaice_init_evp set from the namelist (velocity_solver.F:168-214,
     # constitutive_relation.F:75-164): module variables
     g = I.globals
-    g["strainschemetype"] = g["variational_strain_scheme"]
-    g["stressdivergenceschemetype"] = g["variational_stress_divergence_scheme"]
+    g["strainschemetype"] = g[opts.get("strain_scheme", "variational") + "_strain_scheme"]
+    g["stressdivergenceschemetype"] = g[opts.get("stress_divergence_scheme", "variational") + "_stress_divergence_scheme"]
     g["averagevariationalstrains"] = bool(opts.get("average_variational_strain", False))
     g["oceanstresstype"] = g[{"quadratic": "quadratic_ocean_stress", "linear": "linear_ocean_stress"}[opts.get("ocean_stress_type", "quadratic")]]
     g["constitutiverelationtype"] = g[{"evp": "evp_constitutive_relation", "evp_revised": "revised_evp_constitutive_relation",
@@ -146,8 +172,15 @@ def build(name):
         src[chain[0]] = chain[3] + 1      # a source updated LATER in the sequential loop (the old value is seen)
         src[chain[2]] = chain[1] + 1      # a source updated EARLIER (the new value is seen)
         step["vertexBoundaryType"], step["vertexBoundarySourceLocal"] = vbt, src
+    weak = None
+    if opts.get("strain_scheme") == "weak":
+        from mpas_seaice_b200 import weakmesh
+        weak = weakmesh.weak_fields(mesh)          # INPUTS: the velocity_weak pool's static arrays
+        nC, nV = mesh.nCells, mesh.nVertices
+        for k in WEAK_STATE:
+            step[k] = np.zeros((nV if k.endswith("Vertex") else nC) + 1)
     work = common.clone_step(step)
-    I, domain = interpreter(mesh, var, work, opts, nsub)
+    I, domain = interpreter(mesh, var, work, opts, nsub, weak)
     t0 = time.time()
     I.call("subcycle_velocity_solver", domain, None)
     called = sorted(set(I.trace))
@@ -166,6 +199,13 @@ def build(name):
         out["opt_" + k] = np.array(v)
     for k in common.COMPARE_CELL + common.COMPARE_VERTEX:
         out["out_" + k] = work[k]
+    if weak is not None:
+        for k in WEAK_STATIC:
+            out["weak_" + k] = weak[k]
+        for k in WEAK_MESH + ("nEdges", "on_a_sphere", "sphere_radius"):
+            out["mesh_" + k] = np.array(mesh[k]) if not isinstance(mesh[k], np.ndarray) else mesh[k]
+        for k in WEAK_STATE:
+            out["out_" + k] = work[k]
     return out, called, time.time() - t0
 
 

@@ -23,7 +23,7 @@ FILES = sorted(f for f in glob.glob(os.path.join(HERE, "golden", "*.npz"))
 def _load(path):
     z = np.load(path)
     mesh = meshgen.Mesh()
-    var, step, opts, out = {}, {}, {}, {}
+    var, step, opts, out, weak = {}, {}, {}, {}, {}
     for k in z.files:
         a = z[k]
         a = a.item() if a.ndim == 0 else a
@@ -37,12 +37,31 @@ def _load(path):
             opts[k[4:]] = a
         elif k.startswith("out_"):
             out[k[4:]] = a
+        elif k.startswith("weak_"):
+            weak[k[5:]] = a
+    if weak:                                   # the velocity_weak pool's static arrays (weak operators)
+        var["weak"] = weak
+        nC, nV = int(mesh["nCells"]), int(mesh["nVertices"])
+        for k in WEAK_STATE:
+            step[k] = np.zeros((nV if k.endswith("Vertex") else nC) + 1)
     return mesh, var, step, opts, out, int(z["nsub"])
 
 
-def _check(mesh, step, want, got):
+WEAK_STATE = ("stress11Weak", "stress22Weak", "stress12Weak", "strain11Weak", "strain22Weak", "strain12Weak",
+              "replacementPressureWeak", "strain11Vertex", "strain22Vertex", "strain12Vertex")
+
+
+def _check(mesh, step, want, got, opts=None):
     cm, vm = common.masks_for(mesh, step)
-    for k in common.COMPARE_CELL:
+    opts = opts or {}
+    weak_strain = opts.get("strain_scheme", "variational") == "weak"
+    weak_div = opts.get("stress_divergence_scheme", "variational") == "weak"
+    if weak_strain:
+        nC = mesh.nCells
+        for k in (WEAK_STATE[:7] if weak_div else WEAK_STATE[3:6]):
+            assert np.array_equal(got[k][:nC], want[k][:nC]), k
+        assert np.abs(want["strain11Weak"]).max() > 0
+    for k in (() if weak_div else common.COMPARE_CELL):
         assert np.array_equal(got[k][cm], want[k][cm]), k
     for k in common.COMPARE_VERTEX:
         assert np.array_equal(got[k][vm], want[k][vm]), k
@@ -59,7 +78,7 @@ def test_golden_files_exist():
 def test_oracle_reproduces_golden(path):
     mesh, var, step, opts, want, nsub = _load(path)
     got = common.run_oracle(mesh, var, step, opts, nsub)
-    _check(mesh, step, want, got)
+    _check(mesh, step, want, got, opts)
 
 
 @pytest.mark.gpu
@@ -78,8 +97,13 @@ def test_device_reproduces_golden(evp_lib, path):
             ext["fVertex"] = np.zeros(mesh.nVertices + 1)
             solver.set_mesh_ext(ext, interior)
         solver.update_step(step)
+        if "weak" in var:
+            solver.set_weak_mesh(mesh, var["weak"])
+            solver.update_weak_state({k: step[k] for k in WEAK_STATE[:3]})
         solver.run_subcycles(nsub)
         got = solver.fetch()
+        if "weak" in var:
+            got.update(solver.fetch_weak())
     finally:
         solver.destroy()
-    _check(mesh, step, want, got)
+    _check(mesh, step, want, got, opts)
