@@ -410,6 +410,20 @@ class VarRef:
             self.frame.bind(self.name, v)
 
 
+class CompRef:
+    def __init__(self, obj, field):
+        self.obj, self.field = obj, field
+
+    def get(self):
+        return getattr(self.obj, self.field)
+
+    def set(self, v):
+        setattr(self.obj, self.field, v)
+
+    def bind(self, v):
+        setattr(self.obj, self.field, v)
+
+
 ABSENT = object()
 
 
@@ -494,6 +508,9 @@ def _maxval(x, dim=None):
 
 
 INTRINSICS = {
+    "huge": lambda x: float(np.finfo(np.float64).max) if isinstance(x, float) else 2147483647,
+    "tiny": lambda x: float(np.finfo(np.float64).tiny), "epsilon": lambda x: float(np.finfo(np.float64).eps),
+    "transpose": lambda x: FArray(x.a.T.copy()),
     "dot_product": _dot_product, "spread": _spread, "maxval": _maxval, "matmul": _matmul,
     "maxloc": lambda x: FArray(np.array([int(np.argmax(x.a.T.reshape(-1))) + 1], dtype=np.int64)),
     "any": lambda x: bool(np.any(x.a)) if isinstance(x, FArray) else bool(x),
@@ -555,7 +572,7 @@ class Frame:
 
     def get(self, name):
         v = self.lookup(name)
-        if isinstance(v, (ElemRef, VarRef)):
+        if isinstance(v, (ElemRef, VarRef, CompRef)):
             return v.get()
         return v
 
@@ -567,7 +584,7 @@ class Frame:
             val = float(val)
         if name in self.vars:
             cur = self.vars[name]
-            if isinstance(cur, (ElemRef, VarRef)):
+            if isinstance(cur, (ElemRef, VarRef, CompRef)):
                 cur.set(val)
             elif isinstance(cur, FArray) and not isinstance(val, FArray):
                 cur.a[...] = val
@@ -604,6 +621,7 @@ class Interpreter:
         self.hooks = {}            # name -> python callable(interp, frame, args) replacing a call
         self.trace = []            # names of the interpreted subroutines, in call order
         self.pending = []          # module-level initialisers not resolved yet
+        self.component_types = {}  # lower-case component name -> "int" for integer components allocated by the source
 
     # ---- loading
     def load(self, path):
@@ -717,22 +735,23 @@ class Interpreter:
         nodes = []
         while i < len(stmts):
             no, s = stmts[i]
-            low = re.sub(r"\s+", " ", s.lower()).strip()
-            low = re.sub(r"^\w+\s*:\s*(?=do\b|if\b)", "", low)          # construct names
+            norm = re.sub(r"\s+", " ", s).strip()                      # case kept: string literals are compared as written
+            norm = re.sub(r"^\w+\s*:\s*(?=do\b|if\b)", "", norm, flags=re.I)   # construct names
+            low = norm.lower()
             key = self._ender_key(low)
             if key in enders:
                 return nodes, i
-            m = re.match(r"^do\s+while\s*\((.*)\)$", low)
+            m = re.match(r"^do\s+while\s*\((.*)\)$", norm, re.I)
             if m:
                 body, j = self._block(sub, stmts, i + 1, ("enddo",))
                 nodes.append(("dowhile", no, parse_expr(m.group(1)), body))
                 i = j + 1
                 continue
-            m = re.match(r"^do\s+(\w+)\s*=\s*(.*)$", low)
+            m = re.match(r"^do\s+(\w+)\s*=\s*(.*)$", norm, re.I)
             if m:
                 parts = _split_top(m.group(2))
                 body, j = self._block(sub, stmts, i + 1, ("enddo",))
-                nodes.append(("do", no, m.group(1), [parse_expr(p) for p in parts], body))
+                nodes.append(("do", no, m.group(1).lower(), [parse_expr(p) for p in parts], body))
                 i = j + 1
                 continue
             if low == "do":
@@ -740,17 +759,18 @@ class Interpreter:
                 nodes.append(("dowhile", no, ("num", True), body))
                 i = j + 1
                 continue
-            m = re.match(r"^if\s*\((.*)\)\s*then$", low)
+            m = re.match(r"^if\s*\((.*)\)\s*then$", norm, re.I)
             if m:
                 branches, cond = [], parse_expr(m.group(1))
                 j = i
                 while True:
                     body, j = self._block(sub, stmts, j + 1, ("elseif", "else", "endif"))
                     branches.append((cond, body))
-                    l2 = re.sub(r"\s+", " ", stmts[j][1].lower()).strip()
+                    n2 = re.sub(r"\s+", " ", stmts[j][1]).strip()
+                    l2 = n2.lower()
                     k2 = self._ender_key(l2)
                     if k2 == "elseif":
-                        cond = parse_expr(re.match(r"^else\s*if\s*\((.*)\)\s*then$", l2).group(1))
+                        cond = parse_expr(re.match(r"^else\s*if\s*\((.*)\)\s*then$", n2, re.I).group(1))
                     elif k2 == "else":
                         cond = ("num", True)
                     else:
@@ -758,15 +778,15 @@ class Interpreter:
                 nodes.append(("if", no, branches))
                 i = j + 1
                 continue
-            m = re.match(r"^select\s*case\s*\((.*)\)$", low)
+            m = re.match(r"^select\s*case\s*\((.*)\)$", norm, re.I)
             if m:
                 sel, cases, j = parse_expr(m.group(1)), [], i + 1
                 while self._ender_key(re.sub(r"\s+", " ", stmts[j][1].lower()).strip()) != "endselect":
-                    l2 = re.sub(r"\s+", " ", stmts[j][1].lower()).strip()
-                    mc = re.match(r"^case\s*(default|\((.*)\))$", l2)
+                    l2 = re.sub(r"\s+", " ", stmts[j][1]).strip()
+                    mc = re.match(r"^case\s*(default|\((.*)\))$", l2, re.I)
                     if not mc:
                         raise FortranError("line %d: expected case, found %r" % (stmts[j][0], l2))
-                    vals = None if mc.group(1) == "default" else [parse_expr(x) for x in _split_top(mc.group(2))]
+                    vals = None if mc.group(1).lower() == "default" else [parse_expr(x) for x in _split_top(mc.group(2))]
                     body, j = self._block(sub, stmts, j + 1, ("case", "endselect"))
                     cases.append((vals, body))
                 nodes.append(("select", no, sel, cases))
@@ -774,8 +794,8 @@ class Interpreter:
                 continue
             m = re.match(r"^if\s*\(", low)
             if m:
-                close = _matching_paren(low, low.index("("))
-                cond, rest = parse_expr(low[low.index("(") + 1:close]), s[_matching_paren(s, s.index("(")) + 1:].strip()
+                close = _matching_paren(norm, norm.index("("))
+                cond, rest = parse_expr(norm[norm.index("(") + 1:close]), s[_matching_paren(s, s.index("(")) + 1:].strip()
                 nodes.append(("if", no, [(cond, [self._simple(sub, no, rest)])]))
                 i += 1
                 continue
@@ -1041,15 +1061,29 @@ class Interpreter:
                 raise _Return()
             elif k == "allocate":
                 for item in n[2]:
+                    if item[0] in ("name", "comp"):        # allocate(p): a scalar of derived type
+                        import types as _types
+                        obj = _types.SimpleNamespace()
+                        if item[0] == "name":
+                            fr.bind(item[1], obj)
+                        else:
+                            setattr(self.ev(item[1], fr), item[2], obj)
+                        continue
                     shape = [int(self.ev(a, fr)) for _, a in item[2]]
-                    kind = fr.sub.types.get(item[1][1], "real")
+                    target = item[1]
+                    kind = fr.sub.types.get(target[1], "real") if target[0] == "name" else self.component_types.get(target[2], "real")
                     dt = np.float64 if kind == "real" else (np.int64 if kind == "int" else np.bool_)
                     new = FArray(np.zeros(tuple(reversed(shape)), dtype=dt))
-                    cur = fr.vars.get(item[1][1])
-                    if isinstance(cur, VarRef):            # an allocatable dummy: the caller's variable is allocated
+                    if target[0] == "comp":                # allocate(obj % field(n, m))
+                        setattr(self.ev(target[1], fr), target[2], new)
+                        continue
+                    cur = fr.vars.get(target[1])
+                    if isinstance(cur, (VarRef, CompRef)):   # an allocatable dummy: the caller's variable is allocated
                         cur.bind(new)
+                    elif target[1] not in fr.vars and target[1] not in fr.sub.types:
+                        self.globals[fr.sub.renames.get(target[1], target[1])] = new     # a module-level allocatable
                     else:
-                        fr.bind(item[1][1], new)
+                        fr.bind(target[1], new)
             elif k in ("deallocate", "continue"):
                 pass
             else:
@@ -1059,26 +1093,32 @@ class Interpreter:
         _, no, name, args = n
         if name in self.hooks:
             return self.hooks[name](self, fr, args)
+        if name in self.noop:                       # (also overrides a routine of that name found in a loaded file)
+            return None
         if name in self.POOL_GETTERS:
             return self._pool_get(name, args, fr)
         if name in self.subs:
             self.invoke(name, args, fr)
-            return None
-        if name in self.noop:
             return None
         raise FortranError("%s line %d: call of %r, which is neither loaded, mapped nor declared a no-op" % (fr.sub.name, no, name))
 
     def _pool_get(self, name, args, fr):
         pool = self.ev(args[0][1], fr) if args[0][1][0] == "name" and fr.has(args[0][1][1]) else None
         key = self.ev(args[1][1], fr)
-        target = args[2][1][1]
+        tnode = args[2][1]
+
+        def bind(val):
+            if tnode[0] == "name":
+                fr.bind(tnode[1], val)
+            else:                                          # MPAS_pool_get_array(pool, 'x', obj % field)
+                setattr(self.ev(tnode[1], fr), tnode[2], val)
         if name == "mpas_pool_get_subpool":
-            fr.bind(target, key)
+            bind(key)
             return
         level = self.ev(args[3][1], fr) if len(args) > 3 else None
         for k in ((pool, key, level), (pool, key), (None, key, level), (None, key), key):
             if k in self.pool:
-                fr.bind(target, self.pool[k])
+                bind(self.pool[k])
                 return
         raise FortranError("%s: the harness holds nothing for %s(%r, %r)" % (fr.sub.name, name, pool, key))
 
@@ -1113,7 +1153,7 @@ class Interpreter:
         if node[0] == "name":
             if caller.has(node[1]):
                 v = caller.lookup(node[1])
-                if isinstance(v, (int, float, bool)) and not isinstance(v, (ElemRef, VarRef)):
+                if isinstance(v, (int, float, bool)) and not isinstance(v, (ElemRef, VarRef, CompRef)):
                     return VarRef(caller, node[1])
                 return v
             return VarRef(caller, node[1])                  # an output the callee defines
@@ -1123,6 +1163,19 @@ class Interpreter:
             if any(isinstance(i, slice) for i in idx):
                 return arr.get(idx)                         # a section: a view of the same memory
             return ElemRef(arr, idx)
+        if node[0] == "call" and node[1][0] == "comp":      # obj % array(i, j): an element (or section) of a component
+            arr = self.ev(node[1], caller)
+            if isinstance(arr, FArray):
+                idx = self._index(node[2], caller)
+                if any(isinstance(i, slice) for i in idx):
+                    return arr.get(idx)
+                return ElemRef(arr, idx)
+        if node[0] == "comp":                               # obj % field: arrays and objects by descriptor, scalars by reference
+            obj = self.ev(node[1], caller)
+            val = getattr(obj, node[2], None)
+            if isinstance(val, (int, float, bool)) or val is None:
+                return CompRef(obj, node[2])
+            return val
         return self.ev(node, caller)
 
     def call(self, name, *values, **kw):

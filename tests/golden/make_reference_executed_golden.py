@@ -572,8 +572,222 @@ def build_upwind(kind, nsteps=2):
     return data
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# The incremental-remapping transport: seaice_run_advection_incremental_remap (incremental_remap.F:2338-2730) with
+# everything below it -- volume <-> thickness, incremental_remap_block (:2740), make_masks, construct_linear_tracer_fields
+# (gradients, limiter, barycentres), find_departure_points / _triangles, shift_vertices_of_departure_triangle, the
+# quadrature points, integrate_fluxes_over_triangles, compute_mass_tracer_products, update_mass_and_tracers,
+# zap_small_mass, and with the optional checks on: tracer_local_min_max, sum_tracers, check_tracer_conservation,
+# check_tracer_monotonicity.  The tracer linked list (tracer_type, incremental_remap_tracers.F:26-110) is built here as
+# objects holding the arrays; the geometry of the incremental_remap pool is an INPUT (oracle.ir.init_geometry).
+# ---------------------------------------------------------------------------------------------------------------------
+IR_MESHES = {"hex": ("planar_hex", 6, 7, 1000.0), "quad": ("planar_quad", 6, 6, 1000.0), "ico": ("icosphere", 1),
+             "quad16": ("planar_quad", 16, 16, 1000.0)}
+IR_CASES = {
+    # name: (mesh, categories, ice layers, snow layers, steps, checks)
+    "refexec_ir_hex": ("hex", 2, 2, 1, 2, False),
+    "refexec_ir_ico": ("ico", 2, 2, 1, 2, False),
+    "refexec_ir_quad": ("quad", 2, 2, 1, 2, False),
+    "refexec_ir_hex_checks": ("hex", 2, 2, 1, 2, True),
+    "refexec_ir_quad_checks": ("quad", 2, 1, 0, 1, True),
+    "refexec_ir_quad16_checks": ("quad16", 3, 4, 2, 1, True),       # the reference's monotonicity test fires here (vertexDegree 4)
+}
+
+
+def build_ir(name):
+    from mpas_seaice_b200 import irmesh
+    from oracle import ir as oir                  # INPUTS only: the incremental_remap pool's geometry, the test state
+    from test_oracle_ir import smooth_divergent_velocity, _random_state
+    kind, nK, n_ice, n_snow, nsteps, checks = IR_CASES[name]
+    mesh = init_mesh(IR_MESHES[kind])
+    irf = irmesh.ir_fields(mesh)
+    geom = oir.init_geometry(mesh, irf)
+    nC, nV, nE, M, D = mesh.nCells, mesh.nVertices, mesh.nEdges, mesh.maxEdges, mesh.vertexDegree
+    nQP = 6
+    tracers = _random_state(mesh, np.random.default_rng(21), n_cat=nK, n_ice=n_ice, n_snow=n_snow)
+    u, v = smooth_divergent_velocity(mesh, geom)
+    I = F.Interpreter(defined=())
+    for f in ("src/column/constants/cice/ice_constants_colpkg.F90", "src/shared/mpas_seaice_constants.F",
+              "src/shared/mpas_seaice_advection_incremental_remap.F"):
+        I.load(os.path.join(REF, f))
+    I.resolve_constants()
+    I.noop |= {"mpas_log_write", "mpas_timer_start", "mpas_timer_stop", "seaice_critical_error_write_block",
+               "seaice_set_tracer_array_pointers", "seaice_update_tracer_halo", "seaice_load_balance_timers",
+               "mpas_dmpar_field_halo_exch", "mpas_dmpar_exch_group_full_halo_exch", "mpas_dmpar_exch_group_reuse_halo_exch"}
+    work = [t.array.copy() for t in tracers]
+    objs = []
+    mk = lambda shape, dt=np.float64: F.FArray(np.zeros(shape, dt))
+    for i, t in enumerate(tracers):
+        nl = t.array.shape[2]
+        o = types.SimpleNamespace(tracername=t.name, parentname="", ndims=2 if nl == 1 else 3, parent=None, next=None,
+                                  nextinitial=None, haschild=False, nparents=0, isactive=True)
+        if nl == 1:
+            o.array2d, o.array3d = F.FArray(work[i][:, :, 0]), None
+            for f in ("masstracerproduct2d", "xbarycenter2d", "ybarycenter2d", "center2d", "xgrad2d", "ygrad2d", "localmin2d", "localmax2d"):
+                setattr(o, f, mk((nC + 1, nK)))
+            o.arraymask2d, o.edgeflux2d, o.trianglevalue2d = mk((nC + 1, nK), np.int64), mk((nE + 1, nK)), mk((nE + 1, 6, nQP, nK))
+            o.globalsuminit2d, o.globalsumfinal2d = mk((nK,)), mk((nK,))
+        else:
+            o.array3d, o.array2d = F.FArray(work[i]), None
+            for f in ("masstracerproduct3d", "xbarycenter3d", "ybarycenter3d", "center3d", "xgrad3d", "ygrad3d", "localmin3d", "localmax3d"):
+                setattr(o, f, mk((nC + 1, nK, nl)))
+            o.arraymask3d, o.edgeflux3d = mk((nC + 1, nK, nl), np.int64), mk((nE + 1, nK, nl))
+            o.trianglevalue3d = mk((nE + 1, 6, nQP, nK, nl))
+            o.globalsuminit3d, o.globalsumfinal3d = mk((nK, nl)), mk((nK, nl))
+        objs.append(o)
+    for i, t in enumerate(tracers):
+        if t.parent is not None:
+            objs[i].parent, objs[t.parent].haschild = objs[t.parent], True
+            objs[i].nparents, objs[i].parentname = objs[t.parent].nparents + 1, tracers[t.parent].name
+        if i + 1 < len(objs):
+            objs[i].next = objs[i + 1]
+    P = {k: mesh[k] for k in list(mesh.keys()) if isinstance(mesh[k], np.ndarray)}
+    P.update(verticesOnEdge=irf["verticesOnEdge"], edgesOnVertex=irf["edgesOnVertex"], coeffs_reconstruct=irf["coeffs_reconstruct"],
+             xEdge=irf["xEdge"], yEdge=irf["yEdge"], zEdge=irf["zEdge"],
+             indexToCellID=np.arange(1, nC + 2, dtype=np.int32), indexToVertexID=np.arange(1, nV + 2, dtype=np.int32),
+             indexToEdgeID=np.arange(1, nE + 2, dtype=np.int32))
+    for k in ("xVertexOnCell", "yVertexOnCell", "xVertexOnEdge", "yVertexOnEdge", "remapEdge", "cellsOnEdgeRemap", "edgesOnEdgeRemap",
+              "transGlobalToCell", "minLengthEdgesOnVertex"):
+        P[k] = geom[k]
+    for n in oir.GEOM_NAMES:
+        P[n + "AvgCell"] = geom["geomAvg"][n]
+    P.update(departurePoint=np.zeros((nV + 1, 2)), xTriangle=np.zeros((nE + 1, 6, nQP)), yTriangle=np.zeros((nE + 1, 6, nQP)),
+             iCellTriangle=np.zeros((nE + 1, 6), np.int32), triangleArea=np.zeros((nE + 1, 6)), maskEdge=np.zeros(nE + 1, np.int32),
+             maskCell=np.zeros(nC + 1, np.int32), maskCategoryCell=np.zeros((nC + 1, nK), np.int32),
+             workCategoryCell=np.zeros((nC + 1, nK)), uVelocity=u, vVelocity=v)
+    for k, a in P.items():
+        I.pool[k] = F.FArray(a)
+    I.pool.update(nCells=nC, nCellsSolve=nC, nVertices=nV, nVerticesSolve=nV, nEdges=nE, nEdgesSolve=nE, maxEdges=M, vertexDegree=D,
+                  nCategories=nK, nTriPerEdgeRemap=6, maxCellsPerEdgeRemap=6, maxEdgesPerEdgeRemap=6, maxVerticesPerEdgeRemap=8,
+                  nQuadPoints=nQP, on_a_sphere=bool(mesh.on_a_sphere), sphere_radius=float(getattr(mesh, "sphere_radius", 0.0) or 0.0),
+                  config_rotate_cartesian_grid=False, config_monotonicity_check=bool(checks), config_conservation_check=bool(checks),
+                  config_recover_tracer_means_check=False, config_use_halo_exch=False, dynamicsTimeStep=3600.0)
+    g = I.globals
+    g["nquadpoints"] = nQP
+    w = np.zeros(nQP)
+    w[:3], w[3:] = g["w1triangleqp"], g["w2triangleqp"]          # seaice_init_advection_incremental_remap :779-784
+    g["weightquadpoint"] = F.FArray(w)
+    g["tracershead"] = objs[0]                                    # module variable of ..._incremental_remap_tracers
+    g["mpas_dmpar_noerr"] = 0
+    for k in ("ctest", "etest", "vtest"):
+        g[k] = 1
+    for k in ("ctestonproc", "etestonproc", "vtestonproc"):
+        g[k] = False
+    for k in ("ctestblockid", "etestblockid", "vtestblockid"):
+        g[k] = 0
+    aborts = []
+
+    def sum_real(interp, fr, args):                               # mpas_dmpar_sum_real on one rank: the local sum
+        interp._assign(args[2][1], interp.ev(args[1][1], fr), fr)
+
+    def critical(interp, fr, args):                               # seaice_check_critical_error(domain, abortFlag)
+        try:
+            aborts.append(bool(interp.ev(args[1][1], fr)))
+        except F.FortranError:                                    # the driver's abortFlag (:2398) is only ever SET to .true.
+            aborts.append(False)                                  # (:8190, :8540): never assigned = no check has fired
+
+    I.hooks.update(mpas_dmpar_sum_real=sum_real, seaice_check_critical_error=critical)
+    block = types.SimpleNamespace(structs="structs", configs="configs", dimensions="dimensions", next=None, localblockid=0)
+    domain = types.SimpleNamespace(blocklist=block, configs="configs", dminfo=types.SimpleNamespace(my_proc_id=0))
+    data = {"spec": np.array(repr(IR_MESHES[kind])), "nsteps": np.int64(nsteps), "dt": np.float64(3600.0), "checks": np.array(bool(checks)),
+            "in_uVelocity": u, "in_vVelocity": v, "n_tracers": np.int64(len(tracers))}
+    for i, t in enumerate(tracers):
+        data["in_%d" % i] = t.array.copy()
+        data["meta_%d" % i] = np.array(repr((t.name, t.parent, bool(t.volume_like))))
+    for step in range(1, nsteps + 1):
+        del aborts[:]
+        I.call("seaice_run_advection_incremental_remap", domain, None)
+        for i in range(len(tracers)):
+            data["out%d_%d" % (step, i)] = work[i].copy()
+        if checks:
+            data["out%d_aborts" % step] = np.array(aborts)       # [after update_mass_and_tracers, conservation, monotonicity]
+            for i, o in enumerate(objs):
+                sfx = "2d" if o.ndims == 2 else "3d"
+                data["out%d_sumInit_%d" % (step, i)] = getattr(o, "globalsuminit" + sfx).a.copy()
+                data["out%d_sumFinal_%d" % (step, i)] = getattr(o, "globalsumfinal" + sfx).a.copy()
+    data["provenance"] = np.array("outputs computed by interpreting the reference's Fortran source "
+                                  "(tests/golden/fortran_subset.py): " + ", ".join(sorted(set(I.trace))))
+    return data
+
+
+IR_INIT_MESHES = {"hex": ("planar_hex", 6, 7, 1000.0), "quad": ("planar_quad", 6, 6, 1000.0), "ico": ("icosphere", 1),
+                  "band": ("latlon_band", 24, 10, 60.0)}
+IR_INIT_CASES = {"refexec_irinit_hex": ("hex", False), "refexec_irinit_quad": ("quad", False), "refexec_irinit_ico": ("ico", False),
+                 "refexec_irinit_ico_rotated": ("ico", True), "refexec_irinit_band_rotated": ("band", True)}
+IR_INIT_OUT = ("transGlobalToCell", "xVertexOnCell", "yVertexOnCell", "remapEdge", "cellsOnEdgeRemap", "edgesOnEdgeRemap",
+               "xVertexOnEdge", "yVertexOnEdge", "minLengthEdgesOnVertex")
+
+
+def build_ir_init(name):
+    """seaice_init_advection_incremental_remap (incremental_remap.F:165-816) as written: rotate_global_vectors,
+    define_local_to_global_transformations, get_vertex_on_cell_coordinates, get_geometry_incremental_remap,
+    compute_geometric_cell_averages.  Framework calls mapped to no-ops: the halo-layer check, the tracer linked list (built
+    by the host), mpas_init_reconstruct (coeffs_reconstruct is the framework's, an input of the transport)."""
+    from mpas_seaice_b200 import irmesh
+    from oracle import ir as oir
+    kind, rotate = IR_INIT_CASES[name]
+    mesh = init_mesh(IR_INIT_MESHES[kind])
+    irf = irmesh.ir_fields(mesh)
+    nC, nV, nE, M, D = mesh.nCells, mesh.nVertices, mesh.nEdges, mesh.maxEdges, mesh.vertexDegree
+    I = F.Interpreter(defined=())
+    for f in ("src/column/constants/cice/ice_constants_colpkg.F90", "src/shared/mpas_seaice_constants.F",
+              "src/shared/mpas_seaice_advection_incremental_remap.F"):
+        I.load(os.path.join(REF, f))
+    I.resolve_constants()
+    I.noop |= {"mpas_log_write", "mpas_timer_start", "mpas_timer_stop", "check_halo_layer_number", "seaice_add_tracers_to_linked_list",
+               "seaice_init_update_tracer_halo_exch_group", "mpas_rbf_interp_initialize", "mpas_init_reconstruct",
+               "mpas_dmpar_field_halo_exch"}
+    P = {k: mesh[k] for k in list(mesh.keys()) if isinstance(mesh[k], np.ndarray)}
+    P.update(verticesOnEdge=irf["verticesOnEdge"], edgesOnVertex=irf["edgesOnVertex"], coeffs_reconstruct=irf["coeffs_reconstruct"],
+             xEdge=irf["xEdge"], yEdge=irf["yEdge"], zEdge=irf["zEdge"], indexToCellID=np.arange(1, nC + 2, dtype=np.int32),
+             indexToVertexID=np.arange(1, nV + 2, dtype=np.int32), indexToEdgeID=np.arange(1, nE + 2, dtype=np.int32))
+    out = dict(transGlobalToCell=np.zeros((nC + 1, 3, 3)), xVertexOnCell=np.zeros((nC + 1, M)), yVertexOnCell=np.zeros((nC + 1, M)),
+               remapEdge=np.zeros(nE + 1, np.int32), cellsOnEdgeRemap=np.zeros((nE + 1, 6), np.int32),
+               edgesOnEdgeRemap=np.zeros((nE + 1, 6), np.int32), xVertexOnEdge=np.zeros((nE + 1, 8)),
+               yVertexOnEdge=np.zeros((nE + 1, 8)), minLengthEdgesOnVertex=np.zeros(nV + 1))
+    for n in oir.GEOM_NAMES:
+        out[n + "AvgCell"] = np.zeros(nC + 1)
+    P.update(out)
+    P.update(transCellToGlobal=np.zeros((nC + 1, 3, 3)), transVertexToGlobal=np.zeros((nV + 1, 3, 3)),
+             transGlobalToVertex=np.zeros((nV + 1, 3, 3)), transEdgeToGlobal=np.zeros((nE + 1, 3, 3)),
+             transGlobalToEdge=np.zeros((nE + 1, 3, 3)))
+    for pre, n in (("Cell", nC), ("Vertex", nV), ("Edge", nE)):
+        for ax in "xyz":
+            P[ax + pre + "Rotate"] = np.zeros(n + 1)
+    for k, a in P.items():
+        I.pool[k] = F.FArray(a)
+    I.pool.update(nCells=nC, nCellsSolve=nC, nVertices=nV, nVerticesSolve=nV, nEdges=nE, nEdgesSolve=nE, maxEdges=M, vertexDegree=D,
+                  nQuadPoints=6, nTriPerEdgeRemap=6, maxCellsPerEdgeRemap=6, maxEdgesPerEdgeRemap=6, maxVerticesPerEdgeRemap=8,
+                  on_a_sphere=bool(mesh.on_a_sphere), sphere_radius=float(getattr(mesh, "sphere_radius", 0.0) or 0.0),
+                  config_rotate_cartesian_grid=bool(rotate))
+    I.globals["tracershead"] = None
+    block = types.SimpleNamespace(structs="structs", configs="configs", dimensions="dimensions", next=None, localblockid=0)
+    domain = types.SimpleNamespace(blocklist=block, configs="configs", dminfo=types.SimpleNamespace(my_proc_id=0))
+    I.call("seaice_init_advection_incremental_remap", domain)
+    data = {"spec": np.array(repr(IR_INIT_MESHES[kind])), "rotate": np.array(bool(rotate)), "mesh_xCell": mesh.xCell,
+            "weightQuadPoint": I.globals["weightquadpoint"].a.copy(),
+            "provenance": np.array("outputs computed by interpreting the reference's Fortran source "
+                                   "(tests/golden/fortran_subset.py): " + ", ".join(sorted(set(I.trace))))}
+    for k, v in out.items():
+        data["out_" + k] = v
+    return data
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
+    os.makedirs(os.path.join(HERE, "ir"), exist_ok=True)
+    for name in IR_INIT_CASES:
+        if only and name not in only:
+            continue
+        np.savez_compressed(os.path.join(HERE, "ir", name + ".npz"), **build_ir_init(name))
+        print(name, flush=True)
+    for name in IR_CASES:
+        if only and name not in only:
+            continue
+        t0 = time.time()
+        data = build_ir(name)
+        np.savez_compressed(os.path.join(HERE, "ir", name + ".npz"), **data)
+        print("%s: %.1f s" % (name, time.time() - t0), flush=True)
     os.makedirs(os.path.join(HERE, "options"), exist_ok=True)
     for kind in OPTION_MESHES:
         for rm in (True, False):

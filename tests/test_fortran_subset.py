@@ -170,3 +170,26 @@ def test_reference_executed_fixtures_say_where_they_come_from():
                  "seaice_linear_constitutive_relation", "seaice_average_strains_on_vertex", "ocean_stress_coefficient",
                  "solve_velocity", "solve_velocity_revised"):
         assert name in seen, name
+
+
+def test_string_literals_keep_their_case_in_conditions(tmp_path):
+    src = """
+module m
+contains
+  subroutine pick(name, out)
+    character(len=*), intent(in) :: name
+    integer, intent(out) :: out
+    out = 0
+    if (trim(name) == 'iceAreaCategory') then
+       out = 1
+    elseif (trim(name) == 'iceVolumeCategory' .or. &
+            trim(name) == 'snowVolumeCategory') then
+       out = 2
+    endif
+    if (trim(name) == 'surfaceTemperature') out = 3
+  end subroutine pick
+end module m
+"""
+    I = _interp(src, tmp_path)
+    for name, want in (("iceAreaCategory", 1), ("snowVolumeCategory", 2), ("surfaceTemperature", 3), ("iceareacategory", 0)):
+        assert I.call("pick", name + "   ", 0).vars["out"] == want

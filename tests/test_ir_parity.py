@@ -446,3 +446,113 @@ def test_shipped_library_exports_the_abi():
         assert hasattr(L, name), name
     subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-Wall", "-Wextra", "-x", "c", os.path.join(ROOT, "include", "ir_b200.h")],
                    check=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Reference-executed fixtures (tests/golden/ir/*.npz): seaice_run_advection_incremental_remap with everything below it,
+# interpreted from the reference's own Fortran source by tests/golden/fortran_subset.py (generator:
+# tests/golden/make_reference_executed_golden.py).  The oracle and the kernels must reproduce every tracer bit for bit.
+# ----------------------------------------------------------------------------------------------------------------------
+import ast      # noqa: E402
+import glob     # noqa: E402
+
+REFEXEC_IR = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "ir", "refexec_ir_*.npz")))
+
+
+def test_reference_executed_transport_fixtures_exist():
+    assert len(REFEXEC_IR) >= 6
+    seen = set()
+    for f in REFEXEC_IR:
+        prov = str(np.load(f)["provenance"])
+        assert "interpreting the reference's Fortran source" in prov
+        seen |= {w.strip() for w in prov.split(":", 1)[1].split(",")}
+    for name in ("seaice_run_advection_incremental_remap", "incremental_remap_block", "make_masks", "construct_linear_tracer_fields",
+                 "compute_gradient_2d", "compute_gradient_3d", "limit_tracer_gradient_2d", "limit_tracer_gradient_3d",
+                 "compute_barycenter_coordinates", "find_departure_points", "find_departure_triangles",
+                 "shift_vertices_of_departure_triangle", "get_triangle_quadrature_points", "integrate_fluxes_over_triangles",
+                 "compute_mass_tracer_products", "update_mass_and_tracers", "zap_small_mass", "volume_to_thickness",
+                 "thickness_to_volume", "sum_tracers", "tracer_local_min_max", "check_tracer_conservation",
+                 "check_tracer_monotonicity"):
+        assert name in seen, name
+
+
+@pytest.mark.parametrize("path", REFEXEC_IR, ids=[os.path.basename(f)[11:-4] for f in REFEXEC_IR])
+def test_transport_reproduces_the_reference_executed_steps(path, lib_path):
+    from mpas_seaice_b200 import irmesh, meshgen
+    z = np.load(path)
+    spec = ast.literal_eval(str(z["spec"]))
+    mesh = getattr(meshgen, spec[0])(*spec[1:])
+    irf = irmesh.ir_fields(mesh)
+    geom = ir.init_geometry(mesh, irf)
+    nC = mesh.nCells
+    tracers = []
+    for i in range(int(z["n_tracers"])):
+        name, parent, vol = ast.literal_eval(str(z["meta_%d" % i]))
+        tracers.append(ir.Tracer(name, z["in_%d" % i].copy(), parent, vol))
+    u, v, dt, checks = z["in_uVelocity"], z["in_vVelocity"], float(z["dt"]), bool(z["checks"])
+    ref, dev = clone(tracers), clone(tracers)
+    solver = ir_host.IrTransport(mesh, irf, geom, tracers[0].array.shape[1], lib_path=lib_path)
+    try:
+        solver.set_tracers(dev)
+        if checks:
+            solver.set_checks(conservation=1, monotonicity=1)
+        for step in range(1, int(z["nsteps"]) + 1):
+            # monotonicity_check = 1: the reference's own in-place extension of the bounds
+            d = ir.run(mesh, irf, geom, ref, u, v, dt, check=False, conservation_check=int(checks), monotonicity_check=int(checks))
+            rc = solver.run(dev, u, v, dt, check=False)
+            for i, (x, y) in enumerate(zip(ref, dev)):
+                want = z["out%d_%d" % (step, i)]
+                assert np.array_equal(x.array[:nC], want[:nC]), ("oracle", x.name, step)
+                assert np.array_equal(y.array[:nC], want[:nC]), ("kernels", x.name, step)
+            if checks:
+                aborts = [bool(b) for b in z["out%d_aborts" % step]]        # [.., update, conservation, monotonicity]
+                assert d["error"] == (9 if aborts[-2] else (10 if aborts[-1] else 0))
+                for i, t in enumerate(tracers):
+                    nl = t.array.shape[2]
+                    for key, mine in (("sumInit", d["sumInit"][i]), ("sumFinal", d["sumFinal"][i])):
+                        want = z["out%d_%s_%d" % (step, key, i)].reshape(mine.shape)
+                        assert np.array_equal(mine, want), (key, t.name)                # the oracle adds like the reference
+                    si, sf = solver.conservation_sums(i, nl)
+                    for mine, key in ((si, "sumInit"), (sf, "sumFinal")):
+                        want = z["out%d_%s_%d" % (step, key, i)].reshape(mine.shape)
+                        assert np.all(np.abs(mine - want) <= 1e-13 * np.abs(want).max() + 1e-300), (key, t.name)
+                if aborts[-1]:      # the kernels' order-independent bounds are never looser than the reference's
+                    assert rc == ir_host.IR_ERR_MONOTONICITY
+                elif not aborts[-2]:
+                    assert rc in (0, ir_host.IR_ERR_MONOTONICITY)
+            else:
+                assert rc == 0 and d["error"] == 0
+        assert np.abs(ref[0].array[:nC] - tracers[0].array[:nC]).max() > 1e-6
+    finally:
+        solver.destroy()
+
+
+REFEXEC_IR_INIT = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "ir", "refexec_irinit_*.npz")))
+
+
+@pytest.mark.parametrize("path", REFEXEC_IR_INIT, ids=[os.path.basename(f)[15:-4] for f in REFEXEC_IR_INIT])
+def test_geometry_reproduces_the_reference_executed_init(path, lib_path):
+    """seaice_init_advection_incremental_remap (incremental_remap.F:165-816) as the reference's source executes it:
+    local frames, vertex coordinates in cell and edge frames, remap stencils, minimum edge lengths, the fourteen
+    geometric cell averages -- reproduced bit for bit by the oracle and by ir_init_geometry."""
+    from mpas_seaice_b200 import irmesh, meshgen
+    z = np.load(path)
+    assert "interpreting the reference's Fortran source" in str(z["provenance"]) and "get_geometry_incremental_remap" in str(z["provenance"])
+    spec = ast.literal_eval(str(z["spec"]))
+    mesh = getattr(meshgen, spec[0])(*spec[1:])
+    assert np.array_equal(mesh.xCell, z["mesh_xCell"])
+    irf = irmesh.ir_fields(mesh)
+    rotate = bool(z["rotate"])
+    nC = mesh.nCells
+    for who, got in (("oracle", ir.init_geometry(mesh, irf, rotate=rotate)),
+                     ("kernels", ir_host.init_geometry(mesh, irf, rotate=rotate, lib_path=lib_path))):
+        for k in ("xVertexOnCell", "yVertexOnCell", "remapEdge", "cellsOnEdgeRemap", "edgesOnEdgeRemap", "xVertexOnEdge",
+                  "yVertexOnEdge", "minLengthEdgesOnVertex"):
+            n = got[k].shape[0] - 1
+            assert np.array_equal(got[k][:n], z["out_" + k][:n]), (who, k)
+        if mesh.on_a_sphere:
+            assert np.array_equal(got["transGlobalToCell"][:nC], z["out_transGlobalToCell"][:nC]), who
+        for name in ir.GEOM_NAMES:
+            assert np.array_equal(got["geomAvg"][name][:nC], z["out_" + name + "AvgCell"][:nC]), (who, name)
+    assert np.abs(z["out_xxAvgCell"][:nC]).max() > 0 and (z["out_remapEdge"] == 1).any()
+    assert list(z["weightQuadPoint"]) == [1.09951743655321885e-01] * 3 + [2.23381589678011389e-01] * 3
