@@ -29,10 +29,15 @@
  * is for the reference (incremental_remap.F:744-746).
  *
  * Parity status: the reference cannot be built in this image (no Fortran compiler, no MPAS framework) and its
- * advection test case (testing_and_setup/testcases/advection) stores no numbers, only plots: "parity unpinned".
- * tests/test_oracle_ir.py pins this file by the properties the scheme guarantees (conservation, monotonicity,
- * preservation of uniform fields, exact translation of linear fields) and by the reference test case itself
- * (solid-body rotation of a cosine bell / slotted cylinder on the sphere, error convergence).
+ * advection test case (testing_and_setup/testcases/advection) stores no numbers, only plots.  This file is pinned by
+ * OUTPUTS OF THE REFERENCE'S OWN SOURCE EXECUTED HERE: the Fortran-subset interpreter tests/golden/fortran_subset.py runs
+ * seaice_init_advection_incremental_remap and seaice_run_advection_incremental_remap (with incremental_remap_block and
+ * everything below it, the optional checks included) from the file under /root/reference; the fixtures
+ * (tests/golden/ir/*.npz: the full tracer hierarchy with layers on planar hexagons and quadrilaterals and the sphere,
+ * rotated and not) are reproduced by this file bit for bit (tests/test_ir_parity.py) -- every tracer, the conservation
+ * sums, the abort decisions of both checks, the whole geometry pool.  tests/test_oracle_ir.py adds the properties the
+ * scheme guarantees (conservation, monotonicity, uniform fields, exact translation of linear fields, an independent
+ * exact remap) and the reference's own test case (solid-body rotation on the sphere, second-order convergence).
  *
  * Array conventions (as everywhere in this repo): 1-based index VALUES, numpy C-order == Fortran column-major with
  * the dimensions reversed, a junk slot n+1 at the end of cell / vertex / edge arrays.

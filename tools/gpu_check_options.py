@@ -90,4 +90,19 @@ for kind in ("quad16", "ico3"):
         note("upwind", kind=kind, step=step, fields_identical=bool(same), fluxes_identical=bool(fl), kernel_ms=s.last_run_ms())
         assert same and fl
     s.destroy()
+# 4. the reference-executed transport fixtures (tests/golden/ir, tests/golden/options) on the device
+import glob
+import test_ir_parity as TP
+for path in TP.REFEXEC_IR:
+    TP.test_transport_reproduces_the_reference_executed_steps(path, LIB)
+    note("refexec_ir", fixture=os.path.basename(path), ok=True)
+for path in TP.REFEXEC_IR_INIT:
+    TP.test_geometry_reproduces_the_reference_executed_init(path, LIB)
+    note("refexec_irinit", fixture=os.path.basename(path), ok=True)
+for path in T.NORMAL_FILES:
+    T.test_normal_vectors_reproduce_the_reference_executed_arrays(path, ("cuda", LIB))
+    note("refexec_normals", fixture=os.path.basename(path), ok=True)
+for path in T.UPWIND_FILES:
+    T.test_upwind_reproduces_the_reference_executed_steps(path, LIB)
+    note("refexec_upwind", fixture=os.path.basename(path), ok=True)
 note("done", ok=True)
