@@ -297,6 +297,9 @@ STEP_CASES = {
     "refexec_step_ico2_stateB_6": ("ico2", "B", 3600.0, 6, 1),
     "refexec_step_hex12_square_5": ("hex12", "square", 3600.0, 5, 1),
     "refexec_step_ico2_stateB_3cat_4": ("ico2", "B", 3600.0, 4, 3),
+    # two consecutive steps with a MOVING ice edge (caps poleward of 70 N, then of 50 N): the second step starts from the
+    # first one's velocities, stresses and solveVelocityPrevious -- new_ice_velocities' branches (:1250-1279)
+    "refexec_step_ico2_moving_edge_2x4": ("ico2", "caps:70,50", 3600.0, 4, 1),
 }
 STEP_OUT = {
     "velocity_solver": ("solveStress", "solveVelocity", "solveVelocityPrevious", "icePressure", "airStressCellU", "airStressCellV",
@@ -338,7 +341,22 @@ def build_step(name):
     from mpas_seaice_b200 import variational_init
     kind, state_kind, config_dt, nsub, n_cat = STEP_CASES[name]
     mesh, var = common.mesh_case(kind)
-    state, cat = step_state(mesh, state_kind, n_cat)
+    later = []
+    if state_kind.startswith("caps:"):
+        lats = [float(x) for x in state_kind[5:].split(",")]
+        state, cat = step_state(mesh, "B", n_cat)
+        seq = []
+        for lat0 in lats:
+            cap = (np.degrees(mesh.latCell[:mesh.nCells]) > lat0) | (np.degrees(mesh.latCell[:mesh.nCells]) < -60.0)
+            c = {}
+            for k_cat, val in (("iceAreaCategory", 1.0), ("iceVolumeCategory", 1.0), ("snowVolumeCategory", 0.0)):
+                a = np.zeros((mesh.nCells + 1, 1, 1))
+                a[:mesh.nCells, 0, 0] = np.where(cap, val, 0.0)
+                c[k_cat] = a
+            seq.append(c)
+        cat, later = seq[0], seq[1:]
+    else:
+        state, cat = step_state(mesh, state_kind, n_cat)
     _, opts = common.step_case(mesh)                      # elasticTimeStep, dampingTimescale ... as seaice_init_evp sets them
     opts = dict(opts)
     nC, nV, M, D = mesh.nCells, mesh.nVertices, mesh.maxEdges, mesh.vertexDegree
@@ -442,6 +460,22 @@ def build_step(name):
     for pool, names in STEP_OUT.items():
         for k in names:
             data["out_" + k] = P[(pool, k)].copy()
+    for n_step, c in enumerate(later, 2):              # further steps: new tracers in, the dynamic state carried in the pools
+        for k, a in c.items():
+            P[("tracers", k)][...] = a
+            data["in%d_%s" % (n_step, k)] = a.copy()
+        I.pool["config_use_column_package"] = False
+        I.call("velocity_solver_pre_subcycle", domain)
+        for pool, names in STEP_OUT.items():
+            for k in names:
+                data["pre%d_%s" % (n_step, k)] = P[(pool, k)].copy()
+        I.call("subcycle_velocity_solver", domain, None)
+        I.pool["config_use_column_package"] = True
+        I.call("velocity_solver_post_subcycle", domain)
+        for pool, names in STEP_OUT.items():
+            for k in names:
+                data["out%d_%s" % (n_step, k)] = P[(pool, k)].copy()
+    data["n_steps"] = np.int64(1 + len(later))
     called = sorted(set(I.trace))
     data["provenance"] = np.array("outputs computed by interpreting the reference's Fortran source "
                                   "(tests/golden/fortran_subset.py): " + ", ".join(called))
@@ -773,8 +807,40 @@ def build_ir_init(name):
     return data
 
 
+def build_boundary(kind):
+    """init_boundary (mesh.F:372-630): interiorVertex, interiorCell, interiorEdge -- the integer maps the solver's masks and
+    the upwind fluxes are built on."""
+    mesh = init_mesh(OPTION_MESHES[kind])
+    nC, nV, nE, M, D = mesh.nCells, mesh.nVertices, mesh.nEdges, mesh.maxEdges, mesh.vertexDegree
+    I = F.Interpreter(defined=())
+    I.load(os.path.join(REF, "src/shared/mpas_seaice_mesh.F"))
+    I.noop |= {"mpas_dmpar_field_halo_exch", "mpas_log_write"}
+    out = dict(interiorVertex=np.zeros(nV + 1, np.int32), interiorCell=np.zeros(nC + 1, np.int32), interiorEdge=np.zeros(nE + 1, np.int32),
+               blockIDout=np.zeros(nC + 1, np.int32))
+    for k in ("nEdgesOnCell", "cellsOnCell", "cellsOnVertex", "cellsOnEdge"):
+        I.pool[k] = F.FArray(mesh[k])
+    for k, v in out.items():
+        I.pool[k] = F.FArray(v)
+    I.pool.update(nCells=nC, nCellsSolve=nC, nVertices=nV, nVerticesSolve=nV, nEdges=nE, nEdgesSolve=nE, vertexDegree=D, maxEdges=M)
+    block = types.SimpleNamespace(structs="structs", configs="configs", dimensions="dimensions", next=None, blockid=0)
+    I.call("init_boundary", types.SimpleNamespace(blocklist=block, configs="configs"))
+    data = {"spec": np.array(repr(OPTION_MESHES[kind])), "mesh_xCell": mesh.xCell,
+            "provenance": np.array("outputs computed by interpreting the reference's Fortran source "
+                                   "(tests/golden/fortran_subset.py): " + ", ".join(sorted(set(I.trace))))}
+    for k in ("interiorVertex", "interiorCell", "interiorEdge"):
+        data["out_" + k] = out[k]
+    return data
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
+    os.makedirs(os.path.join(HERE, "options"), exist_ok=True)
+    for kind in OPTION_MESHES:
+        name = "refexec_boundary_%s" % kind
+        if only and name not in only:
+            continue
+        np.savez_compressed(os.path.join(HERE, "options", name + ".npz"), **build_boundary(kind))
+        print(name, flush=True)
     os.makedirs(os.path.join(HERE, "ir"), exist_ok=True)
     for name in IR_INIT_CASES:
         if only and name not in only:

@@ -116,3 +116,32 @@ def test_weak_mesh_helper_geometry(kind):
         ok = e < nE
         acc[ok] += nvt[:nV][ok, s, :] * mesh.dcEdge[e[ok]][:, None]
     assert np.abs(acc[interior]).max() <= tol * mesh.dcEdge[:nE].max()
+
+
+def test_interior_maps_against_the_reference_executed_init_boundary():
+    """interiorVertex / interiorCell / interiorEdge as the reference's own init_boundary (src/shared/mpas_seaice_mesh.F:372-630)
+    computes them -- its Fortran source interpreted by tests/golden/fortran_subset.py, fixtures
+    tests/golden/options/refexec_boundary_*.npz -- against the host-side maps (variational_init.interior_vertex,
+    ir_host.interior_edge) and the oracle's orc_interior_vertices.  Integer maps: bit-exact."""
+    import ast
+    import glob
+    import os
+    import oracle
+    from mpas_seaice_b200 import ir_host, meshgen
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "options", "refexec_boundary_*.npz")))
+    assert len(files) == 4
+    for f in files:
+        z = np.load(f)
+        assert "interior_vertices" in str(z["provenance"]) and "interior_edges" in str(z["provenance"])
+        spec = ast.literal_eval(str(z["spec"]))
+        mesh = getattr(meshgen, spec[0])(*spec[1:])
+        assert np.array_equal(mesh.xCell, z["mesh_xCell"])
+        nC, nV, nE, D = mesh.nCells, mesh.nVertices, mesh.nEdges, mesh.vertexDegree
+        assert np.array_equal(variational_init.interior_vertex(mesh)[:nV], z["out_interiorVertex"][:nV]), f
+        assert np.array_equal(ir_host.interior_edge(mesh)[:nE], z["out_interiorEdge"][:nE]), f
+        mine = np.zeros(nV + 1, dtype=np.int32)
+        oracle.lib().orc_interior_vertices(oracle._p(mine), nV, D, nC, oracle._p(mesh.cellsOnVertex))
+        assert np.array_equal(mine[:nV], z["out_interiorVertex"][:nV]), f
+        coc = mesh.cellsOnCell[:nC]
+        used = np.arange(mesh.maxEdges)[None, :] < mesh.nEdgesOnCell[:nC, None]
+        assert np.array_equal(np.all((coc <= nC) | ~used, axis=1).astype(np.int32), z["out_interiorCell"][:nC]), f

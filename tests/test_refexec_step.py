@@ -41,6 +41,15 @@ def _load(path):
     forcing = {k: z["in_" + k] for k in ("uAirVelocity", "vAirVelocity", "airDensity", "uOceanVelocity", "vOceanVelocity")}
     pre = {k[4:]: z[k] for k in z.files if k.startswith("pre_")}
     out = {k[4:]: z[k] for k in z.files if k.startswith("out_")}
+    n_steps = int(z["n_steps"]) if "n_steps" in z.files else 1
+    if n_steps > 1:        # further steps of the same run: (category tracers, fields after pre, fields after post) each
+        more = []
+        for n in range(2, n_steps + 1):
+            tag = str(n)
+            more.append(({k: z["in%s_%s" % (tag, k)] for k in cat},
+                         {k[len("pre" + tag) + 1:]: z[k] for k in z.files if k.startswith("pre" + tag + "_")},
+                         {k[len("out" + tag) + 1:]: z[k] for k in z.files if k.startswith("out" + tag + "_")}))
+        pre["_more"] = more
     return mesh, var, opts, cat, forcing, pre, out, int(z["nsub"]), float(z["config_dt"]), str(z["provenance"])
 
 
@@ -72,13 +81,19 @@ def test_fixtures_exist_and_name_the_routines_that_ran():
 @pytest.mark.parametrize("path", FILES, ids=IDS)
 def test_oracle_reproduces_the_reference_executed_step(path):
     mesh, var, opts, cat, forcing, pre, out, nsub, config_dt, _ = _load(path)
+    prev = _first_step_prev(mesh)
+    for cat_n, pre_n, out_n in [(cat, pre, out)] + pre.get("_more", []):
+        prev = _oracle_step(mesh, var, opts, cat_n, forcing, pre_n, out_n, nsub, config_dt, prev)
+
+
+def _oracle_step(mesh, var, opts, cat, forcing, pre, out, nsub, config_dt, prev):
     nC, nV = mesh.nCells, mesh.nVertices
     a, vi, vs, mass = oracle.aggregate_mass_and_area(cat["iceAreaCategory"][:, :, 0], cat["iceVolumeCategory"][:, :, 0],
                                                      cat["snowVolumeCategory"][:, :, 0])
     for k, got in (("iceAreaCell", a), ("iceVolumeCell", vi), ("snowVolumeCell", vs), ("totalMassCell", mass)):
         assert np.array_equal(got[:nC], pre[k][:nC]), k
     state = dict(forcing, iceAreaCell=a, iceVolumeCell=vi, snowVolumeCell=vs)
-    step = oracle.pre_subcycle(mesh, state, config_dt, prev=_first_step_prev(mesh))
+    step = oracle.pre_subcycle(mesh, state, config_dt, prev=prev)
     vm = pre["solveVelocity"][:nV] == 1
     assert vm.any() and (pre["solveStress"][:nC] == 1).any()
     for k in ("solveStress", "icePressure"):
@@ -104,6 +119,10 @@ def test_oracle_reproduces_the_reference_executed_step(path):
         assert np.array_equal(got[k][:nV][vm], out[k][:nV][vm]), k
     assert np.abs(out["uVelocity"][:nV][vm]).max() > 0 and np.abs(out["divergence"][:nC]).max() > 0
     assert np.abs(out["oceanStressCellU"][:nC]).max() > 0 and np.abs(out["stress11"][:nC][cm]).max() > 0
+    # vertices that lost their ice are zeroed by the reference (new_ice_velocities :1262-1270): compare everywhere
+    assert np.array_equal(step["uVelocity"][:nV][~vm], out["uVelocity"][:nV][~vm])
+    return dict(uVelocity=step["uVelocity"], vVelocity=step["vVelocity"], stress11=step["stress11"], stress22=step["stress22"],
+                stress12=step["stress12"], solveVelocityPrevious=step["solveVelocityPrevious"])
 
 
 @pytest.mark.gpu
@@ -115,6 +134,51 @@ def test_device_reproduces_the_reference_executed_step(evp_lib, path):
     solver = host.EvpSolver(mesh, var, opts)
     solver.set_mesh_ext(mesh, variational_init.interior_vertex(mesh))
     try:
+        steps = [(cat, pre, out)] + pre.get("_more", [])
+        for n_step, (cat, pre, out) in enumerate(steps):
+            start = host.START_FIRST_STEP if n_step == 0 else host.START_RESIDENT       # the state stays on the device
+            _device_step(solver, host, mesh, cat, forcing, pre, out, nsub, start)
+    finally:
+        solver.destroy()
+
+
+def _device_step(solver, host, mesh, cat, forcing, pre, out, nsub, start):
+    nC, nV = mesh.nCells, mesh.nVertices
+    cm = (pre["solveStress"][:nC] == 1)[:, None] & _valid(mesh)
+    for k in POST_CELL:
+        assert np.array_equal(got[k][:nC], out[k][:nC]), k
+    for k in POST_CELL2D + ("principalStress1", "principalStress2"):
+        assert np.array_equal(got[k][:nC][cm], out[k][:nC][cm]), k
+    for k in POST_VERTEX:
+        assert np.array_equal(got[k][:nV][vm], out[k][:nV][vm]), k
+    assert np.abs(out["uVelocity"][:nV][vm]).max() > 0 and np.abs(out["divergence"][:nC]).max() > 0
+    assert np.abs(out["oceanStressCellU"][:nC]).max() > 0 and np.abs(out["stress11"][:nC][cm]).max() > 0
+    # vertices that lost their ice are zeroed by the reference (new_ice_velocities :1262-1270): compare everywhere
+    assert np.array_equal(step["uVelocity"][:nV][~vm], out["uVelocity"][:nV][~vm])
+    return dict(uVelocity=step["uVelocity"], vVelocity=step["vVelocity"], stress11=step["stress11"], stress22=step["stress22"],
+                stress12=step["stress12"], solveVelocityPrevious=step["solveVelocityPrevious"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", FILES, ids=IDS)
+def test_device_reproduces_the_reference_executed_step(evp_lib, path):
+    from mpas_seaice_b200 import host
+    mesh, var, opts, cat, forcing, pre, out, nsub, config_dt, _ = _load(path)
+    nC, nV = mesh.nCells, mesh.nVertices
+    solver = host.EvpSolver(mesh, var, opts)
+    solver.set_mesh_ext(mesh, variational_init.interior_vertex(mesh))
+    try:
+        steps = [(cat, pre, out)] + pre.get("_more", [])
+        for n_step, (cat, pre, out) in enumerate(steps):
+            start = host.START_FIRST_STEP if n_step == 0 else host.START_RESIDENT       # the state stays on the device
+            _device_step(solver, host, mesh, cat, forcing, pre, out, nsub, start)
+    finally:
+        solver.destroy()
+
+
+def _device_step(solver, host, mesh, cat, forcing, pre, out, nsub, start):
+    nC, nV = mesh.nCells, mesh.nVertices
+    if True:
         # aggregate_mass_and_area and the Hibler strength on the device, from the category tracers
         solver.aggregate(cat["iceAreaCategory"][:, :, 0].copy(), cat["iceVolumeCategory"][:, :, 0].copy(),
                          cat["snowVolumeCategory"][:, :, 0].copy(), hibler_strength=True)
@@ -130,7 +194,7 @@ def test_device_reproduces_the_reference_executed_step(evp_lib, path):
         assert np.all(np.abs(agg["icePressure"][:nC] - p_host[:nC]) <= np.spacing(np.abs(p_host[:nC])))
         cells = dict(forcing, iceAreaCellInitial=agg["iceAreaCell"], iceAreaCell=agg["iceAreaCell"],
                      totalMassCell=agg["totalMassCell"], icePressure=p_host)
-        solver.pre_subcycle(cells, cold_start=host.START_FIRST_STEP)
+        solver.pre_subcycle(cells, cold_start=start)
         got_pre = solver.fetch_pre()
         vm = pre["solveVelocity"][:nV] == 1
         assert np.array_equal(got_pre["solveStress"][:nC], pre["solveStress"][:nC])
@@ -144,8 +208,6 @@ def test_device_reproduces_the_reference_executed_step(evp_lib, path):
         got = solver.post_subcycle(names=host.POST_FIELDS_VARIATIONAL)
         inner = solver.fetch(names=("stress11", "stress22", "stress12", "strain11", "strain22", "strain12",
                                     "replacementPressure", "stressDivergenceU", "stressDivergenceV"))
-    finally:
-        solver.destroy()
     cm = (pre["solveStress"][:nC] == 1)[:, None] & _valid(mesh)
     for k in POST_CELL:
         assert np.array_equal(got[k][:nC], out[k][:nC]), k
