@@ -300,6 +300,10 @@ STEP_CASES = {
     # two consecutive steps with a MOVING ice edge (caps poleward of 70 N, then of 50 N): the second step starts from the
     # first one's velocities, stresses and solveVelocityPrevious -- new_ice_velocities' branches (:1250-1279)
     "refexec_step_ico2_moving_edge_2x4": ("ico2", "caps:70,50", 3600.0, 4, 1),
+    # the namelist switches of the pre-subcycle: config_geostrophic_surface_tilt = false (surface_tilt_ssh_gradient
+    # :2024-2170 from the coupler's sea-surface tilt), config_use_air_stress / config_use_surface_tilt = false
+    "refexec_step_ico2_sshtilt_3": ("ico2", "B", 3600.0, 3, 1, dict(geostrophic_surface_tilt=False)),
+    "refexec_step_ico2_noair_notilt_3": ("ico2", "B", 3600.0, 3, 1, dict(use_air_stress=False, use_surface_tilt=False)),
 }
 STEP_OUT = {
     "velocity_solver": ("solveStress", "solveVelocity", "solveVelocityPrevious", "icePressure", "airStressCellU", "airStressCellV",
@@ -339,7 +343,9 @@ def step_state(mesh, state_kind, n_cat):
 
 def build_step(name):
     from mpas_seaice_b200 import variational_init
-    kind, state_kind, config_dt, nsub, n_cat = STEP_CASES[name]
+    kind, state_kind, config_dt, nsub, n_cat = STEP_CASES[name][:5]
+    sw = dict(use_air_stress=True, use_surface_tilt=True, geostrophic_surface_tilt=True)
+    sw.update(STEP_CASES[name][5] if len(STEP_CASES[name]) > 5 else {})
     mesh, var = common.mesh_case(kind)
     later = []
     if state_kind.startswith("caps:"):
@@ -383,6 +389,9 @@ def build_step(name):
         P[("ocean_coupling", k)] = np.ascontiguousarray(state[k], dtype=np.float64).copy()
     for k in ("seaSurfaceTiltU", "seaSurfaceTiltV"):
         P[("ocean_coupling", k)] = zc()
+    if not sw["geostrophic_surface_tilt"]:
+        P[("ocean_coupling", "seaSurfaceTiltU")][:nC] = 1e-6 * np.sin(3 * mesh.lonCell[:nC]) * np.cos(mesh.latCell[:nC])
+        P[("ocean_coupling", "seaSurfaceTiltV")][:nC] = -2e-6 * np.cos(2 * mesh.lonCell[:nC]) * np.cos(mesh.latCell[:nC])
     P[("ocean_coupling", "landIceMask")] = np.zeros(nC + 1, np.int32)
     P[("ocean_coupling", "landIceMaskVertex")] = np.zeros(nV + 1, np.int32)
     P[("boundary", "interiorVertex")] = variational_init.interior_vertex(mesh).astype(np.int32)
@@ -420,8 +429,9 @@ def build_step(name):
         I.globals[k.lower()] = v
     I.pool.update(config_use_halo_exch=False, config_aggregate_halo_exch=False, config_reuse_halo_exch=False,
                   config_use_column_package=False, config_use_column_vertical_thermodynamics=False,
-                  config_use_air_stress=True, config_use_ocean_stress=True, config_use_surface_tilt=True,
-                  config_geostrophic_surface_tilt=True, config_calc_velocity_masks=True,
+                  config_use_air_stress=bool(sw["use_air_stress"]), config_use_ocean_stress=True,
+                  config_use_surface_tilt=bool(sw["use_surface_tilt"]),
+                  config_geostrophic_surface_tilt=bool(sw["geostrophic_surface_tilt"]), config_calc_velocity_masks=True,
                   config_stress_divergence_scheme="variational", config_strain_scheme="variational",
                   config_elastic_subcycle_number=int(nsub), config_use_special_boundaries_velocity=False,
                   config_use_special_boundaries_velocity_masks=False,
@@ -445,6 +455,10 @@ def build_step(name):
         data["in_" + k] = np.ascontiguousarray(state[k], dtype=np.float64)
     for k, v in opts.items():
         data["opt_" + k] = np.array(v)
+    for k, v in sw.items():
+        data["sw_" + k] = np.array(bool(v))
+    for k in ("seaSurfaceTiltU", "seaSurfaceTiltV"):
+        data["in_" + k] = P[("ocean_coupling", k)].copy()
     t0 = time.time()
     I.call("velocity_solver_pre_subcycle", domain)
     for pool, names in STEP_OUT.items():
@@ -625,6 +639,8 @@ IR_CASES = {
     "refexec_ir_hex_checks": ("hex", 2, 2, 1, 2, True),
     "refexec_ir_quad_checks": ("quad", 2, 1, 0, 1, True),
     "refexec_ir_quad16_checks": ("quad16", 3, 4, 2, 1, True),       # the reference's monotonicity test fires here (vertexDegree 4)
+    "refexec_ir_ico_rotated": ("ico", 2, 2, 1, 2, False, dict(rotate=True)),     # config_rotate_cartesian_grid (Registry default)
+    "refexec_ir_hex_3qp": ("hex", 2, 2, 0, 2, False, dict(nqp=3)),               # nQuadPoints = 3 (:780-782, :6598)
 }
 
 
@@ -632,12 +648,13 @@ def build_ir(name):
     from mpas_seaice_b200 import irmesh
     from oracle import ir as oir                  # INPUTS only: the incremental_remap pool's geometry, the test state
     from test_oracle_ir import smooth_divergent_velocity, _random_state
-    kind, nK, n_ice, n_snow, nsteps, checks = IR_CASES[name]
+    kind, nK, n_ice, n_snow, nsteps, checks = IR_CASES[name][:6]
+    extra = IR_CASES[name][6] if len(IR_CASES[name]) > 6 else {}
+    rotate, nQP = bool(extra.get("rotate", False)), int(extra.get("nqp", 6))
     mesh = init_mesh(IR_MESHES[kind])
     irf = irmesh.ir_fields(mesh)
-    geom = oir.init_geometry(mesh, irf)
+    geom = oir.init_geometry(mesh, irf, rotate=rotate)
     nC, nV, nE, M, D = mesh.nCells, mesh.nVertices, mesh.nEdges, mesh.maxEdges, mesh.vertexDegree
-    nQP = 6
     tracers = _random_state(mesh, np.random.default_rng(21), n_cat=nK, n_ice=n_ice, n_snow=n_snow)
     u, v = smooth_divergent_velocity(mesh, geom)
     I = F.Interpreter(defined=())
@@ -694,12 +711,15 @@ def build_ir(name):
     I.pool.update(nCells=nC, nCellsSolve=nC, nVertices=nV, nVerticesSolve=nV, nEdges=nE, nEdgesSolve=nE, maxEdges=M, vertexDegree=D,
                   nCategories=nK, nTriPerEdgeRemap=6, maxCellsPerEdgeRemap=6, maxEdgesPerEdgeRemap=6, maxVerticesPerEdgeRemap=8,
                   nQuadPoints=nQP, on_a_sphere=bool(mesh.on_a_sphere), sphere_radius=float(getattr(mesh, "sphere_radius", 0.0) or 0.0),
-                  config_rotate_cartesian_grid=False, config_monotonicity_check=bool(checks), config_conservation_check=bool(checks),
+                  config_rotate_cartesian_grid=rotate, config_monotonicity_check=bool(checks), config_conservation_check=bool(checks),
                   config_recover_tracer_means_check=False, config_use_halo_exch=False, dynamicsTimeStep=3600.0)
     g = I.globals
     g["nquadpoints"] = nQP
     w = np.zeros(nQP)
-    w[:3], w[3:] = g["w1triangleqp"], g["w2triangleqp"]          # seaice_init_advection_incremental_remap :779-784
+    if nQP == 3:
+        w[:] = 1.0 / 3.0                                          # seaice_init_advection_incremental_remap :779-784
+    else:
+        w[:3], w[3:] = g["w1triangleqp"], g["w2triangleqp"]
     g["weightquadpoint"] = F.FArray(w)
     g["tracershead"] = objs[0]                                    # module variable of ..._incremental_remap_tracers
     g["mpas_dmpar_noerr"] = 0
@@ -724,6 +744,7 @@ def build_ir(name):
     block = types.SimpleNamespace(structs="structs", configs="configs", dimensions="dimensions", next=None, localblockid=0)
     domain = types.SimpleNamespace(blocklist=block, configs="configs", dminfo=types.SimpleNamespace(my_proc_id=0))
     data = {"spec": np.array(repr(IR_MESHES[kind])), "nsteps": np.int64(nsteps), "dt": np.float64(3600.0), "checks": np.array(bool(checks)),
+            "rotate": np.array(rotate), "nqp": np.int64(nQP),
             "in_uVelocity": u, "in_vVelocity": v, "n_tracers": np.int64(len(tracers))}
     for i, t in enumerate(tracers):
         data["in_%d" % i] = t.array.copy()

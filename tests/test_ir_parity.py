@@ -483,7 +483,9 @@ def test_transport_reproduces_the_reference_executed_steps(path, lib_path):
     spec = ast.literal_eval(str(z["spec"]))
     mesh = getattr(meshgen, spec[0])(*spec[1:])
     irf = irmesh.ir_fields(mesh)
-    geom = ir.init_geometry(mesh, irf)
+    rotate = bool(z["rotate"]) if "rotate" in z.files else False
+    nqp = int(z["nqp"]) if "nqp" in z.files else 6
+    geom = ir.init_geometry(mesh, irf, rotate=rotate)
     nC = mesh.nCells
     tracers = []
     for i in range(int(z["n_tracers"])):
@@ -491,14 +493,15 @@ def test_transport_reproduces_the_reference_executed_steps(path, lib_path):
         tracers.append(ir.Tracer(name, z["in_%d" % i].copy(), parent, vol))
     u, v, dt, checks = z["in_uVelocity"], z["in_vVelocity"], float(z["dt"]), bool(z["checks"])
     ref, dev = clone(tracers), clone(tracers)
-    solver = ir_host.IrTransport(mesh, irf, geom, tracers[0].array.shape[1], lib_path=lib_path)
+    solver = ir_host.IrTransport(mesh, irf, geom, tracers[0].array.shape[1], n_quad_points=nqp, rotate=rotate, lib_path=lib_path)
     try:
         solver.set_tracers(dev)
         if checks:
             solver.set_checks(conservation=1, monotonicity=1)
         for step in range(1, int(z["nsteps"]) + 1):
             # monotonicity_check = 1: the reference's own in-place extension of the bounds
-            d = ir.run(mesh, irf, geom, ref, u, v, dt, check=False, conservation_check=int(checks), monotonicity_check=int(checks))
+            d = ir.run(mesh, irf, geom, ref, u, v, dt, n_quad_points=nqp, rotate=rotate, check=False,
+                       conservation_check=int(checks), monotonicity_check=int(checks))
             rc = solver.run(dev, u, v, dt, check=False)
             for i, (x, y) in enumerate(zip(ref, dev)):
                 want = z["out%d_%d" % (step, i)]

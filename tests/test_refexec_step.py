@@ -39,6 +39,10 @@ def _load(path):
     opts = {k[4:]: (z[k].item() if z[k].ndim == 0 else z[k]) for k in z.files if k.startswith("opt_")}
     cat = {k: z["in_" + k] for k in ("iceAreaCategory", "iceVolumeCategory", "snowVolumeCategory")}
     forcing = {k: z["in_" + k] for k in ("uAirVelocity", "vAirVelocity", "airDensity", "uOceanVelocity", "vOceanVelocity")}
+    sw = {k[3:]: bool(z[k]) for k in z.files if k.startswith("sw_")}          # the pre-subcycle's namelist switches
+    if sw and not sw.get("geostrophic_surface_tilt", True):
+        forcing.update(seaSurfaceTiltU=z["in_seaSurfaceTiltU"], seaSurfaceTiltV=z["in_seaSurfaceTiltV"])
+    opts["_switches"] = sw or dict(use_air_stress=True, use_surface_tilt=True, geostrophic_surface_tilt=True)
     pre = {k[4:]: z[k] for k in z.files if k.startswith("pre_")}
     out = {k[4:]: z[k] for k in z.files if k.startswith("out_")}
     n_steps = int(z["n_steps"]) if "n_steps" in z.files else 1
@@ -93,7 +97,7 @@ def _oracle_step(mesh, var, opts, cat, forcing, pre, out, nsub, config_dt, prev)
     for k, got in (("iceAreaCell", a), ("iceVolumeCell", vi), ("snowVolumeCell", vs), ("totalMassCell", mass)):
         assert np.array_equal(got[:nC], pre[k][:nC]), k
     state = dict(forcing, iceAreaCell=a, iceVolumeCell=vi, snowVolumeCell=vs)
-    step = oracle.pre_subcycle(mesh, state, config_dt, prev=prev)
+    step = oracle.pre_subcycle(mesh, state, config_dt, prev=prev, **opts["_switches"])
     vm = pre["solveVelocity"][:nV] == 1
     assert vm.any() and (pre["solveStress"][:nC] == 1).any()
     for k in ("solveStress", "icePressure"):
@@ -131,18 +135,18 @@ def test_device_reproduces_the_reference_executed_step(evp_lib, path):
     from mpas_seaice_b200 import host
     mesh, var, opts, cat, forcing, pre, out, nsub, config_dt, _ = _load(path)
     nC, nV = mesh.nCells, mesh.nVertices
-    solver = host.EvpSolver(mesh, var, opts)
+    solver = host.EvpSolver(mesh, var, {k: v for k, v in opts.items() if not k.startswith("_")})
     solver.set_mesh_ext(mesh, variational_init.interior_vertex(mesh))
     try:
         steps = [(cat, pre, out)] + pre.get("_more", [])
         for n_step, (cat, pre, out) in enumerate(steps):
             start = host.START_FIRST_STEP if n_step == 0 else host.START_RESIDENT       # the state stays on the device
-            _device_step(solver, host, mesh, cat, forcing, pre, out, nsub, start)
+            _device_step(solver, host, mesh, cat, forcing, pre, out, nsub, start, opts["_switches"])
     finally:
         solver.destroy()
 
 
-def _device_step(solver, host, mesh, cat, forcing, pre, out, nsub, start):
+def _device_step(solver, host, mesh, cat, forcing, pre, out, nsub, start, switches):
     nC, nV = mesh.nCells, mesh.nVertices
     cm = (pre["solveStress"][:nC] == 1)[:, None] & _valid(mesh)
     for k in POST_CELL:
@@ -194,7 +198,7 @@ def _device_step(solver, host, mesh, cat, forcing, pre, out, nsub, start):
         assert np.all(np.abs(agg["icePressure"][:nC] - p_host[:nC]) <= np.spacing(np.abs(p_host[:nC])))
         cells = dict(forcing, iceAreaCellInitial=agg["iceAreaCell"], iceAreaCell=agg["iceAreaCell"],
                      totalMassCell=agg["totalMassCell"], icePressure=p_host)
-        solver.pre_subcycle(cells, cold_start=start)
+        solver.pre_subcycle(cells, cold_start=start, **switches)
         got_pre = solver.fetch_pre()
         vm = pre["solveVelocity"][:nV] == 1
         assert np.array_equal(got_pre["solveStress"][:nC], pre["solveStress"][:nC])
