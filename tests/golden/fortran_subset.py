@@ -368,6 +368,13 @@ class FArray:
         return _scalar(v)
 
     def set(self, idx, val):
+        if self.a.dtype == object:
+            ix = self._ix(idx)
+            if any(isinstance(i, slice) for i in ix):
+                self.a[ix] = val.a if isinstance(val, FArray) else val
+            else:
+                self.a[ix] = val                   # an element of an array of objects / addresses: kept as it is
+            return
         self.a[self._ix(idx)] = val.a if isinstance(val, FArray) else val
 
 
@@ -511,6 +518,9 @@ INTRINSICS = {
     "huge": lambda x: float(np.finfo(np.float64).max) if isinstance(x, float) else 2147483647,
     "tiny": lambda x: float(np.finfo(np.float64).tiny), "epsilon": lambda x: float(np.finfo(np.float64).eps),
     "transpose": lambda x: FArray(x.a.T.copy()),
+    "merge": lambda a, b, mask: a if mask else b,
+    "c_loc": lambda x: x,                                   # the array (or object) itself stands for its address
+    "c_associated": lambda p, *q: p is not None and p != 0,
     "dot_product": _dot_product, "spread": _spread, "maxval": _maxval, "matmul": _matmul,
     "maxloc": lambda x: FArray(np.array([int(np.argmax(x.a.T.reshape(-1))) + 1], dtype=np.int64)),
     "any": lambda x: bool(np.any(x.a)) if isinstance(x, FArray) else bool(x),
@@ -550,6 +560,7 @@ class Sub:
         self.lines = lines
         self.result = None         # name of the result variable of a function
         self.types = {}            # declared type of the names: "int" | "real" | "log" (assignment converts)
+        self.decl_objects = []     # local variables of a derived type: (name, type name)
 
 
 _DECL = re.compile(r"^(real\b|integer\b|logical\b|character\b|double\s+precision\b|type\s*\(|class\s*\()", re.I)
@@ -615,7 +626,12 @@ class Interpreter:
     def __init__(self, defined=()):
         self.defined = tuple(defined)
         self.subs = {}
-        self.globals = {"rkind": 8, "strkind": 512}   # module variables (lower-case names); the MPAS kind parameters
+        self.globals = {"rkind": 8, "strkind": 512,   # module variables (lower-case names); the MPAS kind parameters
+                        "c_int": 4, "c_double": 8, "c_char": 1, "c_null_ptr": None, "c_null_char": "\0"}   # iso_c_binding
+        self.types = {}            # derived types: name -> [(component, kind, dims or None)], kind in int/real/log/ptr/char/type:<name>
+        self.cfuncs = {}           # bind(C) interfaces: name -> dict(args=[...], decl={arg: (kind, value, out, array)}, result=kind)
+        self.func_hooks = {}       # name -> python callable(interp, frame, args) -> value, for functions called in expressions
+        self.module_objects = []   # module-level variables of derived type, created by resolve_constants
         self.pool = {}             # (pool name or None, variable name) -> value for the MPAS_pool_get_* calls
         self.noop = set()          # framework calls that do nothing on a single block
         self.hooks = {}            # name -> python callable(interp, frame, args) replacing a call
@@ -627,10 +643,26 @@ class Interpreter:
     def load(self, path):
         text = preprocess(open(path).read(), self.defined)
         lines = logical_lines(text)
+        self._derived_types(lines)
         self._module_constants(lines)
         i = 0
+        in_interface = False
         while i < len(lines):
             no, s = lines[i]
+            if re.match(r"^interface\b", s, re.I):
+                in_interface = True
+            elif re.match(r"^end\s*interface\b", s, re.I):
+                in_interface = False
+            if in_interface:
+                mi = re.match(r"^(?:function|subroutine)\s+(\w+)\s*\((.*?)\)\s*(?:bind\s*\(.*?\))?\s*(?:result\s*\(\s*(\w+)\s*\))?\s*$", s, re.I)
+                if mi:
+                    j = i + 1
+                    while not re.match(r"^end\s*(subroutine|function)\b", lines[j][1], re.I):
+                        j += 1
+                    self._c_interface(mi, lines[i + 1:j])
+                    i = j
+                i += 1
+                continue
             m = re.match(r"^(?:recursive\s+|pure\s+|elemental\s+)*subroutine\s+(\w+)\s*(?:\((.*)\))?\s*$", s, re.I)
             mf = None if m else re.match(
                 r"^(?:recursive\s+|pure\s+|elemental\s+|real\s*(?:\([^)]*\))?\s+|integer\s+|logical\s+|double\s+precision\s+)*"
@@ -648,6 +680,79 @@ class Interpreter:
                 i = j
             i += 1
 
+    @staticmethod
+    def _decl_kind(attrs_l):
+        a = attrs_l.strip()
+        if a.startswith("integer"):
+            return "int"
+        if a.startswith("real") or a.startswith("double"):
+            return "real"
+        if a.startswith("logical"):
+            return "log"
+        if a.startswith("character"):
+            return "char"
+        m = re.match(r"^type\s*\(\s*(\w+)\s*\)", a)
+        if m:
+            return "ptr" if m.group(1) == "c_ptr" else "type:" + m.group(1)
+        return "real"
+
+    def _derived_types(self, lines):
+        i = 0
+        while i < len(lines):
+            m = re.match(r"^type\s*(?:,[^:]*)?::\s*(\w+)\s*$", lines[i][1], re.I) or re.match(r"^type\s+(\w+)\s*$", lines[i][1], re.I)
+            if m and not re.match(r"^type\s*\(", lines[i][1], re.I):
+                name, comps, j = m.group(1).lower(), [], i + 1
+                while not re.match(r"^end\s*type\b", lines[j][1], re.I):
+                    d = lines[j][1]
+                    if "::" in d:
+                        attrs, items = d.split("::", 1)
+                        kind = self._decl_kind(attrs.lower())
+                        pointer = "pointer" in attrs.lower()
+                        for part in _split_top(items):
+                            mm = re.match(r"^(\w+)\s*(?:\((.*?)\))?", part.strip())
+                            dims = mm.group(2) if (mm.group(2) and ":" not in mm.group(2)) else None
+                            comps.append((mm.group(1).lower(), "ptr" if pointer else kind, dims))
+                    j += 1
+                self.types[name] = comps
+                i = j
+            i += 1
+
+    def new_object(self, typename, fr=None):
+        import types as _types
+        obj = _types.SimpleNamespace(_type=typename)
+        for comp, kind, dims in self.types[typename]:
+            if dims is not None:
+                n = [int(self.ev(parse_expr(x), fr or Frame(self, Sub("<type>", [], [], "")))) for x in _split_top(dims)]
+                if kind in ("int", "real", "log"):
+                    dt = {"int": np.int64, "real": np.float64, "log": np.bool_}[kind]
+                    val = FArray(np.zeros(tuple(reversed(n)), dtype=dt))
+                else:
+                    val = FArray(np.array([None] * int(np.prod(n)), dtype=object).reshape(tuple(reversed(n))))
+            elif kind.startswith("type:") and kind[5:] in self.types:
+                val = self.new_object(kind[5:], fr)
+            else:
+                val = {"int": 0, "real": 0.0, "log": False, "char": ""}.get(kind)
+            setattr(obj, comp, val)
+        return obj
+
+    def _c_interface(self, m, decl_lines):
+        name = m.group(1).lower()
+        args = [a.strip().lower() for a in m.group(2).split(",") if a.strip()]
+        result = (m.group(3) or name).lower()
+        decl = {}
+        for no, d in decl_lines:
+            if "::" not in d:
+                continue
+            attrs, items = d.split("::", 1)
+            al = attrs.lower()
+            kind = self._decl_kind(al)
+            for part in _split_top(items):
+                mm = re.match(r"^(\w+)\s*(\(.*\))?", part.strip())
+                decl[mm.group(1).lower()] = dict(kind=kind, value="value" in al, out="intent(out)" in al.replace(" ", "") or
+                                                 "intent(inout)" in al.replace(" ", ""),
+                                                 array=bool(mm.group(2)) or "dimension" in al)
+        self.cfuncs[name] = dict(args=args, decl=decl, result=decl.get(result, dict(kind="int"))["kind"])
+
     def _module_constants(self, lines):
         """Module-level declarations with an initialiser (`integer, parameter :: A = 1`, `real(kind=RKIND), parameter ::
         puny = 1.0e-11_RKIND`) become globals, evaluated from the reference text; an initialiser that names something not
@@ -658,10 +763,15 @@ class Interpreter:
             if not (_DECL.match(s) and "::" in s):
                 continue
             attrs, items = s.split("::", 1)
+            kind = self._decl_kind(attrs.lower())
+            dim = re.search(r"dimension\s*\(([^()]*(?:\([^()]*\)[^()]*)*)\)", attrs.lower())
             for part in _split_top(items):
                 m = re.match(r"^(\w+)\s*(?:\(.*?\))?\s*=(?!>)\s*(.*)$", part.strip())
                 if m:
                     self.pending.append((m.group(1).lower(), m.group(2)))
+                elif kind.startswith("type:") and kind[5:] in self.types and "pointer" not in attrs.lower():
+                    mm = re.match(r"^(\w+)\s*(?:\((.*?)\))?", part.strip())
+                    self.module_objects.append((mm.group(1).lower(), kind[5:], mm.group(2) or (dim.group(1) if dim else None)))
         self.resolve_constants()
 
     def resolve_constants(self):
@@ -676,6 +786,17 @@ class Interpreter:
                 except FortranError:
                     rest.append((name, init))
             self.pending = rest
+        for name, typename, dims in self.module_objects:
+            if name in self.globals:
+                continue
+            try:
+                if dims is None:
+                    self.globals[name] = self.new_object(typename, fr)
+                else:
+                    n = int(self.ev(parse_expr(dims), fr))
+                    self.globals[name] = FArray(np.array([self.new_object(typename, fr) for _ in range(n)], dtype=object))
+            except FortranError:
+                pass
 
     def _prepare(self, sub):
         if sub.body is not None:
@@ -723,6 +844,10 @@ class Interpreter:
             name, own_dim, init = m.group(1).lower(), m.group(2), m.group(3)
             if not attrs_l.startswith(("type", "class", "character")):
                 sub.types[name] = kind
+            tk = self._decl_kind(attrs_l)
+            if tk.startswith("type:") and tk[5:] in self.types and not deferred and name not in sub.args:
+                sub.decl_objects.append((name, tk[5:]))
+                continue
             shape = own_dim if own_dim else (dim.group(1) if dim else None)
             if shape is not None and not deferred and ":" not in shape and name not in sub.args:
                 sub.decl_arrays.append((name, [parse_expr(x) for x in _split_top(shape)], kind))
@@ -863,6 +988,8 @@ class Interpreter:
             return self.ev(node[1], fr)
         if k == "array":
             vals = [self.ev(x, fr) for x in node[1]]
+            if any(isinstance(v, str) for v in vals):
+                return FArray(np.array(vals, dtype=object))
             return FArray(np.array(vals, dtype=np.float64 if any(isinstance(v, float) for v in vals) else np.int64))
         if k == "name":
             return fr.get(node[1])
@@ -976,6 +1103,8 @@ class Interpreter:
             if name in self.subs and self.subs[name].result:
                 callee = self.invoke(name, args, fr)
                 return callee.get(self.subs[name].result)
+            if name in self.func_hooks:
+                return self.func_hooks[name](self, fr, args)
             if name in INTRINSICS:
                 vals = [self.ev(a, fr) for kw, a in args if kw is None]
                 kws = {kw: self.ev(a, fr) for kw, a in args if kw is not None}
@@ -1139,6 +1268,8 @@ class Interpreter:
             shape = tuple(int(self.ev(x, fr)) for x in dims)
             dt = np.float64 if kind == "real" else (np.int64 if kind == "int" else np.bool_)
             fr.vars[nm] = FArray(np.zeros(tuple(reversed(shape)), dtype=dt))
+        for nm, typename in sub.decl_objects:
+            fr.vars[nm] = self.new_object(typename, fr)
         for nm, init in sub.inits:
             fr.vars[nm] = self.ev(init, fr)
         try:
@@ -1196,6 +1327,8 @@ class Interpreter:
             shape = tuple(int(self.ev(x, fr)) for x in dims)
             dt = np.float64 if kind == "real" else (np.int64 if kind == "int" else np.bool_)
             fr.vars[nm] = FArray(np.zeros(tuple(reversed(shape)), dtype=dt))
+        for nm, typename in sub.decl_objects:
+            fr.vars[nm] = self.new_object(typename, fr)
         for nm, init in sub.inits:
             fr.vars[nm] = self.ev(init, fr)
         try:

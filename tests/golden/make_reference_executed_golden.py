@@ -60,6 +60,11 @@ CASES = {
     "refexec_quad10_evp_avg_6": ("quad10", "evp", 6, {"average_variational_strain": True}),
     "refexec_ico2_evp_lineardrag_6": ("ico2", "evp", 6, {"ocean_stress_type": "linear"}),
     "refexec_hex12_evp_special_boundaries_8": ("hex12", "evp", 8, {"use_special_boundaries_velocity": True}),
+    # the same inputs as the oracle-made vectors of make_golden.py, at their full length: a whole 120-subcycle dynamics
+    # step of the square test case and of the sphere, interpreted (minutes each)
+    "refexec_hex20_evp_120": ("hex20", "evp", 120, {}),
+    "refexec_ico3_revised_40": ("ico3", "evp_revised", 40, {}),
+    "refexec_ico3_evp_120": ("ico3", "evp", 120, {}),
     # the weak operators (src/shared/mpas_seaice_velocity_solver_weak.F) and the weak-strain / variational-divergence mix
     # (interpolate_strains_weak_to_variational, velocity_solver.F:2877-2972)
     "refexec_hex12_weak_evp_8": ("hex12", "evp", 8, {"strain_scheme": "weak", "stress_divergence_scheme": "weak"}),
