@@ -24,6 +24,7 @@ class CBridge:
         self.keep = []
         self._structs = {}
         self.calls = []                       # names of the C functions called, in order
+        self.returns = []                     # (name, return value)
         for name in interp.cfuncs:
             if hasattr(lib, name):
                 interp.func_hooks[name] = self._make(name)
@@ -127,6 +128,7 @@ class CBridge:
             fn.restype = C.c_void_p if cf["result"] == "ptr" else C.c_int
             self.calls.append(name)
             rc = fn(*cargs)
+            self.returns.append((name, rc))
             for target, holder in after:
                 if isinstance(holder, C.Structure):
                     self.from_struct(holder, target)

@@ -144,7 +144,7 @@ _TOKEN = re.compile(r"""
     | (?P<dot>\.(?:and|or|not|eqv|neqv|eq|ne|lt|le|gt|ge|true|false)\.)
     | (?P<name>[A-Za-z_]\w*)
     | (?P<str>'(?:[^']|'')*'|"(?:[^"]|"")*")
-    | (?P<op>\*\*|==|/=|<=|>=|=>|//|[-+*/(),:%<>=])
+    | (?P<op>\*\*|==|/=|<=|>=|=>|//|[-+*/(),:%<>=\[\]])
     )""", re.X | re.I)
 
 _DOT_REL = {".eq.": "==", ".ne.": "/=", ".lt.": "<", ".le.": "<=", ".gt.": ">", ".ge.": ">="}
@@ -300,6 +300,15 @@ class Parser:
         if tok[0] == "str":
             self.take()
             return ("str", tok[1])
+        if tok == ("op", "["):                                # [a, b, c]: the Fortran 2003 array constructor
+            self.take()
+            items = []
+            while not self.at_op("]"):
+                items.append(self.expr())
+                if self.at_op(","):
+                    self.take()
+            self.take("op", "]")
+            return ("array", items)
         if tok == ("op", "(") and self.i + 1 < len(self.t) and self.t[self.i + 1] == ("op", "/"):
             self.take()
             self.take()
@@ -621,7 +630,7 @@ class Frame:
 
 class Interpreter:
     POOL_GETTERS = ("mpas_pool_get_array", "mpas_pool_get_config", "mpas_pool_get_dimension", "mpas_pool_get_subpool",
-                    "mpas_pool_get_field")
+                    "mpas_pool_get_field", "mpas_pool_get_package")
 
     def __init__(self, defined=()):
         self.defined = tuple(defined)
@@ -772,6 +781,12 @@ class Interpreter:
                 elif kind.startswith("type:") and kind[5:] in self.types and "pointer" not in attrs.lower():
                     mm = re.match(r"^(\w+)\s*(?:\((.*?)\))?", part.strip())
                     self.module_objects.append((mm.group(1).lower(), kind[5:], mm.group(2) or (dim.group(1) if dim else None)))
+                else:
+                    # a module variable without an initialiser: it exists (so that assignments inside routines reach it)
+                    mm = re.match(r"^(\w+)\s*(\(.*\))?$", part.strip())
+                    if mm and not mm.group(2) and dim is None and "allocatable" not in attrs.lower() and \
+                            "pointer" not in attrs.lower() and mm.group(1).lower() not in self.globals:
+                        self.globals[mm.group(1).lower()] = {"int": 0, "real": 0.0, "log": False, "char": ""}.get(kind)
         self.resolve_constants()
 
     def resolve_constants(self):
@@ -1122,6 +1137,13 @@ class Interpreter:
             fr.set(lhs[1], val)
         elif lhs[0] == "call":
             arr = self.ev(lhs[1], fr) if lhs[1][0] != "name" else fr.get(lhs[1][1])
+            if isinstance(arr, str) and lhs[1][0] == "name":          # msg(i:j) = "..." : a substring of a character variable
+                idx = self._index(lhs[2], fr)[0]
+                lo, hi = (idx.start or 1, idx.stop or len(arr)) if isinstance(idx, slice) else (idx, idx)
+                chars = list(arr.ljust(hi))
+                chars[lo - 1:hi] = list(str(val).ljust(hi - lo + 1))[:hi - lo + 1]
+                fr.set(lhs[1][1], "".join(chars))
+                return
             if not isinstance(arr, FArray):
                 raise FortranError("assignment to an element of %s, which is not an array" % (lhs[1],))
             arr.set(self._index(lhs[2], fr), val)

@@ -135,3 +135,94 @@ def test_ir_shim_executed_against_the_emulated_library():
 @pytest.mark.gpu
 def test_ir_shim_executed_against_the_cuda_library():
     _check_ir_shim(ir_host.LIB_PATH)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# fortran/seaice_evp_b200.F90: seaice_evp_b200_create / _update / _subcycle / _destroy executed against libevp_b200.so
+# ----------------------------------------------------------------------------------------------------------------------
+
+def _evp_shim(kind="hex20", nsub=20, cr="evp"):
+    from mpas_seaice_b200 import host
+    mesh, var = common.mesh_case(kind)
+    step, opts = common.step_case(mesh, constitutive_relation_type=cr)
+    work = common.clone_step(step)
+    I = F.Interpreter()
+    I.load(os.path.join(ROOT, "fortran", "seaice_evp_b200.F90"))
+    I.resolve_constants()
+    I.noop |= {"seaice_set_special_boundaries_velocity_masks"}
+    I.globals["mpas_log_crit"] = 3
+    bridge = CBridge(I, C.CDLL(host.LIB_PATH))
+    bridge.log = []
+
+    def c_f_pointer(interp, fr, args):            # call c_f_pointer(cptr, fptr, [n]): the C string as a character array
+        addr, n = interp.ev(args[0][1], fr), int(interp.ev(args[2][1], fr).a[0])
+        text = (C.string_at(addr) if addr else b"").decode()[:n - 1]
+        fr.bind(args[1][1][1], F.FArray(np.array(list(text) + ["\0"] * (n - len(text)), dtype=object)))
+
+    def log_write(interp, fr, args):
+        bridge.log.append(interp.ev(args[0][1], fr))
+
+    I.hooks.update(c_f_pointer=c_f_pointer, mpas_log_write=log_write)
+    nC, nV = mesh.nCells, mesh.nVertices
+    for k in ("nEdgesOnCell", "verticesOnCell", "cellsOnVertex"):
+        I.pool[k] = F.FArray(mesh[k])
+    for k in ("cellVerticesAtVertex", "basisGradientU", "basisGradientV", "basisIntegralsU", "basisIntegralsV", "basisIntegralsMetric",
+              "tanLatVertexRotatedOverRadius", "variationalDenominator"):
+        I.pool[k] = F.FArray(var[k])
+    for k, a in work.items():
+        if isinstance(a, np.ndarray):
+            I.pool[k] = F.FArray(a)
+    I.pool.update(nCells=nC, nCellsSolve=nC, nVertices=nV, nVerticesSolve=nV, maxEdges=mesh.maxEdges, vertexDegree=mesh.vertexDegree,
+                  elasticTimeStep=float(opts["elasticTimeStep"]), dynamicsTimeStep=float(opts["dynamicsTimeStep"]),
+                  config_ocean_stress_type="quadratic", config_use_ocean_stress=True, config_use_special_boundaries_velocity=False,
+                  config_use_special_boundaries_velocity_masks=False, config_elastic_subcycle_number=int(nsub),
+                  config_average_variational_strain=False, config_strain_scheme="variational",
+                  config_stress_divergence_scheme="variational", pkgVariationalActive=True)
+    # module variables of seaice_velocity_solver_constitutive_relation the shim uses (constitutive_relation.F:29-59)
+    I.globals.update(constitutiverelationtype={"evp": 1, "evp_revised": 2, "linear": 3}[cr],
+                     dampingtimescale=float(opts["dampingTimescale"]),
+                     numericalinertiacoefficient=float(opts.get("numericalInertiaCoefficient", 0.0)))
+    block = types.SimpleNamespace(structs="structs", configs="configs", dimensions="dimensions", next=None)
+    domain = types.SimpleNamespace(blocklist=block, configs="configs", packages="packages")
+    return I, bridge, domain, mesh, var, step, opts, work
+
+
+def test_evp_shim_reaches_the_library_with_a_valid_descriptor():
+    """Without a device evp_create must fail with EVP_ERR_CUDA (2) -- AFTER it has accepted the mesh descriptor and the
+    options the shim built (an argument error would be 1): the bind(C) types and the interface of evp_create as the shim
+    declares them are what the library expects."""
+    I, bridge, domain, *_ = _evp_shim()
+    assert I.call("seaice_evp_b200_supported", domain).vars["supported"] is True
+    I.call("seaice_evp_b200_create", domain)
+    name, rc = bridge.returns[0]
+    assert name == "evp_create"
+    import subprocess
+    has_gpu = subprocess.run(["nvidia-smi", "-L"], capture_output=True).returncode == 0 if os.path.exists("/usr/bin/nvidia-smi") else False
+    assert rc == (0 if has_gpu else 2), rc
+    if rc == 0:
+        I.call("seaice_evp_b200_destroy", 0)
+    else:       # the shim's own error path: evp_last_error_string() copied character by character into the MPAS log line
+        assert len(bridge.log) == 1 and bridge.log[0].startswith("libevp_b200: evp_create: ") and "cuda" in bridge.log[0].lower()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,cr", [("hex20", "evp"), ("ico3", "evp_revised")])
+def test_evp_shim_executed_against_the_cuda_library(evp_lib, kind, cr):
+    """The shim's own create -> update -> subcycle (evp_set_options, evp_update_step, evp_run_subcycles, evp_fetch into the
+    pool arrays) -> destroy, from the pools of a synthetic step; the pool arrays afterwards hold the oracle's results."""
+    nsub = 20
+    I, bridge, domain, mesh, var, step, opts, work = _evp_shim(kind, nsub, cr)
+    I.call("seaice_evp_b200_create", domain)
+    I.call("seaice_evp_b200_update", domain)
+    I.call("seaice_evp_b200_subcycle", domain)
+    assert [n for n, _ in bridge.returns] == ["evp_create", "evp_set_options", "evp_update_step", "evp_run_subcycles", "evp_fetch"]
+    assert all(rc == 0 for _, rc in bridge.returns), bridge.returns
+    ref = common.run_oracle(mesh, var, step, opts, nsub)
+    cm, vm = common.masks_for(mesh, step)
+    for k in common.COMPARE_CELL:
+        assert np.array_equal(work[k][cm], ref[k][cm]), k
+    for k in common.COMPARE_VERTEX:
+        assert np.array_equal(work[k][vm], ref[k][vm]), k
+    assert np.abs(ref["uVelocity"][vm]).max() > 0
+    I.call("seaice_evp_b200_destroy", 0)
+    assert bridge.returns[-1] == ("evp_destroy", 0) and I.globals["evphandle"] is None
