@@ -148,70 +148,35 @@ def test_device_reproduces_the_reference_executed_step(evp_lib, path):
 
 def _device_step(solver, host, mesh, cat, forcing, pre, out, nsub, start, switches):
     nC, nV = mesh.nCells, mesh.nVertices
-    cm = (pre["solveStress"][:nC] == 1)[:, None] & _valid(mesh)
-    for k in POST_CELL:
-        assert np.array_equal(got[k][:nC], out[k][:nC]), k
-    for k in POST_CELL2D + ("principalStress1", "principalStress2"):
-        assert np.array_equal(got[k][:nC][cm], out[k][:nC][cm]), k
-    for k in POST_VERTEX:
-        assert np.array_equal(got[k][:nV][vm], out[k][:nV][vm]), k
-    assert np.abs(out["uVelocity"][:nV][vm]).max() > 0 and np.abs(out["divergence"][:nC]).max() > 0
-    assert np.abs(out["oceanStressCellU"][:nC]).max() > 0 and np.abs(out["stress11"][:nC][cm]).max() > 0
-    # vertices that lost their ice are zeroed by the reference (new_ice_velocities :1262-1270): compare everywhere
-    assert np.array_equal(step["uVelocity"][:nV][~vm], out["uVelocity"][:nV][~vm])
-    return dict(uVelocity=step["uVelocity"], vVelocity=step["vVelocity"], stress11=step["stress11"], stress22=step["stress22"],
-                stress12=step["stress12"], solveVelocityPrevious=step["solveVelocityPrevious"])
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("path", FILES, ids=IDS)
-def test_device_reproduces_the_reference_executed_step(evp_lib, path):
-    from mpas_seaice_b200 import host
-    mesh, var, opts, cat, forcing, pre, out, nsub, config_dt, _ = _load(path)
-    nC, nV = mesh.nCells, mesh.nVertices
-    solver = host.EvpSolver(mesh, var, opts)
-    solver.set_mesh_ext(mesh, variational_init.interior_vertex(mesh))
-    try:
-        steps = [(cat, pre, out)] + pre.get("_more", [])
-        for n_step, (cat, pre, out) in enumerate(steps):
-            start = host.START_FIRST_STEP if n_step == 0 else host.START_RESIDENT       # the state stays on the device
-            _device_step(solver, host, mesh, cat, forcing, pre, out, nsub, start)
-    finally:
-        solver.destroy()
-
-
-def _device_step(solver, host, mesh, cat, forcing, pre, out, nsub, start):
-    nC, nV = mesh.nCells, mesh.nVertices
-    if True:
-        # aggregate_mass_and_area and the Hibler strength on the device, from the category tracers
-        solver.aggregate(cat["iceAreaCategory"][:, :, 0].copy(), cat["iceVolumeCategory"][:, :, 0].copy(),
-                         cat["snowVolumeCategory"][:, :, 0].copy(), hibler_strength=True)
-        agg = solver.fetch_aggregate(ice_pressure=True)
-        for k in ("iceAreaCell", "iceVolumeCell", "snowVolumeCell", "totalMassCell"):
-            assert np.array_equal(agg[k][:nC], pre[k][:nC]), k
-        # The Hibler strength holds the path's one transcendental: P* h exp(-C (1 - a)) (velocity_solver.F:1419-1436).  CUDA's
-        # exp() is a 1-ulp function, the reference's is the host libm's: the device value is held to 1 ulp here, and the step
-        # continues from the libm value (what a host that keeps ice_strength passes) so that everything after it stays
-        # a bit-for-bit comparison.
-        state = dict(iceAreaCell=agg["iceAreaCell"], iceVolumeCell=agg["iceVolumeCell"])
-        p_host = oracle.hibler_strength_unmasked(state, nC)
-        assert np.all(np.abs(agg["icePressure"][:nC] - p_host[:nC]) <= np.spacing(np.abs(p_host[:nC])))
-        cells = dict(forcing, iceAreaCellInitial=agg["iceAreaCell"], iceAreaCell=agg["iceAreaCell"],
-                     totalMassCell=agg["totalMassCell"], icePressure=p_host)
-        solver.pre_subcycle(cells, cold_start=start, **switches)
-        got_pre = solver.fetch_pre()
-        vm = pre["solveVelocity"][:nV] == 1
-        assert np.array_equal(got_pre["solveStress"][:nC], pre["solveStress"][:nC])
-        assert np.array_equal(got_pre["solveVelocity"][:nV], pre["solveVelocity"][:nV])
-        assert np.array_equal(got_pre["icePressure"][:nC], pre["icePressure"][:nC])
-        for k in ("iceAreaVertex", "totalMassVertex", "totalMassVertexfVertex", "airStressVertexU", "airStressVertexV",
-                  "surfaceTiltForceU", "surfaceTiltForceV", "oceanStressU", "oceanStressV", "uOceanVelocityVertex",
-                  "vOceanVelocityVertex", "uVelocityInitial", "vVelocityInitial"):
-            assert np.array_equal(got_pre[k][:nV][vm], pre[k][:nV][vm]), k
-        solver.run_subcycles(nsub)
-        got = solver.post_subcycle(names=host.POST_FIELDS_VARIATIONAL)
-        inner = solver.fetch(names=("stress11", "stress22", "stress12", "strain11", "strain22", "strain12",
-                                    "replacementPressure", "stressDivergenceU", "stressDivergenceV"))
+    # aggregate_mass_and_area and the Hibler strength on the device, from the category tracers
+    solver.aggregate(cat["iceAreaCategory"][:, :, 0].copy(), cat["iceVolumeCategory"][:, :, 0].copy(),
+                     cat["snowVolumeCategory"][:, :, 0].copy(), hibler_strength=True)
+    agg = solver.fetch_aggregate(ice_pressure=True)
+    for k in ("iceAreaCell", "iceVolumeCell", "snowVolumeCell", "totalMassCell"):
+        assert np.array_equal(agg[k][:nC], pre[k][:nC]), k
+    # The Hibler strength holds the path's one transcendental: P* h exp(-C (1 - a)) (velocity_solver.F:1419-1436).  CUDA's
+    # exp() is a 1-ulp function, the reference's is the host libm's: the device value is held to 1 ulp here, and the step
+    # continues from the libm value (what a host that keeps ice_strength passes) so that everything after it stays
+    # a bit-for-bit comparison.
+    state = dict(iceAreaCell=agg["iceAreaCell"], iceVolumeCell=agg["iceVolumeCell"])
+    p_host = oracle.hibler_strength_unmasked(state, nC)
+    assert np.all(np.abs(agg["icePressure"][:nC] - p_host[:nC]) <= np.spacing(np.abs(p_host[:nC])))
+    cells = dict(forcing, iceAreaCellInitial=agg["iceAreaCell"], iceAreaCell=agg["iceAreaCell"],
+                 totalMassCell=agg["totalMassCell"], icePressure=p_host)
+    solver.pre_subcycle(cells, cold_start=start, **switches)
+    got_pre = solver.fetch_pre()
+    vm = pre["solveVelocity"][:nV] == 1
+    assert np.array_equal(got_pre["solveStress"][:nC], pre["solveStress"][:nC])
+    assert np.array_equal(got_pre["solveVelocity"][:nV], pre["solveVelocity"][:nV])
+    assert np.array_equal(got_pre["icePressure"][:nC], pre["icePressure"][:nC])
+    for k in ("iceAreaVertex", "totalMassVertex", "totalMassVertexfVertex", "airStressVertexU", "airStressVertexV",
+              "surfaceTiltForceU", "surfaceTiltForceV", "oceanStressU", "oceanStressV", "uOceanVelocityVertex",
+              "vOceanVelocityVertex", "uVelocityInitial", "vVelocityInitial"):
+        assert np.array_equal(got_pre[k][:nV][vm], pre[k][:nV][vm]), k
+    solver.run_subcycles(nsub)
+    got = solver.post_subcycle(names=host.POST_FIELDS_VARIATIONAL)
+    inner = solver.fetch(names=("stress11", "stress22", "stress12", "strain11", "strain22", "strain12",
+                                "replacementPressure", "stressDivergenceU", "stressDivergenceV"))
     cm = (pre["solveStress"][:nC] == 1)[:, None] & _valid(mesh)
     for k in POST_CELL:
         assert np.array_equal(got[k][:nC], out[k][:nC]), k
