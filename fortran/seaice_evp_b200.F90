@@ -21,8 +21,9 @@
 !> caller keeps using the original Fortran subcycle -- the ORIGINAL code, not a CPU copy of this one.
 !>
 !> The bind(C) types below mirror include/evp_b200.h field for field (tests/test_fortran_shim.py
-!> checks names, order and types against the header).  This file cannot be compiled in the build
-!> container (no Fortran compiler, no MPAS framework); see INTEGRATION.md.
+!> checks names, order and types against the header).  No Fortran compiler exists in the build
+!> container; the module is executed there by an interpreter that calls the library through these
+!> interface blocks (tests/test_fortran_shim_executed.py); see INTEGRATION.md.
 !
 !-----------------------------------------------------------------------
 

@@ -23,7 +23,8 @@
 !>  (:8416) runs in the library, so the call of check_tracer_monotonicity is skipped on the device path.
 !>
 !>  Not compiled in this repository (no Fortran compiler in the build image); tests/test_fortran_shim.py
-!>  checks the interface blocks against include/ir_b200.h.
+!>  checks the interface blocks against include/ir_b200.h, and tests/test_fortran_shim_executed.py EXECUTES
+!>  this module with an interpreter that calls the library through these interface blocks.
 !
 !-----------------------------------------------------------------------
 
