@@ -107,3 +107,22 @@ def test_device_reproduces_golden(evp_lib, path):
     finally:
         solver.destroy()
     _check(mesh, step, want, got, opts)
+
+
+def test_oracle_made_vectors_equal_their_reference_executed_twins():
+    """hex20_evp_120 / ico3_revised_40 / ico3_evp_120 exist twice: made by the oracle (make_golden.py) and made by
+    interpreting the reference's source from the same inputs at the same length (a whole 120-subcycle dynamics step of the
+    square case and of the sphere).  Same inputs, same outputs on every solved cell and vertex, bit for bit."""
+    pairs = [(f, os.path.join(HERE, "golden", "refexec_" + os.path.basename(f))) for f in FILES
+             if not os.path.basename(f).startswith("refexec_")]
+    pairs = [(a, b) for a, b in pairs if os.path.exists(b)]
+    assert len(pairs) >= 2
+    for a, b in pairs:
+        mesh, var, step, opts, want, nsub = _load(a)
+        mesh2, var2, step2, opts2, want2, nsub2 = _load(b)
+        assert nsub == nsub2 and "interpreting the reference's Fortran source" in str(np.load(b)["provenance"])
+        for k in ("uVelocity", "icePressure", "totalMassVertex", "solveStress", "solveVelocity"):
+            assert np.array_equal(step[k], step2[k]), k
+        for k in ("basisGradientU", "basisIntegralsMetric"):
+            assert np.array_equal(var[k], var2[k]), k
+        _check(mesh, step, want, want2, opts)
