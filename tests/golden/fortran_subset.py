@@ -517,6 +517,12 @@ def _matmul(a, b):
     return FArray(out.T.copy())
 
 
+def _minval(x, dim=None):
+    if dim is None:
+        return _scalar(x.a.min())
+    return FArray(x.a.min(axis=x.a.ndim - int(dim)))
+
+
 def _maxval(x, dim=None):
     if dim is None:
         return _scalar(x.a.max())
@@ -530,7 +536,7 @@ INTRINSICS = {
     "merge": lambda a, b, mask: a if mask else b,
     "c_loc": lambda x: x,                                   # the array (or object) itself stands for its address
     "c_associated": lambda p, *q: p is not None and p != 0,
-    "dot_product": _dot_product, "spread": _spread, "maxval": _maxval, "matmul": _matmul,
+    "dot_product": _dot_product, "spread": _spread, "maxval": _maxval, "minval": _minval, "matmul": _matmul,
     "maxloc": lambda x: FArray(np.array([int(np.argmax(x.a.T.reshape(-1))) + 1], dtype=np.int64)),
     "any": lambda x: bool(np.any(x.a)) if isinstance(x, FArray) else bool(x),
     "all": lambda x: bool(np.all(x.a)) if isinstance(x, FArray) else bool(x),

@@ -833,6 +833,30 @@ def build_ir_init(name):
     return data
 
 
+def build_init_evp():
+    """seaice_init_evp (constitutive_relation.F:75-164): the relation type from the namelist string, dampingTimescale,
+    numericalInertiaCoefficient (Bouillon et al. 2013) from the time steps and the shortest edge of the mesh."""
+    rows = []
+    for kind in ("hex", "ico", "band"):
+        mesh = init_mesh(OPTION_MESHES[kind])
+        for cr, dt_dyn, nsub in (("evp", 3600.0, 120), ("evp_revised", 900.0, 60), ("linear", 120.0, 120), ("none", 1800.0, 1)):
+            I = F.Interpreter(defined=())
+            I.load(os.path.join(REF, "src/shared/mpas_seaice_velocity_solver_constitutive_relation.F"))
+            I.resolve_constants()
+            I.noop |= {"mpas_log_write"}
+            I.hooks["mpas_dmpar_min_real"] = lambda interp, fr, args: interp._assign(args[2][1], interp.ev(args[1][1], fr), fr)
+            I.pool.update(config_constitutive_relation_type=cr, dynamicsTimeStep=dt_dyn, elasticTimeStep=dt_dyn / nsub,
+                          nEdgesSolve=int(mesh.nEdges), dvEdge=F.FArray(mesh.dvEdge))
+            block = types.SimpleNamespace(structs="structs", configs="configs", dimensions="dimensions", next=None)
+            I.call("seaice_init_evp", types.SimpleNamespace(blocklist=block, configs="configs", dminfo=None))
+            g = I.globals
+            rows.append((kind, cr, dt_dyn, nsub, int(g["constitutiverelationtype"]), float(g["dampingtimescale"]),
+                         float(g["numericalinertiacoefficient"]), float(mesh.dvEdge[:mesh.nEdges].min())))
+    return {"rows": np.array([repr(r) for r in rows]),
+            "provenance": np.array("outputs computed by interpreting the reference's Fortran source "
+                                   "(tests/golden/fortran_subset.py): seaice_init_evp")}
+
+
 def build_boundary(kind):
     """init_boundary (mesh.F:372-630): interiorVertex, interiorCell, interiorEdge -- the integer maps the solver's masks and
     the upwind fluxes are built on."""
@@ -861,6 +885,9 @@ def build_boundary(kind):
 if __name__ == "__main__":
     only = sys.argv[1:]
     os.makedirs(os.path.join(HERE, "options"), exist_ok=True)
+    if not only or "refexec_init_evp" in only:
+        np.savez_compressed(os.path.join(HERE, "options", "refexec_init_evp.npz"), **build_init_evp())
+        print("refexec_init_evp", flush=True)
     for kind in OPTION_MESHES:
         name = "refexec_boundary_%s" % kind
         if only and name not in only:

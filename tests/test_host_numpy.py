@@ -145,3 +145,27 @@ def test_interior_maps_against_the_reference_executed_init_boundary():
         coc = mesh.cellsOnCell[:nC]
         used = np.arange(mesh.maxEdges)[None, :] < mesh.nEdgesOnCell[:nC, None]
         assert np.array_equal(np.all((coc <= nC) | ~used, axis=1).astype(np.int32), z["out_interiorCell"][:nC]), f
+
+
+def test_evp_parameters_against_the_reference_executed_seaice_init_evp():
+    """constitutiveRelationType, dampingTimescale and numericalInertiaCoefficient as the reference's own seaice_init_evp
+    (src/shared/mpas_seaice_velocity_solver_constitutive_relation.F:75-164) leaves them -- interpreted from its source,
+    fixture tests/golden/options/refexec_init_evp.npz -- against the host-side synthetic.time_steps /
+    numerical_inertia_coefficient every test's options come from, and the oracle's orc_* functions.  Bit for bit."""
+    import ast
+    import ctypes as C
+    import os
+    import oracle
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "options", "refexec_init_evp.npz"))
+    assert "seaice_init_evp" in str(z["provenance"])
+    L = oracle.lib()
+    L.orc_numerical_inertia_coefficient.restype = C.c_double
+    L.orc_damping_timescale.restype = C.c_double
+    rows = [ast.literal_eval(str(r)) for r in z["rows"]]
+    assert len(rows) == 12
+    for kind, cr, dt_dyn, nsub, cr_type, damping, inertia, dv_min in rows:
+        assert cr_type == {"evp": oracle.EVP, "evp_revised": oracle.EVP_REVISED, "linear": oracle.LINEAR, "none": oracle.NONE}[cr]
+        dt, dte, damp = synthetic.time_steps(dt_dyn, 1, nsub)
+        assert damp == damping and synthetic.numerical_inertia_coefficient(dt, dv_min) == inertia
+        assert L.orc_damping_timescale(C.c_double(dt_dyn)) == damping
+        assert L.orc_numerical_inertia_coefficient(C.c_double(dt_dyn), C.c_double(dv_min)) == inertia
