@@ -857,6 +857,35 @@ def build_init_evp():
                                    "(tests/golden/fortran_subset.py): seaice_init_evp")}
 
 
+def build_weak_post():
+    """seaice_final_divergence_shear_weak (weak.F:654-751), as written: `Delta = sqrt(...)` assigns the whole work array
+    inside the cell loop, so the ridging shear of every cell is computed from the LAST owned cell's Delta."""
+    rng = np.random.default_rng(7)
+    nC = 57
+    strain = [np.zeros(nC + 1) for _ in range(3)]
+    for a in strain:
+        a[:nC] = rng.normal(scale=1e-6, size=nC)
+    out = {k: np.zeros(nC + 1) for k in ("divergence", "shear", "ridgeConvergence", "ridgeShear")}
+    I = F.Interpreter(defined=())
+    I.load(os.path.join(REF, "src/shared/mpas_seaice_velocity_solver_constitutive_relation.F"))
+    I.load(os.path.join(REF, "src/shared/mpas_seaice_velocity_solver_weak.F"))
+    I.resolve_constants()
+    for k, a in zip(("strain11", "strain22", "strain12"), strain):
+        I.pool[("velocity_weak", k)] = F.FArray(a)
+    for k, a in out.items():
+        I.pool[k] = F.FArray(a)
+    I.pool.update(nCellsSolve=nC, nEdgesOnCell=F.FArray(np.full(nC + 1, 6, np.int32)), config_use_column_package=True)
+    block = types.SimpleNamespace(structs="structs", configs="configs", dimensions="dimensions", next=None)
+    I.call("seaice_final_divergence_shear_weak", block)
+    data = {"nCells": np.int64(nC), "provenance": np.array("outputs computed by interpreting the reference's Fortran source "
+                                                          "(tests/golden/fortran_subset.py): seaice_final_divergence_shear_weak")}
+    for k, a in zip(("strain11", "strain22", "strain12"), strain):
+        data["in_" + k] = a
+    for k, a in out.items():
+        data["out_" + k] = a
+    return data
+
+
 def build_boundary(kind):
     """init_boundary (mesh.F:372-630): interiorVertex, interiorCell, interiorEdge -- the integer maps the solver's masks and
     the upwind fluxes are built on."""
@@ -885,6 +914,9 @@ def build_boundary(kind):
 if __name__ == "__main__":
     only = sys.argv[1:]
     os.makedirs(os.path.join(HERE, "options"), exist_ok=True)
+    if not only or "refexec_weak_post" in only:
+        np.savez_compressed(os.path.join(HERE, "options", "refexec_weak_post.npz"), **build_weak_post())
+        print("refexec_weak_post", flush=True)
     if not only or "refexec_init_evp" in only:
         np.savez_compressed(os.path.join(HERE, "options", "refexec_init_evp.npz"), **build_init_evp())
         print("refexec_init_evp", flush=True)

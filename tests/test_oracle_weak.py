@@ -92,3 +92,23 @@ def test_final_divergence_shear_weak_uses_the_last_cells_delta():
     delta_last = np.sqrt(sd * sd + (st * st + ss * ss) / 4.0)
     assert np.allclose(rs, 0.5 * (delta_last - np.abs(div)), rtol=1e-15)
     assert np.array_equal(rc, -np.minimum(div, 0.0))
+
+
+def test_final_divergence_shear_weak_against_the_reference_executed_routine():
+    """seaice_final_divergence_shear_weak (weak.F:654-751) interpreted from the reference's source
+    (tests/golden/options/refexec_weak_post.npz): the oracle reproduces it bit for bit -- including what its
+    whole-array assignment `Delta = sqrt(...)` inside the cell loop does to ridgeShear (every cell sees the last owned
+    cell's Delta), which the device path restates too (tests/test_gpu_weak.py)."""
+    import os
+    import oracle
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "options", "refexec_weak_post.npz"))
+    assert "seaice_final_divergence_shear_weak" in str(z["provenance"])
+    nC = int(z["nCells"])
+    got = {k: np.zeros(nC + 1) for k in ("divergence", "shear", "ridgeConvergence", "ridgeShear")}
+    oracle.lib().orc_final_divergence_shear_weak(nC, oracle._p(z["in_strain11"]), oracle._p(z["in_strain22"]), oracle._p(z["in_strain12"]),
+                                                 *[oracle._p(got[k]) for k in ("divergence", "shear", "ridgeConvergence", "ridgeShear")])
+    for k in got:
+        assert np.array_equal(got[k][:nC], z["out_" + k][:nC]), k
+    # the quirk itself: ridgeShear + |divergence| / 2 is the same number in every cell (half the last cell's Delta)
+    half_delta = z["out_ridgeShear"][:nC] + 0.5 * np.abs(z["out_divergence"][:nC])
+    assert np.ptp(half_delta) <= 1e-21 and half_delta[0] > 0
