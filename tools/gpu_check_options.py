@@ -105,4 +105,16 @@ for path in T.NORMAL_FILES:
 for path in T.UPWIND_FILES:
     T.test_upwind_reproduces_the_reference_executed_steps(path, LIB)
     note("refexec_upwind", fixture=os.path.basename(path), ok=True)
+# 5. the remaining cases of tests/test_transport_options.py, called as plain functions with the shipped library
+T.test_checks_pass_and_leave_the_fields_alone("ico3", LIB)
+T.test_monotonicity_report_matches_oracle("band48", LIB)
+T.test_conservation_report_on_a_partial_block(LIB)
+T.test_checks_call_order_and_arguments(LIB)
+for kind in ("hex16", "band48"):
+    T.test_upwind_matches_oracle(kind, "reference", LIB)
+T.test_upwind_call_order_and_arguments(LIB)
+for kind in ("quad10",):
+    for rm in (True, False):
+        T.test_normal_vectors_match_oracle(kind, rm, ("cuda", LIB))
+note("transport_options_remaining_cases", ok=True)
 note("done", ok=True)
