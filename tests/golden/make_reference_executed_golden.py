@@ -886,6 +886,40 @@ def build_weak_post():
     return data
 
 
+def build_square_testcase():
+    """The synthetic workload of BASELINE.json configs[1] ("square testcase"): init_square_test_case_state / _atmos / _ocean
+    (src/shared/mpas_seaice_testing.F:304-343, 357-422, 436-525) on the cell centres of a planar hex mesh scaled to the
+    test case's 1.28e6 m domain, time = 0."""
+    from mpas_seaice_b200 import meshgen
+    mesh = meshgen.planar_hex(12, 14, 16000.0)
+    nC, nK = mesh.nCells, 1
+    x = mesh.xCell * (1.28e6 / mesh.Lx)
+    y = mesh.yCell * (1.28e6 / mesh.Ly)
+    I = F.Interpreter(defined=())
+    for f in ("src/column/constants/cice/ice_constants_colpkg.F90", "src/shared/mpas_seaice_constants.F", "src/shared/mpas_seaice_testing.F"):
+        I.load(os.path.join(REF, f))
+    I.resolve_constants()
+    out = {k: np.zeros(nC + 1) for k in ("uAirVelocity", "vAirVelocity", "airDensity", "uOceanVelocity", "vOceanVelocity")}
+    cat = {k: np.zeros((nC + 1, nK, 1)) for k in ("iceAreaCategory", "iceVolumeCategory", "snowVolumeCategory")}
+    fa = lambda a: F.FArray(a)
+    I.call("init_square_test_case_atmos", fa(out["uAirVelocity"]), fa(out["vAirVelocity"]), fa(out["airDensity"]), fa(x), fa(y), 0.0)
+    I.call("init_square_test_case_ocean", fa(out["uOceanVelocity"]), fa(out["vOceanVelocity"]), fa(x), fa(y))
+    I.pool.update(nCells=nC, nVertices=int(mesh.nVertices), xCell=fa(x), interiorVertex=fa(np.zeros(mesh.nVertices + 1, np.int32)))
+    for k, a in cat.items():
+        I.pool[("tracers", k, 1)] = fa(a)
+    for k in ("uVelocity", "vVelocity", "uOceanVelocityVertex", "vOceanVelocityVertex"):
+        I.pool[k] = fa(np.zeros(mesh.nVertices + 1))
+    I.pool["uOceanVelocity"], I.pool["vOceanVelocity"] = fa(out["uOceanVelocity"]), fa(out["vOceanVelocity"])
+    I.call("init_square_test_case_state", "mesh", "tracers", "velocity_solver", "ocean_coupling", "boundary")
+    data = {"in_x": x, "in_y": y, "provenance": np.array("outputs computed by interpreting the reference's Fortran source "
+                                                        "(tests/golden/fortran_subset.py): " + ", ".join(sorted(set(I.trace))))}
+    for k, a in out.items():
+        data["out_" + k] = a
+    for k, a in cat.items():
+        data["out_" + k] = a
+    return data
+
+
 def build_boundary(kind):
     """init_boundary (mesh.F:372-630): interiorVertex, interiorCell, interiorEdge -- the integer maps the solver's masks and
     the upwind fluxes are built on."""
@@ -914,6 +948,9 @@ def build_boundary(kind):
 if __name__ == "__main__":
     only = sys.argv[1:]
     os.makedirs(os.path.join(HERE, "options"), exist_ok=True)
+    if not only or "refexec_square_testcase" in only:
+        np.savez_compressed(os.path.join(HERE, "options", "refexec_square_testcase.npz"), **build_square_testcase())
+        print("refexec_square_testcase", flush=True)
     if not only or "refexec_weak_post" in only:
         np.savez_compressed(os.path.join(HERE, "options", "refexec_weak_post.npz"), **build_weak_post())
         print("refexec_weak_post", flush=True)

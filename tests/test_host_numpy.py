@@ -169,3 +169,23 @@ def test_evp_parameters_against_the_reference_executed_seaice_init_evp():
         assert damp == damping and synthetic.numerical_inertia_coefficient(dt, dv_min) == inertia
         assert L.orc_damping_timescale(C.c_double(dt_dyn)) == damping
         assert L.orc_numerical_inertia_coefficient(C.c_double(dt_dyn), C.c_double(dv_min)) == inertia
+
+
+def test_square_test_case_state_against_the_reference_executed_routines():
+    """The synthetic workload of BASELINE configs[1]: synthetic.square_state against init_square_test_case_state / _atmos /
+    _ocean of the reference (src/shared/mpas_seaice_testing.F), interpreted from source
+    (tests/golden/options/refexec_square_testcase.npz).  Inputs of the path, not results of it: held to round-off (numpy
+    evaluates sin() in vector form, whose last bit may differ from libm's)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "options", "refexec_square_testcase.npz"))
+    assert "init_square_test_case_atmos" in str(z["provenance"]) and "init_square_test_case_state" in str(z["provenance"])
+    m = meshgen.Mesh()
+    m.xCell, m.yCell = z["in_x"], z["in_y"]
+    st = synthetic.square_state(m)
+    n = len(z["in_x"]) - 1
+    for k in ("uAirVelocity", "vAirVelocity", "airDensity", "uOceanVelocity", "vOceanVelocity"):
+        assert np.allclose(st[k][:n], z["out_" + k][:n], rtol=1e-14, atol=1e-15), k
+    assert np.array_equal(st["iceAreaCell"][:n], z["out_iceAreaCategory"][:n, 0, 0])
+    assert np.array_equal(st["iceVolumeCell"][:n], z["out_iceVolumeCategory"][:n, 0, 0])
+    assert np.array_equal(st["snowVolumeCell"][:n], z["out_snowVolumeCategory"][:n, 0, 0])
+    assert z["out_iceAreaCategory"].max() == 1.0 and np.abs(z["out_uAirVelocity"]).max() > 5.0
