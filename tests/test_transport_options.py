@@ -542,3 +542,49 @@ def test_upwind_reproduces_the_reference_executed_steps(path, lib_path):
 
 def case_geometry(mesh, irf):
     return ir.init_geometry(mesh, irf)
+
+
+def test_option_kernels_do_not_depend_on_the_thread_order():
+    """The emulation runs blocks and threads first-to-last or last-to-first (IR_EMU_ORDER): the checks (sums, local
+    extremes, the first violation found through atomicMin), the upwind step (edge kernels feeding cell kernels, the in-place
+    rescaling of the old time level) and the normal vectors give the same bits either way -- no thread of a launch depends
+    on another one of the same launch."""
+    lib = _emulation_library()
+    mesh, irf, geom, interior, nve = _upwind_setup("quad16")
+    iv = variational_init.interior_vertex(mesh)
+    tracers = _random_state(mesh, np.random.default_rng(21))
+    var = _upwind_state(mesh, np.random.default_rng(11))
+    u, v = smooth_divergent_velocity(mesh, geom)
+    results = []
+    for order in ("forward", "reverse"):
+        os.environ["IR_EMU_ORDER"] = order
+        try:
+            dev, uw = clone(tracers), _clone_vars(var)
+            s = _solver("quad16", lib, tracers[0].array.shape[1], n_cells_solve=(2 * mesh.nCells) // 3)
+            try:
+                s.set_tracers(dev)
+                s.set_checks(2, 1)
+                rc = s.run(dev, u, v, 3600.0, check=False)
+                rep = s.check_report()
+                sums = [s.conservation_sums(i, t.array.shape[2]) for i, t in enumerate(dev)]
+                s.set_upwind_mesh(interior, mesh.dvEdge, nve)
+                for _ in range(2):
+                    s.run_upwind(uw, u, v, 3600.0)
+                flux = s.upwind_fluxes(1)
+            finally:
+                s.destroy()
+            nv = ir_host.normal_vectors(mesh, irf, iv, lib_path=lib)
+        finally:
+            os.environ.pop("IR_EMU_ORDER", None)
+        results.append((rc, rep, sums, dev, uw, flux, nv))
+    a, b = results
+    assert a[0] == b[0] == ir_host.IR_ERR_MONOTONICITY and a[1] == b[1]
+    for (si0, sf0), (si1, sf1) in zip(a[2], b[2]):
+        assert np.array_equal(si0, si1) and np.array_equal(sf0, sf1)
+    for x, y in zip(a[3], b[3]):
+        assert np.array_equal(x.array, y.array), x.name
+    for x, y in zip(a[4], b[4]):
+        assert np.array_equal(x.array, y.array), x.name
+    assert np.array_equal(a[5][0], b[5][0]) and np.array_equal(a[5][1], b[5][1])
+    for k in a[6]:
+        assert np.array_equal(a[6][k], b[6][k]), k
