@@ -60,6 +60,11 @@ CASES = {
     "refexec_quad10_evp_avg_6": ("quad10", "evp", 6, {"average_variational_strain": True}),
     "refexec_ico2_evp_lineardrag_6": ("ico2", "evp", 6, {"ocean_stress_type": "linear"}),
     "refexec_hex12_evp_special_boundaries_8": ("hex12", "evp", 8, {"use_special_boundaries_velocity": True}),
+    # the piecewise-linear basis (dense gradient arrays: another instantiation of the device's cell kernel), the 'alternate'
+    # denominator, no ocean stress, and config_constitutive_relation_type = 'none'
+    "refexec_hex12_pwl_alt_evp_8": ("hex12", "evp", 8, {"_basis": "pwl", "_denominator": "alternate"}),
+    "refexec_ico2_no_ocean_stress_6": ("ico2", "evp", 6, {"use_ocean_stress": False}),
+    "refexec_quad10_none_3": ("quad10", "none", 3, {}),
     # the same inputs as the oracle-made vectors of make_golden.py, at their full length: a whole 120-subcycle dynamics
     # step of the square test case and of the sphere, interpreted (minutes each)
     "refexec_hex20_evp_120": ("hex20", "evp", 120, {}),
@@ -72,6 +77,7 @@ CASES = {
     "refexec_quad10_weak_revised_5": ("quad10", "evp_revised", 5, {"strain_scheme": "weak", "stress_divergence_scheme": "weak"}),
     "refexec_ico2_weakvar_evp_5": ("ico2", "evp", 5, {"strain_scheme": "weak", "stress_divergence_scheme": "variational"}),
 }
+CPU_ONLY = ("refexec_hex12_pwl_alt_evp_8", "refexec_ico2_no_ocean_stress_6", "refexec_quad10_none_3")
 WEAK_STATIC = ("verticesOnEdge", "edgesOnVertex", "normalVectorPolygon", "normalVectorTriangle", "latCellRotated", "latVertexRotated")
 WEAK_MESH = ("edgesOnCell", "cellsOnEdge", "dvEdge", "dcEdge", "areaTriangle")
 WEAK_STATE = ("stress11Weak", "stress22Weak", "stress12Weak", "strain11Weak", "strain22Weak", "strain12Weak",
@@ -149,9 +155,9 @@ def interpreter(mesh, var, step, opts, nsub, weak=None):
 
 def build(name):
     kind, cr, nsub, extra = CASES[name]
-    mesh, var = common.mesh_case(kind)
-    step, opts = common.step_case(mesh, constitutive_relation_type=cr)
-    opts = dict(opts, **extra)
+    mesh, var = common.mesh_case(kind, basis=extra.get("_basis", "wachspress"), denominator=extra.get("_denominator", "original"))
+    step, opts = common.step_case(mesh, constitutive_relation_type=cr, **({"use_ocean_stress": False} if extra.get("use_ocean_stress") is False else {}))
+    opts = dict(opts, **{k: v for k, v in extra.items() if not k.startswith("_")})
     if cr == "linear":
         # the linear relation leaves the velocities alone (velocity_solver.F:2529-2541): start from a velocity field
         # that is not at rest, the operator test's (square/operators_strain_stress_divergence/create_ics.py:12-18)
@@ -1010,6 +1016,8 @@ if __name__ == "__main__":
         if only and name not in only:
             continue
         data, called, secs = build(name)
-        path = os.path.join(HERE, name + ".npz")
+        # fixtures added after this round's GPU time was spent are replayed through the oracle only (tests/golden/cpu/);
+        # the device runs the same configurations against the oracle in tests/test_gpu_parity.py
+        path = os.path.join(HERE, "cpu" if name in CPU_ONLY else "", name + ".npz")
         np.savez_compressed(path, **data)
         print("%s: %.1f s, %d KB; interpreted: %s" % (name, secs, os.path.getsize(path) // 1024, ", ".join(called)))

@@ -109,6 +109,21 @@ def test_device_reproduces_golden(evp_lib, path):
     _check(mesh, step, want, got, opts)
 
 
+CPU_FILES = sorted(glob.glob(os.path.join(HERE, "golden", "cpu", "refexec_*.npz")))
+
+
+@pytest.mark.parametrize("path", CPU_FILES, ids=[os.path.basename(f)[:-4] for f in CPU_FILES])
+def test_oracle_reproduces_reference_executed_vectors_added_late(path):
+    """Reference-executed vectors generated after the round's GPU time was spent (piecewise-linear basis with the
+    'alternate' denominator, no ocean stress, constitutive relation 'none'): replayed through the oracle here; the device
+    runs the same configurations against the oracle in tests/test_gpu_parity.py (test_device_pwl_precompute_bit_exact,
+    test_no_ocean_stress, test_namelist_options)."""
+    assert len(CPU_FILES) == 3
+    mesh, var, step, opts, want, nsub = _load(path)
+    got = common.run_oracle(mesh, var, step, opts, nsub)
+    _check(mesh, step, want, got, opts)
+
+
 def test_oracle_made_vectors_equal_their_reference_executed_twins():
     """hex20_evp_120 / ico3_revised_40 / ico3_evp_120 exist twice: made by the oracle (make_golden.py) and made by
     interpreting the reference's source from the same inputs at the same length (a whole 120-subcycle dynamics step of the
