@@ -65,6 +65,8 @@ CASES = {
     "refexec_hex12_pwl_alt_evp_8": ("hex12", "evp", 8, {"_basis": "pwl", "_denominator": "alternate"}),
     "refexec_ico2_no_ocean_stress_6": ("ico2", "evp", 6, {"use_ocean_stress": False}),
     "refexec_quad10_none_3": ("quad10", "none", 3, {}),
+    # seaice_set_special_boundaries_velocity_masks (special_boundaries.F:345-401): the masks replaced by given ones
+    "refexec_hex12_special_boundary_masks_6": ("hex12", "evp", 6, {"use_special_boundaries_velocity_masks": True}),
     # the same inputs as the oracle-made vectors of make_golden.py, at their full length: a whole 120-subcycle dynamics
     # step of the square test case and of the sphere, interpreted (minutes each)
     "refexec_hex20_evp_120": ("hex20", "evp", 120, {}),
@@ -77,7 +79,8 @@ CASES = {
     "refexec_quad10_weak_revised_5": ("quad10", "evp_revised", 5, {"strain_scheme": "weak", "stress_divergence_scheme": "weak"}),
     "refexec_ico2_weakvar_evp_5": ("ico2", "evp", 5, {"strain_scheme": "weak", "stress_divergence_scheme": "variational"}),
 }
-CPU_ONLY = ("refexec_hex12_pwl_alt_evp_8", "refexec_ico2_no_ocean_stress_6", "refexec_quad10_none_3")
+CPU_ONLY = ("refexec_hex12_pwl_alt_evp_8", "refexec_ico2_no_ocean_stress_6", "refexec_quad10_none_3",
+            "refexec_hex12_special_boundary_masks_6")
 WEAK_STATIC = ("verticesOnEdge", "edgesOnVertex", "normalVectorPolygon", "normalVectorTriangle", "latCellRotated", "latVertexRotated")
 WEAK_MESH = ("edgesOnCell", "cellsOnEdge", "dvEdge", "dcEdge", "areaTriangle")
 WEAK_STATE = ("stress11Weak", "stress22Weak", "stress12Weak", "strain11Weak", "strain22Weak", "strain12Weak",
@@ -183,6 +186,12 @@ def build(name):
         src[chain[0]] = chain[3] + 1      # a source updated LATER in the sequential loop (the old value is seen)
         src[chain[2]] = chain[1] + 1      # a source updated EARLIER (the new value is seen)
         step["vertexBoundaryType"], step["vertexBoundarySourceLocal"] = vbt, src
+    if opts.get("use_special_boundaries_velocity_masks"):
+        nC, nV = mesh.nCells, mesh.nVertices
+        ss, sv = step["solveStress"].copy(), step["solveVelocity"].copy()
+        sv[:nV:7] = 0
+        ss[:nC:5] = 0
+        step["solveStressSpecialBoundaries"], step["solveVelocitySpecialBoundaries"] = ss, sv
     weak = None
     if opts.get("strain_scheme") == "weak":
         from mpas_seaice_b200 import weakmesh

@@ -118,9 +118,11 @@ def test_oracle_reproduces_reference_executed_vectors_added_late(path):
     'alternate' denominator, no ocean stress, constitutive relation 'none'): replayed through the oracle here; the device
     runs the same configurations against the oracle in tests/test_gpu_parity.py (test_device_pwl_precompute_bit_exact,
     test_no_ocean_stress, test_namelist_options)."""
-    assert len(CPU_FILES) == 3
+    assert len(CPU_FILES) == 4
     mesh, var, step, opts, want, nsub = _load(path)
     got = common.run_oracle(mesh, var, step, opts, nsub)
+    if opts.get("use_special_boundaries_velocity_masks"):      # the masks the subcycle ran with are the special-boundary ones
+        step = dict(step, solveStress=step["solveStressSpecialBoundaries"], solveVelocity=step["solveVelocitySpecialBoundaries"])
     _check(mesh, step, want, got, opts)
 
 
