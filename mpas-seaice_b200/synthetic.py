@@ -138,12 +138,14 @@ def interior_vertex(mesh):
 
 def pre_subcycle(mesh, state, config_dt, *, n_elastic=120, prev=None, use_air_stress=True,
                  use_ocean_stress=True, use_surface_tilt=True, constitutive_relation_type="evp",
-                 masks=None):
+                 masks=None, land_ice_mask=None):
     """velocity_solver_pre_subcycle (velocity_solver.F:613-671) for a single-category state without
     the column package.  ``prev`` carries the state that survives between dynamics steps
     (uVelocity, vVelocity, stress11/22/12, solveVelocityPrevious); None = cold start.
     ``masks`` = (solveStress, solveVelocity) overrides calculation_masks, which is what
     config_calc_velocity_masks = false does for the operator tests (velocity_solver.F:897-901).
+    ``land_ice_mask`` (nCells+1): cells under an ice shelf, excluded from both masks (:1023, :1131 through
+    init_ice_shelve_vertex_mask :481-544); None = none.
     Returns (step_fields, options)."""
     nC, nV, M = mesh.nCells, mesh.nVertices, mesh.maxEdges
     dt_dyn, dte, damping = time_steps(config_dt, 1, n_elastic)
@@ -158,7 +160,7 @@ def pre_subcycle(mesh, state, config_dt, *, n_elastic=120, prev=None, use_air_st
     # calculation_masks (:766-947)
     f["iceAreaVertex"] = interpolate_cell_to_vertex(mesh, ice_area)
     f["totalMassVertex"] = interpolate_cell_to_vertex(mesh, total_mass_cell)
-    land_ice = np.zeros(nC + 1, dtype=np.int32)
+    land_ice = np.zeros(nC + 1, dtype=np.int32) if land_ice_mask is None else np.asarray(land_ice_mask, dtype=np.int32)
     if masks is None:
         # stress_calculation_mask (:961-1059)
         enough = (ice_area > AREA_MIN) & (total_mass_cell > MASS_MIN) & (land_ice == 0)
@@ -172,7 +174,9 @@ def pre_subcycle(mesh, state, config_dt, *, n_elastic=120, prev=None, use_air_st
         # velocity_calculation_mask (:1073-1150)
         interior = interior_vertex(mesh)
         with np.errstate(invalid="ignore"):
-            solve_velocity = ((interior == 1) & (f["iceAreaVertex"] > AREA_MIN) &
+            land_ice_vertex = np.zeros(nV + 1, dtype=bool)
+            land_ice_vertex[:nV] = np.any(land_ice[mesh.cellsOnVertex[:nV] - 1] == 1, axis=1)
+            solve_velocity = ((interior == 1) & ~land_ice_vertex & (f["iceAreaVertex"] > AREA_MIN) &
                               (f["totalMassVertex"] > MASS_MIN)).astype(np.int32)
         solve_velocity[nV] = 0
     else:

@@ -50,6 +50,30 @@ def interior_vertex(mesh):
     return out
 
 
+def land_ice_mask_vertex(mesh, land_ice_mask, n_vertices_solve=None):
+    """init_ice_shelve_vertex_mask (velocity_solver.F:481-544): 1 at the vertices of the owned range that touch a cell
+    under an ice shelf (landIceMask == 1; the junk slot nCells+1 of the mask counts like any cell), 0 elsewhere --
+    the ``landIceMaskVertex`` of evp_mesh_ext (include/evp_b200.h)."""
+    nV = mesh.nVertices
+    nVs = nV if n_vertices_solve is None else int(n_vertices_solve)
+    land = np.asarray(land_ice_mask)
+    assert land.shape == (mesh.nCells + 1,)
+    out = np.zeros(nV + 1, dtype=np.int32)
+    out[:nVs] = np.any(land[mesh.cellsOnVertex[:nVs] - 1] == 1, axis=1)
+    return out
+
+
+def dynamically_locked_cells_mask(mesh, interior_vertex_mask):
+    """dynamically_locked_cell_mask (velocity_solver.F:402-467): 1 at the cells none of whose vertices is an interior
+    vertex (their ice cannot move), the mask the regional statistics read."""
+    nC = mesh.nCells
+    out = np.zeros(nC + 1, dtype=np.int32)
+    valid = np.arange(mesh.maxEdges)[None, :] < mesh.nEdgesOnCell[:nC, None]
+    voc = np.where(valid, mesh.verticesOnCell[:nC] - 1, mesh.nVertices)
+    out[:nC] = ~np.any(valid & (np.asarray(interior_vertex_mask)[voc] == 1), axis=1)
+    return out
+
+
 def local_coords(mesh, rotate=True):
     """seaice_calc_local_coords (variational_shared.F:42-279) with
     seaice_project_3D_vector_onto_local_2D (mesh.F:2021-2061, 2272-2332)."""

@@ -267,13 +267,37 @@ def set_num_threads(n: int) -> None:
 # pre- / post-subcycle (the host side of the boundary, restated so tests can build identical inputs)
 # ---------------------------------------------------------------------------------------------
 
+def land_ice_mask_vertex(mesh, land_ice_mask, n_vertices_solve=None):
+    """init_ice_shelve_vertex_mask (velocity_solver.F:481-544): (nVertices+1) int32"""
+    nV = mesh.nVertices
+    out = np.zeros(nV + 1, dtype=np.int32)
+    land = np.ascontiguousarray(land_ice_mask, dtype=np.int32)
+    assert land.shape == (mesh.nCells + 1,)
+    lib().orc_ice_shelve_vertex_mask(_i(nV), _i(nV if n_vertices_solve is None else n_vertices_solve), _i(mesh.vertexDegree),
+                                     _p(mesh.cellsOnVertex), _p(land), _p(out))
+    return out
+
+
+def dynamically_locked_cells_mask(mesh, interior_vertex):
+    """dynamically_locked_cell_mask (velocity_solver.F:402-467): (nCells+1) int32"""
+    nC = mesh.nCells
+    out = np.zeros(nC + 1, dtype=np.int32)
+    iv = np.ascontiguousarray(interior_vertex, dtype=np.int32)
+    assert iv.shape == (mesh.nVertices + 1,)
+    lib().orc_dynamically_locked_cell_mask(_i(nC), _i(mesh.maxEdges), _p(mesh.nEdgesOnCell), _p(mesh.verticesOnCell),
+                                           _p(iv), _p(out))
+    return out
+
+
 def pre_subcycle(mesh, state, config_dt, *, n_elastic=120, use_air_stress=True, use_ocean_stress=True,
-                 use_surface_tilt=True, interior_vertex=None, prev=None, geostrophic_surface_tilt=True):
+                 use_surface_tilt=True, interior_vertex=None, prev=None, geostrophic_surface_tilt=True,
+                 land_ice_mask=None, land_ice_mask_vertex=None):
     """velocity_solver_pre_subcycle (velocity_solver.F:613-671) from a cold start, single category,
     Hibler strength, constant_air_stress, geostrophic tilt -- call order of the reference.
     ``prev`` (uVelocity, vVelocity, stress11/22/12, solveVelocityPrevious) = the state carried from the previous
     dynamics step instead of a cold start; ``geostrophic_surface_tilt=False`` uses state["seaSurfaceTiltU/V"]
-    (surface_tilt_ssh_gradient, :2024-2170).
+    (surface_tilt_ssh_gradient, :2024-2170).  ``land_ice_mask`` (nCells+1) / ``land_ice_mask_vertex`` (nVertices+1): the
+    ocean_coupling pool's ice-shelf masks read by the calculation masks (:1023, :1131); None = no land ice.
     Returns the same dict of per-step fields as mpas_seaice_b200.synthetic.pre_subcycle."""
     L = lib()
     nC, nV, M, D = mesh.nCells, mesh.nVertices, mesh.maxEdges, mesh.vertexDegree
@@ -294,8 +318,11 @@ def pre_subcycle(mesh, state, config_dt, *, n_elastic=120, use_air_stress=True, 
     with np.errstate(all="ignore"):
         f["iceAreaVertex"] = c2v(area)
         f["totalMassVertex"] = c2v(mass)
-        land = np.zeros(nC + 1, dtype=np.int32)
-        landv = np.zeros(nV + 1, dtype=np.int32)
+        land = (np.zeros(nC + 1, dtype=np.int32) if land_ice_mask is None
+                else np.ascontiguousarray(land_ice_mask, dtype=np.int32))
+        landv = (np.zeros(nV + 1, dtype=np.int32) if land_ice_mask_vertex is None
+                 else np.ascontiguousarray(land_ice_mask_vertex, dtype=np.int32))
+        assert land.shape == (nC + 1,) and landv.shape == (nV + 1,)
         ss = np.zeros(nC + 1, dtype=np.int32)
         L.orc_stress_calculation_mask(_i(nC), _i(M), _p(mesh.nEdgesOnCell), _p(mesh.cellsOnCell), _p(area), _p(mass),
                                       _p(land), _p(ss))

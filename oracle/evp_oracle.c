@@ -746,6 +746,37 @@ void orc_velocity_calculation_mask(int nVerticesSolve, int nVertices, const int 
     for (int i = nVerticesSolve; i < nVertices; i++) solveVelocity[i] = 0;
 }
 
+/* init_ice_shelve_vertex_mask (velocity_solver.F:481-544): a vertex of the owned range touching a land-ice cell */
+void orc_ice_shelve_vertex_mask(int nVertices, int nVerticesSolve, int vertexDegree, const int *cellsOnVertex,
+                                const int *landIceMask, int *landIceMaskVertex)
+{
+    const int D = vertexDegree;
+    for (int i = 0; i < nVertices; i++) landIceMaskVertex[i] = 0;
+    for (int iVertex = 1; iVertex <= nVerticesSolve; iVertex++) {
+        for (int k = 1; k <= D; k++) {
+            const int iCell = cellsOnVertex[IDX2(k, iVertex, D)];
+            if (landIceMask[iCell - 1] == 1) landIceMaskVertex[iVertex - 1] = 1;
+        }
+    }
+}
+
+/* dynamically_locked_cell_mask (velocity_solver.F:402-467): 1 where no vertex of the cell is an interior vertex */
+void orc_dynamically_locked_cell_mask(int nCells, int maxEdges, const int *nEdgesOnCell, const int *verticesOnCell,
+                                      const int *interiorVertex, int *dynamicallyLockedCellsMask)
+{
+    const int M = maxEdges;
+    for (int iCell = 1; iCell <= nCells; iCell++) {
+        dynamicallyLockedCellsMask[iCell - 1] = 1;
+        for (int k = 1; k <= nEdgesOnCell[iCell - 1]; k++) {
+            const int iVertex = verticesOnCell[IDX2(k, iCell, M)];
+            if (interiorVertex[iVertex - 1] == 1) {
+                dynamicallyLockedCellsMask[iCell - 1] = 0;
+                break;
+            }
+        }
+    }
+}
+
 /* ice_strength, Hibler branch (velocity_solver.F:1419-1436) */
 void orc_ice_strength_hibler(int nCellsSolve, const int *solveStress, const double *iceVolumeCell,
                              const double *iceAreaCell, double *icePressure)

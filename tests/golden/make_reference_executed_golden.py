@@ -324,7 +324,12 @@ STEP_CASES = {
     # :2024-2170 from the coupler's sea-surface tilt), config_use_air_stress / config_use_surface_tilt = false
     "refexec_step_ico2_sshtilt_3": ("ico2", "B", 3600.0, 3, 1, dict(geostrophic_surface_tilt=False)),
     "refexec_step_ico2_noair_notilt_3": ("ico2", "B", 3600.0, 3, 1, dict(use_air_stress=False, use_surface_tilt=False)),
+    # ice shelves: landIceMask = 1 on a patch inside the ice cover; init_ice_shelve_vertex_mask (:481-544) and
+    # dynamically_locked_cell_mask (:402-467) run first, the calculation masks (:1023, :1131) then leave the patch out
+    "refexec_step_ico2_landice_3": ("ico2", "B", 3600.0, 3, 1, dict(land_ice=True)),
+    "refexec_step_hex12_landice_3": ("hex12", "square", 3600.0, 3, 1, dict(land_ice=True)),
 }
+STEP_CPU_ONLY = ("refexec_step_ico2_landice_3", "refexec_step_hex12_landice_3")
 STEP_OUT = {
     "velocity_solver": ("solveStress", "solveVelocity", "solveVelocityPrevious", "icePressure", "airStressCellU", "airStressCellV",
                         "uVelocity", "vVelocity", "uVelocityInitial", "vVelocityInitial", "stressDivergenceU", "stressDivergenceV",
@@ -366,6 +371,7 @@ def build_step(name):
     kind, state_kind, config_dt, nsub, n_cat = STEP_CASES[name][:5]
     sw = dict(use_air_stress=True, use_surface_tilt=True, geostrophic_surface_tilt=True)
     sw.update(STEP_CASES[name][5] if len(STEP_CASES[name]) > 5 else {})
+    land_ice = bool(sw.pop("land_ice", False))
     mesh, var = common.mesh_case(kind)
     later = []
     if state_kind.startswith("caps:"):
@@ -413,7 +419,16 @@ def build_step(name):
         P[("ocean_coupling", "seaSurfaceTiltU")][:nC] = 1e-6 * np.sin(3 * mesh.lonCell[:nC]) * np.cos(mesh.latCell[:nC])
         P[("ocean_coupling", "seaSurfaceTiltV")][:nC] = -2e-6 * np.cos(2 * mesh.lonCell[:nC]) * np.cos(mesh.latCell[:nC])
     P[("ocean_coupling", "landIceMask")] = np.zeros(nC + 1, np.int32)
-    P[("ocean_coupling", "landIceMaskVertex")] = np.zeros(nV + 1, np.int32)
+    if land_ice:
+        if mesh.on_a_sphere:
+            lat, lon = np.degrees(mesh.latCell[:nC]), mesh.lonCell[:nC]
+            shelf = (lat < -65.0) | ((lat > 74.0) & (np.cos(lon) > 0.3))
+        else:
+            shelf = (mesh.xCell[:nC] > 0.62 * mesh.Lx) & (mesh.yCell[:nC] > 0.55 * mesh.Ly)
+        assert 0 < shelf.sum() < nC
+        P[("ocean_coupling", "landIceMask")][:nC] = shelf
+    P[("ocean_coupling", "landIceMaskVertex")] = np.full(nV + 1, -7, np.int32)       # written by the reference below
+    P[("velocity_solver", "dynamicallyLockedCellsMask")] = np.full(nC + 1, -7, np.int32)
     P[("boundary", "interiorVertex")] = variational_init.interior_vertex(mesh).astype(np.int32)
     P[("velocity_solver", "solveStress")] = np.zeros(nC + 1, np.int32)
     for k in ("solveVelocity", "solveVelocityPrevious"):
@@ -480,6 +495,16 @@ def build_step(name):
     for k in ("seaSurfaceTiltU", "seaSurfaceTiltV"):
         data["in_" + k] = P[("ocean_coupling", k)].copy()
     t0 = time.time()
+    # seaice_init_velocity_solver's two mask routines (:237-238)
+    if not land_ice:
+        P[("ocean_coupling", "landIceMaskVertex")][:] = 0
+    else:
+        I.call("init_ice_shelve_vertex_mask", domain)
+        I.call("dynamically_locked_cell_mask", domain)
+        data["in_landIceMask"] = P[("ocean_coupling", "landIceMask")].copy()
+        data["ref_landIceMaskVertex"] = P[("ocean_coupling", "landIceMaskVertex")].copy()
+        data["ref_dynamicallyLockedCellsMask"] = P[("velocity_solver", "dynamicallyLockedCellsMask")].copy()
+        data["ref_interiorVertex"] = P[("boundary", "interiorVertex")].copy()
     I.call("velocity_solver_pre_subcycle", domain)
     for pool, names in STEP_OUT.items():
         for k in names:
@@ -960,9 +985,54 @@ def build_boundary(kind):
     return data
 
 
+def culled_quad_mesh():
+    """planar_quad 7 x 6 with two columns of cells culled in the lower rows (their references in cellsOnVertex /
+    cellsOnCell replaced by nCells+1, what the mesh culler leaves): a channel one cell wide whose cells have no
+    interior vertex."""
+    from mpas_seaice_b200 import meshgen
+    spec = ("planar_quad", 7, 6, 1000.0)
+    mesh = meshgen.Mesh(init_mesh(spec))
+    nC = mesh.nCells
+    ix = np.rint(mesh.xCell[:nC] / 1000.0 - 0.5).astype(int)
+    iy = np.rint(mesh.yCell[:nC] / 1000.0 - 0.5).astype(int)
+    culled = np.flatnonzero(((ix == 2) | (ix == 4)) & (iy < 4)) + 1
+    for k in ("cellsOnVertex", "cellsOnCell"):
+        a = mesh[k].copy()
+        a[np.isin(a, culled)] = nC + 1
+        mesh[k] = a
+    return spec, mesh, culled
+
+
+def build_locked_cells():
+    """interior_vertices (mesh.F:423-488) then dynamically_locked_cell_mask (velocity_solver.F:402-467) on the culled mesh"""
+    spec, mesh, culled = culled_quad_mesh()
+    nC, nV, nE, M, D = mesh.nCells, mesh.nVertices, mesh.nEdges, mesh.maxEdges, mesh.vertexDegree
+    I = F.Interpreter(defined=())
+    I.load(os.path.join(REF, "src/shared/mpas_seaice_mesh.F"))
+    I.load(os.path.join(REF, "src/shared/mpas_seaice_velocity_solver.F"))
+    I.noop |= {"mpas_dmpar_field_halo_exch", "mpas_log_write"}
+    out = dict(interiorVertex=np.full(nV + 1, -7, np.int32), dynamicallyLockedCellsMask=np.full(nC + 1, -7, np.int32))
+    for k in ("nEdgesOnCell", "cellsOnCell", "cellsOnVertex", "verticesOnCell"):
+        I.pool[k] = F.FArray(mesh[k])
+    for k, v in out.items():
+        I.pool[k] = F.FArray(v)
+    I.pool.update(nCells=nC, nCellsSolve=nC, nVertices=nV, nVerticesSolve=nV, nEdges=nE, nEdgesSolve=nE, vertexDegree=D, maxEdges=M)
+    block = types.SimpleNamespace(structs="structs", configs="configs", dimensions="dimensions", next=None, blockid=0)
+    domain = types.SimpleNamespace(blocklist=block, configs="configs")
+    I.call("interior_vertices", "mesh", "boundary")
+    I.call("dynamically_locked_cell_mask", domain)
+    return {"spec": np.array(repr(spec)), "culled": culled.astype(np.int32), "out_interiorVertex": out["interiorVertex"],
+            "out_dynamicallyLockedCellsMask": out["dynamicallyLockedCellsMask"],
+            "provenance": np.array("outputs computed by interpreting the reference's Fortran source "
+                                   "(tests/golden/fortran_subset.py): " + ", ".join(sorted(set(I.trace))))}
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     os.makedirs(os.path.join(HERE, "options"), exist_ok=True)
+    if not only or "refexec_locked_cells" in only:
+        np.savez_compressed(os.path.join(HERE, "cpu", "refexec_locked_cells.npz"), **build_locked_cells())
+        print("refexec_locked_cells", flush=True)
     if not only or "refexec_square_testcase" in only:
         np.savez_compressed(os.path.join(HERE, "options", "refexec_square_testcase.npz"), **build_square_testcase())
         print("refexec_square_testcase", flush=True)
@@ -1009,7 +1079,7 @@ if __name__ == "__main__":
         if only and name not in only:
             continue
         data, called, secs = build_step(name)
-        path = os.path.join(HERE, "step", name + ".npz")
+        path = os.path.join(HERE, "cpu" if name in STEP_CPU_ONLY else "step", name + ".npz")
         os.makedirs(os.path.dirname(path), exist_ok=True)
         np.savez_compressed(path, **data)
         print("%s: %.1f s, %d KB; interpreted: %s" % (name, secs, os.path.getsize(path) // 1024, ", ".join(called)), flush=True)

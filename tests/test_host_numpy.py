@@ -147,6 +147,32 @@ def test_interior_maps_against_the_reference_executed_init_boundary():
         assert np.array_equal(np.all((coc <= nC) | ~used, axis=1).astype(np.int32), z["out_interiorCell"][:nC]), f
 
 
+def test_locked_cells_against_the_reference_executed_mask():
+    """dynamically_locked_cell_mask (src/shared/mpas_seaice_velocity_solver.F:402-467) after interior_vertices
+    (mesh.F:423-488), both interpreted from the reference's source on a quadrilateral mesh with two culled columns
+    (tests/golden/cpu/refexec_locked_cells.npz): the cells of the one-cell-wide channel between them have no interior
+    vertex.  Host function and the oracle's restatement, bit-exact (an integer map of SURVEY section 8(c))."""
+    import ast
+    import os
+    import oracle
+    from mpas_seaice_b200 import meshgen
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cpu", "refexec_locked_cells.npz"))
+    assert "dynamically_locked_cell_mask" in str(z["provenance"]) and "interior_vertices" in str(z["provenance"])
+    spec = ast.literal_eval(str(z["spec"]))
+    mesh = meshgen.Mesh(getattr(meshgen, spec[0])(*spec[1:]))
+    nC, nV = mesh.nCells, mesh.nVertices
+    for k in ("cellsOnVertex", "cellsOnCell"):
+        a = mesh[k].copy()
+        a[np.isin(a, z["culled"])] = nC + 1
+        mesh[k] = a
+    interior = variational_init.interior_vertex(mesh)
+    assert np.array_equal(interior[:nV], z["out_interiorVertex"][:nV])
+    ref = z["out_dynamicallyLockedCellsMask"][:nC]
+    assert 0 < ref.sum() < nC
+    assert np.array_equal(variational_init.dynamically_locked_cells_mask(mesh, interior)[:nC], ref)
+    assert np.array_equal(oracle.dynamically_locked_cells_mask(mesh, interior)[:nC], ref)
+
+
 def test_evp_parameters_against_the_reference_executed_seaice_init_evp():
     """constitutiveRelationType, dampingTimescale and numericalInertiaCoefficient as the reference's own seaice_init_evp
     (src/shared/mpas_seaice_velocity_solver_constitutive_relation.F:75-164) leaves them -- interpreted from its source,

@@ -23,6 +23,9 @@ from mpas_seaice_b200 import synthetic, variational_init
 HERE = os.path.dirname(os.path.abspath(__file__))
 FILES = sorted(glob.glob(os.path.join(HERE, "golden", "step", "refexec_step_*.npz")))
 IDS = [os.path.basename(f)[13:-4] for f in FILES]
+# generated after this round's GPU time was spent: replayed on the oracle and the host functions only
+CPU_FILES = sorted(glob.glob(os.path.join(HERE, "golden", "cpu", "refexec_step_*.npz")))
+CPU_IDS = [os.path.basename(f)[13:-4] for f in CPU_FILES]
 
 PRE_CELL = ("solveStress", "icePressure", "totalMassCell", "iceAreaCellInitial", "iceAreaCell", "iceVolumeCell", "snowVolumeCell")
 PRE_VERTEX_ALL = ("solveVelocity", "iceAreaVertex", "totalMassVertex", "uOceanVelocityVertex", "vOceanVelocityVertex")
@@ -43,6 +46,8 @@ def _load(path):
     if sw and not sw.get("geostrophic_surface_tilt", True):
         forcing.update(seaSurfaceTiltU=z["in_seaSurfaceTiltU"], seaSurfaceTiltV=z["in_seaSurfaceTiltV"])
     opts["_switches"] = sw or dict(use_air_stress=True, use_surface_tilt=True, geostrophic_surface_tilt=True)
+    if "in_landIceMask" in z.files:     # ice shelves: the vertex mask is the reference's own (init_ice_shelve_vertex_mask)
+        opts["_switches"].update(land_ice_mask=z["in_landIceMask"], land_ice_mask_vertex=z["ref_landIceMaskVertex"])
     pre = {k[4:]: z[k] for k in z.files if k.startswith("pre_")}
     out = {k[4:]: z[k] for k in z.files if k.startswith("out_")}
     n_steps = int(z["n_steps"]) if "n_steps" in z.files else 1
@@ -82,12 +87,51 @@ def test_fixtures_exist_and_name_the_routines_that_ran():
         assert name in seen, name
 
 
-@pytest.mark.parametrize("path", FILES, ids=IDS)
+@pytest.mark.parametrize("path", FILES + CPU_FILES, ids=IDS + CPU_IDS)
 def test_oracle_reproduces_the_reference_executed_step(path):
     mesh, var, opts, cat, forcing, pre, out, nsub, config_dt, _ = _load(path)
     prev = _first_step_prev(mesh)
     for cat_n, pre_n, out_n in [(cat, pre, out)] + pre.get("_more", []):
         prev = _oracle_step(mesh, var, opts, cat_n, forcing, pre_n, out_n, nsub, config_dt, prev)
+
+
+@pytest.mark.parametrize("path", [f for f in CPU_FILES if "landice" in f], ids=[i for i in CPU_IDS if "landice" in i])
+def test_ice_shelf_masks_reproduce_the_reference_executed_arrays(path):
+    """init_ice_shelve_vertex_mask (velocity_solver.F:481-544) and dynamically_locked_cell_mask (:402-467), integer maps
+    SURVEY section 8(c) lists for bit-exact parity: the oracle's restatements and the host functions against the arrays
+    the reference's statements wrote; and the masks of the step show the shelf (no stress point, no velocity point on
+    it, although there is ice)."""
+    z = np.load(path)
+    mesh, _ = common.mesh_case(str(z["kind"]))
+    nC, nV = mesh.nCells, mesh.nVertices
+    land = z["in_landIceMask"]
+    interior = z["ref_interiorVertex"]
+    assert np.array_equal(variational_init.interior_vertex(mesh), interior)
+    for f in (oracle.land_ice_mask_vertex, variational_init.land_ice_mask_vertex):
+        assert np.array_equal(f(mesh, land)[:nV], z["ref_landIceMaskVertex"][:nV]), f.__module__
+    for f in (oracle.dynamically_locked_cells_mask, variational_init.dynamically_locked_cells_mask):
+        assert np.array_equal(f(mesh, interior)[:nC], z["ref_dynamicallyLockedCellsMask"][:nC]), f.__module__
+    locked = z["ref_dynamicallyLockedCellsMask"][:nC]
+    assert not locked.any()       # every cell of these meshes touches an interior vertex (a mixed case: test_host_numpy.py)
+    lv = z["ref_landIceMaskVertex"][:nV] == 1
+    assert 0 < lv.sum() < nV
+    assert not z["pre_solveVelocity"][:nV][lv].any()
+    # a shelf cell with shelf cells all around has no stress point although it carries ice
+    shelf = land[:nC] == 1
+    ring = np.zeros(nC, dtype=bool)
+    for k in range(mesh.maxEdges):
+        nb = mesh.cellsOnCell[:nC, k] - 1
+        ok = (k < mesh.nEdgesOnCell[:nC]) & (nb < nC)
+        ring |= ok & ~shelf[np.minimum(nb, nC - 1)]
+    deep = shelf & ~ring
+    assert deep.any() and (z["pre_iceAreaCell"][:nC][deep] > 0.1).any()
+    assert not z["pre_solveStress"][:nC][deep].any()
+    # the host mirror of the pre-subcycle gives the reference's masks with the shelf
+    state = dict(iceAreaCell=z["pre_iceAreaCell"], iceVolumeCell=z["pre_iceVolumeCell"], snowVolumeCell=z["pre_snowVolumeCell"],
+                 **{k: z["in_" + k] for k in ("uAirVelocity", "vAirVelocity", "airDensity", "uOceanVelocity", "vOceanVelocity")})
+    step, _ = synthetic.pre_subcycle(mesh, state, float(z["config_dt"]), n_elastic=int(z["nsub"]), land_ice_mask=land)
+    assert np.array_equal(step["solveStress"][:nC], z["pre_solveStress"][:nC])
+    assert np.array_equal(step["solveVelocity"][:nV], z["pre_solveVelocity"][:nV])
 
 
 def _oracle_step(mesh, var, opts, cat, forcing, pre, out, nsub, config_dt, prev):
