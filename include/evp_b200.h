@@ -159,10 +159,17 @@ int evp_set_options(evp_handle *handle, const evp_options *options);
 
 /* Device version of seaice_init_velocity_solver_wachspress
  * (src/shared/mpas_seaice_velocity_solver_wachspress.F:46-161) writing straight into the device layout.
- * xLocal, yLocal: (maxEdges, nCells) from seaice_calc_local_coords.  integrationType 0 = dunavant
- * (orders 1..8), 1 = trapezoidal.  Bit-identical to the FP64 non-FMA evaluation of the reference formulas. */
+ * xLocal, yLocal: (maxEdges, nCells) from seaice_calc_local_coords.  config_wachspress_integration_type /
+ * _order (Registry.xml:603-610): integrationType 0 = 'dunavant' (orders 1..10, 12), 1 = 'trapezoidal' (orders 1..9:
+ * at most 64 points), 2 = 'fekete' (orders 1..6, 8, 9).  Bit-identical to the FP64 non-FMA evaluation of the
+ * reference formulas. */
 int evp_precompute_wachspress(evp_handle *handle, const double *xLocal, const double *yLocal,
                               int integrationType, int integrationOrder);
+
+/* The points, weights and normalisation evp_precompute_wachspress uses for (integrationType, integrationOrder):
+ * get_integration_factors (wachspress.F:1224-1287).  Host-only (no device needed); u, v, w: room for 64 doubles each. */
+int evp_integration_rule(int integrationType, int integrationOrder, int *nPoints, double *u, double *v, double *w,
+                         double *normalizationFactor);
 
 /* Device version of seaice_init_velocity_solver_pwl (src/shared/mpas_seaice_velocity_solver_pwl.F:44-373,
  * config_variational_basis = 'pwl'), incl. the 3x3 LU solves of src/shared/mpas_seaice_numerics.F:44-212.

@@ -18,6 +18,9 @@ __constant__ double cQu[QMAX], cQv[QMAX], cQw[QMAX];
 // reference's truncated literals (wachspress.F:1441-1597) -- the digits must not be "improved".
 struct Rule { int n; double norm; double u[QMAX], v[QMAX], w[QMAX]; };
 
+// dunavant orders 9, 10, 12 and the 'fekete' rules (wachspress.F:1599-1941), generated from the reference's routines
+#include "evp_quadrature_tables.inc"
+
 int make_rule(int type, int order, Rule &r)
 {
     if (type == 1) {   // trapezoidal (wachspress.F:1301-1387)
@@ -41,6 +44,23 @@ int make_rule(int type, int order, Rule &r)
             }
         r.norm = 6.0 * ((double)nT * (double)nT);
         return 0;
+    }
+    if (type != 0 && type != 2) return 1;
+    {
+        int n = 0;
+        double norm = 0.0;
+        const double *t = generated_rule(type, order, n, norm);
+        if (t != nullptr) {
+            if (n > QMAX) return 1;
+            r.n = n;
+            r.norm = norm;
+            for (int k = 0; k < n; k++) {
+                r.u[k] = t[3 * k];
+                r.v[k] = t[3 * k + 1];
+                r.w[k] = t[3 * k + 2];
+            }
+            return 0;
+        }
     }
     if (type != 0) return 1;
     r.norm = 2.0;
@@ -427,6 +447,28 @@ __global__ void __launch_bounds__(64) k_pwl(int nCells, int Mh, const uint8_t *_
 }
 
 }  // namespace
+
+// The rule evp_precompute_wachspress integrates with (get_integration_factors, wachspress.F:1224-1287): host-only, no
+// device needed.  u, v, w: room for 64 points each.
+extern "C" int evp_integration_rule(int integrationType, int integrationOrder, int *nPoints, double *u, double *v,
+                                    double *w, double *normalizationFactor)
+{
+    EVP_REQUIRE(nPoints != nullptr && u != nullptr && v != nullptr && w != nullptr && normalizationFactor != nullptr,
+                "NULL argument");
+    Rule r;
+    if (make_rule(integrationType, integrationOrder, r)) {
+        evp_set_error("unsupported integration rule (type %d, order %d)", integrationType, integrationOrder);
+        return EVP_ERR_ARGUMENT;
+    }
+    *nPoints = r.n;
+    *normalizationFactor = r.norm;
+    for (int k = 0; k < r.n; k++) {
+        u[k] = r.u[k];
+        v[k] = r.v[k];
+        w[k] = r.w[k];
+    }
+    return EVP_OK;
+}
 
 extern "C" int evp_precompute_wachspress(evp_handle *h, const double *xLocal, const double *yLocal,
                                          int integrationType, int integrationOrder)

@@ -37,8 +37,9 @@ EXPORTS = (
     "evp_launch_count", "evp_get_stream", "evp_device_bytes", "evp_set_use_graph", "evp_profile_passes",
     "evp_host_metric_terms", "evp_set_mesh_ext", "evp_set_state", "evp_pre_subcycle", "evp_post_subcycle",
     "evp_fetch_pre", "evp_release_host_memory", "evp_set_weak_mesh", "evp_update_weak_state", "evp_fetch_weak",
-    "evp_precompute_pwl", "evp_halo_mode", "evp_aggregate", "evp_fetch_aggregate",
+    "evp_precompute_pwl", "evp_halo_mode", "evp_aggregate", "evp_fetch_aggregate", "evp_integration_rule",
 )
+INTEGRATION_TYPE = {"dunavant": 0, "trapezoidal": 1, "fekete": 2}     # config_wachspress_integration_type
 
 
 class EvpError(RuntimeError):
@@ -172,6 +173,20 @@ def _ptr(a, dtype):
     return a.ctypes.data
 
 
+def integration_rule(integration_type="dunavant", order=8):
+    """evp_integration_rule: (u, v, weights, normalizationFactor) of get_integration_factors (wachspress.F:1224-1287)
+    as the library holds them; host-only."""
+    lib = load_library()
+    u, v, w = np.zeros(64), np.zeros(64), np.zeros(64)
+    n, norm = C.c_int(0), C.c_double(0.0)
+    rc = lib.evp_integration_rule(C.c_int(INTEGRATION_TYPE[integration_type]), C.c_int(int(order)), C.byref(n),
+                                  C.c_void_p(u.ctypes.data), C.c_void_p(v.ctypes.data), C.c_void_p(w.ctypes.data),
+                                  C.byref(norm))
+    if rc != 0:
+        raise EvpError(f"libevp_b200 error {rc}: {lib.evp_last_error_string().decode()}")
+    return u[:n.value].copy(), v[:n.value].copy(), w[:n.value].copy(), norm.value
+
+
 def host_metric_terms(z_rotated: np.ndarray, sphere_radius: float) -> np.ndarray:
     """evp_host_metric_terms: tan(asin(z/R))/R with the scalar libm (position-independent bits)."""
     lib = load_library()
@@ -254,7 +269,7 @@ class EvpSolver:
                 C.c_int(int(mesh["nEdges"])), C.c_void_p(_ptr(mesh["areaCell"], np.float64))))
         elif local_coords is not None:
             xl, yl = local_coords
-            itype = {"dunavant": 0, "trapezoidal": 1}[integration[0]]
+            itype = INTEGRATION_TYPE[integration[0]]
             self._check(self.lib.evp_precompute_wachspress(self._h, C.c_void_p(_ptr(xl, np.float64)),
                                                            C.c_void_p(_ptr(yl, np.float64)),
                                                            C.c_int(itype), C.c_int(integration[1])))

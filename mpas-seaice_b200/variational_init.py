@@ -50,6 +50,40 @@ def interior_vertex(mesh):
     return out
 
 
+def boundary_source_local(index_to_id, boundary_type, boundary_source):
+    """init_special_boundaries_velocity / init_special_boundaries_tracers (special_boundaries.F:83-150, 164-250):
+    ``vertexBoundarySourceLocal`` (what evp_create's special-boundary arrays take, include/evp_b200.h) /
+    ``tracerBoundarySourceLocal`` from the global IDs in the stream arrays ``vertexBoundarySource`` /
+    ``tracerBoundarySource``.  Arrays carry the extra slot; entities of type 0 get 0.  Like the reference's table
+    (allocated with nVertices / nCells slots) this serves a block whose IDs are a permutation of 1..n; anything else
+    raises instead of indexing out of bounds."""
+    ids = np.asarray(index_to_id)
+    n = len(ids) - 1
+    btype, src = np.asarray(boundary_type), np.asarray(boundary_source)
+    assert btype.shape == (n + 1,) and src.shape == (n + 1,)
+    special = np.flatnonzero(btype[:n] != 0)
+    if np.any(ids[:n] < 1) or np.any(ids[:n] > n) or np.any(src[special] < 1) or np.any(src[special] > n):
+        raise ValueError("global IDs outside 1..n: the reference's globalToLocalID table would be indexed out of bounds")
+    g2l = np.zeros(n + 1, dtype=np.int32)
+    g2l[ids[:n]] = np.arange(1, n + 1, dtype=np.int32)
+    out = np.zeros(n + 1, dtype=np.int32)
+    out[special] = g2l[src[special]]
+    return out
+
+
+def set_special_boundaries_tracers(boundary_type, source_local, *category_arrays):
+    """seaice_set_special_boundaries_tracers (special_boundaries.F:415-485), IN PLACE on the category tracers
+    (first dimension nCells+1): type 1 cells are emptied, type 2 cells take their source cell's values -- in cell order,
+    so a source the loop changed earlier is read changed (the reference's in-place semantics)."""
+    btype = np.asarray(boundary_type)
+    for i in np.flatnonzero(btype[:-1] != 0):
+        for a in category_arrays:
+            if btype[i] == 1:
+                a[i] = 0.0
+            elif btype[i] == 2:
+                a[i] = a[int(source_local[i]) - 1]
+
+
 def land_ice_mask_vertex(mesh, land_ice_mask, n_vertices_solve=None):
     """init_ice_shelve_vertex_mask (velocity_solver.F:481-544): 1 at the vertices of the owned range that touch a cell
     under an ice shelf (landIceMask == 1; the junk slot nCells+1 of the mask counts like any cell), 0 elsewhere --

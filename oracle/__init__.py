@@ -25,7 +25,8 @@ QUADRATIC_OCEAN_STRESS, LINEAR_OCEAN_STRESS = 1, 2
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("evp_oracle.c", "evp_precompute_oracle.c", "ir_oracle.c", "upwind_oracle.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("evp_oracle.c", "evp_precompute_oracle.c", "ir_oracle.c", "upwind_oracle.c", "Makefile",
+                                              "quadrature_tables.inc")]
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
     if force or stale:
@@ -111,7 +112,7 @@ def init_variational(mesh, basis="wachspress", denominator="original", rotate=No
                             _p(mesh.xCell), _p(mesh.yCell), _p(mesh.zCell), _i(rotate), _i(on_sphere))
     GU, GV, SU, SV, SM = (np.zeros((nC + 1, M, M)) for _ in range(5))
     if basis == "wachspress":
-        itype = {"dunavant": 0, "trapezoidal": 1}[integration_type]
+        itype = {"dunavant": 0, "trapezoidal": 1, "fekete": 2}[integration_type]
         err = L.orc_init_velocity_solver_wachspress(_i(nC), _i(M), _p(mesh.nEdgesOnCell), _p(xl), _p(yl),
                                                     _i(itype), _i(integration_order),
                                                     _p(GU), _p(GV), _p(SU), _p(SV), _p(SM))
@@ -140,7 +141,7 @@ def integration_factors(integration_type="dunavant", order=8):
     n = C.c_int(0)
     norm = C.c_double(0)
     u, v, w = np.zeros(512), np.zeros(512), np.zeros(512)
-    err = L.orc_get_integration_factors(_i({"dunavant": 0, "trapezoidal": 1}[integration_type]), _i(order),
+    err = L.orc_get_integration_factors(_i({"dunavant": 0, "trapezoidal": 1, "fekete": 2}[integration_type]), _i(order),
                                         C.byref(n), _p(u), _p(v), _p(w), C.byref(norm))
     assert err == 0
     return u[:n.value].copy(), v[:n.value].copy(), w[:n.value].copy(), norm.value
@@ -266,6 +267,29 @@ def set_num_threads(n: int) -> None:
 # ---------------------------------------------------------------------------------------------
 # pre- / post-subcycle (the host side of the boundary, restated so tests can build identical inputs)
 # ---------------------------------------------------------------------------------------------
+
+def boundary_source_local(index_to_id, boundary_type, boundary_source, out=None):
+    """init_special_boundaries_velocity / _tracers (special_boundaries.F:83-150, 164-250); arrays with the extra slot"""
+    n = len(index_to_id) - 1
+    res = np.zeros(n + 1, dtype=np.int32) if out is None else out
+    a = [np.ascontiguousarray(x, dtype=np.int32) for x in (index_to_id, boundary_type, boundary_source)]
+    L = lib()
+    L.orc_boundary_source_local.restype = C.c_int
+    if L.orc_boundary_source_local(_i(n), _p(a[0]), _p(a[1]), _p(a[2]), _p(res)) != 0:
+        raise ValueError("global IDs outside 1..n: the reference's globalToLocalID table would be indexed out of bounds")
+    return res
+
+
+def set_special_boundaries_tracers(boundary_type, source_local, ice_area_category, ice_volume_category, snow_volume_category):
+    """seaice_set_special_boundaries_tracers (special_boundaries.F:415-485), IN PLACE on (nCells+1, nCategories, 1) arrays"""
+    nC = len(boundary_type) - 1
+    n = int(np.prod(ice_area_category.shape[1:]))
+    for a in (ice_area_category, ice_volume_category, snow_volume_category):
+        assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.shape[0] == nC + 1
+    lib().orc_set_special_boundaries_tracers(_i(nC), _i(n), _p(np.ascontiguousarray(boundary_type, dtype=np.int32)),
+                                             _p(np.ascontiguousarray(source_local, dtype=np.int32)),
+                                             _p(ice_area_category), _p(ice_volume_category), _p(snow_volume_category))
+
 
 def land_ice_mask_vertex(mesh, land_ice_mask, n_vertices_solve=None):
     """init_ice_shelve_vertex_mask (velocity_solver.F:481-544): (nVertices+1) int32"""

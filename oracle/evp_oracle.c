@@ -12,7 +12,7 @@
  * interpreter for the Fortran subset of these routines (tests/golden/fortran_subset.py) runs
  * subcycle_velocity_solver, velocity_solver_pre_subcycle and velocity_solver_post_subcycle with everything below them
  * from the files under /root/reference, one IEEE operation per operator in the written order; the fixtures
- * (tests/golden/refexec_*.npz, tests/golden/step/*.npz) are reproduced by this file bit for bit
+ * (tests/golden/refexec_*.npz, tests/golden/step/refexec_step_*.npz) are reproduced by this file bit for bit
  * (tests/test_golden.py, tests/test_refexec_step.py).  Also: the reference's analytic known answers
  * (testing_and_setup/testcases/square/operators_strain_stress_divergence/create_ics.py:12-48,
  * src/shared/mpas_seaice_testing.F:726-839; tests/test_oracle_kat.py), analytic fields generated with the reference's
@@ -744,6 +744,49 @@ void orc_velocity_calculation_mask(int nVerticesSolve, int nVertices, const int 
             solveVelocity[i] = 1;
     }
     for (int i = nVerticesSolve; i < nVertices; i++) solveVelocity[i] = 0;
+}
+
+/* init_special_boundaries_velocity / init_special_boundaries_tracers (special_boundaries.F:83-150, 164-250): the local
+ * index of every special entity's source, from the global IDs the stream delivers.  globalToLocalID has nEntities slots
+ * in the reference: it serves a block whose global IDs are 1..nEntities (one block per rank, one rank).  Returns 1 when
+ * an ID falls outside (the reference would index out of bounds), leaving the output as far as written. */
+int orc_boundary_source_local(int nEntities, const int *indexToID, const int *boundaryType, const int *boundarySource,
+                              int *boundarySourceLocal)
+{
+    int *globalToLocalID = (int *)calloc((size_t)(nEntities > 0 ? nEntities : 1), sizeof(int));
+    int rc = 0;
+    for (int i = 1; i <= nEntities; i++) {
+        const int id = indexToID[i - 1];
+        if (id < 1 || id > nEntities) { rc = 1; break; }
+        globalToLocalID[id - 1] = i;
+    }
+    for (int i = 1; i <= nEntities && !rc; i++) {
+        if (boundaryType[i - 1] != 0) {
+            const int src = boundarySource[i - 1];
+            if (src < 1 || src > nEntities) { rc = 1; break; }
+            boundarySourceLocal[i - 1] = globalToLocalID[src - 1];
+        }
+    }
+    free(globalToLocalID);
+    return rc;
+}
+
+/* seaice_set_special_boundaries_tracers (special_boundaries.F:415-485): in cell order, in place -- a source changed
+ * earlier in the loop is read changed.  Arrays (nCells, n) with n = nCategories * (the ONE layer). */
+void orc_set_special_boundaries_tracers(int nCells, int n, const int *tracerBoundaryType, const int *tracerBoundarySourceLocal,
+                                        double *iceAreaCategory, double *iceVolumeCategory, double *snowVolumeCategory)
+{
+    double *f[3] = {iceAreaCategory, iceVolumeCategory, snowVolumeCategory};
+    for (int iCell = 1; iCell <= nCells; iCell++) {
+        if (tracerBoundaryType[iCell - 1] == 1) {
+            for (int t = 0; t < 3; t++)
+                for (int k = 0; k < n; k++) f[t][(size_t)(iCell - 1) * n + k] = 0.0;
+        } else if (tracerBoundaryType[iCell - 1] == 2) {
+            const int s = tracerBoundarySourceLocal[iCell - 1];
+            for (int t = 0; t < 3; t++)
+                for (int k = 0; k < n; k++) f[t][(size_t)(iCell - 1) * n + k] = f[t][(size_t)(s - 1) * n + k];
+        }
+    }
 }
 
 /* init_ice_shelve_vertex_mask (velocity_solver.F:481-544): a vertex of the owned range touching a land-ice cell */

@@ -5,7 +5,7 @@
  * (seaice_init_velocity_solver_variational and callees).  Same conventions as evp_oracle.c.  Pinned by outputs of
  * the reference's own source executed here (tests/golden/fortran_subset.py interprets
  * init_velocity_solver_variational_primary_mesh with the Wachspress / PWL routines below it; fixtures
- * tests/golden/init/*.npz, reproduced bit for bit: tests/test_refexec_init.py), by the exact reproduction properties
+ * tests/golden/init/refexec_init_*.npz, reproduced bit for bit: tests/test_refexec_init.py), by the exact reproduction properties
  * of the bases (tests/test_oracle_kat.py) and by an independent closed form (tests/test_wachspress_independent.py).
  *
  * Arrays: Fortran column-major, 1-based index values, junk slot at the end.
@@ -143,6 +143,9 @@ void orc_calc_local_coords(double *xLocal, double *yLocal, int nCells, int maxEd
 #define QMAX 512
 typedef struct { int n; double u[QMAX], v[QMAX], w[QMAX]; double norm; } quad_rule;
 
+/* dunavant 9, 10, 12 and the 'fekete' rules (wachspress.F:1599-1941): generated by executing the reference's routines */
+#include "quadrature_tables.inc"
+
 static int rule_dunavant(int order, quad_rule *q)
 {
     q->norm = 2.0;
@@ -180,7 +183,7 @@ static int rule_dunavant(int order, quad_rule *q)
                      0.89890554336594, 0.05054722831703, 0.72849239295540, 0.00839477740996, 0.26311282963464, 0.26311282963464, 0.00839477740996, 0.72849239295540,
                      0.14431560767779, 0.09509163426728, 0.09509163426728, 0.09509163426728, 0.10321737053472, 0.10321737053472, 0.10321737053472, 0.03245849762320,
                      0.03245849762320, 0.03245849762320, 0.02723031417443, 0.02723031417443, 0.02723031417443, 0.02723031417443, 0.02723031417443, 0.02723031417443); break;
-    default: return 1; /* orders 9, 10, 12 of the reference are not restated */
+    default: return rule_generated(0, order, q);       /* orders 9, 10, 12 */
     }
 #undef SETQ
     return 0;
@@ -213,13 +216,14 @@ static int rule_trapezoidal(int order, quad_rule *q)
     return 0;
 }
 
-/* 0 = dunavant, 1 = trapezoidal ("fekete" of the reference is not restated) */
+/* 0 = dunavant, 1 = trapezoidal, 2 = fekete */
 int orc_get_integration_factors(int integrationType, int integrationOrder, int *n, double *u, double *v,
                                 double *w, double *norm)
 {
     quad_rule q;
     int err = integrationType == 0 ? rule_dunavant(integrationOrder, &q)
-            : integrationType == 1 ? rule_trapezoidal(integrationOrder, &q) : 1;
+            : integrationType == 1 ? rule_trapezoidal(integrationOrder, &q)
+            : integrationType == 2 ? rule_generated(2, integrationOrder, &q) : 1;
     if (err) return err;
     *n = q.n; *norm = q.norm;
     memcpy(u, q.u, sizeof(double) * q.n);
@@ -331,7 +335,8 @@ int orc_init_velocity_solver_wachspress(int nCells, int maxEdges, const int *nEd
     if (M > MAXE) return 2;
     quad_rule q;
     int err = integrationType == 0 ? rule_dunavant(integrationOrder, &q)
-            : integrationType == 1 ? rule_trapezoidal(integrationOrder, &q) : 1;
+            : integrationType == 1 ? rule_trapezoidal(integrationOrder, &q)
+            : integrationType == 2 ? rule_generated(2, integrationOrder, &q) : 1;
     if (err) return err;
     const int nq = q.n;
 

@@ -33,7 +33,7 @@
  * OUTPUTS OF THE REFERENCE'S OWN SOURCE EXECUTED HERE: the Fortran-subset interpreter tests/golden/fortran_subset.py runs
  * seaice_init_advection_incremental_remap and seaice_run_advection_incremental_remap (with incremental_remap_block and
  * everything below it, the optional checks included) from the file under /root/reference; the fixtures
- * (tests/golden/ir/*.npz: the full tracer hierarchy with layers on planar hexagons and quadrilaterals and the sphere,
+ * (tests/golden/ir/refexec_ir*.npz: the full tracer hierarchy with layers on planar hexagons and quadrilaterals and the sphere,
  * rotated and not) are reproduced by this file bit for bit (tests/test_ir_parity.py) -- every tracer, the conservation
  * sums, the abort decisions of both checks, the whole geometry pool.  tests/test_oracle_ir.py adds the properties the
  * scheme guarantees (conservation, monotonicity, uniform fields, exact translation of linear fields, an independent

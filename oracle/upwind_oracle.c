@@ -19,7 +19,7 @@
  * Parity status: the reference cannot be compiled in this image; both parts are pinned by OUTPUTS OF THE
  * REFERENCE'S OWN SOURCE EXECUTED HERE by the Fortran-subset interpreter tests/golden/fortran_subset.py (mesh.F's
  * seaice_normal_vectors; advection_upwind.F's define_tracer_connectivities and seaice_run_advection_upwind with the
- * module's own table and parameters): fixtures tests/golden/options/*.npz, reproduced by this file bit for bit
+ * module's own table and parameters): fixtures tests/golden/options/refexec_*.npz, reproduced by this file bit for bit
  * (tests/test_transport_options.py).  Also: an independent vectorised reading of the normal vectors
  * (mpas-seaice_b200/weakmesh.py), the reference's analytic operator fields through the weak operators
  * (tests/test_analytic_golden.py), conservation, uniform tracers and the closed-form donor-cell update.

@@ -630,7 +630,13 @@ class Frame:
         self.vars[name] = val
 
     def bind(self, name, val):
-        """pointer association / first definition: replaces whatever the name held"""
+        """pointer association / first definition: replaces whatever the name held.  A name the routine does not declare
+        but its module does (a module-level pointer, e.g. special_boundaries.F:29-32) is associated at module level."""
+        if name not in self.vars and name not in self.sub.types and name not in self.sub.args:
+            g = self.sub.renames.get(name, name)
+            if g in self.interp.globals:
+                self.interp.globals[g] = val
+                return
         self.vars[name] = val
 
 
@@ -932,7 +938,16 @@ class Interpreter:
                     mc = re.match(r"^case\s*(default|\((.*)\))$", l2, re.I)
                     if not mc:
                         raise FortranError("line %d: expected case, found %r" % (stmts[j][0], l2))
-                    vals = None if mc.group(1).lower() == "default" else [parse_expr(x) for x in _split_top(mc.group(2))]
+                    if mc.group(1).lower() == "default":
+                        vals = None
+                    else:                      # values and ranges lo:hi (either bound may be missing)
+                        vals = []
+                        for x in _split_top(mc.group(2)):
+                            if ":" in x and not re.search(r"['\"]", x):
+                                lo, hi = [y.strip() for y in x.split(":", 1)]
+                                vals.append(("range", parse_expr(lo) if lo else None, parse_expr(hi) if hi else None))
+                            else:
+                                vals.append(parse_expr(x))
                     body, j = self._block(sub, stmts, j + 1, ("case", "endselect"))
                     cases.append((vals, body))
                 nodes.append(("select", no, sel, cases))
@@ -1201,7 +1216,11 @@ class Interpreter:
             elif k == "select":
                 sel = self.ev(n[2], fr)
                 for vals, body in n[3]:
-                    if vals is None or any(self.ev(x, fr) == sel for x in vals):
+                    def hit(x):
+                        if x[0] == "range":
+                            return (x[1] is None or self.ev(x[1], fr) <= sel) and (x[2] is None or sel <= self.ev(x[2], fr))
+                        return self.ev(x, fr) == sel
+                    if vals is None or any(hit(x) for x in vals):
                         self.run_block(body, fr)
                         break
             elif k == "ptr":

@@ -252,7 +252,12 @@ INIT_CASES = {
     "refexec_init_hex4_trapezoidal": (("planar_hex", 4, 5, 16000.0), "wachspress", "original", "trapezoidal", 3),
     "refexec_init_hex5_pwl": (("planar_hex", 5, 6, 16000.0), "pwl", "original", "dunavant", 8),
     "refexec_init_ico1_pwl": (("icosphere", 1), "pwl", "alternate", "dunavant", 8),
+    # the other rules of config_wachspress_integration_type / _order (Registry.xml:603-610)
+    "refexec_init_hex3_fekete9": (("planar_hex", 3, 4, 16000.0), "wachspress", "original", "fekete", 9),
+    "refexec_init_quad3_dunavant12": (("planar_quad", 3, 3, 16000.0), "wachspress", "alternate", "dunavant", 12),
+    "refexec_init_ico1_fekete5": (("icosphere", 1), "wachspress", "original", "fekete", 5),
 }
+INIT_CPU_ONLY = ("refexec_init_hex3_fekete9", "refexec_init_quad3_dunavant12", "refexec_init_ico1_fekete5")
 
 
 def init_mesh(spec):
@@ -1027,9 +1032,65 @@ def build_locked_cells():
                                    "(tests/golden/fortran_subset.py): " + ", ".join(sorted(set(I.trace))))}
 
 
+def build_special_boundaries_init():
+    """seaice_init_special_boundaries (special_boundaries.F:60-250): vertexBoundarySourceLocal / tracerBoundarySourceLocal
+    from the global IDs of the stream arrays, on a block whose local numbering is a permutation of the global one; then
+    seaice_set_special_boundaries_tracers (:415-485) on category tracers (zeroed cells, copied cells, a copied cell whose
+    source was itself changed earlier in the loop)."""
+    mesh = init_mesh(("planar_hex", 6, 7, 1000.0))
+    nC, nV = mesh.nCells, mesh.nVertices
+    rng = np.random.default_rng(8)
+    idV = np.zeros(nV + 1, np.int32)
+    idV[:nV] = rng.permutation(nV) + 1
+    idC = np.zeros(nC + 1, np.int32)
+    idC[:nC] = rng.permutation(nC) + 1
+    vType, vSrc = np.zeros(nV + 1, np.int32), np.zeros(nV + 1, np.int32)
+    pick = rng.choice(nV, size=18, replace=False)
+    vType[pick] = np.tile([1, 2, 3], 6)
+    vSrc[pick] = idV[rng.choice(nV, size=18)]                       # global IDs, as the stream delivers them
+    cType, cSrc = np.zeros(nC + 1, np.int32), np.zeros(nC + 1, np.int32)
+    pickc = np.sort(rng.choice(nC, size=10, replace=False))
+    cType[pickc] = np.tile([1, 2], 5)
+    cSrc[pickc] = idC[rng.choice(nC, size=10)]
+    cSrc[pickc[-1]] = idC[pickc[1]]                                 # a SET cell whose source is an earlier SET cell
+    cType[pickc[-1]] = 2
+    cSrc[pickc[-2]] = idC[pickc[0]]                                 # ... and one whose source is an earlier ZERO cell
+    cType[pickc[-2]] = 2
+    vLoc, cLoc = np.full(nV + 1, -7, np.int32), np.full(nC + 1, -7, np.int32)
+    nK = 3
+    tr = {k: rng.uniform(0.1, 1.0, size=(nC + 1, nK, 1)) for k in ("iceAreaCategory", "iceVolumeCategory", "snowVolumeCategory")}
+    data = {"in_" + k: v.copy() for k, v in tr.items()}
+    I = F.Interpreter(defined=())
+    I.load(os.path.join(REF, "src/shared/mpas_seaice_special_boundaries.F"))
+    I.noop |= {"mpas_log_write"}
+    for k, v in dict(vertexBoundaryType=vType, vertexBoundarySource=vSrc, vertexBoundarySourceLocal=vLoc, indexToVertexID=idV,
+                     tracerBoundaryType=cType, tracerBoundarySource=cSrc, tracerBoundarySourceLocal=cLoc, indexToCellID=idC,
+                     **tr).items():
+        I.pool[k] = F.FArray(v)
+    I.pool.update(nCells=nC, nVertices=nV, config_use_special_boundaries_velocity=True,
+                  config_use_special_boundaries_velocity_masks=False, config_use_special_boundaries_tracers=True)
+    block = types.SimpleNamespace(structs="structs", configs="configs", dimensions="dimensions", next=None)
+    domain = types.SimpleNamespace(blocklist=block, configs="configs")
+    for k in ("usespecialboundariesvelocity", "usespecialboundariesvelocitymasks", "usespecialboundariestracers"):
+        I.globals[k] = False                  # the module's logical pointers: the init routines point them at the configs
+    I.call("seaice_init_special_boundaries", domain)
+    assert I.globals["usespecialboundariesvelocity"] is True and I.globals["usespecialboundariestracers"] is True
+    I.call("seaice_set_special_boundaries_tracers", domain)
+    data.update(indexToVertexID=idV, vertexBoundaryType=vType, vertexBoundarySource=vSrc, out_vertexBoundarySourceLocal=vLoc,
+                indexToCellID=idC, tracerBoundaryType=cType, tracerBoundarySource=cSrc, out_tracerBoundarySourceLocal=cLoc)
+    for k, v in tr.items():
+        data["out_" + k] = v
+    data["provenance"] = np.array("outputs computed by interpreting the reference's Fortran source "
+                                  "(tests/golden/fortran_subset.py): " + ", ".join(sorted(set(I.trace))))
+    return data
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     os.makedirs(os.path.join(HERE, "options"), exist_ok=True)
+    if not only or "refexec_special_boundaries_init" in only:
+        np.savez_compressed(os.path.join(HERE, "cpu", "refexec_special_boundaries_init.npz"), **build_special_boundaries_init())
+        print("refexec_special_boundaries_init", flush=True)
     if not only or "refexec_locked_cells" in only:
         np.savez_compressed(os.path.join(HERE, "cpu", "refexec_locked_cells.npz"), **build_locked_cells())
         print("refexec_locked_cells", flush=True)
@@ -1087,7 +1148,7 @@ if __name__ == "__main__":
         if only and name not in only:
             continue
         data, called, secs = build_init(name)
-        path = os.path.join(HERE, "init", name + ".npz")
+        path = os.path.join(HERE, "cpu" if name in INIT_CPU_ONLY else "init", name + ".npz")
         os.makedirs(os.path.dirname(path), exist_ok=True)
         np.savez_compressed(path, **data)
         print("%s: %.1f s, %d KB; interpreted: %s" % (name, secs, os.path.getsize(path) // 1024, ", ".join(called)), flush=True)

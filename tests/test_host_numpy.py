@@ -173,6 +173,45 @@ def test_locked_cells_against_the_reference_executed_mask():
     assert np.array_equal(oracle.dynamically_locked_cells_mask(mesh, interior)[:nC], ref)
 
 
+def test_special_boundary_sources_against_the_reference_executed_init():
+    """vertexBoundarySourceLocal / tracerBoundarySourceLocal as seaice_init_special_boundaries
+    (src/shared/mpas_seaice_special_boundaries.F:60-250) computes them and the category tracers after
+    seaice_set_special_boundaries_tracers (:415-485), both interpreted from the reference's source on a block whose local
+    numbering is a permutation of the global IDs (tests/golden/cpu/refexec_special_boundaries_init.npz).  Integer maps
+    bit-exact; the tracer copy is exact too (no arithmetic)."""
+    import os
+    import oracle
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cpu", "refexec_special_boundaries_init.npz"))
+    for name in ("init_special_boundaries_velocity", "init_special_boundaries_tracers", "seaice_set_special_boundaries_tracers"):
+        assert name in str(z["provenance"]), name
+    for ids, btype, src, ref in (("indexToVertexID", "vertexBoundaryType", "vertexBoundarySource", "out_vertexBoundarySourceLocal"),
+                                 ("indexToCellID", "tracerBoundaryType", "tracerBoundarySource", "out_tracerBoundarySourceLocal")):
+        special = z[btype] != 0
+        assert special.sum() >= 10
+        assert not np.array_equal(z[ids][:-1], np.arange(1, len(z[ids])))        # local numbering differs from the global
+        for f in (variational_init.boundary_source_local, oracle.boundary_source_local):
+            got = f(z[ids], z[btype], z[src])
+            assert np.array_equal(got[special], z[ref][special]), (ref, f.__module__)
+            assert np.array_equal(z[ids][got[special] - 1], z[src][special])      # and it IS the inverse map
+    names = ("iceAreaCategory", "iceVolumeCategory", "snowVolumeCategory")
+    btype, loc = z["tracerBoundaryType"], z["out_tracerBoundarySourceLocal"]
+    host = [z["in_" + k].copy() for k in names]
+    orc = [z["in_" + k].copy() for k in names]
+    variational_init.set_special_boundaries_tracers(btype, loc, *host)
+    oracle.set_special_boundaries_tracers(btype, loc, *orc)
+    for k, a, b in zip(names, host, orc):
+        assert np.array_equal(a[:-1], z["out_" + k][:-1]), k
+        assert np.array_equal(b[:-1], z["out_" + k][:-1]), k
+        assert not np.array_equal(z["in_" + k], z["out_" + k])
+    # the chained cells of the fixture: a SET cell whose source was emptied earlier in the loop comes out empty
+    chained = [i for i in np.flatnonzero(btype[:-1] == 2) if btype[loc[i] - 1] == 1 and loc[i] - 1 < i]
+    assert chained and all(np.all(z["out_iceAreaCategory"][i] == 0.0) for i in chained)
+    with pytest.raises(ValueError):
+        variational_init.boundary_source_local(z["indexToCellID"] + 5, btype, z["tracerBoundarySource"])
+    with pytest.raises(ValueError):
+        oracle.boundary_source_local(z["indexToCellID"] + 5, btype, z["tracerBoundarySource"])
+
+
 def test_evp_parameters_against_the_reference_executed_seaice_init_evp():
     """constitutiveRelationType, dampingTimescale and numericalInertiaCoefficient as the reference's own seaice_init_evp
     (src/shared/mpas_seaice_velocity_solver_constitutive_relation.F:75-164) leaves them -- interpreted from its source,

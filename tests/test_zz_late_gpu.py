@@ -1,0 +1,63 @@
+"""Device legs of the reference-executed fixtures that were generated after this round's GPU time was spent
+(tests/golden/cpu/): the oracle and the host functions replay them in tests/test_refexec_step.py / test_refexec_init.py;
+here the library does, through the C ABI, bit for bit.  This file sorts last on purpose: these are the GPU tests that
+have not run on a B200 yet.
+
+* Ice shelves: two whole steps with landIceMask = 1 on a patch of the ice cover (refexec_step_*_landice_3.npz;
+  init_ice_shelve_vertex_mask velocity_solver.F:481-544, the calculation masks :1023 / :1131) through
+  evp_set_mesh_ext(landIceMaskVertex) and evp_pre_subcycle(landIceMask).
+* The quadrature rules added late ('fekete', dunavant order 12: refexec_init_*.npz): evp_precompute_wachspress with
+  integrationType 2 / order 12 -- the kernel is the one the other rules run, only the constant tables differ, and
+  those are checked against the reference's without a GPU in tests/test_quadrature_rules.py."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from mpas_seaice_b200 import variational_init
+import oracle
+import test_refexec_init
+from test_refexec_step import _load, _device_step
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FILES = sorted(glob.glob(os.path.join(HERE, "golden", "cpu", "refexec_step_*landice*.npz")))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[13:-4] for f in FILES])
+def test_device_reproduces_the_reference_executed_step_with_ice_shelves(evp_lib, path):
+    from mpas_seaice_b200 import host
+    mesh, var, opts, cat, forcing, pre, out, nsub, config_dt, _ = _load(path)
+    switches = dict(opts["_switches"])
+    land = np.ascontiguousarray(switches.pop("land_ice_mask"), dtype=np.int32)
+    land_vertex_ref = switches.pop("land_ice_mask_vertex")
+    land_vertex = variational_init.land_ice_mask_vertex(mesh, land)
+    assert np.array_equal(land_vertex[:mesh.nVertices], land_vertex_ref[:mesh.nVertices])
+    solver = host.EvpSolver(mesh, var, {k: v for k, v in opts.items() if not k.startswith("_")})
+    solver.set_mesh_ext(mesh, variational_init.interior_vertex(mesh), land_ice_mask_vertex=land_vertex)
+    try:
+        _device_step(solver, host, mesh, cat, dict(forcing, landIceMask=land), pre, out, nsub, host.START_FIRST_STEP, switches)
+    finally:
+        solver.destroy()
+    lv = land_vertex[:mesh.nVertices] == 1
+    assert lv.any() and not pre["solveVelocity"][:mesh.nVertices][lv].any()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", test_refexec_init.CPU_FILES, ids=[os.path.basename(f)[13:-4] for f in test_refexec_init.CPU_FILES])
+def test_device_precompute_reproduces_the_reference_executed_arrays_of_the_late_rules(evp_lib, path):
+    import common
+    from mpas_seaice_b200 import host
+    mesh, want, kw, _ = test_refexec_init._load(path)
+    var = oracle.init_variational(mesh, **kw)            # xLocal / yLocal and the host-side maps the create call takes
+    step, opts = common.step_case(mesh)
+    solver = host.EvpSolver(mesh, var, opts, local_coords=(var["xLocal"], var["yLocal"]),
+                            integration=(kw["integration_type"], kw["integration_order"]))
+    try:
+        got = solver.fetch_basis()
+    finally:
+        solver.destroy()
+    nC = mesh.nCells
+    for k, a in got.items():
+        assert np.array_equal(a[:nC], want[k][:nC]), k
