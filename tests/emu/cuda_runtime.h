@@ -148,8 +148,8 @@ static void emu_launch_sync(dim3 grid, dim3 block, F body)
 
 typedef int cudaError_t;
 enum { cudaSuccess = 0 };
-typedef int cudaStream_t;
-typedef int cudaEvent_t;
+typedef void *cudaStream_t;
+typedef void *cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
 enum { cudaStreamNonBlocking = 1 };
 
@@ -161,10 +161,10 @@ static inline cudaError_t cudaMalloc(void **p, size_t n) { *p = calloc(n ? n : 1
 static inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
-static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = 1; return cudaSuccess; }
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = (void *)1; return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
-static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = 1; return cudaSuccess; }
+static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = (void *)1; return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
