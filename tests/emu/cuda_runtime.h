@@ -13,6 +13,7 @@
 #include <ucontext.h>
 
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -81,9 +82,28 @@ static void emu_trampoline()
     (*emu_body)();
     emu_fibers[emu_current].done = true;      /* uc_link brings control back to the scheduler */
 }
+/* grid mode (a cooperative launch, emu_launch_grid below): the fibers of ALL blocks are alive at the same time */
+struct EmuGridFiber {
+    ucontext_t ctx;
+    bool done = true, atBarrier = false;
+    unsigned block = 0, thread = 0;
+};
+static bool emu_grid_mode = false;
+static std::vector<EmuGridFiber> emu_gfibers;
+static unsigned long long emu_gcurrent = 0;
 static inline void emu_syncthreads()
 {
+    if (emu_grid_mode) {
+        emu_gfibers[emu_gcurrent].atBarrier = true;
+        swapcontext(&emu_gfibers[emu_gcurrent].ctx, &emu_sched_ctx);
+        return;
+    }
     swapcontext(&emu_fibers[emu_current].ctx, &emu_sched_ctx);
+}
+/* a thread that polls memory written by another block lets the others run */
+static inline void emu_yield()
+{
+    if (emu_grid_mode) swapcontext(&emu_gfibers[emu_gcurrent].ctx, &emu_sched_ctx);
 }
 #define __syncthreads() emu_syncthreads()
 /* __syncthreads_or: two accumulators used alternately; the first fiber to arrive for a generation clears its slot */
@@ -145,6 +165,85 @@ static void emu_launch_sync(dim3 grid, dim3 block, F body)
 }
 #define IR_LAUNCH_SYNC(kernel, grid, block, smem, stream, ...) \
     emu_launch_sync(dim3(grid), dim3(block), [&] { kernel(__VA_ARGS__); })
+
+/* Cooperative launch: every thread of every block is a fiber of its own, resumed round-robin (IR_EMU_ORDER=reverse: last
+ * to first).  __syncthreads() holds a fiber until all living fibers of ITS block have arrived; a fiber spinning on a word
+ * another block will write calls emu_yield() in the loop (the acquire-load helpers do).  Dynamic shared memory: one
+ * buffer per block, *smemVar points at the running block's before every resumption (kernels take the address once, at
+ * their start).  A launch that makes no progress for a long time aborts: a grid barrier that cannot complete. */
+static void emu_gtrampoline()
+{
+    (*emu_body)();
+    emu_gfibers[emu_gcurrent].done = true;
+}
+template <typename F>
+static void emu_launch_grid(dim3 grid, dim3 block, size_t smemBytes, unsigned char **smemVar, F body)
+{
+    gridDim = grid;
+    blockDim = block;
+    const char *order = getenv("IR_EMU_ORDER");
+    const bool reverse = order != nullptr && order[0] == 'r';
+    const unsigned long long nb = (unsigned long long)grid.x * grid.y * grid.z, nt = (unsigned long long)block.x * block.y * block.z;
+    const unsigned long long total = nb * nt;
+    const size_t stackBytes = 64 * 1024, smemPitch = (smemBytes + 127) & ~(size_t)127;
+    char *stacks = (char *)malloc(total * stackBytes);
+    unsigned char *smem = (unsigned char *)aligned_alloc(128, smemPitch * nb + 128);
+    if (!stacks || !smem) abort();
+    memset(smem, 0, smemPitch * nb + 128);
+    emu_gfibers.assign(total, EmuGridFiber());
+    std::function<void()> fn = body;
+    emu_body = &fn;
+    std::vector<unsigned long long> alive(nb, nt), arrived(nb, 0);
+    for (unsigned long long i = 0; i < total; i++) {
+        EmuGridFiber &f = emu_gfibers[i];
+        f.block = (unsigned)(i / nt);
+        f.thread = (unsigned)(i % nt);
+        f.done = false;
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp = stacks + i * stackBytes;
+        f.ctx.uc_stack.ss_size = stackBytes;
+        f.ctx.uc_link = &emu_sched_ctx;
+        makecontext(&f.ctx, emu_gtrampoline, 0);
+    }
+    unsigned char *savedSmem = *smemVar;
+    emu_grid_mode = true;
+    unsigned long long remaining = total, idle = 0;
+    while (remaining > 0) {
+        bool ran = false, changed = false;
+        for (unsigned long long it = 0; it < total; it++) {
+            const unsigned long long i = reverse ? total - 1 - it : it;
+            EmuGridFiber &f = emu_gfibers[i];
+            if (f.done || f.atBarrier) continue;
+            const unsigned long long b = f.block, t = f.thread;
+            blockIdx = dim3((unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y), (unsigned)(b / ((unsigned long long)grid.x * grid.y)));
+            threadIdx = dim3((unsigned)(t % block.x), (unsigned)((t / block.x) % block.y), (unsigned)(t / ((unsigned long long)block.x * block.y)));
+            *smemVar = smem + smemPitch * b;
+            emu_gcurrent = i;
+            swapcontext(&emu_sched_ctx, &f.ctx);
+            ran = true;
+            if (f.done) { remaining--; alive[b]--; changed = true; }
+            else if (f.atBarrier) { arrived[b]++; changed = true; }
+        }
+        for (unsigned long long b = 0; b < nb; b++) {
+            if (alive[b] > 0 && arrived[b] == alive[b]) {
+                for (unsigned long long t = 0; t < nt; t++) emu_gfibers[b * nt + t].atBarrier = false;
+                arrived[b] = 0;
+                changed = true;
+            }
+        }
+        idle = changed ? 0 : idle + 1;
+        if (!ran || idle > 100000) {
+            fprintf(stderr, "emu_launch_grid: no progress (%llu threads left): a barrier that cannot complete\n", remaining);
+            abort();
+        }
+    }
+    emu_grid_mode = false;
+    *smemVar = savedSmem;
+    emu_body = nullptr;
+    emu_gfibers.clear();
+    free(stacks);
+    free(smem);
+}
 
 typedef int cudaError_t;
 enum { cudaSuccess = 0 };

@@ -7,7 +7,7 @@
  * same host code as the product.  What it checks: the kernels' logic (indexing, operation order, masks, the launch
  * sequence, graph capture and replay) against the oracle where no GPU exists, dependence on the thread order (a race
  * on the device) through IR_EMU_ORDER=reverse (the switch of tests/emu/cuda_runtime.h), and out-of-bounds accesses under AddressSanitizer.  What it cannot:
- * timing, memory-model questions, the persistent cooperative kernel (refused here), more than one rank.
+ * timing, memory-model questions, more than one rank.
  */
 #ifndef TESTS_EMU_EVP_CUDA_RUNTIME_H
 #define TESTS_EMU_EVP_CUDA_RUNTIME_H
@@ -30,7 +30,8 @@ static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y
 static inline int2 make_int2(int x, int y) { int2 r; r.x = x; r.y = y; return r; }
 
 /* dynamic shared memory of the block being executed */
-alignas(128) static unsigned char emu_evp_dyn_smem[256 * 1024];
+alignas(128) static unsigned char emu_evp_dyn_smem_one[256 * 1024];
+static unsigned char *emu_evp_dyn_smem = emu_evp_dyn_smem_one;      /* (a cooperative launch points it at the running block's) */
 
 /* ---- warp collectives: every thread of the block calls them (true for the kernels under test); implemented as a block
  * barrier over per-thread predicate slots, two generations alternating like __syncthreads_or ---- */
@@ -154,13 +155,23 @@ static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, con
     return cudaSuccess;
 }
 
-/* one device with 148 multiprocessors; no block of the persistent kernel is ever "resident": that path is refused */
+/* one device with 148 multiprocessors, four resident blocks of the persistent kernel each */
 enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16, cudaDevAttrCooperativeLaunch = 95 };
 static inline cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr a, int) { *v = a == cudaDevAttrMultiProcessorCount ? 148 : 0; return cudaSuccess; }
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 template <typename K> static inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
-template <typename K> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, K, int, size_t) { *n = 0; return cudaSuccess; }
-static inline cudaError_t cudaLaunchCooperativeKernel(const void *, dim3, dim3, void **, size_t, cudaStream_t) { return 902; }
+template <typename K> static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, K, int, size_t) { *n = 4; return cudaSuccess; }
+/* cudaLaunchCooperativeKernel((const void *)kernel, ...) is rewritten into this by tests/emu/evp_emu.py (the typed pointer) */
+template <typename A>
+static cudaError_t emu_launch_cooperative(void (*kernel)(A), dim3 grid, dim3 block, void **args, size_t smem, cudaStream_t)
+{
+    auto pack = std::make_shared<std::decay_t<A>>(*reinterpret_cast<std::decay_t<A> *>(args[0]));
+    emu_enqueue([=] {
+        emu_launches++;
+        emu_launch_grid(grid, block, smem, &emu_evp_dyn_smem, [&] { kernel(*pack); });
+    });
+    return cudaSuccess;
+}
 
 /* peer-to-peer halo exchange: needs a second process with a device of its own -- not emulated */
 struct cudaIpcMemHandle_t { char reserved[64]; };

@@ -8,7 +8,9 @@ makes a rewritten COPY under tests/_build/evp_emu/ with exactly two kinds of cha
   * the bodies of the few helpers written in inline PTX (mbarrier, cp.async.bulk, acquire / release accesses, the global
     timer) -> their plain C++ meaning (a bulk copy is a memcpy that has completed when the call returns; a barrier wait
     therefore never waits); a helper with inline PTX that is not in the table below stops the build;
-  * ``extern __shared__ ... evp_smem_raw[]``  ->  a pointer to the emulated dynamic shared memory.
+  * ``extern __shared__ ... evp_smem_raw[]``  ->  a pointer to the emulated dynamic shared memory;
+  * ``cudaLaunchCooperativeKernel((const void *)kern, ...)``  ->  ``emu_launch_cooperative(kern, ...)`` (the typed pointer):
+    all blocks alive at once, so the persistent kernel's grid barrier works (tests/emu/cuda_runtime.h, emu_launch_grid).
 
 Used by tests/test_evp_emulation.py."""
 import os
@@ -29,7 +31,7 @@ PTX_HELPERS = {
     "mbar_expect_tx": "{ (void)bar; (void)bytes; }",
     "bulk_g2s": "{ memcpy(dst, src, bytes); (void)bar; }",
     "mbar_wait": "{ (void)bar; (void)parity; }",
-    "evp_ld_acquire_gpu_u32": "{ return *(const volatile unsigned *)p; }",
+    "evp_ld_acquire_gpu_u32": "{ emu_yield(); return *(const volatile unsigned *)p; }",   # polled in the grid barrier
     "evp_st_release_gpu_u32": "{ *(volatile unsigned *)p = v; }",
     "evp_ld_acquire_sys": "{ return *(const volatile int *)p; }",
     "evp_st_relaxed_sys": "{ *(volatile int *)p = v; }",
@@ -115,6 +117,7 @@ def rewrite(text, name):
     text = re.sub(r"extern\s+__shared__\s+__align__\(\d+\)\s+unsigned\s+char\s+(\w+)\[\];",
                   r"unsigned char *\1 = emu_evp_dyn_smem;", text)
     text = text.replace("__cvta_generic_to_shared", "(uintptr_t)")
+    text = text.replace("cudaLaunchCooperativeKernel((const void *)kern,", "emu_launch_cooperative(kern,")
     return text
 
 
@@ -143,7 +146,12 @@ def library(asan=False):
              "-I", os.path.join(HERE, "evp"), "-I", os.path.join(BUILD, "csrc")]
     if asan:
         flags += ["-fsanitize=address", "-fno-omit-frame-pointer"]
-    subprocess.run(["g++"] + flags + ["-o", out] + cpps + ["-ldl"], check=True)
+    # one compiler process per translation unit, then the link
+    objs = [c[:-4] + ("_asan.o" if asan else ".o") for c in cpps]
+    procs = [subprocess.Popen(["g++"] + [f for f in flags if f != "-shared"] + ["-c", "-o", o, c]) for c, o in zip(cpps, objs)]
+    if any(p.wait() != 0 for p in procs):
+        raise RuntimeError("the emulated EVP library does not compile")
+    subprocess.run(["g++", "-shared"] + (["-fsanitize=address"] if asan else []) + ["-o", out] + objs + ["-ldl"], check=True)
     return out
 
 

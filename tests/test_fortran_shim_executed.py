@@ -141,7 +141,7 @@ def test_ir_shim_executed_against_the_cuda_library():
 # fortran/seaice_evp_b200.F90: seaice_evp_b200_create / _update / _subcycle / _destroy executed against libevp_b200.so
 # ----------------------------------------------------------------------------------------------------------------------
 
-def _evp_shim(kind="hex20", nsub=20, cr="evp"):
+def _evp_shim(kind="hex20", nsub=20, cr="evp", lib_path=None):
     from mpas_seaice_b200 import host
     mesh, var = common.mesh_case(kind)
     step, opts = common.step_case(mesh, constitutive_relation_type=cr)
@@ -151,7 +151,7 @@ def _evp_shim(kind="hex20", nsub=20, cr="evp"):
     I.resolve_constants()
     I.noop |= {"seaice_set_special_boundaries_velocity_masks"}
     I.globals["mpas_log_crit"] = 3
-    bridge = CBridge(I, C.CDLL(host.LIB_PATH))
+    bridge = CBridge(I, C.CDLL(lib_path or host.LIB_PATH))
     bridge.log = []
 
     def c_f_pointer(interp, fr, args):            # call c_f_pointer(cptr, fptr, [n]): the C string as a character array
@@ -211,8 +211,8 @@ def test_evp_shim_executed_against_the_cuda_library(evp_lib, kind, cr):
     """The shim's own create -> update -> subcycle (evp_set_options, evp_update_step, evp_run_subcycles, evp_fetch into the
     pool arrays) -> destroy, from the pools of a synthetic step; the pool arrays afterwards hold the oracle's results."""
     nsub = 20
-    I, bridge, domain, mesh, var, step, opts, work = _evp_shim(kind, nsub, cr)
-    I.call("seaice_evp_b200_create", domain)
+    I, bridge, domain, mesh, var, step, opts, work = _evp_shim(kind, nsub, cr, lib_path=evp_lib._name)   # (the CUDA build, or
+    I.call("seaice_evp_b200_create", domain)                                                            # its host emulation)
     I.call("seaice_evp_b200_update", domain)
     I.call("seaice_evp_b200_subcycle", domain)
     assert [n for n, _ in bridge.returns] == ["evp_create", "evp_set_options", "evp_update_step", "evp_run_subcycles", "evp_fetch"]
