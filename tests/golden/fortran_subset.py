@@ -544,7 +544,7 @@ INTRINSICS = {
     "sign": lambda a, b: math.copysign(abs(a), b) if isinstance(a, float) or isinstance(b, float) else (abs(a) if b >= 0 else -abs(a)),
     "mod": lambda a, b: math.fmod(a, b) if isinstance(a, float) else int(math.fmod(a, b)),
     "modulo": lambda a, b: a - b * math.floor(a / b) if isinstance(a, float) or isinstance(b, float) else a % b,
-    "real": lambda a, *k: float(a), "dble": float, "int": lambda a, *k: int(a), "nint": lambda a: int(round(a)),
+    "real": lambda a, *k: float(a), "dble": float, "int": lambda a, *k: int(a), "nint": lambda a: int(math.floor(abs(a) + 0.5)) * (1 if a >= 0 else -1),      # half away from zero (not Python's round)
     "sin": math.sin, "cos": math.cos, "tan": math.tan, "asin": math.asin, "acos": math.acos, "atan": math.atan,
     "atan2": math.atan2, "exp": math.exp, "log": math.log, "sum": _sum, "size": _size, "trim": lambda s: s.rstrip(),
 }

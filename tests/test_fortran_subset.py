@@ -45,6 +45,11 @@ def test_expression_semantics():
     assert _eval("sqrt(a*a + (b*b + c*c) / 4.0_RKIND)", a=a, b=b, c=c) == math.sqrt(a * a + (b * b + c * c) / 4.0)
     assert _eval("a > b .or. .not. (a >= b) .and. c == c", a=a, b=b, c=c) is True
     assert _eval("a .lt. b", a=a, b=b) is True and _eval("a /= b", a=a, b=b) is True
+    assert _eval("nint(x)", x=2.5) == 3 and _eval("nint(x)", x=-2.5) == -3 and _eval("nint(x)", x=0.49) == 0   # half away from zero
+    assert _eval("int(x)", x=-2.7) == -2 and _eval("mod(-7, 3)") == -1 and _eval("modulo(-7, 3)") == 2      # sign of the dividend / divisor
+    assert _eval("mod(x, 2.0_RKIND)", x=-5.5) == -1.5 and _eval("real(7, RKIND) / 2") == 3.5
+    assert _eval("abs(x)", x=-0.0) == 0.0 and math.copysign(1.0, _eval("abs(x)", x=-0.0)) == 1.0
+    assert _eval("merge(a, b, a > b)", a=a, b=b) == b
     # a sum written on one line is added left to right: not the same bits as another association
     x = [1.0e16, 1.0, -1.0e16, 1.0]
     assert _eval("p + q + r + s", p=x[0], q=x[1], r=x[2], s=x[3]) == ((x[0] + x[1]) + x[2]) + x[3] == 1.0
