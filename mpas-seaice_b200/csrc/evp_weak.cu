@@ -240,8 +240,9 @@ extern "C" int evp_set_weak_mesh(evp_handle *h, const evp_weak_mesh *m)
         {(void **)&d.eV12, sizeof(double) * nVp}};
     for (auto &x : state) {
         if ((rc = evp_dev_alloc(h, x.p, x.bytes))) return rc;
-        EVP_CUDA(cudaMemset(*x.p, 0, x.bytes));
+        EVP_CUDA(cudaMemsetAsync(*x.p, 0, x.bytes, h->stream));
     }
+    EVP_CUDA(cudaStreamSynchronize(h->stream));
     d.wRadius = m->sphere_radius == 0.0 ? 1.0 : m->sphere_radius;
     h->haveWeak = true;
     return EVP_OK;
@@ -257,13 +258,15 @@ extern "C" int evp_update_weak_state(evp_handle *h, const evp_weak_fields *f)
     const size_t nC = h->nCells, nCp = h->nCp;
     std::vector<double2> s(nCp, make_double2(0.0, 0.0));
     for (size_t c = 0; c < nC; c++) s[c] = make_double2(f->stress11Weak[c], f->stress22Weak[c]);
-    EVP_CUDA(cudaStreamSynchronize(h->stream));
-    EVP_CUDA(cudaMemcpy(d.sigW, s.data(), sizeof(double2) * nCp, cudaMemcpyHostToDevice));
-    if (nC) EVP_CUDA(cudaMemcpy(d.sigW12, f->stress12Weak, sizeof(double) * nC, cudaMemcpyHostToDevice));
+    // everything on the handle's stream (a non-blocking stream is not ordered after the legacy default stream), then one
+    // synchronisation before the staging vector goes out of scope
+    EVP_CUDA(cudaMemcpyAsync(d.sigW, s.data(), sizeof(double2) * nCp, cudaMemcpyHostToDevice, h->stream));
+    if (nC) EVP_CUDA(cudaMemcpyAsync(d.sigW12, f->stress12Weak, sizeof(double) * nC, cudaMemcpyHostToDevice, h->stream));
     // init_subcycle_variables, weak branch (velocity_solver.F:2350-2365): strains start from zero
-    EVP_CUDA(cudaMemset(d.eW11, 0, sizeof(double) * nCp));
-    EVP_CUDA(cudaMemset(d.eW22, 0, sizeof(double) * nCp));
-    EVP_CUDA(cudaMemset(d.eW12, 0, sizeof(double) * nCp));
+    EVP_CUDA(cudaMemsetAsync(d.eW11, 0, sizeof(double) * nCp, h->stream));
+    EVP_CUDA(cudaMemsetAsync(d.eW22, 0, sizeof(double) * nCp, h->stream));
+    EVP_CUDA(cudaMemsetAsync(d.eW12, 0, sizeof(double) * nCp, h->stream));
+    EVP_CUDA(cudaStreamSynchronize(h->stream));
     return EVP_OK;
 }
 
