@@ -333,8 +333,19 @@ STEP_CASES = {
     # dynamically_locked_cell_mask (:402-467) run first, the calculation masks (:1023, :1131) then leave the patch out
     "refexec_step_ico2_landice_3": ("ico2", "B", 3600.0, 3, 1, dict(land_ice=True)),
     "refexec_step_hex12_landice_3": ("hex12", "square", 3600.0, 3, 1, dict(land_ice=True)),
+    # the other namelist options of the subcycle, carried through a WHOLE step (pre-subcycle -> subcycles -> post-subcycle):
+    # revised EVP (init_subcycle_variables' uVelocityInitial feeds solve_velocity_revised), linear ocean drag with
+    # averaged variational strains (seaice_average_strains_on_vertex between strain and stress, the final
+    # divergence / shear from the unaveraged strains)
+    "refexec_step_ico2_revised_4": ("ico2", "B", 3600.0, 4, 1, dict(opts=dict(constitutive_relation_type="evp_revised"))),
+    "refexec_step_hex12_lineardrag_avg_4": ("hex12", "square", 3600.0, 4, 1,
+                                            dict(opts=dict(ocean_stress_type="linear", average_variational_strain=True))),
+    # config_use_ocean_stress = false through the whole step (ocean_stress :1849, ocean_stress_coefficient :3021,
+    # ocean_stress_final :3700 all take their 'off' branch), three categories
+    "refexec_step_ico2_no_ocean_stress_3cat_3": ("ico2", "B", 3600.0, 3, 3, dict(opts=dict(use_ocean_stress=False))),
 }
-STEP_CPU_ONLY = ("refexec_step_ico2_landice_3", "refexec_step_hex12_landice_3")
+STEP_CPU_ONLY = ("refexec_step_ico2_landice_3", "refexec_step_hex12_landice_3", "refexec_step_ico2_revised_4",
+                 "refexec_step_hex12_lineardrag_avg_4", "refexec_step_ico2_no_ocean_stress_3cat_3")
 STEP_OUT = {
     "velocity_solver": ("solveStress", "solveVelocity", "solveVelocityPrevious", "icePressure", "airStressCellU", "airStressCellV",
                         "uVelocity", "vVelocity", "uVelocityInitial", "vVelocityInitial", "stressDivergenceU", "stressDivergenceV",
@@ -377,6 +388,7 @@ def build_step(name):
     sw = dict(use_air_stress=True, use_surface_tilt=True, geostrophic_surface_tilt=True)
     sw.update(STEP_CASES[name][5] if len(STEP_CASES[name]) > 5 else {})
     land_ice = bool(sw.pop("land_ice", False))
+    opt_over = dict(sw.pop("opts", {}))
     mesh, var = common.mesh_case(kind)
     later = []
     if state_kind.startswith("caps:"):
@@ -394,8 +406,9 @@ def build_step(name):
         cat, later = seq[0], seq[1:]
     else:
         state, cat = step_state(mesh, state_kind, n_cat)
-    _, opts = common.step_case(mesh)                      # elasticTimeStep, dampingTimescale ... as seaice_init_evp sets them
-    opts = dict(opts)
+    cr = opt_over.get("constitutive_relation_type", "evp")
+    _, opts = common.step_case(mesh, constitutive_relation_type=cr)   # elasticTimeStep, dampingTimescale ... as seaice_init_evp sets them
+    opts = dict(opts, **opt_over)
     nC, nV, M, D = mesh.nCells, mesh.nVertices, mesh.maxEdges, mesh.vertexDegree
     I = F.Interpreter(defined=())
     for f in STEP_FILES:
@@ -469,7 +482,7 @@ def build_step(name):
         I.globals[k.lower()] = v
     I.pool.update(config_use_halo_exch=False, config_aggregate_halo_exch=False, config_reuse_halo_exch=False,
                   config_use_column_package=False, config_use_column_vertical_thermodynamics=False,
-                  config_use_air_stress=bool(sw["use_air_stress"]), config_use_ocean_stress=True,
+                  config_use_air_stress=bool(sw["use_air_stress"]), config_use_ocean_stress=bool(opts.get("use_ocean_stress", True)),
                   config_use_surface_tilt=bool(sw["use_surface_tilt"]),
                   config_geostrophic_surface_tilt=bool(sw["geostrophic_surface_tilt"]), config_calc_velocity_masks=True,
                   config_stress_divergence_scheme="variational", config_strain_scheme="variational",
@@ -479,9 +492,9 @@ def build_step(name):
     g = I.globals
     g["strainschemetype"] = g["variational_strain_scheme"]
     g["stressdivergenceschemetype"] = g["variational_stress_divergence_scheme"]
-    g["averagevariationalstrains"] = False
-    g["oceanstresstype"] = g["quadratic_ocean_stress"]
-    g["constitutiverelationtype"] = g["evp_constitutive_relation"]
+    g["averagevariationalstrains"] = bool(opts.get("average_variational_strain", False))
+    g["oceanstresstype"] = g[{"quadratic": "quadratic_ocean_stress", "linear": "linear_ocean_stress"}[opts.get("ocean_stress_type", "quadratic")]]
+    g["constitutiverelationtype"] = g[{"evp": "evp_constitutive_relation", "evp_revised": "revised_evp_constitutive_relation"}[cr]]
     g["usespecialboundariesvelocity"] = False
     g["usespecialboundariesvelocitymasks"] = False
     g["dampingtimescale"] = float(opts["dampingTimescale"])

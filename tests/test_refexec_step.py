@@ -141,7 +141,8 @@ def _oracle_step(mesh, var, opts, cat, forcing, pre, out, nsub, config_dt, prev)
     for k, got in (("iceAreaCell", a), ("iceVolumeCell", vi), ("snowVolumeCell", vs), ("totalMassCell", mass)):
         assert np.array_equal(got[:nC], pre[k][:nC]), k
     state = dict(forcing, iceAreaCell=a, iceVolumeCell=vi, snowVolumeCell=vs)
-    step = oracle.pre_subcycle(mesh, state, config_dt, prev=prev, **opts["_switches"])
+    step = oracle.pre_subcycle(mesh, state, config_dt, prev=prev, use_ocean_stress=bool(opts.get("use_ocean_stress", True)),
+                               **opts["_switches"])
     vm = pre["solveVelocity"][:nV] == 1
     assert vm.any() and (pre["solveStress"][:nC] == 1).any()
     for k in ("solveStress", "icePressure"):
@@ -166,7 +167,8 @@ def _oracle_step(mesh, var, opts, cat, forcing, pre, out, nsub, config_dt, prev)
     for k in POST_VERTEX:
         assert np.array_equal(got[k][:nV][vm], out[k][:nV][vm]), k
     assert np.abs(out["uVelocity"][:nV][vm]).max() > 0 and np.abs(out["divergence"][:nC]).max() > 0
-    assert np.abs(out["oceanStressCellU"][:nC]).max() > 0 and np.abs(out["stress11"][:nC][cm]).max() > 0
+    assert np.abs(out["stress11"][:nC][cm]).max() > 0
+    assert (np.abs(out["oceanStressCellU"][:nC]).max() > 0) == bool(opts.get("use_ocean_stress", True))
     # vertices that lost their ice are zeroed by the reference (new_ice_velocities :1262-1270): compare everywhere
     assert np.array_equal(step["uVelocity"][:nV][~vm], out["uVelocity"][:nV][~vm])
     return dict(uVelocity=step["uVelocity"], vVelocity=step["vVelocity"], stress11=step["stress11"], stress22=step["stress22"],

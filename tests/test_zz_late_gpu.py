@@ -6,6 +6,7 @@ have not run on a B200 yet.
 * Ice shelves: two whole steps with landIceMask = 1 on a patch of the ice cover (refexec_step_*_landice_3.npz;
   init_ice_shelve_vertex_mask velocity_solver.F:481-544, the calculation masks :1023 / :1131) through
   evp_set_mesh_ext(landIceMaskVertex) and evp_pre_subcycle(landIceMask).
+* Whole steps under the subcycle's other namelist options (revised EVP; linear drag with averaged strains).
 * The quadrature rules added late ('fekete', dunavant order 12: refexec_init_*.npz): evp_precompute_wachspress with
   integrationType 2 / order 12 -- the kernel is the one the other rules run, only the constant tables differ, and
   those are checked against the reference's without a GPU in tests/test_quadrature_rules.py."""
@@ -42,6 +43,24 @@ def test_device_reproduces_the_reference_executed_step_with_ice_shelves(evp_lib,
         solver.destroy()
     lv = land_vertex[:mesh.nVertices] == 1
     assert lv.any() and not pre["solveVelocity"][:mesh.nVertices][lv].any()
+
+
+OPTION_FILES = [f for f in sorted(glob.glob(os.path.join(HERE, "golden", "cpu", "refexec_step_*.npz"))) if "landice" not in f]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", OPTION_FILES, ids=[os.path.basename(f)[13:-4] for f in OPTION_FILES])
+def test_device_reproduces_the_reference_executed_step_with_other_options(evp_lib, path):
+    """Whole steps under revised EVP and under linear drag + averaged variational strains (refexec_step_ico2_revised_4,
+    refexec_step_hex12_lineardrag_avg_4): evp_aggregate -> evp_pre_subcycle -> evp_run_subcycles -> evp_post_subcycle."""
+    from mpas_seaice_b200 import host
+    mesh, var, opts, cat, forcing, pre, out, nsub, config_dt, _ = _load(path)
+    solver = host.EvpSolver(mesh, var, {k: v for k, v in opts.items() if not k.startswith("_")})
+    solver.set_mesh_ext(mesh, variational_init.interior_vertex(mesh))
+    try:
+        _device_step(solver, host, mesh, cat, forcing, pre, out, nsub, host.START_FIRST_STEP, opts["_switches"])
+    finally:
+        solver.destroy()
 
 
 @pytest.mark.gpu
