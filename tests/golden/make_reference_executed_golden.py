@@ -342,10 +342,15 @@ STEP_CASES = {
                                             dict(opts=dict(ocean_stress_type="linear", average_variational_strain=True))),
     # config_use_ocean_stress = false through the whole step (ocean_stress :1849, ocean_stress_coefficient :3021,
     # ocean_stress_final :3700 all take their 'off' branch), three categories
+    # the weak operators through the whole step: init_subcycle_variables' weak branch (:2350-2365), the weak subcycle,
+    # seaice_final_divergence_shear_weak (weak.F:651-751) and the weak principal stresses (:3500-3515)
+    "refexec_step_ico2_weak_4": ("ico2", "B", 3600.0, 4, 1, dict(opts=dict(strain_scheme="weak", stress_divergence_scheme="weak"))),
+    "refexec_step_hex12_weak_3": ("hex12", "square", 3600.0, 3, 1, dict(opts=dict(strain_scheme="weak", stress_divergence_scheme="weak"))),
     "refexec_step_ico2_no_ocean_stress_3cat_3": ("ico2", "B", 3600.0, 3, 3, dict(opts=dict(use_ocean_stress=False))),
 }
 STEP_CPU_ONLY = ("refexec_step_ico2_landice_3", "refexec_step_hex12_landice_3", "refexec_step_ico2_revised_4",
-                 "refexec_step_hex12_lineardrag_avg_4", "refexec_step_ico2_no_ocean_stress_3cat_3")
+                 "refexec_step_hex12_lineardrag_avg_4", "refexec_step_ico2_no_ocean_stress_3cat_3",
+                 "refexec_step_ico2_weak_4", "refexec_step_hex12_weak_3")
 STEP_OUT = {
     "velocity_solver": ("solveStress", "solveVelocity", "solveVelocityPrevious", "icePressure", "airStressCellU", "airStressCellV",
                         "uVelocity", "vVelocity", "uVelocityInitial", "vVelocityInitial", "stressDivergenceU", "stressDivergenceV",
@@ -411,7 +416,8 @@ def build_step(name):
     opts = dict(opts, **opt_over)
     nC, nV, M, D = mesh.nCells, mesh.nVertices, mesh.maxEdges, mesh.vertexDegree
     I = F.Interpreter(defined=())
-    for f in STEP_FILES:
+    is_weak = opts.get("strain_scheme", "variational") == "weak"
+    for f in STEP_FILES[:-1] + (("src/shared/mpas_seaice_velocity_solver_weak.F",) if is_weak else ()) + STEP_FILES[-1:]:
         I.load(os.path.join(REF, f))
     I.resolve_constants()
     I.noop |= {"mpas_timer_start", "mpas_timer_stop", "mpas_log_write", "seaice_load_balance_timers", "mpas_dmpar_field_halo_exch",
@@ -476,6 +482,15 @@ def build_step(name):
         I.pool.setdefault(k, fa)
         if pool != "velocity_weak":
             I.globals[k.lower()] = fa                  # seaice_mesh_pool's module pointers
+    if is_weak:
+        from mpas_seaice_b200 import weakmesh
+        weak = weakmesh.weak_fields(mesh)          # INPUTS: the velocity_weak pool's static arrays (seaice_normal_vectors)
+        for k in WEAK_STATIC:
+            I.pool[k] = F.FArray(weak[k])
+        for k in WEAK_STATE[7:]:
+            I.pool[("velocity_weak_variational", k)] = F.FArray(zv())
+        I.pool.update(nEdges=int(mesh.nEdges), on_a_sphere=bool(mesh.on_a_sphere),
+                      sphere_radius=float(getattr(mesh, "sphere_radius", 0.0) or 0.0))
     dims = dict(nCells=nC, nVertices=nV, nVerticesSolve=nV, nCellsSolve=nC, vertexDegree=D, maxEdges=M, nCategories=n_cat)
     I.pool.update(dims)
     for k, v in dims.items():
@@ -485,13 +500,14 @@ def build_step(name):
                   config_use_air_stress=bool(sw["use_air_stress"]), config_use_ocean_stress=bool(opts.get("use_ocean_stress", True)),
                   config_use_surface_tilt=bool(sw["use_surface_tilt"]),
                   config_geostrophic_surface_tilt=bool(sw["geostrophic_surface_tilt"]), config_calc_velocity_masks=True,
-                  config_stress_divergence_scheme="variational", config_strain_scheme="variational",
+                  config_stress_divergence_scheme=str(opts.get("stress_divergence_scheme", "variational")),
+                  config_strain_scheme=str(opts.get("strain_scheme", "variational")),
                   config_elastic_subcycle_number=int(nsub), config_use_special_boundaries_velocity=False,
                   config_use_special_boundaries_velocity_masks=False,
                   elasticTimeStep=float(opts["elasticTimeStep"]), dynamicsTimeStep=float(opts["dynamicsTimeStep"]))
     g = I.globals
-    g["strainschemetype"] = g["variational_strain_scheme"]
-    g["stressdivergenceschemetype"] = g["variational_stress_divergence_scheme"]
+    g["strainschemetype"] = g[opts.get("strain_scheme", "variational") + "_strain_scheme"]
+    g["stressdivergenceschemetype"] = g[opts.get("stress_divergence_scheme", "variational") + "_stress_divergence_scheme"]
     g["averagevariationalstrains"] = bool(opts.get("average_variational_strain", False))
     g["oceanstresstype"] = g[{"quadratic": "quadratic_ocean_stress", "linear": "linear_ocean_stress"}[opts.get("ocean_stress_type", "quadratic")]]
     g["constitutiverelationtype"] = g[{"evp": "evp_constitutive_relation", "evp_revised": "revised_evp_constitutive_relation"}[cr]]
@@ -537,6 +553,10 @@ def build_step(name):
     for pool, names in STEP_OUT.items():
         for k in names:
             data["out_" + k] = P[(pool, k)].copy()
+    if is_weak:
+        for k in ("strain11", "strain22", "strain12", "stress11", "stress22", "stress12", "replacementPressure", "principalStress1",
+                  "principalStress2"):
+            data["out_" + k + "Weak"] = P[("velocity_weak", k)].copy()
     for n_step, c in enumerate(later, 2):              # further steps: new tracers in, the dynamic state carried in the pools
         for k, a in c.items():
             P[("tracers", k)][...] = a

@@ -87,7 +87,13 @@ def test_fixtures_exist_and_name_the_routines_that_ran():
         assert name in seen, name
 
 
-@pytest.mark.parametrize("path", FILES + CPU_FILES, ids=IDS + CPU_IDS)
+WEAK_FILES = [f for f in CPU_FILES if "_weak_" in os.path.basename(f)]
+WEAK_IDS = [os.path.basename(f)[13:-4] for f in WEAK_FILES]
+WEAK_CELL = ("stress11Weak", "stress22Weak", "stress12Weak", "strain11Weak", "strain22Weak", "strain12Weak", "replacementPressureWeak")
+
+
+@pytest.mark.parametrize("path", [f for f in FILES + CPU_FILES if f not in WEAK_FILES],
+                         ids=[i for i in IDS + CPU_IDS if i not in WEAK_IDS])
 def test_oracle_reproduces_the_reference_executed_step(path):
     mesh, var, opts, cat, forcing, pre, out, nsub, config_dt, _ = _load(path)
     prev = _first_step_prev(mesh)
@@ -190,6 +196,70 @@ def test_device_reproduces_the_reference_executed_step(evp_lib, path):
             _device_step(solver, host, mesh, cat, forcing, pre, out, nsub, start, opts["_switches"])
     finally:
         solver.destroy()
+
+
+def _oracle_pre(mesh, opts, cat, forcing, pre, config_dt, prev):
+    nC, nV = mesh.nCells, mesh.nVertices
+    a, vi, vs, mass = oracle.aggregate_mass_and_area(cat["iceAreaCategory"][:, :, 0], cat["iceVolumeCategory"][:, :, 0],
+                                                     cat["snowVolumeCategory"][:, :, 0])
+    state = dict(forcing, iceAreaCell=a, iceVolumeCell=vi, snowVolumeCell=vs)
+    step = oracle.pre_subcycle(mesh, state, config_dt, prev=prev, use_ocean_stress=bool(opts.get("use_ocean_stress", True)),
+                               **opts["_switches"])
+    vm = pre["solveVelocity"][:nV] == 1
+    assert vm.any() and (pre["solveStress"][:nC] == 1).any()
+    for k in ("solveStress", "icePressure"):
+        assert np.array_equal(step[k][:nC], pre[k][:nC]), k
+    for k in PRE_VERTEX_ALL + ("solveVelocityPrevious",):
+        assert np.array_equal(step[k][:nV], pre[k][:nV]), k
+    for k in PRE_VERTEX_SOLVED:
+        assert np.array_equal(step[k][:nV][vm], pre[k][:nV][vm]), k
+    return step, vm
+
+
+def _weak_post_oracle(mesh, step):
+    """seaice_final_divergence_shear_weak (weak.F:651-751) and the weak branch of principal_stresses
+    (velocity_solver.F:3500-3515) from the oracle's weak state"""
+    nC = mesh.nCells
+    L = oracle.lib()
+    want = {k: np.zeros(nC + 1) for k in ("divergence", "shear", "ridgeConvergence", "ridgeShear", "principalStress1Weak",
+                                          "principalStress2Weak")}
+    L.orc_final_divergence_shear_weak(nC, oracle._p(step["strain11Weak"]), oracle._p(step["strain22Weak"]),
+                                      oracle._p(step["strain12Weak"]), oracle._p(want["divergence"]), oracle._p(want["shear"]),
+                                      oracle._p(want["ridgeConvergence"]), oracle._p(want["ridgeShear"]))
+    one = np.ones(nC + 1, dtype=np.int32)
+    L.orc_principal_stresses_variational(nC, 1, oracle._p(one), oracle._p(step["stress11Weak"]), oracle._p(step["stress22Weak"]),
+                                         oracle._p(step["stress12Weak"]), oracle._p(step["replacementPressureWeak"]),
+                                         oracle._p(want["principalStress1Weak"]), oracle._p(want["principalStress2Weak"]))
+    return want
+
+
+@pytest.mark.parametrize("path", WEAK_FILES, ids=WEAK_IDS)
+def test_oracle_reproduces_the_reference_executed_weak_step(path):
+    """config_strain_scheme = config_stress_divergence_scheme = 'weak' through a whole step: the pre-subcycle (its
+    weak init_subcycle_variables branch), the weak subcycles, seaice_final_divergence_shear_weak, the weak principal
+    stresses and ocean_stress_final, against the arrays the reference's statements wrote."""
+    from mpas_seaice_b200 import weakmesh
+    mesh, var, opts, cat, forcing, pre, out, nsub, config_dt, prov = _load(path)
+    for name in ("seaice_strain_tensor_weak", "seaice_stress_tensor_weak", "seaice_stress_divergence_weak",
+                 "seaice_final_divergence_shear_weak", "init_subcycle_variables", "principal_stresses"):
+        assert name in prov, name
+    nC, nV = mesh.nCells, mesh.nVertices
+    step, vm = _oracle_pre(mesh, opts, cat, forcing, pre, config_dt, _first_step_prev(mesh))
+    oracle.subcycle_velocity_solver(mesh, dict(var, weak=weakmesh.weak_fields(mesh)), step, opts, nsub)
+    want = _weak_post_oracle(mesh, step)
+    osu, osv, ocu, ocv, coef = oracle.ocean_stress_final(mesh, step, opts, variational_init.interior_vertex(mesh))
+    for k in WEAK_CELL:
+        assert np.array_equal(step[k][:nC], out[k][:nC]), k
+    for k in ("divergence", "shear", "ridgeConvergence", "ridgeShear", "principalStress1Weak", "principalStress2Weak"):
+        assert np.array_equal(want[k][:nC], out[k][:nC]), k
+    for k, got in (("uVelocity", step["uVelocity"]), ("vVelocity", step["vVelocity"]), ("oceanStressU", osu), ("oceanStressV", osv),
+                   ("oceanStressCoeff", coef), ("stressDivergenceU", step["stressDivergenceU"]),
+                   ("stressDivergenceV", step["stressDivergenceV"])):
+        assert np.array_equal(got[:nV][vm], out[k][:nV][vm]), k
+    for k, got in (("oceanStressCellU", ocu), ("oceanStressCellV", ocv)):
+        assert np.array_equal(got[:nC], out[k][:nC]), k
+    assert np.abs(out["stress12Weak"][:nC]).max() > 0 and np.abs(out["ridgeShear"][:nC]).max() > 0
+    assert not out["stress11"].any()                    # the variational pool is not touched by a weak run
 
 
 def _device_step(solver, host, mesh, cat, forcing, pre, out, nsub, start, switches):

@@ -6,7 +6,8 @@ have not run on a B200 yet.
 * Ice shelves: two whole steps with landIceMask = 1 on a patch of the ice cover (refexec_step_*_landice_3.npz;
   init_ice_shelve_vertex_mask velocity_solver.F:481-544, the calculation masks :1023 / :1131) through
   evp_set_mesh_ext(landIceMaskVertex) and evp_pre_subcycle(landIceMask).
-* Whole steps under the subcycle's other namelist options (revised EVP; linear drag with averaged strains).
+* Whole steps under the subcycle's other namelist options (revised EVP; linear drag with averaged strains; no ocean
+  stress) and with the weak operators (pre-subcycle, weak subcycles, weak post-subcycle).
 * The quadrature rules added late ('fekete', dunavant order 12: refexec_init_*.npz): evp_precompute_wachspress with
   integrationType 2 / order 12 -- the kernel is the one the other rules run, only the constant tables differ, and
   those are checked against the reference's without a GPU in tests/test_quadrature_rules.py."""
@@ -19,6 +20,7 @@ import pytest
 from mpas_seaice_b200 import variational_init
 import oracle
 import test_refexec_init
+import test_refexec_step
 from test_refexec_step import _load, _device_step
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -45,7 +47,8 @@ def test_device_reproduces_the_reference_executed_step_with_ice_shelves(evp_lib,
     assert lv.any() and not pre["solveVelocity"][:mesh.nVertices][lv].any()
 
 
-OPTION_FILES = [f for f in sorted(glob.glob(os.path.join(HERE, "golden", "cpu", "refexec_step_*.npz"))) if "landice" not in f]
+OPTION_FILES = [f for f in sorted(glob.glob(os.path.join(HERE, "golden", "cpu", "refexec_step_*.npz")))
+                if "landice" not in f and f not in test_refexec_step.WEAK_FILES]
 
 
 @pytest.mark.gpu
@@ -61,6 +64,54 @@ def test_device_reproduces_the_reference_executed_step_with_other_options(evp_li
         _device_step(solver, host, mesh, cat, forcing, pre, out, nsub, host.START_FIRST_STEP, opts["_switches"])
     finally:
         solver.destroy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", test_refexec_step.WEAK_FILES, ids=test_refexec_step.WEAK_IDS)
+def test_device_reproduces_the_reference_executed_weak_step(evp_lib, path):
+    """The weak operators through a whole step on the device (refexec_step_*_weak_*.npz): evp_aggregate, evp_pre_subcycle
+    (weak branch of init_subcycle_variables), the weak subcycles, evp_post_subcycle (seaice_final_divergence_shear_weak,
+    the weak principal stresses, ocean_stress_final) against the arrays the reference's own statements wrote."""
+    from mpas_seaice_b200 import host, weakmesh
+    mesh, var, opts, cat, forcing, pre, out, nsub, config_dt, _ = _load(path)
+    nC, nV = mesh.nCells, mesh.nVertices
+    solver = host.EvpSolver(mesh, var, {k: v for k, v in opts.items() if not k.startswith("_")})
+    try:
+        solver.set_mesh_ext(mesh, variational_init.interior_vertex(mesh))
+        solver.set_weak_mesh(mesh, weakmesh.weak_fields(mesh))
+        solver.aggregate(cat["iceAreaCategory"][:, :, 0].copy(), cat["iceVolumeCategory"][:, :, 0].copy(),
+                         cat["snowVolumeCategory"][:, :, 0].copy(), hibler_strength=True)
+        agg = solver.fetch_aggregate(ice_pressure=True)
+        for k in ("iceAreaCell", "iceVolumeCell", "snowVolumeCell", "totalMassCell"):
+            assert np.array_equal(agg[k][:nC], pre[k][:nC]), k
+        # exp() of the Hibler strength: the device's to 1 ulp of libm's, the step continues from the libm value
+        p_host = oracle.hibler_strength_unmasked(dict(iceAreaCell=agg["iceAreaCell"], iceVolumeCell=agg["iceVolumeCell"]), nC)
+        assert np.all(np.abs(agg["icePressure"][:nC] - p_host[:nC]) <= np.spacing(np.abs(p_host[:nC])))
+        cells = dict(forcing, iceAreaCellInitial=agg["iceAreaCell"], iceAreaCell=agg["iceAreaCell"],
+                     totalMassCell=agg["totalMassCell"], icePressure=p_host)
+        solver.pre_subcycle(cells, cold_start=host.START_FIRST_STEP, **opts["_switches"])
+        got_pre = solver.fetch_pre()
+        vm = pre["solveVelocity"][:nV] == 1
+        assert np.array_equal(got_pre["solveStress"][:nC], pre["solveStress"][:nC])
+        assert np.array_equal(got_pre["solveVelocity"][:nV], pre["solveVelocity"][:nV])
+        for k in ("totalMassVertexfVertex", "airStressVertexU", "airStressVertexV", "surfaceTiltForceU", "surfaceTiltForceV",
+                  "oceanStressU", "oceanStressV", "uVelocityInitial", "vVelocityInitial"):
+            assert np.array_equal(got_pre[k][:nV][vm], pre[k][:nV][vm]), k
+        solver.run_subcycles(nsub)
+        got = solver.post_subcycle(names=("uVelocity", "vVelocity", "divergence", "shear", "ridgeConvergence", "ridgeShear",
+                                          "oceanStressCellU", "oceanStressCellV", "oceanStressU", "oceanStressV",
+                                          "oceanStressCoeff", "principalStress1Weak", "principalStress2Weak"))
+        wk = solver.fetch_weak()
+    finally:
+        solver.destroy()
+    for k in test_refexec_step.WEAK_CELL:
+        assert np.array_equal(wk[k][:nC], out[k][:nC]), k
+    for k in ("divergence", "shear", "ridgeConvergence", "ridgeShear", "oceanStressCellU", "oceanStressCellV",
+              "principalStress1Weak", "principalStress2Weak"):
+        assert np.array_equal(got[k][:nC], out[k][:nC]), k
+    for k in ("uVelocity", "vVelocity", "oceanStressU", "oceanStressV", "oceanStressCoeff"):
+        assert np.array_equal(got[k][:nV][vm], out[k][:nV][vm]), k
+    assert np.abs(out["ridgeShear"][:nC]).max() > 0 and np.abs(out["stress12Weak"][:nC]).max() > 0
 
 
 @pytest.mark.gpu
