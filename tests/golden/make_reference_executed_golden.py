@@ -346,11 +346,14 @@ STEP_CASES = {
     # seaice_final_divergence_shear_weak (weak.F:651-751) and the weak principal stresses (:3500-3515)
     "refexec_step_ico2_weak_4": ("ico2", "B", 3600.0, 4, 1, dict(opts=dict(strain_scheme="weak", stress_divergence_scheme="weak"))),
     "refexec_step_hex12_weak_3": ("hex12", "square", 3600.0, 3, 1, dict(opts=dict(strain_scheme="weak", stress_divergence_scheme="weak"))),
+    # weak strains interpolated to the variational stress points (interpolate_strains_weak_to_variational :2877-2972),
+    # variational stress divergence, the variational post-subcycle
+    "refexec_step_ico2_weakvar_3": ("ico2", "B", 3600.0, 3, 1, dict(opts=dict(strain_scheme="weak", stress_divergence_scheme="variational"))),
     "refexec_step_ico2_no_ocean_stress_3cat_3": ("ico2", "B", 3600.0, 3, 3, dict(opts=dict(use_ocean_stress=False))),
 }
 STEP_CPU_ONLY = ("refexec_step_ico2_landice_3", "refexec_step_hex12_landice_3", "refexec_step_ico2_revised_4",
                  "refexec_step_hex12_lineardrag_avg_4", "refexec_step_ico2_no_ocean_stress_3cat_3",
-                 "refexec_step_ico2_weak_4", "refexec_step_hex12_weak_3")
+                 "refexec_step_ico2_weak_4", "refexec_step_hex12_weak_3", "refexec_step_ico2_weakvar_3")
 STEP_OUT = {
     "velocity_solver": ("solveStress", "solveVelocity", "solveVelocityPrevious", "icePressure", "airStressCellU", "airStressCellV",
                         "uVelocity", "vVelocity", "uVelocityInitial", "vVelocityInitial", "stressDivergenceU", "stressDivergenceV",

@@ -157,6 +157,9 @@ def _oracle_step(mesh, var, opts, cat, forcing, pre, out, nsub, config_dt, prev)
         assert np.array_equal(step[k][:nV], pre[k][:nV]), k
     for k in PRE_VERTEX_SOLVED:
         assert np.array_equal(step[k][:nV][vm], pre[k][:nV][vm]), k
+    if opts.get("strain_scheme", "variational") == "weak":     # weak strains, variational stress divergence
+        from mpas_seaice_b200 import weakmesh
+        var = dict(var, weak=weakmesh.weak_fields(mesh))
     oracle.subcycle_velocity_solver(mesh, var, step, opts, nsub)
     interior = variational_init.interior_vertex(mesh)
     ds = oracle.final_divergence_shear(mesh, step)

@@ -61,6 +61,9 @@ def test_device_reproduces_the_reference_executed_step_with_other_options(evp_li
     solver = host.EvpSolver(mesh, var, {k: v for k, v in opts.items() if not k.startswith("_")})
     solver.set_mesh_ext(mesh, variational_init.interior_vertex(mesh))
     try:
+        if opts.get("strain_scheme", "variational") == "weak":
+            from mpas_seaice_b200 import weakmesh
+            solver.set_weak_mesh(mesh, weakmesh.weak_fields(mesh))
         _device_step(solver, host, mesh, cat, forcing, pre, out, nsub, host.START_FIRST_STEP, opts["_switches"])
     finally:
         solver.destroy()
