@@ -47,7 +47,7 @@ QUICK = ("evp_subcycles_match_oracle[hex20,7]", "evp_subcycles_match_oracle[hex8
          "graph_and_stream_paths_agree[hex20]", "average_variational_strain[hex20]", "weak_weak_matches_oracle[evp,hex20]",
          "weak_strain_variational_divergence_matches_oracle[hex20]", "weak_full_dynamics_step", "special_boundaries_velocity",
          "set_masks", "no_ice_anywhere", "host_max_edges", "no_ocean_stress", "pwl_basis_dense", "device_pwl_precompute_bit_exact[hex20]",
-         "device_wachspress_precompute_bit_exact[ico3]", "refexec_step", "refexec_init", "zz_late_gpu", "pre_subcycle_",
+         "device_wachspress_precompute_bit_exact[ico3]", "refexec_step", "refexec_init", "zz_late_gpu.device_", "state_resident[0]", "on_one_handle[1]", "pre_subcycle_",
          "device_aggregate", "random_configurations_match_oracle[1]", "random_configurations_match_oracle[7]",
          "fortran_shim_executed", "golden.")
 SKIP_NAMES = {"test_linearity_of_the_stress_divergence_at_full_size", "test_split_subcycle_counts_at_full_size",
@@ -87,7 +87,7 @@ SMALLEST = ("evp_subcycles_match_oracle[hex20,7]", "namelist_options[hex20,evp_r
             "average_variational_strain[hex20]", "weak_weak_matches_oracle[evp,hex20]",
             "weak_strain_variational_divergence_matches_oracle[hex20]", "special_boundaries_velocity", "no_ice_anywhere",
             "host_max_edges", "device_pwl_precompute_bit_exact[hex20]", "device_wachspress_precompute_bit_exact[ico3]",
-            "refexec_step", "zz_late_gpu", "pre_subcycle_cold_start_matches_oracle[ico4", "random_configurations_match_oracle[7]")
+            "refexec_step", "zz_late_gpu.device_", "state_resident[0]", "on_one_handle[1]", "pre_subcycle_cold_start_matches_oracle[ico4", "random_configurations_match_oracle[7]")
 CASES = _cases()
 if os.environ.get("EVP_EMU_SUBSET") == "quick":
     CASES = [c for c in CASES if any(q in c.id for q in QUICK)]

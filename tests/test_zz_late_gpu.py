@@ -134,3 +134,146 @@ def test_device_precompute_reproduces_the_reference_executed_arrays_of_the_late_
     nC = mesh.nCells
     for k, a in got.items():
         assert np.array_equal(a[:nC], want[k][:nC]), k
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Fuzz of what a handle keeps BETWEEN calls (tile and vertex-block lists, contrib rows, the instantiated graph or the
+# persistent kernel, the resident state): sequences of steps with a different random ice cover each.  200 seeds of each
+# kind ran on the emulated library when these were written (persistent and graph path): all bit-identical.
+# ---------------------------------------------------------------------------------------------------------------------
+def _random_cover(rng, mesh):
+    nC = mesh.nCells
+    mode = rng.integers(0, 5)
+    if mode == 0:                                   # random holes
+        on = rng.uniform(size=nC) < rng.uniform(0.05, 0.95)
+    elif mode == 1:                                 # an ice edge
+        x = mesh.latCell[:nC] if mesh.on_a_sphere else mesh.xCell[:nC] / mesh.xCell[:nC].max()
+        t = rng.uniform(x.min(), x.max())
+        on = x > t if rng.uniform() < 0.5 else x < t
+    elif mode == 2:                                 # a run of cell indices: whole tiles without work
+        lo = int(rng.integers(0, nC))
+        on = np.zeros(nC, bool)
+        on[lo:min(nC, lo + int(rng.integers(1, nC)))] = True
+    elif mode == 3:
+        on = np.ones(nC, bool)
+    else:                                           # a few isolated cells
+        on = np.zeros(nC, bool)
+        on[rng.integers(0, nC, size=int(rng.integers(1, 6)))] = True
+    area = np.where(on, rng.uniform(0.2, 1.0, nC), 0.0)
+    return area, np.where(on, area * rng.uniform(0.2, 3.0, nC), 0.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(4))
+def test_random_ice_cover_sequences_with_the_state_resident(evp_lib, seed):
+    """Five whole steps (evp_pre_subcycle -> evp_run_subcycles -> evp_post_subcycle) on one handle, the ice cover redrawn
+    every step, u / v / stresses / solveVelocityPrevious never re-uploaded; the oracle chain carries them explicitly.
+    Compared on ALL vertices and cells (what new_ice_velocities zeroes, what a cell that lost its ice keeps)."""
+    import test_gpu_prepost as P
+    from mpas_seaice_b200 import host, synthetic
+    rng = np.random.default_rng(7000 + seed)
+    mesh, var = common_mesh(["hex20", "ico3", "quad40", "ico4"][seed % 4])
+    base = P._state(mesh, "B" if mesh.on_a_sphere else "square")
+    nC, nV = mesh.nCells, mesh.nVertices
+    interior = variational_init.interior_vertex(mesh)
+    _, opts = synthetic.pre_subcycle(mesh, base, 3600.0, constitutive_relation_type=str(rng.choice(["evp", "evp_revised"])))
+    opts = dict(opts, ocean_stress_type=str(rng.choice(["quadratic", "linear"])))
+    valid = np.arange(mesh.maxEdges)[None, :] < mesh.nEdgesOnCell[:nC, None]
+    solver = P._solver(mesh, var, opts)
+    prev = None
+    try:
+        for it in range(5):
+            state = dict(base)
+            area, vol = _random_cover(rng, mesh)
+            for k, a in (("iceAreaCell", area), ("iceVolumeCell", vol), ("snowVolumeCell", 0.1 * vol)):
+                z = np.zeros(nC + 1)
+                z[:nC] = a
+                state[k] = z
+            n_sub = int(rng.integers(1, 8))
+            ref_step = oracle.pre_subcycle(mesh, state, 3600.0, prev=prev)
+            solver.pre_subcycle(P._cells(mesh, state), cold_start=(it == 0))
+            got_pre = solver.fetch_pre()
+            for k, n in (("solveStress", nC), ("solveVelocity", nV), ("solveVelocityPrevious", nV)):
+                assert np.array_equal(got_pre[k][:n], ref_step[k][:n]), (it, k)
+            oracle.subcycle_velocity_solver(mesh, var, ref_step, opts, n_sub)
+            solver.run_subcycles(n_sub)
+            ref = P._post_reference(mesh, ref_step, opts, interior)
+            got = solver.post_subcycle(names=host.POST_FIELDS_VARIATIONAL)
+            inner = solver.fetch(names=("stress11", "stress22", "stress12"))
+            vm = ref_step["solveVelocity"][:nV] == 1
+            for k in ("divergence", "shear", "ridgeConvergence", "ridgeShear", "oceanStressCellU", "oceanStressCellV"):
+                assert np.array_equal(got[k][:nC], ref[k][:nC]), (it, k)
+            for k in ("uVelocity", "vVelocity"):
+                assert np.array_equal(got[k][:nV], ref[k][:nV]), (it, k)
+            for k in ("oceanStressU", "oceanStressV", "oceanStressCoeff"):
+                assert np.array_equal(got[k][:nV][vm], ref[k][:nV][vm]), (it, k)
+            for k in ("stress11", "stress22", "stress12"):
+                assert np.array_equal(inner[k][:nC][valid], ref_step[k][:nC][valid]), (it, k)
+            prev = {k: ref_step[k] for k in ("uVelocity", "vVelocity", "stress11", "stress22", "stress12", "solveVelocityPrevious")}
+    finally:
+        solver.destroy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(4))
+def test_random_mask_sequences_on_one_handle(evp_lib, seed):
+    """evp_update_step -> evp_run_subcycles (sometimes split in two calls) -> evp_fetch, five times on one handle with new
+    masks, state and subcycle count each time: nothing a previous step left on the device may show."""
+    from mpas_seaice_b200 import host
+    from test_gpu_parity import _compare
+    import common
+    rng = np.random.default_rng(9000 + seed)
+    mesh, var = common_mesh(["hex20", "quad40", "ico3", "ico4"][seed % 4])
+    state_kind = "auto" if not mesh.on_a_sphere else str(rng.choice(["A", "B"]))
+    base, opts = common.step_case(mesh, state_kind=state_kind, constitutive_relation_type=str(rng.choice(["evp", "evp_revised"])))
+    opts = dict(opts, ocean_stress_type=str(rng.choice(["quadratic", "linear"])),
+                average_variational_strain=bool(rng.uniform() < 0.2))
+    nC, nV = mesh.nCells, mesh.nVertices
+    solver = host.EvpSolver(mesh, var, opts)
+    try:
+        if opts["average_variational_strain"]:
+            solver.set_mesh_ext(mesh, variational_init.interior_vertex(mesh))
+        for it in range(5):
+            step = common.clone_step(base)
+            mode = rng.integers(0, 4)
+            if mode == 0:
+                step["solveStress"][:nC][rng.uniform(size=nC) < rng.uniform(0, 0.9)] = 0
+                step["solveVelocity"][:nV][rng.uniform(size=nV) < rng.uniform(0, 0.9)] = 0
+            elif mode == 1:
+                lo = int(rng.integers(0, nC))
+                keep = np.zeros(nC, bool)
+                keep[lo:min(nC, lo + int(rng.integers(1, nC)))] = True
+                step["solveStress"][:nC][~keep] = 0
+                lo = int(rng.integers(0, nV))
+                keep = np.zeros(nV, bool)
+                keep[lo:min(nV, lo + int(rng.integers(1, nV)))] = True
+                step["solveVelocity"][:nV][~keep] = 0
+            elif mode == 2:
+                if rng.uniform() < 0.3:
+                    step["solveStress"][:] = 0
+                if rng.uniform() < 0.3:
+                    step["solveVelocity"][:] = 0
+            on_v = step["solveVelocity"] == 1
+            step["uVelocity"] = np.where(on_v, rng.uniform(-0.2, 0.2, nV + 1), 0.0)
+            step["vVelocity"] = np.where(on_v, rng.uniform(-0.2, 0.2, nV + 1), 0.0)
+            if "uVelocityInitial" in step:
+                step["uVelocityInitial"], step["vVelocityInitial"] = step["uVelocity"].copy(), step["vVelocity"].copy()
+            on_c = (step["solveStress"] == 1)[:, None]
+            for k in ("stress11", "stress22", "stress12"):
+                step[k] = np.where(on_c, rng.uniform(-500.0, 500.0, step[k].shape), 0.0)
+            n_sub = int(rng.integers(1, 7))
+            ref = common.run_oracle(mesh, var, step, opts, n_sub)
+            solver.update_step(step)
+            first = int(rng.integers(0, n_sub + 1)) if rng.uniform() < 0.5 else n_sub
+            if first:
+                solver.run_subcycles(first)
+            if n_sub - first:
+                solver.run_subcycles(n_sub - first)
+            _compare(mesh, step, ref, solver.fetch())
+    finally:
+        solver.destroy()
+
+
+def common_mesh(kind):
+    import common
+    return common.mesh_case(kind)
