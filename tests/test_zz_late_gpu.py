@@ -274,6 +274,67 @@ def test_random_mask_sequences_on_one_handle(evp_lib, seed):
         solver.destroy()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(4))
+def test_options_switched_on_one_handle(evp_lib, seed):
+    """evp_set_options between the steps of one handle: constitutive relation (evp / evp_revised / linear / none), drag law,
+    ocean stress on / off, averaged strains and the operator schemes (variational, weak, weak strain + variational
+    divergence; the weak mesh is set once) redrawn every step, masks and state too.  104 seeds x 6 steps on the emulated
+    library when this was written: all bit-identical."""
+    import common
+    from mpas_seaice_b200 import host, weakmesh
+    from test_gpu_parity import _compare
+    rng = np.random.default_rng(11000 + seed)
+    mesh, var = common_mesh(["hex20", "quad40", "ico3", "ico4"][seed % 4])
+    weak = weakmesh.weak_fields(mesh)
+    state = "auto" if not mesh.on_a_sphere else str(rng.choice(["A", "B"]))
+    base, opts0 = common.step_case(mesh, state_kind=state)
+    nC, nV = mesh.nCells, mesh.nVertices
+    solver = host.EvpSolver(mesh, var, opts0)
+    try:
+        solver.set_mesh_ext(mesh, variational_init.interior_vertex(mesh))
+        solver.set_weak_mesh(mesh, weak)
+        for it in range(6):
+            cr = str(rng.choice(["evp", "evp_revised", "linear", "none"]))
+            _, o = common.step_case(mesh, state_kind=state, constitutive_relation_type=cr)
+            scheme = [("variational", "variational"), ("weak", "weak"), ("weak", "variational")][int(rng.integers(0, 3))]
+            opts = dict(o, ocean_stress_type=str(rng.choice(["quadratic", "linear"])), use_ocean_stress=bool(rng.uniform() < 0.8),
+                        average_variational_strain=bool(scheme[0] == "variational" and rng.uniform() < 0.3),
+                        strain_scheme=scheme[0], stress_divergence_scheme=scheme[1])
+            step = common.clone_step(base)
+            step["solveStress"][:nC][rng.uniform(size=nC) < rng.uniform(0, 0.5)] = 0
+            step["solveVelocity"][:nV][rng.uniform(size=nV) < rng.uniform(0, 0.5)] = 0
+            on_v = step["solveVelocity"] == 1
+            step["uVelocity"] = np.where(on_v, rng.uniform(-0.2, 0.2, nV + 1), 0.0)
+            step["vVelocity"] = np.where(on_v, rng.uniform(-0.2, 0.2, nV + 1), 0.0)
+            step["uVelocityInitial"], step["vVelocityInitial"] = step["uVelocity"].copy(), step["vVelocity"].copy()
+            on_c = step["solveStress"] == 1
+            for k in ("stress11", "stress22", "stress12"):
+                step[k] = np.where(on_c[:, None], rng.uniform(-500.0, 500.0, step[k].shape), 0.0)
+            if scheme[0] == "weak":
+                for k in ("stress11Weak", "stress22Weak", "stress12Weak"):
+                    step[k] = np.where(on_c, rng.uniform(-500.0, 500.0, nC + 1), 0.0)
+            n_sub = int(rng.integers(1, 6))
+            ref = common.run_oracle(mesh, dict(var, weak=weak), step, opts, n_sub)
+            solver.set_options(opts)
+            solver.update_step(step)
+            if scheme[0] == "weak":
+                solver.update_weak_state({k: step[k] for k in ("stress11Weak", "stress22Weak", "stress12Weak")})
+            solver.run_subcycles(n_sub)
+            out = solver.fetch()
+            if scheme == ("weak", "weak"):
+                wk = solver.fetch_weak()
+                _, vm = common.masks_for(mesh, step)
+                for k in ("uVelocity", "vVelocity"):
+                    assert np.array_equal(out[k][vm], ref[k][vm]), (it, cr, k)
+                for k in ("stress11Weak", "stress22Weak", "stress12Weak"):
+                    assert np.array_equal(wk[k][:nC], ref[k][:nC]), (it, cr, k)
+            else:
+                _compare(mesh, step, ref, out)
+    finally:
+        solver.destroy()
+
+
 def common_mesh(kind):
     import common
     return common.mesh_case(kind)
