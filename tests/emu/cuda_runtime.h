@@ -256,7 +256,17 @@ static inline const char *cudaGetErrorString(cudaError_t) { return "emulation"; 
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
-static inline cudaError_t cudaMalloc(void **p, size_t n) { *p = calloc(n ? n : 1, 1); return *p ? cudaSuccess : 2; }
+/* cudaMalloc does not clear memory.  IR_EMU_POISON=1 fills every allocation with 0xFF bytes (NaN as a double, -1 as an int):
+ * code that counts on fresh device memory being zero gives wrong results here instead of passing by luck. */
+static inline cudaError_t cudaMalloc(void **p, size_t n)
+{
+    *p = calloc(n ? n : 1, 1);
+    if (*p) {
+        static const int poison = [] { const char *e = getenv("IR_EMU_POISON"); return (e && e[0] == '1') ? 1 : 0; }();
+        if (poison) memset(*p, 0xFF, n ? n : 1);
+    }
+    return *p ? cudaSuccess : 2;
+}
 static inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }

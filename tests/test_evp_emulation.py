@@ -8,7 +8,8 @@ reference-executed fixtures).
 
 What this adds to the GPU legs: it runs in the build container (where there is no device), so a change of a kernel, of
 the launch sequence or of the ABI meets the oracle before any GPU time is spent; IR_EMU_ORDER=reverse runs blocks and
-threads last to first (a result that changes would be a race on the device); and an AddressSanitizer build reports any
+threads last to first (a result that changes would be a race on the device) and fills fresh device memory with 0xFF
+bytes instead of zeros (IR_EMU_POISON=1); and an AddressSanitizer build reports any
 access past the end of a device array (device memory is plain calloc memory of exactly the requested size).
 What it does not: timing, the memory model, the peer-to-peer exchange and more than one rank (refused by the emulated
 runtime), the device's own libm (exp() here is the host's).
@@ -126,8 +127,11 @@ def test_child_run_with_blocks_and_threads_in_reverse_order():
     the cooperative launch are resumed last to first.  The results must still be the oracle's, bit for bit -- a kernel
     whose threads depend on one another within a launch (a race on the device) would not survive both orders.  That
     covers the two fused kernels with their shared-memory phases, the persistent kernel with its grid barrier, the
-    tile / vertex-block compaction and the pre- / post-subcycle kernels."""
-    r = _child(dict(IR_EMU_ORDER="reverse"), 900)
+    tile / vertex-block compaction and the pre- / post-subcycle kernels.
+    The same child also runs with IR_EMU_POISON=1: every cudaMalloc'ed byte starts as 0xFF (NaN as a double, -1 as an int)
+    instead of calloc's zero, so anything that counts on fresh device memory being clear shows here (cudaMalloc does not
+    clear memory on the device either)."""
+    r = _child(dict(IR_EMU_ORDER="reverse", IR_EMU_POISON="1"), 900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert " passed" in r.stdout and "failed" not in r.stdout
 

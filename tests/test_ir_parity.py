@@ -264,7 +264,8 @@ def test_emulated_kernels_are_clean_under_address_sanitizer(tmp_path):
     lib = str(tmp_path / "libir_emu_asan.so")
     subprocess.run(["g++", "-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer", "-ffp-contract=off", "-std=c++17",
                     "-fPIC", "-shared", "-x", "c++", "-Wno-unknown-pragmas", "-I", EMU_DIR, "-o", lib, SRC], check=True)
-    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0")
+    # IR_EMU_POISON: fresh "device" memory holds 0xFF bytes, not zeros (cudaMalloc does not clear memory either)
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0", IR_EMU_POISON="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_ir_asan_worker.py"), lib], env=env, capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0 and "AddressSanitizer" not in r.stderr, r.stderr[-3000:]
