@@ -189,7 +189,10 @@ static void emu_launch_grid(dim3 grid, dim3 block, size_t smemBytes, unsigned ch
     char *stacks = (char *)malloc(total * stackBytes);
     unsigned char *smem = (unsigned char *)aligned_alloc(128, smemPitch * nb + 128);
     if (!stacks || !smem) abort();
-    memset(smem, 0, smemPitch * nb + 128);
+    {   /* shared memory of a fresh block is not clear on a device either: 0xFF bytes under IR_EMU_POISON=1 */
+        const char *e = getenv("IR_EMU_POISON");
+        memset(smem, (e && e[0] == '1') ? 0xFF : 0, smemPitch * nb + 128);
+    }
     emu_gfibers.assign(total, EmuGridFiber());
     std::function<void()> fn = body;
     emu_body = &fn;
