@@ -24,8 +24,10 @@
 #define __constant__ static
 #define __ldcg(p) (*(p))
 
-struct double2 { double x, y; };
-struct int2 { int x, y; };
+/* aligned like the device's vector types: a misaligned double2 / int2 access faults on a GPU and is reported by
+ * -fsanitize=alignment in the AddressSanitizer build (evp_emu.library(asan=True)) */
+struct alignas(16) double2 { double x, y; };
+struct alignas(8) int2 { int x, y; };
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
 static inline int2 make_int2(int x, int y) { int2 r; r.x = x; r.y = y; return r; }
 

@@ -140,7 +140,9 @@ def test_child_run_with_blocks_and_threads_in_reverse_order():
 def test_child_run_under_address_sanitizer():
     """Device-memory bounds where there is no device: the library built with -fsanitize=address, every "device" buffer a
     calloc of exactly the requested size (evp_dev_alloc -> cudaMalloc -> calloc), so an index past the end of a device
-    array -- in a kernel, a layout transform or a copy -- aborts the child."""
+    array -- in a kernel, a layout transform or a copy -- aborts the child.  The same build carries
+    -fsanitize=alignment with double2 / int2 aligned as on the device (16 / 8 bytes): a vector access at a misaligned
+    address, which faults on a GPU and works silently on x86, aborts it too."""
     asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
     if not os.path.isabs(asan) or not os.path.exists(asan):
         pytest.skip("libasan is not installed")
