@@ -25,7 +25,7 @@
 #define __ldcg(p) (*(p))
 
 /* aligned like the device's vector types: a misaligned double2 / int2 access faults on a GPU and is reported by
- * -fsanitize=alignment in the AddressSanitizer build (evp_emu.library(asan=True)) */
+ * -fsanitize=undefined in the AddressSanitizer build (evp_emu.library(asan=True)) */
 struct alignas(16) double2 { double x, y; };
 struct alignas(8) int2 { int x, y; };
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }

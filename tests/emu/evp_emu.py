@@ -145,13 +145,13 @@ def library(asan=False):
              "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-unused-variable", "-Wno-sign-compare",
              "-I", os.path.join(HERE, "evp"), "-I", os.path.join(BUILD, "csrc")]
     if asan:
-        flags += ["-fsanitize=address", "-fsanitize=alignment", "-fno-sanitize-recover=alignment", "-fno-omit-frame-pointer"]
+        flags += ["-fsanitize=address", "-fsanitize=undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer"]
     # one compiler process per translation unit, then the link
     objs = [c[:-4] + ("_asan.o" if asan else ".o") for c in cpps]
     procs = [subprocess.Popen(["g++"] + [f for f in flags if f != "-shared"] + ["-c", "-o", o, c]) for c, o in zip(cpps, objs)]
     if any(p.wait() != 0 for p in procs):
         raise RuntimeError("the emulated EVP library does not compile")
-    subprocess.run(["g++", "-shared"] + (["-fsanitize=address", "-fsanitize=alignment"] if asan else []) + ["-o", out] + objs + ["-ldl"],
+    subprocess.run(["g++", "-shared"] + (["-fsanitize=address", "-fsanitize=undefined"] if asan else []) + ["-o", out] + objs + ["-ldl"],
                    check=True)
     return out
 

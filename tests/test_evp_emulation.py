@@ -141,8 +141,9 @@ def test_child_run_under_address_sanitizer():
     """Device-memory bounds where there is no device: the library built with -fsanitize=address, every "device" buffer a
     calloc of exactly the requested size (evp_dev_alloc -> cudaMalloc -> calloc), so an index past the end of a device
     array -- in a kernel, a layout transform or a copy -- aborts the child.  The same build carries
-    -fsanitize=alignment with double2 / int2 aligned as on the device (16 / 8 bytes): a vector access at a misaligned
-    address, which faults on a GPU and works silently on x86, aborts it too."""
+    -fsanitize=undefined (no recovery) with double2 / int2 aligned as on the device (16 / 8 bytes): a vector access at a
+    misaligned address -- a fault on a GPU, silent on x86 --, a signed overflow in an index expression, an out-of-range
+    shift or an index past a fixed-size local array aborts it too."""
     asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
     if not os.path.isabs(asan) or not os.path.exists(asan):
         pytest.skip("libasan is not installed")
