@@ -256,13 +256,13 @@ def test_emulated_kernels_do_not_depend_on_the_thread_order():
 
 def test_emulated_kernels_are_clean_under_address_sanitizer(tmp_path):
     """Device-memory bounds, checked where there is no device: the kernels compiled for the host with
-    -fsanitize=address, every "device" buffer a calloc of exactly the requested size."""
+    -fsanitize=address,undefined (no recovery), every "device" buffer a calloc of exactly the requested size, poisoned."""
     import sys
     asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
     if not os.path.isabs(asan) or not os.path.exists(asan):
         pytest.skip("libasan is not installed")
     lib = str(tmp_path / "libir_emu_asan.so")
-    subprocess.run(["g++", "-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer", "-ffp-contract=off", "-std=c++17",
+    subprocess.run(["g++", "-O1", "-g", "-fsanitize=address", "-fsanitize=undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer", "-ffp-contract=off", "-std=c++17",
                     "-fPIC", "-shared", "-x", "c++", "-Wno-unknown-pragmas", "-I", EMU_DIR, "-o", lib, SRC], check=True)
     # IR_EMU_POISON: fresh "device" memory holds 0xFF bytes, not zeros (cudaMalloc does not clear memory either)
     env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0", IR_EMU_POISON="1")
