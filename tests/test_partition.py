@@ -170,3 +170,55 @@ def test_cell_exchange_lists_are_consistent(kind, n_parts, n_halos):
             theirs = qsidx[qsoff[kk]:qsoff[kk + 1]] - 1
             assert np.array_equal(b.indexToCellID[mine], blocks[q].indexToCellID[theirs])
             assert np.all(b.cellOwner[mine] == q)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_cell_assignments_reproduce_the_single_block_run(seed):
+    """Any cell-to-rank assignment must do -- the reference takes whatever graph.info.part.N holds: every cell drawn at
+    random, a partition with a tenth of its cells reassigned, a part of two cells, index runs of random lengths (some
+    empty).  Blocks, halo lists and the decomposed run against the single-block oracle, bit for bit.  (144 seeds when this
+    was written: no difference.)"""
+    import oracle
+    rng = np.random.default_rng(31000 + seed)
+    mesh, var = common.mesh_case(["hex20", "ico3", "quad40"][seed % 3])
+    nC, nV = mesh.nCells, mesh.nVertices
+    n_parts = int(rng.integers(2, 7))
+    mode = seed % 4
+    if mode == 0:
+        part = rng.integers(0, n_parts, nC)
+    elif mode == 1:
+        part = partition.partition_cells(mesh, n_parts, "rcb").copy()
+        flip = rng.uniform(size=nC) < 0.1
+        part[flip] = rng.integers(0, n_parts, int(flip.sum()))
+    elif mode == 2:
+        part = partition.partition_cells(mesh, n_parts - 1, "block").copy() if n_parts > 2 else np.zeros(nC, int)
+        part[rng.integers(0, nC, 2)] = n_parts - 1
+    else:
+        part = np.searchsorted(np.sort(rng.integers(0, nC, n_parts - 1)), np.arange(nC), side="right")
+    part = np.asarray(part, dtype=np.int64)
+    step, opts = common.step_case(mesh)
+    step["solveStress"][:nC][rng.uniform(size=nC) < 0.2] = 0
+    step["solveVelocity"][:nV][rng.uniform(size=nV) < 0.2] = 0
+    n_sub = int(rng.integers(2, 6))
+    ref = common.run_oracle(mesh, var, step, opts, n_sub)
+    blocks = [partition.build_block(mesh, part, r, None) for r in range(n_parts)]
+    requests = {r: partition.halo_requests(b) for r, b in enumerate(blocks)}
+    lists = [partition.exchange_lists(b, requests) for b in blocks]
+    bvars = [oracle.init_variational(b) if b.nCells > 0 else None for b in blocks]
+    bsteps = [partition.restrict_step(b, step, nC, nV) for b in blocks]
+    for _ in range(n_sub):
+        for b, v, s in zip(blocks, bvars, bsteps):
+            if b.nCells > 0:
+                oracle.subcycle_velocity_solver(b, v, s, dict(opts, nVerticesSolve=int(b.nVerticesSolve)), 1)
+        common.exchange_halos(bsteps, lists)
+    out = {k: np.zeros_like(step[k]) for k in common.COMPARE_CELL + common.COMPARE_VERTEX}
+    for b, s in zip(blocks, bsteps):
+        for k in common.COMPARE_CELL:
+            partition.scatter_owned(b, s[k], out[k], "cell")
+        for k in common.COMPARE_VERTEX:
+            partition.scatter_owned(b, s[k], out[k], "vertex")
+    cm, vm = common.masks_for(mesh, step)
+    for k in common.COMPARE_CELL:
+        assert np.array_equal(out[k][cm], ref[k][cm]), k
+    for k in common.COMPARE_VERTEX:
+        assert np.array_equal(out[k][vm], ref[k][vm]), k
