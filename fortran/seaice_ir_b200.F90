@@ -361,7 +361,7 @@ contains
 
     ! config_conservation_check / config_monotonicity_check (:2574, :2590).  Conservation in mode 2: the
     ! library computes this block's sums, check_tracer_conservation (:8126) keeps adding the ranks and testing.
-    ! Monotonicity is tested by the library (every bound it needs lies within the two halo layers).
+    ! Monotonicity is tested by the library (every bound it needs lies within the halo layers check_halo_layer_number asks for).
     call MPAS_pool_get_config(block % configs, 'config_conservation_check', configConservationCheck)
     call MPAS_pool_get_config(block % configs, 'config_monotonicity_check', configMonotonicityCheck)
     consMode = 0

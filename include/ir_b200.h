@@ -138,7 +138,7 @@ int ir_run(ir_handle *h, int nTracers, const ir_tracer_desc *tracers, const doub
  *   monotonicity  for every tracer with a parent, the range of the old values over a cell and its edge neighbours
  *                 (tracer_local_min_max :8268), widened by one more ring, against the new value
  *                 (check_tracer_monotonicity :8416): outside by more than 1e-11 * max(1, |bound|) returns
- *                 IR_ERR_MONOTONICITY.  Needs the two halo layers the scheme itself requires (:829).
+ *                 IR_ERR_MONOTONICITY.  Needs the halo layers the scheme itself requires (two; three on quadrilaterals, :829-852).
  * The transported fields are the same with and without the checks.  0 / 0 switches them off again. */
 int ir_set_checks(ir_handle *h, int conservation, int monotonicity);
 

@@ -106,3 +106,57 @@ def test_device_blocks_reproduce_the_single_block_run(lib_path):
             s.destroy()
     for a, g in zip(single, gathered):
         assert np.array_equal(a.array[:mesh.nCells], g.array[:mesh.nCells]), a.name
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 5, 8])
+def test_random_cell_assignments_reproduce_the_single_block_run(seed):
+    """Blocks of ANY cell-to-rank assignment (a partition with scattered cells reassigned, index runs, every cell at
+    random), with the halo layers check_halo_layer_number asks for: two on vertexDegree-3 meshes, THREE on quadrilaterals
+    (incremental_remap.F:848-852 -- a diagonal source cell's gradient reaches three edge steps from the owned cell; with
+    two layers the scattered assignments of seeds 5 and 8 differ from the single-block run, as they should).  Oracle blocks
+    + tracer halo update against the single block, bit for bit; 60 seeds when this was written."""
+    rng = np.random.default_rng(41000 + seed)
+    kind = ["hex16", "ico3", "quad16"][seed % 3]
+    mesh, irf, geom = case(kind)
+    nC = mesh.nCells
+    n_parts = int(rng.integers(2, 5))
+    mode = seed % 3
+    if mode == 0:
+        part = partition.partition_cells(mesh, n_parts).copy()
+        flip = rng.uniform(size=nC) < 0.08
+        part[flip] = rng.integers(0, n_parts, int(flip.sum()))
+    elif mode == 1:
+        part = np.searchsorted(np.sort(rng.integers(1, nC - 1, n_parts - 1)), np.arange(nC), side="right")
+    else:
+        part = rng.integers(0, n_parts, nC)
+    part = np.asarray(part, dtype=np.int64)
+    tracers = _random_state(mesh, rng, n_cat=int(rng.integers(1, 3)), n_ice=int(rng.integers(1, 3)), n_snow=int(rng.integers(0, 2)))
+    u, v = smooth_divergent_velocity(mesh, geom, cfl=rng.uniform(0.1, 0.5))
+
+    def decomposed(n_halos):
+        blocks = [partition.build_block(mesh, part, r, n_halos) for r in range(n_parts)]
+        birfs = [partition.restrict_ir(b, mesh, irf) for b in blocks]
+        gathered = clone(tracers)
+        btr = [[ir.Tracer(t.name, partition.restrict_field(b, t.array, mesh.nCells, mesh.nVertices), t.parent, t.volume_like)
+                for t in tracers] for b in blocks]
+        live = [b.nCellsSolve > 0 for b in blocks]
+        bgeom = [ir.init_geometry(b, f, n_cells_solve=b.nCellsSolve, check=False) if ok else None
+                 for b, f, ok in zip(blocks, birfs, live)]
+        for _ in range(2):
+            for b, f, g, tr, ok in zip(blocks, birfs, bgeom, btr, live):
+                if ok:
+                    ir.run(b, f, g, tr, partition.restrict_field(b, u, mesh.nCells, mesh.nVertices),
+                           partition.restrict_field(b, v, mesh.nCells, mesh.nVertices), 3600.0, n_cells_solve=b.nCellsSolve,
+                           check=False)
+            _halo_update(mesh, blocks, btr, gathered)
+        return gathered
+
+    single = clone(tracers)
+    for _ in range(2):
+        ir.run(mesh, irf, geom, single, u, v, 3600.0)
+    quads = int(mesh.vertexDegree) == 4
+    for a, g in zip(single, decomposed(3 if quads else 2)):
+        assert np.array_equal(a.array[:nC], g.array[:nC]), a.name
+    if quads and seed in (5, 8):
+        two = decomposed(2)
+        assert not all(np.array_equal(a.array[:nC], g.array[:nC]) for a, g in zip(single, two))
