@@ -222,3 +222,39 @@ def test_random_cell_assignments_reproduce_the_single_block_run(seed):
         assert np.array_equal(out[k][cm], ref[k][cm]), k
     for k in common.COMPARE_VERTEX:
         assert np.array_equal(out[k][vm], ref[k][vm]), k
+
+
+def test_weak_strain_variational_divergence_is_rank_count_dependent_in_the_reference():
+    """config_strain_scheme = 'weak' with config_stress_divergence_scheme = 'variational' is NOT decomposition-invariant in
+    the reference: interpolate_strains_weak_to_variational fills strain11/22/12Vertex for iVertex <= nVerticesSolve only
+    (velocity_solver.F:2933) and nothing updates their halo (Registry.xml:3769-3771 are never exchanged), so an owned
+    cell reads a stale vertex strain at every vertex another rank owns.  The oracle restates the routine as written, block
+    by block; this test pins that behaviour (a decomposed run of this mix differs from the single-block run, starting at
+    the block boundary) so that nobody 'fixes' it on one side only.  The weak / weak pair above and every
+    variational configuration are invariant."""
+    from mpas_seaice_b200 import weakmesh
+    mesh, var = common.mesh_case("hex20")
+    gweak = weakmesh.weak_fields(mesh)
+    step, opts = common.step_case(mesh)
+    opts = dict(opts, strain_scheme="weak", stress_divergence_scheme="variational")
+    nsub = 3
+    ref = common.run_oracle(mesh, dict(var, weak=gweak), step, opts, nsub)
+    part, blocks, lists = common.make_blocks(mesh, 2, "block", n_halos=2)
+    bsteps = [partition.restrict_step(b, step, mesh.nCells, mesh.nVertices) for b in blocks]
+    bvars = []
+    for b in blocks:
+        v = oracle.init_variational(b)
+        v["weak"] = partition.restrict_weak(b, mesh, gweak)
+        bvars.append(v)
+    for _ in range(nsub):
+        for b, v, s in zip(blocks, bvars, bsteps):
+            oracle.subcycle_velocity_solver(b, v, s, dict(opts, nVerticesSolve=int(b.nVerticesSolve)), 1)
+        common.exchange_halos(bsteps, lists)
+    differing, total = 0, 0
+    for r, (b, s) in enumerate(zip(blocks, bsteps)):
+        nCs = int(b.nCellsSolve)
+        gc = b.indexToCellID[:nCs].astype(np.int64) - 1
+        bad = np.any(s["stress11"][:nCs] != ref["stress11"][gc], axis=1)
+        differing += int(bad.sum())
+        total += nCs
+    assert 0 < differing < total            # next to the block boundary, spreading a ring per subcycle; the far side is untouched
