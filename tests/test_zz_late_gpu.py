@@ -379,6 +379,81 @@ def test_precompute_on_distorted_cells(evp_lib, seed):
         assert np.array_equal(np.ascontiguousarray(a[:nC]).view(np.int64), np.ascontiguousarray(var[k][:nC]).view(np.int64)), k
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(4))
+def test_random_switches_ice_shelves_and_categories(evp_lib, seed):
+    """Three resident steps with the pre-subcycle's namelist switches (air stress, surface tilt, geostrophic or
+    sea-surface-height tilt), an ice-shelf mask and 1-3 thickness categories (evp_aggregate) drawn at random, the cover
+    redrawn every step.  132 seeds on the emulated library when this was written: all bit-identical."""
+    import test_gpu_prepost as P
+    from mpas_seaice_b200 import host, synthetic
+    rng = np.random.default_rng(61000 + seed)
+    mesh, var = common_mesh(["hex20", "ico3", "quad40", "ico4"][seed % 4])
+    base = P._state(mesh, "B" if mesh.on_a_sphere else "square")
+    nC, nV, M = mesh.nCells, mesh.nVertices, mesh.maxEdges
+    interior = variational_init.interior_vertex(mesh)
+    _, opts = synthetic.pre_subcycle(mesh, base, 3600.0)
+    sw = dict(use_air_stress=bool(rng.uniform() < 0.7), use_surface_tilt=bool(rng.uniform() < 0.7),
+              geostrophic_surface_tilt=bool(rng.uniform() < 0.6))
+    land = land_vertex = None
+    if seed % 2 == 0:
+        land = np.zeros(nC + 1, np.int32)
+        land[:nC] = rng.uniform(size=nC) < rng.uniform(0.05, 0.4)
+        land_vertex = variational_init.land_ice_mask_vertex(mesh, land)
+    n_cat = int(rng.integers(1, 4))
+    solver = host.EvpSolver(mesh, var, opts)
+    solver.set_mesh_ext(mesh, interior, **({"land_ice_mask_vertex": land_vertex} if land is not None else {}))
+    prev = dict(uVelocity=np.zeros(nV + 1), vVelocity=np.zeros(nV + 1), solveVelocityPrevious=np.zeros(nV + 1, dtype=np.int32),
+                stress11=np.zeros((nC + 1, M)), stress22=np.zeros((nC + 1, M)), stress12=np.zeros((nC + 1, M)))
+    try:
+        for it in range(3):
+            w = rng.uniform(0.1, 1.0, n_cat)
+            w /= w.sum()
+            area = np.where(rng.uniform(size=nC) < rng.uniform(0.2, 1.0), rng.uniform(0.2, 1.0, nC), 0.0)
+            a, vi, vs = (np.zeros((nC + 1, n_cat)) for _ in range(3))
+            for k in range(n_cat):
+                a[:nC, k] = area * w[k]
+                vi[:nC, k] = area * w[k] * rng.uniform(0.3, 3.0, nC)
+                vs[:nC, k] = 0.1 * vi[:nC, k]
+            A, VI, VS, mass = oracle.aggregate_mass_and_area(a, vi, vs)
+            state = dict(base, iceAreaCell=A, iceVolumeCell=VI, snowVolumeCell=VS)
+            forcing = {}
+            if not sw["geostrophic_surface_tilt"]:
+                forcing = dict(seaSurfaceTiltU=1e-6 * rng.uniform(-1, 1, nC + 1), seaSurfaceTiltV=1e-6 * rng.uniform(-1, 1, nC + 1))
+                state.update(forcing)
+            kw = dict(sw, **(dict(land_ice_mask=land, land_ice_mask_vertex=land_vertex) if land is not None else {}))
+            ref_step = oracle.pre_subcycle(mesh, state, 3600.0, prev=prev, **kw)
+            solver.aggregate(a.copy(), vi.copy(), vs.copy(), hibler_strength=False)
+            agg = solver.fetch_aggregate(ice_pressure=False)
+            for k, want in (("iceAreaCell", A), ("iceVolumeCell", VI), ("snowVolumeCell", VS), ("totalMassCell", mass)):
+                assert np.array_equal(agg[k][:nC], want[:nC]), (it, k)
+            cells = dict({k: np.ascontiguousarray(state[k], dtype=np.float64)
+                          for k in ("uOceanVelocity", "vOceanVelocity", "uAirVelocity", "vAirVelocity", "airDensity")},
+                         iceAreaCellInitial=agg["iceAreaCell"], iceAreaCell=agg["iceAreaCell"], totalMassCell=agg["totalMassCell"],
+                         icePressure=oracle.hibler_strength_unmasked(state, nC), **forcing)
+            if land is not None:
+                cells["landIceMask"] = land
+            n_sub = int(rng.integers(1, 6))
+            solver.pre_subcycle(cells, cold_start=(host.START_FIRST_STEP if it == 0 else host.START_RESIDENT), **sw)
+            got_pre = solver.fetch_pre()
+            for k, n in (("solveStress", nC), ("solveVelocity", nV), ("solveVelocityPrevious", nV)):
+                assert np.array_equal(got_pre[k][:n], ref_step[k][:n]), (it, k)
+            vm = ref_step["solveVelocity"][:nV] == 1
+            for k in ("airStressVertexU", "surfaceTiltForceU", "surfaceTiltForceV", "oceanStressU", "totalMassVertexfVertex"):
+                assert np.array_equal(got_pre[k][:nV][vm], ref_step[k][:nV][vm]), (it, k)
+            oracle.subcycle_velocity_solver(mesh, var, ref_step, opts, n_sub)
+            solver.run_subcycles(n_sub)
+            ref = P._post_reference(mesh, ref_step, opts, interior)
+            got = solver.post_subcycle(names=host.POST_FIELDS_VARIATIONAL)
+            for k in ("divergence", "shear", "ridgeConvergence", "ridgeShear", "oceanStressCellU", "oceanStressCellV"):
+                assert np.array_equal(got[k][:nC], ref[k][:nC]), (it, k)
+            for k in ("uVelocity", "vVelocity"):
+                assert np.array_equal(got[k][:nV], ref[k][:nV]), (it, k)
+            prev = {k: ref_step[k] for k in ("uVelocity", "vVelocity", "stress11", "stress22", "stress12", "solveVelocityPrevious")}
+    finally:
+        solver.destroy()
+
+
 def common_mesh(kind):
     import common
     return common.mesh_case(kind)
